@@ -1,0 +1,551 @@
+"""ctypes binding of the CPU ORACLE (oracle/libopm_oracle.so).
+
+TEST INFRASTRUCTURE ONLY.  May be imported from tests/, __graft_entry__.smoke() and the
+cpu_baseline / --impl reference legs of bench.py.  The product package (opossum_b200) never
+imports this module.
+
+The arithmetic lives in opm_oracle.c (a C restatement of the reference, every function citing
+the reference file:line).  This file only marshals arrays and mirrors the reference's *control
+flow* that is O(#nodes): the node -> surface builders, `pass_through_surface`, the ray-trace
+walk and the ghost-focus pass loop (see oracle/scene.py).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+from pathlib import Path
+
+import numpy as np
+
+_HERE = Path(__file__).resolve().parent
+_LIB_PATH = _HERE / "libopm_oracle.so"
+
+
+def build(force: bool = False) -> Path:
+    """Compile oracle/libopm_oracle.so with the committed Makefile (gcc only)."""
+    src = _HERE / "opm_oracle.c"
+    hdr = _HERE / "opm_oracle.h"
+    if force or not _LIB_PATH.exists() or _LIB_PATH.stat().st_mtime < max(src.stat().st_mtime, hdr.stat().st_mtime):
+        env = dict(os.environ)
+        env.pop("CC", None)
+        subprocess.run(["make", "-C", str(_HERE), "-B" if force else "-s"], check=True, env=env,
+                       stdout=subprocess.DEVNULL)
+    return _LIB_PATH
+
+
+# ---------------------------------------------------------------------------
+# layouts
+# ---------------------------------------------------------------------------
+RAY_DTYPE = np.dtype(
+    [("pos", "<f8", 3), ("dir", "<f8", 3), ("e", "<f8"), ("wvl", "<f8"), ("opl", "<f8"), ("n", "<f8"),
+     ("bounces", "<u4"), ("refr", "<u4"), ("valid", "<u4"), ("id", "<u4")], align=True)
+assert RAY_DTYPE.itemsize == 96
+HIT_DTYPE = np.dtype([("x", "<f8"), ("y", "<f8"), ("z", "<f8"), ("e", "<f8"), ("bounce", "<u4"), ("id", "<u4")],
+                     align=True)
+assert HIT_DTYPE.itemsize == 40
+
+
+class Iso3(C.Structure):
+    _fields_ = [("q", C.c_double * 4), ("t", C.c_double * 3)]
+
+
+class Isometry(C.Structure):
+    """Mirror of utils/geom_transformation.rs `Isometry` (transform + cached inverse)."""
+    _fields_ = [("fwd", Iso3), ("inv", Iso3)]
+
+    @staticmethod
+    def identity() -> "Isometry":
+        o = Isometry()
+        lib().orc_iso_identity(C.byref(o))
+        return o
+
+    @staticmethod
+    def new(translation, euler_xyz=(0.0, 0.0, 0.0)) -> "Isometry":
+        """Isometry::new(translation [m], axes_angles [rad]) geom_transformation.rs:44-72."""
+        o = Isometry()
+        lib().orc_iso_new((C.c_double * 3)(*translation), (C.c_double * 3)(*euler_xyz), C.byref(o))
+        return o
+
+    @staticmethod
+    def new_along_z(z: float) -> "Isometry":
+        return Isometry.new((0.0, 0.0, z), (0.0, 0.0, 0.0))
+
+    @staticmethod
+    def from_view(p, direction, up) -> "Isometry":
+        o = Isometry()
+        lib().orc_iso_from_view((C.c_double * 3)(*p), (C.c_double * 3)(*direction), (C.c_double * 3)(*up), C.byref(o))
+        return o
+
+    def append(self, rhs: "Isometry") -> "Isometry":
+        o = Isometry()
+        lib().orc_iso_append(C.byref(self), C.byref(rhs), C.byref(o))
+        return o
+
+    def _apply(self, fn, v):
+        out = (C.c_double * 3)()
+        fn(C.byref(self), (C.c_double * 3)(*v), out)
+        return np.array(out[:])
+
+    def transform_point(self, p):
+        return self._apply(lib().orc_iso_transform_point, p)
+
+    def inverse_transform_point(self, p):
+        return self._apply(lib().orc_iso_inverse_transform_point, p)
+
+    def transform_vector(self, v):
+        return self._apply(lib().orc_iso_transform_vector, v)
+
+    def inverse_transform_vector(self, v):
+        return self._apply(lib().orc_iso_inverse_transform_vector, v)
+
+    def matrices(self):
+        """(rot_fwd[9], t_fwd[3], rot_inv[9], t_inv[3]) -- for cross-checking the product's 3x3 form."""
+        rf, tf, ri, ti = (C.c_double * 9)(), (C.c_double * 3)(), (C.c_double * 9)(), (C.c_double * 3)()
+        lib().orc_iso_to_matrix(C.byref(self.fwd), rf, tf)
+        lib().orc_iso_to_matrix(C.byref(self.inv), ri, ti)
+        return np.array(rf[:]), np.array(tf[:]), np.array(ri[:]), np.array(ti[:])
+
+
+GEOM_PLANE, GEOM_SPHERE, GEOM_CYLINDER, GEOM_PARABOLA = 0, 1, 2, 3
+COAT_IDEAL_AR, COAT_CONSTANT_R, COAT_FRESNEL = 0, 1, 2
+IDX_CONST, IDX_SELLMEIER1, IDX_SCHOTT, IDX_CONRADY = 0, 1, 2, 3
+MISS_STOP, MISS_IGNORE = 0, 1
+AP_NONE, AP_CIRCLE, AP_RECT, AP_POLYGON, AP_GAUSSIAN, AP_STACK = 0, 1, 2, 3, 4, 5
+
+
+class Surface(C.Structure):
+    _fields_ = [("geom", C.c_int32), ("coating", C.c_int32), ("param", C.c_double), ("coating_r", C.c_double),
+                ("iso", Isometry)]
+
+
+class IndexModel(C.Structure):
+    _fields_ = [("type", C.c_int32), ("_pad", C.c_int32), ("c", C.c_double * 6), ("wvl_lo", C.c_double),
+                ("wvl_hi", C.c_double)]
+
+    @staticmethod
+    def const(n: float) -> "IndexModel":
+        m = IndexModel(type=IDX_CONST)
+        m.c[0] = n
+        return m
+
+    @staticmethod
+    def sellmeier1(k1, k2, k3, l1, l2, l3, lo, hi) -> "IndexModel":
+        m = IndexModel(type=IDX_SELLMEIER1, wvl_lo=lo, wvl_hi=hi)
+        m.c[:] = [k1, k2, k3, l1, l2, l3]
+        return m
+
+    @staticmethod
+    def schott(a0, a1, a2, a3, a4, a5, lo, hi) -> "IndexModel":
+        m = IndexModel(type=IDX_SCHOTT, wvl_lo=lo, wvl_hi=hi)
+        m.c[:] = [a0, a1, a2, a3, a4, a5]
+        return m
+
+    @staticmethod
+    def conrady(n0, a, b, lo, hi) -> "IndexModel":
+        m = IndexModel(type=IDX_CONRADY, wvl_lo=lo, wvl_hi=hi)
+        m.c[:] = [n0, a, b, 0.0, 0.0, 0.0]
+        return m
+
+    def get_refractive_index(self, wvl: float) -> float:
+        out = C.c_double()
+        _check(lib().orc_refractive_index(C.byref(self), wvl, C.byref(out)))
+        return out.value
+
+
+class Aperture(C.Structure):
+    pass
+
+
+Aperture._fields_ = [("type", C.c_int32), ("obstruction", C.c_int32), ("p", C.c_double * 4), ("n_sub", C.c_int32),
+                     ("_pad", C.c_int32), ("tris", C.POINTER(C.c_double)), ("sub", C.POINTER(Aperture))]
+
+
+def ap_none() -> Aperture:
+    return Aperture(type=AP_NONE)
+
+
+def ap_circle(r, cx=0.0, cy=0.0, obstruction=False) -> Aperture:
+    a = Aperture(type=AP_CIRCLE, obstruction=int(obstruction))
+    a.p[:] = [r, cx, cy, 0.0]
+    return a
+
+
+def ap_rect(w, h, cx=0.0, cy=0.0, obstruction=False) -> Aperture:
+    a = Aperture(type=AP_RECT, obstruction=int(obstruction))
+    a.p[:] = [w, h, cx, cy]
+    return a
+
+
+def ap_gaussian(sx, sy, cx=0.0, cy=0.0, obstruction=False) -> Aperture:
+    a = Aperture(type=AP_GAUSSIAN, obstruction=int(obstruction))
+    a.p[:] = [sx, sy, cx, cy]
+    return a
+
+
+def ap_polygon(triangles, obstruction=False) -> Aperture:
+    """triangles: (k,3,2) array of already ear-cut triangles (the reference uses `earcutr`, construction only)."""
+    t = np.ascontiguousarray(np.asarray(triangles, dtype=np.float64).reshape(-1, 6))
+    a = Aperture(type=AP_POLYGON, obstruction=int(obstruction), n_sub=t.shape[0])
+    a._keep = t
+    a.tris = t.ctypes.data_as(C.POINTER(C.c_double))
+    return a
+
+
+def ap_stack(items, obstruction=False) -> Aperture:
+    arr = (Aperture * len(items))(*items)
+    a = Aperture(type=AP_STACK, obstruction=int(obstruction), n_sub=len(items))
+    a._keep = (arr, items)
+    a.sub = C.cast(arr, C.POINTER(Aperture))
+    return a
+
+
+class RefractStats(C.Structure):
+    _fields_ = [("n_children", C.c_uint64), ("n_hits", C.c_uint64), ("n_interactions", C.c_uint64),
+                ("rays_missed", C.c_int32), ("valid_rays_found", C.c_int32)]
+
+
+class OracleError(RuntimeError):
+    def __init__(self, code: int):
+        self.code = code
+        super().__init__(lib().orc_strerror(code).decode())
+
+
+def _check(rc: int):
+    if rc != 0:
+        raise OracleError(rc)
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is not None:
+        return _lib
+    build()
+    L = C.CDLL(str(_LIB_PATH))
+    dp = C.POINTER(C.c_double)
+    vp = C.c_void_p
+    L.orc_strerror.restype = C.c_char_p
+    L.orc_strerror.argtypes = [C.c_int]
+    L.orc_max_threads.restype = C.c_int
+    for name in ("orc_iso_transform_point", "orc_iso_inverse_transform_point", "orc_iso_transform_vector",
+                 "orc_iso_inverse_transform_vector"):
+        getattr(L, name).argtypes = [C.POINTER(Isometry), dp, dp]
+        getattr(L, name).restype = None
+    L.orc_iso_identity.argtypes = [C.POINTER(Isometry)]
+    L.orc_iso_new.argtypes = [dp, dp, C.POINTER(Isometry)]
+    L.orc_iso_append.argtypes = [C.POINTER(Isometry)] * 3
+    L.orc_iso_from_view.argtypes = [dp, dp, dp, C.POINTER(Isometry)]
+    L.orc_iso_to_matrix.argtypes = [C.POINTER(Iso3), dp, dp]
+    L.orc_find_roots_quadratic.argtypes = [C.c_double] * 3 + [dp]
+    L.orc_find_roots_quadratic.restype = C.c_int
+    L.orc_powi.argtypes = [C.c_double, C.c_int]
+    L.orc_powi.restype = C.c_double
+    L.orc_refractive_index.argtypes = [C.POINTER(IndexModel), C.c_double, dp]
+    L.orc_fresnel_reflectivity.argtypes = [dp, dp, C.c_double, C.c_double]
+    L.orc_fresnel_reflectivity.restype = C.c_double
+    L.orc_apodization_factor.argtypes = [C.POINTER(Aperture), C.c_double, C.c_double]
+    L.orc_apodization_factor.restype = C.c_double
+    L.orc_intersect.argtypes = [C.POINTER(Surface), dp, dp, dp, dp]
+    L.orc_intersect.restype = C.c_int
+    L.orc_ray_new.argtypes = [dp, dp, C.c_double, C.c_double, vp]
+    L.orc_ray_refract_on_surface.argtypes = [vp, C.POINTER(Surface), C.c_int, C.c_double, C.c_int, vp,
+                                             C.POINTER(C.c_int), vp, C.POINTER(C.c_int)]
+    L.orc_rays_refract_on_surface.argtypes = [vp, C.c_uint64, C.POINTER(Surface), C.POINTER(IndexModel), C.c_int,
+                                              C.c_int, vp, vp, C.POINTER(RefractStats), C.c_int]
+    L.orc_rays_apodize.argtypes = [vp, C.c_uint64, C.POINTER(Aperture), C.POINTER(Isometry), C.POINTER(C.c_int),
+                                   C.c_int]
+    L.orc_rays_threshold.argtypes = [vp, C.c_uint64, C.c_double, C.c_int]
+    L.orc_rays_filter_bounces.argtypes = [vp, C.c_uint64, C.c_uint64]
+    L.orc_rays_filter_bounces.restype = None
+    L.orc_rays_filter_refractions.argtypes = [vp, C.c_uint64, C.c_uint64]
+    L.orc_rays_filter_refractions.restype = None
+    L.orc_rays_filter_energy.argtypes = [vp, C.c_uint64, C.c_double]
+    L.orc_rays_split.argtypes = [vp, C.c_uint64, C.c_double, vp]
+    L.orc_rays_refract_paraxial.argtypes = [vp, C.c_uint64, C.c_double, C.POINTER(Isometry)]
+    L.orc_rays_transform.argtypes = [vp, C.c_uint64, C.POINTER(Isometry), C.c_int]
+    L.orc_rays_transform.restype = None
+    L.orc_rays_total_energy.argtypes = [vp, C.c_uint64]
+    L.orc_rays_total_energy.restype = C.c_double
+    L.orc_rays_count.argtypes = [vp, C.c_uint64, C.c_int]
+    L.orc_rays_count.restype = C.c_uint64
+    for name in ("orc_rays_centroid", "orc_rays_energy_weighted_centroid"):
+        getattr(L, name).argtypes = [vp, C.c_uint64, dp]
+    for name in ("orc_rays_beam_radius_geo", "orc_rays_beam_radius_rms", "orc_rays_energy_weighted_beam_radius_rms"):
+        getattr(L, name).argtypes = [vp, C.c_uint64, dp]
+    L.orc_rays_bounce_lvl.argtypes = [vp, C.c_uint64]
+    L.orc_rays_bounce_lvl.restype = C.c_uint32
+    L.orc_hits_bounding_box.argtypes = [vp, C.c_uint64, dp]
+    L.orc_fluence_binning.argtypes = [vp, C.c_uint64, C.c_uint64, C.c_uint64, dp, dp, dp]
+    L.orc_fluence_peak.argtypes = [dp, C.c_uint64]
+    L.orc_fluence_peak.restype = C.c_double
+    L.orc_fluence_total_energy.argtypes = [dp, C.c_uint64, C.c_uint64, dp]
+    L.orc_fluence_total_energy.restype = C.c_double
+    L.orc_grid.argtypes = [C.c_uint64, C.c_uint64, C.c_double, C.c_double, dp]
+    L.orc_grid.restype = None
+    L.orc_fibonacci_rectangle.argtypes = [C.c_uint64, C.c_double, C.c_double, dp]
+    L.orc_fibonacci_rectangle.restype = None
+    L.orc_fibonacci_ellipse.argtypes = [C.c_uint64, C.c_double, C.c_double, dp]
+    L.orc_fibonacci_ellipse.restype = None
+    L.orc_hexapolar_count.argtypes = [C.c_uint32]
+    L.orc_hexapolar_count.restype = C.c_uint64
+    L.orc_hexapolar.argtypes = [C.c_uint32, C.c_double, dp]
+    L.orc_hexapolar.restype = None
+    L.orc_energy_uniform.argtypes = [C.c_uint64, C.c_double, dp]
+    L.orc_energy_uniform.restype = None
+    L.orc_energy_general_gaussian.argtypes = [dp, C.c_uint64] + [C.c_double] * 7 + [C.c_int, dp]
+    L.orc_energy_general_gaussian.restype = None
+    L.orc_linspace.argtypes = [C.c_double, C.c_double, C.c_uint64, dp]
+    L.orc_spectrum_gaussian.argtypes = [C.c_double, C.c_double, C.c_uint64, C.c_double, C.c_double, C.c_double, dp, dp]
+    L.orc_spectrum_gaussian.restype = None
+    L.orc_rays_collimated_with_spectrum.argtypes = [dp, dp, C.c_uint64, dp, dp, C.c_uint64, vp]
+    _lib = L
+    return L
+
+
+def _dptr(a: np.ndarray):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def _vp(a: np.ndarray):
+    return C.c_void_p(a.ctypes.data)
+
+
+# ---------------------------------------------------------------------------
+# thin functional API over arrays of RAY_DTYPE
+# ---------------------------------------------------------------------------
+def max_threads() -> int:
+    return lib().orc_max_threads()
+
+
+def find_roots_quadratic(a2, a1, a0):
+    r = (C.c_double * 2)()
+    n = lib().orc_find_roots_quadratic(a2, a1, a0, r)
+    return list(r[:n])
+
+
+def fresnel(direction, normal, n1, n2) -> float:
+    return lib().orc_fresnel_reflectivity((C.c_double * 3)(*direction), (C.c_double * 3)(*normal), n1, n2)
+
+
+def apodization_factor(ap: Aperture, x: float, y: float) -> float:
+    return lib().orc_apodization_factor(C.byref(ap), x, y)
+
+
+def intersect(surf: Surface, pos, direction):
+    q, n = (C.c_double * 3)(), (C.c_double * 3)()
+    hit = lib().orc_intersect(C.byref(surf), (C.c_double * 3)(*pos), (C.c_double * 3)(*direction), q, n)
+    return (np.array(q[:]), np.array(n[:])) if hit else None
+
+
+def ray_new(pos, direction, wvl, e) -> np.ndarray:
+    """Ray::new (ray.rs:108-140) -> 1-element RAY_DTYPE array."""
+    out = np.zeros(1, dtype=RAY_DTYPE)
+    _check(lib().orc_ray_new((C.c_double * 3)(*pos), (C.c_double * 3)(*direction), wvl, e, _vp(out)))
+    return out
+
+
+def rays_from_arrays(pos, direction, e, wvl) -> np.ndarray:
+    n = len(e)
+    out = np.zeros(n, dtype=RAY_DTYPE)
+    out["pos"] = pos
+    d = np.asarray(direction, dtype=np.float64)
+    out["dir"] = d / np.sqrt((d * d).sum(axis=-1, keepdims=True))
+    out["e"], out["wvl"], out["n"], out["valid"] = e, wvl, 1.0, 1
+    out["id"] = np.arange(n, dtype=np.uint32)
+    return out
+
+
+def ray_refract_on_surface(ray: np.ndarray, surf: Surface, n2, strategy=MISS_STOP):
+    """Ray::refract_on_surface (ray.rs:580-688) on a 1-element array, in place. Returns (child|None, hit|None)."""
+    child = np.zeros(1, dtype=RAY_DTYPE)
+    hit = np.zeros(1, dtype=HIT_DTYPE)
+    hc, hh = C.c_int(), C.c_int()
+    _check(lib().orc_ray_refract_on_surface(_vp(ray), C.byref(surf), int(n2 is not None), float(n2 or 0.0), strategy,
+                                            _vp(child), C.byref(hc), _vp(hit), C.byref(hh)))
+    return (child if hc.value else None), (hit if hh.value else None)
+
+
+def rays_refract_on_surface(rays: np.ndarray, surf: Surface, idx: IndexModel | None, refraction_intended=True,
+                            strategy=MISS_STOP, n_threads=1):
+    """Rays::refract_on_surface (rays.rs:976-1047), in place. Returns (children, hits, stats)."""
+    n = len(rays)
+    children = np.zeros(max(n, 1), dtype=RAY_DTYPE)
+    hits = np.zeros(max(n, 1), dtype=HIT_DTYPE)
+    st = RefractStats()
+    _check(lib().orc_rays_refract_on_surface(_vp(rays), n, C.byref(surf), C.byref(idx) if idx is not None else None,
+                                             int(refraction_intended), strategy, _vp(children), _vp(hits),
+                                             C.byref(st), n_threads))
+    return children[: st.n_children].copy(), hits[: st.n_hits].copy(), st
+
+
+def rays_apodize(rays, ap: Aperture, iso: Isometry, n_threads=1) -> bool:
+    inv = C.c_int()
+    _check(lib().orc_rays_apodize(_vp(rays), len(rays), C.byref(ap), C.byref(iso), C.byref(inv), n_threads))
+    return bool(inv.value)
+
+
+def rays_threshold(rays, min_energy: float, n_threads=1):
+    _check(lib().orc_rays_threshold(_vp(rays), len(rays), min_energy, n_threads))
+
+
+def rays_filter_bounces(rays, max_bounces: int):
+    lib().orc_rays_filter_bounces(_vp(rays), len(rays), max_bounces)
+
+
+def rays_filter_refractions(rays, max_refr: int):
+    lib().orc_rays_filter_refractions(_vp(rays), len(rays), max_refr)
+
+
+def rays_filter_energy(rays, t: float):
+    _check(lib().orc_rays_filter_energy(_vp(rays), len(rays), t))
+
+
+def rays_split(rays, ratio: float) -> np.ndarray:
+    out = np.zeros(len(rays), dtype=RAY_DTYPE)
+    _check(lib().orc_rays_split(_vp(rays), len(rays), ratio, _vp(out)))
+    return out
+
+
+def rays_refract_paraxial(rays, f: float, iso: Isometry):
+    _check(lib().orc_rays_refract_paraxial(_vp(rays), len(rays), f, C.byref(iso)))
+
+
+def rays_transform(rays, iso: Isometry, inverse=False):
+    lib().orc_rays_transform(_vp(rays), len(rays), C.byref(iso), int(inverse))
+
+
+def total_energy(rays) -> float:
+    return lib().orc_rays_total_energy(_vp(rays), len(rays))
+
+
+def nr_of_rays(rays, valid_only=True) -> int:
+    return lib().orc_rays_count(_vp(rays), len(rays), int(valid_only))
+
+
+def _opt3(fn, rays):
+    c = (C.c_double * 3)()
+    return np.array(c[:]) if fn(_vp(rays), len(rays), c) else None
+
+
+def centroid(rays):
+    return _opt3(lib().orc_rays_centroid, rays)
+
+
+def energy_weighted_centroid(rays):
+    return _opt3(lib().orc_rays_energy_weighted_centroid, rays)
+
+
+def _opt1(fn, rays):
+    c = C.c_double()
+    return c.value if fn(_vp(rays), len(rays), C.byref(c)) else None
+
+
+def beam_radius_geo(rays):
+    return _opt1(lib().orc_rays_beam_radius_geo, rays)
+
+
+def beam_radius_rms(rays):
+    return _opt1(lib().orc_rays_beam_radius_rms, rays)
+
+
+def energy_weighted_beam_radius_rms(rays):
+    return _opt1(lib().orc_rays_energy_weighted_beam_radius_rms, rays)
+
+
+def bounce_lvl(rays) -> int:
+    return lib().orc_rays_bounce_lvl(_vp(rays), len(rays))
+
+
+def hits_from_xye(x, y, e, z=None) -> np.ndarray:
+    h = np.zeros(len(x), dtype=HIT_DTYPE)
+    h["x"], h["y"], h["e"] = x, y, e
+    if z is not None:
+        h["z"] = z
+    return h
+
+
+def fluence_binning(hits: np.ndarray, nx: int, ny: int, ranges=None):
+    """calc_fluence_with_binning (rays_hit_map.rs:330-391). Returns (map[ny,nx], (left,right,top,bottom))."""
+    m = np.zeros(nx * ny, dtype=np.float64)
+    lrtb = (C.c_double * 4)()
+    rg = (C.c_double * 4)(*ranges) if ranges is not None else None
+    _check(lib().orc_fluence_binning(_vp(hits), len(hits), nx, ny, rg, _dptr(m), lrtb))
+    return m.reshape(nx, ny).T.copy(), tuple(lrtb[:])  # column-major ny x nx -> [row=y, col=x]
+
+
+def fluence_peak(fmap: np.ndarray) -> float:
+    m = np.ascontiguousarray(fmap, dtype=np.float64).ravel()
+    return lib().orc_fluence_peak(_dptr(m), m.size)
+
+
+def fluence_total_energy(fmap: np.ndarray, lrtb) -> float:
+    ny, nx = fmap.shape
+    m = np.ascontiguousarray(fmap, dtype=np.float64).ravel()
+    return lib().orc_fluence_total_energy(_dptr(m), nx, ny, (C.c_double * 4)(*lrtb))
+
+
+# ---- sources -------------------------------------------------------------
+def grid(nx, ny, side_x, side_y) -> np.ndarray:
+    out = np.zeros((max(nx, 1) * max(ny, 1), 3))
+    lib().orc_grid(nx, ny, side_x, side_y, _dptr(out))
+    return out
+
+
+def fibonacci_rectangle(n, sx, sy) -> np.ndarray:
+    out = np.zeros((n, 3))
+    lib().orc_fibonacci_rectangle(n, sx, sy, _dptr(out))
+    return out
+
+
+def fibonacci_ellipse(n, rx, ry) -> np.ndarray:
+    out = np.zeros((n, 3))
+    lib().orc_fibonacci_ellipse(n, rx, ry, _dptr(out))
+    return out
+
+
+def hexapolar(rings, radius) -> np.ndarray:
+    out = np.zeros((lib().orc_hexapolar_count(rings), 3))
+    lib().orc_hexapolar(rings, radius, _dptr(out))
+    return out if radius != 0.0 else out[:1]
+
+
+def energy_uniform(n, total) -> np.ndarray:
+    out = np.zeros(n)
+    lib().orc_energy_uniform(n, total, _dptr(out))
+    return out
+
+
+def energy_general_gaussian(xyz, total, mu=(0.0, 0.0), sigma=(1.0, 1.0), power=1.0, theta=0.0,
+                            rectangular=False) -> np.ndarray:
+    xyz = np.ascontiguousarray(xyz, dtype=np.float64)
+    out = np.zeros(len(xyz))
+    lib().orc_energy_general_gaussian(_dptr(xyz), len(xyz), total, mu[0], mu[1], sigma[0], sigma[1], power, theta,
+                                      int(rectangular), _dptr(out))
+    return out
+
+
+def linspace(start, end, num) -> np.ndarray:
+    out = np.zeros(num)
+    _check(lib().orc_linspace(start, end, num, _dptr(out)))
+    return out
+
+
+def spectrum_gaussian(lo, hi, num, mu, fwhm, power=1.0):
+    wvl, w = np.zeros(num), np.zeros(num)
+    lib().orc_spectrum_gaussian(lo, hi, num, mu, fwhm, power, _dptr(wvl), _dptr(w))
+    return wvl, w
+
+
+def rays_collimated_with_spectrum(xyz, e_pos, wvl, w) -> np.ndarray:
+    """Rays::new_collimated_with_spectrum (rays.rs:264-297): position-major, wavelength-minor."""
+    xyz = np.ascontiguousarray(xyz, dtype=np.float64)
+    e_pos = np.ascontiguousarray(e_pos, dtype=np.float64)
+    wvl = np.ascontiguousarray(np.atleast_1d(wvl), dtype=np.float64)
+    w = np.ascontiguousarray(np.atleast_1d(w), dtype=np.float64)
+    out = np.zeros(len(xyz) * len(wvl), dtype=RAY_DTYPE)
+    _check(lib().orc_rays_collimated_with_spectrum(_dptr(xyz), _dptr(e_pos), len(xyz), _dptr(wvl), _dptr(w),
+                                                   len(wvl), _vp(out)))
+    return out

@@ -1,0 +1,532 @@
+"""Known-answer tests that PIN THE ORACLE to the reference.
+
+Every test is a transcription of one of the reference's own unit tests for the ray-propagation
+path (file:line under /root/reference/opossum/src given in each docstring).  `assert_eq!` in the
+reference is transcribed as exact equality, `assert_abs_diff_eq!` as |a-b| <= f64::EPSILON (its
+default), `assert_relative_eq!` as relative f64::EPSILON unless the test states a tolerance.
+"""
+import math
+
+import numpy as np
+import pytest
+
+from oracle import oracle as orc
+
+EPS = np.finfo(np.float64).eps
+
+
+def mm(*v):
+    """uom `millimeter!(x)`: value * 1e-3 (base unit metre)."""
+    r = tuple(x * 1.0e-3 for x in v)
+    return r[0] if len(r) == 1 else r
+
+
+def nm(x):
+    return x * 1.0e-9
+
+
+def plane(z_mm=0.0, coating=orc.COAT_IDEAL_AR, r=0.0):
+    return orc.Surface(geom=orc.GEOM_PLANE, coating=coating, coating_r=r, iso=orc.Isometry.new_along_z(mm(z_mm)))
+
+
+def sphere_at(radius, pos):
+    """Sphere::new_at_position (sphere.rs:30-41): iso = T(pos.x, pos.y, pos.z + radius)."""
+    return orc.Surface(geom=orc.GEOM_SPHERE, param=radius,
+                       iso=orc.Isometry.new((pos[0], pos[1], pos[2] + radius)))
+
+
+Z = (0.0, 0.0, 1.0)
+
+
+# ---------------------------------------------------------------- ray.rs
+def test_ray_new():
+    """ray.rs:897-927"""
+    r = orc.ray_new(mm(1.0, 2.0, 3.0), (0.0, 0.0, 2.0), nm(1053.0), 1.0)[0]
+    assert tuple(r["pos"]) == mm(1.0, 2.0, 3.0)
+    assert tuple(r["dir"]) == Z
+    assert r["opl"] == 0.0 and r["n"] == 1.0 and r["valid"] == 1 and r["bounces"] == 0 and r["refr"] == 0
+    for bad_wvl in (0.0, nm(-10.0), math.nan, math.inf, -math.inf):
+        with pytest.raises(orc.OracleError):
+            orc.ray_new((0, 0, 0), Z, bad_wvl, 1.0)
+    for bad_e in (-0.1, math.nan, math.inf):
+        with pytest.raises(orc.OracleError):
+            orc.ray_new((0, 0, 0), Z, nm(1053.0), bad_e)
+    with pytest.raises(orc.OracleError):
+        orc.ray_new((0, 0, 0), (0.0, 0.0, 0.0), nm(1053.0), 1.0)
+    orc.ray_new((0, 0, 0), Z, nm(1053.0), 0.0)  # ray.rs:948 zero energy is ok
+
+
+def test_refract_on_surface_collimated():
+    """ray.rs:1203-1290: plane z=10 mm, n 1 -> 1.5, ConstantR 0.2"""
+    s = plane(10.0, orc.COAT_CONSTANT_R, 0.2)
+    ray = orc.ray_new((0.0, 0.0, 0.0), Z, nm(1054.0), 1.0)
+    for bad in (0.9, math.nan, math.inf):
+        with pytest.raises(orc.OracleError):
+            orc.ray_refract_on_surface(ray.copy(), s, bad)
+    child, hit = orc.ray_refract_on_surface(ray, s, 1.5)
+    r, c = ray[0], child[0]
+    assert tuple(r["pos"]) == mm(0.0, 0.0, 10.0)
+    assert r["n"] == 1.5
+    assert tuple(r["dir"]) == Z
+    assert r["opl"] == mm(10.0)
+    assert r["bounces"] == 0 and r["refr"] == 1
+    assert r["e"] == (1.0 - 0.2) * 1.0
+    assert tuple(c["pos"]) == mm(0.0, 0.0, 10.0)
+    assert c["n"] == 1.0
+    assert tuple(c["dir"]) == (0.0, 0.0, -1.0)
+    assert c["opl"] == mm(10.0)
+    assert c["bounces"] == 1 and c["refr"] == 0
+    assert c["e"] == 0.2 * 1.0
+    # hit map entry: surface frame, INPUT energy, filed under the refracted ray's bounce count (ray.rs:640-654)
+    assert (hit[0]["x"], hit[0]["y"], hit[0]["z"], hit[0]["e"], hit[0]["bounce"]) == (0.0, 0.0, 0.0, 1.0, 0)
+    ray = orc.ray_new(mm(0.0, 1.0, 0.0), Z, nm(1054.0), 1.0)
+    orc.ray_refract_on_surface(ray, s, 1.5)
+    assert tuple(ray[0]["pos"]) == mm(0.0, 1.0, 10.0)
+    assert tuple(ray[0]["dir"]) == Z
+    assert ray[0]["opl"] == mm(10.0)
+    assert ray[0]["bounces"] == 0 and ray[0]["refr"] == 1
+
+
+def test_refract_on_surface_same_index():
+    """ray.rs:1291-1318: passive surface, OPL = n * sqrt(2) * z"""
+    ray = orc.ray_new((0.0, 0.0, 0.0), (0.0, 1.0, 1.0), nm(1054.0), 1.0)
+    ray["n"] = 2.0
+    orc.ray_refract_on_surface(ray, plane(10.0), None)
+    d = np.array([0.0, 1.0, 1.0]) / math.sqrt(2.0)
+    assert tuple(ray[0]["pos"]) == mm(0.0, 10.0, 10.0)
+    assert ray[0]["dir"][0] == 0.0
+    assert abs(ray[0]["dir"][1] - d[1]) <= EPS and abs(ray[0]["dir"][2] - d[2]) <= EPS
+    assert abs(ray[0]["opl"] - 2.0 * math.sqrt(2.0) * mm(10.0)) <= EPS
+    assert ray[0]["refr"] == 0  # n2 = None does not count as a refraction (ray.rs:636-638)
+
+
+def test_refract_on_surface_non_intersecting():
+    """ray.rs:1319-1346"""
+    ray = orc.ray_new((0.0, 0.0, 0.0), (0.0, 0.0, -1.0), nm(1054.0), 1.0)
+    child, hit = orc.ray_refract_on_surface(ray, plane(10.0), 1.5, orc.MISS_STOP)
+    r = ray[0]
+    assert child is None and hit is None
+    assert tuple(r["pos"]) == (0.0, 0.0, 0.0) and tuple(r["dir"]) == (0.0, 0.0, -1.0)
+    assert r["n"] == 1.0 and r["opl"] == 0.0 and r["bounces"] == 0 and r["refr"] == 0
+    assert r["valid"] == 0  # ray.rs:683 (Stop); not asserted by the reference test
+    ray = orc.ray_new((0.0, 0.0, 0.0), (0.0, 0.0, -1.0), nm(1054.0), 1.0)
+    orc.ray_refract_on_surface(ray, plane(10.0), 1.5, orc.MISS_IGNORE)
+    assert ray[0]["valid"] == 1
+
+
+def test_refract_on_surface_non_collimated():
+    """ray.rs:1347-1428: dir = (0, 0.4714045207910317, 0.8819171036881969) at 45 deg into n=1.5"""
+    s = plane(10.0)
+    ray = orc.ray_new((0.0, 0.0, 0.0), (0.0, 1.0, 1.0), nm(1054.0), 1.0)
+    orc.ray_refract_on_surface(ray, s, 1.0)
+    d = np.array([0.0, 1.0, 1.0]) / math.sqrt(2.0)
+    assert tuple(ray[0]["pos"]) == mm(0.0, 10.0, 10.0)
+    assert ray[0]["dir"][0] == 0.0
+    assert abs(ray[0]["dir"][1] - d[1]) <= EPS and abs(ray[0]["dir"][2] - d[2]) <= EPS
+    assert abs(ray[0]["opl"] - math.sqrt(2.0) * mm(10.0)) <= EPS
+    ray = orc.ray_new((0.0, 0.0, 0.0), (0.0, 1.0, 1.0), nm(1054.0), 1.0)
+    orc.ray_refract_on_surface(ray, s, 1.5)
+    assert ray[0]["bounces"] == 0 and ray[0]["refr"] == 1
+    assert tuple(ray[0]["pos"]) == mm(0.0, 10.0, 10.0)
+    assert ray[0]["dir"][0] == 0.0
+    assert abs(ray[0]["dir"][1] - 0.4714045207910317) <= EPS
+    assert abs(ray[0]["dir"][2] - 0.8819171036881969) <= EPS
+    ray = orc.ray_new((0.0, 0.0, 0.0), (1.0, 0.0, 1.0), nm(1054.0), 1.0)
+    orc.ray_refract_on_surface(ray, s, 1.5)
+    assert tuple(ray[0]["pos"]) == mm(10.0, 0.0, 10.0)
+    assert ray[0]["dir"][0] == 0.4714045207910317  # assert_eq! in the reference (ray.rs:1425)
+    assert abs(ray[0]["dir"][1]) <= EPS
+    assert abs(ray[0]["dir"][2] - 0.8819171036881969) <= EPS
+
+
+def test_refract_on_surface_total_reflection():
+    """ray.rs:1429-1458"""
+    ray = orc.ray_new((0.0, 0.0, 0.0), (0.0, 2.0, 1.0), nm(1054.0), 1.0)
+    ray["n"] = 1.5
+    child, hit = orc.ray_refract_on_surface(ray, plane(10.0), 1.0)
+    assert child is None and hit is None
+    assert tuple(ray[0]["pos"]) == mm(0.0, 20.0, 10.0)
+    t = np.array([0.0, 2.0, -1.0]) / math.sqrt(5.0)
+    assert np.all(np.abs(ray[0]["dir"] - t) <= EPS)
+    assert ray[0]["bounces"] == 1 and ray[0]["e"] == 1.0 and ray[0]["n"] == 1.5
+
+
+def test_filter_and_split():
+    """ray.rs:1459-1473, 1503-1515"""
+    ray = orc.ray_new(mm(0.0, 1.0, 0.0), Z, nm(1054.0), 1.0)
+    orc.rays_filter_energy(ray, 0.3)
+    assert ray[0]["e"] == 0.3
+    for bad in (-0.1, 1.1):
+        with pytest.raises(orc.OracleError):
+            orc.rays_filter_energy(ray, bad)
+    ray = orc.ray_new((0.0, 0.0, 0.0), Z, nm(1054.0), 1.0)
+    for bad in (1.1, -0.1):
+        with pytest.raises(orc.OracleError):
+            orc.rays_split(ray, bad)
+    sp = orc.rays_split(ray, 0.1)
+    assert ray[0]["e"] == 0.1 and sp[0]["e"] == 0.9
+    assert tuple(ray[0]["pos"]) == tuple(sp[0]["pos"]) and tuple(ray[0]["dir"]) == tuple(sp[0]["dir"])
+
+
+def test_refract_paraxial():
+    """ray.rs:1142-1202 (refract_paraxial_collimated, refract_paraxial_recollimate)"""
+    iso = orc.Isometry.identity()
+    pos = mm(1.0, 2.0, 0.0)
+    for f_mm, t in ((100.0, (-1.0, -2.0, 100.0)), (-100.0, (1.0, 2.0, 100.0))):
+        ray = orc.ray_new(pos, Z, nm(1053.0), 1.0)
+        orc.rays_refract_paraxial(ray, mm(f_mm), iso)
+        t = np.array(t) / np.sqrt(np.dot(t, t))
+        assert tuple(ray[0]["pos"]) == pos
+        assert np.all(np.abs(ray[0]["dir"] - t) <= EPS)
+        assert ray[0]["refr"] == 1
+    ray = orc.ray_new(mm(0.0, 10.0, 0.0), Z, nm(1053.0), 1.0)
+    orc.rays_refract_paraxial(ray, mm(10.0), iso)
+    assert abs(ray[0]["opl"] / 1e-3 - (-1.0 * (math.sqrt(200.0) - 10.0))) <= 10 * EPS
+    pos = mm(0.0, 100.0, 0.0)
+    ray = orc.ray_new(pos, Z, nm(1053.0), 1.0)
+    orc.rays_refract_paraxial(ray, mm(100.0), iso)
+    t = np.array([0.0, -100.0, 100.0]) / math.sqrt(20000.0)
+    assert tuple(ray[0]["pos"]) == pos and np.all(np.abs(ray[0]["dir"] - t) <= EPS)
+    pos = mm(0.0, 100.0, 100.0)
+    ray = orc.ray_new(pos, (0.0, 1.0, 1.0), nm(1053.0), 1.0)
+    orc.rays_refract_paraxial(ray, mm(100.0), iso)
+    assert tuple(ray[0]["pos"]) == pos and tuple(ray[0]["dir"]) == Z
+    ray = orc.ray_new(pos, (0.0, -1.0, 1.0), nm(1053.0), 1.0)
+    orc.rays_refract_paraxial(ray, mm(-100.0), iso)
+    assert tuple(ray[0]["pos"]) == pos and tuple(ray[0]["dir"]) == Z
+    with pytest.raises(orc.OracleError):
+        orc.rays_refract_paraxial(ray, 0.0, iso)
+
+
+def test_transformed_ray():
+    """ray.rs:1588-1651"""
+    ray = orc.ray_new((0.0, 0.0, 0.0), Z, nm(1053.0), 1.0)
+    r = ray.copy()
+    orc.rays_transform(r, orc.Isometry.new_along_z(1.0))
+    assert tuple(r[0]["pos"]) == (0.0, 0.0, 1.0) and tuple(r[0]["dir"]) == Z
+    r = ray.copy()
+    orc.rays_transform(r, orc.Isometry.new((0, 0, 0), (0.0, math.radians(90.0), 0.0)))
+    assert np.allclose(r[0]["dir"], (1.0, 0.0, 0.0), rtol=0, atol=EPS)
+    r = orc.ray_new((1.0, 1.0, 1.0), Z, nm(1053.0), 1.0)
+    orc.rays_transform(r, orc.Isometry.new((0.0, 1.0, 0.0), (0.0, 0.0, math.radians(90.0))))
+    assert abs(r[0]["pos"][0] + 1.0) <= 2 * EPS and r[0]["pos"][1] == pytest.approx(2.0, rel=EPS)
+    assert r[0]["pos"][2] == pytest.approx(1.0, rel=EPS)
+    r = ray.copy()
+    orc.rays_transform(r, orc.Isometry.new_along_z(1.0), inverse=True)
+    assert tuple(r[0]["pos"]) == (0.0, 0.0, -1.0)
+    r = ray.copy()
+    orc.rays_transform(r, orc.Isometry.new((0, 0, 0), (0.0, math.radians(90.0), 0.0)), inverse=True)
+    assert np.allclose(r[0]["dir"], (-1.0, 0.0, 0.0), rtol=0, atol=EPS)
+    r = orc.ray_new((-1.0, 2.0, 1.0), Z, nm(1053.0), 1.0)
+    orc.rays_transform(r, orc.Isometry.new((0.0, 1.0, 0.0), (0.0, 0.0, math.radians(90.0))), inverse=True)
+    assert abs(r[0]["pos"][0] - 1.0) <= 5 * EPS and r[0]["pos"][1] == pytest.approx(1.0, rel=EPS)
+
+
+# ---------------------------------------------------------------- surfaces
+def test_plane_kats():
+    """surface/plane.rs:118-165"""
+    s = plane(10.0)
+    q, n = orc.intersect(s, (0, 0, 0), Z)
+    assert tuple(q) == mm(0.0, 0.0, 10.0) and tuple(n) == (0.0, 0.0, -1.0)
+    assert orc.intersect(plane(-10.0), (0, 0, 0), Z) is None
+    q, n = orc.intersect(plane(0.0), (0, 0, 0), Z)
+    assert tuple(q) == (0.0, 0.0, 0.0) and tuple(n) == (0.0, 0.0, -1.0)
+    q, n = orc.intersect(s, mm(0.0, 1.0, 1.0), Z)
+    assert tuple(q) == mm(0.0, 1.0, 10.0) and tuple(n) == (0.0, 0.0, -1.0)
+    d = np.array([0.0, 1.0, 1.0]) / np.sqrt(2.0)  # Ray::new normalises
+    q, n = orc.intersect(s, mm(0.0, 1.0, 0.0), tuple(orc.ray_new(mm(0.0, 1.0, 0.0), (0.0, 1.0, 1.0), nm(1053.0), 1.0)[0]["dir"]))
+    assert tuple(q) == mm(0.0, 11.0, 10.0) and tuple(n) == (0.0, 0.0, -1.0)
+
+
+@pytest.mark.parametrize("radius_mm", [10.0, -10.0])
+def test_sphere_on_axis_forward(radius_mm):
+    """surface/sphere.rs:213-276"""
+    s = sphere_at(mm(radius_mm), (0.0, 0.0, 0.0))
+    q, n = orc.intersect(s, mm(0.0, 0.0, -5.0), Z)
+    assert tuple(q) == (0.0, 0.0, 0.0) and tuple(n) == (0.0, 0.0, -1.0)
+    q, _ = orc.intersect(s, mm(0.0, 0.0, -15.0), Z)
+    assert np.all(np.abs(q) <= EPS)
+    assert orc.intersect(s, mm(0.0, 0.0, 5.0), Z) is None
+    assert orc.intersect(s, mm(0.0, 0.0, 15.0), Z) is None
+
+
+@pytest.mark.parametrize("radius_mm", [10.0, -10.0])
+def test_sphere_on_axis_backward(radius_mm):
+    """surface/sphere.rs:277-366"""
+    s = sphere_at(mm(radius_mm), (0.0, 0.0, 0.0))
+    back = (0.0, 0.0, -1.0)
+    q, n = orc.intersect(s, mm(0.0, 0.0, 5.0), back)
+    assert tuple(q) == (0.0, 0.0, 0.0) and tuple(n) == (0.0, 0.0, 1.0)
+    q, _ = orc.intersect(s, mm(0.0, 0.0, 15.0), back)
+    assert np.all(np.abs(q) <= EPS)
+    assert orc.intersect(s, mm(0.0, 0.0, -5.0), back) is None
+    assert orc.intersect(s, mm(0.0, 0.0, -15.0), back) is None
+
+
+def test_sphere_collinear():
+    """surface/sphere.rs:367-402: miss, and the tangent ray that needs disc == 0 exactly (Roots::One)"""
+    s = sphere_at(mm(1.0), mm(0.0, 0.0, 10.0))
+    assert orc.intersect(s, mm(0.0, 1.1, 0.0), Z) is None
+    assert orc.intersect(s, mm(0.0, -1.1, 0.0), Z) is None
+    q, n = orc.intersect(s, mm(0.0, 1.0, 0.0), Z)
+    assert tuple(q) == mm(0.0, 1.0, 11.0) and tuple(n) == (0.0, 1.0, 0.0)
+    q, n = orc.intersect(s, mm(0.0, -1.0, -1.0), Z)
+    assert q[0] == 0.0 and abs(q[1] + 0.001) <= EPS and abs(q[2] - 0.011) <= 1000 * EPS
+    assert np.all(np.abs(n - np.array([0.0, -1.0, 0.0])) <= EPS)
+
+
+def test_parabola_kats():
+    """surface/parabola.rs:140-235"""
+    ident = orc.Isometry.identity()
+    p = orc.Surface(geom=orc.GEOM_PARABOLA, param=1.0, iso=ident)
+    q, n = orc.intersect(p, (-1.0, -1.0, -10.0), Z)
+    assert tuple(q) == (-1.0, -1.0, 0.5) and tuple(n) == (-1.0, -1.0, -2.0)
+    pn = orc.Surface(geom=orc.GEOM_PARABOLA, param=-1.0, iso=ident)
+    d = orc.ray_new((0, 0, -1.0), (0.0, 1.0, 0.75), nm(1000.0), 1.0)[0]["dir"]
+    assert orc.intersect(pn, (0.0, 0.0, -1.0), tuple(d)) is not None
+    d = orc.ray_new((0, 0, 0), (0.0, 0.5, 2.0), nm(1000.0), 1.0)[0]["dir"]
+    assert orc.intersect(p, (0.0, -0.5, -1.0), tuple(d)) is not None
+    q, n = orc.intersect(p, (0.0, -1.0, 0.0), (0.0, 1.0, 0.0))
+    assert tuple(q) == (0.0, 0.0, 0.0)
+    assert tuple(n / np.sqrt((n * n).sum())) == (0.0, 0.0, -1.0)
+    assert orc.intersect(p, (0.0, -1.0, -1.0), (0.0, 1.0, 0.0)) is None
+    assert orc.intersect(p, (0.0, 0.0, -1.0), (0.0, 0.0, -1.0)) is None
+
+
+def test_cylinder_kats():
+    """surface/cylinder.rs:170-228 (Cylinder::new takes the isometry of the cylinder axis)"""
+    s = orc.Surface(geom=orc.GEOM_CYLINDER, param=mm(1.0), iso=orc.Isometry.new_along_z(mm(10.0)))
+    for y in (0.0, 1.0):
+        q, n = orc.intersect(s, mm(0.0, y, 0.0), Z)
+        assert abs(q[0]) <= EPS and abs(q[1] - mm(y)) <= EPS and abs(q[2] - 0.009) <= EPS
+        assert np.all(np.abs(n - np.array([0.0, 0.0, -1.0])) <= EPS)
+    sb = orc.Surface(geom=orc.GEOM_CYLINDER, param=mm(1.0), iso=orc.Isometry.new_along_z(mm(-10.0)))
+    assert orc.intersect(sb, (0, 0, 0), Z) is None
+    assert orc.intersect(s, mm(1.1, 0.0, 0.0), Z) is None
+    q, n = orc.intersect(s, mm(1.0, 0.0, 0.0), Z)
+    assert tuple(q) == mm(1.0, 0.0, 10.0) and tuple(n) == (1.0, 0.0, 0.0)
+    q, n = orc.intersect(s, mm(-1.0, 0.0, 0.0), Z)
+    assert q[1] == 0.0 and abs(q[0] + 0.001) <= EPS and abs(q[2] - 0.01) <= 1000 * EPS
+    assert np.all(np.abs(n - np.array([-1.0, 0.0, 0.0])) <= EPS)
+
+
+# ---------------------------------------------------------------- coatings / index
+def test_fresnel_kats():
+    """coatings/fresnel.rs:54-83"""
+    nrm = (0.0, 0.0, -1.0)
+    assert orc.fresnel(Z, nrm, 1.0, 1.0) == 0.0
+    assert orc.fresnel(Z, nrm, 2.0, 2.0) == 0.0
+    assert abs(orc.fresnel(Z, nrm, 1.0, 1.5) - 0.04) <= EPS
+    # set_direction does not normalise (ray.rs:269-275)
+    assert abs(orc.fresnel((0.0, 1.0, 1.0), nrm, 1.0, 1.5) - 0.05023991101223595) <= EPS
+
+
+def test_constant_r_rejects_zero():
+    """coatings/constant_r.rs:22-29 (`!is_normal` rejects 0.0) -- surfaces at trace time via coatings/mod.rs:49"""
+    for bad in (0.0, -0.1, 1.1, math.nan, math.inf):
+        ray = orc.ray_new((0, 0, 0), Z, nm(1000.0), 1.0)
+        with pytest.raises(orc.OracleError):
+            orc.ray_refract_on_surface(ray, plane(10.0, orc.COAT_CONSTANT_R, bad), 1.5)
+    ray = orc.ray_new((0, 0, 0), Z, nm(1000.0), 1.0)
+    orc.ray_refract_on_surface(ray, plane(10.0, orc.COAT_CONSTANT_R, 1.0), 1.5)
+    assert ray[0]["e"] == 0.0
+
+
+HK9L = (6.14555251E-1, 6.56775017E-1, 1.02699346E+0, 1.45987884E-2, 2.87769588E-3, 1.07653051E+2)
+
+
+def test_index_models():
+    """refr_index_sellmeier1.rs:234-251, refr_index_schott.rs:251-268, refr_index_conrady.rs:121-133"""
+    lo, hi = nm(500.0), nm(2000.0)
+    m = orc.IndexModel.sellmeier1(*HK9L, lo, hi)
+    assert m.get_refractive_index(nm(1054.0)) == pytest.approx(1.5068, rel=1e-4)
+    m2 = orc.IndexModel.schott(3.26760058E+000, -2.05384566E-002, 3.51507672E-002, 7.70151348E-003,
+                               -9.08139817E-004, 7.52649555E-005, lo, hi)
+    assert m2.get_refractive_index(nm(1054.0)) == pytest.approx(1.8116, rel=1e-4)
+    m3 = orc.IndexModel.conrady(1.0, 1.0, 1.0, lo, hi)
+    assert m3.get_refractive_index(nm(1054.0)) == pytest.approx(2.7806, rel=1e-4)
+    for mod in (m, m2, m3):
+        for bad in (nm(499.0), nm(2001.0)):
+            with pytest.raises(orc.OracleError):
+                mod.get_refractive_index(bad)
+        mod.get_refractive_index(lo)          # Range is end-exclusive: start ok ...
+        with pytest.raises(orc.OracleError):  # ... end is not
+            mod.get_refractive_index(hi)
+    assert orc.IndexModel.const(1.5).get_refractive_index(nm(1.0)) == 1.5
+    with pytest.raises(orc.OracleError):      # refractive_index/mod.rs:54-58
+        orc.IndexModel.conrady(0.5, 0.0, 0.0, lo, hi).get_refractive_index(nm(1000.0))
+
+
+def test_roots_branches():
+    """roots 0.0.8 branch structure: No / One / Two ascending / linear"""
+    assert orc.find_roots_quadratic(1.0, 0.0, 1.0) == []
+    assert orc.find_roots_quadratic(1.0, -2.0, 1.0) == [1.0]
+    assert orc.find_roots_quadratic(1.0, 0.0, -1.0) == [-1.0, 1.0]
+    assert orc.find_roots_quadratic(1.0, -3.0, 2.0) == [1.0, 2.0]
+    assert orc.find_roots_quadratic(0.0, 2.0, -4.0) == [2.0]
+    assert orc.find_roots_quadratic(0.0, 0.0, 1.0) == []
+    assert orc.find_roots_quadratic(0.0, 0.0, 0.0) == [0.0]
+
+
+# ---------------------------------------------------------------- apertures
+def test_apertures():
+    """aperture.rs doc example :26-33 and tests :470-640 (circle, rect, gaussian, stack, obstruction)"""
+    c = orc.ap_circle(mm(1.0), *mm(1.0, 1.0))
+    assert orc.apodization_factor(c, *mm(1.0, 1.0)) == 1.0 and orc.apodization_factor(c, 0.0, 0.0) == 0.0
+    c0 = orc.ap_circle(1.0)
+    assert orc.apodization_factor(c0, 1.0, 0.0) == 1.0 and orc.apodization_factor(c0, 0.0, 1.0) == 1.0  # `<=` on the rim
+    assert orc.apodization_factor(c0, 1.0, 1.0) == 0.0
+    co = orc.ap_circle(1.0, obstruction=True)
+    assert orc.apodization_factor(co, 0.0, 0.0) == 0.0 and orc.apodization_factor(co, 2.0, 0.0) == 1.0
+    r = orc.ap_rect(1.0, 2.0, 1.0, 1.0)
+    assert orc.apodization_factor(r, 1.0, 1.0) == 1.0 and orc.apodization_factor(r, 0.5, 0.0) == 1.0  # corner, `<=`
+    assert orc.apodization_factor(r, 0.0, 0.0) == 0.0 and orc.apodization_factor(r, 1.6, 1.0) == 0.0
+    g = orc.ap_gaussian(1.0, 1.0)
+    assert orc.apodization_factor(g, 0.0, 0.0) == 1.0
+    assert orc.apodization_factor(g, 1.0, 0.0) == math.exp(-0.5)
+    st = orc.ap_stack([orc.ap_circle(1.0), orc.ap_rect(1.0, 1.0)])
+    assert orc.apodization_factor(st, 0.4, 0.4) == 1.0 and orc.apodization_factor(st, 0.9, 0.0) == 0.0
+    tri = orc.ap_polygon([[(0.0, 0.0), (1.0, 0.0), (0.0, 1.0)]])
+    assert orc.apodization_factor(tri, 0.25, 0.25) == 1.0 and orc.apodization_factor(tri, 0.75, 0.75) == 0.0
+
+
+# ---------------------------------------------------------------- bundles
+def _bundle(items):
+    rays = np.concatenate([orc.ray_new(p, Z, nm(1053.0), e) for p, e in items])
+    return rays
+
+
+def test_total_energy_centroid_radius():
+    """rays.rs:2019-2106"""
+    rays = _bundle([((0, 0, 0), 1.0), ((0, 0, 0), 1.0), ((0, 0, 0), 1.0)])
+    rays[2]["valid"] = 0
+    assert orc.total_energy(rays) == 2.0
+    assert orc.total_energy(rays[:0]) == 0.0
+    rays = _bundle([(mm(1.0, 2.0, 0.0), 1.0), (mm(2.0, 3.0, 0.0), 1.0), (mm(2.0, 3.0, 0.0), 1.0)])
+    rays[2]["valid"] = 0
+    assert orc.centroid(rays[:0]) is None
+    assert tuple(orc.centroid(rays)) == mm(1.5, 2.5, 0.0)
+    assert orc.beam_radius_geo(rays[:0]) is None
+    assert orc.beam_radius_geo(rays) == mm(math.sqrt(0.5))
+    rays = _bundle([(mm(1.0, 1.0, 0.0), 1.0)])
+    assert orc.beam_radius_rms(rays) == 0.0
+    rays = _bundle([(mm(1.0, 1.0, 0.0), 1.0), ((0, 0, 0), 1.0), (mm(1.0, 15.0, 0.0), 1.0)])
+    rays[2]["valid"] = 0
+    assert orc.beam_radius_rms(rays) == mm(math.sqrt(2.0) / 2.0)
+
+
+def test_energy_weighted_centroid():
+    """rays.rs:2696-2734"""
+    rays = _bundle([(mm(-1.0, 0.0, 0.0), 1.0), (mm(1.0, 0.0, 0.0), 1.0)])
+    assert tuple(orc.energy_weighted_centroid(rays)) == (0.0, 0.0, 0.0)
+    rays = _bundle([(mm(-1.0, 0.0, 0.0), 1.0), (mm(1.0, 0.0, 0.0), 0.5)])
+    c = orc.energy_weighted_centroid(rays)
+    assert c[0] / 1e-3 == pytest.approx(-1.0 / 3.0, rel=EPS) and c[1] == 0.0 and c[2] == 0.0
+    rays[1]["valid"] = 0
+    assert orc.energy_weighted_centroid(rays)[0] / 1e-3 == pytest.approx(-1.0, rel=EPS)
+    assert orc.energy_weighted_centroid(rays[:0]) is None
+    # energy-weighted rms radius is unpinned by the reference (mutants.out/missed.txt rays.rs:694,698):
+    rays = _bundle([(mm(-1.0, 0.0, 0.0), 1.0), (mm(1.0, 0.0, 0.0), 1.0)])
+    assert orc.energy_weighted_beam_radius_rms(rays) == pytest.approx(1e-3, rel=1e-15)
+
+
+def test_bundle_refract_missed_and_energy():
+    """rays.rs:2246-2286"""
+    default_surface = plane(0.0)
+    vac = orc.IndexModel.const(1.0)
+    rays = _bundle([(mm(0.0, 0.0, 1.0), 1.0)])
+    children, hits, st = orc.rays_refract_on_surface(rays, default_surface, vac, True, orc.MISS_STOP)
+    assert len(children) == 0 and st.rays_missed == 1
+    rays = _bundle([(mm(0.0, 0.0, -1.0), 1.0)])
+    s = plane(0.0, orc.COAT_CONSTANT_R, 0.2)
+    children, hits, st = orc.rays_refract_on_surface(rays, s, vac, True, orc.MISS_STOP)
+    assert orc.total_energy(rays) == 0.8 and orc.total_energy(children) == 0.2
+    assert st.n_interactions == 1 and st.n_children == 1 and st.n_hits == 1
+
+
+def test_threshold_and_apodize():
+    """rays.rs:2307-2350"""
+    empty = _bundle([((0, 0, 0), 1.0)])[:0]
+    for bad in (math.nan, math.inf):
+        with pytest.raises(orc.OracleError):
+            orc.rays_threshold(empty, bad)
+    orc.rays_threshold(empty, -0.1)
+    rays = _bundle([((0, 0, 0), 1.0), ((0, 0, 0), 0.1)])
+    orc.rays_threshold(rays, -0.1)
+    assert orc.nr_of_rays(rays) == 2
+    orc.rays_threshold(rays, 0.1)
+    assert orc.nr_of_rays(rays) == 2
+    orc.rays_threshold(rays, 0.5)
+    assert orc.nr_of_rays(rays) == 1
+    orc.rays_threshold(rays, 1.1)
+    assert orc.nr_of_rays(rays) == 0
+    rays = _bundle([((0, 0, 0), 1.0), (mm(1.0, 1.0, 0.0), 1.0)])
+    inv = orc.rays_apodize(rays, orc.ap_circle(mm(0.5)), orc.Isometry.identity())
+    assert inv and orc.total_energy(rays) == 1.0
+
+
+def test_limits():
+    """rays.rs:1386-1404: bounces `>` max, refractions `>=` max"""
+    rays = _bundle([((0, 0, 0), 1.0)] * 3)
+    rays["bounces"] = [0, 1, 2]
+    orc.rays_filter_bounces(rays, 1)
+    assert list(rays["valid"]) == [1, 1, 0]
+    rays = _bundle([((0, 0, 0), 1.0)] * 3)
+    rays["refr"] = [0, 1, 2]
+    orc.rays_filter_refractions(rays, 1)
+    assert list(rays["valid"]) == [1, 0, 0]
+
+
+# ---------------------------------------------------------------- binning
+def test_binning_kat():
+    """surface/hit_map/mod.rs:1200-1240: 51x51, centre bin = 2601.0 (both point sets, merged)"""
+    pos1 = [(-0.5, -0.5), (0.0, 0.0), (-0.5, 0.5), (0.5, 0.5), (0.5, -0.5)]
+    h = orc.hits_from_xye([p[0] for p in pos1], [p[1] for p in pos1], [1.0] * 5)
+    fmap, lrtb = orc.fluence_binning(h, 51, 51)
+    assert fmap.shape == (51, 51)
+    assert fmap[25, 25] == pytest.approx(2601.0, rel=EPS)
+    assert lrtb == (-0.5, 0.5, 0.5, -0.5)
+    r = math.sqrt(0.5)
+    pos2 = [(r, 0.0), (0.0, r), (-r, 0.0), (0.0, -r), (0.0, 0.0)]
+    h2 = orc.hits_from_xye([p[0] for p in pos1 + pos2], [p[1] for p in pos1 + pos2], [1.0] * 10)
+    fmap2, _ = orc.fluence_binning(h2, 51, 51)
+    # the reference asserts 2601.0 again although two points now sit on the centre: it only holds
+    # because the merged map spans +-sqrt(0.5): bin_area doubles, (2 J)/(2/2601) = 2601
+    assert fmap2[25, 25] == pytest.approx(2601.0, rel=4 * EPS)
+    with pytest.raises(orc.OracleError):
+        orc.fluence_binning(h[:0], 51, 51)
+    assert orc.fluence_peak(fmap) == fmap.max()
+    # corner hits drop their outside taps: sum(map)*bin_area == 5 J here because every hit sits on a node
+    assert orc.fluence_total_energy(fmap, lrtb) == pytest.approx(5.0, rel=1e-14)
+
+
+# ---------------------------------------------------------------- sources
+def test_grid_kats():
+    """position_distributions/grid.rs:119-143"""
+    p = orc.grid(2, 2, mm(1.0), mm(1.0))
+    assert [tuple(x) for x in p] == [mm(-0.5, -0.5, 0.0), mm(-0.5, 0.5, 0.0), mm(0.5, -0.5, 0.0), mm(0.5, 0.5, 0.0)]
+    assert [tuple(x) for x in orc.grid(1, 1, mm(1.0), mm(1.0))] == [(0.0, 0.0, 0.0)]
+    assert [tuple(x) for x in orc.grid(1, 2, mm(1.0), mm(1.0))] == [mm(0.0, -0.5, 0.0), mm(0.0, 0.5, 0.0)]
+
+
+def test_hexapolar_counts():
+    """position_distributions/hexapolar.rs:74-99"""
+    assert len(orc.hexapolar(1, 0.0)) == 1 and len(orc.hexapolar(0, mm(1.0))) == 1
+    for rings, n in ((1, 7), (2, 19), (6, 127), (7, 169), (255, 195841)):
+        assert len(orc.hexapolar(rings, mm(1.0))) == n
+
+
+def test_fibonacci_and_spectrum_properties():
+    """fibonacci.rs:53-65,113-126; spectral_distribution/gaussian.rs:78-96 (weights Kahan-normalised to 1)"""
+    p = orc.fibonacci_rectangle(1000, 2.0, 4.0)
+    assert np.all(np.abs(p[:, 0]) <= 1.0) and np.all(np.abs(p[:, 1]) <= 2.0) and np.all(p[:, 2] == 0.0)
+    assert tuple(p[0]) == (-1.0, -2.0, 0.0)
+    p = orc.fibonacci_ellipse(1000, 1.0, 2.0)
+    assert np.all((p[:, 0] / 1.0) ** 2 + (p[:, 1] / 2.0) ** 2 <= 1.0 + 1e-12)
+    wvl, w = orc.spectrum_gaussian(nm(950.0), nm(1150.0), 64, nm(1053.0), nm(50.0))
+    assert wvl[0] == nm(950.0) and abs(wvl[-1] - nm(1150.0)) < 1e-18 and abs(w.sum() - 1.0) < 1e-14
+    e = orc.energy_general_gaussian(orc.fibonacci_ellipse(500, 0.01, 0.01), 1.0, sigma=(0.004, 0.004), power=5.0)
+    assert abs(e.sum() - 1.0) < 1e-13 and np.all(e >= 0.0)
+    rays = orc.rays_collimated_with_spectrum(orc.grid(2, 2, 1.0, 1.0), orc.energy_uniform(4, 1.0), wvl[:3], w[:3])
+    assert len(rays) == 12 and list(rays["wvl"][:3]) == list(wvl[:3])  # position-major, wavelength-minor
+    assert rays["e"][1] == 0.25 * w[1]
