@@ -1,0 +1,342 @@
+/*
+ * opossum_b200.h -- C ABI of the B200-native ray-propagation engine.
+ *
+ * This is the drop-in boundary for OPOSSUM's ray-propagation hot path.  The reference
+ * (opossum-labs/opossum v0.6.0, pure Rust) has no FFI: its extension point for this path is the
+ * set of `Rays` bundle methods that every node's `analyze` calls through
+ * `AnalysisRayTrace::pass_through_surface` (analyzers/raytrace.rs:96-140).  Each entry point
+ * below names the reference interface it replaces (file:line under opossum/src/).  A Rust host
+ * binds these with a plain `extern "C"` block; plain pointers and sizes
+ * only, no C++/torch types.
+ *
+ * Conventions
+ *  - SI base units like the reference's `uom` quantities: metres, joules, radians.
+ *  - Every function returns an OpmStatus (0 = ok).  `opm_last_error()` gives the message of the
+ *    last failure on the calling thread; messages mirror the reference's `OpossumError` strings.
+ *  - Ownership: the caller owns every handle it creates and destroys it; the library never frees
+ *    caller memory.  Handles belong to the context (device + stream) they were created on and
+ *    are not thread-safe (the reference's analyzers are single-threaded per scenery).
+ *  - There is NO CPU fallback.  Every compute entry point fails with OPM_ERR_CUDA when no
+ *    sm_100 device / driver is present.
+ */
+#ifndef OPOSSUM_B200_H
+#define OPOSSUM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OPM_ABI_VERSION 1
+#define OPM_MAX_APERTURE_ITEMS 4
+#define OPM_MAX_PROGRAM_OPS 64
+
+typedef int32_t OpmStatus;
+enum {
+    OPM_OK = 0,
+    OPM_ERR_N2_INVALID = 1,      /* "the refractive index must be >=1.0 and finite"            ray.rs:588-592 */
+    OPM_ERR_WVL_RANGE = 2,       /* "wavelength outside valid range"                           refr_index_sellmeier1.rs:79-81 */
+    OPM_ERR_INDEX_MODEL = 3,     /* "refractive index calculated by model is <1.0 or not finite" refractive_index/mod.rs:54-58 */
+    OPM_ERR_COATING = 4,         /* "reflectivity must be within [0.0, 1.0] and finite."       coatings/constant_r.rs:23-27 */
+    OPM_ERR_APODIZE_FACTOR = 5,  /* "transmission factor must be within (0.0..=1.0)"           ray.rs:705-709 */
+    OPM_ERR_THRESHOLD = 6,       /* "threshold energy must be finite"                          rays.rs:1150-1154 */
+    OPM_ERR_HITPOINT = 7,        /* hit point energy/position not finite                       rays_hit_map.rs:59-66 */
+    OPM_ERR_SPLIT_RATIO = 8,     /* "splitting_ratio must be within [0.0;1.0]"                 ray.rs:763-767 */
+    OPM_ERR_FOCAL_LENGTH = 9,    /* "focal length must be !=0.0 and finite"                    rays.rs:944-948 */
+    OPM_ERR_EMPTY_HITMAP = 10,   /* "could not calculate bounding box"                         rays_hit_map.rs:526-531 */
+    OPM_ERR_BIN_RANGE = 11,      /* hit outside an explicit map range (the reference panics)   rays_hit_map.rs:364-374 */
+    OPM_ERR_ARG = 12,            /* invalid argument / handle */
+    OPM_ERR_CAPACITY = 13,       /* an output bundle / hit map is too small */
+    OPM_ERR_CUDA = 14            /* CUDA runtime failure (including: no device) */
+};
+
+/* ------------------------------------------------------------------------------------------
+ * Plain-old-data descriptors
+ * ---------------------------------------------------------------------------------------- */
+
+/* Host-side array-of-structs mirror of the parity fields of `struct Ray` (ray.rs:66-96).  Used only by
+ * upload/download; on the device rays live as struct-of-arrays f64 buffers. */
+typedef struct {
+    double pos[3];
+    double dir[3];
+    double e;         /* energy, J */
+    double wvl;       /* wavelength, m */
+    double opl;       /* path_length, m */
+    double n;         /* refractive_index of the medium the ray is in */
+    uint32_t bounces; /* number_of_bounces */
+    uint32_t refr;    /* number_of_refractions */
+    uint32_t valid;   /* 0 invalid, 1 valid */
+    uint32_t id;      /* index of the seed ray (not in the reference; keys unordered outputs) */
+} OpmRay;             /* 96 bytes */
+
+/* Rigid transform p' = rot * p + t (rot row-major).  `Isometry` (utils/geom_transformation.rs:27-31)
+ * keeps the transform and its cached inverse; so do we. */
+typedef struct { double rot[9]; double t[3]; } OpmIso;
+typedef struct { OpmIso fwd; OpmIso inv; } OpmIsometry;
+
+typedef enum { OPM_GEOM_PLANE = 0, OPM_GEOM_SPHERE = 1, OPM_GEOM_CYLINDER = 2, OPM_GEOM_PARABOLA = 3 } OpmGeom;
+typedef enum { OPM_COAT_IDEAL_AR = 0, OPM_COAT_CONSTANT_R = 1, OPM_COAT_FRESNEL = 2 } OpmCoating;
+typedef enum { OPM_IDX_CONST = 0, OPM_IDX_SELLMEIER1 = 1, OPM_IDX_SCHOTT = 2, OPM_IDX_CONRADY = 3 } OpmIndexType;
+typedef enum { OPM_MISS_STOP = 0, OPM_MISS_IGNORE = 1 } OpmMissedSurfaceStrategy; /* analyzers/raytrace.rs:282-293 */
+typedef enum { OPM_AP_NONE = 0, OPM_AP_CIRCLE = 1, OPM_AP_RECT = 2, OPM_AP_POLYGON = 3, OPM_AP_GAUSSIAN = 4 } OpmApertureType;
+
+/* `OpticSurface` geometry + coating (surface/optic_surface.rs:29-43, surface/geo_surface.rs:19-47).
+ * `iso` is the isometry of the GEO surface: for spheres/cylinders the frame of the centre of
+ * curvature (node_iso o T(0,0,R), nodes/lens/mod.rs:238-247). */
+typedef struct {
+    int32_t geom;        /* OpmGeom */
+    int32_t coating;     /* OpmCoating */
+    double geom_param;   /* radius of curvature (sphere, cylinder) or focal length (parabola) */
+    double coating_r;    /* ConstantR reflectivity */
+    OpmIsometry iso;
+} OpmSurface;
+
+/* `RefractiveIndexType` (refractive_index/mod.rs:20-32) */
+typedef struct {
+    int32_t type;        /* OpmIndexType */
+    int32_t _pad;
+    double c[6];         /* Const: n | Sellmeier1: k1,k2,k3,l1,l2,l3 | Schott: a0..a5 | Conrady: n0,a,b */
+    double wvl_lo, wvl_hi; /* valid range [lo, hi) in metres (ignored for Const) */
+} OpmIndexModel;
+
+/* `Aperture` (aperture.rs:66-84).  n_items = 0 is Aperture::None; is_stack = 1 multiplies the items
+ * (aperture.rs:407-416).  One level of stacking, at most OPM_MAX_APERTURE_ITEMS members. */
+typedef struct {
+    int32_t type;        /* OpmApertureType */
+    int32_t obstruction; /* ApertureType::Obstruction */
+    double p[4];         /* circle: r,cx,cy | rect: w,h,cx,cy | gaussian: sigma_x,sigma_y,cx,cy */
+} OpmApertureItem;
+typedef struct {
+    int32_t n_items;
+    int32_t is_stack;
+    int32_t stack_obstruction;
+    int32_t n_tris;          /* polygon only: number of triangles in `tris` */
+    OpmApertureItem items[OPM_MAX_APERTURE_ITEMS];
+    const double* tris;      /* HOST pointer, n_tris*6 doubles (x1,y1,x2,y2,x3,y3), ear-cut by the caller */
+} OpmAperture;
+
+/* `RayTraceConfig` (analyzers/raytrace.rs:302-323) */
+typedef struct {
+    double min_energy_per_ray;       /* default 1e-12 J */
+    uint64_t max_number_of_bounces;  /* default 1000 */
+    uint64_t max_number_of_refractions; /* default 1000 */
+    int32_t missed_surface_strategy; /* default OPM_MISS_STOP */
+    int32_t _pad;
+} OpmRayTraceConfig;
+
+/* Counters of one launch.  `rays_missed` / `valid_rays_found` drive the reference's warnings
+ * (rays.rs:1026-1031); `interactions` is the benchmark unit: one valid ray through one
+ * `refract_on_surface`. */
+typedef struct {
+    uint64_t interactions;
+    uint64_t children;       /* reflected rays emitted */
+    uint64_t hits;           /* hit-map entries recorded */
+    uint64_t missed;         /* valid rays that missed or were totally reflected */
+    uint64_t apodized;       /* rays invalidated by an aperture (rays.rs:557-573 return value != 0) */
+    uint64_t valid_out;      /* valid rays in the bundle after the call */
+    uint64_t alive_out;      /* rays in the bundle after the call (valid or not) */
+    uint32_t status_bits;    /* bit k set = OpmStatus k raised by some ray */
+    uint32_t _pad;
+} OpmTraceStats;
+
+typedef struct OpmContext OpmContext;
+typedef struct OpmRays OpmRays;        /* device ray bundle, struct-of-arrays */
+typedef struct OpmHitMap OpmHitMap;    /* device hit-point record of one surface pass (rays_hit_map.rs:43-49) */
+
+/* ------------------------------------------------------------------------------------------
+ * Fused surface-sequence program: one kernel launch runs all ops over every ray, ray state in
+ * registers, op descriptors staged in shared memory.  One op = one `Rays` method call.
+ * ---------------------------------------------------------------------------------------- */
+typedef enum {
+    OPM_OP_REFRACT = 1,    /* Rays::refract_on_surface            rays.rs:976-1047  */
+    OPM_OP_APODIZE = 2,    /* Rays::apodize                       rays.rs:557-573   */
+    OPM_OP_THRESHOLD = 3,  /* Rays::invalidate_by_threshold_energy rays.rs:1145-1162 */
+    OPM_OP_LIMITS = 4,     /* filter_by_nr_of_bounces / _refractions rays.rs:1386-1404 */
+    OPM_OP_FILTER = 5,     /* Rays::filter_energy(Constant)       rays.rs:1119-1133 */
+    OPM_OP_PARAXIAL = 6,   /* Rays::refract_paraxial              rays.rs:943-959   */
+    OPM_OP_SPLIT = 7,      /* Rays::split(Ratio)                  rays.rs:1253-1264 */
+    OPM_OP_SNAPSHOT = 8    /* copy of the bundle a detector node keeps (analyzers/raytrace.rs:186-205) */
+} OpmOpKind;
+
+enum {
+    OPM_REFRACT_EMIT_CHILDREN = 1,   /* append reflected rays to `children` (warp-aggregated atomics) */
+    OPM_REFRACT_CONTINUE_AS_CHILD = 2 /* mirror in a sequence: the reflected ray continues, rays without one leave the bundle
+                                        (refraction_intended = false, nodes/thin_mirror.rs:209-250) */
+};
+
+typedef struct {
+    OpmSurface surface;
+    OpmIndexModel index;          /* medium behind the surface; used when has_index != 0 */
+    int32_t has_index;            /* 0 = `None`: passive surface, n2 = n of the ray (ray.rs:587) */
+    int32_t refraction_intended;  /* rays.rs:979; 0 decrements the child's bounce counter (rays.rs:1016) */
+    int32_t strategy;             /* OpmMissedSurfaceStrategy */
+    int32_t flags;                /* OPM_REFRACT_* */
+    OpmHitMap* hits;              /* optional: record (surface-frame xyz, input energy, bounce) per refracted ray */
+    OpmRays* children;            /* optional: reflected bundle (appended) */
+} OpmRefractOp;
+
+typedef struct { OpmIsometry iso; OpmAperture aperture; } OpmApodizeOp; /* iso = effective_surface_iso (optic_node.rs:372-382) */
+typedef struct { double min_energy; } OpmThresholdOp;
+typedef struct { uint64_t max_bounces; uint64_t max_refractions; int32_t check_refractions; int32_t _pad; } OpmLimitsOp;
+typedef struct { double transmission; } OpmFilterOp;
+typedef struct { double focal_length; OpmIsometry iso; } OpmParaxialOp;
+typedef struct { double ratio; OpmRays* split_out; } OpmSplitOp;   /* split_out: slot-indexed copy with E*(1-ratio) */
+typedef struct { OpmRays* out; } OpmSnapshotOp;                     /* slot-indexed copy of the bundle at this point */
+
+typedef struct {
+    int32_t kind; /* OpmOpKind */
+    int32_t _pad;
+    union {
+        OpmRefractOp refract;
+        OpmApodizeOp apodize;
+        OpmThresholdOp threshold;
+        OpmLimitsOp limits;
+        OpmFilterOp filter;
+        OpmParaxialOp paraxial;
+        OpmSplitOp split;
+        OpmSnapshotOp snapshot;
+    } u;
+} OpmOp;
+
+enum {
+    OPM_TRACE_COMPACT = 1,  /* write survivors densely into `out` (warp-ballot aggregated append) instead of in place */
+    OPM_TRACE_STRICT = 2    /* kernel variant compiled without FMA contraction: reference operation order */
+};
+
+/* ------------------------------------------------------------------------------------------
+ * Entry points
+ * ---------------------------------------------------------------------------------------- */
+int32_t opm_abi_version(void);
+const char* opm_last_error(void);
+const char* opm_status_string(OpmStatus s);
+
+/* device: CUDA ordinal; stream: a cudaStream_t the caller owns, or NULL for a library-owned stream */
+OpmStatus opm_context_create(int32_t device, void* stream, OpmContext** out);
+void opm_context_destroy(OpmContext* ctx);
+OpmStatus opm_context_synchronize(OpmContext* ctx);
+void* opm_context_stream(OpmContext* ctx);
+/* number of kernels launched through this context so far (bench.py "gpu_launches") */
+uint64_t opm_context_launch_count(const OpmContext* ctx);
+
+/* host helpers mirroring utils/geom_transformation.rs (pure host math, no device needed) */
+void opm_isometry_identity(OpmIsometry* out);
+OpmStatus opm_isometry_new(const double translation[3], const double euler_xyz[3], OpmIsometry* out); /* :44-72 */
+void opm_isometry_append(const OpmIsometry* a, const OpmIsometry* b, OpmIsometry* out);              /* :216-223 */
+void opm_raytrace_config_default(OpmRayTraceConfig* out);                                             /* analyzers/raytrace.rs:315-322 */
+
+/* ---- struct Rays (rays.rs:62-73) */
+OpmStatus opm_rays_create(OpmContext* ctx, uint64_t capacity, OpmRays** out);
+void opm_rays_destroy(OpmRays* rays);
+uint64_t opm_rays_len(const OpmRays* rays);        /* slots in use (includes invalid and removed rays) */
+uint64_t opm_rays_capacity(const OpmRays* rays);
+OpmStatus opm_rays_clear(OpmRays* rays);
+OpmStatus opm_rays_reserve(OpmRays* rays, uint64_t capacity);
+OpmStatus opm_rays_upload(OpmRays* rays, const OpmRay* host, uint64_t n);                 /* Rays::from(Vec<Ray>) */
+/* struct-of-arrays upload from (pinned) host memory; opl/n/bounces/refr/valid take their `Ray::new` defaults */
+OpmStatus opm_rays_upload_soa(OpmRays* rays, const double* pos_xyz[3], const double* dir_xyz[3],
+                              const double* e, const double* wvl, uint64_t n);
+OpmStatus opm_rays_download(const OpmRays* rays, OpmRay* host, uint64_t capacity, uint64_t* n_out); /* skips removed rays */
+OpmStatus opm_rays_copy(const OpmRays* src, OpmRays* dst);                                 /* Rays::clone */
+OpmStatus opm_rays_append(OpmRays* dst, const OpmRays* src);                               /* Rays::add_rays / merge rays.rs:932,1268 */
+OpmStatus opm_rays_compact(OpmRays* rays);                    /* drop removed rays, order preserving */
+/* raw device pointer of one field ("px","py","pz","dx","dy","dz","e","wvl","opl","n","bounces","refr","id","valid") */
+void* opm_rays_field_ptr(OpmRays* rays, const char* field);
+
+/* Rays::refract_on_surface (rays.rs:976-1047) as a stand-alone call */
+OpmStatus opm_rays_refract_on_surface(OpmRays* rays, const OpmSurface* surface, const OpmIndexModel* n2_or_null,
+                                      int32_t refraction_intended, int32_t strategy,
+                                      OpmRays* reflected_out_or_null, OpmHitMap* hits_or_null, OpmTraceStats* stats);
+OpmStatus opm_rays_apodize(OpmRays* rays, const OpmAperture* aperture, const OpmIsometry* iso, int32_t* invalidated); /* rays.rs:557 */
+OpmStatus opm_rays_invalidate_by_threshold_energy(OpmRays* rays, double min_energy_per_ray);   /* rays.rs:1145 */
+OpmStatus opm_rays_filter_by_nr_of_bounces(OpmRays* rays, uint64_t max_bounces);               /* rays.rs:1396 */
+OpmStatus opm_rays_filter_by_nr_of_refractions(OpmRays* rays, uint64_t max_refractions);       /* rays.rs:1386 */
+OpmStatus opm_rays_filter_energy(OpmRays* rays, double transmission);                          /* rays.rs:1119 */
+OpmStatus opm_rays_split(OpmRays* rays, double ratio, OpmRays* split_out);                     /* rays.rs:1253 */
+OpmStatus opm_rays_refract_paraxial(OpmRays* rays, double focal_length, const OpmIsometry* iso); /* rays.rs:943 */
+OpmStatus opm_rays_transform(OpmRays* rays, const OpmIsometry* iso, int32_t inverse);          /* Rays::transformed_by_iso */
+
+/* fused sequence: replaces the per-node chain of the calls above (analyzers/raytrace.rs:96-140,
+ * nodes/node_group/analysis_raytrace.rs:29-91).  `out` may be NULL or == rays for in-place operation. */
+OpmStatus opm_trace_sequence(OpmRays* rays, const OpmOp* ops, int32_t n_ops, int32_t flags, OpmRays* out,
+                             OpmTraceStats* stats);
+
+/* ---- bundle statistics (rays.rs:521-701) */
+typedef struct {
+    uint64_t n_valid;           /* nr_of_rays(true)  rays.rs:535-540 */
+    uint64_t n_total;           /* nr_of_rays(false) */
+    double total_energy;        /* rays.rs:521-530 */
+    double centroid[3];         /* rays.rs:599-612 */
+    double energy_centroid[3];  /* rays.rs:618-637 */
+    double beam_radius_geo;     /* rays.rs:642-660 */
+    double beam_radius_rms;     /* rays.rs:666-684 */
+    double energy_beam_radius_rms; /* rays.rs:690-701 */
+    uint32_t bounce_lvl;        /* rays.rs:183-194 (bounce count of the valid ray with the lowest id) */
+    uint32_t _pad;
+} OpmSpotStats;
+/* frame: NULL or the detector's effective surface isometry (positions are inverse-transformed into it,
+ * nodes/spot_diagram.rs:106-112) */
+OpmStatus opm_rays_spot_stats(const OpmRays* rays, const OpmIsometry* frame_or_null, OpmSpotStats* out);
+/* per-bounce-order tallies: counts[b] valid rays and energy[b] their energy, b < n_orders (last bin = overflow) */
+OpmStatus opm_rays_tally(const OpmRays* rays, uint32_t n_orders, uint64_t* counts, double* energy);
+
+/* ---- hit map + Binning fluence (surface/hit_map/rays_hit_map.rs) */
+OpmStatus opm_hitmap_create(OpmContext* ctx, uint64_t capacity, OpmHitMap** out);
+void opm_hitmap_destroy(OpmHitMap* h);
+uint64_t opm_hitmap_capacity(const OpmHitMap* h);
+uint64_t opm_hitmap_len(const OpmHitMap* h);       /* slots written by the last pass (entries with e < 0 are empty) */
+OpmStatus opm_hitmap_upload(OpmHitMap* h, const double* x, const double* y, const double* z, const double* e,
+                            const uint32_t* bounce_or_null, uint64_t n);
+/* packed download of the non-empty entries */
+OpmStatus opm_hitmap_download(const OpmHitMap* h, double* x, double* y, double* z, double* e, uint32_t* bounce,
+                              uint64_t capacity, uint64_t* n_out);
+/* calc_2d_bounding_box (rays_hit_map.rs:522-562) over several hit maps (merged, hit_map/mod.rs:161-175);
+ * bounce_filter < 0 = all bounces.  lrtb = left,right,top,bottom. */
+OpmStatus opm_hitmaps_bounding_box(OpmHitMap* const* maps, int32_t n_maps, int64_t bounce_filter, double lrtb[4],
+                                   uint64_t* n_hits);
+/* calc_fluence_with_binning (rays_hit_map.rs:330-391).  ranges: NULL (auto bounding box) or
+ * {ax1.start, ax1.end, ax2.start, ax2.end}.  map_dev: DEVICE buffer of nx*ny doubles, column-major ny x nx like
+ * nalgebra's DMatrix; zeroed by the call unless accumulate != 0.  lrtb_out receives the range used. */
+OpmStatus opm_fluence_binning(OpmHitMap* const* maps, int32_t n_maps, int64_t bounce_filter, uint64_t nx, uint64_t ny,
+                              const double* ranges, const double* lrtb_override, int32_t accumulate, double* map_dev,
+                              double lrtb_out[4]);
+/* FluenceData::new peak (fluence_data.rs:45-68) and total_energy (:130-141) of a device map */
+OpmStatus opm_fluence_peak_total(OpmContext* ctx, const double* map_dev, uint64_t nx, uint64_t ny, const double lrtb[4],
+                                 double* peak, double* total_energy);
+/* device buffers for maps (so callers need no CUDA runtime of their own) */
+OpmStatus opm_device_alloc(OpmContext* ctx, uint64_t bytes, void** out);
+void opm_device_free(OpmContext* ctx, void* p);
+OpmStatus opm_device_to_host(OpmContext* ctx, void* host, const void* dev, uint64_t bytes);
+OpmStatus opm_host_to_device(OpmContext* ctx, void* dev, const void* host, uint64_t bytes);
+OpmStatus opm_host_alloc_pinned(uint64_t bytes, void** out);
+void opm_host_free_pinned(void* p);
+
+/* ---- on-device sources (rays.rs:264-297 with the generators of position_distributions/) */
+typedef enum { OPM_POS_GRID = 0, OPM_POS_FIBONACCI_RECT = 1, OPM_POS_FIBONACCI_ELLIPSE = 2 } OpmPosDist;
+typedef enum { OPM_EDIST_UNIFORM = 0, OPM_EDIST_GENERAL_GAUSSIAN = 1 } OpmEnergyDist;
+typedef struct {
+    int32_t pos_dist;         /* OpmPosDist */
+    int32_t energy_dist;      /* OpmEnergyDist */
+    uint64_t n_positions;     /* total positions of the whole source (all ranks) */
+    uint64_t grid_nx, grid_ny;/* Grid: points in x (outer) and y (inner)  grid.rs:58-92 */
+    double size_x, size_y;    /* Grid/FibonacciRect: side lengths; FibonacciEllipse: radii */
+    double total_energy;      /* J */
+    double mu[2], sigma[2], power, theta; int32_t rectangular; int32_t _pad; /* General2DGaussian general_gaussian.rs:93-120 */
+    double energy_norm;       /* General2DGaussian: sum of the unnormalised weights over ALL positions; 0 = compute it */
+    uint32_t n_wavelengths;   /* spectrum lines per position (position-major order, rays.rs:284-289) */
+    uint32_t _pad2;
+    const double* wavelengths;/* HOST, n_wavelengths, metres */
+    const double* weights;    /* HOST, n_wavelengths, normalised */
+    OpmIsometry iso;          /* source isometry applied to the bundle (nodes/source.rs:205-210) */
+} OpmSourceDesc;
+/* generates positions [pos_begin, pos_end) x all wavelengths into `rays` (ids = global ray index mod 2^32) */
+OpmStatus opm_source_generate(OpmRays* rays, const OpmSourceDesc* desc, uint64_t pos_begin, uint64_t pos_end);
+/* sum of unnormalised General2DGaussian weights over [pos_begin,pos_end) (for multi-GPU: allreduce, then set energy_norm) */
+OpmStatus opm_source_energy_norm(OpmContext* ctx, const OpmSourceDesc* desc, uint64_t pos_begin, uint64_t pos_end,
+                                 double* partial_sum);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OPOSSUM_B200_H */

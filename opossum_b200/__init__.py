@@ -1,0 +1,14 @@
+"""opossum_b200 -- B200-native ray-propagation engine behind OPOSSUM's `Rays` API.
+
+The package is a thin host layer over libopossum_b200.so (hand-written sm_100a CUDA kernels behind the C ABI
+of include/opossum_b200.h).  There is no CPU implementation: importing works anywhere, but creating a
+`Context` needs a B200 and raises otherwise.
+"""
+from . import _ffi as ffi  # noqa: F401
+from .api import (Aperture, Context, FluenceData, HitMap, Isometry, OpossumError, OpticSurface, Program, RAY_DTYPE,  # noqa: F401
+                  RayTraceConfig, Rays, RefractiveIndex, SourceDesc, TraceStats, fluence_binning, hitmaps_bounding_box,
+                  refr_index_vaccuum)
+
+__all__ = ["Aperture", "Context", "FluenceData", "HitMap", "Isometry", "OpossumError", "OpticSurface", "Program",
+           "RAY_DTYPE", "RayTraceConfig", "Rays", "RefractiveIndex", "SourceDesc", "TraceStats", "fluence_binning",
+           "hitmaps_bounding_box", "refr_index_vaccuum", "ffi"]

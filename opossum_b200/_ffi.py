@@ -1,0 +1,243 @@
+"""ctypes declarations of the C ABI in include/opossum_b200.h (1:1, no logic).
+
+The shared library is built in-tree by `opossum_b200/csrc/Makefile` (nvcc, sm_100a).  There is no
+fallback: if the library is missing or no B200 is visible, loading / context creation raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+from pathlib import Path
+
+PKG = Path(__file__).resolve().parent
+LIB_PATH = PKG / "lib" / "libopossum_b200.so"
+
+OPM_MAX_APERTURE_ITEMS = 4
+OPM_MAX_PROGRAM_OPS = 64
+
+# status codes
+(OPM_OK, OPM_ERR_N2_INVALID, OPM_ERR_WVL_RANGE, OPM_ERR_INDEX_MODEL, OPM_ERR_COATING, OPM_ERR_APODIZE_FACTOR,
+ OPM_ERR_THRESHOLD, OPM_ERR_HITPOINT, OPM_ERR_SPLIT_RATIO, OPM_ERR_FOCAL_LENGTH, OPM_ERR_EMPTY_HITMAP,
+ OPM_ERR_BIN_RANGE, OPM_ERR_ARG, OPM_ERR_CAPACITY, OPM_ERR_CUDA) = range(15)
+
+GEOM_PLANE, GEOM_SPHERE, GEOM_CYLINDER, GEOM_PARABOLA = range(4)
+COAT_IDEAL_AR, COAT_CONSTANT_R, COAT_FRESNEL = range(3)
+IDX_CONST, IDX_SELLMEIER1, IDX_SCHOTT, IDX_CONRADY = range(4)
+MISS_STOP, MISS_IGNORE = 0, 1
+AP_NONE, AP_CIRCLE, AP_RECT, AP_POLYGON, AP_GAUSSIAN = range(5)
+OP_REFRACT, OP_APODIZE, OP_THRESHOLD, OP_LIMITS, OP_FILTER, OP_PARAXIAL, OP_SPLIT, OP_SNAPSHOT = range(1, 9)
+REFRACT_EMIT_CHILDREN, REFRACT_CONTINUE_AS_CHILD = 1, 2
+TRACE_COMPACT, TRACE_STRICT = 1, 2
+POS_GRID, POS_FIBONACCI_RECT, POS_FIBONACCI_ELLIPSE = range(3)
+EDIST_UNIFORM, EDIST_GENERAL_GAUSSIAN = 0, 1
+
+
+class OpmRay(C.Structure):
+    _fields_ = [("pos", C.c_double * 3), ("dir", C.c_double * 3), ("e", C.c_double), ("wvl", C.c_double),
+                ("opl", C.c_double), ("n", C.c_double), ("bounces", C.c_uint32), ("refr", C.c_uint32),
+                ("valid", C.c_uint32), ("id", C.c_uint32)]
+
+
+class OpmIso(C.Structure):
+    _fields_ = [("rot", C.c_double * 9), ("t", C.c_double * 3)]
+
+
+class OpmIsometry(C.Structure):
+    _fields_ = [("fwd", OpmIso), ("inv", OpmIso)]
+
+
+class OpmSurface(C.Structure):
+    _fields_ = [("geom", C.c_int32), ("coating", C.c_int32), ("geom_param", C.c_double), ("coating_r", C.c_double),
+                ("iso", OpmIsometry)]
+
+
+class OpmIndexModel(C.Structure):
+    _fields_ = [("type", C.c_int32), ("_pad", C.c_int32), ("c", C.c_double * 6), ("wvl_lo", C.c_double),
+                ("wvl_hi", C.c_double)]
+
+
+class OpmApertureItem(C.Structure):
+    _fields_ = [("type", C.c_int32), ("obstruction", C.c_int32), ("p", C.c_double * 4)]
+
+
+class OpmAperture(C.Structure):
+    _fields_ = [("n_items", C.c_int32), ("is_stack", C.c_int32), ("stack_obstruction", C.c_int32),
+                ("n_tris", C.c_int32), ("items", OpmApertureItem * OPM_MAX_APERTURE_ITEMS),
+                ("tris", C.POINTER(C.c_double))]
+
+
+class OpmRayTraceConfig(C.Structure):
+    _fields_ = [("min_energy_per_ray", C.c_double), ("max_number_of_bounces", C.c_uint64),
+                ("max_number_of_refractions", C.c_uint64), ("missed_surface_strategy", C.c_int32), ("_pad", C.c_int32)]
+
+
+class OpmTraceStats(C.Structure):
+    _fields_ = [("interactions", C.c_uint64), ("children", C.c_uint64), ("hits", C.c_uint64), ("missed", C.c_uint64),
+                ("apodized", C.c_uint64), ("valid_out", C.c_uint64), ("alive_out", C.c_uint64),
+                ("status_bits", C.c_uint32), ("_pad", C.c_uint32)]
+
+
+class OpmRefractOp(C.Structure):
+    _fields_ = [("surface", OpmSurface), ("index", OpmIndexModel), ("has_index", C.c_int32),
+                ("refraction_intended", C.c_int32), ("strategy", C.c_int32), ("flags", C.c_int32),
+                ("hits", C.c_void_p), ("children", C.c_void_p)]
+
+
+class OpmApodizeOp(C.Structure):
+    _fields_ = [("iso", OpmIsometry), ("aperture", OpmAperture)]
+
+
+class OpmThresholdOp(C.Structure):
+    _fields_ = [("min_energy", C.c_double)]
+
+
+class OpmLimitsOp(C.Structure):
+    _fields_ = [("max_bounces", C.c_uint64), ("max_refractions", C.c_uint64), ("check_refractions", C.c_int32),
+                ("_pad", C.c_int32)]
+
+
+class OpmFilterOp(C.Structure):
+    _fields_ = [("transmission", C.c_double)]
+
+
+class OpmParaxialOp(C.Structure):
+    _fields_ = [("focal_length", C.c_double), ("iso", OpmIsometry)]
+
+
+class OpmSplitOp(C.Structure):
+    _fields_ = [("ratio", C.c_double), ("split_out", C.c_void_p)]
+
+
+class OpmSnapshotOp(C.Structure):
+    _fields_ = [("out", C.c_void_p)]
+
+
+class _OpUnion(C.Union):
+    _fields_ = [("refract", OpmRefractOp), ("apodize", OpmApodizeOp), ("threshold", OpmThresholdOp),
+                ("limits", OpmLimitsOp), ("filter", OpmFilterOp), ("paraxial", OpmParaxialOp), ("split", OpmSplitOp),
+                ("snapshot", OpmSnapshotOp)]
+
+
+class OpmOp(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("_pad", C.c_int32), ("u", _OpUnion)]
+
+
+class OpmSpotStats(C.Structure):
+    _fields_ = [("n_valid", C.c_uint64), ("n_total", C.c_uint64), ("total_energy", C.c_double),
+                ("centroid", C.c_double * 3), ("energy_centroid", C.c_double * 3), ("beam_radius_geo", C.c_double),
+                ("beam_radius_rms", C.c_double), ("energy_beam_radius_rms", C.c_double), ("bounce_lvl", C.c_uint32),
+                ("_pad", C.c_uint32)]
+
+
+class OpmSourceDesc(C.Structure):
+    _fields_ = [("pos_dist", C.c_int32), ("energy_dist", C.c_int32), ("n_positions", C.c_uint64),
+                ("grid_nx", C.c_uint64), ("grid_ny", C.c_uint64), ("size_x", C.c_double), ("size_y", C.c_double),
+                ("total_energy", C.c_double), ("mu", C.c_double * 2), ("sigma", C.c_double * 2), ("power", C.c_double),
+                ("theta", C.c_double), ("rectangular", C.c_int32), ("_pad", C.c_int32), ("energy_norm", C.c_double),
+                ("n_wavelengths", C.c_uint32), ("_pad2", C.c_uint32), ("wavelengths", C.POINTER(C.c_double)),
+                ("weights", C.POINTER(C.c_double)), ("iso", OpmIsometry)]
+
+
+# every symbol include/opossum_b200.h declares (tests/test_abi.py checks the library exports all of them)
+EXPORTS = [
+    "opm_abi_version", "opm_last_error", "opm_status_string", "opm_context_create", "opm_context_destroy",
+    "opm_context_synchronize", "opm_context_stream", "opm_context_launch_count", "opm_isometry_identity",
+    "opm_isometry_new", "opm_isometry_append", "opm_raytrace_config_default", "opm_rays_create", "opm_rays_destroy",
+    "opm_rays_len", "opm_rays_capacity", "opm_rays_clear", "opm_rays_reserve", "opm_rays_upload",
+    "opm_rays_upload_soa", "opm_rays_download", "opm_rays_copy", "opm_rays_append", "opm_rays_compact",
+    "opm_rays_field_ptr", "opm_rays_refract_on_surface", "opm_rays_apodize",
+    "opm_rays_invalidate_by_threshold_energy", "opm_rays_filter_by_nr_of_bounces",
+    "opm_rays_filter_by_nr_of_refractions", "opm_rays_filter_energy", "opm_rays_split", "opm_rays_refract_paraxial",
+    "opm_rays_transform", "opm_trace_sequence", "opm_rays_spot_stats", "opm_rays_tally", "opm_hitmap_create",
+    "opm_hitmap_destroy", "opm_hitmap_capacity", "opm_hitmap_len", "opm_hitmap_upload", "opm_hitmap_download",
+    "opm_hitmaps_bounding_box", "opm_fluence_binning", "opm_fluence_peak_total", "opm_device_alloc",
+    "opm_device_free", "opm_device_to_host", "opm_host_to_device", "opm_host_alloc_pinned", "opm_host_free_pinned",
+    "opm_source_generate", "opm_source_energy_norm",
+]
+
+_lib = None
+
+
+def build(force: bool = False) -> Path:
+    """Compile the CUDA library in-tree (nvcc cross-compiles sm_100a without a GPU)."""
+    env = dict(os.environ)
+    cmd = ["make", "-C", str(PKG / "csrc"), "-j4"] + (["-B"] if force else [])
+    subprocess.run(cmd, check=True, env=env, stdout=subprocess.DEVNULL)
+    return LIB_PATH
+
+
+def lib() -> C.CDLL:
+    """Load libopossum_b200.so.  Raises if it has not been built: there is no other implementation."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        raise RuntimeError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                           "(the CUDA extension is the only implementation of this package)")
+    L = C.CDLL(str(LIB_PATH))
+    vp, dp, i32, u64, i64 = C.c_void_p, C.POINTER(C.c_double), C.c_int32, C.c_uint64, C.c_int64
+    pp = C.POINTER(vp)
+    sig = {
+        "opm_abi_version": (i32, []),
+        "opm_last_error": (C.c_char_p, []),
+        "opm_status_string": (C.c_char_p, [i32]),
+        "opm_context_create": (i32, [i32, vp, pp]),
+        "opm_context_destroy": (None, [vp]),
+        "opm_context_synchronize": (i32, [vp]),
+        "opm_context_stream": (vp, [vp]),
+        "opm_context_launch_count": (u64, [vp]),
+        "opm_isometry_identity": (None, [C.POINTER(OpmIsometry)]),
+        "opm_isometry_new": (i32, [dp, dp, C.POINTER(OpmIsometry)]),
+        "opm_isometry_append": (None, [C.POINTER(OpmIsometry)] * 3),
+        "opm_raytrace_config_default": (None, [C.POINTER(OpmRayTraceConfig)]),
+        "opm_rays_create": (i32, [vp, u64, pp]),
+        "opm_rays_destroy": (None, [vp]),
+        "opm_rays_len": (u64, [vp]),
+        "opm_rays_capacity": (u64, [vp]),
+        "opm_rays_clear": (i32, [vp]),
+        "opm_rays_reserve": (i32, [vp, u64]),
+        "opm_rays_upload": (i32, [vp, vp, u64]),
+        "opm_rays_upload_soa": (i32, [vp, C.POINTER(dp), C.POINTER(dp), dp, dp, u64]),
+        "opm_rays_download": (i32, [vp, vp, u64, C.POINTER(u64)]),
+        "opm_rays_copy": (i32, [vp, vp]),
+        "opm_rays_append": (i32, [vp, vp]),
+        "opm_rays_compact": (i32, [vp]),
+        "opm_rays_field_ptr": (vp, [vp, C.c_char_p]),
+        "opm_rays_refract_on_surface": (i32, [vp, C.POINTER(OpmSurface), C.POINTER(OpmIndexModel), i32, i32, vp, vp,
+                                              C.POINTER(OpmTraceStats)]),
+        "opm_rays_apodize": (i32, [vp, C.POINTER(OpmAperture), C.POINTER(OpmIsometry), C.POINTER(i32)]),
+        "opm_rays_invalidate_by_threshold_energy": (i32, [vp, C.c_double]),
+        "opm_rays_filter_by_nr_of_bounces": (i32, [vp, u64]),
+        "opm_rays_filter_by_nr_of_refractions": (i32, [vp, u64]),
+        "opm_rays_filter_energy": (i32, [vp, C.c_double]),
+        "opm_rays_split": (i32, [vp, C.c_double, vp]),
+        "opm_rays_refract_paraxial": (i32, [vp, C.c_double, C.POINTER(OpmIsometry)]),
+        "opm_rays_transform": (i32, [vp, C.POINTER(OpmIsometry), i32]),
+        "opm_trace_sequence": (i32, [vp, C.POINTER(OpmOp), i32, i32, vp, C.POINTER(OpmTraceStats)]),
+        "opm_rays_spot_stats": (i32, [vp, C.POINTER(OpmIsometry), C.POINTER(OpmSpotStats)]),
+        "opm_rays_tally": (i32, [vp, C.c_uint32, C.POINTER(u64), dp]),
+        "opm_hitmap_create": (i32, [vp, u64, pp]),
+        "opm_hitmap_destroy": (None, [vp]),
+        "opm_hitmap_capacity": (u64, [vp]),
+        "opm_hitmap_len": (u64, [vp]),
+        "opm_hitmap_upload": (i32, [vp, dp, dp, dp, dp, C.POINTER(C.c_uint32), u64]),
+        "opm_hitmap_download": (i32, [vp, dp, dp, dp, dp, C.POINTER(C.c_uint32), u64, C.POINTER(u64)]),
+        "opm_hitmaps_bounding_box": (i32, [pp, i32, i64, dp, C.POINTER(u64)]),
+        "opm_fluence_binning": (i32, [pp, i32, i64, u64, u64, dp, dp, i32, vp, dp]),
+        "opm_fluence_peak_total": (i32, [vp, vp, u64, u64, dp, dp, dp]),
+        "opm_device_alloc": (i32, [vp, u64, pp]),
+        "opm_device_free": (None, [vp, vp]),
+        "opm_device_to_host": (i32, [vp, vp, vp, u64]),
+        "opm_host_to_device": (i32, [vp, vp, vp, u64]),
+        "opm_host_alloc_pinned": (i32, [u64, pp]),
+        "opm_host_free_pinned": (None, [vp]),
+        "opm_source_generate": (i32, [vp, C.POINTER(OpmSourceDesc), u64, u64]),
+        "opm_source_energy_norm": (i32, [vp, C.POINTER(OpmSourceDesc), u64, u64, dp]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(L, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = L
+    return L

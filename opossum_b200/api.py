@@ -1,0 +1,647 @@
+"""Host-side mirror of the reference's ray API over the C ABI (include/opossum_b200.h).
+
+Names follow the reference (opossum/src): `Rays` (rays.rs), `OpticSurface` (surface/optic_surface.rs),
+`Isometry` (utils/geom_transformation.rs), `RefractiveIndex*` (refractive_index/), `Aperture`
+(aperture.rs), `CoatingType` (coatings/mod.rs), `HitMap`/fluence (surface/hit_map/).  Every method is a
+thin call into libopossum_b200.so -- all ray arithmetic runs in the CUDA kernels; nothing here
+computes on rays with numpy.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import _ffi as F
+
+RAY_DTYPE = np.dtype(
+    [("pos", "<f8", 3), ("dir", "<f8", 3), ("e", "<f8"), ("wvl", "<f8"), ("opl", "<f8"), ("n", "<f8"),
+     ("bounces", "<u4"), ("refr", "<u4"), ("valid", "<u4"), ("id", "<u4")], align=True)
+assert RAY_DTYPE.itemsize == C.sizeof(F.OpmRay) == 96
+
+
+class OpossumError(RuntimeError):
+    """Mirror of `OpossumError` (error.rs:9-28): carries the status code and the reference's message."""
+
+    def __init__(self, code: int, message: str):
+        self.code = code
+        super().__init__(message)
+
+
+def _check(rc: int):
+    if rc != F.OPM_OK:
+        msg = F.lib().opm_last_error().decode() or F.lib().opm_status_string(rc).decode()
+        raise OpossumError(rc, msg)
+
+
+def _d3(v):
+    return (C.c_double * 3)(*[float(x) for x in v])
+
+
+# ---------------------------------------------------------------------------------------------
+class Isometry:
+    """utils/geom_transformation.rs `Isometry` (transform + cached inverse), 3x3 + t form."""
+
+    def __init__(self, c: F.OpmIsometry | None = None):
+        self.c = c if c is not None else F.OpmIsometry()
+        if c is None:
+            F.lib().opm_isometry_identity(C.byref(self.c))
+
+    @staticmethod
+    def identity() -> "Isometry":
+        return Isometry()
+
+    @staticmethod
+    def new(translation, euler_xyz=(0.0, 0.0, 0.0)) -> "Isometry":
+        """Isometry::new(translation [m], axes angles [rad], applied x -> y -> z) :44-72"""
+        o = F.OpmIsometry()
+        _check(F.lib().opm_isometry_new(_d3(translation), _d3(euler_xyz), C.byref(o)))
+        return Isometry(o)
+
+    @staticmethod
+    def new_along_z(z: float) -> "Isometry":
+        return Isometry.new((0.0, 0.0, z))
+
+    def append(self, rhs: "Isometry") -> "Isometry":
+        o = F.OpmIsometry()
+        F.lib().opm_isometry_append(C.byref(self.c), C.byref(rhs.c), C.byref(o))
+        return Isometry(o)
+
+    def matrices(self):
+        return (np.array(self.c.fwd.rot[:]), np.array(self.c.fwd.t[:]), np.array(self.c.inv.rot[:]),
+                np.array(self.c.inv.t[:]))
+
+
+class RefractiveIndex:
+    """refractive_index/mod.rs `RefractiveIndexType`"""
+
+    def __init__(self, c: F.OpmIndexModel):
+        self.c = c
+
+    @staticmethod
+    def const(n: float) -> "RefractiveIndex":
+        m = F.OpmIndexModel(type=F.IDX_CONST)
+        m.c[0] = n
+        return RefractiveIndex(m)
+
+    @staticmethod
+    def sellmeier1(k1, k2, k3, l1, l2, l3, lo, hi) -> "RefractiveIndex":
+        m = F.OpmIndexModel(type=F.IDX_SELLMEIER1, wvl_lo=lo, wvl_hi=hi)
+        m.c[:] = [k1, k2, k3, l1, l2, l3]
+        return RefractiveIndex(m)
+
+    @staticmethod
+    def schott(a0, a1, a2, a3, a4, a5, lo, hi) -> "RefractiveIndex":
+        m = F.OpmIndexModel(type=F.IDX_SCHOTT, wvl_lo=lo, wvl_hi=hi)
+        m.c[:] = [a0, a1, a2, a3, a4, a5]
+        return RefractiveIndex(m)
+
+    @staticmethod
+    def conrady(n0, a, b, lo, hi) -> "RefractiveIndex":
+        m = F.OpmIndexModel(type=F.IDX_CONRADY, wvl_lo=lo, wvl_hi=hi)
+        m.c[:] = [n0, a, b, 0.0, 0.0, 0.0]
+        return RefractiveIndex(m)
+
+
+def refr_index_vaccuum() -> RefractiveIndex:
+    return RefractiveIndex.const(1.0)
+
+
+class Aperture:
+    """aperture.rs `Aperture`"""
+
+    def __init__(self):
+        self.c = F.OpmAperture()
+        self._keep = None
+
+    @staticmethod
+    def none() -> "Aperture":
+        return Aperture()
+
+    @staticmethod
+    def _single(t, p, obstruction) -> "Aperture":
+        a = Aperture()
+        a.c.n_items = 1
+        a.c.items[0].type = t
+        a.c.items[0].obstruction = int(obstruction)
+        a.c.items[0].p[:] = p
+        return a
+
+    @staticmethod
+    def circle(r, cx=0.0, cy=0.0, obstruction=False) -> "Aperture":
+        return Aperture._single(F.AP_CIRCLE, [r, cx, cy, 0.0], obstruction)
+
+    @staticmethod
+    def rect(w, h, cx=0.0, cy=0.0, obstruction=False) -> "Aperture":
+        return Aperture._single(F.AP_RECT, [w, h, cx, cy], obstruction)
+
+    @staticmethod
+    def gaussian(sx, sy, cx=0.0, cy=0.0, obstruction=False) -> "Aperture":
+        return Aperture._single(F.AP_GAUSSIAN, [sx, sy, cx, cy], obstruction)
+
+    @staticmethod
+    def polygon(triangles, obstruction=False) -> "Aperture":
+        t = np.ascontiguousarray(np.asarray(triangles, dtype=np.float64).reshape(-1, 6))
+        a = Aperture._single(F.AP_POLYGON, [0.0] * 4, obstruction)
+        a._keep = t
+        a.c.n_tris = t.shape[0]
+        a.c.tris = t.ctypes.data_as(C.POINTER(C.c_double))
+        return a
+
+    @staticmethod
+    def stack(items, obstruction=False) -> "Aperture":
+        if len(items) > F.OPM_MAX_APERTURE_ITEMS:
+            raise OpossumError(F.OPM_ERR_ARG, "aperture stack too deep")
+        a = Aperture()
+        a.c.n_items = len(items)
+        a.c.is_stack = 1
+        a.c.stack_obstruction = int(obstruction)
+        for k, it in enumerate(items):
+            if it.c.n_items != 1 or it.c.is_stack:
+                raise OpossumError(F.OPM_ERR_ARG, "only flat stacks of simple apertures are supported")
+            a.c.items[k] = it.c.items[0]
+            if it.c.n_tris:
+                a.c.n_tris, a.c.tris, a._keep = it.c.n_tris, it.c.tris, it._keep
+        return a
+
+
+class OpticSurface:
+    """surface/optic_surface.rs `OpticSurface`: geometry + isometry of the geo surface + coating."""
+
+    def __init__(self, geom=F.GEOM_PLANE, param=0.0, iso: Isometry | None = None, coating=F.COAT_IDEAL_AR,
+                 reflectivity=0.0):
+        self.c = F.OpmSurface(geom=geom, coating=coating, geom_param=param, coating_r=reflectivity)
+        self.c.iso = (iso or Isometry.identity()).c
+
+    @staticmethod
+    def plane(iso=None, **kw):
+        return OpticSurface(F.GEOM_PLANE, 0.0, iso, **kw)
+
+    @staticmethod
+    def sphere(radius, iso, **kw):
+        """`iso` is the isometry of the centre of curvature (node_iso o T(0,0,R))."""
+        return OpticSurface(F.GEOM_SPHERE, radius, iso, **kw)
+
+    @staticmethod
+    def sphere_at_position(radius, pos, **kw):
+        """Sphere::new_at_position (surface/sphere.rs:30-41)"""
+        return OpticSurface(F.GEOM_SPHERE, radius, Isometry.new((pos[0], pos[1], pos[2] + radius)), **kw)
+
+    @staticmethod
+    def cylinder(radius, iso, **kw):
+        return OpticSurface(F.GEOM_CYLINDER, radius, iso, **kw)
+
+    @staticmethod
+    def parabola(focal_length, iso, **kw):
+        return OpticSurface(F.GEOM_PARABOLA, focal_length, iso, **kw)
+
+
+@dataclass
+class RayTraceConfig:
+    """analyzers/raytrace.rs:302-323"""
+    min_energy_per_ray: float = 1.0 * 1.0e-12
+    max_number_of_bounces: int = 1000
+    max_number_of_refractions: int = 1000
+    missed_surface_strategy: int = F.MISS_STOP
+
+
+# ---------------------------------------------------------------------------------------------
+class Context:
+    """One CUDA device + stream.  Raises OpossumError(OPM_ERR_CUDA) when no B200 is visible (no CPU fallback)."""
+
+    def __init__(self, device: int = 0, stream: int | None = None):
+        h = C.c_void_p()
+        _check(F.lib().opm_context_create(device, C.c_void_p(stream) if stream else None, C.byref(h)))
+        self.h = h
+        self.device = device
+
+    def synchronize(self):
+        _check(F.lib().opm_context_synchronize(self.h))
+
+    @property
+    def stream(self) -> int:
+        return F.lib().opm_context_stream(self.h) or 0
+
+    @property
+    def launch_count(self) -> int:
+        return F.lib().opm_context_launch_count(self.h)
+
+    def close(self):
+        if self.h:
+            F.lib().opm_context_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # device buffers for fluence maps
+    def device_alloc(self, nbytes: int) -> int:
+        p = C.c_void_p()
+        _check(F.lib().opm_device_alloc(self.h, nbytes, C.byref(p)))
+        return p.value
+
+    def device_free(self, p: int):
+        F.lib().opm_device_free(self.h, C.c_void_p(p))
+
+    def to_host(self, dev: int, arr: np.ndarray):
+        _check(F.lib().opm_device_to_host(self.h, C.c_void_p(arr.ctypes.data), C.c_void_p(dev), arr.nbytes))
+
+    def to_device(self, dev: int, arr: np.ndarray):
+        _check(F.lib().opm_host_to_device(self.h, C.c_void_p(dev), C.c_void_p(arr.ctypes.data), arr.nbytes))
+
+
+class HitMap:
+    """Device hit-point record of one surface (rays_hit_map.rs:43-49): surface-frame xyz + input energy + bounce."""
+
+    def __init__(self, ctx: Context, capacity: int):
+        self.ctx = ctx
+        h = C.c_void_p()
+        _check(F.lib().opm_hitmap_create(ctx.h, capacity, C.byref(h)))
+        self.h = h
+
+    def __len__(self):
+        return F.lib().opm_hitmap_len(self.h)
+
+    def upload(self, x, y, e, z=None, bounce=None):
+        x, y, e = (np.ascontiguousarray(v, dtype=np.float64) for v in (x, y, e))
+        dp = C.POINTER(C.c_double)
+        zz = np.ascontiguousarray(z, dtype=np.float64) if z is not None else None
+        bb = np.ascontiguousarray(bounce, dtype=np.uint32) if bounce is not None else None
+        _check(F.lib().opm_hitmap_upload(self.h, x.ctypes.data_as(dp), y.ctypes.data_as(dp),
+                                         zz.ctypes.data_as(dp) if zz is not None else None, e.ctypes.data_as(dp),
+                                         bb.ctypes.data_as(C.POINTER(C.c_uint32)) if bb is not None else None, len(x)))
+
+    def download(self):
+        n = len(self)
+        x, y, z, e = (np.zeros(max(n, 1)) for _ in range(4))
+        b = np.zeros(max(n, 1), dtype=np.uint32)
+        dp = C.POINTER(C.c_double)
+        k = C.c_uint64()
+        _check(F.lib().opm_hitmap_download(self.h, x.ctypes.data_as(dp), y.ctypes.data_as(dp), z.ctypes.data_as(dp),
+                                           e.ctypes.data_as(dp), b.ctypes.data_as(C.POINTER(C.c_uint32)), max(n, 1),
+                                           C.byref(k)))
+        k = k.value
+        return x[:k], y[:k], z[:k], e[:k], b[:k]
+
+    def close(self):
+        if self.h:
+            F.lib().opm_hitmap_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+@dataclass
+class TraceStats:
+    interactions: int = 0
+    children: int = 0
+    hits: int = 0
+    missed: int = 0
+    apodized: int = 0
+    valid_out: int = 0
+    alive_out: int = 0
+
+    @staticmethod
+    def of(s: F.OpmTraceStats) -> "TraceStats":
+        return TraceStats(s.interactions, s.children, s.hits, s.missed, s.apodized, s.valid_out, s.alive_out)
+
+
+class Rays:
+    """rays.rs `Rays`: a bundle held as struct-of-arrays f64 buffers in HBM."""
+
+    def __init__(self, ctx: Context, capacity: int = 1):
+        self.ctx = ctx
+        h = C.c_void_p()
+        _check(F.lib().opm_rays_create(ctx.h, capacity, C.byref(h)))
+        self.h = h
+
+    # ---- construction / inspection
+    @staticmethod
+    def from_array(ctx: Context, rays: np.ndarray) -> "Rays":
+        """Rays::from(Vec<Ray>)"""
+        a = np.ascontiguousarray(rays, dtype=RAY_DTYPE)
+        r = Rays(ctx, max(len(a), 1))
+        _check(F.lib().opm_rays_upload(r.h, C.c_void_p(a.ctypes.data), len(a)))
+        return r
+
+    def upload_soa(self, pos, direction, e, wvl):
+        """SoA upload (one H2D copy per field, from pinned memory when the arrays are pinned)."""
+        dp = C.POINTER(C.c_double)
+        P = (dp * 3)(*[p.ctypes.data_as(dp) for p in pos])
+        D = (dp * 3)(*[d.ctypes.data_as(dp) for d in direction])
+        _check(F.lib().opm_rays_upload_soa(self.h, P, D, e.ctypes.data_as(dp), wvl.ctypes.data_as(dp), len(e)))
+
+    def to_array(self) -> np.ndarray:
+        n = len(self)
+        out = np.zeros(max(n, 1), dtype=RAY_DTYPE)
+        k = C.c_uint64()
+        _check(F.lib().opm_rays_download(self.h, C.c_void_p(out.ctypes.data), max(n, 1), C.byref(k)))
+        return out[: k.value]
+
+    def __len__(self):
+        return F.lib().opm_rays_len(self.h)
+
+    def clone(self) -> "Rays":
+        r = Rays(self.ctx, max(len(self), 1))
+        _check(F.lib().opm_rays_copy(self.h, r.h))
+        return r
+
+    def add_rays(self, other: "Rays"):
+        _check(F.lib().opm_rays_append(self.h, other.h))
+
+    merge = add_rays
+
+    def compact(self):
+        _check(F.lib().opm_rays_compact(self.h))
+
+    def clear(self):
+        _check(F.lib().opm_rays_clear(self.h))
+
+    def field_ptr(self, name: str) -> int:
+        return F.lib().opm_rays_field_ptr(self.h, name.encode()) or 0
+
+    def close(self):
+        if self.h:
+            F.lib().opm_rays_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- the reference's bundle methods
+    def refract_on_surface(self, surface: OpticSurface, refractive_index: RefractiveIndex | None,
+                           refraction_intended: bool = True, missed_surface_strategy: int = F.MISS_STOP,
+                           hit_map: HitMap | None = None, want_reflected: bool = True):
+        """Rays::refract_on_surface (rays.rs:976-1047) -> (reflected Rays, TraceStats)."""
+        reflected = Rays(self.ctx, max(len(self), 1)) if want_reflected else None
+        st = F.OpmTraceStats()
+        _check(F.lib().opm_rays_refract_on_surface(
+            self.h, C.byref(surface.c), C.byref(refractive_index.c) if refractive_index is not None else None,
+            int(refraction_intended), missed_surface_strategy, reflected.h if reflected else None,
+            hit_map.h if hit_map else None, C.byref(st)))
+        return reflected, TraceStats.of(st)
+
+    def apodize(self, aperture: Aperture, iso: Isometry) -> bool:
+        inv = C.c_int32()
+        _check(F.lib().opm_rays_apodize(self.h, C.byref(aperture.c), C.byref(iso.c), C.byref(inv)))
+        return bool(inv.value)
+
+    def invalidate_by_threshold_energy(self, min_energy_per_ray: float):
+        _check(F.lib().opm_rays_invalidate_by_threshold_energy(self.h, min_energy_per_ray))
+
+    def filter_by_nr_of_bounces(self, max_bounces: int):
+        _check(F.lib().opm_rays_filter_by_nr_of_bounces(self.h, max_bounces))
+
+    def filter_by_nr_of_refractions(self, max_refractions: int):
+        _check(F.lib().opm_rays_filter_by_nr_of_refractions(self.h, max_refractions))
+
+    def filter_energy(self, transmission: float):
+        _check(F.lib().opm_rays_filter_energy(self.h, transmission))
+
+    def split(self, ratio: float) -> "Rays":
+        out = Rays(self.ctx, max(len(self), 1))
+        _check(F.lib().opm_rays_split(self.h, ratio, out.h))
+        return out
+
+    def refract_paraxial(self, focal_length: float, iso: Isometry):
+        _check(F.lib().opm_rays_refract_paraxial(self.h, focal_length, C.byref(iso.c)))
+
+    def transformed_by_iso(self, iso: Isometry, inverse: bool = False):
+        _check(F.lib().opm_rays_transform(self.h, C.byref(iso.c), int(inverse)))
+
+    # ---- statistics
+    def spot_stats(self, frame: Isometry | None = None) -> F.OpmSpotStats:
+        s = F.OpmSpotStats()
+        _check(F.lib().opm_rays_spot_stats(self.h, C.byref(frame.c) if frame else None, C.byref(s)))
+        return s
+
+    def total_energy(self) -> float:
+        return self.spot_stats().total_energy
+
+    def nr_of_rays(self, valid_only: bool = True) -> int:
+        s = self.spot_stats()
+        return s.n_valid if valid_only else s.n_total
+
+    def centroid(self):
+        s = self.spot_stats()
+        return np.array(s.centroid[:]) if s.n_valid else None
+
+    def energy_weighted_centroid(self):
+        s = self.spot_stats()
+        return np.array(s.energy_centroid[:]) if s.n_valid else None
+
+    def beam_radius_geo(self):
+        s = self.spot_stats()
+        return s.beam_radius_geo if s.n_valid else None
+
+    def beam_radius_rms(self):
+        s = self.spot_stats()
+        return s.beam_radius_rms if s.n_valid else None
+
+    def energy_weighted_beam_radius_rms(self):
+        s = self.spot_stats()
+        return s.energy_beam_radius_rms if s.n_valid else None
+
+    def bounce_lvl(self) -> int:
+        s = self.spot_stats()
+        return s.bounce_lvl if s.n_valid else 0
+
+    def tally(self, n_orders: int = 8):
+        counts = (C.c_uint64 * n_orders)()
+        energy = (C.c_double * n_orders)()
+        _check(F.lib().opm_rays_tally(self.h, n_orders, counts, energy))
+        return np.array(counts[:], dtype=np.uint64), np.array(energy[:])
+
+
+# ---------------------------------------------------------------------------------------------
+class Program:
+    """A fused surface sequence: ops run back to back in ONE kernel launch (opm_trace_sequence)."""
+
+    def __init__(self):
+        self.ops: list[F.OpmOp] = []
+        self._keep: list = []
+
+    def refract(self, surface: OpticSurface, index: RefractiveIndex | None, refraction_intended=True,
+                strategy=F.MISS_STOP, hit_map: HitMap | None = None, children: Rays | None = None,
+                continue_as_child=False) -> "Program":
+        op = F.OpmOp(kind=F.OP_REFRACT)
+        r = op.u.refract
+        r.surface = surface.c
+        if index is not None:
+            r.index = index.c
+            r.has_index = 1
+        r.refraction_intended = int(refraction_intended)
+        r.strategy = strategy
+        r.flags = (F.REFRACT_EMIT_CHILDREN if children is not None else 0) | \
+                  (F.REFRACT_CONTINUE_AS_CHILD if continue_as_child else 0)
+        r.hits = hit_map.h if hit_map else None
+        r.children = children.h if children else None
+        self._keep += [hit_map, children]
+        self.ops.append(op)
+        return self
+
+    def mirror(self, surface: OpticSurface, strategy=F.MISS_STOP, hit_map=None) -> "Program":
+        """nodes/thin_mirror.rs:209-250: n2 = None, refraction_intended = false, the reflected bundle continues."""
+        return self.refract(surface, None, refraction_intended=False, strategy=strategy, hit_map=hit_map,
+                            continue_as_child=True)
+
+    def apodize(self, aperture: Aperture, iso: Isometry) -> "Program":
+        op = F.OpmOp(kind=F.OP_APODIZE)
+        op.u.apodize.iso = iso.c
+        op.u.apodize.aperture = aperture.c
+        self._keep.append(aperture)
+        self.ops.append(op)
+        return self
+
+    def threshold(self, min_energy: float) -> "Program":
+        op = F.OpmOp(kind=F.OP_THRESHOLD)
+        op.u.threshold.min_energy = min_energy
+        self.ops.append(op)
+        return self
+
+    def limits(self, max_bounces: int, max_refractions: int | None) -> "Program":
+        op = F.OpmOp(kind=F.OP_LIMITS)
+        op.u.limits.max_bounces = max_bounces
+        op.u.limits.max_refractions = max_refractions if max_refractions is not None else 0
+        op.u.limits.check_refractions = int(max_refractions is not None)
+        self.ops.append(op)
+        return self
+
+    def filter(self, transmission: float) -> "Program":
+        op = F.OpmOp(kind=F.OP_FILTER)
+        op.u.filter.transmission = transmission
+        self.ops.append(op)
+        return self
+
+    def paraxial(self, focal_length: float, iso: Isometry) -> "Program":
+        op = F.OpmOp(kind=F.OP_PARAXIAL)
+        op.u.paraxial.focal_length = focal_length
+        op.u.paraxial.iso = iso.c
+        self.ops.append(op)
+        return self
+
+    def split(self, ratio: float, split_out: Rays) -> "Program":
+        op = F.OpmOp(kind=F.OP_SPLIT)
+        op.u.split.ratio = ratio
+        op.u.split.split_out = split_out.h
+        self._keep.append(split_out)
+        self.ops.append(op)
+        return self
+
+    def snapshot(self, out: Rays) -> "Program":
+        op = F.OpmOp(kind=F.OP_SNAPSHOT)
+        op.u.snapshot.out = out.h
+        self._keep.append(out)
+        self.ops.append(op)
+        return self
+
+    def run(self, rays: Rays, out: Rays | None = None, compact=False, strict=False, sync=True) -> TraceStats | None:
+        arr = (F.OpmOp * max(len(self.ops), 1))(*self.ops)
+        flags = (F.TRACE_COMPACT if compact else 0) | (F.TRACE_STRICT if strict else 0)
+        st = F.OpmTraceStats()
+        _check(F.lib().opm_trace_sequence(rays.h, arr, len(self.ops), flags, out.h if out else None,
+                                          C.byref(st) if sync else None))
+        return TraceStats.of(st) if sync else None
+
+
+# ---------------------------------------------------------------------------------------------
+@dataclass
+class FluenceData:
+    """nodes/fluence_detector/fluence_data.rs `FluenceData` (Binning estimator)."""
+    map: np.ndarray          # [ny, nx] (rows = y like nalgebra's DMatrix)
+    lrtb: tuple              # left, right, top, bottom
+    peak: float
+    total_energy: float
+
+
+def fluence_binning(ctx: Context, hit_maps, nx: int, ny: int, ranges=None, lrtb=None, bounce=-1,
+                    map_dev: int | None = None, accumulate=False, download=True) -> FluenceData:
+    """HitMap::calc_fluence_map(.., FluenceEstimator::Binning) (hit_map/mod.rs:363-379, rays_hit_map.rs:330-391)."""
+    L = F.lib()
+    own = map_dev is None
+    if own:
+        map_dev = ctx.device_alloc(nx * ny * 8)
+    try:
+        arr = (C.c_void_p * len(hit_maps))(*[h.h for h in hit_maps])
+        rg = (C.c_double * 4)(*ranges) if ranges is not None else None
+        ov = (C.c_double * 4)(*lrtb) if lrtb is not None else None
+        out = (C.c_double * 4)()
+        _check(L.opm_fluence_binning(arr, len(hit_maps), bounce, nx, ny, rg, ov, int(accumulate), C.c_void_p(map_dev), out))
+        peak, tot = C.c_double(), C.c_double()
+        _check(L.opm_fluence_peak_total(ctx.h, C.c_void_p(map_dev), nx, ny, out, C.byref(peak), C.byref(tot)))
+        m = None
+        if download:
+            flat = np.zeros(nx * ny)
+            ctx.to_host(map_dev, flat)
+            m = flat.reshape(nx, ny).T.copy()  # column-major ny x nx
+        return FluenceData(m, tuple(out[:]), peak.value, tot.value)
+    finally:
+        if own:
+            ctx.device_free(map_dev)
+
+
+def hitmaps_bounding_box(hit_maps, bounce=-1):
+    arr = (C.c_void_p * len(hit_maps))(*[h.h for h in hit_maps])
+    out = (C.c_double * 4)()
+    n = C.c_uint64()
+    _check(F.lib().opm_hitmaps_bounding_box(arr, len(hit_maps), bounce, out, C.byref(n)))
+    return tuple(out[:]), n.value
+
+
+# ---------------------------------------------------------------------------------------------
+class SourceDesc:
+    """Deterministic collimated source generated on the device (rays.rs:264-297)."""
+
+    def __init__(self, n_positions: int, wavelengths, weights=None, total_energy=1.0, iso: Isometry | None = None):
+        self.c = F.OpmSourceDesc()
+        self.c.n_positions = n_positions
+        self.c.total_energy = total_energy
+        self._w = np.ascontiguousarray(np.atleast_1d(wavelengths), dtype=np.float64)
+        self._g = np.ascontiguousarray(np.atleast_1d(weights if weights is not None else [1.0]), dtype=np.float64)
+        self.c.n_wavelengths = len(self._w)
+        self.c.wavelengths = self._w.ctypes.data_as(C.POINTER(C.c_double))
+        self.c.weights = self._g.ctypes.data_as(C.POINTER(C.c_double))
+        self.c.iso = (iso or Isometry.identity()).c
+        self.c.power = 1.0
+        self.c.sigma[:] = [1.0, 1.0]
+
+    def grid(self, nx, ny, side_x, side_y):
+        self.c.pos_dist, self.c.grid_nx, self.c.grid_ny, self.c.size_x, self.c.size_y = F.POS_GRID, nx, ny, side_x, side_y
+        return self
+
+    def fibonacci_rectangle(self, sx, sy):
+        self.c.pos_dist, self.c.size_x, self.c.size_y = F.POS_FIBONACCI_RECT, sx, sy
+        return self
+
+    def fibonacci_ellipse(self, rx, ry):
+        self.c.pos_dist, self.c.size_x, self.c.size_y = F.POS_FIBONACCI_ELLIPSE, rx, ry
+        return self
+
+    def general_gaussian(self, mu=(0.0, 0.0), sigma=(1.0, 1.0), power=1.0, theta=0.0, rectangular=False, norm=0.0):
+        self.c.energy_dist = F.EDIST_GENERAL_GAUSSIAN
+        self.c.mu[:], self.c.sigma[:] = list(mu), list(sigma)
+        self.c.power, self.c.theta, self.c.rectangular, self.c.energy_norm = power, theta, int(rectangular), norm
+        return self
+
+    def energy_norm(self, ctx: Context, begin=0, end=None) -> float:
+        out = C.c_double()
+        _check(F.lib().opm_source_energy_norm(ctx.h, C.byref(self.c), begin, end if end is not None else self.c.n_positions,
+                                              C.byref(out)))
+        return out.value
+
+    def generate(self, ctx: Context, begin=0, end=None, rays: Rays | None = None) -> Rays:
+        end = end if end is not None else self.c.n_positions
+        r = rays or Rays(ctx, max((end - begin) * self.c.n_wavelengths, 1))
+        _check(F.lib().opm_source_generate(r.h, C.byref(self.c), begin, end))
+        return r

@@ -1,0 +1,1056 @@
+// opm_api.cu -- implementation of the C ABI declared in include/opossum_b200.h.
+//
+// Host-side bookkeeping only: handle lifetimes, descriptor validation (same error conditions as the
+// reference's OpmResult paths), conversion of public op descriptors into the device program, launches.
+// All arithmetic on rays happens in the CUDA kernels (opm_trace.cu, opm_kernels.cu); there is no CPU path.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "opm_internal.h"
+#include "opm_kernels.h"
+
+using namespace opm;
+
+// ---------------------------------------------------------------------------------------------
+// handles
+// ---------------------------------------------------------------------------------------------
+struct OpmContext {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    int sms = 148;
+    uint64_t launches = 0;
+    DevStats* d_stats = nullptr;
+    DevStats* h_stats = nullptr;  // pinned
+    DevOp* d_ops = nullptr;
+    // pinned staging ring for op programs: launches stay asynchronous (a pageable source would make every
+    // cudaMemcpyAsync a stream synchronisation point)
+    static constexpr int kRing = 8;
+    DevOp* h_ops_ring = nullptr;
+    cudaEvent_t ring_ev[kRing] = {};
+    int ring_pos = 0;
+    unsigned char* d_scratch = nullptr;  // small accumulators
+    unsigned char* h_scratch = nullptr;  // pinned mirror
+    static constexpr size_t kScratch = 4096;
+};
+
+struct OpmRays {
+    OpmContext* ctx = nullptr;
+    uint64_t cap = 0, len = 0;
+    void* base = nullptr;
+    DevRays v{};
+    unsigned long long* d_tail = nullptr;
+    bool len_dirty = false;  // the device tail counter is ahead of `len` (asynchronous append)
+};
+
+struct OpmHitMap {
+    OpmContext* ctx = nullptr;
+    uint64_t cap = 0, len = 0;
+    void* base = nullptr;
+    DevHits v{};
+};
+
+// ---------------------------------------------------------------------------------------------
+// errors
+// ---------------------------------------------------------------------------------------------
+static thread_local std::string g_last_error;
+
+static OpmStatus fail(OpmStatus s, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_last_error = buf;
+    return s;
+}
+#define CU(expr)                                                                                         \
+    do {                                                                                                 \
+        cudaError_t _e = (expr);                                                                         \
+        if (_e != cudaSuccess) return fail(OPM_ERR_CUDA, "CUDA error %s at %s:%d (%s)", cudaGetErrorName(_e), \
+                                           __FILE__, __LINE__, cudaGetErrorString(_e));                  \
+    } while (0)
+#define KL(expr)                                                                                         \
+    do {                                                                                                 \
+        int _e = (expr);                                                                                 \
+        if (_e != 0) return fail(OPM_ERR_CUDA, "kernel launch failed: %s at %s:%d",                      \
+                                 cudaGetErrorString((cudaError_t)_e), __FILE__, __LINE__);               \
+    } while (0)
+
+extern "C" const char* opm_status_string(OpmStatus s) {
+    switch (s) {
+        case OPM_OK: return "ok";
+        case OPM_ERR_N2_INVALID: return "the refractive index must be >=1.0 and finite";
+        case OPM_ERR_WVL_RANGE: return "wavelength outside valid range";
+        case OPM_ERR_INDEX_MODEL: return "refractive index calculated by model is <1.0 or not finite";
+        case OPM_ERR_COATING: return "reflectivity must be within [0.0, 1.0] and finite.";
+        case OPM_ERR_APODIZE_FACTOR: return "transmission factor must be within (0.0..=1.0)";
+        case OPM_ERR_THRESHOLD: return "threshold energy must be finite";
+        case OPM_ERR_HITPOINT: return "hit point: value must be positive and finite, position must be finite";
+        case OPM_ERR_SPLIT_RATIO: return "splitting_ratio must be within [0.0;1.0]";
+        case OPM_ERR_FOCAL_LENGTH: return "focal length must be !=0.0 and finite";
+        case OPM_ERR_EMPTY_HITMAP: return "could not calculate bounding box";
+        case OPM_ERR_BIN_RANGE: return "hit point outside the given fluence map range";
+        case OPM_ERR_ARG: return "invalid argument";
+        case OPM_ERR_CAPACITY: return "output bundle or hit map too small";
+        case OPM_ERR_CUDA: return "CUDA failure";
+        default: return "unknown status";
+    }
+}
+extern "C" const char* opm_last_error(void) { return g_last_error.c_str(); }
+extern "C" int32_t opm_abi_version(void) { return OPM_ABI_VERSION; }
+
+static OpmStatus status_from_bits(uint32_t bits) {
+    if (!bits) return OPM_OK;
+    for (int k = 1; k < 32; ++k)
+        if (bits & (1u << k)) return fail((OpmStatus)k, "%s", opm_status_string((OpmStatus)k));
+    return OPM_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// context
+// ---------------------------------------------------------------------------------------------
+extern "C" OpmStatus opm_context_create(int32_t device, void* stream, OpmContext** out) {
+    if (!out) return fail(OPM_ERR_ARG, "out is NULL");
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return fail(OPM_ERR_CUDA, "no CUDA device available (%s): opossum_b200 has no CPU fallback",
+                    e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+    if (device < 0 || device >= count) return fail(OPM_ERR_ARG, "device %d out of range (%d devices)", device, count);
+    CU(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10)
+        return fail(OPM_ERR_CUDA, "device %d is sm_%d%d; this library carries sm_100a code only", device, prop.major, prop.minor);
+    OpmContext* c = new OpmContext();
+    c->device = device;
+    c->sms = prop.multiProcessorCount;
+    if (stream) { c->stream = (cudaStream_t)stream; c->own_stream = false; }
+    else { CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)); c->own_stream = true; }
+    CU(cudaMalloc(&c->d_stats, sizeof(DevStats)));
+    CU(cudaMallocHost(&c->h_stats, sizeof(DevStats)));
+    CU(cudaMalloc(&c->d_ops, sizeof(DevOp) * OPM_MAX_PROGRAM_OPS * OpmContext::kRing));
+    CU(cudaMallocHost(&c->h_ops_ring, sizeof(DevOp) * OPM_MAX_PROGRAM_OPS * OpmContext::kRing));
+    for (int k = 0; k < OpmContext::kRing; ++k) CU(cudaEventCreateWithFlags(&c->ring_ev[k], cudaEventDisableTiming));
+    CU(cudaMalloc(&c->d_scratch, OpmContext::kScratch));
+    CU(cudaMallocHost(&c->h_scratch, OpmContext::kScratch));
+    *out = c;
+    return OPM_OK;
+}
+extern "C" void opm_context_destroy(OpmContext* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    for (int k = 0; k < OpmContext::kRing; ++k) if (c->ring_ev[k]) cudaEventDestroy(c->ring_ev[k]);
+    cudaFreeHost(c->h_ops_ring);
+    cudaFree(c->d_stats); cudaFreeHost(c->h_stats); cudaFree(c->d_ops); cudaFree(c->d_scratch); cudaFreeHost(c->h_scratch);
+    if (c->own_stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+extern "C" OpmStatus opm_context_synchronize(OpmContext* c) {
+    if (!c) return fail(OPM_ERR_ARG, "context is NULL");
+    CU(cudaSetDevice(c->device));
+    CU(cudaStreamSynchronize(c->stream));
+    return OPM_OK;
+}
+extern "C" void* opm_context_stream(OpmContext* c) { return c ? (void*)c->stream : nullptr; }
+extern "C" uint64_t opm_context_launch_count(const OpmContext* c) { return c ? c->launches : 0; }
+
+// ---------------------------------------------------------------------------------------------
+// isometry (utils/geom_transformation.rs) -- host math in 3x3 + t form
+// ---------------------------------------------------------------------------------------------
+static void iso_invert(const OpmIso& f, OpmIso& inv) {  // (R^T, -R^T t)  geom_transformation.rs:226-229
+    for (int r = 0; r < 3; ++r)
+        for (int c = 0; c < 3; ++c) inv.rot[r * 3 + c] = f.rot[c * 3 + r];
+    for (int r = 0; r < 3; ++r)
+        inv.t[r] = -(inv.rot[r * 3 + 0] * f.t[0] + inv.rot[r * 3 + 1] * f.t[1] + inv.rot[r * 3 + 2] * f.t[2]);
+}
+extern "C" void opm_isometry_identity(OpmIsometry* o) {
+    memset(o, 0, sizeof *o);
+    o->fwd.rot[0] = o->fwd.rot[4] = o->fwd.rot[8] = 1.0;
+    o->inv.rot[0] = o->inv.rot[4] = o->inv.rot[8] = 1.0;
+}
+// Isometry::new: rotation applied in the order x -> y -> z, i.e. R = Rz(az) * Ry(ay) * Rx(ax)
+// (nalgebra Rotation3::from_euler_angles(roll, pitch, yaw), geom_transformation.rs:44-72)
+extern "C" OpmStatus opm_isometry_new(const double t[3], const double e[3], OpmIsometry* o) {
+    for (int k = 0; k < 3; ++k) {
+        if (!std::isfinite(t[k])) return fail(OPM_ERR_ARG, "translation coordinates must be finite");
+        if (!std::isfinite(e[k])) return fail(OPM_ERR_ARG, "axis angles must be finite");
+    }
+    double sr = sin(e[0]), cr = cos(e[0]), sp = sin(e[1]), cp = cos(e[1]), sy = sin(e[2]), cy = cos(e[2]);
+    double m[9] = {cy * cp, cy * sp * sr - sy * cr, cy * sp * cr + sy * sr,
+                   sy * cp, sy * sp * sr + cy * cr, sy * sp * cr - cy * sr,
+                   -sp,     cp * sr,                cp * cr};
+    memcpy(o->fwd.rot, m, sizeof m);
+    memcpy(o->fwd.t, t, 3 * sizeof(double));
+    iso_invert(o->fwd, o->inv);
+    return OPM_OK;
+}
+extern "C" void opm_isometry_append(const OpmIsometry* a, const OpmIsometry* b, OpmIsometry* o) {  // a o b: b first (:216-223)
+    OpmIso f;
+    for (int r = 0; r < 3; ++r)
+        for (int c = 0; c < 3; ++c)
+            f.rot[r * 3 + c] = a->fwd.rot[r * 3 + 0] * b->fwd.rot[0 * 3 + c] + a->fwd.rot[r * 3 + 1] * b->fwd.rot[1 * 3 + c] +
+                               a->fwd.rot[r * 3 + 2] * b->fwd.rot[2 * 3 + c];
+    for (int r = 0; r < 3; ++r)
+        f.t[r] = a->fwd.rot[r * 3 + 0] * b->fwd.t[0] + a->fwd.rot[r * 3 + 1] * b->fwd.t[1] + a->fwd.rot[r * 3 + 2] * b->fwd.t[2] + a->fwd.t[r];
+    o->fwd = f;
+    iso_invert(o->fwd, o->inv);
+}
+extern "C" void opm_raytrace_config_default(OpmRayTraceConfig* c) {  // analyzers/raytrace.rs:315-322
+    c->min_energy_per_ray = 1.0 * 1.0E-12;
+    c->max_number_of_bounces = 1000;
+    c->max_number_of_refractions = 1000;
+    c->missed_surface_strategy = OPM_MISS_STOP;
+    c->_pad = 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// rays storage
+// ---------------------------------------------------------------------------------------------
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+static size_t rays_layout(uint64_t cap, void* base, DevRays* v, unsigned long long** tail) {
+    size_t off = 0;
+    unsigned char* b = (unsigned char*)base;
+    auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return b ? b + o : nullptr; };
+    double** d[10] = {&v->px, &v->py, &v->pz, &v->dx, &v->dy, &v->dz, &v->e, &v->wvl, &v->opl, &v->n};
+    for (auto p : d) *p = (double*)take(cap * 8);
+    v->bounces = (uint32_t*)take(cap * 4);
+    v->refr = (uint32_t*)take(cap * 4);
+    v->id = (uint32_t*)take(cap * 4);
+    v->valid = (uint8_t*)take(cap);
+    *tail = (unsigned long long*)take(8);
+    return off;
+}
+
+static OpmStatus rays_alloc(OpmRays* r, uint64_t cap) {
+    DevRays tmp; unsigned long long* t;
+    size_t bytes = rays_layout(cap, nullptr, &tmp, &t);
+    void* base = nullptr;
+    CU(cudaMalloc(&base, bytes));
+    r->base = base; r->cap = cap;
+    rays_layout(cap, base, &r->v, &r->d_tail);
+    CU(cudaMemsetAsync(r->d_tail, 0, 8, r->ctx->stream));
+    return OPM_OK;
+}
+
+extern "C" OpmStatus opm_rays_create(OpmContext* ctx, uint64_t capacity, OpmRays** out) {
+    if (!ctx || !out) return fail(OPM_ERR_ARG, "NULL argument");
+    CU(cudaSetDevice(ctx->device));
+    OpmRays* r = new OpmRays();
+    r->ctx = ctx;
+    OpmStatus s = rays_alloc(r, capacity ? capacity : 1);
+    if (s != OPM_OK) { delete r; return s; }
+    *out = r;
+    return OPM_OK;
+}
+extern "C" void opm_rays_destroy(OpmRays* r) {
+    if (!r) return;
+    cudaSetDevice(r->ctx->device);
+    cudaStreamSynchronize(r->ctx->stream);
+    cudaFree(r->base);
+    delete r;
+}
+static OpmStatus rays_refresh_len(OpmRays* r) {
+    if (!r->len_dirty) return OPM_OK;
+    unsigned long long t = 0;
+    CU(cudaMemcpyAsync(&t, r->d_tail, 8, cudaMemcpyDeviceToHost, r->ctx->stream));
+    CU(cudaStreamSynchronize(r->ctx->stream));
+    r->len = t > r->cap ? r->cap : t;
+    r->len_dirty = false;
+    return OPM_OK;
+}
+extern "C" uint64_t opm_rays_len(const OpmRays* r) {
+    if (!r) return 0;
+    rays_refresh_len(const_cast<OpmRays*>(r));
+    return r->len;
+}
+extern "C" uint64_t opm_rays_capacity(const OpmRays* r) { return r ? r->cap : 0; }
+extern "C" OpmStatus opm_rays_clear(OpmRays* r) {
+    if (!r) return fail(OPM_ERR_ARG, "rays is NULL");
+    r->len = 0; r->len_dirty = false;
+    CU(cudaMemsetAsync(r->d_tail, 0, 8, r->ctx->stream));
+    return OPM_OK;
+}
+static OpmStatus copy_fields(const DevRays& s, uint64_t soff, const DevRays& d, uint64_t doff, uint64_t n, cudaStream_t st) {
+    if (n == 0) return OPM_OK;
+    const double* sd[10] = {s.px, s.py, s.pz, s.dx, s.dy, s.dz, s.e, s.wvl, s.opl, s.n};
+    double* dd[10] = {d.px, d.py, d.pz, d.dx, d.dy, d.dz, d.e, d.wvl, d.opl, d.n};
+    for (int k = 0; k < 10; ++k) CU(cudaMemcpyAsync(dd[k] + doff, sd[k] + soff, n * 8, cudaMemcpyDeviceToDevice, st));
+    CU(cudaMemcpyAsync(d.bounces + doff, s.bounces + soff, n * 4, cudaMemcpyDeviceToDevice, st));
+    CU(cudaMemcpyAsync(d.refr + doff, s.refr + soff, n * 4, cudaMemcpyDeviceToDevice, st));
+    CU(cudaMemcpyAsync(d.id + doff, s.id + soff, n * 4, cudaMemcpyDeviceToDevice, st));
+    CU(cudaMemcpyAsync(d.valid + doff, s.valid + soff, n, cudaMemcpyDeviceToDevice, st));
+    return OPM_OK;
+}
+extern "C" OpmStatus opm_rays_reserve(OpmRays* r, uint64_t capacity) {
+    if (!r) return fail(OPM_ERR_ARG, "rays is NULL");
+    if (capacity <= r->cap) return OPM_OK;
+    CU(cudaSetDevice(r->ctx->device));
+    OpmStatus s = rays_refresh_len(r);
+    if (s) return s;
+    OpmRays old = *r;
+    s = rays_alloc(r, capacity);
+    if (s) { *r = old; return s; }
+    s = copy_fields(old.v, 0, r->v, 0, old.len, r->ctx->stream);
+    if (s) return s;
+    KL(k_set_u64(r->d_tail, r->len, r->ctx->stream));
+    CU(cudaStreamSynchronize(r->ctx->stream));
+    cudaFree(old.base);
+    return OPM_OK;
+}
+static OpmStatus rays_set_len(OpmRays* r, uint64_t n) {
+    r->len = n; r->len_dirty = false;
+    KL(k_set_u64(r->d_tail, n, r->ctx->stream));  // value travels as a kernel argument: no host staging, fully asynchronous
+    r->ctx->launches++;
+    return OPM_OK;
+}
+
+extern "C" OpmStatus opm_rays_upload(OpmRays* r, const OpmRay* host, uint64_t n) {
+    if (!r || (!host && n)) return fail(OPM_ERR_ARG, "NULL argument");
+    OpmContext* c = r->ctx;
+    CU(cudaSetDevice(c->device));
+    OpmStatus s = opm_rays_reserve(r, n);
+    if (s) return s;
+    if (n) {
+        OpmRay* d_aos = nullptr;
+        CU(cudaMalloc(&d_aos, n * sizeof(OpmRay)));
+        CU(cudaMemcpyAsync(d_aos, host, n * sizeof(OpmRay), cudaMemcpyHostToDevice, c->stream));
+        KL(k_aos_to_soa(d_aos, r->v, 0, n, c->sms, c->stream)); c->launches++;
+        CU(cudaStreamSynchronize(c->stream));
+        cudaFree(d_aos);
+    }
+    return rays_set_len(r, n);
+}
+extern "C" OpmStatus opm_rays_upload_soa(OpmRays* r, const double* pos[3], const double* dir[3], const double* e,
+                                         const double* wvl, uint64_t n) {
+    if (!r || !pos || !dir || !e || !wvl) return fail(OPM_ERR_ARG, "NULL argument");
+    OpmContext* c = r->ctx;
+    CU(cudaSetDevice(c->device));
+    OpmStatus s = opm_rays_reserve(r, n);
+    if (s) return s;
+    if (n) {
+        double* dst[8] = {r->v.px, r->v.py, r->v.pz, r->v.dx, r->v.dy, r->v.dz, r->v.e, r->v.wvl};
+        const double* src[8] = {pos[0], pos[1], pos[2], dir[0], dir[1], dir[2], e, wvl};
+        for (int k = 0; k < 8; ++k) CU(cudaMemcpyAsync(dst[k], src[k], n * 8, cudaMemcpyHostToDevice, c->stream));
+        KL(k_soa_defaults(r->v, n, c->sms, c->stream)); c->launches++;
+    }
+    return rays_set_len(r, n);
+}
+extern "C" OpmStatus opm_rays_download(const OpmRays* rc, OpmRay* host, uint64_t capacity, uint64_t* n_out) {
+    OpmRays* r = const_cast<OpmRays*>(rc);
+    if (!r || !n_out) return fail(OPM_ERR_ARG, "NULL argument");
+    OpmContext* c = r->ctx;
+    CU(cudaSetDevice(c->device));
+    OpmStatus s = rays_refresh_len(r);
+    if (s) return s;
+    uint64_t n = r->len;
+    *n_out = 0;
+    if (n == 0) return OPM_OK;
+    OpmRay* d_aos = nullptr;
+    CU(cudaMalloc(&d_aos, n * sizeof(OpmRay)));
+    KL(k_soa_to_aos(r->v, d_aos, n, c->sms, c->stream)); c->launches++;
+    std::vector<OpmRay> tmp(n);
+    CU(cudaMemcpyAsync(tmp.data(), d_aos, n * sizeof(OpmRay), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    cudaFree(d_aos);
+    uint64_t k = 0;
+    for (uint64_t i = 0; i < n; ++i) {
+        if (tmp[i].valid == RAY_REMOVED) continue;
+        if (k >= capacity) return fail(OPM_ERR_CAPACITY, "download buffer too small");
+        host[k++] = tmp[i];
+    }
+    *n_out = k;
+    return OPM_OK;
+}
+extern "C" OpmStatus opm_rays_copy(const OpmRays* src, OpmRays* dst) {
+    if (!src || !dst) return fail(OPM_ERR_ARG, "NULL argument");
+    CU(cudaSetDevice(dst->ctx->device));
+    OpmStatus s = rays_refresh_len(const_cast<OpmRays*>(src));
+    if (s) return s;
+    s = opm_rays_reserve(dst, src->len);
+    if (s) return s;
+    s = copy_fields(src->v, 0, dst->v, 0, src->len, dst->ctx->stream);
+    if (s) return s;
+    return rays_set_len(dst, src->len);
+}
+extern "C" OpmStatus opm_rays_append(OpmRays* dst, const OpmRays* src) {
+    if (!src || !dst) return fail(OPM_ERR_ARG, "NULL argument");
+    CU(cudaSetDevice(dst->ctx->device));
+    OpmStatus s = rays_refresh_len(const_cast<OpmRays*>(src));
+    if (s) return s;
+    s = rays_refresh_len(dst);
+    if (s) return s;
+    s = opm_rays_reserve(dst, dst->len + src->len);
+    if (s) return s;
+    s = copy_fields(src->v, 0, dst->v, dst->len, src->len, dst->ctx->stream);
+    if (s) return s;
+    return rays_set_len(dst, dst->len + src->len);
+}
+extern "C" OpmStatus opm_rays_compact(OpmRays* r) {
+    if (!r) return fail(OPM_ERR_ARG, "rays is NULL");
+    OpmContext* c = r->ctx;
+    CU(cudaSetDevice(c->device));
+    OpmStatus s = rays_refresh_len(r);
+    if (s) return s;
+    uint64_t n = r->len;
+    if (n == 0) return OPM_OK;
+    uint64_t nb = (n + 1023) / 1024;
+    unsigned* counts = nullptr; unsigned long long* offsets = nullptr;
+    CU(cudaMalloc(&counts, nb * sizeof(unsigned)));
+    CU(cudaMalloc(&offsets, (nb + 1) * sizeof(unsigned long long)));
+    OpmRays old = *r;
+    s = rays_alloc(r, old.cap);
+    if (s) { *r = old; cudaFree(counts); cudaFree(offsets); return s; }
+    int rc = k_compact(old.v, r->v, n, counts, offsets, r->d_tail, c->stream);
+    c->launches += 3;
+    unsigned long long total = 0;
+    cudaMemcpyAsync(&total, r->d_tail, 8, cudaMemcpyDeviceToHost, c->stream);
+    cudaError_t e = cudaStreamSynchronize(c->stream);
+    cudaFree(counts); cudaFree(offsets); cudaFree(old.base);
+    if (rc != 0 || e != cudaSuccess) return fail(OPM_ERR_CUDA, "compaction failed: %s", cudaGetErrorString(e));
+    r->len = total; r->len_dirty = false;
+    return OPM_OK;
+}
+extern "C" void* opm_rays_field_ptr(OpmRays* r, const char* f) {
+    if (!r || !f) return nullptr;
+    struct { const char* n; void* p; } tab[] = {
+        {"px", r->v.px}, {"py", r->v.py}, {"pz", r->v.pz}, {"dx", r->v.dx}, {"dy", r->v.dy}, {"dz", r->v.dz},
+        {"e", r->v.e}, {"wvl", r->v.wvl}, {"opl", r->v.opl}, {"n", r->v.n}, {"bounces", r->v.bounces},
+        {"refr", r->v.refr}, {"id", r->v.id}, {"valid", r->v.valid}};
+    for (auto& t : tab) if (!strcmp(t.n, f)) return t.p;
+    return nullptr;
+}
+
+// ---------------------------------------------------------------------------------------------
+// hit maps
+// ---------------------------------------------------------------------------------------------
+static size_t hits_layout(uint64_t cap, void* base, DevHits* v) {
+    size_t off = 0;
+    unsigned char* b = (unsigned char*)base;
+    auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return b ? b + o : nullptr; };
+    v->x = (double*)take(cap * 8); v->y = (double*)take(cap * 8); v->z = (double*)take(cap * 8); v->e = (double*)take(cap * 8);
+    v->bounce = (uint32_t*)take(cap * 4);
+    return off;
+}
+extern "C" OpmStatus opm_hitmap_create(OpmContext* ctx, uint64_t capacity, OpmHitMap** out) {
+    if (!ctx || !out) return fail(OPM_ERR_ARG, "NULL argument");
+    CU(cudaSetDevice(ctx->device));
+    OpmHitMap* h = new OpmHitMap();
+    h->ctx = ctx; h->cap = capacity ? capacity : 1;
+    DevHits tmp;
+    size_t bytes = hits_layout(h->cap, nullptr, &tmp);
+    cudaError_t e = cudaMalloc(&h->base, bytes);
+    if (e != cudaSuccess) { delete h; return fail(OPM_ERR_CUDA, "cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e)); }
+    hits_layout(h->cap, h->base, &h->v);
+    *out = h;
+    return OPM_OK;
+}
+extern "C" void opm_hitmap_destroy(OpmHitMap* h) {
+    if (!h) return;
+    cudaSetDevice(h->ctx->device);
+    cudaStreamSynchronize(h->ctx->stream);
+    cudaFree(h->base);
+    delete h;
+}
+extern "C" uint64_t opm_hitmap_capacity(const OpmHitMap* h) { return h ? h->cap : 0; }
+extern "C" uint64_t opm_hitmap_len(const OpmHitMap* h) { return h ? h->len : 0; }
+extern "C" OpmStatus opm_hitmap_upload(OpmHitMap* h, const double* x, const double* y, const double* z, const double* e,
+                                       const uint32_t* bounce, uint64_t n) {
+    if (!h || !x || !y || !e) return fail(OPM_ERR_ARG, "NULL argument");
+    if (n > h->cap) return fail(OPM_ERR_CAPACITY, "hit map capacity %llu < %llu", (unsigned long long)h->cap, (unsigned long long)n);
+    cudaStream_t st = h->ctx->stream;
+    CU(cudaSetDevice(h->ctx->device));
+    CU(cudaMemcpyAsync(h->v.x, x, n * 8, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(h->v.y, y, n * 8, cudaMemcpyHostToDevice, st));
+    if (z) CU(cudaMemcpyAsync(h->v.z, z, n * 8, cudaMemcpyHostToDevice, st));
+    else CU(cudaMemsetAsync(h->v.z, 0, n * 8, st));
+    CU(cudaMemcpyAsync(h->v.e, e, n * 8, cudaMemcpyHostToDevice, st));
+    if (bounce) CU(cudaMemcpyAsync(h->v.bounce, bounce, n * 4, cudaMemcpyHostToDevice, st));
+    else CU(cudaMemsetAsync(h->v.bounce, 0, n * 4, st));
+    CU(cudaStreamSynchronize(st));
+    h->len = n;
+    return OPM_OK;
+}
+extern "C" OpmStatus opm_hitmap_download(const OpmHitMap* h, double* x, double* y, double* z, double* e, uint32_t* bounce,
+                                         uint64_t capacity, uint64_t* n_out) {
+    if (!h || !n_out) return fail(OPM_ERR_ARG, "NULL argument");
+    cudaStream_t st = h->ctx->stream;
+    CU(cudaSetDevice(h->ctx->device));
+    uint64_t n = h->len;
+    std::vector<double> tx(n), ty(n), tz(n), te(n);
+    std::vector<uint32_t> tb(n);
+    if (n) {
+        CU(cudaMemcpyAsync(tx.data(), h->v.x, n * 8, cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(ty.data(), h->v.y, n * 8, cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(tz.data(), h->v.z, n * 8, cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(te.data(), h->v.e, n * 8, cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(tb.data(), h->v.bounce, n * 4, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+    }
+    uint64_t k = 0;
+    for (uint64_t i = 0; i < n; ++i) {
+        if (!(te[i] >= 0.0)) continue;
+        if (k >= capacity) return fail(OPM_ERR_CAPACITY, "download buffer too small");
+        if (x) x[k] = tx[i];
+        if (y) y[k] = ty[i];
+        if (z) z[k] = tz[i];
+        if (e) e[k] = te[i];
+        if (bounce) bounce[k] = tb[i];
+        ++k;
+    }
+    *n_out = k;
+    return OPM_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// program compilation: public op descriptors -> device ops
+// ---------------------------------------------------------------------------------------------
+static void to_dev_iso(const OpmIso& s, DevIso& d) { memcpy(d.r, s.rot, sizeof d.r); memcpy(d.t, s.t, sizeof d.t); }
+
+struct Compiled {
+    std::vector<DevOp> ops;
+    std::vector<void*> temp_dev;        // polygon triangle uploads, freed after the launch
+    std::vector<OpmRays*> appended;     // bundles that receive appended rays (children)
+    std::vector<OpmRays*> slot_outputs; // split / snapshot outputs (len = n)
+    std::vector<OpmHitMap*> hitmaps;
+};
+
+static OpmStatus compile_aperture(OpmContext* c, const OpmAperture& a, DevAperture& d, Compiled& out) {
+    memset(&d, 0, sizeof d);
+    if (a.n_items < 0 || a.n_items > OPM_MAX_APERTURE_ITEMS) return fail(OPM_ERR_ARG, "aperture n_items out of range");
+    d.n_items = a.n_items; d.is_stack = a.is_stack; d.stack_obstruction = a.stack_obstruction; d.n_tris = 0;
+    for (int k = 0; k < a.n_items; ++k) {
+        d.items[k].type = a.items[k].type; d.items[k].obstruction = a.items[k].obstruction;
+        memcpy(d.items[k].p, a.items[k].p, sizeof d.items[k].p);
+        if (a.items[k].type == OPM_AP_POLYGON) {
+            if (a.n_tris <= 0 || !a.tris) return fail(OPM_ERR_ARG, "polygon aperture without triangles");
+            double* dt = nullptr;
+            CU(cudaMalloc(&dt, (size_t)a.n_tris * 6 * sizeof(double)));
+            out.temp_dev.push_back(dt);
+            CU(cudaMemcpyAsync(dt, a.tris, (size_t)a.n_tris * 6 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+            d.tris = dt; d.n_tris = a.n_tris;
+        }
+    }
+    return OPM_OK;
+}
+
+static OpmStatus compile_ops(OpmContext* c, const OpmOp* ops, int n_ops, uint64_t n_rays, Compiled& out) {
+    if (n_ops < 0 || n_ops > OPM_MAX_PROGRAM_OPS) return fail(OPM_ERR_ARG, "program has %d ops (max %d)", n_ops, OPM_MAX_PROGRAM_OPS);
+    for (int k = 0; k < n_ops; ++k) {
+        const OpmOp& p = ops[k];
+        DevOp d;
+        memset(&d, 0, sizeof d);
+        switch (p.kind) {
+            case OPM_OP_REFRACT: {
+                const OpmRefractOp& r = p.u.refract;
+                DevRefract& o = d.u.refract;
+                d.kind = OPK_REFRACT;
+                if (r.surface.geom < OPM_GEOM_PLANE || r.surface.geom > OPM_GEOM_PARABOLA) return fail(OPM_ERR_ARG, "unknown surface geometry %d", r.surface.geom);
+                if (r.surface.geom != OPM_GEOM_PLANE) {  // sphere.rs:48-57, cylinder.rs:30-37, parabola.rs:31-42: is_normal
+                    if (!std::isnormal(r.surface.geom_param)) return fail(OPM_ERR_ARG, "radius of curvature / focal length must be != 0.0 and finite");
+                }
+                o.geom = r.surface.geom; o.coating = r.surface.coating; o.param = r.surface.geom_param; o.coating_r = r.surface.coating_r;
+                to_dev_iso(r.surface.iso.fwd, o.fwd); to_dev_iso(r.surface.iso.inv, o.inv);
+                o.has_index = r.has_index ? 1 : 0; o.refraction_intended = r.refraction_intended ? 1 : 0;
+                o.strategy = r.strategy; o.flags = r.flags; o.index_type = r.index.type;
+                memcpy(o.ic, r.index.c, sizeof o.ic); o.wlo = r.index.wvl_lo; o.whi = r.index.wvl_hi;
+                if (r.hits) {
+                    if (r.hits->cap < n_rays) return fail(OPM_ERR_CAPACITY, "hit map capacity %llu < %llu rays", (unsigned long long)r.hits->cap, (unsigned long long)n_rays);
+                    o.hits = r.hits->v;
+                    out.hitmaps.push_back(r.hits);
+                }
+                if (r.flags & OPM_REFRACT_EMIT_CHILDREN) {
+                    if (!r.children) return fail(OPM_ERR_ARG, "OPM_REFRACT_EMIT_CHILDREN without a children bundle");
+                    OpmStatus s = rays_refresh_len(r.children);
+                    if (s) return s;
+                    s = opm_rays_reserve(r.children, r.children->len + n_rays);
+                    if (s) return s;
+                    o.children = r.children->v; o.child_tail = r.children->d_tail; o.child_cap = r.children->cap;
+                    out.appended.push_back(r.children);
+                }
+                break;
+            }
+            case OPM_OP_APODIZE: {
+                d.kind = OPK_APODIZE;
+                to_dev_iso(p.u.apodize.iso.inv, d.u.apodize.inv);
+                OpmStatus s = compile_aperture(c, p.u.apodize.aperture, d.u.apodize.ap, out);
+                if (s) return s;
+                if (d.u.apodize.ap.n_items == 0) continue;  // Aperture::None: factor 1.0 for every ray
+                break;
+            }
+            case OPM_OP_THRESHOLD: {  // rays.rs:1145-1154
+                double t = p.u.threshold.min_energy;
+                if (std::signbit(t)) continue;  // "negative threshold energy given. Ray bundle unmodified."
+                if (!std::isfinite(t)) return fail(OPM_ERR_THRESHOLD, "%s", opm_status_string(OPM_ERR_THRESHOLD));
+                d.kind = OPK_THRESHOLD; d.u.threshold.min_energy = t;
+                break;
+            }
+            case OPM_OP_LIMITS:
+                d.kind = OPK_LIMITS; d.u.limits.max_bounces = p.u.limits.max_bounces; d.u.limits.max_refr = p.u.limits.max_refractions;
+                d.u.limits.check_refr = p.u.limits.check_refractions;
+                break;
+            case OPM_OP_FILTER: {  // rays.rs:1120-1126
+                double t = p.u.filter.transmission;
+                if (!(t >= 0.0 && t <= 1.0)) return fail(OPM_ERR_APODIZE_FACTOR, "transmission value must be in the range [0.0;1.0]");
+                d.kind = OPK_FILTER; d.u.filter.t = t;
+                break;
+            }
+            case OPM_OP_PARAXIAL: {  // rays.rs:944-948
+                double f = p.u.paraxial.focal_length;
+                if (f == 0.0 || !std::isfinite(f)) return fail(OPM_ERR_FOCAL_LENGTH, "%s", opm_status_string(OPM_ERR_FOCAL_LENGTH));
+                d.kind = OPK_PARAXIAL; d.u.paraxial.f = f;
+                to_dev_iso(p.u.paraxial.iso.fwd, d.u.paraxial.fwd); to_dev_iso(p.u.paraxial.iso.inv, d.u.paraxial.inv);
+                break;
+            }
+            case OPM_OP_SPLIT: {  // ray.rs:763-767
+                double ratio = p.u.split.ratio;
+                if (!(ratio >= 0.0 && ratio <= 1.0)) return fail(OPM_ERR_SPLIT_RATIO, "%s", opm_status_string(OPM_ERR_SPLIT_RATIO));
+                if (!p.u.split.split_out) return fail(OPM_ERR_ARG, "split without output bundle");
+                OpmStatus s = opm_rays_reserve(p.u.split.split_out, n_rays);
+                if (s) return s;
+                d.kind = OPK_SPLIT; d.u.split.ratio = ratio; d.u.split.out = p.u.split.split_out->v;
+                out.slot_outputs.push_back(p.u.split.split_out);
+                break;
+            }
+            case OPM_OP_SNAPSHOT: {
+                if (!p.u.snapshot.out) return fail(OPM_ERR_ARG, "snapshot without output bundle");
+                OpmStatus s = opm_rays_reserve(p.u.snapshot.out, n_rays);
+                if (s) return s;
+                d.kind = OPK_SNAPSHOT; d.u.snapshot.out = p.u.snapshot.out->v;
+                out.slot_outputs.push_back(p.u.snapshot.out);
+                break;
+            }
+            default: return fail(OPM_ERR_ARG, "unknown op kind %d", p.kind);
+        }
+        out.ops.push_back(d);
+    }
+    return OPM_OK;
+}
+
+static void stats_to_public(const DevStats& d, OpmTraceStats* s) {
+    s->interactions = d.interactions; s->children = d.children; s->hits = d.hits; s->missed = d.missed;
+    s->apodized = d.apodized; s->valid_out = d.valid_out; s->alive_out = d.alive_out; s->status_bits = d.status_bits; s->_pad = 0;
+}
+
+// The one place that launches the fused kernel.  stats == NULL: fully asynchronous (no host sync).
+static OpmStatus run_program(OpmRays* rays, const OpmOp* ops, int n_ops, int flags, OpmRays* out, OpmTraceStats* stats) {
+    if (!rays || (!ops && n_ops)) return fail(OPM_ERR_ARG, "NULL argument");
+    OpmContext* c = rays->ctx;
+    CU(cudaSetDevice(c->device));
+    OpmStatus s = rays_refresh_len(rays);
+    if (s) return s;
+    const uint64_t n = rays->len;
+    const bool compact = (flags & OPM_TRACE_COMPACT) != 0;
+    if (stats) memset(stats, 0, sizeof *stats);
+    if (compact && (!out || out == rays)) return fail(OPM_ERR_ARG, "OPM_TRACE_COMPACT needs a distinct output bundle");
+    OpmRays* dst = (out && out != rays) ? out : rays;
+
+    Compiled prog;
+    s = compile_ops(c, ops, n_ops, n, prog);
+    auto free_temps = [&]() { for (void* p : prog.temp_dev) cudaFree(p); };
+    if (s) { free_temps(); return s; }
+
+    if (compact) {
+        s = rays_refresh_len(dst);
+        if (!s) s = opm_rays_reserve(dst, dst->len + n);
+        if (s) { free_temps(); return s; }
+    } else if (dst != rays) {
+        s = opm_rays_reserve(dst, n);
+        if (s) { free_temps(); return s; }
+    }
+    // a program whose ops were all elided (Aperture::None, negative threshold) still has to honour out/compact
+    if (n > 0 && (!prog.ops.empty() || dst != rays)) {
+        if (prog.ops.empty()) {  // pure copy: keep the kernel path uniform with a no-op limits check
+            DevOp d; memset(&d, 0, sizeof d);
+            d.kind = OPK_LIMITS; d.u.limits.max_bounces = ~0ull; d.u.limits.max_refr = ~0ull; d.u.limits.check_refr = 0;
+            prog.ops.push_back(d);
+        }
+        const int slot = c->ring_pos;
+        c->ring_pos = (c->ring_pos + 1) % OpmContext::kRing;
+        DevOp* h_slot = c->h_ops_ring + (size_t)slot * OPM_MAX_PROGRAM_OPS;
+        DevOp* d_slot = c->d_ops + (size_t)slot * OPM_MAX_PROGRAM_OPS;
+        CU(cudaEventSynchronize(c->ring_ev[slot]));  // the copy that last used this pinned slot has drained
+        memcpy(h_slot, prog.ops.data(), prog.ops.size() * sizeof(DevOp));
+        CU(cudaMemcpyAsync(d_slot, h_slot, prog.ops.size() * sizeof(DevOp), cudaMemcpyHostToDevice, c->stream));
+        CU(cudaEventRecord(c->ring_ev[slot], c->stream));
+        CU(cudaMemsetAsync(c->d_stats, 0, sizeof(DevStats), c->stream));
+        TraceLaunch L;
+        L.ops = d_slot; L.n_ops = (int)prog.ops.size();
+        L.in = rays->v; L.out = dst->v; L.n = n; L.out_cap = dst->cap; L.out_tail = dst->d_tail;
+        L.stats = c->d_stats; L.compact = compact ? 1 : 0; L.block = 256; L.stream = c->stream;
+        const bool strict = (flags & OPM_TRACE_STRICT) != 0;
+        size_t smem = prog.ops.size() * sizeof(DevOp);
+        int occ = strict ? trace_occupancy_strict(L.block, smem) : trace_occupancy_fast(L.block, smem);
+        uint64_t tiles = (n + L.block - 1) / L.block;
+        uint64_t maxg = (uint64_t)c->sms * occ;
+        L.grid = (int)(tiles < maxg ? tiles : maxg);
+        int rc = strict ? launch_trace_strict(L) : launch_trace_fast(L);
+        c->launches++;
+        if (rc != 0) { free_temps(); return fail(OPM_ERR_CUDA, "trace kernel launch failed: %s", cudaGetErrorString((cudaError_t)rc)); }
+    }
+    // host-side lengths
+    for (OpmHitMap* h : prog.hitmaps) h->len = n;
+    for (OpmRays* r : prog.slot_outputs) { s = rays_set_len(r, n); if (s) { free_temps(); return s; } }
+    for (OpmRays* r : prog.appended) r->len_dirty = true;
+    if (compact) dst->len_dirty = true;
+    else if (dst != rays) { s = rays_set_len(dst, n); if (s) { free_temps(); return s; } }
+
+    if (stats || !prog.temp_dev.empty()) {
+        if (n > 0 && !prog.ops.empty())
+            CU(cudaMemcpyAsync(c->h_stats, c->d_stats, sizeof(DevStats), cudaMemcpyDeviceToHost, c->stream));
+        else memset(c->h_stats, 0, sizeof(DevStats));
+        cudaError_t e = cudaStreamSynchronize(c->stream);
+        free_temps();
+        if (e != cudaSuccess) return fail(OPM_ERR_CUDA, "kernel execution failed: %s", cudaGetErrorString(e));
+        for (OpmRays* r : prog.appended) { s = rays_refresh_len(r); if (s) return s; }
+        if (compact) { s = rays_refresh_len(dst); if (s) return s; }
+        if (stats) {
+            stats_to_public(*c->h_stats, stats);
+            return status_from_bits(stats->status_bits);
+        }
+    }
+    return OPM_OK;
+}
+
+extern "C" OpmStatus opm_trace_sequence(OpmRays* rays, const OpmOp* ops, int32_t n_ops, int32_t flags, OpmRays* out,
+                                        OpmTraceStats* stats) {
+    return run_program(rays, ops, n_ops, flags, out, stats);
+}
+
+// ---------------------------------------------------------------------------------------------
+// stand-alone `Rays` methods: 1-op programs through the same kernel
+// ---------------------------------------------------------------------------------------------
+extern "C" OpmStatus opm_rays_refract_on_surface(OpmRays* rays, const OpmSurface* surface, const OpmIndexModel* n2,
+                                                 int32_t refraction_intended, int32_t strategy, OpmRays* reflected,
+                                                 OpmHitMap* hits, OpmTraceStats* stats) {
+    if (!rays || !surface) return fail(OPM_ERR_ARG, "NULL argument");
+    OpmOp op;
+    memset(&op, 0, sizeof op);
+    op.kind = OPM_OP_REFRACT;
+    op.u.refract.surface = *surface;
+    if (n2) { op.u.refract.index = *n2; op.u.refract.has_index = 1; }
+    op.u.refract.refraction_intended = refraction_intended;
+    op.u.refract.strategy = strategy;
+    op.u.refract.flags = reflected ? OPM_REFRACT_EMIT_CHILDREN : 0;
+    op.u.refract.hits = hits;
+    op.u.refract.children = reflected;
+    OpmTraceStats local;
+    return run_program(rays, &op, 1, 0, nullptr, stats ? stats : &local);
+}
+extern "C" OpmStatus opm_rays_apodize(OpmRays* rays, const OpmAperture* ap, const OpmIsometry* iso, int32_t* invalidated) {
+    if (!rays || !ap || !iso) return fail(OPM_ERR_ARG, "NULL argument");
+    OpmOp op;
+    memset(&op, 0, sizeof op);
+    op.kind = OPM_OP_APODIZE; op.u.apodize.iso = *iso; op.u.apodize.aperture = *ap;
+    OpmTraceStats st;
+    OpmStatus s = run_program(rays, &op, 1, 0, nullptr, &st);
+    if (invalidated) *invalidated = st.apodized ? 1 : 0;
+    return s;
+}
+static OpmStatus run_simple(OpmRays* rays, OpmOp& op) {
+    OpmTraceStats st;
+    return run_program(rays, &op, 1, 0, nullptr, &st);
+}
+extern "C" OpmStatus opm_rays_invalidate_by_threshold_energy(OpmRays* rays, double min_energy) {
+    OpmOp op; memset(&op, 0, sizeof op);
+    op.kind = OPM_OP_THRESHOLD; op.u.threshold.min_energy = min_energy;
+    return run_simple(rays, op);
+}
+extern "C" OpmStatus opm_rays_filter_by_nr_of_bounces(OpmRays* rays, uint64_t max_bounces) {
+    OpmOp op; memset(&op, 0, sizeof op);
+    op.kind = OPM_OP_LIMITS; op.u.limits.max_bounces = max_bounces; op.u.limits.check_refractions = 0;
+    return run_simple(rays, op);
+}
+extern "C" OpmStatus opm_rays_filter_by_nr_of_refractions(OpmRays* rays, uint64_t max_refr) {
+    OpmOp op; memset(&op, 0, sizeof op);
+    op.kind = OPM_OP_LIMITS; op.u.limits.max_bounces = ~0ull; op.u.limits.max_refractions = max_refr; op.u.limits.check_refractions = 1;
+    return run_simple(rays, op);
+}
+extern "C" OpmStatus opm_rays_filter_energy(OpmRays* rays, double t) {
+    OpmOp op; memset(&op, 0, sizeof op);
+    op.kind = OPM_OP_FILTER; op.u.filter.transmission = t;
+    return run_simple(rays, op);
+}
+extern "C" OpmStatus opm_rays_split(OpmRays* rays, double ratio, OpmRays* split_out) {
+    OpmOp op; memset(&op, 0, sizeof op);
+    op.kind = OPM_OP_SPLIT; op.u.split.ratio = ratio; op.u.split.split_out = split_out;
+    return run_simple(rays, op);
+}
+extern "C" OpmStatus opm_rays_refract_paraxial(OpmRays* rays, double f, const OpmIsometry* iso) {
+    if (!iso) return fail(OPM_ERR_ARG, "NULL argument");
+    OpmOp op; memset(&op, 0, sizeof op);
+    op.kind = OPM_OP_PARAXIAL; op.u.paraxial.focal_length = f; op.u.paraxial.iso = *iso;
+    return run_simple(rays, op);
+}
+extern "C" OpmStatus opm_rays_transform(OpmRays* rays, const OpmIsometry* iso, int32_t inverse) {
+    if (!rays || !iso) return fail(OPM_ERR_ARG, "NULL argument");
+    OpmContext* c = rays->ctx;
+    CU(cudaSetDevice(c->device));
+    OpmStatus s = rays_refresh_len(rays);
+    if (s) return s;
+    if (rays->len == 0) return OPM_OK;
+    DevIso I;
+    to_dev_iso(inverse ? iso->inv : iso->fwd, I);
+    KL(k_transform(rays->v, I, rays->len, c->sms, c->stream)); c->launches++;
+    return OPM_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// statistics
+// ---------------------------------------------------------------------------------------------
+extern "C" OpmStatus opm_rays_spot_stats(const OpmRays* rc, const OpmIsometry* frame, OpmSpotStats* out) {
+    OpmRays* r = const_cast<OpmRays*>(rc);
+    if (!r || !out) return fail(OPM_ERR_ARG, "NULL argument");
+    OpmContext* c = r->ctx;
+    CU(cudaSetDevice(c->device));
+    OpmStatus s = rays_refresh_len(r);
+    if (s) return s;
+    memset(out, 0, sizeof *out);
+    SpotAccum init;
+    memset(&init, 0, sizeof init);
+    init.first_key = ~0ull;
+    init.max_d2_key = double_to_key(0.0);
+    SpotAccum* d_acc = (SpotAccum*)c->d_scratch;
+    SpotAccum* h_acc = (SpotAccum*)c->h_scratch;
+    CU(cudaMemcpyAsync(d_acc, &init, sizeof init, cudaMemcpyHostToDevice, c->stream));
+    DevIso inv;
+    memset(&inv, 0, sizeof inv);
+    if (frame) to_dev_iso(frame->inv, inv);
+    if (r->len) { KL(k_spot(r->v, r->len, frame ? 1 : 0, inv, d_acc, c->sms, c->stream)); c->launches += 2; }
+    CU(cudaMemcpyAsync(h_acc, d_acc, sizeof init, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    const SpotAccum& a = *h_acc;
+    out->n_valid = a.n_valid; out->n_total = a.n_total; out->total_energy = a.sum[6];
+    const double nan = std::nan("");
+    if (a.n_valid == 0) {  // the reference returns None
+        for (int k = 0; k < 3; ++k) out->centroid[k] = out->energy_centroid[k] = nan;
+        out->beam_radius_geo = out->beam_radius_rms = out->energy_beam_radius_rms = nan;
+        return OPM_OK;
+    }
+    double len = (double)a.n_valid;
+    for (int k = 0; k < 3; ++k) { out->centroid[k] = a.sum[k] / len; out->energy_centroid[k] = a.sum[3 + k] / a.sum[6]; }
+    out->beam_radius_geo = std::sqrt(key_to_double(a.max_d2_key)) * 1.0E-3;  // millimeter!(max_dist)
+    out->beam_radius_rms = std::sqrt(a.sum_d2 / len) * 1.0E-3;
+    out->energy_beam_radius_rms = std::sqrt(a.sum_ed2 / a.sum[6]);
+    out->bounce_lvl = (uint32_t)(a.first_key & 0xffffffffull);
+    return OPM_OK;
+}
+extern "C" OpmStatus opm_rays_tally(const OpmRays* rc, uint32_t n_orders, uint64_t* counts, double* energy) {
+    OpmRays* r = const_cast<OpmRays*>(rc);
+    if (!r || !counts || !energy || n_orders == 0 || n_orders > 128) return fail(OPM_ERR_ARG, "bad argument (n_orders in 1..128)");
+    OpmContext* c = r->ctx;
+    CU(cudaSetDevice(c->device));
+    OpmStatus s = rays_refresh_len(r);
+    if (s) return s;
+    double* d_e = (double*)c->d_scratch;
+    unsigned long long* d_c = (unsigned long long*)(c->d_scratch + n_orders * 8);
+    CU(cudaMemsetAsync(c->d_scratch, 0, n_orders * 16, c->stream));
+    if (r->len) { KL(k_tally(r->v, r->len, n_orders, d_c, d_e, c->sms, c->stream)); c->launches++; }
+    CU(cudaMemcpyAsync(c->h_scratch, c->d_scratch, n_orders * 16, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    memcpy(energy, c->h_scratch, n_orders * 8);
+    memcpy(counts, c->h_scratch + n_orders * 8, n_orders * 8);
+    return OPM_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// fluence
+// ---------------------------------------------------------------------------------------------
+static OpmStatus check_same_ctx(OpmHitMap* const* maps, int n_maps, OpmContext** ctx) {
+    if (!maps || n_maps <= 0) return fail(OPM_ERR_ARG, "no hit maps given");
+    *ctx = maps[0]->ctx;
+    for (int k = 0; k < n_maps; ++k)
+        if (!maps[k] || maps[k]->ctx != *ctx) return fail(OPM_ERR_ARG, "hit maps must share one context");
+    return OPM_OK;
+}
+extern "C" OpmStatus opm_hitmaps_bounding_box(OpmHitMap* const* maps, int32_t n_maps, int64_t bounce_filter, double lrtb[4],
+                                              uint64_t* n_hits) {
+    OpmContext* c;
+    OpmStatus s = check_same_ctx(maps, n_maps, &c);
+    if (s) return s;
+    CU(cudaSetDevice(c->device));
+    BBoxAccum init;
+    init.key[0] = ~0ull; init.key[1] = 0; init.key[2] = 0; init.key[3] = ~0ull; init.count = 0;
+    BBoxAccum* d_acc = (BBoxAccum*)c->d_scratch;
+    CU(cudaMemcpyAsync(d_acc, &init, sizeof init, cudaMemcpyHostToDevice, c->stream));
+    for (int k = 0; k < n_maps; ++k)
+        if (maps[k]->len) { KL(k_hits_bbox(maps[k]->v, maps[k]->len, bounce_filter, d_acc, c->sms, c->stream)); c->launches++; }
+    CU(cudaMemcpyAsync(c->h_scratch, d_acc, sizeof init, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    const BBoxAccum& a = *(BBoxAccum*)c->h_scratch;
+    if (n_hits) *n_hits = a.count;
+    if (a.count == 0) return fail(OPM_ERR_EMPTY_HITMAP, "%s", opm_status_string(OPM_ERR_EMPTY_HITMAP));
+    for (int k = 0; k < 4; ++k) lrtb[k] = key_to_double(a.key[k]);
+    return OPM_OK;
+}
+extern "C" OpmStatus opm_fluence_binning(OpmHitMap* const* maps, int32_t n_maps, int64_t bounce_filter, uint64_t nx, uint64_t ny,
+                                         const double* ranges, const double* lrtb_override, int32_t accumulate, double* map_dev,
+                                         double lrtb_out[4]) {
+    OpmContext* c;
+    OpmStatus s = check_same_ctx(maps, n_maps, &c);
+    if (s) return s;
+    if (!map_dev || nx == 0 || ny == 0) return fail(OPM_ERR_ARG, "bad map arguments");
+    CU(cudaSetDevice(c->device));
+    double l, r, t, b;
+    if (ranges) { l = ranges[0]; r = ranges[1]; t = ranges[2]; b = ranges[3]; }  // rays_hit_map.rs:337-339 (sic)
+    else if (lrtb_override) { l = lrtb_override[0]; r = lrtb_override[1]; t = lrtb_override[2]; b = lrtb_override[3]; }
+    else {
+        double box[4];
+        s = opm_hitmaps_bounding_box(maps, n_maps, bounce_filter, box, nullptr);
+        if (s) return s;
+        l = box[0]; r = box[1]; t = box[2]; b = box[3];
+    }
+    BinParams P;
+    P.nx = nx; P.ny = ny; P.left = l; P.bottom = b;
+    double bin_width = (r - l) / (double)nx;
+    double bin_height = (t - b) / (double)ny;
+    P.bin_area = bin_width * bin_height;
+    P.width_step = (r - l) / (double)(nx - 1);
+    P.height_step = (t - b) / (double)(ny - 1);
+    if (!accumulate) CU(cudaMemsetAsync(map_dev, 0, nx * ny * sizeof(double), c->stream));
+    unsigned* d_status = (unsigned*)(c->d_scratch + 1024);
+    CU(cudaMemsetAsync(d_status, 0, 4, c->stream));
+    for (int k = 0; k < n_maps; ++k)
+        if (maps[k]->len) { KL(k_binning(maps[k]->v, maps[k]->len, bounce_filter, P, map_dev, d_status, c->sms, c->stream)); c->launches++; }
+    unsigned* h_status = (unsigned*)(c->h_scratch + 1024);
+    CU(cudaMemcpyAsync(h_status, d_status, 4, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    if (lrtb_out) { lrtb_out[0] = l; lrtb_out[1] = r; lrtb_out[2] = t; lrtb_out[3] = b; }
+    return status_from_bits(*h_status);
+}
+extern "C" OpmStatus opm_fluence_peak_total(OpmContext* c, const double* map_dev, uint64_t nx, uint64_t ny, const double lrtb[4],
+                                            double* peak, double* total) {
+    if (!c || !map_dev || !lrtb) return fail(OPM_ERR_ARG, "NULL argument");
+    CU(cudaSetDevice(c->device));
+    double dx = (lrtb[1] - lrtb[0]) / (double)nx;  // fluence_data.rs:131-133, x_range = left..right, y_range = bottom..top
+    double dy = (lrtb[2] - lrtb[3]) / (double)ny;
+    PeakAccum init;
+    init.peak_key = double_to_key(-INFINITY); init.total = 0.0;
+    PeakAccum* d_acc = (PeakAccum*)c->d_scratch;
+    CU(cudaMemcpyAsync(d_acc, &init, sizeof init, cudaMemcpyHostToDevice, c->stream));
+    KL(k_peak_total(map_dev, nx * ny, dx * dy, d_acc, c->sms, c->stream)); c->launches++;
+    CU(cudaMemcpyAsync(c->h_scratch, d_acc, sizeof init, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    const PeakAccum& a = *(PeakAccum*)c->h_scratch;
+    if (peak) *peak = key_to_double(a.peak_key);
+    if (total) *total = a.total;
+    return OPM_OK;
+}
+
+extern "C" OpmStatus opm_device_alloc(OpmContext* c, uint64_t bytes, void** out) {
+    if (!c || !out) return fail(OPM_ERR_ARG, "NULL argument");
+    CU(cudaSetDevice(c->device));
+    CU(cudaMalloc(out, bytes ? bytes : 1));
+    return OPM_OK;
+}
+extern "C" void opm_device_free(OpmContext* c, void* p) {
+    if (!c || !p) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    cudaFree(p);
+}
+extern "C" OpmStatus opm_device_to_host(OpmContext* c, void* host, const void* dev, uint64_t bytes) {
+    if (!c) return fail(OPM_ERR_ARG, "NULL argument");
+    CU(cudaSetDevice(c->device));
+    CU(cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return OPM_OK;
+}
+extern "C" OpmStatus opm_host_to_device(OpmContext* c, void* dev, const void* host, uint64_t bytes) {
+    if (!c) return fail(OPM_ERR_ARG, "NULL argument");
+    CU(cudaSetDevice(c->device));
+    CU(cudaMemcpyAsync(dev, host, bytes, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return OPM_OK;
+}
+extern "C" OpmStatus opm_host_alloc_pinned(uint64_t bytes, void** out) {
+    if (!out) return fail(OPM_ERR_ARG, "NULL argument");
+    CU(cudaMallocHost(out, bytes ? bytes : 1));
+    return OPM_OK;
+}
+extern "C" void opm_host_free_pinned(void* p) { if (p) cudaFreeHost(p); }
+
+// ---------------------------------------------------------------------------------------------
+// sources
+// ---------------------------------------------------------------------------------------------
+static OpmStatus source_params(const OpmSourceDesc* d, SourceParams& S) {
+    memset(&S, 0, sizeof S);
+    if (!d) return fail(OPM_ERR_ARG, "desc is NULL");
+    if (d->n_positions == 0) return fail(OPM_ERR_ARG, "source has no positions");
+    S.pos_dist = d->pos_dist; S.energy_dist = d->energy_dist; S.rectangular = d->rectangular;
+    S.n_positions = d->n_positions; S.n_wavelengths = d->n_wavelengths ? d->n_wavelengths : 1;
+    S.size_x = d->size_x; S.size_y = d->size_y;
+    S.golden = (1.0 + std::sqrt(5.0)) / 2.0;  // f64::midpoint(1., sqrt(5.)) fibonacci.rs:56
+    if (d->pos_dist == OPM_POS_GRID) {  // grid.rs:58-80
+        uint64_t nx = d->grid_nx < 1 ? 1 : d->grid_nx, ny = d->grid_ny < 1 ? 1 : d->grid_ny;
+        if (nx * ny != d->n_positions) return fail(OPM_ERR_ARG, "grid_nx*grid_ny != n_positions");
+        S.grid_ny = ny;
+        S.dist_x = nx > 1 ? d->size_x / (double)(nx - 1) : 0.0;
+        S.dist_y = ny > 1 ? d->size_y / (double)(ny - 1) : 0.0;
+        S.off_x = nx > 1 ? d->size_x / 2.0 : 0.0;
+        S.off_y = ny > 1 ? d->size_y / 2.0 : 0.0;
+    }
+    S.total_energy = d->total_energy;
+    S.e_uniform = d->total_energy / (double)d->n_positions;  // uniform.rs:39
+    S.energy_norm = d->energy_norm;
+    S.mu[0] = d->mu[0]; S.mu[1] = d->mu[1]; S.sigma[0] = d->sigma[0]; S.sigma[1] = d->sigma[1]; S.power = d->power;
+    S.sin_t = std::sin(d->theta); S.cos_t = std::cos(d->theta);
+    to_dev_iso(d->iso.fwd, S.iso);
+    return OPM_OK;
+}
+extern "C" OpmStatus opm_source_energy_norm(OpmContext* c, const OpmSourceDesc* desc, uint64_t pos_begin, uint64_t pos_end, double* partial) {
+    if (!c || !partial) return fail(OPM_ERR_ARG, "NULL argument");
+    SourceParams S;
+    OpmStatus s = source_params(desc, S);
+    if (s) return s;
+    if (pos_end > desc->n_positions || pos_begin > pos_end) return fail(OPM_ERR_ARG, "position range out of bounds");
+    CU(cudaSetDevice(c->device));
+    double* d_sum = (double*)c->d_scratch;
+    CU(cudaMemsetAsync(d_sum, 0, 8, c->stream));
+    if (pos_end > pos_begin) { KL(k_source_norm(S, pos_begin, pos_end, d_sum, c->sms, c->stream)); c->launches++; }
+    CU(cudaMemcpyAsync(c->h_scratch, d_sum, 8, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    *partial = *(double*)c->h_scratch;
+    return OPM_OK;
+}
+extern "C" OpmStatus opm_source_generate(OpmRays* rays, const OpmSourceDesc* desc, uint64_t pos_begin, uint64_t pos_end) {
+    if (!rays) return fail(OPM_ERR_ARG, "rays is NULL");
+    OpmContext* c = rays->ctx;
+    SourceParams S;
+    OpmStatus s = source_params(desc, S);
+    if (s) return s;
+    if (pos_end > desc->n_positions || pos_begin > pos_end) return fail(OPM_ERR_ARG, "position range out of bounds");
+    CU(cudaSetDevice(c->device));
+    if (S.energy_dist == OPM_EDIST_GENERAL_GAUSSIAN && !(S.energy_norm > 0.0)) {
+        double norm = 0.0;
+        s = opm_source_energy_norm(c, desc, 0, desc->n_positions, &norm);
+        if (s) return s;
+        S.energy_norm = norm;
+    }
+    uint64_t n_rays = (pos_end - pos_begin) * S.n_wavelengths;
+    s = opm_rays_reserve(rays, n_rays);
+    if (s) return s;
+    double one = 1.0, *d_w = nullptr;
+    CU(cudaMalloc(&d_w, (size_t)S.n_wavelengths * 16));
+    const double* hw = desc->n_wavelengths ? desc->wavelengths : nullptr;
+    const double* hg = desc->n_wavelengths ? desc->weights : nullptr;
+    if (!hw) { cudaFree(d_w); return fail(OPM_ERR_ARG, "source needs at least one wavelength"); }
+    CU(cudaMemcpyAsync(d_w, hw, (size_t)S.n_wavelengths * 8, cudaMemcpyHostToDevice, c->stream));
+    if (hg) CU(cudaMemcpyAsync(d_w + S.n_wavelengths, hg, (size_t)S.n_wavelengths * 8, cudaMemcpyHostToDevice, c->stream));
+    else CU(cudaMemcpyAsync(d_w + S.n_wavelengths, &one, 8, cudaMemcpyHostToDevice, c->stream));
+    if (n_rays) { KL(k_source_generate(S, rays->v, pos_begin, n_rays, d_w, d_w + S.n_wavelengths, c->sms, c->stream)); c->launches++; }
+    cudaError_t e = cudaStreamSynchronize(c->stream);
+    cudaFree(d_w);
+    if (e != cudaSuccess) return fail(OPM_ERR_CUDA, "source generation failed: %s", cudaGetErrorString(e));
+    return rays_set_len(rays, n_rays);
+}

@@ -1,0 +1,97 @@
+// opm_internal.h -- device-side POD layouts shared by the kernels and the C-ABI host code.
+// Not part of the public boundary (include/opossum_b200.h is).
+#pragma once
+#include <cstdint>
+
+#include "../../include/opossum_b200.h"
+
+namespace opm {
+
+// valid byte of a ray slot
+enum : uint8_t { RAY_INVALID = 0, RAY_VALID = 1, RAY_REMOVED = 2 };
+
+// Struct-of-arrays view of a ray bundle in HBM: 10 f64 + 3 u32 + 1 u8 = 93 B per ray.
+struct DevRays {
+    double *px, *py, *pz, *dx, *dy, *dz, *e, *wvl, *opl, *n;
+    uint32_t *bounces, *refr, *id;
+    uint8_t* valid;
+};
+constexpr int kRayBytes = 10 * 8 + 3 * 4 + 1;
+
+// Slot-indexed hit record of one surface pass: 4 f64 + u32 = 36 B per slot, e < 0 marks "no hit".
+struct DevHits {
+    double *x, *y, *z, *e;
+    uint32_t* bounce;
+};
+
+struct DevIso { double r[9]; double t[3]; };
+
+struct DevApItem { int32_t type, obstruction; double p[4]; };
+struct DevAperture {
+    int32_t n_items, is_stack, stack_obstruction, n_tris;
+    DevApItem items[OPM_MAX_APERTURE_ITEMS];
+    const double* tris;  // device
+};
+
+enum : int32_t { OPK_REFRACT = 1, OPK_APODIZE, OPK_THRESHOLD, OPK_LIMITS, OPK_FILTER, OPK_PARAXIAL, OPK_SPLIT, OPK_SNAPSHOT };
+
+struct DevRefract {
+    int32_t geom, coating, has_index, refraction_intended, strategy, flags, index_type, _pad;
+    double param, coating_r;
+    DevIso fwd, inv;
+    double ic[6];
+    double wlo, whi;
+    DevHits hits;                    // hits.e == nullptr: not recorded
+    DevRays children;                // children.px == nullptr: not emitted
+    unsigned long long* child_tail;  // device counter = current length of the children bundle
+    uint64_t child_cap;
+};
+struct DevApodize { DevIso inv; DevAperture ap; };
+struct DevThreshold { double min_energy; };
+struct DevLimits { uint64_t max_bounces, max_refr; int32_t check_refr, _pad; };
+struct DevFilter { double t; };
+struct DevParaxial { double f; DevIso fwd, inv; };
+struct DevSplit { double ratio; DevRays out; };
+struct DevSnapshot { DevRays out; };
+
+struct alignas(16) DevOp {
+    int32_t kind, _pad;
+    union {
+        DevRefract refract;
+        DevApodize apodize;
+        DevThreshold threshold;
+        DevLimits limits;
+        DevFilter filter;
+        DevParaxial paraxial;
+        DevSplit split;
+        DevSnapshot snapshot;
+    } u;
+};
+static_assert(sizeof(DevOp) % 16 == 0, "DevOp must be a multiple of 16 B for the bulk copy into shared memory");
+
+// device mirror of OpmTraceStats (all counters are atomically accumulated)
+struct DevStats {
+    unsigned long long interactions, children, hits, missed, apodized, valid_out, alive_out;
+    unsigned int status_bits, _pad;
+};
+
+struct TraceLaunch {
+    const DevOp* ops;  // device
+    int32_t n_ops;
+    DevRays in, out;
+    uint64_t n;
+    uint64_t out_cap;
+    unsigned long long* out_tail;  // compact mode: device counter of `out`
+    DevStats* stats;
+    int32_t compact;
+    int32_t grid, block;
+    void* stream;
+};
+
+// launchers implemented in opm_trace.cu (compiled twice: contracted "fast" and -fmad=false "strict")
+int launch_trace_fast(const TraceLaunch& L);
+int launch_trace_strict(const TraceLaunch& L);
+int trace_occupancy_fast(int block, size_t smem);
+int trace_occupancy_strict(int block, size_t smem);
+
+}  // namespace opm

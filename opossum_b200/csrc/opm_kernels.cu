@@ -1,0 +1,535 @@
+// opm_kernels.cu -- bundle plumbing, detector and source kernels (sm_100a).
+//
+//   * AoS<->SoA staging for upload/download, defaults of Ray::new (ray.rs:108-140)
+//   * Rays::transformed_by_iso
+//   * spot-diagram statistics (rays.rs:521-701, nodes/spot_diagram.rs:101-163): two fused passes
+//   * per-bounce-order tallies
+//   * hit-map bounding box (rays_hit_map.rs:522-562) and the Binning fluence estimator
+//     (rays_hit_map.rs:330-391): shared-memory privatised map when it fits, otherwise warp-run
+//     aggregated global f64 atomics
+//   * FluenceData peak / total energy (fluence_data.rs:45-68,130-141)
+//   * on-device sources (position_distributions/{grid,fibonacci}.rs, energy_distributions/, rays.rs:264-297)
+//   * order-preserving compaction of removed rays (ballot + popc ranks, block offsets from a scan)
+// All kernels are HBM-bound streaming kernels: coalesced SoA accesses, persistent grids sized from the
+// SM count, reductions through warp shuffles before any atomic.
+#include <cuda_runtime.h>
+
+#include <cfloat>
+
+#include "opm_device.cuh"
+#include "opm_kernels.h"
+
+namespace opm {
+
+// ---------------------------------------------------------------------------------------------
+// helpers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ double warp_min(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ unsigned long long warp_sum_u64(unsigned long long v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+// monotonic double <-> uint64 key so atomicMin/atomicMax work on doubles of any sign
+__device__ __forceinline__ unsigned long long dkey(double d) {
+    unsigned long long b = (unsigned long long)__double_as_longlong(d);
+    return (b & 0x8000000000000000ull) ? ~b : (b | 0x8000000000000000ull);
+}
+
+// ---------------------------------------------------------------------------------------------
+// AoS <-> SoA
+// ---------------------------------------------------------------------------------------------
+__global__ void aos_to_soa_kernel(const OpmRay* __restrict__ a, DevRays R, uint64_t off, uint64_t n) {
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        OpmRay r = a[i];
+        uint64_t j = off + i;
+        R.px[j] = r.pos[0]; R.py[j] = r.pos[1]; R.pz[j] = r.pos[2];
+        R.dx[j] = r.dir[0]; R.dy[j] = r.dir[1]; R.dz[j] = r.dir[2];
+        R.e[j] = r.e; R.wvl[j] = r.wvl; R.opl[j] = r.opl; R.n[j] = r.n;
+        R.bounces[j] = r.bounces; R.refr[j] = r.refr; R.id[j] = r.id;
+        R.valid[j] = r.valid ? RAY_VALID : RAY_INVALID;
+    }
+}
+__global__ void soa_to_aos_kernel(DevRays R, OpmRay* __restrict__ a, uint64_t n) {
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        OpmRay r;
+        r.pos[0] = R.px[i]; r.pos[1] = R.py[i]; r.pos[2] = R.pz[i];
+        r.dir[0] = R.dx[i]; r.dir[1] = R.dy[i]; r.dir[2] = R.dz[i];
+        r.e = R.e[i]; r.wvl = R.wvl[i]; r.opl = R.opl[i]; r.n = R.n[i];
+        r.bounces = R.bounces[i]; r.refr = R.refr[i]; r.id = R.id[i];
+        r.valid = R.valid[i];  // 2 = removed: dropped by the host side of download
+        a[i] = r;
+    }
+}
+// Ray::new defaults after a struct-of-arrays upload: normalised direction, opl 0, n 1, counters 0, valid
+__global__ void soa_defaults_kernel(DevRays R, uint64_t n) {
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        V3 d = v3(R.dx[i], R.dy[i], R.dz[i]);
+        double nn = sqrt(dot(d, d));
+        R.dx[i] = d.x / nn; R.dy[i] = d.y / nn; R.dz[i] = d.z / nn;
+        R.opl[i] = 0.0; R.n[i] = 1.0; R.bounces[i] = 0; R.refr[i] = 0; R.id[i] = (uint32_t)i; R.valid[i] = RAY_VALID;
+    }
+}
+__global__ void transform_kernel(DevRays R, DevIso I, uint64_t n) {  // ray.rs:787-804
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        if (R.valid[i] == RAY_REMOVED) continue;
+        V3 p = iso_point(I, v3(R.px[i], R.py[i], R.pz[i]));
+        V3 d = iso_vector(I, v3(R.dx[i], R.dy[i], R.dz[i]));
+        R.px[i] = p.x; R.py[i] = p.y; R.pz[i] = p.z;
+        R.dx[i] = d.x; R.dy[i] = d.y; R.dz[i] = d.z;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// spot statistics
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) spot_pass1_kernel(DevRays R, uint64_t n, int use_frame, DevIso inv, SpotAccum* acc) {
+    double s[7] = {0, 0, 0, 0, 0, 0, 0};  // x y z ex ey ez e
+    unsigned long long nv = 0, nt = 0, first = ~0ull;
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        uint8_t v = R.valid[i];
+        if (v == RAY_REMOVED) continue;
+        nt++;
+        if (v != RAY_VALID) continue;
+        nv++;
+        V3 p = v3(R.px[i], R.py[i], R.pz[i]);
+        if (use_frame) p = iso_point(inv, p);
+        double e = R.e[i];
+        s[0] += p.x; s[1] += p.y; s[2] += p.z;
+        s[3] += p.x * e; s[4] += p.y * e; s[5] += p.z * e; s[6] += e;
+        unsigned long long key = ((unsigned long long)R.id[i] << 32) | R.bounces[i];
+        first = key < first ? key : first;
+    }
+    __shared__ double sh[8][7];
+    __shared__ unsigned long long shn[8][3];
+    int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+#pragma unroll
+    for (int j = 0; j < 7; ++j) s[j] = warp_sum(s[j]);
+    nv = warp_sum_u64(nv); nt = warp_sum_u64(nt);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { unsigned long long t = __shfl_xor_sync(0xffffffffu, first, o); first = t < first ? t : first; }
+    if (l == 0) { for (int j = 0; j < 7; ++j) sh[w][j] = s[j]; shn[w][0] = nv; shn[w][1] = nt; shn[w][2] = first; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t[7] = {0, 0, 0, 0, 0, 0, 0};
+        unsigned long long a = 0, b = 0, f = ~0ull;
+        for (int k = 0; k < (int)(blockDim.x >> 5); ++k) {
+            for (int j = 0; j < 7; ++j) t[j] += sh[k][j];
+            a += shn[k][0]; b += shn[k][1]; f = shn[k][2] < f ? shn[k][2] : f;
+        }
+        for (int j = 0; j < 7; ++j) atomicAdd(&acc->sum[j], t[j]);
+        atomicAdd(&acc->n_valid, a); atomicAdd(&acc->n_total, b); atomicMin(&acc->first_key, f);
+    }
+}
+__global__ void __launch_bounds__(256) spot_pass2_kernel(DevRays R, uint64_t n, int use_frame, DevIso inv, SpotAccum* acc) {
+    const double nvalid = (double)acc->n_valid;
+    // rays.rs:599-612 / 618-637: centroid = sum / len ; energy centroid = sum(e*p) / sum(e)
+    const double cx = acc->sum[0] / nvalid, cy = acc->sum[1] / nvalid;
+    const double ex = acc->sum[3] / acc->sum[6], ey = acc->sum[4] / acc->sum[6];
+    const double cxm = cx / 1.0E-3, cym = cy / 1.0E-3;  // get::<millimeter>()
+    double mx = 0.0, s2 = 0.0, se = 0.0;
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        if (R.valid[i] != RAY_VALID) continue;
+        V3 p = v3(R.px[i], R.py[i], R.pz[i]);
+        if (use_frame) p = iso_point(inv, p);
+        double dx = cxm - p.x / 1.0E-3, dy = cym - p.y / 1.0E-3;
+        double d2 = dx * dx + dy * dy;
+        mx = fmax(mx, d2);     // max of sqrt == sqrt of max (rays.rs:642-660)
+        s2 += d2;              // rays.rs:666-684: distance(..).powi(2)
+        double ux = ex - p.x, uy = ey - p.y;
+        se += (ux * ux + uy * uy) * R.e[i];  // rays.rs:690-701
+    }
+    __shared__ double sh[8][3];
+    int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    mx = warp_max(mx); s2 = warp_sum(s2); se = warp_sum(se);
+    if (l == 0) { sh[w][0] = mx; sh[w][1] = s2; sh[w][2] = se; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double a = 0, b = 0, c = 0;
+        for (int k = 0; k < (int)(blockDim.x >> 5); ++k) { a = fmax(a, sh[k][0]); b += sh[k][1]; c += sh[k][2]; }
+        atomicMax(&acc->max_d2_key, dkey(a));
+        atomicAdd(&acc->sum_d2, b); atomicAdd(&acc->sum_ed2, c);
+    }
+}
+__global__ void __launch_bounds__(256) tally_kernel(DevRays R, uint64_t n, uint32_t n_orders, unsigned long long* counts, double* energy) {
+    extern __shared__ unsigned char tsm[];
+    double* se = reinterpret_cast<double*>(tsm);
+    unsigned long long* sc = reinterpret_cast<unsigned long long*>(se + n_orders);
+    for (uint32_t k = threadIdx.x; k < n_orders; k += blockDim.x) { se[k] = 0.0; sc[k] = 0; }
+    __syncthreads();
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        if (R.valid[i] != RAY_VALID) continue;
+        uint32_t b = R.bounces[i];
+        if (b >= n_orders) b = n_orders - 1;
+        atomicAdd(&se[b], R.e[i]);
+        atomicAdd(&sc[b], 1ull);
+    }
+    __syncthreads();
+    for (uint32_t k = threadIdx.x; k < n_orders; k += blockDim.x)
+        if (sc[k]) { atomicAdd(&energy[k], se[k]); atomicAdd(&counts[k], sc[k]); }
+}
+
+// ---------------------------------------------------------------------------------------------
+// hit map: bounding box and Binning
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) hits_bbox_kernel(DevHits H, uint64_t n, long long bounce_filter, BBoxAccum* acc) {
+    double xmin = DBL_MAX, xmax = -DBL_MAX, ymin = DBL_MAX, ymax = -DBL_MAX;
+    unsigned long long cnt = 0;
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        double e = __ldcs(H.e + i);
+        if (!(e >= 0.0)) continue;
+        if (bounce_filter >= 0 && (long long)H.bounce[i] != bounce_filter) continue;
+        double x = __ldcs(H.x + i), y = __ldcs(H.y + i);
+        xmin = fmin(xmin, x); xmax = fmax(xmax, x); ymin = fmin(ymin, y); ymax = fmax(ymax, y);
+        cnt++;
+    }
+    xmin = warp_min(xmin); xmax = warp_max(xmax); ymin = warp_min(ymin); ymax = warp_max(ymax); cnt = warp_sum_u64(cnt);
+    if ((threadIdx.x & 31) == 0 && cnt) {
+        atomicMin(&acc->key[0], dkey(xmin)); atomicMax(&acc->key[1], dkey(xmax));
+        atomicMax(&acc->key[2], dkey(ymax)); atomicMin(&acc->key[3], dkey(ymin));
+        atomicAdd(&acc->count, cnt);
+    }
+}
+
+// Rust `f64 as usize` (saturating, NaN -> 0)
+__device__ __forceinline__ unsigned long long f64_to_usize(double v) {
+    if (!(v > 0.0)) return 0ull;
+    if (v >= 18446744073709551615.0) return ~0ull;
+    return (unsigned long long)v;
+}
+
+struct BinTaps { unsigned long long base; double w00, w10, w01, w11; bool ok, has_x, has_y; };
+
+// rays_hit_map.rs:352-376 for one hit
+__device__ __forceinline__ BinTaps bin_taps(const BinParams& P, double x, double y, double e, unsigned* status) {
+    BinTaps t;
+    double ipx, ipy;
+    double fx = modf((x - P.left) / P.width_step, &ipx);
+    double fy = modf((y - P.bottom) / P.height_step, &ipy);
+    unsigned long long xi = f64_to_usize(ipx), yi = f64_to_usize(ipy);
+    double fl = e / P.bin_area;
+    t.w00 = (1.0 - fx) * (1.0 - fy) * fl;
+    t.w10 = fx * (1.0 - fy) * fl;
+    t.w01 = (1.0 - fx) * fy * fl;
+    t.w11 = fx * fy * fl;
+    t.ok = (xi < P.nx) && (yi < P.ny);
+    if (!t.ok) *status |= 1u << OPM_ERR_BIN_RANGE;  // the reference panics (index out of bounds)
+    t.has_x = xi < P.nx - 1;
+    t.has_y = yi < P.ny - 1;
+    t.base = xi * P.ny + yi;  // column-major ny x nx
+    return t;
+}
+
+// map fits in shared memory: privatise the whole map per CTA, flush non-zero bins with global atomics
+__global__ void __launch_bounds__(256) binning_smem_kernel(DevHits H, uint64_t n, long long bounce_filter, BinParams P,
+                                                           double* __restrict__ map, unsigned* status_out) {
+    extern __shared__ double smap[];
+    const unsigned long long bins = P.nx * P.ny;
+    for (unsigned long long k = threadIdx.x; k < bins; k += blockDim.x) smap[k] = 0.0;
+    __syncthreads();
+    unsigned status = 0;
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        double e = __ldcs(H.e + i);
+        if (!(e >= 0.0)) continue;
+        if (bounce_filter >= 0 && (long long)H.bounce[i] != bounce_filter) continue;
+        BinTaps t = bin_taps(P, __ldcs(H.x + i), __ldcs(H.y + i), e, &status);
+        if (!t.ok) continue;
+        atomicAdd(&smap[t.base], t.w00);
+        if (t.has_x) {
+            atomicAdd(&smap[t.base + P.ny], t.w10);
+            if (t.has_y) atomicAdd(&smap[t.base + P.ny + 1], t.w11);
+        }
+        if (t.has_y) atomicAdd(&smap[t.base + 1], t.w01);
+    }
+    __syncthreads();
+    for (unsigned long long k = threadIdx.x; k < bins; k += blockDim.x) {
+        double v = smap[k];
+        if (v != 0.0) atomicAdd(&map[k], v);
+    }
+    if (status) atomicOr(status_out, status);
+}
+
+// large maps: consecutive lanes that fall into the same bin (a run) are summed with a segmented warp
+// scan first, the run head issues the global f64 atomics
+__global__ void __launch_bounds__(256) binning_global_kernel(DevHits H, uint64_t n, long long bounce_filter, BinParams P,
+                                                             double* __restrict__ map, unsigned* status_out) {
+    unsigned status = 0;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    const uint64_t n_round = (n + 31) / 32 * 32;
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n_round; i += stride) {
+        BinTaps t;
+        t.ok = false; t.base = ~0ull; t.w00 = t.w10 = t.w01 = t.w11 = 0.0; t.has_x = t.has_y = false;
+        if (i < n) {
+            double e = __ldcs(H.e + i);
+            if (e >= 0.0 && !(bounce_filter >= 0 && (long long)H.bounce[i] != bounce_filter))
+                t = bin_taps(P, __ldcs(H.x + i), __ldcs(H.y + i), e, &status);
+        }
+        const int lane = threadIdx.x & 31;
+        // runs of consecutive lanes that hit the same base bin: run id = number of run heads at or below this lane
+        const unsigned long long key = t.ok ? t.base : (~0ull - (unsigned long long)lane);  // invalid lanes never join a run
+        const unsigned long long prev = __shfl_up_sync(0xffffffffu, key, 1);
+        const bool head = (lane == 0) || (prev != key);
+        const unsigned heads = __ballot_sync(0xffffffffu, head);
+        const int rid = __popc(heads & (0xffffffffu >> (31 - lane)));
+        // segmented suffix sum (Hillis-Steele): run ids are monotonic, so equal ids at distance o mean one run
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int r2 = __shfl_down_sync(0xffffffffu, rid, o);
+            double a = __shfl_down_sync(0xffffffffu, t.w00, o), b = __shfl_down_sync(0xffffffffu, t.w10, o);
+            double c = __shfl_down_sync(0xffffffffu, t.w01, o), d = __shfl_down_sync(0xffffffffu, t.w11, o);
+            if (lane + o < 32 && r2 == rid) { t.w00 += a; t.w10 += b; t.w01 += c; t.w11 += d; }
+        }
+        if (t.ok && head) {
+            atomicAdd(&map[t.base], t.w00);
+            if (t.has_x) {
+                atomicAdd(&map[t.base + P.ny], t.w10);
+                if (t.has_y) atomicAdd(&map[t.base + P.ny + 1], t.w11);
+            }
+            if (t.has_y) atomicAdd(&map[t.base + 1], t.w01);
+        }
+    }
+    if (status) atomicOr(status_out, status);
+}
+
+// fluence_data.rs:45-68 (peak over finite bins) and :130-141 (sum over non-NaN bins)
+__global__ void __launch_bounds__(256) peak_total_kernel(const double* __restrict__ map, uint64_t bins, double area, PeakAccum* acc) {
+    double peak = -INFINITY, tot = 0.0;
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < bins; i += (uint64_t)gridDim.x * blockDim.x) {
+        double v = map[i];
+        if (isfinite(v)) peak = fmax(peak, v);
+        if (!isnan(v)) tot += area * v;
+    }
+    peak = warp_max(peak); tot = warp_sum(tot);
+    if ((threadIdx.x & 31) == 0) { atomicMax(&acc->peak_key, dkey(peak)); atomicAdd(&acc->total, tot); }
+}
+
+// ---------------------------------------------------------------------------------------------
+// sources
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ double fract(double x) { return x - trunc(x); }
+__device__ __forceinline__ void source_position(const SourceParams& S, uint64_t ip, double& x, double& y) {
+    switch (S.pos_dist) {
+        case OPM_POS_GRID: {  // position_distributions/grid.rs:58-92 (x outer, y inner)
+            uint64_t ix = ip / S.grid_ny, iy = ip % S.grid_ny;
+            x = (double)ix * S.dist_x - S.off_x;
+            y = (double)iy * S.dist_y - S.off_y;
+            break;
+        }
+        case OPM_POS_FIBONACCI_RECT: {  // fibonacci.rs:53-65
+            double fi = (double)ip;
+            x = S.size_x * (fract(fi / S.golden) - 0.5);
+            y = S.size_y * ((fi / (double)S.n_positions) - 0.5);
+            break;
+        }
+        default: {  // fibonacci.rs:113-126
+            double sn, cs;
+            sincos(2.0 * 3.14159265358979323846 * fract((double)ip / S.golden), &sn, &cs);
+            double sr = sqrt((double)ip / (double)S.n_positions);
+            x = S.size_x * sn * sr;
+            y = S.size_y * cs * sr;
+            break;
+        }
+    }
+}
+// utils/math_distribution_functions.rs:54-70,133-150
+__device__ __forceinline__ double general_gaussian_weight(const SourceParams& S, double px, double py) {
+    double x_rot = fma(px - S.mu[0], S.cos_t, -((py - S.mu[1]) * S.sin_t));
+    double y_rot = fma(py - S.mu[1], S.cos_t, (px - S.mu[0]) * S.sin_t);
+    double ax = x_rot / S.sigma[0], ay = y_rot / S.sigma[1];
+    if (S.rectangular) return exp(-pow(0.5 * (ax * ax), S.power) - pow(0.5 * (ay * ay), S.power));
+    return exp(-pow(0.5 * fma(ax, ax, ay * ay), S.power));
+}
+__global__ void __launch_bounds__(256) source_norm_kernel(SourceParams S, uint64_t pos_begin, uint64_t pos_end, double* out) {
+    double s = 0.0;
+    for (uint64_t ip = pos_begin + blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; ip < pos_end; ip += (uint64_t)gridDim.x * blockDim.x) {
+        double x, y;
+        source_position(S, ip, x, y);
+        s += general_gaussian_weight(S, x, y);
+    }
+    s = warp_sum(s);
+    if ((threadIdx.x & 31) == 0) atomicAdd(out, s);
+}
+// rays.rs:264-297 (position-major, wavelength-minor) + nodes/source.rs:205-210 (source isometry)
+__global__ void __launch_bounds__(256) source_generate_kernel(SourceParams S, DevRays R, uint64_t pos_begin, uint64_t n_rays,
+                                                              const double* __restrict__ wvl, const double* __restrict__ wgt) {
+    const V3 zdir = iso_vector(S.iso, v3(0.0, 0.0, 1.0));
+    for (uint64_t k = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; k < n_rays; k += (uint64_t)gridDim.x * blockDim.x) {
+        uint64_t ip = pos_begin + k / S.n_wavelengths;
+        uint32_t iw = (uint32_t)(k % S.n_wavelengths);
+        double x, y;
+        source_position(S, ip, x, y);
+        double e_pos = S.energy_dist == OPM_EDIST_UNIFORM ? S.e_uniform
+                                                          : S.total_energy * general_gaussian_weight(S, x, y) / S.energy_norm;
+        V3 p = iso_point(S.iso, v3(x, y, 0.0));
+        R.px[k] = p.x; R.py[k] = p.y; R.pz[k] = p.z;
+        R.dx[k] = zdir.x; R.dy[k] = zdir.y; R.dz[k] = zdir.z;
+        R.e[k] = e_pos * wgt[iw]; R.wvl[k] = wvl[iw]; R.opl[k] = 0.0; R.n[k] = 1.0;
+        R.bounces[k] = 0; R.refr[k] = 0; R.id[k] = (uint32_t)(ip * S.n_wavelengths + iw); R.valid[k] = RAY_VALID;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// order-preserving compaction of removed rays
+// ---------------------------------------------------------------------------------------------
+constexpr int kCompactBlock = 1024;
+__global__ void __launch_bounds__(kCompactBlock) compact_count_kernel(const uint8_t* __restrict__ valid, uint64_t n, unsigned* counts) {
+    uint64_t i = blockIdx.x * (uint64_t)kCompactBlock + threadIdx.x;
+    bool keep = i < n && valid[i] != RAY_REMOVED;
+    int c = __syncthreads_count(keep);
+    if (threadIdx.x == 0) counts[blockIdx.x] = (unsigned)c;
+}
+// single-CTA exclusive scan of the block counts (nb is ~n/1024, tiny next to the ray traffic)
+__global__ void __launch_bounds__(1024) compact_scan_kernel(const unsigned* __restrict__ counts, unsigned long long* offsets, uint64_t nb,
+                                                            unsigned long long* total) {
+    __shared__ unsigned long long wsum[32];
+    __shared__ unsigned long long carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (uint64_t base = 0; base < nb; base += 1024) {
+        uint64_t i = base + threadIdx.x;
+        unsigned long long v = i < nb ? counts[i] : 0ull;
+        unsigned long long x = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { unsigned long long t = __shfl_up_sync(0xffffffffu, x, o); if ((threadIdx.x & 31) >= o) x += t; }
+        if ((threadIdx.x & 31) == 31) wsum[threadIdx.x >> 5] = x;
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            unsigned long long w = wsum[threadIdx.x], y = w;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { unsigned long long t = __shfl_up_sync(0xffffffffu, y, o); if (threadIdx.x >= o) y += t; }
+            wsum[threadIdx.x] = y - w;
+        }
+        __syncthreads();
+        unsigned long long incl = x + wsum[threadIdx.x >> 5] + carry;
+        if (i < nb) offsets[i] = incl - v;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry = incl;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *total = carry;
+}
+__global__ void __launch_bounds__(kCompactBlock) compact_scatter_kernel(DevRays S, DevRays D, uint64_t n, const unsigned long long* __restrict__ offsets) {
+    __shared__ unsigned wcount[32];
+    uint64_t i = blockIdx.x * (uint64_t)kCompactBlock + threadIdx.x;
+    bool keep = i < n && S.valid[i] != RAY_REMOVED;
+    unsigned mask = __ballot_sync(0xffffffffu, keep);
+    int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    if (l == 0) wcount[w] = __popc(mask);
+    __syncthreads();
+    if (w == 0) {
+        unsigned c = wcount[l], x = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { unsigned t = __shfl_up_sync(0xffffffffu, x, o); if (l >= o) x += t; }
+        wcount[l] = x - c;
+    }
+    __syncthreads();
+    if (keep) {
+        uint64_t j = offsets[blockIdx.x] + wcount[w] + __popc(mask & ((1u << l) - 1u));
+        D.px[j] = S.px[i]; D.py[j] = S.py[i]; D.pz[j] = S.pz[i];
+        D.dx[j] = S.dx[i]; D.dy[j] = S.dy[i]; D.dz[j] = S.dz[i];
+        D.e[j] = S.e[i]; D.wvl[j] = S.wvl[i]; D.opl[j] = S.opl[i]; D.n[j] = S.n[i];
+        D.bounces[j] = S.bounces[i]; D.refr[j] = S.refr[i]; D.id[j] = S.id[i]; D.valid[j] = S.valid[i];
+    }
+}
+__global__ void fill_u8_kernel(uint8_t* p, uint8_t v, uint64_t n) {
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) p[i] = v;
+}
+__global__ void set_u64_kernel(unsigned long long* p, unsigned long long v) { *p = v; }
+
+// ---------------------------------------------------------------------------------------------
+// host launchers
+// ---------------------------------------------------------------------------------------------
+static inline int grid_for(uint64_t n, int block, int max_blocks) {
+    uint64_t g = (n + block - 1) / block;
+    if (g < 1) g = 1;
+    if (g > (uint64_t)max_blocks) g = max_blocks;
+    return (int)g;
+}
+#define ST ((cudaStream_t)stream)
+
+int k_aos_to_soa(const OpmRay* a, DevRays R, uint64_t off, uint64_t n, int sms, void* stream) {
+    aos_to_soa_kernel<<<grid_for(n, 256, sms * 8), 256, 0, ST>>>(a, R, off, n);
+    return (int)cudaGetLastError();
+}
+int k_soa_to_aos(DevRays R, OpmRay* a, uint64_t n, int sms, void* stream) {
+    soa_to_aos_kernel<<<grid_for(n, 256, sms * 8), 256, 0, ST>>>(R, a, n);
+    return (int)cudaGetLastError();
+}
+int k_soa_defaults(DevRays R, uint64_t n, int sms, void* stream) {
+    soa_defaults_kernel<<<grid_for(n, 256, sms * 8), 256, 0, ST>>>(R, n);
+    return (int)cudaGetLastError();
+}
+int k_transform(DevRays R, DevIso I, uint64_t n, int sms, void* stream) {
+    transform_kernel<<<grid_for(n, 256, sms * 8), 256, 0, ST>>>(R, I, n);
+    return (int)cudaGetLastError();
+}
+int k_spot(DevRays R, uint64_t n, int use_frame, DevIso inv, SpotAccum* acc, int sms, void* stream) {
+    int g = grid_for(n, 256, sms * 4);
+    spot_pass1_kernel<<<g, 256, 0, ST>>>(R, n, use_frame, inv, acc);
+    spot_pass2_kernel<<<g, 256, 0, ST>>>(R, n, use_frame, inv, acc);
+    return (int)cudaGetLastError();
+}
+int k_tally(DevRays R, uint64_t n, uint32_t n_orders, unsigned long long* counts, double* energy, int sms, void* stream) {
+    tally_kernel<<<grid_for(n, 256, sms * 2), 256, n_orders * 16, ST>>>(R, n, n_orders, counts, energy);
+    return (int)cudaGetLastError();
+}
+int k_hits_bbox(DevHits H, uint64_t n, long long bounce_filter, BBoxAccum* acc, int sms, void* stream) {
+    hits_bbox_kernel<<<grid_for(n, 256, sms * 4), 256, 0, ST>>>(H, n, bounce_filter, acc);
+    return (int)cudaGetLastError();
+}
+int k_binning(DevHits H, uint64_t n, long long bounce_filter, const BinParams& P, double* map, unsigned* status, int sms, void* stream) {
+    size_t bytes = (size_t)(P.nx * P.ny) * sizeof(double);
+    if (bytes <= 160 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(binning_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+        if (e != cudaSuccess) return (int)e;
+        binning_smem_kernel<<<grid_for(n, 256, sms), 256, bytes, ST>>>(H, n, bounce_filter, P, map, status);
+    } else {
+        binning_global_kernel<<<grid_for(n, 256, sms * 8), 256, 0, ST>>>(H, n, bounce_filter, P, map, status);
+    }
+    return (int)cudaGetLastError();
+}
+int k_peak_total(const double* map, uint64_t bins, double area, PeakAccum* acc, int sms, void* stream) {
+    peak_total_kernel<<<grid_for(bins, 256, sms * 4), 256, 0, ST>>>(map, bins, area, acc);
+    return (int)cudaGetLastError();
+}
+int k_source_norm(const SourceParams& S, uint64_t b, uint64_t e, double* out, int sms, void* stream) {
+    source_norm_kernel<<<grid_for(e - b, 256, sms * 4), 256, 0, ST>>>(S, b, e, out);
+    return (int)cudaGetLastError();
+}
+int k_source_generate(const SourceParams& S, DevRays R, uint64_t pos_begin, uint64_t n_rays, const double* wvl, const double* wgt,
+                      int sms, void* stream) {
+    source_generate_kernel<<<grid_for(n_rays, 256, sms * 8), 256, 0, ST>>>(S, R, pos_begin, n_rays, wvl, wgt);
+    return (int)cudaGetLastError();
+}
+int k_compact(DevRays S, DevRays D, uint64_t n, unsigned* counts, unsigned long long* offsets, unsigned long long* total, void* stream) {
+    uint64_t nb = (n + kCompactBlock - 1) / kCompactBlock;
+    if (nb == 0) return 0;
+    compact_count_kernel<<<(unsigned)nb, kCompactBlock, 0, ST>>>(S.valid, n, counts);
+    compact_scan_kernel<<<1, 1024, 0, ST>>>(counts, offsets, nb, total);
+    compact_scatter_kernel<<<(unsigned)nb, kCompactBlock, 0, ST>>>(S, D, n, offsets);
+    return (int)cudaGetLastError();
+}
+int k_set_u64(unsigned long long* p, unsigned long long v, void* stream) {
+    set_u64_kernel<<<1, 1, 0, ST>>>(p, v);
+    return (int)cudaGetLastError();
+}
+int k_fill_u8(uint8_t* p, uint8_t v, uint64_t n, int sms, void* stream) {
+    fill_u8_kernel<<<grid_for(n, 256, sms * 8), 256, 0, ST>>>(p, v, n);
+    return (int)cudaGetLastError();
+}
+
+}  // namespace opm

@@ -1,0 +1,59 @@
+// opm_kernels.h -- launchers of the plumbing / detector / source kernels (opm_kernels.cu).
+#pragma once
+#include "opm_internal.h"
+
+namespace opm {
+
+struct SpotAccum {
+    double sum[7];  // x y z e*x e*y e*z e  (valid rays)
+    unsigned long long n_valid, n_total, first_key;  // first_key = min (id << 32 | bounces) over valid rays
+    unsigned long long max_d2_key;                   // ordered key of max squared distance [mm^2] from the centroid
+    double sum_d2, sum_ed2;
+};
+struct BBoxAccum { unsigned long long key[4]; unsigned long long count; };  // left,right,top,bottom as ordered keys
+struct PeakAccum { unsigned long long peak_key; double total; };
+struct BinParams {
+    unsigned long long nx, ny;
+    double left, bottom, width_step, height_step, bin_area;
+};
+struct SourceParams {
+    int32_t pos_dist, energy_dist, rectangular, _pad;
+    uint64_t n_positions, grid_ny;
+    uint32_t n_wavelengths, _pad2;
+    double dist_x, dist_y, off_x, off_y;  // grid.rs:61-80
+    double size_x, size_y, golden;
+    double total_energy, e_uniform, energy_norm;
+    double mu[2], sigma[2], power, sin_t, cos_t;
+    DevIso iso;
+};
+
+// host-side inverse of the ordered-key encoding used by the atomicMin/Max reductions
+inline double key_to_double(unsigned long long k) {
+    unsigned long long b = (k & 0x8000000000000000ull) ? (k & 0x7fffffffffffffffull) : ~k;
+    double d;
+    __builtin_memcpy(&d, &b, sizeof d);
+    return d;
+}
+inline unsigned long long double_to_key(double d) {
+    unsigned long long b;
+    __builtin_memcpy(&b, &d, sizeof b);
+    return (b & 0x8000000000000000ull) ? ~b : (b | 0x8000000000000000ull);
+}
+
+int k_aos_to_soa(const OpmRay* a, DevRays R, uint64_t off, uint64_t n, int sms, void* stream);
+int k_soa_to_aos(DevRays R, OpmRay* a, uint64_t n, int sms, void* stream);
+int k_soa_defaults(DevRays R, uint64_t n, int sms, void* stream);
+int k_transform(DevRays R, DevIso I, uint64_t n, int sms, void* stream);
+int k_spot(DevRays R, uint64_t n, int use_frame, DevIso inv, SpotAccum* acc, int sms, void* stream);
+int k_tally(DevRays R, uint64_t n, uint32_t n_orders, unsigned long long* counts, double* energy, int sms, void* stream);
+int k_hits_bbox(DevHits H, uint64_t n, long long bounce_filter, BBoxAccum* acc, int sms, void* stream);
+int k_binning(DevHits H, uint64_t n, long long bounce_filter, const BinParams& P, double* map, unsigned* status, int sms, void* stream);
+int k_peak_total(const double* map, uint64_t bins, double area, PeakAccum* acc, int sms, void* stream);
+int k_source_norm(const SourceParams& S, uint64_t b, uint64_t e, double* out, int sms, void* stream);
+int k_source_generate(const SourceParams& S, DevRays R, uint64_t pos_begin, uint64_t n_rays, const double* wvl, const double* wgt,
+                      int sms, void* stream);
+int k_compact(DevRays S, DevRays D, uint64_t n, unsigned* counts, unsigned long long* offsets, unsigned long long* total, void* stream);
+int k_set_u64(unsigned long long* p, unsigned long long v, void* stream);
+int k_fill_u8(uint8_t* p, uint8_t v, uint64_t n, int sms, void* stream);
+
+}  // namespace opm

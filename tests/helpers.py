@@ -1,0 +1,115 @@
+"""Shared builders for the parity tests: the same neutral description -> oracle objects and product objects."""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+
+import opossum_b200 as ob
+from opossum_b200 import ffi as F
+from oracle import oracle as orc
+
+RTOL = 1e-9  # BASELINE.json north_star: per-ray positions, directions, energies and OPL within 1e-9 relative
+
+HK9L = (6.14555251E-1, 6.56775017E-1, 1.02699346E+0, 1.45987884E-2, 2.87769588E-3, 1.07653051E+2)
+HZF52 = (3.26760058E+000, -2.05384566E-002, 3.51507672E-002, 7.70151348E-003, -9.08139817E-004, 7.52649555E-005)
+
+
+def mm(*v):
+    r = tuple(x * 1.0e-3 for x in v)
+    return r[0] if len(r) == 1 else r
+
+
+def nm(x):
+    return x * 1.0e-9
+
+
+def iso_pair(translation=(0.0, 0.0, 0.0), euler=(0.0, 0.0, 0.0)):
+    return orc.Isometry.new(translation, euler), ob.Isometry.new(translation, euler)
+
+
+def append_pair(a, b):
+    return a[0].append(b[0]), a[1].append(b[1])
+
+
+def surface_pair(geom, param=0.0, iso=None, coating=0, r=0.0):
+    """geom/coating ints are shared enum values (checked in test_abi)."""
+    iso = iso or iso_pair()
+    return (orc.Surface(geom=geom, coating=coating, param=param, coating_r=r, iso=iso[0]),
+            ob.OpticSurface(geom, param, iso[1], coating, r))
+
+
+def node_sphere_pair(radius, node_iso, **kw):
+    """Sphere as a lens/mirror node builds it: geo iso = node_iso o T(0,0,R) (nodes/lens/mod.rs:238-247)."""
+    return surface_pair(F.GEOM_SPHERE, radius, append_pair(node_iso, iso_pair((0.0, 0.0, radius))), **kw)
+
+
+def index_pair(kind, *a):
+    return getattr(orc.IndexModel, kind)(*a), getattr(ob.RefractiveIndex, kind)(*a)
+
+
+def aperture_pair(kind, *a, **kw):
+    if kind == "none":
+        return orc.ap_none(), ob.Aperture.none()
+    if kind == "stack":
+        items = a[0]
+        return orc.ap_stack([i[0] for i in items], **kw), ob.Aperture.stack([i[1] for i in items], **kw)
+    return getattr(orc, "ap_" + kind)(*a, **kw), getattr(ob.Aperture, kind)(*a, **kw)
+
+
+def make_bundle(n=4096, radius=mm(8.0), z=0.0, divergence=0.02, seed=7, wvl=(nm(600.0), nm(1500.0))):
+    """Deterministic, boundary-avoiding bundle: Fibonacci ellipse positions, smoothly varying directions/energies."""
+    i = np.arange(n, dtype=np.float64)
+    xyz = orc.fibonacci_ellipse(n, radius, radius)
+    xyz[:, 2] = z
+    rng = np.random.default_rng(seed)
+    d = np.stack([divergence * (xyz[:, 0] / radius) + 0.003 * rng.standard_normal(n),
+                  divergence * (xyz[:, 1] / radius) + 0.003 * rng.standard_normal(n), np.ones(n)], axis=1)
+    e = 1.0e-3 * (1.0 + 0.5 * np.sin(0.37 * i))
+    w = wvl[0] + (wvl[1] - wvl[0]) * ((i * 0.6180339887498949) % 1.0)
+    return orc.rays_from_arrays(xyz, d, e, w)
+
+
+def sort_by_id(a: np.ndarray) -> np.ndarray:
+    return a[np.argsort(a["id"], kind="stable")]
+
+
+def assert_rays_match(gpu: np.ndarray, ref: np.ndarray, rtol=RTOL, keyed=False, what="rays"):
+    """Counts and integer state bit-exact; pos/dir/e/opl/n within rtol (vector norms for pos/dir)."""
+    assert len(gpu) == len(ref), f"{what}: bundle length {len(gpu)} != {len(ref)}"
+    if len(ref) == 0:
+        return
+    if keyed:
+        gpu, ref = sort_by_id(gpu), sort_by_id(ref)
+    for f in ("id", "valid", "bounces", "refr"):
+        assert np.array_equal(gpu[f], ref[f]), f"{what}: field {f} differs at {np.flatnonzero(gpu[f] != ref[f])[:5]}"
+    scale_p = np.maximum(np.linalg.norm(ref["pos"], axis=1), 1e-3)
+    dp = np.linalg.norm(gpu["pos"] - ref["pos"], axis=1) / scale_p
+    assert dp.max() <= rtol, f"{what}: pos rel err {dp.max():.3e} at {dp.argmax()}"
+    dd = np.linalg.norm(gpu["dir"] - ref["dir"], axis=1) / np.maximum(np.linalg.norm(ref["dir"], axis=1), 1e-300)
+    assert dd.max() <= rtol, f"{what}: dir rel err {dd.max():.3e} at {dd.argmax()}"
+    for f, floor in (("e", 1e-30), ("opl", 1e-12), ("n", 1e-30), ("wvl", 1e-30)):
+        err = np.abs(gpu[f] - ref[f]) / np.maximum(np.abs(ref[f]), floor)
+        assert err.max() <= rtol, f"{what}: {f} rel err {err.max():.3e} at {err.argmax()}"
+
+
+def assert_hits_match(gpu_xyzeb, ref_hits: np.ndarray, rtol=RTOL):
+    x, y, z, e, b = gpu_xyzeb
+    assert len(x) == len(ref_hits), f"hit count {len(x)} != {len(ref_hits)}"
+    if len(x) == 0:
+        return
+    assert np.array_equal(b, ref_hits["bounce"])
+    p = np.stack([x, y, z], axis=1)
+    q = np.stack([ref_hits["x"], ref_hits["y"], ref_hits["z"]], axis=1)
+    scale = np.maximum(np.linalg.norm(q, axis=1), 1e-3)
+    assert (np.linalg.norm(p - q, axis=1) / scale).max() <= rtol
+    assert (np.abs(e - ref_hits["e"]) / np.maximum(np.abs(ref_hits["e"]), 1e-30)).max() <= rtol
+
+
+def assert_map_match(gpu_map, ref_map, rtol=RTOL):
+    """fluence maps within 1e-9 relative per bin, absolute floor 1e-9 * peak."""
+    assert gpu_map.shape == ref_map.shape
+    peak = np.nanmax(np.abs(ref_map)) if ref_map.size else 0.0
+    err = np.abs(gpu_map - ref_map)
+    tol = rtol * np.maximum(np.abs(ref_map), peak)
+    assert np.all(err <= tol), f"fluence map max err {np.max(err / np.maximum(tol, 1e-300)):.3e} x tol"

@@ -1,0 +1,83 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library builds, loads and exports every symbol that
+include/opossum_b200.h declares; enum values shared with the oracle agree; the host isometry math agrees
+with the oracle's nalgebra restatement; without a GPU the library refuses loudly (no CPU fallback)."""
+import ctypes as C
+import math
+import re
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+import opossum_b200 as ob
+from opossum_b200 import ffi as F
+from oracle import oracle as orc
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = (ROOT / "include" / "opossum_b200.h").read_text()
+    declared = set(re.findall(r"\b(opm_[a-z0-9_]+)\s*\(", hdr))
+    assert declared == set(F.EXPORTS), declared ^ set(F.EXPORTS)
+    L = F.lib()
+    for name in declared:
+        assert hasattr(L, name), name
+    assert L.opm_abi_version() == 1
+
+
+def test_struct_layouts():
+    assert C.sizeof(F.OpmRay) == 96 == ob.RAY_DTYPE.itemsize == orc.RAY_DTYPE.itemsize
+    assert C.sizeof(F.OpmIsometry) == 192 and C.sizeof(F.OpmSurface) == 216 and C.sizeof(F.OpmIndexModel) == 72
+    assert C.sizeof(F.OpmOp) == 384 and C.sizeof(F.OpmTraceStats) == 64
+
+
+def test_enums_match_oracle():
+    assert (F.GEOM_PLANE, F.GEOM_SPHERE, F.GEOM_CYLINDER, F.GEOM_PARABOLA) == (
+        orc.GEOM_PLANE, orc.GEOM_SPHERE, orc.GEOM_CYLINDER, orc.GEOM_PARABOLA)
+    assert (F.COAT_IDEAL_AR, F.COAT_CONSTANT_R, F.COAT_FRESNEL) == (orc.COAT_IDEAL_AR, orc.COAT_CONSTANT_R, orc.COAT_FRESNEL)
+    assert (F.MISS_STOP, F.MISS_IGNORE) == (orc.MISS_STOP, orc.MISS_IGNORE)
+
+
+def test_no_gpu_fails_loudly():
+    try:
+        import torch
+        if torch.cuda.is_available():
+            pytest.skip("a GPU is present")
+    except ImportError:
+        pass
+    with pytest.raises(ob.OpossumError) as ei:
+        ob.Context(0)
+    assert ei.value.code == F.OPM_ERR_CUDA and "no CPU fallback" in str(ei.value)
+
+
+@pytest.mark.parametrize("t,e", [((0, 0, 0), (0, 0, 0)), ((0.0, 0.0, 0.01), (0.0, 0.0, 0.0)),
+                                 ((0.1, -0.2, 0.3), (0.3, -0.7, 1.1)), ((0, 0.05, 1.0), (math.pi / 4, 0, 0)),
+                                 ((1, 2, 3), (0.0, math.radians(90.0), 0.0))])
+def test_isometry_matches_oracle(t, e):
+    """3x3 form (product) vs unit-quaternion form (oracle, nalgebra) agree to 1e-15; identity rotations exactly."""
+    a, b = orc.Isometry.new(t, e), ob.Isometry.new(t, e)
+    for x, y in zip(a.matrices(), b.matrices()):
+        assert np.allclose(x, y, rtol=0, atol=4e-16)
+    if e == (0, 0, 0) or e == (0.0, 0.0, 0.0):
+        for x, y in zip(a.matrices(), b.matrices()):
+            assert np.array_equal(x, y)
+    t2, e2 = (0.0, 0.0, 0.2), (0.05, 0.0, -0.2)
+    a2, b2 = a.append(orc.Isometry.new(t2, e2)), b.append(ob.Isometry.new(t2, e2))
+    for x, y in zip(a2.matrices(), b2.matrices()):
+        assert np.allclose(x, y, rtol=0, atol=1e-15)
+
+
+def test_default_config():
+    c = F.OpmRayTraceConfig()
+    F.lib().opm_raytrace_config_default(C.byref(c))
+    assert (c.min_energy_per_ray, c.max_number_of_bounces, c.max_number_of_refractions, c.missed_surface_strategy) == (
+        1e-12, 1000, 1000, F.MISS_STOP)
+    assert ob.RayTraceConfig() == ob.RayTraceConfig(1e-12, 1000, 1000, F.MISS_STOP)
+
+
+def test_isometry_rejects_non_finite():
+    with pytest.raises(ob.OpossumError):
+        ob.Isometry.new((math.nan, 0, 0))
+    with pytest.raises(ob.OpossumError):
+        ob.Isometry.new((0, 0, 0), (0, math.inf, 0))

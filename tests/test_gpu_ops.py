@@ -1,0 +1,378 @@
+"""GPU parity tests of the bundle operations: CUDA path (through the C ABI) vs the CPU oracle on the same
+seeded inputs.  Bar: counts / valid / bounce / refraction state bit-exact, per-ray pos/dir/E/OPL within 1e-9
+relative (helpers.RTOL).  Also transcribes the reference's exact-equality KATs onto the GPU (strict kernel)."""
+import math
+
+import numpy as np
+import pytest
+
+import opossum_b200 as ob
+from opossum_b200 import ffi as F
+from oracle import oracle as orc
+from helpers import (HK9L, HZF52, RTOL, aperture_pair, append_pair, assert_hits_match, assert_rays_match, index_pair,
+                     iso_pair, make_bundle, mm, nm, node_sphere_pair, surface_pair)
+
+pytestmark = pytest.mark.gpu
+EPS = np.finfo(np.float64).eps
+Z = (0.0, 0.0, 1.0)
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = ob.Context(0)
+    yield c
+    c.close()
+
+
+def gpu_refract(ctx, rays_np, surf, idx, refraction_intended=True, strategy=F.MISS_STOP, strict=False):
+    """one REFRACT op through the fused kernel; returns (rays, children, hits, stats) as numpy"""
+    r = ob.Rays.from_array(ctx, rays_np)
+    hm = ob.HitMap(ctx, max(len(rays_np), 1))
+    ch = ob.Rays(ctx, max(len(rays_np), 1))
+    st = ob.Program().refract(surf, idx, refraction_intended, strategy, hit_map=hm, children=ch).run(r, strict=strict)
+    return r.to_array(), ch.to_array(), hm.download(), st
+
+
+# ------------------------------------------------------------------ reference KATs on the GPU
+def test_kat_refract_collimated(ctx):
+    """ray.rs:1203-1290 on the GPU (strict kernel: exact equality like the reference's assert_eq!)"""
+    _, s = surface_pair(F.GEOM_PLANE, iso=iso_pair(mm(0.0, 0.0, 10.0)), coating=F.COAT_CONSTANT_R, r=0.2)
+    _, n15 = index_pair("const", 1.5)
+    ray = orc.ray_new((0.0, 0.0, 0.0), Z, nm(1054.0), 1.0)
+    out, ch, hits, st = gpu_refract(ctx, ray, s, n15, strict=True)
+    r, c = out[0], ch[0]
+    assert tuple(r["pos"]) == mm(0.0, 0.0, 10.0) and r["n"] == 1.5 and tuple(r["dir"]) == Z
+    assert r["opl"] == mm(10.0) and r["bounces"] == 0 and r["refr"] == 1 and r["e"] == (1.0 - 0.2) * 1.0
+    assert tuple(c["pos"]) == mm(0.0, 0.0, 10.0) and c["n"] == 1.0 and tuple(c["dir"]) == (0.0, 0.0, -1.0)
+    assert c["opl"] == mm(10.0) and c["bounces"] == 1 and c["refr"] == 0 and c["e"] == 0.2 * 1.0
+    assert (hits[0][0], hits[1][0], hits[2][0], hits[3][0], hits[4][0]) == (0.0, 0.0, 0.0, 1.0, 0)
+    assert (st.interactions, st.children, st.hits, st.missed) == (1, 1, 1, 0)
+    for bad in (0.9, math.nan, math.inf):
+        with pytest.raises(ob.OpossumError) as ei:
+            gpu_refract(ctx, ray, s, index_pair("const", bad)[1])
+        assert ei.value.code in (F.OPM_ERR_N2_INVALID, F.OPM_ERR_INDEX_MODEL)
+
+
+def test_kat_refract_45deg_and_tir(ctx):
+    """ray.rs:1347-1458: dir (0, 0.4714045207910317, 0.8819171036881969); total internal reflection"""
+    _, s = surface_pair(F.GEOM_PLANE, iso=iso_pair(mm(0.0, 0.0, 10.0)))
+    ray = orc.ray_new((0.0, 0.0, 0.0), (1.0, 0.0, 1.0), nm(1054.0), 1.0)
+    out, _, _, _ = gpu_refract(ctx, ray, s, index_pair("const", 1.5)[1], strict=True)
+    assert tuple(out[0]["pos"]) == mm(10.0, 0.0, 10.0)
+    assert out[0]["dir"][0] == 0.4714045207910317 and abs(out[0]["dir"][1]) <= EPS
+    assert abs(out[0]["dir"][2] - 0.8819171036881969) <= EPS
+    ray = orc.ray_new((0.0, 0.0, 0.0), (0.0, 2.0, 1.0), nm(1054.0), 1.0)
+    ray["n"] = 1.5
+    out, ch, hits, st = gpu_refract(ctx, ray, s, index_pair("const", 1.0)[1], strict=True)
+    assert len(ch) == 0 and len(hits[0]) == 0 and st.missed == 1
+    assert tuple(out[0]["pos"]) == mm(0.0, 20.0, 10.0)
+    t = np.array([0.0, 2.0, -1.0]) / math.sqrt(5.0)
+    assert np.all(np.abs(out[0]["dir"] - t) <= EPS) and out[0]["bounces"] == 1 and out[0]["e"] == 1.0
+
+
+def test_kat_miss_strategies(ctx):
+    """ray.rs:1319-1346, rays.rs:2246-2266"""
+    _, s = surface_pair(F.GEOM_PLANE, iso=iso_pair(mm(0.0, 0.0, 10.0)))
+    ray = orc.ray_new((0.0, 0.0, 0.0), (0.0, 0.0, -1.0), nm(1054.0), 1.0)
+    for strat, valid in ((F.MISS_STOP, 0), (F.MISS_IGNORE, 1)):
+        out, ch, _, st = gpu_refract(ctx, ray, s, index_pair("const", 1.5)[1], strategy=strat)
+        assert len(ch) == 0 and st.missed == 1 and out[0]["valid"] == valid
+        assert tuple(out[0]["pos"]) == (0.0, 0.0, 0.0) and out[0]["opl"] == 0.0 and out[0]["n"] == 1.0
+
+
+def test_kat_sphere_and_fresnel(ctx):
+    """surface/sphere.rs:213-402 (exact on-axis hits, tangent ray) and coatings/fresnel.rs:54-83 via the energy split"""
+    for radius in (mm(10.0), mm(-10.0)):
+        s = ob.OpticSurface.sphere_at_position(radius, (0.0, 0.0, 0.0))
+        out, _, _, _ = gpu_refract(ctx, orc.ray_new(mm(0.0, 0.0, -5.0), Z, nm(1053.0), 1.0), s, None, strict=True)
+        assert tuple(out[0]["pos"]) == (0.0, 0.0, 0.0)
+        out, _, _, st = gpu_refract(ctx, orc.ray_new(mm(0.0, 0.0, 5.0), Z, nm(1053.0), 1.0), s, None, strict=True)
+        assert st.missed == 1 and out[0]["valid"] == 0
+    s = ob.OpticSurface.sphere_at_position(mm(1.0), mm(0.0, 0.0, 10.0))
+    out, _, _, st = gpu_refract(ctx, orc.ray_new(mm(0.0, 1.0, 0.0), Z, nm(1053.0), 1.0), s, None, strict=True)
+    assert tuple(out[0]["pos"]) == mm(0.0, 1.0, 11.0) and st.missed == 0  # disc == 0 exactly -> Roots::One
+    out, _, _, st = gpu_refract(ctx, orc.ray_new(mm(0.0, 1.1, 0.0), Z, nm(1053.0), 1.0), s, None, strict=True)
+    assert st.missed == 1
+    fs = ob.OpticSurface.plane(ob.Isometry.new_along_z(mm(1.0)), coating=F.COAT_FRESNEL)
+    out, ch, _, _ = gpu_refract(ctx, orc.ray_new((0, 0, 0), Z, nm(1000.0), 1.0), fs, index_pair("const", 1.5)[1], strict=True)
+    assert abs(ch[0]["e"] - 0.04) <= 4 * EPS
+    out, ch, _, _ = gpu_refract(ctx, orc.ray_new((0, 0, 0), (0.0, 1.0, 1.0), nm(1000.0), 1.0), fs, index_pair("const", 1.5)[1], strict=True)
+    assert abs(ch[0]["e"] - 0.05023991101223595) <= 8 * EPS  # CUDA libm vs glibc: a few ulp in acos/sin/cos
+
+
+# ------------------------------------------------------------------ seeded bundles vs the oracle
+GEOMS = {
+    "plane": lambda node: surface_pair(F.GEOM_PLANE, iso=node),
+    "sphere_convex": lambda node: node_sphere_pair(mm(120.0), node),
+    "sphere_concave": lambda node: node_sphere_pair(mm(-90.0), node),
+    "cylinder": lambda node: surface_pair(F.GEOM_CYLINDER, mm(150.0), append_pair(node, iso_pair((0.0, 0.0, mm(150.0))))),
+    "cylinder_neg": lambda node: surface_pair(F.GEOM_CYLINDER, mm(-150.0), append_pair(node, iso_pair((0.0, 0.0, mm(-150.0))))),
+    "parabola": lambda node: surface_pair(F.GEOM_PARABOLA, mm(-200.0), node),
+    "parabola_pos": lambda node: surface_pair(F.GEOM_PARABOLA, mm(200.0), node),
+}
+NODE_ISOS = {
+    "axis": ((0.0, 0.0, mm(50.0)), (0.0, 0.0, 0.0)),
+    "tilted": ((mm(0.7), mm(-0.4), mm(60.0)), (0.11, -0.07, 0.3)),
+}
+INDICES = {
+    "none": None,
+    "const": ("const", 1.5068),
+    "sellmeier": ("sellmeier1", *HK9L, nm(500.0), nm(2000.0)),
+    "schott": ("schott", *HZF52, nm(500.0), nm(2000.0)),
+    "conrady": ("conrady", 1.45, 0.012, 0.0004, nm(500.0), nm(2000.0)),
+}
+
+
+def _with_coating(pair, coating, r=0.0):
+    o, g = pair
+    o.coating, o.coating_r = coating, r
+    g.c.coating, g.c.coating_r = coating, r
+    return o, g
+
+
+@pytest.mark.parametrize("strict", [False, True], ids=["fast", "strict"])
+@pytest.mark.parametrize("iso_name", list(NODE_ISOS))
+@pytest.mark.parametrize("geom", list(GEOMS))
+def test_refract_geometries(ctx, geom, iso_name, strict):
+    """every surface solver x placement; Sellmeier glass, Fresnel coating (a4, a5, a7, a8 of SURVEY 8a)"""
+    so, sg = _with_coating(GEOMS[geom](iso_pair(*NODE_ISOS[iso_name])), F.COAT_FRESNEL)
+    io, ig = index_pair(*INDICES["sellmeier"])
+    rays = make_bundle(4096)
+    ref = rays.copy()
+    ch_ref, hits_ref, st_ref = orc.rays_refract_on_surface(ref, so, io, True, orc.MISS_STOP)
+    out, ch, hits, st = gpu_refract(ctx, rays, sg, ig, strict=strict)
+    assert (st.interactions, st.children, st.hits) == (st_ref.n_interactions, st_ref.n_children, st_ref.n_hits)
+    assert bool(st.missed) == bool(st_ref.rays_missed)
+    assert st_ref.n_children > 0
+    assert_rays_match(out, ref, what=f"{geom} refracted")
+    assert_rays_match(ch, ch_ref, keyed=True, what=f"{geom} reflected")
+    assert_hits_match(hits, hits_ref)  # hits are slot-indexed: already in ray order
+    assert st.valid_out == orc.nr_of_rays(ref) and st.alive_out == len(ref)
+
+
+@pytest.mark.parametrize("index", list(INDICES))
+@pytest.mark.parametrize("coating", [(F.COAT_IDEAL_AR, 0.0), (F.COAT_CONSTANT_R, 0.05), (F.COAT_FRESNEL, 0.0)])
+def test_refract_index_and_coating(ctx, index, coating):
+    """all four index models + passive surface x all three coatings, leaving glass (n1 > n2 -> some TIR)"""
+    so, sg = _with_coating(node_sphere_pair(mm(-40.0), iso_pair((0.0, 0.0, mm(30.0)), (0.02, 0.01, 0.0))), *coating)
+    rays = make_bundle(4096, divergence=0.35)
+    rays["n"] = 1.7  # rays travel inside glass
+    io = ig = None
+    if INDICES[index] is not None:
+        io, ig = index_pair(*INDICES[index])
+    ref = rays.copy()
+    ch_ref, hits_ref, st_ref = orc.rays_refract_on_surface(ref, so, io, True, orc.MISS_IGNORE)
+    out, ch, hits, st = gpu_refract(ctx, rays, sg, ig, strategy=F.MISS_IGNORE)
+    assert (st.interactions, st.children, st.hits) == (st_ref.n_interactions, st_ref.n_children, st_ref.n_hits)
+    assert_rays_match(out, ref, what="refracted")
+    assert_rays_match(ch, ch_ref, keyed=True, what="reflected")
+    assert_hits_match(hits, hits_ref)
+
+
+def test_total_internal_reflection_bundle(ctx):
+    """ray.rs:674-679: steep glass->vacuum incidence; part of the bundle is totally reflected (bounce +1, no child,
+    no hit-map entry), the rest refracts"""
+    so, sg = surface_pair(F.GEOM_PLANE, iso=iso_pair((0.0, 0.0, mm(30.0)), (math.radians(33.0), 0.0, 0.0)))
+    rays = make_bundle(4096, divergence=0.25)
+    rays["n"] = 1.7
+    io, ig = index_pair("const", 1.0)
+    ref = rays.copy()
+    ch_ref, hits_ref, st_ref = orc.rays_refract_on_surface(ref, so, io, True, orc.MISS_STOP)
+    out, ch, hits, st = gpu_refract(ctx, rays, sg, ig)
+    n_tir = int((ref["bounces"] == 1).sum())
+    assert 0 < n_tir < len(rays), n_tir
+    assert st.missed == n_tir and st.children == len(ch_ref) == len(rays) - n_tir
+    assert_rays_match(out, ref, what="TIR bundle")
+    assert_rays_match(ch, ch_ref, keyed=True, what="TIR children")
+    assert_hits_match(hits, hits_ref)
+
+
+def test_refract_errors_match_reference(ctx):
+    """wavelength outside the model range aborts (refr_index_sellmeier1.rs:79-81); ConstantR 0.0 is an error at trace
+    time (coatings/mod.rs:49, constant_r.rs:23)"""
+    so, sg = surface_pair(F.GEOM_PLANE, iso=iso_pair((0, 0, mm(10.0))))
+    io, ig = index_pair("sellmeier1", *HK9L, nm(500.0), nm(2000.0))
+    rays = make_bundle(64, wvl=(nm(400.0), nm(2100.0)))
+    with pytest.raises(orc.OracleError) as eo:
+        orc.rays_refract_on_surface(rays.copy(), so, io)
+    with pytest.raises(ob.OpossumError) as eg:
+        gpu_refract(ctx, rays, sg, ig)
+    assert eg.value.code == F.OPM_ERR_WVL_RANGE and eo.value.code == 2
+    assert str(eg.value) == str(eo.value)
+    so, sg = surface_pair(F.GEOM_PLANE, iso=iso_pair((0, 0, mm(10.0))), coating=F.COAT_CONSTANT_R, r=0.0)
+    with pytest.raises(ob.OpossumError) as eg:
+        gpu_refract(ctx, make_bundle(64), sg, index_pair("const", 1.5)[1])
+    assert eg.value.code == F.OPM_ERR_COATING
+
+
+def test_mirror_drops_and_keeps_order(ctx):
+    """refraction_intended = false (nodes/thin_mirror.rs:209-250, SURVEY C-1): the reflected bundle continues,
+    invalid and missing rays leave the bundle; compact and in-place outputs agree"""
+    node = iso_pair((0.0, 0.0, mm(40.0)), (math.pi / 4, 0.0, 0.0))
+    so, sg = _with_coating(surface_pair(F.GEOM_PLANE, iso=node), F.COAT_CONSTANT_R, 1.0)
+    rays = make_bundle(4096, divergence=0.6)
+    rays["valid"][::7] = 0
+    rays["dir"][::11] *= -1.0  # these fly away from the mirror -> miss
+    ref = rays.copy()
+    ch_ref, hits_ref, st_ref = orc.rays_refract_on_surface(ref, so, None, False, orc.MISS_STOP)
+    assert 0 < len(ch_ref) < len(rays)
+    # in place: rays without a child are flagged removed and skipped by download
+    r = ob.Rays.from_array(ctx, rays)
+    st = ob.Program().mirror(sg).run(r)
+    assert st.alive_out == len(ch_ref)
+    assert_rays_match(r.to_array(), ch_ref, what="mirror in place")  # slot order == reference order
+    assert r.nr_of_rays(False) == len(ch_ref)
+    r.compact()
+    assert len(r) == len(ch_ref)
+    assert_rays_match(r.to_array(), ch_ref, what="mirror + stable compaction")
+    # compacted by the trace kernel itself (warp-ballot aggregated append): same set, order keyed by id
+    r2 = ob.Rays.from_array(ctx, rays)
+    out = ob.Rays(ctx, len(rays))
+    st2 = ob.Program().mirror(sg).run(r2, out=out, compact=True)
+    assert len(out) == len(ch_ref) == st2.alive_out
+    assert_rays_match(out.to_array(), ch_ref, keyed=True, what="mirror compact")
+
+
+APERTURES = {
+    "circle": ("circle", mm(5.0), mm(0.3), mm(-0.2)),
+    "circle_obstruction": ("circle", mm(2.0), 0.0, 0.0),
+    "rect": ("rect", mm(9.0), mm(6.0), mm(0.5), 0.0),
+    "gaussian": ("gaussian", mm(4.0), mm(6.0), 0.0, mm(1.0)),
+    "polygon": ("polygon", [[(-0.006, -0.006), (0.006, -0.006), (0.0, 0.007)], [(0.0, 0.007), (0.006, -0.006), (0.008, 0.008)]]),
+}
+
+
+@pytest.mark.parametrize("name", list(APERTURES) + ["stack", "none"])
+def test_apodize(ctx, name):
+    """rays.rs:557-573 + aperture.rs (circle/rect/polygon/gaussian/stack, hole and obstruction)"""
+    if name == "stack":
+        ao, ag = aperture_pair("stack", [aperture_pair("circle", mm(6.0)), aperture_pair("rect", mm(8.0), mm(8.0)),
+                                         aperture_pair("gaussian", mm(5.0), mm(5.0))])
+    elif name == "none":
+        ao, ag = aperture_pair("none")
+    else:
+        kind, *a = APERTURES[name]
+        ao, ag = aperture_pair(kind, *a, obstruction=name.endswith("obstruction"))
+    io, ig = iso_pair((mm(0.2), 0.0, mm(3.0)), (0.05, -0.02, 0.4))
+    rays = make_bundle(4096)
+    rays["valid"][::9] = 0
+    ref = rays.copy()
+    inv_ref = orc.rays_apodize(ref, ao, io)
+    r = ob.Rays.from_array(ctx, rays)
+    inv = r.apodize(ag, ig)
+    assert inv == inv_ref
+    assert_rays_match(r.to_array(), ref, what=f"apodize {name}")
+    if name in ("circle", "rect", "polygon"):
+        assert 0 < orc.nr_of_rays(ref) < int(rays["valid"].sum())
+
+
+def test_threshold_limits_filter_split(ctx):
+    """rays.rs:1145-1162, 1386-1404, 1119-1133, 1253-1264 incl. their error conditions"""
+    rays = make_bundle(2048)
+    rays["bounces"] = np.arange(len(rays)) % 5
+    rays["refr"] = np.arange(len(rays)) % 3
+    rays["valid"][::13] = 0
+    ref = rays.copy()
+    r = ob.Rays.from_array(ctx, rays)
+    thr = float(np.median(rays["e"]))
+    orc.rays_threshold(ref, thr); r.invalidate_by_threshold_energy(thr)
+    assert_rays_match(r.to_array(), ref, what="threshold")
+    orc.rays_threshold(ref, -1.0); r.invalidate_by_threshold_energy(-1.0)  # negative: warning, unmodified
+    assert_rays_match(r.to_array(), ref, what="negative threshold")
+    for bad in (math.nan, math.inf):
+        with pytest.raises(ob.OpossumError) as ei:
+            r.invalidate_by_threshold_energy(bad)
+        assert ei.value.code == F.OPM_ERR_THRESHOLD
+    orc.rays_filter_bounces(ref, 3); r.filter_by_nr_of_bounces(3)
+    assert_rays_match(r.to_array(), ref, what="bounces")
+    orc.rays_filter_refractions(ref, 2); r.filter_by_nr_of_refractions(2)
+    assert_rays_match(r.to_array(), ref, what="refractions")
+    assert orc.nr_of_rays(ref) > 0
+    orc.rays_filter_energy(ref, 0.3); r.filter_energy(0.3)
+    assert_rays_match(r.to_array(), ref, what="filter")
+    for bad in (-0.1, 1.1):
+        with pytest.raises(ob.OpossumError):
+            r.filter_energy(bad)
+        with pytest.raises(ob.OpossumError) as ei:
+            r.split(bad)
+        assert ei.value.code == F.OPM_ERR_SPLIT_RATIO
+    sp_ref = orc.rays_split(ref, 0.6)
+    sp = r.split(0.6)
+    assert_rays_match(r.to_array(), ref, what="split kept")
+    assert_rays_match(sp.to_array(), sp_ref, what="split off")  # invalid rays are copied too (rays.rs:1260)
+    assert len(sp) == len(rays)
+
+
+def test_paraxial_and_transform(ctx):
+    """rays.rs:943-959 / ray.rs:443-471 and Rays::transformed_by_iso"""
+    io, ig = iso_pair((mm(0.1), mm(-0.3), mm(20.0)), (0.02, 0.03, -0.1))
+    rays = make_bundle(2048, z=mm(20.0))
+    rays["valid"][::5] = 0
+    ref = rays.copy()
+    r = ob.Rays.from_array(ctx, rays)
+    orc.rays_refract_paraxial(ref, mm(150.0), io); r.refract_paraxial(mm(150.0), ig)
+    assert_rays_match(r.to_array(), ref, what="paraxial")
+    orc.rays_refract_paraxial(ref, mm(-80.0), io); r.refract_paraxial(mm(-80.0), ig)
+    assert_rays_match(r.to_array(), ref, what="paraxial negative")
+    for bad in (0.0, math.inf, math.nan):
+        with pytest.raises(ob.OpossumError) as ei:
+            r.refract_paraxial(bad, ig)
+        assert ei.value.code == F.OPM_ERR_FOCAL_LENGTH
+    for inverse in (False, True):
+        orc.rays_transform(ref, io, inverse); r.transformed_by_iso(ig, inverse)
+        assert_rays_match(r.to_array(), ref, what="transform")
+
+
+def test_bundle_statistics(ctx):
+    """rays.rs:521-701 + reference KATs rays.rs:2019-2106, 2696-2734"""
+    rays = make_bundle(100_000, radius=mm(3.0))
+    rays["pos"][:, 0] += mm(1.5)
+    rays["valid"][::17] = 0
+    rays["bounces"] = 2
+    r = ob.Rays.from_array(ctx, rays)
+    s = r.spot_stats()
+    assert s.n_valid == orc.nr_of_rays(rays) and s.n_total == len(rays) and s.bounce_lvl == orc.bounce_lvl(rays) == 2
+    assert s.total_energy == pytest.approx(orc.total_energy(rays), rel=RTOL)
+    assert np.allclose(s.centroid[:], orc.centroid(rays), rtol=RTOL, atol=1e-15)
+    assert np.allclose(s.energy_centroid[:], orc.energy_weighted_centroid(rays), rtol=RTOL, atol=1e-15)
+    assert s.beam_radius_geo == pytest.approx(orc.beam_radius_geo(rays), rel=RTOL)
+    assert s.beam_radius_rms == pytest.approx(orc.beam_radius_rms(rays), rel=RTOL)
+    assert s.energy_beam_radius_rms == pytest.approx(orc.energy_weighted_beam_radius_rms(rays), rel=RTOL)
+    io, ig = iso_pair((mm(1.0), 0.0, mm(5.0)), (0.1, 0.2, 0.0))  # detector frame (nodes/spot_diagram.rs:106-112)
+    loc = rays.copy()
+    orc.rays_transform(loc, io, inverse=True)
+    s = r.spot_stats(ig)
+    assert np.allclose(s.energy_centroid[:], orc.energy_weighted_centroid(loc), rtol=RTOL, atol=1e-15)
+    assert s.beam_radius_geo == pytest.approx(orc.beam_radius_geo(loc), rel=RTOL)
+    # reference KATs
+    k = np.concatenate([orc.ray_new(mm(1.0, 2.0, 0.0), Z, nm(1053.0), 1.0), orc.ray_new(mm(2.0, 3.0, 0.0), Z, nm(1053.0), 1.0),
+                        orc.ray_new(mm(2.0, 3.0, 0.0), Z, nm(1053.0), 1.0)])
+    k[2]["valid"] = 0
+    rk = ob.Rays.from_array(ctx, k)
+    assert tuple(rk.centroid()) == mm(1.5, 2.5, 0.0) and rk.beam_radius_geo() == mm(math.sqrt(0.5))
+    assert rk.total_energy() == 2.0 and rk.nr_of_rays() == 2 and rk.nr_of_rays(False) == 3
+    k = np.concatenate([orc.ray_new(mm(-1.0, 0.0, 0.0), Z, nm(1054.0), 1.0), orc.ray_new(mm(1.0, 0.0, 0.0), Z, nm(1054.0), 0.5)])
+    assert ob.Rays.from_array(ctx, k).energy_weighted_centroid()[0] / 1e-3 == pytest.approx(-1.0 / 3.0, rel=4 * EPS)
+    empty = ob.Rays(ctx, 1)
+    assert empty.centroid() is None and empty.beam_radius_geo() is None and empty.total_energy() == 0.0
+    counts, energy = r.tally(4)
+    assert counts[2] == orc.nr_of_rays(rays) and counts.sum() == counts[2]
+    assert energy[2] == pytest.approx(orc.total_energy(rays), rel=RTOL)
+
+
+def test_upload_download_roundtrip_and_soa(ctx):
+    rays = make_bundle(1000)
+    rays["valid"][::3] = 0
+    r = ob.Rays.from_array(ctx, rays)
+    back = r.to_array()
+    assert back.tobytes() == rays.tobytes()
+    c = r.clone(); c.add_rays(r)
+    assert len(c) == 2000 and c.to_array()[1000:].tobytes() == rays.tobytes()
+    soa = ob.Rays(ctx, 1000)
+    pos = [np.ascontiguousarray(rays["pos"][:, k]) for k in range(3)]
+    d = [np.ascontiguousarray(2.0 * rays["dir"][:, k]) for k in range(3)]  # Ray::new normalises (ray.rs:127)
+    soa.upload_soa(pos, d, np.ascontiguousarray(rays["e"]), np.ascontiguousarray(rays["wvl"]))
+    got = soa.to_array()
+    fresh = rays.copy(); fresh["valid"] = 1
+    assert_rays_match(got, fresh, what="soa upload")
+    assert len(ob.Rays.from_array(ctx, rays[:0]).to_array()) == 0  # empty bundle
