@@ -388,8 +388,8 @@ class Rays:
         st = F.OpmTraceStats()
         _check(F.lib().opm_rays_refract_on_surface(
             self.h, C.byref(surface.c), C.byref(refractive_index.c) if refractive_index is not None else None,
-            int(refraction_intended), missed_surface_strategy, reflected.h if reflected else None,
-            hit_map.h if hit_map else None, C.byref(st)))
+            int(refraction_intended), missed_surface_strategy, reflected.h if reflected is not None else None,
+            hit_map.h if hit_map is not None else None, C.byref(st)))
         return reflected, TraceStats.of(st)
 
     def apodize(self, aperture: Aperture, iso: Isometry) -> bool:
@@ -423,7 +423,7 @@ class Rays:
     # ---- statistics
     def spot_stats(self, frame: Isometry | None = None) -> F.OpmSpotStats:
         s = F.OpmSpotStats()
-        _check(F.lib().opm_rays_spot_stats(self.h, C.byref(frame.c) if frame else None, C.byref(s)))
+        _check(F.lib().opm_rays_spot_stats(self.h, C.byref(frame.c) if frame is not None else None, C.byref(s)))
         return s
 
     def total_energy(self) -> float:
@@ -485,8 +485,8 @@ class Program:
         r.strategy = strategy
         r.flags = (F.REFRACT_EMIT_CHILDREN if children is not None else 0) | \
                   (F.REFRACT_CONTINUE_AS_CHILD if continue_as_child else 0)
-        r.hits = hit_map.h if hit_map else None
-        r.children = children.h if children else None
+        r.hits = hit_map.h if hit_map is not None else None
+        r.children = children.h if children is not None else None
         self._keep += [hit_map, children]
         self.ops.append(op)
         return self
@@ -550,7 +550,7 @@ class Program:
         arr = (F.OpmOp * max(len(self.ops), 1))(*self.ops)
         flags = (F.TRACE_COMPACT if compact else 0) | (F.TRACE_STRICT if strict else 0)
         st = F.OpmTraceStats()
-        _check(F.lib().opm_trace_sequence(rays.h, arr, len(self.ops), flags, out.h if out else None,
+        _check(F.lib().opm_trace_sequence(rays.h, arr, len(self.ops), flags, out.h if out is not None else None,
                                           C.byref(st) if sync else None))
         return TraceStats.of(st) if sync else None
 
@@ -642,6 +642,6 @@ class SourceDesc:
 
     def generate(self, ctx: Context, begin=0, end=None, rays: Rays | None = None) -> Rays:
         end = end if end is not None else self.c.n_positions
-        r = rays or Rays(ctx, max((end - begin) * self.c.n_wavelengths, 1))
+        r = rays if rays is not None else Rays(ctx, max((end - begin) * self.c.n_wavelengths, 1))
         _check(F.lib().opm_source_generate(r.h, C.byref(self.c), begin, end))
         return r

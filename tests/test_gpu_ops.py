@@ -165,7 +165,9 @@ def test_refract_index_and_coating(ctx, index, coating):
     out, ch, hits, st = gpu_refract(ctx, rays, sg, ig, strategy=F.MISS_IGNORE)
     assert (st.interactions, st.children, st.hits) == (st_ref.n_interactions, st_ref.n_children, st_ref.n_hits)
     assert_rays_match(out, ref, what="refracted")
-    assert_rays_match(ch, ch_ref, keyed=True, what="reflected")
+    # Fresnel at n1 == n2 (passive surface) is exactly 0 analytically; off axis both sides return ~1e-33 of rounding
+    # noise (coatings/fresnel.rs:21-33 cancels), so child energies are compared on the scale of the parent energy
+    assert_rays_match(ch, ch_ref, keyed=True, what="reflected", e_floor=1e-15 * float(rays["e"].max()))
     assert_hits_match(hits, hits_ref)
 
 
