@@ -157,7 +157,8 @@ typedef enum {
     OPM_OP_FILTER = 5,     /* Rays::filter_energy(Constant)       rays.rs:1119-1133 */
     OPM_OP_PARAXIAL = 6,   /* Rays::refract_paraxial              rays.rs:943-959   */
     OPM_OP_SPLIT = 7,      /* Rays::split(Ratio)                  rays.rs:1253-1264 */
-    OPM_OP_SNAPSHOT = 8    /* copy of the bundle a detector node keeps (analyzers/raytrace.rs:186-205) */
+    OPM_OP_SNAPSHOT = 8,   /* copy of the bundle a detector node keeps (analyzers/raytrace.rs:186-205) */
+    OPM_OP_TRANSFORM = 9   /* Rays::transformed_by_iso (nodes/source.rs:205-210)                      */
 } OpmOpKind;
 
 enum {
@@ -182,8 +183,9 @@ typedef struct { double min_energy; } OpmThresholdOp;
 typedef struct { uint64_t max_bounces; uint64_t max_refractions; int32_t check_refractions; int32_t _pad; } OpmLimitsOp;
 typedef struct { double transmission; } OpmFilterOp;
 typedef struct { double focal_length; OpmIsometry iso; } OpmParaxialOp;
-typedef struct { double ratio; OpmRays* split_out; } OpmSplitOp;   /* split_out: slot-indexed copy with E*(1-ratio) */
+typedef struct { double ratio; OpmRays* split_out; } OpmSplitOp;   /* split_out: slot-indexed copy with E*(1-ratio); NULL = discard it */
 typedef struct { OpmRays* out; } OpmSnapshotOp;                     /* slot-indexed copy of the bundle at this point */
+typedef struct { OpmIsometry iso; int32_t inverse; int32_t _pad; } OpmTransformOp;
 
 typedef struct {
     int32_t kind; /* OpmOpKind */
@@ -197,6 +199,7 @@ typedef struct {
         OpmParaxialOp paraxial;
         OpmSplitOp split;
         OpmSnapshotOp snapshot;
+        OpmTransformOp transform;
     } u;
 } OpmOp;
 
@@ -278,6 +281,8 @@ typedef struct {
 /* frame: NULL or the detector's effective surface isometry (positions are inverse-transformed into it,
  * nodes/spot_diagram.rs:106-112) */
 OpmStatus opm_rays_spot_stats(const OpmRays* rays, const OpmIsometry* frame_or_null, OpmSpotStats* out);
+/* Rays::bounce_lvl (rays.rs:183-194): bounce count of the first valid ray (lowest id); 0 for none */
+OpmStatus opm_rays_bounce_lvl(const OpmRays* rays, uint32_t* bounce_lvl);
 /* per-bounce-order tallies: counts[b] valid rays and energy[b] their energy, b < n_orders (last bin = overflow) */
 OpmStatus opm_rays_tally(const OpmRays* rays, uint32_t n_orders, uint64_t* counts, double* energy);
 

@@ -1,0 +1,133 @@
+/*
+ * opossum_b200_scene.h -- host-side mirror of the reference's node / analyzer layer for the
+ * ray-propagation path, written in C++ above the C ABI of opossum_b200.h and exported with C linkage.
+ *
+ * What it replaces in the reference (opossum/src/):
+ *   - the node -> surface compilers `OpticNode::update_surfaces` of Lens (nodes/lens/mod.rs:226-293),
+ *     CylindricLens (nodes/cylindric_lens/mod.rs:146-214), Wedge (nodes/wedge/mod.rs:116-160), ThinMirror
+ *     (nodes/thin_mirror.rs:121-155), ParabolicMirror on axis (nodes/parabolic_mirror.rs:388-421), and the flat
+ *     single-surface nodes (optic_node.rs:62-80): BeamSplitter, Dummy, IdealFilter, ParaxialSurface, Source,
+ *     SpotDiagram, FluenceDetector;
+ *   - each node's `AnalysisRayTrace::analyze` / `AnalysisGhostFocus::analyze` and the shared
+ *     `pass_through_surface` / `pass_through_detector_surface` (analyzers/raytrace.rs:96-207);
+ *   - the drivers `RayTracingAnalyzer::analyze` (analyzers/raytrace.rs:36-49 with the walk of
+ *     nodes/node_group/analysis_raytrace.rs:29-91) and `GhostFocusAnalyzer::analyze`
+ *     (analyzers/ghostfocus.rs:82-122 with nodes/node_group/analysis_ghostfocus.rs:22-109).
+ *
+ * Scope limits (SURVEY.md 8f "next"): the scene is a chain of nodes with explicit isometries (node
+ * positioning from an axis ray and .opm ingestion are out of scope); a beam splitter may feed a side chain
+ * from its second output.  Only the Binning fluence estimator exists on the device.
+ */
+#ifndef OPOSSUM_B200_SCENE_H
+#define OPOSSUM_B200_SCENE_H
+
+#include "opossum_b200.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+    OPM_NODE_SOURCE = 0,
+    OPM_NODE_LENS = 1,
+    OPM_NODE_CYLINDRIC_LENS = 2,
+    OPM_NODE_WEDGE = 3,
+    OPM_NODE_THIN_MIRROR = 4,
+    OPM_NODE_PARABOLIC_MIRROR = 5,
+    OPM_NODE_BEAM_SPLITTER = 6,
+    OPM_NODE_DUMMY = 7,
+    OPM_NODE_IDEAL_FILTER = 8,
+    OPM_NODE_PARAXIAL_SURFACE = 9,
+    OPM_NODE_SPOT_DIAGRAM = 10,
+    OPM_NODE_FLUENCE_DETECTOR = 11
+} OpmNodeType;
+
+typedef struct { int32_t type; int32_t _pad; double reflectivity; } OpmCoatingDesc; /* coatings/mod.rs:17-29 */
+
+/* One optic node.  Geometry parameters p[]:
+ *   LENS / CYLINDRIC_LENS : p[0] front curvature, p[1] rear curvature (+-INFINITY = flat), p[2] centre thickness
+ *   WEDGE                 : p[0] centre thickness, p[1] wedge angle [rad]
+ *   THIN_MIRROR           : p[0] curvature (INFINITY = flat)
+ *   PARABOLIC_MIRROR      : p[0] focal length (on axis)
+ *   BEAM_SPLITTER         : p[0] splitting ratio (SplittingConfig::Ratio, ray.rs:36-46)
+ *   IDEAL_FILTER          : p[0] transmission (FilterType::Constant)
+ *   PARAXIAL_SURFACE      : p[0] focal length
+ */
+typedef struct {
+    int32_t type;              /* OpmNodeType */
+    int32_t parent;            /* index of the node whose output feeds this one; -1 = the previous node */
+    int32_t parent_port;       /* 0 = main output, 1 = second output of a beam splitter */
+    int32_t has_alignment;     /* local decenter/tilt appended to the node isometry (optic_node.rs:356-363) */
+    OpmIsometry iso;           /* node isometry */
+    OpmIsometry alignment;
+    double p[4];
+    OpmIndexModel index;       /* glass of LENS / CYLINDRIC_LENS / WEDGE */
+    OpmCoatingDesc coating_in, coating_out; /* per optic surface (input_1 / output_1) */
+    OpmAperture aperture_in, aperture_out;
+    double lidt;               /* J/m^2; 0 = the default 1 J/cm^2 (surface/optic_surface.rs:55) */
+} OpmNodeDesc;
+
+/* defaults of the reference's node constructors: IdealAR coatings (mirrors: ConstantR 1.0), no apertures */
+void opm_node_desc_init(OpmNodeDesc* d, int32_t type);
+
+typedef struct OpmScene OpmScene;
+
+OpmStatus opm_scene_create(OpmContext* ctx, OpmScene** out);
+void opm_scene_destroy(OpmScene* scene);
+/* SceneryResources::ambient_refr_index (optic_scenery_rsc.rs:8-20); default vacuum */
+OpmStatus opm_scene_set_ambient(OpmScene* scene, const OpmIndexModel* ambient);
+OpmStatus opm_scene_add_node(OpmScene* scene, const OpmNodeDesc* desc, int32_t* node_index);
+int32_t opm_scene_node_count(const OpmScene* scene);
+/* OpticNode::reset_data: clears hit maps, ray caches and stored detector data (optic_node.rs:84-95) */
+OpmStatus opm_scene_reset_data(OpmScene* scene);
+
+enum {
+    OPM_SCENE_STRICT = 2,           /* same value as OPM_TRACE_STRICT */
+    OPM_SCENE_PER_SURFACE = 4,      /* one launch per reference call instead of one fused launch per chain */
+    OPM_SCENE_RECORD_ALL_HITS = 8,  /* keep the hit map of every surface (the reference always does); default: detectors only */
+    OPM_SCENE_NO_SNAPSHOTS = 16,    /* detectors keep hit maps but no copy of the bundle (no spot statistics) */
+    OPM_SCENE_ASYNC = 32            /* do not synchronise / read counters back (throughput runs) */
+};
+
+/* RayTracingAnalyzer::analyze.  `source_rays` is the bundle the Source node's light-data builder produced, in
+ * the source's local frame; it is traced in place and holds the main chain's output afterwards. */
+OpmStatus opm_scene_raytrace(OpmScene* scene, OpmRays* source_rays, const OpmRayTraceConfig* config, int32_t flags,
+                             OpmTraceStats* stats);
+
+/* detector read-out (node_report of SpotDiagram / FluenceDetector) */
+OpmRays* opm_scene_node_rays(OpmScene* scene, int32_t node);           /* bundle stored at a detector / split-off bundle of a splitter */
+OpmStatus opm_scene_node_spot(OpmScene* scene, int32_t node, OpmSpotStats* out); /* nodes/spot_diagram.rs:101-163 */
+/* nodes/fluence_detector/mod.rs:91-135 with FluenceEstimator::Binning: map_host (nx*ny, column-major ny x nx) may be NULL */
+OpmStatus opm_scene_node_fluence(OpmScene* scene, int32_t node, uint64_t nx, uint64_t ny, double* map_host, double lrtb[4],
+                                 double* peak, double* total_energy);
+/* hit maps recorded on surface `surface` (0 = input_1, 1 = output_1) of a node: fills up to `capacity` handles */
+int32_t opm_scene_node_hitmaps(OpmScene* scene, int32_t node, int32_t surface, OpmHitMap** out, int32_t capacity);
+
+/* ---- ghost focus (analyzers/ghostfocus.rs) */
+typedef struct { uint64_t max_bounces; } OpmGhostFocusConfig;  /* estimator: Binning */
+typedef struct {
+    uint64_t interactions;
+    uint64_t launches;
+    uint64_t bundles;          /* ray bundles that reached a sink over all passes */
+    uint32_t passes;
+    uint32_t _pad;
+} OpmGhostFocusStats;
+OpmStatus opm_scene_ghostfocus(OpmScene* scene, OpmRays* source_rays, const OpmGhostFocusConfig* config, int32_t flags,
+                               OpmGhostFocusStats* stats);
+/* accumulated rays per pass (scenery.add_to_accumulated_rays, analyzers/ghostfocus.rs:117-119): per-bounce-order tallies
+ * of the bundles collected in pass `pass` */
+OpmStatus opm_scene_gf_pass_tally(OpmScene* scene, uint32_t pass, uint32_t n_orders, uint64_t* counts, double* energy,
+                                  uint64_t* n_bundles, uint64_t* n_rays);
+/* bundles collected in a pass (ray_collection): returns the number written */
+int32_t opm_scene_gf_pass_bundles(OpmScene* scene, uint32_t pass, OpmRays** out, int32_t capacity);
+/* critical fluences of a surface (hit_map/mod.rs:121-146): peak fluence [J/m^2] per offending bundle */
+typedef struct { uint64_t bundle_uuid; double peak_fluence; uint32_t bounce; uint32_t _pad; } OpmCriticalFluence;
+int32_t opm_scene_node_critical_fluences(OpmScene* scene, int32_t node, int32_t surface, OpmCriticalFluence* out,
+                                         int32_t capacity);
+/* peak of the per-bundle 101x101 Binning maps evaluated on a surface during the analysis (max over bundles) */
+OpmStatus opm_scene_node_peak_fluence(OpmScene* scene, int32_t node, int32_t surface, double* peak);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -26,7 +26,7 @@ COAT_IDEAL_AR, COAT_CONSTANT_R, COAT_FRESNEL = range(3)
 IDX_CONST, IDX_SELLMEIER1, IDX_SCHOTT, IDX_CONRADY = range(4)
 MISS_STOP, MISS_IGNORE = 0, 1
 AP_NONE, AP_CIRCLE, AP_RECT, AP_POLYGON, AP_GAUSSIAN = range(5)
-OP_REFRACT, OP_APODIZE, OP_THRESHOLD, OP_LIMITS, OP_FILTER, OP_PARAXIAL, OP_SPLIT, OP_SNAPSHOT = range(1, 9)
+OP_REFRACT, OP_APODIZE, OP_THRESHOLD, OP_LIMITS, OP_FILTER, OP_PARAXIAL, OP_SPLIT, OP_SNAPSHOT, OP_TRANSFORM = range(1, 10)
 REFRACT_EMIT_CHILDREN, REFRACT_CONTINUE_AS_CHILD = 1, 2
 TRACE_COMPACT, TRACE_STRICT = 1, 2
 POS_GRID, POS_FIBONACCI_RECT, POS_FIBONACCI_ELLIPSE = range(3)
@@ -113,10 +113,14 @@ class OpmSnapshotOp(C.Structure):
     _fields_ = [("out", C.c_void_p)]
 
 
+class OpmTransformOp(C.Structure):
+    _fields_ = [("iso", OpmIsometry), ("inverse", C.c_int32), ("_pad", C.c_int32)]
+
+
 class _OpUnion(C.Union):
     _fields_ = [("refract", OpmRefractOp), ("apodize", OpmApodizeOp), ("threshold", OpmThresholdOp),
                 ("limits", OpmLimitsOp), ("filter", OpmFilterOp), ("paraxial", OpmParaxialOp), ("split", OpmSplitOp),
-                ("snapshot", OpmSnapshotOp)]
+                ("snapshot", OpmSnapshotOp), ("transform", OpmTransformOp)]
 
 
 class OpmOp(C.Structure):
@@ -139,6 +143,43 @@ class OpmSourceDesc(C.Structure):
                 ("weights", C.POINTER(C.c_double)), ("iso", OpmIsometry)]
 
 
+(NODE_SOURCE, NODE_LENS, NODE_CYLINDRIC_LENS, NODE_WEDGE, NODE_THIN_MIRROR, NODE_PARABOLIC_MIRROR, NODE_BEAM_SPLITTER,
+ NODE_DUMMY, NODE_IDEAL_FILTER, NODE_PARAXIAL_SURFACE, NODE_SPOT_DIAGRAM, NODE_FLUENCE_DETECTOR) = range(12)
+SCENE_STRICT, SCENE_PER_SURFACE, SCENE_RECORD_ALL_HITS, SCENE_NO_SNAPSHOTS, SCENE_ASYNC = 2, 4, 8, 16, 32
+
+
+class OpmCoatingDesc(C.Structure):
+    _fields_ = [("type", C.c_int32), ("_pad", C.c_int32), ("reflectivity", C.c_double)]
+
+
+class OpmNodeDesc(C.Structure):
+    _fields_ = [("type", C.c_int32), ("parent", C.c_int32), ("parent_port", C.c_int32), ("has_alignment", C.c_int32),
+                ("iso", OpmIsometry), ("alignment", OpmIsometry), ("p", C.c_double * 4), ("index", OpmIndexModel),
+                ("coating_in", OpmCoatingDesc), ("coating_out", OpmCoatingDesc), ("aperture_in", OpmAperture),
+                ("aperture_out", OpmAperture), ("lidt", C.c_double)]
+
+
+class OpmGhostFocusConfig(C.Structure):
+    _fields_ = [("max_bounces", C.c_uint64)]
+
+
+class OpmGhostFocusStats(C.Structure):
+    _fields_ = [("interactions", C.c_uint64), ("launches", C.c_uint64), ("bundles", C.c_uint64), ("passes", C.c_uint32),
+                ("_pad", C.c_uint32)]
+
+
+class OpmCriticalFluence(C.Structure):
+    _fields_ = [("bundle_uuid", C.c_uint64), ("peak_fluence", C.c_double), ("bounce", C.c_uint32), ("_pad", C.c_uint32)]
+
+
+# every symbol include/opossum_b200_scene.h declares
+SCENE_EXPORTS = [
+    "opm_node_desc_init", "opm_scene_create", "opm_scene_destroy", "opm_scene_set_ambient", "opm_scene_add_node",
+    "opm_scene_node_count", "opm_scene_reset_data", "opm_scene_raytrace", "opm_scene_node_rays", "opm_scene_node_spot",
+    "opm_scene_node_fluence", "opm_scene_node_hitmaps", "opm_scene_ghostfocus", "opm_scene_gf_pass_tally",
+    "opm_scene_gf_pass_bundles", "opm_scene_node_critical_fluences", "opm_scene_node_peak_fluence",
+]
+
 # every symbol include/opossum_b200.h declares (tests/test_abi.py checks the library exports all of them)
 EXPORTS = [
     "opm_abi_version", "opm_last_error", "opm_status_string", "opm_context_create", "opm_context_destroy",
@@ -149,7 +190,7 @@ EXPORTS = [
     "opm_rays_field_ptr", "opm_rays_refract_on_surface", "opm_rays_apodize",
     "opm_rays_invalidate_by_threshold_energy", "opm_rays_filter_by_nr_of_bounces",
     "opm_rays_filter_by_nr_of_refractions", "opm_rays_filter_energy", "opm_rays_split", "opm_rays_refract_paraxial",
-    "opm_rays_transform", "opm_trace_sequence", "opm_rays_spot_stats", "opm_rays_tally", "opm_hitmap_create",
+    "opm_rays_transform", "opm_trace_sequence", "opm_rays_spot_stats", "opm_rays_bounce_lvl", "opm_rays_tally", "opm_hitmap_create",
     "opm_hitmap_destroy", "opm_hitmap_capacity", "opm_hitmap_len", "opm_hitmap_upload", "opm_hitmap_download",
     "opm_hitmaps_bounding_box", "opm_fluence_binning", "opm_fluence_peak_total", "opm_device_alloc",
     "opm_device_free", "opm_device_to_host", "opm_host_to_device", "opm_host_alloc_pinned", "opm_host_free_pinned",
@@ -216,6 +257,7 @@ def lib() -> C.CDLL:
         "opm_rays_transform": (i32, [vp, C.POINTER(OpmIsometry), i32]),
         "opm_trace_sequence": (i32, [vp, C.POINTER(OpmOp), i32, i32, vp, C.POINTER(OpmTraceStats)]),
         "opm_rays_spot_stats": (i32, [vp, C.POINTER(OpmIsometry), C.POINTER(OpmSpotStats)]),
+        "opm_rays_bounce_lvl": (i32, [vp, C.POINTER(C.c_uint32)]),
         "opm_rays_tally": (i32, [vp, C.c_uint32, C.POINTER(u64), dp]),
         "opm_hitmap_create": (i32, [vp, u64, pp]),
         "opm_hitmap_destroy": (None, [vp]),
@@ -235,6 +277,25 @@ def lib() -> C.CDLL:
         "opm_source_generate": (i32, [vp, C.POINTER(OpmSourceDesc), u64, u64]),
         "opm_source_energy_norm": (i32, [vp, C.POINTER(OpmSourceDesc), u64, u64, dp]),
     }
+    sig.update({
+        "opm_node_desc_init": (None, [C.POINTER(OpmNodeDesc), i32]),
+        "opm_scene_create": (i32, [vp, pp]),
+        "opm_scene_destroy": (None, [vp]),
+        "opm_scene_set_ambient": (i32, [vp, C.POINTER(OpmIndexModel)]),
+        "opm_scene_add_node": (i32, [vp, C.POINTER(OpmNodeDesc), C.POINTER(i32)]),
+        "opm_scene_node_count": (i32, [vp]),
+        "opm_scene_reset_data": (i32, [vp]),
+        "opm_scene_raytrace": (i32, [vp, vp, C.POINTER(OpmRayTraceConfig), i32, C.POINTER(OpmTraceStats)]),
+        "opm_scene_node_rays": (vp, [vp, i32]),
+        "opm_scene_node_spot": (i32, [vp, i32, C.POINTER(OpmSpotStats)]),
+        "opm_scene_node_fluence": (i32, [vp, i32, u64, u64, dp, dp, dp, dp]),
+        "opm_scene_node_hitmaps": (i32, [vp, i32, i32, pp, i32]),
+        "opm_scene_ghostfocus": (i32, [vp, vp, C.POINTER(OpmGhostFocusConfig), i32, C.POINTER(OpmGhostFocusStats)]),
+        "opm_scene_gf_pass_tally": (i32, [vp, C.c_uint32, C.c_uint32, C.POINTER(u64), dp, C.POINTER(u64), C.POINTER(u64)]),
+        "opm_scene_gf_pass_bundles": (i32, [vp, C.c_uint32, pp, i32]),
+        "opm_scene_node_critical_fluences": (i32, [vp, i32, i32, C.POINTER(OpmCriticalFluence), i32]),
+        "opm_scene_node_peak_fluence": (i32, [vp, i32, i32, dp]),
+    })
     for name, (res, args) in sig.items():
         fn = getattr(L, name)
         fn.restype = res

@@ -454,8 +454,9 @@ class Rays:
         return s.energy_beam_radius_rms if s.n_valid else None
 
     def bounce_lvl(self) -> int:
-        s = self.spot_stats()
-        return s.bounce_lvl if s.n_valid else 0
+        out = C.c_uint32()
+        _check(F.lib().opm_rays_bounce_lvl(self.h, C.byref(out)))
+        return out.value
 
     def tally(self, n_orders: int = 8):
         counts = (C.c_uint64 * n_orders)()
@@ -531,10 +532,17 @@ class Program:
         self.ops.append(op)
         return self
 
-    def split(self, ratio: float, split_out: Rays) -> "Program":
+    def transform(self, iso: Isometry, inverse=False) -> "Program":
+        op = F.OpmOp(kind=F.OP_TRANSFORM)
+        op.u.transform.iso = iso.c
+        op.u.transform.inverse = int(inverse)
+        self.ops.append(op)
+        return self
+
+    def split(self, ratio: float, split_out: Rays | None) -> "Program":
         op = F.OpmOp(kind=F.OP_SPLIT)
         op.u.split.ratio = ratio
-        op.u.split.split_out = split_out.h
+        op.u.split.split_out = split_out.h if split_out is not None else None
         self._keep.append(split_out)
         self.ops.append(op)
         return self

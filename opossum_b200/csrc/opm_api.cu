@@ -615,11 +615,13 @@ static OpmStatus compile_ops(OpmContext* c, const OpmOp* ops, int n_ops, uint64_
             case OPM_OP_SPLIT: {  // ray.rs:763-767
                 double ratio = p.u.split.ratio;
                 if (!(ratio >= 0.0 && ratio <= 1.0)) return fail(OPM_ERR_SPLIT_RATIO, "%s", opm_status_string(OPM_ERR_SPLIT_RATIO));
-                if (!p.u.split.split_out) return fail(OPM_ERR_ARG, "split without output bundle");
-                OpmStatus s = opm_rays_reserve(p.u.split.split_out, n_rays);
-                if (s) return s;
-                d.kind = OPK_SPLIT; d.u.split.ratio = ratio; d.u.split.out = p.u.split.split_out->v;
-                out.slot_outputs.push_back(p.u.split.split_out);
+                d.kind = OPK_SPLIT; d.u.split.ratio = ratio;
+                if (p.u.split.split_out) {
+                    OpmStatus s = opm_rays_reserve(p.u.split.split_out, n_rays);
+                    if (s) return s;
+                    d.u.split.out = p.u.split.split_out->v;
+                    out.slot_outputs.push_back(p.u.split.split_out);
+                }
                 break;
             }
             case OPM_OP_SNAPSHOT: {
@@ -630,6 +632,10 @@ static OpmStatus compile_ops(OpmContext* c, const OpmOp* ops, int n_ops, uint64_
                 out.slot_outputs.push_back(p.u.snapshot.out);
                 break;
             }
+            case OPM_OP_TRANSFORM:
+                d.kind = OPK_TRANSFORM;
+                to_dev_iso(p.u.transform.inverse ? p.u.transform.iso.inv : p.u.transform.iso.fwd, d.u.transform.iso);
+                break;
             default: return fail(OPM_ERR_ARG, "unknown op kind %d", p.kind);
         }
         out.ops.push_back(d);
@@ -782,6 +788,7 @@ extern "C" OpmStatus opm_rays_filter_energy(OpmRays* rays, double t) {
     return run_simple(rays, op);
 }
 extern "C" OpmStatus opm_rays_split(OpmRays* rays, double ratio, OpmRays* split_out) {
+    if (!split_out) return fail(OPM_ERR_ARG, "split without output bundle");
     OpmOp op; memset(&op, 0, sizeof op);
     op.kind = OPM_OP_SPLIT; op.u.split.ratio = ratio; op.u.split.split_out = split_out;
     return run_simple(rays, op);
@@ -843,6 +850,24 @@ extern "C" OpmStatus opm_rays_spot_stats(const OpmRays* rc, const OpmIsometry* f
     out->beam_radius_rms = std::sqrt(a.sum_d2 / len) * 1.0E-3;
     out->energy_beam_radius_rms = std::sqrt(a.sum_ed2 / a.sum[6]);
     out->bounce_lvl = (uint32_t)(a.first_key & 0xffffffffull);
+    return OPM_OK;
+}
+extern "C" OpmStatus opm_rays_bounce_lvl(const OpmRays* rc, uint32_t* out) {
+    OpmRays* r = const_cast<OpmRays*>(rc);
+    if (!r || !out) return fail(OPM_ERR_ARG, "NULL argument");
+    OpmContext* c = r->ctx;
+    CU(cudaSetDevice(c->device));
+    OpmStatus s = rays_refresh_len(r);
+    if (s) return s;
+    *out = 0;
+    if (r->len == 0) return OPM_OK;
+    unsigned long long* d_key = (unsigned long long*)c->d_scratch;
+    CU(cudaMemsetAsync(d_key, 0xff, 8, c->stream));
+    KL(k_bounce_lvl(r->v, r->len, d_key, c->sms, c->stream)); c->launches++;
+    CU(cudaMemcpyAsync(c->h_scratch, d_key, 8, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    unsigned long long key = *(unsigned long long*)c->h_scratch;
+    if (key != ~0ull) *out = (uint32_t)(key & 0xffffffffull);
     return OPM_OK;
 }
 extern "C" OpmStatus opm_rays_tally(const OpmRays* rc, uint32_t n_orders, uint64_t* counts, double* energy) {

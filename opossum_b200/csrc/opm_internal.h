@@ -33,7 +33,7 @@ struct DevAperture {
     const double* tris;  // device
 };
 
-enum : int32_t { OPK_REFRACT = 1, OPK_APODIZE, OPK_THRESHOLD, OPK_LIMITS, OPK_FILTER, OPK_PARAXIAL, OPK_SPLIT, OPK_SNAPSHOT };
+enum : int32_t { OPK_REFRACT = 1, OPK_APODIZE, OPK_THRESHOLD, OPK_LIMITS, OPK_FILTER, OPK_PARAXIAL, OPK_SPLIT, OPK_SNAPSHOT, OPK_TRANSFORM };
 
 struct DevRefract {
     int32_t geom, coating, has_index, refraction_intended, strategy, flags, index_type, _pad;
@@ -53,6 +53,7 @@ struct DevFilter { double t; };
 struct DevParaxial { double f; DevIso fwd, inv; };
 struct DevSplit { double ratio; DevRays out; };
 struct DevSnapshot { DevRays out; };
+struct DevTransform { DevIso iso; };
 
 struct alignas(16) DevOp {
     int32_t kind, _pad;
@@ -65,6 +66,7 @@ struct alignas(16) DevOp {
         DevParaxial paraxial;
         DevSplit split;
         DevSnapshot snapshot;
+        DevTransform transform;
     } u;
 };
 static_assert(sizeof(DevOp) % 16 == 0, "DevOp must be a multiple of 16 B for the bulk copy into shared memory");

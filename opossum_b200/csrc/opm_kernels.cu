@@ -165,6 +165,17 @@ __global__ void __launch_bounds__(256) spot_pass2_kernel(DevRays R, uint64_t n, 
         atomicAdd(&acc->sum_d2, b); atomicAdd(&acc->sum_ed2, c);
     }
 }
+__global__ void __launch_bounds__(256) bounce_lvl_kernel(DevRays R, uint64_t n, unsigned long long* first_key) {
+    unsigned long long first = ~0ull;
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        if (R.valid[i] != RAY_VALID) continue;
+        unsigned long long key = ((unsigned long long)R.id[i] << 32) | R.bounces[i];
+        first = key < first ? key : first;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { unsigned long long t = __shfl_xor_sync(0xffffffffu, first, o); first = t < first ? t : first; }
+    if ((threadIdx.x & 31) == 0 && first != ~0ull) atomicMin(first_key, first);
+}
 __global__ void __launch_bounds__(256) tally_kernel(DevRays R, uint64_t n, uint32_t n_orders, unsigned long long* counts, double* energy) {
     extern __shared__ unsigned char tsm[];
     double* se = reinterpret_cast<double*>(tsm);
@@ -481,6 +492,10 @@ int k_spot(DevRays R, uint64_t n, int use_frame, DevIso inv, SpotAccum* acc, int
     int g = grid_for(n, 256, sms * 4);
     spot_pass1_kernel<<<g, 256, 0, ST>>>(R, n, use_frame, inv, acc);
     spot_pass2_kernel<<<g, 256, 0, ST>>>(R, n, use_frame, inv, acc);
+    return (int)cudaGetLastError();
+}
+int k_bounce_lvl(DevRays R, uint64_t n, unsigned long long* first_key, int sms, void* stream) {
+    bounce_lvl_kernel<<<grid_for(n, 256, sms * 4), 256, 0, ST>>>(R, n, first_key);
     return (int)cudaGetLastError();
 }
 int k_tally(DevRays R, uint64_t n, uint32_t n_orders, unsigned long long* counts, double* energy, int sms, void* stream) {

@@ -45,6 +45,7 @@ int k_soa_to_aos(DevRays R, OpmRay* a, uint64_t n, int sms, void* stream);
 int k_soa_defaults(DevRays R, uint64_t n, int sms, void* stream);
 int k_transform(DevRays R, DevIso I, uint64_t n, int sms, void* stream);
 int k_spot(DevRays R, uint64_t n, int use_frame, DevIso inv, SpotAccum* acc, int sms, void* stream);
+int k_bounce_lvl(DevRays R, uint64_t n, unsigned long long* first_key, int sms, void* stream);
 int k_tally(DevRays R, uint64_t n, uint32_t n_orders, unsigned long long* counts, double* energy, int sms, void* stream);
 int k_hits_bbox(DevHits H, uint64_t n, long long bounce_filter, BBoxAccum* acc, int sms, void* stream);
 int k_binning(DevHits H, uint64_t n, long long bounce_filter, const BinParams& P, double* map, unsigned* status, int sms, void* stream);

@@ -1,0 +1,518 @@
+// opm_scene.cpp -- host-side mirror of the reference's node / analyzer layer (see include/opossum_b200_scene.h).
+//
+// Pure host bookkeeping, O(#nodes): it compiles optic nodes into surface descriptors and `Rays` op programs
+// and drives them through the public C ABI (opossum_b200.h) exactly as a Rust host would through FFI.  No ray
+// arithmetic happens here.  Reference file:line citations are relative to opossum/src/.
+#include <cmath>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/opossum_b200_scene.h"
+
+namespace {
+
+struct HitEntry { uint64_t uuid; OpmHitMap* map; };
+
+// One bundle of the ghost-focus analysis (struct Rays: uuid, parent_id; rays.rs:62-73)
+struct Bundle {
+    OpmRays* rays = nullptr;
+    uint64_t uuid = 0;
+    uint64_t parent = 0;
+};
+
+// surface/optic_surface.rs:29-43
+struct SurfaceState {
+    OpmSurface surf{};
+    OpmIsometry eff_iso{};   // effective_surface_iso = effective_node_iso o anchor_point_iso (optic_node.rs:372-382)
+    OpmAperture aperture{};
+    double lidt = 1.0e4;     // 1 J/cm^2 in J/m^2
+    std::vector<HitEntry> hits;
+    std::vector<std::shared_ptr<Bundle>> fwd_cache, bwd_cache;  // optic_surface.rs:92-143
+    std::vector<OpmCriticalFluence> critical;
+    double peak_seen = -INFINITY;
+};
+
+struct Node {
+    OpmNodeDesc d{};
+    int parent = -1;
+    SurfaceState s[2];          // input_1, output_1
+    std::vector<double> tris[2];  // polygon aperture storage
+    OpmRays* stored = nullptr;  // bundle kept by a detector (LightData::Geometric, analyzers/raytrace.rs:186-205)
+    OpmRays* split = nullptr;   // second output of a beam splitter
+    std::vector<std::shared_ptr<Bundle>> stored_gf;  // LightData::GhostFocus kept by a detector
+    int main_child = -1, split_child = -1;
+};
+
+OpmIsometry iso_z(double z) {
+    OpmIsometry o;
+    double t[3] = {0.0, 0.0, z}, e[3] = {0.0, 0.0, 0.0};
+    opm_isometry_new(t, e, &o);
+    return o;
+}
+OpmIsometry iso_append(const OpmIsometry& a, const OpmIsometry& b) {
+    OpmIsometry o;
+    opm_isometry_append(&a, &b, &o);
+    return o;
+}
+
+}  // namespace
+
+struct OpmScene {
+    OpmContext* ctx = nullptr;
+    OpmIndexModel ambient{};
+    std::vector<std::unique_ptr<Node>> nodes;
+    uint64_t next_uuid = 1;
+    std::vector<std::vector<std::shared_ptr<Bundle>>> passes;  // ray_collection of every ghost-focus pass
+    std::vector<OpmRays*> owned_rays;                           // every device bundle the scene allocated for GF
+    std::vector<OpmHitMap*> owned_hits;
+    std::string err;
+};
+
+namespace {
+
+OpmStatus scene_fail(OpmStatus s) { return s; }
+
+void free_node_data(OpmScene* sc, Node& n) {
+    for (auto& s : n.s) {
+        for (auto& h : s.hits) opm_hitmap_destroy(h.map);
+        s.hits.clear(); s.fwd_cache.clear(); s.bwd_cache.clear(); s.critical.clear(); s.peak_seen = -INFINITY;
+    }
+    if (n.stored) { opm_rays_destroy(n.stored); n.stored = nullptr; }
+    if (n.split) { opm_rays_destroy(n.split); n.split = nullptr; }
+    n.stored_gf.clear();
+    (void)sc;
+}
+
+// ---- node -> surfaces (OpticNode::update_surfaces)
+OpmSurface make_surface(int geom, double param, const OpmIsometry& iso, const OpmCoatingDesc& c) {
+    OpmSurface s;
+    memset(&s, 0, sizeof s);
+    s.geom = geom; s.geom_param = param; s.iso = iso; s.coating = c.type; s.coating_r = c.reflectivity;
+    return s;
+}
+
+OpmStatus update_surfaces(Node& n) {
+    const OpmNodeDesc& d = n.d;
+    OpmIsometry node_iso = d.has_alignment ? iso_append(d.iso, d.alignment) : d.iso;  // effective_node_iso (optic_node.rs:356-363)
+    OpmIsometry ident;
+    opm_isometry_identity(&ident);
+    OpmIsometry anchor[2] = {ident, ident};
+    const OpmCoatingDesc* coat[2] = {&d.coating_in, &d.coating_out};
+    switch (d.type) {
+        case OPM_NODE_LENS:
+        case OPM_NODE_CYLINDRIC_LENS: {  // nodes/lens/mod.rs:226-293, nodes/cylindric_lens/mod.rs:146-214
+            const int curved = d.type == OPM_NODE_LENS ? OPM_GEOM_SPHERE : OPM_GEOM_CYLINDER;
+            const double front = d.p[0], rear = d.p[1], thick = d.p[2];
+            if (std::isnan(front) || std::isnan(rear) || front == 0.0 || rear == 0.0) return OPM_ERR_ARG;
+            if (!(thick >= 0.0) || !std::isfinite(thick)) return OPM_ERR_ARG;  // nodes/lens/mod.rs:110-116
+            if (std::isinf(front)) n.s[0].surf = make_surface(OPM_GEOM_PLANE, 0.0, node_iso, *coat[0]);
+            else {
+                anchor[0] = iso_z(front);
+                n.s[0].surf = make_surface(curved, front, iso_append(node_iso, anchor[0]), *coat[0]);
+            }
+            if (std::isinf(rear)) {
+                anchor[1] = iso_z(thick);
+                n.s[1].surf = make_surface(OPM_GEOM_PLANE, 0.0, iso_append(node_iso, anchor[1]), *coat[1]);
+            } else {
+                anchor[1] = iso_z(rear + thick);
+                n.s[1].surf = make_surface(curved, rear, iso_append(node_iso, anchor[1]), *coat[1]);
+            }
+            break;
+        }
+        case OPM_NODE_WEDGE: {  // nodes/wedge/mod.rs:116-160
+            const double thick = d.p[0], angle = d.p[1];
+            if (!(thick >= 0.0) || !std::isfinite(thick) || !std::isfinite(angle) || std::fabs(angle) >= M_PI / 2) return OPM_ERR_ARG;
+            n.s[0].surf = make_surface(OPM_GEOM_PLANE, 0.0, node_iso, *coat[0]);
+            OpmIsometry wedge_iso;
+            double t0[3] = {0, 0, 0}, e[3] = {angle, 0.0, 0.0};
+            opm_isometry_new(t0, e, &wedge_iso);
+            anchor[1] = iso_append(iso_z(thick), wedge_iso);
+            n.s[1].surf = make_surface(OPM_GEOM_PLANE, 0.0, iso_append(node_iso, anchor[1]), *coat[1]);
+            break;
+        }
+        case OPM_NODE_THIN_MIRROR: {  // nodes/thin_mirror.rs:121-155: both ports share the geometry
+            const double curv = d.p[0];
+            if (std::isnan(curv) || curv == 0.0) return OPM_ERR_ARG;
+            for (int k = 0; k < 2; ++k) {
+                if (std::isinf(curv)) n.s[k].surf = make_surface(OPM_GEOM_PLANE, 0.0, node_iso, *coat[k]);
+                else {
+                    anchor[k] = iso_z(curv);
+                    n.s[k].surf = make_surface(OPM_GEOM_SPHERE, curv, iso_append(node_iso, anchor[k]), *coat[k]);
+                }
+            }
+            break;
+        }
+        case OPM_NODE_PARABOLIC_MIRROR: {  // nodes/parabolic_mirror.rs:388-421 with oa angle 0: Parabola(-f)
+            const double f = d.p[0];
+            if (!std::isnormal(f)) return OPM_ERR_ARG;
+            for (int k = 0; k < 2; ++k) n.s[k].surf = make_surface(OPM_GEOM_PARABOLA, -1.0 * f, node_iso, *coat[k]);
+            break;
+        }
+        default:  // optic_node.rs:62-80 update_flat_single_surfaces
+            for (int k = 0; k < 2; ++k) n.s[k].surf = make_surface(OPM_GEOM_PLANE, 0.0, node_iso, *coat[k]);
+            break;
+    }
+    const OpmAperture* ap[2] = {&d.aperture_in, &d.aperture_out};
+    for (int k = 0; k < 2; ++k) {
+        n.s[k].eff_iso = iso_append(node_iso, anchor[k]);
+        n.s[k].aperture = *ap[k];
+        if (ap[k]->n_tris > 0 && ap[k]->tris) {  // the polygon triangles are caller memory: keep a copy
+            n.tris[k].assign(ap[k]->tris, ap[k]->tris + (size_t)ap[k]->n_tris * 6);
+            n.s[k].aperture.tris = n.tris[k].data();
+        }
+        n.s[k].lidt = d.lidt > 0.0 ? d.lidt : 1.0e4;
+    }
+    return OPM_OK;
+}
+
+// ---- op builders (one op = one `Rays` method call of the reference)
+OpmOp op_refract(const SurfaceState& s, const OpmIndexModel* index, bool intended, int strategy, int flags, OpmHitMap* hits,
+                 OpmRays* children) {
+    OpmOp op;
+    memset(&op, 0, sizeof op);
+    op.kind = OPM_OP_REFRACT;
+    op.u.refract.surface = s.surf;
+    if (index) { op.u.refract.index = *index; op.u.refract.has_index = 1; }
+    op.u.refract.refraction_intended = intended ? 1 : 0;
+    op.u.refract.strategy = strategy;
+    op.u.refract.flags = flags;
+    op.u.refract.hits = hits;
+    op.u.refract.children = children;
+    return op;
+}
+OpmOp op_apodize(const OpmAperture& ap, const OpmIsometry& iso) {
+    OpmOp op;
+    memset(&op, 0, sizeof op);
+    op.kind = OPM_OP_APODIZE; op.u.apodize.aperture = ap; op.u.apodize.iso = iso;
+    return op;
+}
+OpmOp op_threshold(double e) {
+    OpmOp op;
+    memset(&op, 0, sizeof op);
+    op.kind = OPM_OP_THRESHOLD; op.u.threshold.min_energy = e;
+    return op;
+}
+OpmOp op_limits(uint64_t max_bounces, uint64_t max_refr, bool check_refr) {
+    OpmOp op;
+    memset(&op, 0, sizeof op);
+    op.kind = OPM_OP_LIMITS; op.u.limits.max_bounces = max_bounces; op.u.limits.max_refractions = max_refr;
+    op.u.limits.check_refractions = check_refr ? 1 : 0;
+    return op;
+}
+
+// Runs an op list, splitting it into several launches when it exceeds OPM_MAX_PROGRAM_OPS or when every reference
+// call should be its own launch (OPM_SCENE_PER_SURFACE: the un-fused baseline).
+struct Runner {
+    OpmRays* rays;
+    int flags;
+    OpmTraceStats total{};
+    std::vector<OpmOp> ops;
+    OpmStatus status = OPM_OK;
+
+    void push(const OpmOp& op) {
+        if (status) return;
+        ops.push_back(op);
+        if ((flags & OPM_SCENE_PER_SURFACE) || ops.size() == OPM_MAX_PROGRAM_OPS) flush();
+    }
+    void flush() {
+        if (status || ops.empty()) return;
+        OpmTraceStats st;
+        memset(&st, 0, sizeof st);
+        const bool async = (flags & OPM_SCENE_ASYNC) != 0;
+        status = opm_trace_sequence(rays, ops.data(), (int32_t)ops.size(), flags & OPM_TRACE_STRICT, nullptr, async ? nullptr : &st);
+        ops.clear();
+        total.interactions += st.interactions; total.children += st.children; total.hits += st.hits; total.missed += st.missed;
+        total.apodized += st.apodized; total.valid_out = st.valid_out; total.alive_out = st.alive_out; total.status_bits |= st.status_bits;
+    }
+};
+
+bool is_detector(int type) { return type == OPM_NODE_SPOT_DIAGRAM || type == OPM_NODE_FLUENCE_DETECTOR; }
+
+OpmHitMap* new_hitmap(OpmScene* sc, SurfaceState& s, uint64_t uuid, uint64_t n, OpmStatus* st) {
+    OpmHitMap* h = nullptr;
+    *st = opm_hitmap_create(sc->ctx, n ? n : 1, &h);
+    if (*st) return nullptr;
+    s.hits.push_back({uuid, h});
+    return h;
+}
+
+// `AnalysisRayTrace::analyze` of one node, forward direction, appended to the runner's program
+OpmStatus compile_node_rt(OpmScene* sc, Node& n, const OpmRayTraceConfig& cfg, int flags, uint64_t n_rays, Runner& R) {
+    const int strat = cfg.missed_surface_strategy;
+    const double thr = cfg.min_energy_per_ray;
+    OpmStatus st = OPM_OK;
+    auto hits_for = [&](SurfaceState& s) -> OpmHitMap* {
+        if (!(flags & OPM_SCENE_RECORD_ALL_HITS) && !is_detector(n.d.type)) return nullptr;
+        return new_hitmap(sc, s, 1, n_rays, &st);
+    };
+    switch (n.d.type) {
+        case OPM_NODE_SOURCE: {  // nodes/source.rs:189-235
+            OpmOp op;
+            memset(&op, 0, sizeof op);
+            op.kind = OPM_OP_TRANSFORM; op.u.transform.iso = n.s[0].eff_iso; op.u.transform.inverse = 0;
+            R.push(op);
+            R.push(op_apodize(n.s[1].aperture, n.s[0].eff_iso));
+            R.push(op_threshold(thr));
+            break;
+        }
+        case OPM_NODE_LENS:
+        case OPM_NODE_CYLINDRIC_LENS:
+        case OPM_NODE_WEDGE: {  // nodes/lens/analysis_raytrace.rs:11-55 -> pass_through_surface x2 (analyzers/raytrace.rs:96-140)
+            OpmHitMap* h0 = hits_for(n.s[0]);
+            if (st) return st;
+            R.push(op_refract(n.s[0], &n.d.index, true, strat, 0, h0, nullptr));
+            R.push(op_apodize(n.s[0].aperture, n.s[0].eff_iso));
+            R.push(op_threshold(thr));
+            OpmHitMap* h1 = hits_for(n.s[1]);
+            if (st) return st;
+            R.push(op_refract(n.s[1], &sc->ambient, true, strat, 0, h1, nullptr));
+            R.push(op_apodize(n.s[1].aperture, n.s[1].eff_iso));
+            R.push(op_threshold(thr));
+            break;
+        }
+        case OPM_NODE_THIN_MIRROR:
+        case OPM_NODE_PARABOLIC_MIRROR: {  // nodes/thin_mirror.rs:209-250, nodes/parabolic_mirror.rs:474-517
+            OpmHitMap* h0 = hits_for(n.s[0]);
+            if (st) return st;
+            R.push(op_refract(n.s[0], nullptr, false, strat, OPM_REFRACT_CONTINUE_AS_CHILD, h0, nullptr));
+            R.push(op_apodize(n.s[0].aperture, n.s[0].eff_iso));
+            R.push(op_threshold(thr));
+            break;
+        }
+        case OPM_NODE_BEAM_SPLITTER: {  // nodes/beam_splitter/mod.rs:158-293 (one input)
+            OpmHitMap* h0 = hits_for(n.s[0]);
+            if (st) return st;
+            R.push(op_refract(n.s[0], nullptr, true, strat, 0, h0, nullptr));
+            R.push(op_apodize(n.s[0].aperture, n.s[0].eff_iso));
+            if (n.split_child >= 0 && !n.split) {
+                st = opm_rays_create(sc->ctx, n_rays ? n_rays : 1, &n.split);
+                if (st) return st;
+            }
+            OpmOp op;
+            memset(&op, 0, sizeof op);
+            op.kind = OPM_OP_SPLIT; op.u.split.ratio = n.d.p[0]; op.u.split.split_out = n.split;
+            R.push(op);
+            R.push(op_apodize(n.s[1].aperture, n.s[1].eff_iso));  // out1 aperture, iso of out1_port
+            R.push(op_threshold(thr));
+            break;
+        }
+        case OPM_NODE_DUMMY:
+        case OPM_NODE_IDEAL_FILTER:
+        case OPM_NODE_PARAXIAL_SURFACE: {  // nodes/dummy.rs:83-135, ideal_filter.rs:203-250, paraxial_surface.rs:169-230
+            OpmHitMap* h0 = hits_for(n.s[0]);
+            if (st) return st;
+            R.push(op_refract(n.s[0], nullptr, true, strat, 0, h0, nullptr));
+            if (n.d.type == OPM_NODE_IDEAL_FILTER) {
+                OpmOp op;
+                memset(&op, 0, sizeof op);
+                op.kind = OPM_OP_FILTER; op.u.filter.transmission = n.d.p[0];
+                R.push(op);
+            } else if (n.d.type == OPM_NODE_PARAXIAL_SURFACE) {
+                OpmOp op;
+                memset(&op, 0, sizeof op);
+                op.kind = OPM_OP_PARAXIAL; op.u.paraxial.focal_length = n.d.p[0]; op.u.paraxial.iso = n.s[0].eff_iso;
+                R.push(op);
+            }
+            R.push(op_apodize(n.s[0].aperture, n.s[0].eff_iso));
+            R.push(op_threshold(thr));
+            R.push(op_apodize(n.s[1].aperture, n.s[0].eff_iso));  // output aperture in the INPUT surface frame
+            R.push(op_threshold(thr));
+            break;
+        }
+        case OPM_NODE_SPOT_DIAGRAM:
+        case OPM_NODE_FLUENCE_DETECTOR: {  // pass_through_detector_surface analyzers/raytrace.rs:150-207
+            OpmHitMap* h0 = hits_for(n.s[0]);
+            if (st) return st;
+            R.push(op_refract(n.s[0], nullptr, true, strat, 0, h0, nullptr));
+            R.push(op_apodize(n.s[0].aperture, n.s[0].eff_iso));
+            R.push(op_threshold(thr));
+            if (!(flags & OPM_SCENE_NO_SNAPSHOTS)) {
+                if (!n.stored) {
+                    st = opm_rays_create(sc->ctx, n_rays ? n_rays : 1, &n.stored);
+                    if (st) return st;
+                }
+                OpmOp op;
+                memset(&op, 0, sizeof op);
+                op.kind = OPM_OP_SNAPSHOT; op.u.snapshot.out = n.stored;
+                R.push(op);
+            }
+            break;
+        }
+        default: return OPM_ERR_ARG;
+    }
+    // filter_ray_limits after every node (nodes/node_group/analysis_raytrace.rs:20-27,66)
+    R.push(op_limits(cfg.max_number_of_bounces, cfg.max_number_of_refractions, true));
+    return R.status;
+}
+
+OpmStatus link_nodes(OpmScene* sc) {
+    const int N = (int)sc->nodes.size();
+    for (int i = 0; i < N; ++i) { sc->nodes[i]->main_child = -1; sc->nodes[i]->split_child = -1; }
+    for (int i = 0; i < N; ++i) {
+        Node& n = *sc->nodes[i];
+        n.parent = n.d.parent < 0 ? i - 1 : n.d.parent;
+        if (i == 0) { n.parent = -1; continue; }
+        if (n.parent < 0 || n.parent >= i) return OPM_ERR_ARG;
+        Node& p = *sc->nodes[n.parent];
+        if (n.d.parent_port == 1) {
+            if (p.d.type != OPM_NODE_BEAM_SPLITTER || p.split_child >= 0) return OPM_ERR_ARG;
+            p.split_child = i;
+        } else {
+            if (p.main_child >= 0) return OPM_ERR_ARG;
+            p.main_child = i;
+        }
+    }
+    return OPM_OK;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------
+extern "C" void opm_node_desc_init(OpmNodeDesc* d, int32_t type) {
+    memset(d, 0, sizeof *d);
+    d->type = type;
+    d->parent = -1;
+    opm_isometry_identity(&d->iso);
+    opm_isometry_identity(&d->alignment);
+    d->index.type = OPM_IDX_CONST; d->index.c[0] = 1.5;  // nodes/lens/mod.rs:81, nodes/wedge/mod.rs:63
+    d->coating_in.type = d->coating_out.type = OPM_COAT_IDEAL_AR;  // surface/optic_surface.rs:54
+    if (type == OPM_NODE_THIN_MIRROR || type == OPM_NODE_PARABOLIC_MIRROR) {  // nodes/thin_mirror.rs:67-82
+        d->coating_in.type = d->coating_out.type = OPM_COAT_CONSTANT_R;
+        d->coating_in.reflectivity = d->coating_out.reflectivity = 1.0;
+    }
+    switch (type) {
+        case OPM_NODE_LENS: case OPM_NODE_CYLINDRIC_LENS: d->p[0] = 500.0 * 1e-3; d->p[1] = -500.0 * 1e-3; d->p[2] = 10.0 * 1e-3; break;
+        case OPM_NODE_WEDGE: d->p[0] = 10.0 * 1e-3; d->p[1] = 0.0; break;
+        case OPM_NODE_THIN_MIRROR: d->p[0] = INFINITY; break;
+        case OPM_NODE_PARABOLIC_MIRROR: d->p[0] = 1.0; break;
+        case OPM_NODE_BEAM_SPLITTER: d->p[0] = 0.5; break;
+        case OPM_NODE_IDEAL_FILTER: d->p[0] = 1.0; break;
+        case OPM_NODE_PARAXIAL_SURFACE: d->p[0] = 10.0 * 1e-3; break;
+        default: break;
+    }
+    d->lidt = 1.0e4;
+}
+
+extern "C" OpmStatus opm_scene_create(OpmContext* ctx, OpmScene** out) {
+    if (!ctx || !out) return OPM_ERR_ARG;
+    OpmScene* s = new OpmScene();
+    s->ctx = ctx;
+    memset(&s->ambient, 0, sizeof s->ambient);
+    s->ambient.type = OPM_IDX_CONST; s->ambient.c[0] = 1.0;  // vacuum (optic_scenery_rsc.rs:14-19)
+    *out = s;
+    return OPM_OK;
+}
+extern "C" OpmStatus opm_scene_reset_data(OpmScene* sc) {
+    if (!sc) return OPM_ERR_ARG;
+    for (auto& n : sc->nodes) free_node_data(sc, *n);
+    sc->passes.clear();
+    for (OpmRays* r : sc->owned_rays) opm_rays_destroy(r);
+    sc->owned_rays.clear();
+    return OPM_OK;
+}
+extern "C" void opm_scene_destroy(OpmScene* sc) {
+    if (!sc) return;
+    opm_scene_reset_data(sc);
+    delete sc;
+}
+extern "C" OpmStatus opm_scene_set_ambient(OpmScene* sc, const OpmIndexModel* a) {
+    if (!sc || !a) return OPM_ERR_ARG;
+    sc->ambient = *a;
+    return OPM_OK;
+}
+extern "C" OpmStatus opm_scene_add_node(OpmScene* sc, const OpmNodeDesc* d, int32_t* idx) {
+    if (!sc || !d) return OPM_ERR_ARG;
+    if (sc->nodes.empty() && d->type != OPM_NODE_SOURCE) return OPM_ERR_ARG;  // the chain starts at a Source
+    auto n = std::make_unique<Node>();
+    n->d = *d;
+    OpmStatus st = update_surfaces(*n);
+    if (st) return st;
+    sc->nodes.push_back(std::move(n));
+    if (idx) *idx = (int32_t)sc->nodes.size() - 1;
+    return link_nodes(sc);
+}
+extern "C" int32_t opm_scene_node_count(const OpmScene* sc) { return sc ? (int32_t)sc->nodes.size() : 0; }
+
+// RayTracingAnalyzer::analyze (analyzers/raytrace.rs:36-49): reset_data, then the topological walk
+extern "C" OpmStatus opm_scene_raytrace(OpmScene* sc, OpmRays* rays, const OpmRayTraceConfig* cfg_in, int32_t flags,
+                                        OpmTraceStats* stats) {
+    if (!sc || !rays || sc->nodes.empty()) return OPM_ERR_ARG;
+    OpmRayTraceConfig cfg;
+    if (cfg_in) cfg = *cfg_in; else opm_raytrace_config_default(&cfg);
+    OpmStatus st = opm_scene_reset_data(sc);
+    if (st) return st;
+    const uint64_t n_rays = opm_rays_len(rays);
+    OpmTraceStats total;
+    memset(&total, 0, sizeof total);
+    // main chain, then the side chains hanging off beam splitters
+    struct Job { int start; OpmRays* rays; int splitter; };
+    std::vector<Job> jobs;
+    jobs.push_back({0, rays, -1});
+    for (size_t j = 0; j < jobs.size(); ++j) {
+        Runner R{jobs[j].rays, flags};
+        if (jobs[j].splitter >= 0) {  // second output: apodize(out2 aperture, iso of out1) + threshold + limits
+            Node& sp = *sc->nodes[jobs[j].splitter];
+            R.push(op_apodize(sp.s[1].aperture, sp.s[1].eff_iso));
+            R.push(op_threshold(cfg.min_energy_per_ray));
+            R.push(op_limits(cfg.max_number_of_bounces, cfg.max_number_of_refractions, true));
+        }
+        for (int i = jobs[j].start; i >= 0; i = sc->nodes[i]->main_child) {
+            Node& n = *sc->nodes[i];
+            st = compile_node_rt(sc, n, cfg, flags, n_rays, R);
+            if (st) return st;
+            if (n.d.type == OPM_NODE_BEAM_SPLITTER && n.split_child >= 0) jobs.push_back({n.split_child, n.split, i});
+        }
+        R.flush();
+        if (R.status) return R.status;
+        total.interactions += R.total.interactions; total.children += R.total.children; total.hits += R.total.hits;
+        total.missed += R.total.missed; total.apodized += R.total.apodized; total.status_bits |= R.total.status_bits;
+        if (j == 0) { total.valid_out = R.total.valid_out; total.alive_out = R.total.alive_out; }
+    }
+    if (stats) *stats = total;
+    return OPM_OK;
+}
+
+extern "C" OpmRays* opm_scene_node_rays(OpmScene* sc, int32_t node) {
+    if (!sc || node < 0 || node >= (int)sc->nodes.size()) return nullptr;
+    Node& n = *sc->nodes[node];
+    return n.d.type == OPM_NODE_BEAM_SPLITTER ? n.split : n.stored;
+}
+extern "C" OpmStatus opm_scene_node_spot(OpmScene* sc, int32_t node, OpmSpotStats* out) {
+    if (!sc || !out || node < 0 || node >= (int)sc->nodes.size()) return OPM_ERR_ARG;
+    Node& n = *sc->nodes[node];
+    if (!n.stored) return OPM_ERR_ARG;
+    return opm_rays_spot_stats(n.stored, &n.s[0].eff_iso, out);  // nodes/spot_diagram.rs:106-112
+}
+extern "C" int32_t opm_scene_node_hitmaps(OpmScene* sc, int32_t node, int32_t surface, OpmHitMap** out, int32_t cap) {
+    if (!sc || node < 0 || node >= (int)sc->nodes.size() || surface < 0 || surface > 1) return 0;
+    auto& hits = sc->nodes[node]->s[surface].hits;
+    int32_t k = 0;
+    for (auto& h : hits) { if (out && k < cap) out[k] = h.map; ++k; }
+    return k;
+}
+extern "C" OpmStatus opm_scene_node_fluence(OpmScene* sc, int32_t node, uint64_t nx, uint64_t ny, double* map_host, double lrtb[4],
+                                            double* peak, double* total) {
+    if (!sc || node < 0 || node >= (int)sc->nodes.size()) return OPM_ERR_ARG;
+    Node& n = *sc->nodes[node];
+    std::vector<OpmHitMap*> maps;
+    for (auto& h : n.s[0].hits) maps.push_back(h.map);  // hit_maps()["input_1"], all bounces and bundles merged
+    if (maps.empty()) return OPM_ERR_EMPTY_HITMAP;
+    void* dev = nullptr;
+    OpmStatus st = opm_device_alloc(sc->ctx, nx * ny * sizeof(double), &dev);
+    if (st) return st;
+    double box[4];
+    st = opm_fluence_binning(maps.data(), (int32_t)maps.size(), -1, nx, ny, nullptr, nullptr, 0, (double*)dev, box);
+    if (!st) st = opm_fluence_peak_total(sc->ctx, (const double*)dev, nx, ny, box, peak, total);
+    if (!st && map_host) st = opm_device_to_host(sc->ctx, map_host, dev, nx * ny * sizeof(double));
+    if (lrtb) memcpy(lrtb, box, sizeof box);
+    opm_device_free(sc->ctx, dev);
+    return st;
+}
+
+// ---------------------------------------------------------------------------------------------
+// ghost focus: see opm_scene_gf.inc
+// ---------------------------------------------------------------------------------------------
+#include "opm_scene_gf.inc"

@@ -185,8 +185,8 @@ trace_kernel(const DevOp* __restrict__ g_ops, int n_ops, DevRays in, DevRays out
                         if (alive) {
                             RayState s = r;
                             if (valid) { r.e *= o.ratio; s.e *= 1.0 - o.ratio; }
-                            store_ray<true>(o.out, i, s, valid ? RAY_VALID : RAY_INVALID);
-                        } else {
+                            if (o.out.px != nullptr) store_ray<true>(o.out, i, s, valid ? RAY_VALID : RAY_INVALID);
+                        } else if (o.out.px != nullptr) {
                             o.out.valid[i] = RAY_REMOVED;
                         }
                     }
@@ -200,6 +200,12 @@ trace_kernel(const DevOp* __restrict__ g_ops, int n_ops, DevRays in, DevRays out
                     }
                     break;
                 }
+                case OPK_TRANSFORM:  // ray.rs:787-804
+                    if (alive) {
+                        r.pos = iso_point(op.u.transform.iso, r.pos);
+                        r.dir = iso_vector(op.u.transform.iso, r.dir);
+                    }
+                    break;
                 default: break;
             }
         }

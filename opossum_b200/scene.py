@@ -1,0 +1,264 @@
+"""Python veneer over the C++ scene layer (include/opossum_b200_scene.h): node constructors named after the
+reference's nodes (opossum/src/nodes/*) and the two analyzers.  Marshalling only -- the node -> surface
+compilation and the analysis drivers live in opossum_b200/csrc/opm_scene.cpp."""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import _ffi as F
+from .api import (Aperture, Context, FluenceData, HitMap, Isometry, Rays, RayTraceConfig, RefractiveIndex, TraceStats,
+                  _check)
+
+
+@dataclass
+class CoatingType:
+    """coatings/mod.rs `CoatingType`"""
+    type: int = F.COAT_IDEAL_AR
+    reflectivity: float = 0.0
+
+    @staticmethod
+    def ideal_ar():
+        return CoatingType(F.COAT_IDEAL_AR)
+
+    @staticmethod
+    def constant_r(reflectivity: float):
+        return CoatingType(F.COAT_CONSTANT_R, reflectivity)
+
+    @staticmethod
+    def fresnel():
+        return CoatingType(F.COAT_FRESNEL)
+
+
+class Node:
+    """Common part of an optic node: isometry, alignment, coatings and apertures of input_1 / output_1."""
+
+    def __init__(self, node_type: int, iso: Isometry | None = None):
+        self.c = F.OpmNodeDesc()
+        F.lib().opm_node_desc_init(C.byref(self.c), node_type)
+        if iso is not None:
+            self.c.iso = iso.c
+        self._keep = []
+
+    def with_alignment(self, decenter, tilt):
+        """OpticNode::set_alignment (optic_node.rs:383-393)"""
+        self.c.has_alignment = 1
+        self.c.alignment = Isometry.new(decenter, tilt).c
+        return self
+
+    def with_coatings(self, input_1: CoatingType | None = None, output_1: CoatingType | None = None):
+        if input_1 is not None:
+            self.c.coating_in.type, self.c.coating_in.reflectivity = input_1.type, input_1.reflectivity
+        if output_1 is not None:
+            self.c.coating_out.type, self.c.coating_out.reflectivity = output_1.type, output_1.reflectivity
+        return self
+
+    def with_apertures(self, input_1: Aperture | None = None, output_1: Aperture | None = None):
+        if input_1 is not None:
+            self.c.aperture_in = input_1.c
+            self._keep.append(input_1)
+        if output_1 is not None:
+            self.c.aperture_out = output_1.c
+            self._keep.append(output_1)
+        return self
+
+    def with_lidt(self, lidt_j_per_m2: float):
+        self.c.lidt = lidt_j_per_m2
+        return self
+
+    def fed_by(self, parent: int, port: int = 0):
+        self.c.parent, self.c.parent_port = parent, port
+        return self
+
+
+def Source(iso=None):
+    return Node(F.NODE_SOURCE, iso)
+
+
+def Lens(front_curvature, rear_curvature, center_thickness, refractive_index: RefractiveIndex, iso=None):
+    """Lens::new (nodes/lens/mod.rs:98-140); curvature +-inf = flat"""
+    n = Node(F.NODE_LENS, iso)
+    n.c.p[0], n.c.p[1], n.c.p[2] = front_curvature, rear_curvature, center_thickness
+    n.c.index = refractive_index.c
+    return n
+
+
+def CylindricLens(front_curvature, rear_curvature, center_thickness, refractive_index: RefractiveIndex, iso=None):
+    n = Node(F.NODE_CYLINDRIC_LENS, iso)
+    n.c.p[0], n.c.p[1], n.c.p[2] = front_curvature, rear_curvature, center_thickness
+    n.c.index = refractive_index.c
+    return n
+
+
+def Wedge(center_thickness, wedge_angle, refractive_index: RefractiveIndex, iso=None):
+    n = Node(F.NODE_WEDGE, iso)
+    n.c.p[0], n.c.p[1] = center_thickness, wedge_angle
+    n.c.index = refractive_index.c
+    return n
+
+
+def ThinMirror(curvature=math.inf, iso=None):
+    n = Node(F.NODE_THIN_MIRROR, iso)
+    n.c.p[0] = curvature
+    return n
+
+
+def ParabolicMirror(focal_length, iso=None):
+    n = Node(F.NODE_PARABOLIC_MIRROR, iso)
+    n.c.p[0] = focal_length
+    return n
+
+
+def BeamSplitter(ratio, iso=None):
+    n = Node(F.NODE_BEAM_SPLITTER, iso)
+    n.c.p[0] = ratio
+    return n
+
+
+def Dummy(iso=None):
+    return Node(F.NODE_DUMMY, iso)
+
+
+def IdealFilter(transmission, iso=None):
+    n = Node(F.NODE_IDEAL_FILTER, iso)
+    n.c.p[0] = transmission
+    return n
+
+
+def ParaxialSurface(focal_length, iso=None):
+    n = Node(F.NODE_PARAXIAL_SURFACE, iso)
+    n.c.p[0] = focal_length
+    return n
+
+
+def SpotDiagram(iso=None):
+    return Node(F.NODE_SPOT_DIAGRAM, iso)
+
+
+def FluenceDetector(iso=None):
+    return Node(F.NODE_FLUENCE_DETECTOR, iso)
+
+
+class _BorrowedRays(Rays):
+    """A bundle owned by the scene (never destroyed from Python)."""
+
+    def __init__(self, ctx, handle):
+        self.ctx, self.h = ctx, C.c_void_p(handle)
+
+    def close(self):
+        self.h = None
+
+
+class _BorrowedHitMap(HitMap):
+    def __init__(self, ctx, handle):
+        self.ctx, self.h = ctx, C.c_void_p(handle)
+
+    def close(self):
+        self.h = None
+
+
+class Scene:
+    """A chain of optic nodes starting at a Source (NodeGroup of the reference, restricted to explicit isometries)."""
+
+    def __init__(self, ctx: Context):
+        self.ctx = ctx
+        h = C.c_void_p()
+        _check(F.lib().opm_scene_create(ctx.h, C.byref(h)))
+        self.h = h
+        self._nodes = []
+
+    def set_ambient(self, index: RefractiveIndex):
+        _check(F.lib().opm_scene_set_ambient(self.h, C.byref(index.c)))
+
+    def add_node(self, node: Node) -> int:
+        idx = C.c_int32()
+        _check(F.lib().opm_scene_add_node(self.h, C.byref(node.c), C.byref(idx)))
+        self._nodes.append(node)
+        return idx.value
+
+    def raytrace(self, source_rays: Rays, config: RayTraceConfig | None = None, strict=False, per_surface=False,
+                 record_all_hits=False, snapshots=True, sync=True) -> TraceStats | None:
+        """RayTracingAnalyzer::analyze (analyzers/raytrace.rs:36-49); traces `source_rays` in place."""
+        cfg = F.OpmRayTraceConfig()
+        c = config or RayTraceConfig()
+        cfg.min_energy_per_ray, cfg.max_number_of_bounces = c.min_energy_per_ray, c.max_number_of_bounces
+        cfg.max_number_of_refractions, cfg.missed_surface_strategy = c.max_number_of_refractions, c.missed_surface_strategy
+        flags = ((F.SCENE_STRICT if strict else 0) | (F.SCENE_PER_SURFACE if per_surface else 0) |
+                 (F.SCENE_RECORD_ALL_HITS if record_all_hits else 0) | (0 if snapshots else F.SCENE_NO_SNAPSHOTS) |
+                 (0 if sync else F.SCENE_ASYNC))
+        st = F.OpmTraceStats()
+        _check(F.lib().opm_scene_raytrace(self.h, source_rays.h, C.byref(cfg), flags, C.byref(st)))
+        return TraceStats.of(st) if sync else None
+
+    def node_rays(self, node: int) -> Rays | None:
+        h = F.lib().opm_scene_node_rays(self.h, node)
+        return _BorrowedRays(self.ctx, h) if h else None
+
+    def node_spot(self, node: int) -> F.OpmSpotStats:
+        s = F.OpmSpotStats()
+        _check(F.lib().opm_scene_node_spot(self.h, node, C.byref(s)))
+        return s
+
+    def node_fluence(self, node: int, nx=100, ny=83, download=True) -> FluenceData:
+        """FluenceDetector::node_report (nodes/fluence_detector/mod.rs:91-135), Binning estimator"""
+        m = np.zeros(nx * ny) if download else None
+        lrtb = (C.c_double * 4)()
+        peak, tot = C.c_double(), C.c_double()
+        _check(F.lib().opm_scene_node_fluence(self.h, node, nx, ny,
+                                              m.ctypes.data_as(C.POINTER(C.c_double)) if download else None, lrtb,
+                                              C.byref(peak), C.byref(tot)))
+        return FluenceData(m.reshape(nx, ny).T.copy() if download else None, tuple(lrtb[:]), peak.value, tot.value)
+
+    def node_hitmaps(self, node: int, surface: int = 0):
+        n = F.lib().opm_scene_node_hitmaps(self.h, node, surface, None, 0)
+        arr = (C.c_void_p * max(n, 1))()
+        F.lib().opm_scene_node_hitmaps(self.h, node, surface, arr, n)
+        return [_BorrowedHitMap(self.ctx, arr[k]) for k in range(n)]
+
+    # ---- ghost focus
+    def ghostfocus(self, source_rays: Rays, max_bounces: int = 1, strict=False) -> F.OpmGhostFocusStats:
+        """GhostFocusAnalyzer::analyze (analyzers/ghostfocus.rs:82-122), FluenceEstimator::Binning"""
+        cfg = F.OpmGhostFocusConfig(max_bounces=max_bounces)
+        st = F.OpmGhostFocusStats()
+        _check(F.lib().opm_scene_ghostfocus(self.h, source_rays.h, C.byref(cfg), F.SCENE_STRICT if strict else 0, C.byref(st)))
+        return st
+
+    def gf_pass_tally(self, gf_pass: int, n_orders: int = 8):
+        counts, energy = (C.c_uint64 * n_orders)(), (C.c_double * n_orders)()
+        nb, nr = C.c_uint64(), C.c_uint64()
+        _check(F.lib().opm_scene_gf_pass_tally(self.h, gf_pass, n_orders, counts, energy, C.byref(nb), C.byref(nr)))
+        return np.array(counts[:], dtype=np.uint64), np.array(energy[:]), nb.value, nr.value
+
+    def gf_pass_bundles(self, gf_pass: int):
+        n = F.lib().opm_scene_gf_pass_bundles(self.h, gf_pass, None, 0)
+        arr = (C.c_void_p * max(n, 1))()
+        F.lib().opm_scene_gf_pass_bundles(self.h, gf_pass, arr, n)
+        return [_BorrowedRays(self.ctx, arr[k]) for k in range(n)]
+
+    def node_critical_fluences(self, node: int, surface: int = 0):
+        n = F.lib().opm_scene_node_critical_fluences(self.h, node, surface, None, 0)
+        arr = (F.OpmCriticalFluence * max(n, 1))()
+        F.lib().opm_scene_node_critical_fluences(self.h, node, surface, arr, n)
+        return [(arr[k].bundle_uuid, arr[k].peak_fluence, arr[k].bounce) for k in range(n)]
+
+    def node_peak_fluence(self, node: int, surface: int = 0) -> float:
+        p = C.c_double()
+        _check(F.lib().opm_scene_node_peak_fluence(self.h, node, surface, C.byref(p)))
+        return p.value
+
+    def reset_data(self):
+        _check(F.lib().opm_scene_reset_data(self.h))
+
+    def close(self):
+        if self.h:
+            F.lib().opm_scene_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

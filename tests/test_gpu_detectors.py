@@ -1,0 +1,152 @@
+"""GPU parity of the detector and source kernels against the oracle: Binning fluence estimator
+(rays_hit_map.rs:330-391; shared-memory privatised and global-atomic paths), bounding box, peak/total
+(fluence_data.rs), on-device sources (position/energy/spectral distributions, rays.rs:264-297)."""
+import math
+
+import numpy as np
+import pytest
+
+import opossum_b200 as ob
+from opossum_b200 import ffi as F
+from oracle import oracle as orc
+from helpers import RTOL, assert_map_match, assert_rays_match, iso_pair, mm, nm
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = ob.Context(0)
+    yield c
+    c.close()
+
+
+def hitmap_from(ctx, x, y, e, bounce=None):
+    h = ob.HitMap(ctx, max(len(x), 1))
+    h.upload(x, y, e, bounce=bounce)
+    return h
+
+
+def seeded_hits(n, seed=3, spread=mm(4.0)):
+    rng = np.random.default_rng(seed)
+    x = spread * rng.standard_normal(n) * 0.4 + mm(0.3)
+    y = spread * rng.standard_normal(n) * 0.25 - mm(0.1)
+    e = 1e-6 * (1.0 + rng.random(n))
+    return x, y, e
+
+
+def test_binning_reference_kat(ctx):
+    """surface/hit_map/mod.rs:1200-1240: 5 x 1 J on a 51x51 map -> centre bin 2601.0, again after merging 5 more"""
+    p1 = [(-0.5, -0.5), (0.0, 0.0), (-0.5, 0.5), (0.5, 0.5), (0.5, -0.5)]
+    h1 = hitmap_from(ctx, [p[0] for p in p1], [p[1] for p in p1], [1.0] * 5)
+    fd = ob.fluence_binning(ctx, [h1], 51, 51)
+    assert fd.map[25, 25] == pytest.approx(2601.0, rel=4e-16) and fd.lrtb == (-0.5, 0.5, 0.5, -0.5)
+    assert fd.peak == fd.map.max() and fd.total_energy == pytest.approx(5.0, rel=1e-14)
+    r = math.sqrt(0.5)
+    p2 = [(r, 0.0), (0.0, r), (-r, 0.0), (0.0, -r), (0.0, 0.0)]
+    h2 = hitmap_from(ctx, [p[0] for p in p2], [p[1] for p in p2], [1.0] * 5)
+    fd = ob.fluence_binning(ctx, [h1, h2], 51, 51)  # merged hit maps (hit_map/mod.rs:161-175)
+    assert fd.map[25, 25] == pytest.approx(2601.0, rel=1e-15)
+
+
+@pytest.mark.parametrize("nx,ny", [(100, 83), (101, 101), (51, 7), (400, 300), (1024, 1024)])
+def test_binning_auto_bbox_matches_oracle(ctx, nx, ny):
+    """data-dependent bounding box (rays_hit_map.rs:522-562), the FluenceDetector's only mode (hit_map/mod.rs:369);
+    100x83 / 101x101 use the shared-memory privatised map, the larger ones warp-run aggregated global atomics"""
+    x, y, e = seeded_hits(200_000)
+    ref_map, ref_lrtb = orc.fluence_binning(orc.hits_from_xye(x, y, e), nx, ny)
+    h = hitmap_from(ctx, x, y, e)
+    box, n = ob.hitmaps_bounding_box([h])
+    assert n == len(x) and box == ref_lrtb == (x.min(), x.max(), y.max(), y.min())
+    fd = ob.fluence_binning(ctx, [h], nx, ny)
+    assert fd.lrtb == ref_lrtb
+    assert_map_match(fd.map, ref_map)
+    assert fd.peak == pytest.approx(orc.fluence_peak(ref_map), rel=RTOL)
+    assert fd.total_energy == pytest.approx(orc.fluence_total_energy(ref_map, ref_lrtb), rel=RTOL)
+
+
+def test_binning_coherent_runs(ctx):
+    """grid-ordered hits: long runs of consecutive hits in the same bin exercise the warp segmented reduction"""
+    g = orc.grid(600, 500, mm(10.0), mm(8.0))
+    x, y = g[:, 0].copy(), g[:, 1].copy()
+    e = 1e-6 * (1.0 + 0.3 * np.cos(1e3 * x) * np.sin(2e3 * y))
+    ref_map, ref_lrtb = orc.fluence_binning(orc.hits_from_xye(x, y, e), 300, 200)
+    fd = ob.fluence_binning(ctx, [hitmap_from(ctx, x, y, e)], 300, 200)
+    assert_map_match(fd.map, ref_map)
+    assert fd.total_energy == pytest.approx(orc.fluence_total_energy(ref_map, ref_lrtb), rel=RTOL)
+
+
+def test_binning_explicit_ranges_and_errors(ctx):
+    """explicit ranges follow rays_hit_map.rs:337-339 literally: (left,right,top,bottom) = (r1.start,r1.end,r2.start,r2.end);
+    hits right of / above the range index out of bounds (the reference panics) -> error; empty map -> error"""
+    x, y, e = seeded_hits(50_000, spread=mm(1.0))
+    lo, hi = mm(-6.0), mm(6.0)
+    ranges = (lo, hi, hi, lo)  # ax2 given as top..bottom so that y indices run upwards
+    ref_map, ref_lrtb = orc.fluence_binning(orc.hits_from_xye(x, y, e), 64, 48, ranges)
+    h = hitmap_from(ctx, x, y, e)
+    fd = ob.fluence_binning(ctx, [h], 64, 48, ranges=ranges)
+    assert fd.lrtb == ref_lrtb == ranges
+    assert_map_match(fd.map, ref_map)
+    with pytest.raises(orc.OracleError):
+        orc.fluence_binning(orc.hits_from_xye(x, y, e), 64, 48, (lo, mm(0.1), hi, lo))
+    with pytest.raises(ob.OpossumError) as ei:
+        ob.fluence_binning(ctx, [h], 64, 48, ranges=(lo, mm(0.1), hi, lo))
+    assert ei.value.code == F.OPM_ERR_BIN_RANGE
+    empty = hitmap_from(ctx, x, y, -np.ones_like(e))  # e < 0 marks "no hit recorded in this slot"
+    with pytest.raises(ob.OpossumError) as ei:
+        ob.fluence_binning(ctx, [empty], 10, 10)
+    assert ei.value.code == F.OPM_ERR_EMPTY_HITMAP
+
+
+def test_binning_bounce_filter_and_accumulate(ctx):
+    """hit maps are keyed by bounce level (hit_map/mod.rs:101-115): filter one level; accumulate two passes into one map"""
+    x, y, e = seeded_hits(80_000)
+    b = (np.arange(len(x)) % 3).astype(np.uint32)
+    h = hitmap_from(ctx, x, y, e, bounce=b)
+    sel = b == 1
+    ref_map, ref_lrtb = orc.fluence_binning(orc.hits_from_xye(x[sel], y[sel], e[sel]), 101, 101)
+    fd = ob.fluence_binning(ctx, [h], 101, 101, bounce=1)
+    assert fd.lrtb == ref_lrtb
+    assert_map_match(fd.map, ref_map)
+    # two shards binned into one device map with a shared (externally reduced) bounding box: the multi-GPU pattern
+    full_map, full_lrtb = orc.fluence_binning(orc.hits_from_xye(x, y, e), 200, 150)
+    half = len(x) // 2
+    ha, hb = hitmap_from(ctx, x[:half], y[:half], e[:half]), hitmap_from(ctx, x[half:], y[half:], e[half:])
+    (la, _), (lb, _) = ob.hitmaps_bounding_box([ha]), ob.hitmaps_bounding_box([hb])
+    box = (min(la[0], lb[0]), max(la[1], lb[1]), max(la[2], lb[2]), min(la[3], lb[3]))
+    assert box == full_lrtb
+    dev = ctx.device_alloc(200 * 150 * 8)
+    ob.fluence_binning(ctx, [ha], 200, 150, lrtb=box, map_dev=dev, download=False)
+    fd = ob.fluence_binning(ctx, [hb], 200, 150, lrtb=box, map_dev=dev, accumulate=True)
+    ctx.device_free(dev)
+    assert_map_match(fd.map, full_map)
+
+
+def test_sources_match_oracle(ctx):
+    """rays.rs:264-297 with grid.rs:58-92, fibonacci.rs:53-65,113-126, uniform.rs:37-41, general_gaussian.rs:93-120,
+    spectral_distribution/gaussian.rs:78-96; position-major / wavelength-minor order; source isometry"""
+    wvl, w = orc.spectrum_gaussian(nm(950.0), nm(1150.0), 8, nm(1053.0), nm(50.0))
+    io, ig = iso_pair((mm(1.0), mm(-2.0), mm(5.0)), (0.01, -0.02, 0.3))
+    cases = {
+        "grid": (lambda: orc.grid(37, 29, mm(20.0), mm(15.0)), lambda s: s.grid(37, 29, mm(20.0), mm(15.0)), 37 * 29),
+        "fib_rect": (lambda: orc.fibonacci_rectangle(1000, mm(20.0), mm(10.0)), lambda s: s.fibonacci_rectangle(mm(20.0), mm(10.0)), 1000),
+        "fib_ellipse": (lambda: orc.fibonacci_ellipse(1000, mm(10.0), mm(7.0)), lambda s: s.fibonacci_ellipse(mm(10.0), mm(7.0)), 1000),
+    }
+    for name, (opos, gset, npos) in cases.items():
+        for gauss in (False, True):
+            xyz = opos()
+            e_pos = (orc.energy_general_gaussian(xyz, 2.0, (mm(0.5), 0.0), (mm(4.0), mm(3.0)), 5.0, 0.2, name == "grid")
+                     if gauss else orc.energy_uniform(npos, 2.0))
+            ref = orc.rays_collimated_with_spectrum(xyz, e_pos, wvl, w)
+            orc.rays_transform(ref, io)
+            sd = gset(ob.SourceDesc(npos, wvl, w, total_energy=2.0, iso=ig))
+            if gauss:
+                sd.general_gaussian((mm(0.5), 0.0), (mm(4.0), mm(3.0)), 5.0, 0.2, rectangular=(name == "grid"))
+            got = sd.generate(ctx).to_array()
+            assert_rays_match(got, ref, what=f"source {name} gauss={gauss}")
+            # a shard [begin, end) of positions equals the same slice of the full source (multi-GPU sharding by index)
+            b, e_ = npos // 3, 2 * npos // 3
+            if gauss:
+                sd.c.energy_norm = sd.energy_norm(ctx)
+            part = sd.generate(ctx, b, e_).to_array()
+            assert_rays_match(part, ref[b * len(wvl): e_ * len(wvl)], what=f"source shard {name}")

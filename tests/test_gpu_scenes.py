@@ -1,0 +1,175 @@
+"""End-to-end parity of the BASELINE.json configs (reduced ray counts) through the scene layer and the fused kernel:
+product (C++ scene layer -> C ABI -> CUDA) vs the oracle's restatement of the reference's node / analyzer flow."""
+import numpy as np
+import pytest
+
+import opossum_b200 as ob
+import scenes
+from oracle import oracle as orc
+from helpers import RTOL, assert_hits_match, assert_map_match, assert_rays_match
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = ob.Context(0)
+    yield c
+    c.close()
+
+
+def run_both(ctx, nodes, src, **kw):
+    osc = scenes.to_oracle(nodes)
+    ref_out = osc.raytrace(scenes.source_to_oracle(src))
+    psc = scenes.to_product(ctx, nodes)
+    rays = scenes.source_to_product(src).generate(ctx)
+    st = psc.raytrace(rays, **kw)
+    return osc, ref_out, psc, rays, st
+
+
+def check_detector(osc, psc, node, nx=100, ny=83):
+    fmap, lrtb, peak, tot = osc.node_fluence(node, nx, ny)
+    fd = psc.node_fluence(node, nx, ny)
+    assert np.allclose(fd.lrtb, lrtb, rtol=RTOL, atol=0.0)
+    if fd.lrtb == lrtb:  # identical bounding box: bins comparable one to one
+        assert_map_match(fd.map, fmap)
+    assert fd.peak == pytest.approx(peak, rel=1e-6 if fd.lrtb != lrtb else RTOL)
+    assert fd.total_energy == pytest.approx(tot, rel=1e-6 if fd.lrtb != lrtb else RTOL)
+
+
+@pytest.mark.parametrize("strict", [False, True], ids=["fast", "strict"])
+def test_c1_single_lens(ctx, strict):
+    """configs[0]: 10^4-ray grid, lens, spot diagram + 100x83 fluence map; full per-ray compare"""
+    osc, ref_out, psc, rays, st = run_both(ctx, scenes.c1_single_lens(), scenes.c1_source(), strict=strict, record_all_hits=True)
+    assert st.interactions == osc.interactions == 40000
+    assert_rays_match(rays.to_array(), ref_out, what="C1 final bundle")
+    ref_spot, s = osc.node_spot(2), psc.node_spot(2)
+    assert s.n_valid == ref_spot["n_valid"] and s.total_energy == pytest.approx(ref_spot["total_energy"], rel=RTOL)
+    assert np.allclose(s.energy_centroid[:2], ref_spot["centroid"][:2], rtol=RTOL, atol=1e-15)
+    assert s.beam_radius_geo == pytest.approx(ref_spot["geo"], rel=RTOL)
+    assert s.energy_beam_radius_rms == pytest.approx(ref_spot["rms"], rel=RTOL)
+    check_detector(osc, psc, 3)
+    if strict:  # axis-aligned scene + strict kernel: the map range is bit-identical to the oracle's
+        assert psc.node_fluence(3).lrtb == osc.node_fluence(3)[1]
+    for node in (1, 2, 3):  # hit maps of every surface (RECORD_ALL_HITS): lens front/rear, detectors
+        for surf in (0, 1):
+            ref_hits = osc.nodes[node].s[surf].merged_hits()
+            maps = psc.node_hitmaps(node, surf)
+            assert (len(maps) > 0) == (len(ref_hits) > 0)
+            if maps:
+                assert_hits_match(maps[0].download(), ref_hits)
+
+
+@pytest.mark.parametrize("mode", ["fused", "per_surface", "strict"])
+def test_c2_laser_chain(ctx, mode):
+    """configs[1] at 20k rays: lens, two 45 deg mirrors (rays clipped at the first leave the bundle at the second), wedge
+    (Sellmeier), beam splitter with a detector on the second output, lens, filter, spot diagram, fluence detector"""
+    kw = {"fused": {}, "per_surface": {"per_surface": True}, "strict": {"strict": True}}[mode]
+    osc, ref_out, psc, rays, st = run_both(ctx, scenes.c2_laser_chain(), scenes.c2_source(20000), **kw)
+    assert st.interactions == osc.interactions
+    got = rays.to_array()  # removed rays (dropped at the mirrors) are skipped by download
+    assert len(got) == len(ref_out) == st.alive_out and st.valid_out == orc.nr_of_rays(ref_out)
+    assert 0 < len(ref_out) < 20000
+    assert_rays_match(got, ref_out, what="C2 main chain")
+    split = psc.node_rays(5).to_array()
+    assert_rays_match(split, osc.nodes[5].split, what="C2 split-off bundle")
+    ref_spot, s = osc.node_spot(8), psc.node_spot(8)
+    assert s.n_valid == ref_spot["n_valid"] and s.total_energy == pytest.approx(ref_spot["total_energy"], rel=RTOL)
+    assert np.allclose(s.energy_centroid[:2], ref_spot["centroid"][:2], rtol=RTOL, atol=1e-15)
+    assert s.beam_radius_geo == pytest.approx(ref_spot["geo"], rel=RTOL)
+    check_detector(osc, psc, 9)
+    check_detector(osc, psc, 10)
+    if mode == "per_surface":
+        assert ctx.launch_count > 40
+
+
+def test_c2_single_surface_nodes_and_limits(ctx):
+    """dummy, paraxial surface, cylindric lens, parabolic mirror + the limits after every node
+    (bounces > max, refractions >= max, node_group/analysis_raytrace.rs:20-27)"""
+    MM = scenes.MM
+    nodes = [scenes.node("source", ap_out=("rect", 18 * MM, 14 * MM, 0.0, 0.0)),
+             scenes.node("dummy", z=20 * MM, ap_in=("circle", 9 * MM, 0.0, 0.0), ap_out=("gaussian", 6 * MM, 6 * MM, 0.0, 0.0)),
+             scenes.node("cylindric_lens", z=40 * MM, p=(300 * MM, float("-inf"), 4 * MM), index=scenes.HK9L),
+             scenes.node("paraxial_surface", z=80 * MM, p=(400 * MM,)),
+             scenes.node("parabolic_mirror", z=200 * MM, p=(500 * MM,), alignment=((0.0, 0.0, 0.0), (0.01, 0.0, 0.0))),
+             scenes.node("fluence_detector", z=100 * MM, euler=(3.14159, 0.0, 0.0))]
+    src = {"pos": ("fibonacci_rectangle", 5000, 20 * MM, 16 * MM), "energy": ("uniform", 1.0), "wvl": [800 * scenes.NM], "w": [1.0]}
+    for max_refr in (1000, 3):
+        cfg_o = __import__("oracle.scene", fromlist=["x"]).RayTraceConfig(max_number_of_refractions=max_refr)
+        osc = scenes.to_oracle(nodes)
+        ref_out = osc.raytrace(scenes.source_to_oracle(src), cfg_o)
+        psc = scenes.to_product(ctx, nodes)
+        rays = scenes.source_to_product(src).generate(ctx)
+        st = psc.raytrace(rays, ob.RayTraceConfig(max_number_of_refractions=max_refr))
+        assert st.interactions == osc.interactions
+        assert_rays_match(rays.to_array(), ref_out, what=f"single-surface chain max_refr={max_refr}")
+        if max_refr == 1000:
+            assert orc.nr_of_rays(ref_out) > 1000
+            check_detector(osc, psc, 5, 64, 48)
+        else:
+            assert orc.nr_of_rays(ref_out) == 0  # cylinder front + rear + paraxial = 3 refractions -> `>= 3` invalidates
+
+
+def test_c4_fluence_map(ctx):
+    """configs[3] reduced: grid source, lens, detector, 512x512 Binning map with the data-dependent bounding box"""
+    osc, ref_out, psc, rays, st = run_both(ctx, scenes.c4_fluence(), scenes.c4_source(300), strict=True, snapshots=False)
+    assert st.interactions == osc.interactions == 3 * 90000
+    check_detector(osc, psc, 2, 512, 512)
+    assert psc.node_rays(2) is None  # OPM_SCENE_NO_SNAPSHOTS
+
+
+def test_c5_broadband(ctx):
+    """configs[4] reduced: 2000 positions x 16 wavelengths (position-major) through Sellmeier + Schott prisms"""
+    src = scenes.c5_source(2000, 16)
+    osc, ref_out, psc, rays, st = run_both(ctx, scenes.c5_broadband(), src)
+    assert st.interactions == osc.interactions and len(ref_out) == 32000
+    assert_rays_match(rays.to_array(), ref_out, what="C5")
+    wv = np.unique(ref_out["wvl"])
+    assert len(wv) == 16
+    # dispersion is real: the mean detector position depends on wavelength
+    y_by_w = [ref_out["pos"][ref_out["wvl"] == w][:, 1].mean() for w in wv]
+    assert np.ptp(y_by_w) > 1e-6
+    check_detector(osc, psc, 4, 128, 96)
+
+
+@pytest.mark.parametrize("max_bounces", [1, 2, 3])
+def test_c3_ghost_focus(ctx, max_bounces):
+    """configs[2] reduced: 3000 seed rays, bounce orders up to 3 incl. the reference's cache re-injection at pass 3
+    (SURVEY appendix C-6).  Per pass: number of bundles, per-bounce-order valid counts (bit-exact) and energies,
+    every collected bundle ray by ray (keyed by seed id); per surface: peak fluence of the per-bundle 101x101 maps."""
+    nodes = scenes.c3_telescope()
+    src = scenes.c3_source(3000)
+    osc = scenes.to_oracle(nodes)
+    ref_passes = osc.ghostfocus(scenes.source_to_oracle(src), max_bounces)
+    psc = scenes.to_product(ctx, nodes)
+    rays = scenes.source_to_product(src).generate(ctx)
+    st = psc.ghostfocus(rays, max_bounces)
+    assert st.passes == max_bounces + 1 and st.interactions == osc.interactions
+    for p, ref_bundles in enumerate(ref_passes):
+        got = psc.gf_pass_bundles(p)
+        assert len(got) == len(ref_bundles), f"pass {p}"
+        counts, energy, nb, nr = psc.gf_pass_tally(p, 6)
+        ref_counts = np.zeros(6, dtype=np.uint64)
+        ref_energy = np.zeros(6)
+        for g, r in zip(got, ref_bundles):
+            assert_rays_match(g.to_array(), r.rays, keyed=True, what=f"pass {p} bundle {r.uuid}", e_floor=1e-25)
+            v = r.rays[r.rays["valid"] == 1]
+            for b in np.unique(v["bounces"]):
+                ref_counts[b] += int((v["bounces"] == b).sum())
+                ref_energy[b] += float(v["e"][v["bounces"] == b].sum())
+        assert np.array_equal(counts, ref_counts), f"pass {p}"
+        assert np.allclose(energy, ref_energy, rtol=RTOL, atol=1e-30)
+        assert nr == sum(len(r.rays) for r in ref_bundles)
+    for node in (0, 1, 2, 3):
+        for surf in (0, 1):
+            ref_peak = osc.nodes[node].s[surf].peak_seen
+            got_peak = psc.node_peak_fluence(node, surf)
+            if np.isfinite(ref_peak):
+                assert got_peak == pytest.approx(ref_peak, rel=1e-6), (node, surf)
+            else:
+                assert not np.isfinite(got_peak)
+            ref_crit = sorted((pk, b) for pk, b in osc.nodes[node].s[surf].critical.values())
+            got_crit = sorted((pk, b) for _, pk, b in psc.node_critical_fluences(node, surf))
+            assert len(ref_crit) == len(got_crit)
+            for (a, ab), (b, bb) in zip(ref_crit, got_crit):
+                assert ab == bb and b == pytest.approx(a, rel=1e-6)
