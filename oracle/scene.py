@@ -141,6 +141,7 @@ class OScene:
             n.stored = n.split = None
         self.passes = []
         self.interactions = 0
+        self.chain_out: dict[int, np.ndarray] = {}
 
     # ---- shared helpers
     def _refract(self, rays, s: OSurface, idx, intended, strategy, uuid=1, record=True):
@@ -206,6 +207,7 @@ class OScene:
         main_out = None
         while jobs:
             i, rays = jobs.pop(0)
+            start = i
             first = main_out is None
             while i is not None:
                 n = self.nodes[i]
@@ -217,6 +219,7 @@ class OScene:
                         jobs.append((k, n.split.copy()))
                 nxt = self._children_of(i, 0)
                 i = nxt[0] if nxt else None
+            self.chain_out[start] = rays  # final bundle of every chain, keyed by its first node
             if first:
                 main_out = rays
         return main_out

@@ -71,8 +71,8 @@ def test_c2_laser_chain(ctx, mode):
     assert len(got) == len(ref_out) == st.alive_out and st.valid_out == orc.nr_of_rays(ref_out)
     assert 0 < len(ref_out) < 20000
     assert_rays_match(got, ref_out, what="C2 main chain")
-    split = psc.node_rays(5).to_array()
-    assert_rays_match(split, osc.nodes[5].split, what="C2 split-off bundle")
+    split = psc.node_rays(5).to_array()  # the splitter's second output, traced in place through its side chain (node 10)
+    assert_rays_match(split, osc.chain_out[10], what="C2 split-off bundle after the side chain")
     ref_spot, s = osc.node_spot(8), psc.node_spot(8)
     assert s.n_valid == ref_spot["n_valid"] and s.total_energy == pytest.approx(ref_spot["total_energy"], rel=RTOL)
     assert np.allclose(s.energy_centroid[:2], ref_spot["centroid"][:2], rtol=RTOL, atol=1e-15)
