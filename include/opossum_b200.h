@@ -240,6 +240,10 @@ OpmStatus opm_rays_upload(OpmRays* rays, const OpmRay* host, uint64_t n);       
 /* struct-of-arrays upload from (pinned) host memory; opl/n/bounces/refr/valid take their `Ray::new` defaults */
 OpmStatus opm_rays_upload_soa(OpmRays* rays, const double* pos_xyz[3], const double* dir_xyz[3],
                               const double* e, const double* wvl, uint64_t n);
+/* Rays::new_collimated_with_spectrum (rays.rs:264-297): pos_xyz = n_pos x 3 (the PositionDistribution's points), e_pos = n_pos
+ * (the EnergyDistribution's energies), spectrum = (wavelength, weight) pairs; rays are expanded on the device, position-major */
+OpmStatus opm_rays_new_collimated_with_spectrum(OpmRays* rays, const double* pos_xyz, const double* e_pos, uint64_t n_pos,
+                                                const double* wavelengths, const double* weights, uint32_t n_wavelengths);
 OpmStatus opm_rays_download(const OpmRays* rays, OpmRay* host, uint64_t capacity, uint64_t* n_out); /* skips removed rays */
 OpmStatus opm_rays_copy(const OpmRays* src, OpmRays* dst);                                 /* Rays::clone */
 OpmStatus opm_rays_append(OpmRays* dst, const OpmRays* src);                               /* Rays::add_rays / merge rays.rs:932,1268 */
@@ -309,6 +313,8 @@ OpmStatus opm_fluence_binning(OpmHitMap* const* maps, int32_t n_maps, int64_t bo
 /* FluenceData::new peak (fluence_data.rs:45-68) and total_energy (:130-141) of a device map */
 OpmStatus opm_fluence_peak_total(OpmContext* ctx, const double* map_dev, uint64_t nx, uint64_t ny, const double lrtb[4],
                                  double* peak, double* total_energy);
+/* measured FP64 FMA throughput of the device in TFLOP/s (FMA = 2 flop): roofline denominator of the fused trace kernel */
+OpmStatus opm_measure_fp64_peak(OpmContext* ctx, double* tflops);
 /* device buffers for maps (so callers need no CUDA runtime of their own) */
 OpmStatus opm_device_alloc(OpmContext* ctx, uint64_t bytes, void** out);
 void opm_device_free(OpmContext* ctx, void* p);

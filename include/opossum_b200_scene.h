@@ -86,13 +86,17 @@ enum {
     OPM_SCENE_PER_SURFACE = 4,      /* one launch per reference call instead of one fused launch per chain */
     OPM_SCENE_RECORD_ALL_HITS = 8,  /* keep the hit map of every surface (the reference always does); default: detectors only */
     OPM_SCENE_NO_SNAPSHOTS = 16,    /* detectors keep hit maps but no copy of the bundle (no spot statistics) */
-    OPM_SCENE_ASYNC = 32            /* do not synchronise / read counters back (throughput runs) */
+    OPM_SCENE_ASYNC = 32,           /* do not synchronise / read counters back (throughput runs) */
+    OPM_SCENE_KEEP_SOURCE = 64      /* leave `source_rays` untouched: the main chain's output goes to opm_scene_output_rays() */
 };
 
 /* RayTracingAnalyzer::analyze.  `source_rays` is the bundle the Source node's light-data builder produced, in
  * the source's local frame; it is traced in place and holds the main chain's output afterwards. */
 OpmStatus opm_scene_raytrace(OpmScene* scene, OpmRays* source_rays, const OpmRayTraceConfig* config, int32_t flags,
                              OpmTraceStats* stats);
+
+/* output bundle of the main chain when OPM_SCENE_KEEP_SOURCE was given (owned by the scene), else NULL */
+OpmRays* opm_scene_output_rays(OpmScene* scene);
 
 /* detector read-out (node_report of SpotDiagram / FluenceDetector) */
 OpmRays* opm_scene_node_rays(OpmScene* scene, int32_t node);           /* bundle stored at a detector / split-off bundle of a splitter */

@@ -145,7 +145,7 @@ class OpmSourceDesc(C.Structure):
 
 (NODE_SOURCE, NODE_LENS, NODE_CYLINDRIC_LENS, NODE_WEDGE, NODE_THIN_MIRROR, NODE_PARABOLIC_MIRROR, NODE_BEAM_SPLITTER,
  NODE_DUMMY, NODE_IDEAL_FILTER, NODE_PARAXIAL_SURFACE, NODE_SPOT_DIAGRAM, NODE_FLUENCE_DETECTOR) = range(12)
-SCENE_STRICT, SCENE_PER_SURFACE, SCENE_RECORD_ALL_HITS, SCENE_NO_SNAPSHOTS, SCENE_ASYNC = 2, 4, 8, 16, 32
+SCENE_STRICT, SCENE_PER_SURFACE, SCENE_RECORD_ALL_HITS, SCENE_NO_SNAPSHOTS, SCENE_ASYNC, SCENE_KEEP_SOURCE = 2, 4, 8, 16, 32, 64
 
 
 class OpmCoatingDesc(C.Structure):
@@ -175,7 +175,7 @@ class OpmCriticalFluence(C.Structure):
 # every symbol include/opossum_b200_scene.h declares
 SCENE_EXPORTS = [
     "opm_node_desc_init", "opm_scene_create", "opm_scene_destroy", "opm_scene_set_ambient", "opm_scene_add_node",
-    "opm_scene_node_count", "opm_scene_reset_data", "opm_scene_raytrace", "opm_scene_node_rays", "opm_scene_node_spot",
+    "opm_scene_node_count", "opm_scene_reset_data", "opm_scene_raytrace", "opm_scene_output_rays", "opm_scene_node_rays", "opm_scene_node_spot",
     "opm_scene_node_fluence", "opm_scene_node_hitmaps", "opm_scene_ghostfocus", "opm_scene_gf_pass_tally",
     "opm_scene_gf_pass_bundles", "opm_scene_node_critical_fluences", "opm_scene_node_peak_fluence",
 ]
@@ -186,13 +186,13 @@ EXPORTS = [
     "opm_context_synchronize", "opm_context_stream", "opm_context_launch_count", "opm_isometry_identity",
     "opm_isometry_new", "opm_isometry_append", "opm_raytrace_config_default", "opm_rays_create", "opm_rays_destroy",
     "opm_rays_len", "opm_rays_capacity", "opm_rays_clear", "opm_rays_reserve", "opm_rays_upload",
-    "opm_rays_upload_soa", "opm_rays_download", "opm_rays_copy", "opm_rays_append", "opm_rays_compact",
+    "opm_rays_upload_soa", "opm_rays_new_collimated_with_spectrum", "opm_rays_download", "opm_rays_copy", "opm_rays_append", "opm_rays_compact",
     "opm_rays_field_ptr", "opm_rays_refract_on_surface", "opm_rays_apodize",
     "opm_rays_invalidate_by_threshold_energy", "opm_rays_filter_by_nr_of_bounces",
     "opm_rays_filter_by_nr_of_refractions", "opm_rays_filter_energy", "opm_rays_split", "opm_rays_refract_paraxial",
     "opm_rays_transform", "opm_trace_sequence", "opm_rays_spot_stats", "opm_rays_bounce_lvl", "opm_rays_tally", "opm_hitmap_create",
     "opm_hitmap_destroy", "opm_hitmap_capacity", "opm_hitmap_len", "opm_hitmap_upload", "opm_hitmap_download",
-    "opm_hitmaps_bounding_box", "opm_fluence_binning", "opm_fluence_peak_total", "opm_device_alloc",
+    "opm_hitmaps_bounding_box", "opm_fluence_binning", "opm_fluence_peak_total", "opm_measure_fp64_peak", "opm_device_alloc",
     "opm_device_free", "opm_device_to_host", "opm_host_to_device", "opm_host_alloc_pinned", "opm_host_free_pinned",
     "opm_source_generate", "opm_source_energy_norm",
 ]
@@ -240,6 +240,7 @@ def lib() -> C.CDLL:
         "opm_rays_reserve": (i32, [vp, u64]),
         "opm_rays_upload": (i32, [vp, vp, u64]),
         "opm_rays_upload_soa": (i32, [vp, C.POINTER(dp), C.POINTER(dp), dp, dp, u64]),
+        "opm_rays_new_collimated_with_spectrum": (i32, [vp, vp, vp, u64, dp, dp, C.c_uint32]),
         "opm_rays_download": (i32, [vp, vp, u64, C.POINTER(u64)]),
         "opm_rays_copy": (i32, [vp, vp]),
         "opm_rays_append": (i32, [vp, vp]),
@@ -268,6 +269,7 @@ def lib() -> C.CDLL:
         "opm_hitmaps_bounding_box": (i32, [pp, i32, i64, dp, C.POINTER(u64)]),
         "opm_fluence_binning": (i32, [pp, i32, i64, u64, u64, dp, dp, i32, vp, dp]),
         "opm_fluence_peak_total": (i32, [vp, vp, u64, u64, dp, dp, dp]),
+        "opm_measure_fp64_peak": (i32, [vp, dp]),
         "opm_device_alloc": (i32, [vp, u64, pp]),
         "opm_device_free": (None, [vp, vp]),
         "opm_device_to_host": (i32, [vp, vp, vp, u64]),
@@ -286,6 +288,7 @@ def lib() -> C.CDLL:
         "opm_scene_node_count": (i32, [vp]),
         "opm_scene_reset_data": (i32, [vp]),
         "opm_scene_raytrace": (i32, [vp, vp, C.POINTER(OpmRayTraceConfig), i32, C.POINTER(OpmTraceStats)]),
+        "opm_scene_output_rays": (vp, [vp]),
         "opm_scene_node_rays": (vp, [vp, i32]),
         "opm_scene_node_spot": (i32, [vp, i32, C.POINTER(OpmSpotStats)]),
         "opm_scene_node_fluence": (i32, [vp, i32, u64, u64, dp, dp, dp, dp]),

@@ -238,6 +238,12 @@ class Context:
         except Exception:
             pass
 
+    def measure_fp64_peak(self) -> float:
+        """DFMA throughput of this GPU in TFLOP/s (microbenchmark kernel in the library)"""
+        out = C.c_double()
+        _check(F.lib().opm_measure_fp64_peak(self.h, C.byref(out)))
+        return out.value
+
     # device buffers for fluence maps
     def device_alloc(self, nbytes: int) -> int:
         p = C.c_void_p()
@@ -338,6 +344,15 @@ class Rays:
         P = (dp * 3)(*[p.ctypes.data_as(dp) for p in pos])
         D = (dp * 3)(*[d.ctypes.data_as(dp) for d in direction])
         _check(F.lib().opm_rays_upload_soa(self.h, P, D, e.ctypes.data_as(dp), wvl.ctypes.data_as(dp), len(e)))
+
+    def new_collimated_with_spectrum(self, pos_xyz_ptr: int, e_pos_ptr: int, n_pos: int, wvl, weights):
+        """Rays::new_collimated_with_spectrum (rays.rs:264-297) from host buffers (ideally pinned): raw addresses of the
+        n_pos x 3 positions and the n_pos energies; asynchronous on the context's stream."""
+        wv = np.ascontiguousarray(wvl, dtype=np.float64)
+        wg = np.ascontiguousarray(weights, dtype=np.float64)
+        dp = C.POINTER(C.c_double)
+        _check(F.lib().opm_rays_new_collimated_with_spectrum(self.h, C.c_void_p(pos_xyz_ptr), C.c_void_p(e_pos_ptr), n_pos,
+                                                             wv.ctypes.data_as(dp), wg.ctypes.data_as(dp), len(wv)))
 
     def to_array(self) -> np.ndarray:
         n = len(self)

@@ -35,6 +35,8 @@ struct OpmContext {
     DevOp* h_ops_ring = nullptr;
     cudaEvent_t ring_ev[kRing] = {};
     int ring_pos = 0;
+    unsigned char* d_staging = nullptr;  // grows on demand: host uploads that are expanded on the device
+    size_t staging_bytes = 0;
     unsigned char* d_scratch = nullptr;  // small accumulators
     unsigned char* h_scratch = nullptr;  // pinned mirror
     static constexpr size_t kScratch = 4096;
@@ -151,6 +153,7 @@ extern "C" void opm_context_destroy(OpmContext* c) {
     cudaStreamSynchronize(c->stream);
     for (int k = 0; k < OpmContext::kRing; ++k) if (c->ring_ev[k]) cudaEventDestroy(c->ring_ev[k]);
     cudaFreeHost(c->h_ops_ring);
+    cudaFree(c->d_staging);
     cudaFree(c->d_stats); cudaFreeHost(c->h_stats); cudaFree(c->d_ops); cudaFree(c->d_scratch); cudaFreeHost(c->h_scratch);
     if (c->own_stream) cudaStreamDestroy(c->stream);
     delete c;
@@ -345,6 +348,36 @@ extern "C" OpmStatus opm_rays_upload_soa(OpmRays* r, const double* pos[3], const
         KL(k_soa_defaults(r->v, n, c->sms, c->stream)); c->launches++;
     }
     return rays_set_len(r, n);
+}
+// Rays::new_collimated_with_spectrum (rays.rs:264-297): the host passes what the reference's position / energy /
+// spectral distribution generators return (32 B per position + the spectrum table); the bundle is expanded on the device
+extern "C" OpmStatus opm_rays_new_collimated_with_spectrum(OpmRays* r, const double* pos_xyz, const double* e_pos, uint64_t n_pos,
+                                                            const double* wvl, const double* weights, uint32_t n_wvl) {
+    if (!r || !pos_xyz || !e_pos || !wvl || !weights || n_wvl == 0) return fail(OPM_ERR_ARG, "NULL argument");
+    OpmContext* c = r->ctx;
+    CU(cudaSetDevice(c->device));
+    for (uint32_t k = 0; k < n_wvl; ++k)  // Ray::new (ray.rs:114-116)
+        if (!(wvl[k] > 0.0) || !std::isfinite(wvl[k])) return fail(OPM_ERR_ARG, "wavelength must be >0");
+    const uint64_t n_rays = n_pos * n_wvl;
+    OpmStatus s = opm_rays_reserve(r, n_rays);
+    if (s) return s;
+    const size_t need = align_up(n_pos * 32, 256) + (size_t)n_wvl * 16;
+    if (need > c->staging_bytes) {
+        CU(cudaStreamSynchronize(c->stream));
+        cudaFree(c->d_staging);
+        c->d_staging = nullptr; c->staging_bytes = 0;
+        CU(cudaMalloc(&c->d_staging, need));
+        c->staging_bytes = need;
+    }
+    double* d_xyz = (double*)c->d_staging;
+    double* d_e = d_xyz + 3 * n_pos;
+    double* d_w = (double*)(c->d_staging + align_up(n_pos * 32, 256));
+    CU(cudaMemcpyAsync(d_xyz, pos_xyz, n_pos * 24, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(d_e, e_pos, n_pos * 8, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(d_w, wvl, (size_t)n_wvl * 8, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(d_w + n_wvl, weights, (size_t)n_wvl * 8, cudaMemcpyHostToDevice, c->stream));
+    if (n_rays) { KL(k_expand_collimated(d_xyz, d_e, d_w, d_w + n_wvl, n_wvl, r->v, n_rays, c->sms, c->stream)); c->launches++; }
+    return rays_set_len(r, n_rays);
 }
 extern "C" OpmStatus opm_rays_download(const OpmRays* rc, OpmRay* host, uint64_t capacity, uint64_t* n_out) {
     OpmRays* r = const_cast<OpmRays*>(rc);
@@ -972,6 +1005,28 @@ extern "C" OpmStatus opm_fluence_peak_total(OpmContext* c, const double* map_dev
     return OPM_OK;
 }
 
+// measured FP64 FMA throughput of this device (TFLOP/s, FMA = 2 flop): the roofline denominator of the fused kernel
+extern "C" OpmStatus opm_measure_fp64_peak(OpmContext* c, double* tflops) {
+    if (!c || !tflops) return fail(OPM_ERR_ARG, "NULL argument");
+    CU(cudaSetDevice(c->device));
+    const int iters = 1 << 15, blocks = c->sms * 8;
+    cudaEvent_t a, b;
+    CU(cudaEventCreate(&a)); CU(cudaEventCreate(&b));
+    double best = 0.0;
+    for (int rep = 0; rep < 4; ++rep) {
+        CU(cudaEventRecord(a, c->stream));
+        KL(k_fp64_peak((double*)c->d_scratch, iters, blocks, c->stream)); c->launches++;
+        CU(cudaEventRecord(b, c->stream));
+        CU(cudaEventSynchronize(b));
+        float ms = 0.f;
+        CU(cudaEventElapsedTime(&ms, a, b));
+        double tf = (double)blocks * 256.0 * iters * 8.0 * 2.0 / (ms * 1e-3) / 1e12;
+        if (rep > 0 && tf > best) best = tf;
+    }
+    cudaEventDestroy(a); cudaEventDestroy(b);
+    *tflops = best;
+    return OPM_OK;
+}
 extern "C" OpmStatus opm_device_alloc(OpmContext* c, uint64_t bytes, void** out) {
     if (!c || !out) return fail(OPM_ERR_ARG, "NULL argument");
     CU(cudaSetDevice(c->device));

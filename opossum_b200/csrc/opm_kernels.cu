@@ -393,6 +393,21 @@ __global__ void __launch_bounds__(256) source_generate_kernel(SourceParams S, De
     }
 }
 
+// Rays::new_collimated_with_spectrum (rays.rs:264-297) from host-generated positions and energies: position-major,
+// wavelength-minor, direction +z, E = E_pos * w
+__global__ void __launch_bounds__(256) expand_collimated_kernel(const double* __restrict__ xyz, const double* __restrict__ e_pos,
+                                                                const double* __restrict__ wvl, const double* __restrict__ wgt,
+                                                                uint32_t n_wvl, DevRays R, uint64_t n_rays) {
+    for (uint64_t k = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; k < n_rays; k += (uint64_t)gridDim.x * blockDim.x) {
+        uint64_t ip = k / n_wvl;
+        uint32_t iw = (uint32_t)(k % n_wvl);
+        R.px[k] = xyz[3 * ip]; R.py[k] = xyz[3 * ip + 1]; R.pz[k] = xyz[3 * ip + 2];
+        R.dx[k] = 0.0; R.dy[k] = 0.0; R.dz[k] = 1.0;
+        R.e[k] = e_pos[ip] * wgt[iw]; R.wvl[k] = wvl[iw]; R.opl[k] = 0.0; R.n[k] = 1.0;
+        R.bounces[k] = 0; R.refr[k] = 0; R.id[k] = (uint32_t)k; R.valid[k] = RAY_VALID;
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // order-preserving compaction of removed rays
 // ---------------------------------------------------------------------------------------------
@@ -458,6 +473,18 @@ __global__ void __launch_bounds__(kCompactBlock) compact_scatter_kernel(DevRays 
 }
 __global__ void fill_u8_kernel(uint8_t* p, uint8_t v, uint64_t n) {
     for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) p[i] = v;
+}
+// FP64 pipe peak: 8 independent DFMA chains per thread (roofline denominator of the FP64-bound fused kernel)
+__global__ void __launch_bounds__(256) fp64_peak_kernel(double* out, int iters, double seed) {
+    double a0 = seed + threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+    const double m = 0.999999, c = 1e-9;
+#pragma unroll 4
+    for (int i = 0; i < iters; ++i) {
+        a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+        a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+    }
+    double s = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+    if (s == 12345.678) out[0] = s;  // keeps the chains alive
 }
 __global__ void set_u64_kernel(unsigned long long* p, unsigned long long v) { *p = v; }
 
@@ -530,12 +557,21 @@ int k_source_generate(const SourceParams& S, DevRays R, uint64_t pos_begin, uint
     source_generate_kernel<<<grid_for(n_rays, 256, sms * 8), 256, 0, ST>>>(S, R, pos_begin, n_rays, wvl, wgt);
     return (int)cudaGetLastError();
 }
+int k_expand_collimated(const double* xyz, const double* e_pos, const double* wvl, const double* wgt, uint32_t n_wvl, DevRays R,
+                        uint64_t n_rays, int sms, void* stream) {
+    expand_collimated_kernel<<<grid_for(n_rays, 256, sms * 8), 256, 0, ST>>>(xyz, e_pos, wvl, wgt, n_wvl, R, n_rays);
+    return (int)cudaGetLastError();
+}
 int k_compact(DevRays S, DevRays D, uint64_t n, unsigned* counts, unsigned long long* offsets, unsigned long long* total, void* stream) {
     uint64_t nb = (n + kCompactBlock - 1) / kCompactBlock;
     if (nb == 0) return 0;
     compact_count_kernel<<<(unsigned)nb, kCompactBlock, 0, ST>>>(S.valid, n, counts);
     compact_scan_kernel<<<1, 1024, 0, ST>>>(counts, offsets, nb, total);
     compact_scatter_kernel<<<(unsigned)nb, kCompactBlock, 0, ST>>>(S, D, n, offsets);
+    return (int)cudaGetLastError();
+}
+int k_fp64_peak(double* out, int iters, int blocks, void* stream) {
+    fp64_peak_kernel<<<blocks, 256, 0, ST>>>(out, iters, 1.0);
     return (int)cudaGetLastError();
 }
 int k_set_u64(unsigned long long* p, unsigned long long v, void* stream) {

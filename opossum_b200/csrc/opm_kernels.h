@@ -53,7 +53,10 @@ int k_peak_total(const double* map, uint64_t bins, double area, PeakAccum* acc, 
 int k_source_norm(const SourceParams& S, uint64_t b, uint64_t e, double* out, int sms, void* stream);
 int k_source_generate(const SourceParams& S, DevRays R, uint64_t pos_begin, uint64_t n_rays, const double* wvl, const double* wgt,
                       int sms, void* stream);
+int k_expand_collimated(const double* xyz, const double* e_pos, const double* wvl, const double* wgt, uint32_t n_wvl, DevRays R,
+                        uint64_t n_rays, int sms, void* stream);
 int k_compact(DevRays S, DevRays D, uint64_t n, unsigned* counts, unsigned long long* offsets, unsigned long long* total, void* stream);
+int k_fp64_peak(double* out, int iters, int blocks, void* stream);
 int k_set_u64(unsigned long long* p, unsigned long long v, void* stream);
 int k_fill_u8(uint8_t* p, uint8_t v, uint64_t n, int sms, void* stream);
 

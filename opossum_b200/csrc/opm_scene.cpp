@@ -67,23 +67,47 @@ struct OpmScene {
     uint64_t next_uuid = 1;
     std::vector<std::vector<std::shared_ptr<Bundle>>> passes;  // ray_collection of every ghost-focus pass
     std::vector<OpmRays*> owned_rays;                           // every device bundle the scene allocated for GF
-    std::vector<OpmHitMap*> owned_hits;
-    std::string err;
+    OpmRays* main_out = nullptr;                                // output of the main chain with OPM_SCENE_KEEP_SOURCE
+    // device buffers are recycled across analyses (cudaMalloc / cudaFree are synchronous and cost milliseconds)
+    std::vector<OpmRays*> pool_rays;
+    std::vector<OpmHitMap*> pool_hits;
 };
 
 namespace {
 
-OpmStatus scene_fail(OpmStatus s) { return s; }
+OpmStatus acquire_rays(OpmScene* sc, uint64_t cap, OpmRays** out) {
+    int best = -1;
+    for (size_t k = 0; k < sc->pool_rays.size(); ++k)
+        if (opm_rays_capacity(sc->pool_rays[k]) >= cap &&
+            (best < 0 || opm_rays_capacity(sc->pool_rays[k]) < opm_rays_capacity(sc->pool_rays[best]))) best = (int)k;
+    if (best >= 0) {
+        *out = sc->pool_rays[best];
+        sc->pool_rays.erase(sc->pool_rays.begin() + best);
+        return opm_rays_clear(*out);
+    }
+    return opm_rays_create(sc->ctx, cap ? cap : 1, out);
+}
+OpmStatus acquire_hitmap(OpmScene* sc, uint64_t cap, OpmHitMap** out) {
+    int best = -1;
+    for (size_t k = 0; k < sc->pool_hits.size(); ++k)
+        if (opm_hitmap_capacity(sc->pool_hits[k]) >= cap &&
+            (best < 0 || opm_hitmap_capacity(sc->pool_hits[k]) < opm_hitmap_capacity(sc->pool_hits[best]))) best = (int)k;
+    if (best >= 0) {
+        *out = sc->pool_hits[best];
+        sc->pool_hits.erase(sc->pool_hits.begin() + best);
+        return OPM_OK;
+    }
+    return opm_hitmap_create(sc->ctx, cap ? cap : 1, out);
+}
 
 void free_node_data(OpmScene* sc, Node& n) {
     for (auto& s : n.s) {
-        for (auto& h : s.hits) opm_hitmap_destroy(h.map);
+        for (auto& h : s.hits) sc->pool_hits.push_back(h.map);
         s.hits.clear(); s.fwd_cache.clear(); s.bwd_cache.clear(); s.critical.clear(); s.peak_seen = -INFINITY;
     }
-    if (n.stored) { opm_rays_destroy(n.stored); n.stored = nullptr; }
-    if (n.split) { opm_rays_destroy(n.split); n.split = nullptr; }
+    if (n.stored) { sc->pool_rays.push_back(n.stored); n.stored = nullptr; }
+    if (n.split) { sc->pool_rays.push_back(n.split); n.split = nullptr; }
     n.stored_gf.clear();
-    (void)sc;
 }
 
 // ---- node -> surfaces (OpticNode::update_surfaces)
@@ -208,6 +232,7 @@ OpmOp op_limits(uint64_t max_bounces, uint64_t max_refr, bool check_refr) {
 struct Runner {
     OpmRays* rays;
     int flags;
+    OpmRays* first_out = nullptr;  // OPM_SCENE_KEEP_SOURCE: the first launch reads `rays` and writes here, later ones run on it in place
     OpmTraceStats total{};
     std::vector<OpmOp> ops;
     OpmStatus status = OPM_OK;
@@ -222,7 +247,8 @@ struct Runner {
         OpmTraceStats st;
         memset(&st, 0, sizeof st);
         const bool async = (flags & OPM_SCENE_ASYNC) != 0;
-        status = opm_trace_sequence(rays, ops.data(), (int32_t)ops.size(), flags & OPM_TRACE_STRICT, nullptr, async ? nullptr : &st);
+        status = opm_trace_sequence(rays, ops.data(), (int32_t)ops.size(), flags & OPM_TRACE_STRICT, first_out, async ? nullptr : &st);
+        if (first_out) { rays = first_out; first_out = nullptr; }
         ops.clear();
         total.interactions += st.interactions; total.children += st.children; total.hits += st.hits; total.missed += st.missed;
         total.apodized += st.apodized; total.valid_out = st.valid_out; total.alive_out = st.alive_out; total.status_bits |= st.status_bits;
@@ -233,7 +259,7 @@ bool is_detector(int type) { return type == OPM_NODE_SPOT_DIAGRAM || type == OPM
 
 OpmHitMap* new_hitmap(OpmScene* sc, SurfaceState& s, uint64_t uuid, uint64_t n, OpmStatus* st) {
     OpmHitMap* h = nullptr;
-    *st = opm_hitmap_create(sc->ctx, n ? n : 1, &h);
+    *st = acquire_hitmap(sc, n ? n : 1, &h);
     if (*st) return nullptr;
     s.hits.push_back({uuid, h});
     return h;
@@ -288,7 +314,7 @@ OpmStatus compile_node_rt(OpmScene* sc, Node& n, const OpmRayTraceConfig& cfg, i
             R.push(op_refract(n.s[0], nullptr, true, strat, 0, h0, nullptr));
             R.push(op_apodize(n.s[0].aperture, n.s[0].eff_iso));
             if (n.split_child >= 0 && !n.split) {
-                st = opm_rays_create(sc->ctx, n_rays ? n_rays : 1, &n.split);
+                st = acquire_rays(sc, n_rays ? n_rays : 1, &n.split);
                 if (st) return st;
             }
             OpmOp op;
@@ -331,7 +357,7 @@ OpmStatus compile_node_rt(OpmScene* sc, Node& n, const OpmRayTraceConfig& cfg, i
             R.push(op_threshold(thr));
             if (!(flags & OPM_SCENE_NO_SNAPSHOTS)) {
                 if (!n.stored) {
-                    st = opm_rays_create(sc->ctx, n_rays ? n_rays : 1, &n.stored);
+                    st = acquire_rays(sc, n_rays ? n_rays : 1, &n.stored);
                     if (st) return st;
                 }
                 OpmOp op;
@@ -409,13 +435,16 @@ extern "C" OpmStatus opm_scene_reset_data(OpmScene* sc) {
     if (!sc) return OPM_ERR_ARG;
     for (auto& n : sc->nodes) free_node_data(sc, *n);
     sc->passes.clear();
-    for (OpmRays* r : sc->owned_rays) opm_rays_destroy(r);
+    for (OpmRays* r : sc->owned_rays) sc->pool_rays.push_back(r);
     sc->owned_rays.clear();
+    if (sc->main_out) { sc->pool_rays.push_back(sc->main_out); sc->main_out = nullptr; }
     return OPM_OK;
 }
 extern "C" void opm_scene_destroy(OpmScene* sc) {
     if (!sc) return;
     opm_scene_reset_data(sc);
+    for (OpmRays* r : sc->pool_rays) opm_rays_destroy(r);
+    for (OpmHitMap* h : sc->pool_hits) opm_hitmap_destroy(h);
     delete sc;
 }
 extern "C" OpmStatus opm_scene_set_ambient(OpmScene* sc, const OpmIndexModel* a) {
@@ -451,8 +480,13 @@ extern "C" OpmStatus opm_scene_raytrace(OpmScene* sc, OpmRays* rays, const OpmRa
     struct Job { int start; OpmRays* rays; int splitter; };
     std::vector<Job> jobs;
     jobs.push_back({0, rays, -1});
+    if (flags & OPM_SCENE_KEEP_SOURCE) {
+        st = acquire_rays(sc, n_rays ? n_rays : 1, &sc->main_out);
+        if (st) return st;
+    }
     for (size_t j = 0; j < jobs.size(); ++j) {
         Runner R{jobs[j].rays, flags};
+        if (j == 0) R.first_out = sc->main_out;
         if (jobs[j].splitter >= 0) {  // second output: apodize(out2 aperture, iso of out1) + threshold + limits
             Node& sp = *sc->nodes[jobs[j].splitter];
             R.push(op_apodize(sp.s[1].aperture, sp.s[1].eff_iso));
@@ -475,6 +509,7 @@ extern "C" OpmStatus opm_scene_raytrace(OpmScene* sc, OpmRays* rays, const OpmRa
     return OPM_OK;
 }
 
+extern "C" OpmRays* opm_scene_output_rays(OpmScene* sc) { return sc ? sc->main_out : nullptr; }
 extern "C" OpmRays* opm_scene_node_rays(OpmScene* sc, int32_t node) {
     if (!sc || node < 0 || node >= (int)sc->nodes.size()) return nullptr;
     Node& n = *sc->nodes[node];

@@ -180,7 +180,7 @@ class Scene:
         return idx.value
 
     def raytrace(self, source_rays: Rays, config: RayTraceConfig | None = None, strict=False, per_surface=False,
-                 record_all_hits=False, snapshots=True, sync=True) -> TraceStats | None:
+                 record_all_hits=False, snapshots=True, sync=True, keep_source=False) -> TraceStats | None:
         """RayTracingAnalyzer::analyze (analyzers/raytrace.rs:36-49); traces `source_rays` in place."""
         cfg = F.OpmRayTraceConfig()
         c = config or RayTraceConfig()
@@ -188,10 +188,15 @@ class Scene:
         cfg.max_number_of_refractions, cfg.missed_surface_strategy = c.max_number_of_refractions, c.missed_surface_strategy
         flags = ((F.SCENE_STRICT if strict else 0) | (F.SCENE_PER_SURFACE if per_surface else 0) |
                  (F.SCENE_RECORD_ALL_HITS if record_all_hits else 0) | (0 if snapshots else F.SCENE_NO_SNAPSHOTS) |
-                 (0 if sync else F.SCENE_ASYNC))
+                 (0 if sync else F.SCENE_ASYNC) | (F.SCENE_KEEP_SOURCE if keep_source else 0))
         st = F.OpmTraceStats()
         _check(F.lib().opm_scene_raytrace(self.h, source_rays.h, C.byref(cfg), flags, C.byref(st)))
         return TraceStats.of(st) if sync else None
+
+    def output_rays(self) -> Rays | None:
+        """output bundle of the main chain after raytrace(keep_source=True)"""
+        h = F.lib().opm_scene_output_rays(self.h)
+        return _BorrowedRays(self.ctx, h) if h else None
 
     def node_rays(self, node: int) -> Rays | None:
         h = F.lib().opm_scene_node_rays(self.h, node)
