@@ -222,6 +222,10 @@ OpmStatus opm_context_synchronize(OpmContext* ctx);
 void* opm_context_stream(OpmContext* ctx);
 /* number of kernels launched through this context so far (bench.py "gpu_launches") */
 uint64_t opm_context_launch_count(const OpmContext* ctx);
+/* measurement: while enabled every launch of the fused trace kernel is bracketed by a CUDA event pair on the
+ * context's stream; opm_context_kernel_timing drains them (blocking) and returns the accumulated device time */
+OpmStatus opm_context_set_kernel_timing(OpmContext* ctx, int32_t enable);
+OpmStatus opm_context_kernel_timing(OpmContext* ctx, double* total_ms, uint64_t* launches, int32_t reset);
 
 /* host helpers mirroring utils/geom_transformation.rs (pure host math, no device needed) */
 void opm_isometry_identity(OpmIsometry* out);

@@ -9,6 +9,7 @@ computes on rays with numpy.
 from __future__ import annotations
 
 import ctypes as C
+import weakref
 from dataclasses import dataclass
 
 import numpy as np
@@ -215,6 +216,10 @@ class Context:
         _check(F.lib().opm_context_create(device, C.c_void_p(stream) if stream else None, C.byref(h)))
         self.h = h
         self.device = device
+        self._children = weakref.WeakSet()  # bundles / hit maps / scenes living on this context
+
+    def _adopt(self, child):
+        self._children.add(child)
 
     def synchronize(self):
         _check(F.lib().opm_context_synchronize(self.h))
@@ -228,7 +233,10 @@ class Context:
         return F.lib().opm_context_launch_count(self.h)
 
     def close(self):
+        """destroys the context after every handle that still lives on it (device buffers hold a pointer to it)"""
         if self.h:
+            for child in sorted(self._children, key=lambda c: getattr(c, "_close_order", 1)):
+                child.close()
             F.lib().opm_context_destroy(self.h)
             self.h = None
 
@@ -237,6 +245,16 @@ class Context:
             self.close()
         except Exception:
             pass
+
+    def set_kernel_timing(self, enable: bool):
+        """bracket every launch of the fused trace kernel with CUDA events on this context's stream"""
+        _check(F.lib().opm_context_set_kernel_timing(self.h, int(enable)))
+
+    def kernel_timing(self, reset=True):
+        """(accumulated trace-kernel device time in ms, number of launches); blocks until the events have completed"""
+        ms, n = C.c_double(), C.c_uint64()
+        _check(F.lib().opm_context_kernel_timing(self.h, C.byref(ms), C.byref(n), int(reset)))
+        return ms.value, n.value
 
     def measure_fp64_peak(self) -> float:
         """DFMA throughput of this GPU in TFLOP/s (microbenchmark kernel in the library)"""
@@ -268,6 +286,7 @@ class HitMap:
         h = C.c_void_p()
         _check(F.lib().opm_hitmap_create(ctx.h, capacity, C.byref(h)))
         self.h = h
+        ctx._adopt(self)
 
     def __len__(self):
         return F.lib().opm_hitmap_len(self.h)
@@ -328,6 +347,7 @@ class Rays:
         h = C.c_void_p()
         _check(F.lib().opm_rays_create(ctx.h, capacity, C.byref(h)))
         self.h = h
+        ctx._adopt(self)
 
     # ---- construction / inspection
     @staticmethod
@@ -612,6 +632,15 @@ def fluence_binning(ctx: Context, hit_maps, nx: int, ny: int, ranges=None, lrtb=
     finally:
         if own:
             ctx.device_free(map_dev)
+
+
+def fluence_peak_total(ctx: Context, map_dev: int, nx: int, ny: int, lrtb) -> FluenceData:
+    """FluenceData::new peak (fluence_data.rs:45-68) and total_energy (:130-141) of a map that already sits on the device
+    (e.g. after an all-reduce of per-GPU maps)."""
+    box = (C.c_double * 4)(*lrtb)
+    peak, tot = C.c_double(), C.c_double()
+    _check(F.lib().opm_fluence_peak_total(ctx.h, C.c_void_p(map_dev), nx, ny, box, C.byref(peak), C.byref(tot)))
+    return FluenceData(None, tuple(lrtb), peak.value, tot.value)
 
 
 def hitmaps_bounding_box(hit_maps, bounce=-1):

@@ -37,6 +37,12 @@ struct OpmContext {
     int ring_pos = 0;
     unsigned char* d_staging = nullptr;  // grows on demand: host uploads that are expanded on the device
     size_t staging_bytes = 0;
+    // optional per-launch timing of the fused trace kernel (CUDA events on the launching stream)
+    bool timing = false;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timing_events;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timing_free;
+    double timing_ms = 0.0;
+    uint64_t timing_launches = 0;
     unsigned char* d_scratch = nullptr;  // small accumulators
     unsigned char* h_scratch = nullptr;  // pinned mirror
     static constexpr size_t kScratch = 4096;
@@ -153,6 +159,8 @@ extern "C" void opm_context_destroy(OpmContext* c) {
     cudaStreamSynchronize(c->stream);
     for (int k = 0; k < OpmContext::kRing; ++k) if (c->ring_ev[k]) cudaEventDestroy(c->ring_ev[k]);
     cudaFreeHost(c->h_ops_ring);
+    for (auto* v : {&c->timing_events, &c->timing_free})
+        for (auto& p : *v) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
     cudaFree(c->d_staging);
     cudaFree(c->d_stats); cudaFreeHost(c->h_stats); cudaFree(c->d_ops); cudaFree(c->d_scratch); cudaFreeHost(c->h_scratch);
     if (c->own_stream) cudaStreamDestroy(c->stream);
@@ -165,6 +173,29 @@ extern "C" OpmStatus opm_context_synchronize(OpmContext* c) {
     return OPM_OK;
 }
 extern "C" void* opm_context_stream(OpmContext* c) { return c ? (void*)c->stream : nullptr; }
+// per-launch device time of the fused trace kernel: an event pair around every launch while enabled
+extern "C" OpmStatus opm_context_set_kernel_timing(OpmContext* c, int32_t enable) {
+    if (!c) return fail(OPM_ERR_ARG, "context is NULL");
+    c->timing = enable != 0;
+    return OPM_OK;
+}
+extern "C" OpmStatus opm_context_kernel_timing(OpmContext* c, double* total_ms, uint64_t* launches, int32_t reset) {
+    if (!c) return fail(OPM_ERR_ARG, "context is NULL");
+    CU(cudaSetDevice(c->device));
+    for (auto& p : c->timing_events) {
+        CU(cudaEventSynchronize(p.second));
+        float ms = 0.f;
+        CU(cudaEventElapsedTime(&ms, p.first, p.second));
+        c->timing_ms += ms;
+        c->timing_launches++;
+        c->timing_free.push_back(p);
+    }
+    c->timing_events.clear();
+    if (total_ms) *total_ms = c->timing_ms;
+    if (launches) *launches = c->timing_launches;
+    if (reset) { c->timing_ms = 0.0; c->timing_launches = 0; }
+    return OPM_OK;
+}
 extern "C" uint64_t opm_context_launch_count(const OpmContext* c) { return c ? c->launches : 0; }
 
 // ---------------------------------------------------------------------------------------------
@@ -593,6 +624,7 @@ static OpmStatus compile_ops(OpmContext* c, const OpmOp* ops, int n_ops, uint64_
                     if (!std::isnormal(r.surface.geom_param)) return fail(OPM_ERR_ARG, "radius of curvature / focal length must be != 0.0 and finite");
                 }
                 o.geom = r.surface.geom; o.coating = r.surface.coating; o.param = r.surface.geom_param; o.coating_r = r.surface.coating_r;
+                o.inv_abs_param = r.surface.geom != OPM_GEOM_PLANE ? 1.0 / std::fabs(r.surface.geom_param) : 0.0;
                 to_dev_iso(r.surface.iso.fwd, o.fwd); to_dev_iso(r.surface.iso.inv, o.inv);
                 o.has_index = r.has_index ? 1 : 0; o.refraction_intended = r.refraction_intended ? 1 : 0;
                 o.strategy = r.strategy; o.flags = r.flags; o.index_type = r.index.type;
@@ -733,8 +765,15 @@ static OpmStatus run_program(OpmRays* rays, const OpmOp* ops, int n_ops, int fla
         uint64_t tiles = (n + L.block - 1) / L.block;
         uint64_t maxg = (uint64_t)c->sms * occ;
         L.grid = (int)(tiles < maxg ? tiles : maxg);
+        std::pair<cudaEvent_t, cudaEvent_t> tev{nullptr, nullptr};
+        if (c->timing) {
+            if (!c->timing_free.empty()) { tev = c->timing_free.back(); c->timing_free.pop_back(); }
+            else { CU(cudaEventCreate(&tev.first)); CU(cudaEventCreate(&tev.second)); }
+            CU(cudaEventRecord(tev.first, c->stream));
+        }
         int rc = strict ? launch_trace_strict(L) : launch_trace_fast(L);
         c->launches++;
+        if (c->timing) { CU(cudaEventRecord(tev.second, c->stream)); c->timing_events.push_back(tev); }
         if (rc != 0) { free_temps(); return fail(OPM_ERR_CUDA, "trace kernel launch failed: %s", cudaGetErrorString((cudaError_t)rc)); }
     }
     // host-side lengths

@@ -38,6 +38,7 @@ enum : int32_t { OPK_REFRACT = 1, OPK_APODIZE, OPK_THRESHOLD, OPK_LIMITS, OPK_FI
 struct DevRefract {
     int32_t geom, coating, has_index, refraction_intended, strategy, flags, index_type, _pad;
     double param, coating_r;
+    double inv_abs_param;            // 1 / |param| (sphere / cylinder normals in the contracted build)
     DevIso fwd, inv;
     double ic[6];
     double wlo, whi;

@@ -114,12 +114,11 @@ trace_kernel(const DevOp* __restrict__ g_ops, int n_ops, DevRays in, DevRays out
             switch (op.kind) {  // warp-uniform
                 case OPK_REFRACT: {
                     const DevRefract& o = op.u.refract;
-                    RayState child;
                     RefractResult res;
                     res.has_child = false; res.hit_e = -1.0; res.hit_bounce = 0; res.hit_local = v3(0, 0, 0);
                     if (valid) {
                         c.interactions++;
-                        res = refract_on_surface(o, r, child);
+                        res = refract_on_surface(o, r);
                         if (res.status != OPM_OK) { c.status |= 1u << res.status; valid = false; res.has_child = false; res.hit_e = -1.0; }
                         else {
                             if (res.missed) c.missed++;
@@ -137,13 +136,17 @@ trace_kernel(const DevOp* __restrict__ g_ops, int n_ops, DevRays in, DevRays out
                     if (o.flags & OPM_REFRACT_EMIT_CHILDREN) {
                         unsigned long long slot = warp_reserve(res.has_child, o.child_tail);
                         if (res.has_child) {
-                            if (slot < o.child_cap) { store_ray<true>(o.children, slot, child, RAY_VALID); c.children++; }
-                            else c.status |= 1u << OPM_ERR_CAPACITY;
+                            if (slot < o.child_cap) {
+                                RayState child = r;
+                                child_into(res, child);
+                                store_ray<true>(o.children, slot, child, RAY_VALID);
+                                c.children++;
+                            } else c.status |= 1u << OPM_ERR_CAPACITY;
                         }
                     }
                     if (o.flags & OPM_REFRACT_CONTINUE_AS_CHILD) {  // mirror: only reflected rays stay in the bundle
                         if (alive) {
-                            if (res.has_child) r = child;
+                            if (res.has_child) child_into(res, r);
                             else { alive = false; valid = false; }
                         }
                     }

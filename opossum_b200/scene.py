@@ -162,6 +162,7 @@ class _BorrowedHitMap(HitMap):
 
 class Scene:
     """A chain of optic nodes starting at a Source (NodeGroup of the reference, restricted to explicit isometries)."""
+    _close_order = 0  # a closing context destroys scenes before stand-alone bundles
 
     def __init__(self, ctx: Context):
         self.ctx = ctx
@@ -169,6 +170,7 @@ class Scene:
         _check(F.lib().opm_scene_create(ctx.h, C.byref(h)))
         self.h = h
         self._nodes = []
+        ctx._adopt(self)
 
     def set_ambient(self, index: RefractiveIndex):
         _check(F.lib().opm_scene_set_ambient(self.h, C.byref(index.c)))
