@@ -186,6 +186,7 @@ def run_product(args):
 
     import opossum_b200 as ob
     import scenes
+    from opossum_b200 import sharding
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -202,44 +203,23 @@ def run_product(args):
         ctx = ob.Context(local, stream=stream.cuda_stream)
         scene = scenes.to_product(ctx, scenes.c2_laser_chain())
         sd = scenes.source_to_product(scenes.c2_source(n * world))
-        src = sd.generate(ctx, rank * n, (rank + 1) * n)  # this rank's shard of the global source, generated on the device
+        begin, end = sharding.shard_range(n * world, rank, world)
+        src = sd.generate(ctx, begin, end)  # this rank's shard of the global source, generated on the device
 
         maps = [torch.zeros(MAP_NX * MAP_NY, dtype=torch.float64, device=dev) for _ in range(2)]
-        red = torch.zeros(8, dtype=torch.float64, device=dev)
-        h_red = torch.zeros(8, dtype=torch.float64).pin_memory()
         h_maps = [torch.zeros(MAP_NX * MAP_NY, dtype=torch.float64).pin_memory() for _ in range(2)]
 
-        def allreduce_host(vals, op):
-            """tiny host-value all-reduce over NCCL (map ranges, tallies)"""
-            if world == 1:
-                return list(vals)
-            k = len(vals)
-            h_red[:k] = torch.tensor(vals, dtype=torch.float64)
-            red[:k].copy_(h_red[:k], non_blocking=True)
-            dist.all_reduce(red[:k], op=op)
-            h_red[:k].copy_(red[:k], non_blocking=True)
-            stream.synchronize()
-            return h_red[:k].tolist()
-
         def read_out(download: bool):
-            """detector reports: FluenceDetector x2 (Binning 100x83, data-dependent range) + SpotDiagram"""
+            """detector reports: FluenceDetector x2 (Binning 100x83, data-dependent range) + SpotDiagram; with N > 1 the map
+            ranges, maps and spot accumulators are all-reduced over NCCL (opossum_b200/sharding.py)"""
             out = {}
             for j, node in enumerate((9, 10)):
-                hm = scene.node_hitmaps(node, 0)
-                (l, r, t, b), _ = ob.hitmaps_bounding_box(hm)
-                if world > 1:  # global map range: min left/bottom, max right/top
-                    l, b = (-v for v in allreduce_host([-l, -b], dist.ReduceOp.MAX))
-                    r, t = allreduce_host([r, t], dist.ReduceOp.MAX)
-                fd = ob.fluence_binning(ctx, hm, MAP_NX, MAP_NY, lrtb=(l, r, t, b), map_dev=maps[j].data_ptr(), download=False)
-                if world > 1:
-                    dist.all_reduce(maps[j], op=dist.ReduceOp.SUM)
-                    fd = ob.fluence_peak_total(ctx, maps[j].data_ptr(), MAP_NX, MAP_NY, fd.lrtb)
+                fd = sharding.fluence_map(ctx, scene.node_hitmaps(node, 0), MAP_NX, MAP_NY, maps[j])
                 if download:
                     h_maps[j].copy_(maps[j], non_blocking=True)
                 out[node] = (fd.peak, fd.total_energy)
-            s = scene.node_spot(8)
-            tally = [float(s.n_valid), s.total_energy, s.total_energy * s.energy_centroid[0], s.total_energy * s.energy_centroid[1]]
-            out["spot"] = allreduce_host(tally, dist.ReduceOp.SUM) if world > 1 else tally
+            s = sharding.spot_stats(scene, 8, dev)
+            out["spot"] = [float(s.n_valid), s.total_energy, s.energy_centroid[0], s.energy_centroid[1], s.beam_radius_geo]
             if download:
                 stream.synchronize()
             return out

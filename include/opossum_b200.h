@@ -289,6 +289,21 @@ typedef struct {
 /* frame: NULL or the detector's effective surface isometry (positions are inverse-transformed into it,
  * nodes/spot_diagram.rs:106-112) */
 OpmStatus opm_rays_spot_stats(const OpmRays* rays, const OpmIsometry* frame_or_null, OpmSpotStats* out);
+/* The same statistics in two phases, for bundles sharded over several GPUs (rays.rs:599-701 need the GLOBAL centroids
+ * before the radii): phase 1 fills the sums, the caller all-reduces them (sum[]: SUM, n_*: SUM, first_key: MIN), phase 2
+ * fills the radius accumulators about the centroids those sums define (max_d2_mm2: MAX, sum_*: SUM), and
+ * opm_spot_stats_from_partial turns the reduced accumulators into the report values. */
+typedef struct {
+    double sum[7];              /* x y z e*x e*y e*z e over valid rays */
+    uint64_t n_valid, n_total;
+    uint64_t first_key;         /* min over valid rays of (id << 32 | bounces) */
+    double max_d2_mm2;          /* max squared distance [mm^2] from the (unweighted) centroid */
+    double sum_d2_mm2;          /* sum of squared distances [mm^2] from the centroid */
+    double sum_ed2;             /* sum of e * squared distance [m^2] from the energy-weighted centroid */
+} OpmSpotPartial;
+OpmStatus opm_rays_spot_partial_sums(const OpmRays* rays, const OpmIsometry* frame_or_null, OpmSpotPartial* out);
+OpmStatus opm_rays_spot_partial_radii(const OpmRays* rays, const OpmIsometry* frame_or_null, OpmSpotPartial* inout);
+void opm_spot_stats_from_partial(const OpmSpotPartial* reduced, OpmSpotStats* out);
 /* Rays::bounce_lvl (rays.rs:183-194): bounce count of the first valid ray (lowest id); 0 for none */
 OpmStatus opm_rays_bounce_lvl(const OpmRays* rays, uint32_t* bounce_lvl);
 /* per-bounce-order tallies: counts[b] valid rays and energy[b] their energy, b < n_orders (last bin = overflow) */

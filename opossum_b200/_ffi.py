@@ -134,6 +134,11 @@ class OpmSpotStats(C.Structure):
                 ("_pad", C.c_uint32)]
 
 
+class OpmSpotPartial(C.Structure):
+    _fields_ = [("sum", C.c_double * 7), ("n_valid", C.c_uint64), ("n_total", C.c_uint64), ("first_key", C.c_uint64),
+                ("max_d2_mm2", C.c_double), ("sum_d2_mm2", C.c_double), ("sum_ed2", C.c_double)]
+
+
 class OpmSourceDesc(C.Structure):
     _fields_ = [("pos_dist", C.c_int32), ("energy_dist", C.c_int32), ("n_positions", C.c_uint64),
                 ("grid_nx", C.c_uint64), ("grid_ny", C.c_uint64), ("size_x", C.c_double), ("size_y", C.c_double),
@@ -176,6 +181,7 @@ class OpmCriticalFluence(C.Structure):
 SCENE_EXPORTS = [
     "opm_node_desc_init", "opm_scene_create", "opm_scene_destroy", "opm_scene_set_ambient", "opm_scene_add_node",
     "opm_scene_node_count", "opm_scene_reset_data", "opm_scene_raytrace", "opm_scene_output_rays", "opm_scene_node_rays", "opm_scene_node_spot",
+    "opm_scene_node_spot_partial",
     "opm_scene_node_fluence", "opm_scene_node_hitmaps", "opm_scene_ghostfocus", "opm_scene_gf_pass_tally",
     "opm_scene_gf_pass_bundles", "opm_scene_node_critical_fluences", "opm_scene_node_peak_fluence",
 ]
@@ -191,7 +197,8 @@ EXPORTS = [
     "opm_rays_field_ptr", "opm_rays_refract_on_surface", "opm_rays_apodize",
     "opm_rays_invalidate_by_threshold_energy", "opm_rays_filter_by_nr_of_bounces",
     "opm_rays_filter_by_nr_of_refractions", "opm_rays_filter_energy", "opm_rays_split", "opm_rays_refract_paraxial",
-    "opm_rays_transform", "opm_trace_sequence", "opm_rays_spot_stats", "opm_rays_bounce_lvl", "opm_rays_tally", "opm_hitmap_create",
+    "opm_rays_transform", "opm_trace_sequence", "opm_rays_spot_stats", "opm_rays_spot_partial_sums",
+    "opm_rays_spot_partial_radii", "opm_spot_stats_from_partial", "opm_rays_bounce_lvl", "opm_rays_tally", "opm_hitmap_create",
     "opm_hitmap_destroy", "opm_hitmap_capacity", "opm_hitmap_len", "opm_hitmap_upload", "opm_hitmap_download",
     "opm_hitmaps_bounding_box", "opm_fluence_binning", "opm_fluence_peak_total", "opm_measure_fp64_peak", "opm_device_alloc",
     "opm_device_free", "opm_device_to_host", "opm_host_to_device", "opm_host_alloc_pinned", "opm_host_free_pinned",
@@ -261,6 +268,9 @@ def lib() -> C.CDLL:
         "opm_rays_transform": (i32, [vp, C.POINTER(OpmIsometry), i32]),
         "opm_trace_sequence": (i32, [vp, C.POINTER(OpmOp), i32, i32, vp, C.POINTER(OpmTraceStats)]),
         "opm_rays_spot_stats": (i32, [vp, C.POINTER(OpmIsometry), C.POINTER(OpmSpotStats)]),
+        "opm_rays_spot_partial_sums": (i32, [vp, C.POINTER(OpmIsometry), C.POINTER(OpmSpotPartial)]),
+        "opm_rays_spot_partial_radii": (i32, [vp, C.POINTER(OpmIsometry), C.POINTER(OpmSpotPartial)]),
+        "opm_spot_stats_from_partial": (None, [C.POINTER(OpmSpotPartial), C.POINTER(OpmSpotStats)]),
         "opm_rays_bounce_lvl": (i32, [vp, C.POINTER(C.c_uint32)]),
         "opm_rays_tally": (i32, [vp, C.c_uint32, C.POINTER(u64), dp]),
         "opm_hitmap_create": (i32, [vp, u64, pp]),
@@ -294,6 +304,7 @@ def lib() -> C.CDLL:
         "opm_scene_output_rays": (vp, [vp]),
         "opm_scene_node_rays": (vp, [vp, i32]),
         "opm_scene_node_spot": (i32, [vp, i32, C.POINTER(OpmSpotStats)]),
+        "opm_scene_node_spot_partial": (i32, [vp, i32, i32, C.POINTER(OpmSpotPartial)]),
         "opm_scene_node_fluence": (i32, [vp, i32, u64, u64, dp, dp, dp, dp]),
         "opm_scene_node_hitmaps": (i32, [vp, i32, i32, pp, i32]),
         "opm_scene_ghostfocus": (i32, [vp, vp, C.POINTER(OpmGhostFocusConfig), i32, C.POINTER(OpmGhostFocusStats)]),

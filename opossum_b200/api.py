@@ -461,6 +461,17 @@ class Rays:
         _check(F.lib().opm_rays_spot_stats(self.h, C.byref(frame.c) if frame is not None else None, C.byref(s)))
         return s
 
+    def spot_partial(self, frame: Isometry | None = None, reduced: "F.OpmSpotPartial | None" = None) -> F.OpmSpotPartial:
+        """two-phase statistics for sharded bundles: without `reduced` phase 1 (sums), with the all-reduced sums phase 2
+        (radius accumulators about the global centroids); see sharding.spot_stats"""
+        fr = C.byref(frame.c) if frame is not None else None
+        if reduced is None:
+            p = F.OpmSpotPartial()
+            _check(F.lib().opm_rays_spot_partial_sums(self.h, fr, C.byref(p)))
+            return p
+        _check(F.lib().opm_rays_spot_partial_radii(self.h, fr, C.byref(reduced)))
+        return reduced
+
     def total_energy(self) -> float:
         return self.spot_stats().total_energy
 

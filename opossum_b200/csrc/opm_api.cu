@@ -887,41 +887,73 @@ extern "C" OpmStatus opm_rays_transform(OpmRays* rays, const OpmIsometry* iso, i
 // ---------------------------------------------------------------------------------------------
 // statistics
 // ---------------------------------------------------------------------------------------------
-extern "C" OpmStatus opm_rays_spot_stats(const OpmRays* rc, const OpmIsometry* frame, OpmSpotStats* out) {
-    OpmRays* r = const_cast<OpmRays*>(rc);
-    if (!r || !out) return fail(OPM_ERR_ARG, "NULL argument");
+// Two-phase form (multi-GPU: the partial accumulators are all-reduced between the phases):
+// phase 1 = sums over valid rays, phase 2 = radii about the centroids the (global) sums define.
+static OpmStatus spot_phase(OpmRays* r, const OpmIsometry* frame, OpmSpotPartial* p, int phase) {
     OpmContext* c = r->ctx;
     CU(cudaSetDevice(c->device));
     OpmStatus s = rays_refresh_len(r);
     if (s) return s;
-    memset(out, 0, sizeof *out);
     SpotAccum init;
     memset(&init, 0, sizeof init);
     init.first_key = ~0ull;
     init.max_d2_key = double_to_key(0.0);
+    if (phase == 2) { memcpy(init.sum, p->sum, sizeof init.sum); init.n_valid = p->n_valid; init.n_total = p->n_total; init.first_key = p->first_key; }
     SpotAccum* d_acc = (SpotAccum*)c->d_scratch;
     SpotAccum* h_acc = (SpotAccum*)c->h_scratch;
     CU(cudaMemcpyAsync(d_acc, &init, sizeof init, cudaMemcpyHostToDevice, c->stream));
     DevIso inv;
     memset(&inv, 0, sizeof inv);
     if (frame) to_dev_iso(frame->inv, inv);
-    if (r->len) { KL(k_spot(r->v, r->len, frame ? 1 : 0, inv, d_acc, c->sms, c->stream)); c->launches += 2; }
+    if (r->len && (phase == 1 || p->n_valid)) {
+        if (phase == 1) KL(k_spot_pass1(r->v, r->len, frame ? 1 : 0, inv, d_acc, c->sms, c->stream));
+        else KL(k_spot_pass2(r->v, r->len, frame ? 1 : 0, inv, d_acc, c->sms, c->stream));
+        c->launches++;
+    }
     CU(cudaMemcpyAsync(h_acc, d_acc, sizeof init, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
     const SpotAccum& a = *h_acc;
-    out->n_valid = a.n_valid; out->n_total = a.n_total; out->total_energy = a.sum[6];
+    if (phase == 1) {
+        memset(p, 0, sizeof *p);
+        memcpy(p->sum, a.sum, sizeof p->sum);
+        p->n_valid = a.n_valid; p->n_total = a.n_total; p->first_key = a.first_key;
+    } else {
+        p->max_d2_mm2 = key_to_double(a.max_d2_key); p->sum_d2_mm2 = a.sum_d2; p->sum_ed2 = a.sum_ed2;
+    }
+    return OPM_OK;
+}
+extern "C" OpmStatus opm_rays_spot_partial_sums(const OpmRays* rays, const OpmIsometry* frame, OpmSpotPartial* out) {
+    if (!rays || !out) return fail(OPM_ERR_ARG, "NULL argument");
+    return spot_phase(const_cast<OpmRays*>(rays), frame, out, 1);
+}
+extern "C" OpmStatus opm_rays_spot_partial_radii(const OpmRays* rays, const OpmIsometry* frame, OpmSpotPartial* inout) {
+    if (!rays || !inout) return fail(OPM_ERR_ARG, "NULL argument");
+    return spot_phase(const_cast<OpmRays*>(rays), frame, inout, 2);
+}
+extern "C" void opm_spot_stats_from_partial(const OpmSpotPartial* a, OpmSpotStats* out) {
+    memset(out, 0, sizeof *out);
+    out->n_valid = a->n_valid; out->n_total = a->n_total; out->total_energy = a->sum[6];
     const double nan = std::nan("");
-    if (a.n_valid == 0) {  // the reference returns None
+    if (a->n_valid == 0) {  // the reference returns None
         for (int k = 0; k < 3; ++k) out->centroid[k] = out->energy_centroid[k] = nan;
         out->beam_radius_geo = out->beam_radius_rms = out->energy_beam_radius_rms = nan;
-        return OPM_OK;
+        return;
     }
-    double len = (double)a.n_valid;
-    for (int k = 0; k < 3; ++k) { out->centroid[k] = a.sum[k] / len; out->energy_centroid[k] = a.sum[3 + k] / a.sum[6]; }
-    out->beam_radius_geo = std::sqrt(key_to_double(a.max_d2_key)) * 1.0E-3;  // millimeter!(max_dist)
-    out->beam_radius_rms = std::sqrt(a.sum_d2 / len) * 1.0E-3;
-    out->energy_beam_radius_rms = std::sqrt(a.sum_ed2 / a.sum[6]);
-    out->bounce_lvl = (uint32_t)(a.first_key & 0xffffffffull);
+    double len = (double)a->n_valid;
+    for (int k = 0; k < 3; ++k) { out->centroid[k] = a->sum[k] / len; out->energy_centroid[k] = a->sum[3 + k] / a->sum[6]; }
+    out->beam_radius_geo = std::sqrt(a->max_d2_mm2) * 1.0E-3;  // millimeter!(max_dist)
+    out->beam_radius_rms = std::sqrt(a->sum_d2_mm2 / len) * 1.0E-3;
+    out->energy_beam_radius_rms = std::sqrt(a->sum_ed2 / a->sum[6]);
+    out->bounce_lvl = (uint32_t)(a->first_key & 0xffffffffull);
+}
+extern "C" OpmStatus opm_rays_spot_stats(const OpmRays* rc, const OpmIsometry* frame, OpmSpotStats* out) {
+    OpmRays* r = const_cast<OpmRays*>(rc);
+    if (!r || !out) return fail(OPM_ERR_ARG, "NULL argument");
+    OpmSpotPartial p;
+    OpmStatus s = spot_phase(r, frame, &p, 1);
+    if (!s) s = spot_phase(r, frame, &p, 2);
+    if (s) return s;
+    opm_spot_stats_from_partial(&p, out);
     return OPM_OK;
 }
 extern "C" OpmStatus opm_rays_bounce_lvl(const OpmRays* rc, uint32_t* out) {

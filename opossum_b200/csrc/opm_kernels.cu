@@ -515,10 +515,12 @@ int k_transform(DevRays R, DevIso I, uint64_t n, int sms, void* stream) {
     transform_kernel<<<grid_for(n, 256, sms * 8), 256, 0, ST>>>(R, I, n);
     return (int)cudaGetLastError();
 }
-int k_spot(DevRays R, uint64_t n, int use_frame, DevIso inv, SpotAccum* acc, int sms, void* stream) {
-    int g = grid_for(n, 256, sms * 4);
-    spot_pass1_kernel<<<g, 256, 0, ST>>>(R, n, use_frame, inv, acc);
-    spot_pass2_kernel<<<g, 256, 0, ST>>>(R, n, use_frame, inv, acc);
+int k_spot_pass1(DevRays R, uint64_t n, int use_frame, DevIso inv, SpotAccum* acc, int sms, void* stream) {
+    spot_pass1_kernel<<<grid_for(n, 256, sms * 4), 256, 0, ST>>>(R, n, use_frame, inv, acc);
+    return (int)cudaGetLastError();
+}
+int k_spot_pass2(DevRays R, uint64_t n, int use_frame, DevIso inv, SpotAccum* acc, int sms, void* stream) {
+    spot_pass2_kernel<<<grid_for(n, 256, sms * 4), 256, 0, ST>>>(R, n, use_frame, inv, acc);
     return (int)cudaGetLastError();
 }
 int k_bounce_lvl(DevRays R, uint64_t n, unsigned long long* first_key, int sms, void* stream) {

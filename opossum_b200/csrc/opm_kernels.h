@@ -44,7 +44,8 @@ int k_aos_to_soa(const OpmRay* a, DevRays R, uint64_t off, uint64_t n, int sms, 
 int k_soa_to_aos(DevRays R, OpmRay* a, uint64_t n, int sms, void* stream);
 int k_soa_defaults(DevRays R, uint64_t n, int sms, void* stream);
 int k_transform(DevRays R, DevIso I, uint64_t n, int sms, void* stream);
-int k_spot(DevRays R, uint64_t n, int use_frame, DevIso inv, SpotAccum* acc, int sms, void* stream);
+int k_spot_pass1(DevRays R, uint64_t n, int use_frame, DevIso inv, SpotAccum* acc, int sms, void* stream);
+int k_spot_pass2(DevRays R, uint64_t n, int use_frame, DevIso inv, SpotAccum* acc, int sms, void* stream);
 int k_bounce_lvl(DevRays R, uint64_t n, unsigned long long* first_key, int sms, void* stream);
 int k_tally(DevRays R, uint64_t n, uint32_t n_orders, unsigned long long* counts, double* energy, int sms, void* stream);
 int k_hits_bbox(DevHits H, uint64_t n, long long bounce_filter, BBoxAccum* acc, int sms, void* stream);

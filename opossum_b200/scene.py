@@ -209,6 +209,12 @@ class Scene:
         _check(F.lib().opm_scene_node_spot(self.h, node, C.byref(s)))
         return s
 
+    def node_spot_partial(self, node: int, reduced: "F.OpmSpotPartial | None" = None) -> F.OpmSpotPartial:
+        """SpotDiagram report in two phases for a bundle sharded over GPUs (sharding.spot_stats drives it)"""
+        p = reduced if reduced is not None else F.OpmSpotPartial()
+        _check(F.lib().opm_scene_node_spot_partial(self.h, node, 1 if reduced is None else 2, C.byref(p)))
+        return p
+
     def node_fluence(self, node: int, nx=100, ny=83, download=True) -> FluenceData:
         """FluenceDetector::node_report (nodes/fluence_detector/mod.rs:91-135), Binning estimator"""
         m = np.zeros(nx * ny) if download else None

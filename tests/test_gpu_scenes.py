@@ -173,3 +173,58 @@ def test_c3_ghost_focus(ctx, max_bounces):
             assert len(ref_crit) == len(got_crit)
             for (a, ab), (b, bb) in zip(ref_crit, got_crit):
                 assert ab == bb and b == pytest.approx(a, rel=1e-6)
+
+
+def test_sharded_trace_equals_whole_source(ctx):
+    """SURVEY 8e on one GPU: two shards of the C2 source traced separately (as two ranks would), detector results combined
+    with the shard API (common map range + accumulate binning = all-reduce of maps; two-phase spot partials) must equal
+    the whole-source run: counts bit-exact, map bins and statistics to 1e-12 (only the summation order differs)."""
+    import ctypes as C
+
+    from opossum_b200 import ffi as F
+    from opossum_b200 import sharding
+    nodes, n = scenes.c2_laser_chain(), 30000
+    sd = scenes.source_to_product(scenes.c2_source(n))
+    whole = scenes.to_product(ctx, nodes)
+    st_whole = whole.raytrace(sd.generate(ctx))
+    ref_fd = whole.node_fluence(9)
+    ref_spot = whole.node_spot(8)
+    shards, stats = [], []
+    for g in range(2):
+        b, e = sharding.shard_range(n, g, 2)
+        sc = scenes.to_product(ctx, nodes)
+        stats.append(sc.raytrace(sd.generate(ctx, b, e)))
+        shards.append(sc)
+    assert sum(s.interactions for s in stats) == st_whole.interactions
+    assert sum(s.valid_out for s in stats) == st_whole.valid_out and sum(s.alive_out for s in stats) == st_whole.alive_out
+    # fluence: global range = min/max of the shard ranges, both shards binned into the same device map
+    boxes = [ob.hitmaps_bounding_box(sc.node_hitmaps(9, 0))[0] for sc in shards]
+    lrtb = (min(b[0] for b in boxes), max(b[1] for b in boxes), max(b[2] for b in boxes), min(b[3] for b in boxes))
+    assert lrtb == ref_fd.lrtb
+    dev_map = ctx.device_alloc(100 * 83 * 8)
+    for g, sc in enumerate(shards):
+        fd = ob.fluence_binning(ctx, sc.node_hitmaps(9, 0), 100, 83, lrtb=lrtb, map_dev=dev_map, accumulate=g > 0, download=g == 1)
+    ctx.device_free(dev_map)
+    assert_map_match(fd.map, ref_fd.map, rtol=1e-12)
+    assert fd.peak == pytest.approx(ref_fd.peak, rel=1e-12) and fd.total_energy == pytest.approx(ref_fd.total_energy, rel=1e-12)
+    # spot diagram: phase-1 partials summed, phase 2 about the global centroids, radius accumulators combined
+    parts = [sc.node_spot_partial(8) for sc in shards]
+    glob = F.OpmSpotPartial()
+    for j in range(7):
+        glob.sum[j] = parts[0].sum[j] + parts[1].sum[j]
+    glob.n_valid, glob.n_total = parts[0].n_valid + parts[1].n_valid, parts[0].n_total + parts[1].n_total
+    glob.first_key = parts[0].first_key if parts[0].n_valid else parts[1].first_key
+    radii = []
+    for sc in shards:
+        p = F.OpmSpotPartial.from_buffer_copy(glob)
+        sc.node_spot_partial(8, reduced=p)
+        radii.append(p)
+    glob.max_d2_mm2 = max(p.max_d2_mm2 for p in radii)
+    glob.sum_d2_mm2 = sum(p.sum_d2_mm2 for p in radii)
+    glob.sum_ed2 = sum(p.sum_ed2 for p in radii)
+    got = F.OpmSpotStats()
+    F.lib().opm_spot_stats_from_partial(C.byref(glob), C.byref(got))
+    assert got.n_valid == ref_spot.n_valid and got.n_total == ref_spot.n_total and got.bounce_lvl == ref_spot.bounce_lvl
+    for f in ("total_energy", "beam_radius_geo", "beam_radius_rms", "energy_beam_radius_rms"):
+        assert getattr(got, f) == pytest.approx(getattr(ref_spot, f), rel=1e-12), f
+    assert np.allclose(got.energy_centroid[:], ref_spot.energy_centroid[:], rtol=1e-9, atol=1e-15)
