@@ -657,10 +657,20 @@ static OpmStatus compile_ops(OpmContext* c, const OpmOp* ops, int n_ops, uint64_
                 double t = p.u.threshold.min_energy;
                 if (std::signbit(t)) continue;  // "negative threshold energy given. Ray bundle unmodified."
                 if (!std::isfinite(t)) return fail(OPM_ERR_THRESHOLD, "%s", opm_status_string(OPM_ERR_THRESHOLD));
+                if (!out.ops.empty() && out.ops.back().epi_flags == 0) {  // fold into the epilogue of the op it follows
+                    out.ops.back().epi_flags = EPI_THRESHOLD; out.ops.back().epi_min_energy = t;
+                    continue;
+                }
                 d.kind = OPK_THRESHOLD; d.u.threshold.min_energy = t;
                 break;
             }
             case OPM_OP_LIMITS:
+                if (!out.ops.empty() && !(out.ops.back().epi_flags & EPI_LIMITS)) {  // the epilogue runs threshold, then limits
+                    DevOp& b = out.ops.back();
+                    b.epi_flags |= EPI_LIMITS | (p.u.limits.check_refractions ? EPI_CHECK_REFR : 0);
+                    b.epi_max_bounces = p.u.limits.max_bounces; b.epi_max_refr = p.u.limits.max_refractions;
+                    continue;
+                }
                 d.kind = OPK_LIMITS; d.u.limits.max_bounces = p.u.limits.max_bounces; d.u.limits.max_refr = p.u.limits.max_refractions;
                 d.u.limits.check_refr = p.u.limits.check_refractions;
                 break;

@@ -56,8 +56,14 @@ struct DevSplit { double ratio; DevRays out; };
 struct DevSnapshot { DevRays out; };
 struct DevTransform { DevIso iso; };
 
+// Every op carries an epilogue: the energy threshold (rays.rs:1145-1162) and the bounce / refraction limits
+// (rays.rs:1386-1404) that the reference applies after nearly every surface are folded into the op they follow, so
+// a surface costs one dispatch instead of three.
+enum : int32_t { EPI_THRESHOLD = 1, EPI_LIMITS = 2, EPI_CHECK_REFR = 4 };
 struct alignas(16) DevOp {
-    int32_t kind, _pad;
+    int32_t kind, epi_flags;
+    double epi_min_energy;
+    uint64_t epi_max_bounces, epi_max_refr;
     union {
         DevRefract refract;
         DevApodize apodize;

@@ -246,7 +246,7 @@ __device__ __forceinline__ BinTaps bin_taps(const BinParams& P, double x, double
 }
 
 // map fits in shared memory: privatise the whole map per CTA, flush non-zero bins with global atomics
-__global__ void __launch_bounds__(256) binning_smem_kernel(DevHits H, uint64_t n, long long bounce_filter, BinParams P,
+__global__ void __launch_bounds__(1024) binning_smem_kernel(DevHits H, uint64_t n, long long bounce_filter, BinParams P,
                                                            double* __restrict__ map, unsigned* status_out) {
     extern __shared__ double smap[];
     const unsigned long long bins = P.nx * P.ny;
@@ -540,7 +540,8 @@ int k_binning(DevHits H, uint64_t n, long long bounce_filter, const BinParams& P
     if (bytes <= 160 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(binning_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
         if (e != cudaSuccess) return (int)e;
-        binning_smem_kernel<<<grid_for(n, 256, sms), 256, bytes, ST>>>(H, n, bounce_filter, P, map, status);
+        // the privatised map takes most of an SM's shared memory: one CTA per SM, as many warps as it can hold
+        binning_smem_kernel<<<grid_for(n, 1024, sms), 1024, bytes, ST>>>(H, n, bounce_filter, P, map, status);
     } else {
         binning_global_kernel<<<grid_for(n, 256, sms * 8), 256, 0, ST>>>(H, n, bounce_filter, P, map, status);
     }

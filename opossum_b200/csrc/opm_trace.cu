@@ -211,6 +211,14 @@ trace_kernel(const DevOp* __restrict__ g_ops, int n_ops, DevRays in, DevRays out
                     break;
                 default: break;
             }
+            if (op.epi_flags && alive) {  // folded threshold + limits (rays.rs:1145-1162, 1386-1404)
+                const int f = op.epi_flags;
+                if ((f & EPI_THRESHOLD) && r.e < op.epi_min_energy) valid = false;
+                if (f & EPI_LIMITS) {
+                    if ((uint64_t)r.bounces > op.epi_max_bounces) valid = false;
+                    if ((f & EPI_CHECK_REFR) && (uint64_t)r.refr >= op.epi_max_refr) valid = false;
+                }
+            }
         }
 
         if (alive) { c.alive_out++; if (valid) c.valid_out++; }
