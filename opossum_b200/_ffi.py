@@ -11,7 +11,7 @@ import subprocess
 from pathlib import Path
 
 PKG = Path(__file__).resolve().parent
-LIB_PATH = PKG / "lib" / "libopossum_b200.so"
+LIB_PATH = Path(os.environ["OPM_B200_LIB"]) if os.environ.get("OPM_B200_LIB") else PKG / "lib" / "libopossum_b200.so"  # override: tuning builds
 
 OPM_MAX_APERTURE_ITEMS = 4
 OPM_MAX_PROGRAM_OPS = 64

@@ -768,8 +768,8 @@ static OpmStatus run_program(OpmRays* rays, const OpmOp* ops, int n_ops, int fla
         TraceLaunch L;
         L.ops = d_slot; L.n_ops = (int)prog.ops.size();
         L.in = rays->v; L.out = dst->v; L.n = n; L.out_cap = dst->cap; L.out_tail = dst->d_tail;
-        L.stats = c->d_stats; L.compact = compact ? 1 : 0; L.block = 256; L.stream = c->stream;
         const bool strict = (flags & OPM_TRACE_STRICT) != 0;
+        L.stats = c->d_stats; L.compact = compact ? 1 : 0; L.block = strict ? trace_block_strict() : trace_block_fast(); L.stream = c->stream;
         size_t smem = prog.ops.size() * sizeof(DevOp);
         int occ = strict ? trace_occupancy_strict(L.block, smem) : trace_occupancy_fast(L.block, smem);
         uint64_t tiles = (n + L.block - 1) / L.block;

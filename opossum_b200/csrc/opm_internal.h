@@ -100,6 +100,8 @@ struct TraceLaunch {
 // launchers implemented in opm_trace.cu (compiled twice: contracted "fast" and -fmad=false "strict")
 int launch_trace_fast(const TraceLaunch& L);
 int launch_trace_strict(const TraceLaunch& L);
+int trace_block_fast();
+int trace_block_strict();
 int trace_occupancy_fast(int block, size_t smem);
 int trace_occupancy_strict(int block, size_t smem);
 

@@ -28,6 +28,14 @@
 #define OPM_VARIANT(name) name##_fast
 #endif
 
+// CTA shape of the fused kernel: threads per CTA and the CTAs per SM the register allocation is bounded for
+#ifndef OPM_TRACE_BLOCK
+#define OPM_TRACE_BLOCK 256
+#endif
+#ifndef OPM_TRACE_MIN_CTAS
+#define OPM_TRACE_MIN_CTAS 2
+#endif
+
 namespace opm {
 namespace {
 
@@ -66,12 +74,16 @@ __device__ __forceinline__ void store_ray(const DevRays& R, uint64_t i, const Ra
     R.valid[i] = valid;
 }
 
+// Per-tile event counters, two 16-bit fields per register (a warp's sum of a field is at most 32 lanes x 64 ops):
+// a = interactions | hits << 16, b = missed | children << 16.  Each tile ends with one REDUX per register and one
+// shared-memory atomic per field from lane 0; the CTA flushes its totals to the global statistics once.
 struct Counters {
-    unsigned interactions, children, hits, missed, apodized, valid_out, alive_out, status;
+    unsigned a, b, apodized, status;
 };
+enum { CNT_INTERACTIONS = 0, CNT_CHILDREN, CNT_HITS, CNT_MISSED, CNT_APODIZED, CNT_VALID_OUT, CNT_ALIVE_OUT, CNT_N };
 
 template <bool COMPACT>
-__global__ void __launch_bounds__(256, 2)
+__global__ void __launch_bounds__(OPM_TRACE_BLOCK, OPM_TRACE_MIN_CTAS)
 trace_kernel(const DevOp* __restrict__ g_ops, int n_ops, DevRays in, DevRays out, uint64_t n, uint64_t out_cap,
              unsigned long long* out_tail, DevStats* stats) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -94,10 +106,16 @@ trace_kernel(const DevOp* __restrict__ g_ops, int n_ops, DevRays in, DevRays out
     }
     bar.wait(std::move(token));
 
-    Counters c = {0, 0, 0, 0, 0, 0, 0, 0};
-    const uint64_t tiles = (n + blockDim.x - 1) / blockDim.x;
-    for (uint64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-        const uint64_t i = tile * blockDim.x + threadIdx.x;
+    __shared__ unsigned long long s_cnt[CNT_N];
+    __shared__ unsigned s_status;
+    if (threadIdx.x < CNT_N) s_cnt[threadIdx.x] = 0ull;
+    if (threadIdx.x == 0) s_status = 0u;
+    __syncthreads();
+
+    const unsigned tiles = (unsigned)((n + blockDim.x - 1) / blockDim.x);
+    for (unsigned tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        Counters c = {0, 0, 0, 0};
+        const uint64_t i = (uint64_t)tile * blockDim.x + threadIdx.x;
         const bool in_range = i < n;
         RayState r;
         r.pos = v3(0, 0, 0); r.dir = v3(0, 0, 1); r.e = 0; r.wvl = 0; r.opl = 0; r.n = 1; r.bounces = 0; r.refr = 0; r.id = 0;
@@ -117,11 +135,11 @@ trace_kernel(const DevOp* __restrict__ g_ops, int n_ops, DevRays in, DevRays out
                     RefractResult res;
                     res.has_child = false; res.hit_e = -1.0; res.hit_bounce = 0; res.hit_local = v3(0, 0, 0);
                     if (valid) {
-                        c.interactions++;
+                        c.a += 1u;
                         res = refract_on_surface(o, r);
                         if (res.status != OPM_OK) { c.status |= 1u << res.status; valid = false; res.has_child = false; res.hit_e = -1.0; }
                         else {
-                            if (res.missed) c.missed++;
+                            if (res.missed) c.b += 1u;
                             if (res.invalidated) valid = false;
                         }
                     }
@@ -130,7 +148,7 @@ trace_kernel(const DevOp* __restrict__ g_ops, int n_ops, DevRays in, DevRays out
                         if (res.hit_e >= 0.0) {
                             __stcs(o.hits.x + i, res.hit_local.x); __stcs(o.hits.y + i, res.hit_local.y);
                             __stcs(o.hits.z + i, res.hit_local.z); __stcs(o.hits.bounce + i, res.hit_bounce);
-                            c.hits++;
+                            c.a += 1u << 16;
                         }
                     }
                     if (o.flags & OPM_REFRACT_EMIT_CHILDREN) {
@@ -140,7 +158,7 @@ trace_kernel(const DevOp* __restrict__ g_ops, int n_ops, DevRays in, DevRays out
                                 RayState child = r;
                                 child_into(res, child);
                                 store_ray<true>(o.children, slot, child, RAY_VALID);
-                                c.children++;
+                                c.b += 1u << 16;
                             } else c.status |= 1u << OPM_ERR_CAPACITY;
                         }
                     }
@@ -161,7 +179,7 @@ trace_kernel(const DevOp* __restrict__ g_ops, int n_ops, DevRays in, DevRays out
                         if (f > 0.0) {
                             if (!(f <= 1.0)) c.status |= 1u << OPM_ERR_APODIZE_FACTOR;
                             else r.e *= f;
-                        } else { valid = false; c.apodized++; }
+                        } else { valid = false; c.apodized += 1u; }
                     }
                     break;
                 }
@@ -221,7 +239,6 @@ trace_kernel(const DevOp* __restrict__ g_ops, int n_ops, DevRays in, DevRays out
             }
         }
 
-        if (alive) { c.alive_out++; if (valid) c.valid_out++; }
         if (COMPACT) {
             unsigned long long slot = warp_reserve(alive, out_tail);
             if (alive) {
@@ -236,23 +253,33 @@ trace_kernel(const DevOp* __restrict__ g_ops, int n_ops, DevRays in, DevRays out
                 out.valid[i] = RAY_REMOVED;
             }
         }
+        // ---- tile counters: one warp reduction per register, lane 0 adds the fields to the CTA totals
+        {
+            const unsigned ra = __reduce_add_sync(0xffffffffu, c.a), rb = __reduce_add_sync(0xffffffffu, c.b);
+            const unsigned rp = __reduce_add_sync(0xffffffffu, c.apodized);
+            const unsigned live = __ballot_sync(0xffffffffu, alive), ok = __ballot_sync(0xffffffffu, valid && alive);
+            const unsigned st = __reduce_or_sync(0xffffffffu, c.status);
+            if ((threadIdx.x & 31) == 0) {
+                if (ra & 0xffffu) atomicAdd(&s_cnt[CNT_INTERACTIONS], (unsigned long long)(ra & 0xffffu));
+                if (ra >> 16) atomicAdd(&s_cnt[CNT_HITS], (unsigned long long)(ra >> 16));
+                if (rb & 0xffffu) atomicAdd(&s_cnt[CNT_MISSED], (unsigned long long)(rb & 0xffffu));
+                if (rb >> 16) atomicAdd(&s_cnt[CNT_CHILDREN], (unsigned long long)(rb >> 16));
+                if (rp) atomicAdd(&s_cnt[CNT_APODIZED], (unsigned long long)rp);
+                if (live) atomicAdd(&s_cnt[CNT_ALIVE_OUT], (unsigned long long)__popc(live));
+                if (ok) atomicAdd(&s_cnt[CNT_VALID_OUT], (unsigned long long)__popc(ok));
+                if (st) atomicOr(&s_status, st);
+            }
+        }
     }
 
-    // ---- counters: warp shuffle reduction, one atomic per warp and counter
-    unsigned vals[7] = {c.interactions, c.children, c.hits, c.missed, c.apodized, c.valid_out, c.alive_out};
-    unsigned long long* dst[7] = {&stats->interactions, &stats->children, &stats->hits, &stats->missed,
-                                  &stats->apodized, &stats->valid_out, &stats->alive_out};
-#pragma unroll
-    for (int j = 0; j < 7; ++j) {
-        unsigned v = vals[j];
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-        if ((threadIdx.x & 31) == 0 && v) atomicAdd(dst[j], (unsigned long long)v);
+    // ---- CTA totals -> global statistics
+    __syncthreads();
+    if (threadIdx.x < CNT_N && s_cnt[threadIdx.x]) {
+        unsigned long long* dst[CNT_N] = {&stats->interactions, &stats->children, &stats->hits, &stats->missed,
+                                          &stats->apodized, &stats->valid_out, &stats->alive_out};
+        atomicAdd(dst[threadIdx.x], s_cnt[threadIdx.x]);
     }
-    unsigned s = c.status;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) s |= __shfl_xor_sync(0xffffffffu, s, o);
-    if ((threadIdx.x & 31) == 0 && s) atomicOr(&stats->status_bits, s);
+    if (threadIdx.x == 0 && s_status) atomicOr(&stats->status_bits, s_status);
 }
 
 }  // namespace
@@ -272,6 +299,8 @@ int OPM_VARIANT(launch_trace)(const TraceLaunch& L) {
     }
     return (int)cudaGetLastError();
 }
+
+int OPM_VARIANT(trace_block)() { return OPM_TRACE_BLOCK; }
 
 int OPM_VARIANT(trace_occupancy)(int block, size_t smem) {
     int nb = 0;
