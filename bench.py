@@ -237,12 +237,20 @@ def run_product(args):
             pos_h[:, k] = torch.from_numpy(tmp)
         ctx.to_host(src.field_ptr("e"), tmp)
         e_h.copy_(torch.from_numpy(tmp))
-        e2e_rays = ob.Rays(ctx, n)
+        e2e_rays = [ob.Rays(ctx, n), ob.Rays(ctx, n)]
         wvl, w = scenes.spectrum_of(scenes.c2_source(n))
+        e2e_k = [0]
+
+        def upload(rays):
+            rays.new_collimated_with_spectrum(pos_h.data_ptr(), e_h.data_ptr(), n, wvl, w)
 
         def step_e2e():
-            e2e_rays.new_collimated_with_spectrum(pos_h.data_ptr(), e_h.data_ptr(), n, wvl, w)
-            scene.raytrace(e2e_rays, sync=False)
+            """host buffers -> reports.  Two bundles alternate: the upload of the NEXT step's inputs runs on the library's
+            copy stream while this step traces, so every step still pays one full host->device copy inside the timed region."""
+            cur, nxt = e2e_rays[e2e_k[0] % 2], e2e_rays[(e2e_k[0] + 1) % 2]
+            e2e_k[0] += 1
+            upload(nxt)
+            scene.raytrace(cur, sync=False)
             return read_out(True)
 
         def barrier():
@@ -281,6 +289,7 @@ def run_product(args):
         ctx.set_kernel_timing(False)
 
         # ---- e2e: host buffers in, reports out
+        upload(e2e_rays[0])
         for _ in range(max(args.warmup, 1)):
             step_e2e()
         barrier()
@@ -332,7 +341,8 @@ def run_product(args):
                        "l2": f"inputs larger than L2: {n * RAY_BYTES / 1e6:.0f} MB source bundle per GPU vs 126 MB",
                        "collective": "NCCL all-reduce of map ranges (min/max), fluence maps and tallies (sum)" if world > 1 else "none (1 GPU)"},
             "e2e": {"value": inter_total * args.steps / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": e2e_ms / args.steps},
+                    "ms_per_step": e2e_ms / args.steps,
+                    "pipeline": "two bundles: H2D of step k+1 (copy stream) overlaps trace + read-out of step k"},
             "gpu_launches": launches_per_step * args.steps,
             "clocks": clk,
             "roofline": {"bound": "hbm", "kernel": "opm::trace_kernel (fused surface sequence)", "achieved": achieved, "peak": hbm_peak,

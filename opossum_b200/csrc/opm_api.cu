@@ -17,6 +17,8 @@
 
 using namespace opm;
 
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
 // ---------------------------------------------------------------------------------------------
 // handles
 // ---------------------------------------------------------------------------------------------
@@ -35,8 +37,14 @@ struct OpmContext {
     DevOp* h_ops_ring = nullptr;
     cudaEvent_t ring_ev[kRing] = {};
     int ring_pos = 0;
-    unsigned char* d_staging = nullptr;  // grows on demand: host uploads that are expanded on the device
-    size_t staging_bytes = 0;
+    // small host -> device parameter blocks (accumulator initial values): pinned + mapped ring read by a fetch kernel,
+    // so they never queue behind a bulk upload on the H2D copy engine
+    static constexpr int kPutSlots = 32;
+    static constexpr size_t kPutBytes = 256;
+    unsigned char* h_put_ring = nullptr;
+    cudaEvent_t put_ev[kPutSlots] = {};
+    int put_pos = 0;
+    cudaStream_t copy_stream = nullptr;  // host uploads that are expanded on the device run here, overlapping the main stream
     // optional per-launch timing of the fused trace kernel (CUDA events on the launching stream)
     bool timing = false;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timing_events;
@@ -55,6 +63,17 @@ struct OpmRays {
     DevRays v{};
     unsigned long long* d_tail = nullptr;
     bool len_dirty = false;  // the device tail counter is ahead of `len` (asynchronous append)
+    // host upload in flight (opm_rays_new_collimated_with_spectrum): positions / energies / spectrum are copied into
+    // this bundle's staging buffer on the context's copy stream; the expansion into the SoA arrays is enqueued on the
+    // main stream the first time the bundle is used, so the copy overlaps whatever the main stream is doing until then
+    unsigned char* d_stage = nullptr;
+    size_t stage_bytes = 0;
+    double* h_spec = nullptr;  // pinned copy of the spectrum table (a pageable source would make the copy synchronous)
+    size_t h_spec_bytes = 0;
+    cudaEvent_t ev_uploaded = nullptr, ev_expanded = nullptr;
+    bool pending = false;
+    uint64_t pend_n_pos = 0;
+    uint32_t pend_n_wvl = 0;
 };
 
 struct OpmHitMap {
@@ -90,6 +109,20 @@ static OpmStatus fail(OpmStatus s, const char* fmt, ...) {
         if (_e != 0) return fail(OPM_ERR_CUDA, "kernel launch failed: %s at %s:%d",                      \
                                  cudaGetErrorString((cudaError_t)_e), __FILE__, __LINE__);               \
     } while (0)
+
+// asynchronous host -> device transfer of a small parameter block (bytes <= kPutBytes, multiple of 8) on the main stream
+static OpmStatus dev_put(OpmContext* c, void* dst, const void* src, size_t bytes) {
+    if (bytes > OpmContext::kPutBytes || (bytes & 7)) return fail(OPM_ERR_ARG, "dev_put: bad size %zu", bytes);
+    const int slot = c->put_pos;
+    c->put_pos = (c->put_pos + 1) % OpmContext::kPutSlots;
+    CU(cudaEventSynchronize(c->put_ev[slot]));  // the fetch that last used this slot has run
+    unsigned char* h = c->h_put_ring + (size_t)slot * OpmContext::kPutBytes;
+    memcpy(h, src, bytes);
+    KL(k_fetch_from_host(dst, h, bytes, c->stream));
+    c->launches++;
+    CU(cudaEventRecord(c->put_ev[slot], c->stream));
+    return OPM_OK;
+}
 
 extern "C" const char* opm_status_string(OpmStatus s) {
     switch (s) {
@@ -143,6 +176,9 @@ extern "C" OpmStatus opm_context_create(int32_t device, void* stream, OpmContext
     c->sms = prop.multiProcessorCount;
     if (stream) { c->stream = (cudaStream_t)stream; c->own_stream = false; }
     else { CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)); c->own_stream = true; }
+    CU(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    CU(cudaMallocHost(&c->h_put_ring, OpmContext::kPutSlots * OpmContext::kPutBytes));
+    for (int k = 0; k < OpmContext::kPutSlots; ++k) CU(cudaEventCreateWithFlags(&c->put_ev[k], cudaEventDisableTiming));
     CU(cudaMalloc(&c->d_stats, sizeof(DevStats)));
     CU(cudaMallocHost(&c->h_stats, sizeof(DevStats)));
     CU(cudaMalloc(&c->d_ops, sizeof(DevOp) * OPM_MAX_PROGRAM_OPS * OpmContext::kRing));
@@ -161,7 +197,9 @@ extern "C" void opm_context_destroy(OpmContext* c) {
     cudaFreeHost(c->h_ops_ring);
     for (auto* v : {&c->timing_events, &c->timing_free})
         for (auto& p : *v) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
-    cudaFree(c->d_staging);
+    if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }
+    for (int k = 0; k < OpmContext::kPutSlots; ++k) if (c->put_ev[k]) cudaEventDestroy(c->put_ev[k]);
+    cudaFreeHost(c->h_put_ring);
     cudaFree(c->d_stats); cudaFreeHost(c->h_stats); cudaFree(c->d_ops); cudaFree(c->d_scratch); cudaFreeHost(c->h_scratch);
     if (c->own_stream) cudaStreamDestroy(c->stream);
     delete c;
@@ -250,7 +288,6 @@ extern "C" void opm_raytrace_config_default(OpmRayTraceConfig* c) {  // analyzer
 // ---------------------------------------------------------------------------------------------
 // rays storage
 // ---------------------------------------------------------------------------------------------
-static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 static size_t rays_layout(uint64_t cap, void* base, DevRays* v, unsigned long long** tail) {
     size_t off = 0;
@@ -290,11 +327,32 @@ extern "C" OpmStatus opm_rays_create(OpmContext* ctx, uint64_t capacity, OpmRays
 extern "C" void opm_rays_destroy(OpmRays* r) {
     if (!r) return;
     cudaSetDevice(r->ctx->device);
+    if (r->d_stage) cudaStreamSynchronize(r->ctx->copy_stream);
     cudaStreamSynchronize(r->ctx->stream);
     cudaFree(r->base);
+    cudaFree(r->d_stage);
+    cudaFreeHost(r->h_spec);
+    if (r->ev_uploaded) cudaEventDestroy(r->ev_uploaded);
+    if (r->ev_expanded) cudaEventDestroy(r->ev_expanded);
     delete r;
 }
+// enqueues the expansion of a pending host upload on the main stream (after the copy has landed)
+static OpmStatus rays_materialize(OpmRays* r) {
+    if (!r->pending) return OPM_OK;
+    OpmContext* c = r->ctx;
+    r->pending = false;
+    const uint64_t n_pos = r->pend_n_pos, n_rays = n_pos * r->pend_n_wvl;
+    double* d_xyz = (double*)r->d_stage;
+    double* d_e = d_xyz + 3 * n_pos;
+    double* d_w = (double*)(r->d_stage + align_up(n_pos * 32, 256));
+    CU(cudaStreamWaitEvent(c->stream, r->ev_uploaded, 0));
+    if (n_rays) { KL(k_expand_collimated(d_xyz, d_e, d_w, d_w + r->pend_n_wvl, r->pend_n_wvl, r->v, n_rays, c->sms, c->stream)); c->launches++; }
+    CU(cudaEventRecord(r->ev_expanded, c->stream));
+    KL(k_set_u64(r->d_tail, n_rays, c->stream)); c->launches++;
+    return OPM_OK;
+}
 static OpmStatus rays_refresh_len(OpmRays* r) {
+    if (r->pending) { OpmStatus s = rays_materialize(r); if (s) return s; }
     if (!r->len_dirty) return OPM_OK;
     unsigned long long t = 0;
     CU(cudaMemcpyAsync(&t, r->d_tail, 8, cudaMemcpyDeviceToHost, r->ctx->stream));
@@ -311,7 +369,7 @@ extern "C" uint64_t opm_rays_len(const OpmRays* r) {
 extern "C" uint64_t opm_rays_capacity(const OpmRays* r) { return r ? r->cap : 0; }
 extern "C" OpmStatus opm_rays_clear(OpmRays* r) {
     if (!r) return fail(OPM_ERR_ARG, "rays is NULL");
-    r->len = 0; r->len_dirty = false;
+    r->len = 0; r->len_dirty = false; r->pending = false;
     CU(cudaMemsetAsync(r->d_tail, 0, 8, r->ctx->stream));
     return OPM_OK;
 }
@@ -351,6 +409,7 @@ static OpmStatus rays_set_len(OpmRays* r, uint64_t n) {
 
 extern "C" OpmStatus opm_rays_upload(OpmRays* r, const OpmRay* host, uint64_t n) {
     if (!r || (!host && n)) return fail(OPM_ERR_ARG, "NULL argument");
+    r->pending = false;
     OpmContext* c = r->ctx;
     CU(cudaSetDevice(c->device));
     OpmStatus s = opm_rays_reserve(r, n);
@@ -370,6 +429,7 @@ extern "C" OpmStatus opm_rays_upload_soa(OpmRays* r, const double* pos[3], const
     if (!r || !pos || !dir || !e || !wvl) return fail(OPM_ERR_ARG, "NULL argument");
     OpmContext* c = r->ctx;
     CU(cudaSetDevice(c->device));
+    r->pending = false;
     OpmStatus s = opm_rays_reserve(r, n);
     if (s) return s;
     if (n) {
@@ -390,25 +450,46 @@ extern "C" OpmStatus opm_rays_new_collimated_with_spectrum(OpmRays* r, const dou
     for (uint32_t k = 0; k < n_wvl; ++k)  // Ray::new (ray.rs:114-116)
         if (!(wvl[k] > 0.0) || !std::isfinite(wvl[k])) return fail(OPM_ERR_ARG, "wavelength must be >0");
     const uint64_t n_rays = n_pos * n_wvl;
+    r->pending = false;  // an earlier upload that was never used is superseded
     OpmStatus s = opm_rays_reserve(r, n_rays);
     if (s) return s;
     const size_t need = align_up(n_pos * 32, 256) + (size_t)n_wvl * 16;
-    if (need > c->staging_bytes) {
+    if (need > r->stage_bytes) {
+        CU(cudaStreamSynchronize(c->copy_stream));
         CU(cudaStreamSynchronize(c->stream));
-        cudaFree(c->d_staging);
-        c->d_staging = nullptr; c->staging_bytes = 0;
-        CU(cudaMalloc(&c->d_staging, need));
-        c->staging_bytes = need;
+        cudaFree(r->d_stage);
+        r->d_stage = nullptr; r->stage_bytes = 0;
+        CU(cudaMalloc(&r->d_stage, need));
+        r->stage_bytes = need;
     }
-    double* d_xyz = (double*)c->d_staging;
+    if (!r->ev_uploaded) {
+        CU(cudaEventCreateWithFlags(&r->ev_uploaded, cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&r->ev_expanded, cudaEventDisableTiming));
+        CU(cudaEventRecord(r->ev_expanded, c->stream));
+        CU(cudaEventRecord(r->ev_uploaded, c->copy_stream));
+    }
+    double* d_xyz = (double*)r->d_stage;
     double* d_e = d_xyz + 3 * n_pos;
-    double* d_w = (double*)(c->d_staging + align_up(n_pos * 32, 256));
-    CU(cudaMemcpyAsync(d_xyz, pos_xyz, n_pos * 24, cudaMemcpyHostToDevice, c->stream));
-    CU(cudaMemcpyAsync(d_e, e_pos, n_pos * 8, cudaMemcpyHostToDevice, c->stream));
-    CU(cudaMemcpyAsync(d_w, wvl, (size_t)n_wvl * 8, cudaMemcpyHostToDevice, c->stream));
-    CU(cudaMemcpyAsync(d_w + n_wvl, weights, (size_t)n_wvl * 8, cudaMemcpyHostToDevice, c->stream));
-    if (n_rays) { KL(k_expand_collimated(d_xyz, d_e, d_w, d_w + n_wvl, n_wvl, r->v, n_rays, c->sms, c->stream)); c->launches++; }
-    return rays_set_len(r, n_rays);
+    double* d_w = (double*)(r->d_stage + align_up(n_pos * 32, 256));
+    // the staging buffer may still be read by the expansion of the previous upload; the bundle's arrays are only
+    // touched on the main stream, which orders the expansion after everything that used them before
+    CU(cudaEventSynchronize(r->ev_uploaded));  // the previous upload of THIS bundle has left the pinned spectrum table
+    if ((size_t)n_wvl * 16 > r->h_spec_bytes) {
+        cudaFreeHost(r->h_spec);
+        r->h_spec = nullptr; r->h_spec_bytes = 0;
+        CU(cudaMallocHost(&r->h_spec, (size_t)n_wvl * 16));
+        r->h_spec_bytes = (size_t)n_wvl * 16;
+    }
+    memcpy(r->h_spec, wvl, (size_t)n_wvl * 8);
+    memcpy(r->h_spec + n_wvl, weights, (size_t)n_wvl * 8);
+    CU(cudaStreamWaitEvent(c->copy_stream, r->ev_expanded, 0));
+    CU(cudaMemcpyAsync(d_xyz, pos_xyz, n_pos * 24, cudaMemcpyHostToDevice, c->copy_stream));
+    CU(cudaMemcpyAsync(d_e, e_pos, n_pos * 8, cudaMemcpyHostToDevice, c->copy_stream));
+    CU(cudaMemcpyAsync(d_w, r->h_spec, (size_t)n_wvl * 16, cudaMemcpyHostToDevice, c->copy_stream));
+    CU(cudaEventRecord(r->ev_uploaded, c->copy_stream));
+    r->pending = true; r->pend_n_pos = n_pos; r->pend_n_wvl = n_wvl;
+    r->len = n_rays; r->len_dirty = false;  // the device-side length is set when the expansion is enqueued
+    return OPM_OK;
 }
 extern "C" OpmStatus opm_rays_download(const OpmRays* rc, OpmRay* host, uint64_t capacity, uint64_t* n_out) {
     OpmRays* r = const_cast<OpmRays*>(rc);
@@ -487,6 +568,7 @@ extern "C" OpmStatus opm_rays_compact(OpmRays* r) {
 }
 extern "C" void* opm_rays_field_ptr(OpmRays* r, const char* f) {
     if (!r || !f) return nullptr;
+    if (rays_refresh_len(r)) return nullptr;
     struct { const char* n; void* p; } tab[] = {
         {"px", r->v.px}, {"py", r->v.py}, {"pz", r->v.pz}, {"dx", r->v.dx}, {"dy", r->v.dy}, {"dz", r->v.dz},
         {"e", r->v.e}, {"wvl", r->v.wvl}, {"opl", r->v.opl}, {"n", r->v.n}, {"bounces", r->v.bounces},
@@ -762,7 +844,8 @@ static OpmStatus run_program(OpmRays* rays, const OpmOp* ops, int n_ops, int fla
         DevOp* d_slot = c->d_ops + (size_t)slot * OPM_MAX_PROGRAM_OPS;
         CU(cudaEventSynchronize(c->ring_ev[slot]));  // the copy that last used this pinned slot has drained
         memcpy(h_slot, prog.ops.data(), prog.ops.size() * sizeof(DevOp));
-        CU(cudaMemcpyAsync(d_slot, h_slot, prog.ops.size() * sizeof(DevOp), cudaMemcpyHostToDevice, c->stream));
+        KL(k_fetch_from_host(d_slot, h_slot, prog.ops.size() * sizeof(DevOp), c->stream));  // not a copy-engine transfer: see dev_put
+        c->launches++;
         CU(cudaEventRecord(c->ring_ev[slot], c->stream));
         CU(cudaMemsetAsync(c->d_stats, 0, sizeof(DevStats), c->stream));
         TraceLaunch L;
@@ -911,7 +994,7 @@ static OpmStatus spot_phase(OpmRays* r, const OpmIsometry* frame, OpmSpotPartial
     if (phase == 2) { memcpy(init.sum, p->sum, sizeof init.sum); init.n_valid = p->n_valid; init.n_total = p->n_total; init.first_key = p->first_key; }
     SpotAccum* d_acc = (SpotAccum*)c->d_scratch;
     SpotAccum* h_acc = (SpotAccum*)c->h_scratch;
-    CU(cudaMemcpyAsync(d_acc, &init, sizeof init, cudaMemcpyHostToDevice, c->stream));
+    { OpmStatus ps = dev_put(c, d_acc, &init, sizeof init); if (ps) return ps; }
     DevIso inv;
     memset(&inv, 0, sizeof inv);
     if (frame) to_dev_iso(frame->inv, inv);
@@ -1021,7 +1104,7 @@ extern "C" OpmStatus opm_hitmaps_bounding_box(OpmHitMap* const* maps, int32_t n_
     BBoxAccum init;
     init.key[0] = ~0ull; init.key[1] = 0; init.key[2] = 0; init.key[3] = ~0ull; init.count = 0;
     BBoxAccum* d_acc = (BBoxAccum*)c->d_scratch;
-    CU(cudaMemcpyAsync(d_acc, &init, sizeof init, cudaMemcpyHostToDevice, c->stream));
+    { OpmStatus ps = dev_put(c, d_acc, &init, sizeof init); if (ps) return ps; }
     for (int k = 0; k < n_maps; ++k)
         if (maps[k]->len) { KL(k_hits_bbox(maps[k]->v, maps[k]->len, bounce_filter, d_acc, c->sms, c->stream)); c->launches++; }
     CU(cudaMemcpyAsync(c->h_scratch, d_acc, sizeof init, cudaMemcpyDeviceToHost, c->stream));
@@ -1076,7 +1159,7 @@ extern "C" OpmStatus opm_fluence_peak_total(OpmContext* c, const double* map_dev
     PeakAccum init;
     init.peak_key = double_to_key(-INFINITY); init.total = 0.0;
     PeakAccum* d_acc = (PeakAccum*)c->d_scratch;
-    CU(cudaMemcpyAsync(d_acc, &init, sizeof init, cudaMemcpyHostToDevice, c->stream));
+    { OpmStatus ps = dev_put(c, d_acc, &init, sizeof init); if (ps) return ps; }
     KL(k_peak_total(map_dev, nx * ny, dx * dy, d_acc, c->sms, c->stream)); c->launches++;
     CU(cudaMemcpyAsync(c->h_scratch, d_acc, sizeof init, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));

@@ -487,6 +487,12 @@ __global__ void __launch_bounds__(256) fp64_peak_kernel(double* out, int iters, 
     if (s == 12345.678) out[0] = s;  // keeps the chains alive
 }
 __global__ void set_u64_kernel(unsigned long long* p, unsigned long long v) { *p = v; }
+// small host -> device transfers that must not queue behind bulk uploads on the copy engine: the source is pinned host
+// memory mapped into the device address space (unified addressing), read over PCIe by one CTA
+__global__ void __launch_bounds__(256) fetch_from_host_kernel(unsigned long long* __restrict__ dst, const unsigned long long* __restrict__ src_host,
+                                                              unsigned words) {
+    for (unsigned k = threadIdx.x; k < words; k += blockDim.x) dst[k] = src_host[k];
+}
 
 // ---------------------------------------------------------------------------------------------
 // host launchers
@@ -575,6 +581,10 @@ int k_compact(DevRays S, DevRays D, uint64_t n, unsigned* counts, unsigned long 
 }
 int k_fp64_peak(double* out, int iters, int blocks, void* stream) {
     fp64_peak_kernel<<<blocks, 256, 0, ST>>>(out, iters, 1.0);
+    return (int)cudaGetLastError();
+}
+int k_fetch_from_host(void* dst, const void* src_host, size_t bytes, void* stream) {
+    fetch_from_host_kernel<<<1, 256, 0, ST>>>((unsigned long long*)dst, (const unsigned long long*)src_host, (unsigned)(bytes / 8));
     return (int)cudaGetLastError();
 }
 int k_set_u64(unsigned long long* p, unsigned long long v, void* stream) {

@@ -58,6 +58,7 @@ int k_expand_collimated(const double* xyz, const double* e_pos, const double* wv
                         uint64_t n_rays, int sms, void* stream);
 int k_compact(DevRays S, DevRays D, uint64_t n, unsigned* counts, unsigned long long* offsets, unsigned long long* total, void* stream);
 int k_fp64_peak(double* out, int iters, int blocks, void* stream);
+int k_fetch_from_host(void* dst, const void* src_host, size_t bytes, void* stream);  // bytes % 8 == 0, src pinned + mapped
 int k_set_u64(unsigned long long* p, unsigned long long v, void* stream);
 int k_fill_u8(uint8_t* p, uint8_t v, uint64_t n, int sms, void* stream);
 

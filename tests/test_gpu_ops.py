@@ -378,3 +378,29 @@ def test_upload_download_roundtrip_and_soa(ctx):
     fresh = rays.copy(); fresh["valid"] = 1
     assert_rays_match(got, fresh, what="soa upload")
     assert len(ob.Rays.from_array(ctx, rays[:0]).to_array()) == 0  # empty bundle
+
+
+def test_new_collimated_with_spectrum_from_host_buffers(ctx):
+    """Rays::new_collimated_with_spectrum (rays.rs:264-297) from host positions / energies: position-major, wavelength-minor,
+    E = E_pos * w.  The copy runs on the library's copy stream and is expanded at first use; re-uploading into a bundle
+    that was just traced (double buffering) must give the new contents."""
+    xyz = np.ascontiguousarray(orc.fibonacci_ellipse(3000, mm(5.0), mm(4.0)))
+    e = np.ascontiguousarray(orc.energy_general_gaussian(xyz, 2.0, (0.0, 0.0), (mm(3.0), mm(3.0)), 2.0, 0.0, False))
+    wvl, w = [nm(900.0), nm(1000.0), nm(1100.0)], [0.2, 0.5, 0.3]
+    ref = orc.rays_collimated_with_spectrum(xyz, e, wvl, w)
+    bufs = [ob.Rays(ctx, 1), ob.Rays(ctx, 1)]
+    surf = surface_pair(F.GEOM_PLANE, iso=iso_pair((0.0, 0.0, mm(30.0))))
+    for k in range(4):
+        r = bufs[k % 2]
+        scale = 1.0 + k
+        ek = np.ascontiguousarray(e * scale)
+        r.new_collimated_with_spectrum(xyz.ctypes.data, ek.ctypes.data, len(xyz), wvl, w)
+        assert len(r) == len(ref) == 9000
+        got = r.to_array()
+        exp = ref.copy()
+        exp["e"] *= scale
+        assert_rays_match(got, exp, what=f"upload {k}")
+        assert np.array_equal(got["wvl"], ref["wvl"]) and np.array_equal(got["pos"], ref["pos"])
+        r.refract_on_surface(surf[1], None, want_reflected=False)  # leaves the bundle modified before its next upload
+    with pytest.raises(ob.OpossumError):
+        bufs[0].new_collimated_with_spectrum(xyz.ctypes.data, e.ctypes.data, len(xyz), [0.0], [1.0])  # Ray::new: wavelength must be > 0
