@@ -206,22 +206,16 @@ def run_product(args):
         begin, end = sharding.shard_range(n * world, rank, world)
         src = sd.generate(ctx, begin, end)  # this rank's shard of the global source, generated on the device
 
-        maps = [torch.zeros(MAP_NX * MAP_NY, dtype=torch.float64, device=dev) for _ in range(2)]
-        h_maps = [torch.zeros(MAP_NX * MAP_NY, dtype=torch.float64).pin_memory() for _ in range(2)]
+
+        readout = sharding.DetectorReadout(ctx, scene, (9, 10), (8,), MAP_NX, MAP_NY, dev)
 
         def read_out(download: bool):
-            """detector reports: FluenceDetector x2 (Binning 100x83, data-dependent range) + SpotDiagram; with N > 1 the map
-            ranges, maps and spot accumulators are all-reduced over NCCL (opossum_b200/sharding.py)"""
-            out = {}
-            for j, node in enumerate((9, 10)):
-                fd = sharding.fluence_map(ctx, scene.node_hitmaps(node, 0), MAP_NX, MAP_NY, maps[j])
-                if download:
-                    h_maps[j].copy_(maps[j], non_blocking=True)
-                out[node] = (fd.peak, fd.total_energy)
-            s = sharding.spot_stats(scene, 8, dev)
+            """detector reports: FluenceDetector x2 (Binning 100x83, data-dependent range) + SpotDiagram, chained on the device
+            (opossum_b200/sharding.py); with N > 1 the map ranges, maps and spot accumulators meet in three NCCL collectives"""
+            rep = readout.run(download_maps=download)
+            s = rep[8]
+            out = {n: (rep[n]["peak"], rep[n]["total_energy"]) for n in (9, 10)}
             out["spot"] = [float(s.n_valid), s.total_energy, s.energy_centroid[0], s.energy_centroid[1], s.beam_radius_geo]
-            if download:
-                stream.synchronize()
             return out
 
         def step_resident():
@@ -339,7 +333,7 @@ def run_product(args):
             "config": {"workload": WORKLOAD_NAME, "rays_per_gpu": n, "rays_total": n * world, "surfaces_per_ray": 13,
                        "interactions_per_step": int(inter_total), "fluence_map": f"{MAP_NX}x{MAP_NY} x2 (Binning, data-dependent range)",
                        "l2": f"inputs larger than L2: {n * RAY_BYTES / 1e6:.0f} MB source bundle per GPU vs 126 MB",
-                       "collective": "NCCL all-reduce of map ranges (min/max), fluence maps and tallies (sum)" if world > 1 else "none (1 GPU)"},
+                       "collective": "3 NCCL collectives per step: all_gather(map ranges | spot sums), all_reduce(sum) of the fluence maps, all_gather(spot radii)" if world > 1 else "none (1 GPU)"},
             "e2e": {"value": inter_total * args.steps / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_ms / args.steps,
                     "pipeline": "two bundles: H2D of step k+1 (copy stream) overlaps trace + read-out of step k"},

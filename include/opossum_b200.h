@@ -296,7 +296,7 @@ OpmStatus opm_rays_spot_stats(const OpmRays* rays, const OpmIsometry* frame_or_n
 typedef struct {
     double sum[7];              /* x y z e*x e*y e*z e over valid rays */
     uint64_t n_valid, n_total;
-    uint64_t first_key;         /* min over valid rays of (id << 32 | bounces) */
+    uint64_t first_key;         /* bounce count of the first valid ray (lowest id); ~0 if there is none */
     double max_d2_mm2;          /* max squared distance [mm^2] from the (unweighted) centroid */
     double sum_d2_mm2;          /* sum of squared distances [mm^2] from the centroid */
     double sum_ed2;             /* sum of e * squared distance [m^2] from the energy-weighted centroid */
@@ -304,6 +304,12 @@ typedef struct {
 OpmStatus opm_rays_spot_partial_sums(const OpmRays* rays, const OpmIsometry* frame_or_null, OpmSpotPartial* out);
 OpmStatus opm_rays_spot_partial_radii(const OpmRays* rays, const OpmIsometry* frame_or_null, OpmSpotPartial* inout);
 void opm_spot_stats_from_partial(const OpmSpotPartial* reduced, OpmSpotStats* out);
+/* Device-chained forms of the two phases: asynchronous on the context's stream, no host synchronisation; the
+ * accumulators stay on the device in layouts an all-reduce can combine directly (multi-GPU: NCCL on the same buffers):
+ *   sums_dev[10] = x y z e*x e*y e*z e | n_valid | n_total (all SUM) | bounce count of the first valid ray, -1 if none
+ *   radii_dev[3] = max d^2 [mm^2] (MAX) | sum d^2 [mm^2] | sum e*d^2 [m^2] (SUM)                                       */
+OpmStatus opm_rays_spot_sums_async(const OpmRays* rays, const OpmIsometry* frame_or_null, double* sums_dev);
+OpmStatus opm_rays_spot_radii_async(const OpmRays* rays, const OpmIsometry* frame_or_null, const double* sums_dev, double* radii_dev);
 /* Rays::bounce_lvl (rays.rs:183-194): bounce count of the first valid ray (lowest id); 0 for none */
 OpmStatus opm_rays_bounce_lvl(const OpmRays* rays, uint32_t* bounce_lvl);
 /* per-bounce-order tallies: counts[b] valid rays and energy[b] their energy, b < n_orders (last bin = overflow) */
@@ -329,6 +335,15 @@ OpmStatus opm_hitmaps_bounding_box(OpmHitMap* const* maps, int32_t n_maps, int64
 OpmStatus opm_fluence_binning(OpmHitMap* const* maps, int32_t n_maps, int64_t bounce_filter, uint64_t nx, uint64_t ny,
                               const double* ranges, const double* lrtb_override, int32_t accumulate, double* map_dev,
                               double lrtb_out[4]);
+/* Device-chained forms (asynchronous, no host synchronisation).  The map range lives on the device as
+ * range_dev[4] = (-left, right, top, -bottom): one element-wise MAX all-reduce merges the ranges of several GPUs and -inf
+ * is the identity of a GPU without hits.  status_dev accumulates OpmStatus bits (OPM_ERR_BIN_RANGE). */
+OpmStatus opm_hitmaps_bounding_box_async(OpmHitMap* const* maps, int32_t n_maps, int64_t bounce_filter_or_minus1, double* range_dev);
+OpmStatus opm_fluence_binning_async(OpmHitMap* const* maps, int32_t n_maps, int64_t bounce_filter_or_minus1, uint64_t nx, uint64_t ny,
+                                    const double* range_dev, int32_t accumulate, double* map_dev, uint32_t* status_dev);
+/* peak_total_dev[2] = peak fluence (J/m^2), total energy (J) */
+OpmStatus opm_fluence_peak_total_async(OpmContext* ctx, const double* map_dev, uint64_t nx, uint64_t ny, const double* range_dev,
+                                       double* peak_total_dev);
 /* FluenceData::new peak (fluence_data.rs:45-68) and total_energy (:130-141) of a device map */
 OpmStatus opm_fluence_peak_total(OpmContext* ctx, const double* map_dev, uint64_t nx, uint64_t ny, const double lrtb[4],
                                  double* peak, double* total_energy);

@@ -181,7 +181,7 @@ class OpmCriticalFluence(C.Structure):
 SCENE_EXPORTS = [
     "opm_node_desc_init", "opm_scene_create", "opm_scene_destroy", "opm_scene_set_ambient", "opm_scene_add_node",
     "opm_scene_node_count", "opm_scene_reset_data", "opm_scene_raytrace", "opm_scene_output_rays", "opm_scene_node_rays", "opm_scene_node_spot",
-    "opm_scene_node_spot_partial",
+    "opm_scene_node_spot_partial", "opm_scene_node_spot_async",
     "opm_scene_node_fluence", "opm_scene_node_hitmaps", "opm_scene_ghostfocus", "opm_scene_gf_pass_tally",
     "opm_scene_gf_pass_bundles", "opm_scene_node_critical_fluences", "opm_scene_node_peak_fluence",
 ]
@@ -198,9 +198,10 @@ EXPORTS = [
     "opm_rays_invalidate_by_threshold_energy", "opm_rays_filter_by_nr_of_bounces",
     "opm_rays_filter_by_nr_of_refractions", "opm_rays_filter_energy", "opm_rays_split", "opm_rays_refract_paraxial",
     "opm_rays_transform", "opm_trace_sequence", "opm_rays_spot_stats", "opm_rays_spot_partial_sums",
-    "opm_rays_spot_partial_radii", "opm_spot_stats_from_partial", "opm_rays_bounce_lvl", "opm_rays_tally", "opm_hitmap_create",
+    "opm_rays_spot_partial_radii", "opm_spot_stats_from_partial", "opm_rays_spot_sums_async", "opm_rays_spot_radii_async", "opm_rays_bounce_lvl", "opm_rays_tally", "opm_hitmap_create",
     "opm_hitmap_destroy", "opm_hitmap_capacity", "opm_hitmap_len", "opm_hitmap_upload", "opm_hitmap_download",
-    "opm_hitmaps_bounding_box", "opm_fluence_binning", "opm_fluence_peak_total", "opm_measure_fp64_peak", "opm_device_alloc",
+    "opm_hitmaps_bounding_box", "opm_fluence_binning", "opm_fluence_peak_total", "opm_hitmaps_bounding_box_async",
+    "opm_fluence_binning_async", "opm_fluence_peak_total_async", "opm_measure_fp64_peak", "opm_device_alloc",
     "opm_device_free", "opm_device_to_host", "opm_host_to_device", "opm_host_alloc_pinned", "opm_host_free_pinned",
     "opm_source_generate", "opm_source_energy_norm",
 ]
@@ -271,6 +272,11 @@ def lib() -> C.CDLL:
         "opm_rays_spot_partial_sums": (i32, [vp, C.POINTER(OpmIsometry), C.POINTER(OpmSpotPartial)]),
         "opm_rays_spot_partial_radii": (i32, [vp, C.POINTER(OpmIsometry), C.POINTER(OpmSpotPartial)]),
         "opm_spot_stats_from_partial": (None, [C.POINTER(OpmSpotPartial), C.POINTER(OpmSpotStats)]),
+        "opm_rays_spot_sums_async": (i32, [vp, C.POINTER(OpmIsometry), vp]),
+        "opm_rays_spot_radii_async": (i32, [vp, C.POINTER(OpmIsometry), vp, vp]),
+        "opm_hitmaps_bounding_box_async": (i32, [pp, i32, i64, vp]),
+        "opm_fluence_binning_async": (i32, [pp, i32, i64, u64, u64, vp, i32, vp, vp]),
+        "opm_fluence_peak_total_async": (i32, [vp, vp, u64, u64, vp, vp]),
         "opm_rays_bounce_lvl": (i32, [vp, C.POINTER(C.c_uint32)]),
         "opm_rays_tally": (i32, [vp, C.c_uint32, C.POINTER(u64), dp]),
         "opm_hitmap_create": (i32, [vp, u64, pp]),
@@ -305,6 +311,7 @@ def lib() -> C.CDLL:
         "opm_scene_node_rays": (vp, [vp, i32]),
         "opm_scene_node_spot": (i32, [vp, i32, C.POINTER(OpmSpotStats)]),
         "opm_scene_node_spot_partial": (i32, [vp, i32, i32, C.POINTER(OpmSpotPartial)]),
+        "opm_scene_node_spot_async": (i32, [vp, i32, i32, vp, vp]),
         "opm_scene_node_fluence": (i32, [vp, i32, u64, u64, dp, dp, dp, dp]),
         "opm_scene_node_hitmaps": (i32, [vp, i32, i32, pp, i32]),
         "opm_scene_ghostfocus": (i32, [vp, vp, C.POINTER(OpmGhostFocusConfig), i32, C.POINTER(OpmGhostFocusStats)]),

@@ -110,6 +110,13 @@ static OpmStatus fail(OpmStatus s, const char* fmt, ...) {
                                  cudaGetErrorString((cudaError_t)_e), __FILE__, __LINE__);               \
     } while (0)
 
+// device scratch layout: [0,1024) accumulators, [1024,1028) status, [2048,2080) range, [2112,2192) spot sums,
+// [2240,2264) spot radii, [2304,2320) peak/total
+static double* scratch_range(OpmContext* c) { return (double*)(c->d_scratch + 2048); }
+static double* scratch_sums(OpmContext* c) { return (double*)(c->d_scratch + 2112); }
+static double* scratch_radii(OpmContext* c) { return (double*)(c->d_scratch + 2240); }
+static double* scratch_peak(OpmContext* c) { return (double*)(c->d_scratch + 2304); }
+
 // asynchronous host -> device transfer of a small parameter block (bytes <= kPutBytes, multiple of 8) on the main stream
 static OpmStatus dev_put(OpmContext* c, void* dst, const void* src, size_t bytes) {
     if (bytes > OpmContext::kPutBytes || (bytes & 7)) return fail(OPM_ERR_ARG, "dev_put: bad size %zu", bytes);
@@ -981,8 +988,11 @@ extern "C" OpmStatus opm_rays_transform(OpmRays* rays, const OpmIsometry* iso, i
 // statistics
 // ---------------------------------------------------------------------------------------------
 // Two-phase form (multi-GPU: the partial accumulators are all-reduced between the phases):
-// phase 1 = sums over valid rays, phase 2 = radii about the centroids the (global) sums define.
-static OpmStatus spot_phase(OpmRays* r, const OpmIsometry* frame, OpmSpotPartial* p, int phase) {
+// phase 1 = sums over valid rays, phase 2 = radii about the centroids the (global) sums define.  The device-chained
+// forms keep both on the device in reduce-friendly double layouts (see opm_kernels.cu) and never synchronise.
+extern "C" OpmStatus opm_rays_spot_sums_async(const OpmRays* rc, const OpmIsometry* frame, double* sums_dev) {
+    OpmRays* r = const_cast<OpmRays*>(rc);
+    if (!r || !sums_dev) return fail(OPM_ERR_ARG, "NULL argument");
     OpmContext* c = r->ctx;
     CU(cudaSetDevice(c->device));
     OpmStatus s = rays_refresh_len(r);
@@ -991,37 +1001,68 @@ static OpmStatus spot_phase(OpmRays* r, const OpmIsometry* frame, OpmSpotPartial
     memset(&init, 0, sizeof init);
     init.first_key = ~0ull;
     init.max_d2_key = double_to_key(0.0);
-    if (phase == 2) { memcpy(init.sum, p->sum, sizeof init.sum); init.n_valid = p->n_valid; init.n_total = p->n_total; init.first_key = p->first_key; }
     SpotAccum* d_acc = (SpotAccum*)c->d_scratch;
-    SpotAccum* h_acc = (SpotAccum*)c->h_scratch;
-    { OpmStatus ps = dev_put(c, d_acc, &init, sizeof init); if (ps) return ps; }
+    s = dev_put(c, d_acc, &init, sizeof init);
+    if (s) return s;
     DevIso inv;
     memset(&inv, 0, sizeof inv);
     if (frame) to_dev_iso(frame->inv, inv);
-    if (r->len && (phase == 1 || p->n_valid)) {
-        if (phase == 1) KL(k_spot_pass1(r->v, r->len, frame ? 1 : 0, inv, d_acc, c->sms, c->stream));
-        else KL(k_spot_pass2(r->v, r->len, frame ? 1 : 0, inv, d_acc, c->sms, c->stream));
-        c->launches++;
-    }
-    CU(cudaMemcpyAsync(h_acc, d_acc, sizeof init, cudaMemcpyDeviceToHost, c->stream));
-    CU(cudaStreamSynchronize(c->stream));
-    const SpotAccum& a = *h_acc;
-    if (phase == 1) {
-        memset(p, 0, sizeof *p);
-        memcpy(p->sum, a.sum, sizeof p->sum);
-        p->n_valid = a.n_valid; p->n_total = a.n_total; p->first_key = a.first_key;
-    } else {
-        p->max_d2_mm2 = key_to_double(a.max_d2_key); p->sum_d2_mm2 = a.sum_d2; p->sum_ed2 = a.sum_ed2;
-    }
+    if (r->len) { KL(k_spot_pass1(r->v, r->len, frame ? 1 : 0, inv, d_acc, c->sms, c->stream)); c->launches++; }
+    KL(k_spot_sums_store(d_acc, sums_dev, c->stream)); c->launches++;
     return OPM_OK;
+}
+extern "C" OpmStatus opm_rays_spot_radii_async(const OpmRays* rc, const OpmIsometry* frame, const double* sums_dev, double* radii_dev) {
+    OpmRays* r = const_cast<OpmRays*>(rc);
+    if (!r || !sums_dev || !radii_dev) return fail(OPM_ERR_ARG, "NULL argument");
+    OpmContext* c = r->ctx;
+    CU(cudaSetDevice(c->device));
+    OpmStatus s = rays_refresh_len(r);
+    if (s) return s;
+    SpotAccum* d_acc = (SpotAccum*)c->d_scratch;
+    KL(k_spot_sums_load(sums_dev, d_acc, c->stream)); c->launches++;
+    DevIso inv;
+    memset(&inv, 0, sizeof inv);
+    if (frame) to_dev_iso(frame->inv, inv);
+    if (r->len) { KL(k_spot_pass2(r->v, r->len, frame ? 1 : 0, inv, d_acc, c->sms, c->stream)); c->launches++; }
+    KL(k_spot_radii_store(d_acc, radii_dev, c->stream)); c->launches++;
+    return OPM_OK;
+}
+static void partial_from_sums(const double* h, OpmSpotPartial* p) {
+    memset(p, 0, sizeof *p);
+    memcpy(p->sum, h, sizeof p->sum);
+    p->n_valid = (uint64_t)h[7]; p->n_total = (uint64_t)h[8];
+    p->first_key = h[9] < 0.0 ? ~0ull : (uint64_t)h[9];
+}
+static void sums_from_partial(const OpmSpotPartial* p, double* h) {
+    memcpy(h, p->sum, sizeof p->sum);
+    h[7] = (double)p->n_valid; h[8] = (double)p->n_total;
+    h[9] = (p->first_key == ~0ull || p->n_valid == 0) ? -1.0 : (double)(p->first_key & 0xffffffffull);
 }
 extern "C" OpmStatus opm_rays_spot_partial_sums(const OpmRays* rays, const OpmIsometry* frame, OpmSpotPartial* out) {
     if (!rays || !out) return fail(OPM_ERR_ARG, "NULL argument");
-    return spot_phase(const_cast<OpmRays*>(rays), frame, out, 1);
+    OpmContext* c = rays->ctx;
+    OpmStatus s = opm_rays_spot_sums_async(rays, frame, scratch_sums(c));
+    if (s) return s;
+    double* h = (double*)(c->h_scratch + 2112);
+    CU(cudaMemcpyAsync(h, scratch_sums(c), 80, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    partial_from_sums(h, out);
+    return OPM_OK;
 }
 extern "C" OpmStatus opm_rays_spot_partial_radii(const OpmRays* rays, const OpmIsometry* frame, OpmSpotPartial* inout) {
     if (!rays || !inout) return fail(OPM_ERR_ARG, "NULL argument");
-    return spot_phase(const_cast<OpmRays*>(rays), frame, inout, 2);
+    OpmContext* c = rays->ctx;
+    CU(cudaSetDevice(c->device));
+    double enc[10];
+    sums_from_partial(inout, enc);
+    OpmStatus s = dev_put(c, scratch_sums(c), enc, sizeof enc);
+    if (!s) s = opm_rays_spot_radii_async(rays, frame, scratch_sums(c), scratch_radii(c));
+    if (s) return s;
+    double* h = (double*)(c->h_scratch + 2240);
+    CU(cudaMemcpyAsync(h, scratch_radii(c), 24, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    inout->max_d2_mm2 = h[0]; inout->sum_d2_mm2 = h[1]; inout->sum_ed2 = h[2];
+    return OPM_OK;
 }
 extern "C" void opm_spot_stats_from_partial(const OpmSpotPartial* a, OpmSpotStats* out) {
     memset(out, 0, sizeof *out);
@@ -1040,12 +1081,18 @@ extern "C" void opm_spot_stats_from_partial(const OpmSpotPartial* a, OpmSpotStat
     out->bounce_lvl = (uint32_t)(a->first_key & 0xffffffffull);
 }
 extern "C" OpmStatus opm_rays_spot_stats(const OpmRays* rc, const OpmIsometry* frame, OpmSpotStats* out) {
-    OpmRays* r = const_cast<OpmRays*>(rc);
-    if (!r || !out) return fail(OPM_ERR_ARG, "NULL argument");
-    OpmSpotPartial p;
-    OpmStatus s = spot_phase(r, frame, &p, 1);
-    if (!s) s = spot_phase(r, frame, &p, 2);
+    if (!rc || !out) return fail(OPM_ERR_ARG, "NULL argument");
+    OpmContext* c = rc->ctx;
+    OpmStatus s = opm_rays_spot_sums_async(rc, frame, scratch_sums(c));          // both phases chained on the device,
+    if (!s) s = opm_rays_spot_radii_async(rc, frame, scratch_sums(c), scratch_radii(c));  // one synchronisation
     if (s) return s;
+    double* h = (double*)(c->h_scratch + 2112);
+    CU(cudaMemcpyAsync(h, scratch_sums(c), 80 + 48 + 24, cudaMemcpyDeviceToHost, c->stream));  // sums .. radii are contiguous in the scratch
+    CU(cudaStreamSynchronize(c->stream));
+    OpmSpotPartial p;
+    partial_from_sums(h, &p);
+    const double* hr = (const double*)(c->h_scratch + 2240);
+    p.max_d2_mm2 = hr[0]; p.sum_d2_mm2 = hr[1]; p.sum_ed2 = hr[2];
     opm_spot_stats_from_partial(&p, out);
     return OPM_OK;
 }
@@ -1095,11 +1142,15 @@ static OpmStatus check_same_ctx(OpmHitMap* const* maps, int n_maps, OpmContext**
         if (!maps[k] || maps[k]->ctx != *ctx) return fail(OPM_ERR_ARG, "hit maps must share one context");
     return OPM_OK;
 }
-extern "C" OpmStatus opm_hitmaps_bounding_box(OpmHitMap* const* maps, int32_t n_maps, int64_t bounce_filter, double lrtb[4],
-                                              uint64_t* n_hits) {
+// ---- device-chained forms: asynchronous on the context's stream, results stay on the device ------------------
+// scratch layout: [0,1024) accumulators, [1024,1028) status, [2048,2080) range, [2112,2192) spot sums, [2240,2264) radii,
+// [2304,2320) peak/total
+
+extern "C" OpmStatus opm_hitmaps_bounding_box_async(OpmHitMap* const* maps, int32_t n_maps, int64_t bounce_filter, double* range_dev) {
     OpmContext* c;
     OpmStatus s = check_same_ctx(maps, n_maps, &c);
     if (s) return s;
+    if (!range_dev) return fail(OPM_ERR_ARG, "range_dev is NULL");
     CU(cudaSetDevice(c->device));
     BBoxAccum init;
     init.key[0] = ~0ull; init.key[1] = 0; init.key[2] = 0; init.key[3] = ~0ull; init.count = 0;
@@ -1107,12 +1158,59 @@ extern "C" OpmStatus opm_hitmaps_bounding_box(OpmHitMap* const* maps, int32_t n_
     { OpmStatus ps = dev_put(c, d_acc, &init, sizeof init); if (ps) return ps; }
     for (int k = 0; k < n_maps; ++k)
         if (maps[k]->len) { KL(k_hits_bbox(maps[k]->v, maps[k]->len, bounce_filter, d_acc, c->sms, c->stream)); c->launches++; }
-    CU(cudaMemcpyAsync(c->h_scratch, d_acc, sizeof init, cudaMemcpyDeviceToHost, c->stream));
+    KL(k_bbox_finalize(d_acc, range_dev, c->stream)); c->launches++;
+    return OPM_OK;
+}
+extern "C" OpmStatus opm_fluence_binning_async(OpmHitMap* const* maps, int32_t n_maps, int64_t bounce_filter, uint64_t nx, uint64_t ny,
+                                               const double* range_dev, int32_t accumulate, double* map_dev, uint32_t* status_dev) {
+    OpmContext* c;
+    OpmStatus s = check_same_ctx(maps, n_maps, &c);
+    if (s) return s;
+    if (!map_dev || !range_dev || !status_dev || nx == 0 || ny == 0) return fail(OPM_ERR_ARG, "bad map arguments");
+    CU(cudaSetDevice(c->device));
+    if (!accumulate) CU(cudaMemsetAsync(map_dev, 0, nx * ny * sizeof(double), c->stream));
+    for (int k = 0; k < n_maps; ++k)
+        if (maps[k]->len) { KL(k_binning(maps[k]->v, maps[k]->len, bounce_filter, nx, ny, range_dev, map_dev, status_dev, c->sms, c->stream)); c->launches++; }
+    return OPM_OK;
+}
+extern "C" OpmStatus opm_fluence_peak_total_async(OpmContext* c, const double* map_dev, uint64_t nx, uint64_t ny, const double* range_dev,
+                                                  double* peak_total_dev) {
+    if (!c || !map_dev || !range_dev || !peak_total_dev) return fail(OPM_ERR_ARG, "NULL argument");
+    CU(cudaSetDevice(c->device));
+    PeakAccum init;
+    init.peak_key = double_to_key(-INFINITY); init.total = 0.0;
+    PeakAccum* d_acc = (PeakAccum*)c->d_scratch;
+    { OpmStatus ps = dev_put(c, d_acc, &init, sizeof init); if (ps) return ps; }
+    KL(k_peak_total(map_dev, nx, ny, range_dev, d_acc, peak_total_dev, c->sms, c->stream)); c->launches += 2;
+    return OPM_OK;
+}
+
+// ---- synchronous forms (one host synchronisation each) ----------------------------------------------------------
+static OpmStatus range_to_host(OpmContext* c, const double* range_dev, double lrtb[4], const unsigned* status_dev, unsigned* status) {
+    double* h = (double*)(c->h_scratch + 2048);
+    CU(cudaMemcpyAsync(h, range_dev, 32, cudaMemcpyDeviceToHost, c->stream));
+    unsigned* hs = (unsigned*)(c->h_scratch + 1024);
+    if (status_dev) CU(cudaMemcpyAsync(hs, status_dev, 4, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
+    lrtb[0] = -h[0]; lrtb[1] = h[1]; lrtb[2] = h[2]; lrtb[3] = -h[3];
+    if (status) *status = status_dev ? *hs : 0u;
+    return OPM_OK;
+}
+extern "C" OpmStatus opm_hitmaps_bounding_box(OpmHitMap* const* maps, int32_t n_maps, int64_t bounce_filter, double lrtb[4],
+                                              uint64_t* n_hits) {
+    OpmContext* c;
+    OpmStatus s = check_same_ctx(maps, n_maps, &c);
+    if (s) return s;
+    s = opm_hitmaps_bounding_box_async(maps, n_maps, bounce_filter, scratch_range(c));
+    if (s) return s;
+    CU(cudaMemcpyAsync(c->h_scratch, c->d_scratch, sizeof(BBoxAccum), cudaMemcpyDeviceToHost, c->stream));
+    double box[4];
+    s = range_to_host(c, scratch_range(c), box, nullptr, nullptr);
+    if (s) return s;
     const BBoxAccum& a = *(BBoxAccum*)c->h_scratch;
     if (n_hits) *n_hits = a.count;
     if (a.count == 0) return fail(OPM_ERR_EMPTY_HITMAP, "%s", opm_status_string(OPM_ERR_EMPTY_HITMAP));
-    for (int k = 0; k < 4; ++k) lrtb[k] = key_to_double(a.key[k]);
+    memcpy(lrtb, box, sizeof box);
     return OPM_OK;
 }
 extern "C" OpmStatus opm_fluence_binning(OpmHitMap* const* maps, int32_t n_maps, int64_t bounce_filter, uint64_t nx, uint64_t ny,
@@ -1123,49 +1221,40 @@ extern "C" OpmStatus opm_fluence_binning(OpmHitMap* const* maps, int32_t n_maps,
     if (s) return s;
     if (!map_dev || nx == 0 || ny == 0) return fail(OPM_ERR_ARG, "bad map arguments");
     CU(cudaSetDevice(c->device));
-    double l, r, t, b;
-    if (ranges) { l = ranges[0]; r = ranges[1]; t = ranges[2]; b = ranges[3]; }  // rays_hit_map.rs:337-339 (sic)
-    else if (lrtb_override) { l = lrtb_override[0]; r = lrtb_override[1]; t = lrtb_override[2]; b = lrtb_override[3]; }
-    else {
-        double box[4];
-        s = opm_hitmaps_bounding_box(maps, n_maps, bounce_filter, box, nullptr);
-        if (s) return s;
-        l = box[0]; r = box[1]; t = box[2]; b = box[3];
+    const double* given = ranges ? ranges : lrtb_override;  // rays_hit_map.rs:337-339: (left, right, top, bottom) (sic)
+    if (given) {
+        double enc[4] = {-given[0], given[1], given[2], -given[3]};
+        s = dev_put(c, scratch_range(c), enc, sizeof enc);
+    } else {
+        s = opm_hitmaps_bounding_box_async(maps, n_maps, bounce_filter, scratch_range(c));
     }
-    BinParams P;
-    P.nx = nx; P.ny = ny; P.left = l; P.bottom = b;
-    double bin_width = (r - l) / (double)nx;
-    double bin_height = (t - b) / (double)ny;
-    P.bin_area = bin_width * bin_height;
-    P.width_step = (r - l) / (double)(nx - 1);
-    P.height_step = (t - b) / (double)(ny - 1);
-    if (!accumulate) CU(cudaMemsetAsync(map_dev, 0, nx * ny * sizeof(double), c->stream));
+    if (s) return s;
     unsigned* d_status = (unsigned*)(c->d_scratch + 1024);
     CU(cudaMemsetAsync(d_status, 0, 4, c->stream));
-    for (int k = 0; k < n_maps; ++k)
-        if (maps[k]->len) { KL(k_binning(maps[k]->v, maps[k]->len, bounce_filter, P, map_dev, d_status, c->sms, c->stream)); c->launches++; }
-    unsigned* h_status = (unsigned*)(c->h_scratch + 1024);
-    CU(cudaMemcpyAsync(h_status, d_status, 4, cudaMemcpyDeviceToHost, c->stream));
-    CU(cudaStreamSynchronize(c->stream));
-    if (lrtb_out) { lrtb_out[0] = l; lrtb_out[1] = r; lrtb_out[2] = t; lrtb_out[3] = b; }
-    return status_from_bits(*h_status);
+    s = opm_fluence_binning_async(maps, n_maps, bounce_filter, nx, ny, scratch_range(c), accumulate, map_dev, d_status);
+    if (s) return s;
+    double box[4];
+    unsigned status = 0;
+    s = range_to_host(c, scratch_range(c), box, d_status, &status);
+    if (s) return s;
+    if (!given && !(std::isfinite(box[0]) && std::isfinite(box[1]) && std::isfinite(box[2]) && std::isfinite(box[3])))
+        return fail(OPM_ERR_EMPTY_HITMAP, "%s", opm_status_string(OPM_ERR_EMPTY_HITMAP));
+    if (lrtb_out) memcpy(lrtb_out, box, sizeof box);
+    return status_from_bits(status);
 }
 extern "C" OpmStatus opm_fluence_peak_total(OpmContext* c, const double* map_dev, uint64_t nx, uint64_t ny, const double lrtb[4],
                                             double* peak, double* total) {
     if (!c || !map_dev || !lrtb) return fail(OPM_ERR_ARG, "NULL argument");
     CU(cudaSetDevice(c->device));
-    double dx = (lrtb[1] - lrtb[0]) / (double)nx;  // fluence_data.rs:131-133, x_range = left..right, y_range = bottom..top
-    double dy = (lrtb[2] - lrtb[3]) / (double)ny;
-    PeakAccum init;
-    init.peak_key = double_to_key(-INFINITY); init.total = 0.0;
-    PeakAccum* d_acc = (PeakAccum*)c->d_scratch;
-    { OpmStatus ps = dev_put(c, d_acc, &init, sizeof init); if (ps) return ps; }
-    KL(k_peak_total(map_dev, nx * ny, dx * dy, d_acc, c->sms, c->stream)); c->launches++;
-    CU(cudaMemcpyAsync(c->h_scratch, d_acc, sizeof init, cudaMemcpyDeviceToHost, c->stream));
+    double enc[4] = {-lrtb[0], lrtb[1], lrtb[2], -lrtb[3]};
+    OpmStatus s = dev_put(c, scratch_range(c), enc, sizeof enc);
+    if (!s) s = opm_fluence_peak_total_async(c, map_dev, nx, ny, scratch_range(c), scratch_peak(c));
+    if (s) return s;
+    double* h = (double*)(c->h_scratch + 2304);
+    CU(cudaMemcpyAsync(h, scratch_peak(c), 16, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
-    const PeakAccum& a = *(PeakAccum*)c->h_scratch;
-    if (peak) *peak = key_to_double(a.peak_key);
-    if (total) *total = a.total;
+    if (peak) *peak = h[0];
+    if (total) *total = h[1];
     return OPM_OK;
 }
 

@@ -225,6 +225,29 @@ __device__ __forceinline__ unsigned long long f64_to_usize(double v) {
 
 struct BinTaps { unsigned long long base; double w00, w10, w01, w11; bool ok, has_x, has_y; };
 
+__device__ __forceinline__ double dkey_inv(unsigned long long k) {
+    unsigned long long b = (k & 0x8000000000000000ull) ? (k & 0x7fffffffffffffffull) : ~k;
+    return __longlong_as_double((long long)b);
+}
+// Map ranges travel on the device as (-left, right, top, -bottom): one element-wise MAX merges the ranges of several
+// GPUs, and -inf is the identity of a GPU without hits.
+__global__ void bbox_finalize_kernel(const BBoxAccum* acc, double* range) {
+    if (acc->count == 0) { range[0] = range[1] = range[2] = range[3] = -INFINITY; return; }
+    range[0] = -dkey_inv(acc->key[0]); range[1] = dkey_inv(acc->key[1]);
+    range[2] = dkey_inv(acc->key[2]); range[3] = -dkey_inv(acc->key[3]);
+}
+// rays_hit_map.rs:343-350 from a device-resident range (same operations as the host formula)
+__device__ __forceinline__ bool bin_params_from_range(unsigned long long nx, unsigned long long ny, const double* range, BinParams& P) {
+    double l = -range[0], r = range[1], t = range[2], b = -range[3];
+    P.nx = nx; P.ny = ny; P.left = l; P.bottom = b;
+    double bin_width = (r - l) / (double)nx;
+    double bin_height = (t - b) / (double)ny;
+    P.bin_area = bin_width * bin_height;
+    P.width_step = (r - l) / (double)(nx - 1);
+    P.height_step = (t - b) / (double)(ny - 1);
+    return isfinite(l) && isfinite(r) && isfinite(t) && isfinite(b);
+}
+
 // rays_hit_map.rs:352-376 for one hit
 __device__ __forceinline__ BinTaps bin_taps(const BinParams& P, double x, double y, double e, unsigned* status) {
     BinTaps t;
@@ -246,9 +269,12 @@ __device__ __forceinline__ BinTaps bin_taps(const BinParams& P, double x, double
 }
 
 // map fits in shared memory: privatise the whole map per CTA, flush non-zero bins with global atomics
-__global__ void __launch_bounds__(1024) binning_smem_kernel(DevHits H, uint64_t n, long long bounce_filter, BinParams P,
-                                                           double* __restrict__ map, unsigned* status_out) {
+__global__ void __launch_bounds__(1024) binning_smem_kernel(DevHits H, uint64_t n, long long bounce_filter, unsigned long long nx,
+                                                            unsigned long long ny, const double* __restrict__ range,
+                                                            double* __restrict__ map, unsigned* status_out) {
     extern __shared__ double smap[];
+    BinParams P;
+    if (!bin_params_from_range(nx, ny, range, P)) return;  // no hit on any GPU: nothing to bin
     const unsigned long long bins = P.nx * P.ny;
     for (unsigned long long k = threadIdx.x; k < bins; k += blockDim.x) smap[k] = 0.0;
     __syncthreads();
@@ -276,8 +302,11 @@ __global__ void __launch_bounds__(1024) binning_smem_kernel(DevHits H, uint64_t 
 
 // large maps: consecutive lanes that fall into the same bin (a run) are summed with a segmented warp
 // scan first, the run head issues the global f64 atomics
-__global__ void __launch_bounds__(256) binning_global_kernel(DevHits H, uint64_t n, long long bounce_filter, BinParams P,
+__global__ void __launch_bounds__(256) binning_global_kernel(DevHits H, uint64_t n, long long bounce_filter, unsigned long long nx,
+                                                             unsigned long long ny, const double* __restrict__ range,
                                                              double* __restrict__ map, unsigned* status_out) {
+    BinParams P;
+    if (!bin_params_from_range(nx, ny, range, P)) return;
     unsigned status = 0;
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     const uint64_t n_round = (n + 31) / 32 * 32;
@@ -317,7 +346,12 @@ __global__ void __launch_bounds__(256) binning_global_kernel(DevHits H, uint64_t
 }
 
 // fluence_data.rs:45-68 (peak over finite bins) and :130-141 (sum over non-NaN bins)
-__global__ void __launch_bounds__(256) peak_total_kernel(const double* __restrict__ map, uint64_t bins, double area, PeakAccum* acc) {
+__global__ void __launch_bounds__(256) peak_total_kernel(const double* __restrict__ map, uint64_t nx, uint64_t ny,
+                                                         const double* __restrict__ range, PeakAccum* acc) {
+    const uint64_t bins = nx * ny;
+    // fluence_data.rs:131-133, x_range = left..right, y_range = bottom..top
+    const double dx = (range[1] - (-range[0])) / (double)nx, dy = (range[2] - (-range[3])) / (double)ny;
+    const double area = dx * dy;
     double peak = -INFINITY, tot = 0.0;
     for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < bins; i += (uint64_t)gridDim.x * blockDim.x) {
         double v = map[i];
@@ -541,20 +575,56 @@ int k_hits_bbox(DevHits H, uint64_t n, long long bounce_filter, BBoxAccum* acc, 
     hits_bbox_kernel<<<grid_for(n, 256, sms * 4), 256, 0, ST>>>(H, n, bounce_filter, acc);
     return (int)cudaGetLastError();
 }
-int k_binning(DevHits H, uint64_t n, long long bounce_filter, const BinParams& P, double* map, unsigned* status, int sms, void* stream) {
-    size_t bytes = (size_t)(P.nx * P.ny) * sizeof(double);
+int k_bbox_finalize(const BBoxAccum* acc, double* range_dev, void* stream) {
+    bbox_finalize_kernel<<<1, 1, 0, ST>>>(acc, range_dev);
+    return (int)cudaGetLastError();
+}
+int k_binning(DevHits H, uint64_t n, long long bounce_filter, uint64_t nx, uint64_t ny, const double* range_dev, double* map,
+              unsigned* status, int sms, void* stream) {
+    size_t bytes = (size_t)(nx * ny) * sizeof(double);
     if (bytes <= 160 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(binning_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
         if (e != cudaSuccess) return (int)e;
         // the privatised map takes most of an SM's shared memory: one CTA per SM, as many warps as it can hold
-        binning_smem_kernel<<<grid_for(n, 1024, sms), 1024, bytes, ST>>>(H, n, bounce_filter, P, map, status);
+        binning_smem_kernel<<<grid_for(n, 1024, sms), 1024, bytes, ST>>>(H, n, bounce_filter, nx, ny, range_dev, map, status);
     } else {
-        binning_global_kernel<<<grid_for(n, 256, sms * 8), 256, 0, ST>>>(H, n, bounce_filter, P, map, status);
+        binning_global_kernel<<<grid_for(n, 256, sms * 8), 256, 0, ST>>>(H, n, bounce_filter, nx, ny, range_dev, map, status);
     }
     return (int)cudaGetLastError();
 }
-int k_peak_total(const double* map, uint64_t bins, double area, PeakAccum* acc, int sms, void* stream) {
-    peak_total_kernel<<<grid_for(bins, 256, sms * 4), 256, 0, ST>>>(map, bins, area, acc);
+__global__ void peak_finalize_kernel(const PeakAccum* acc, double* out2) { out2[0] = dkey_inv(acc->peak_key); out2[1] = acc->total; }
+int k_peak_total(const double* map, uint64_t nx, uint64_t ny, const double* range_dev, PeakAccum* acc, double* out2_dev, int sms, void* stream) {
+    peak_total_kernel<<<grid_for(nx * ny, 256, sms * 4), 256, 0, ST>>>(map, nx, ny, range_dev, acc);
+    if (out2_dev) peak_finalize_kernel<<<1, 1, 0, ST>>>(acc, out2_dev);
+    return (int)cudaGetLastError();
+}
+// spot statistics: accumulator <-> the reduce-friendly double layouts
+//   sums[10]  = x y z e*x e*y e*z e | n_valid | n_total | bounce count of the first valid ray (-1: none)
+//   radii[3]  = max d^2 [mm^2] | sum d^2 [mm^2] | sum e*d^2 [m^2]
+__global__ void spot_sums_store_kernel(const SpotAccum* acc, double* sums) {
+    for (int j = 0; j < 7; ++j) sums[j] = acc->sum[j];
+    sums[7] = (double)acc->n_valid; sums[8] = (double)acc->n_total;
+    sums[9] = acc->n_valid ? (double)(acc->first_key & 0xffffffffull) : -1.0;
+}
+__global__ void spot_sums_load_kernel(const double* sums, SpotAccum* acc) {
+    for (int j = 0; j < 7; ++j) acc->sum[j] = sums[j];
+    acc->n_valid = (unsigned long long)sums[7]; acc->n_total = (unsigned long long)sums[8];
+    acc->first_key = sums[9] < 0.0 ? ~0ull : (unsigned long long)sums[9];
+    acc->max_d2_key = dkey(0.0); acc->sum_d2 = 0.0; acc->sum_ed2 = 0.0;
+}
+__global__ void spot_radii_store_kernel(const SpotAccum* acc, double* radii) {
+    radii[0] = dkey_inv(acc->max_d2_key); radii[1] = acc->sum_d2; radii[2] = acc->sum_ed2;
+}
+int k_spot_sums_store(const SpotAccum* acc, double* sums_dev, void* stream) {
+    spot_sums_store_kernel<<<1, 1, 0, ST>>>(acc, sums_dev);
+    return (int)cudaGetLastError();
+}
+int k_spot_sums_load(const double* sums_dev, SpotAccum* acc, void* stream) {
+    spot_sums_load_kernel<<<1, 1, 0, ST>>>(sums_dev, acc);
+    return (int)cudaGetLastError();
+}
+int k_spot_radii_store(const SpotAccum* acc, double* radii_dev, void* stream) {
+    spot_radii_store_kernel<<<1, 1, 0, ST>>>(acc, radii_dev);
     return (int)cudaGetLastError();
 }
 int k_source_norm(const SourceParams& S, uint64_t b, uint64_t e, double* out, int sms, void* stream) {

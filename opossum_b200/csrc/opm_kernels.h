@@ -49,8 +49,14 @@ int k_spot_pass2(DevRays R, uint64_t n, int use_frame, DevIso inv, SpotAccum* ac
 int k_bounce_lvl(DevRays R, uint64_t n, unsigned long long* first_key, int sms, void* stream);
 int k_tally(DevRays R, uint64_t n, uint32_t n_orders, unsigned long long* counts, double* energy, int sms, void* stream);
 int k_hits_bbox(DevHits H, uint64_t n, long long bounce_filter, BBoxAccum* acc, int sms, void* stream);
-int k_binning(DevHits H, uint64_t n, long long bounce_filter, const BinParams& P, double* map, unsigned* status, int sms, void* stream);
-int k_peak_total(const double* map, uint64_t bins, double area, PeakAccum* acc, int sms, void* stream);
+// device-resident chaining: the map range lives on the device as (-left, right, top, -bottom), see opm_kernels.cu
+int k_bbox_finalize(const BBoxAccum* acc, double* range_dev, void* stream);
+int k_binning(DevHits H, uint64_t n, long long bounce_filter, uint64_t nx, uint64_t ny, const double* range_dev, double* map,
+              unsigned* status, int sms, void* stream);
+int k_peak_total(const double* map, uint64_t nx, uint64_t ny, const double* range_dev, PeakAccum* acc, double* out2_dev, int sms, void* stream);
+int k_spot_sums_store(const SpotAccum* acc, double* sums_dev, void* stream);
+int k_spot_sums_load(const double* sums_dev, SpotAccum* acc, void* stream);
+int k_spot_radii_store(const SpotAccum* acc, double* radii_dev, void* stream);
 int k_source_norm(const SourceParams& S, uint64_t b, uint64_t e, double* out, int sms, void* stream);
 int k_source_generate(const SourceParams& S, DevRays R, uint64_t pos_begin, uint64_t n_rays, const double* wvl, const double* wgt,
                       int sms, void* stream);

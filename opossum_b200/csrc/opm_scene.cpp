@@ -528,6 +528,13 @@ extern "C" OpmStatus opm_scene_node_spot_partial(OpmScene* sc, int32_t node, int
     return phase == 1 ? opm_rays_spot_partial_sums(n.stored, &n.s[0].eff_iso, inout)
                       : opm_rays_spot_partial_radii(n.stored, &n.s[0].eff_iso, inout);
 }
+extern "C" OpmStatus opm_scene_node_spot_async(OpmScene* sc, int32_t node, int32_t phase, double* sums_dev, double* radii_dev) {
+    if (!sc || !sums_dev || node < 0 || node >= (int)sc->nodes.size() || (phase != 1 && phase != 2)) return OPM_ERR_ARG;
+    Node& n = *sc->nodes[node];
+    if (!n.stored) return OPM_ERR_ARG;
+    return phase == 1 ? opm_rays_spot_sums_async(n.stored, &n.s[0].eff_iso, sums_dev)
+                      : opm_rays_spot_radii_async(n.stored, &n.s[0].eff_iso, sums_dev, radii_dev);
+}
 extern "C" int32_t opm_scene_node_hitmaps(OpmScene* sc, int32_t node, int32_t surface, OpmHitMap** out, int32_t cap) {
     if (!sc || node < 0 || node >= (int)sc->nodes.size() || surface < 0 || surface > 1) return 0;
     auto& hits = sc->nodes[node]->s[surface].hits;

@@ -89,6 +89,129 @@ def reduce_spot_radii(p, device="cpu"):
 
 
 # ---------------------------------------------------------------------------------------------------------------
+# device-chained detector read-out (GPU): every phase stays on the device, the ranks meet in three small collectives and
+# the host synchronises once, when it reads the reports
+# ---------------------------------------------------------------------------------------------------------------
+class DetectorReadout:
+    """Reports of the detectors of a scene whose rays are sharded over the ranks: Binning fluence maps
+    (`FluenceDetector::node_report`, nodes/fluence_detector/mod.rs:91-135) and spot-diagram statistics
+    (`SpotDiagram::node_report`, nodes/spot_diagram.rs:101-163).
+
+        phase A  per detector: bounding box of its hits -> range (-l, r, t, -b); spot sums                 [local, async]
+        gather 1 all_gather of (ranges | sums): element-wise max of the ranges, sum of the sums               [1 collective]
+        phase B  per detector: Binning into the common grid; spot radii about the global centroids           [local, async]
+        reduce   all_reduce(sum) of all maps in one buffer; all_gather of the radius accumulators            [2 collectives]
+        phase C  peak / total of every (global) map                                                          [local, async]
+        read     one device->host copy of the scalars (and the maps if asked), one synchronisation
+    """
+
+    def __init__(self, ctx, scene, fluence_nodes, spot_nodes, nx: int, ny: int, device):
+        import ctypes as C
+
+        from . import _ffi as F
+        self.C, self.F = C, F
+        self.ctx, self.scene, self.nx, self.ny = ctx, scene, nx, ny
+        self.fl, self.sp = list(fluence_nodes), list(spot_nodes)
+        nf, ns = len(self.fl), len(self.sp)
+        self.nA = 4 * nf + 10 * ns                       # ranges | spot sums
+        self.nB = 3 * ns                                 # spot radii
+        self.buf = torch.zeros(self.nA + self.nB + 2 * nf, dtype=torch.float64, device=device)
+        self.maps = torch.zeros((max(nf, 1), nx * ny), dtype=torch.float64, device=device)
+        self.status = torch.zeros(max(nf, 1), dtype=torch.int32, device=device)
+        self.h_buf = torch.zeros(self.buf.numel(), dtype=torch.float64).pin_memory()
+        self.h_status = torch.zeros(self.status.numel(), dtype=torch.int32).pin_memory()
+        self.h_maps = torch.zeros_like(self.maps, device="cpu").pin_memory()
+        w = world()[1]
+        self.gA = torch.zeros((w, self.nA), dtype=torch.float64, device=device) if w > 1 else None
+        self.gB = torch.zeros((w, max(self.nB, 1)), dtype=torch.float64, device=device) if w > 1 else None
+
+    def _ptr(self, t: torch.Tensor, offset: int = 0) -> int:
+        return t.data_ptr() + 8 * offset
+
+    def _hit_arrays(self, node):
+        hm = self.scene.node_hitmaps(node, 0)
+        return (self.C.c_void_p * len(hm))(*[h.h for h in hm]), len(hm)
+
+    def run(self, download_maps: bool = False) -> dict:
+        L, C, F = self.F.lib(), self.C, self.F
+        from .api import _check
+        rank, w = world()
+        nf, ns, nx, ny = len(self.fl), len(self.sp), self.nx, self.ny
+        hits = [self._hit_arrays(n) for n in self.fl]
+        # ---- phase A
+        for j, (arr, n) in enumerate(hits):
+            _check(L.opm_hitmaps_bounding_box_async(arr, n, -1, C.c_void_p(self._ptr(self.buf, 4 * j))))
+        for k, node in enumerate(self.sp):
+            _check(L.opm_scene_node_spot_async(self.scene.h, node, 1, C.c_void_p(self._ptr(self.buf, 4 * nf + 10 * k)), None))
+        if w > 1:
+            A = self.buf[: self.nA]
+            dist.all_gather_into_tensor(self.gA.view(-1), A)
+            if nf:
+                A[: 4 * nf] = self.gA[:, : 4 * nf].max(dim=0).values
+            for k in range(ns):
+                o = 4 * nf + 10 * k
+                A[o: o + 9] = self.gA[:, o: o + 9].sum(dim=0)
+                # bounce level: the first valid ray of the lowest rank that has one (shards are ordered by rank)
+                has = self.gA[:, o + 7] > 0
+                first = torch.argmax(has.to(torch.int32))
+                A[o + 9] = torch.where(has.any(), self.gA[first, o + 9], torch.full_like(A[o + 9], -1.0))
+        # ---- phase B
+        self.status.zero_()
+        for j, (arr, n) in enumerate(hits):
+            _check(L.opm_fluence_binning_async(arr, n, -1, nx, ny, C.c_void_p(self._ptr(self.buf, 4 * j)), 0,
+                                               C.c_void_p(self.maps[j].data_ptr()), C.c_void_p(self.status.data_ptr() + 4 * j)))
+        for k, node in enumerate(self.sp):
+            _check(L.opm_scene_node_spot_async(self.scene.h, node, 2, C.c_void_p(self._ptr(self.buf, 4 * nf + 10 * k)),
+                                               C.c_void_p(self._ptr(self.buf, self.nA + 3 * k))))
+        if w > 1:
+            if nf:
+                dist.all_reduce(self.maps, op=dist.ReduceOp.SUM)
+            if ns:
+                B = self.buf[self.nA: self.nA + self.nB]
+                dist.all_gather_into_tensor(self.gB.view(-1), B)
+                g = self.gB.view(w, ns, 3)
+                B.view(ns, 3)[:, 0] = g[:, :, 0].max(dim=0).values
+                B.view(ns, 3)[:, 1:] = g[:, :, 1:].sum(dim=0)
+        # ---- phase C
+        for j in range(nf):
+            _check(L.opm_fluence_peak_total_async(self.ctx.h, C.c_void_p(self.maps[j].data_ptr()), nx, ny,
+                                                  C.c_void_p(self._ptr(self.buf, 4 * j)),
+                                                  C.c_void_p(self._ptr(self.buf, self.nA + self.nB + 2 * j))))
+        # ---- read
+        self.h_buf.copy_(self.buf, non_blocking=True)
+        self.h_status.copy_(self.status, non_blocking=True)
+        if download_maps and nf:
+            self.h_maps.copy_(self.maps, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        h = self.h_buf
+        out = {}
+        for j, node in enumerate(self.fl):
+            r = h[4 * j: 4 * j + 4].tolist()
+            lrtb = (-r[0], r[1], r[2], -r[3])
+            if not all(math.isfinite(v) for v in lrtb):
+                raise ValueError("could not calculate bounding box")
+            st = int(self.h_status[j])
+            if st:
+                raise RuntimeError(f"fluence binning raised status bits {st:#x}")
+            pk = h[self.nA + self.nB + 2 * j: self.nA + self.nB + 2 * j + 2].tolist()
+            out[node] = {"lrtb": lrtb, "peak": pk[0], "total_energy": pk[1],
+                         "map": self.h_maps[j].numpy().reshape(nx, ny).T.copy() if download_maps else None}
+        for k, node in enumerate(self.sp):
+            s = h[4 * nf + 10 * k: 4 * nf + 10 * k + 10].tolist()
+            rr = h[self.nA + 3 * k: self.nA + 3 * k + 3].tolist()
+            p = F.OpmSpotPartial()
+            for i in range(7):
+                p.sum[i] = s[i]
+            p.n_valid, p.n_total = int(s[7]), int(s[8])
+            p.first_key = 0xFFFFFFFFFFFFFFFF if s[9] < 0 else int(s[9])
+            p.max_d2_mm2, p.sum_d2_mm2, p.sum_ed2 = rr
+            st = F.OpmSpotStats()
+            L.opm_spot_stats_from_partial(C.byref(p), C.byref(st))
+            out[node] = st
+        return out
+
+
+# ---------------------------------------------------------------------------------------------------------------
 # drivers over the product API (GPU): used by bench.py and by applications that shard a scene over the GPUs of a box
 # ---------------------------------------------------------------------------------------------------------------
 def fluence_map(ctx, hit_maps, nx: int, ny: int, map_tensor: torch.Tensor):

@@ -228,3 +228,31 @@ def test_sharded_trace_equals_whole_source(ctx):
     for f in ("total_energy", "beam_radius_geo", "beam_radius_rms", "energy_beam_radius_rms"):
         assert getattr(got, f) == pytest.approx(getattr(ref_spot, f), rel=1e-12), f
     assert np.allclose(got.energy_centroid[:], ref_spot.energy_centroid[:], rtol=1e-9, atol=1e-15)
+
+
+def test_device_chained_readout_equals_stepwise_reports(ctx):
+    """sharding.DetectorReadout (device-chained: bbox -> Binning -> peak/total and spot sums -> radii without host round
+    trips) must give the same reports as the stepwise calls, which are checked against the oracle above."""
+    import torch
+
+    from opossum_b200 import sharding
+    psc = scenes.to_product(ctx, scenes.c2_laser_chain())
+    rays = scenes.source_to_product(scenes.c2_source(25000)).generate(ctx)
+    psc.raytrace(rays)
+    ref = {n: psc.node_fluence(n, 100, 83) for n in (9, 10)}
+    ref_spot = psc.node_spot(8)
+    ro = sharding.DetectorReadout(ctx, psc, (9, 10), (8,), 100, 83, torch.device("cuda", 0))
+    for _ in range(2):  # buffers are reused across calls
+        torch.cuda.synchronize()
+        got = ro.run(download_maps=True)
+        ctx.synchronize()
+        for n in (9, 10):
+            assert got[n]["lrtb"] == ref[n].lrtb
+            assert np.allclose(got[n]["map"], ref[n].map, rtol=1e-12, atol=1e-12 * ref[n].peak)
+            assert got[n]["peak"] == pytest.approx(ref[n].peak, rel=1e-12)
+            assert got[n]["total_energy"] == pytest.approx(ref[n].total_energy, rel=1e-12)
+        s = got[8]
+        assert s.n_valid == ref_spot.n_valid and s.n_total == ref_spot.n_total and s.bounce_lvl == ref_spot.bounce_lvl
+        for f in ("total_energy", "beam_radius_geo", "beam_radius_rms", "energy_beam_radius_rms"):
+            assert getattr(s, f) == pytest.approx(getattr(ref_spot, f), rel=1e-12), f
+        assert np.allclose(s.energy_centroid[:], ref_spot.energy_centroid[:], rtol=1e-12, atol=1e-18)
