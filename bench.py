@@ -203,8 +203,11 @@ def run_product(args):
         ctx = ob.Context(local, stream=stream.cuda_stream)
         scene = scenes.to_product(ctx, scenes.c2_laser_chain())
         sd = scenes.source_to_product(scenes.c2_source(n * world))
-        begin, end = sharding.shard_range(n * world, rank, world)
-        src = sd.generate(ctx, begin, end)  # this rank's shard of the global source, generated on the device
+        # this rank's shard of the global source, generated on the device: interleaved indices {rank, rank + G, ...} so that
+        # every GPU sees the same mix of clipped and surviving rays (a contiguous split leaves the outer, clipped part of the
+        # Fibonacci index range to the last rank)
+        first, count, stride = sharding.shard_strided(n * world, rank, world)
+        src = sd.generate_strided(ctx, first, count, stride)
 
 
         readout = sharding.DetectorReadout(ctx, scene, (9, 10), (8,), MAP_NX, MAP_NY, dev)
@@ -330,7 +333,7 @@ def run_product(args):
             "metric": METRIC, "value": inter_total * args.steps / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": WORKLOAD_NAME, "rays_per_gpu": n, "rays_total": n * world, "surfaces_per_ray": 13,
+            "config": {"workload": WORKLOAD_NAME, "rays_per_gpu": n, "rays_total": n * world, "sharding": "source index i -> rank i mod N (interleaved)", "surfaces_per_ray": 13,
                        "interactions_per_step": int(inter_total), "fluence_map": f"{MAP_NX}x{MAP_NY} x2 (Binning, data-dependent range)",
                        "l2": f"inputs larger than L2: {n * RAY_BYTES / 1e6:.0f} MB source bundle per GPU vs 126 MB",
                        "collective": "3 NCCL collectives per step: all_gather(map ranges | spot sums), all_reduce(sum) of the fluence maps, all_gather(spot radii)" if world > 1 else "none (1 GPU)"},

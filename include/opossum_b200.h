@@ -296,7 +296,7 @@ OpmStatus opm_rays_spot_stats(const OpmRays* rays, const OpmIsometry* frame_or_n
 typedef struct {
     double sum[7];              /* x y z e*x e*y e*z e over valid rays */
     uint64_t n_valid, n_total;
-    uint64_t first_key;         /* bounce count of the first valid ray (lowest id); ~0 if there is none */
+    uint64_t first_key;         /* (id << 32 | bounces) of the first valid ray (lowest id); ~0 if there is none */
     double max_d2_mm2;          /* max squared distance [mm^2] from the (unweighted) centroid */
     double sum_d2_mm2;          /* sum of squared distances [mm^2] from the centroid */
     double sum_ed2;             /* sum of e * squared distance [m^2] from the energy-weighted centroid */
@@ -306,7 +306,8 @@ OpmStatus opm_rays_spot_partial_radii(const OpmRays* rays, const OpmIsometry* fr
 void opm_spot_stats_from_partial(const OpmSpotPartial* reduced, OpmSpotStats* out);
 /* Device-chained forms of the two phases: asynchronous on the context's stream, no host synchronisation; the
  * accumulators stay on the device in layouts an all-reduce can combine directly (multi-GPU: NCCL on the same buffers):
- *   sums_dev[10] = x y z e*x e*y e*z e | n_valid | n_total (all SUM) | bounce count of the first valid ray, -1 if none
+ *   sums_dev[11] = x y z e*x e*y e*z e | n_valid | n_total (all SUM) | bounce count and id of the first valid ray (-1: none;
+ *                  across GPUs: the entry with the smallest id, ties to the lowest rank)
  *   radii_dev[3] = max d^2 [mm^2] (MAX) | sum d^2 [mm^2] | sum e*d^2 [m^2] (SUM)                                       */
 OpmStatus opm_rays_spot_sums_async(const OpmRays* rays, const OpmIsometry* frame_or_null, double* sums_dev);
 OpmStatus opm_rays_spot_radii_async(const OpmRays* rays, const OpmIsometry* frame_or_null, const double* sums_dev, double* radii_dev);
@@ -377,6 +378,9 @@ typedef struct {
 } OpmSourceDesc;
 /* generates positions [pos_begin, pos_end) x all wavelengths into `rays` (ids = global ray index mod 2^32) */
 OpmStatus opm_source_generate(OpmRays* rays, const OpmSourceDesc* desc, uint64_t pos_begin, uint64_t pos_end);
+/* positions first_pos, first_pos + stride, ... (n_pos of them): a load-balanced shard of the source for rank g of G is
+ * (first_pos = g, stride = G) -- rays are independent, so any partition of the source index set is a valid sharding */
+OpmStatus opm_source_generate_strided(OpmRays* rays, const OpmSourceDesc* desc, uint64_t first_pos, uint64_t n_pos, uint64_t stride);
 /* sum of unnormalised General2DGaussian weights over [pos_begin,pos_end) (for multi-GPU: allreduce, then set energy_norm) */
 OpmStatus opm_source_energy_norm(OpmContext* ctx, const OpmSourceDesc* desc, uint64_t pos_begin, uint64_t pos_end,
                                  double* partial_sum);

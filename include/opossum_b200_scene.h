@@ -103,7 +103,7 @@ OpmRays* opm_scene_node_rays(OpmScene* scene, int32_t node);           /* bundle
 OpmStatus opm_scene_node_spot(OpmScene* scene, int32_t node, OpmSpotStats* out); /* nodes/spot_diagram.rs:101-163 */
 /* the same report in two phases for a bundle sharded over GPUs (see OpmSpotPartial): phase 1 = sums, phase 2 = radii */
 OpmStatus opm_scene_node_spot_partial(OpmScene* scene, int32_t node, int32_t phase, OpmSpotPartial* inout);
-/* device-chained form: phase 1 writes sums_dev[10], phase 2 reads sums_dev and writes radii_dev[3] (opm_rays_spot_*_async) */
+/* device-chained form: phase 1 writes sums_dev[11], phase 2 reads sums_dev and writes radii_dev[3] (opm_rays_spot_*_async) */
 OpmStatus opm_scene_node_spot_async(OpmScene* scene, int32_t node, int32_t phase, double* sums_dev, double* radii_dev);
 /* nodes/fluence_detector/mod.rs:91-135 with FluenceEstimator::Binning: map_host (nx*ny, column-major ny x nx) may be NULL */
 OpmStatus opm_scene_node_fluence(OpmScene* scene, int32_t node, uint64_t nx, uint64_t ny, double* map_host, double lrtb[4],

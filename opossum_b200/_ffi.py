@@ -203,7 +203,7 @@ EXPORTS = [
     "opm_hitmaps_bounding_box", "opm_fluence_binning", "opm_fluence_peak_total", "opm_hitmaps_bounding_box_async",
     "opm_fluence_binning_async", "opm_fluence_peak_total_async", "opm_measure_fp64_peak", "opm_device_alloc",
     "opm_device_free", "opm_device_to_host", "opm_host_to_device", "opm_host_alloc_pinned", "opm_host_free_pinned",
-    "opm_source_generate", "opm_source_energy_norm",
+    "opm_source_generate", "opm_source_generate_strided", "opm_source_energy_norm",
 ]
 
 _lib = None
@@ -296,6 +296,7 @@ def lib() -> C.CDLL:
         "opm_host_alloc_pinned": (i32, [u64, pp]),
         "opm_host_free_pinned": (None, [vp]),
         "opm_source_generate": (i32, [vp, C.POINTER(OpmSourceDesc), u64, u64]),
+        "opm_source_generate_strided": (i32, [vp, C.POINTER(OpmSourceDesc), u64, u64, u64]),
         "opm_source_energy_norm": (i32, [vp, C.POINTER(OpmSourceDesc), u64, u64, dp]),
     }
     sig.update({

@@ -703,6 +703,12 @@ class SourceDesc:
                                               C.byref(out)))
         return out.value
 
+    def generate_strided(self, ctx: Context, first: int, count: int, stride: int, rays: Rays | None = None) -> Rays:
+        """positions first, first + stride, ...: the load-balanced shard (first = rank, stride = world size)"""
+        r = rays if rays is not None else Rays(ctx, max(count * self.c.n_wavelengths, 1))
+        _check(F.lib().opm_source_generate_strided(r.h, C.byref(self.c), first, count, stride))
+        return r
+
     def generate(self, ctx: Context, begin=0, end=None, rays: Rays | None = None) -> Rays:
         end = end if end is not None else self.c.n_positions
         r = rays if rays is not None else Rays(ctx, max((end - begin) * self.c.n_wavelengths, 1))

@@ -1031,12 +1031,14 @@ static void partial_from_sums(const double* h, OpmSpotPartial* p) {
     memset(p, 0, sizeof *p);
     memcpy(p->sum, h, sizeof p->sum);
     p->n_valid = (uint64_t)h[7]; p->n_total = (uint64_t)h[8];
-    p->first_key = h[9] < 0.0 ? ~0ull : (uint64_t)h[9];
+    p->first_key = h[9] < 0.0 ? ~0ull : (((uint64_t)h[10] << 32) | (uint64_t)h[9]);
 }
 static void sums_from_partial(const OpmSpotPartial* p, double* h) {
     memcpy(h, p->sum, sizeof p->sum);
     h[7] = (double)p->n_valid; h[8] = (double)p->n_total;
-    h[9] = (p->first_key == ~0ull || p->n_valid == 0) ? -1.0 : (double)(p->first_key & 0xffffffffull);
+    const bool none = p->first_key == ~0ull || p->n_valid == 0;
+    h[9] = none ? -1.0 : (double)(p->first_key & 0xffffffffull);
+    h[10] = none ? -1.0 : (double)(p->first_key >> 32);
 }
 extern "C" OpmStatus opm_rays_spot_partial_sums(const OpmRays* rays, const OpmIsometry* frame, OpmSpotPartial* out) {
     if (!rays || !out) return fail(OPM_ERR_ARG, "NULL argument");
@@ -1044,7 +1046,7 @@ extern "C" OpmStatus opm_rays_spot_partial_sums(const OpmRays* rays, const OpmIs
     OpmStatus s = opm_rays_spot_sums_async(rays, frame, scratch_sums(c));
     if (s) return s;
     double* h = (double*)(c->h_scratch + 2112);
-    CU(cudaMemcpyAsync(h, scratch_sums(c), 80, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(h, scratch_sums(c), 88, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
     partial_from_sums(h, out);
     return OPM_OK;
@@ -1053,7 +1055,7 @@ extern "C" OpmStatus opm_rays_spot_partial_radii(const OpmRays* rays, const OpmI
     if (!rays || !inout) return fail(OPM_ERR_ARG, "NULL argument");
     OpmContext* c = rays->ctx;
     CU(cudaSetDevice(c->device));
-    double enc[10];
+    double enc[11];
     sums_from_partial(inout, enc);
     OpmStatus s = dev_put(c, scratch_sums(c), enc, sizeof enc);
     if (!s) s = opm_rays_spot_radii_async(rays, frame, scratch_sums(c), scratch_radii(c));
@@ -1356,13 +1358,23 @@ extern "C" OpmStatus opm_source_energy_norm(OpmContext* c, const OpmSourceDesc* 
     *partial = *(double*)c->h_scratch;
     return OPM_OK;
 }
+static OpmStatus source_generate(OpmRays* rays, const OpmSourceDesc* desc, uint64_t pos_begin, uint64_t n_pos, uint64_t stride);
 extern "C" OpmStatus opm_source_generate(OpmRays* rays, const OpmSourceDesc* desc, uint64_t pos_begin, uint64_t pos_end) {
+    if (pos_begin > pos_end) return fail(OPM_ERR_ARG, "position range out of bounds");
+    return source_generate(rays, desc, pos_begin, pos_end - pos_begin, 1);
+}
+extern "C" OpmStatus opm_source_generate_strided(OpmRays* rays, const OpmSourceDesc* desc, uint64_t first_pos, uint64_t n_pos,
+                                                 uint64_t stride) {
+    if (stride == 0) return fail(OPM_ERR_ARG, "stride must be >= 1");
+    return source_generate(rays, desc, first_pos, n_pos, stride);
+}
+static OpmStatus source_generate(OpmRays* rays, const OpmSourceDesc* desc, uint64_t pos_begin, uint64_t n_pos, uint64_t stride) {
     if (!rays) return fail(OPM_ERR_ARG, "rays is NULL");
     OpmContext* c = rays->ctx;
     SourceParams S;
     OpmStatus s = source_params(desc, S);
     if (s) return s;
-    if (pos_end > desc->n_positions || pos_begin > pos_end) return fail(OPM_ERR_ARG, "position range out of bounds");
+    if (n_pos && pos_begin + (n_pos - 1) * stride >= desc->n_positions) return fail(OPM_ERR_ARG, "position range out of bounds");
     CU(cudaSetDevice(c->device));
     if (S.energy_dist == OPM_EDIST_GENERAL_GAUSSIAN && !(S.energy_norm > 0.0)) {
         double norm = 0.0;
@@ -1370,7 +1382,8 @@ extern "C" OpmStatus opm_source_generate(OpmRays* rays, const OpmSourceDesc* des
         if (s) return s;
         S.energy_norm = norm;
     }
-    uint64_t n_rays = (pos_end - pos_begin) * S.n_wavelengths;
+    rays->pending = false;
+    uint64_t n_rays = n_pos * S.n_wavelengths;
     s = opm_rays_reserve(rays, n_rays);
     if (s) return s;
     double one = 1.0, *d_w = nullptr;
@@ -1381,7 +1394,7 @@ extern "C" OpmStatus opm_source_generate(OpmRays* rays, const OpmSourceDesc* des
     CU(cudaMemcpyAsync(d_w, hw, (size_t)S.n_wavelengths * 8, cudaMemcpyHostToDevice, c->stream));
     if (hg) CU(cudaMemcpyAsync(d_w + S.n_wavelengths, hg, (size_t)S.n_wavelengths * 8, cudaMemcpyHostToDevice, c->stream));
     else CU(cudaMemcpyAsync(d_w + S.n_wavelengths, &one, 8, cudaMemcpyHostToDevice, c->stream));
-    if (n_rays) { KL(k_source_generate(S, rays->v, pos_begin, n_rays, d_w, d_w + S.n_wavelengths, c->sms, c->stream)); c->launches++; }
+    if (n_rays) { KL(k_source_generate(S, rays->v, pos_begin, stride, n_rays, d_w, d_w + S.n_wavelengths, c->sms, c->stream)); c->launches++; }
     cudaError_t e = cudaStreamSynchronize(c->stream);
     cudaFree(d_w);
     if (e != cudaSuccess) return fail(OPM_ERR_CUDA, "source generation failed: %s", cudaGetErrorString(e));

@@ -409,11 +409,12 @@ __global__ void __launch_bounds__(256) source_norm_kernel(SourceParams S, uint64
     if ((threadIdx.x & 31) == 0) atomicAdd(out, s);
 }
 // rays.rs:264-297 (position-major, wavelength-minor) + nodes/source.rs:205-210 (source isometry)
-__global__ void __launch_bounds__(256) source_generate_kernel(SourceParams S, DevRays R, uint64_t pos_begin, uint64_t n_rays,
-                                                              const double* __restrict__ wvl, const double* __restrict__ wgt) {
+__global__ void __launch_bounds__(256) source_generate_kernel(SourceParams S, DevRays R, uint64_t pos_begin, uint64_t pos_stride,
+                                                              uint64_t n_rays, const double* __restrict__ wvl,
+                                                              const double* __restrict__ wgt) {
     const V3 zdir = iso_vector(S.iso, v3(0.0, 0.0, 1.0));
     for (uint64_t k = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; k < n_rays; k += (uint64_t)gridDim.x * blockDim.x) {
-        uint64_t ip = pos_begin + k / S.n_wavelengths;
+        uint64_t ip = pos_begin + (k / S.n_wavelengths) * pos_stride;
         uint32_t iw = (uint32_t)(k % S.n_wavelengths);
         double x, y;
         source_position(S, ip, x, y);
@@ -599,17 +600,18 @@ int k_peak_total(const double* map, uint64_t nx, uint64_t ny, const double* rang
     return (int)cudaGetLastError();
 }
 // spot statistics: accumulator <-> the reduce-friendly double layouts
-//   sums[10]  = x y z e*x e*y e*z e | n_valid | n_total | bounce count of the first valid ray (-1: none)
+//   sums[11]  = x y z e*x e*y e*z e | n_valid | n_total | bounce count and id of the first valid ray (-1: none)
 //   radii[3]  = max d^2 [mm^2] | sum d^2 [mm^2] | sum e*d^2 [m^2]
 __global__ void spot_sums_store_kernel(const SpotAccum* acc, double* sums) {
     for (int j = 0; j < 7; ++j) sums[j] = acc->sum[j];
     sums[7] = (double)acc->n_valid; sums[8] = (double)acc->n_total;
     sums[9] = acc->n_valid ? (double)(acc->first_key & 0xffffffffull) : -1.0;
+    sums[10] = acc->n_valid ? (double)(acc->first_key >> 32) : -1.0;
 }
 __global__ void spot_sums_load_kernel(const double* sums, SpotAccum* acc) {
     for (int j = 0; j < 7; ++j) acc->sum[j] = sums[j];
     acc->n_valid = (unsigned long long)sums[7]; acc->n_total = (unsigned long long)sums[8];
-    acc->first_key = sums[9] < 0.0 ? ~0ull : (unsigned long long)sums[9];
+    acc->first_key = sums[9] < 0.0 ? ~0ull : (((unsigned long long)sums[10] << 32) | (unsigned long long)sums[9]);
     acc->max_d2_key = dkey(0.0); acc->sum_d2 = 0.0; acc->sum_ed2 = 0.0;
 }
 __global__ void spot_radii_store_kernel(const SpotAccum* acc, double* radii) {
@@ -631,9 +633,9 @@ int k_source_norm(const SourceParams& S, uint64_t b, uint64_t e, double* out, in
     source_norm_kernel<<<grid_for(e - b, 256, sms * 4), 256, 0, ST>>>(S, b, e, out);
     return (int)cudaGetLastError();
 }
-int k_source_generate(const SourceParams& S, DevRays R, uint64_t pos_begin, uint64_t n_rays, const double* wvl, const double* wgt,
-                      int sms, void* stream) {
-    source_generate_kernel<<<grid_for(n_rays, 256, sms * 8), 256, 0, ST>>>(S, R, pos_begin, n_rays, wvl, wgt);
+int k_source_generate(const SourceParams& S, DevRays R, uint64_t pos_begin, uint64_t pos_stride, uint64_t n_rays, const double* wvl,
+                      const double* wgt, int sms, void* stream) {
+    source_generate_kernel<<<grid_for(n_rays, 256, sms * 8), 256, 0, ST>>>(S, R, pos_begin, pos_stride, n_rays, wvl, wgt);
     return (int)cudaGetLastError();
 }
 int k_expand_collimated(const double* xyz, const double* e_pos, const double* wvl, const double* wgt, uint32_t n_wvl, DevRays R,

@@ -58,8 +58,8 @@ int k_spot_sums_store(const SpotAccum* acc, double* sums_dev, void* stream);
 int k_spot_sums_load(const double* sums_dev, SpotAccum* acc, void* stream);
 int k_spot_radii_store(const SpotAccum* acc, double* radii_dev, void* stream);
 int k_source_norm(const SourceParams& S, uint64_t b, uint64_t e, double* out, int sms, void* stream);
-int k_source_generate(const SourceParams& S, DevRays R, uint64_t pos_begin, uint64_t n_rays, const double* wvl, const double* wgt,
-                      int sms, void* stream);
+int k_source_generate(const SourceParams& S, DevRays R, uint64_t pos_begin, uint64_t pos_stride, uint64_t n_rays, const double* wvl,
+                      const double* wgt, int sms, void* stream);
 int k_expand_collimated(const double* xyz, const double* e_pos, const double* wvl, const double* wgt, uint32_t n_wvl, DevRays R,
                         uint64_t n_rays, int sms, void* stream);
 int k_compact(DevRays S, DevRays D, uint64_t n, unsigned* counts, unsigned long long* offsets, unsigned long long* total, void* stream);

@@ -25,6 +25,15 @@ def world() -> tuple[int, int]:
     return 0, 1
 
 
+def shard_strided(n_positions: int, rank: int, world_size: int) -> tuple[int, int, int]:
+    """(first, count, stride) of the interleaved shard {rank, rank + G, rank + 2G, ...}: every rank sees the same mix of
+    rays (load balance when apertures clip a contiguous part of the index range); rays are independent, so any
+    partition of the source index set is a valid sharding (SURVEY 8e uses contiguous ranges)"""
+    if world_size < 1 or not (0 <= rank < world_size):
+        raise ValueError(f"rank {rank} outside world of {world_size}")
+    return rank, (n_positions - rank + world_size - 1) // world_size, world_size
+
+
 def shard_range(n_positions: int, rank: int, world_size: int) -> tuple[int, int]:
     """contiguous index range [g*N/G, (g+1)*N/G) of the source POSITIONS owned by `rank`"""
     if world_size < 1 or not (0 <= rank < world_size):
@@ -113,7 +122,7 @@ class DetectorReadout:
         self.ctx, self.scene, self.nx, self.ny = ctx, scene, nx, ny
         self.fl, self.sp = list(fluence_nodes), list(spot_nodes)
         nf, ns = len(self.fl), len(self.sp)
-        self.nA = 4 * nf + 10 * ns                       # ranges | spot sums
+        self.nA = 4 * nf + 11 * ns                       # ranges | spot sums
         self.nB = 3 * ns                                 # spot radii
         self.buf = torch.zeros(self.nA + self.nB + 2 * nf, dtype=torch.float64, device=device)
         self.maps = torch.zeros((max(nf, 1), nx * ny), dtype=torch.float64, device=device)
@@ -142,26 +151,26 @@ class DetectorReadout:
         for j, (arr, n) in enumerate(hits):
             _check(L.opm_hitmaps_bounding_box_async(arr, n, -1, C.c_void_p(self._ptr(self.buf, 4 * j))))
         for k, node in enumerate(self.sp):
-            _check(L.opm_scene_node_spot_async(self.scene.h, node, 1, C.c_void_p(self._ptr(self.buf, 4 * nf + 10 * k)), None))
+            _check(L.opm_scene_node_spot_async(self.scene.h, node, 1, C.c_void_p(self._ptr(self.buf, 4 * nf + 11 * k)), None))
         if w > 1:
             A = self.buf[: self.nA]
             dist.all_gather_into_tensor(self.gA.view(-1), A)
             if nf:
                 A[: 4 * nf] = self.gA[:, : 4 * nf].max(dim=0).values
             for k in range(ns):
-                o = 4 * nf + 10 * k
+                o = 4 * nf + 11 * k
                 A[o: o + 9] = self.gA[:, o: o + 9].sum(dim=0)
-                # bounce level: the first valid ray of the lowest rank that has one (shards are ordered by rank)
-                has = self.gA[:, o + 7] > 0
-                first = torch.argmax(has.to(torch.int32))
-                A[o + 9] = torch.where(has.any(), self.gA[first, o + 9], torch.full_like(A[o + 9], -1.0))
+                # bounce level = bounce count of the first valid ray (rays.rs:183-194): smallest id, ties to the lowest rank
+                ids = self.gA[:, o + 10]
+                first = torch.argmin(torch.where(ids < 0, torch.full_like(ids, math.inf), ids))
+                A[o + 9: o + 11] = self.gA[first, o + 9: o + 11]
         # ---- phase B
         self.status.zero_()
         for j, (arr, n) in enumerate(hits):
             _check(L.opm_fluence_binning_async(arr, n, -1, nx, ny, C.c_void_p(self._ptr(self.buf, 4 * j)), 0,
                                                C.c_void_p(self.maps[j].data_ptr()), C.c_void_p(self.status.data_ptr() + 4 * j)))
         for k, node in enumerate(self.sp):
-            _check(L.opm_scene_node_spot_async(self.scene.h, node, 2, C.c_void_p(self._ptr(self.buf, 4 * nf + 10 * k)),
+            _check(L.opm_scene_node_spot_async(self.scene.h, node, 2, C.c_void_p(self._ptr(self.buf, 4 * nf + 11 * k)),
                                                C.c_void_p(self._ptr(self.buf, self.nA + 3 * k))))
         if w > 1:
             if nf:
@@ -197,13 +206,13 @@ class DetectorReadout:
             out[node] = {"lrtb": lrtb, "peak": pk[0], "total_energy": pk[1],
                          "map": self.h_maps[j].numpy().reshape(nx, ny).T.copy() if download_maps else None}
         for k, node in enumerate(self.sp):
-            s = h[4 * nf + 10 * k: 4 * nf + 10 * k + 10].tolist()
+            s = h[4 * nf + 11 * k: 4 * nf + 11 * k + 11].tolist()
             rr = h[self.nA + 3 * k: self.nA + 3 * k + 3].tolist()
             p = F.OpmSpotPartial()
             for i in range(7):
                 p.sum[i] = s[i]
             p.n_valid, p.n_total = int(s[7]), int(s[8])
-            p.first_key = 0xFFFFFFFFFFFFFFFF if s[9] < 0 else int(s[9])
+            p.first_key = 0xFFFFFFFFFFFFFFFF if s[9] < 0 else ((int(s[10]) << 32) | int(s[9]))
             p.max_d2_mm2, p.sum_d2_mm2, p.sum_ed2 = rr
             st = F.OpmSpotStats()
             L.opm_spot_stats_from_partial(C.byref(p), C.byref(st))

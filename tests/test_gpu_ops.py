@@ -404,3 +404,20 @@ def test_new_collimated_with_spectrum_from_host_buffers(ctx):
         r.refract_on_surface(surf[1], None, want_reflected=False)  # leaves the bundle modified before its next upload
     with pytest.raises(ob.OpossumError):
         bufs[0].new_collimated_with_spectrum(xyz.ctypes.data, e.ctypes.data, len(xyz), [0.0], [1.0])  # Ray::new: wavelength must be > 0
+
+
+def test_source_generate_strided_is_a_slice_of_the_source(ctx):
+    """opm_source_generate_strided: rank g of G gets positions g, g+G, ... of the same global source (ids stay global)"""
+    sd = ob.SourceDesc(1001, [nm(1000.0), nm(1100.0)], [0.4, 0.6], total_energy=2.0).fibonacci_ellipse(mm(6.0), mm(5.0))
+    sd.general_gaussian((0.0, 0.0), (mm(3.0), mm(3.0)), 3.0)
+    # the normalisation sum is a parallel reduction (order-dependent in the last digit): fix it once for all shards
+    sd.general_gaussian((0.0, 0.0), (mm(3.0), mm(3.0)), 3.0, norm=sd.energy_norm(ctx))
+    full = sd.generate(ctx).to_array().reshape(1001, 2)
+    for g, G in ((0, 3), (2, 3), (7, 8)):
+        first, count, stride = g, len(range(g, 1001, G)), G
+        got = sd.generate_strided(ctx, first, count, stride).to_array().reshape(count, 2)
+        ref = full[g::G]
+        for f in ("pos", "dir", "e", "wvl", "id", "valid"):
+            assert np.array_equal(got[f], ref[f]), f
+    with pytest.raises(ob.OpossumError):
+        sd.generate_strided(ctx, 5, 1000, 3)

@@ -135,3 +135,14 @@ def test_two_rank_reduction_equals_single_process():
     assert np.allclose(got["centroid"][:2], ref["centroid"][:2], rtol=1e-9, atol=1e-15)
     assert got["geo"] == pytest.approx(ref["geo"], rel=1e-9)
     assert got["rms"] == pytest.approx(ref["rms"], rel=1e-9)
+
+
+def test_shard_strided_partitions_every_index_once():
+    for n, g in ((10, 3), (10_000_000, 8), (7, 8), (0, 2)):
+        seen = []
+        for r in range(g):
+            first, count, stride = sharding.shard_strided(n, r, g)
+            seen += [first + k * stride for k in range(count)] if n < 1000 else []
+            assert count == len(range(r, n, g))
+        if n < 1000:
+            assert sorted(seen) == list(range(n))
