@@ -139,6 +139,8 @@ typedef struct {
     uint64_t alive_out;      /* rays in the bundle after the call (valid or not) */
     uint32_t status_bits;    /* bit k set = OpmStatus k raised by some ray */
     uint32_t _pad;
+    uint64_t first_valid_key; /* (id << 32 | bounces) of the valid ray with the lowest id after the call, ~0 if none:
+                                 Rays::bounce_lvl (rays.rs:183-194) without a second pass over the bundle */
 } OpmTraceStats;
 
 typedef struct OpmContext OpmContext;
@@ -353,6 +355,7 @@ OpmStatus opm_measure_fp64_peak(OpmContext* ctx, double* tflops);
 /* device buffers for maps (so callers need no CUDA runtime of their own) */
 OpmStatus opm_device_alloc(OpmContext* ctx, uint64_t bytes, void** out);
 void opm_device_free(OpmContext* ctx, void* p);
+OpmStatus opm_device_memset(OpmContext* ctx, void* dev, int32_t value, uint64_t bytes);  /* asynchronous on the context's stream */
 OpmStatus opm_device_to_host(OpmContext* ctx, void* host, const void* dev, uint64_t bytes);
 OpmStatus opm_host_to_device(OpmContext* ctx, void* dev, const void* host, uint64_t bytes);
 OpmStatus opm_host_alloc_pinned(uint64_t bytes, void** out);
@@ -377,6 +380,9 @@ typedef struct {
     OpmIsometry iso;          /* source isometry applied to the bundle (nodes/source.rs:205-210) */
 } OpmSourceDesc;
 /* generates positions [pos_begin, pos_end) x all wavelengths into `rays` (ids = global ray index mod 2^32) */
+/* Gaussian spectrum (spectral_distribution/gaussian.rs:78-96): num wavelengths over [lo, hi] and their normalised weights (host math) */
+OpmStatus opm_spectrum_gaussian(double lo, double hi, uint64_t num, double mu, double fwhm, double power, double* wavelengths,
+                                double* weights);
 OpmStatus opm_source_generate(OpmRays* rays, const OpmSourceDesc* desc, uint64_t pos_begin, uint64_t pos_end);
 /* positions first_pos, first_pos + stride, ... (n_pos of them): a load-balanced shard of the source for rank g of G is
  * (first_pos = g, stride = G) -- rays are independent, so any partition of the source index set is a valid sharding */

@@ -75,7 +75,7 @@ class OpmRayTraceConfig(C.Structure):
 class OpmTraceStats(C.Structure):
     _fields_ = [("interactions", C.c_uint64), ("children", C.c_uint64), ("hits", C.c_uint64), ("missed", C.c_uint64),
                 ("apodized", C.c_uint64), ("valid_out", C.c_uint64), ("alive_out", C.c_uint64),
-                ("status_bits", C.c_uint32), ("_pad", C.c_uint32)]
+                ("status_bits", C.c_uint32), ("_pad", C.c_uint32), ("first_valid_key", C.c_uint64)]
 
 
 class OpmRefractOp(C.Structure):
@@ -202,8 +202,8 @@ EXPORTS = [
     "opm_hitmap_destroy", "opm_hitmap_capacity", "opm_hitmap_len", "opm_hitmap_upload", "opm_hitmap_download",
     "opm_hitmaps_bounding_box", "opm_fluence_binning", "opm_fluence_peak_total", "opm_hitmaps_bounding_box_async",
     "opm_fluence_binning_async", "opm_fluence_peak_total_async", "opm_measure_fp64_peak", "opm_device_alloc",
-    "opm_device_free", "opm_device_to_host", "opm_host_to_device", "opm_host_alloc_pinned", "opm_host_free_pinned",
-    "opm_source_generate", "opm_source_generate_strided", "opm_source_energy_norm",
+    "opm_device_free", "opm_device_memset", "opm_device_to_host", "opm_host_to_device", "opm_host_alloc_pinned", "opm_host_free_pinned",
+    "opm_spectrum_gaussian", "opm_source_generate", "opm_source_generate_strided", "opm_source_energy_norm",
 ]
 
 _lib = None
@@ -291,12 +291,14 @@ def lib() -> C.CDLL:
         "opm_measure_fp64_peak": (i32, [vp, dp]),
         "opm_device_alloc": (i32, [vp, u64, pp]),
         "opm_device_free": (None, [vp, vp]),
+        "opm_device_memset": (i32, [vp, vp, i32, u64]),
         "opm_device_to_host": (i32, [vp, vp, vp, u64]),
         "opm_host_to_device": (i32, [vp, vp, vp, u64]),
         "opm_host_alloc_pinned": (i32, [u64, pp]),
         "opm_host_free_pinned": (None, [vp]),
         "opm_source_generate": (i32, [vp, C.POINTER(OpmSourceDesc), u64, u64]),
         "opm_source_generate_strided": (i32, [vp, C.POINTER(OpmSourceDesc), u64, u64, u64]),
+        "opm_spectrum_gaussian": (i32, [C.c_double, C.c_double, u64, C.c_double, C.c_double, C.c_double, dp, dp]),
         "opm_source_energy_norm": (i32, [vp, C.POINTER(OpmSourceDesc), u64, u64, dp]),
     }
     sig.update({

@@ -663,6 +663,14 @@ def hitmaps_bounding_box(hit_maps, bounce=-1):
 
 
 # ---------------------------------------------------------------------------------------------
+def spectrum_gaussian(lo: float, hi: float, num: int, mu: float, fwhm: float, power: float = 1.0):
+    """spectral_distribution/gaussian.rs:78-96: (wavelengths, normalised weights); host math in the library"""
+    wv, w = np.zeros(num), np.zeros(num)
+    dp = C.POINTER(C.c_double)
+    _check(F.lib().opm_spectrum_gaussian(lo, hi, num, mu, fwhm, power, wv.ctypes.data_as(dp), w.ctypes.data_as(dp)))
+    return wv, w
+
+
 class SourceDesc:
     """Deterministic collimated source generated on the device (rays.rs:264-297)."""
 

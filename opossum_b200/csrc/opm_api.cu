@@ -810,6 +810,7 @@ static OpmStatus compile_ops(OpmContext* c, const OpmOp* ops, int n_ops, uint64_
 static void stats_to_public(const DevStats& d, OpmTraceStats* s) {
     s->interactions = d.interactions; s->children = d.children; s->hits = d.hits; s->missed = d.missed;
     s->apodized = d.apodized; s->valid_out = d.valid_out; s->alive_out = d.alive_out; s->status_bits = d.status_bits; s->_pad = 0;
+    s->first_valid_key = d.first_inv ? ~d.first_inv : ~0ull;
 }
 
 // The one place that launches the fused kernel.  stats == NULL: fully asynchronous (no host sync).
@@ -1294,6 +1295,12 @@ extern "C" void opm_device_free(OpmContext* c, void* p) {
     cudaStreamSynchronize(c->stream);
     cudaFree(p);
 }
+extern "C" OpmStatus opm_device_memset(OpmContext* c, void* dev, int32_t value, uint64_t bytes) {  // asynchronous
+    if (!c || !dev) return fail(OPM_ERR_ARG, "NULL argument");
+    CU(cudaSetDevice(c->device));
+    CU(cudaMemsetAsync(dev, value, bytes, c->stream));
+    return OPM_OK;
+}
 extern "C" OpmStatus opm_device_to_host(OpmContext* c, void* host, const void* dev, uint64_t bytes) {
     if (!c) return fail(OPM_ERR_ARG, "NULL argument");
     CU(cudaSetDevice(c->device));
@@ -1318,6 +1325,27 @@ extern "C" void opm_host_free_pinned(void* p) { if (p) cudaFreeHost(p); }
 // ---------------------------------------------------------------------------------------------
 // sources
 // ---------------------------------------------------------------------------------------------
+// spectral_distribution/gaussian.rs:78-96 (+ linspace utils/griddata.rs:211-231, gaussian() math_distribution_functions.rs:168-176):
+// `num` wavelengths equally spaced over [lo, hi], generalised-Gaussian weights normalised (Kahan sum) to 1.  Host math.
+extern "C" OpmStatus opm_spectrum_gaussian(double lo, double hi, uint64_t num, double mu, double fwhm, double power, double* wvl,
+                                           double* weights) {
+    if (!wvl || !weights || num == 0) return fail(OPM_ERR_ARG, "NULL argument");
+    if (!std::isfinite(lo) || !std::isfinite(hi)) return fail(OPM_ERR_ARG, "wavelength range must be finite");
+    const double bin = num > 1 ? (hi - lo) / (double)(num - 1) : 0.0;
+    for (uint64_t i = 0; i < num; ++i) wvl[i] = lo + (double)i * bin;
+    const double sigma = fwhm / (2.0 * std::sqrt(2.0 * std::pow(std::log(2.0), 1.0 / power)));
+    double sum = 0.0, comp = 0.0;  // kahan 0.1.4
+    for (uint64_t i = 0; i < num; ++i) {
+        const double u = (wvl[i] - mu) / sigma;
+        weights[i] = std::exp(-std::pow(0.5 * (u * u), power));
+        const double y = weights[i] - comp, t = sum + y;
+        comp = (t - sum) - y;
+        sum = t;
+    }
+    for (uint64_t i = 0; i < num; ++i) weights[i] = weights[i] / sum;
+    return OPM_OK;
+}
+
 static OpmStatus source_params(const OpmSourceDesc* d, SourceParams& S) {
     memset(&S, 0, sizeof S);
     if (!d) return fail(OPM_ERR_ARG, "desc is NULL");

@@ -82,6 +82,7 @@ static_assert(sizeof(DevOp) % 16 == 0, "DevOp must be a multiple of 16 B for the
 struct DevStats {
     unsigned long long interactions, children, hits, missed, apodized, valid_out, alive_out;
     unsigned int status_bits, _pad;
+    unsigned long long first_inv;  // max over valid rays of ~(id << 32 | bounces); 0 = no valid ray (zero-initialised)
 };
 
 struct TraceLaunch {

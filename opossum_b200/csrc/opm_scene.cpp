@@ -71,6 +71,10 @@ struct OpmScene {
     // device buffers are recycled across analyses (cudaMalloc / cudaFree are synchronous and cost milliseconds)
     std::vector<OpmRays*> pool_rays;
     std::vector<OpmHitMap*> pool_hits;
+    // ghost focus: device scratch of the per-bundle 101x101 fluence check (map | range[4] | peak,total[2] | status) and its
+    // pinned mirror of the scalars, so a check costs one synchronisation and no allocation
+    void* gf_scratch = nullptr;
+    void* gf_host = nullptr;
 };
 
 namespace {
@@ -252,6 +256,7 @@ struct Runner {
         ops.clear();
         total.interactions += st.interactions; total.children += st.children; total.hits += st.hits; total.missed += st.missed;
         total.apodized += st.apodized; total.valid_out = st.valid_out; total.alive_out = st.alive_out; total.status_bits |= st.status_bits;
+        total.first_valid_key = st.first_valid_key;
     }
 };
 
@@ -445,6 +450,8 @@ extern "C" void opm_scene_destroy(OpmScene* sc) {
     opm_scene_reset_data(sc);
     for (OpmRays* r : sc->pool_rays) opm_rays_destroy(r);
     for (OpmHitMap* h : sc->pool_hits) opm_hitmap_destroy(h);
+    if (sc->gf_scratch) opm_device_free(sc->ctx, sc->gf_scratch);
+    if (sc->gf_host) opm_host_free_pinned(sc->gf_host);
     delete sc;
 }
 extern "C" OpmStatus opm_scene_set_ambient(OpmScene* sc, const OpmIndexModel* a) {
@@ -503,7 +510,7 @@ extern "C" OpmStatus opm_scene_raytrace(OpmScene* sc, OpmRays* rays, const OpmRa
         if (R.status) return R.status;
         total.interactions += R.total.interactions; total.children += R.total.children; total.hits += R.total.hits;
         total.missed += R.total.missed; total.apodized += R.total.apodized; total.status_bits |= R.total.status_bits;
-        if (j == 0) { total.valid_out = R.total.valid_out; total.alive_out = R.total.alive_out; }
+        if (j == 0) { total.valid_out = R.total.valid_out; total.alive_out = R.total.alive_out; total.first_valid_key = R.total.first_valid_key; }
     }
     if (stats) *stats = total;
     return OPM_OK;

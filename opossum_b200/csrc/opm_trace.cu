@@ -108,8 +108,9 @@ trace_kernel(const DevOp* __restrict__ g_ops, int n_ops, DevRays in, DevRays out
 
     __shared__ unsigned long long s_cnt[CNT_N];
     __shared__ unsigned s_status;
+    __shared__ unsigned long long s_first_inv;  // max of ~(id << 32 | bounces) over the valid rays this CTA wrote
     if (threadIdx.x < CNT_N) s_cnt[threadIdx.x] = 0ull;
-    if (threadIdx.x == 0) s_status = 0u;
+    if (threadIdx.x == 0) { s_status = 0u; s_first_inv = 0ull; }
     __syncthreads();
 
     const unsigned tiles = (unsigned)((n + blockDim.x - 1) / blockDim.x);
@@ -259,6 +260,12 @@ trace_kernel(const DevOp* __restrict__ g_ops, int n_ops, DevRays in, DevRays out
             const unsigned rp = __reduce_add_sync(0xffffffffu, c.apodized);
             const unsigned live = __ballot_sync(0xffffffffu, alive), ok = __ballot_sync(0xffffffffu, valid && alive);
             const unsigned st = __reduce_or_sync(0xffffffffu, c.status);
+            if (ok) {  // first valid ray of the warp = lowest id: ~key is largest there
+                unsigned long long inv = (valid && alive) ? ~(((unsigned long long)r.id << 32) | r.bounces) : 0ull;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) { unsigned long long t = __shfl_xor_sync(0xffffffffu, inv, o); inv = t > inv ? t : inv; }
+                if ((threadIdx.x & 31) == 0) atomicMax(&s_first_inv, inv);
+            }
             if ((threadIdx.x & 31) == 0) {
                 if (ra & 0xffffu) atomicAdd(&s_cnt[CNT_INTERACTIONS], (unsigned long long)(ra & 0xffffu));
                 if (ra >> 16) atomicAdd(&s_cnt[CNT_HITS], (unsigned long long)(ra >> 16));
@@ -280,6 +287,7 @@ trace_kernel(const DevOp* __restrict__ g_ops, int n_ops, DevRays in, DevRays out
         atomicAdd(dst[threadIdx.x], s_cnt[threadIdx.x]);
     }
     if (threadIdx.x == 0 && s_status) atomicOr(&stats->status_bits, s_status);
+    if (threadIdx.x == 0 && s_first_inv) atomicMax(&stats->first_inv, s_first_inv);
 }
 
 }  // namespace

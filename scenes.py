@@ -165,13 +165,16 @@ def to_oracle(nodes, n_threads=1):
     return OS.OScene(out, n_threads=n_threads)
 
 
-def spectrum_of(src):
-    """(wavelengths, weights) of a source description; Gaussian spectra come from the oracle's restatement of
-    spectral_distribution/gaussian.rs (host-side input preparation, O(#wavelengths))"""
+def spectrum_of(src, backend="product"):
+    """(wavelengths, weights) of a source description; Gaussian spectra (spectral_distribution/gaussian.rs:78-96) come
+    from the library's host helper for the product and from the oracle's own restatement for the oracle"""
     if "spectrum" in src:
-        from oracle import oracle as orc
         _, lo, hi, n, mu, fwhm, power = src["spectrum"]
-        return orc.spectrum_gaussian(lo, hi, n, mu, fwhm, power)
+        if backend == "oracle":
+            from oracle import oracle as orc
+            return orc.spectrum_gaussian(lo, hi, n, mu, fwhm, power)
+        import opossum_b200 as ob
+        return ob.spectrum_gaussian(lo, hi, n, mu, fwhm, power)
     import numpy as np
     return np.asarray(src["wvl"], dtype=float), np.asarray(src["w"], dtype=float)
 
@@ -200,7 +203,7 @@ def source_to_oracle(src, wvl=None, w=None):
     """source description -> oracle ray array (Rays::new_collimated_with_spectrum, rays.rs:264-297)"""
     from oracle import oracle as orc
     if wvl is None:
-        wvl, w = spectrum_of(src)
+        wvl, w = spectrum_of(src, backend="oracle")
     pos = src["pos"]
     if pos[0] == "grid":
         xyz = orc.grid(pos[1], pos[2], pos[3], pos[4])

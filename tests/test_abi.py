@@ -29,7 +29,7 @@ def test_library_exports_every_declared_symbol():
 def test_struct_layouts():
     assert C.sizeof(F.OpmRay) == 96 == ob.RAY_DTYPE.itemsize == orc.RAY_DTYPE.itemsize
     assert C.sizeof(F.OpmIsometry) == 192 and C.sizeof(F.OpmSurface) == 216 and C.sizeof(F.OpmIndexModel) == 72
-    assert C.sizeof(F.OpmOp) == 384 and C.sizeof(F.OpmTraceStats) == 64
+    assert C.sizeof(F.OpmOp) == 384 and C.sizeof(F.OpmTraceStats) == 72
 
 
 def test_enums_match_oracle():
@@ -81,3 +81,16 @@ def test_isometry_rejects_non_finite():
         ob.Isometry.new((math.nan, 0, 0))
     with pytest.raises(ob.OpossumError):
         ob.Isometry.new((0, 0, 0), (0, math.inf, 0))
+
+
+def test_spectrum_gaussian_host_helper_matches_the_oracle():
+    """opm_spectrum_gaussian (spectral_distribution/gaussian.rs:78-96) is host math: same wavelengths and weights as the oracle"""
+    import numpy as np
+
+    import opossum_b200 as ob
+    from oracle import oracle as orc
+    for args in ((950e-9, 1150e-9, 64, 1053e-9, 50e-9, 1.0), (400e-9, 800e-9, 7, 600e-9, 120e-9, 2.5), (1e-6, 1e-6, 1, 1e-6, 1e-8, 1.0)):
+        wv, w = ob.spectrum_gaussian(*args)
+        rv, rw = orc.spectrum_gaussian(*args)
+        assert np.array_equal(wv, rv)
+        assert np.allclose(w, rw, rtol=1e-14, atol=0) and abs(w.sum() - 1.0) < 1e-14
