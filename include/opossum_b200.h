@@ -22,8 +22,17 @@
 #ifndef OPOSSUM_B200_H
 #define OPOSSUM_B200_H
 
+#ifndef __CUDACC_RTC__
 #include <stddef.h>
 #include <stdint.h>
+#else /* compiled at run time by NVRTC (the library's own kernels): no system headers there */
+typedef signed char int8_t;
+typedef unsigned char uint8_t;
+typedef int int32_t;
+typedef unsigned int uint32_t;
+typedef long long int64_t;
+typedef unsigned long long uint64_t;
+#endif
 
 #ifdef __cplusplus
 extern "C" {
@@ -228,6 +237,17 @@ uint64_t opm_context_launch_count(const OpmContext* ctx);
  * context's stream; opm_context_kernel_timing drains them (blocking) and returns the accumulated device time */
 OpmStatus opm_context_set_kernel_timing(OpmContext* ctx, int32_t enable);
 OpmStatus opm_context_kernel_timing(OpmContext* ctx, double* total_ms, uint64_t* launches, int32_t reset);
+
+/* Run-time specialised kernels: for bundles of at least `min_rays` rays the contracted build compiles (NVRTC, cached per
+ * program STRUCTURE: op kinds, geometries, coatings, index models, flags -- not the numbers) the straight-line kernel of
+ * the op program instead of interpreting it; any failure falls back to the interpreter kernel.  Defaults: enabled,
+ * 200000 rays; environment OPM_B200_JIT=0|1, OPM_B200_JIT_MIN_RAYS=n. */
+OpmStatus opm_context_set_jit(OpmContext* ctx, int32_t enable, uint64_t min_rays);
+OpmStatus opm_context_jit_stats(const OpmContext* ctx, uint64_t* kernels_compiled, uint64_t* compile_failures, uint64_t* launches,
+                                double* compile_ms);
+/* build check that needs no GPU: compiles a program with every op kind to an sm_100a cubin; returns its size, 0 on failure
+ * (reason in log) */
+uint64_t opm_jit_selftest(char* log, uint64_t log_capacity);
 
 /* host helpers mirroring utils/geom_transformation.rs (pure host math, no device needed) */
 void opm_isometry_identity(OpmIsometry* out);

@@ -256,6 +256,15 @@ class Context:
         _check(F.lib().opm_context_kernel_timing(self.h, C.byref(ms), C.byref(n), int(reset)))
         return ms.value, n.value
 
+    def set_jit(self, enable: bool, min_rays: int = 200000):
+        """run-time specialised trace kernels (NVRTC, cached per program structure) for bundles of >= min_rays rays"""
+        _check(F.lib().opm_context_set_jit(self.h, int(enable), min_rays))
+
+    def jit_stats(self) -> dict:
+        a, b, c, ms = C.c_uint64(), C.c_uint64(), C.c_uint64(), C.c_double()
+        _check(F.lib().opm_context_jit_stats(self.h, C.byref(a), C.byref(b), C.byref(c), C.byref(ms)))
+        return {"kernels_compiled": a.value, "compile_failures": b.value, "launches": c.value, "compile_ms": ms.value}
+
     def measure_fp64_peak(self) -> float:
         """DFMA throughput of this GPU in TFLOP/s (microbenchmark kernel in the library)"""
         out = C.c_double()

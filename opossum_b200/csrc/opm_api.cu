@@ -44,6 +44,11 @@ struct OpmContext {
     unsigned char* h_put_ring = nullptr;
     cudaEvent_t put_ev[kPutSlots] = {};
     int put_pos = 0;
+    // run-time specialised trace kernels: used by the contracted build for bundles of at least jit_min_rays rays
+    JitCache* jit = nullptr;
+    bool jit_enabled = true;
+    uint64_t jit_min_rays = 200000;
+    bool jit_warned = false;
     cudaStream_t copy_stream = nullptr;  // host uploads that are expanded on the device run here, overlapping the main stream
     // optional per-launch timing of the fused trace kernel (CUDA events on the launching stream)
     bool timing = false;
@@ -184,6 +189,9 @@ extern "C" OpmStatus opm_context_create(int32_t device, void* stream, OpmContext
     if (stream) { c->stream = (cudaStream_t)stream; c->own_stream = false; }
     else { CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)); c->own_stream = true; }
     CU(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    c->jit = jit_cache_create();
+    if (const char* e = getenv("OPM_B200_JIT")) c->jit_enabled = atoi(e) != 0;
+    if (const char* e = getenv("OPM_B200_JIT_MIN_RAYS")) c->jit_min_rays = strtoull(e, nullptr, 10);
     CU(cudaMallocHost(&c->h_put_ring, OpmContext::kPutSlots * OpmContext::kPutBytes));
     for (int k = 0; k < OpmContext::kPutSlots; ++k) CU(cudaEventCreateWithFlags(&c->put_ev[k], cudaEventDisableTiming));
     CU(cudaMalloc(&c->d_stats, sizeof(DevStats)));
@@ -205,6 +213,7 @@ extern "C" void opm_context_destroy(OpmContext* c) {
     for (auto* v : {&c->timing_events, &c->timing_free})
         for (auto& p : *v) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
     if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }
+    jit_cache_destroy(c->jit);
     for (int k = 0; k < OpmContext::kPutSlots; ++k) if (c->put_ev[k]) cudaEventDestroy(c->put_ev[k]);
     cudaFreeHost(c->h_put_ring);
     cudaFree(c->d_stats); cudaFreeHost(c->h_stats); cudaFree(c->d_ops); cudaFree(c->d_scratch); cudaFreeHost(c->h_scratch);
@@ -215,6 +224,20 @@ extern "C" OpmStatus opm_context_synchronize(OpmContext* c) {
     if (!c) return fail(OPM_ERR_ARG, "context is NULL");
     CU(cudaSetDevice(c->device));
     CU(cudaStreamSynchronize(c->stream));
+    return OPM_OK;
+}
+// ---- run-time specialised kernels (opm_jit.cu)
+extern "C" uint64_t opm_jit_selftest(char* log, uint64_t cap) { return jit_selftest(log, cap); }
+extern "C" OpmStatus opm_context_set_jit(OpmContext* c, int32_t enable, uint64_t min_rays) {
+    if (!c) return fail(OPM_ERR_ARG, "context is NULL");
+    c->jit_enabled = enable != 0;
+    c->jit_min_rays = min_rays;
+    return OPM_OK;
+}
+extern "C" OpmStatus opm_context_jit_stats(const OpmContext* c, uint64_t* kernels_compiled, uint64_t* compile_failures,
+                                           uint64_t* launches, double* compile_ms) {
+    if (!c) return fail(OPM_ERR_ARG, "context is NULL");
+    jit_cache_stats(c->jit, kernels_compiled, compile_failures, launches, compile_ms);
     return OPM_OK;
 }
 extern "C" void* opm_context_stream(OpmContext* c) { return c ? (void*)c->stream : nullptr; }
@@ -852,17 +875,30 @@ static OpmStatus run_program(OpmRays* rays, const OpmOp* ops, int n_ops, int fla
         DevOp* d_slot = c->d_ops + (size_t)slot * OPM_MAX_PROGRAM_OPS;
         CU(cudaEventSynchronize(c->ring_ev[slot]));  // the copy that last used this pinned slot has drained
         memcpy(h_slot, prog.ops.data(), prog.ops.size() * sizeof(DevOp));
-        KL(k_fetch_from_host(d_slot, h_slot, prog.ops.size() * sizeof(DevOp), c->stream));  // not a copy-engine transfer: see dev_put
-        c->launches++;
-        CU(cudaEventRecord(c->ring_ev[slot], c->stream));
+        const bool strict = (flags & OPM_TRACE_STRICT) != 0;
+        const int block = strict ? trace_block_strict() : trace_block_fast();
+        // large bundles run the kernel compiled for the structure of this program (opm_jit.cu); otherwise, and whenever
+        // that kernel cannot be had, the interpreter
+        const JitKernel* jk = nullptr;
+        if (!strict && c->jit_enabled && n >= c->jit_min_rays) {
+            const char* why = nullptr;
+            jk = jit_get(c->jit, prog.ops.data(), (int)prog.ops.size(), compact, block, 2, &why);
+            if (!jk && !c->jit_warned) {
+                c->jit_warned = true;
+                fprintf(stderr, "opossum_b200: run-time kernel specialisation unavailable, using the interpreter kernel (%s)\n", why ? why : "?");
+            }
+        }
+        if (!jk) {
+            KL(k_fetch_from_host(d_slot, h_slot, prog.ops.size() * sizeof(DevOp), c->stream));  // not a copy-engine transfer: see dev_put
+            c->launches++;
+        }
         CU(cudaMemsetAsync(c->d_stats, 0, sizeof(DevStats), c->stream));
         TraceLaunch L;
         L.ops = d_slot; L.n_ops = (int)prog.ops.size();
         L.in = rays->v; L.out = dst->v; L.n = n; L.out_cap = dst->cap; L.out_tail = dst->d_tail;
-        const bool strict = (flags & OPM_TRACE_STRICT) != 0;
-        L.stats = c->d_stats; L.compact = compact ? 1 : 0; L.block = strict ? trace_block_strict() : trace_block_fast(); L.stream = c->stream;
+        L.stats = c->d_stats; L.compact = compact ? 1 : 0; L.block = block; L.stream = c->stream;
         size_t smem = prog.ops.size() * sizeof(DevOp);
-        int occ = strict ? trace_occupancy_strict(L.block, smem) : trace_occupancy_fast(L.block, smem);
+        int occ = jk ? jit_occupancy(jk) : strict ? trace_occupancy_strict(L.block, smem) : trace_occupancy_fast(L.block, smem);
         uint64_t tiles = (n + L.block - 1) / L.block;
         uint64_t maxg = (uint64_t)c->sms * occ;
         L.grid = (int)(tiles < maxg ? tiles : maxg);
@@ -872,8 +908,9 @@ static OpmStatus run_program(OpmRays* rays, const OpmOp* ops, int n_ops, int fla
             else { CU(cudaEventCreate(&tev.first)); CU(cudaEventCreate(&tev.second)); }
             CU(cudaEventRecord(tev.first, c->stream));
         }
-        int rc = strict ? launch_trace_strict(L) : launch_trace_fast(L);
-        c->launches++;
+        int rc = jk ? jit_launch(c->jit, jk, L, h_slot) : strict ? launch_trace_strict(L) : launch_trace_fast(L);
+        c->launches += jk ? 2 : 1;
+        CU(cudaEventRecord(c->ring_ev[slot], c->stream));  // the pinned slot is free once the fetch kernel has read it
         if (c->timing) { CU(cudaEventRecord(tev.second, c->stream)); c->timing_events.push_back(tev); }
         if (rc != 0) { free_temps(); return fail(OPM_ERR_CUDA, "trace kernel launch failed: %s", cudaGetErrorString((cudaError_t)rc)); }
     }

@@ -1,7 +1,9 @@
 // opm_internal.h -- device-side POD layouts shared by the kernels and the C-ABI host code.
 // Not part of the public boundary (include/opossum_b200.h is).
 #pragma once
+#ifndef __CUDACC_RTC__
 #include <cstdint>
+#endif
 
 #include "../../include/opossum_b200.h"
 
@@ -105,5 +107,16 @@ int trace_block_fast();
 int trace_block_strict();
 int trace_occupancy_fast(int block, size_t smem);
 int trace_occupancy_strict(int block, size_t smem);
+
+// run-time specialised trace kernels (opm_jit.cu)
+struct JitKernel;
+struct JitCache;
+JitCache* jit_cache_create();
+void jit_cache_destroy(JitCache* c);
+void jit_cache_stats(const JitCache* c, uint64_t* compiled, uint64_t* failures, uint64_t* launches, double* compile_ms);
+const JitKernel* jit_get(JitCache* cache, const DevOp* ops, int n_ops, bool compact, int block, int min_ctas, const char** why);
+int jit_occupancy(const JitKernel* k);
+int jit_launch(JitCache* cache, const JitKernel* k, const TraceLaunch& L, const void* h_ops_pinned);
+size_t jit_selftest(char* why, size_t cap);  // compiles a program with every op kind to a cubin (no GPU needed); 0 = failed
 
 }  // namespace opm

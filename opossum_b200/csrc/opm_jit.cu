@@ -1,0 +1,286 @@
+// opm_jit.cu -- run-time specialisation of the fused surface-sequence kernel.
+//
+// The interpreter kernel (opm_trace.cu) pays a dispatch, a set of structural branches (which geometry? which coating?
+// index model? hit record? epilogue flags?) and shared-memory descriptor loads for every op of every ray.  For a bundle
+// that is large enough to amortise a compilation, the library instead generates the straight-line kernel of THIS
+// program: the op bodies of opm_trace_ops.cuh called back to back with the structural facts as template arguments
+// (RefractCt / ApertureCt / EpilogueCt), and the descriptors in __constant__ memory at compile-time indices, so the
+// numbers (isometries, radii, coefficients) become constant-bank operands of the FP64 instructions.  Only the STRUCTURE
+// is baked in: scenes that differ in numbers alone (parameter sweeps, tolerancing) reuse the kernel.
+//
+// NVRTC is loaded lazily with dlopen and the cubin through the runtime's cudaLibrary API, so the library has no link-time
+// dependency on libnvrtc / libcuda; if either step fails the caller falls back to the interpreter.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nvrtc.h>
+
+#include <chrono>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "opm_internal.h"
+#include "opm_jit_headers.inc"
+#include "opm_kernels.h"
+
+namespace opm {
+
+struct JitKernel {
+    cudaLibrary_t lib = nullptr;
+    cudaKernel_t kernel = nullptr;
+    void* d_const = nullptr;  // device address of the kernel's __constant__ op array
+    size_t const_bytes = 0;
+    int n_ops = 0;
+    int occupancy = 1;
+    bool failed = false;
+    std::string why;
+};
+
+struct JitCache {
+    std::map<std::string, JitKernel> kernels;
+    uint64_t compiled = 0, failures = 0, launches = 0;
+    double compile_ms = 0.0;
+};
+
+namespace {
+
+struct Nvrtc {
+    void* h = nullptr;
+    bool tried = false;
+    nvrtcResult (*CreateProgram)(nvrtcProgram*, const char*, const char*, int, const char* const*, const char* const*) = nullptr;
+    nvrtcResult (*CompileProgram)(nvrtcProgram, int, const char* const*) = nullptr;
+    nvrtcResult (*GetCUBINSize)(nvrtcProgram, size_t*) = nullptr;
+    nvrtcResult (*GetCUBIN)(nvrtcProgram, char*) = nullptr;
+    nvrtcResult (*GetProgramLogSize)(nvrtcProgram, size_t*) = nullptr;
+    nvrtcResult (*GetProgramLog)(nvrtcProgram, char*) = nullptr;
+    nvrtcResult (*DestroyProgram)(nvrtcProgram*) = nullptr;
+};
+Nvrtc g_nvrtc;
+
+bool nvrtc_load(std::string* why) {
+    Nvrtc& N = g_nvrtc;
+    if (N.tried) { if (!N.h && why) *why = "libnvrtc not available"; return N.h != nullptr; }
+    N.tried = true;
+    const char* names[] = {"libnvrtc.so.12", "libnvrtc.so", "/usr/local/cuda/lib64/libnvrtc.so.12", "/usr/local/cuda/lib64/libnvrtc.so"};
+    for (const char* nm : names) { N.h = dlopen(nm, RTLD_NOW | RTLD_LOCAL); if (N.h) break; }
+    if (!N.h) { if (why) *why = "libnvrtc not available"; return false; }
+#define OPM_SYM(field, name) *(void**)(&N.field) = dlsym(N.h, name); if (!N.field) { dlclose(N.h); N.h = nullptr; if (why) *why = "libnvrtc lacks " name; return false; }
+    OPM_SYM(CreateProgram, "nvrtcCreateProgram")
+    OPM_SYM(CompileProgram, "nvrtcCompileProgram")
+    OPM_SYM(GetCUBINSize, "nvrtcGetCUBINSize")
+    OPM_SYM(GetCUBIN, "nvrtcGetCUBIN")
+    OPM_SYM(GetProgramLogSize, "nvrtcGetProgramLogSize")
+    OPM_SYM(GetProgramLog, "nvrtcGetProgramLog")
+    OPM_SYM(DestroyProgram, "nvrtcDestroyProgram")
+#undef OPM_SYM
+    return true;
+}
+
+void appendf(std::string& s, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    s += buf;
+}
+
+// one line of kernel body per op; the same text is the structural cache key
+std::string op_line(const DevOp& op, int k) {
+    std::string s;
+    switch (op.kind) {
+        case OPK_REFRACT: {
+            const DevRefract& o = op.u.refract;
+            appendf(s, "        exec_refract(RefractCt<%d, %d, %d, %d, %d, %d, %d, %d>(opm_jit_ops[%d].u.refract), x);\n", o.geom, o.coating,
+                    o.has_index ? 1 : 0, o.index_type, o.strategy, o.flags, o.refraction_intended ? 1 : 0, o.hits.e ? 1 : 0, k);
+            break;
+        }
+        case OPK_APODIZE: {
+            const DevAperture& a = op.u.apodize.ap;
+            unsigned to = 0;
+            for (int j = 0; j < a.n_items && j < OPM_MAX_APERTURE_ITEMS; ++j)
+                to |= ((unsigned)(a.items[j].type & 7) | (a.items[j].obstruction ? 8u : 0u)) << (4 * j);
+            appendf(s, "        exec_apodize(ApertureCt<%d, %d, %d, 0x%xu>(opm_jit_ops[%d].u.apodize.ap), opm_jit_ops[%d].u.apodize.inv, x);\n",
+                    a.n_items, a.is_stack ? 1 : 0, a.stack_obstruction ? 1 : 0, to, k, k);
+            break;
+        }
+        case OPK_THRESHOLD: appendf(s, "        exec_threshold(opm_jit_ops[%d].u.threshold, x);\n", k); break;
+        case OPK_LIMITS: appendf(s, "        exec_limits(opm_jit_ops[%d].u.limits, x);\n", k); break;
+        case OPK_FILTER: appendf(s, "        exec_filter(opm_jit_ops[%d].u.filter, x);\n", k); break;
+        case OPK_PARAXIAL: appendf(s, "        exec_paraxial(opm_jit_ops[%d].u.paraxial, x);\n", k); break;
+        case OPK_SPLIT: appendf(s, "        exec_split(opm_jit_ops[%d].u.split, x);\n", k); break;
+        case OPK_SNAPSHOT: appendf(s, "        exec_snapshot(opm_jit_ops[%d].u.snapshot, x);\n", k); break;
+        case OPK_TRANSFORM: appendf(s, "        exec_transform(opm_jit_ops[%d].u.transform, x);\n", k); break;
+        default: appendf(s, "        /* op %d: unknown kind %d */\n", k, op.kind); break;
+    }
+    if (op.epi_flags) appendf(s, "        exec_epilogue(EpilogueCt<%d>(), opm_jit_ops[%d], x);\n", op.epi_flags, k);
+    return s;
+}
+
+std::string make_source(const DevOp* ops, int n_ops, bool compact, int block, int min_ctas) {
+    std::string body;
+    for (int k = 0; k < n_ops; ++k) body += op_line(ops[k], k);
+    std::string s;
+    s += "#include \"opm_trace_ops.cuh\"\nnamespace opm {\n";
+    appendf(s, "extern \"C\" __constant__ DevOp opm_jit_ops[%d];\n", n_ops);
+    appendf(s, "extern \"C\" __global__ void __launch_bounds__(%d, %d)\n", block, min_ctas);
+    s += "opm_jit_trace(DevRays in, DevRays out, unsigned long long n, unsigned long long out_cap, unsigned long long* out_tail,\n"
+         "              DevStats* stats) {\n"
+         "    __shared__ unsigned long long s_cnt[CNT_N];\n"
+         "    __shared__ unsigned s_status;\n"
+         "    __shared__ unsigned long long s_first_inv;\n"
+         "    if (threadIdx.x < CNT_N) s_cnt[threadIdx.x] = 0ull;\n"
+         "    if (threadIdx.x == 0) { s_status = 0u; s_first_inv = 0ull; }\n"
+         "    __syncthreads();\n"
+         "    const unsigned tiles = (unsigned)((n + blockDim.x - 1) / blockDim.x);\n"
+         "    for (unsigned tile = blockIdx.x; tile < tiles; tile += gridDim.x) {\n"
+         "        RayCtx x;\n"
+         "        uint8_t vb;\n"
+         "        tile_load(in, (uint64_t)tile * blockDim.x + threadIdx.x, n, x, vb);\n";
+    s += body;
+    appendf(s, "        tile_store<%s>(in, out, out_cap, out_tail, x, vb);\n", compact ? "true" : "false");
+    s += "        tile_count(x, s_cnt, &s_status, &s_first_inv);\n"
+         "    }\n"
+         "    __syncthreads();\n"
+         "    cta_flush(stats, s_cnt, s_status, s_first_inv);\n"
+         "}\n}  // namespace opm\n";
+    return s;
+}
+
+// source -> sm_100a cubin (needs no GPU)
+bool compile_cubin(const std::string& src, std::vector<char>& cubin, std::string& why) {
+    Nvrtc& N = g_nvrtc;
+    nvrtcProgram prog = nullptr;
+    if (N.CreateProgram(&prog, src.c_str(), "opm_jit_trace.cu", kJitHeaderCount, kJitHeaderSources, kJitHeaderNames) != NVRTC_SUCCESS) {
+        why = "nvrtcCreateProgram failed";
+        return false;
+    }
+    // -default-device: the public header declares the (host) entry points without execution-space annotations
+    const char* opts[] = {"--gpu-architecture=sm_100a", "-std=c++17", "-lineinfo", "-default-device"};
+    nvrtcResult rc = N.CompileProgram(prog, 4, opts);
+    if (rc != NVRTC_SUCCESS) {
+        size_t ls = 0;
+        N.GetProgramLogSize(prog, &ls);
+        std::string log(ls, '\0');
+        if (ls) N.GetProgramLog(prog, &log[0]);
+        why = "nvrtc compilation failed: " + log.substr(0, 3000);
+        N.DestroyProgram(&prog);
+        return false;
+    }
+    size_t cs = 0;
+    N.GetCUBINSize(prog, &cs);
+    cubin.resize(cs);
+    N.GetCUBIN(prog, cubin.data());
+    N.DestroyProgram(&prog);
+    return true;
+}
+
+bool compile(JitKernel& K, const std::string& src, int n_ops, int block) {
+    std::vector<char> cubin;
+    if (!compile_cubin(src, cubin, K.why)) return false;
+    cudaError_t e = cudaLibraryLoadData(&K.lib, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0);
+    if (e != cudaSuccess) { K.why = std::string("cudaLibraryLoadData: ") + cudaGetErrorString(e); cudaGetLastError(); return false; }
+    e = cudaLibraryGetKernel(&K.kernel, K.lib, "opm_jit_trace");
+    if (e == cudaSuccess) e = cudaLibraryGetGlobal(&K.d_const, &K.const_bytes, K.lib, "opm_jit_ops");
+    if (e != cudaSuccess) { K.why = std::string("cudaLibraryGetKernel/Global: ") + cudaGetErrorString(e); cudaGetLastError(); return false; }
+    if (K.const_bytes < (size_t)n_ops * sizeof(DevOp)) { K.why = "constant array smaller than the program"; return false; }
+    int nb = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, (const void*)K.kernel, block, 0) != cudaSuccess || nb < 1) { nb = 1; cudaGetLastError(); }
+    K.occupancy = nb;
+    K.n_ops = n_ops;
+    return true;
+}
+
+}  // namespace
+
+JitCache* jit_cache_create() { return new JitCache(); }
+void jit_cache_destroy(JitCache* c) {
+    if (!c) return;
+    for (auto& kv : c->kernels) if (kv.second.lib) cudaLibraryUnload(kv.second.lib);
+    delete c;
+}
+void jit_cache_stats(const JitCache* c, uint64_t* compiled, uint64_t* failures, uint64_t* launches, double* compile_ms) {
+    if (compiled) *compiled = c ? c->compiled : 0;
+    if (failures) *failures = c ? c->failures : 0;
+    if (launches) *launches = c ? c->launches : 0;
+    if (compile_ms) *compile_ms = c ? c->compile_ms : 0.0;
+}
+std::string jit_debug_source(const DevOp* ops, int n_ops, bool compact) { return make_source(ops, n_ops, compact, 256, 2); }
+
+const JitKernel* jit_get(JitCache* cache, const DevOp* ops, int n_ops, bool compact, int block, int min_ctas, const char** why) {
+    static std::string s_why;
+    if (!cache || n_ops <= 0) { if (why) *why = "no program"; return nullptr; }
+    std::string src = make_source(ops, n_ops, compact, block, min_ctas);
+    auto it = cache->kernels.find(src);
+    if (it == cache->kernels.end()) {
+        JitKernel K;
+        if (!nvrtc_load(&K.why)) K.failed = true;
+        else {
+            const auto t0 = std::chrono::steady_clock::now();
+            K.failed = !compile(K, src, n_ops, block);
+            cache->compile_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        }
+        if (K.failed) cache->failures++; else cache->compiled++;
+        it = cache->kernels.emplace(std::move(src), std::move(K)).first;
+    }
+    if (it->second.failed) { s_why = it->second.why; if (why) *why = s_why.c_str(); return nullptr; }
+    return &it->second;
+}
+
+int jit_occupancy(const JitKernel* K) { return K ? K->occupancy : 1; }
+
+// Build check without a GPU: a program with one op of every kind, every geometry and coating is turned into source and
+// compiled to an sm_100a cubin.  Returns the cubin size, or 0 with the reason in `why`.
+static size_t jit_selftest_impl(std::string& why) {
+    if (!nvrtc_load(&why)) return 0;
+    std::vector<DevOp> ops;
+    auto push = [&](int kind) { DevOp d; memset(&d, 0, sizeof d); d.kind = kind; ops.push_back(d); return &ops.back(); };
+    for (int geom = OPM_GEOM_PLANE; geom <= OPM_GEOM_PARABOLA; ++geom) {
+        DevOp* d = push(OPK_REFRACT);
+        d->u.refract.geom = geom; d->u.refract.coating = geom % 3; d->u.refract.has_index = 1; d->u.refract.index_type = geom;
+        d->u.refract.refraction_intended = 1; d->u.refract.hits.e = (double*)8; d->epi_flags = EPI_THRESHOLD | EPI_LIMITS | EPI_CHECK_REFR;
+    }
+    {
+        DevOp* d = push(OPK_REFRACT);  // mirror that also emits its children
+        d->u.refract.flags = OPM_REFRACT_EMIT_CHILDREN | OPM_REFRACT_CONTINUE_AS_CHILD; d->u.refract.coating = OPM_COAT_CONSTANT_R;
+    }
+    {
+        DevOp* d = push(OPK_APODIZE);
+        d->u.apodize.ap.n_items = 4; d->u.apodize.ap.is_stack = 1;
+        for (int j = 0; j < 4; ++j) d->u.apodize.ap.items[j].type = OPM_AP_CIRCLE + j;
+    }
+    for (int kind : {OPK_THRESHOLD, OPK_LIMITS, OPK_FILTER, OPK_PARAXIAL, OPK_SPLIT, OPK_SNAPSHOT, OPK_TRANSFORM}) push(kind);
+    std::vector<char> cubin;
+    for (bool compact : {false, true}) {
+        std::string src = make_source(ops.data(), (int)ops.size(), compact, 256, 2);
+        if (!compile_cubin(src, cubin, why)) return 0;
+    }
+    return cubin.size();
+}
+size_t jit_selftest(char* why, size_t cap) {
+    std::string w;
+    size_t n = jit_selftest_impl(w);
+    if (why && cap) { snprintf(why, cap, "%s", w.c_str()); }
+    return n;
+}
+
+// h_ops: the pinned, mapped copy of the program (the descriptors' numbers and pointers of THIS launch)
+int jit_launch(JitCache* cache, const JitKernel* K, const TraceLaunch& L, const void* h_ops) {
+    cudaStream_t st = (cudaStream_t)L.stream;
+    int rc = k_fetch_from_host(K->d_const, h_ops, (size_t)L.n_ops * sizeof(DevOp), L.stream);
+    if (rc) return rc;
+    DevRays in = L.in, out = L.out;
+    unsigned long long n = L.n, cap = L.out_cap;
+    unsigned long long* tail = L.out_tail;
+    DevStats* stats = L.stats;
+    void* args[] = {&in, &out, &n, &cap, &tail, &stats};
+    cudaError_t e = cudaLaunchKernel((const void*)K->kernel, dim3(L.grid), dim3(L.block), args, 0, st);
+    if (e != cudaSuccess) return (int)e;
+    cache->launches++;
+    return (int)cudaGetLastError();
+}
+
+}  // namespace opm

@@ -1,0 +1,252 @@
+// opm_trace_ops.cuh -- the per-op bodies of the fused surface-sequence kernel.
+//
+// One function per `Rays` method of the reference (file:line cited), operating on a ray held in registers (RayCtx).
+// Shared by the two kernels that run an op program:
+//   * the interpreter (opm_trace.cu): ops staged in shared memory, dispatched by a warp-uniform switch, structural facts
+//     read at run time (RefractRt / ApertureRt / EpilogueRt views);
+//   * the run-time-compiled kernel of a fixed program (opm_jit.cpp): the same functions called back to back with the
+//     structural facts as template arguments (*Ct views), descriptors read from constant memory.
+#pragma once
+#include "opm_device.cuh"
+
+namespace opm {
+
+__device__ __forceinline__ unsigned lanemask_lt() {
+    unsigned m;
+    asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+    return m;
+}
+
+// warp-aggregated reservation of `want ? 1 : 0` slots per lane; returns this lane's slot
+__device__ __forceinline__ unsigned long long warp_reserve(bool want, unsigned long long* tail) {
+    unsigned mask = __ballot_sync(0xffffffffu, want);
+    if (mask == 0) return 0;
+    int leader = __ffs(mask) - 1;
+    unsigned long long base = 0;
+    if ((threadIdx.x & 31) == leader) base = atomicAdd(tail, (unsigned long long)__popc(mask));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    return base + __popc(mask & lanemask_lt());
+}
+
+__device__ __forceinline__ void load_ray(const DevRays& R, uint64_t i, RayState& r) {
+    r.pos = v3(__ldcs(R.px + i), __ldcs(R.py + i), __ldcs(R.pz + i));
+    r.dir = v3(__ldcs(R.dx + i), __ldcs(R.dy + i), __ldcs(R.dz + i));
+    r.e = __ldcs(R.e + i); r.wvl = __ldcs(R.wvl + i); r.opl = __ldcs(R.opl + i); r.n = __ldcs(R.n + i);
+    r.bounces = __ldcs(R.bounces + i); r.refr = __ldcs(R.refr + i); r.id = __ldcs(R.id + i);
+}
+template <bool FULL>
+__device__ __forceinline__ void store_ray(const DevRays& R, uint64_t i, const RayState& r, uint8_t valid) {
+    __stcs(R.px + i, r.pos.x); __stcs(R.py + i, r.pos.y); __stcs(R.pz + i, r.pos.z);
+    __stcs(R.dx + i, r.dir.x); __stcs(R.dy + i, r.dir.y); __stcs(R.dz + i, r.dir.z);
+    __stcs(R.e + i, r.e); __stcs(R.opl + i, r.opl); __stcs(R.n + i, r.n);
+    __stcs(R.bounces + i, r.bounces); __stcs(R.refr + i, r.refr);
+    if (FULL) { __stcs(R.wvl + i, r.wvl); __stcs(R.id + i, r.id); }  // wavelength and id never change in place
+    R.valid[i] = valid;
+}
+
+// Per-tile event counters, two 16-bit fields per register (a warp's sum of a field is at most 32 lanes x 64 ops):
+// a = interactions | hits << 16, b = missed | children << 16.  Each tile ends with one REDUX per register and one
+// shared-memory atomic per field from lane 0; the CTA flushes its totals to the global statistics once.
+struct Counters {
+    unsigned a, b, apodized, status;
+};
+enum { CNT_INTERACTIONS = 0, CNT_CHILDREN, CNT_HITS, CNT_MISSED, CNT_APODIZED, CNT_VALID_OUT, CNT_ALIVE_OUT, CNT_N };
+
+// one ray of the current tile
+struct RayCtx {
+    RayState r;
+    uint64_t i;      // slot in the bundle
+    bool in_range;   // i < n
+    bool alive;      // part of the bundle (not removed)
+    bool valid;      // Ray::valid
+    Counters c;
+};
+
+// folded threshold + limits (rays.rs:1145-1162, 1386-1404): EPI_* flags
+struct EpilogueRt {
+    int f;
+    __device__ __forceinline__ explicit EpilogueRt(int f_) : f(f_) {}
+    __device__ __forceinline__ int flags() const { return f; }
+};
+template <int FLAGS>
+struct EpilogueCt {
+    __device__ __forceinline__ static constexpr int flags() { return FLAGS; }
+};
+template <class E>
+__device__ __forceinline__ void exec_epilogue(const E& e, const DevOp& op, RayCtx& x) {
+    const int f = e.flags();
+    if (f == 0 || !x.alive) return;
+    if ((f & EPI_THRESHOLD) && x.r.e < op.epi_min_energy) x.valid = false;
+    if (f & EPI_LIMITS) {
+        if ((uint64_t)x.r.bounces > op.epi_max_bounces) x.valid = false;
+        if ((f & EPI_CHECK_REFR) && (uint64_t)x.r.refr >= op.epi_max_refr) x.valid = false;
+    }
+}
+
+// Rays::refract_on_surface (rays.rs:976-1047) for one ray + hit record + child emission / mirror continuation
+template <class V>
+__device__ __forceinline__ void exec_refract(const V& v, RayCtx& x) {
+    const DevRefract& o = v.d();
+    RefractResult res;
+    res.has_child = false; res.hit_e = -1.0; res.hit_bounce = 0; res.hit_local = v3(0, 0, 0);
+    if (x.valid) {
+        x.c.a += 1u;
+        res = refract_on_surface(v, x.r);
+        if (res.status != OPM_OK) { x.c.status |= 1u << res.status; x.valid = false; res.has_child = false; res.hit_e = -1.0; }
+        else {
+            if (res.missed) x.c.b += 1u;
+            if (res.invalidated) x.valid = false;
+        }
+    }
+    if (v.has_hits() && x.in_range) {  // slot-indexed hit record, e < 0 = empty
+        __stcs(o.hits.e + x.i, res.hit_e);
+        if (res.hit_e >= 0.0) {
+            __stcs(o.hits.x + x.i, res.hit_local.x); __stcs(o.hits.y + x.i, res.hit_local.y);
+            __stcs(o.hits.z + x.i, res.hit_local.z); __stcs(o.hits.bounce + x.i, res.hit_bounce);
+            x.c.a += 1u << 16;
+        }
+    }
+    if (v.flags() & OPM_REFRACT_EMIT_CHILDREN) {
+        unsigned long long slot = warp_reserve(res.has_child, o.child_tail);
+        if (res.has_child) {
+            if (slot < o.child_cap) {
+                RayState child = x.r;
+                child_into(res, child);
+                store_ray<true>(o.children, slot, child, RAY_VALID);
+                x.c.b += 1u << 16;
+            } else x.c.status |= 1u << OPM_ERR_CAPACITY;
+        }
+    }
+    if (v.flags() & OPM_REFRACT_CONTINUE_AS_CHILD) {  // mirror: only reflected rays stay in the bundle
+        if (x.alive) {
+            if (res.has_child) child_into(res, x.r);
+            else { x.alive = false; x.valid = false; }
+        }
+    }
+}
+
+// Rays::apodize (rays.rs:557-573)
+template <class A>
+__device__ __forceinline__ void exec_apodize(const A& av, const DevIso& inv, RayCtx& x) {
+    if (!x.valid) return;
+    double lx = inv.r[0] * x.r.pos.x + inv.r[1] * x.r.pos.y + inv.r[2] * x.r.pos.z + inv.t[0];
+    double ly = inv.r[3] * x.r.pos.x + inv.r[4] * x.r.pos.y + inv.r[5] * x.r.pos.z + inv.t[1];
+    double f = aperture_factor(av, lx, ly);
+    if (f > 0.0) {
+        if (!(f <= 1.0)) x.c.status |= 1u << OPM_ERR_APODIZE_FACTOR;
+        else x.r.e *= f;
+    } else { x.valid = false; x.c.apodized += 1u; }
+}
+
+// rays.rs:1145-1162 (all rays; a no-op for already invalid ones)
+__device__ __forceinline__ void exec_threshold(const DevThreshold& o, RayCtx& x) {
+    if (x.alive && x.r.e < o.min_energy) x.valid = false;
+}
+// rays.rs:1386-1404
+__device__ __forceinline__ void exec_limits(const DevLimits& o, RayCtx& x) {
+    if (!x.alive) return;
+    if ((uint64_t)x.r.bounces > o.max_bounces) x.valid = false;
+    if (o.check_refr && (uint64_t)x.r.refr >= o.max_refr) x.valid = false;
+}
+// rays.rs:1119-1133
+__device__ __forceinline__ void exec_filter(const DevFilter& o, RayCtx& x) {
+    if (x.valid) x.r.e *= o.t;
+}
+// rays.rs:943-959
+__device__ __forceinline__ void exec_paraxial(const DevParaxial& o, RayCtx& x) {
+    if (x.valid) refract_paraxial(o, x.r);
+}
+// rays.rs:1253-1264, ray.rs:752-772
+__device__ __forceinline__ void exec_split(const DevSplit& o, RayCtx& x) {
+    if (!x.in_range) return;
+    if (x.alive) {
+        RayState s = x.r;
+        if (x.valid) { x.r.e *= o.ratio; s.e *= 1.0 - o.ratio; }
+        if (o.out.px != nullptr) store_ray<true>(o.out, x.i, s, x.valid ? RAY_VALID : RAY_INVALID);
+    } else if (o.out.px != nullptr) {
+        o.out.valid[x.i] = RAY_REMOVED;
+    }
+}
+// copy of the bundle a detector node keeps (analyzers/raytrace.rs:186-205)
+__device__ __forceinline__ void exec_snapshot(const DevSnapshot& o, RayCtx& x) {
+    if (!x.in_range) return;
+    if (x.alive) store_ray<true>(o.out, x.i, x.r, x.valid ? RAY_VALID : RAY_INVALID);
+    else o.out.valid[x.i] = RAY_REMOVED;
+}
+// ray.rs:787-804
+__device__ __forceinline__ void exec_transform(const DevTransform& o, RayCtx& x) {
+    if (!x.alive) return;
+    x.r.pos = iso_point(o.iso, x.r.pos);
+    x.r.dir = iso_vector(o.iso, x.r.dir);
+}
+
+// ---- tile prologue / epilogue shared by both kernels -----------------------------------------------------------
+__device__ __forceinline__ void tile_load(const DevRays& in, uint64_t i, uint64_t n, RayCtx& x, uint8_t& vb) {
+    x.i = i;
+    x.in_range = i < n;
+    x.c.a = 0; x.c.b = 0; x.c.apodized = 0; x.c.status = 0;
+    x.r.pos = v3(0, 0, 0); x.r.dir = v3(0, 0, 1); x.r.e = 0; x.r.wvl = 0; x.r.opl = 0; x.r.n = 1; x.r.bounces = 0; x.r.refr = 0; x.r.id = 0;
+    vb = RAY_REMOVED;
+    if (x.in_range) {
+        vb = in.valid[i];
+        if (vb != RAY_REMOVED) load_ray(in, i, x.r);
+    }
+    x.alive = vb != RAY_REMOVED;
+    x.valid = vb == RAY_VALID;
+}
+
+template <bool COMPACT>
+__device__ __forceinline__ void tile_store(const DevRays& in, const DevRays& out, uint64_t out_cap, unsigned long long* out_tail,
+                                           RayCtx& x, uint8_t vb) {
+    if (COMPACT) {
+        unsigned long long slot = warp_reserve(x.alive, out_tail);
+        if (x.alive) {
+            if (slot < out_cap) store_ray<true>(out, slot, x.r, x.valid ? RAY_VALID : RAY_INVALID);
+            else x.c.status |= 1u << OPM_ERR_CAPACITY;
+        }
+    } else if (x.in_range) {
+        if (x.alive) {
+            if (out.px == in.px) store_ray<false>(out, x.i, x.r, x.valid ? RAY_VALID : RAY_INVALID);
+            else store_ray<true>(out, x.i, x.r, x.valid ? RAY_VALID : RAY_INVALID);
+        } else if (vb != RAY_REMOVED || out.px != in.px) {
+            out.valid[x.i] = RAY_REMOVED;
+        }
+    }
+}
+
+// tile counters: one warp reduction per register, lane 0 adds the fields to the CTA totals in shared memory
+__device__ __forceinline__ void tile_count(const RayCtx& x, unsigned long long* s_cnt, unsigned* s_status, unsigned long long* s_first_inv) {
+    const unsigned ra = __reduce_add_sync(0xffffffffu, x.c.a), rb = __reduce_add_sync(0xffffffffu, x.c.b);
+    const unsigned rp = __reduce_add_sync(0xffffffffu, x.c.apodized);
+    const unsigned live = __ballot_sync(0xffffffffu, x.alive), ok = __ballot_sync(0xffffffffu, x.valid && x.alive);
+    const unsigned st = __reduce_or_sync(0xffffffffu, x.c.status);
+    if (ok) {  // first valid ray of the warp = lowest id: ~key is largest there
+        unsigned long long inv = (x.valid && x.alive) ? ~(((unsigned long long)x.r.id << 32) | x.r.bounces) : 0ull;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { unsigned long long t = __shfl_xor_sync(0xffffffffu, inv, o); inv = t > inv ? t : inv; }
+        if ((threadIdx.x & 31) == 0) atomicMax(s_first_inv, inv);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (ra & 0xffffu) atomicAdd(&s_cnt[CNT_INTERACTIONS], (unsigned long long)(ra & 0xffffu));
+        if (ra >> 16) atomicAdd(&s_cnt[CNT_HITS], (unsigned long long)(ra >> 16));
+        if (rb & 0xffffu) atomicAdd(&s_cnt[CNT_MISSED], (unsigned long long)(rb & 0xffffu));
+        if (rb >> 16) atomicAdd(&s_cnt[CNT_CHILDREN], (unsigned long long)(rb >> 16));
+        if (rp) atomicAdd(&s_cnt[CNT_APODIZED], (unsigned long long)rp);
+        if (live) atomicAdd(&s_cnt[CNT_ALIVE_OUT], (unsigned long long)__popc(live));
+        if (ok) atomicAdd(&s_cnt[CNT_VALID_OUT], (unsigned long long)__popc(ok));
+        if (st) atomicOr(s_status, st);
+    }
+}
+
+// CTA totals -> global statistics (call after __syncthreads())
+__device__ __forceinline__ void cta_flush(DevStats* stats, const unsigned long long* s_cnt, unsigned s_status, unsigned long long s_first_inv) {
+    if (threadIdx.x < CNT_N && s_cnt[threadIdx.x]) {
+        unsigned long long* dst[CNT_N] = {&stats->interactions, &stats->children, &stats->hits, &stats->missed,
+                                          &stats->apodized, &stats->valid_out, &stats->alive_out};
+        atomicAdd(dst[threadIdx.x], s_cnt[threadIdx.x]);
+    }
+    if (threadIdx.x == 0 && s_status) atomicOr(&stats->status_bits, s_status);
+    if (threadIdx.x == 0 && s_first_inv) atomicMax(&stats->first_inv, s_first_inv);
+}
+
+}  // namespace opm

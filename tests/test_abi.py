@@ -94,3 +94,12 @@ def test_spectrum_gaussian_host_helper_matches_the_oracle():
         rv, rw = orc.spectrum_gaussian(*args)
         assert np.array_equal(wv, rv)
         assert np.allclose(w, rw, rtol=1e-14, atol=0) and abs(w.sum() - 1.0) < 1e-14
+
+
+def test_jit_source_compiles_without_a_gpu():
+    """the run-time specialised kernel (opm_jit.cu): a program with every op kind, geometry and coating is generated and
+    compiled by NVRTC for sm_100a against the embedded device headers -- the build check of the JIT path"""
+    import ctypes as C
+    buf = C.create_string_buffer(4096)
+    n = F.lib().opm_jit_selftest(buf, 4096)
+    assert n > 10_000, buf.value.decode()

@@ -256,3 +256,48 @@ def test_device_chained_readout_equals_stepwise_reports(ctx):
         for f in ("total_energy", "beam_radius_geo", "beam_radius_rms", "energy_beam_radius_rms"):
             assert getattr(s, f) == pytest.approx(getattr(ref_spot, f), rel=1e-12), f
         assert np.allclose(s.energy_centroid[:], ref_spot.energy_centroid[:], rtol=1e-12, atol=1e-18)
+
+
+@pytest.fixture(scope="module")
+def jit_ctx():
+    c = ob.Context(0)
+    c.set_jit(True, 1)  # every launch of the contracted build runs the kernel compiled for its program structure
+    yield c
+    c.close()
+
+
+@pytest.mark.parametrize("case", ["c1", "c2", "c4", "c5"])
+def test_specialised_kernel_matches_oracle(jit_ctx, case):
+    """the run-time compiled straight-line kernel (opm_jit.cu) against the oracle on the BASELINE scenes"""
+    nodes, src, dets, spot = {
+        "c1": (scenes.c1_single_lens(), scenes.c1_source(60), [3], 2),
+        "c2": (scenes.c2_laser_chain(), scenes.c2_source(20000), [9, 10], 8),
+        "c4": (scenes.c4_fluence(), scenes.c4_source(150), [2], None),
+        "c5": (scenes.c5_broadband(), scenes.c5_source(1500, 8), [4], None)}[case]
+    before = jit_ctx.jit_stats()
+    osc, ref_out, psc, rays, st = run_both(jit_ctx, nodes, src)
+    after = jit_ctx.jit_stats()
+    assert after["launches"] > before["launches"] and after["compile_failures"] == 0, after
+    assert st.interactions == osc.interactions
+    assert_rays_match(rays.to_array(), ref_out, what=f"{case} specialised kernel")
+    for node in dets:
+        check_detector(osc, psc, node)
+    if spot is not None:
+        ref_spot, s = osc.node_spot(spot), psc.node_spot(spot)
+        assert s.n_valid == ref_spot["n_valid"] and s.total_energy == pytest.approx(ref_spot["total_energy"], rel=RTOL)
+        assert s.beam_radius_geo == pytest.approx(ref_spot["geo"], rel=RTOL)
+
+
+def test_specialised_kernel_ghost_focus(jit_ctx):
+    """ghost focus (child emission with warp-aggregated appends, mirrors, limits) through the specialised kernels"""
+    nodes, src = scenes.c3_telescope(), scenes.c3_source(2000)
+    osc = scenes.to_oracle(nodes)
+    ref_passes = osc.ghostfocus(scenes.source_to_oracle(src), 2)
+    psc = scenes.to_product(jit_ctx, nodes)
+    st = psc.ghostfocus(scenes.source_to_product(src).generate(jit_ctx), 2)
+    assert st.interactions == osc.interactions and jit_ctx.jit_stats()["compile_failures"] == 0
+    for p, ref_bundles in enumerate(ref_passes):
+        got = psc.gf_pass_bundles(p)
+        assert len(got) == len(ref_bundles)
+        for g, r in zip(got, ref_bundles):
+            assert_rays_match(g.to_array(), r.rays, keyed=True, what=f"pass {p} bundle {r.uuid}", e_floor=1e-25)
