@@ -309,6 +309,7 @@ def run_product(args):
             inter_total = float(inter_per_step)
 
         fp64_peak = ctx.measure_fp64_peak() if rank == 0 else 0.0
+        jit = ctx.jit_stats()
 
     if rank == 0:
         peaks_file = ROOT / "MEASURED_PEAKS.json"
@@ -342,7 +343,9 @@ def run_product(args):
                     "pipeline": "two bundles: H2D of step k+1 (copy stream) overlaps trace + read-out of step k"},
             "gpu_launches": launches_per_step * args.steps,
             "clocks": clk,
-            "roofline": {"bound": "hbm", "kernel": "opm::trace_kernel (fused surface sequence)", "achieved": achieved, "peak": hbm_peak,
+            "roofline": {"bound": "hbm", "kernel": ("opm_jit_trace (fused surface sequence, compiled at run time for this op program)" if jit["launches"] else
+                                                   "opm::trace_kernel (fused surface sequence, interpreter)"),
+                         "jit": jit, "achieved": achieved, "peak": hbm_peak,
                          "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": bytes_step / max(launches_trace, 1), "launches_per_step": launches_trace,
                          "kernel_ms_per_launch": kern_ms_step / max(launches_trace, 1), "kernel_share_of_step": kern_ms_step / (ms / args.steps),

@@ -49,6 +49,7 @@ struct OpmContext {
     bool jit_enabled = true;
     uint64_t jit_min_rays = 200000;
     bool jit_warned = false;
+    int jit_block = 128, jit_min_ctas = 5;  // CTA shape of the specialised kernels (tunable: OPM_B200_JIT_BLOCK / _MIN_CTAS)
     cudaStream_t copy_stream = nullptr;  // host uploads that are expanded on the device run here, overlapping the main stream
     // optional per-launch timing of the fused trace kernel (CUDA events on the launching stream)
     bool timing = false;
@@ -192,6 +193,8 @@ extern "C" OpmStatus opm_context_create(int32_t device, void* stream, OpmContext
     c->jit = jit_cache_create();
     if (const char* e = getenv("OPM_B200_JIT")) c->jit_enabled = atoi(e) != 0;
     if (const char* e = getenv("OPM_B200_JIT_MIN_RAYS")) c->jit_min_rays = strtoull(e, nullptr, 10);
+    if (const char* e = getenv("OPM_B200_JIT_BLOCK")) { int v = atoi(e); if (v >= 32 && v <= 1024 && v % 32 == 0) c->jit_block = v; }
+    if (const char* e = getenv("OPM_B200_JIT_MIN_CTAS")) { int v = atoi(e); if (v >= 1 && v <= 16) c->jit_min_ctas = v; }
     CU(cudaMallocHost(&c->h_put_ring, OpmContext::kPutSlots * OpmContext::kPutBytes));
     for (int k = 0; k < OpmContext::kPutSlots; ++k) CU(cudaEventCreateWithFlags(&c->put_ev[k], cudaEventDisableTiming));
     CU(cudaMalloc(&c->d_stats, sizeof(DevStats)));
@@ -876,13 +879,14 @@ static OpmStatus run_program(OpmRays* rays, const OpmOp* ops, int n_ops, int fla
         CU(cudaEventSynchronize(c->ring_ev[slot]));  // the copy that last used this pinned slot has drained
         memcpy(h_slot, prog.ops.data(), prog.ops.size() * sizeof(DevOp));
         const bool strict = (flags & OPM_TRACE_STRICT) != 0;
-        const int block = strict ? trace_block_strict() : trace_block_fast();
+        int block = strict ? trace_block_strict() : trace_block_fast();
         // large bundles run the kernel compiled for the structure of this program (opm_jit.cu); otherwise, and whenever
         // that kernel cannot be had, the interpreter
         const JitKernel* jk = nullptr;
         if (!strict && c->jit_enabled && n >= c->jit_min_rays) {
             const char* why = nullptr;
-            jk = jit_get(c->jit, prog.ops.data(), (int)prog.ops.size(), compact, block, 2, &why);
+            jk = jit_get(c->jit, prog.ops.data(), (int)prog.ops.size(), compact, c->jit_block, c->jit_min_ctas, &why);
+            if (jk) block = c->jit_block;
             if (!jk && !c->jit_warned) {
                 c->jit_warned = true;
                 fprintf(stderr, "opossum_b200: run-time kernel specialisation unavailable, using the interpreter kernel (%s)\n", why ? why : "?");

@@ -17,6 +17,8 @@
 #include <cfloat>
 
 #include "opm_device.cuh"
+#include <cstdlib>
+
 #include "opm_kernels.h"
 
 namespace opm {
@@ -100,19 +102,34 @@ __global__ void transform_kernel(DevRays R, DevIso I, uint64_t n) {  // ray.rs:7
 __global__ void __launch_bounds__(256) spot_pass1_kernel(DevRays R, uint64_t n, int use_frame, DevIso inv, SpotAccum* acc) {
     double s[7] = {0, 0, 0, 0, 0, 0, 0};  // x y z ex ey ez e
     unsigned long long nv = 0, nt = 0, first = ~0ull;
-    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
-        uint8_t v = R.valid[i];
-        if (v == RAY_REMOVED) continue;
-        nt++;
-        if (v != RAY_VALID) continue;
-        nv++;
-        V3 p = v3(R.px[i], R.py[i], R.pz[i]);
-        if (use_frame) p = iso_point(inv, p);
-        double e = R.e[i];
-        s[0] += p.x; s[1] += p.y; s[2] += p.z;
-        s[3] += p.x * e; s[4] += p.y * e; s[5] += p.z * e; s[6] += e;
-        unsigned long long key = ((unsigned long long)R.id[i] << 32) | R.bounces[i];
-        first = key < first ? key : first;
+    // four independent slots per thread and iteration: the loads of a batch are in flight together
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t base = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; base < n; base += 4 * stride) {
+        uint8_t v[4];
+        double px[4], py[4], pz[4], e[4];
+        uint32_t id[4], bn[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const uint64_t i = base + u * stride;
+            const bool in = i < n;
+            v[u] = in ? R.valid[i] : (uint8_t)RAY_REMOVED;
+            const bool ld = in && v[u] == RAY_VALID;
+            px[u] = ld ? __ldcs(R.px + i) : 0.0; py[u] = ld ? __ldcs(R.py + i) : 0.0; pz[u] = ld ? __ldcs(R.pz + i) : 0.0;
+            e[u] = ld ? __ldcs(R.e + i) : 0.0; id[u] = ld ? __ldcs(R.id + i) : 0u; bn[u] = ld ? __ldcs(R.bounces + i) : 0u;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            if (v[u] == RAY_REMOVED) continue;
+            nt++;
+            if (v[u] != RAY_VALID) continue;
+            nv++;
+            V3 p = v3(px[u], py[u], pz[u]);
+            if (use_frame) p = iso_point(inv, p);
+            s[0] += p.x; s[1] += p.y; s[2] += p.z;
+            s[3] += p.x * e[u]; s[4] += p.y * e[u]; s[5] += p.z * e[u]; s[6] += e[u];
+            unsigned long long key = ((unsigned long long)id[u] << 32) | bn[u];
+            first = key < first ? key : first;
+        }
     }
     __shared__ double sh[8][7];
     __shared__ unsigned long long shn[8][3];
@@ -142,16 +159,29 @@ __global__ void __launch_bounds__(256) spot_pass2_kernel(DevRays R, uint64_t n, 
     const double ex = acc->sum[3] / acc->sum[6], ey = acc->sum[4] / acc->sum[6];
     const double cxm = cx / 1.0E-3, cym = cy / 1.0E-3;  // get::<millimeter>()
     double mx = 0.0, s2 = 0.0, se = 0.0;
-    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
-        if (R.valid[i] != RAY_VALID) continue;
-        V3 p = v3(R.px[i], R.py[i], R.pz[i]);
-        if (use_frame) p = iso_point(inv, p);
-        double dx = cxm - p.x / 1.0E-3, dy = cym - p.y / 1.0E-3;
-        double d2 = dx * dx + dy * dy;
-        mx = fmax(mx, d2);     // max of sqrt == sqrt of max (rays.rs:642-660)
-        s2 += d2;              // rays.rs:666-684: distance(..).powi(2)
-        double ux = ex - p.x, uy = ey - p.y;
-        se += (ux * ux + uy * uy) * R.e[i];  // rays.rs:690-701
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t base = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; base < n; base += 4 * stride) {
+        bool ok[4];
+        double px[4], py[4], pz[4], e[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const uint64_t i = base + u * stride;
+            ok[u] = i < n && R.valid[i] == RAY_VALID;
+            px[u] = ok[u] ? __ldcs(R.px + i) : 0.0; py[u] = ok[u] ? __ldcs(R.py + i) : 0.0; pz[u] = ok[u] ? __ldcs(R.pz + i) : 0.0;
+            e[u] = ok[u] ? __ldcs(R.e + i) : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            if (!ok[u]) continue;
+            V3 p = v3(px[u], py[u], pz[u]);
+            if (use_frame) p = iso_point(inv, p);
+            double dx = cxm - p.x / 1.0E-3, dy = cym - p.y / 1.0E-3;
+            double d2 = dx * dx + dy * dy;
+            mx = fmax(mx, d2);     // max of sqrt == sqrt of max (rays.rs:642-660)
+            s2 += d2;              // rays.rs:666-684: distance(..).powi(2)
+            double ux = ex - p.x, uy = ey - p.y;
+            se += (ux * ux + uy * uy) * e[u];  // rays.rs:690-701
+        }
     }
     __shared__ double sh[8][3];
     int w = threadIdx.x >> 5, l = threadIdx.x & 31;
@@ -200,13 +230,25 @@ __global__ void __launch_bounds__(256) tally_kernel(DevRays R, uint64_t n, uint3
 __global__ void __launch_bounds__(256) hits_bbox_kernel(DevHits H, uint64_t n, long long bounce_filter, BBoxAccum* acc) {
     double xmin = DBL_MAX, xmax = -DBL_MAX, ymin = DBL_MAX, ymax = -DBL_MAX;
     unsigned long long cnt = 0;
-    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
-        double e = __ldcs(H.e + i);
-        if (!(e >= 0.0)) continue;
-        if (bounce_filter >= 0 && (long long)H.bounce[i] != bounce_filter) continue;
-        double x = __ldcs(H.x + i), y = __ldcs(H.y + i);
-        xmin = fmin(xmin, x); xmax = fmax(xmax, x); ymin = fmin(ymin, y); ymax = fmax(ymax, y);
-        cnt++;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t base = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; base < n; base += 4 * stride) {
+        double e[4], x[4], y[4];
+        bool ok[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {  // four independent slots: their loads are in flight together
+            const uint64_t i = base + u * stride;
+            const bool in = i < n;
+            e[u] = in ? __ldcs(H.e + i) : -1.0;
+            ok[u] = e[u] >= 0.0;
+            if (ok[u] && bounce_filter >= 0) ok[u] = (long long)H.bounce[i] == bounce_filter;
+            x[u] = ok[u] ? __ldcs(H.x + i) : 0.0; y[u] = ok[u] ? __ldcs(H.y + i) : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            if (!ok[u]) continue;
+            xmin = fmin(xmin, x[u]); xmax = fmax(xmax, x[u]); ymin = fmin(ymin, y[u]); ymax = fmax(ymax, y[u]);
+            cnt++;
+        }
     }
     xmin = warp_min(xmin); xmax = warp_max(xmax); ymin = warp_min(ymin); ymax = warp_max(ymax); cnt = warp_sum_u64(cnt);
     if ((threadIdx.x & 31) == 0 && cnt) {
@@ -557,11 +599,11 @@ int k_transform(DevRays R, DevIso I, uint64_t n, int sms, void* stream) {
     return (int)cudaGetLastError();
 }
 int k_spot_pass1(DevRays R, uint64_t n, int use_frame, DevIso inv, SpotAccum* acc, int sms, void* stream) {
-    spot_pass1_kernel<<<grid_for(n, 256, sms * 4), 256, 0, ST>>>(R, n, use_frame, inv, acc);
+    spot_pass1_kernel<<<grid_for(n, 256 * 4, sms * 8), 256, 0, ST>>>(R, n, use_frame, inv, acc);
     return (int)cudaGetLastError();
 }
 int k_spot_pass2(DevRays R, uint64_t n, int use_frame, DevIso inv, SpotAccum* acc, int sms, void* stream) {
-    spot_pass2_kernel<<<grid_for(n, 256, sms * 4), 256, 0, ST>>>(R, n, use_frame, inv, acc);
+    spot_pass2_kernel<<<grid_for(n, 256 * 4, sms * 8), 256, 0, ST>>>(R, n, use_frame, inv, acc);
     return (int)cudaGetLastError();
 }
 int k_bounce_lvl(DevRays R, uint64_t n, unsigned long long* first_key, int sms, void* stream) {
@@ -573,7 +615,7 @@ int k_tally(DevRays R, uint64_t n, uint32_t n_orders, unsigned long long* counts
     return (int)cudaGetLastError();
 }
 int k_hits_bbox(DevHits H, uint64_t n, long long bounce_filter, BBoxAccum* acc, int sms, void* stream) {
-    hits_bbox_kernel<<<grid_for(n, 256, sms * 4), 256, 0, ST>>>(H, n, bounce_filter, acc);
+    hits_bbox_kernel<<<grid_for(n, 256 * 4, sms * 8), 256, 0, ST>>>(H, n, bounce_filter, acc);
     return (int)cudaGetLastError();
 }
 int k_bbox_finalize(const BBoxAccum* acc, double* range_dev, void* stream) {
@@ -583,7 +625,8 @@ int k_bbox_finalize(const BBoxAccum* acc, double* range_dev, void* stream) {
 int k_binning(DevHits H, uint64_t n, long long bounce_filter, uint64_t nx, uint64_t ny, const double* range_dev, double* map,
               unsigned* status, int sms, void* stream) {
     size_t bytes = (size_t)(nx * ny) * sizeof(double);
-    if (bytes <= 160 * 1024) {
+    static const bool force_global = getenv("OPM_B200_BINNING_GLOBAL") != nullptr;  // tuning switch
+    if (bytes <= 160 * 1024 && !force_global) {
         cudaError_t e = cudaFuncSetAttribute(binning_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
         if (e != cudaSuccess) return (int)e;
         // the privatised map takes most of an SM's shared memory: one CTA per SM, as many warps as it can hold
