@@ -369,16 +369,17 @@ def ray_refract_on_surface(ray: np.ndarray, surf: Surface, n2, strategy=MISS_STO
 
 
 def rays_refract_on_surface(rays: np.ndarray, surf: Surface, idx: IndexModel | None, refraction_intended=True,
-                            strategy=MISS_STOP, n_threads=1):
-    """Rays::refract_on_surface (rays.rs:976-1047), in place. Returns (children, hits, stats)."""
+                            strategy=MISS_STOP, n_threads=1, want_children=True, want_hits=True):
+    """Rays::refract_on_surface (rays.rs:976-1047), in place. Returns (children, hits, stats); outputs that are not wanted
+    are not materialised (None)."""
     n = len(rays)
-    children = np.zeros(max(n, 1), dtype=RAY_DTYPE)
-    hits = np.zeros(max(n, 1), dtype=HIT_DTYPE)
+    children = np.empty(max(n, 1), dtype=RAY_DTYPE) if want_children else None
+    hits = np.empty(max(n, 1), dtype=HIT_DTYPE) if want_hits else None
     st = RefractStats()
     _check(lib().orc_rays_refract_on_surface(_vp(rays), n, C.byref(surf), C.byref(idx) if idx is not None else None,
-                                             int(refraction_intended), strategy, _vp(children), _vp(hits),
-                                             C.byref(st), n_threads))
-    return children[: st.n_children].copy(), hits[: st.n_hits].copy(), st
+                                             int(refraction_intended), strategy, _vp(children) if want_children else None,
+                                             _vp(hits) if want_hits else None, C.byref(st), n_threads))
+    return (children[: st.n_children].copy() if want_children else None, hits[: st.n_hits].copy() if want_hits else None, st)
 
 
 def rays_apodize(rays, ap: Aperture, iso: Isometry, n_threads=1) -> bool:

@@ -144,8 +144,9 @@ class OScene:
         self.chain_out: dict[int, np.ndarray] = {}
 
     # ---- shared helpers
-    def _refract(self, rays, s: OSurface, idx, intended, strategy, uuid=1, record=True):
-        ch, hits, st = orc.rays_refract_on_surface(rays, s.surf, idx, intended, strategy, self.nt)
+    def _refract(self, rays, s: OSurface, idx, intended, strategy, uuid=1, record=True, want_children=True):
+        ch, hits, st = orc.rays_refract_on_surface(rays, s.surf, idx, intended, strategy, self.nt, want_children=want_children,
+                                                   want_hits=record)
         self.interactions += st.n_interactions
         if record:
             s.add_hits(hits, uuid)
@@ -164,7 +165,7 @@ class OScene:
             orc.rays_threshold(rays, thr, self.nt)
         elif t in (LENS, CYLINDRIC_LENS, WEDGE):  # lens/analysis_raytrace.rs + pass_through_surface (raytrace.rs:96-140)
             for s, idx in ((n.s[0], n.index), (n.s[1], self.ambient)):
-                self._refract(rays, s, idx, True, strat, record=record_all)
+                self._refract(rays, s, idx, True, strat, record=record_all, want_children=False)
                 orc.rays_apodize(rays, s.aperture, s.eff_iso, self.nt)
                 orc.rays_threshold(rays, thr, self.nt)
         elif t in (THIN_MIRROR, PARABOLIC_MIRROR):  # thin_mirror.rs:209-250
@@ -172,7 +173,7 @@ class OScene:
             orc.rays_apodize(rays, n.s[0].aperture, n.s[0].eff_iso, self.nt)
             orc.rays_threshold(rays, thr, self.nt)
         elif t == BEAM_SPLITTER:  # beam_splitter/mod.rs:158-293
-            self._refract(rays, n.s[0], None, True, strat, record=record_all)
+            self._refract(rays, n.s[0], None, True, strat, record=record_all, want_children=False)
             orc.rays_apodize(rays, n.s[0].aperture, n.s[0].eff_iso, self.nt)
             split = orc.rays_split(rays, n.p[0])
             orc.rays_apodize(rays, n.s[1].aperture, n.s[1].eff_iso, self.nt)
@@ -181,7 +182,7 @@ class OScene:
             orc.rays_threshold(split, thr, self.nt)
             n.split = split
         elif t in (DUMMY, IDEAL_FILTER, PARAXIAL_SURFACE):  # dummy.rs:83-135, ideal_filter.rs:203-250, paraxial_surface.rs:169-230
-            self._refract(rays, n.s[0], None, True, strat, record=record_all)
+            self._refract(rays, n.s[0], None, True, strat, record=record_all, want_children=False)
             if t == IDEAL_FILTER:
                 orc.rays_filter_energy(rays, n.p[0])
             if t == PARAXIAL_SURFACE:
@@ -190,7 +191,7 @@ class OScene:
                 orc.rays_apodize(rays, ap, n.s[0].eff_iso, self.nt)
                 orc.rays_threshold(rays, thr, self.nt)
         else:  # detectors: pass_through_detector_surface (raytrace.rs:150-207)
-            self._refract(rays, n.s[0], None, True, strat, record=True)
+            self._refract(rays, n.s[0], None, True, strat, record=True, want_children=False)
             orc.rays_apodize(rays, n.s[0].aperture, n.s[0].eff_iso, self.nt)
             orc.rays_threshold(rays, thr, self.nt)
             n.stored = rays.copy()
