@@ -240,9 +240,12 @@ OpmStatus opm_context_kernel_timing(OpmContext* ctx, double* total_ms, uint64_t*
 
 /* Run-time specialised kernels: for bundles of at least `min_rays` rays the contracted build compiles (NVRTC, cached per
  * program STRUCTURE: op kinds, geometries, coatings, index models, flags -- not the numbers) the straight-line kernel of
- * the op program instead of interpreting it; any failure falls back to the interpreter kernel.  Defaults: enabled,
- * 200000 rays; environment OPM_B200_JIT=0|1, OPM_B200_JIT_MIN_RAYS=n. */
+ * the op program instead of interpreting it.  The compiler runs on a worker thread: launches use the interpreter kernel
+ * until the specialised one is ready (enable = 1) or wait for it (enable = 2); any failure falls back to the interpreter.
+ * Defaults: 1, 200000 rays; environment OPM_B200_JIT=0|1|2, OPM_B200_JIT_MIN_RAYS=n.  opm_context_jit_wait blocks until no
+ * compilation is in flight (benchmarks: measure the steady state). */
 OpmStatus opm_context_set_jit(OpmContext* ctx, int32_t enable, uint64_t min_rays);
+OpmStatus opm_context_jit_wait(OpmContext* ctx);
 OpmStatus opm_context_jit_stats(const OpmContext* ctx, uint64_t* kernels_compiled, uint64_t* compile_failures, uint64_t* launches,
                                 double* compile_ms);
 /* build check that needs no GPU: compiles a program with every op kind to an sm_100a cubin; returns its size, 0 on failure

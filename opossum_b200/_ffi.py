@@ -190,7 +190,7 @@ SCENE_EXPORTS = [
 EXPORTS = [
     "opm_abi_version", "opm_last_error", "opm_status_string", "opm_context_create", "opm_context_destroy",
     "opm_context_synchronize", "opm_context_stream", "opm_context_launch_count", "opm_context_set_kernel_timing",
-    "opm_context_kernel_timing", "opm_context_set_jit", "opm_context_jit_stats", "opm_jit_selftest", "opm_isometry_identity",
+    "opm_context_kernel_timing", "opm_context_set_jit", "opm_context_jit_wait", "opm_context_jit_stats", "opm_jit_selftest", "opm_isometry_identity",
     "opm_isometry_new", "opm_isometry_append", "opm_raytrace_config_default", "opm_rays_create", "opm_rays_destroy",
     "opm_rays_len", "opm_rays_capacity", "opm_rays_clear", "opm_rays_reserve", "opm_rays_upload",
     "opm_rays_upload_soa", "opm_rays_new_collimated_with_spectrum", "opm_rays_download", "opm_rays_copy", "opm_rays_append", "opm_rays_compact",
@@ -240,6 +240,7 @@ def lib() -> C.CDLL:
         "opm_context_set_kernel_timing": (i32, [vp, i32]),
         "opm_context_kernel_timing": (i32, [vp, dp, C.POINTER(u64), i32]),
         "opm_context_set_jit": (i32, [vp, i32, u64]),
+        "opm_context_jit_wait": (i32, [vp]),
         "opm_context_jit_stats": (i32, [vp, C.POINTER(u64), C.POINTER(u64), C.POINTER(u64), dp]),
         "opm_jit_selftest": (u64, [C.c_char_p, u64]),
         "opm_isometry_identity": (None, [C.POINTER(OpmIsometry)]),

@@ -256,9 +256,14 @@ class Context:
         _check(F.lib().opm_context_kernel_timing(self.h, C.byref(ms), C.byref(n), int(reset)))
         return ms.value, n.value
 
-    def set_jit(self, enable: bool, min_rays: int = 200000):
-        """run-time specialised trace kernels (NVRTC, cached per program structure) for bundles of >= min_rays rays"""
+    def set_jit(self, enable, min_rays: int = 200000):
+        """run-time specialised trace kernels (NVRTC, cached per program structure) for bundles of >= min_rays rays.
+        enable: 0 off, 1 compile in the background and interpret meanwhile (default), 2 wait for the compiler"""
         _check(F.lib().opm_context_set_jit(self.h, int(enable), min_rays))
+
+    def jit_wait(self):
+        """block until no kernel compilation is in flight"""
+        _check(F.lib().opm_context_jit_wait(self.h))
 
     def jit_stats(self) -> dict:
         a, b, c, ms = C.c_uint64(), C.c_uint64(), C.c_uint64(), C.c_double()

@@ -47,6 +47,7 @@ struct OpmContext {
     // run-time specialised trace kernels: used by the contracted build for bundles of at least jit_min_rays rays
     JitCache* jit = nullptr;
     bool jit_enabled = true;
+    bool jit_sync = false;  // wait for the compiler instead of interpreting until the kernel is ready
     uint64_t jit_min_rays = 200000;
     bool jit_warned = false;
     int jit_block = 128, jit_min_ctas = 5;  // CTA shape of the specialised kernels (tunable: OPM_B200_JIT_BLOCK / _MIN_CTAS)
@@ -191,7 +192,7 @@ extern "C" OpmStatus opm_context_create(int32_t device, void* stream, OpmContext
     else { CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)); c->own_stream = true; }
     CU(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
     c->jit = jit_cache_create();
-    if (const char* e = getenv("OPM_B200_JIT")) c->jit_enabled = atoi(e) != 0;
+    if (const char* e = getenv("OPM_B200_JIT")) { c->jit_enabled = atoi(e) != 0; c->jit_sync = atoi(e) == 2; }
     if (const char* e = getenv("OPM_B200_JIT_MIN_RAYS")) c->jit_min_rays = strtoull(e, nullptr, 10);
     if (const char* e = getenv("OPM_B200_JIT_BLOCK")) { int v = atoi(e); if (v >= 32 && v <= 1024 && v % 32 == 0) c->jit_block = v; }
     if (const char* e = getenv("OPM_B200_JIT_MIN_CTAS")) { int v = atoi(e); if (v >= 1 && v <= 16) c->jit_min_ctas = v; }
@@ -234,7 +235,13 @@ extern "C" uint64_t opm_jit_selftest(char* log, uint64_t cap) { return jit_selft
 extern "C" OpmStatus opm_context_set_jit(OpmContext* c, int32_t enable, uint64_t min_rays) {
     if (!c) return fail(OPM_ERR_ARG, "context is NULL");
     c->jit_enabled = enable != 0;
+    c->jit_sync = enable == 2;
     c->jit_min_rays = min_rays;
+    return OPM_OK;
+}
+extern "C" OpmStatus opm_context_jit_wait(OpmContext* c) {
+    if (!c) return fail(OPM_ERR_ARG, "context is NULL");
+    jit_cache_wait(c->jit);
     return OPM_OK;
 }
 extern "C" OpmStatus opm_context_jit_stats(const OpmContext* c, uint64_t* kernels_compiled, uint64_t* compile_failures,
@@ -885,9 +892,9 @@ static OpmStatus run_program(OpmRays* rays, const OpmOp* ops, int n_ops, int fla
         const JitKernel* jk = nullptr;
         if (!strict && c->jit_enabled && n >= c->jit_min_rays) {
             const char* why = nullptr;
-            jk = jit_get(c->jit, prog.ops.data(), (int)prog.ops.size(), compact, c->jit_block, c->jit_min_ctas, &why);
+            jk = jit_get(c->jit, prog.ops.data(), (int)prog.ops.size(), compact, c->jit_block, c->jit_min_ctas, c->jit_sync, &why);
             if (jk) block = c->jit_block;
-            if (!jk && !c->jit_warned) {
+            if (!jk && why && !c->jit_warned) {  // why == NULL: still compiling, interpret meanwhile
                 c->jit_warned = true;
                 fprintf(stderr, "opossum_b200: run-time kernel specialisation unavailable, using the interpreter kernel (%s)\n", why ? why : "?");
             }

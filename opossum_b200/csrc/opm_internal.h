@@ -114,7 +114,9 @@ struct JitCache;
 JitCache* jit_cache_create();
 void jit_cache_destroy(JitCache* c);
 void jit_cache_stats(const JitCache* c, uint64_t* compiled, uint64_t* failures, uint64_t* launches, double* compile_ms);
-const JitKernel* jit_get(JitCache* cache, const DevOp* ops, int n_ops, bool compact, int block, int min_ctas, const char** why);
+void jit_cache_wait(JitCache* c);
+const JitKernel* jit_get(JitCache* cache, const DevOp* ops, int n_ops, bool compact, int block, int min_ctas, bool wait,
+                         const char** why);
 int jit_occupancy(const JitKernel* k);
 int jit_launch(JitCache* cache, const JitKernel* k, const TraceLaunch& L, const void* h_ops_pinned);
 size_t jit_selftest(char* why, size_t cap);  // compiles a program with every op kind to a cubin (no GPU needed); 0 = failed

@@ -18,8 +18,11 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <atomic>
 #include <map>
+#include <memory>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "opm_internal.h"
@@ -28,19 +31,25 @@
 
 namespace opm {
 
+// NVRTC runs on a worker thread (state COMPILING); the thread that owns the CUDA context loads the finished cubin the next
+// time the program is looked up.  Until then, and after a failure, launches use the interpreter kernel.
+enum JitState : int { JIT_COMPILING = 0, JIT_CUBIN_READY = 1, JIT_LOADED = 2, JIT_FAILED = 3 };
 struct JitKernel {
+    std::atomic<int> state{JIT_COMPILING};
+    std::thread worker;
+    std::vector<char> cubin;
+    double compile_ms = 0.0;
     cudaLibrary_t lib = nullptr;
     cudaKernel_t kernel = nullptr;
     void* d_const = nullptr;  // device address of the kernel's __constant__ op array
     size_t const_bytes = 0;
     int n_ops = 0;
     int occupancy = 1;
-    bool failed = false;
     std::string why;
 };
 
 struct JitCache {
-    std::map<std::string, JitKernel> kernels;
+    std::map<std::string, std::unique_ptr<JitKernel>> kernels;
     uint64_t compiled = 0, failures = 0, launches = 0;
     double compile_ms = 0.0;
 };
@@ -178,10 +187,9 @@ bool compile_cubin(const std::string& src, std::vector<char>& cubin, std::string
     return true;
 }
 
-bool compile(JitKernel& K, const std::string& src, int n_ops, int block) {
-    std::vector<char> cubin;
-    if (!compile_cubin(src, cubin, K.why)) return false;
-    cudaError_t e = cudaLibraryLoadData(&K.lib, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0);
+// cubin -> kernel handle + address of its constant op array (on the thread that owns the CUDA context)
+bool load(JitKernel& K, int n_ops, int block) {
+    cudaError_t e = cudaLibraryLoadData(&K.lib, K.cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0);
     if (e != cudaSuccess) { K.why = std::string("cudaLibraryLoadData: ") + cudaGetErrorString(e); cudaGetLastError(); return false; }
     e = cudaLibraryGetKernel(&K.kernel, K.lib, "opm_jit_trace");
     if (e == cudaSuccess) e = cudaLibraryGetGlobal(&K.d_const, &K.const_bytes, K.lib, "opm_jit_ops");
@@ -191,6 +199,8 @@ bool compile(JitKernel& K, const std::string& src, int n_ops, int block) {
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, (const void*)K.kernel, block, 0) != cudaSuccess || nb < 1) { nb = 1; cudaGetLastError(); }
     K.occupancy = nb;
     K.n_ops = n_ops;
+    K.cubin.clear();
+    K.cubin.shrink_to_fit();
     return true;
 }
 
@@ -199,7 +209,10 @@ bool compile(JitKernel& K, const std::string& src, int n_ops, int block) {
 JitCache* jit_cache_create() { return new JitCache(); }
 void jit_cache_destroy(JitCache* c) {
     if (!c) return;
-    for (auto& kv : c->kernels) if (kv.second.lib) cudaLibraryUnload(kv.second.lib);
+    for (auto& kv : c->kernels) {
+        if (kv.second->worker.joinable()) kv.second->worker.join();
+        if (kv.second->lib) cudaLibraryUnload(kv.second->lib);
+    }
     delete c;
 }
 void jit_cache_stats(const JitCache* c, uint64_t* compiled, uint64_t* failures, uint64_t* launches, double* compile_ms) {
@@ -208,26 +221,56 @@ void jit_cache_stats(const JitCache* c, uint64_t* compiled, uint64_t* failures, 
     if (launches) *launches = c ? c->launches : 0;
     if (compile_ms) *compile_ms = c ? c->compile_ms : 0.0;
 }
-std::string jit_debug_source(const DevOp* ops, int n_ops, bool compact) { return make_source(ops, n_ops, compact, 256, 2); }
+// blocks until no compilation is in flight (benchmarks and tests: measure / check the specialised kernels, not the hand-over)
+void jit_cache_wait(JitCache* c) {
+    if (!c) return;
+    for (auto& kv : c->kernels) if (kv.second->worker.joinable()) kv.second->worker.join();
+}
 
-const JitKernel* jit_get(JitCache* cache, const DevOp* ops, int n_ops, bool compact, int block, int min_ctas, const char** why) {
-    static std::string s_why;
+// wait = false: returns nullptr while the kernel of this program is still being compiled (the caller interprets meanwhile)
+const JitKernel* jit_get(JitCache* cache, const DevOp* ops, int n_ops, bool compact, int block, int min_ctas, bool wait,
+                         const char** why) {
+    static thread_local std::string s_why;
+    if (why) *why = nullptr;
     if (!cache || n_ops <= 0) { if (why) *why = "no program"; return nullptr; }
     std::string src = make_source(ops, n_ops, compact, block, min_ctas);
     auto it = cache->kernels.find(src);
     if (it == cache->kernels.end()) {
-        JitKernel K;
-        if (!nvrtc_load(&K.why)) K.failed = true;
-        else {
-            const auto t0 = std::chrono::steady_clock::now();
-            K.failed = !compile(K, src, n_ops, block);
-            cache->compile_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        it = cache->kernels.emplace(std::move(src), std::unique_ptr<JitKernel>(new JitKernel())).first;
+        JitKernel* k = it->second.get();
+        if (!nvrtc_load(&k->why)) {
+            k->state = JIT_FAILED;
+            cache->failures++;
+        } else {
+            const std::string* text = &it->first;  // map nodes are stable: the worker reads the key in place
+            k->worker = std::thread([k, text]() {
+                const auto t0 = std::chrono::steady_clock::now();
+                const bool ok = compile_cubin(*text, k->cubin, k->why);
+                k->compile_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+                k->state.store(ok ? JIT_CUBIN_READY : JIT_FAILED, std::memory_order_release);
+            });
         }
-        if (K.failed) cache->failures++; else cache->compiled++;
-        it = cache->kernels.emplace(std::move(src), std::move(K)).first;
     }
-    if (it->second.failed) { s_why = it->second.why; if (why) *why = s_why.c_str(); return nullptr; }
-    return &it->second;
+    JitKernel& K = *it->second;
+    int st = K.state.load(std::memory_order_acquire);
+    if (st == JIT_COMPILING && wait) {
+        if (K.worker.joinable()) K.worker.join();
+        st = K.state.load(std::memory_order_acquire);
+    }
+    if (st == JIT_CUBIN_READY) {
+        if (K.worker.joinable()) K.worker.join();
+        cache->compile_ms += K.compile_ms;
+        if (load(K, n_ops, block)) { K.state = JIT_LOADED; cache->compiled++; }
+        else { K.state = JIT_FAILED; cache->failures++; }
+        st = K.state.load();
+    } else if (st == JIT_FAILED && K.worker.joinable()) {
+        K.worker.join();
+        cache->failures++;
+        cache->compile_ms += K.compile_ms;
+    }
+    if (st == JIT_LOADED) return &K;
+    if (st == JIT_FAILED) { s_why = K.why; if (why) *why = s_why.c_str(); }
+    return nullptr;
 }
 
 int jit_occupancy(const JitKernel* K) { return K ? K->occupancy : 1; }

@@ -23,6 +23,8 @@ import scenes  # noqa: E402
 
 def timed(fn, ctx, reps=3):
     fn()
+    ctx.jit_wait()  # specialised kernels are compiled in the background: time the steady state
+    fn()
     ctx.synchronize()
     best = 1e30
     for _ in range(reps):

@@ -261,7 +261,7 @@ def test_device_chained_readout_equals_stepwise_reports(ctx):
 @pytest.fixture(scope="module")
 def jit_ctx():
     c = ob.Context(0)
-    c.set_jit(True, 1)  # every launch of the contracted build runs the kernel compiled for its program structure
+    c.set_jit(2, 1)  # every launch of the contracted build waits for and runs the kernel compiled for its program structure
     yield c
     c.close()
 
