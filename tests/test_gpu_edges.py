@@ -1,0 +1,139 @@
+"""Edge cases of the GPU path against the oracle: empty and ragged bundles, a single ray, bundles without a valid ray,
+programs longer than one launch, detectors that nothing hits, zero-energy rays, and the interpreter / run-time
+specialised kernels against each other."""
+import numpy as np
+import pytest
+
+import opossum_b200 as ob
+import scenes
+from opossum_b200 import ffi as F
+from oracle import oracle as orc
+from helpers import RTOL, assert_rays_match, index_pair, iso_pair, make_bundle, mm, nm, node_sphere_pair, surface_pair
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = ob.Context(0)
+    yield c
+    c.close()
+
+
+def lens_program(hm=None):
+    node = iso_pair((0.0, 0.0, mm(30.0)))
+    front = node_sphere_pair(mm(120.0), node, coating=F.COAT_FRESNEL)
+    rear = surface_pair(F.GEOM_PLANE, iso=iso_pair((0.0, 0.0, mm(34.0))), coating=F.COAT_CONSTANT_R, r=0.02)
+    glass, vac = index_pair("sellmeier1", 6.14555251E-1, 6.56775017E-1, 1.02699346E+0, 1.45987884E-2, 2.87769588E-3,
+                            1.07653051E+2, nm(300.0), nm(2000.0)), index_pair("const", 1.0)
+
+    def oracle(rays):
+        orc.rays_refract_on_surface(rays, front[0], glass[0])
+        orc.rays_threshold(rays, 1e-12)
+        _, hits, _ = orc.rays_refract_on_surface(rays, rear[0], vac[0])
+        orc.rays_threshold(rays, 1e-12)
+        return hits
+    prog = (ob.Program().refract(front[1], glass[1]).threshold(1e-12).refract(rear[1], vac[1], hit_map=hm).threshold(1e-12))
+    return oracle, prog
+
+
+@pytest.mark.parametrize("n", [0, 1, 31, 32, 33, 255, 256, 257, 1000])
+def test_ragged_bundle_sizes(ctx, n):
+    """tile boundaries of the persistent kernel (256-ray tiles, 32-lane warps), the single ray and the empty bundle"""
+    rays = make_bundle(max(n, 1), wvl=(nm(700.0), nm(1400.0)))[:n]
+    hm = ob.HitMap(ctx, max(n, 1))
+    oracle, prog = lens_program(hm)
+    ref = rays.copy()
+    hits = oracle(ref)
+    r = ob.Rays.from_array(ctx, rays)
+    assert len(r) == n
+    st = prog.run(r)
+    assert st.interactions == 2 * n and st.alive_out == n and st.hits == len(hits)
+    assert_rays_match(r.to_array(), ref, what=f"n={n}")
+    if n == 0:
+        assert r.total_energy() == 0.0 and r.centroid() is None
+
+
+def test_bundle_without_valid_rays_and_zero_energy_rays(ctx):
+    """invalid rays are carried along untouched (rays.rs:987: only valid rays are refracted); zero-energy rays stay valid
+    and still spawn (zero-energy) children unless a positive threshold removes them"""
+    rays = make_bundle(500)
+    rays["valid"][:] = 0
+    oracle, prog = lens_program()
+    r = ob.Rays.from_array(ctx, rays)
+    st = prog.run(r)
+    assert st.interactions == 0 and st.valid_out == 0 and st.alive_out == 500
+    got = r.to_array()
+    assert np.array_equal(got["pos"], rays["pos"]) and np.array_equal(got["opl"], rays["opl"])
+    zero = make_bundle(300)
+    zero["e"][::2] = 0.0
+    surf = surface_pair(F.GEOM_PLANE, iso=iso_pair((0.0, 0.0, mm(20.0))), coating=F.COAT_CONSTANT_R, r=0.1)
+    ref = zero.copy()
+    ch_ref, _, _ = orc.rays_refract_on_surface(ref, surf[0], index_pair("const", 1.5)[0])
+    g = ob.Rays.from_array(ctx, zero)
+    ch, st = g.refract_on_surface(surf[1], index_pair("const", 1.5)[1])
+    assert st.children == len(ch_ref) == 300  # the zero-energy half reflects zero-energy children
+    assert_rays_match(ch.to_array(), ch_ref, keyed=True, what="children incl. zero energy")
+    assert_rays_match(g.to_array(), ref, what="parents incl. zero energy")
+    g.invalidate_by_threshold_energy(1e-15)
+    orc.rays_threshold(ref, 1e-15)
+    assert g.nr_of_rays() == orc.nr_of_rays(ref) == 150
+
+
+def test_program_longer_than_one_launch(ctx):
+    """a chain whose op list exceeds OPM_MAX_PROGRAM_OPS is split into several launches by the scene layer"""
+    MM = scenes.MM
+    nodes = [scenes.node("source")]
+    for k in range(30):  # 30 dummies -> 30 x (refract, 2 apodize, thresholds, limits): far more than 64 ops
+        # radii chosen off the source's own radii 9 mm * sqrt(i / 4000): a ray exactly ON an aperture edge is decided by the
+        # last bit of its position (the `<=` of aperture.rs:158-180) and is not a parity case
+        nodes.append(scenes.node("dummy", z=(10 + 5 * k) * MM, ap_in=("circle", (9.03 - 0.1 * k) * MM, 0.0, 0.0)))
+    nodes.append(scenes.node("fluence_detector", z=200 * MM))
+    src = {"pos": ("fibonacci_ellipse", 4000, 9 * MM, 9 * MM), "energy": ("uniform", 1.0), "wvl": [1000 * scenes.NM], "w": [1.0]}
+    osc = scenes.to_oracle(nodes)
+    ref = osc.raytrace(scenes.source_to_oracle(src))
+    psc = scenes.to_product(ctx, nodes)
+    rays = scenes.source_to_product(src).generate(ctx)
+    l0 = ctx.launch_count
+    st = psc.raytrace(rays)
+    assert st.interactions == osc.interactions and st.valid_out == orc.nr_of_rays(ref) and 0 < st.valid_out < 4000
+    assert ctx.launch_count - l0 >= 4  # at least two trace launches (each with its program fetch)
+    assert_rays_match(rays.to_array(), ref, what="long chain")
+
+
+def test_detector_that_nothing_hits(ctx):
+    """every ray is clipped before the detector: Binning raises the reference's 'could not calculate bounding box'
+    (rays_hit_map.rs:526-531), the spot statistics report no valid ray"""
+    MM = scenes.MM
+    nodes = [scenes.node("source"), scenes.node("dummy", z=10 * MM, ap_in=("circle", 1 * MM, 0.05, 0.0)),
+             scenes.node("spot_diagram", z=20 * MM), scenes.node("fluence_detector", z=30 * MM)]
+    src = {"pos": ("grid", 20, 20, 20 * MM, 20 * MM), "energy": ("uniform", 1.0), "wvl": [1000 * scenes.NM], "w": [1.0]}
+    psc = scenes.to_product(ctx, nodes)
+    rays = scenes.source_to_product(src).generate(ctx)
+    st = psc.raytrace(rays)
+    assert st.valid_out == 0 and st.alive_out == 400
+    with pytest.raises(ob.OpossumError) as e:
+        psc.node_fluence(3)
+    assert e.value.code == F.OPM_ERR_EMPTY_HITMAP
+    s = psc.node_spot(2)
+    assert s.n_valid == 0 and s.n_total == 400 and np.isnan(s.beam_radius_geo)
+
+
+def test_interpreter_and_specialised_kernels_agree(ctx):
+    """the same program through the interpreter kernel and through the kernel compiled for it: identical counts and
+    flags, values equal to rounding (both are the contracted build; only instruction scheduling differs)"""
+    rays = make_bundle(5000, divergence=0.05)
+    outs = []
+    for jit in (0, 2):
+        ctx.set_jit(jit, 1)
+        hm = ob.HitMap(ctx, len(rays))
+        _, prog = lens_program(hm)
+        r = ob.Rays.from_array(ctx, rays)
+        st = prog.run(r)
+        outs.append((r.to_array(), hm.download(), st))
+    ctx.set_jit(1, 200000)
+    (a, ha, sa), (b, hb, sb) = outs
+    assert sa == sb
+    assert_rays_match(b, a, rtol=1e-13, what="specialised vs interpreter")
+    assert np.array_equal(ha[4], hb[4]) and np.allclose(ha[0], hb[0], rtol=1e-13, atol=1e-18)
+    assert ctx.jit_stats()["launches"] >= 1 and ctx.jit_stats()["compile_failures"] == 0
