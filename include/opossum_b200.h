@@ -58,7 +58,8 @@ enum {
     OPM_ERR_BIN_RANGE = 11,      /* hit outside an explicit map range (the reference panics)   rays_hit_map.rs:364-374 */
     OPM_ERR_ARG = 12,            /* invalid argument / handle */
     OPM_ERR_CAPACITY = 13,       /* an output bundle / hit map is too small */
-    OPM_ERR_CUDA = 14            /* CUDA runtime failure (including: no device) */
+    OPM_ERR_CUDA = 14,           /* CUDA runtime failure (including: no device) */
+    OPM_ERR_KDE_BANDWIDTH = 15   /* "bandwidth must be != 0.0 and finite"                      kde/mod.rs:36-42 */
 };
 
 /* ------------------------------------------------------------------------------------------
@@ -370,6 +371,12 @@ OpmStatus opm_fluence_binning_async(OpmHitMap* const* maps, int32_t n_maps, int6
 /* peak_total_dev[2] = peak fluence (J/m^2), total energy (J) */
 OpmStatus opm_fluence_peak_total_async(OpmContext* ctx, const double* map_dev, uint64_t nx, uint64_t ny, const double* range_dev,
                                        double* peak_total_dev);
+/* HitMap::calc_fluence_map(.., FluenceEstimator::KDE): RaysHitMap::calc_fluence_with_kde (rays_hit_map.rs:575-613) with
+ * Kde::bandwidth_estimate / kde_2d (kde/mod.rs:83-134, Gaussian2D kde/gaussian.rs).  ranges: NULL (bounding box + 3 band
+ * widths) or {r1.start, r1.end, r2.start, r2.end}, read as (left, right, top, bottom) like the reference does.  O(hits^2)
+ * memory for the bandwidth estimate: at most 50000 hit points. */
+OpmStatus opm_fluence_kde(OpmHitMap* const* maps, int32_t n_maps, int64_t bounce_filter_or_minus1, uint64_t nx, uint64_t ny,
+                          const double* ranges_or_null, double* map_dev, double lrtb_out[4], double* band_width_out);
 /* FluenceData::new peak (fluence_data.rs:45-68) and total_energy (:130-141) of a device map */
 OpmStatus opm_fluence_peak_total(OpmContext* ctx, const double* map_dev, uint64_t nx, uint64_t ny, const double lrtb[4],
                                  double* peak, double* total_energy);

@@ -108,6 +108,9 @@ OpmStatus opm_scene_node_spot_async(OpmScene* scene, int32_t node, int32_t phase
 /* nodes/fluence_detector/mod.rs:91-135 with FluenceEstimator::Binning: map_host (nx*ny, column-major ny x nx) may be NULL */
 OpmStatus opm_scene_node_fluence(OpmScene* scene, int32_t node, uint64_t nx, uint64_t ny, double* map_host, double lrtb[4],
                                  double* peak, double* total_energy);
+/* the same report with FluenceEstimator::KDE (rays_hit_map.rs:575-613, kde/mod.rs); band_width = the estimated kernel width */
+OpmStatus opm_scene_node_fluence_kde(OpmScene* scene, int32_t node, uint64_t nx, uint64_t ny, double* map_host, double lrtb[4],
+                                     double* peak, double* total_energy, double* band_width);
 /* hit maps recorded on surface `surface` (0 = input_1, 1 = output_1) of a node: fills up to `capacity` handles */
 int32_t opm_scene_node_hitmaps(OpmScene* scene, int32_t node, int32_t surface, OpmHitMap** out, int32_t capacity);
 

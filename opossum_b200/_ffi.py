@@ -19,7 +19,7 @@ OPM_MAX_PROGRAM_OPS = 64
 # status codes
 (OPM_OK, OPM_ERR_N2_INVALID, OPM_ERR_WVL_RANGE, OPM_ERR_INDEX_MODEL, OPM_ERR_COATING, OPM_ERR_APODIZE_FACTOR,
  OPM_ERR_THRESHOLD, OPM_ERR_HITPOINT, OPM_ERR_SPLIT_RATIO, OPM_ERR_FOCAL_LENGTH, OPM_ERR_EMPTY_HITMAP,
- OPM_ERR_BIN_RANGE, OPM_ERR_ARG, OPM_ERR_CAPACITY, OPM_ERR_CUDA) = range(15)
+ OPM_ERR_BIN_RANGE, OPM_ERR_ARG, OPM_ERR_CAPACITY, OPM_ERR_CUDA, OPM_ERR_KDE_BANDWIDTH) = range(16)
 
 GEOM_PLANE, GEOM_SPHERE, GEOM_CYLINDER, GEOM_PARABOLA = range(4)
 COAT_IDEAL_AR, COAT_CONSTANT_R, COAT_FRESNEL = range(3)
@@ -182,7 +182,7 @@ SCENE_EXPORTS = [
     "opm_node_desc_init", "opm_scene_create", "opm_scene_destroy", "opm_scene_set_ambient", "opm_scene_add_node",
     "opm_scene_node_count", "opm_scene_reset_data", "opm_scene_raytrace", "opm_scene_output_rays", "opm_scene_node_rays", "opm_scene_node_spot",
     "opm_scene_node_spot_partial", "opm_scene_node_spot_async",
-    "opm_scene_node_fluence", "opm_scene_node_hitmaps", "opm_scene_ghostfocus", "opm_scene_gf_pass_tally",
+    "opm_scene_node_fluence", "opm_scene_node_fluence_kde", "opm_scene_node_hitmaps", "opm_scene_ghostfocus", "opm_scene_gf_pass_tally",
     "opm_scene_gf_pass_bundles", "opm_scene_node_critical_fluences", "opm_scene_node_peak_fluence",
 ]
 
@@ -201,7 +201,7 @@ EXPORTS = [
     "opm_rays_spot_partial_radii", "opm_spot_stats_from_partial", "opm_rays_spot_sums_async", "opm_rays_spot_radii_async", "opm_rays_bounce_lvl", "opm_rays_tally", "opm_hitmap_create",
     "opm_hitmap_destroy", "opm_hitmap_capacity", "opm_hitmap_len", "opm_hitmap_upload", "opm_hitmap_download",
     "opm_hitmaps_bounding_box", "opm_fluence_binning", "opm_fluence_peak_total", "opm_hitmaps_bounding_box_async",
-    "opm_fluence_binning_async", "opm_fluence_peak_total_async", "opm_measure_fp64_peak", "opm_device_alloc",
+    "opm_fluence_binning_async", "opm_fluence_peak_total_async", "opm_fluence_kde", "opm_measure_fp64_peak", "opm_device_alloc",
     "opm_device_free", "opm_device_memset", "opm_device_to_host", "opm_host_to_device", "opm_host_alloc_pinned", "opm_host_free_pinned",
     "opm_spectrum_gaussian", "opm_source_generate", "opm_source_generate_strided", "opm_source_energy_norm",
 ]
@@ -281,6 +281,7 @@ def lib() -> C.CDLL:
         "opm_hitmaps_bounding_box_async": (i32, [pp, i32, i64, vp]),
         "opm_fluence_binning_async": (i32, [pp, i32, i64, u64, u64, vp, i32, vp, vp]),
         "opm_fluence_peak_total_async": (i32, [vp, vp, u64, u64, vp, vp]),
+        "opm_fluence_kde": (i32, [pp, i32, i64, u64, u64, dp, vp, dp, dp]),
         "opm_rays_bounce_lvl": (i32, [vp, C.POINTER(C.c_uint32)]),
         "opm_rays_tally": (i32, [vp, C.c_uint32, C.POINTER(u64), dp]),
         "opm_hitmap_create": (i32, [vp, u64, pp]),
@@ -320,6 +321,7 @@ def lib() -> C.CDLL:
         "opm_scene_node_spot_partial": (i32, [vp, i32, i32, C.POINTER(OpmSpotPartial)]),
         "opm_scene_node_spot_async": (i32, [vp, i32, i32, vp, vp]),
         "opm_scene_node_fluence": (i32, [vp, i32, u64, u64, dp, dp, dp, dp]),
+        "opm_scene_node_fluence_kde": (i32, [vp, i32, u64, u64, dp, dp, dp, dp, dp]),
         "opm_scene_node_hitmaps": (i32, [vp, i32, i32, pp, i32]),
         "opm_scene_ghostfocus": (i32, [vp, vp, C.POINTER(OpmGhostFocusConfig), i32, C.POINTER(OpmGhostFocusStats)]),
         "opm_scene_gf_pass_tally": (i32, [vp, C.c_uint32, C.c_uint32, C.POINTER(u64), dp, C.POINTER(u64), C.POINTER(u64)]),

@@ -659,6 +659,25 @@ def fluence_binning(ctx: Context, hit_maps, nx: int, ny: int, ranges=None, lrtb=
             ctx.device_free(map_dev)
 
 
+def fluence_kde(ctx: Context, hit_maps, nx: int, ny: int, ranges=None, bounce=-1):
+    """HitMap::calc_fluence_map(.., FluenceEstimator::KDE) (rays_hit_map.rs:575-613, kde/mod.rs) -> (FluenceData, band width)"""
+    L = F.lib()
+    map_dev = ctx.device_alloc(nx * ny * 8)
+    try:
+        arr = (C.c_void_p * len(hit_maps))(*[h.h for h in hit_maps])
+        rg = (C.c_double * 4)(*ranges) if ranges is not None else None
+        out = (C.c_double * 4)()
+        bw = C.c_double()
+        _check(L.opm_fluence_kde(arr, len(hit_maps), bounce, nx, ny, rg, C.c_void_p(map_dev), out, C.byref(bw)))
+        peak, tot = C.c_double(), C.c_double()
+        _check(L.opm_fluence_peak_total(ctx.h, C.c_void_p(map_dev), nx, ny, out, C.byref(peak), C.byref(tot)))
+        flat = np.zeros(nx * ny)
+        ctx.to_host(map_dev, flat)
+        return FluenceData(flat.reshape(nx, ny).T.copy(), tuple(out[:]), peak.value, tot.value), bw.value
+    finally:
+        ctx.device_free(map_dev)
+
+
 def fluence_peak_total(ctx: Context, map_dev: int, nx: int, ny: int, lrtb) -> FluenceData:
     """FluenceData::new peak (fluence_data.rs:45-68) and total_energy (:130-141) of a map that already sits on the device
     (e.g. after an all-reduce of per-GPU maps)."""

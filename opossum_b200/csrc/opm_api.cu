@@ -155,6 +155,7 @@ extern "C" const char* opm_status_string(OpmStatus s) {
         case OPM_ERR_ARG: return "invalid argument";
         case OPM_ERR_CAPACITY: return "output bundle or hit map too small";
         case OPM_ERR_CUDA: return "CUDA failure";
+        case OPM_ERR_KDE_BANDWIDTH: return "bandwidth must be != 0.0 and finite";
         default: return "unknown status";
     }
 }
@@ -1306,6 +1307,95 @@ extern "C" OpmStatus opm_fluence_peak_total(OpmContext* c, const double* map_dev
     CU(cudaStreamSynchronize(c->stream));
     if (peak) *peak = h[0];
     if (total) *total = h[1];
+    return OPM_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// KDE fluence estimator: RaysHitMap::calc_fluence_with_kde (rays_hit_map.rs:575-613), Kde (kde/mod.rs) -- SURVEY 8f-1
+// ---------------------------------------------------------------------------------------------
+extern "C" OpmStatus opm_fluence_kde(OpmHitMap* const* maps, int32_t n_maps, int64_t bounce_filter, uint64_t nx, uint64_t ny,
+                                     const double* ranges, double* map_dev, double lrtb_out[4], double* band_width_out) {
+    OpmContext* c;
+    OpmStatus s = check_same_ctx(maps, n_maps, &c);
+    if (s) return s;
+    if (!map_dev || nx == 0 || ny == 0) return fail(OPM_ERR_ARG, "bad map arguments");
+    CU(cudaSetDevice(c->device));
+    uint64_t slots = 0;
+    for (int k = 0; k < n_maps; ++k) slots += maps[k]->len;
+    // dense hit list
+    double *hx = nullptr, *hy = nullptr, *he = nullptr, *dist = nullptr, *sorted = nullptr;
+    void* temp = nullptr;
+    auto cleanup = [&]() { cudaFree(hx); cudaFree(dist); cudaFree(sorted); cudaFree(temp); };
+    CU(cudaMalloc(&hx, (slots ? slots : 1) * 3 * sizeof(double)));
+    hy = hx + (slots ? slots : 1); he = hy + (slots ? slots : 1);
+    unsigned long long* d_count = (unsigned long long*)(c->d_scratch + 3072);  // count | sum of distances | sum of squared deviations
+    double* d_sums = (double*)(d_count + 1);
+    cudaMemsetAsync(d_count, 0, 24, c->stream);
+    for (int k = 0; k < n_maps; ++k)
+        if (maps[k]->len) {
+            int rc = k_hits_pack(maps[k]->v, maps[k]->len, bounce_filter, hx, hy, he, d_count, slots, c->sms, c->stream);
+            c->launches++;
+            if (rc) { cleanup(); return fail(OPM_ERR_CUDA, "hit packing failed"); }
+        }
+    unsigned long long n = 0;
+    cudaMemcpyAsync(&n, d_count, 8, cudaMemcpyDeviceToHost, c->stream);
+    if (cudaStreamSynchronize(c->stream) != cudaSuccess) { cleanup(); return fail(OPM_ERR_CUDA, "hit packing failed"); }
+    // Kde::bandwidth_estimate (kde/mod.rs:83-106)
+    const double nan = std::nan("");
+    double bw = nan;
+    std::vector<double> first(4, 0.0);
+    if (n == 2) {
+        cudaMemcpyAsync(first.data(), hx, 16, cudaMemcpyDeviceToHost, c->stream);
+        cudaMemcpyAsync(first.data() + 2, hy, 16, cudaMemcpyDeviceToHost, c->stream);
+        cudaStreamSynchronize(c->stream);
+        double dx = first[1] - first[0], dy = first[3] - first[2];
+        bw = 0.5 * std::sqrt(dx * dx + dy * dy);
+        if (bw == 0.0) bw = nan;
+    } else if (n > 2) {
+        if (n > 50000) { cleanup(); return fail(OPM_ERR_CAPACITY, "KDE bandwidth estimate over %llu hit points needs %llu pair distances", n, n * (n - 1) / 2); }
+        const uint64_t m = n * (n - 1) / 2;
+        size_t temp_bytes = 0;
+        k_sort_doubles(nullptr, nullptr, m, nullptr, &temp_bytes, c->stream);
+        if (cudaMalloc(&dist, m * 8) != cudaSuccess || cudaMalloc(&sorted, m * 8) != cudaSuccess || cudaMalloc(&temp, temp_bytes ? temp_bytes : 8) != cudaSuccess) {
+            cleanup(); cudaGetLastError();
+            return fail(OPM_ERR_CUDA, "out of device memory for the KDE pair distances");
+        }
+        int rc = k_kde_pair_distances(hx, hy, n, dist, d_sums, d_sums + 1, c->sms, c->stream);
+        if (!rc) rc = k_sort_doubles(dist, sorted, m, temp, &temp_bytes, c->stream);
+        c->launches += 3;
+        if (rc) { cleanup(); return fail(OPM_ERR_CUDA, "KDE bandwidth kernels failed: %s", cudaGetErrorString((cudaError_t)rc)); }
+        // Kde::distances_iqr (kde/mod.rs:65-81)
+        const double quart = 0.75 * (double)m;
+        double ip;
+        const bool whole = std::modf(quart, &ip) == 0.0;
+        const uint64_t q = whole ? (uint64_t)quart - 1 : (uint64_t)std::floor(quart);
+        double qv[2] = {0.0, 0.0}, sums[2] = {0.0, 0.0};
+        cudaMemcpyAsync(qv, sorted + q, whole ? 16 : 8, cudaMemcpyDeviceToHost, c->stream);
+        cudaMemcpyAsync(sums, d_sums, 16, cudaMemcpyDeviceToHost, c->stream);
+        if (cudaStreamSynchronize(c->stream) != cudaSuccess) { cleanup(); return fail(OPM_ERR_CUDA, "KDE bandwidth kernels failed"); }
+        const double iqr = whole ? 0.5 * (qv[0] + qv[1]) : qv[0];
+        const double std_dev = std::sqrt(sums[1] / (double)m);
+        bw = 0.9 * std::fmin(std_dev, iqr / 1.34) * std::pow((double)n, -0.2);  // Silverman's rule of thumb
+    }
+    if (band_width_out) *band_width_out = bw;
+    if (!std::isnormal(bw)) { cleanup(); return fail(OPM_ERR_KDE_BANDWIDTH, "%s", opm_status_string(OPM_ERR_KDE_BANDWIDTH)); }
+    // map range: given ranges (left, right, top, bottom like the reference reads them) or bounding box + 3 bandwidths
+    double l, r, t, b;
+    if (ranges) { l = ranges[0]; r = ranges[1]; t = ranges[2]; b = ranges[3]; }
+    else {
+        double box[4];
+        s = opm_hitmaps_bounding_box(maps, n_maps, bounce_filter, box, nullptr);
+        if (s) { cleanup(); return s; }
+        const double margin = 3. * bw;
+        l = box[0] - margin; r = box[1] + margin; b = box[3] - margin; t = box[2] + margin;
+    }
+    const double dx = (r - l) / (double)nx, dy = (t - b) / (double)ny;
+    int rc = k_kde_2d(hx, hy, he, n, bw, l, b, dx, dy, nx, ny, map_dev, c->stream);
+    c->launches++;
+    cudaError_t e = cudaStreamSynchronize(c->stream);
+    cleanup();
+    if (rc || e != cudaSuccess) return fail(OPM_ERR_CUDA, "KDE map kernel failed");
+    if (lrtb_out) { lrtb_out[0] = l; lrtb_out[1] = r; lrtb_out[2] = t; lrtb_out[3] = b; }
     return OPM_OK;
 }
 

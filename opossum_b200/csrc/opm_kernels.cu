@@ -19,6 +19,8 @@
 #include "opm_device.cuh"
 #include <cstdlib>
 
+#include <cub/device/device_radix_sort.cuh>
+
 #include "opm_kernels.h"
 
 namespace opm {
@@ -405,6 +407,90 @@ __global__ void __launch_bounds__(256) peak_total_kernel(const double* __restric
 }
 
 // ---------------------------------------------------------------------------------------------
+// kernel density estimator (kde/mod.rs, kde/gaussian.rs): the KDE fluence estimator
+// ---------------------------------------------------------------------------------------------
+// dense (x, y, e) list of the recorded hits of a slot-indexed hit map (warp-aggregated append; order is not kept)
+__global__ void __launch_bounds__(256) hits_pack_kernel(DevHits H, uint64_t n, long long bounce_filter, double* __restrict__ x,
+                                                        double* __restrict__ y, double* __restrict__ e, unsigned long long* count,
+                                                        unsigned long long cap) {
+    const uint64_t n_round = (n + 31) / 32 * 32;
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n_round; i += (uint64_t)gridDim.x * blockDim.x) {
+        bool ok = false;
+        double ev = -1.0;
+        if (i < n) {
+            ev = H.e[i];
+            ok = ev >= 0.0 && !(bounce_filter >= 0 && (long long)H.bounce[i] != bounce_filter);
+        }
+        const unsigned mask = __ballot_sync(0xffffffffu, ok);
+        if (!mask) continue;
+        const int lane = threadIdx.x & 31, leader = __ffs(mask) - 1;
+        unsigned long long base = 0;
+        if (lane == leader) base = atomicAdd(count, (unsigned long long)__popc(mask));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if (ok) {
+            unsigned long long slot = base + __popc(mask & ((1u << lane) - 1u));
+            if (slot < cap) { x[slot] = H.x[i]; y[slot] = H.y[i]; e[slot] = ev; }
+        }
+    }
+}
+// Kde::point_distances_std_dev, first half (kde/mod.rs:44-56): every pair distance (i < j) at its place in the
+// reference's order, and their sum
+__global__ void __launch_bounds__(256) kde_pair_distance_kernel(const double* __restrict__ x, const double* __restrict__ y, uint64_t n,
+                                                                double* __restrict__ dist, double* sum) {
+    const uint64_t i = blockIdx.y;
+    const double xi = x[i], yi = y[i];
+    const uint64_t base = i * (2 * n - i - 1) / 2;
+    double s = 0.0;
+    for (uint64_t j = i + 1 + blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; j < n; j += (uint64_t)gridDim.x * blockDim.x) {
+        double dx = x[j] - xi, dy = y[j] - yi;  // math_utils::distance_2d_point
+        double d = sqrt(dx * dx + dy * dy);
+        dist[base + (j - i - 1)] = d;
+        s += d;
+    }
+    s = warp_sum(s);
+    if ((threadIdx.x & 31) == 0 && s != 0.0) atomicAdd(sum, s);
+}
+// second half (kde/mod.rs:57-63): sum of squared deviations from the mean distance
+__global__ void __launch_bounds__(256) kde_deviation_kernel(const double* __restrict__ dist, uint64_t m, const double* __restrict__ sum,
+                                                            double* dev) {
+    const double avg = *sum / (double)m;
+    double s = 0.0;
+    for (uint64_t k = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; k < m; k += (uint64_t)gridDim.x * blockDim.x) {
+        double d = dist[k] - avg;
+        s += d * d;
+    }
+    s = warp_sum(s);
+    if ((threadIdx.x & 31) == 0 && s != 0.0) atomicAdd(dev, s);
+}
+// Kde::kde_2d (kde/mod.rs:114-134): one thread per map point, the hit list streamed through shared memory, summed in hit
+// order like the reference's iterator sum.  map: column-major ny x nx.
+__global__ void __launch_bounds__(256) kde_2d_kernel(const double* __restrict__ hx, const double* __restrict__ hy,
+                                                     const double* __restrict__ he, uint64_t n, double band_width, double left,
+                                                     double bottom, double dx, double dy, uint64_t nx, uint64_t ny,
+                                                     double* __restrict__ map) {
+    __shared__ double sx[256], sy[256], sa[256];
+    const uint64_t k = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    const bool in = k < nx * ny;
+    const uint64_t col = in ? k / ny : 0, row = in ? k % ny : 0;
+    const double px = left + (double)col * dx, py = bottom + (double)row * dy;
+    const double FRAC_1_2PI = 0.15915494309189535;
+    const double sigma_square = band_width * band_width;
+    double sum = 0.0;
+    for (uint64_t t0 = 0; t0 < n; t0 += 256) {
+        const uint64_t j = t0 + threadIdx.x;
+        __syncthreads();
+        if (j < n) { sx[threadIdx.x] = hx[j]; sy[threadIdx.x] = hy[j]; sa[threadIdx.x] = he[j] * FRAC_1_2PI / sigma_square; }
+        __syncthreads();
+        const int cnt = (int)((n - t0) < 256 ? (n - t0) : 256);
+        for (int q = 0; q < cnt; ++q) {  // Gaussian2D::value (kde/gaussian.rs:24-27)
+            double dist_square = (px - sx[q]) * (px - sx[q]) + (py - sy[q]) * (py - sy[q]);
+            sum += sa[q] * exp(-dist_square / (2. * sigma_square));
+        }
+    }
+    if (in) map[k] = sum;
+}
+
+// ---------------------------------------------------------------------------------------------
 // sources
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ double fract(double x) { return x - trunc(x); }
@@ -637,6 +723,31 @@ int k_binning(DevHits H, uint64_t n, long long bounce_filter, uint64_t nx, uint6
     return (int)cudaGetLastError();
 }
 __global__ void peak_finalize_kernel(const PeakAccum* acc, double* out2) { out2[0] = dkey_inv(acc->peak_key); out2[1] = acc->total; }
+int k_hits_pack(DevHits H, uint64_t n, long long bounce_filter, double* x, double* y, double* e, unsigned long long* count,
+                unsigned long long cap, int sms, void* stream) {
+    hits_pack_kernel<<<grid_for(n, 256, sms * 8), 256, 0, ST>>>(H, n, bounce_filter, x, y, e, count, cap);
+    return (int)cudaGetLastError();
+}
+int k_kde_pair_distances(const double* x, const double* y, uint64_t n, double* dist, double* sum, double* dev, int sms, void* stream) {
+    if (n < 2) return 0;
+    const uint64_t m = n * (n - 1) / 2;
+    unsigned gx = (unsigned)((n + 255) / 256);
+    if (gx > 64) gx = 64;
+    kde_pair_distance_kernel<<<dim3(gx, (unsigned)(n - 1)), 256, 0, ST>>>(x, y, n, dist, sum);
+    kde_deviation_kernel<<<grid_for(m, 256, sms * 8), 256, 0, ST>>>(dist, m, sum, dev);
+    return (int)cudaGetLastError();
+}
+// ascending sort of the pair distances (the 75 % quantile of kde/mod.rs:65-81 is read from the sorted list)
+int k_sort_doubles(const double* in, double* out, uint64_t m, void* temp, size_t* temp_bytes, void* stream) {
+    if (m > 0x7fffffffull) return (int)cudaErrorInvalidValue;
+    return (int)cub::DeviceRadixSort::SortKeys(temp, *temp_bytes, in, out, (int)m, 0, 64, ST);
+}
+int k_kde_2d(const double* hx, const double* hy, const double* he, uint64_t n, double band_width, double left, double bottom, double dx,
+             double dy, uint64_t nx, uint64_t ny, double* map, void* stream) {
+    const uint64_t pts = nx * ny;
+    kde_2d_kernel<<<(unsigned)((pts + 255) / 256), 256, 0, ST>>>(hx, hy, he, n, band_width, left, bottom, dx, dy, nx, ny, map);
+    return (int)cudaGetLastError();
+}
 int k_peak_total(const double* map, uint64_t nx, uint64_t ny, const double* range_dev, PeakAccum* acc, double* out2_dev, int sms, void* stream) {
     peak_total_kernel<<<grid_for(nx * ny, 256, sms * 4), 256, 0, ST>>>(map, nx, ny, range_dev, acc);
     if (out2_dev) peak_finalize_kernel<<<1, 1, 0, ST>>>(acc, out2_dev);

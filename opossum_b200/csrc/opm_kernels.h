@@ -54,6 +54,13 @@ int k_bbox_finalize(const BBoxAccum* acc, double* range_dev, void* stream);
 int k_binning(DevHits H, uint64_t n, long long bounce_filter, uint64_t nx, uint64_t ny, const double* range_dev, double* map,
               unsigned* status, int sms, void* stream);
 int k_peak_total(const double* map, uint64_t nx, uint64_t ny, const double* range_dev, PeakAccum* acc, double* out2_dev, int sms, void* stream);
+// kernel density estimator (kde/mod.rs)
+int k_hits_pack(DevHits H, uint64_t n, long long bounce_filter, double* x, double* y, double* e, unsigned long long* count,
+                unsigned long long cap, int sms, void* stream);
+int k_kde_pair_distances(const double* x, const double* y, uint64_t n, double* dist, double* sum, double* dev, int sms, void* stream);
+int k_sort_doubles(const double* in, double* out, uint64_t m, void* temp, size_t* temp_bytes, void* stream);
+int k_kde_2d(const double* hx, const double* hy, const double* he, uint64_t n, double band_width, double left, double bottom, double dx,
+             double dy, uint64_t nx, uint64_t ny, double* map, void* stream);
 int k_spot_sums_store(const SpotAccum* acc, double* sums_dev, void* stream);
 int k_spot_sums_load(const double* sums_dev, SpotAccum* acc, void* stream);
 int k_spot_radii_store(const SpotAccum* acc, double* radii_dev, void* stream);

@@ -568,6 +568,26 @@ extern "C" OpmStatus opm_scene_node_fluence(OpmScene* sc, int32_t node, uint64_t
     return st;
 }
 
+// FluenceDetector::node_report with FluenceEstimator::KDE (nodes/fluence_detector/mod.rs:91-135, rays_hit_map.rs:575-613)
+extern "C" OpmStatus opm_scene_node_fluence_kde(OpmScene* sc, int32_t node, uint64_t nx, uint64_t ny, double* map_host, double lrtb[4],
+                                                double* peak, double* total, double* band_width) {
+    if (!sc || node < 0 || node >= (int)sc->nodes.size()) return OPM_ERR_ARG;
+    Node& n = *sc->nodes[node];
+    std::vector<OpmHitMap*> maps;
+    for (auto& h : n.s[0].hits) maps.push_back(h.map);
+    if (maps.empty()) return OPM_ERR_EMPTY_HITMAP;
+    void* dev = nullptr;
+    OpmStatus st = opm_device_alloc(sc->ctx, nx * ny * sizeof(double), &dev);
+    if (st) return st;
+    double box[4];
+    st = opm_fluence_kde(maps.data(), (int32_t)maps.size(), -1, nx, ny, nullptr, (double*)dev, box, band_width);
+    if (!st) st = opm_fluence_peak_total(sc->ctx, (const double*)dev, nx, ny, box, peak, total);
+    if (!st && map_host) st = opm_device_to_host(sc->ctx, map_host, dev, nx * ny * sizeof(double));
+    if (lrtb) memcpy(lrtb, box, sizeof box);
+    opm_device_free(sc->ctx, dev);
+    return st;
+}
+
 // ---------------------------------------------------------------------------------------------
 // ghost focus: see opm_scene_gf.inc
 // ---------------------------------------------------------------------------------------------

@@ -215,11 +215,21 @@ class Scene:
         _check(F.lib().opm_scene_node_spot_partial(self.h, node, 1 if reduced is None else 2, C.byref(p)))
         return p
 
-    def node_fluence(self, node: int, nx=100, ny=83, download=True) -> FluenceData:
-        """FluenceDetector::node_report (nodes/fluence_detector/mod.rs:91-135), Binning estimator"""
+    def node_fluence(self, node: int, nx=100, ny=83, download=True, estimator="binning") -> FluenceData:
+        """FluenceDetector::node_report (nodes/fluence_detector/mod.rs:91-135); estimator "binning" or "kde"
+        (FluenceEstimator::Binning / ::KDE)"""
         m = np.zeros(nx * ny) if download else None
         lrtb = (C.c_double * 4)()
         peak, tot = C.c_double(), C.c_double()
+        if estimator == "kde":
+            bw = C.c_double()
+            _check(F.lib().opm_scene_node_fluence_kde(self.h, node, nx, ny, m.ctypes.data_as(C.POINTER(C.c_double)) if download else None,
+                                                      lrtb, C.byref(peak), C.byref(tot), C.byref(bw)))
+            fd = FluenceData(m.reshape(nx, ny).T.copy() if download else None, tuple(lrtb[:]), peak.value, tot.value)
+            fd.band_width = bw.value
+            return fd
+        if estimator != "binning":
+            raise ValueError("estimator must be 'binning' or 'kde' (the Voronoi estimator is out of scope, SURVEY 8f-1)")
         _check(F.lib().opm_scene_node_fluence(self.h, node, nx, ny,
                                               m.ctypes.data_as(C.POINTER(C.c_double)) if download else None, lrtb,
                                               C.byref(peak), C.byref(tot)))

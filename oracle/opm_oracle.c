@@ -808,6 +808,108 @@ int orc_hits_bounding_box(const OrcHit* h, uint64_t n, double lrtb[4]) { /* rays
     lrtb[0] = left - 0.0; lrtb[1] = right + 0.0; lrtb[2] = top + 0.0; lrtb[3] = bottom - 0.0;
     return ORC_OK;
 }
+/* ---- kernel density estimator (kde/mod.rs, kde/gaussian.rs) ---------------------------------- */
+static int cmp_double(const void* a, const void* b) {
+    double x = *(const double*)a, y = *(const double*)b;
+    return (x > y) - (x < y);
+}
+/* Kde::distances_iqr (kde/mod.rs:65-81): despite its name the 75 % quantile of the values */
+double orc_kde_distances_iqr(const double* values, uint64_t n) {
+    if (n == 0) return NAN;
+    double* v = (double*)malloc(n * sizeof(double));
+    if (!v) return NAN;
+    memcpy(v, values, n * sizeof(double));
+    qsort(v, n, sizeof(double), cmp_double);
+    double quart = 0.75 * (double)n, ip;
+    double out;
+    if (modf(quart, &ip) == 0.0) out = 0.5 * (v[(uint64_t)quart - 1] + v[(uint64_t)quart]);
+    else out = v[(uint64_t)floor(quart)];
+    free(v);
+    return out;
+}
+/* Kde::point_distances_std_dev (kde/mod.rs:44-64): all pair distances (i < j, in that order) and their population std dev */
+int orc_kde_point_distances(const OrcHit* h, uint64_t n, double* distances, double* std_dev) {
+    uint64_t m = 0;
+    double sum = 0.0;
+    for (uint64_t i = 0; i < n; ++i)
+        for (uint64_t j = i + 1; j < n; ++j) {
+            double dx = h[j].x - h[i].x, dy = h[j].y - h[i].y;  /* math_utils::distance_2d_point: ((x2-x1)^2 + (y2-y1)^2).sqrt() */
+            double d = sqrt(dx * dx + dy * dy);
+            if (distances) distances[m] = d;
+            ++m;
+            sum += d;
+        }
+    double nr = (double)m, avg = sum / nr, dev = 0.0;
+    m = 0;
+    for (uint64_t i = 0; i < n; ++i)
+        for (uint64_t j = i + 1; j < n; ++j) {
+            double dx = h[j].x - h[i].x, dy = h[j].y - h[i].y;
+            double d = distances ? distances[m] : sqrt(dx * dx + dy * dy);
+            ++m;
+            dev += (d - avg) * (d - avg);
+        }
+    *std_dev = sqrt(dev / nr);
+    return ORC_OK;
+}
+/* Kde::bandwidth_estimate (kde/mod.rs:83-106): Silverman's rule of thumb on the pair distances */
+double orc_kde_bandwidth_estimate(const OrcHit* h, uint64_t n) {
+    if (n < 2) return NAN;
+    if (n == 2) {
+        double dx = h[1].x - h[0].x, dy = h[1].y - h[0].y;
+        double bw = 0.5 * sqrt(dx * dx + dy * dy);
+        return bw == 0.0 ? NAN : bw;
+    }
+    uint64_t m = n * (n - 1) / 2;
+    double* d = (double*)malloc(m * sizeof(double));
+    if (!d) return NAN;
+    double sd;
+    orc_kde_point_distances(h, n, d, &sd);
+    double iqr = orc_kde_distances_iqr(d, m);
+    free(d);
+    double a = iqr / 1.34;
+    double mn = sd < a ? sd : a;  /* uom Length::min == f64::min (NaN-ignoring) */
+    if (isnan(sd)) mn = a;
+    if (isnan(a)) mn = sd;
+    return 0.9 * mn * pow((double)n, -0.2);
+}
+/* Gaussian2D::value summed over the hit map (kde/gaussian.rs:12-28, kde/mod.rs:107-113), in hit order */
+double orc_kde_value(const OrcHit* h, uint64_t n, double band_width, double px, double py) {
+    const double FRAC_1_2PI = 0.15915494309189535;
+    double sigma_square = band_width * band_width, sum = 0.0;
+    for (uint64_t i = 0; i < n; ++i) {
+        double amplitude = h[i].e * FRAC_1_2PI / sigma_square;
+        double dist_square = (px - h[i].x) * (px - h[i].x) + (py - h[i].y) * (py - h[i].y);
+        sum += amplitude * exp(-dist_square / (2. * sigma_square));
+    }
+    return sum;
+}
+/* RaysHitMap::calc_fluence_with_kde (rays_hit_map.rs:575-613) + Kde::kde_2d (kde/mod.rs:114-134).  ranges: NULL or
+ * {r1.start, r1.end, r2.start, r2.end} taken as (left, right, top, bottom) like the reference does.  map: ny rows x nx
+ * columns, column-major.  Errors: bandwidth not normal -> ORC_ERR_ARG ("bandwidth must be != 0.0 and finite"). */
+int orc_fluence_kde(const OrcHit* h, uint64_t n, uint64_t nx, uint64_t ny, const double* ranges, double* map, double lrtb_out[4],
+                    double* band_width_out, int n_threads) {
+    double bw = orc_kde_bandwidth_estimate(h, n);
+    if (band_width_out) *band_width_out = bw;
+    if (!isnormal(bw)) return ORC_ERR_ARG;
+    double left, right, top, bottom;
+    if (ranges) { left = ranges[0]; right = ranges[1]; top = ranges[2]; bottom = ranges[3]; }
+    else {
+        double b[4];
+        int rc = orc_hits_bounding_box(h, n, b);
+        if (rc) return rc;
+        double margin = 3. * bw;
+        left = b[0] - margin; right = b[1] + margin; bottom = b[3] - margin; top = b[2] + margin;
+    }
+    double dx = (right - left) / (double)nx, dy = (top - bottom) / (double)ny;
+    (void)n_threads;
+#pragma omp parallel for schedule(static) num_threads(n_threads > 0 ? n_threads : 1) if (n_threads > 1)
+    for (int64_t col = 0; col < (int64_t)nx; ++col)
+        for (uint64_t row = 0; row < ny; ++row)
+            map[(uint64_t)col * ny + row] = orc_kde_value(h, n, bw, left + (double)col * dx, bottom + (double)row * dy);
+    lrtb_out[0] = left; lrtb_out[1] = right; lrtb_out[2] = top; lrtb_out[3] = bottom;
+    return ORC_OK;
+}
+
 /* Rust `f64 as usize`: saturating, NaN -> 0 */
 static inline uint64_t f64_to_usize(double v) {
     if (isnan(v) || v <= 0.0) return 0;

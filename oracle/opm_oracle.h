@@ -172,6 +172,14 @@ int orc_fluence_binning(const OrcHit* hits, uint64_t n, uint64_t nx, uint64_t ny
 double orc_fluence_peak(const double* map, uint64_t n);                                /* fluence_data.rs:45-68 */
 double orc_fluence_total_energy(const double* map, uint64_t nx, uint64_t ny, const double lrtb[4]); /* :130-141 */
 
+/* ---- kernel density estimator (kde/mod.rs, kde/gaussian.rs): the KDE fluence estimator, SURVEY 8f-1 */
+double orc_kde_distances_iqr(const double* values, uint64_t n);                       /* kde/mod.rs:65-81 */
+int orc_kde_point_distances(const OrcHit* hits, uint64_t n, double* distances_or_null, double* std_dev); /* :44-64 */
+double orc_kde_bandwidth_estimate(const OrcHit* hits, uint64_t n);                    /* :83-106 */
+double orc_kde_value(const OrcHit* hits, uint64_t n, double band_width, double px, double py); /* :107-113, gaussian.rs:12-28 */
+int orc_fluence_kde(const OrcHit* hits, uint64_t n, uint64_t nx, uint64_t ny, const double* ranges, double* map, double lrtb_out[4],
+                    double* band_width_out, int n_threads);                           /* rays_hit_map.rs:575-613 */
+
 /* ---- sources */
 void orc_grid(uint64_t nx, uint64_t ny, double side_x, double side_y, double* xyz);   /* position_distributions/grid.rs:58-92 */
 void orc_fibonacci_rectangle(uint64_t n, double side_x, double side_y, double* xyz);   /* fibonacci.rs:53-65 */

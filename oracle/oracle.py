@@ -279,6 +279,14 @@ def lib():
     L.orc_rays_bounce_lvl.restype = C.c_uint32
     L.orc_hits_bounding_box.argtypes = [vp, C.c_uint64, dp]
     L.orc_fluence_binning.argtypes = [vp, C.c_uint64, C.c_uint64, C.c_uint64, dp, dp, dp]
+    L.orc_kde_distances_iqr.argtypes = [dp, C.c_uint64]
+    L.orc_kde_distances_iqr.restype = C.c_double
+    L.orc_kde_point_distances.argtypes = [vp, C.c_uint64, dp, dp]
+    L.orc_kde_bandwidth_estimate.argtypes = [vp, C.c_uint64]
+    L.orc_kde_bandwidth_estimate.restype = C.c_double
+    L.orc_kde_value.argtypes = [vp, C.c_uint64, C.c_double, C.c_double, C.c_double]
+    L.orc_kde_value.restype = C.c_double
+    L.orc_fluence_kde.argtypes = [vp, C.c_uint64, C.c_uint64, C.c_uint64, dp, dp, dp, dp, C.c_int]
     L.orc_fluence_peak.argtypes = [dp, C.c_uint64]
     L.orc_fluence_peak.restype = C.c_double
     L.orc_fluence_total_energy.argtypes = [dp, C.c_uint64, C.c_uint64, dp]
@@ -475,6 +483,38 @@ def fluence_binning(hits: np.ndarray, nx: int, ny: int, ranges=None):
     rg = (C.c_double * 4)(*ranges) if ranges is not None else None
     _check(lib().orc_fluence_binning(_vp(hits), len(hits), nx, ny, rg, _dptr(m), lrtb))
     return m.reshape(nx, ny).T.copy(), tuple(lrtb[:])  # column-major ny x nx -> [row=y, col=x]
+
+
+def kde_distances_iqr(values) -> float:
+    v = np.ascontiguousarray(values, dtype=np.float64)
+    return lib().orc_kde_distances_iqr(_dptr(v), len(v))
+
+
+def kde_point_distances(hits: np.ndarray):
+    """Kde::point_distances_std_dev (kde/mod.rs:44-64) -> (distances, std_dev)"""
+    n = len(hits)
+    d = np.zeros(max(n * (n - 1) // 2, 1))
+    sd = C.c_double()
+    lib().orc_kde_point_distances(_vp(hits), n, _dptr(d), C.byref(sd))
+    return d[: n * (n - 1) // 2], sd.value
+
+
+def kde_bandwidth_estimate(hits: np.ndarray) -> float:
+    return lib().orc_kde_bandwidth_estimate(_vp(hits), len(hits))
+
+
+def kde_value(hits: np.ndarray, band_width: float, px: float, py: float) -> float:
+    return lib().orc_kde_value(_vp(hits), len(hits), band_width, px, py)
+
+
+def fluence_kde(hits: np.ndarray, nx: int, ny: int, ranges=None, n_threads=1):
+    """calc_fluence_with_kde (rays_hit_map.rs:575-613). Returns (map[ny,nx], (left,right,top,bottom), band width)."""
+    m = np.zeros(nx * ny, dtype=np.float64)
+    lrtb = (C.c_double * 4)()
+    rg = (C.c_double * 4)(*ranges) if ranges is not None else None
+    bw = C.c_double()
+    _check(lib().orc_fluence_kde(_vp(hits), len(hits), nx, ny, rg, _dptr(m), lrtb, C.byref(bw), n_threads))
+    return m.reshape(nx, ny).T.copy(), tuple(lrtb[:]), bw.value
 
 
 def fluence_peak(fmap: np.ndarray) -> float:

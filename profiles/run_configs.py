@@ -148,11 +148,30 @@ def c5(ctx, n_pos, n_wvl=64, chunk_pos=1_562_500, nx=512, ny=512):
                        "map_energy_below_source": bool(fd.total_energy < float(np.sum(w))), "lrtb": lrtb}}
 
 
+def kde(ctx, n=20000, nx=100, ny=83):
+    """the KDE fluence estimator (kde/mod.rs) on the C1 detector's hit map: O(n^2) bandwidth estimate
+    (2*10^8 pair distances, sorted) + n x pixels Gaussian sum, against the oracle on the host cores"""
+    from oracle import oracle as orc
+    side = int(round(n ** 0.5))
+    sc = scenes.to_product(ctx, scenes.c1_single_lens())
+    sc.raytrace(scenes.source_to_product(scenes.c1_source(side)).generate(ctx))
+    fd, dt = timed(lambda: sc.node_fluence(3, nx, ny, estimator="kde"), ctx, reps=2)
+    x, y, z, e, b = sc.node_hitmaps(3, 0)[0].download()
+    hits = orc.hits_from_xye(x, y, e)
+    t = time.perf_counter()
+    ref_map, _, ref_bw = orc.fluence_kde(hits, nx, ny, n_threads=orc.max_threads())
+    dt_cpu = time.perf_counter() - t
+    err = float(np.max(np.abs(fd.map - ref_map)) / ref_map.max())
+    return {"config": f"KDE fluence estimator, {len(x)} hit points -> {nx}x{ny} map", "rays": len(x), "interactions": len(x) * nx * ny,
+            "seconds": dt, "cpu_oracle_seconds": dt_cpu, "cpu_threads": orc.max_threads(),
+            "checks": {"band_width": fd.band_width, "band_width_oracle": ref_bw, "max_abs_err_over_peak": err, "within_1e-9": bool(err < 1e-9)}}
+
+
 def main():
     which = sys.argv[1:] or ["c1", "c2", "c3", "c4", "c5"]
     ctx = ob.Context(0)
     table = {"c1": lambda: c1(ctx), "c2": lambda: c2(ctx), "c3": lambda: c3(ctx), "c4": lambda: c4(ctx),
-             "c5": lambda: c5(ctx, 1_562_500), "c5full": lambda: c5(ctx, 100_000_000)}
+             "c5": lambda: c5(ctx, 1_562_500), "c5full": lambda: c5(ctx, 100_000_000), "kde": lambda: kde(ctx)}
     for k in which:
         out = table[k]()
         out["interactions_per_s"] = out.get("traced_interactions", out["interactions"]) / out["seconds"]

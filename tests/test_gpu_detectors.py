@@ -150,3 +150,59 @@ def test_sources_match_oracle(ctx):
                 sd.c.energy_norm = sd.energy_norm(ctx)
             part = sd.generate(ctx, b, e_).to_array()
             assert_rays_match(part, ref[b * len(wvl): e_ * len(wvl)], what=f"source shard {name}")
+
+
+# ------------------------------------------------------------------ KDE estimator (kde/mod.rs)
+def _kde_hits(ctx, xyz, e):
+    hm = ob.HitMap(ctx, len(e))
+    hm.upload(xyz[:, 0], xyz[:, 1], e)
+    return hm, orc.hits_from_xye(xyz[:, 0], xyz[:, 1], e)
+
+
+@pytest.mark.parametrize("case", ["hexapolar37", "fibonacci2000", "three_points", "explicit_ranges"])
+def test_kde_fluence_matches_oracle(ctx, case):
+    """calc_fluence_with_kde (rays_hit_map.rs:575-613): bandwidth (Silverman on all pair distances: std dev, 75 % quantile),
+    map range (bounding box + 3 bandwidths) and the Gaussian sum per map point against the oracle.  hexapolar37 -> 30x30
+    is the hit set of the reference's own `kde` criterion bench (benches/fluence_estimator.rs:12-24)."""
+    ranges = None
+    if case == "hexapolar37":
+        xyz, nx, ny = orc.hexapolar(3, mm(5.0)), 30, 30
+    elif case == "fibonacci2000":
+        xyz, nx, ny = orc.fibonacci_ellipse(2000, mm(4.0), mm(3.0)), 64, 48
+    elif case == "three_points":
+        xyz, nx, ny = np.array([[0.0, 0.0, 0.0], [1e-3, 0.0, 0.0], [-1e-3, 0.0, 0.0]]), 20, 10
+    else:
+        xyz, nx, ny = orc.fibonacci_rectangle(500, mm(6.0), mm(6.0)), 40, 40
+        ranges = (mm(-2.0), mm(2.5), mm(3.0), mm(-1.0))  # (left, right, top, bottom) as the reference reads them
+    e = 1e-3 * (1.0 + 0.3 * np.cos(np.arange(len(xyz))))
+    hm, hits = _kde_hits(ctx, xyz, e)
+    ref_map, ref_lrtb, ref_bw = orc.fluence_kde(hits, nx, ny, ranges)
+    fd, bw = ob.fluence_kde(ctx, [hm], nx, ny, ranges)
+    assert bw == pytest.approx(ref_bw, rel=1e-12)
+    if case == "three_points":
+        assert abs(bw - 0.00034057440111656337) < 1e-15  # kde/mod.rs:255-261
+    assert np.allclose(fd.lrtb, ref_lrtb, rtol=1e-12, atol=1e-18)
+    assert_map_match(fd.map, ref_map)
+    assert fd.peak == pytest.approx(orc.fluence_peak(ref_map), rel=RTOL)
+
+
+def test_kde_errors_and_bounce_filter(ctx):
+    """fewer than two hit points or coincident points: 'bandwidth must be != 0.0 and finite' (kde/mod.rs:36-42,83-98);
+    the bounce filter selects the hit points of one bounce level (hit_map/mod.rs:101-115)"""
+    xyz = orc.fibonacci_ellipse(300, mm(3.0), mm(3.0))
+    e = np.full(300, 1e-3)
+    hm = ob.HitMap(ctx, 300)
+    bounce = (np.arange(300) % 3).astype(np.uint32)
+    hm.upload(xyz[:, 0], xyz[:, 1], e, bounce=bounce)
+    sel = bounce == 1
+    ref_map, _, ref_bw = orc.fluence_kde(orc.hits_from_xye(xyz[sel, 0], xyz[sel, 1], e[sel]), 32, 32)
+    fd, bw = ob.fluence_kde(ctx, [hm], 32, 32, bounce=1)
+    assert bw == pytest.approx(ref_bw, rel=1e-12)
+    assert_map_match(fd.map, ref_map)
+    for pts in ([[0.0, 0.0, 0.0]], [[1e-3, 2e-3, 0.0], [1e-3, 2e-3, 0.0]]):
+        p = np.array(pts)
+        h1 = ob.HitMap(ctx, len(p))
+        h1.upload(p[:, 0], p[:, 1], np.ones(len(p)))
+        with pytest.raises(ob.OpossumError) as ei:
+            ob.fluence_kde(ctx, [h1], 8, 8)
+        assert ei.value.code == F.OPM_ERR_KDE_BANDWIDTH

@@ -301,3 +301,19 @@ def test_specialised_kernel_ghost_focus(jit_ctx):
         assert len(got) == len(ref_bundles)
         for g, r in zip(got, ref_bundles):
             assert_rays_match(g.to_array(), r.rays, keyed=True, what=f"pass {p} bundle {r.uuid}", e_floor=1e-25)
+
+
+def test_fluence_detector_with_kde_estimator(ctx):
+    """FluenceDetector with FluenceEstimator::KDE (SURVEY 8f-1) end to end: C1 scene at 1500 rays, detector map 40x33"""
+    nodes, src = scenes.c1_single_lens(), scenes.c1_source(39)
+    osc = scenes.to_oracle(nodes)
+    osc.raytrace(scenes.source_to_oracle(src))
+    ref_map, ref_lrtb, ref_bw = orc.fluence_kde(osc.nodes[3].s[0].merged_hits(), 40, 33)
+    psc = scenes.to_product(ctx, nodes)
+    psc.raytrace(scenes.source_to_product(src).generate(ctx))
+    fd = psc.node_fluence(3, 40, 33, estimator="kde")
+    assert fd.band_width == pytest.approx(ref_bw, rel=1e-9)
+    assert np.allclose(fd.lrtb, ref_lrtb, rtol=1e-9, atol=1e-15)
+    assert_map_match(fd.map, ref_map, rtol=1e-8)  # the map range itself carries the 1e-9 of the hit positions
+    with pytest.raises(ValueError):
+        psc.node_fluence(3, 40, 33, estimator="voronoi")

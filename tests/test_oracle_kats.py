@@ -530,3 +530,56 @@ def test_fibonacci_and_spectrum_properties():
     rays = orc.rays_collimated_with_spectrum(orc.grid(2, 2, 1.0, 1.0), orc.energy_uniform(4, 1.0), wvl[:3], w[:3])
     assert len(rays) == 12 and list(rays["wvl"][:3]) == list(wvl[:3])  # position-major, wavelength-minor
     assert rays["e"][1] == 0.25 * w[1]
+
+
+# ------------------------------------------------------------------ kernel density estimator
+def _hits_xy(points, e=None):
+    p = np.asarray(points, dtype=float)
+    return orc.hits_from_xye(p[:, 0], p[:, 1], np.zeros(len(p)) if e is None else e)
+
+
+def test_kde_point_distances_std_dev():
+    """kde/mod.rs:178-209"""
+    d, sd = orc.kde_point_distances(_hits_xy([(0.0, 0.0), (1e-3, 0.0)]))
+    assert list(d) == [1e-3] and sd == 0.0
+    d, sd = orc.kde_point_distances(_hits_xy([(0.0, 0.0), (1.0, 0.0), (-1.0, 0.0)]))
+    assert list(d) == [1.0, 1.0, 2.0] and sd == math.sqrt(2.0 / 9.0)
+    _, sd = orc.kde_point_distances(_hits_xy([(0.0, 0.0)]))
+    assert math.isnan(sd)
+
+
+def test_kde_distances_iqr():
+    """kde/mod.rs:210-240 (incl. the Wikipedia example)"""
+    assert math.isnan(orc.kde_distances_iqr([]))
+    assert orc.kde_distances_iqr([1.0]) == 1.0
+    assert orc.kde_distances_iqr([0.0, 1.0]) == 1.0
+    assert orc.kde_distances_iqr([0.0, 1.0, 2.0]) == 2.0
+    assert orc.kde_distances_iqr([0.0, 1.0, 2.0, 3.0]) == 2.5
+    assert orc.kde_distances_iqr([25.0, 28.0, 4.0, 28.0, 19.0, 3.0, 9.0, 17.0, 29.0, 29.0]) == 28.0
+
+
+def test_kde_bandwidth_estimate():
+    """kde/mod.rs:241-262"""
+    assert math.isnan(orc.kde_bandwidth_estimate(_hits_xy([(0.0, 0.0)])))
+    assert orc.kde_bandwidth_estimate(_hits_xy([(0.0, 0.0), (1e-3, 0.0)])) == 0.5e-3
+    bw = orc.kde_bandwidth_estimate(_hits_xy([(0.0, 0.0), (1e-3, 0.0), (-1e-3, 0.0)]))
+    assert abs(bw - 0.00034057440111656337) < 1e-15  # assert_abs_diff_eq! default epsilon
+
+
+def test_kde_gaussian_norm():
+    """kde/gaussian.rs:40-58: a 1 J Gaussian of sigma 5 mm integrates to 1 J over a 200 mm square (2 %)"""
+    h = _hits_xy([(0.0, 0.0)], e=[1.0])
+    xs = np.linspace(-0.1, 0.1, 120)
+    total = sum(orc.kde_value(h, 5e-3, x, y) for x in xs for y in xs) * (0.2 * 0.2 / (120 * 120))
+    assert abs(total - 1.0) < 0.02
+
+
+def test_kde_fluence_map_conserves_energy():
+    """calc_fluence_with_kde (rays_hit_map.rs:575-613): the map over the 3-bandwidth margin holds (nearly) all the energy"""
+    xyz = orc.hexapolar(3, 5e-3)  # the hit set of the reference's own `kde` criterion bench (benches/fluence_estimator.rs:12-24)
+    assert len(xyz) == 37
+    h = orc.hits_from_xye(xyz[:, 0], xyz[:, 1], np.full(37, 1.0 / 37))
+    fmap, (l, r, t, b), bw = orc.fluence_kde(h, 30, 30)
+    assert bw > 0 and l == xyz[:, 0].min() - 3 * bw and t == xyz[:, 1].max() + 3 * bw
+    energy = fmap.sum() * ((r - l) / 30) * ((t - b) / 30)
+    assert abs(energy - 1.0) < 0.05
