@@ -170,7 +170,8 @@ typedef enum {
     OPM_OP_PARAXIAL = 6,   /* Rays::refract_paraxial              rays.rs:943-959   */
     OPM_OP_SPLIT = 7,      /* Rays::split(Ratio)                  rays.rs:1253-1264 */
     OPM_OP_SNAPSHOT = 8,   /* copy of the bundle a detector node keeps (analyzers/raytrace.rs:186-205) */
-    OPM_OP_TRANSFORM = 9   /* Rays::transformed_by_iso (nodes/source.rs:205-210)                      */
+    OPM_OP_TRANSFORM = 9,  /* Rays::transformed_by_iso (nodes/source.rs:205-210)                      */
+    OPM_OP_DIFFRACT = 10   /* Rays::diffract_on_periodic_surface  rays.rs:1058-1111 (reflective grating) */
 } OpmOpKind;
 
 enum {
@@ -189,6 +190,20 @@ typedef struct {
     OpmHitMap* hits;              /* optional: record (surface-frame xyz, input energy, bounce) per refracted ray */
     OpmRays* children;            /* optional: reflected bundle (appended) */
 } OpmRefractOp;
+
+/* Reflective grating: the diffracted (reflected) clone of every valid ray that hits the surface in a supported order goes
+ * to `children` and / or continues in the bundle (flags OPM_REFRACT_*, as for mirrors); rays in an evanescent order are
+ * invalidated; the grating vector is given in the WORLD frame, |grating_vector| = 2 pi * line density */
+typedef struct {
+    OpmSurface surface;
+    OpmIndexModel index;          /* medium behind the surface: only validated (ray.rs:489-493) */
+    double grating_vector[3];
+    int32_t order;                /* diffraction order */
+    int32_t refraction_intended;  /* 0 (ReflectiveGrating node) takes the bounce back from the clones (rays.rs:1081) */
+    int32_t flags;                /* OPM_REFRACT_* */
+    int32_t _pad;
+    OpmRays* children;            /* optional: diffracted bundle (appended) */
+} OpmDiffractOp;
 
 typedef struct { OpmIsometry iso; OpmAperture aperture; } OpmApodizeOp; /* iso = effective_surface_iso (optic_node.rs:372-382) */
 typedef struct { double min_energy; } OpmThresholdOp;
@@ -212,6 +227,7 @@ typedef struct {
         OpmSplitOp split;
         OpmSnapshotOp snapshot;
         OpmTransformOp transform;
+        OpmDiffractOp diffract;
     } u;
 } OpmOp;
 
@@ -285,6 +301,10 @@ void* opm_rays_field_ptr(OpmRays* rays, const char* field);
 OpmStatus opm_rays_refract_on_surface(OpmRays* rays, const OpmSurface* surface, const OpmIndexModel* n2_or_null,
                                       int32_t refraction_intended, int32_t strategy,
                                       OpmRays* reflected_out_or_null, OpmHitMap* hits_or_null, OpmTraceStats* stats);
+/* Rays::diffract_on_periodic_surface (rays.rs:1058-1111): in place; the diffracted clones are appended to `diffracted` */
+OpmStatus opm_rays_diffract_on_periodic_surface(OpmRays* rays, const OpmSurface* surface, const OpmIndexModel* refractive_index,
+                                                const double grating_vector[3], int32_t diffraction_order, int32_t refraction_intended,
+                                                OpmRays* diffracted, OpmTraceStats* stats);
 OpmStatus opm_rays_apodize(OpmRays* rays, const OpmAperture* aperture, const OpmIsometry* iso, int32_t* invalidated); /* rays.rs:557 */
 OpmStatus opm_rays_invalidate_by_threshold_energy(OpmRays* rays, double min_energy_per_ray);   /* rays.rs:1145 */
 OpmStatus opm_rays_filter_by_nr_of_bounces(OpmRays* rays, uint64_t max_bounces);               /* rays.rs:1396 */

@@ -39,7 +39,8 @@ typedef enum {
     OPM_NODE_IDEAL_FILTER = 8,
     OPM_NODE_PARAXIAL_SURFACE = 9,
     OPM_NODE_SPOT_DIAGRAM = 10,
-    OPM_NODE_FLUENCE_DETECTOR = 11
+    OPM_NODE_FLUENCE_DETECTOR = 11,
+    OPM_NODE_REFLECTIVE_GRATING = 12 /* nodes/reflective_grating.rs */
 } OpmNodeType;
 
 typedef struct { int32_t type; int32_t _pad; double reflectivity; } OpmCoatingDesc; /* coatings/mod.rs:17-29 */
@@ -52,6 +53,7 @@ typedef struct { int32_t type; int32_t _pad; double reflectivity; } OpmCoatingDe
  *   BEAM_SPLITTER         : p[0] splitting ratio (SplittingConfig::Ratio, ray.rs:36-46)
  *   IDEAL_FILTER          : p[0] transmission (FilterType::Constant)
  *   PARAXIAL_SURFACE      : p[0] focal length
+ *   REFLECTIVE_GRATING    : p[0] line density [1/m] (default 1740/mm), p[1] diffraction order (default -1)
  */
 typedef struct {
     int32_t type;              /* OpmNodeType */

@@ -26,7 +26,7 @@ COAT_IDEAL_AR, COAT_CONSTANT_R, COAT_FRESNEL = range(3)
 IDX_CONST, IDX_SELLMEIER1, IDX_SCHOTT, IDX_CONRADY = range(4)
 MISS_STOP, MISS_IGNORE = 0, 1
 AP_NONE, AP_CIRCLE, AP_RECT, AP_POLYGON, AP_GAUSSIAN = range(5)
-OP_REFRACT, OP_APODIZE, OP_THRESHOLD, OP_LIMITS, OP_FILTER, OP_PARAXIAL, OP_SPLIT, OP_SNAPSHOT, OP_TRANSFORM = range(1, 10)
+OP_REFRACT, OP_APODIZE, OP_THRESHOLD, OP_LIMITS, OP_FILTER, OP_PARAXIAL, OP_SPLIT, OP_SNAPSHOT, OP_TRANSFORM, OP_DIFFRACT = range(1, 11)
 REFRACT_EMIT_CHILDREN, REFRACT_CONTINUE_AS_CHILD = 1, 2
 TRACE_COMPACT, TRACE_STRICT = 1, 2
 POS_GRID, POS_FIBONACCI_RECT, POS_FIBONACCI_ELLIPSE = range(3)
@@ -117,10 +117,15 @@ class OpmTransformOp(C.Structure):
     _fields_ = [("iso", OpmIsometry), ("inverse", C.c_int32), ("_pad", C.c_int32)]
 
 
+class OpmDiffractOp(C.Structure):
+    _fields_ = [("surface", OpmSurface), ("index", OpmIndexModel), ("grating_vector", C.c_double * 3), ("order", C.c_int32),
+                ("refraction_intended", C.c_int32), ("flags", C.c_int32), ("_pad", C.c_int32), ("children", C.c_void_p)]
+
+
 class _OpUnion(C.Union):
     _fields_ = [("refract", OpmRefractOp), ("apodize", OpmApodizeOp), ("threshold", OpmThresholdOp),
                 ("limits", OpmLimitsOp), ("filter", OpmFilterOp), ("paraxial", OpmParaxialOp), ("split", OpmSplitOp),
-                ("snapshot", OpmSnapshotOp), ("transform", OpmTransformOp)]
+                ("snapshot", OpmSnapshotOp), ("transform", OpmTransformOp), ("diffract", OpmDiffractOp)]
 
 
 class OpmOp(C.Structure):
@@ -149,7 +154,7 @@ class OpmSourceDesc(C.Structure):
 
 
 (NODE_SOURCE, NODE_LENS, NODE_CYLINDRIC_LENS, NODE_WEDGE, NODE_THIN_MIRROR, NODE_PARABOLIC_MIRROR, NODE_BEAM_SPLITTER,
- NODE_DUMMY, NODE_IDEAL_FILTER, NODE_PARAXIAL_SURFACE, NODE_SPOT_DIAGRAM, NODE_FLUENCE_DETECTOR) = range(12)
+ NODE_DUMMY, NODE_IDEAL_FILTER, NODE_PARAXIAL_SURFACE, NODE_SPOT_DIAGRAM, NODE_FLUENCE_DETECTOR, NODE_REFLECTIVE_GRATING) = range(13)
 SCENE_STRICT, SCENE_PER_SURFACE, SCENE_RECORD_ALL_HITS, SCENE_NO_SNAPSHOTS, SCENE_ASYNC, SCENE_KEEP_SOURCE = 2, 4, 8, 16, 32, 64
 
 
@@ -194,7 +199,7 @@ EXPORTS = [
     "opm_isometry_new", "opm_isometry_append", "opm_raytrace_config_default", "opm_rays_create", "opm_rays_destroy",
     "opm_rays_len", "opm_rays_capacity", "opm_rays_clear", "opm_rays_reserve", "opm_rays_upload",
     "opm_rays_upload_soa", "opm_rays_new_collimated_with_spectrum", "opm_rays_download", "opm_rays_copy", "opm_rays_append", "opm_rays_compact",
-    "opm_rays_field_ptr", "opm_rays_refract_on_surface", "opm_rays_apodize",
+    "opm_rays_field_ptr", "opm_rays_refract_on_surface", "opm_rays_diffract_on_periodic_surface", "opm_rays_apodize",
     "opm_rays_invalidate_by_threshold_energy", "opm_rays_filter_by_nr_of_bounces",
     "opm_rays_filter_by_nr_of_refractions", "opm_rays_filter_energy", "opm_rays_split", "opm_rays_refract_paraxial",
     "opm_rays_transform", "opm_trace_sequence", "opm_rays_spot_stats", "opm_rays_spot_partial_sums",
@@ -263,6 +268,8 @@ def lib() -> C.CDLL:
         "opm_rays_field_ptr": (vp, [vp, C.c_char_p]),
         "opm_rays_refract_on_surface": (i32, [vp, C.POINTER(OpmSurface), C.POINTER(OpmIndexModel), i32, i32, vp, vp,
                                               C.POINTER(OpmTraceStats)]),
+        "opm_rays_diffract_on_periodic_surface": (i32, [vp, C.POINTER(OpmSurface), C.POINTER(OpmIndexModel), dp, i32, i32, vp,
+                                                        C.POINTER(OpmTraceStats)]),
         "opm_rays_apodize": (i32, [vp, C.POINTER(OpmAperture), C.POINTER(OpmIsometry), C.POINTER(i32)]),
         "opm_rays_invalidate_by_threshold_energy": (i32, [vp, C.c_double]),
         "opm_rays_filter_by_nr_of_bounces": (i32, [vp, u64]),

@@ -441,6 +441,16 @@ class Rays:
             hit_map.h if hit_map is not None else None, C.byref(st)))
         return reflected, TraceStats.of(st)
 
+    def diffract_on_periodic_surface(self, surface: OpticSurface, refractive_index: RefractiveIndex, grating_vector,
+                                     diffraction_order: int, refraction_intended: bool = False):
+        """Rays::diffract_on_periodic_surface (rays.rs:1058-1111) -> (diffracted Rays, TraceStats)"""
+        out = Rays(self.ctx, max(len(self), 1))
+        st = F.OpmTraceStats()
+        g = (C.c_double * 3)(*[float(x) for x in grating_vector])
+        _check(F.lib().opm_rays_diffract_on_periodic_surface(self.h, C.byref(surface.c), C.byref(refractive_index.c), g,
+                                                             int(diffraction_order), int(refraction_intended), out.h, C.byref(st)))
+        return out, TraceStats.of(st)
+
     def apodize(self, aperture: Aperture, iso: Isometry) -> bool:
         inv = C.c_int32()
         _check(F.lib().opm_rays_apodize(self.h, C.byref(aperture.c), C.byref(iso.c), C.byref(inv)))
@@ -556,6 +566,20 @@ class Program:
         """nodes/thin_mirror.rs:209-250: n2 = None, refraction_intended = false, the reflected bundle continues."""
         return self.refract(surface, None, refraction_intended=False, strategy=strategy, hit_map=hit_map,
                             continue_as_child=True)
+
+    def diffract(self, surface: OpticSurface, index: RefractiveIndex, grating_vector, order: int, refraction_intended=False,
+                 children: Rays | None = None, continue_as_child=True) -> "Program":
+        """reflective grating (rays.rs:1058-1111); continue_as_child: the diffracted bundle continues (the node's behaviour)"""
+        op = F.OpmOp(kind=F.OP_DIFFRACT)
+        g = op.u.diffract
+        g.surface, g.index = surface.c, index.c
+        g.grating_vector[:] = [float(x) for x in grating_vector]
+        g.order, g.refraction_intended = int(order), int(refraction_intended)
+        g.flags = (F.REFRACT_EMIT_CHILDREN if children is not None else 0) | (F.REFRACT_CONTINUE_AS_CHILD if continue_as_child else 0)
+        g.children = children.h if children is not None else None
+        self._keep.append(children)
+        self.ops.append(op)
+        return self
 
     def apodize(self, aperture: Aperture, iso: Isometry) -> "Program":
         op = F.OpmOp(kind=F.OP_APODIZE)

@@ -830,6 +830,32 @@ static OpmStatus compile_ops(OpmContext* c, const OpmOp* ops, int n_ops, uint64_
                 out.slot_outputs.push_back(p.u.snapshot.out);
                 break;
             }
+            case OPM_OP_DIFFRACT: {
+                const OpmDiffractOp& g = p.u.diffract;
+                DevDiffract& o = d.u.diffract;
+                d.kind = OPK_DIFFRACT;
+                if (g.surface.geom < OPM_GEOM_PLANE || g.surface.geom > OPM_GEOM_PARABOLA) return fail(OPM_ERR_ARG, "unknown surface geometry %d", g.surface.geom);
+                if (g.surface.geom != OPM_GEOM_PLANE && !std::isnormal(g.surface.geom_param)) return fail(OPM_ERR_ARG, "radius of curvature / focal length must be != 0.0 and finite");
+                o.surf.geom = g.surface.geom; o.surf.coating = g.surface.coating; o.surf.param = g.surface.geom_param; o.surf.coating_r = g.surface.coating_r;
+                o.surf.inv_abs_param = g.surface.geom != OPM_GEOM_PLANE ? 1.0 / std::fabs(g.surface.geom_param) : 0.0;
+                to_dev_iso(g.surface.iso.fwd, o.surf.fwd); to_dev_iso(g.surface.iso.inv, o.surf.inv);
+                o.surf.has_index = 1; o.surf.refraction_intended = g.refraction_intended ? 1 : 0; o.surf.strategy = OPM_MISS_IGNORE;
+                o.surf.flags = g.flags; o.surf.index_type = g.index.type;
+                memcpy(o.surf.ic, g.index.c, sizeof o.surf.ic); o.surf.wlo = g.index.wvl_lo; o.surf.whi = g.index.wvl_hi;
+                for (int j = 0; j < 3; ++j) o.gvec[j] = g.grating_vector[j];
+                o.gnorm = std::sqrt(0.0 + (g.grating_vector[0] * g.grating_vector[0] + g.grating_vector[1] * g.grating_vector[1]) + g.grating_vector[2] * g.grating_vector[2]);
+                o.order = (double)g.order;
+                if (g.flags & OPM_REFRACT_EMIT_CHILDREN) {
+                    if (!g.children) return fail(OPM_ERR_ARG, "OPM_REFRACT_EMIT_CHILDREN without a children bundle");
+                    OpmStatus s = rays_refresh_len(g.children);
+                    if (s) return s;
+                    s = opm_rays_reserve(g.children, g.children->len + n_rays);
+                    if (s) return s;
+                    o.surf.children = g.children->v; o.surf.child_tail = g.children->d_tail; o.surf.child_cap = g.children->cap;
+                    out.appended.push_back(g.children);
+                }
+                break;
+            }
             case OPM_OP_TRANSFORM:
                 d.kind = OPK_TRANSFORM;
                 to_dev_iso(p.u.transform.inverse ? p.u.transform.iso.inv : p.u.transform.iso.fwd, d.u.transform.iso);
@@ -972,6 +998,23 @@ extern "C" OpmStatus opm_rays_refract_on_surface(OpmRays* rays, const OpmSurface
     op.u.refract.flags = reflected ? OPM_REFRACT_EMIT_CHILDREN : 0;
     op.u.refract.hits = hits;
     op.u.refract.children = reflected;
+    OpmTraceStats local;
+    return run_program(rays, &op, 1, 0, nullptr, stats ? stats : &local);
+}
+extern "C" OpmStatus opm_rays_diffract_on_periodic_surface(OpmRays* rays, const OpmSurface* surface, const OpmIndexModel* index,
+                                                           const double gvec[3], int32_t order, int32_t refraction_intended,
+                                                           OpmRays* diffracted, OpmTraceStats* stats) {
+    if (!rays || !surface || !index || !gvec) return fail(OPM_ERR_ARG, "NULL argument");
+    OpmOp op;
+    memset(&op, 0, sizeof op);
+    op.kind = OPM_OP_DIFFRACT;
+    op.u.diffract.surface = *surface;
+    op.u.diffract.index = *index;
+    for (int j = 0; j < 3; ++j) op.u.diffract.grating_vector[j] = gvec[j];
+    op.u.diffract.order = order;
+    op.u.diffract.refraction_intended = refraction_intended;
+    op.u.diffract.flags = diffracted ? OPM_REFRACT_EMIT_CHILDREN : 0;
+    op.u.diffract.children = diffracted;
     OpmTraceStats local;
     return run_program(rays, &op, 1, 0, nullptr, stats ? stats : &local);
 }

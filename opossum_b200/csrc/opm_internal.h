@@ -35,7 +35,8 @@ struct DevAperture {
     const double* tris;  // device
 };
 
-enum : int32_t { OPK_REFRACT = 1, OPK_APODIZE, OPK_THRESHOLD, OPK_LIMITS, OPK_FILTER, OPK_PARAXIAL, OPK_SPLIT, OPK_SNAPSHOT, OPK_TRANSFORM };
+enum : int32_t { OPK_REFRACT = 1, OPK_APODIZE, OPK_THRESHOLD, OPK_LIMITS, OPK_FILTER, OPK_PARAXIAL, OPK_SPLIT, OPK_SNAPSHOT, OPK_TRANSFORM,
+                 OPK_DIFFRACT };
 
 struct DevRefract {
     int32_t geom, coating, has_index, refraction_intended, strategy, flags, index_type, _pad;
@@ -49,6 +50,9 @@ struct DevRefract {
     unsigned long long* child_tail;  // device counter = current length of the children bundle
     uint64_t child_cap;
 };
+// Rays::diffract_on_periodic_surface (rays.rs:1058-1111): the surface part (geometry, index model for the n2 check, children,
+// flags) is a DevRefract; gvec = grating vector in the world frame, gnorm = |gvec|, order = diffraction order
+struct DevDiffract { DevRefract surf; double gvec[3]; double gnorm; double order; };
 struct DevApodize { DevIso inv; DevAperture ap; };
 struct DevThreshold { double min_energy; };
 struct DevLimits { uint64_t max_bounces, max_refr; int32_t check_refr, _pad; };
@@ -76,6 +80,7 @@ struct alignas(16) DevOp {
         DevSplit split;
         DevSnapshot snapshot;
         DevTransform transform;
+        DevDiffract diffract;
     } u;
 };
 static_assert(sizeof(DevOp) % 16 == 0, "DevOp must be a multiple of 16 B for the bulk copy into shared memory");

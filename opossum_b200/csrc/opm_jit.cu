@@ -123,6 +123,12 @@ std::string op_line(const DevOp& op, int k) {
         case OPK_SPLIT: appendf(s, "        exec_split(opm_jit_ops[%d].u.split, x);\n", k); break;
         case OPK_SNAPSHOT: appendf(s, "        exec_snapshot(opm_jit_ops[%d].u.snapshot, x);\n", k); break;
         case OPK_TRANSFORM: appendf(s, "        exec_transform(opm_jit_ops[%d].u.transform, x);\n", k); break;
+        case OPK_DIFFRACT: {
+            const DevRefract& o = op.u.diffract.surf;
+            appendf(s, "        exec_diffract(RefractCt<%d, %d, %d, %d, %d, %d, %d, %d>(opm_jit_ops[%d].u.diffract.surf), opm_jit_ops[%d].u.diffract, x);\n",
+                    o.geom, o.coating, o.has_index ? 1 : 0, o.index_type, o.strategy, o.flags, o.refraction_intended ? 1 : 0, 0, k, k);
+            break;
+        }
         default: appendf(s, "        /* op %d: unknown kind %d */\n", k, op.kind); break;
     }
     if (op.epi_flags) appendf(s, "        exec_epilogue(EpilogueCt<%d>(), opm_jit_ops[%d], x);\n", op.epi_flags, k);
@@ -295,7 +301,7 @@ static size_t jit_selftest_impl(std::string& why) {
         d->u.apodize.ap.n_items = 4; d->u.apodize.ap.is_stack = 1;
         for (int j = 0; j < 4; ++j) d->u.apodize.ap.items[j].type = OPM_AP_CIRCLE + j;
     }
-    for (int kind : {OPK_THRESHOLD, OPK_LIMITS, OPK_FILTER, OPK_PARAXIAL, OPK_SPLIT, OPK_SNAPSHOT, OPK_TRANSFORM}) push(kind);
+    for (int kind : {OPK_THRESHOLD, OPK_LIMITS, OPK_FILTER, OPK_PARAXIAL, OPK_SPLIT, OPK_SNAPSHOT, OPK_TRANSFORM, OPK_DIFFRACT}) push(kind);
     std::vector<char> cubin;
     for (bool compact : {false, true}) {
         std::string src = make_source(ops.data(), (int)ops.size(), compact, 256, 2);

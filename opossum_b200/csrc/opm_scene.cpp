@@ -231,6 +231,24 @@ OpmOp op_limits(uint64_t max_bounces, uint64_t max_refr, bool check_refr) {
     return op;
 }
 
+// ReflectiveGrating RT analyze (nodes/reflective_grating.rs:209-262): grating vector 2 pi * line density * (effective
+// surface iso applied to x), vacuum behind the surface, refraction_intended = false, the diffracted bundle continues
+OpmOp op_diffract(const Node& n, const SurfaceState& s, int extra_flags, OpmRays* children) {
+    OpmOp op;
+    memset(&op, 0, sizeof op);
+    op.kind = OPM_OP_DIFFRACT;
+    OpmDiffractOp& g = op.u.diffract;
+    g.surface = s.surf;
+    g.index.type = OPM_IDX_CONST; g.index.c[0] = 1.0;  // refr_index_vaccuum()
+    const double dens = n.d.p[0];
+    for (int k = 0; k < 3; ++k) g.grating_vector[k] = 2. * M_PI * dens * s.eff_iso.fwd.rot[3 * k + 0];  // iso.transform_vector(x)
+    g.order = (int32_t)n.d.p[1];
+    g.refraction_intended = 0;
+    g.flags = OPM_REFRACT_CONTINUE_AS_CHILD | extra_flags;
+    g.children = children;
+    return op;
+}
+
 // Runs an op list, splitting it into several launches when it exceeds OPM_MAX_PROGRAM_OPS or when every reference
 // call should be its own launch (OPM_SCENE_PER_SURFACE: the un-fused baseline).
 struct Runner {
@@ -309,6 +327,12 @@ OpmStatus compile_node_rt(OpmScene* sc, Node& n, const OpmRayTraceConfig& cfg, i
             OpmHitMap* h0 = hits_for(n.s[0]);
             if (st) return st;
             R.push(op_refract(n.s[0], nullptr, false, strat, OPM_REFRACT_CONTINUE_AS_CHILD, h0, nullptr));
+            R.push(op_apodize(n.s[0].aperture, n.s[0].eff_iso));
+            R.push(op_threshold(thr));
+            break;
+        }
+        case OPM_NODE_REFLECTIVE_GRATING: {  // nodes/reflective_grating.rs:209-262
+            R.push(op_diffract(n, n.s[0], 0, nullptr));
             R.push(op_apodize(n.s[0].aperture, n.s[0].eff_iso));
             R.push(op_threshold(thr));
             break;
@@ -422,6 +446,7 @@ extern "C" void opm_node_desc_init(OpmNodeDesc* d, int32_t type) {
         case OPM_NODE_BEAM_SPLITTER: d->p[0] = 0.5; break;
         case OPM_NODE_IDEAL_FILTER: d->p[0] = 1.0; break;
         case OPM_NODE_PARAXIAL_SURFACE: d->p[0] = 10.0 * 1e-3; break;
+        case OPM_NODE_REFLECTIVE_GRATING: d->p[0] = 1740.0 * 1.0e3; d->p[1] = -1.0; break;  // nodes/reflective_grating.rs:60-75
         default: break;
     }
     d->lidt = 1.0e4;

@@ -89,6 +89,7 @@ trace_kernel(const DevOp* __restrict__ g_ops, int n_ops, DevRays in, DevRays out
                 case OPK_SPLIT: exec_split(op.u.split, x); break;
                 case OPK_SNAPSHOT: exec_snapshot(op.u.snapshot, x); break;
                 case OPK_TRANSFORM: exec_transform(op.u.transform, x); break;
+                case OPK_DIFFRACT: exec_diffract(RefractRt(op.u.diffract.surf), op.u.diffract, x); break;
                 default: break;
             }
             exec_epilogue(EpilogueRt(op.epi_flags), op, x);

@@ -83,6 +83,30 @@ __device__ __forceinline__ void exec_epilogue(const E& e, const DevOp& op, RayCt
     }
 }
 
+// what happens to the reflected clone of a refract / diffract op: appended to the children bundle (ghost focus) and / or
+// taking the parent's place in the bundle (mirrors, gratings: rays without a clone leave the bundle)
+template <class V>
+__device__ __forceinline__ void finish_children(const V& v, const RefractResult& res, RayCtx& x) {
+    const DevRefract& o = v.d();
+    if (v.flags() & OPM_REFRACT_EMIT_CHILDREN) {
+        unsigned long long slot = warp_reserve(res.has_child, o.child_tail);
+        if (res.has_child) {
+            if (slot < o.child_cap) {
+                RayState child = x.r;
+                child_into(res, child);
+                store_ray<true>(o.children, slot, child, RAY_VALID);
+                x.c.b += 1u << 16;
+            } else x.c.status |= 1u << OPM_ERR_CAPACITY;
+        }
+    }
+    if (v.flags() & OPM_REFRACT_CONTINUE_AS_CHILD) {  // mirror: only reflected rays stay in the bundle
+        if (x.alive) {
+            if (res.has_child) child_into(res, x.r);
+            else { x.alive = false; x.valid = false; }
+        }
+    }
+}
+
 // Rays::refract_on_surface (rays.rs:976-1047) for one ray + hit record + child emission / mirror continuation
 template <class V>
 __device__ __forceinline__ void exec_refract(const V& v, RayCtx& x) {
@@ -106,23 +130,24 @@ __device__ __forceinline__ void exec_refract(const V& v, RayCtx& x) {
             x.c.a += 1u << 16;
         }
     }
-    if (v.flags() & OPM_REFRACT_EMIT_CHILDREN) {
-        unsigned long long slot = warp_reserve(res.has_child, o.child_tail);
-        if (res.has_child) {
-            if (slot < o.child_cap) {
-                RayState child = x.r;
-                child_into(res, child);
-                store_ray<true>(o.children, slot, child, RAY_VALID);
-                x.c.b += 1u << 16;
-            } else x.c.status |= 1u << OPM_ERR_CAPACITY;
+    finish_children(v, res, x);
+}
+
+// Rays::diffract_on_periodic_surface (rays.rs:1058-1111) for one ray: reflective grating
+template <class V>
+__device__ __forceinline__ void exec_diffract(const V& v, const DevDiffract& o, RayCtx& x) {
+    RefractResult res;
+    res.has_child = false;
+    if (x.valid) {
+        x.c.a += 1u;
+        res = diffract_on_periodic_surface(v, o, x.r);
+        if (res.status != OPM_OK) { x.c.status |= 1u << res.status; x.valid = false; res.has_child = false; }
+        else {
+            if (res.missed) x.c.b += 1u;
+            if (res.invalidated) x.valid = false;
         }
     }
-    if (v.flags() & OPM_REFRACT_CONTINUE_AS_CHILD) {  // mirror: only reflected rays stay in the bundle
-        if (x.alive) {
-            if (res.has_child) child_into(res, x.r);
-            else { x.alive = false; x.valid = false; }
-        }
-    }
+    finish_children(v, res, x);
 }
 
 // Rays::apodize (rays.rs:557-573)

@@ -134,6 +134,20 @@ def ParaxialSurface(focal_length, iso=None):
     return n
 
 
+def ReflectiveGrating(line_density_per_m=1740.0e3, diffraction_order=-1, iso=None):
+    """ReflectiveGrating::new (nodes/reflective_grating.rs:84-105): line density in 1/m, grating vector along the node's x"""
+    if not (math.isfinite(line_density_per_m) and line_density_per_m > 0.0):
+        raise ValueError("Only positive finite values are allowed for a grating line density")
+    n = Node(F.NODE_REFLECTIVE_GRATING, iso)
+    n.c.p[0], n.c.p[1] = line_density_per_m, float(diffraction_order)
+    return n
+
+
+def littrow_angle(line_density_per_m, diffraction_order, wavelength):
+    """with_rot_from_littrow (nodes/reflective_grating.rs:107-128): tilt about y that puts `wavelength` in Littrow"""
+    return math.asin(diffraction_order * wavelength * line_density_per_m / 2.0)
+
+
 def SpotDiagram(iso=None):
     return Node(F.NODE_SPOT_DIAGRAM, iso)
 

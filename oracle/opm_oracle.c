@@ -556,6 +556,53 @@ int orc_ray_refract_on_surface(OrcRay* ray, const OrcSurface* s, int has_n2, dou
     return ORC_OK;
 }
 
+/* Ray::diffract_on_periodic_surface (ray.rs:482-556): reflective grating, diffraction order m, grating vector G (world
+ * frame, |G| = 2 pi line density).  On a supported order the ray moves to the hit point, takes the diffracted direction,
+ * counts a bounce, *child_out is its clone and the ray itself is left with zero energy; an evanescent order invalidates
+ * the ray; a miss leaves it untouched.  SURVEY 8f-3. */
+int orc_ray_diffract_on_periodic_surface(OrcRay* ray, const OrcSurface* s, double n2, const double gvec[3], int32_t order,
+                                         OrcRay* child_out, int* has_child) {
+    *has_child = 0;
+    if (n2 < 1.0 || !isfinite(n2)) return ORC_ERR_N2_INVALID;
+    double q[3], normal[3];
+    if (!orc_intersect(s, ray->pos, ray->dir, q, normal)) return ORC_OK;
+    const double PI = 3.14159265358979323846264338327950288;
+    double N[3];
+    normalize3(normal, N);
+    double ray_dir_norm = norm3(ray->dir);
+    double k0_n = 2. * PI * ray->n / ray->wvl;
+    double k_vec[3] = { ray->dir[0] * k0_n / ray_dir_norm, ray->dir[1] * k0_n / ray_dir_norm, ray->dir[2] * k0_n / ray_dir_norm };
+    double kxn[3], k_para[3];
+    cross3(k_vec, N, kxn);
+    cross3(N, kxn, k_para);
+    double kn = dot3(k_vec, N);
+    double k_perp[3] = { N[0] * kn, N[1] * kn, N[2] * kn };
+    double m = (double)order;
+    double k_para_out[3] = { k_para[0] + m * gvec[0], k_para[1] + m * gvec[1], k_para[2] + m * gvec[2] };
+    double kpo = norm3(k_para_out);
+    double k_perp_norm_out = sqrt(fma(k0_n, k0_n, -(kpo * kpo)));  /* norm().powi(2) */
+    double dp[3] = { ray->pos[0] - q[0], ray->pos[1] - q[1], ray->pos[2] - q[2] };
+    ray->opl += ray->n * norm3(dp);
+    double ql[3];
+    iso3_point(&s->iso.inv, q, ql);
+    ray->opl += m * norm3(gvec) / 2. / PI * ql[0] * ray->wvl;
+    ray->pos[0] = q[0]; ray->pos[1] = q[1]; ray->pos[2] = q[2];
+    if (isfinite(k_perp_norm_out)) {
+        double kpn[3];
+        normalize3(k_perp, kpn);
+        double out[3] = { -kpn[0] * k_perp_norm_out + k_para_out[0], -kpn[1] * k_perp_norm_out + k_para_out[1],
+                          -kpn[2] * k_perp_norm_out + k_para_out[2] };
+        normalize3(out, ray->dir);
+        ray->bounces += 1;
+        *child_out = *ray;
+        *has_child = 1;
+        ray->e = 0.;
+    } else {
+        ray->valid = 0;
+    }
+    return ORC_OK;
+}
+
 /* ray.rs:443-471 */
 int orc_ray_refract_paraxial(OrcRay* ray, double f, const OrcIsometry* iso) {
     if (f == 0.0 || !isfinite(f)) return ORC_ERR_FOCAL_LENGTH;
@@ -691,6 +738,32 @@ int orc_rays_split(OrcRay* rays, uint64_t n, double ratio, OrcRay* out) { /* :12
             out[i] = rays[i];
         }
     }
+    return ORC_OK;
+}
+/* Rays::diffract_on_periodic_surface (rays.rs:1058-1111): valid rays only, n2 from the index model per ray; the diffracted
+ * clones are returned in ray order (children must hold n entries); refraction_intended == 0 takes the bounce back from the
+ * clones (reduce_bounce_counter), as the ReflectiveGrating node does */
+int orc_rays_diffract_on_periodic_surface(OrcRay* rays, uint64_t n, const OrcSurface* s, const OrcIndexModel* idx, const double gvec[3],
+                                          int32_t order, int refraction_intended, OrcRay* children, OrcRefractStats* stats) {
+    OrcRefractStats st;
+    memset(&st, 0, sizeof st);
+    for (uint64_t i = 0; i < n; ++i) {
+        if (!rays[i].valid) continue;
+        double n2;
+        int rc = orc_refractive_index(idx, rays[i].wvl, &n2);
+        if (rc) return rc;
+        OrcRay child;
+        int has_child = 0;
+        rc = orc_ray_diffract_on_periodic_surface(&rays[i], s, n2, gvec, order, &child, &has_child);
+        if (rc) return rc;
+        st.n_interactions++;
+        if (has_child) {
+            if (!refraction_intended) child.bounces -= 1;
+            children[st.n_children++] = child;
+        } else st.rays_missed = 1;
+        st.valid_rays_found = 1;
+    }
+    if (stats) *stats = st;
     return ORC_OK;
 }
 int orc_rays_refract_paraxial(OrcRay* rays, uint64_t n, double f, const OrcIsometry* iso) { /* :943-959 */

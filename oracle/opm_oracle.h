@@ -131,6 +131,9 @@ int orc_ray_new(const double pos[3], const double dir[3], double wvl, double e, 
 int orc_ray_refract_on_surface(OrcRay* ray, const OrcSurface* s, int has_n2, double n2, int strategy,
                                OrcRay* child_out, int* has_child, OrcHit* hit_out, int* has_hit);
 int orc_ray_refract_paraxial(OrcRay* ray, double focal_length, const OrcIsometry* iso);          /* :443-471 */
+/* :482-556 reflective grating: gvec = grating vector in the world frame, |gvec| = 2 pi line density */
+int orc_ray_diffract_on_periodic_surface(OrcRay* ray, const OrcSurface* s, double n2, const double gvec[3], int32_t order,
+                                         OrcRay* child_out, int* has_child);
 
 /* ---- bundles (rays.rs).  All loops are over `n` rays in order; OpenMP variants keep the order. */
 typedef struct {
@@ -152,6 +155,8 @@ void orc_rays_filter_refractions(OrcRay* rays, uint64_t n, uint64_t max_refr);  
 int orc_rays_filter_energy(OrcRay* rays, uint64_t n, double transmission);             /* :1119-1133 */
 int orc_rays_split(OrcRay* rays, uint64_t n, double ratio, OrcRay* split_out);         /* :1253-1264 */
 int orc_rays_refract_paraxial(OrcRay* rays, uint64_t n, double focal_length, const OrcIsometry* iso); /* :943-959 */
+int orc_rays_diffract_on_periodic_surface(OrcRay* rays, uint64_t n, const OrcSurface* s, const OrcIndexModel* idx, const double gvec[3],
+                                          int32_t order, int refraction_intended, OrcRay* children, OrcRefractStats* stats); /* :1058-1111 */
 void orc_rays_transform(OrcRay* rays, uint64_t n, const OrcIsometry* iso, int inverse);/* ray.rs:787-804 */
 
 /* statistics (rays.rs:521-701) */

@@ -279,6 +279,8 @@ def lib():
     L.orc_rays_bounce_lvl.restype = C.c_uint32
     L.orc_hits_bounding_box.argtypes = [vp, C.c_uint64, dp]
     L.orc_fluence_binning.argtypes = [vp, C.c_uint64, C.c_uint64, C.c_uint64, dp, dp, dp]
+    L.orc_rays_diffract_on_periodic_surface.argtypes = [vp, C.c_uint64, C.POINTER(Surface), C.POINTER(IndexModel), dp, C.c_int32, C.c_int, vp,
+                                                         C.POINTER(RefractStats)]
     L.orc_kde_distances_iqr.argtypes = [dp, C.c_uint64]
     L.orc_kde_distances_iqr.restype = C.c_double
     L.orc_kde_point_distances.argtypes = [vp, C.c_uint64, dp, dp]
@@ -420,6 +422,17 @@ def rays_split(rays, ratio: float) -> np.ndarray:
 
 def rays_refract_paraxial(rays, f: float, iso: Isometry):
     _check(lib().orc_rays_refract_paraxial(_vp(rays), len(rays), f, C.byref(iso)))
+
+
+def rays_diffract_on_periodic_surface(rays, surf: Surface, idx: IndexModel, grating_vector, order: int, refraction_intended=False):
+    """Rays::diffract_on_periodic_surface (rays.rs:1058-1111), in place -> (diffracted clones, stats)"""
+    n = len(rays)
+    children = np.empty(max(n, 1), dtype=RAY_DTYPE)
+    g = (C.c_double * 3)(*[float(x) for x in grating_vector])
+    st = RefractStats()
+    _check(lib().orc_rays_diffract_on_periodic_surface(_vp(rays), n, C.byref(surf), C.byref(idx), g, int(order),
+                                                       int(refraction_intended), _vp(children), C.byref(st)))
+    return children[: st.n_children].copy(), st
 
 
 def rays_transform(rays, iso: Isometry, inverse=False):

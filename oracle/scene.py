@@ -14,7 +14,7 @@ import numpy as np
 from . import oracle as orc
 
 (SOURCE, LENS, CYLINDRIC_LENS, WEDGE, THIN_MIRROR, PARABOLIC_MIRROR, BEAM_SPLITTER, DUMMY, IDEAL_FILTER, PARAXIAL_SURFACE,
- SPOT_DIAGRAM, FLUENCE_DETECTOR) = range(12)
+ SPOT_DIAGRAM, FLUENCE_DETECTOR, REFLECTIVE_GRATING) = range(13)
 
 
 @dataclass
@@ -171,6 +171,14 @@ class OScene:
         elif t in (THIN_MIRROR, PARABOLIC_MIRROR):  # thin_mirror.rs:209-250
             rays = self._refract(rays, n.s[0], None, False, strat, record=record_all)
             orc.rays_apodize(rays, n.s[0].aperture, n.s[0].eff_iso, self.nt)
+            orc.rays_threshold(rays, thr, self.nt)
+        elif t == REFLECTIVE_GRATING:  # nodes/reflective_grating.rs:209-262
+            iso = n.s[0].eff_iso
+            gx = iso.transform_vector((1.0, 0.0, 0.0))
+            gvec = [2. * math.pi * n.p[0] * c for c in gx]
+            rays, st = orc.rays_diffract_on_periodic_surface(rays, n.s[0].surf, orc.IndexModel.const(1.0), gvec, int(n.p[1]), False)
+            self.interactions += st.n_interactions
+            orc.rays_apodize(rays, n.s[0].aperture, iso, self.nt)
             orc.rays_threshold(rays, thr, self.nt)
         elif t == BEAM_SPLITTER:  # beam_splitter/mod.rs:158-293
             self._refract(rays, n.s[0], None, True, strat, record=record_all, want_children=False)

@@ -421,3 +421,44 @@ def test_source_generate_strided_is_a_slice_of_the_source(ctx):
             assert np.array_equal(got[f], ref[f]), f
     with pytest.raises(ob.OpossumError):
         sd.generate_strided(ctx, 5, 1000, 3)
+
+
+# ------------------------------------------------------------------ reflective grating
+@pytest.mark.parametrize("strict", [False, True], ids=["fast", "strict"])
+@pytest.mark.parametrize("order", [-1, 1, 0, -2])
+def test_diffract_on_periodic_surface(ctx, order, strict):
+    """Rays::diffract_on_periodic_surface (rays.rs:1058-1111) on a tilted, decentred grating: a divergent polychromatic
+    bundle, supported and evanescent orders mixed, invalid rays carried along; diffracted clones, parents (zero energy) and
+    counts against the oracle; the bundle-continues form (ReflectiveGrating node) against the clones"""
+    dens = 600e3
+    node = iso_pair((mm(0.3), mm(-0.2), mm(60.0)), (0.05, 0.4, 0.1))
+    so, sg = surface_pair(F.GEOM_PLANE, iso=node)
+    gvec = [2 * math.pi * dens * c for c in node[0].transform_vector((1.0, 0.0, 0.0))]
+    rays = make_bundle(3000, divergence=0.25, wvl=(nm(500.0), nm(1600.0)))
+    rays["valid"][::13] = 0
+    ref = rays.copy()
+    ch_ref, st_ref = orc.rays_diffract_on_periodic_surface(ref, so, orc.IndexModel.const(1.0), gvec, order, False)
+    r = ob.Rays.from_array(ctx, rays)
+    out = ob.Rays(ctx, len(rays))
+    prog = ob.Program().diffract(sg, ob.RefractiveIndex.const(1.0), gvec, order, children=out, continue_as_child=False)
+    st = prog.run(r, strict=strict)
+    assert st.interactions == st_ref.n_interactions and st.children == len(ch_ref)
+    if order == -2:
+        assert 0 < len(ch_ref) < st_ref.n_interactions  # some wavelengths are evanescent in second order
+    assert_rays_match(out.to_array(), ch_ref, keyed=True, what=f"diffracted order {order}", e_floor=1e-25)
+    assert_rays_match(r.to_array(), ref, what=f"parents order {order}", e_floor=1e-25)
+    r2 = ob.Rays.from_array(ctx, rays)
+    st2 = ob.Program().diffract(sg, ob.RefractiveIndex.const(1.0), gvec, order).run(r2, strict=strict)
+    assert st2.alive_out == len(ch_ref)
+    assert_rays_match(r2.to_array(), ch_ref, what=f"bundle continues, order {order}", e_floor=1e-25)
+
+
+def test_diffract_index_error(ctx):
+    """the medium behind the grating is only validated: an index < 1 is already refused by the index model
+    (refractive_index/mod.rs:54-58, called at rays.rs:1071) before ray.rs:489-493 sees it"""
+    node = iso_pair((0.0, 0.0, mm(10.0)))
+    so, sg = surface_pair(F.GEOM_PLANE, iso=node)
+    r = ob.Rays.from_array(ctx, make_bundle(64))
+    with pytest.raises(ob.OpossumError) as e:
+        r.diffract_on_periodic_surface(sg, ob.RefractiveIndex.const(0.5), (1e6, 0.0, 0.0), -1)
+    assert e.value.code == F.OPM_ERR_INDEX_MODEL

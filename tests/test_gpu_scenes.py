@@ -317,3 +317,47 @@ def test_fluence_detector_with_kde_estimator(ctx):
     assert_map_match(fd.map, ref_map, rtol=1e-8)  # the map range itself carries the 1e-9 of the hit positions
     with pytest.raises(ValueError):
         psc.node_fluence(3, 40, 33, estimator="voronoi")
+
+
+@pytest.mark.parametrize("jit", [0, 2], ids=["interpreter", "specialised"])
+def test_reflective_grating_node(ctx, jit):
+    """ReflectiveGrating (nodes/reflective_grating.rs): the reference's Littrow KATs through the scene layer, and a
+    stretcher-like chain (lens, grating near Littrow, detector) against the oracle"""
+    import math
+
+    from opossum_b200 import scene as S
+    MM, NM = scenes.MM, scenes.NM
+    ctx.set_jit(jit, 1)
+    try:
+        for extra in (0.0, math.radians(1.0)):  # reflective_grating.rs:386-443
+            tilt = S.littrow_angle(1740e3, -1, 1000 * NM) + extra
+            nodes = [scenes.node("source"), scenes.node("reflective_grating", z=0.0, euler=(0.0, tilt, 0.0), p=(1740e3, -1))]
+            src = {"pos": ("grid", 1, 1, 0.0, 0.0), "energy": ("uniform", 1.0), "wvl": [1000 * NM], "w": [1.0]}
+            psc = scenes.to_product(ctx, nodes)
+            rays = scenes.source_to_product(src).generate(ctx)
+            st = psc.raytrace(rays)
+            got = rays.to_array()
+            assert st.valid_out == 1 and np.array_equal(got["pos"][0], [0.0, 0.0, 0.0])
+            if extra == 0.0:
+                expect = np.array([0.0, 0.0, -1.0])
+            else:
+                ia = math.asin(-1000e-9 * 1740000. / 2.) + extra
+                da = math.asin(-1740000. * 1000e-9 - math.sin(ia))
+                expect = np.array([math.sin(-ia + da), 0.0, -math.cos(-ia + da)])
+            assert np.all(np.abs(got["dir"][0] - expect) <= 4e-15)
+        tilt = S.littrow_angle(1740e3, -1, 1030 * NM) + math.radians(8.0)
+        nodes = [scenes.node("source"),
+                 scenes.node("lens", z=50 * MM, p=(800 * MM, -800 * MM, 4 * MM), index=scenes.HK9L),
+                 scenes.node("reflective_grating", z=250 * MM, euler=(0.0, tilt, 0.0), p=(1740e3, -1), ap_in=("rect", 30 * MM, 20 * MM, 0.0, 0.0)),
+                 scenes.node("fluence_detector", z=100 * MM, xy=(-40 * MM, 0.0), euler=(0.0, math.pi + 0.3, 0.0))]
+        src = {"pos": ("fibonacci_ellipse", 3000, 6 * MM, 6 * MM), "energy": ("uniform", 1.0),
+               "spectrum": ("gaussian", 1010 * NM, 1050 * NM, 9, 1030 * NM, 10 * NM, 1.0)}
+        osc, ref_out, psc, rays, st = run_both(ctx, nodes, src)
+        assert st.interactions == osc.interactions and orc.nr_of_rays(ref_out) > 20000
+        assert_rays_match(rays.to_array(), ref_out, what="lens + grating + detector")
+        wv = np.unique(ref_out["wvl"])
+        x_by_w = [ref_out["pos"][(ref_out["wvl"] == w) & (ref_out["valid"] == 1)][:, 0].mean() for w in wv]
+        assert np.all(np.diff(x_by_w) != 0.0) and np.ptp(x_by_w) > 1e-4  # angular dispersion reaches the detector
+        check_detector(osc, psc, 3, 64, 48)
+    finally:
+        ctx.set_jit(1, 200000)

@@ -583,3 +583,41 @@ def test_kde_fluence_map_conserves_energy():
     assert bw > 0 and l == xyz[:, 0].min() - 3 * bw and t == xyz[:, 1].max() + 3 * bw
     energy = fmap.sum() * ((r - l) / 30) * ((t - b) / 30)
     assert abs(energy - 1.0) < 0.05
+
+
+# ------------------------------------------------------------------ reflective grating
+def _grating(extra_tilt, wvl=1000e-9, dens=1740e3, order=-1):
+    littrow = math.asin(order * wvl * dens / 2.)  # with_rot_from_littrow (nodes/reflective_grating.rs:107-128)
+    iso = orc.Isometry.new((0.0, 0.0, 0.0), (0.0, littrow + extra_tilt, 0.0))
+    surf = orc.Surface(geom=orc.GEOM_PLANE, coating=orc.COAT_IDEAL_AR, param=0.0, coating_r=0.0, iso=iso)
+    gvec = [2 * math.pi * dens * c for c in iso.transform_vector((1.0, 0.0, 0.0))]
+    return surf, gvec
+
+
+def test_grating_littrow_and_one_degree_off():
+    """nodes/reflective_grating.rs:386-443: 1740 lines/mm, order -1, 1000 nm ray along z from the origin"""
+    for extra in (0.0, math.radians(1.0)):
+        surf, gvec = _grating(extra)
+        rays = orc.rays_from_arrays(np.zeros((1, 3)), np.array([[0.0, 0.0, 1.0]]), np.array([1.0]), np.array([1000e-9]))
+        out, st = orc.rays_diffract_on_periodic_surface(rays, surf, orc.IndexModel.const(1.0), gvec, -1, False)
+        assert len(out) == 1 and out["valid"][0] == 1 and np.array_equal(out["pos"][0], [0.0, 0.0, 0.0])
+        assert out["bounces"][0] == 0 and out["e"][0] == 1.0 and rays["e"][0] == 0.0  # bounce taken back, energy moved to the clone
+        if extra == 0.0:
+            expect = np.array([0.0, 0.0, -1.0])
+        else:
+            input_angle = math.asin(-1000e-9 * 1740000. / 2.) + extra
+            diffraction_angle = math.asin(-1740000. * 1000e-9 - math.sin(input_angle))
+            expect = np.array([math.sin(-input_angle + diffraction_angle), 0.0, -math.cos(-input_angle + diffraction_angle)])
+        assert np.all(np.abs(out["dir"][0] - expect) <= 1e-15 * np.maximum(1.0, np.abs(expect)))  # assert_relative_eq!(.., epsilon = 1e-15)
+
+
+def test_grating_evanescent_order_and_miss():
+    """ray.rs:541-551: an order whose in-plane k exceeds k0 invalidates the ray (no clone); a miss leaves it untouched"""
+    surf, gvec = _grating(0.0)
+    rays = orc.rays_from_arrays(np.zeros((2, 3)), np.array([[0.0, 0.0, 1.0], [0.0, 0.0, -1.0]]), np.ones(2), np.full(2, 1000e-9))
+    rays["pos"][1] = (0.0, 0.0, -1e-3)  # flies away from the grating plane
+    before = rays.copy()
+    out, st = orc.rays_diffract_on_periodic_surface(rays, surf, orc.IndexModel.const(1.0), gvec, -3, False)
+    assert len(out) == 0 and st.rays_missed == 1
+    assert rays["valid"][0] == 0 and rays["valid"][1] == 1
+    assert np.array_equal(rays["pos"][1], before["pos"][1]) and rays["e"][1] == 1.0
