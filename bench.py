@@ -319,13 +319,15 @@ def run_product(args):
             hbm_peak, peak_src = json.loads(peaks_file.read_text())["hbm_gbs"], "MEASURED_PEAKS.json hbm_gbs (measured copy)"
         else:
             hbm_peak, peak_src = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
-        # algorithmic bytes of the trace launches of ONE step on this rank (DESIGN.md "byte model"):
-        #   main chain launch: read n x 93; write the output bundle + split-off bundle + 2 detector snapshots (93 B each)
-        #   and 2 hit records (36 B) for the rays still in the bundle
-        #   side chain launch: read + in-place write of the split-off bundle, 1 snapshot, 1 hit record
-        bytes_step = (n * RAY_BYTES + alive_main * (4 * RAY_BYTES + 2 * HIT_BYTES)
-                      + alive_side * (RAY_BYTES + RAY_BYTES_INPLACE + RAY_BYTES + HIT_BYTES))
+        # algorithmic bytes of the trace launches of ONE step on this rank (DESIGN.md "byte model"): every buffer the step
+        # must read or write, once.  Read the source bundle (n x 93 B); for the rays still in the bundle write the main
+        # output bundle, 2 detector snapshots (93 B each) and 2 hit records (36 B) of the main chain, and the split-off
+        # bundle after its side chain, its detector snapshot and hit record.  When the side chain is its own launch
+        # (2 trace launches per step) the split-off bundle is additionally written by the main launch and read back.
         launches_trace = kern_launches / args.steps
+        bytes_step = (n * RAY_BYTES + alive_main * (3 * RAY_BYTES + 2 * HIT_BYTES) + alive_side * (2 * RAY_BYTES + HIT_BYTES))
+        if launches_trace > 1.5:
+            bytes_step += alive_side * (RAY_BYTES + RAY_BYTES_INPLACE)
         kern_ms_step = kern_ms / args.steps
         achieved = bytes_step / (kern_ms_step * 1e-3) / 1e9
         unfused = inter_per_step * 146.0 / (kern_ms_step * 1e-3) / 1e9  # 146 B per stand-alone interaction

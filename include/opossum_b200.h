@@ -40,7 +40,7 @@ extern "C" {
 
 #define OPM_ABI_VERSION 1
 #define OPM_MAX_APERTURE_ITEMS 4
-#define OPM_MAX_PROGRAM_OPS 64
+#define OPM_MAX_PROGRAM_OPS 128
 
 typedef int32_t OpmStatus;
 enum {
@@ -171,7 +171,11 @@ typedef enum {
     OPM_OP_SPLIT = 7,      /* Rays::split(Ratio)                  rays.rs:1253-1264 */
     OPM_OP_SNAPSHOT = 8,   /* copy of the bundle a detector node keeps (analyzers/raytrace.rs:186-205) */
     OPM_OP_TRANSFORM = 9,  /* Rays::transformed_by_iso (nodes/source.rs:205-210)                      */
-    OPM_OP_DIFFRACT = 10   /* Rays::diffract_on_periodic_surface  rays.rs:1058-1111 (reflective grating) */
+    OPM_OP_DIFFRACT = 10,  /* Rays::diffract_on_periodic_surface  rays.rs:1058-1111 (reflective grating) */
+    OPM_OP_FORK = 11,      /* Rays::split(Ratio) whose split-off bundle is traced in the SAME launch: the ops up to the matching
+                              OPM_OP_JOIN run on the split-off rays (E*(1-ratio)) while the main bundle (E*ratio) is parked in
+                              shared memory; the beam splitter's second output never takes a round trip through HBM */
+    OPM_OP_JOIN = 12       /* stores the split-off bundle (slot-indexed, like OPM_OP_SPLIT's output) and resumes the main bundle */
 } OpmOpKind;
 
 enum {
@@ -211,6 +215,8 @@ typedef struct { uint64_t max_bounces; uint64_t max_refractions; int32_t check_r
 typedef struct { double transmission; } OpmFilterOp;
 typedef struct { double focal_length; OpmIsometry iso; } OpmParaxialOp;
 typedef struct { double ratio; OpmRays* split_out; } OpmSplitOp;   /* split_out: slot-indexed copy with E*(1-ratio); NULL = discard it */
+typedef struct { double ratio; } OpmForkOp;
+typedef struct { OpmRays* out; } OpmJoinOp;                         /* out: the split-off bundle after its side chain; NULL = discard */
 typedef struct { OpmRays* out; } OpmSnapshotOp;                     /* slot-indexed copy of the bundle at this point */
 typedef struct { OpmIsometry iso; int32_t inverse; int32_t _pad; } OpmTransformOp;
 
@@ -228,6 +234,8 @@ typedef struct {
         OpmSnapshotOp snapshot;
         OpmTransformOp transform;
         OpmDiffractOp diffract;
+        OpmForkOp fork;
+        OpmJoinOp join;
     } u;
 } OpmOp;
 

@@ -14,7 +14,7 @@ PKG = Path(__file__).resolve().parent
 LIB_PATH = Path(os.environ["OPM_B200_LIB"]) if os.environ.get("OPM_B200_LIB") else PKG / "lib" / "libopossum_b200.so"  # override: tuning builds
 
 OPM_MAX_APERTURE_ITEMS = 4
-OPM_MAX_PROGRAM_OPS = 64
+OPM_MAX_PROGRAM_OPS = 128
 
 # status codes
 (OPM_OK, OPM_ERR_N2_INVALID, OPM_ERR_WVL_RANGE, OPM_ERR_INDEX_MODEL, OPM_ERR_COATING, OPM_ERR_APODIZE_FACTOR,
@@ -26,7 +26,8 @@ COAT_IDEAL_AR, COAT_CONSTANT_R, COAT_FRESNEL = range(3)
 IDX_CONST, IDX_SELLMEIER1, IDX_SCHOTT, IDX_CONRADY = range(4)
 MISS_STOP, MISS_IGNORE = 0, 1
 AP_NONE, AP_CIRCLE, AP_RECT, AP_POLYGON, AP_GAUSSIAN = range(5)
-OP_REFRACT, OP_APODIZE, OP_THRESHOLD, OP_LIMITS, OP_FILTER, OP_PARAXIAL, OP_SPLIT, OP_SNAPSHOT, OP_TRANSFORM, OP_DIFFRACT = range(1, 11)
+(OP_REFRACT, OP_APODIZE, OP_THRESHOLD, OP_LIMITS, OP_FILTER, OP_PARAXIAL, OP_SPLIT, OP_SNAPSHOT, OP_TRANSFORM, OP_DIFFRACT, OP_FORK,
+ OP_JOIN) = range(1, 13)
 REFRACT_EMIT_CHILDREN, REFRACT_CONTINUE_AS_CHILD = 1, 2
 TRACE_COMPACT, TRACE_STRICT = 1, 2
 POS_GRID, POS_FIBONACCI_RECT, POS_FIBONACCI_ELLIPSE = range(3)
@@ -122,10 +123,18 @@ class OpmDiffractOp(C.Structure):
                 ("refraction_intended", C.c_int32), ("flags", C.c_int32), ("_pad", C.c_int32), ("children", C.c_void_p)]
 
 
+class OpmForkOp(C.Structure):
+    _fields_ = [("ratio", C.c_double)]
+
+
+class OpmJoinOp(C.Structure):
+    _fields_ = [("out", C.c_void_p)]
+
+
 class _OpUnion(C.Union):
     _fields_ = [("refract", OpmRefractOp), ("apodize", OpmApodizeOp), ("threshold", OpmThresholdOp),
                 ("limits", OpmLimitsOp), ("filter", OpmFilterOp), ("paraxial", OpmParaxialOp), ("split", OpmSplitOp),
-                ("snapshot", OpmSnapshotOp), ("transform", OpmTransformOp), ("diffract", OpmDiffractOp)]
+                ("snapshot", OpmSnapshotOp), ("transform", OpmTransformOp), ("diffract", OpmDiffractOp), ("fork", OpmForkOp), ("join", OpmJoinOp)]
 
 
 class OpmOp(C.Structure):

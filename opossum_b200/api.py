@@ -631,6 +631,21 @@ class Program:
         self.ops.append(op)
         return self
 
+    def fork(self, ratio: float) -> "Program":
+        """Rays::split whose split-off bundle (E * (1 - ratio)) runs the ops up to the matching join() in the same launch"""
+        op = F.OpmOp(kind=F.OP_FORK)
+        op.u.fork.ratio = ratio
+        self.ops.append(op)
+        return self
+
+    def join(self, out: Rays | None) -> "Program":
+        """stores the split-off bundle (slot-indexed) and resumes the main bundle"""
+        op = F.OpmOp(kind=F.OP_JOIN)
+        op.u.join.out = out.h if out is not None else None
+        self._keep.append(out)
+        self.ops.append(op)
+        return self
+
     def snapshot(self, out: Rays) -> "Program":
         op = F.OpmOp(kind=F.OP_SNAPSHOT)
         op.u.snapshot.out = out.h

@@ -710,6 +710,8 @@ struct Compiled {
     std::vector<OpmRays*> appended;     // bundles that receive appended rays (children)
     std::vector<OpmRays*> slot_outputs; // split / snapshot outputs (len = n)
     std::vector<OpmHitMap*> hitmaps;
+    int fork_depth = 0;                 // inside an OPM_OP_FORK .. OPM_OP_JOIN range
+    bool has_fork = false;
 };
 
 static OpmStatus compile_aperture(OpmContext* c, const OpmAperture& a, DevAperture& d, Compiled& out) {
@@ -822,6 +824,26 @@ static OpmStatus compile_ops(OpmContext* c, const OpmOp* ops, int n_ops, uint64_
                 }
                 break;
             }
+            case OPM_OP_FORK: {  // ray.rs:763-767
+                double ratio = p.u.fork.ratio;
+                if (!(ratio >= 0.0 && ratio <= 1.0)) return fail(OPM_ERR_SPLIT_RATIO, "%s", opm_status_string(OPM_ERR_SPLIT_RATIO));
+                if (out.fork_depth != 0) return fail(OPM_ERR_ARG, "OPM_OP_FORK inside a fork: one level only");
+                out.fork_depth = 1; out.has_fork = true;
+                d.kind = OPK_FORK; d.u.fork.ratio = ratio;
+                break;
+            }
+            case OPM_OP_JOIN: {
+                if (out.fork_depth != 1) return fail(OPM_ERR_ARG, "OPM_OP_JOIN without a matching OPM_OP_FORK");
+                out.fork_depth = 0;
+                d.kind = OPK_JOIN;
+                if (p.u.join.out) {
+                    OpmStatus s = opm_rays_reserve(p.u.join.out, n_rays);
+                    if (s) return s;
+                    d.u.join.out = p.u.join.out->v;
+                    out.slot_outputs.push_back(p.u.join.out);
+                }
+                break;
+            }
             case OPM_OP_SNAPSHOT: {
                 if (!p.u.snapshot.out) return fail(OPM_ERR_ARG, "snapshot without output bundle");
                 OpmStatus s = opm_rays_reserve(p.u.snapshot.out, n_rays);
@@ -864,6 +886,7 @@ static OpmStatus compile_ops(OpmContext* c, const OpmOp* ops, int n_ops, uint64_
         }
         out.ops.push_back(d);
     }
+    if (out.fork_depth != 0) return fail(OPM_ERR_ARG, "OPM_OP_FORK without a matching OPM_OP_JOIN in the same program");
     return OPM_OK;
 }
 
@@ -917,7 +940,7 @@ static OpmStatus run_program(OpmRays* rays, const OpmOp* ops, int n_ops, int fla
         // large bundles run the kernel compiled for the structure of this program (opm_jit.cu); otherwise, and whenever
         // that kernel cannot be had, the interpreter
         const JitKernel* jk = nullptr;
-        if (!strict && c->jit_enabled && n >= c->jit_min_rays) {
+        if (!strict && c->jit_enabled && n >= c->jit_min_rays && prog.ops.size() * sizeof(DevOp) <= 60 * 1024) {  // __constant__ holds 64 KB
             const char* why = nullptr;
             jk = jit_get(c->jit, prog.ops.data(), (int)prog.ops.size(), compact, c->jit_block, c->jit_min_ctas, c->jit_sync, &why);
             if (jk) block = c->jit_block;
@@ -935,7 +958,8 @@ static OpmStatus run_program(OpmRays* rays, const OpmOp* ops, int n_ops, int fla
         L.ops = d_slot; L.n_ops = (int)prog.ops.size();
         L.in = rays->v; L.out = dst->v; L.n = n; L.out_cap = dst->cap; L.out_tail = dst->d_tail;
         L.stats = c->d_stats; L.compact = compact ? 1 : 0; L.block = block; L.stream = c->stream;
-        size_t smem = prog.ops.size() * sizeof(DevOp);
+        L.has_fork = prog.has_fork ? 1 : 0;
+        size_t smem = prog.ops.size() * sizeof(DevOp) + (prog.has_fork ? (size_t)block * kStashWords * 4 : 0);
         int occ = jk ? jit_occupancy(jk) : strict ? trace_occupancy_strict(L.block, smem) : trace_occupancy_fast(L.block, smem);
         uint64_t tiles = (n + L.block - 1) / L.block;
         uint64_t maxg = (uint64_t)c->sms * occ;

@@ -36,7 +36,7 @@ struct DevAperture {
 };
 
 enum : int32_t { OPK_REFRACT = 1, OPK_APODIZE, OPK_THRESHOLD, OPK_LIMITS, OPK_FILTER, OPK_PARAXIAL, OPK_SPLIT, OPK_SNAPSHOT, OPK_TRANSFORM,
-                 OPK_DIFFRACT };
+                 OPK_DIFFRACT, OPK_FORK, OPK_JOIN };
 
 struct DevRefract {
     int32_t geom, coating, has_index, refraction_intended, strategy, flags, index_type, _pad;
@@ -60,6 +60,9 @@ struct DevFilter { double t; };
 struct DevParaxial { double f; DevIso fwd, inv; };
 struct DevSplit { double ratio; DevRays out; };
 struct DevSnapshot { DevRays out; };
+struct DevFork { double ratio; };
+struct DevJoin { DevRays out; };
+constexpr int kStashWords = 21;  // parked main-bundle ray of a FORK: pos, dir, e, opl, n (18 words) + bounces, refr, flags
 struct DevTransform { DevIso iso; };
 
 // Every op carries an epilogue: the energy threshold (rays.rs:1145-1162) and the bounce / refraction limits
@@ -81,6 +84,8 @@ struct alignas(16) DevOp {
         DevSnapshot snapshot;
         DevTransform transform;
         DevDiffract diffract;
+        DevFork fork;
+        DevJoin join;
     } u;
 };
 static_assert(sizeof(DevOp) % 16 == 0, "DevOp must be a multiple of 16 B for the bulk copy into shared memory");
@@ -101,6 +106,7 @@ struct TraceLaunch {
     unsigned long long* out_tail;  // compact mode: device counter of `out`
     DevStats* stats;
     int32_t compact;
+    int32_t has_fork;  // the program parks rays in shared memory: kStashWords * 4 bytes per thread
     int32_t grid, block;
     void* stream;
 };

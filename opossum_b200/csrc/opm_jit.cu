@@ -123,6 +123,8 @@ std::string op_line(const DevOp& op, int k) {
         case OPK_SPLIT: appendf(s, "        exec_split(opm_jit_ops[%d].u.split, x);\n", k); break;
         case OPK_SNAPSHOT: appendf(s, "        exec_snapshot(opm_jit_ops[%d].u.snapshot, x);\n", k); break;
         case OPK_TRANSFORM: appendf(s, "        exec_transform(opm_jit_ops[%d].u.transform, x);\n", k); break;
+        case OPK_FORK: appendf(s, "        exec_fork(opm_jit_ops[%d].u.fork, x, opm_jit_stash);\n", k); break;
+        case OPK_JOIN: appendf(s, "        exec_join(opm_jit_ops[%d].u.join, x, opm_jit_stash);\n", k); break;
         case OPK_DIFFRACT: {
             const DevRefract& o = op.u.diffract.surf;
             appendf(s, "        exec_diffract(RefractCt<%d, %d, %d, %d, %d, %d, %d, %d>(opm_jit_ops[%d].u.diffract.surf), opm_jit_ops[%d].u.diffract, x);\n",
@@ -144,6 +146,7 @@ std::string make_source(const DevOp* ops, int n_ops, bool compact, int block, in
     appendf(s, "extern \"C\" __global__ void __launch_bounds__(%d, %d)\n", block, min_ctas);
     s += "opm_jit_trace(DevRays in, DevRays out, unsigned long long n, unsigned long long out_cap, unsigned long long* out_tail,\n"
          "              DevStats* stats) {\n"
+         "    extern __shared__ unsigned opm_jit_stash[];  // parked main-bundle rays of a FORK (sized by the launch)\n"
          "    __shared__ unsigned long long s_cnt[CNT_N];\n"
          "    __shared__ unsigned s_status;\n"
          "    __shared__ unsigned long long s_first_inv;\n"
@@ -301,7 +304,7 @@ static size_t jit_selftest_impl(std::string& why) {
         d->u.apodize.ap.n_items = 4; d->u.apodize.ap.is_stack = 1;
         for (int j = 0; j < 4; ++j) d->u.apodize.ap.items[j].type = OPM_AP_CIRCLE + j;
     }
-    for (int kind : {OPK_THRESHOLD, OPK_LIMITS, OPK_FILTER, OPK_PARAXIAL, OPK_SPLIT, OPK_SNAPSHOT, OPK_TRANSFORM, OPK_DIFFRACT}) push(kind);
+    for (int kind : {OPK_THRESHOLD, OPK_LIMITS, OPK_FILTER, OPK_PARAXIAL, OPK_SPLIT, OPK_SNAPSHOT, OPK_TRANSFORM, OPK_DIFFRACT, OPK_FORK, OPK_JOIN}) push(kind);
     std::vector<char> cubin;
     for (bool compact : {false, true}) {
         std::string src = make_source(ops.data(), (int)ops.size(), compact, 256, 2);
@@ -326,7 +329,8 @@ int jit_launch(JitCache* cache, const JitKernel* K, const TraceLaunch& L, const 
     unsigned long long* tail = L.out_tail;
     DevStats* stats = L.stats;
     void* args[] = {&in, &out, &n, &cap, &tail, &stats};
-    cudaError_t e = cudaLaunchKernel((const void*)K->kernel, dim3(L.grid), dim3(L.block), args, 0, st);
+    const size_t smem = L.has_fork ? (size_t)L.block * kStashWords * 4 : 0;
+    cudaError_t e = cudaLaunchKernel((const void*)K->kernel, dim3(L.grid), dim3(L.block), args, smem, st);
     if (e != cudaSuccess) return (int)e;
     cache->launches++;
     return (int)cudaGetLastError();

@@ -44,6 +44,7 @@ struct Node {
     OpmRays* split = nullptr;   // second output of a beam splitter
     std::vector<std::shared_ptr<Bundle>> stored_gf;  // LightData::GhostFocus kept by a detector
     int main_child = -1, split_child = -1;
+    bool side_inlined = false;  // the second output's side chain ran inside the main launch (OPM_OP_FORK .. OPM_OP_JOIN)
 };
 
 OpmIsometry iso_z(double z) {
@@ -289,7 +290,21 @@ OpmHitMap* new_hitmap(OpmScene* sc, SurfaceState& s, uint64_t uuid, uint64_t n, 
 }
 
 // `AnalysisRayTrace::analyze` of one node, forward direction, appended to the runner's program
-OpmStatus compile_node_rt(OpmScene* sc, Node& n, const OpmRayTraceConfig& cfg, int flags, uint64_t n_rays, Runner& R) {
+OpmStatus compile_node_rt(OpmScene* sc, Node& n, const OpmRayTraceConfig& cfg, int flags, uint64_t n_rays, Runner& R, int depth = 0);
+
+// the side chain hanging off a splitter's second output, inlined between OPM_OP_FORK and OPM_OP_JOIN: true when the side
+// chain (no further splitter with a second output in it) and the rest fit comfortably into the current launch
+bool can_inline_side_chain(OpmScene* sc, const Node& sp, int flags, const Runner& R, int depth) {
+    if ((flags & OPM_SCENE_PER_SURFACE) || depth != 0 || sp.split_child < 0) return false;
+    size_t nodes = 0;
+    for (int i = sp.split_child; i >= 0; i = sc->nodes[i]->main_child) {
+        if (sc->nodes[i]->d.type == OPM_NODE_BEAM_SPLITTER && sc->nodes[i]->split_child >= 0) return false;
+        ++nodes;
+    }
+    return R.ops.size() + 8 * (nodes + 1) + 8 <= OPM_MAX_PROGRAM_OPS;
+}
+
+OpmStatus compile_node_rt(OpmScene* sc, Node& n, const OpmRayTraceConfig& cfg, int flags, uint64_t n_rays, Runner& R, int depth) {
     const int strat = cfg.missed_surface_strategy;
     const double thr = cfg.min_energy_per_ray;
     OpmStatus st = OPM_OK;
@@ -348,8 +363,26 @@ OpmStatus compile_node_rt(OpmScene* sc, Node& n, const OpmRayTraceConfig& cfg, i
             }
             OpmOp op;
             memset(&op, 0, sizeof op);
-            op.kind = OPM_OP_SPLIT; op.u.split.ratio = n.d.p[0]; op.u.split.split_out = n.split;
-            R.push(op);
+            n.side_inlined = can_inline_side_chain(sc, n, flags, R, depth);
+            if (n.side_inlined) {
+                // the second output's side chain runs in this launch on the split-off rays (same ops the separate launch
+                // would run: out2 aperture in the frame of out1, threshold, limits, then the side chain's nodes)
+                op.kind = OPM_OP_FORK; op.u.fork.ratio = n.d.p[0];
+                R.push(op);
+                R.push(op_apodize(n.s[1].aperture, n.s[1].eff_iso));
+                R.push(op_threshold(thr));
+                R.push(op_limits(cfg.max_number_of_bounces, cfg.max_number_of_refractions, true));
+                for (int i = n.split_child; i >= 0; i = sc->nodes[i]->main_child) {
+                    st = compile_node_rt(sc, *sc->nodes[i], cfg, flags, n_rays, R, depth + 1);
+                    if (st) return st;
+                }
+                memset(&op, 0, sizeof op);
+                op.kind = OPM_OP_JOIN; op.u.join.out = n.split;
+                R.push(op);
+            } else {
+                op.kind = OPM_OP_SPLIT; op.u.split.ratio = n.d.p[0]; op.u.split.split_out = n.split;
+                R.push(op);
+            }
             R.push(op_apodize(n.s[1].aperture, n.s[1].eff_iso));  // out1 aperture, iso of out1_port
             R.push(op_threshold(thr));
             break;
@@ -529,7 +562,7 @@ extern "C" OpmStatus opm_scene_raytrace(OpmScene* sc, OpmRays* rays, const OpmRa
             Node& n = *sc->nodes[i];
             st = compile_node_rt(sc, n, cfg, flags, n_rays, R);
             if (st) return st;
-            if (n.d.type == OPM_NODE_BEAM_SPLITTER && n.split_child >= 0) jobs.push_back({n.split_child, n.split, i});
+            if (n.d.type == OPM_NODE_BEAM_SPLITTER && n.split_child >= 0 && !n.side_inlined) jobs.push_back({n.split_child, n.split, i});
         }
         R.flush();
         if (R.status) return R.status;

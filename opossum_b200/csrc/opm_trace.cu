@@ -47,6 +47,7 @@ trace_kernel(const DevOp* __restrict__ g_ops, int n_ops, DevRays in, DevRays out
              unsigned long long* out_tail, DevStats* stats) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     DevOp* ops = reinterpret_cast<DevOp*>(smem_raw);
+    unsigned* stash = reinterpret_cast<unsigned*>(smem_raw + (size_t)n_ops * sizeof(DevOp));  // only sized when the program forks
     __shared__ barrier_t bar;
 
     // ---- stage the program in shared memory: one TMA bulk copy per CTA
@@ -90,6 +91,8 @@ trace_kernel(const DevOp* __restrict__ g_ops, int n_ops, DevRays in, DevRays out
                 case OPK_SNAPSHOT: exec_snapshot(op.u.snapshot, x); break;
                 case OPK_TRANSFORM: exec_transform(op.u.transform, x); break;
                 case OPK_DIFFRACT: exec_diffract(RefractRt(op.u.diffract.surf), op.u.diffract, x); break;
+                case OPK_FORK: exec_fork(op.u.fork, x, stash); break;
+                case OPK_JOIN: exec_join(op.u.join, x, stash); break;
                 default: break;
             }
             exec_epilogue(EpilogueRt(op.epi_flags), op, x);
@@ -104,7 +107,7 @@ trace_kernel(const DevOp* __restrict__ g_ops, int n_ops, DevRays in, DevRays out
 }  // namespace
 
 int OPM_VARIANT(launch_trace)(const TraceLaunch& L) {
-    size_t smem = (size_t)L.n_ops * sizeof(DevOp);
+    size_t smem = (size_t)L.n_ops * sizeof(DevOp) + (L.has_fork ? (size_t)L.block * kStashWords * 4 : 0);
     cudaStream_t st = (cudaStream_t)L.stream;
     cudaError_t err;
     if (L.compact) {

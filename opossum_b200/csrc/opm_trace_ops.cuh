@@ -192,6 +192,39 @@ __device__ __forceinline__ void exec_split(const DevSplit& o, RayCtx& x) {
         o.out.valid[x.i] = RAY_REMOVED;
     }
 }
+// OPM_OP_FORK / OPM_OP_JOIN: Rays::split (rays.rs:1253-1264, ray.rs:752-772) whose split-off bundle runs its side chain in the
+// same launch.  The main-bundle ray (E * ratio) is parked in shared memory, one 32-bit word per field and thread
+// (field-major, so consecutive lanes hit consecutive banks); the ops up to the JOIN see the split-off ray (E * (1 - ratio)).
+__device__ __forceinline__ void stash_put(unsigned* stash, int f, double v) {
+    stash[(2 * f) * blockDim.x + threadIdx.x] = (unsigned)__double2loint(v);
+    stash[(2 * f + 1) * blockDim.x + threadIdx.x] = (unsigned)__double2hiint(v);
+}
+__device__ __forceinline__ double stash_get(const unsigned* stash, int f) {
+    return __hiloint2double((int)stash[(2 * f + 1) * blockDim.x + threadIdx.x], (int)stash[(2 * f) * blockDim.x + threadIdx.x]);
+}
+__device__ __forceinline__ void exec_fork(const DevFork& o, RayCtx& x, unsigned* stash) {
+    const double e_main = x.valid ? x.r.e * o.ratio : x.r.e;  // invalid rays are copied unchanged (rays.rs:1258-1262)
+    stash_put(stash, 0, x.r.pos.x); stash_put(stash, 1, x.r.pos.y); stash_put(stash, 2, x.r.pos.z);
+    stash_put(stash, 3, x.r.dir.x); stash_put(stash, 4, x.r.dir.y); stash_put(stash, 5, x.r.dir.z);
+    stash_put(stash, 6, e_main); stash_put(stash, 7, x.r.opl); stash_put(stash, 8, x.r.n);
+    stash[18 * blockDim.x + threadIdx.x] = x.r.bounces;
+    stash[19 * blockDim.x + threadIdx.x] = x.r.refr;
+    stash[20 * blockDim.x + threadIdx.x] = (x.alive ? 1u : 0u) | (x.valid ? 2u : 0u);
+    if (x.valid) x.r.e *= 1.0 - o.ratio;
+}
+__device__ __forceinline__ void exec_join(const DevJoin& o, RayCtx& x, const unsigned* stash) {
+    if (x.in_range && o.out.px != nullptr) {
+        if (x.alive) store_ray<true>(o.out, x.i, x.r, x.valid ? RAY_VALID : RAY_INVALID);
+        else o.out.valid[x.i] = RAY_REMOVED;
+    }
+    x.r.pos = v3(stash_get(stash, 0), stash_get(stash, 1), stash_get(stash, 2));
+    x.r.dir = v3(stash_get(stash, 3), stash_get(stash, 4), stash_get(stash, 5));
+    x.r.e = stash_get(stash, 6); x.r.opl = stash_get(stash, 7); x.r.n = stash_get(stash, 8);
+    x.r.bounces = stash[18 * blockDim.x + threadIdx.x];
+    x.r.refr = stash[19 * blockDim.x + threadIdx.x];
+    const unsigned fl = stash[20 * blockDim.x + threadIdx.x];
+    x.alive = (fl & 1u) != 0; x.valid = (fl & 2u) != 0;
+}
 // copy of the bundle a detector node keeps (analyzers/raytrace.rs:186-205)
 __device__ __forceinline__ void exec_snapshot(const DevSnapshot& o, RayCtx& x) {
     if (!x.in_range) return;

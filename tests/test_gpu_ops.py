@@ -462,3 +462,46 @@ def test_diffract_index_error(ctx):
     with pytest.raises(ob.OpossumError) as e:
         r.diffract_on_periodic_surface(sg, ob.RefractiveIndex.const(0.5), (1e6, 0.0, 0.0), -1)
     assert e.value.code == F.OPM_ERR_INDEX_MODEL
+
+
+def test_fork_join_equals_split_and_separate_trace(ctx):
+    """OPM_OP_FORK .. OPM_OP_JOIN (the split-off bundle of Rays::split, rays.rs:1253-1264, traced inside the same launch, its
+    parent parked in shared memory) against OPM_OP_SPLIT followed by a separate launch over the split-off bundle, in both
+    ways of running a program; main bundle, side bundle, hit records and counts must agree exactly"""
+    node = iso_pair((0.0, 0.0, mm(30.0)))
+    front = node_sphere_pair(mm(150.0), node, coating=F.COAT_FRESNEL)[1]
+    side_surf = surface_pair(F.GEOM_PLANE, iso=iso_pair((0.0, 0.0, mm(50.0)), (0.02, -0.01, 0.0)), coating=F.COAT_CONSTANT_R, r=0.3)[1]
+    main_surf = surface_pair(F.GEOM_PLANE, iso=iso_pair((0.0, 0.0, mm(70.0))))[1]
+    glass = ob.RefractiveIndex.const(1.5)
+    ap = ob.Aperture.circle(mm(6.0))
+    rays = make_bundle(5000, divergence=0.05)
+    rays["valid"][::9] = 0
+    for jit in (0, 2):
+        ctx.set_jit(jit, 1)
+        # reference form: split, then the side chain as its own launch
+        a = ob.Rays.from_array(ctx, rays)
+        side_a = ob.Rays(ctx, len(rays))
+        hm_a = ob.HitMap(ctx, len(rays))
+        st_a = (ob.Program().refract(front, glass).threshold(1e-12).split(0.3, side_a).refract(main_surf, None).limits(10, 10)).run(a)
+        st_a2 = (ob.Program().apodize(ap, ob.Isometry.identity()).threshold(1e-12).refract(side_surf, None, hit_map=hm_a).limits(10, 10)).run(side_a)
+        # fused form
+        b = ob.Rays.from_array(ctx, rays)
+        side_b = ob.Rays(ctx, len(rays))
+        hm_b = ob.HitMap(ctx, len(rays))
+        st_b = (ob.Program().refract(front, glass).threshold(1e-12)
+                .fork(0.3).apodize(ap, ob.Isometry.identity()).threshold(1e-12).refract(side_surf, None, hit_map=hm_b).limits(10, 10).join(side_b)
+                .refract(main_surf, None).limits(10, 10)).run(b)
+        assert st_b.interactions == st_a.interactions + st_a2.interactions and st_b.hits == st_a2.hits
+        assert st_b.valid_out == st_a.valid_out and st_b.alive_out == st_a.alive_out and st_b.apodized == st_a2.apodized
+        ga, gb = a.to_array(), b.to_array()
+        sa, sb = side_a.to_array(), side_b.to_array()
+        for f in ga.dtype.names:
+            assert np.array_equal(ga[f], gb[f]), f"main bundle field {f} (jit={jit})"
+            assert np.array_equal(sa[f], sb[f]), f"side bundle field {f} (jit={jit})"
+        for u, w in zip(hm_a.download(), hm_b.download()):
+            assert np.array_equal(u, w)
+    ctx.set_jit(1, 200000)
+    with pytest.raises(ob.OpossumError):
+        ob.Program().fork(0.5).refract(main_surf, None).run(ob.Rays.from_array(ctx, rays))  # FORK without JOIN
+    with pytest.raises(ob.OpossumError):
+        ob.Program().join(None).run(ob.Rays.from_array(ctx, rays))  # JOIN without FORK
