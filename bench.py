@@ -179,6 +179,29 @@ WORKLOAD_NAME = "C2 multi-element laser chain (lens, 2 mirrors, Sellmeier wedge,
 # ---------------------------------------------------------------------------------------------------------------
 # product arm
 # ---------------------------------------------------------------------------------------------------------------
+def bind_to_gpu_numa_node(local: int) -> str:
+    """Best effort: run this rank on the CPUs of the NUMA node its GPU hangs off, so that the pinned host buffers it allocates
+    (first touch) are local to the GPU's PCIe root and H2D copies do not cross the socket interconnect."""
+    try:
+        import torch
+        p = torch.cuda.get_device_properties(local)
+        bdf = f"{p.pci_domain_id:04x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0"
+        base = Path("/sys/bus/pci/devices") / bdf
+        node = int((base / "numa_node").read_text().strip())
+        cpus = (base / "local_cpulist").read_text().strip()
+        ids = set()
+        for part in cpus.split(","):
+            a, _, b = part.partition("-")
+            ids.update(range(int(a), int(b or a) + 1))
+        ids &= os.sched_getaffinity(0)
+        if node >= 0 and ids:
+            os.sched_setaffinity(0, ids)
+            return f"numa node {node} ({len(ids)} cpus)"
+        return "no numa information"
+    except Exception as e:  # noqa: BLE001
+        return f"not bound ({type(e).__name__})"
+
+
 def run_product(args):
     import numpy as np
     import torch
@@ -195,6 +218,7 @@ def run_product(args):
         raise RuntimeError("bench.py needs a CUDA device: opossum_b200 has no CPU fallback")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa = bind_to_gpu_numa_node(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     stream = torch.cuda.Stream(device=dev)
@@ -344,7 +368,8 @@ def run_product(args):
                        "collective": "3 NCCL collectives per step: all_gather(map ranges | spot sums), all_reduce(sum) of the fluence maps, all_gather(spot radii)" if world > 1 else "none (1 GPU)"},
             "e2e": {"value": inter_total * args.steps / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_ms / args.steps,
-                    "pipeline": "two bundles: H2D of step k+1 (copy stream) overlaps trace + read-out of step k"},
+                    "pipeline": "two bundles: H2D of step k+1 (copy stream) overlaps trace + read-out of step k",
+                    "host_binding": numa},
             "gpu_launches": launches_per_step * args.steps,
             "clocks": clk,
             "roofline": {"bound": "hbm", "kernel": ("opm_jit_trace (fused surface sequence, compiled at run time for this op program)" if jit["launches"] else

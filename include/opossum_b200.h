@@ -420,14 +420,15 @@ OpmStatus opm_host_alloc_pinned(uint64_t bytes, void** out);
 void opm_host_free_pinned(void* p);
 
 /* ---- on-device sources (rays.rs:264-297 with the generators of position_distributions/) */
-typedef enum { OPM_POS_GRID = 0, OPM_POS_FIBONACCI_RECT = 1, OPM_POS_FIBONACCI_ELLIPSE = 2 } OpmPosDist;
+typedef enum { OPM_POS_GRID = 0, OPM_POS_FIBONACCI_RECT = 1, OPM_POS_FIBONACCI_ELLIPSE = 2, OPM_POS_HEXAPOLAR = 3 } OpmPosDist;
 typedef enum { OPM_EDIST_UNIFORM = 0, OPM_EDIST_GENERAL_GAUSSIAN = 1 } OpmEnergyDist;
 typedef struct {
     int32_t pos_dist;         /* OpmPosDist */
     int32_t energy_dist;      /* OpmEnergyDist */
     uint64_t n_positions;     /* total positions of the whole source (all ranks) */
-    uint64_t grid_nx, grid_ny;/* Grid: points in x (outer) and y (inner)  grid.rs:58-92 */
-    double size_x, size_y;    /* Grid/FibonacciRect: side lengths; FibonacciEllipse: radii */
+    uint64_t grid_nx, grid_ny;/* Grid: points in x (outer) and y (inner)  grid.rs:58-92; Hexapolar: grid_nx = number of rings
+                                 (n_positions = 1 + 3 rings (rings + 1), hexapolar.rs:38-56) */
+    double size_x, size_y;    /* Grid/FibonacciRect: side lengths; FibonacciEllipse: radii; Hexapolar: size_x = radius */
     double total_energy;      /* J */
     double mu[2], sigma[2], power, theta; int32_t rectangular; int32_t _pad; /* General2DGaussian general_gaussian.rs:93-120 */
     double energy_norm;       /* General2DGaussian: sum of the unnormalised weights over ALL positions; 0 = compute it */

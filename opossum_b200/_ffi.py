@@ -30,7 +30,7 @@ AP_NONE, AP_CIRCLE, AP_RECT, AP_POLYGON, AP_GAUSSIAN = range(5)
  OP_JOIN) = range(1, 13)
 REFRACT_EMIT_CHILDREN, REFRACT_CONTINUE_AS_CHILD = 1, 2
 TRACE_COMPACT, TRACE_STRICT = 1, 2
-POS_GRID, POS_FIBONACCI_RECT, POS_FIBONACCI_ELLIPSE = range(3)
+POS_GRID, POS_FIBONACCI_RECT, POS_FIBONACCI_ELLIPSE, POS_HEXAPOLAR = range(4)
 EDIST_UNIFORM, EDIST_GENERAL_GAUSSIAN = 0, 1
 
 

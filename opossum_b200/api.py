@@ -763,6 +763,11 @@ class SourceDesc:
         self.c.pos_dist, self.c.grid_nx, self.c.grid_ny, self.c.size_x, self.c.size_y = F.POS_GRID, nx, ny, side_x, side_y
         return self
 
+    def hexapolar(self, rings: int, radius: float):
+        """Hexapolar (position_distributions/hexapolar.rs): n_positions must be 1 + 3 rings (rings + 1)"""
+        self.c.pos_dist, self.c.grid_nx, self.c.size_x = F.POS_HEXAPOLAR, rings, radius
+        return self
+
     def fibonacci_rectangle(self, sx, sy):
         self.c.pos_dist, self.c.size_x, self.c.size_y = F.POS_FIBONACCI_RECT, sx, sy
         return self

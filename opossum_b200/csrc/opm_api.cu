@@ -1568,6 +1568,14 @@ static OpmStatus source_params(const OpmSourceDesc* d, SourceParams& S) {
         S.off_x = nx > 1 ? d->size_x / 2.0 : 0.0;
         S.off_y = ny > 1 ? d->size_y / 2.0 : 0.0;
     }
+    if (d->pos_dist == OPM_POS_HEXAPOLAR) {  // hexapolar.rs:24-36,38-56
+        const uint64_t rings = d->grid_nx;
+        if (rings > 255) return fail(OPM_ERR_ARG, "hexapolar: nr_of_rings is a u8");
+        if (std::signbit(d->size_x) || !std::isfinite(d->size_x)) return fail(OPM_ERR_ARG, "radius must be positive and finite");
+        const uint64_t expect = d->size_x == 0.0 ? 1 : 1 + 3 * rings * (rings + 1);
+        if (expect != d->n_positions) return fail(OPM_ERR_ARG, "hexapolar: n_positions must be 1 + 3 rings (rings + 1)");
+        S.dist_x = rings ? d->size_x / (double)rings : 0.0;  // radius_step
+    }
     S.total_energy = d->total_energy;
     S.e_uniform = d->total_energy / (double)d->n_positions;  // uniform.rs:39
     S.energy_norm = d->energy_norm;

@@ -508,6 +508,20 @@ __device__ __forceinline__ void source_position(const SourceParams& S, uint64_t 
             y = S.size_y * ((fi / (double)S.n_positions) - 0.5);
             break;
         }
+        case OPM_POS_HEXAPOLAR: {  // hexapolar.rs:38-56: centre, then ring r (1-based) with 6 r points at radius r * R / rings
+            x = 0.0; y = 0.0;
+            if (ip == 0 || S.size_x == 0.0) break;
+            uint64_t ring = (uint64_t)((sqrt(12.0 * (double)(ip - 1) + 9.0) - 3.0) / 6.0);  // 0-based: 1 + 3 ring (ring + 1) <= ip
+            while (1 + 3 * ring * (ring + 1) > ip) --ring;
+            while (1 + 3 * (ring + 1) * (ring + 2) <= ip) ++ring;
+            const uint64_t point_nr = ip - (1 + 3 * ring * (ring + 1));
+            const double radius = (double)(ring + 1) * S.dist_x;  // dist_x = radius_step
+            const double angle_step = 2.0 * 3.14159265358979323846 / (double)(6 * (ring + 1));
+            double sn, cs;
+            sincos((double)point_nr * angle_step, &sn, &cs);
+            x = radius * sn; y = radius * cs;
+            break;
+        }
         default: {  // fibonacci.rs:113-126
             double sn, cs;
             sincos(2.0 * 3.14159265358979323846 * fract((double)ip / S.golden), &sn, &cs);

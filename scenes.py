@@ -185,13 +185,15 @@ def source_to_product(src, wvl=None, w=None):
     if wvl is None:
         wvl, w = spectrum_of(src)
     pos = src["pos"]
-    n_pos = pos[1] * pos[2] if pos[0] == "grid" else pos[1]
+    n_pos = pos[1] * pos[2] if pos[0] == "grid" else (1 + 3 * pos[1] * (pos[1] + 1) if pos[0] == "hexapolar" else pos[1])
     en = src["energy"]
     sd = ob.SourceDesc(n_pos, wvl, w, total_energy=en[1])
     if pos[0] == "grid":
         sd.grid(pos[1], pos[2], pos[3], pos[4])
     elif pos[0] == "fibonacci_rectangle":
         sd.fibonacci_rectangle(pos[2], pos[3])
+    elif pos[0] == "hexapolar":
+        sd.hexapolar(pos[1], pos[2])
     else:
         sd.fibonacci_ellipse(pos[2], pos[3])
     if en[0] == "general_gaussian":
@@ -209,6 +211,8 @@ def source_to_oracle(src, wvl=None, w=None):
         xyz = orc.grid(pos[1], pos[2], pos[3], pos[4])
     elif pos[0] == "fibonacci_rectangle":
         xyz = orc.fibonacci_rectangle(pos[1], pos[2], pos[3])
+    elif pos[0] == "hexapolar":
+        xyz = orc.hexapolar(pos[1], pos[2])
     else:
         xyz = orc.fibonacci_ellipse(pos[1], pos[2], pos[3])
     en = src["energy"]

@@ -124,13 +124,15 @@ def test_binning_bounce_filter_and_accumulate(ctx):
 
 def test_sources_match_oracle(ctx):
     """rays.rs:264-297 with grid.rs:58-92, fibonacci.rs:53-65,113-126, uniform.rs:37-41, general_gaussian.rs:93-120,
-    spectral_distribution/gaussian.rs:78-96; position-major / wavelength-minor order; source isometry"""
+    hexapolar.rs:38-56, spectral_distribution/gaussian.rs:78-96; position-major / wavelength-minor order; source isometry"""
     wvl, w = orc.spectrum_gaussian(nm(950.0), nm(1150.0), 8, nm(1053.0), nm(50.0))
     io, ig = iso_pair((mm(1.0), mm(-2.0), mm(5.0)), (0.01, -0.02, 0.3))
     cases = {
         "grid": (lambda: orc.grid(37, 29, mm(20.0), mm(15.0)), lambda s: s.grid(37, 29, mm(20.0), mm(15.0)), 37 * 29),
         "fib_rect": (lambda: orc.fibonacci_rectangle(1000, mm(20.0), mm(10.0)), lambda s: s.fibonacci_rectangle(mm(20.0), mm(10.0)), 1000),
         "fib_ellipse": (lambda: orc.fibonacci_ellipse(1000, mm(10.0), mm(7.0)), lambda s: s.fibonacci_ellipse(mm(10.0), mm(7.0)), 1000),
+        "hexapolar": (lambda: orc.hexapolar(17, mm(8.0)), lambda s: s.hexapolar(17, mm(8.0)), 1 + 3 * 17 * 18),
+        "hexapolar255": (lambda: orc.hexapolar(255, mm(8.0)), lambda s: s.hexapolar(255, mm(8.0)), 1 + 3 * 255 * 256),
     }
     for name, (opos, gset, npos) in cases.items():
         for gauss in (False, True):
