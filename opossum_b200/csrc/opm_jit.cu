@@ -17,6 +17,7 @@
 #include <chrono>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <atomic>
 #include <map>
@@ -177,8 +178,20 @@ bool compile_cubin(const std::string& src, std::vector<char>& cubin, std::string
         return false;
     }
     // -default-device: the public header declares the (host) entry points without execution-space annotations
-    const char* opts[] = {"--gpu-architecture=sm_100a", "-std=c++17", "-lineinfo", "-default-device"};
-    nvrtcResult rc = N.CompileProgram(prog, 4, opts);
+    std::vector<std::string> extra;  // tuning: OPM_B200_JIT_DEFINES="-DOPM_STORE_CG -D..." is passed through to the compiler
+    if (const char* e = getenv("OPM_B200_JIT_DEFINES")) {
+        std::string all(e);
+        size_t pos = 0;
+        while (pos < all.size()) {
+            size_t sp = all.find(' ', pos);
+            if (sp == std::string::npos) sp = all.size();
+            if (sp > pos) extra.push_back(all.substr(pos, sp - pos));
+            pos = sp + 1;
+        }
+    }
+    std::vector<const char*> opts = {"--gpu-architecture=sm_100a", "-std=c++17", "-lineinfo", "-default-device"};
+    for (auto& x : extra) opts.push_back(x.c_str());
+    nvrtcResult rc = N.CompileProgram(prog, (int)opts.size(), opts.data());
     if (rc != NVRTC_SUCCESS) {
         size_t ls = 0;
         N.GetProgramLogSize(prog, &ls);

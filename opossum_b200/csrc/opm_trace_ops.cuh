@@ -28,6 +28,15 @@ __device__ __forceinline__ unsigned long long warp_reserve(bool want, unsigned l
     return base + __popc(mask & lanemask_lt());
 }
 
+// cache operator of the bundle / hit-record stores (tuning: -DOPM_STORE_PLAIN / -DOPM_STORE_CG through OPM_B200_JIT_DEFINES)
+#if defined(OPM_STORE_PLAIN)
+#define OPM_ST(ptr, v) (*(ptr) = (v))
+#elif defined(OPM_STORE_CG)
+#define OPM_ST(ptr, v) __stcg((ptr), (v))
+#else
+#define OPM_ST(ptr, v) __stcs((ptr), (v))
+#endif
+
 __device__ __forceinline__ void load_ray(const DevRays& R, uint64_t i, RayState& r) {
     r.pos = v3(__ldcs(R.px + i), __ldcs(R.py + i), __ldcs(R.pz + i));
     r.dir = v3(__ldcs(R.dx + i), __ldcs(R.dy + i), __ldcs(R.dz + i));
@@ -36,12 +45,21 @@ __device__ __forceinline__ void load_ray(const DevRays& R, uint64_t i, RayState&
 }
 template <bool FULL>
 __device__ __forceinline__ void store_ray(const DevRays& R, uint64_t i, const RayState& r, uint8_t valid) {
-    __stcs(R.px + i, r.pos.x); __stcs(R.py + i, r.pos.y); __stcs(R.pz + i, r.pos.z);
-    __stcs(R.dx + i, r.dir.x); __stcs(R.dy + i, r.dir.y); __stcs(R.dz + i, r.dir.z);
-    __stcs(R.e + i, r.e); __stcs(R.opl + i, r.opl); __stcs(R.n + i, r.n);
-    __stcs(R.bounces + i, r.bounces); __stcs(R.refr + i, r.refr);
-    if (FULL) { __stcs(R.wvl + i, r.wvl); __stcs(R.id + i, r.id); }  // wavelength and id never change in place
+    OPM_ST(R.px + i, r.pos.x); OPM_ST(R.py + i, r.pos.y); OPM_ST(R.pz + i, r.pos.z);
+    OPM_ST(R.dx + i, r.dir.x); OPM_ST(R.dy + i, r.dir.y); OPM_ST(R.dz + i, r.dir.z);
+    OPM_ST(R.e + i, r.e); OPM_ST(R.opl + i, r.opl); OPM_ST(R.n + i, r.n);
+#ifndef OPM_DIAG_NO_U32  // diagnosis builds only (profiles/store_variants.sh): which stores cause the ECC read traffic?
+    OPM_ST(R.bounces + i, r.bounces); OPM_ST(R.refr + i, r.refr);
+#endif
+    if (FULL) {  // wavelength and id never change in place
+        OPM_ST(R.wvl + i, r.wvl);
+#ifndef OPM_DIAG_NO_U32
+        OPM_ST(R.id + i, r.id);
+#endif
+    }
+#ifndef OPM_DIAG_NO_U8
     R.valid[i] = valid;
+#endif
 }
 
 // Per-tile event counters, two 16-bit fields per register (a warp's sum of a field is at most 32 lanes x 64 ops):
@@ -123,10 +141,10 @@ __device__ __forceinline__ void exec_refract(const V& v, RayCtx& x) {
         }
     }
     if (v.has_hits() && x.in_range) {  // slot-indexed hit record, e < 0 = empty
-        __stcs(o.hits.e + x.i, res.hit_e);
+        OPM_ST(o.hits.e + x.i, res.hit_e);
         if (res.hit_e >= 0.0) {
-            __stcs(o.hits.x + x.i, res.hit_local.x); __stcs(o.hits.y + x.i, res.hit_local.y);
-            __stcs(o.hits.z + x.i, res.hit_local.z); __stcs(o.hits.bounce + x.i, res.hit_bounce);
+            OPM_ST(o.hits.x + x.i, res.hit_local.x); OPM_ST(o.hits.y + x.i, res.hit_local.y);
+            OPM_ST(o.hits.z + x.i, res.hit_local.z); OPM_ST(o.hits.bounce + x.i, res.hit_bounce);
             x.c.a += 1u << 16;
         }
     }
