@@ -21,7 +21,9 @@
 #include <cstring>
 #include <atomic>
 #include <map>
+#include <condition_variable>
 #include <memory>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
@@ -228,6 +230,26 @@ bool load(JitKernel& K, int n_ops, int block) {
 
 }  // namespace
 
+// A process may end while a compilation is still in flight (a context that was never destroyed, an exception on the
+// caller's side): the exit handler below waits for the workers, so that NVRTC is not torn down under a running compile.
+static std::mutex g_inflight_mu;
+static std::condition_variable g_inflight_cv;
+static int g_inflight = 0;
+static void wait_for_workers_at_exit() {
+    std::unique_lock<std::mutex> lk(g_inflight_mu);
+    g_inflight_cv.wait(lk, [] { return g_inflight == 0; });
+}
+static void worker_begin() {
+    static std::once_flag once;  // registered after NVRTC was loaded, so it runs before NVRTC's own exit handlers
+    std::call_once(once, [] { atexit(wait_for_workers_at_exit); });
+    std::lock_guard<std::mutex> lk(g_inflight_mu);
+    ++g_inflight;
+}
+static void worker_end() {
+    std::lock_guard<std::mutex> lk(g_inflight_mu);
+    if (--g_inflight == 0) g_inflight_cv.notify_all();
+}
+
 JitCache* jit_cache_create() { return new JitCache(); }
 void jit_cache_destroy(JitCache* c) {
     if (!c) return;
@@ -265,11 +287,13 @@ const JitKernel* jit_get(JitCache* cache, const DevOp* ops, int n_ops, bool comp
             cache->failures++;
         } else {
             const std::string* text = &it->first;  // map nodes are stable: the worker reads the key in place
+            worker_begin();
             k->worker = std::thread([k, text]() {
                 const auto t0 = std::chrono::steady_clock::now();
                 const bool ok = compile_cubin(*text, k->cubin, k->why);
                 k->compile_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
                 k->state.store(ok ? JIT_CUBIN_READY : JIT_FAILED, std::memory_order_release);
+                worker_end();
             });
         }
     }
