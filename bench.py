@@ -358,6 +358,14 @@ def run_product(args):
         flop_per_inter = 300.0  # SURVEY 8d estimate (FMA = 2 flop), sqrt/div counted as one
         h2d = n * 32 + 16 * len(wvl)
         d2h = 2 * MAP_NX * MAP_NY * 8 + 2 * 48 + 64
+        # DRAM bytes of the same launch from the committed `ncu --set full` capture (never measured under the profiler here)
+        traffic = None
+        try:
+            tr = json.loads((ROOT / "profiles" / "r1_traffic.json").read_text())
+            if jit["launches"] and tr["workload_rays_per_gpu"] == n and tr["launches_per_step"] == launches_trace:
+                traffic = tr["dram_bytes_read"] + tr["dram_bytes_write"]
+        except (OSError, ValueError, KeyError):
+            pass
         line = {
             "metric": METRIC, "value": inter_total * args.steps / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -375,7 +383,7 @@ def run_product(args):
             "roofline": {"bound": "hbm", "kernel": ("opm_jit_trace (fused surface sequence, compiled at run time for this op program)" if jit["launches"] else
                                                    "opm::trace_kernel (fused surface sequence, interpreter)"),
                          "jit": jit, "achieved": achieved, "peak": hbm_peak,
-                         "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
+                         "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": bytes_step / max(launches_trace, 1), "launches_per_step": launches_trace,
                          "kernel_ms_per_launch": kern_ms_step / max(launches_trace, 1), "kernel_share_of_step": kern_ms_step / (ms / args.steps),
                          "unfused_equivalent_gbs": unfused,

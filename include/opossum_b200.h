@@ -302,6 +302,21 @@ OpmStatus opm_rays_download(const OpmRays* rays, OpmRay* host, uint64_t capacity
 OpmStatus opm_rays_copy(const OpmRays* src, OpmRays* dst);                                 /* Rays::clone */
 OpmStatus opm_rays_append(OpmRays* dst, const OpmRays* src);                               /* Rays::add_rays / merge rays.rs:932,1268 */
 OpmStatus opm_rays_compact(OpmRays* rays);                    /* drop removed rays, order preserving */
+/* Per-ray position history (`pos_hist` ray.rs:70): once enabled, every call that pushes a position in the
+ * reference logs it for the bundle's rays -- refract_on_surface (the position the ray leaves, ray.rs:616; also on total
+ * reflection, not on a miss), diffract_on_periodic_surface (:537), apodize for the rays it invalidates (rays.rs:566).
+ * Split-off and stored copies (OPM_OP_SPLIT / OPM_OP_SNAPSHOT, opm_rays_copy) inherit the history like a cloned Ray;
+ * reflected children (refraction_intended) start without one (rays.rs:1014); uploading or generating rays clears it.
+ * Bundles with a history run on the interpreter kernel, cannot be compacted and cannot use OPM_OP_FORK.
+ * levels_hint = expected number of logging calls (the log grows on demand). */
+OpmStatus opm_rays_enable_position_history(OpmRays* rays, uint32_t levels_hint);
+OpmStatus opm_rays_disable_position_history(OpmRays* rays);
+OpmStatus opm_rays_clear_position_history(OpmRays* rays);                 /* Ray::clear_pos_hist ray.rs:225-227 */
+int32_t opm_rays_position_history_levels(const OpmRays* rays);            /* logging calls so far = max positions per ray; -1: disabled */
+/* Ray::position_history / position_history_with_current (ray.rs:296-327) of every ray, in the order of opm_rays_download:
+ * xyz_out[(ray * pos_cap + k) * 3 + c] for k < len_out[ray]; OPM_ERR_CAPACITY if a ray has more than pos_cap positions */
+OpmStatus opm_rays_position_history(const OpmRays* rays, int32_t with_current, double* xyz_out, uint32_t* len_out,
+                                    uint64_t ray_cap, uint32_t pos_cap, uint64_t* n_rays_out);
 /* raw device pointer of one field ("px","py","pz","dx","dy","dz","e","wvl","opl","n","bounces","refr","id","valid") */
 void* opm_rays_field_ptr(OpmRays* rays, const char* field);
 

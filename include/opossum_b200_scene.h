@@ -40,7 +40,9 @@ typedef enum {
     OPM_NODE_PARAXIAL_SURFACE = 9,
     OPM_NODE_SPOT_DIAGRAM = 10,
     OPM_NODE_FLUENCE_DETECTOR = 11,
-    OPM_NODE_REFLECTIVE_GRATING = 12 /* nodes/reflective_grating.rs */
+    OPM_NODE_REFLECTIVE_GRATING = 12, /* nodes/reflective_grating.rs */
+    OPM_NODE_RAY_PROPAGATION_VISUALIZER = 13 /* nodes/ray_propagation_visualizer.rs: a single-surface detector that keeps the bundle;
+                                                 with OPM_SCENE_POSITION_HISTORY its rays carry their paths */
 } OpmNodeType;
 
 typedef struct { int32_t type; int32_t _pad; double reflectivity; } OpmCoatingDesc; /* coatings/mod.rs:17-29 */
@@ -89,7 +91,9 @@ enum {
     OPM_SCENE_RECORD_ALL_HITS = 8,  /* keep the hit map of every surface (the reference always does); default: detectors only */
     OPM_SCENE_NO_SNAPSHOTS = 16,    /* detectors keep hit maps but no copy of the bundle (no spot statistics) */
     OPM_SCENE_ASYNC = 32,           /* do not synchronise / read counters back (throughput runs) */
-    OPM_SCENE_KEEP_SOURCE = 64      /* leave `source_rays` untouched: the main chain's output goes to opm_scene_output_rays() */
+    OPM_SCENE_KEEP_SOURCE = 64,     /* leave `source_rays` untouched: the main chain's output goes to opm_scene_output_rays() */
+    OPM_SCENE_POSITION_HISTORY = 128 /* keep the per-ray position history (`pos_hist`): read it with opm_rays_position_history() from the
+                                       bundles of opm_scene_node_rays() / opm_scene_output_rays() / the traced source bundle */
 };
 
 /* RayTracingAnalyzer::analyze.  `source_rays` is the bundle the Source node's light-data builder produced, in

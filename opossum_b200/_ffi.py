@@ -163,8 +163,10 @@ class OpmSourceDesc(C.Structure):
 
 
 (NODE_SOURCE, NODE_LENS, NODE_CYLINDRIC_LENS, NODE_WEDGE, NODE_THIN_MIRROR, NODE_PARABOLIC_MIRROR, NODE_BEAM_SPLITTER,
- NODE_DUMMY, NODE_IDEAL_FILTER, NODE_PARAXIAL_SURFACE, NODE_SPOT_DIAGRAM, NODE_FLUENCE_DETECTOR, NODE_REFLECTIVE_GRATING) = range(13)
+ NODE_DUMMY, NODE_IDEAL_FILTER, NODE_PARAXIAL_SURFACE, NODE_SPOT_DIAGRAM, NODE_FLUENCE_DETECTOR, NODE_REFLECTIVE_GRATING,
+ NODE_RAY_PROPAGATION_VISUALIZER) = range(14)
 SCENE_STRICT, SCENE_PER_SURFACE, SCENE_RECORD_ALL_HITS, SCENE_NO_SNAPSHOTS, SCENE_ASYNC, SCENE_KEEP_SOURCE = 2, 4, 8, 16, 32, 64
+SCENE_POSITION_HISTORY = 128
 
 
 class OpmCoatingDesc(C.Structure):
@@ -208,6 +210,8 @@ EXPORTS = [
     "opm_isometry_new", "opm_isometry_append", "opm_raytrace_config_default", "opm_rays_create", "opm_rays_destroy",
     "opm_rays_len", "opm_rays_capacity", "opm_rays_clear", "opm_rays_reserve", "opm_rays_upload",
     "opm_rays_upload_soa", "opm_rays_new_collimated_with_spectrum", "opm_rays_download", "opm_rays_copy", "opm_rays_append", "opm_rays_compact",
+    "opm_rays_enable_position_history", "opm_rays_disable_position_history", "opm_rays_clear_position_history",
+    "opm_rays_position_history_levels", "opm_rays_position_history",
     "opm_rays_field_ptr", "opm_rays_refract_on_surface", "opm_rays_diffract_on_periodic_surface", "opm_rays_apodize",
     "opm_rays_invalidate_by_threshold_energy", "opm_rays_filter_by_nr_of_bounces",
     "opm_rays_filter_by_nr_of_refractions", "opm_rays_filter_energy", "opm_rays_split", "opm_rays_refract_paraxial",
@@ -274,6 +278,11 @@ def lib() -> C.CDLL:
         "opm_rays_copy": (i32, [vp, vp]),
         "opm_rays_append": (i32, [vp, vp]),
         "opm_rays_compact": (i32, [vp]),
+        "opm_rays_enable_position_history": (i32, [vp, C.c_uint32]),
+        "opm_rays_disable_position_history": (i32, [vp]),
+        "opm_rays_clear_position_history": (i32, [vp]),
+        "opm_rays_position_history_levels": (i32, [vp]),
+        "opm_rays_position_history": (i32, [vp, i32, vp, vp, u64, C.c_uint32, C.POINTER(u64)]),
         "opm_rays_field_ptr": (vp, [vp, C.c_char_p]),
         "opm_rays_refract_on_surface": (i32, [vp, C.POINTER(OpmSurface), C.POINTER(OpmIndexModel), i32, i32, vp, vp,
                                               C.POINTER(OpmTraceStats)]),

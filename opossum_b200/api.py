@@ -372,6 +372,11 @@ class Rays:
         _check(F.lib().opm_rays_upload(r.h, C.c_void_p(a.ctypes.data), len(a)))
         return r
 
+    def upload(self, rays: np.ndarray):
+        """replaces the bundle's rays (a position history, if kept, starts over)"""
+        a = np.ascontiguousarray(rays, dtype=RAY_DTYPE)
+        _check(F.lib().opm_rays_upload(self.h, C.c_void_p(a.ctypes.data), len(a)))
+
     def upload_soa(self, pos, direction, e, wvl):
         """SoA upload (one H2D copy per field, from pinned memory when the arrays are pinned)."""
         dp = C.POINTER(C.c_double)
@@ -413,6 +418,36 @@ class Rays:
 
     def clear(self):
         _check(F.lib().opm_rays_clear(self.h))
+
+    # ---- per-ray position history (`pos_hist`, ray.rs:70)
+    def enable_position_history(self, levels_hint: int = 16):
+        """from now on every refract / diffract / clipping apodize call logs the positions the reference pushes"""
+        _check(F.lib().opm_rays_enable_position_history(self.h, levels_hint))
+
+    def disable_position_history(self):
+        _check(F.lib().opm_rays_disable_position_history(self.h))
+
+    def clear_position_history(self):
+        """Ray::clear_pos_hist (ray.rs:225-227) for every ray"""
+        _check(F.lib().opm_rays_clear_position_history(self.h))
+
+    @property
+    def position_history_levels(self) -> int:
+        return F.lib().opm_rays_position_history_levels(self.h)
+
+    def position_history(self, with_current: bool = True):
+        """Rays::get_rays_position_history (rays.rs:1357-1383) without the wavelength grouping: one (len_i, 3) array per
+        ray in bundle order -- Ray::position_history_with_current / position_history (ray.rs:296-327)"""
+        levels = self.position_history_levels
+        if levels < 0:
+            raise OpossumError(F.OPM_ERR_ARG, "the bundle keeps no position history")
+        n, cap = len(self), levels + 1
+        xyz = np.zeros((max(n, 1), cap, 3), dtype=np.float64)
+        ln = np.zeros(max(n, 1), dtype=np.uint32)
+        k = C.c_uint64()
+        _check(F.lib().opm_rays_position_history(self.h, 1 if with_current else 0, C.c_void_p(xyz.ctypes.data),
+                                                 C.c_void_p(ln.ctypes.data), max(n, 1), cap, C.byref(k)))
+        return [xyz[i, : ln[i]].copy() for i in range(k.value)]
 
     def field_ptr(self, name: str) -> int:
         return F.lib().opm_rays_field_ptr(self.h, name.encode()) or 0

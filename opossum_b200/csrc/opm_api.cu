@@ -81,6 +81,11 @@ struct OpmRays {
     bool pending = false;
     uint64_t pend_n_pos = 0;
     uint32_t pend_n_wvl = 0;
+    // optional per-ray position history (`pos_hist`, ray.rs:70): level-major log, see HistParams.
+    // Levels [0, hist_next) are in use; a slot's NaN rows are levels at which that ray logged nothing.
+    double* d_hist = nullptr;
+    uint32_t hist_levels = 0, hist_next = 0;
+    uint64_t hist_stride = 0;
 };
 
 struct OpmHitMap {
@@ -89,6 +94,9 @@ struct OpmHitMap {
     void* base = nullptr;
     DevHits v{};
 };
+
+static OpmStatus hist_resize(OpmRays* r, uint32_t levels, uint64_t stride);
+static OpmStatus hist_clear(OpmRays* r);
 
 // ---------------------------------------------------------------------------------------------
 // errors
@@ -371,6 +379,7 @@ extern "C" void opm_rays_destroy(OpmRays* r) {
     if (r->d_stage) cudaStreamSynchronize(r->ctx->copy_stream);
     cudaStreamSynchronize(r->ctx->stream);
     cudaFree(r->base);
+    cudaFree(r->d_hist);
     cudaFree(r->d_stage);
     cudaFreeHost(r->h_spec);
     if (r->ev_uploaded) cudaEventDestroy(r->ev_uploaded);
@@ -411,6 +420,7 @@ extern "C" uint64_t opm_rays_capacity(const OpmRays* r) { return r ? r->cap : 0;
 extern "C" OpmStatus opm_rays_clear(OpmRays* r) {
     if (!r) return fail(OPM_ERR_ARG, "rays is NULL");
     r->len = 0; r->len_dirty = false; r->pending = false;
+    if (r->d_hist) { OpmStatus hs = hist_clear(r); if (hs) return hs; }  // new rays start without a history (ray.rs:126)
     CU(cudaMemsetAsync(r->d_tail, 0, 8, r->ctx->stream));
     return OPM_OK;
 }
@@ -439,6 +449,7 @@ extern "C" OpmStatus opm_rays_reserve(OpmRays* r, uint64_t capacity) {
     KL(k_set_u64(r->d_tail, r->len, r->ctx->stream));
     CU(cudaStreamSynchronize(r->ctx->stream));
     cudaFree(old.base);
+    if (r->d_hist && r->hist_stride < capacity) return hist_resize(r, r->hist_levels, capacity);
     return OPM_OK;
 }
 static OpmStatus rays_set_len(OpmRays* r, uint64_t n) {
@@ -448,11 +459,124 @@ static OpmStatus rays_set_len(OpmRays* r, uint64_t n) {
     return OPM_OK;
 }
 
+// ---- position history ---------------------------------------------------------------------------
+// (re)allocates the log for `levels` levels of `stride` slots; used levels are carried over, everything else reads NaN
+static OpmStatus hist_resize(OpmRays* r, uint32_t levels, uint64_t stride) {
+    if (levels < 1) levels = 1;
+    if (stride < r->cap) stride = r->cap;
+    if (stride < 1) stride = 1;
+    OpmContext* c = r->ctx;
+    double* nb = nullptr;
+    const size_t bytes = (size_t)levels * 3 * stride * sizeof(double);
+    CU(cudaMalloc(&nb, bytes));
+    CU(cudaMemsetAsync(nb, 0xFF, bytes, c->stream));  // all-ones = a quiet NaN
+    if (r->d_hist) {
+        const uint32_t keep = r->hist_next < levels ? r->hist_next : levels;
+        const uint64_t w = r->hist_stride < stride ? r->hist_stride : stride;
+        if (keep && w)
+            CU(cudaMemcpy2DAsync(nb, stride * sizeof(double), r->d_hist, r->hist_stride * sizeof(double), w * sizeof(double),
+                                 (size_t)keep * 3, cudaMemcpyDeviceToDevice, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+        cudaFree(r->d_hist);
+        if (r->hist_next > levels) r->hist_next = levels;
+    }
+    r->d_hist = nb; r->hist_levels = levels; r->hist_stride = stride;
+    return OPM_OK;
+}
+// Ray::clear_pos_hist (ray.rs:225-227) for the whole bundle
+static OpmStatus hist_clear(OpmRays* r) {
+    if (r->d_hist && r->hist_next)
+        CU(cudaMemsetAsync(r->d_hist, 0xFF, (size_t)r->hist_next * 3 * r->hist_stride * sizeof(double), r->ctx->stream));
+    r->hist_next = 0;
+    return OPM_OK;
+}
+// dst's history := the first `levels` levels of src's (a clone of the rays carries their history, ray.rs:625 / :752-772)
+static OpmStatus hist_copy(const OpmRays* src, OpmRays* dst, uint32_t levels, uint64_t n) {
+    OpmStatus s = OPM_OK;
+    if (!dst->d_hist || dst->hist_levels < levels || dst->hist_stride < n) {
+        dst->hist_next = 0;  // nothing worth carrying over
+        s = hist_resize(dst, levels > dst->hist_levels ? levels : dst->hist_levels, n > dst->hist_stride ? n : dst->hist_stride);
+    } else s = hist_clear(dst);
+    if (s) return s;
+    if (src && src->d_hist && levels && n) {
+        if (levels > src->hist_next) levels = src->hist_next;
+        if (levels)
+            CU(cudaMemcpy2DAsync(dst->d_hist, dst->hist_stride * sizeof(double), src->d_hist, src->hist_stride * sizeof(double),
+                                 n * sizeof(double), (size_t)levels * 3, cudaMemcpyDeviceToDevice, dst->ctx->stream));
+    }
+    dst->hist_next = (src && src->d_hist) ? levels : 0;
+    return OPM_OK;
+}
+extern "C" OpmStatus opm_rays_enable_position_history(OpmRays* r, uint32_t levels_hint) {
+    if (!r) return fail(OPM_ERR_ARG, "rays is NULL");
+    CU(cudaSetDevice(r->ctx->device));
+    if (r->d_hist) return OPM_OK;
+    return hist_resize(r, levels_hint ? levels_hint : 16, r->cap);
+}
+extern "C" OpmStatus opm_rays_disable_position_history(OpmRays* r) {
+    if (!r) return fail(OPM_ERR_ARG, "rays is NULL");
+    if (!r->d_hist) return OPM_OK;
+    CU(cudaSetDevice(r->ctx->device));
+    CU(cudaStreamSynchronize(r->ctx->stream));
+    cudaFree(r->d_hist);
+    r->d_hist = nullptr; r->hist_levels = r->hist_next = 0; r->hist_stride = 0;
+    return OPM_OK;
+}
+extern "C" OpmStatus opm_rays_clear_position_history(OpmRays* r) {
+    if (!r) return fail(OPM_ERR_ARG, "rays is NULL");
+    CU(cudaSetDevice(r->ctx->device));
+    return hist_clear(r);
+}
+extern "C" int32_t opm_rays_position_history_levels(const OpmRays* r) { return (r && r->d_hist) ? (int32_t)r->hist_next : -1; }
+// Ray::position_history / position_history_with_current (ray.rs:296-327) of every ray of the bundle, in the order of
+// opm_rays_download: xyz_out[(ray * pos_cap + k) * 3 + c], len_out[ray] positions each
+extern "C" OpmStatus opm_rays_position_history(const OpmRays* rc, int32_t with_current, double* xyz_out, uint32_t* len_out,
+                                               uint64_t ray_cap, uint32_t pos_cap, uint64_t* n_out) {
+    OpmRays* r = const_cast<OpmRays*>(rc);
+    if (!r || !xyz_out || !len_out || !n_out) return fail(OPM_ERR_ARG, "NULL argument");
+    if (!r->d_hist) return fail(OPM_ERR_ARG, "the bundle keeps no position history (opm_rays_enable_position_history)");
+    OpmContext* c = r->ctx;
+    CU(cudaSetDevice(c->device));
+    OpmStatus s = rays_materialize(r);
+    if (!s) s = rays_refresh_len(r);
+    if (s) return s;
+    *n_out = 0;
+    const uint64_t n = r->len;
+    if (n == 0) return OPM_OK;
+    if (pos_cap == 0) return fail(OPM_ERR_CAPACITY, "position capacity is 0");
+    double* d_xyz = nullptr;
+    uint32_t* d_len = nullptr;
+    CU(cudaMalloc(&d_xyz, (size_t)n * pos_cap * 3 * sizeof(double)));
+    CU(cudaMalloc(&d_len, (size_t)n * sizeof(uint32_t)));
+    HistParams hp;
+    hp.base = r->d_hist; hp.stride = r->hist_stride;
+    int rc2 = k_history_gather(hp, r->hist_next, r->v, n, with_current ? 1 : 0, pos_cap, d_xyz, d_len, c->sms, c->stream);
+    c->launches++;
+    std::vector<double> h_xyz((size_t)n * pos_cap * 3);
+    std::vector<uint32_t> h_len(n);
+    cudaError_t e = rc2 ? (cudaError_t)rc2 : cudaMemcpyAsync(h_xyz.data(), d_xyz, h_xyz.size() * sizeof(double), cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(h_len.data(), d_len, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    cudaFree(d_xyz); cudaFree(d_len);
+    if (e != cudaSuccess) return fail(OPM_ERR_CUDA, "position history read-out failed: %s", cudaGetErrorString(e));
+    uint64_t k = 0;
+    for (uint64_t i = 0; i < n; ++i) {
+        if (h_len[i] == 0xFFFFFFFFu) continue;  // removed slot (not part of the bundle)
+        if (k >= ray_cap) return fail(OPM_ERR_CAPACITY, "position history buffer holds %llu rays, the bundle has more", (unsigned long long)ray_cap);
+        if (h_len[i] > pos_cap) return fail(OPM_ERR_CAPACITY, "a ray has %u positions, the buffer holds %u per ray", h_len[i], pos_cap);
+        memcpy(xyz_out + k * pos_cap * 3, h_xyz.data() + i * pos_cap * 3, (size_t)pos_cap * 3 * sizeof(double));
+        len_out[k++] = h_len[i];
+    }
+    *n_out = k;
+    return OPM_OK;
+}
+
 extern "C" OpmStatus opm_rays_upload(OpmRays* r, const OpmRay* host, uint64_t n) {
     if (!r || (!host && n)) return fail(OPM_ERR_ARG, "NULL argument");
     r->pending = false;
     OpmContext* c = r->ctx;
     CU(cudaSetDevice(c->device));
+    if (r->d_hist) { OpmStatus hs = hist_clear(r); if (hs) return hs; }  // new rays start without a history (ray.rs:126)
     OpmStatus s = opm_rays_reserve(r, n);
     if (s) return s;
     if (n) {
@@ -471,6 +595,7 @@ extern "C" OpmStatus opm_rays_upload_soa(OpmRays* r, const double* pos[3], const
     OpmContext* c = r->ctx;
     CU(cudaSetDevice(c->device));
     r->pending = false;
+    if (r->d_hist) { OpmStatus hs = hist_clear(r); if (hs) return hs; }  // new rays start without a history (ray.rs:126)
     OpmStatus s = opm_rays_reserve(r, n);
     if (s) return s;
     if (n) {
@@ -492,6 +617,7 @@ extern "C" OpmStatus opm_rays_new_collimated_with_spectrum(OpmRays* r, const dou
         if (!(wvl[k] > 0.0) || !std::isfinite(wvl[k])) return fail(OPM_ERR_ARG, "wavelength must be >0");
     const uint64_t n_rays = n_pos * n_wvl;
     r->pending = false;  // an earlier upload that was never used is superseded
+    if (r->d_hist) { OpmStatus hs = hist_clear(r); if (hs) return hs; }  // new rays start without a history (ray.rs:126)
     OpmStatus s = opm_rays_reserve(r, n_rays);
     if (s) return s;
     const size_t need = align_up(n_pos * 32, 256) + (size_t)n_wvl * 16;
@@ -567,6 +693,8 @@ extern "C" OpmStatus opm_rays_copy(const OpmRays* src, OpmRays* dst) {
     if (s) return s;
     s = copy_fields(src->v, 0, dst->v, 0, src->len, dst->ctx->stream);
     if (s) return s;
+    if (src->d_hist) { s = hist_copy(src, dst, src->hist_next, src->len); if (s) return s; }
+    else if (dst->d_hist) { s = hist_clear(dst); if (s) return s; }
     return rays_set_len(dst, src->len);
 }
 extern "C" OpmStatus opm_rays_append(OpmRays* dst, const OpmRays* src) {
@@ -576,6 +704,7 @@ extern "C" OpmStatus opm_rays_append(OpmRays* dst, const OpmRays* src) {
     if (s) return s;
     s = rays_refresh_len(dst);
     if (s) return s;
+    if (dst->d_hist) return fail(OPM_ERR_ARG, "a bundle with a position history cannot take appended rays");
     s = opm_rays_reserve(dst, dst->len + src->len);
     if (s) return s;
     s = copy_fields(src->v, 0, dst->v, dst->len, src->len, dst->ctx->stream);
@@ -590,6 +719,7 @@ extern "C" OpmStatus opm_rays_compact(OpmRays* r) {
     if (s) return s;
     uint64_t n = r->len;
     if (n == 0) return OPM_OK;
+    if (r->d_hist) return fail(OPM_ERR_ARG, "a bundle with a position history cannot be compacted (the log is indexed by slot)");
     uint64_t nb = (n + 1023) / 1024;
     unsigned* counts = nullptr; unsigned long long* offsets = nullptr;
     CU(cudaMalloc(&counts, nb * sizeof(unsigned)));
@@ -709,6 +839,7 @@ struct Compiled {
     std::vector<void*> temp_dev;        // polygon triangle uploads, freed after the launch
     std::vector<OpmRays*> appended;     // bundles that receive appended rays (children)
     std::vector<OpmRays*> slot_outputs; // split / snapshot outputs (len = n)
+    std::vector<std::pair<int, OpmRays*>> slot_output_ops;  // the same with the index of their device op (position history)
     std::vector<OpmHitMap*> hitmaps;
     int fork_depth = 0;                 // inside an OPM_OP_FORK .. OPM_OP_JOIN range
     bool has_fork = false;
@@ -821,6 +952,7 @@ static OpmStatus compile_ops(OpmContext* c, const OpmOp* ops, int n_ops, uint64_
                     if (s) return s;
                     d.u.split.out = p.u.split.split_out->v;
                     out.slot_outputs.push_back(p.u.split.split_out);
+                    out.slot_output_ops.push_back({(int)out.ops.size(), p.u.split.split_out});
                 }
                 break;
             }
@@ -850,6 +982,7 @@ static OpmStatus compile_ops(OpmContext* c, const OpmOp* ops, int n_ops, uint64_
                 if (s) return s;
                 d.kind = OPK_SNAPSHOT; d.u.snapshot.out = p.u.snapshot.out->v;
                 out.slot_outputs.push_back(p.u.snapshot.out);
+                out.slot_output_ops.push_back({(int)out.ops.size(), p.u.snapshot.out});
                 break;
             }
             case OPM_OP_DIFFRACT: {
@@ -922,6 +1055,29 @@ static OpmStatus run_program(OpmRays* rays, const OpmOp* ops, int n_ops, int fla
         s = opm_rays_reserve(dst, n);
         if (s) { free_temps(); return s; }
     }
+    // position history: the bundle the program leaves its rays in logs one level per pushing op
+    HistParams hp;
+    const bool use_hist = rays->d_hist != nullptr || dst->d_hist != nullptr;
+    std::vector<uint32_t> level_before;  // per device op: levels in use when it starts
+    if (use_hist) {
+        if (compact) { free_temps(); return fail(OPM_ERR_ARG, "a bundle with a position history cannot be compacted by a trace"); }
+        if (prog.has_fork) { free_temps(); return fail(OPM_ERR_ARG, "OPM_OP_FORK needs bundles without a position history (use OPM_OP_SPLIT)"); }
+        if (dst != rays) { s = hist_copy(rays, dst, rays->d_hist ? rays->hist_next : 0, n); if (s) { free_temps(); return s; } }
+        uint32_t need = dst->hist_next;
+        for (const DevOp& d : prog.ops) need += (d.kind == OPK_REFRACT || d.kind == OPK_DIFFRACT || d.kind == OPK_APODIZE) ? 1u : 0u;
+        if (need > dst->hist_levels || dst->hist_stride < n) {
+            s = hist_resize(dst, need > 2 * dst->hist_levels ? need : 2 * dst->hist_levels, n);
+            if (s) { free_temps(); return s; }
+        }
+        uint32_t lv = dst->hist_next;
+        for (size_t k = 0; k < prog.ops.size(); ++k) {
+            const int kind = prog.ops[k].kind;
+            level_before.push_back(lv);
+            hp.level[k] = (kind == OPK_REFRACT || kind == OPK_DIFFRACT || kind == OPK_APODIZE) ? (short)lv++ : (short)-1;
+        }
+        hp.base = dst->d_hist; hp.stride = dst->hist_stride;
+        dst->hist_next = lv;
+    }
     // a program whose ops were all elided (Aperture::None, negative threshold) still has to honour out/compact
     if (n > 0 && (!prog.ops.empty() || dst != rays)) {
         if (prog.ops.empty()) {  // pure copy: keep the kernel path uniform with a no-op limits check
@@ -940,7 +1096,7 @@ static OpmStatus run_program(OpmRays* rays, const OpmOp* ops, int n_ops, int fla
         // large bundles run the kernel compiled for the structure of this program (opm_jit.cu); otherwise, and whenever
         // that kernel cannot be had, the interpreter
         const JitKernel* jk = nullptr;
-        if (!strict && c->jit_enabled && n >= c->jit_min_rays && prog.ops.size() * sizeof(DevOp) <= 60 * 1024) {  // __constant__ holds 64 KB
+        if (!strict && !use_hist && c->jit_enabled && n >= c->jit_min_rays && prog.ops.size() * sizeof(DevOp) <= 60 * 1024) {  // __constant__ holds 64 KB
             const char* why = nullptr;
             jk = jit_get(c->jit, prog.ops.data(), (int)prog.ops.size(), compact, c->jit_block, c->jit_min_ctas, c->jit_sync, &why);
             if (jk) block = c->jit_block;
@@ -959,6 +1115,7 @@ static OpmStatus run_program(OpmRays* rays, const OpmOp* ops, int n_ops, int fla
         L.in = rays->v; L.out = dst->v; L.n = n; L.out_cap = dst->cap; L.out_tail = dst->d_tail;
         L.stats = c->d_stats; L.compact = compact ? 1 : 0; L.block = block; L.stream = c->stream;
         L.has_fork = prog.has_fork ? 1 : 0;
+        L.hist = use_hist ? &hp : nullptr;
         size_t smem = prog.ops.size() * sizeof(DevOp) + (prog.has_fork ? (size_t)block * kStashWords * 4 : 0);
         int occ = jk ? jit_occupancy(jk) : strict ? trace_occupancy_strict(L.block, smem) : trace_occupancy_fast(L.block, smem);
         uint64_t tiles = (n + L.block - 1) / L.block;
@@ -976,6 +1133,13 @@ static OpmStatus run_program(OpmRays* rays, const OpmOp* ops, int n_ops, int fla
         if (c->timing) { CU(cudaEventRecord(tev.second, c->stream)); c->timing_events.push_back(tev); }
         if (rc != 0) { free_temps(); return fail(OPM_ERR_CUDA, "trace kernel launch failed: %s", cudaGetErrorString((cudaError_t)rc)); }
     }
+    // a split-off or stored copy of the rays carries the history they had at that op (clone, ray.rs:752-772)
+    if (use_hist)
+        for (auto& so : prog.slot_output_ops) {
+            const uint32_t lv = (size_t)so.first < level_before.size() ? level_before[so.first] : dst->hist_next;
+            s = hist_copy(dst, so.second, lv, n);
+            if (s) { free_temps(); return s; }
+        }
     // host-side lengths
     for (OpmHitMap* h : prog.hitmaps) h->len = n;
     for (OpmRays* r : prog.slot_outputs) { s = rays_set_len(r, n); if (s) { free_temps(); return s; } }
@@ -1624,6 +1788,7 @@ static OpmStatus source_generate(OpmRays* rays, const OpmSourceDesc* desc, uint6
         S.energy_norm = norm;
     }
     rays->pending = false;
+    if (rays->d_hist) { OpmStatus hs = hist_clear(rays); if (hs) return hs; }  // new rays start without a history (ray.rs:126)
     uint64_t n_rays = n_pos * S.n_wavelengths;
     s = opm_rays_reserve(rays, n_rays);
     if (s) return s;

@@ -90,6 +90,15 @@ struct alignas(16) DevOp {
 };
 static_assert(sizeof(DevOp) % 16 == 0, "DevOp must be a multiple of 16 B for the bulk copy into shared memory");
 
+// Optional per-ray position history (`pos_hist`, ray.rs:70): a level-major log beside the bundle,
+// base[(level * 3 + c) * stride + slot], NaN = the ray has no entry at this level.  Every op that pushes in the
+// reference (refract :616, diffract :537, apodize of a ray it invalidates rays.rs:566) owns one level per launch.
+struct HistParams {
+    double* base;
+    uint64_t stride;
+    short level[OPM_MAX_PROGRAM_OPS];  // per device op, -1 = logs nothing
+};
+
 // device mirror of OpmTraceStats (all counters are atomically accumulated)
 struct DevStats {
     unsigned long long interactions, children, hits, missed, apodized, valid_out, alive_out;
@@ -109,6 +118,7 @@ struct TraceLaunch {
     int32_t has_fork;  // the program parks rays in shared memory: kStashWords * 4 bytes per thread
     int32_t grid, block;
     void* stream;
+    const HistParams* hist = nullptr;  // host pointer; non-NULL: the interpreter variant that logs positions (never compact)
 };
 
 // launchers implemented in opm_trace.cu (compiled twice: contracted "fast" and -fmad=false "strict")

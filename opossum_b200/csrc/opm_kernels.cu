@@ -736,6 +736,34 @@ int k_binning(DevHits H, uint64_t n, long long bounce_filter, uint64_t nx, uint6
     }
     return (int)cudaGetLastError();
 }
+// Ray::position_history / position_history_with_current (ray.rs:296-327): the logged positions of every slot in level
+// order (NaN rows = levels at which the ray logged nothing), ray-major; len = 0xFFFFFFFF marks a removed slot
+__global__ void __launch_bounds__(256) history_gather_kernel(const double* __restrict__ base, uint64_t stride, uint32_t levels, DevRays R,
+                                                             uint64_t n, int with_current, uint32_t pos_cap, double* __restrict__ xyz,
+                                                             uint32_t* __restrict__ len) {
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        if (R.valid[i] == RAY_REMOVED) { len[i] = 0xFFFFFFFFu; continue; }
+        uint32_t k = 0;
+        double* out = xyz + i * (uint64_t)pos_cap * 3;
+        for (uint32_t l = 0; l < levels; ++l) {
+            const double* row = base + (size_t)l * 3 * stride + i;
+            const double x = row[0];
+            if (isnan(x)) continue;
+            if (k < pos_cap) { out[3 * k] = x; out[3 * k + 1] = row[stride]; out[3 * k + 2] = row[2 * stride]; }
+            ++k;
+        }
+        if (with_current) {
+            if (k < pos_cap) { out[3 * k] = R.px[i]; out[3 * k + 1] = R.py[i]; out[3 * k + 2] = R.pz[i]; }
+            ++k;
+        }
+        len[i] = k;
+    }
+}
+int k_history_gather(const HistParams& hp, uint32_t levels, DevRays R, uint64_t n, int with_current, uint32_t pos_cap, double* xyz,
+                     uint32_t* len, int sms, void* stream) {
+    history_gather_kernel<<<grid_for(n, 256, sms * 8), 256, 0, ST>>>(hp.base, hp.stride, levels, R, n, with_current, pos_cap, xyz, len);
+    return (int)cudaGetLastError();
+}
 __global__ void peak_finalize_kernel(const PeakAccum* acc, double* out2) { out2[0] = dkey_inv(acc->peak_key); out2[1] = acc->total; }
 int k_hits_pack(DevHits H, uint64_t n, long long bounce_filter, double* x, double* y, double* e, unsigned long long* count,
                 unsigned long long cap, int sms, void* stream) {

@@ -70,6 +70,8 @@ int k_source_generate(const SourceParams& S, DevRays R, uint64_t pos_begin, uint
 int k_expand_collimated(const double* xyz, const double* e_pos, const double* wvl, const double* wgt, uint32_t n_wvl, DevRays R,
                         uint64_t n_rays, int sms, void* stream);
 int k_compact(DevRays S, DevRays D, uint64_t n, unsigned* counts, unsigned long long* offsets, unsigned long long* total, void* stream);
+int k_history_gather(const HistParams& hp, uint32_t levels, DevRays R, uint64_t n, int with_current, uint32_t pos_cap, double* xyz,
+                     uint32_t* len, int sms, void* stream);
 int k_fp64_peak(double* out, int iters, int blocks, void* stream);
 int k_fetch_from_host(void* dst, const void* src_host, size_t bytes, void* stream);  // bytes % 8 == 0, src pinned + mapped
 int k_set_u64(unsigned long long* p, unsigned long long v, void* stream);

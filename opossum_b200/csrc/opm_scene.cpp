@@ -88,7 +88,8 @@ OpmStatus acquire_rays(OpmScene* sc, uint64_t cap, OpmRays** out) {
     if (best >= 0) {
         *out = sc->pool_rays[best];
         sc->pool_rays.erase(sc->pool_rays.begin() + best);
-        return opm_rays_clear(*out);
+        OpmStatus st = opm_rays_disable_position_history(*out);  // a pooled bundle starts without the log of its last use
+        return st ? st : opm_rays_clear(*out);
     }
     return opm_rays_create(sc->ctx, cap ? cap : 1, out);
 }
@@ -279,7 +280,9 @@ struct Runner {
     }
 };
 
-bool is_detector(int type) { return type == OPM_NODE_SPOT_DIAGRAM || type == OPM_NODE_FLUENCE_DETECTOR; }
+bool is_detector(int type) {
+    return type == OPM_NODE_SPOT_DIAGRAM || type == OPM_NODE_FLUENCE_DETECTOR || type == OPM_NODE_RAY_PROPAGATION_VISUALIZER;
+}
 
 OpmHitMap* new_hitmap(OpmScene* sc, SurfaceState& s, uint64_t uuid, uint64_t n, OpmStatus* st) {
     OpmHitMap* h = nullptr;
@@ -295,7 +298,7 @@ OpmStatus compile_node_rt(OpmScene* sc, Node& n, const OpmRayTraceConfig& cfg, i
 // the side chain hanging off a splitter's second output, inlined between OPM_OP_FORK and OPM_OP_JOIN: true when the side
 // chain (no further splitter with a second output in it) and the rest fit comfortably into the current launch
 bool can_inline_side_chain(OpmScene* sc, const Node& sp, int flags, const Runner& R, int depth) {
-    if ((flags & OPM_SCENE_PER_SURFACE) || depth != 0 || sp.split_child < 0) return false;
+    if ((flags & (OPM_SCENE_PER_SURFACE | OPM_SCENE_POSITION_HISTORY)) || depth != 0 || sp.split_child < 0) return false;
     size_t nodes = 0;
     for (int i = sp.split_child; i >= 0; i = sc->nodes[i]->main_child) {
         if (sc->nodes[i]->d.type == OPM_NODE_BEAM_SPLITTER && sc->nodes[i]->split_child >= 0) return false;
@@ -411,6 +414,7 @@ OpmStatus compile_node_rt(OpmScene* sc, Node& n, const OpmRayTraceConfig& cfg, i
             break;
         }
         case OPM_NODE_SPOT_DIAGRAM:
+        case OPM_NODE_RAY_PROPAGATION_VISUALIZER:
         case OPM_NODE_FLUENCE_DETECTOR: {  // pass_through_detector_surface analyzers/raytrace.rs:150-207
             OpmHitMap* h0 = hits_for(n.s[0]);
             if (st) return st;
@@ -547,6 +551,10 @@ extern "C" OpmStatus opm_scene_raytrace(OpmScene* sc, OpmRays* rays, const OpmRa
     jobs.push_back({0, rays, -1});
     if (flags & OPM_SCENE_KEEP_SOURCE) {
         st = acquire_rays(sc, n_rays ? n_rays : 1, &sc->main_out);
+        if (st) return st;
+    }
+    if (flags & OPM_SCENE_POSITION_HISTORY) {  // the working bundle logs; stored and split-off copies inherit (opm_trace_sequence)
+        st = opm_rays_enable_position_history(sc->main_out ? sc->main_out : rays, 2 * (uint32_t)sc->nodes.size() + 4);
         if (st) return st;
     }
     for (size_t j = 0; j < jobs.size(); ++j) {

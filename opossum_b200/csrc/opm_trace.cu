@@ -41,10 +41,14 @@ namespace {
 
 using barrier_t = cuda::barrier<cuda::thread_scope_block>;
 
-template <bool COMPACT>
-__global__ void __launch_bounds__(OPM_TRACE_BLOCK, OPM_TRACE_MIN_CTAS)
-trace_kernel(const DevOp* __restrict__ g_ops, int n_ops, DevRays in, DevRays out, uint64_t n, uint64_t out_cap,
-             unsigned long long* out_tail, DevStats* stats) {
+__device__ __forceinline__ void hist_push(const HistParams& hp, int level, uint64_t slot, const V3& p) {
+    double* row = hp.base + (size_t)level * 3 * hp.stride + slot;
+    row[0] = p.x; row[hp.stride] = p.y; row[2 * hp.stride] = p.z;
+}
+
+template <bool COMPACT, bool HIST>
+__device__ __forceinline__ void trace_body(const DevOp* __restrict__ g_ops, int n_ops, const DevRays& in, const DevRays& out, uint64_t n,
+                                           uint64_t out_cap, unsigned long long* out_tail, DevStats* stats, const HistParams& hp) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     DevOp* ops = reinterpret_cast<DevOp*>(smem_raw);
     unsigned* stash = reinterpret_cast<unsigned*>(smem_raw + (size_t)n_ops * sizeof(DevOp));  // only sized when the program forks
@@ -81,8 +85,17 @@ trace_kernel(const DevOp* __restrict__ g_ops, int n_ops, DevRays in, DevRays out
         for (int k = 0; k < n_ops; ++k) {
             const DevOp& op = ops[k];
             switch (op.kind) {  // warp-uniform
-                case OPK_REFRACT: exec_refract(RefractRt(op.u.refract), x); break;
-                case OPK_APODIZE: exec_apodize(ApertureRt(op.u.apodize.ap), op.u.apodize.inv, x); break;
+                case OPK_REFRACT: {
+                    const V3 p0 = x.r.pos;
+                    const bool moved = exec_refract(RefractRt(op.u.refract), x);
+                    if (HIST && moved && hp.level[k] >= 0) hist_push(hp, hp.level[k], x.i, p0);
+                    break;
+                }
+                case OPK_APODIZE: {
+                    const bool clipped = exec_apodize(ApertureRt(op.u.apodize.ap), op.u.apodize.inv, x);
+                    if (HIST && clipped && hp.level[k] >= 0) hist_push(hp, hp.level[k], x.i, x.r.pos);
+                    break;
+                }
                 case OPK_THRESHOLD: exec_threshold(op.u.threshold, x); break;
                 case OPK_LIMITS: exec_limits(op.u.limits, x); break;
                 case OPK_FILTER: exec_filter(op.u.filter, x); break;
@@ -90,7 +103,12 @@ trace_kernel(const DevOp* __restrict__ g_ops, int n_ops, DevRays in, DevRays out
                 case OPK_SPLIT: exec_split(op.u.split, x); break;
                 case OPK_SNAPSHOT: exec_snapshot(op.u.snapshot, x); break;
                 case OPK_TRANSFORM: exec_transform(op.u.transform, x); break;
-                case OPK_DIFFRACT: exec_diffract(RefractRt(op.u.diffract.surf), op.u.diffract, x); break;
+                case OPK_DIFFRACT: {
+                    const V3 p0 = x.r.pos;
+                    const bool moved = exec_diffract(RefractRt(op.u.diffract.surf), op.u.diffract, x);
+                    if (HIST && moved && hp.level[k] >= 0) hist_push(hp, hp.level[k], x.i, p0);
+                    break;
+                }
                 case OPK_FORK: exec_fork(op.u.fork, x, stash); break;
                 case OPK_JOIN: exec_join(op.u.join, x, stash); break;
                 default: break;
@@ -104,13 +122,32 @@ trace_kernel(const DevOp* __restrict__ g_ops, int n_ops, DevRays in, DevRays out
     cta_flush(stats, s_cnt, s_status, s_first_inv);
 }
 
+template <bool COMPACT>
+__global__ void __launch_bounds__(OPM_TRACE_BLOCK, OPM_TRACE_MIN_CTAS)
+trace_kernel(const DevOp* __restrict__ g_ops, int n_ops, DevRays in, DevRays out, uint64_t n, uint64_t out_cap,
+             unsigned long long* out_tail, DevStats* stats) {
+    HistParams none;  // never read: HIST = false
+    trace_body<COMPACT, false>(g_ops, n_ops, in, out, n, out_cap, out_tail, stats, none);
+}
+// the same program with the per-ray position log: a separate kernel, so that the common one carries no trace of it
+__global__ void __launch_bounds__(OPM_TRACE_BLOCK, OPM_TRACE_MIN_CTAS)
+trace_history_kernel(const DevOp* __restrict__ g_ops, int n_ops, DevRays in, DevRays out, uint64_t n, DevStats* stats,
+                     const __grid_constant__ HistParams hp) {
+    trace_body<false, true>(g_ops, n_ops, in, out, n, 0, nullptr, stats, hp);
+}
+
 }  // namespace
 
 int OPM_VARIANT(launch_trace)(const TraceLaunch& L) {
     size_t smem = (size_t)L.n_ops * sizeof(DevOp) + (L.has_fork ? (size_t)L.block * kStashWords * 4 : 0);
     cudaStream_t st = (cudaStream_t)L.stream;
     cudaError_t err;
-    if (L.compact) {
+    if (L.hist) {
+        if (L.compact) return (int)cudaErrorInvalidValue;
+        err = cudaFuncSetAttribute(trace_history_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (err != cudaSuccess) return (int)err;
+        trace_history_kernel<<<L.grid, L.block, smem, st>>>(L.ops, L.n_ops, L.in, L.out, L.n, L.stats, *L.hist);
+    } else if (L.compact) {
         err = cudaFuncSetAttribute(trace_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (err != cudaSuccess) return (int)err;
         trace_kernel<true><<<L.grid, L.block, smem, st>>>(L.ops, L.n_ops, L.in, L.out, L.n, L.out_cap, L.out_tail, L.stats);

@@ -125,12 +125,13 @@ __device__ __forceinline__ void finish_children(const V& v, const RefractResult&
     }
 }
 
-// Rays::refract_on_surface (rays.rs:976-1047) for one ray + hit record + child emission / mirror continuation
+// Rays::refract_on_surface (rays.rs:976-1047) for one ray + hit record + child emission / mirror continuation.  Returns
+// true when the ray reached the surface, i.e. when the reference pushes the old position to `pos_hist` (ray.rs:616).
 template <class V>
-__device__ __forceinline__ void exec_refract(const V& v, RayCtx& x) {
+__device__ __forceinline__ bool exec_refract(const V& v, RayCtx& x) {
     const DevRefract& o = v.d();
     RefractResult res;
-    res.has_child = false; res.hit_e = -1.0; res.hit_bounce = 0; res.hit_local = v3(0, 0, 0);
+    res.has_child = false; res.moved = false; res.hit_e = -1.0; res.hit_bounce = 0; res.hit_local = v3(0, 0, 0);
     if (x.valid) {
         x.c.a += 1u;
         res = refract_on_surface(v, x.r);
@@ -149,13 +150,15 @@ __device__ __forceinline__ void exec_refract(const V& v, RayCtx& x) {
         }
     }
     finish_children(v, res, x);
+    return res.moved;
 }
 
-// Rays::diffract_on_periodic_surface (rays.rs:1058-1111) for one ray: reflective grating
+// Rays::diffract_on_periodic_surface (rays.rs:1058-1111) for one ray: reflective grating; returns like
+// exec_refract (ray.rs:537)
 template <class V>
-__device__ __forceinline__ void exec_diffract(const V& v, const DevDiffract& o, RayCtx& x) {
+__device__ __forceinline__ bool exec_diffract(const V& v, const DevDiffract& o, RayCtx& x) {
     RefractResult res;
-    res.has_child = false;
+    res.has_child = false; res.moved = false;
     if (x.valid) {
         x.c.a += 1u;
         res = diffract_on_periodic_surface(v, o, x.r);
@@ -166,19 +169,21 @@ __device__ __forceinline__ void exec_diffract(const V& v, const DevDiffract& o, 
         }
     }
     finish_children(v, res, x);
+    return res.moved;
 }
 
-// Rays::apodize (rays.rs:557-573)
+// Rays::apodize (rays.rs:557-573); returns true for a ray this call invalidated (its position goes to `pos_hist`, :566)
 template <class A>
-__device__ __forceinline__ void exec_apodize(const A& av, const DevIso& inv, RayCtx& x) {
-    if (!x.valid) return;
+__device__ __forceinline__ bool exec_apodize(const A& av, const DevIso& inv, RayCtx& x) {
+    if (!x.valid) return false;
     double lx = inv.r[0] * x.r.pos.x + inv.r[1] * x.r.pos.y + inv.r[2] * x.r.pos.z + inv.t[0];
     double ly = inv.r[3] * x.r.pos.x + inv.r[4] * x.r.pos.y + inv.r[5] * x.r.pos.z + inv.t[1];
     double f = aperture_factor(av, lx, ly);
     if (f > 0.0) {
         if (!(f <= 1.0)) x.c.status |= 1u << OPM_ERR_APODIZE_FACTOR;
         else x.r.e *= f;
-    } else { x.valid = false; x.c.apodized += 1u; }
+    } else { x.valid = false; x.c.apodized += 1u; return true; }
+    return false;
 }
 
 // rays.rs:1145-1162 (all rays; a no-op for already invalid ones)

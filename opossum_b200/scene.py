@@ -156,6 +156,12 @@ def FluenceDetector(iso=None):
     return Node(F.NODE_FLUENCE_DETECTOR, iso)
 
 
+def RayPropagationVisualizer(iso=None):
+    """nodes/ray_propagation_visualizer.rs: a single-surface detector that keeps the bundle; after
+    raytrace(position_history=True) its rays (Scene.node_rays) carry their paths (Rays.position_history)"""
+    return Node(F.NODE_RAY_PROPAGATION_VISUALIZER, iso)
+
+
 class _BorrowedRays(Rays):
     """A bundle owned by the scene (never destroyed from Python)."""
 
@@ -196,7 +202,7 @@ class Scene:
         return idx.value
 
     def raytrace(self, source_rays: Rays, config: RayTraceConfig | None = None, strict=False, per_surface=False,
-                 record_all_hits=False, snapshots=True, sync=True, keep_source=False) -> TraceStats | None:
+                 record_all_hits=False, snapshots=True, sync=True, keep_source=False, position_history=False) -> TraceStats | None:
         """RayTracingAnalyzer::analyze (analyzers/raytrace.rs:36-49); traces `source_rays` in place."""
         cfg = F.OpmRayTraceConfig()
         c = config or RayTraceConfig()
@@ -204,7 +210,8 @@ class Scene:
         cfg.max_number_of_refractions, cfg.missed_surface_strategy = c.max_number_of_refractions, c.missed_surface_strategy
         flags = ((F.SCENE_STRICT if strict else 0) | (F.SCENE_PER_SURFACE if per_surface else 0) |
                  (F.SCENE_RECORD_ALL_HITS if record_all_hits else 0) | (0 if snapshots else F.SCENE_NO_SNAPSHOTS) |
-                 (0 if sync else F.SCENE_ASYNC) | (F.SCENE_KEEP_SOURCE if keep_source else 0))
+                 (0 if sync else F.SCENE_ASYNC) | (F.SCENE_KEEP_SOURCE if keep_source else 0) |
+                 (F.SCENE_POSITION_HISTORY if position_history else 0))
         st = F.OpmTraceStats()
         _check(F.lib().opm_scene_raytrace(self.h, source_rays.h, C.byref(cfg), flags, C.byref(st)))
         return TraceStats.of(st) if sync else None

@@ -498,6 +498,28 @@ int orc_ray_new(const double pos[3], const double dir[3], double wvl, double e, 
 }
 
 /* ray.rs:580-688 */
+/* ---- position history (`pos_hist`, ray.rs:70).  While a sink is attached, every push of the reference
+ * (refract ray.rs:616, diffract :537, apodize of a ray it invalidates rays.rs:566) on a ray of [base, base + n) is
+ * appended to that ray's list xyz[(i * cap + k) * 3 + c], k < len[i].  One sink at a time (single-threaded callers). */
+static struct { const OrcRay* base; uint64_t n; double* xyz; uint32_t* len; uint32_t cap; int overflow; } g_hist;
+void orc_history_attach(const OrcRay* base, uint64_t n, double* xyz, uint32_t* len, uint32_t cap) {
+    g_hist.base = base; g_hist.n = n; g_hist.xyz = xyz; g_hist.len = len; g_hist.cap = cap; g_hist.overflow = 0;
+}
+int orc_history_detach(void) {
+    int ov = g_hist.overflow;
+    memset(&g_hist, 0, sizeof g_hist);
+    return ov;
+}
+static void hist_push(const OrcRay* ray, const double pos[3]) {
+    if (!g_hist.base || ray < g_hist.base || ray >= g_hist.base + g_hist.n) return;
+    uint64_t i = (uint64_t)(ray - g_hist.base);
+    uint32_t k = g_hist.len[i];
+    if (k >= g_hist.cap) { g_hist.overflow = 1; return; }
+    double* d = g_hist.xyz + ((size_t)i * g_hist.cap + k) * 3;
+    d[0] = pos[0]; d[1] = pos[1]; d[2] = pos[2];
+    g_hist.len[i] = k + 1;
+}
+
 int orc_ray_refract_on_surface(OrcRay* ray, const OrcSurface* s, int has_n2, double n2, int strategy,
                                OrcRay* child_out, int* has_child, OrcHit* hit_out, int* has_hit) {
     *has_child = 0;
@@ -516,6 +538,7 @@ int orc_ray_refract_on_surface(OrcRay* ray, const OrcSurface* s, int has_n2, dou
         double refl[3] = { s1[0] - k * N[0], s1[1] - k * N[1], s1[2] - k * N[2] };
         double dp[3] = { ray->pos[0] - q[0], ray->pos[1] - q[1], ray->pos[2] - q[2] };
         ray->opl += ray->n * norm3(dp);
+        hist_push(ray, ray->pos); /* ray.rs:616 */
         ray->pos[0] = q[0]; ray->pos[1] = q[1]; ray->pos[2] = q[2];
         if (!signbit(dis)) {
             OrcRay child = *ray;
@@ -586,6 +609,7 @@ int orc_ray_diffract_on_periodic_surface(OrcRay* ray, const OrcSurface* s, doubl
     double ql[3];
     iso3_point(&s->iso.inv, q, ql);
     ray->opl += m * norm3(gvec) / 2. / PI * ql[0] * ray->wvl;
+    hist_push(ray, ray->pos); /* ray.rs:537 */
     ray->pos[0] = q[0]; ray->pos[1] = q[1]; ray->pos[2] = q[2];
     if (isfinite(k_perp_norm_out)) {
         double kpn[3];
@@ -698,6 +722,7 @@ int orc_rays_apodize(OrcRay* rays, uint64_t n, const OrcAperture* ap, const OrcI
             if (!(f >= 0.0 && f <= 1.0)) { err = ORC_ERR_APODIZE_FACTOR; continue; } /* ray.rs:705-709 */
             ray->e *= f;
         } else {
+            hist_push(ray, ray->pos); /* rays.rs:566 */
             ray->valid = 0;
             inv = 1;
         }

@@ -159,6 +159,11 @@ int orc_rays_diffract_on_periodic_surface(OrcRay* rays, uint64_t n, const OrcSur
                                           int32_t order, int refraction_intended, OrcRay* children, OrcRefractStats* stats); /* :1058-1111 */
 void orc_rays_transform(OrcRay* rays, uint64_t n, const OrcIsometry* iso, int inverse);/* ray.rs:787-804 */
 
+/* position history (`pos_hist`, ray.rs:70): while attached, the pushes of ray.rs:537,616 and rays.rs:566 on rays of
+ * [base, base + n) are appended to xyz[(i * cap + k) * 3 + c], k < len[i]; detach returns 1 if a list overflowed */
+void orc_history_attach(const OrcRay* base, uint64_t n, double* xyz, uint32_t* len, uint32_t cap);
+int orc_history_detach(void);
+
 /* statistics (rays.rs:521-701) */
 double orc_rays_total_energy(const OrcRay* rays, uint64_t n);                          /* Kahan, valid only */
 uint64_t orc_rays_count(const OrcRay* rays, uint64_t n, int valid_only);

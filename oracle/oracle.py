@@ -311,6 +311,9 @@ def lib():
     L.orc_spectrum_gaussian.argtypes = [C.c_double, C.c_double, C.c_uint64, C.c_double, C.c_double, C.c_double, dp, dp]
     L.orc_spectrum_gaussian.restype = None
     L.orc_rays_collimated_with_spectrum.argtypes = [dp, dp, C.c_uint64, dp, dp, C.c_uint64, vp]
+    L.orc_history_attach.argtypes = [vp, C.c_uint64, dp, vp, C.c_uint32]
+    L.orc_history_attach.restype = None
+    L.orc_history_detach.restype = C.c_int
     _lib = L
     return L
 
@@ -433,6 +436,43 @@ def rays_diffract_on_periodic_surface(rays, surf: Surface, idx: IndexModel, grat
     _check(lib().orc_rays_diffract_on_periodic_surface(_vp(rays), n, C.byref(surf), C.byref(idx), g, int(order),
                                                        int(refraction_intended), _vp(children), C.byref(st)))
     return children[: st.n_children].copy(), st
+
+
+class History:
+    """`pos_hist` of every ray of one bundle (ray.rs:70): positions xyz[i, k], k < len[i], row i = ray i of the array the
+    history is attached to.  attach() makes the C oracle record the reference's pushes (ray.rs:537,616; rays.rs:566) for
+    the rays of that array until detach()."""
+
+    def __init__(self, n: int, cap: int = 64):
+        self.xyz = np.zeros((max(n, 1), cap, 3), dtype=np.float64)
+        self.len = np.zeros(max(n, 1), dtype=np.uint32)
+        self.n = n
+
+    def attach(self, rays: np.ndarray):
+        assert len(rays) == self.n and rays.flags["C_CONTIGUOUS"]
+        lib().orc_history_attach(_vp(rays), len(rays), _dptr(self.xyz), _vp(self.len), self.xyz.shape[1])
+
+    @staticmethod
+    def detach():
+        if lib().orc_history_detach():
+            raise RuntimeError("oracle position history overflow: raise History(cap=...)")
+
+    def select(self, rows) -> "History":
+        """history of clones of the rays `rows` (a cloned Ray carries its pos_hist)"""
+        rows = np.asarray(rows, dtype=np.int64)
+        h = History(len(rows), self.xyz.shape[1])
+        if len(rows):
+            h.xyz[: len(rows)] = self.xyz[rows]
+            h.len[: len(rows)] = self.len[rows]
+        return h
+
+    def copy(self) -> "History":
+        return self.select(np.arange(self.n))
+
+    def of(self, i: int, rays: np.ndarray | None = None) -> np.ndarray:
+        """Ray::position_history (ray.rs:296-308), or with `rays` position_history_with_current (:313-327)"""
+        h = self.xyz[i, : self.len[i]]
+        return np.vstack([h, rays["pos"][i][None, :]]) if rays is not None else h.copy()
 
 
 def rays_transform(rays, iso: Isometry, inverse=False):

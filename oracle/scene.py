@@ -14,7 +14,7 @@ import numpy as np
 from . import oracle as orc
 
 (SOURCE, LENS, CYLINDRIC_LENS, WEDGE, THIN_MIRROR, PARABOLIC_MIRROR, BEAM_SPLITTER, DUMMY, IDEAL_FILTER, PARAXIAL_SURFACE,
- SPOT_DIAGRAM, FLUENCE_DETECTOR, REFLECTIVE_GRATING) = range(13)
+ SPOT_DIAGRAM, FLUENCE_DETECTOR, REFLECTIVE_GRATING, RAY_PROPAGATION_VISUALIZER) = range(14)
 
 
 @dataclass
@@ -123,6 +123,7 @@ class ONode:
         self.s = [OSurface(s0, node_iso.append(anchor[0]), aps[0], lidt), OSurface(s1, node_iso.append(anchor[1]), aps[1], lidt)]
         self.stored: np.ndarray | None = None
         self.split: np.ndarray | None = None
+        self.stored_hist = self.split_hist = None  # orc.History of those bundles (raytrace(history=True))
 
 
 class OScene:
@@ -139,6 +140,7 @@ class OScene:
             for s in n.s:
                 s.reset()
             n.stored = n.split = None
+            n.stored_hist = n.split_hist = None
         self.passes = []
         self.interactions = 0
         self.chain_out: dict[int, np.ndarray] = {}
@@ -151,6 +153,19 @@ class OScene:
         if record:
             s.add_hits(hits, uuid)
         return ch
+
+    def _rebind_history(self, parents: np.ndarray, clones: np.ndarray) -> np.ndarray:
+        """the reflected / diffracted clones continue as the bundle (rays.rs:1016-1019): each carries the pos_hist of the
+        ray it was cloned from (same id), the sink moves to the new array"""
+        if self.hist is None:
+            return clones
+        row = {int(i): k for k, i in enumerate(parents["id"])}
+        assert len(row) == len(parents), "history tracking needs unique ray ids within a bundle"
+        orc.History.detach()
+        self.hist = self.hist.select([row[int(i)] for i in clones["id"]])
+        clones = np.ascontiguousarray(clones)
+        self.hist.attach(clones)
+        return clones
 
     def _children_of(self, i, port=0):
         return [k for k, n in enumerate(self.nodes) if k > 0 and (n.parent if n.parent >= 0 else k - 1) == i and n.parent_port == port]
@@ -169,14 +184,15 @@ class OScene:
                 orc.rays_apodize(rays, s.aperture, s.eff_iso, self.nt)
                 orc.rays_threshold(rays, thr, self.nt)
         elif t in (THIN_MIRROR, PARABOLIC_MIRROR):  # thin_mirror.rs:209-250
-            rays = self._refract(rays, n.s[0], None, False, strat, record=record_all)
+            rays = self._rebind_history(rays, self._refract(rays, n.s[0], None, False, strat, record=record_all))
             orc.rays_apodize(rays, n.s[0].aperture, n.s[0].eff_iso, self.nt)
             orc.rays_threshold(rays, thr, self.nt)
         elif t == REFLECTIVE_GRATING:  # nodes/reflective_grating.rs:209-262
             iso = n.s[0].eff_iso
             gx = iso.transform_vector((1.0, 0.0, 0.0))
             gvec = [2. * math.pi * n.p[0] * c for c in gx]
-            rays, st = orc.rays_diffract_on_periodic_surface(rays, n.s[0].surf, orc.IndexModel.const(1.0), gvec, int(n.p[1]), False)
+            out, st = orc.rays_diffract_on_periodic_surface(rays, n.s[0].surf, orc.IndexModel.const(1.0), gvec, int(n.p[1]), False)
+            rays = self._rebind_history(rays, out)
             self.interactions += st.n_interactions
             orc.rays_apodize(rays, n.s[0].aperture, iso, self.nt)
             orc.rays_threshold(rays, thr, self.nt)
@@ -186,8 +202,15 @@ class OScene:
             split = orc.rays_split(rays, n.p[0])
             orc.rays_apodize(rays, n.s[1].aperture, n.s[1].eff_iso, self.nt)
             orc.rays_threshold(rays, thr, self.nt)
+            if self.hist is not None:  # the split-off clones carry the history up to here; their own pushes go to their copy
+                n.split_hist = self.hist.copy()
+                orc.History.detach()
+                n.split_hist.attach(split)
             orc.rays_apodize(split, n.s[1].aperture, n.s[1].eff_iso, self.nt)
             orc.rays_threshold(split, thr, self.nt)
+            if self.hist is not None:
+                orc.History.detach()
+                self.hist.attach(rays)
             n.split = split
         elif t in (DUMMY, IDEAL_FILTER, PARAXIAL_SURFACE):  # dummy.rs:83-135, ideal_filter.rs:203-250, paraxial_surface.rs:169-230
             self._refract(rays, n.s[0], None, True, strat, record=record_all, want_children=False)
@@ -203,19 +226,35 @@ class OScene:
             orc.rays_apodize(rays, n.s[0].aperture, n.s[0].eff_iso, self.nt)
             orc.rays_threshold(rays, thr, self.nt)
             n.stored = rays.copy()
+            n.stored_hist = self.hist.copy() if self.hist is not None else None
         return rays
 
     def _limits_rt(self, rays, cfg):  # node_group/analysis_raytrace.rs:20-27
         orc.rays_filter_bounces(rays, cfg.max_number_of_bounces)
         orc.rays_filter_refractions(rays, cfg.max_number_of_refractions)
 
-    def raytrace(self, source_rays: np.ndarray, cfg: RayTraceConfig | None = None, record_all=True) -> np.ndarray:
+    def raytrace(self, source_rays: np.ndarray, cfg: RayTraceConfig | None = None, record_all=True, history=False) -> np.ndarray:
+        """history=True: every bundle's pos_hist is tracked (orc.History); see chain_hist, ONode.stored_hist"""
         cfg = cfg or RayTraceConfig()
         self.reset_data()
-        jobs = [(0, source_rays.copy())]
+        self.chain_hist: dict[int, orc.History] = {}
+        jobs = [(0, np.ascontiguousarray(source_rays.copy()), orc.History(len(source_rays)) if history else None)]
+        main_out = None
+        try:
+            return self._raytrace_jobs(jobs, cfg, record_all)
+        finally:
+            if history:
+                orc.lib().orc_history_detach()
+            self.hist = None
+
+    hist = None  # History of the bundle being traced
+
+    def _raytrace_jobs(self, jobs, cfg, record_all):
         main_out = None
         while jobs:
-            i, rays = jobs.pop(0)
+            i, rays, self.hist = jobs.pop(0)
+            if self.hist is not None:
+                self.hist.attach(rays)
             start = i
             first = main_out is None
             while i is not None:
@@ -225,10 +264,13 @@ class OScene:
                 if n.type == BEAM_SPLITTER:
                     self._limits_rt(n.split, cfg)
                     for k in self._children_of(i, 1):
-                        jobs.append((k, n.split.copy()))
+                        jobs.append((k, np.ascontiguousarray(n.split.copy()), n.split_hist.copy() if n.split_hist is not None else None))
                 nxt = self._children_of(i, 0)
                 i = nxt[0] if nxt else None
             self.chain_out[start] = rays  # final bundle of every chain, keyed by its first node
+            if self.hist is not None:
+                orc.History.detach()
+                self.chain_hist[start] = self.hist
             if first:
                 main_out = rays
         return main_out

@@ -621,3 +621,45 @@ def test_grating_evanescent_order_and_miss():
     assert len(out) == 0 and st.rays_missed == 1
     assert rays["valid"][0] == 0 and rays["valid"][1] == 1
     assert np.array_equal(rays["pos"][1], before["pos"][1]) and rays["e"][1] == 1.0
+
+
+# ---- position history ------------------------------------------------------------------------------
+def test_position_history_refract_kat():
+    """ray.rs:1236-1272: after refract_on_surface at a plane 10 mm ahead `ray.pos_hist == [(0,0,0)]` and the reflected
+    clone carries the same history (it is cloned after the push, ray.rs:616-625)"""
+    ray = np.ascontiguousarray(orc.ray_new((0.0, 0.0, 0.0), (0.0, 0.0, 1.0), 1053e-9, 1.0))
+    plane = orc.Surface(geom=orc.GEOM_PLANE, coating=orc.COAT_CONSTANT_R, coating_r=0.2, param=0.0,
+                        iso=orc.Isometry.new((0.0, 0.0, 10e-3), (0.0, 0.0, 0.0)))
+    H = orc.History(1, cap=4)
+    H.attach(ray)
+    try:
+        ch, _, st = orc.rays_refract_on_surface(ray, plane, orc.IndexModel.const(1.5))
+    finally:
+        orc.History.detach()
+    assert st.n_children == 1 and H.len[0] == 1
+    assert np.array_equal(H.of(0), [[0.0, 0.0, 0.0]])
+    assert np.array_equal(H.of(0, ray), [[0.0, 0.0, 0.0], [0.0, 0.0, 10e-3]])  # position_history_with_current
+    assert np.array_equal(ch["pos"][0], [0.0, 0.0, 10e-3])
+
+
+def test_position_history_push_rules():
+    """a miss pushes nothing (ray.rs:680-686), total reflection pushes (the surface was reached, :616), apodize pushes the
+    position of exactly the rays it invalidates (rays.rs:566), invalid rays never push"""
+    rays = np.ascontiguousarray(orc.rays_from_arrays(
+        pos=[(0, 0, 0), (0, 0, 0), (0, 0, 0), (0, 5e-3, 0)], direction=[(0, 0, 1), (0, 0, -1), (0, 0.8, 0.6), (0, 0, 1)],
+        e=[1.0] * 4, wvl=[1e-6] * 4))
+    rays["n"][2] = 1.5  # steep ray inside glass -> total internal reflection at the plane
+    plane = orc.Surface(geom=orc.GEOM_PLANE, coating=orc.COAT_IDEAL_AR, coating_r=0.0, param=0.0,
+                        iso=orc.Isometry.new((0.0, 0.0, 10e-3), (0.0, 0.0, 0.0)))
+    H = orc.History(4, cap=4)
+    H.attach(rays)
+    try:
+        orc.rays_refract_on_surface(rays, plane, orc.IndexModel.const(1.0), strategy=orc.MISS_IGNORE)
+        assert list(H.len) == [1, 0, 1, 1] and rays["bounces"][2] == 1
+        orc.rays_apodize(rays, orc.ap_circle(2e-3), orc.Isometry.identity())
+        assert list(H.len) == [1, 0, 2, 2] and list(rays["valid"]) == [1, 1, 0, 0]
+        assert np.array_equal(H.of(3), [[0.0, 5e-3, 0.0], [0.0, 5e-3, 10e-3]])
+        orc.rays_refract_on_surface(rays, plane, orc.IndexModel.const(1.0), strategy=orc.MISS_IGNORE)
+        assert list(H.len) == [2, 0, 2, 2]
+    finally:
+        orc.History.detach()
