@@ -56,6 +56,8 @@ const char* orc_strerror(int code) {
         case ORC_ERR_SPLIT_RATIO: return "splitting_ratio must be within [0.0;1.0]";
         case ORC_ERR_FOCAL_LENGTH: return "focal length must be !=0.0 and finite";
         case ORC_ERR_EMPTY_HITMAP: return "could not calculate bounding box";
+        case ORC_ERR_SPECTRUM: return "spectrum: wavelength outside the spectrum / no valid rays / invalid range or resolution";
+        case ORC_ERR_EMPTY_WAVEFRONT: return "Empty wavefront-data vector!";
         default: return "invalid argument";
     }
 }
@@ -1181,5 +1183,168 @@ int orc_rays_collimated_with_spectrum(const double* xyz, const double* e_pos, ui
             out[k].id = (uint32_t)k;
             ++k;
         }
+    return ORC_OK;
+}
+
+/* ---------------------------------------------------------------------------------------------
+ * spectrum.rs: Spectrum = Vec<(wavelength in micrometers, value in 1/micrometers)>, here two arrays.
+ * uom: micrometer!(x) = x * 1e-6, get::<micrometer>() = value / 1e-6, get::<nanometer>() = value / 1e-9
+ * ------------------------------------------------------------------------------------------- */
+/* Spectrum::new (spectrum.rs:47-73); lambda == NULL: only the number of slots is returned */
+int orc_spectrum_new(double start_m, double end_m, double res_m, double* lambda, double* data, uint64_t cap, uint64_t* n_out) {
+    if (res_m <= 0.0) return ORC_ERR_SPECTRUM;              /* "resolution must be positive" */
+    if (start_m >= end_m) return ORC_ERR_SPECTRUM;          /* "wavelength range must be in ascending order and not empty" */
+    if (signbit(start_m) || signbit(end_m)) return ORC_ERR_SPECTRUM;
+    double cnt = round((end_m - start_m) / res_m);
+    uint64_t n = cnt > 0.0 ? (uint64_t)cnt : 0;             /* f64_to_usize: `as usize` */
+    double start = start_m / 1e-6, step = res_m / 1e-6;
+    if (n_out) *n_out = n;
+    if (!lambda) return ORC_OK;
+    if (n > cap) return ORC_ERR_ARG;
+    for (uint64_t i = 0; i < n; ++i) { lambda[i] = fma((double)i, step, start); if (data) data[i] = 0.0; }
+    return ORC_OK;
+}
+/* Spectrum::add_single_peak (spectrum.rs:193-227) */
+int orc_spectrum_add_single_peak(const double* lambda, double* data, uint64_t n, double wl_m, double value) {
+    if (n == 0) return ORC_ERR_SPECTRUM;
+    double r0 = lambda[0] * 1e-6, r1 = lambda[n - 1] * 1e-6;     /* range(): micrometer!(first)..micrometer!(last) */
+    if (!(r0 <= wl_m && wl_m < r1)) return ORC_OK;               /* warn!("peak wavelength is not in spectrum range. Spectrum unmodified.") */
+    if (value < 0.0) return ORC_ERR_SPECTRUM;                    /* "energy must be positive" */
+    double w = wl_m / 1e-6;
+    if (n < 2) return ORC_ERR_SPECTRUM;                          /* "spectrum size is too small" */
+    uint64_t idx = n;
+    for (uint64_t i = 0; i < n; ++i) if (lambda[i] >= w) { idx = i; break; }
+    if (idx == n) return ORC_ERR_SPECTRUM;                       /* "insertion point not found" */
+    if (idx == 0) {
+        double delta = lambda[1] - lambda[0];
+        data[0] += value / delta;
+    } else {
+        double lower = lambda[idx - 1], upper = lambda[idx];
+        double delta = upper - lower;
+        double epm = value / delta;
+        double part = epm * (w - lower) / delta;
+        data[idx] += part;
+        data[idx - 1] += epm - part;
+    }
+    return ORC_OK;
+}
+/* Spectrum::from_laser_lines (spectrum.rs:126-148) */
+int orc_spectrum_from_laser_lines(const double* wl_m, const double* e, uint64_t n_lines, double res_m, double* lambda, double* data,
+                                  uint64_t cap, uint64_t* n_out) {
+    if (n_lines == 0) return ORC_ERR_SPECTRUM;                   /* "no laser lines provided" */
+    if (res_m <= 0.0) return ORC_ERR_SPECTRUM;
+    double mn = wl_m[0], mx = wl_m[0];
+    for (uint64_t i = 0; i < n_lines; ++i) { if (wl_m[i] < mn) mn = wl_m[i]; if (wl_m[i] > mx) mx = wl_m[i]; }
+    uint64_t n = 0;
+    int rc = orc_spectrum_new(mn, mx + 2.0 * res_m, res_m, lambda, data, cap, &n);
+    if (n_out) *n_out = n;
+    if (rc || !lambda) return rc;
+    for (uint64_t i = 0; i < n_lines; ++i) {
+        rc = orc_spectrum_add_single_peak(lambda, data, n, wl_m[i], e[i]);
+        if (rc) return rc;
+    }
+    return ORC_OK;
+}
+/* Rays::to_spectrum (rays.rs:1209-1223): the valid rays as laser lines */
+int orc_rays_to_spectrum(const OrcRay* rays, uint64_t n, double res_m, double* lambda, double* data, uint64_t cap, uint64_t* n_out) {
+    uint64_t nv = orc_rays_count(rays, n, 1);
+    if (nv == 0) return ORC_ERR_SPECTRUM;                        /* "ray bundle is empty - cannot create spectrum" */
+    double* wl = (double*)malloc(nv * sizeof(double));
+    double* e = (double*)malloc(nv * sizeof(double));
+    if (!wl || !e) { free(wl); free(e); return ORC_ERR_ARG; }
+    uint64_t k = 0;
+    for (uint64_t i = 0; i < n; ++i) if (rays[i].valid) { wl[k] = rays[i].wvl; e[k] = rays[i].e; ++k; }
+    int rc = orc_spectrum_from_laser_lines(wl, e, nv, res_m, lambda, data, cap, n_out);
+    free(wl); free(e);
+    return rc;
+}
+/* Spectrum::total_energy (spectrum.rs:289-298) */
+double orc_spectrum_total_energy(const double* lambda, const double* data, uint64_t n) {
+    Kahan k = { 0.0, 0.0 };
+    for (uint64_t i = 0; i + 1 < n; ++i) kahan_add(&k, (lambda[i + 1] - lambda[i]) * data[i]);
+    return k.sum;
+}
+/* Spectrum::center_wavelength (spectrum.rs:304-316); returns metres */
+double orc_spectrum_center_wavelength(const double* lambda, const double* data, uint64_t n) {
+    double weighted_sum = 0.0, total_weight = 0.0;
+    for (uint64_t i = 0; i + 1 < n; ++i) {
+        double bin_width = lambda[i + 1] - lambda[i];
+        double bin_weight = data[i] * bin_width;
+        weighted_sum += lambda[i] * bin_weight;
+        total_weight += bin_weight;
+    }
+    return (weighted_sum / total_weight) * 1e-6;
+}
+/* Spectrum::get_value (spectrum.rs:321-349): returns 1 = Some(*out), 0 = None */
+int orc_spectrum_get_value(const double* lambda, const double* data, uint64_t n, double wl_m, double* out) {
+    if (n == 0) return 0;
+    double w = wl_m / 1e-6;
+    if (w == lambda[n - 1]) { *out = data[n - 1]; return 1; }
+    double r0 = lambda[0] * 1e-6, r1 = lambda[n - 1] * 1e-6;
+    if (!(r0 <= wl_m && wl_m < r1)) return 0;
+    uint64_t idx = n;
+    for (uint64_t i = 0; i < n; ++i) if (lambda[i] >= w) { idx = i; break; }
+    if (idx == n) return 0;
+    uint64_t l = idx == 0 ? 0 : idx - 1, r = idx == 0 ? 1 : idx;
+    double ratio = (w - lambda[l]) / (lambda[r] - lambda[l]);
+    *out = fma(data[l], 1.0 - ratio, data[r] * ratio);
+    return 1;
+}
+/* Ray::filter_energy with FilterType::Spectrum (ray.rs:712-721) over the valid rays (rays.rs:1119-1133) */
+int orc_rays_filter_energy_spectrum(OrcRay* rays, uint64_t n, const double* lambda, const double* data, uint64_t ns) {
+    for (uint64_t i = 0; i < n; ++i) {
+        if (!rays[i].valid) continue;
+        double t;
+        if (!orc_spectrum_get_value(lambda, data, ns, rays[i].wvl, &t)) return ORC_ERR_SPECTRUM; /* "wavelength of ray outside filter spectrum" */
+        rays[i].e *= t;
+    }
+    return ORC_OK;
+}
+/* Ray::split with SplittingConfig::Spectrum (ray.rs:752-772) over the bundle (rays.rs:1253-1264: invalid rays are copied unchanged) */
+int orc_rays_split_spectrum(OrcRay* rays, uint64_t n, const double* lambda, const double* data, uint64_t ns, OrcRay* split_out) {
+    for (uint64_t i = 0; i < n; ++i) {
+        split_out[i] = rays[i];
+        if (!rays[i].valid) continue;
+        double ratio;
+        if (!orc_spectrum_get_value(lambda, data, ns, rays[i].wvl, &ratio)) return ORC_ERR_SPECTRUM; /* "ray splitting failed. wavelength outside given spectrum" */
+        if (!(ratio >= 0.0 && ratio <= 1.0)) return ORC_ERR_SPLIT_RATIO;
+        rays[i].e *= ratio;
+        split_out[i].e *= 1.0 - ratio;
+    }
+    return ORC_OK;
+}
+
+/* Rays::wavefront_error_at_pos_in_units_of_wvl (rays.rs:769-802): rows (x mm, y mm, wavefront error in wavelengths) of the
+ * valid rays in order, relative to the ray closest to the monitor axis (the first one on ties) */
+int orc_rays_wavefront_error(const OrcRay* rays, uint64_t n, double wavelength_m, const OrcIsometry* monitor_iso, double* xyw,
+                             uint64_t* n_out) {
+    double wvl = wavelength_m / 1e-9;
+    double min_radius = INFINITY, center = 0.0;
+    uint64_t k = 0;
+    for (uint64_t i = 0; i < n; ++i) {
+        if (!rays[i].valid) continue;
+        double p[3];
+        iso3_point(&monitor_iso->inv, rays[i].pos, p);
+        double x = p[0] / 1e-3, y = p[1] / 1e-3;
+        xyw[3 * k] = x; xyw[3 * k + 1] = y;
+        xyw[3 * k + 2] = -(rays[i].opl / 1e-9);
+        double radius = fma(x, x, y * y);
+        if (radius < min_radius) { min_radius = radius; center = xyw[3 * k + 2]; }
+        ++k;
+    }
+    for (uint64_t j = 0; j < k; ++j) { xyw[3 * j + 2] -= center; xyw[3 * j + 2] /= wvl; }
+    if (n_out) *n_out = k;
+    return ORC_OK;
+}
+/* WaveFrontErrorMap::calc_wavefront_statistics (nodes/wavefront.rs:145-164): (ptv, rms) of column 3 (stride 3) */
+int orc_wavefront_statistics(const double* xyw, uint64_t n, double* ptv, double* rms) {
+    if (n == 0) return ORC_ERR_EMPTY_WAVEFRONT;                  /* "Empty wavefront-data vector!" */
+    double mx = xyw[2], mn = xyw[2], sum = 0.0;
+    for (uint64_t i = 0; i < n; ++i) { double v = xyw[3 * i + 2]; if (v > mx) mx = v; if (v < mn) mn = v; sum += v; }
+    double avg = sum / (double)n;
+    double s2 = 0.0;
+    for (uint64_t i = 0; i < n; ++i) { double d = xyw[3 * i + 2] - avg; s2 += d * d; }
+    *ptv = mx - mn;
+    *rms = sqrt(s2 / (double)(int32_t)n);
     return ORC_OK;
 }

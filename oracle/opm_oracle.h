@@ -67,7 +67,9 @@ enum {
     ORC_ERR_SPLIT_RATIO = 8,       /* ray.rs:763-767 */
     ORC_ERR_FOCAL_LENGTH = 9,      /* rays.rs:944-948 */
     ORC_ERR_EMPTY_HITMAP = 10,     /* rays_hit_map.rs:526-531 */
-    ORC_ERR_ARG = 11
+    ORC_ERR_ARG = 11,
+    ORC_ERR_SPECTRUM = 12,         /* OpossumError::Spectrum (spectrum.rs) and the spectrum look-ups of ray.rs:712-721,755-761 */
+    ORC_ERR_EMPTY_WAVEFRONT = 13   /* nodes/wavefront.rs:121-123,146-148 */
 };
 
 typedef struct {
@@ -205,6 +207,21 @@ void orc_spectrum_gaussian(double lo, double hi, uint64_t num, double mu, double
 /* rays.rs:264-297: position-major, wavelength-minor; E = E_pos * w */
 int orc_rays_collimated_with_spectrum(const double* xyz, const double* e_pos, uint64_t n_pos,
                                       const double* wvl, const double* w, uint64_t n_wvl, OrcRay* out);
+
+/* ---- spectrum.rs, nodes/spectrometer.rs, nodes/wavefront.rs: wavelengths of a Spectrum in micrometers */
+int orc_spectrum_new(double start_m, double end_m, double res_m, double* lambda, double* data, uint64_t cap, uint64_t* n_out); /* :47-73 */
+int orc_spectrum_add_single_peak(const double* lambda, double* data, uint64_t n, double wl_m, double value);                 /* :193-227 */
+int orc_spectrum_from_laser_lines(const double* wl_m, const double* e, uint64_t n_lines, double res_m, double* lambda, double* data,
+                                  uint64_t cap, uint64_t* n_out);                                                              /* :126-148 */
+int orc_rays_to_spectrum(const OrcRay* rays, uint64_t n, double res_m, double* lambda, double* data, uint64_t cap, uint64_t* n_out); /* rays.rs:1209-1223 */
+double orc_spectrum_total_energy(const double* lambda, const double* data, uint64_t n);                                       /* :289-298 */
+double orc_spectrum_center_wavelength(const double* lambda, const double* data, uint64_t n);                                  /* :304-316, metres */
+int orc_spectrum_get_value(const double* lambda, const double* data, uint64_t n, double wl_m, double* out);                   /* :321-349 */
+int orc_rays_filter_energy_spectrum(OrcRay* rays, uint64_t n, const double* lambda, const double* data, uint64_t ns);         /* ray.rs:712-721 */
+int orc_rays_split_spectrum(OrcRay* rays, uint64_t n, const double* lambda, const double* data, uint64_t ns, OrcRay* split_out); /* ray.rs:752-772 */
+int orc_rays_wavefront_error(const OrcRay* rays, uint64_t n, double wavelength_m, const OrcIsometry* monitor_iso, double* xyw,
+                             uint64_t* n_out);                                                                                 /* rays.rs:769-802 */
+int orc_wavefront_statistics(const double* xyw, uint64_t n, double* ptv, double* rms);                                        /* nodes/wavefront.rs:145-164 */
 
 int orc_max_threads(void);
 

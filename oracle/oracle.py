@@ -311,6 +311,20 @@ def lib():
     L.orc_spectrum_gaussian.argtypes = [C.c_double, C.c_double, C.c_uint64, C.c_double, C.c_double, C.c_double, dp, dp]
     L.orc_spectrum_gaussian.restype = None
     L.orc_rays_collimated_with_spectrum.argtypes = [dp, dp, C.c_uint64, dp, dp, C.c_uint64, vp]
+    u64p = C.POINTER(C.c_uint64)
+    L.orc_spectrum_new.argtypes = [C.c_double, C.c_double, C.c_double, dp, dp, C.c_uint64, u64p]
+    L.orc_spectrum_add_single_peak.argtypes = [dp, dp, C.c_uint64, C.c_double, C.c_double]
+    L.orc_spectrum_from_laser_lines.argtypes = [dp, dp, C.c_uint64, C.c_double, dp, dp, C.c_uint64, u64p]
+    L.orc_rays_to_spectrum.argtypes = [vp, C.c_uint64, C.c_double, dp, dp, C.c_uint64, u64p]
+    L.orc_spectrum_total_energy.argtypes = [dp, dp, C.c_uint64]
+    L.orc_spectrum_total_energy.restype = C.c_double
+    L.orc_spectrum_center_wavelength.argtypes = [dp, dp, C.c_uint64]
+    L.orc_spectrum_center_wavelength.restype = C.c_double
+    L.orc_spectrum_get_value.argtypes = [dp, dp, C.c_uint64, C.c_double, dp]
+    L.orc_rays_filter_energy_spectrum.argtypes = [vp, C.c_uint64, dp, dp, C.c_uint64]
+    L.orc_rays_split_spectrum.argtypes = [vp, C.c_uint64, dp, dp, C.c_uint64, vp]
+    L.orc_rays_wavefront_error.argtypes = [vp, C.c_uint64, C.c_double, C.POINTER(Isometry), dp, u64p]
+    L.orc_wavefront_statistics.argtypes = [dp, C.c_uint64, dp, dp]
     L.orc_history_attach.argtypes = [vp, C.c_uint64, dp, vp, C.c_uint32]
     L.orc_history_attach.restype = None
     L.orc_history_detach.restype = C.c_int
@@ -643,3 +657,78 @@ def rays_collimated_with_spectrum(xyz, e_pos, wvl, w) -> np.ndarray:
     _check(lib().orc_rays_collimated_with_spectrum(_dptr(xyz), _dptr(e_pos), len(xyz), _dptr(wvl), _dptr(w),
                                                    len(wvl), _vp(out)))
     return out
+
+
+# ---------------------------------------------------------------------------
+# spectrum.rs / nodes/spectrometer.rs / nodes/wavefront.rs.  A Spectrum is (lambda [um], value [1/um]).
+# ---------------------------------------------------------------------------
+def spectrum_new(start_m: float, end_m: float, res_m: float):
+    n = C.c_uint64()
+    _check(lib().orc_spectrum_new(start_m, end_m, res_m, None, None, 0, C.byref(n)))
+    lam, data = np.zeros(max(n.value, 1)), np.zeros(max(n.value, 1))
+    _check(lib().orc_spectrum_new(start_m, end_m, res_m, _dptr(lam), _dptr(data), n.value, C.byref(n)))
+    return lam[: n.value], data[: n.value]
+
+
+def spectrum_add_single_peak(lam, data, wl_m: float, value: float):
+    _check(lib().orc_spectrum_add_single_peak(_dptr(lam), _dptr(data), len(lam), wl_m, value))
+
+
+def spectrum_from_laser_lines(wl_m, e, res_m: float):
+    wl, e = np.ascontiguousarray(wl_m, dtype=np.float64), np.ascontiguousarray(e, dtype=np.float64)
+    n = C.c_uint64()
+    _check(lib().orc_spectrum_from_laser_lines(_dptr(wl), _dptr(e), len(wl), res_m, None, None, 0, C.byref(n)))
+    lam, data = np.zeros(max(n.value, 1)), np.zeros(max(n.value, 1))
+    _check(lib().orc_spectrum_from_laser_lines(_dptr(wl), _dptr(e), len(wl), res_m, _dptr(lam), _dptr(data), n.value, C.byref(n)))
+    return lam[: n.value], data[: n.value]
+
+
+def rays_to_spectrum(rays, res_m: float):
+    """Rays::to_spectrum (rays.rs:1209-1223)"""
+    n = C.c_uint64()
+    _check(lib().orc_rays_to_spectrum(_vp(rays), len(rays), res_m, None, None, 0, C.byref(n)))
+    lam, data = np.zeros(max(n.value, 1)), np.zeros(max(n.value, 1))
+    _check(lib().orc_rays_to_spectrum(_vp(rays), len(rays), res_m, _dptr(lam), _dptr(data), n.value, C.byref(n)))
+    return lam[: n.value], data[: n.value]
+
+
+def spectrum_total_energy(lam, data) -> float:
+    return lib().orc_spectrum_total_energy(_dptr(lam), _dptr(data), len(lam))
+
+
+def spectrum_center_wavelength(lam, data) -> float:
+    return lib().orc_spectrum_center_wavelength(_dptr(lam), _dptr(data), len(lam))
+
+
+def spectrum_get_value(lam, data, wl_m: float):
+    lam, data = np.ascontiguousarray(lam, dtype=np.float64), np.ascontiguousarray(data, dtype=np.float64)
+    v = C.c_double()
+    return v.value if lib().orc_spectrum_get_value(_dptr(lam), _dptr(data), len(lam), wl_m, C.byref(v)) else None
+
+
+def rays_filter_energy_spectrum(rays, lam, data):
+    lam, data = np.ascontiguousarray(lam, dtype=np.float64), np.ascontiguousarray(data, dtype=np.float64)
+    _check(lib().orc_rays_filter_energy_spectrum(_vp(rays), len(rays), _dptr(lam), _dptr(data), len(lam)))
+
+
+def rays_split_spectrum(rays, lam, data) -> np.ndarray:
+    lam, data = np.ascontiguousarray(lam, dtype=np.float64), np.ascontiguousarray(data, dtype=np.float64)
+    out = np.zeros(len(rays), dtype=RAY_DTYPE)
+    _check(lib().orc_rays_split_spectrum(_vp(rays), len(rays), _dptr(lam), _dptr(data), len(lam), _vp(out)))
+    return out
+
+
+def rays_wavefront_error(rays, wavelength_m: float, monitor_iso: Isometry) -> np.ndarray:
+    """Rays::wavefront_error_at_pos_in_units_of_wvl (rays.rs:769-802): (n_valid, 3) rows x [mm], y [mm], error [wavelengths]"""
+    out = np.zeros((max(len(rays), 1), 3))
+    n = C.c_uint64()
+    _check(lib().orc_rays_wavefront_error(_vp(rays), len(rays), wavelength_m, C.byref(monitor_iso), _dptr(out), C.byref(n)))
+    return out[: n.value]
+
+
+def wavefront_statistics(xyw: np.ndarray):
+    """WaveFrontErrorMap::calc_wavefront_statistics (nodes/wavefront.rs:145-164) -> (ptv, rms)"""
+    xyw = np.ascontiguousarray(xyw, dtype=np.float64)
+    ptv, rms = C.c_double(), C.c_double()
+    _check(lib().orc_wavefront_statistics(_dptr(xyw), len(xyw), C.byref(ptv), C.byref(rms)))
+    return ptv.value, rms.value

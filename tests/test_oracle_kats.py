@@ -663,3 +663,77 @@ def test_position_history_push_rules():
         assert list(H.len) == [2, 0, 2, 2]
     finally:
         orc.History.detach()
+
+
+# ---- spectrum.rs / wavefront -------------------------------------------------------------------------
+UM = 1e-6
+
+
+def _prep():  # spectrum.rs:657-659: Spectrum::new(1.0..4.0 um, 0.5 um)
+    return orc.spectrum_new(1.0 * UM, 4.0 * UM, 0.5 * UM)
+
+
+def test_spectrum_new_and_single_peak_kats():
+    """spectrum.rs:661-675 (new), :800-833 (set_single_peak*), :875-886 (total_energy*)"""
+    lam, data = _prep()
+    assert np.allclose(lam, [1.0, 1.5, 2.0, 2.5, 3.0, 3.5], rtol=0, atol=1e-15) and not data.any()
+    for bad in ((1.0 * UM, 4.0 * UM, -0.5 * UM), (4.0 * UM, 1.0 * UM, 0.5 * UM), (-1.0 * UM, 4.0 * UM, 0.5 * UM)):
+        with pytest.raises(orc.OracleError):
+            orc.spectrum_new(*bad)
+    orc.spectrum_add_single_peak(lam, data, 2.0 * UM, 1.0)
+    assert data[2] == 2.0 and orc.spectrum_total_energy(lam, data) == 1.0
+    orc.spectrum_add_single_peak(lam, data, 2.0 * UM, 1.0)
+    assert data[2] == 4.0  # additive
+    lam, data = _prep()
+    orc.spectrum_add_single_peak(lam, data, 2.25 * UM, 1.0)
+    assert data[2] == 1.0 and data[3] == 1.0  # interpolated
+    lam, data = _prep()
+    orc.spectrum_add_single_peak(lam, data, 2.0 * UM, 1.0)
+    orc.spectrum_add_single_peak(lam, data, 2.25 * UM, 1.0)
+    assert data[2] == 3.0 and data[3] == 1.0
+    lam, data = _prep()
+    orc.spectrum_add_single_peak(lam, data, 1.0 * UM, 1.0)
+    assert data[0] == 2.0  # lower bound
+    before = data.copy()
+    orc.spectrum_add_single_peak(lam, data, 0.5 * UM, 1.0)  # outside: warning, unmodified
+    orc.spectrum_add_single_peak(lam, data, 4.0 * UM, 1.0)
+    assert np.array_equal(data, before)
+    with pytest.raises(orc.OracleError):
+        orc.spectrum_add_single_peak(lam, data, 1.5 * UM, -1.0)
+    lam, data = orc.spectrum_new(1.0 * UM, 4.0 * UM, 1.0 * UM)
+    orc.spectrum_add_single_peak(lam, data, 1.5 * UM, 1.0)
+    assert orc.spectrum_total_energy(lam, data) == 1.0
+
+
+def test_spectrum_from_laser_lines_kats():
+    """spectrum.rs:726-756"""
+    lam, data = orc.spectrum_from_laser_lines([1.0 * UM], [1.0], 1e-9)
+    assert orc.spectrum_total_energy(lam, data) == 1.0
+    assert abs(lam[0] - 1.0) < 1e-12 and abs(lam[1] - 1.001) < 1e-12 and abs(data[0] - 1000.0) < 1e-9 and data[1] == 0.0
+    lam, data = orc.spectrum_from_laser_lines([1.0 * UM, 1.010 * UM], [1.0, 0.5], 1e-9)
+    assert abs(orc.spectrum_total_energy(lam, data) - 1.5) < 1e-9
+    assert abs(data[0] - 1000.0) < 1e-9 and data[1] == 0.0 and data[2] == 0.0 and abs(lam[10] - 1.010) < 1e-12
+    assert abs(data[10] - 500.0) < 1e-9 and data[11] == 0.0 and abs(lam[11] - 1.011) < 1e-12
+
+
+def test_spectrum_get_value_kat():
+    """spectrum.rs:887-909"""
+    lam, data = [1.0, 2.0, 3.0], [1.0, 2.0, 4.0]
+    want = {0.9: None, 1.0: 1.0, 1.2: 1.2, 2.0: 2.0, 2.75: 3.5, 3.0: 4.0, 3.1: None}
+    for w, v in want.items():
+        got = orc.spectrum_get_value(lam, data, w * UM)
+        assert (got is None) if v is None else abs(got - v) < 1e-12, (w, got, v)
+    assert orc.spectrum_get_value([1.0], [1.0], 0.9 * UM) is None and orc.spectrum_get_value([1.0], [1.0], 1.0 * UM) == 1.0
+
+
+def test_wavefront_statistics_kat():
+    """nodes/wavefront.rs:353-368: two rays at the origin, one an extra wavelength along -> ptv 1.0, rms 0.5"""
+    wvl = 1000e-9
+    rays = np.ascontiguousarray(orc.rays_from_arrays(pos=[(0, 0, 0), (0, 0, wvl)], direction=[(0, 0, 1)] * 2, e=[1.0] * 2, wvl=[wvl] * 2))
+    rays["opl"][1] = wvl  # Ray::propagate(wvl) in vacuum
+    xyw = orc.rays_wavefront_error(rays, wvl, orc.Isometry.identity())
+    assert xyw.shape == (2, 3) and xyw[0, 2] == 0.0 and abs(xyw[1, 2] + 1.0) < 1e-12
+    ptv, rms = orc.wavefront_statistics(xyw)
+    assert abs(ptv - 1.0) < 1e-12 and abs(rms - 0.5) < 1e-12
+    with pytest.raises(orc.OracleError):
+        orc.wavefront_statistics(np.zeros((0, 3)))
