@@ -59,7 +59,10 @@ enum {
     OPM_ERR_ARG = 12,            /* invalid argument / handle */
     OPM_ERR_CAPACITY = 13,       /* an output bundle / hit map is too small */
     OPM_ERR_CUDA = 14,           /* CUDA runtime failure (including: no device) */
-    OPM_ERR_KDE_BANDWIDTH = 15   /* "bandwidth must be != 0.0 and finite"                      kde/mod.rs:36-42 */
+    OPM_ERR_KDE_BANDWIDTH = 15,  /* "bandwidth must be != 0.0 and finite"                      kde/mod.rs:36-42 */
+    OPM_ERR_SPECTRUM = 16,       /* OpossumError::Spectrum; "wavelength of ray outside filter spectrum" ray.rs:716-720, :757-761;
+                                    "ray bundle is empty - cannot create spectrum" rays.rs:1216-1220 */
+    OPM_ERR_EMPTY_WAVEFRONT = 17 /* "Empty wavefront-data vector!"                             nodes/wavefront.rs:121-123 */
 };
 
 /* ------------------------------------------------------------------------------------------
@@ -212,10 +215,12 @@ typedef struct {
 typedef struct { OpmIsometry iso; OpmAperture aperture; } OpmApodizeOp; /* iso = effective_surface_iso (optic_node.rs:372-382) */
 typedef struct { double min_energy; } OpmThresholdOp;
 typedef struct { uint64_t max_bounces; uint64_t max_refractions; int32_t check_refractions; int32_t _pad; } OpmLimitsOp;
-typedef struct { double transmission; } OpmFilterOp;
+typedef struct OpmSpectrum OpmSpectrum;   /* a Spectrum resident on the device, see opm_spectrum_create() */
+typedef struct { double transmission; const OpmSpectrum* spectrum; } OpmFilterOp;   /* spectrum != NULL: FilterType::Spectrum (ray.rs:712-721) */
 typedef struct { double focal_length; OpmIsometry iso; } OpmParaxialOp;
-typedef struct { double ratio; OpmRays* split_out; } OpmSplitOp;   /* split_out: slot-indexed copy with E*(1-ratio); NULL = discard it */
-typedef struct { double ratio; } OpmForkOp;
+/* split_out: slot-indexed copy with E*(1-ratio), NULL = discard it; spectrum != NULL: SplittingConfig::Spectrum (ray.rs:755-761) */
+typedef struct { double ratio; OpmRays* split_out; const OpmSpectrum* spectrum; } OpmSplitOp;
+typedef struct { double ratio; const OpmSpectrum* spectrum; } OpmForkOp;
 typedef struct { OpmRays* out; } OpmJoinOp;                         /* out: the split-off bundle after its side chain; NULL = discard */
 typedef struct { OpmRays* out; } OpmSnapshotOp;                     /* slot-indexed copy of the bundle at this point */
 typedef struct { OpmIsometry iso; int32_t inverse; int32_t _pad; } OpmTransformOp;
@@ -248,6 +253,9 @@ enum {
  * Entry points
  * ---------------------------------------------------------------------------------------- */
 int32_t opm_abi_version(void);
+/* sizeof() of a public structure as this library was compiled ("OpmRay", "OpmOp", "OpmSurface", "OpmAperture", "OpmTraceStats",
+ * "OpmSpotStats", "OpmSourceDesc", "OpmWavefrontStats", "OpmNodeDesc", ...); 0 = unknown name.  Lets a binding check its mirror. */
+uint64_t opm_abi_sizeof(const char* struct_name);
 const char* opm_last_error(void);
 const char* opm_status_string(OpmStatus s);
 
@@ -423,6 +431,37 @@ OpmStatus opm_fluence_kde(OpmHitMap* const* maps, int32_t n_maps, int64_t bounce
 /* FluenceData::new peak (fluence_data.rs:45-68) and total_energy (:130-141) of a device map */
 OpmStatus opm_fluence_peak_total(OpmContext* ctx, const double* map_dev, uint64_t nx, uint64_t ny, const double lrtb[4],
                                  double* peak, double* total_energy);
+/* ---- spectra, spectrometer, wavefront (spectrum.rs, nodes/spectrometer.rs, nodes/wavefront.rs) ------------
+ * A Spectrum (spectrum.rs:35-37) is a pair of arrays: ascending wavelength slots in micrometers and values in 1/um. */
+/* device-resident copy for the spectrum-driven ops (OpmFilterOp / OpmSplitOp / OpmForkOp); n >= 1, slots ascending */
+OpmStatus opm_spectrum_create(OpmContext* ctx, const double* lambda_um, const double* values, uint64_t n, OpmSpectrum** out);
+void opm_spectrum_destroy(OpmSpectrum* spectrum);
+/* host helpers on a spectrum's arrays: Spectrum::total_energy (:289-298, Kahan), center_wavelength (:304-316, metres),
+ * get_value (:321-349; returns 1 = Some(*out), 0 = None) */
+double opm_spectrum_total_energy(const double* lambda_um, const double* values, uint64_t n);
+double opm_spectrum_center_wavelength(const double* lambda_um, const double* values, uint64_t n);
+int32_t opm_spectrum_get_value(const double* lambda_um, const double* values, uint64_t n, double wavelength_m, double* out);
+/* smallest / largest wavelength and number of the valid rays (multi-GPU: reduce with min / max / sum, then pass the common
+ * range to opm_rays_to_spectrum on every rank and sum the values) */
+OpmStatus opm_rays_wavelength_range(const OpmRays* rays, double min_max_m[2], uint64_t* n_valid);
+/* Rays::to_spectrum (rays.rs:1209-1223) = Spectrum::from_laser_lines (spectrum.rs:126-148) of the valid rays: slots from
+ * the smallest wavelength to the largest + 2 resolutions, every ray's energy spread over its two neighbouring slots
+ * (add_single_peak, :193-227).  range_m: NULL (this bundle's own) or {min, max}.  lambda_um == NULL: only *n_out. */
+OpmStatus opm_rays_to_spectrum(const OpmRays* rays, double resolution_m, const double* range_m, double* lambda_um, double* values,
+                               uint64_t cap, uint64_t* n_out);
+/* Rays::filter_energy(FilterType::Spectrum) (rays.rs:1119-1133, ray.rs:712-721), Rays::split(SplittingConfig::Spectrum)
+ * (rays.rs:1253-1264, ray.rs:752-772): a ray whose wavelength is outside the spectrum fails the call (OPM_ERR_SPECTRUM) */
+OpmStatus opm_rays_filter_energy_spectrum(OpmRays* rays, const OpmSpectrum* spectrum);
+OpmStatus opm_rays_split_spectrum(OpmRays* rays, const OpmSpectrum* spectrum, OpmRays* split_out);
+/* Rays::wavefront_error_at_pos_in_units_of_wvl (rays.rs:769-802) + WaveFrontErrorMap::calc_wavefront_statistics
+ * (nodes/wavefront.rs:145-164): per valid ray (x [mm], y [mm] in the monitor frame, wavefront error in wavelengths relative
+ * to the ray closest to the monitor axis), peak-to-valley and rms (about the mean).  wavelength_m <= 0: the centre wavelength
+ * of to_spectrum(1 nm), what WaveFront::node_report uses (nodes/wavefront.rs:180, rays.rs:719-726).
+ * xyw_out: NULL or cap rows of 3 doubles (bundle order). */
+typedef struct { double wavelength_m, ptv, rms; uint64_t n_rays; } OpmWavefrontStats;
+OpmStatus opm_rays_wavefront_error(const OpmRays* rays, const OpmIsometry* monitor_iso, double wavelength_m, double* xyw_out,
+                                   uint64_t cap, OpmWavefrontStats* out);
+
 /* measured FP64 FMA throughput of the device in TFLOP/s (FMA = 2 flop): roofline denominator of the fused trace kernel */
 OpmStatus opm_measure_fp64_peak(OpmContext* ctx, double* tflops);
 /* device buffers for maps (so callers need no CUDA runtime of their own) */

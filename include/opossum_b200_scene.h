@@ -41,8 +41,10 @@ typedef enum {
     OPM_NODE_SPOT_DIAGRAM = 10,
     OPM_NODE_FLUENCE_DETECTOR = 11,
     OPM_NODE_REFLECTIVE_GRATING = 12, /* nodes/reflective_grating.rs */
-    OPM_NODE_RAY_PROPAGATION_VISUALIZER = 13 /* nodes/ray_propagation_visualizer.rs: a single-surface detector that keeps the bundle;
+    OPM_NODE_RAY_PROPAGATION_VISUALIZER = 13, /* nodes/ray_propagation_visualizer.rs: a single-surface detector that keeps the bundle;
                                                  with OPM_SCENE_POSITION_HISTORY its rays carry their paths */
+    OPM_NODE_SPECTROMETER = 14,  /* nodes/spectrometer.rs: detector, report = Rays::to_spectrum(0.2 nm) */
+    OPM_NODE_WAVEFRONT = 15      /* nodes/wavefront.rs: detector, report = wavefront error map, PtV, RMS */
 } OpmNodeType;
 
 typedef struct { int32_t type; int32_t _pad; double reflectivity; } OpmCoatingDesc; /* coatings/mod.rs:17-29 */
@@ -52,8 +54,8 @@ typedef struct { int32_t type; int32_t _pad; double reflectivity; } OpmCoatingDe
  *   WEDGE                 : p[0] centre thickness, p[1] wedge angle [rad]
  *   THIN_MIRROR           : p[0] curvature (INFINITY = flat)
  *   PARABOLIC_MIRROR      : p[0] focal length (on axis)
- *   BEAM_SPLITTER         : p[0] splitting ratio (SplittingConfig::Ratio, ray.rs:36-46)
- *   IDEAL_FILTER          : p[0] transmission (FilterType::Constant)
+ *   BEAM_SPLITTER         : p[0] splitting ratio (SplittingConfig::Ratio, ray.rs:36-46), or `spectrum` (SplittingConfig::Spectrum)
+ *   IDEAL_FILTER          : p[0] transmission (FilterType::Constant), or `spectrum` (FilterType::Spectrum)
  *   PARAXIAL_SURFACE      : p[0] focal length
  *   REFLECTIVE_GRATING    : p[0] line density [1/m] (default 1740/mm), p[1] diffraction order (default -1)
  */
@@ -69,6 +71,7 @@ typedef struct {
     OpmCoatingDesc coating_in, coating_out; /* per optic surface (input_1 / output_1) */
     OpmAperture aperture_in, aperture_out;
     double lidt;               /* J/m^2; 0 = the default 1 J/cm^2 (surface/optic_surface.rs:55) */
+    const OpmSpectrum* spectrum; /* IDEAL_FILTER / BEAM_SPLITTER: transmission spectrum (must outlive the scene); NULL = use p[0] */
 } OpmNodeDesc;
 
 /* defaults of the reference's node constructors: IdealAR coatings (mirrors: ConstantR 1.0), no apertures */
@@ -117,6 +120,13 @@ OpmStatus opm_scene_node_fluence(OpmScene* scene, int32_t node, uint64_t nx, uin
 /* the same report with FluenceEstimator::KDE (rays_hit_map.rs:575-613, kde/mod.rs); band_width = the estimated kernel width */
 OpmStatus opm_scene_node_fluence_kde(OpmScene* scene, int32_t node, uint64_t nx, uint64_t ny, double* map_host, double lrtb[4],
                                      double* peak, double* total_energy, double* band_width);
+/* Spectrometer::node_report (nodes/spectrometer.rs:155-175): Rays::to_spectrum of the bundle the node keeps; resolution_m <= 0:
+ * the node's 0.2 nm.  lambda_um == NULL: only *n_out.  Arguments as opm_rays_to_spectrum. */
+OpmStatus opm_scene_node_spectrum(OpmScene* scene, int32_t node, double resolution_m, const double* range_m, double* lambda_um,
+                                  double* values, uint64_t cap, uint64_t* n_out);
+/* WaveFront::node_report (nodes/wavefront.rs:173-235): wavefront error map of the kept bundle in the frame of the node's
+ * surface, at the centre wavelength of its spectrum, with PtV and RMS.  Arguments as opm_rays_wavefront_error. */
+OpmStatus opm_scene_node_wavefront(OpmScene* scene, int32_t node, double* xyw_out, uint64_t cap, OpmWavefrontStats* out);
 /* hit maps recorded on surface `surface` (0 = input_1, 1 = output_1) of a node: fills up to `capacity` handles */
 int32_t opm_scene_node_hitmaps(OpmScene* scene, int32_t node, int32_t surface, OpmHitMap** out, int32_t capacity);
 

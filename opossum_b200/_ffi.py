@@ -19,7 +19,8 @@ OPM_MAX_PROGRAM_OPS = 128
 # status codes
 (OPM_OK, OPM_ERR_N2_INVALID, OPM_ERR_WVL_RANGE, OPM_ERR_INDEX_MODEL, OPM_ERR_COATING, OPM_ERR_APODIZE_FACTOR,
  OPM_ERR_THRESHOLD, OPM_ERR_HITPOINT, OPM_ERR_SPLIT_RATIO, OPM_ERR_FOCAL_LENGTH, OPM_ERR_EMPTY_HITMAP,
- OPM_ERR_BIN_RANGE, OPM_ERR_ARG, OPM_ERR_CAPACITY, OPM_ERR_CUDA, OPM_ERR_KDE_BANDWIDTH) = range(16)
+ OPM_ERR_BIN_RANGE, OPM_ERR_ARG, OPM_ERR_CAPACITY, OPM_ERR_CUDA, OPM_ERR_KDE_BANDWIDTH,
+ OPM_ERR_SPECTRUM, OPM_ERR_EMPTY_WAVEFRONT) = range(18)
 
 GEOM_PLANE, GEOM_SPHERE, GEOM_CYLINDER, GEOM_PARABOLA = range(4)
 COAT_IDEAL_AR, COAT_CONSTANT_R, COAT_FRESNEL = range(3)
@@ -99,7 +100,7 @@ class OpmLimitsOp(C.Structure):
 
 
 class OpmFilterOp(C.Structure):
-    _fields_ = [("transmission", C.c_double)]
+    _fields_ = [("transmission", C.c_double), ("spectrum", C.c_void_p)]
 
 
 class OpmParaxialOp(C.Structure):
@@ -107,7 +108,7 @@ class OpmParaxialOp(C.Structure):
 
 
 class OpmSplitOp(C.Structure):
-    _fields_ = [("ratio", C.c_double), ("split_out", C.c_void_p)]
+    _fields_ = [("ratio", C.c_double), ("split_out", C.c_void_p), ("spectrum", C.c_void_p)]
 
 
 class OpmSnapshotOp(C.Structure):
@@ -124,7 +125,7 @@ class OpmDiffractOp(C.Structure):
 
 
 class OpmForkOp(C.Structure):
-    _fields_ = [("ratio", C.c_double)]
+    _fields_ = [("ratio", C.c_double), ("spectrum", C.c_void_p)]
 
 
 class OpmJoinOp(C.Structure):
@@ -164,7 +165,7 @@ class OpmSourceDesc(C.Structure):
 
 (NODE_SOURCE, NODE_LENS, NODE_CYLINDRIC_LENS, NODE_WEDGE, NODE_THIN_MIRROR, NODE_PARABOLIC_MIRROR, NODE_BEAM_SPLITTER,
  NODE_DUMMY, NODE_IDEAL_FILTER, NODE_PARAXIAL_SURFACE, NODE_SPOT_DIAGRAM, NODE_FLUENCE_DETECTOR, NODE_REFLECTIVE_GRATING,
- NODE_RAY_PROPAGATION_VISUALIZER) = range(14)
+ NODE_RAY_PROPAGATION_VISUALIZER, NODE_SPECTROMETER, NODE_WAVEFRONT) = range(16)
 SCENE_STRICT, SCENE_PER_SURFACE, SCENE_RECORD_ALL_HITS, SCENE_NO_SNAPSHOTS, SCENE_ASYNC, SCENE_KEEP_SOURCE = 2, 4, 8, 16, 32, 64
 SCENE_POSITION_HISTORY = 128
 
@@ -177,7 +178,11 @@ class OpmNodeDesc(C.Structure):
     _fields_ = [("type", C.c_int32), ("parent", C.c_int32), ("parent_port", C.c_int32), ("has_alignment", C.c_int32),
                 ("iso", OpmIsometry), ("alignment", OpmIsometry), ("p", C.c_double * 4), ("index", OpmIndexModel),
                 ("coating_in", OpmCoatingDesc), ("coating_out", OpmCoatingDesc), ("aperture_in", OpmAperture),
-                ("aperture_out", OpmAperture), ("lidt", C.c_double)]
+                ("aperture_out", OpmAperture), ("lidt", C.c_double), ("spectrum", C.c_void_p)]
+
+
+class OpmWavefrontStats(C.Structure):
+    _fields_ = [("wavelength_m", C.c_double), ("ptv", C.c_double), ("rms", C.c_double), ("n_rays", C.c_uint64)]
 
 
 class OpmGhostFocusConfig(C.Structure):
@@ -198,13 +203,13 @@ SCENE_EXPORTS = [
     "opm_node_desc_init", "opm_scene_create", "opm_scene_destroy", "opm_scene_set_ambient", "opm_scene_add_node",
     "opm_scene_node_count", "opm_scene_reset_data", "opm_scene_raytrace", "opm_scene_output_rays", "opm_scene_node_rays", "opm_scene_node_spot",
     "opm_scene_node_spot_partial", "opm_scene_node_spot_async",
-    "opm_scene_node_fluence", "opm_scene_node_fluence_kde", "opm_scene_node_hitmaps", "opm_scene_ghostfocus", "opm_scene_gf_pass_tally",
+    "opm_scene_node_fluence", "opm_scene_node_fluence_kde", "opm_scene_node_spectrum", "opm_scene_node_wavefront", "opm_scene_node_hitmaps", "opm_scene_ghostfocus", "opm_scene_gf_pass_tally",
     "opm_scene_gf_pass_bundles", "opm_scene_node_critical_fluences", "opm_scene_node_peak_fluence",
 ]
 
 # every symbol include/opossum_b200.h declares (tests/test_abi.py checks the library exports all of them)
 EXPORTS = [
-    "opm_abi_version", "opm_last_error", "opm_status_string", "opm_context_create", "opm_context_destroy",
+    "opm_abi_version", "opm_abi_sizeof", "opm_last_error", "opm_status_string", "opm_context_create", "opm_context_destroy",
     "opm_context_synchronize", "opm_context_stream", "opm_context_launch_count", "opm_context_set_kernel_timing",
     "opm_context_kernel_timing", "opm_context_set_jit", "opm_context_jit_wait", "opm_context_jit_stats", "opm_jit_selftest", "opm_isometry_identity",
     "opm_isometry_new", "opm_isometry_append", "opm_raytrace_config_default", "opm_rays_create", "opm_rays_destroy",
@@ -219,7 +224,10 @@ EXPORTS = [
     "opm_rays_spot_partial_radii", "opm_spot_stats_from_partial", "opm_rays_spot_sums_async", "opm_rays_spot_radii_async", "opm_rays_bounce_lvl", "opm_rays_tally", "opm_hitmap_create",
     "opm_hitmap_destroy", "opm_hitmap_capacity", "opm_hitmap_len", "opm_hitmap_upload", "opm_hitmap_download",
     "opm_hitmaps_bounding_box", "opm_fluence_binning", "opm_fluence_peak_total", "opm_hitmaps_bounding_box_async",
-    "opm_fluence_binning_async", "opm_fluence_peak_total_async", "opm_fluence_kde", "opm_measure_fp64_peak", "opm_device_alloc",
+    "opm_fluence_binning_async", "opm_fluence_peak_total_async", "opm_fluence_kde",
+    "opm_spectrum_create", "opm_spectrum_destroy", "opm_spectrum_total_energy", "opm_spectrum_center_wavelength", "opm_spectrum_get_value",
+    "opm_rays_wavelength_range", "opm_rays_to_spectrum", "opm_rays_filter_energy_spectrum", "opm_rays_split_spectrum",
+    "opm_rays_wavefront_error", "opm_measure_fp64_peak", "opm_device_alloc",
     "opm_device_free", "opm_device_memset", "opm_device_to_host", "opm_host_to_device", "opm_host_alloc_pinned", "opm_host_free_pinned",
     "opm_spectrum_gaussian", "opm_source_generate", "opm_source_generate_strided", "opm_source_energy_norm",
 ]
@@ -269,6 +277,7 @@ def lib() -> C.CDLL:
         "opm_rays_destroy": (None, [vp]),
         "opm_rays_len": (u64, [vp]),
         "opm_rays_capacity": (u64, [vp]),
+        "opm_abi_sizeof": (u64, [C.c_char_p]),
         "opm_rays_clear": (i32, [vp]),
         "opm_rays_reserve": (i32, [vp, u64]),
         "opm_rays_upload": (i32, [vp, vp, u64]),
@@ -307,6 +316,16 @@ def lib() -> C.CDLL:
         "opm_fluence_binning_async": (i32, [pp, i32, i64, u64, u64, vp, i32, vp, vp]),
         "opm_fluence_peak_total_async": (i32, [vp, vp, u64, u64, vp, vp]),
         "opm_fluence_kde": (i32, [pp, i32, i64, u64, u64, dp, vp, dp, dp]),
+        "opm_spectrum_create": (i32, [vp, dp, dp, u64, pp]),
+        "opm_spectrum_destroy": (None, [vp]),
+        "opm_spectrum_total_energy": (C.c_double, [dp, dp, u64]),
+        "opm_spectrum_center_wavelength": (C.c_double, [dp, dp, u64]),
+        "opm_spectrum_get_value": (i32, [dp, dp, u64, C.c_double, dp]),
+        "opm_rays_wavelength_range": (i32, [vp, dp, C.POINTER(u64)]),
+        "opm_rays_to_spectrum": (i32, [vp, C.c_double, dp, dp, dp, u64, C.POINTER(u64)]),
+        "opm_rays_filter_energy_spectrum": (i32, [vp, vp]),
+        "opm_rays_split_spectrum": (i32, [vp, vp, vp]),
+        "opm_rays_wavefront_error": (i32, [vp, C.POINTER(OpmIsometry), C.c_double, dp, u64, C.POINTER(OpmWavefrontStats)]),
         "opm_rays_bounce_lvl": (i32, [vp, C.POINTER(C.c_uint32)]),
         "opm_rays_tally": (i32, [vp, C.c_uint32, C.POINTER(u64), dp]),
         "opm_hitmap_create": (i32, [vp, u64, pp]),
@@ -347,6 +366,8 @@ def lib() -> C.CDLL:
         "opm_scene_node_spot_async": (i32, [vp, i32, i32, vp, vp]),
         "opm_scene_node_fluence": (i32, [vp, i32, u64, u64, dp, dp, dp, dp]),
         "opm_scene_node_fluence_kde": (i32, [vp, i32, u64, u64, dp, dp, dp, dp, dp]),
+        "opm_scene_node_spectrum": (i32, [vp, i32, C.c_double, dp, dp, dp, u64, C.POINTER(u64)]),
+        "opm_scene_node_wavefront": (i32, [vp, i32, dp, u64, C.POINTER(OpmWavefrontStats)]),
         "opm_scene_node_hitmaps": (i32, [vp, i32, i32, pp, i32]),
         "opm_scene_ghostfocus": (i32, [vp, vp, C.POINTER(OpmGhostFocusConfig), i32, C.POINTER(OpmGhostFocusStats)]),
         "opm_scene_gf_pass_tally": (i32, [vp, C.c_uint32, C.c_uint32, C.POINTER(u64), dp, C.POINTER(u64), C.POINTER(u64)]),

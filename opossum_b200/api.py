@@ -353,6 +353,51 @@ class TraceStats:
         return TraceStats(s.interactions, s.children, s.hits, s.missed, s.apodized, s.valid_out, s.alive_out)
 
 
+class Spectrum:
+    """spectrum.rs `Spectrum` resident on the device (for the spectrum-driven filter / splitter ops): ascending wavelength
+    slots in micrometers and their values.  total_energy / center_wavelength / get_value are the library's host helpers."""
+
+    def __init__(self, ctx: Context, lambda_um, values):
+        self.ctx = ctx
+        self.lam = np.ascontiguousarray(lambda_um, dtype=np.float64)
+        self.val = np.ascontiguousarray(values, dtype=np.float64)
+        dp = C.POINTER(C.c_double)
+        h = C.c_void_p()
+        _check(F.lib().opm_spectrum_create(ctx.h, self.lam.ctypes.data_as(dp), self.val.ctypes.data_as(dp), len(self.lam), C.byref(h)))
+        self.h = h
+        ctx._adopt(self)
+
+    def close(self):
+        if self.h:
+            F.lib().opm_spectrum_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def spectrum_total_energy(lam, val) -> float:
+    lam, val = np.ascontiguousarray(lam, dtype=np.float64), np.ascontiguousarray(val, dtype=np.float64)
+    dp = C.POINTER(C.c_double)
+    return F.lib().opm_spectrum_total_energy(lam.ctypes.data_as(dp), val.ctypes.data_as(dp), len(lam))
+
+
+def spectrum_center_wavelength(lam, val) -> float:
+    lam, val = np.ascontiguousarray(lam, dtype=np.float64), np.ascontiguousarray(val, dtype=np.float64)
+    dp = C.POINTER(C.c_double)
+    return F.lib().opm_spectrum_center_wavelength(lam.ctypes.data_as(dp), val.ctypes.data_as(dp), len(lam))
+
+
+def spectrum_get_value(lam, val, wavelength: float):
+    lam, val = np.ascontiguousarray(lam, dtype=np.float64), np.ascontiguousarray(val, dtype=np.float64)
+    dp = C.POINTER(C.c_double)
+    v = C.c_double()
+    return v.value if F.lib().opm_spectrum_get_value(lam.ctypes.data_as(dp), val.ctypes.data_as(dp), len(lam), wavelength, C.byref(v)) else None
+
+
 class Rays:
     """rays.rs `Rays`: a bundle held as struct-of-arrays f64 buffers in HBM."""
 
@@ -418,6 +463,45 @@ class Rays:
 
     def clear(self):
         _check(F.lib().opm_rays_clear(self.h))
+
+    # ---- spectra / wavefront (spectrum.rs, nodes/spectrometer.rs, nodes/wavefront.rs)
+    def wavelength_range(self):
+        """(min, max, n_valid) of the valid rays' wavelengths"""
+        mm = (C.c_double * 2)()
+        nv = C.c_uint64()
+        _check(F.lib().opm_rays_wavelength_range(self.h, mm, C.byref(nv)))
+        return mm[0], mm[1], nv.value
+
+    def to_spectrum(self, resolution: float, wavelength_range=None):
+        """Rays::to_spectrum (rays.rs:1209-1223) -> (wavelength slots [um], values [1/um]); wavelength_range = (min, max) of
+        all shards when the bundle is one shard of several (then the values of the shards add up)"""
+        rng = (C.c_double * 2)(*wavelength_range) if wavelength_range is not None else None
+        n = C.c_uint64()
+        _check(F.lib().opm_rays_to_spectrum(self.h, resolution, rng, None, None, 0, C.byref(n)))
+        lam, val = np.zeros(max(n.value, 1)), np.zeros(max(n.value, 1))
+        dp = C.POINTER(C.c_double)
+        _check(F.lib().opm_rays_to_spectrum(self.h, resolution, rng, lam.ctypes.data_as(dp), val.ctypes.data_as(dp), n.value, C.byref(n)))
+        return lam[: n.value], val[: n.value]
+
+    def filter_energy_spectrum(self, spectrum: "Spectrum"):
+        """Rays::filter_energy(FilterType::Spectrum) (rays.rs:1119-1133, ray.rs:712-721)"""
+        _check(F.lib().opm_rays_filter_energy_spectrum(self.h, spectrum.h))
+
+    def split_spectrum(self, spectrum: "Spectrum") -> "Rays":
+        """Rays::split(SplittingConfig::Spectrum) (rays.rs:1253-1264, ray.rs:752-772)"""
+        out = Rays(self.ctx, max(len(self), 1))
+        _check(F.lib().opm_rays_split_spectrum(self.h, spectrum.h, out.h))
+        return out
+
+    def wavefront_error(self, monitor_iso: "Isometry", wavelength: float = 0.0, want_map: bool = True):
+        """Rays::wavefront_error_at_pos_in_units_of_wvl (rays.rs:769-802) + calc_wavefront_statistics (nodes/wavefront.rs:145-164)
+        -> (OpmWavefrontStats, (n_valid, 3) array or None); wavelength <= 0: centre wavelength of to_spectrum(1 nm)"""
+        st = F.OpmWavefrontStats()
+        n = len(self)
+        xyw = np.zeros((max(n, 1), 3)) if want_map else None
+        _check(F.lib().opm_rays_wavefront_error(self.h, C.byref(monitor_iso.c), wavelength,
+                                                xyw.ctypes.data_as(C.POINTER(C.c_double)) if want_map else None, max(n, 1), C.byref(st)))
+        return st, (xyw[: st.n_rays] if want_map else None)
 
     # ---- per-ray position history (`pos_hist`, ray.rs:70; SURVEY 8f-2)
     def enable_position_history(self, levels_hint: int = 16):
@@ -638,9 +722,12 @@ class Program:
         self.ops.append(op)
         return self
 
-    def filter(self, transmission: float) -> "Program":
+    def filter(self, transmission: float = 1.0, spectrum: "Spectrum | None" = None) -> "Program":
+        """FilterType::Constant(transmission) or, with `spectrum`, FilterType::Spectrum (ray.rs:702-727)"""
         op = F.OpmOp(kind=F.OP_FILTER)
         op.u.filter.transmission = transmission
+        op.u.filter.spectrum = spectrum.h if spectrum is not None else None
+        self._keep.append(spectrum)
         self.ops.append(op)
         return self
 
@@ -658,18 +745,22 @@ class Program:
         self.ops.append(op)
         return self
 
-    def split(self, ratio: float, split_out: Rays | None) -> "Program":
+    def split(self, ratio: float, split_out: Rays | None, spectrum: "Spectrum | None" = None) -> "Program":
+        """SplittingConfig::Ratio(ratio) or, with `spectrum`, SplittingConfig::Spectrum (ray.rs:752-772)"""
         op = F.OpmOp(kind=F.OP_SPLIT)
         op.u.split.ratio = ratio
         op.u.split.split_out = split_out.h if split_out is not None else None
-        self._keep.append(split_out)
+        op.u.split.spectrum = spectrum.h if spectrum is not None else None
+        self._keep += [split_out, spectrum]
         self.ops.append(op)
         return self
 
-    def fork(self, ratio: float) -> "Program":
+    def fork(self, ratio: float, spectrum: "Spectrum | None" = None) -> "Program":
         """Rays::split whose split-off bundle (E * (1 - ratio)) runs the ops up to the matching join() in the same launch"""
         op = F.OpmOp(kind=F.OP_FORK)
         op.u.fork.ratio = ratio
+        op.u.fork.spectrum = spectrum.h if spectrum is not None else None
+        self._keep.append(spectrum)
         self.ops.append(op)
         return self
 

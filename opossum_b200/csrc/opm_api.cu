@@ -14,6 +14,7 @@
 
 #include "opm_internal.h"
 #include "opm_kernels.h"
+#include "../../include/opossum_b200_scene.h"
 
 using namespace opm;
 
@@ -86,6 +87,12 @@ struct OpmRays {
     double* d_hist = nullptr;
     uint32_t hist_levels = 0, hist_next = 0;
     uint64_t hist_stride = 0;
+};
+
+struct OpmSpectrum {  // spectrum.rs:35-37 on the device: [lam(n) | val(n)] in one allocation
+    OpmContext* ctx = nullptr;
+    uint64_t n = 0;
+    double* d = nullptr;
 };
 
 struct OpmHitMap {
@@ -164,11 +171,23 @@ extern "C" const char* opm_status_string(OpmStatus s) {
         case OPM_ERR_CAPACITY: return "output bundle or hit map too small";
         case OPM_ERR_CUDA: return "CUDA failure";
         case OPM_ERR_KDE_BANDWIDTH: return "bandwidth must be != 0.0 and finite";
+        case OPM_ERR_SPECTRUM: return "spectrum: wavelength outside the spectrum, no valid rays, or invalid range / resolution";
+        case OPM_ERR_EMPTY_WAVEFRONT: return "Empty wavefront-data vector!";
         default: return "unknown status";
     }
 }
 extern "C" const char* opm_last_error(void) { return g_last_error.c_str(); }
 extern "C" int32_t opm_abi_version(void) { return OPM_ABI_VERSION; }
+extern "C" uint64_t opm_abi_sizeof(const char* name) {
+    if (!name) return 0;
+#define OPM_SZ(T) if (!strcmp(name, #T)) return sizeof(T);
+    OPM_SZ(OpmRay) OPM_SZ(OpmIso) OPM_SZ(OpmIsometry) OPM_SZ(OpmSurface) OPM_SZ(OpmIndexModel) OPM_SZ(OpmApertureItem) OPM_SZ(OpmAperture)
+    OPM_SZ(OpmTraceStats) OPM_SZ(OpmRefractOp) OPM_SZ(OpmDiffractOp) OPM_SZ(OpmFilterOp) OPM_SZ(OpmSplitOp) OPM_SZ(OpmForkOp) OPM_SZ(OpmOp)
+    OPM_SZ(OpmSpotStats) OPM_SZ(OpmSpotPartial) OPM_SZ(OpmSourceDesc) OPM_SZ(OpmRayTraceConfig) OPM_SZ(OpmWavefrontStats)
+    OPM_SZ(OpmNodeDesc) OPM_SZ(OpmCoatingDesc) OPM_SZ(OpmGhostFocusConfig) OPM_SZ(OpmGhostFocusStats) OPM_SZ(OpmCriticalFluence)
+#undef OPM_SZ
+    return 0;
+}
 
 static OpmStatus status_from_bits(uint32_t bits) {
     if (!bits) return OPM_OK;
@@ -864,6 +883,12 @@ static OpmStatus compile_aperture(OpmContext* c, const OpmAperture& a, DevApertu
     return OPM_OK;
 }
 
+static DevSpectrum dev_spectrum(const OpmSpectrum* sp) {
+    DevSpectrum d;
+    d.lam = sp->d; d.val = sp->d + sp->n; d.n = sp->n;
+    return d;
+}
+
 static OpmStatus compile_ops(OpmContext* c, const OpmOp* ops, int n_ops, uint64_t n_rays, Compiled& out) {
     if (n_ops < 0 || n_ops > OPM_MAX_PROGRAM_OPS) return fail(OPM_ERR_ARG, "program has %d ops (max %d)", n_ops, OPM_MAX_PROGRAM_OPS);
     for (int k = 0; k < n_ops; ++k) {
@@ -932,8 +957,15 @@ static OpmStatus compile_ops(OpmContext* c, const OpmOp* ops, int n_ops, uint64_
                 break;
             case OPM_OP_FILTER: {  // rays.rs:1120-1126
                 double t = p.u.filter.transmission;
+                d.kind = OPK_FILTER;
+                if (p.u.filter.spectrum) {  // FilterType::Spectrum: the transmission is looked up per ray (ray.rs:712-721)
+                    if (p.u.filter.spectrum->ctx != c) return fail(OPM_ERR_ARG, "spectrum belongs to another context");
+                    d.u.filter.s = dev_spectrum(p.u.filter.spectrum);
+                    d.u.filter.t = 1.0;
+                    break;
+                }
                 if (!(t >= 0.0 && t <= 1.0)) return fail(OPM_ERR_APODIZE_FACTOR, "transmission value must be in the range [0.0;1.0]");
-                d.kind = OPK_FILTER; d.u.filter.t = t;
+                d.u.filter.t = t;
                 break;
             }
             case OPM_OP_PARAXIAL: {  // rays.rs:944-948
@@ -945,6 +977,11 @@ static OpmStatus compile_ops(OpmContext* c, const OpmOp* ops, int n_ops, uint64_
             }
             case OPM_OP_SPLIT: {  // ray.rs:763-767
                 double ratio = p.u.split.ratio;
+                if (p.u.split.spectrum) {  // SplittingConfig::Spectrum (ray.rs:755-761)
+                    if (p.u.split.spectrum->ctx != c) return fail(OPM_ERR_ARG, "spectrum belongs to another context");
+                    d.u.split.s = dev_spectrum(p.u.split.spectrum);
+                    ratio = 1.0;
+                }
                 if (!(ratio >= 0.0 && ratio <= 1.0)) return fail(OPM_ERR_SPLIT_RATIO, "%s", opm_status_string(OPM_ERR_SPLIT_RATIO));
                 d.kind = OPK_SPLIT; d.u.split.ratio = ratio;
                 if (p.u.split.split_out) {
@@ -958,6 +995,11 @@ static OpmStatus compile_ops(OpmContext* c, const OpmOp* ops, int n_ops, uint64_
             }
             case OPM_OP_FORK: {  // ray.rs:763-767
                 double ratio = p.u.fork.ratio;
+                if (p.u.fork.spectrum) {
+                    if (p.u.fork.spectrum->ctx != c) return fail(OPM_ERR_ARG, "spectrum belongs to another context");
+                    d.u.fork.s = dev_spectrum(p.u.fork.spectrum);
+                    ratio = 1.0;
+                }
                 if (!(ratio >= 0.0 && ratio <= 1.0)) return fail(OPM_ERR_SPLIT_RATIO, "%s", opm_status_string(OPM_ERR_SPLIT_RATIO));
                 if (out.fork_depth != 0) return fail(OPM_ERR_ARG, "OPM_OP_FORK inside a fork: one level only");
                 out.fork_depth = 1; out.has_fork = true;
@@ -1246,6 +1288,19 @@ extern "C" OpmStatus opm_rays_split(OpmRays* rays, double ratio, OpmRays* split_
     op.kind = OPM_OP_SPLIT; op.u.split.ratio = ratio; op.u.split.split_out = split_out;
     return run_simple(rays, op);
 }
+extern "C" OpmStatus opm_rays_filter_energy_spectrum(OpmRays* rays, const OpmSpectrum* spectrum) {
+    if (!spectrum) return fail(OPM_ERR_ARG, "NULL spectrum");
+    OpmOp op; memset(&op, 0, sizeof op);
+    op.kind = OPM_OP_FILTER; op.u.filter.spectrum = spectrum;
+    return run_simple(rays, op);
+}
+extern "C" OpmStatus opm_rays_split_spectrum(OpmRays* rays, const OpmSpectrum* spectrum, OpmRays* split_out) {
+    if (!spectrum) return fail(OPM_ERR_ARG, "NULL spectrum");
+    if (!split_out) return fail(OPM_ERR_ARG, "split without output bundle");
+    OpmOp op; memset(&op, 0, sizeof op);
+    op.kind = OPM_OP_SPLIT; op.u.split.split_out = split_out; op.u.split.spectrum = spectrum;
+    return run_simple(rays, op);
+}
 extern "C" OpmStatus opm_rays_refract_paraxial(OpmRays* rays, double f, const OpmIsometry* iso) {
     if (!iso) return fail(OPM_ERR_ARG, "NULL argument");
     OpmOp op; memset(&op, 0, sizeof op);
@@ -1262,6 +1317,196 @@ extern "C" OpmStatus opm_rays_transform(OpmRays* rays, const OpmIsometry* iso, i
     DevIso I;
     to_dev_iso(inverse ? iso->inv : iso->fwd, I);
     KL(k_transform(rays->v, I, rays->len, c->sms, c->stream)); c->launches++;
+    return OPM_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// spectra, spectrometer, wavefront (spectrum.rs, nodes/spectrometer.rs, nodes/wavefront.rs)
+// ---------------------------------------------------------------------------------------------
+extern "C" OpmStatus opm_spectrum_create(OpmContext* c, const double* lambda_um, const double* values, uint64_t n, OpmSpectrum** out) {
+    if (!c || !lambda_um || !values || !out || n == 0) return fail(OPM_ERR_ARG, "NULL argument or empty spectrum");
+    for (uint64_t i = 1; i < n; ++i)
+        if (!(lambda_um[i] > lambda_um[i - 1])) return fail(OPM_ERR_SPECTRUM, "spectrum wavelengths must be ascending");
+    CU(cudaSetDevice(c->device));
+    OpmSpectrum* sp = new OpmSpectrum();
+    sp->ctx = c; sp->n = n;
+    cudaError_t e = cudaMalloc(&sp->d, 2 * n * sizeof(double));
+    if (e == cudaSuccess) e = cudaMemcpyAsync(sp->d, lambda_um, n * sizeof(double), cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(sp->d + n, values, n * sizeof(double), cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);  // the caller's arrays may go away
+    if (e != cudaSuccess) { cudaFree(sp->d); delete sp; return fail(OPM_ERR_CUDA, "spectrum upload failed: %s", cudaGetErrorString(e)); }
+    *out = sp;
+    return OPM_OK;
+}
+extern "C" void opm_spectrum_destroy(OpmSpectrum* sp) {
+    if (!sp) return;
+    cudaSetDevice(sp->ctx->device);
+    cudaStreamSynchronize(sp->ctx->stream);
+    cudaFree(sp->d);
+    delete sp;
+}
+// Spectrum::total_energy (spectrum.rs:289-298): Kahan sum (kahan 0.1.4) of slot width x value
+extern "C" double opm_spectrum_total_energy(const double* lambda_um, const double* values, uint64_t n) {
+    double sum = 0.0, err = 0.0;
+    for (uint64_t i = 0; i + 1 < n; ++i) {
+        const double x = (lambda_um[i + 1] - lambda_um[i]) * values[i];
+        const double y = x - err, t = sum + y;
+        err = (t - sum) - y;
+        sum = t;
+    }
+    return sum;
+}
+// Spectrum::center_wavelength (spectrum.rs:304-316), returned in metres (micrometer!(x) = x * 1e-6)
+extern "C" double opm_spectrum_center_wavelength(const double* lambda_um, const double* values, uint64_t n) {
+    double weighted_sum = 0.0, total_weight = 0.0;
+    for (uint64_t i = 0; i + 1 < n; ++i) {
+        const double bin_width = lambda_um[i + 1] - lambda_um[i];
+        const double bin_weight = values[i] * bin_width;
+        weighted_sum += lambda_um[i] * bin_weight;
+        total_weight += bin_weight;
+    }
+    return (weighted_sum / total_weight) * 1e-6;
+}
+// Spectrum::get_value (spectrum.rs:321-349)
+extern "C" int32_t opm_spectrum_get_value(const double* lam, const double* val, uint64_t n, double wl_m, double* out) {
+    if (!lam || !val || !out || n == 0) return 0;
+    const double w = wl_m / 1e-6;
+    if (w == lam[n - 1]) { *out = val[n - 1]; return 1; }
+    if (!(lam[0] * 1e-6 <= wl_m && wl_m < lam[n - 1] * 1e-6)) return 0;
+    uint64_t idx = n;
+    for (uint64_t i = 0; i < n; ++i) if (lam[i] >= w) { idx = i; break; }
+    if (idx == n) return 0;
+    const uint64_t l = idx == 0 ? 0 : idx - 1, r = idx == 0 ? 1 : idx;
+    const double ratio = (w - lam[l]) / (lam[r] - lam[l]);
+    *out = std::fma(val[l], 1.0 - ratio, val[r] * ratio);
+    return 1;
+}
+extern "C" OpmStatus opm_rays_wavelength_range(const OpmRays* rc, double min_max_m[2], uint64_t* n_valid) {
+    OpmRays* r = const_cast<OpmRays*>(rc);
+    if (!r || !min_max_m) return fail(OPM_ERR_ARG, "NULL argument");
+    OpmContext* c = r->ctx;
+    CU(cudaSetDevice(c->device));
+    OpmStatus s = rays_materialize(r);
+    if (!s) s = rays_refresh_len(r);
+    if (s) return s;
+    WvlAccum init;
+    init.min_key = double_to_key(INFINITY); init.max_key = double_to_key(-INFINITY); init.count = 0;
+    WvlAccum* d_acc = (WvlAccum*)(c->d_scratch + 3200);
+    s = dev_put(c, d_acc, &init, sizeof init);
+    if (s) return s;
+    if (r->len) { KL(k_wavelength_range(r->v, r->len, d_acc, c->sms, c->stream)); c->launches++; }
+    WvlAccum* h = (WvlAccum*)(c->h_scratch + 3200);
+    CU(cudaMemcpyAsync(h, d_acc, sizeof *h, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    min_max_m[0] = key_to_double(h->min_key); min_max_m[1] = key_to_double(h->max_key);
+    if (n_valid) *n_valid = h->count;
+    return OPM_OK;
+}
+// Spectrum::new (spectrum.rs:47-73): slot count and the two numbers every slot wavelength derives from
+static OpmStatus spectrum_grid(double start_m, double end_m, double res_m, uint64_t* n, double* start_um, double* step_um) {
+    if (!(res_m > 0.0)) return fail(OPM_ERR_SPECTRUM, "resolution must be positive");
+    if (start_m >= end_m) return fail(OPM_ERR_SPECTRUM, "wavelength range must be in ascending order and not empty");
+    if (std::signbit(start_m) || std::signbit(end_m)) return fail(OPM_ERR_SPECTRUM, "wavelength range limits must both be positive");
+    const double cnt = std::round((end_m - start_m) / res_m);
+    *n = cnt > 0.0 ? (uint64_t)cnt : 0;  // f64_to_usize (utils/math_utils.rs:38-43)
+    *start_um = start_m / 1e-6; *step_um = res_m / 1e-6;
+    return OPM_OK;
+}
+extern "C" OpmStatus opm_rays_to_spectrum(const OpmRays* rc, double resolution_m, const double* range_m, double* lambda_um, double* values,
+                                          uint64_t cap, uint64_t* n_out) {
+    OpmRays* r = const_cast<OpmRays*>(rc);
+    if (!r || !n_out) return fail(OPM_ERR_ARG, "NULL argument");
+    OpmContext* c = r->ctx;
+    double mm[2];
+    if (range_m) { mm[0] = range_m[0]; mm[1] = range_m[1]; }
+    else {
+        uint64_t nv = 0;
+        OpmStatus s = opm_rays_wavelength_range(r, mm, &nv);
+        if (s) return s;
+        if (nv == 0) return fail(OPM_ERR_SPECTRUM, "ray bundle is empty - cannot create spectrum");  // rays.rs:1216-1220
+    }
+    if (!(resolution_m > 0.0)) return fail(OPM_ERR_SPECTRUM, "resolution must be positive");
+    uint64_t n = 0;
+    double start = 0.0, step = 0.0;
+    OpmStatus s = spectrum_grid(mm[0], mm[1] + 2.0 * resolution_m, resolution_m, &n, &start, &step);  // spectrum.rs:143
+    if (s) return s;
+    *n_out = n;
+    if (!lambda_um) return OPM_OK;
+    if (!values || cap < n) return fail(OPM_ERR_CAPACITY, "spectrum has %llu slots, the buffers hold %llu", (unsigned long long)n, (unsigned long long)cap);
+    for (uint64_t i = 0; i < n; ++i) lambda_um[i] = std::fma((double)i, step, start);
+    if (n == 0) return OPM_OK;
+    CU(cudaSetDevice(c->device));
+    s = rays_materialize(r);
+    if (!s) s = rays_refresh_len(r);
+    if (s) return s;
+    double* d_data = nullptr;
+    CU(cudaMalloc(&d_data, n * sizeof(double)));
+    unsigned* d_status = (unsigned*)(c->d_scratch + 1024);
+    cudaError_t e = cudaMemsetAsync(d_data, 0, n * sizeof(double), c->stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(d_status, 0, 4, c->stream);
+    if (e == cudaSuccess && r->len) { e = (cudaError_t)k_spectrum_splat(r->v, r->len, start, step, n, d_data, d_status, c->sms, c->stream); c->launches++; }
+    unsigned* h_status = (unsigned*)(c->h_scratch + 1024);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(values, d_data, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(h_status, d_status, 4, cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    cudaFree(d_data);
+    if (e != cudaSuccess) return fail(OPM_ERR_CUDA, "spectrum kernel failed: %s", cudaGetErrorString(e));
+    return status_from_bits(*h_status);
+}
+extern "C" OpmStatus opm_rays_wavefront_error(const OpmRays* rc, const OpmIsometry* monitor_iso, double wavelength_m, double* xyw_out,
+                                              uint64_t cap, OpmWavefrontStats* out) {
+    OpmRays* r = const_cast<OpmRays*>(rc);
+    if (!r || !monitor_iso || !out) return fail(OPM_ERR_ARG, "NULL argument");
+    OpmContext* c = r->ctx;
+    memset(out, 0, sizeof *out);
+    if (!(wavelength_m > 0.0)) {  // WaveFront::node_report: centre wavelength of to_spectrum(1 nm) (rays.rs:719-726)
+        uint64_t ns = 0;
+        OpmStatus s = opm_rays_to_spectrum(r, 1.0e-9, nullptr, nullptr, nullptr, 0, &ns);
+        if (s) return s;
+        std::vector<double> lam(ns ? ns : 1), val(ns ? ns : 1);
+        s = opm_rays_to_spectrum(r, 1.0e-9, nullptr, lam.data(), val.data(), ns, &ns);
+        if (s) return s;
+        wavelength_m = opm_spectrum_center_wavelength(lam.data(), val.data(), ns);
+    }
+    CU(cudaSetDevice(c->device));
+    OpmStatus s = rays_materialize(r);
+    if (!s) s = rays_refresh_len(r);
+    if (s) return s;
+    const uint64_t n = r->len;
+    WfAccum init;
+    memset(&init, 0, sizeof init);
+    init.min_r_key = double_to_key(INFINITY); init.first_slot = ~0ull;
+    init.max_key = double_to_key(-INFINITY); init.min_key = double_to_key(INFINITY);
+    WfAccum* d_acc = (WfAccum*)(c->d_scratch + 3200);
+    s = dev_put(c, d_acc, &init, sizeof init);
+    if (s) return s;
+    double* d_xyw = nullptr;
+    if (xyw_out && n) CU(cudaMalloc(&d_xyw, n * 3 * sizeof(double)));
+    DevIso inv;
+    to_dev_iso(monitor_iso->inv, inv);
+    cudaError_t e = cudaSuccess;
+    if (n) { e = (cudaError_t)k_wavefront(r->v, n, inv, wavelength_m / 1e-9, d_acc, d_xyw, c->sms, c->stream); c->launches += 4; }
+    WfAccum* h = (WfAccum*)(c->h_scratch + 3200);
+    std::vector<double> tmp;
+    if (e == cudaSuccess) e = cudaMemcpyAsync(h, d_acc, sizeof *h, cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess && d_xyw) { tmp.resize(n * 3); e = cudaMemcpyAsync(tmp.data(), d_xyw, n * 3 * sizeof(double), cudaMemcpyDeviceToHost, c->stream); }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    cudaFree(d_xyw);
+    if (e != cudaSuccess) return fail(OPM_ERR_CUDA, "wavefront kernels failed: %s", cudaGetErrorString(e));
+    out->wavelength_m = wavelength_m;
+    out->n_rays = h->count;
+    if (h->count == 0) return fail(OPM_ERR_EMPTY_WAVEFRONT, "%s", opm_status_string(OPM_ERR_EMPTY_WAVEFRONT));  // nodes/wavefront.rs:121-123
+    out->ptv = key_to_double(h->max_key) - key_to_double(h->min_key);
+    out->rms = std::sqrt(h->sum2 / (double)(int32_t)h->count);
+    if (xyw_out) {
+        uint64_t k = 0;
+        for (uint64_t i = 0; i < n; ++i) {
+            if (std::isnan(tmp[3 * i])) continue;  // not a valid ray
+            if (k >= cap) return fail(OPM_ERR_CAPACITY, "wavefront buffer holds %llu rows, the bundle has %llu valid rays", (unsigned long long)cap, (unsigned long long)h->count);
+            memcpy(xyw_out + 3 * k, tmp.data() + 3 * i, 3 * sizeof(double));
+            ++k;
+        }
+    }
     return OPM_OK;
 }
 

@@ -56,11 +56,13 @@ struct DevDiffract { DevRefract surf; double gvec[3]; double gnorm; double order
 struct DevApodize { DevIso inv; DevAperture ap; };
 struct DevThreshold { double min_energy; };
 struct DevLimits { uint64_t max_bounces, max_refr; int32_t check_refr, _pad; };
-struct DevFilter { double t; };
+// a Spectrum (spectrum.rs:35-37) on the device: ascending wavelength slots [um] and their values; lam == nullptr: none
+struct DevSpectrum { const double* lam; const double* val; uint64_t n; };
+struct DevFilter { double t; DevSpectrum s; };   // s.lam != nullptr: FilterType::Spectrum (ray.rs:712-721)
 struct DevParaxial { double f; DevIso fwd, inv; };
-struct DevSplit { double ratio; DevRays out; };
+struct DevSplit { double ratio; DevRays out; DevSpectrum s; };  // s.lam != nullptr: SplittingConfig::Spectrum (ray.rs:755-761)
 struct DevSnapshot { DevRays out; };
-struct DevFork { double ratio; };
+struct DevFork { double ratio; DevSpectrum s; };
 struct DevJoin { DevRays out; };
 constexpr int kStashWords = 21;  // parked main-bundle ray of a FORK: pos, dir, e, opl, n (18 words) + bounces, refr, flags
 struct DevTransform { DevIso iso; };

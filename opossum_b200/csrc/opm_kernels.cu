@@ -864,4 +864,155 @@ int k_fill_u8(uint8_t* p, uint8_t v, uint64_t n, int sms, void* stream) {
     return (int)cudaGetLastError();
 }
 
+// ---------------------------------------------------------------------------------------------
+// spectrometer and wavefront detectors (spectrum.rs, nodes/spectrometer.rs, nodes/wavefront.rs)
+// ---------------------------------------------------------------------------------------------
+// smallest / largest wavelength and number of the valid rays (Spectrum::from_laser_lines, spectrum.rs:133-142)
+__global__ void __launch_bounds__(256) wavelength_range_kernel(DevRays R, uint64_t n, WvlAccum* acc) {
+    double mn = INFINITY, mx = -INFINITY;
+    unsigned long long cnt = 0;
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        if (R.valid[i] != RAY_VALID) continue;
+        const double w = R.wvl[i];
+        mn = fmin(mn, w); mx = fmax(mx, w); cnt++;
+    }
+    mn = warp_min(mn); mx = warp_max(mx); cnt = warp_sum_u64(cnt);
+    if ((threadIdx.x & 31) == 0 && cnt) {
+        atomicMin(&acc->min_key, dkey(mn)); atomicMax(&acc->max_key, dkey(mx)); atomicAdd(&acc->count, cnt);
+    }
+}
+// Spectrum::add_single_peak (spectrum.rs:193-227) for every valid ray: slot i holds wavelength fma(i, step, start) [um]; the
+// ray's energy per micrometer goes to the two slots around its wavelength.  Slots privatised per CTA in shared memory.
+__global__ void __launch_bounds__(256) spectrum_splat_kernel(DevRays R, uint64_t n, double start, double step, unsigned long long nslots,
+                                                             double* __restrict__ data, int use_smem, unsigned* status_out) {
+    extern __shared__ double sdata[];
+    if (use_smem) {
+        for (unsigned long long k = threadIdx.x; k < nslots; k += blockDim.x) sdata[k] = 0.0;
+        __syncthreads();
+    }
+    double* dst = use_smem ? sdata : data;
+    const double r0 = start * 1e-6;                                    // range(): micrometer!(first)..micrometer!(last)
+    const double r1 = fma((double)(nslots - 1), step, start) * 1e-6;
+    unsigned status = 0;
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        if (R.valid[i] != RAY_VALID) continue;
+        const double wl = R.wvl[i], value = R.e[i];
+        if (!(r0 <= wl && wl < r1)) continue;                          // "peak wavelength is not in spectrum range. Spectrum unmodified."
+        if (value < 0.0 || nslots < 2) { status |= 1u << OPM_ERR_SPECTRUM; continue; }
+        const double w = wl / 1e-6;
+        // first slot with lambda >= w: estimate, then settle with the slots' own arithmetic
+        double g = ceil((w - start) / step);
+        long long idx = g > 0.0 ? (g < (double)nslots ? (long long)g : (long long)nslots) : 0;
+        while (idx > 0 && fma((double)(idx - 1), step, start) >= w) --idx;
+        while (idx < (long long)nslots && fma((double)idx, step, start) < w) ++idx;
+        if (idx >= (long long)nslots) { status |= 1u << OPM_ERR_SPECTRUM; continue; }  // "insertion point not found"
+        if (idx == 0) {
+            const double delta = fma(1.0, step, start) - start;
+            atomicAdd(&dst[0], value / delta);
+        } else {
+            const double lower = fma((double)(idx - 1), step, start), upper = fma((double)idx, step, start);
+            const double delta = upper - lower;
+            const double epm = value / delta;
+            const double part = epm * (w - lower) / delta;
+            atomicAdd(&dst[idx], part);
+            atomicAdd(&dst[idx - 1], epm - part);
+        }
+    }
+    if (use_smem) {
+        __syncthreads();
+        for (unsigned long long k = threadIdx.x; k < nslots; k += blockDim.x) {
+            const double v = sdata[k];
+            if (v != 0.0) atomicAdd(&data[k], v);
+        }
+    }
+    if (status) atomicOr(status_out, status);
+}
+
+// Rays::wavefront_error_at_pos_in_units_of_wvl (rays.rs:769-802).  x, y in mm in the monitor frame; the reference ray is
+// the valid ray with the smallest x^2 + y^2, the first one in bundle order on ties.
+__device__ __forceinline__ void wf_xy(const DevRays& R, uint64_t i, const DevIso& inv, double& x, double& y) {
+    const V3 p = iso_point(inv, v3(R.px[i], R.py[i], R.pz[i]));
+    x = p.x / 1e-3; y = p.y / 1e-3;
+}
+__global__ void __launch_bounds__(256) wavefront_center1_kernel(DevRays R, uint64_t n, DevIso inv, WfAccum* acc) {
+    double mn = INFINITY;
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        if (R.valid[i] != RAY_VALID) continue;
+        double x, y;
+        wf_xy(R, i, inv, x, y);
+        mn = fmin(mn, fma(x, x, y * y));
+    }
+    mn = warp_min(mn);
+    if ((threadIdx.x & 31) == 0 && mn < INFINITY) atomicMin(&acc->min_r_key, dkey(mn));
+}
+__global__ void __launch_bounds__(256) wavefront_center2_kernel(DevRays R, uint64_t n, DevIso inv, WfAccum* acc) {
+    const unsigned long long key = acc->min_r_key;
+    unsigned long long first = ~0ull;
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        if (R.valid[i] != RAY_VALID) continue;
+        double x, y;
+        wf_xy(R, i, inv, x, y);
+        if (dkey(fma(x, x, y * y)) == key && i < first) first = i;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { unsigned long long t = __shfl_xor_sync(0xffffffffu, first, o); first = t < first ? t : first; }
+    if ((threadIdx.x & 31) == 0 && first != ~0ull) atomicMin(&acc->first_slot, first);
+}
+// pass 3: error of every valid ray (optionally written slot-indexed, NaN = not a valid ray), max / min / sum / count;
+// pass 4 (second = 1): sum of squared deviations from the mean of pass 3
+__global__ void __launch_bounds__(256) wavefront_stats_kernel(DevRays R, uint64_t n, DevIso inv, double wvl_nm, WfAccum* acc,
+                                                              double* __restrict__ xyw, int second) {
+    const unsigned long long fs = acc->first_slot;
+    const double center = fs != ~0ull ? -(R.opl[fs] / 1e-9) : 0.0;
+    const double avg = second ? acc->sum / (double)acc->count : 0.0;
+    double mx = -INFINITY, mn = INFINITY, sum = 0.0;
+    unsigned long long cnt = 0;
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        const bool ok = R.valid[i] == RAY_VALID;
+        double x = NAN, y = NAN, wf = NAN;
+        if (ok) {
+            wf_xy(R, i, inv, x, y);
+            wf = -(R.opl[i] / 1e-9);
+            wf -= center;
+            wf /= wvl_nm;
+            if (second) { const double d = wf - avg; sum += d * d; }
+            else { mx = fmax(mx, wf); mn = fmin(mn, wf); sum += wf; cnt++; }
+        }
+        if (!second && xyw) { xyw[3 * i] = x; xyw[3 * i + 1] = y; xyw[3 * i + 2] = wf; }
+    }
+    sum = warp_sum(sum);
+    if (second) {
+        if ((threadIdx.x & 31) == 0) atomicAdd(&acc->sum2, sum);
+        return;
+    }
+    mx = warp_max(mx); mn = warp_min(mn); cnt = warp_sum_u64(cnt);
+    if ((threadIdx.x & 31) == 0 && cnt) {
+        atomicMax(&acc->max_key, dkey(mx)); atomicMin(&acc->min_key, dkey(mn)); atomicAdd(&acc->sum, sum); atomicAdd(&acc->count, cnt);
+    }
+}
+
+int k_wavelength_range(DevRays R, uint64_t n, WvlAccum* acc, int sms, void* stream) {
+    wavelength_range_kernel<<<grid_for(n, 256, sms * 8), 256, 0, ST>>>(R, n, acc);
+    return (int)cudaGetLastError();
+}
+int k_spectrum_splat(DevRays R, uint64_t n, double start_um, double step_um, uint64_t nslots, double* data, unsigned* status, int sms,
+                     void* stream) {
+    const size_t bytes = (size_t)nslots * sizeof(double);
+    const int use_smem = bytes <= 96 * 1024;
+    if (use_smem) {
+        cudaError_t e = cudaFuncSetAttribute(spectrum_splat_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+        if (e != cudaSuccess) return (int)e;
+    }
+    spectrum_splat_kernel<<<grid_for(n, 256, sms * 2), 256, use_smem ? bytes : 0, ST>>>(R, n, start_um, step_um, nslots, data, use_smem, status);
+    return (int)cudaGetLastError();
+}
+int k_wavefront(DevRays R, uint64_t n, DevIso inv, double wvl_nm, WfAccum* acc, double* xyw, int sms, void* stream) {
+    const int g = grid_for(n, 256, sms * 8);
+    wavefront_center1_kernel<<<g, 256, 0, ST>>>(R, n, inv, acc);
+    wavefront_center2_kernel<<<g, 256, 0, ST>>>(R, n, inv, acc);
+    wavefront_stats_kernel<<<g, 256, 0, ST>>>(R, n, inv, wvl_nm, acc, xyw, 0);
+    wavefront_stats_kernel<<<g, 256, 0, ST>>>(R, n, inv, wvl_nm, acc, nullptr, 1);
+    return (int)cudaGetLastError();
+}
+
 }  // namespace opm

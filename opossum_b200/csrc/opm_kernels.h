@@ -12,6 +12,9 @@ struct SpotAccum {
 };
 struct BBoxAccum { unsigned long long key[4]; unsigned long long count; };  // left,right,top,bottom as ordered keys
 struct PeakAccum { unsigned long long peak_key; double total; };
+struct WvlAccum { unsigned long long min_key, max_key, count; };  // init: key(+inf), key(-inf), 0
+// wavefront detector accumulators; init: min_r_key = key(+inf), first_slot = ~0, max_key = key(-inf), min_key = key(+inf), rest 0
+struct WfAccum { unsigned long long min_r_key, first_slot, max_key, min_key, count; double sum, sum2; };
 struct BinParams {
     unsigned long long nx, ny;
     double left, bottom, width_step, height_step, bin_area;
@@ -72,6 +75,10 @@ int k_expand_collimated(const double* xyz, const double* e_pos, const double* wv
 int k_compact(DevRays S, DevRays D, uint64_t n, unsigned* counts, unsigned long long* offsets, unsigned long long* total, void* stream);
 int k_history_gather(const HistParams& hp, uint32_t levels, DevRays R, uint64_t n, int with_current, uint32_t pos_cap, double* xyz,
                      uint32_t* len, int sms, void* stream);
+int k_wavelength_range(DevRays R, uint64_t n, WvlAccum* acc, int sms, void* stream);
+int k_spectrum_splat(DevRays R, uint64_t n, double start_um, double step_um, uint64_t nslots, double* data, unsigned* status, int sms,
+                     void* stream);
+int k_wavefront(DevRays R, uint64_t n, DevIso inv, double wvl_nm, WfAccum* acc, double* xyw, int sms, void* stream);
 int k_fp64_peak(double* out, int iters, int blocks, void* stream);
 int k_fetch_from_host(void* dst, const void* src_host, size_t bytes, void* stream);  // bytes % 8 == 0, src pinned + mapped
 int k_set_u64(unsigned long long* p, unsigned long long v, void* stream);

@@ -281,7 +281,8 @@ struct Runner {
 };
 
 bool is_detector(int type) {
-    return type == OPM_NODE_SPOT_DIAGRAM || type == OPM_NODE_FLUENCE_DETECTOR || type == OPM_NODE_RAY_PROPAGATION_VISUALIZER;
+    return type == OPM_NODE_SPOT_DIAGRAM || type == OPM_NODE_FLUENCE_DETECTOR || type == OPM_NODE_RAY_PROPAGATION_VISUALIZER ||
+           type == OPM_NODE_SPECTROMETER || type == OPM_NODE_WAVEFRONT;
 }
 
 OpmHitMap* new_hitmap(OpmScene* sc, SurfaceState& s, uint64_t uuid, uint64_t n, OpmStatus* st) {
@@ -370,7 +371,7 @@ OpmStatus compile_node_rt(OpmScene* sc, Node& n, const OpmRayTraceConfig& cfg, i
             if (n.side_inlined) {
                 // the second output's side chain runs in this launch on the split-off rays (same ops the separate launch
                 // would run: out2 aperture in the frame of out1, threshold, limits, then the side chain's nodes)
-                op.kind = OPM_OP_FORK; op.u.fork.ratio = n.d.p[0];
+                op.kind = OPM_OP_FORK; op.u.fork.ratio = n.d.p[0]; op.u.fork.spectrum = n.d.spectrum;
                 R.push(op);
                 R.push(op_apodize(n.s[1].aperture, n.s[1].eff_iso));
                 R.push(op_threshold(thr));
@@ -383,7 +384,7 @@ OpmStatus compile_node_rt(OpmScene* sc, Node& n, const OpmRayTraceConfig& cfg, i
                 op.kind = OPM_OP_JOIN; op.u.join.out = n.split;
                 R.push(op);
             } else {
-                op.kind = OPM_OP_SPLIT; op.u.split.ratio = n.d.p[0]; op.u.split.split_out = n.split;
+                op.kind = OPM_OP_SPLIT; op.u.split.ratio = n.d.p[0]; op.u.split.split_out = n.split; op.u.split.spectrum = n.d.spectrum;
                 R.push(op);
             }
             R.push(op_apodize(n.s[1].aperture, n.s[1].eff_iso));  // out1 aperture, iso of out1_port
@@ -399,7 +400,7 @@ OpmStatus compile_node_rt(OpmScene* sc, Node& n, const OpmRayTraceConfig& cfg, i
             if (n.d.type == OPM_NODE_IDEAL_FILTER) {
                 OpmOp op;
                 memset(&op, 0, sizeof op);
-                op.kind = OPM_OP_FILTER; op.u.filter.transmission = n.d.p[0];
+                op.kind = OPM_OP_FILTER; op.u.filter.transmission = n.d.p[0]; op.u.filter.spectrum = n.d.spectrum;
                 R.push(op);
             } else if (n.d.type == OPM_NODE_PARAXIAL_SURFACE) {
                 OpmOp op;
@@ -415,6 +416,8 @@ OpmStatus compile_node_rt(OpmScene* sc, Node& n, const OpmRayTraceConfig& cfg, i
         }
         case OPM_NODE_SPOT_DIAGRAM:
         case OPM_NODE_RAY_PROPAGATION_VISUALIZER:
+        case OPM_NODE_SPECTROMETER:
+        case OPM_NODE_WAVEFRONT:
         case OPM_NODE_FLUENCE_DETECTOR: {  // pass_through_detector_surface analyzers/raytrace.rs:150-207
             OpmHitMap* h0 = hits_for(n.s[0]);
             if (st) return st;
@@ -607,6 +610,21 @@ extern "C" OpmStatus opm_scene_node_spot_async(OpmScene* sc, int32_t node, int32
     if (!n.stored) return OPM_ERR_ARG;
     return phase == 1 ? opm_rays_spot_sums_async(n.stored, &n.s[0].eff_iso, sums_dev)
                       : opm_rays_spot_radii_async(n.stored, &n.s[0].eff_iso, sums_dev, radii_dev);
+}
+// Spectrometer::node_report (nodes/spectrometer.rs:155-175): to_spectrum(0.2 nm) of the kept bundle
+extern "C" OpmStatus opm_scene_node_spectrum(OpmScene* sc, int32_t node, double resolution_m, const double* range_m, double* lambda_um,
+                                             double* values, uint64_t cap, uint64_t* n_out) {
+    if (!sc || node < 0 || node >= (int)sc->nodes.size()) return OPM_ERR_ARG;
+    Node& n = *sc->nodes[node];
+    if (!n.stored) return OPM_ERR_ARG;
+    return opm_rays_to_spectrum(n.stored, resolution_m > 0.0 ? resolution_m : 0.2e-9, range_m, lambda_um, values, cap, n_out);
+}
+// WaveFront::node_report (nodes/wavefront.rs:173-235): monitor frame = effective_surface_iso("input_1")
+extern "C" OpmStatus opm_scene_node_wavefront(OpmScene* sc, int32_t node, double* xyw_out, uint64_t cap, OpmWavefrontStats* out) {
+    if (!sc || !out || node < 0 || node >= (int)sc->nodes.size()) return OPM_ERR_ARG;
+    Node& n = *sc->nodes[node];
+    if (!n.stored) return OPM_ERR_ARG;
+    return opm_rays_wavefront_error(n.stored, &n.s[0].eff_iso, 0.0, xyw_out, cap, out);
 }
 extern "C" int32_t opm_scene_node_hitmaps(OpmScene* sc, int32_t node, int32_t surface, OpmHitMap** out, int32_t cap) {
     if (!sc || node < 0 || node >= (int)sc->nodes.size() || surface < 0 || surface > 1) return 0;

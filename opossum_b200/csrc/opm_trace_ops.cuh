@@ -196,9 +196,21 @@ __device__ __forceinline__ void exec_limits(const DevLimits& o, RayCtx& x) {
     if ((uint64_t)x.r.bounces > o.max_bounces) x.valid = false;
     if (o.check_refr && (uint64_t)x.r.refr >= o.max_refr) x.valid = false;
 }
+// the per-ray splitting ratio / transmission of a spectrum-driven op (ray.rs:712-721, 755-761); false = the wavelength is
+// outside the spectrum (the reference returns an error: the ray raises OPM_ERR_SPECTRUM)
+__device__ __forceinline__ bool spectral_factor(const DevSpectrum& s, double fixed, RayCtx& x, double& f) {
+    f = fixed;
+    if (s.lam == nullptr) return true;
+    if (spectrum_get_value(s, x.r.wvl, f)) return true;
+    x.c.status |= 1u << OPM_ERR_SPECTRUM;
+    x.valid = false;
+    return false;
+}
 // rays.rs:1119-1133
 __device__ __forceinline__ void exec_filter(const DevFilter& o, RayCtx& x) {
-    if (x.valid) x.r.e *= o.t;
+    if (!x.valid) return;
+    double t;
+    if (spectral_factor(o.s, o.t, x, t)) x.r.e *= t;
 }
 // rays.rs:943-959
 __device__ __forceinline__ void exec_paraxial(const DevParaxial& o, RayCtx& x) {
@@ -209,8 +221,15 @@ __device__ __forceinline__ void exec_split(const DevSplit& o, RayCtx& x) {
     if (!x.in_range) return;
     if (x.alive) {
         RayState s = x.r;
-        if (x.valid) { x.r.e *= o.ratio; s.e *= 1.0 - o.ratio; }
-        if (o.out.px != nullptr) store_ray<true>(o.out, x.i, s, x.valid ? RAY_VALID : RAY_INVALID);
+        const bool was_valid = x.valid;
+        if (x.valid) {
+            double ratio;
+            if (spectral_factor(o.s, o.ratio, x, ratio)) {
+                if (o.s.lam != nullptr && !(ratio >= 0.0 && ratio <= 1.0)) { x.c.status |= 1u << OPM_ERR_SPLIT_RATIO; x.valid = false; }
+                else { x.r.e *= ratio; s.e *= 1.0 - ratio; }
+            }
+        }
+        if (o.out.px != nullptr) store_ray<true>(o.out, x.i, s, was_valid && x.valid ? RAY_VALID : RAY_INVALID);
     } else if (o.out.px != nullptr) {
         o.out.valid[x.i] = RAY_REMOVED;
     }
@@ -226,14 +245,18 @@ __device__ __forceinline__ double stash_get(const unsigned* stash, int f) {
     return __hiloint2double((int)stash[(2 * f + 1) * blockDim.x + threadIdx.x], (int)stash[(2 * f) * blockDim.x + threadIdx.x]);
 }
 __device__ __forceinline__ void exec_fork(const DevFork& o, RayCtx& x, unsigned* stash) {
-    const double e_main = x.valid ? x.r.e * o.ratio : x.r.e;  // invalid rays are copied unchanged (rays.rs:1258-1262)
+    double ratio = o.ratio;
+    if (x.valid && spectral_factor(o.s, o.ratio, x, ratio) && o.s.lam != nullptr && !(ratio >= 0.0 && ratio <= 1.0)) {
+        x.c.status |= 1u << OPM_ERR_SPLIT_RATIO; x.valid = false;
+    }
+    const double e_main = x.valid ? x.r.e * ratio : x.r.e;  // invalid rays are copied unchanged (rays.rs:1258-1262)
     stash_put(stash, 0, x.r.pos.x); stash_put(stash, 1, x.r.pos.y); stash_put(stash, 2, x.r.pos.z);
     stash_put(stash, 3, x.r.dir.x); stash_put(stash, 4, x.r.dir.y); stash_put(stash, 5, x.r.dir.z);
     stash_put(stash, 6, e_main); stash_put(stash, 7, x.r.opl); stash_put(stash, 8, x.r.n);
     stash[18 * blockDim.x + threadIdx.x] = x.r.bounces;
     stash[19 * blockDim.x + threadIdx.x] = x.r.refr;
     stash[20 * blockDim.x + threadIdx.x] = (x.alive ? 1u : 0u) | (x.valid ? 2u : 0u);
-    if (x.valid) x.r.e *= 1.0 - o.ratio;
+    if (x.valid) x.r.e *= 1.0 - ratio;
 }
 __device__ __forceinline__ void exec_join(const DevJoin& o, RayCtx& x, const unsigned* stash) {
     if (x.in_range && o.out.px != nullptr) {

@@ -69,6 +69,12 @@ class Node:
         self.c.lidt = lidt_j_per_m2
         return self
 
+    def with_spectrum(self, spectrum):
+        """IdealFilter: FilterType::Spectrum; BeamSplitter: SplittingConfig::Spectrum (api.Spectrum, kept alive by the node)"""
+        self._spectrum = spectrum
+        self.c.spectrum = spectrum.h if spectrum is not None else None
+        return self
+
     def fed_by(self, parent: int, port: int = 0):
         self.c.parent, self.c.parent_port = parent, port
         return self
@@ -154,6 +160,16 @@ def SpotDiagram(iso=None):
 
 def FluenceDetector(iso=None):
     return Node(F.NODE_FLUENCE_DETECTOR, iso)
+
+
+def Spectrometer(iso=None):
+    """nodes/spectrometer.rs: detector whose report is Rays::to_spectrum(0.2 nm) of the bundle it keeps (Scene.node_spectrum)"""
+    return Node(F.NODE_SPECTROMETER, iso)
+
+
+def WaveFront(iso=None):
+    """nodes/wavefront.rs: detector whose report is the wavefront error map with PtV and RMS (Scene.node_wavefront)"""
+    return Node(F.NODE_WAVEFRONT, iso)
 
 
 def RayPropagationVisualizer(iso=None):
@@ -255,6 +271,27 @@ class Scene:
                                               m.ctypes.data_as(C.POINTER(C.c_double)) if download else None, lrtb,
                                               C.byref(peak), C.byref(tot)))
         return FluenceData(m.reshape(nx, ny).T.copy() if download else None, tuple(lrtb[:]), peak.value, tot.value)
+
+    def node_spectrum(self, node: int, resolution: float = 0.0, wavelength_range=None):
+        """Spectrometer::node_report (nodes/spectrometer.rs:155-175) -> (slots [um], values [1/um])"""
+        rng = (C.c_double * 2)(*wavelength_range) if wavelength_range is not None else None
+        n = C.c_uint64()
+        _check(F.lib().opm_scene_node_spectrum(self.h, node, resolution, rng, None, None, 0, C.byref(n)))
+        lam, val = np.zeros(max(n.value, 1)), np.zeros(max(n.value, 1))
+        dp = C.POINTER(C.c_double)
+        _check(F.lib().opm_scene_node_spectrum(self.h, node, resolution, rng, lam.ctypes.data_as(dp), val.ctypes.data_as(dp), n.value,
+                                               C.byref(n)))
+        return lam[: n.value], val[: n.value]
+
+    def node_wavefront(self, node: int, want_map: bool = True):
+        """WaveFront::node_report (nodes/wavefront.rs:173-235) -> (OpmWavefrontStats, (n_valid, 3) rows x mm, y mm, error in wavelengths)"""
+        st = F.OpmWavefrontStats()
+        r = self.node_rays(node)
+        n = len(r) if r is not None else 0
+        xyw = np.zeros((max(n, 1), 3)) if want_map else None
+        _check(F.lib().opm_scene_node_wavefront(self.h, node, xyw.ctypes.data_as(C.POINTER(C.c_double)) if want_map else None,
+                                                max(n, 1), C.byref(st)))
+        return st, (xyw[: st.n_rays] if want_map else None)
 
     def node_hitmaps(self, node: int, surface: int = 0):
         n = F.lib().opm_scene_node_hitmaps(self.h, node, surface, None, 0)

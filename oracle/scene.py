@@ -14,7 +14,7 @@ import numpy as np
 from . import oracle as orc
 
 (SOURCE, LENS, CYLINDRIC_LENS, WEDGE, THIN_MIRROR, PARABOLIC_MIRROR, BEAM_SPLITTER, DUMMY, IDEAL_FILTER, PARAXIAL_SURFACE,
- SPOT_DIAGRAM, FLUENCE_DETECTOR, REFLECTIVE_GRATING, RAY_PROPAGATION_VISUALIZER) = range(14)
+ SPOT_DIAGRAM, FLUENCE_DETECTOR, REFLECTIVE_GRATING, RAY_PROPAGATION_VISUALIZER, SPECTROMETER, WAVEFRONT) = range(16)
 
 
 @dataclass
@@ -77,8 +77,9 @@ def _surface(geom, param, iso, coating):
 
 class ONode:
     def __init__(self, node_type, iso=None, p=(), index=None, coating_in=None, coating_out=None, aperture_in=None,
-                 aperture_out=None, alignment=None, lidt=1.0e4, parent=-1, parent_port=0):
+                 aperture_out=None, alignment=None, lidt=1.0e4, parent=-1, parent_port=0, spectrum=None):
         self.type, self.p, self.index = node_type, tuple(p), index
+        self.spectrum = spectrum  # (slots [um], values): FilterType::Spectrum / SplittingConfig::Spectrum
         self.parent, self.parent_port = parent, parent_port
         mirror = node_type in (THIN_MIRROR, PARABOLIC_MIRROR)
         default_coat = (orc.COAT_CONSTANT_R, 1.0) if mirror else (orc.COAT_IDEAL_AR, 0.0)  # thin_mirror.rs:67-82
@@ -199,7 +200,7 @@ class OScene:
         elif t == BEAM_SPLITTER:  # beam_splitter/mod.rs:158-293
             self._refract(rays, n.s[0], None, True, strat, record=record_all, want_children=False)
             orc.rays_apodize(rays, n.s[0].aperture, n.s[0].eff_iso, self.nt)
-            split = orc.rays_split(rays, n.p[0])
+            split = orc.rays_split_spectrum(rays, *n.spectrum) if n.spectrum is not None else orc.rays_split(rays, n.p[0])
             orc.rays_apodize(rays, n.s[1].aperture, n.s[1].eff_iso, self.nt)
             orc.rays_threshold(rays, thr, self.nt)
             if self.hist is not None:  # the split-off clones carry the history up to here; their own pushes go to their copy
@@ -215,7 +216,10 @@ class OScene:
         elif t in (DUMMY, IDEAL_FILTER, PARAXIAL_SURFACE):  # dummy.rs:83-135, ideal_filter.rs:203-250, paraxial_surface.rs:169-230
             self._refract(rays, n.s[0], None, True, strat, record=record_all, want_children=False)
             if t == IDEAL_FILTER:
-                orc.rays_filter_energy(rays, n.p[0])
+                if n.spectrum is not None:
+                    orc.rays_filter_energy_spectrum(rays, *n.spectrum)
+                else:
+                    orc.rays_filter_energy(rays, n.p[0])
             if t == PARAXIAL_SURFACE:
                 orc.rays_refract_paraxial(rays, n.p[0], n.s[0].eff_iso)
             for ap in (n.s[0].aperture, n.s[1].aperture):
@@ -278,6 +282,16 @@ class OScene:
     def node_fluence(self, node: int, nx=100, ny=83):  # fluence_detector/mod.rs:91-135 (Binning)
         fmap, lrtb = orc.fluence_binning(self.nodes[node].s[0].merged_hits(), nx, ny)
         return fmap, lrtb, orc.fluence_peak(fmap), orc.fluence_total_energy(fmap, lrtb)
+
+    def node_spectrum(self, node: int, resolution=0.2e-9):  # nodes/spectrometer.rs:155-175
+        return orc.rays_to_spectrum(self.nodes[node].stored, resolution)
+
+    def node_wavefront(self, node: int):  # nodes/wavefront.rs:173-235, rays.rs:713-726
+        n = self.nodes[node]
+        wvl = orc.spectrum_center_wavelength(*orc.rays_to_spectrum(n.stored, 1.0e-9))
+        xyw = orc.rays_wavefront_error(n.stored, wvl, n.s[0].eff_iso)
+        ptv, rms = orc.wavefront_statistics(xyw)
+        return {"wavelength": wvl, "ptv": ptv, "rms": rms, "map": xyw}
 
     def node_spot(self, node: int):  # spot_diagram.rs:101-163
         n = self.nodes[node]

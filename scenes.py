@@ -112,7 +112,7 @@ def c5_source(n_pos, n_wvl=64):
 # ---------------------------------------------------------------------------------------------------------------
 KIND_IDS = {"source": 0, "lens": 1, "cylindric_lens": 2, "wedge": 3, "thin_mirror": 4, "parabolic_mirror": 5, "beam_splitter": 6,
             "dummy": 7, "ideal_filter": 8, "paraxial_surface": 9, "spot_diagram": 10, "fluence_detector": 11, "reflective_grating": 12,
-            "ray_propagation_visualizer": 13}
+            "ray_propagation_visualizer": 13, "spectrometer": 14, "wavefront": 15}
 
 
 def to_product(ctx, nodes):
@@ -139,6 +139,8 @@ def to_product(ctx, nodes):
             n.with_alignment(*d["alignment"])
         if "lidt" in d:
             n.with_lidt(d["lidt"])
+        if "spectrum" in d:  # (wavelength slots [um], values): FilterType::Spectrum / SplittingConfig::Spectrum
+            n.with_spectrum(ob.Spectrum(ctx, *d["spectrum"]))
         n.fed_by(d.get("parent", -1), d.get("parent_port", 0))
         sc.add_node(n)
     return sc
@@ -162,7 +164,7 @@ def to_oracle(nodes, n_threads=1):
         align = orc.Isometry.new(*d["alignment"]) if "alignment" in d else None
         out.append(OS.ONode(KIND_IDS[d["kind"]], orc.Isometry.new(d["t"], d["euler"]), d.get("p", ()), idx, coat(d.get("coat_in")),
                             coat(d.get("coat_out")), ap(d.get("ap_in")), ap(d.get("ap_out")), align, d.get("lidt", 1.0e4),
-                            d.get("parent", -1), d.get("parent_port", 0)))
+                            d.get("parent", -1), d.get("parent_port", 0), spectrum=d.get("spectrum")))
     return OS.OScene(out, n_threads=n_threads)
 
 

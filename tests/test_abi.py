@@ -32,6 +32,21 @@ def test_struct_layouts():
     assert C.sizeof(F.OpmOp) == 384 and C.sizeof(F.OpmTraceStats) == 72
 
 
+def test_ctypes_mirrors_have_the_sizes_the_library_was_compiled_with():
+    """every structure of include/*.h that the Python binding mirrors: sizeof on the C side == ctypes.sizeof"""
+    L = F.lib()
+    names = ["OpmRay", "OpmIso", "OpmIsometry", "OpmSurface", "OpmIndexModel", "OpmApertureItem", "OpmAperture", "OpmTraceStats",
+             "OpmRefractOp", "OpmDiffractOp", "OpmFilterOp", "OpmSplitOp", "OpmForkOp", "OpmOp", "OpmSpotStats", "OpmSpotPartial",
+             "OpmSourceDesc", "OpmRayTraceConfig", "OpmWavefrontStats", "OpmNodeDesc", "OpmCoatingDesc", "OpmGhostFocusConfig",
+             "OpmGhostFocusStats", "OpmCriticalFluence"]
+    for name in names:
+        c_size = L.opm_abi_sizeof(name.encode())
+        assert c_size > 0, name
+        assert hasattr(F, name), f"no ctypes mirror of {name}"
+        assert C.sizeof(getattr(F, name)) == c_size, f"{name}: ctypes {C.sizeof(getattr(F, name))} vs C {c_size}"
+    assert L.opm_abi_sizeof(b"NoSuchStruct") == 0
+
+
 def test_enums_match_oracle():
     assert (F.GEOM_PLANE, F.GEOM_SPHERE, F.GEOM_CYLINDER, F.GEOM_PARABOLA) == (
         orc.GEOM_PLANE, orc.GEOM_SPHERE, orc.GEOM_CYLINDER, orc.GEOM_PARABOLA)
