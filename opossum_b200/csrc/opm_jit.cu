@@ -48,6 +48,8 @@ struct JitKernel {
     size_t const_bytes = 0;
     int n_ops = 0;
     int occupancy = 1;
+    bool has_fork = false;
+    size_t smem = 0;  // dynamic shared memory per CTA
     std::string why;
 };
 
@@ -140,7 +142,27 @@ std::string op_line(const DevOp& op, int k) {
     return s;
 }
 
+// staged tile loads (tile_load_staged, opm_trace_ops.cuh): OPM_B200_JIT_PIPE=1.  Off by default: measured on the C2 chain the
+// kernel takes 1.954 ms with them and 1.955 ms without (profiles/r1_summary.md) -- the other resident CTAs already hide the
+// load latency of a tile.
+static bool jit_pipe_enabled() {
+    static const bool on = [] { const char* e = getenv("OPM_B200_JIT_PIPE"); return e && e[0] == '1'; }();
+    return on;
+}
+static size_t jit_stage_bytes(int block) { return ((size_t)block * kRayBytes + 127) & ~(size_t)127; }
+static bool program_has_fork(const DevOp* ops, int n_ops) {
+    for (int k = 0; k < n_ops; ++k) if (ops[k].kind == OPK_FORK) return true;
+    return false;
+}
+// dynamic shared memory of a specialised kernel: [parked rays of a FORK | stage 0 | stage 1]
+static size_t jit_stash_bytes(bool has_fork, int block) { return has_fork ? (((size_t)block * kStashWords * 4 + 127) & ~(size_t)127) : 0; }
+size_t jit_dynamic_smem(bool has_fork, int block) {
+    return jit_stash_bytes(has_fork, block) + (jit_pipe_enabled() && block % 16 == 0 ? 2 * jit_stage_bytes(block) : 0);
+}
+
 std::string make_source(const DevOp* ops, int n_ops, bool compact, int block, int min_ctas) {
+    const bool pipe = jit_pipe_enabled() && block % 16 == 0;
+    const size_t stash = jit_stash_bytes(program_has_fork(ops, n_ops), block);
     std::string body;
     for (int k = 0; k < n_ops; ++k) body += op_line(ops[k], k);
     std::string s;
@@ -149,18 +171,25 @@ std::string make_source(const DevOp* ops, int n_ops, bool compact, int block, in
     appendf(s, "extern \"C\" __global__ void __launch_bounds__(%d, %d)\n", block, min_ctas);
     s += "opm_jit_trace(DevRays in, DevRays out, unsigned long long n, unsigned long long out_cap, unsigned long long* out_tail,\n"
          "              DevStats* stats) {\n"
-         "    extern __shared__ unsigned opm_jit_stash[];  // parked main-bundle rays of a FORK (sized by the launch)\n"
+         "    extern __shared__ __align__(128) unsigned char opm_jit_smem[];  // [parked rays of a FORK | tile stages], sized by the launch\n"
+         "    unsigned* opm_jit_stash = reinterpret_cast<unsigned*>(opm_jit_smem);\n"
          "    __shared__ unsigned long long s_cnt[CNT_N];\n"
          "    __shared__ unsigned s_status;\n"
          "    __shared__ unsigned long long s_first_inv;\n"
          "    if (threadIdx.x < CNT_N) s_cnt[threadIdx.x] = 0ull;\n"
          "    if (threadIdx.x == 0) { s_status = 0u; s_first_inv = 0ull; }\n"
          "    __syncthreads();\n"
-         "    const unsigned tiles = (unsigned)((n + blockDim.x - 1) / blockDim.x);\n"
-         "    for (unsigned tile = blockIdx.x; tile < tiles; tile += gridDim.x) {\n"
+         "    const unsigned tiles = (unsigned)((n + blockDim.x - 1) / blockDim.x);\n";
+    if (pipe) {
+        s += "    __shared__ unsigned long long s_bar[2];\n"
+             "    TilePipe pipe;\n";
+        appendf(s, "    tile_pipe_init(pipe, opm_jit_smem + %zu, s_bar, in, n);\n", stash);
+    }
+    s += "    for (unsigned tile = blockIdx.x; tile < tiles; tile += gridDim.x) {\n"
          "        RayCtx x;\n"
-         "        uint8_t vb;\n"
-         "        tile_load(in, (uint64_t)tile * blockDim.x + threadIdx.x, n, x, vb);\n";
+         "        uint8_t vb;\n";
+    s += pipe ? "        tile_load_staged(pipe, in, tile, n, x, vb);\n"
+              : "        tile_load(in, (uint64_t)tile * blockDim.x + threadIdx.x, n, x, vb);\n";
     s += body;
     appendf(s, "        tile_store<%s>(in, out, out_cap, out_tail, x, vb);\n", compact ? "true" : "false");
     s += "        tile_count(x, s_cnt, &s_status, &s_first_inv);\n"
@@ -220,7 +249,12 @@ bool load(JitKernel& K, int n_ops, int block) {
     if (e != cudaSuccess) { K.why = std::string("cudaLibraryGetKernel/Global: ") + cudaGetErrorString(e); cudaGetLastError(); return false; }
     if (K.const_bytes < (size_t)n_ops * sizeof(DevOp)) { K.why = "constant array smaller than the program"; return false; }
     int nb = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, (const void*)K.kernel, block, 0) != cudaSuccess || nb < 1) { nb = 1; cudaGetLastError(); }
+    K.smem = jit_dynamic_smem(K.has_fork, block);
+    if (K.smem > 48 * 1024 &&
+        cudaFuncSetAttribute((const void*)K.kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K.smem) != cudaSuccess) {
+        K.why = "dynamic shared memory of the specialised kernel not available"; cudaGetLastError(); return false;
+    }
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, (const void*)K.kernel, block, K.smem) != cudaSuccess || nb < 1) { nb = 1; cudaGetLastError(); }
     K.occupancy = nb;
     K.n_ops = n_ops;
     K.cubin.clear();
@@ -282,6 +316,7 @@ const JitKernel* jit_get(JitCache* cache, const DevOp* ops, int n_ops, bool comp
     if (it == cache->kernels.end()) {
         it = cache->kernels.emplace(std::move(src), std::unique_ptr<JitKernel>(new JitKernel())).first;
         JitKernel* k = it->second.get();
+        k->has_fork = program_has_fork(ops, n_ops);
         if (!nvrtc_load(&k->why)) {
             k->state = JIT_FAILED;
             cache->failures++;
@@ -366,8 +401,7 @@ int jit_launch(JitCache* cache, const JitKernel* K, const TraceLaunch& L, const 
     unsigned long long* tail = L.out_tail;
     DevStats* stats = L.stats;
     void* args[] = {&in, &out, &n, &cap, &tail, &stats};
-    const size_t smem = L.has_fork ? (size_t)L.block * kStashWords * 4 : 0;
-    cudaError_t e = cudaLaunchKernel((const void*)K->kernel, dim3(L.grid), dim3(L.block), args, smem, st);
+    cudaError_t e = cudaLaunchKernel((const void*)K->kernel, dim3(L.grid), dim3(L.block), args, K->smem, st);
     if (e != cudaSuccess) return (int)e;
     cache->launches++;
     return (int)cudaGetLastError();

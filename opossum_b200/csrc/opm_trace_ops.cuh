@@ -299,6 +299,100 @@ __device__ __forceinline__ void tile_load(const DevRays& in, uint64_t i, uint64_
     x.valid = vb == RAY_VALID;
 }
 
+// ---- staged tile loads (run-time specialised kernel) ---------------------------------------------------------------
+// One elected thread copies whole tiles of the bundle -- 14 contiguous field segments of blockDim.x rays -- into shared
+// memory with TMA bulk copies (cp.async.bulk -> UBLKCP) two tiles ahead of the compute; the CTA's warps find their ray
+// state on chip when they get to the tile instead of waiting on 14 global loads each.  Two stages, one mbarrier per
+// stage; a stage is re-armed after a block barrier that follows the last read of it.  A trailing partial tile takes the
+// direct path (tile_load).
+__device__ __forceinline__ unsigned smem_addr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+    unsigned done;
+    do {  // try_wait suspends the thread in hardware until the phase completes or a time limit passes
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(done)
+                     : "r"(smem_addr(bar)), "r"(parity)
+                     : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_addr(dst)), "l"(src),
+                 "r"(bytes), "r"(smem_addr(bar))
+                 : "memory");
+}
+constexpr int kStageBytesPerRay = 10 * 8 + 3 * 4 + 1;  // = kRayBytes, laid out field-major in a stage
+struct TilePipe {
+    unsigned char* stage[2];
+    unsigned long long* bar;  // [2]
+    unsigned iter;            // tiles of this CTA consumed so far through the stages
+    unsigned tiles;           // number of tiles of the launch
+    unsigned full_tiles;      // tiles [0, full_tiles) hold blockDim.x rays
+};
+// thread 0: arm the stage's barrier and start the 14 copies of one full tile
+__device__ __forceinline__ void tile_issue(const DevRays& in, unsigned tile, unsigned char* st, unsigned long long* bar) {
+    const unsigned B = blockDim.x;
+    const size_t off = (size_t)tile * B;
+    mbar_expect_tx(bar, B * kStageBytesPerRay);
+    const double* f64[10] = {in.px, in.py, in.pz, in.dx, in.dy, in.dz, in.e, in.wvl, in.opl, in.n};
+#pragma unroll
+    for (int f = 0; f < 10; ++f) bulk_g2s(st + (size_t)f * B * 8, f64[f] + off, B * 8, bar);
+    const uint32_t* u32[3] = {in.bounces, in.refr, in.id};
+#pragma unroll
+    for (int f = 0; f < 3; ++f) bulk_g2s(st + (size_t)B * 80 + (size_t)f * B * 4, u32[f] + off, B * 4, bar);
+    bulk_g2s(st + (size_t)B * 92, in.valid + off, B, bar);
+}
+__device__ __forceinline__ void tile_pipe_init(TilePipe& p, unsigned char* smem, unsigned long long* bar, const DevRays& in, uint64_t n) {
+    const unsigned B = blockDim.x;
+    const unsigned stage_bytes = (B * kStageBytesPerRay + 127u) & ~127u;
+    p.stage[0] = smem; p.stage[1] = smem + stage_bytes;
+    p.bar = bar; p.iter = 0;
+    p.tiles = (unsigned)((n + B - 1) / B);
+    p.full_tiles = (unsigned)(n / B);
+    if (threadIdx.x == 0) {
+        mbar_init(&bar[0], 1); mbar_init(&bar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned t0 = blockIdx.x, t1 = blockIdx.x + gridDim.x;
+        if (t0 < p.full_tiles) tile_issue(in, t0, p.stage[0], &bar[0]);
+        if (t1 < p.full_tiles) tile_issue(in, t1, p.stage[1], &bar[1]);
+    }
+}
+__device__ __forceinline__ void tile_load_staged(TilePipe& p, const DevRays& in, unsigned tile, uint64_t n, RayCtx& x, uint8_t& vb) {
+    const uint64_t i = (uint64_t)tile * blockDim.x + threadIdx.x;
+    if (tile >= p.full_tiles) { tile_load(in, i, n, x, vb); return; }  // the trailing partial tile
+    const unsigned s = p.iter & 1u, B = blockDim.x, t = threadIdx.x;
+    unsigned char* st = p.stage[s];
+    mbar_wait(&p.bar[s], (p.iter >> 1) & 1u);
+    x.i = i; x.in_range = true;
+    x.c.a = 0; x.c.b = 0; x.c.apodized = 0; x.c.status = 0;
+    const double* d = reinterpret_cast<const double*>(st);
+    x.r.pos = v3(d[t], d[B + t], d[2 * B + t]);
+    x.r.dir = v3(d[3 * B + t], d[4 * B + t], d[5 * B + t]);
+    x.r.e = d[6 * B + t]; x.r.wvl = d[7 * B + t]; x.r.opl = d[8 * B + t]; x.r.n = d[9 * B + t];
+    const uint32_t* u = reinterpret_cast<const uint32_t*>(st + (size_t)B * 80);
+    x.r.bounces = u[t]; x.r.refr = u[B + t]; x.r.id = u[2 * B + t];
+    vb = st[(size_t)B * 92 + t];
+    if (vb == RAY_REMOVED) {  // what tile_load leaves for a slot that is not part of the bundle
+        x.r.pos = v3(0, 0, 0); x.r.dir = v3(0, 0, 1); x.r.e = 0; x.r.wvl = 0; x.r.opl = 0; x.r.n = 1; x.r.bounces = 0; x.r.refr = 0; x.r.id = 0;
+    }
+    x.alive = vb != RAY_REMOVED;
+    x.valid = vb == RAY_VALID;
+    __syncthreads();  // every thread has its ray in registers: the stage can take the tile after next
+    if (t == 0) {
+        const unsigned next = tile + 2u * gridDim.x;
+        if (next < p.full_tiles) tile_issue(in, next, st, &p.bar[s]);
+    }
+    p.iter++;
+}
+
 template <bool COMPACT>
 __device__ __forceinline__ void tile_store(const DevRays& in, const DevRays& out, uint64_t out_cap, unsigned long long* out_tail,
                                            RayCtx& x, uint8_t vb) {
