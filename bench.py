@@ -345,11 +345,12 @@ def run_product(args):
             hbm_peak, peak_src = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
         # algorithmic bytes of the trace launches of ONE step on this rank (DESIGN.md "byte model"): every buffer the step
         # must read or write, once.  Read the source bundle (n x 93 B); for the rays still in the bundle write the main
-        # output bundle, 2 detector snapshots (93 B each) and 2 hit records (36 B) of the main chain, and the split-off
-        # bundle after its side chain, its detector snapshot and hit record.  When the side chain is its own launch
+        # output bundle, the spot diagram's copy of the bundle (93 B) and the fluence detector's hit record (36 B), and the
+        # split-off bundle after its side chain with its hit record.  (The fluence detectors keep only hit maps: their
+        # report reads nothing else, nodes/fluence_detector/mod.rs:91-135.)  When the side chain is its own launch
         # (2 trace launches per step) the split-off bundle is additionally written by the main launch and read back.
         launches_trace = kern_launches / args.steps
-        bytes_step = (n * RAY_BYTES + alive_main * (3 * RAY_BYTES + 2 * HIT_BYTES) + alive_side * (2 * RAY_BYTES + HIT_BYTES))
+        bytes_step = (n * RAY_BYTES + alive_main * (2 * RAY_BYTES + HIT_BYTES) + alive_side * (RAY_BYTES + HIT_BYTES))
         if launches_trace > 1.5:
             bytes_step += alive_side * (RAY_BYTES + RAY_BYTES_INPLACE)
         kern_ms_step = kern_ms / args.steps

@@ -91,10 +91,12 @@ OpmStatus opm_scene_reset_data(OpmScene* scene);
 enum {
     OPM_SCENE_STRICT = 2,           /* same value as OPM_TRACE_STRICT */
     OPM_SCENE_PER_SURFACE = 4,      /* one launch per reference call instead of one fused launch per chain */
-    OPM_SCENE_RECORD_ALL_HITS = 8,  /* keep the hit map of every surface (the reference always does); default: detectors only */
+    OPM_SCENE_RECORD_ALL_HITS = 8,  /* keep the hit map of every surface (the reference always does); default: FluenceDetector nodes only */
     OPM_SCENE_NO_SNAPSHOTS = 16,    /* detectors keep hit maps but no copy of the bundle (no spot statistics) */
     OPM_SCENE_ASYNC = 32,           /* do not synchronise / read counters back (throughput runs) */
     OPM_SCENE_KEEP_SOURCE = 64,     /* leave `source_rays` untouched: the main chain's output goes to opm_scene_output_rays() */
+    OPM_SCENE_KEEP_LIGHT_DATA = 256, /* FluenceDetector nodes also keep a copy of the bundle (the reference's `light_data`); no report
+                                       reads it (nodes/fluence_detector/mod.rs:91-135), so by default only their hit map is kept */
     OPM_SCENE_POSITION_HISTORY = 128 /* keep the per-ray position history (`pos_hist`): read it with opm_rays_position_history() from the
                                        bundles of opm_scene_node_rays() / opm_scene_output_rays() / the traced source bundle */
 };

@@ -167,7 +167,7 @@ class OpmSourceDesc(C.Structure):
  NODE_DUMMY, NODE_IDEAL_FILTER, NODE_PARAXIAL_SURFACE, NODE_SPOT_DIAGRAM, NODE_FLUENCE_DETECTOR, NODE_REFLECTIVE_GRATING,
  NODE_RAY_PROPAGATION_VISUALIZER, NODE_SPECTROMETER, NODE_WAVEFRONT) = range(16)
 SCENE_STRICT, SCENE_PER_SURFACE, SCENE_RECORD_ALL_HITS, SCENE_NO_SNAPSHOTS, SCENE_ASYNC, SCENE_KEEP_SOURCE = 2, 4, 8, 16, 32, 64
-SCENE_POSITION_HISTORY = 128
+SCENE_POSITION_HISTORY, SCENE_KEEP_LIGHT_DATA = 128, 256
 
 
 class OpmCoatingDesc(C.Structure):

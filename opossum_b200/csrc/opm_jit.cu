@@ -312,6 +312,9 @@ const JitKernel* jit_get(JitCache* cache, const DevOp* ops, int n_ops, bool comp
     if (why) *why = nullptr;
     if (!cache || n_ops <= 0) { if (why) *why = "no program"; return nullptr; }
     std::string src = make_source(ops, n_ops, compact, block, min_ctas);
+    if (const char* dump = getenv("OPM_B200_JIT_DUMP")) {  // diagnosis: the generated source, to compile offline with nvcc -Xptxas -v
+        if (FILE* f = fopen(dump, "w")) { fwrite(src.data(), 1, src.size(), f); fclose(f); }
+    }
     auto it = cache->kernels.find(src);
     if (it == cache->kernels.end()) {
         it = cache->kernels.emplace(std::move(src), std::unique_ptr<JitKernel>(new JitKernel())).first;

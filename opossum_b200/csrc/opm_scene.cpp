@@ -313,7 +313,8 @@ OpmStatus compile_node_rt(OpmScene* sc, Node& n, const OpmRayTraceConfig& cfg, i
     const double thr = cfg.min_energy_per_ray;
     OpmStatus st = OPM_OK;
     auto hits_for = [&](SurfaceState& s) -> OpmHitMap* {
-        if (!(flags & OPM_SCENE_RECORD_ALL_HITS) && !is_detector(n.d.type)) return nullptr;
+        // by default only where a report reads the hit map: FluenceDetector (the other detectors report from their copy of the bundle)
+        if (!(flags & OPM_SCENE_RECORD_ALL_HITS) && n.d.type != OPM_NODE_FLUENCE_DETECTOR) return nullptr;
         return new_hitmap(sc, s, 1, n_rays, &st);
     };
     switch (n.d.type) {
@@ -424,7 +425,10 @@ OpmStatus compile_node_rt(OpmScene* sc, Node& n, const OpmRayTraceConfig& cfg, i
             R.push(op_refract(n.s[0], nullptr, true, strat, 0, h0, nullptr));
             R.push(op_apodize(n.s[0].aperture, n.s[0].eff_iso));
             R.push(op_threshold(thr));
-            if (!(flags & OPM_SCENE_NO_SNAPSHOTS)) {
+            // the detector's `light_data` (analyzers/raytrace.rs:186-205).  FluenceDetector::node_report reads only the hit map
+            // (nodes/fluence_detector/mod.rs:91-135): its copy of the bundle is written only on request
+            const bool keep = n.d.type != OPM_NODE_FLUENCE_DETECTOR || (flags & OPM_SCENE_KEEP_LIGHT_DATA);
+            if (keep && !(flags & OPM_SCENE_NO_SNAPSHOTS)) {
                 if (!n.stored) {
                     st = acquire_rays(sc, n_rays ? n_rays : 1, &n.stored);
                     if (st) return st;
