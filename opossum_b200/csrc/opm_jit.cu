@@ -123,12 +123,12 @@ std::string op_line(const DevOp& op, int k) {
         }
         case OPK_THRESHOLD: appendf(s, "        exec_threshold(opm_jit_ops[%d].u.threshold, x);\n", k); break;
         case OPK_LIMITS: appendf(s, "        exec_limits(opm_jit_ops[%d].u.limits, x);\n", k); break;
-        case OPK_FILTER: appendf(s, "        exec_filter(opm_jit_ops[%d].u.filter, x);\n", k); break;
+        case OPK_FILTER: appendf(s, "        exec_filter<%s>(opm_jit_ops[%d].u.filter, x);\n", op.u.filter.s.lam ? "true" : "false", k); break;
         case OPK_PARAXIAL: appendf(s, "        exec_paraxial(opm_jit_ops[%d].u.paraxial, x);\n", k); break;
-        case OPK_SPLIT: appendf(s, "        exec_split(opm_jit_ops[%d].u.split, x);\n", k); break;
+        case OPK_SPLIT: appendf(s, "        exec_split<%s>(opm_jit_ops[%d].u.split, x);\n", op.u.split.s.lam ? "true" : "false", k); break;
         case OPK_SNAPSHOT: appendf(s, "        exec_snapshot(opm_jit_ops[%d].u.snapshot, x);\n", k); break;
         case OPK_TRANSFORM: appendf(s, "        exec_transform(opm_jit_ops[%d].u.transform, x);\n", k); break;
-        case OPK_FORK: appendf(s, "        exec_fork(opm_jit_ops[%d].u.fork, x, opm_jit_stash);\n", k); break;
+        case OPK_FORK: appendf(s, "        exec_fork<%s>(opm_jit_ops[%d].u.fork, x, opm_jit_stash);\n", op.u.fork.s.lam ? "true" : "false", k); break;
         case OPK_JOIN: appendf(s, "        exec_join(opm_jit_ops[%d].u.join, x, opm_jit_stash);\n", k); break;
         case OPK_DIFFRACT: {
             const DevRefract& o = op.u.diffract.surf;

@@ -198,25 +198,29 @@ __device__ __forceinline__ void exec_limits(const DevLimits& o, RayCtx& x) {
 }
 // the per-ray splitting ratio / transmission of a spectrum-driven op (ray.rs:712-721, 755-761); false = the wavelength is
 // outside the spectrum (the reference returns an error: the ray raises OPM_ERR_SPECTRUM)
+// SPECTRAL = false: the program is known to use the fixed factor (run-time specialised kernel), the look-up is compiled out
+template <bool SPECTRAL = true>
 __device__ __forceinline__ bool spectral_factor(const DevSpectrum& s, double fixed, RayCtx& x, double& f) {
     f = fixed;
-    if (s.lam == nullptr) return true;
+    if (!SPECTRAL || s.lam == nullptr) return true;
     if (spectrum_get_value(s, x.r.wvl, f)) return true;
     x.c.status |= 1u << OPM_ERR_SPECTRUM;
     x.valid = false;
     return false;
 }
 // rays.rs:1119-1133
+template <bool SPECTRAL = true>
 __device__ __forceinline__ void exec_filter(const DevFilter& o, RayCtx& x) {
     if (!x.valid) return;
     double t;
-    if (spectral_factor(o.s, o.t, x, t)) x.r.e *= t;
+    if (spectral_factor<SPECTRAL>(o.s, o.t, x, t)) x.r.e *= t;
 }
 // rays.rs:943-959
 __device__ __forceinline__ void exec_paraxial(const DevParaxial& o, RayCtx& x) {
     if (x.valid) refract_paraxial(o, x.r);
 }
 // rays.rs:1253-1264, ray.rs:752-772
+template <bool SPECTRAL = true>
 __device__ __forceinline__ void exec_split(const DevSplit& o, RayCtx& x) {
     if (!x.in_range) return;
     if (x.alive) {
@@ -224,8 +228,8 @@ __device__ __forceinline__ void exec_split(const DevSplit& o, RayCtx& x) {
         const bool was_valid = x.valid;
         if (x.valid) {
             double ratio;
-            if (spectral_factor(o.s, o.ratio, x, ratio)) {
-                if (o.s.lam != nullptr && !(ratio >= 0.0 && ratio <= 1.0)) { x.c.status |= 1u << OPM_ERR_SPLIT_RATIO; x.valid = false; }
+            if (spectral_factor<SPECTRAL>(o.s, o.ratio, x, ratio)) {
+                if (SPECTRAL && o.s.lam != nullptr && !(ratio >= 0.0 && ratio <= 1.0)) { x.c.status |= 1u << OPM_ERR_SPLIT_RATIO; x.valid = false; }
                 else { x.r.e *= ratio; s.e *= 1.0 - ratio; }
             }
         }
@@ -244,9 +248,10 @@ __device__ __forceinline__ void stash_put(unsigned* stash, int f, double v) {
 __device__ __forceinline__ double stash_get(const unsigned* stash, int f) {
     return __hiloint2double((int)stash[(2 * f + 1) * blockDim.x + threadIdx.x], (int)stash[(2 * f) * blockDim.x + threadIdx.x]);
 }
+template <bool SPECTRAL = true>
 __device__ __forceinline__ void exec_fork(const DevFork& o, RayCtx& x, unsigned* stash) {
     double ratio = o.ratio;
-    if (x.valid && spectral_factor(o.s, o.ratio, x, ratio) && o.s.lam != nullptr && !(ratio >= 0.0 && ratio <= 1.0)) {
+    if (SPECTRAL && x.valid && spectral_factor<true>(o.s, o.ratio, x, ratio) && o.s.lam != nullptr && !(ratio >= 0.0 && ratio <= 1.0)) {
         x.c.status |= 1u << OPM_ERR_SPLIT_RATIO; x.valid = false;
     }
     const double e_main = x.valid ? x.r.e * ratio : x.r.e;  // invalid rays are copied unchanged (rays.rs:1258-1262)
