@@ -51,7 +51,10 @@ struct OpmContext {
     bool jit_sync = false;  // wait for the compiler instead of interpreting until the kernel is ready
     uint64_t jit_min_rays = 200000;
     bool jit_warned = false;
-    int jit_block = 128, jit_min_ctas = 5;  // CTA shape of the specialised kernels (tunable: OPM_B200_JIT_BLOCK / _MIN_CTAS)
+    // CTA shape of the specialised kernels (tunable: OPM_B200_JIT_BLOCK / _MIN_CTAS).  One CTA of 32 warps per SM at 64 registers
+    // per thread measured best on the C2 chain (profiles/r1_summary.md, CTA-shape sweep): the warps of one CTA walk the 70 KB of
+    // straight-line code together and share its instruction-cache lines.
+    int jit_block = 1024, jit_min_ctas = 1;
     cudaStream_t copy_stream = nullptr;  // host uploads that are expanded on the device run here, overlapping the main stream
     // optional per-launch timing of the fused trace kernel (CUDA events on the launching stream)
     bool timing = false;
@@ -1053,10 +1056,15 @@ static OpmStatus compile_ops(OpmContext* c, const OpmOp* ops, int n_ops, uint64_
                 }
                 break;
             }
-            case OPM_OP_TRANSFORM:
+            case OPM_OP_TRANSFORM: {
                 d.kind = OPK_TRANSFORM;
                 to_dev_iso(p.u.transform.inverse ? p.u.transform.iso.inv : p.u.transform.iso.fwd, d.u.transform.iso);
+                const DevIso& I = d.u.transform.iso;  // the identity moves nothing (rotation by the unit matrix and adding 0.0 are exact)
+                const bool ident = I.r[0] == 1.0 && I.r[4] == 1.0 && I.r[8] == 1.0 && I.r[1] == 0.0 && I.r[2] == 0.0 && I.r[3] == 0.0 &&
+                                   I.r[5] == 0.0 && I.r[6] == 0.0 && I.r[7] == 0.0 && I.t[0] == 0.0 && I.t[1] == 0.0 && I.t[2] == 0.0;
+                if (ident) continue;
                 break;
+            }
             default: return fail(OPM_ERR_ARG, "unknown op kind %d", p.kind);
         }
         out.ops.push_back(d);

@@ -1,5 +1,4 @@
-# CTA shapes of the run-time specialised kernel: value, step ms and kernel ms per step of bench.py
-for v in "128 5" "128 6" "128 4" "256 3" "256 2" "64 10" "64 12"; do
+for v in "384 2" "768 1" "640 1" "512 1" "1024 1" "448 2" "512 2"; do
   set -- $v
   OPM_B200_JIT_BLOCK=$1 OPM_B200_JIT_MIN_CTAS=$2 python bench.py --no-cpu-baseline --steps 20 2>/dev/null | tail -1 | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('$1 x $2', round(d['value']/1e9,2), round(d['ms_per_step'],3), round(d['roofline']['kernel_ms_per_launch']*d['roofline']['launches_per_step'],3))"
 done
