@@ -363,7 +363,8 @@ def run_product(args):
         traffic = None
         try:
             tr = json.loads((ROOT / "profiles" / "r1_traffic.json").read_text())
-            if jit["launches"] and tr["workload_rays_per_gpu"] == n and tr["launches_per_step"] == launches_trace:
+            same_bytes = abs(tr["algorithmic_bytes_per_launch"] - bytes_step / max(launches_trace, 1)) < 0.02 * tr["algorithmic_bytes_per_launch"]
+            if jit["launches"] and tr["workload_rays_per_gpu"] == n and tr["launches_per_step"] == launches_trace and same_bytes:
                 traffic = tr["dram_bytes_read"] + tr["dram_bytes_write"]
         except (OSError, ValueError, KeyError):
             pass
@@ -374,7 +375,7 @@ def run_product(args):
             "config": {"workload": WORKLOAD_NAME, "rays_per_gpu": n, "rays_total": n * world, "sharding": "source index i -> rank i mod N (interleaved)", "surfaces_per_ray": 13,
                        "interactions_per_step": int(inter_total), "fluence_map": f"{MAP_NX}x{MAP_NY} x2 (Binning, data-dependent range)",
                        "l2": f"inputs larger than L2: {n * RAY_BYTES / 1e6:.0f} MB source bundle per GPU vs 126 MB",
-                       "collective": "3 NCCL collectives per step: all_gather(map ranges | spot sums), all_reduce(sum) of the fluence maps, all_gather(spot radii)" if world > 1 else "none (1 GPU)"},
+                       "collective": "2 NCCL collectives per step: all_gather(map ranges | spot sums), all_gather(fluence maps | spot radii), each combined in rank order by one kernel" if world > 1 else "none (1 GPU)"},
             "e2e": {"value": inter_total * args.steps / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_ms / args.steps,
                     "pipeline": "two bundles: H2D of step k+1 (copy stream) overlaps trace + read-out of step k",
@@ -423,7 +424,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="product", choices=["product", "reference"])
     ap.add_argument("--rays", type=int, default=10_000_000, help="rays per GPU (BASELINE.json configs[1]: 10^7)")
-    ap.add_argument("--cpu-rays-per-core", type=int, default=200_000)
+    ap.add_argument("--cpu-rays-per-core", type=int, default=1_000_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "product" else args.warmup

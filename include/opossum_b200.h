@@ -462,6 +462,16 @@ typedef struct { double wavelength_m, ptv, rms; uint64_t n_rays; } OpmWavefrontS
 OpmStatus opm_rays_wavefront_error(const OpmRays* rays, const OpmIsometry* monitor_iso, double wavelength_m, double* xyw_out,
                                    uint64_t cap, OpmWavefrontStats* out);
 
+/* ---- multi-GPU detector read-out (host side: opossum_b200/sharding.py) ----------------------------------------
+ * Every rank all-gathers a small block, then combines the `world` rows in rank order with one launch (bit-identical on all ranks):
+ *  block A = [4 x n_fluence map ranges as (-l, r, t, -b) | 11 x n_spot spot sums of opm_rays_spot_sums_async]: ranges by max,
+ *            sums by sum, the first-valid-ray pair from the rank holding the smallest ray id;
+ *  block B = [maps_len fluence bins | 3 x n_spot radius accumulators of opm_rays_spot_radii_async]: bins and sums by sum, max by max. */
+OpmStatus opm_readout_combine_ranges_sums(OpmContext* ctx, const double* gathered_dev, int32_t world, int32_t n_fluence, int32_t n_spot,
+                                          double* out_dev);
+OpmStatus opm_readout_combine_maps_radii(OpmContext* ctx, const double* gathered_dev, int32_t world, uint64_t maps_len, int32_t n_spot,
+                                         double* out_dev);
+
 /* measured FP64 FMA throughput of the device in TFLOP/s (FMA = 2 flop): roofline denominator of the fused trace kernel */
 OpmStatus opm_measure_fp64_peak(OpmContext* ctx, double* tflops);
 /* device buffers for maps (so callers need no CUDA runtime of their own) */

@@ -1329,6 +1329,24 @@ extern "C" OpmStatus opm_rays_transform(OpmRays* rays, const OpmIsometry* iso, i
 }
 
 // ---------------------------------------------------------------------------------------------
+// multi-GPU detector read-out: combine the blocks an all-gather collected
+// ---------------------------------------------------------------------------------------------
+extern "C" OpmStatus opm_readout_combine_ranges_sums(OpmContext* c, const double* gathered_dev, int32_t world, int32_t n_fluence,
+                                                     int32_t n_spot, double* out_dev) {
+    if (!c || !gathered_dev || !out_dev || world < 1 || n_fluence < 0 || n_spot < 0) return fail(OPM_ERR_ARG, "bad argument");
+    CU(cudaSetDevice(c->device));
+    KL(k_readout_combine_a(gathered_dev, world, n_fluence, n_spot, out_dev, c->stream)); c->launches++;
+    return OPM_OK;
+}
+extern "C" OpmStatus opm_readout_combine_maps_radii(OpmContext* c, const double* gathered_dev, int32_t world, uint64_t maps_len,
+                                                    int32_t n_spot, double* out_dev) {
+    if (!c || !gathered_dev || !out_dev || world < 1 || n_spot < 0) return fail(OPM_ERR_ARG, "bad argument");
+    CU(cudaSetDevice(c->device));
+    KL(k_readout_combine_b(gathered_dev, world, maps_len, n_spot, out_dev, c->sms, c->stream)); c->launches++;
+    return OPM_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
 // spectra, spectrometer, wavefront (spectrum.rs, nodes/spectrometer.rs, nodes/wavefront.rs)
 // ---------------------------------------------------------------------------------------------
 extern "C" OpmStatus opm_spectrum_create(OpmContext* c, const double* lambda_um, const double* values, uint64_t n, OpmSpectrum** out) {

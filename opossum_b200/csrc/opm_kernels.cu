@@ -1015,4 +1015,59 @@ int k_wavefront(DevRays R, uint64_t n, DevIso inv, double wvl_nm, WfAccum* acc, 
     return (int)cudaGetLastError();
 }
 
+// ---------------------------------------------------------------------------------------------
+// multi-GPU detector read-out: what one all-gather collected from `w` ranks, combined in rank order (every rank
+// gets bit-identical results).  Row r of `g` is rank r's block.
+// ---------------------------------------------------------------------------------------------
+// block A = [4 x nf map ranges as (-l, r, t, -b) | 11 x ns spot sums]: ranges by max; sums[0..8] by sum; sums[9..10] =
+// (bounces, id) of the first valid ray = the rank with the smallest id >= 0, the lowest rank on ties (rays.rs:183-194)
+__global__ void readout_combine_a_kernel(const double* __restrict__ g, int w, int nf, int ns, double* __restrict__ out) {
+    const int nA = 4 * nf + 11 * ns;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nA) return;
+    if (i < 4 * nf) {
+        double m = g[i];
+        for (int r = 1; r < w; ++r) m = fmax(m, g[(size_t)r * nA + i]);
+        out[i] = m;
+        return;
+    }
+    const int k = (i - 4 * nf) / 11, c = (i - 4 * nf) % 11, o = 4 * nf + 11 * k;
+    if (c < 9) {
+        double s = 0.0;
+        for (int r = 0; r < w; ++r) s += g[(size_t)r * nA + i];
+        out[i] = s;
+    } else {
+        int first = 0;
+        double best = INFINITY;
+        for (int r = 0; r < w; ++r) {
+            const double id = g[(size_t)r * nA + o + 10];
+            if (id >= 0.0 && id < best) { best = id; first = r; }
+        }
+        out[i] = g[(size_t)first * nA + i];
+    }
+}
+// block B = [maps_len map bins | 3 x ns spot radius accumulators (max d^2, sum d^2, sum E d^2)]: bins and sums by sum, max by max
+__global__ void __launch_bounds__(256) readout_combine_b_kernel(const double* __restrict__ g, int w, uint64_t maps_len, int ns,
+                                                                double* __restrict__ out) {
+    const uint64_t len = maps_len + 3ull * ns;
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < len; i += (uint64_t)gridDim.x * blockDim.x) {
+        const bool is_max = i >= maps_len && (i - maps_len) % 3 == 0;
+        double a = g[i];
+        for (int r = 1; r < w; ++r) { const double v = g[(size_t)r * len + i]; a = is_max ? fmax(a, v) : a + v; }
+        out[i] = a;
+    }
+}
+int k_readout_combine_a(const double* g, int w, int nf, int ns, double* out, void* stream) {
+    const int nA = 4 * nf + 11 * ns;
+    if (nA <= 0) return 0;
+    readout_combine_a_kernel<<<(nA + 127) / 128, 128, 0, ST>>>(g, w, nf, ns, out);
+    return (int)cudaGetLastError();
+}
+int k_readout_combine_b(const double* g, int w, uint64_t maps_len, int ns, double* out, int sms, void* stream) {
+    const uint64_t len = maps_len + 3ull * ns;
+    if (len == 0) return 0;
+    readout_combine_b_kernel<<<grid_for(len, 256, sms * 8), 256, 0, ST>>>(g, w, maps_len, ns, out);
+    return (int)cudaGetLastError();
+}
+
 }  // namespace opm

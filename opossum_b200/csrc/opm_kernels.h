@@ -79,6 +79,8 @@ int k_wavelength_range(DevRays R, uint64_t n, WvlAccum* acc, int sms, void* stre
 int k_spectrum_splat(DevRays R, uint64_t n, double start_um, double step_um, uint64_t nslots, double* data, unsigned* status, int sms,
                      void* stream);
 int k_wavefront(DevRays R, uint64_t n, DevIso inv, double wvl_nm, WfAccum* acc, double* xyw, int sms, void* stream);
+int k_readout_combine_a(const double* g, int w, int nf, int ns, double* out, void* stream);
+int k_readout_combine_b(const double* g, int w, uint64_t maps_len, int ns, double* out, int sms, void* stream);
 int k_fp64_peak(double* out, int iters, int blocks, void* stream);
 int k_fetch_from_host(void* dst, const void* src_host, size_t bytes, void* stream);  // bytes % 8 == 0, src pinned + mapped
 int k_set_u64(unsigned long long* p, unsigned long long v, void* stream);

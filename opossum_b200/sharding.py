@@ -101,18 +101,44 @@ def reduce_spot_radii(p, device="cpu"):
 # device-chained detector read-out (GPU): every phase stays on the device, the ranks meet in three small collectives and
 # the host synchronises once, when it reads the reports
 # ---------------------------------------------------------------------------------------------------------------
+def combine_ranges_sums_reference(gA: torch.Tensor, nf: int, ns: int) -> torch.Tensor:
+    """what opm_readout_combine_ranges_sums computes, in torch ops (CPU or GPU tensors): the specification the kernel is
+    tested against and the form the world-size-2 gloo test runs"""
+    out = torch.empty(gA.shape[1], dtype=gA.dtype, device=gA.device)
+    if nf:
+        out[: 4 * nf] = gA[:, : 4 * nf].max(dim=0).values
+    for k in range(ns):
+        o = 4 * nf + 11 * k
+        out[o: o + 9] = gA[:, o: o + 9].sum(dim=0)
+        # bounce level = bounce count of the first valid ray (rays.rs:183-194): smallest id, ties to the lowest rank
+        ids = gA[:, o + 10]
+        first = int(torch.argmin(torch.where(ids < 0, torch.full_like(ids, math.inf), ids)))
+        out[o + 9: o + 11] = gA[first, o + 9: o + 11]
+    return out
+
+
+def combine_maps_radii_reference(gB: torch.Tensor, maps_len: int, ns: int) -> torch.Tensor:
+    """what opm_readout_combine_maps_radii computes, in torch ops"""
+    out = gB.sum(dim=0)
+    if ns:
+        out[maps_len::3] = gB[:, maps_len::3].max(dim=0).values
+    return out
+
+
 class DetectorReadout:
     """Reports of the detectors of a scene whose rays are sharded over the ranks: Binning fluence maps
     (`FluenceDetector::node_report`, nodes/fluence_detector/mod.rs:91-135) and spot-diagram statistics
     (`SpotDiagram::node_report`, nodes/spot_diagram.rs:101-163).
 
         phase A  per detector: bounding box of its hits -> range (-l, r, t, -b); spot sums                 [local, async]
-        gather 1 all_gather of (ranges | sums): element-wise max of the ranges, sum of the sums               [1 collective]
+        gather 1 all_gather of (ranges | sums), combined in rank order by one kernel                          [1 collective]
         phase B  per detector: Binning into the common grid; spot radii about the global centroids           [local, async]
-        reduce   all_reduce(sum) of all maps in one buffer; all_gather of the radius accumulators            [2 collectives]
+        gather 2 all_gather of (maps | radius accumulators), summed in rank order by one kernel               [1 collective]
+                 (maps too large to gather -- more than FUSED_LIMIT doubles over all ranks -- are all-reduced instead)
         phase C  peak / total of every (global) map                                                          [local, async]
         read     one device->host copy of the scalars (and the maps if asked), one synchronisation
     """
+    FUSED_LIMIT = 8 * 1024 * 1024  # doubles in the gathered (maps | radii) buffer
 
     def __init__(self, ctx, scene, fluence_nodes, spot_nodes, nx: int, ny: int, device):
         import ctypes as C
@@ -124,15 +150,20 @@ class DetectorReadout:
         nf, ns = len(self.fl), len(self.sp)
         self.nA = 4 * nf + 11 * ns                       # ranges | spot sums
         self.nB = 3 * ns                                 # spot radii
-        self.buf = torch.zeros(self.nA + self.nB + 2 * nf, dtype=torch.float64, device=device)
-        self.maps = torch.zeros((max(nf, 1), nx * ny), dtype=torch.float64, device=device)
+        self.maps_len = max(nf, 1) * nx * ny
+        self.buf = torch.zeros(self.nA + 2 * nf, dtype=torch.float64, device=device)        # A | peak, total per map
+        self.mb = torch.zeros(self.maps_len + self.nB, dtype=torch.float64, device=device)  # maps | B
+        self.maps = self.mb[: self.maps_len].view(max(nf, 1), nx * ny)
         self.status = torch.zeros(max(nf, 1), dtype=torch.int32, device=device)
         self.h_buf = torch.zeros(self.buf.numel(), dtype=torch.float64).pin_memory()
+        self.h_B = torch.zeros(max(self.nB, 1), dtype=torch.float64).pin_memory()
         self.h_status = torch.zeros(self.status.numel(), dtype=torch.int32).pin_memory()
         self.h_maps = torch.zeros_like(self.maps, device="cpu").pin_memory()
         w = world()[1]
+        self.fused = w > 1 and self.mb.numel() * w <= self.FUSED_LIMIT
         self.gA = torch.zeros((w, self.nA), dtype=torch.float64, device=device) if w > 1 else None
-        self.gB = torch.zeros((w, max(self.nB, 1)), dtype=torch.float64, device=device) if w > 1 else None
+        self.gMB = torch.zeros((w, self.mb.numel()), dtype=torch.float64, device=device) if self.fused else None
+        self.gB = torch.zeros((w, max(self.nB, 1)), dtype=torch.float64, device=device) if (w > 1 and not self.fused) else None
 
     def _ptr(self, t: torch.Tensor, offset: int = 0) -> int:
         return t.data_ptr() + 8 * offset
@@ -147,47 +178,40 @@ class DetectorReadout:
         rank, w = world()
         nf, ns, nx, ny = len(self.fl), len(self.sp), self.nx, self.ny
         hits = [self._hit_arrays(n) for n in self.fl]
+        vp = C.c_void_p
         # ---- phase A
         for j, (arr, n) in enumerate(hits):
-            _check(L.opm_hitmaps_bounding_box_async(arr, n, -1, C.c_void_p(self._ptr(self.buf, 4 * j))))
+            _check(L.opm_hitmaps_bounding_box_async(arr, n, -1, vp(self._ptr(self.buf, 4 * j))))
         for k, node in enumerate(self.sp):
-            _check(L.opm_scene_node_spot_async(self.scene.h, node, 1, C.c_void_p(self._ptr(self.buf, 4 * nf + 11 * k)), None))
-        if w > 1:
-            A = self.buf[: self.nA]
-            dist.all_gather_into_tensor(self.gA.view(-1), A)
-            if nf:
-                A[: 4 * nf] = self.gA[:, : 4 * nf].max(dim=0).values
-            for k in range(ns):
-                o = 4 * nf + 11 * k
-                A[o: o + 9] = self.gA[:, o: o + 9].sum(dim=0)
-                # bounce level = bounce count of the first valid ray (rays.rs:183-194): smallest id, ties to the lowest rank
-                ids = self.gA[:, o + 10]
-                first = torch.argmin(torch.where(ids < 0, torch.full_like(ids, math.inf), ids))
-                A[o + 9: o + 11] = self.gA[first, o + 9: o + 11]
+            _check(L.opm_scene_node_spot_async(self.scene.h, node, 1, vp(self._ptr(self.buf, 4 * nf + 11 * k)), None))
+        if w > 1 and self.nA:
+            dist.all_gather_into_tensor(self.gA.view(-1), self.buf[: self.nA])
+            _check(L.opm_readout_combine_ranges_sums(self.ctx.h, vp(self.gA.data_ptr()), w, nf, ns, vp(self.buf.data_ptr())))
         # ---- phase B
         self.status.zero_()
         for j, (arr, n) in enumerate(hits):
-            _check(L.opm_fluence_binning_async(arr, n, -1, nx, ny, C.c_void_p(self._ptr(self.buf, 4 * j)), 0,
-                                               C.c_void_p(self.maps[j].data_ptr()), C.c_void_p(self.status.data_ptr() + 4 * j)))
+            _check(L.opm_fluence_binning_async(arr, n, -1, nx, ny, vp(self._ptr(self.buf, 4 * j)), 0,
+                                               vp(self.maps[j].data_ptr()), vp(self.status.data_ptr() + 4 * j)))
         for k, node in enumerate(self.sp):
-            _check(L.opm_scene_node_spot_async(self.scene.h, node, 2, C.c_void_p(self._ptr(self.buf, 4 * nf + 11 * k)),
-                                               C.c_void_p(self._ptr(self.buf, self.nA + 3 * k))))
-        if w > 1:
+            _check(L.opm_scene_node_spot_async(self.scene.h, node, 2, vp(self._ptr(self.buf, 4 * nf + 11 * k)),
+                                               vp(self._ptr(self.mb, self.maps_len + 3 * k))))
+        if self.fused:
+            dist.all_gather_into_tensor(self.gMB.view(-1), self.mb)
+            _check(L.opm_readout_combine_maps_radii(self.ctx.h, vp(self.gMB.data_ptr()), w, self.maps_len, ns, vp(self.mb.data_ptr())))
+        elif w > 1:
             if nf:
                 dist.all_reduce(self.maps, op=dist.ReduceOp.SUM)
             if ns:
-                B = self.buf[self.nA: self.nA + self.nB]
-                dist.all_gather_into_tensor(self.gB.view(-1), B)
-                g = self.gB.view(w, ns, 3)
-                B.view(ns, 3)[:, 0] = g[:, :, 0].max(dim=0).values
-                B.view(ns, 3)[:, 1:] = g[:, :, 1:].sum(dim=0)
+                dist.all_gather_into_tensor(self.gB.view(-1), self.mb[self.maps_len:])
+                _check(L.opm_readout_combine_maps_radii(self.ctx.h, vp(self.gB.data_ptr()), w, 0, ns, vp(self._ptr(self.mb, self.maps_len))))
         # ---- phase C
         for j in range(nf):
-            _check(L.opm_fluence_peak_total_async(self.ctx.h, C.c_void_p(self.maps[j].data_ptr()), nx, ny,
-                                                  C.c_void_p(self._ptr(self.buf, 4 * j)),
-                                                  C.c_void_p(self._ptr(self.buf, self.nA + self.nB + 2 * j))))
+            _check(L.opm_fluence_peak_total_async(self.ctx.h, vp(self.maps[j].data_ptr()), nx, ny, vp(self._ptr(self.buf, 4 * j)),
+                                                  vp(self._ptr(self.buf, self.nA + 2 * j))))
         # ---- read
         self.h_buf.copy_(self.buf, non_blocking=True)
+        if ns:
+            self.h_B.copy_(self.mb[self.maps_len:], non_blocking=True)
         self.h_status.copy_(self.status, non_blocking=True)
         if download_maps and nf:
             self.h_maps.copy_(self.maps, non_blocking=True)
@@ -202,12 +226,12 @@ class DetectorReadout:
             st = int(self.h_status[j])
             if st:
                 raise RuntimeError(f"fluence binning raised status bits {st:#x}")
-            pk = h[self.nA + self.nB + 2 * j: self.nA + self.nB + 2 * j + 2].tolist()
+            pk = h[self.nA + 2 * j: self.nA + 2 * j + 2].tolist()
             out[node] = {"lrtb": lrtb, "peak": pk[0], "total_energy": pk[1],
                          "map": self.h_maps[j].numpy().reshape(nx, ny).T.copy() if download_maps else None}
         for k, node in enumerate(self.sp):
             s = h[4 * nf + 11 * k: 4 * nf + 11 * k + 11].tolist()
-            rr = h[self.nA + 3 * k: self.nA + 3 * k + 3].tolist()
+            rr = self.h_B[3 * k: 3 * k + 3].tolist()
             p = F.OpmSpotPartial()
             for i in range(7):
                 p.sum[i] = s[i]

@@ -1,5 +1,7 @@
 """End-to-end parity of the BASELINE.json configs (reduced ray counts) through the scene layer and the fused kernel:
 product (C++ scene layer -> C ABI -> CUDA) vs the oracle's restatement of the reference's node / analyzer flow."""
+import math
+
 import numpy as np
 import pytest
 
@@ -256,6 +258,46 @@ def test_device_chained_readout_equals_stepwise_reports(ctx):
         for f in ("total_energy", "beam_radius_geo", "beam_radius_rms", "energy_beam_radius_rms"):
             assert getattr(s, f) == pytest.approx(getattr(ref_spot, f), rel=1e-12), f
         assert np.allclose(s.energy_centroid[:], ref_spot.energy_centroid[:], rtol=1e-12, atol=1e-18)
+
+
+@pytest.mark.parametrize("world", [1, 2, 8])
+def test_readout_combine_kernels_match_their_specification(ctx, world):
+    """opm_readout_combine_ranges_sums / _maps_radii (what every rank runs on an all-gathered block) against the torch
+    restatement that the world-size-2 gloo test exercises on CPU; rank order makes the sums reproducible bit for bit"""
+    import ctypes as C
+
+    import torch
+
+    from opossum_b200 import ffi as F
+    from opossum_b200 import sharding
+    dev = torch.device("cuda", 0)
+    g = torch.Generator().manual_seed(world)
+    nf, ns, maps_len = 2, 3, 2 * 100 * 83
+    nA = 4 * nf + 11 * ns
+    gA = torch.rand((world, nA), generator=g, dtype=torch.float64) * 10 - 3
+    for k in range(ns):  # ids (o + 10) of the first valid ray: some ranks have none (-1), some tie
+        o = 4 * nf + 11 * k
+        gA[:, o + 10] = torch.tensor([(-1.0, 5.0, 5.0, 2.0, -1.0, 7.0, 2.0, 9.0)[(r + k) % 8] for r in range(world)])
+        gA[:, o + 9] = torch.arange(world, dtype=torch.float64) + 10 * k
+    gA[0, 1] = -math.inf  # a rank without hits contributes -inf to the ranges
+    gB = torch.rand((world, maps_len + 3 * ns), generator=g, dtype=torch.float64)
+    L, vp = F.lib(), C.c_void_p
+    dA, dB = gA.to(dev), gB.to(dev)
+    outA, outB = torch.zeros(nA, dtype=torch.float64, device=dev), torch.zeros(maps_len + 3 * ns, dtype=torch.float64, device=dev)
+    stream = torch.cuda.current_stream()
+    stream.synchronize()
+    assert L.opm_readout_combine_ranges_sums(ctx.h, vp(dA.data_ptr()), world, nf, ns, vp(outA.data_ptr())) == 0
+    assert L.opm_readout_combine_maps_radii(ctx.h, vp(dB.data_ptr()), world, maps_len, ns, vp(outB.data_ptr())) == 0
+    ctx.synchronize()
+    refA = sharding.combine_ranges_sums_reference(gA, nf, ns)
+    refB = sharding.combine_maps_radii_reference(gB, maps_len, ns)
+    assert torch.allclose(outA.cpu(), refA, rtol=1e-15, atol=0)
+    assert torch.equal(outA.cpu()[: 4 * nf], refA[: 4 * nf])
+    for k in range(ns):
+        o = 4 * nf + 11 * k
+        assert torch.equal(outA.cpu()[o + 9: o + 11], refA[o + 9: o + 11])  # the same rank's pair, ties to the lowest rank
+    assert torch.allclose(outB.cpu(), refB, rtol=1e-14, atol=0)
+    assert torch.equal(outB.cpu()[maps_len::3], refB[maps_len::3])
 
 
 @pytest.fixture(scope="module")

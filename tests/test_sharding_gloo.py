@@ -78,10 +78,33 @@ def _worker(rank, world_size, port, q):
         sharding.reduce_spot_radii(p)
         st = F.OpmSpotStats()
         F.lib().opm_spot_stats_from_partial(C.byref(p), C.byref(st))
+        # the gathered-block form DetectorReadout uses on the GPU (one all-gather per phase, rows combined in rank order):
+        # block A = [map range as (-l, r, t, -b) | 11 spot sums], block B = [map bins | 3 radius accumulators]
+        pl = _partial_sums(stored, iso)
+        first = (-1.0, -1.0) if pl.first_key == 0xFFFFFFFFFFFFFFFF else (float(pl.first_key & 0xFFFFFFFF), float(pl.first_key >> 32))
+        a = torch.tensor([-lrtb_local[0], lrtb_local[1], lrtb_local[2], -lrtb_local[3]] + list(pl.sum) +
+                         [float(pl.n_valid), float(pl.n_total), *first], dtype=torch.float64)
+        ga = [torch.zeros_like(a) for _ in range(world_size)]
+        dist.all_gather(ga, a)
+        A = sharding.combine_ranges_sums_reference(torch.stack(ga), 1, 1)
+        pg = F.OpmSpotPartial()
+        for j in range(7):
+            pg.sum[j] = float(A[4 + j])
+        pg.n_valid, pg.n_total = int(A[11]), int(A[12])
+        _partial_radii(stored, iso, pg)
+        fmap_g, _ = orc.fluence_binning(hits, NX, NY, ranges=(-float(A[0]), float(A[1]), float(A[2]), -float(A[3])))
+        b_blk = torch.cat([torch.from_numpy(np.ascontiguousarray(fmap_g)).reshape(-1),
+                           torch.tensor([pg.max_d2_mm2, pg.sum_d2_mm2, pg.sum_ed2], dtype=torch.float64)])
+        gb = [torch.zeros_like(b_blk) for _ in range(world_size)]
+        dist.all_gather(gb, b_blk)
+        B = sharding.combine_maps_radii_reference(torch.stack(gb), NX * NY, 1)
+        blocks_ok = (torch.equal(B[: NX * NY].reshape(t.shape), t) and float(B[NX * NY]) == p.max_d2_mm2 and
+                     abs(float(B[NX * NY + 1]) - p.sum_d2_mm2) <= 1e-12 * p.sum_d2_mm2 and int(A[13]) == 0 and int(A[14]) == 0 and
+                     (-float(A[0]), float(A[1]), float(A[2]), -float(A[3])) == tuple(lrtb))
         if rank == 0:
             q.put({"lrtb": lrtb, "map": t.numpy().copy(), "counts": counts, "energy": energy, "n_valid": st.n_valid,
                    "total_energy": st.total_energy, "centroid": list(st.energy_centroid), "geo": st.beam_radius_geo,
-                   "rms": st.energy_beam_radius_rms, "bounce_lvl": st.bounce_lvl, "shard": (b, e)})
+                   "rms": st.energy_beam_radius_rms, "bounce_lvl": st.bounce_lvl, "shard": (b, e), "blocks_ok": bool(blocks_ok)})
     finally:
         dist.destroy_process_group()
 
@@ -124,6 +147,7 @@ def test_two_rank_reduction_equals_single_process():
     osc, out = _trace(src_all)
     fmap, lrtb = orc.fluence_binning(osc.nodes[3].s[0].merged_hits(), NX, NY)
     assert got["shard"] == (0, len(src_all) // 2)
+    assert got["blocks_ok"]  # the gathered-block combination gives the same map, range, radii and first ray as the all-reduces
     assert got["lrtb"] == pytest.approx(lrtb, rel=0, abs=0)  # min/max are exact
     peak = fmap.max()
     assert np.all(np.abs(got["map"] - fmap) <= 1e-12 * np.maximum(np.abs(fmap), peak))  # only the summation order differs
