@@ -312,6 +312,33 @@ __device__ __forceinline__ BinTaps bin_taps(const BinParams& P, double x, double
     return t;
 }
 
+// x / d from the correctly rounded reciprocal of a loop-invariant d: one multiplication and one residual correction
+// (Markstein); equal to the IEEE quotient except in rare last-bit cases, where it is one ulp off
+__device__ __forceinline__ double div_by_invariant(double x, double d, double inv) {
+    const double q = x * inv;
+    return fma(fma(-q, d, x), inv, q);
+}
+struct BinInv { double width_step, height_step, bin_area; };
+// bin_taps with the three divisions by loop-invariant numbers replaced by div_by_invariant
+__device__ __forceinline__ BinTaps bin_taps_inv(const BinParams& P, const BinInv& I, double x, double y, double e, unsigned* status) {
+    BinTaps t;
+    double ipx, ipy;
+    double fx = modf(div_by_invariant(x - P.left, P.width_step, I.width_step), &ipx);
+    double fy = modf(div_by_invariant(y - P.bottom, P.height_step, I.height_step), &ipy);
+    unsigned long long xi = f64_to_usize(ipx), yi = f64_to_usize(ipy);
+    double fl = div_by_invariant(e, P.bin_area, I.bin_area);
+    t.w00 = (1.0 - fx) * (1.0 - fy) * fl;
+    t.w10 = fx * (1.0 - fy) * fl;
+    t.w01 = (1.0 - fx) * fy * fl;
+    t.w11 = fx * fy * fl;
+    t.ok = (xi < P.nx) && (yi < P.ny);
+    if (!t.ok) *status |= 1u << OPM_ERR_BIN_RANGE;
+    t.has_x = xi < P.nx - 1;
+    t.has_y = yi < P.ny - 1;
+    t.base = xi * P.ny + yi;
+    return t;
+}
+
 // map fits in shared memory: privatise the whole map per CTA, flush non-zero bins with global atomics
 __global__ void __launch_bounds__(1024) binning_smem_kernel(DevHits H, uint64_t n, long long bounce_filter, unsigned long long nx,
                                                             unsigned long long ny, const double* __restrict__ range,
@@ -340,6 +367,89 @@ __global__ void __launch_bounds__(1024) binning_smem_kernel(DevHits H, uint64_t 
     for (unsigned long long k = threadIdx.x; k < bins; k += blockDim.x) {
         double v = smap[k];
         if (v != 0.0) atomicAdd(&map[k], v);
+    }
+    if (status) atomicOr(status_out, status);
+}
+
+// The same splat with the CTA-private map held as 64-bit FIXED-POINT sums split over two 32-bit words per bin. Shared-memory
+// f64 (and u64) adds are compare-and-swap loops on sm_100a (ATOMS.CAST.SPIN.64); 32-bit integer adds are native (ATOMS.ADD), so a
+// tap costs two fire-and-forget adds: the low word (its returned old value tells whether the add wrapped) and the high word plus
+// that carry. The unit is a power of two chosen per CTA from the largest energy among the CTA's slots so that no bin can exceed
+// 2^62 units: a tap is rounded to 2^-62 x (slots per CTA) of the largest possible tap (<= 2^-45 relative to it for 10^5 slots per
+// CTA), and the CTA's sums do not depend on the order of the adds. Taps, indices and the flush into the global f64 map are
+// those of the kernel above.
+template <int BLOCK, int MIN_CTAS, int UNROLL, bool FASTDIV>
+__global__ void __launch_bounds__(BLOCK, MIN_CTAS) binning_smem_fixed_kernel(DevHits H, uint64_t n, long long bounce_filter,
+                                                                             unsigned long long nx, unsigned long long ny,
+                                                                             const double* __restrict__ range, double* __restrict__ map,
+                                                                             unsigned* status_out) {
+    extern __shared__ unsigned sfix[];
+    __shared__ unsigned long long s_emax_key;
+    BinParams P;
+    if (!bin_params_from_range(nx, ny, range, P)) return;
+    const unsigned long long bins = P.nx * P.ny;
+    unsigned* lo = sfix;
+    unsigned* hi = sfix + bins;
+    for (unsigned long long k = threadIdx.x; k < 2 * bins; k += BLOCK) sfix[k] = 0u;
+    if (threadIdx.x == 0) s_emax_key = 0ull;
+    __syncthreads();
+    const uint64_t stride = (uint64_t)gridDim.x * BLOCK;
+    const uint64_t first = blockIdx.x * (uint64_t)BLOCK + threadIdx.x;
+    const uint64_t cta_first = blockIdx.x * (uint64_t)BLOCK;
+    const uint64_t cta_slots = cta_first < n ? (n - cta_first + stride - 1) / stride * BLOCK : 0;  // upper bound, CTA-uniform
+    double emax = 0.0;
+    for (uint64_t i = first; i < n; i += stride) emax = fmax(emax, H.e[i]);  // NaN / negative (= no hit) lose against 0
+    emax = warp_max(emax);
+    if ((threadIdx.x & 31) == 0 && emax > 0.0) atomicMax(&s_emax_key, (unsigned long long)__double_as_longlong(emax));  // >= 0: bits are ordered
+    __syncthreads();
+    const double flmax = __longlong_as_double((long long)s_emax_key) / P.bin_area;
+    // every bin of this CTA stays below flmax * (slots of the CTA) < 2^ex; one unit = 2^(ex-62)
+    int ex = 0;
+    (void)frexp(flmax * (double)cta_slots, &ex);
+    ex = max(-900, min(ex, 1000));
+    const double inv_unit = ldexp(1.0, 62 - ex), unit = ldexp(1.0, ex - 62);
+    unsigned status = 0;
+    const BinInv I{1.0 / P.width_step, 1.0 / P.height_step, 1.0 / P.bin_area};
+    const bool scaled = flmax > 0.0 && isfinite(flmax);
+    {
+        auto add = [&](unsigned long long b, double w) {
+            if (w == 0.0) return;
+            // NaN / infinite taps (a NaN hit position, an infinite energy) go to the global map as they are, like the f64 kernel's
+            if (!scaled || !isfinite(w)) { atomicAdd(&map[b], w); return; }
+            const unsigned long long q = __double2ull_rn(w * inv_unit);
+            const unsigned l = (unsigned)q;
+            unsigned h = (unsigned)(q >> 32);
+            if (l) { const unsigned old = atomicAdd(&lo[b], l); h += (unsigned)(old + l < old); }
+            if (h) atomicAdd(&hi[b], h);
+        };
+        auto splat = [&](uint64_t i, double x, double y, double e) {
+            if (!(e >= 0.0)) return;
+            if (bounce_filter >= 0 && (long long)H.bounce[i] != bounce_filter) return;
+            BinTaps t = FASTDIV ? bin_taps_inv(P, I, x, y, e, &status) : bin_taps(P, x, y, e, &status);
+            if (!t.ok) return;
+            add(t.base, t.w00);
+            if (t.has_x) {
+                add(t.base + P.ny, t.w10);
+                if (t.has_y) add(t.base + P.ny + 1, t.w11);
+            }
+            if (t.has_y) add(t.base + 1, t.w01);
+        };
+        // the loads of UNROLL slots are issued before the first splat (atomics order memory operations: the compiler does not
+        // move the next slot's loads above them)
+        uint64_t i = first;
+        for (; i + (UNROLL - 1) * stride < n; i += UNROLL * stride) {
+            double x[UNROLL], y[UNROLL], e[UNROLL];
+#pragma unroll
+            for (int u = 0; u < UNROLL; ++u) { e[u] = H.e[i + u * stride]; x[u] = __ldcs(H.x + i + u * stride); y[u] = __ldcs(H.y + i + u * stride); }
+#pragma unroll
+            for (int u = 0; u < UNROLL; ++u) splat(i + u * stride, x[u], y[u], e[u]);
+        }
+        for (; i < n; i += stride) splat(i, __ldcs(H.x + i), __ldcs(H.y + i), H.e[i]);
+    }
+    __syncthreads();
+    for (unsigned long long k = threadIdx.x; k < bins; k += BLOCK) {
+        const unsigned long long q = ((unsigned long long)hi[k] << 32) | lo[k];
+        if (q) atomicAdd(&map[k], (double)q * unit);
     }
     if (status) atomicOr(status_out, status);
 }
@@ -726,7 +836,17 @@ int k_binning(DevHits H, uint64_t n, long long bounce_filter, uint64_t nx, uint6
               unsigned* status, int sms, void* stream) {
     size_t bytes = (size_t)(nx * ny) * sizeof(double);
     static const bool force_global = getenv("OPM_B200_BINNING_GLOBAL") != nullptr;  // tuning switch
-    if (bytes <= 160 * 1024 && !force_global) {
+    // OPM_B200_BINNING_FIXED=0: the f64 compare-and-swap kernel (tuning switch; profiles/binning_variants.sh)
+    static const bool fixed = [] { const char* e = getenv("OPM_B200_BINNING_FIXED"); return e ? atoi(e) != 0 : true; }();
+    if (bytes <= 160 * 1024 && !force_global && fixed) {
+        // two CTAs of 1024 threads per SM when two private maps fit in its shared memory (all 64 warps of the SM hide the
+        // latency of the adds), else one; measured on the C2 detectors (10^7 slots, 100 x 83): 200 -> 85 us per map
+        const int ctas = (2 * (bytes + 1024) <= 227 * 1024) ? 2 : 1;
+        cudaError_t e = cudaFuncSetAttribute(binning_smem_fixed_kernel<1024, 2, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+        if (e != cudaSuccess) return (int)e;
+        binning_smem_fixed_kernel<1024, 2, 2, true><<<grid_for(n, 1024, sms * ctas), 1024, bytes, ST>>>(H, n, bounce_filter, nx, ny, range_dev,
+                                                                                                      map, status);
+    } else if (bytes <= 160 * 1024 && !force_global) {
         cudaError_t e = cudaFuncSetAttribute(binning_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
         if (e != cudaSuccess) return (int)e;
         // the privatised map takes most of an SM's shared memory: one CTA per SM, as many warps as it can hold
