@@ -102,14 +102,26 @@ void appendf(std::string& s, const char* fmt, ...) {
     s += buf;
 }
 
+// rotation exactly the identity: the isometry is a pure translation, a structural fact the kernel is specialised for
+bool rot_is_identity(const DevIso& I) {
+    for (int j = 0; j < 9; ++j)
+        if (I.r[j] != ((j % 4 == 0) ? 1.0 : 0.0)) return false;
+    return true;
+}
+bool jit_rot_id_enabled() {
+    static const bool on = [] { const char* e = getenv("OPM_B200_JIT_ROT_ID"); return !(e && e[0] == '0'); }();  // tuning switch
+    return on;
+}
+
 // one line of kernel body per op; the same text is the structural cache key
 std::string op_line(const DevOp& op, int k) {
     std::string s;
     switch (op.kind) {
         case OPK_REFRACT: {
             const DevRefract& o = op.u.refract;
-            appendf(s, "        exec_refract(RefractCt<%d, %d, %d, %d, %d, %d, %d, %d>(opm_jit_ops[%d].u.refract), x);\n", o.geom, o.coating,
-                    o.has_index ? 1 : 0, o.index_type, o.strategy, o.flags, o.refraction_intended ? 1 : 0, o.hits.e ? 1 : 0, k);
+            const int rot_id = jit_rot_id_enabled() && rot_is_identity(o.inv) && rot_is_identity(o.fwd) ? 1 : 0;
+            appendf(s, "        exec_refract(RefractCt<%d, %d, %d, %d, %d, %d, %d, %d, %d>(opm_jit_ops[%d].u.refract), x);\n", o.geom, o.coating,
+                    o.has_index ? 1 : 0, o.index_type, o.strategy, o.flags, o.refraction_intended ? 1 : 0, o.hits.e ? 1 : 0, rot_id, k);
             break;
         }
         case OPK_APODIZE: {
@@ -117,8 +129,9 @@ std::string op_line(const DevOp& op, int k) {
             unsigned to = 0;
             for (int j = 0; j < a.n_items && j < OPM_MAX_APERTURE_ITEMS; ++j)
                 to |= ((unsigned)(a.items[j].type & 7) | (a.items[j].obstruction ? 8u : 0u)) << (4 * j);
-            appendf(s, "        exec_apodize(ApertureCt<%d, %d, %d, 0x%xu>(opm_jit_ops[%d].u.apodize.ap), opm_jit_ops[%d].u.apodize.inv, x);\n",
-                    a.n_items, a.is_stack ? 1 : 0, a.stack_obstruction ? 1 : 0, to, k, k);
+            appendf(s, "        exec_apodize<%s>(ApertureCt<%d, %d, %d, 0x%xu>(opm_jit_ops[%d].u.apodize.ap), opm_jit_ops[%d].u.apodize.inv, x);\n",
+                    jit_rot_id_enabled() && rot_is_identity(op.u.apodize.inv) ? "true" : "false", a.n_items, a.is_stack ? 1 : 0,
+                    a.stack_obstruction ? 1 : 0, to, k, k);
             break;
         }
         case OPK_THRESHOLD: appendf(s, "        exec_threshold(opm_jit_ops[%d].u.threshold, x);\n", k); break;

@@ -173,11 +173,12 @@ __device__ __forceinline__ bool exec_diffract(const V& v, const DevDiffract& o, 
 }
 
 // Rays::apodize (rays.rs:557-573); returns true for a ray this call invalidated (its position goes to `pos_hist`, :566)
-template <class A>
+// ROT_ID: `inv` is a pure translation (see RefractCt)
+template <bool ROT_ID = false, class A>
 __device__ __forceinline__ bool exec_apodize(const A& av, const DevIso& inv, RayCtx& x) {
     if (!x.valid) return false;
-    double lx = inv.r[0] * x.r.pos.x + inv.r[1] * x.r.pos.y + inv.r[2] * x.r.pos.z + inv.t[0];
-    double ly = inv.r[3] * x.r.pos.x + inv.r[4] * x.r.pos.y + inv.r[5] * x.r.pos.z + inv.t[1];
+    double lx = ROT_ID ? x.r.pos.x + inv.t[0] : inv.r[0] * x.r.pos.x + inv.r[1] * x.r.pos.y + inv.r[2] * x.r.pos.z + inv.t[0];
+    double ly = ROT_ID ? x.r.pos.y + inv.t[1] : inv.r[3] * x.r.pos.x + inv.r[4] * x.r.pos.y + inv.r[5] * x.r.pos.z + inv.t[1];
     double f = aperture_factor(av, lx, ly);
     if (f > 0.0) {
         if (!(f <= 1.0)) x.c.status |= 1u << OPM_ERR_APODIZE_FACTOR;
