@@ -137,6 +137,10 @@ class DetectorReadout:
                  (maps too large to gather -- more than FUSED_LIMIT doubles over all ranks -- are all-reduced instead)
         phase C  peak / total of every (global) map                                                          [local, async]
         read     one device->host copy of the scalars (and the maps if asked), one synchronisation
+
+    `run()` does all of it; `launch(slot)` / `collect(slot)` split it at the synchronisation so that a caller that analyses
+    one scene after another (a sweep, a tolerancing run) can queue the next trace before it reads the previous reports:
+    two sets of pinned host buffers, one CUDA event each, the device buffers are reused in stream order.
     """
     FUSED_LIMIT = 8 * 1024 * 1024  # doubles in the gathered (maps | radii) buffer
 
@@ -155,10 +159,10 @@ class DetectorReadout:
         self.mb = torch.zeros(self.maps_len + self.nB, dtype=torch.float64, device=device)  # maps | B
         self.maps = self.mb[: self.maps_len].view(max(nf, 1), nx * ny)
         self.status = torch.zeros(max(nf, 1), dtype=torch.int32, device=device)
-        self.h_buf = torch.zeros(self.buf.numel(), dtype=torch.float64).pin_memory()
-        self.h_B = torch.zeros(max(self.nB, 1), dtype=torch.float64).pin_memory()
-        self.h_status = torch.zeros(self.status.numel(), dtype=torch.int32).pin_memory()
-        self.h_maps = torch.zeros_like(self.maps, device="cpu").pin_memory()
+        self.host = [{"buf": torch.zeros(self.buf.numel(), dtype=torch.float64).pin_memory(),
+                      "B": torch.zeros(max(self.nB, 1), dtype=torch.float64).pin_memory(),
+                      "status": torch.zeros(self.status.numel(), dtype=torch.int32).pin_memory(),
+                      "maps": None, "event": None, "with_maps": False} for _ in range(2)]
         w = world()[1]
         self.fused = w > 1 and self.mb.numel() * w <= self.FUSED_LIMIT
         self.gA = torch.zeros((w, self.nA), dtype=torch.float64, device=device) if w > 1 else None
@@ -173,6 +177,11 @@ class DetectorReadout:
         return (self.C.c_void_p * len(hm))(*[h.h for h in hm]), len(hm)
 
     def run(self, download_maps: bool = False) -> dict:
+        self.launch(download_maps, 0)
+        return self.collect(0)
+
+    def launch(self, download_maps: bool = False, slot: int = 0):
+        """queue the whole read-out and its device->host copies on the current stream; nothing waits"""
         L, C, F = self.F.lib(), self.C, self.F
         from .api import _check
         rank, w = world()
@@ -209,29 +218,42 @@ class DetectorReadout:
             _check(L.opm_fluence_peak_total_async(self.ctx.h, vp(self.maps[j].data_ptr()), nx, ny, vp(self._ptr(self.buf, 4 * j)),
                                                   vp(self._ptr(self.buf, self.nA + 2 * j))))
         # ---- read
-        self.h_buf.copy_(self.buf, non_blocking=True)
+        H = self.host[slot]
+        H["buf"].copy_(self.buf, non_blocking=True)
         if ns:
-            self.h_B.copy_(self.mb[self.maps_len:], non_blocking=True)
-        self.h_status.copy_(self.status, non_blocking=True)
-        if download_maps and nf:
-            self.h_maps.copy_(self.maps, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
-        h = self.h_buf
+            H["B"].copy_(self.mb[self.maps_len:], non_blocking=True)
+        H["status"].copy_(self.status, non_blocking=True)
+        H["with_maps"] = bool(download_maps and nf)
+        if H["with_maps"]:
+            if H["maps"] is None:
+                H["maps"] = torch.zeros_like(self.maps, device="cpu").pin_memory()
+            H["maps"].copy_(self.maps, non_blocking=True)
+        if H["event"] is None:
+            H["event"] = torch.cuda.Event()
+        H["event"].record(torch.cuda.current_stream())
+
+    def collect(self, slot: int = 0) -> dict:
+        """wait for the read-out queued in `slot` and build the reports"""
+        L, C, F = self.F.lib(), self.C, self.F
+        nf, nx, ny = len(self.fl), self.nx, self.ny
+        H = self.host[slot]
+        H["event"].synchronize()
+        h, download_maps = H["buf"], H["with_maps"]
         out = {}
         for j, node in enumerate(self.fl):
             r = h[4 * j: 4 * j + 4].tolist()
             lrtb = (-r[0], r[1], r[2], -r[3])
             if not all(math.isfinite(v) for v in lrtb):
                 raise ValueError("could not calculate bounding box")
-            st = int(self.h_status[j])
+            st = int(H["status"][j])
             if st:
                 raise RuntimeError(f"fluence binning raised status bits {st:#x}")
             pk = h[self.nA + 2 * j: self.nA + 2 * j + 2].tolist()
             out[node] = {"lrtb": lrtb, "peak": pk[0], "total_energy": pk[1],
-                         "map": self.h_maps[j].numpy().reshape(nx, ny).T.copy() if download_maps else None}
+                         "map": H["maps"][j].numpy().reshape(nx, ny).T.copy() if download_maps else None}
         for k, node in enumerate(self.sp):
             s = h[4 * nf + 11 * k: 4 * nf + 11 * k + 11].tolist()
-            rr = self.h_B[3 * k: 3 * k + 3].tolist()
+            rr = H["B"][3 * k: 3 * k + 3].tolist()
             p = F.OpmSpotPartial()
             for i in range(7):
                 p.sum[i] = s[i]
