@@ -115,7 +115,7 @@ __global__ void __launch_bounds__(256) spot_pass1_kernel(DevRays R, uint64_t n, 
             const uint64_t i = base + u * stride;
             const bool in = i < n;
             v[u] = in ? R.valid[i] : (uint8_t)RAY_REMOVED;
-            const bool ld = in && v[u] == RAY_VALID;
+            const bool ld = in;  // not `valid`: the loads would wait for the flag (two round trips); most slots are valid anyway
             px[u] = ld ? __ldcs(R.px + i) : 0.0; py[u] = ld ? __ldcs(R.py + i) : 0.0; pz[u] = ld ? __ldcs(R.pz + i) : 0.0;
             e[u] = ld ? __ldcs(R.e + i) : 0.0; id[u] = ld ? __ldcs(R.id + i) : 0u; bn[u] = ld ? __ldcs(R.bounces + i) : 0u;
         }
@@ -168,9 +168,10 @@ __global__ void __launch_bounds__(256) spot_pass2_kernel(DevRays R, uint64_t n, 
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
             const uint64_t i = base + u * stride;
-            ok[u] = i < n && R.valid[i] == RAY_VALID;
-            px[u] = ok[u] ? __ldcs(R.px + i) : 0.0; py[u] = ok[u] ? __ldcs(R.py + i) : 0.0; pz[u] = ok[u] ? __ldcs(R.pz + i) : 0.0;
-            e[u] = ok[u] ? __ldcs(R.e + i) : 0.0;
+            const bool in = i < n;  // loads do not wait for the flag
+            ok[u] = in && R.valid[i] == RAY_VALID;
+            px[u] = in ? __ldcs(R.px + i) : 0.0; py[u] = in ? __ldcs(R.py + i) : 0.0; pz[u] = in ? __ldcs(R.pz + i) : 0.0;
+            e[u] = in ? __ldcs(R.e + i) : 0.0;
         }
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
@@ -241,9 +242,10 @@ __global__ void __launch_bounds__(256) hits_bbox_kernel(DevHits H, uint64_t n, l
             const uint64_t i = base + u * stride;
             const bool in = i < n;
             e[u] = in ? __ldcs(H.e + i) : -1.0;
+            // x and y do not wait for e (one round trip instead of two; empty slots cost their bytes)
+            x[u] = in ? __ldcs(H.x + i) : 0.0; y[u] = in ? __ldcs(H.y + i) : 0.0;
             ok[u] = e[u] >= 0.0;
             if (ok[u] && bounce_filter >= 0) ok[u] = (long long)H.bounce[i] == bounce_filter;
-            x[u] = ok[u] ? __ldcs(H.x + i) : 0.0; y[u] = ok[u] ? __ldcs(H.y + i) : 0.0;
         }
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
