@@ -289,6 +289,9 @@ uint64_t opm_jit_selftest(char* log, uint64_t log_capacity);
 void opm_isometry_identity(OpmIsometry* out);
 OpmStatus opm_isometry_new(const double translation[3], const double euler_xyz[3], OpmIsometry* out); /* :44-72 */
 void opm_isometry_append(const OpmIsometry* a, const OpmIsometry* b, OpmIsometry* out);              /* :216-223 */
+/* Isometry::new_from_view (:166-185): origin at `pos`, local z along `dir`, local y as close to `up` as orthogonality allows
+ * (nalgebra Isometry3::face_towards(pos, pos + dir, up)); `up` must not be collinear with `dir` */
+OpmStatus opm_isometry_from_view(const double pos[3], const double dir[3], const double up[3], OpmIsometry* out);
 void opm_raytrace_config_default(OpmRayTraceConfig* out);                                             /* analyzers/raytrace.rs:315-322 */
 
 /* ---- struct Rays (rays.rs:62-73) */

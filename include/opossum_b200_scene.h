@@ -14,9 +14,12 @@
  *     nodes/node_group/analysis_raytrace.rs:29-91) and `GhostFocusAnalyzer::analyze`
  *     (analyzers/ghostfocus.rs:82-122 with nodes/node_group/analysis_ghostfocus.rs:22-109).
  *
- * Scope limits (SURVEY.md 8f "next"): the scene is a chain of nodes with explicit isometries (node
- * positioning from an axis ray and .opm ingestion are out of scope); a beam splitter may feed a side chain
- * from its second output.  Only the Binning fluence estimator exists on the device.
+ *   - node positioning from the optical axis: `NodeGroup::connect_nodes(.., distance)` + `calc_node_positions`
+ *     (nodes/node_group/analysis_raytrace.rs:92-212, nodes/node_group/optic_graph.rs:878-926).
+ *
+ * Scope limits (SURVEY.md 8f "next"): the scene is a chain of nodes (explicit isometries, or edge distances placed by
+ * opm_scene_calc_node_positions); a beam splitter may feed a side chain from its second output; .opm ingestion is out of
+ * scope.  Fluence estimators on the device: Binning and KDE.
  */
 #ifndef OPOSSUM_B200_SCENE_H
 #define OPOSSUM_B200_SCENE_H
@@ -85,6 +88,24 @@ void opm_scene_destroy(OpmScene* scene);
 OpmStatus opm_scene_set_ambient(OpmScene* scene, const OpmIndexModel* ambient);
 OpmStatus opm_scene_add_node(OpmScene* scene, const OpmNodeDesc* desc, int32_t* node_index);
 int32_t opm_scene_node_count(const OpmScene* scene);
+
+/* ---- node positioning from the optical axis
+ * NodeGroup::add_node + connect_nodes(predecessor, port, node, "input_1", distance) for a node WITHOUT an isometry of its own
+ * (desc->iso is ignored; desc->parent / parent_port name the predecessor's output as in opm_scene_add_node; the local
+ * `alignment` still applies, optic_node.rs:356-363).  The node cannot be analysed before it has been placed. */
+OpmStatus opm_scene_add_node_at_distance(OpmScene* scene, const OpmNodeDesc* desc, double distance_m, int32_t* node_index);
+/* AnalysisRayTrace::calc_node_positions of the node group (nodes/node_group/analysis_raytrace.rs:92-212), which
+ * RayTracingAnalyzer::analyze runs before the analysis proper (analyzers/raytrace.rs:44): ONE axis ray -- Rays::
+ * get_optical_axis_ray = Ray::new_collimated(origin, axis_wavelength, 1 J) in the source's frame (nodes/source.rs:236-268,
+ * rays.rs:1414-1421) -- is passed from node to node through each node's own analysis on the device (beam splitter: only its
+ * input surface, both outputs carry the ray; beam_splitter/analysis_raytrace.rs:40-93); every node that has not been placed
+ * gets Isometry::new_from_view(position of the ray after Ray::propagate(distance), its direction, up) (optic_graph.rs:
+ * 878-926, ray.rs:408-434); `up` starts as Ray::define_up_direction of the source's axis ray (ray.rs:818-838) and is rotated by
+ * each node's last direction change (Ray::calc_new_up_direction, ray.rs:842-860).  Nodes are walked in index order (the
+ * reference: topological order).  Ends with reset_data like the reference.  config NULL = RayTraceConfig::default(). */
+OpmStatus opm_scene_calc_node_positions(OpmScene* scene, double axis_wavelength_m, const OpmRayTraceConfig* config);
+/* OpticNode::isometry(): the node isometry (without the local alignment); OPM_ERR_ARG while the node is not placed */
+OpmStatus opm_scene_node_isometry(const OpmScene* scene, int32_t node, OpmIsometry* out);
 /* OpticNode::reset_data: clears hit maps, ray caches and stored detector data (optic_node.rs:84-95) */
 OpmStatus opm_scene_reset_data(OpmScene* scene);
 

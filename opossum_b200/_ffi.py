@@ -201,6 +201,7 @@ class OpmCriticalFluence(C.Structure):
 # every symbol include/opossum_b200_scene.h declares
 SCENE_EXPORTS = [
     "opm_node_desc_init", "opm_scene_create", "opm_scene_destroy", "opm_scene_set_ambient", "opm_scene_add_node",
+    "opm_scene_add_node_at_distance", "opm_scene_calc_node_positions", "opm_scene_node_isometry",
     "opm_scene_node_count", "opm_scene_reset_data", "opm_scene_raytrace", "opm_scene_output_rays", "opm_scene_node_rays", "opm_scene_node_spot",
     "opm_scene_node_spot_partial", "opm_scene_node_spot_async",
     "opm_scene_node_fluence", "opm_scene_node_fluence_kde", "opm_scene_node_spectrum", "opm_scene_node_wavefront", "opm_scene_node_hitmaps", "opm_scene_ghostfocus", "opm_scene_gf_pass_tally",
@@ -212,7 +213,7 @@ EXPORTS = [
     "opm_abi_version", "opm_abi_sizeof", "opm_last_error", "opm_status_string", "opm_context_create", "opm_context_destroy",
     "opm_context_synchronize", "opm_context_stream", "opm_context_launch_count", "opm_context_set_kernel_timing",
     "opm_context_kernel_timing", "opm_context_set_jit", "opm_context_jit_wait", "opm_context_jit_stats", "opm_jit_selftest", "opm_isometry_identity",
-    "opm_isometry_new", "opm_isometry_append", "opm_raytrace_config_default", "opm_rays_create", "opm_rays_destroy",
+    "opm_isometry_new", "opm_isometry_append", "opm_isometry_from_view", "opm_raytrace_config_default", "opm_rays_create", "opm_rays_destroy",
     "opm_rays_len", "opm_rays_capacity", "opm_rays_clear", "opm_rays_reserve", "opm_rays_upload",
     "opm_rays_upload_soa", "opm_rays_new_collimated_with_spectrum", "opm_rays_download", "opm_rays_copy", "opm_rays_append", "opm_rays_compact",
     "opm_rays_enable_position_history", "opm_rays_disable_position_history", "opm_rays_clear_position_history",
@@ -272,6 +273,7 @@ def lib() -> C.CDLL:
         "opm_isometry_identity": (None, [C.POINTER(OpmIsometry)]),
         "opm_isometry_new": (i32, [dp, dp, C.POINTER(OpmIsometry)]),
         "opm_isometry_append": (None, [C.POINTER(OpmIsometry)] * 3),
+        "opm_isometry_from_view": (i32, [dp, dp, dp, C.POINTER(OpmIsometry)]),
         "opm_raytrace_config_default": (None, [C.POINTER(OpmRayTraceConfig)]),
         "opm_rays_create": (i32, [vp, u64, pp]),
         "opm_rays_destroy": (None, [vp]),
@@ -358,6 +360,9 @@ def lib() -> C.CDLL:
         "opm_scene_destroy": (None, [vp]),
         "opm_scene_set_ambient": (i32, [vp, C.POINTER(OpmIndexModel)]),
         "opm_scene_add_node": (i32, [vp, C.POINTER(OpmNodeDesc), C.POINTER(i32)]),
+        "opm_scene_add_node_at_distance": (i32, [vp, C.POINTER(OpmNodeDesc), C.c_double, C.POINTER(i32)]),
+        "opm_scene_calc_node_positions": (i32, [vp, C.c_double, C.POINTER(OpmRayTraceConfig)]),
+        "opm_scene_node_isometry": (i32, [vp, i32, C.POINTER(OpmIsometry)]),
         "opm_scene_node_count": (i32, [vp]),
         "opm_scene_reset_data": (i32, [vp]),
         "opm_scene_raytrace": (i32, [vp, vp, C.POINTER(OpmRayTraceConfig), i32, C.POINTER(OpmTraceStats)]),

@@ -64,6 +64,13 @@ class Isometry:
     def new_along_z(z: float) -> "Isometry":
         return Isometry.new((0.0, 0.0, z))
 
+    @staticmethod
+    def new_from_view(view_point, view_direction, up_direction) -> "Isometry":
+        """Isometry::new_from_view :166-185 (origin at the view point, local z along the view direction)"""
+        o = F.OpmIsometry()
+        _check(F.lib().opm_isometry_from_view(_d3(view_point), _d3(view_direction), _d3(up_direction), C.byref(o)))
+        return Isometry(o)
+
     def append(self, rhs: "Isometry") -> "Isometry":
         o = F.OpmIsometry()
         F.lib().opm_isometry_append(C.byref(self.c), C.byref(rhs.c), C.byref(o))

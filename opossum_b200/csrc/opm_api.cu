@@ -348,6 +348,34 @@ extern "C" void opm_isometry_append(const OpmIsometry* a, const OpmIsometry* b, 
     o->fwd = f;
     iso_invert(o->fwd, o->inv);
 }
+// Isometry::new_from_view (geom_transformation.rs:166-185) = Isometry3::face_towards(eye, eye + dir, up): rotation columns
+// x = unit(up x z), y = unit(z x x), z = unit((eye + dir) - eye); nalgebra keeps the rotation as a unit quaternion, here it stays
+// the matrix (the round trip through the quaternion only adds rounding)
+extern "C" OpmStatus opm_isometry_from_view(const double p[3], const double dir[3], const double up[3], OpmIsometry* o) {
+    if (!p || !dir || !up || !o) return fail(OPM_ERR_ARG, "null argument");
+    double z[3], x[3], y[3];
+    for (int k = 0; k < 3; ++k) z[k] = (p[k] + dir[k]) - p[k];
+    auto unit = [](double v[3]) {
+        const double n = sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
+        for (int k = 0; k < 3; ++k) v[k] /= n;
+        return n;
+    };
+    auto cross = [](const double a[3], const double b[3], double c[3]) {
+        c[0] = a[1] * b[2] - a[2] * b[1]; c[1] = a[2] * b[0] - a[0] * b[2]; c[2] = a[0] * b[1] - a[1] * b[0];
+    };
+    if (!(unit(z) > 0.0)) return fail(OPM_ERR_ARG, "view direction must not be zero");
+    cross(up, z, x);
+    if (!(unit(x) > 0.0)) return fail(OPM_ERR_ARG, "up direction must not be collinear to the view direction");
+    cross(z, x, y);
+    unit(y);
+    for (int r = 0; r < 3; ++r) {
+        o->fwd.rot[3 * r + 0] = x[r]; o->fwd.rot[3 * r + 1] = y[r]; o->fwd.rot[3 * r + 2] = z[r];
+        o->fwd.t[r] = p[r];
+        if (!std::isfinite(p[r]) || !std::isfinite(x[r]) || !std::isfinite(y[r]) || !std::isfinite(z[r])) return fail(OPM_ERR_ARG, "view must be finite");
+    }
+    iso_invert(o->fwd, o->inv);
+    return OPM_OK;
+}
 extern "C" void opm_raytrace_config_default(OpmRayTraceConfig* c) {  // analyzers/raytrace.rs:315-322
     c->min_energy_per_ray = 1.0 * 1.0E-12;
     c->max_number_of_bounces = 1000;

@@ -44,6 +44,8 @@ struct Node {
     OpmRays* split = nullptr;   // second output of a beam splitter
     std::vector<std::shared_ptr<Bundle>> stored_gf;  // LightData::GhostFocus kept by a detector
     int main_child = -1, split_child = -1;
+    bool placed = true;         // false: waits for opm_scene_calc_node_positions (a node without an isometry of its own)
+    double distance = 0.0;      // edge distance from the predecessor (NodeGroup::connect_nodes)
     bool side_inlined = false;  // the second output's side chain ran inside the main launch (OPM_OP_FORK .. OPM_OP_JOIN)
 };
 
@@ -541,12 +543,179 @@ extern "C" OpmStatus opm_scene_add_node(OpmScene* sc, const OpmNodeDesc* d, int3
 }
 extern "C" int32_t opm_scene_node_count(const OpmScene* sc) { return sc ? (int32_t)sc->nodes.size() : 0; }
 
+// ---------------------------------------------------------------------------------------------
+// node positioning from the optical axis
+// ---------------------------------------------------------------------------------------------
+extern "C" OpmStatus opm_scene_add_node_at_distance(OpmScene* sc, const OpmNodeDesc* d, double distance, int32_t* idx) {
+    if (!sc || !d || !std::isfinite(distance)) return OPM_ERR_ARG;  // "propagation length must be finite" (ray.rs:414-418)
+    if (sc->nodes.empty()) return OPM_ERR_ARG;                      // the source carries an isometry of its own
+    OpmNodeDesc copy = *d;
+    opm_isometry_identity(&copy.iso);  // placeholder: validates the parameters, replaced when the node is placed
+    int32_t i = -1;
+    OpmStatus st = opm_scene_add_node(sc, &copy, &i);
+    if (st) return st;
+    sc->nodes[i]->placed = false;
+    sc->nodes[i]->distance = distance;
+    if (idx) *idx = i;
+    return OPM_OK;
+}
+extern "C" OpmStatus opm_scene_node_isometry(const OpmScene* sc, int32_t node, OpmIsometry* out) {
+    if (!sc || !out || node < 0 || node >= (int)sc->nodes.size() || !sc->nodes[node]->placed) return OPM_ERR_ARG;
+    *out = sc->nodes[node]->d.iso;
+    return OPM_OK;
+}
+
+namespace {
+struct AxisRay { OpmRay ray; bool has_prev = false; double prev_dir[3] = {0, 0, 0}; bool set = false; };
+
+// Ray::define_up_direction (ray.rs:818-838)
+void define_up_direction(const double dir_in[3], double up[3]) {
+    auto cross_norm = [](const double a[3], const double b[3]) {
+        const double c[3] = {a[1] * b[2] - a[2] * b[1], a[2] * b[0] - a[0] * b[2], a[0] * b[1] - a[1] * b[0]};
+        return std::sqrt(c[0] * c[0] + c[1] * c[1] + c[2] * c[2]);
+    };
+    const double len = std::sqrt(dir_in[0] * dir_in[0] + dir_in[1] * dir_in[1] + dir_in[2] * dir_in[2]);
+    const double dir[3] = {dir_in[0] / len, dir_in[1] / len, dir_in[2] / len};
+    const double X[3] = {1, 0, 0}, Y[3] = {0, 1, 0}, Z[3] = {0, 0, 1};
+    const double eps = 2.220446049250313e-16;
+    if (cross_norm(dir, X) < eps || cross_norm(dir, Z) < eps) { up[0] = 0; up[1] = 1; up[2] = 0; return; }
+    if (cross_norm(dir, Y) < eps) { up[0] = 1; up[1] = 0; up[2] = 0; return; }
+    const double k = dir[1];  // y . dir
+    double pr[3] = {-k * dir[0], 1.0 - k * dir[1], -k * dir[2]};
+    const double pl = std::sqrt(pr[0] * pr[0] + pr[1] * pr[1] + pr[2] * pr[2]);
+    for (int c = 0; c < 3; ++c) up[c] = pr[c] / pl;
+}
+// Ray::calc_new_up_direction (ray.rs:842-860): up <- Rotation3::rotation_between(prev_dir, dir) * up when the direction changed
+// by more than 1000 eps (axis = unit(a x b), angle = acos(a . b), Rodrigues matrix; parallel: identity, anti-parallel: untouched)
+void calc_new_up_direction(const double prev[3], const double dir[3], double up[3]) {
+    const double eps = 2.220446049250313e-16;
+    auto norm = [](const double v[3]) { return std::sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]); };
+    const double d[3] = {prev[0] - dir[0], prev[1] - dir[1], prev[2] - dir[2]};
+    if (!(norm(d) > eps * 1000.)) return;
+    const double la = norm(prev), lb = norm(dir);
+    if (!(la > 0.0) || !(lb > 0.0)) return;
+    const double a[3] = {prev[0] / la, prev[1] / la, prev[2] / la}, b[3] = {dir[0] / lb, dir[1] / lb, dir[2] / lb};
+    const double c[3] = {a[1] * b[2] - a[2] * b[1], a[2] * b[0] - a[0] * b[2], a[0] * b[1] - a[1] * b[0]};
+    const double cn = norm(c);
+    if (!(cn > eps)) return;
+    const double ux = c[0] / cn, uy = c[1] / cn, uz = c[2] / cn;
+    const double angle = std::acos(a[0] * b[0] + a[1] * b[1] + a[2] * b[2]);
+    if (angle == 0.0) return;
+    const double sn = std::sin(angle), cs = std::cos(angle), omc = 1.0 - cs;
+    const double m[9] = {ux * ux + (1.0 - ux * ux) * cs, ux * uy * omc - uz * sn,       ux * uz * omc + uy * sn,
+                         ux * uy * omc + uz * sn,       uy * uy + (1.0 - uy * uy) * cs, uy * uz * omc - ux * sn,
+                         ux * uz * omc - uy * sn,       uy * uz * omc + ux * sn,       uz * uz + (1.0 - uz * uz) * cs};
+    const double v[3] = {up[0], up[1], up[2]};
+    for (int r = 0; r < 3; ++r) up[r] = m[3 * r] * v[0] + m[3 * r + 1] * v[1] + m[3 * r + 2] * v[2];
+}
+
+// passes the one-ray bundle through `ops`, one op per launch; the ray is read back after every op that can change its
+// direction, so that `prev_dir` (the direction before the last surface that was reached: ray.rs:450,541,628-631,676) is known
+OpmStatus run_axis_ops(OpmRays* bundle, const std::vector<OpmOp>& ops, int flags, AxisRay& a) {
+    for (const OpmOp& op : ops) {
+        const bool turns = op.kind == OPM_OP_REFRACT || op.kind == OPM_OP_DIFFRACT || op.kind == OPM_OP_PARAXIAL;
+        OpmTraceStats st;
+        memset(&st, 0, sizeof st);
+        OpmStatus rc = opm_trace_sequence(bundle, &op, 1, flags & OPM_TRACE_STRICT, nullptr, &st);
+        if (rc) return rc;
+        if (!turns) continue;
+        OpmRay after;
+        uint64_t n = 0;
+        rc = opm_rays_download(bundle, &after, 1, &n);
+        if (rc) return rc;
+        if (n != 1) return OPM_ERR_ARG;  // "no rays in this ray bundle. cannot position nodes" (optic_graph.rs:919-923)
+        const bool was_valid = a.ray.valid != 0;
+        const bool reached = op.kind == OPM_OP_PARAXIAL ? was_valid
+                                                        : (was_valid && st.interactions == 1 && (st.missed == 0 || after.bounces != a.ray.bounces));
+        if (reached) { a.has_prev = true; memcpy(a.prev_dir, a.ray.dir, sizeof a.prev_dir); }
+        a.ray = after;
+    }
+    uint64_t n = 0;
+    OpmStatus rc = opm_rays_download(bundle, &a.ray, 1, &n);  // energy / validity after the trailing apodize, threshold, limits
+    if (rc) return rc;
+    return n == 1 ? OPM_OK : OPM_ERR_ARG;
+}
+}  // namespace
+
+extern "C" OpmStatus opm_scene_calc_node_positions(OpmScene* sc, double wavelength, const OpmRayTraceConfig* cfg_in) {
+    if (!sc || sc->nodes.empty() || !(wavelength > 0.0) || !std::isfinite(wavelength)) return OPM_ERR_ARG;
+    OpmRayTraceConfig cfg;
+    if (cfg_in) cfg = *cfg_in; else opm_raytrace_config_default(&cfg);
+    OpmStatus st = opm_scene_reset_data(sc);
+    if (st) return st;
+    const int N = (int)sc->nodes.size();
+    std::vector<AxisRay> out_main(N), out_split(N);
+    double up[3] = {0.0, 1.0, 0.0};  // analysis_raytrace.rs:103
+    OpmRays* bundle = nullptr;
+    st = acquire_rays(sc, 1, &bundle);
+    if (st) return st;
+    auto done = [&](OpmStatus rc) { sc->pool_rays.push_back(bundle); opm_scene_reset_data(sc); return rc; };
+    const int flags = 0;
+    for (int i = 0; i < N; ++i) {
+        Node& n = *sc->nodes[i];
+        AxisRay a;
+        if (i == 0) {  // nodes/source.rs:236-268: Ray::new_collimated(origin, wavelength, 1 J) moved into the source's frame
+            memset(&a.ray, 0, sizeof a.ray);
+            a.ray.dir[2] = 1.0; a.ray.e = 1.0; a.ray.wvl = wavelength; a.ray.n = 1.0; a.ray.valid = 1;
+            st = opm_rays_upload(bundle, &a.ray, 1);
+            if (st) return done(st);
+            OpmOp op;
+            memset(&op, 0, sizeof op);
+            op.kind = OPM_OP_TRANSFORM; op.u.transform.iso = n.s[0].eff_iso; op.u.transform.inverse = 0;
+            st = run_axis_ops(bundle, {op}, flags, a);
+            if (st) return done(st);
+            define_up_direction(a.ray.dir, up);
+            a.set = true;
+            out_main[0] = a;
+            continue;
+        }
+        const AxisRay& in = (n.d.parent_port == 1 ? out_split : out_main)[n.parent];
+        if (!in.set) return done(OPM_ERR_ARG);
+        a = in;  // prev_dir is a field of the ray: it survives a node whose surface the ray does not reach
+        if (!n.placed) {  // optic_graph.rs:878-926: ray.propagate(distance), Isometry::new_from_view(position, direction, up)
+            double pos[3];
+            for (int c = 0; c < 3; ++c) pos[c] = a.ray.pos[c] + n.distance * a.ray.dir[c];
+            st = opm_isometry_from_view(pos, a.ray.dir, up, &n.d.iso);
+            if (st) return done(st);
+            st = update_surfaces(n);
+            if (st) return done(st);
+            n.placed = true;
+        }
+        st = opm_rays_upload(bundle, &a.ray, 1);
+        if (st) return done(st);
+        Runner R{bundle, flags};
+        int edges = 1;
+        if (n.d.type == OPM_NODE_BEAM_SPLITTER) {  // beam_splitter/analysis_raytrace.rs:40-93: the input surface only
+            R.ops.push_back(op_refract(n.s[0], nullptr, true, cfg.missed_surface_strategy, 0, nullptr, nullptr));
+            edges = 2;
+        } else {
+            st = compile_node_rt(sc, n, cfg, OPM_SCENE_NO_SNAPSHOTS, 1, R);  // ops are collected, not launched (a node has < 128 ops)
+            if (st) return done(st);
+        }
+        std::vector<OpmOp> ops;
+        ops.swap(R.ops);
+        for (OpmOp& op : ops)  // the axis ray records nothing (the reference resets the data afterwards)
+            if (op.kind == OPM_OP_REFRACT) op.u.refract.hits = nullptr;
+        st = run_axis_ops(bundle, ops, flags, a);
+        if (st) return done(st);
+        a.set = true;
+        out_main[i] = a;
+        if (edges == 2) out_split[i] = a;
+        for (int e = 0; e < edges; ++e) {  // once per outgoing edge (analysis_raytrace.rs:199-208)
+            if (!a.has_prev) return done(OPM_ERR_ARG);  // "no previous direction of ray defined to calculate new up-direction!"
+            calc_new_up_direction(a.prev_dir, a.ray.dir, up);
+        }
+    }
+    return done(OPM_OK);
+}
+
 // RayTracingAnalyzer::analyze (analyzers/raytrace.rs:36-49): reset_data, then the topological walk
 extern "C" OpmStatus opm_scene_raytrace(OpmScene* sc, OpmRays* rays, const OpmRayTraceConfig* cfg_in, int32_t flags,
                                         OpmTraceStats* stats) {
     if (!sc || !rays || sc->nodes.empty()) return OPM_ERR_ARG;
     OpmRayTraceConfig cfg;
     if (cfg_in) cfg = *cfg_in; else opm_raytrace_config_default(&cfg);
+    for (auto& n : sc->nodes) if (!n->placed) return OPM_ERR_ARG;  // "no effective isometry defined" (analyzers/raytrace.rs:108-112)
     OpmStatus st = opm_scene_reset_data(sc);
     if (st) return st;
     const uint64_t n_rays = opm_rays_len(rays);

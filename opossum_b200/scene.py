@@ -211,11 +211,34 @@ class Scene:
     def set_ambient(self, index: RefractiveIndex):
         _check(F.lib().opm_scene_set_ambient(self.h, C.byref(index.c)))
 
-    def add_node(self, node: Node) -> int:
+    def add_node(self, node: Node, distance: float | None = None) -> int:
+        """NodeGroup::add_node (+ connect_nodes to the node named by `fed_by`, default the previous one).  distance = None: the
+        node sits at its own isometry; else it has none and `calc_node_positions` places it `distance` [m] behind its
+        predecessor along the optical axis (NodeGroup::connect_nodes(.., distance))"""
         idx = C.c_int32()
-        _check(F.lib().opm_scene_add_node(self.h, C.byref(node.c), C.byref(idx)))
+        if distance is None:
+            _check(F.lib().opm_scene_add_node(self.h, C.byref(node.c), C.byref(idx)))
+        else:
+            _check(F.lib().opm_scene_add_node_at_distance(self.h, C.byref(node.c), float(distance), C.byref(idx)))
         self._nodes.append(node)
         return idx.value
+
+    def calc_node_positions(self, axis_wavelength: float, config: RayTraceConfig | None = None):
+        """AnalysisRayTrace::calc_node_positions of the node group (nodes/node_group/analysis_raytrace.rs:92-212): places
+        every node that was added with a distance; `axis_wavelength` [m] is the source's alignment wavelength (or the
+        energy-weighted centre wavelength of its rays, rays.rs:1166-1175)"""
+        cfg = None
+        if config is not None:
+            cfg = F.OpmRayTraceConfig()
+            cfg.min_energy_per_ray, cfg.max_number_of_bounces = config.min_energy_per_ray, config.max_number_of_bounces
+            cfg.max_number_of_refractions, cfg.missed_surface_strategy = config.max_number_of_refractions, config.missed_surface_strategy
+        _check(F.lib().opm_scene_calc_node_positions(self.h, float(axis_wavelength), C.byref(cfg) if cfg is not None else None))
+
+    def node_isometry(self, node: int) -> Isometry:
+        """OpticNode::isometry()"""
+        o = F.OpmIsometry()
+        _check(F.lib().opm_scene_node_isometry(self.h, node, C.byref(o)))
+        return Isometry(o)
 
     def raytrace(self, source_rays: Rays, config: RayTraceConfig | None = None, strict=False, per_surface=False,
                  record_all_hits=False, snapshots=True, sync=True, keep_source=False, position_history=False, keep_light_data=False) -> TraceStats | None:

@@ -8,6 +8,7 @@
  */
 #include "opm_oracle.h"
 
+#include <float.h>
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>
@@ -191,6 +192,48 @@ void orc_iso_from_view(const double p[3], const double dir[3], const double up[3
     quat_from_matrix(m, tr.q);
     tr.t[0] = p[0]; tr.t[1] = p[1]; tr.t[2] = p[2];
     iso_from_transform(&tr, out);
+}
+/* ---- node positioning helpers (test infrastructure like everything here) */
+/* Ray::define_up_direction (ray.rs:818-838) */
+void orc_define_up_direction(const double dir_in[3], double up[3]) {
+    const double X[3] = { 1, 0, 0 }, Y[3] = { 0, 1, 0 }, Z[3] = { 0, 0, 1 };
+    double dir[3], c[3];
+    normalize3(dir_in, dir);
+    cross3(dir, X, c);
+    const double nx = norm3(c);
+    cross3(dir, Z, c);
+    const double nz = norm3(c);
+    if (nx < DBL_EPSILON || nz < DBL_EPSILON) { up[0] = 0; up[1] = 1; up[2] = 0; return; }
+    cross3(dir, Y, c);
+    if (norm3(c) < DBL_EPSILON) { up[0] = 1; up[1] = 0; up[2] = 0; return; }
+    const double k = dot3(Y, dir);
+    double proj[3] = { Y[0] - k * dir[0], Y[1] - k * dir[1], Y[2] - k * dir[2] };
+    normalize3(proj, up);
+}
+/* Ray::calc_new_up_direction (ray.rs:842-860): up <- rotation_between(prev_dir, dir) * up when the direction changed by more
+ * than 1000 eps.  nalgebra 0.33.2 Rotation3::rotation_between = scaled_rotation_between(a, b, 1): axis = unit(na x nb) (None
+ * below the default epsilon), angle = acos(na . nb), Rotation3::from_axis_angle (Rodrigues matrix); parallel vectors give the
+ * identity, anti-parallel ones None (the reference then leaves `up` alone). */
+void orc_calc_new_up_direction(const double prev_dir[3], const double dir[3], double up[3]) {
+    double d[3] = { prev_dir[0] - dir[0], prev_dir[1] - dir[1], prev_dir[2] - dir[2] };
+    if (!(norm3(d) > DBL_EPSILON * 1000.)) return;  /* relative_ne!(norm, 0, epsilon = 1000 eps) */
+    double na[3], nb[3], c[3];
+    if (!(norm3(prev_dir) > 0.0) || !(norm3(dir) > 0.0)) return;  /* try_normalize(0) fails: identity */
+    normalize3(prev_dir, na);
+    normalize3(dir, nb);
+    cross3(na, nb, c);
+    const double cn = norm3(c);
+    if (!(cn > DBL_EPSILON)) return;  /* zero angle: identity; pi: None */
+    const double ux = c[0] / cn, uy = c[1] / cn, uz = c[2] / cn;
+    const double angle = acos(dot3(na, nb));
+    if (angle == 0.0) return;
+    const double sn = sin(angle), cs = cos(angle), omc = 1.0 - cs;
+    const double sqx = ux * ux, sqy = uy * uy, sqz = uz * uz;
+    const double m[9] = { sqx + (1.0 - sqx) * cs,     ux * uy * omc - uz * sn, ux * uz * omc + uy * sn,
+                          ux * uy * omc + uz * sn, sqy + (1.0 - sqy) * cs,     uy * uz * omc - ux * sn,
+                          ux * uz * omc - uy * sn, uy * uz * omc + ux * sn, sqz + (1.0 - sqz) * cs };
+    const double v[3] = { up[0], up[1], up[2] };
+    for (int r = 0; r < 3; ++r) up[r] = m[3 * r] * v[0] + m[3 * r + 1] * v[1] + m[3 * r + 2] * v[2];
 }
 void orc_iso_transform_point(const OrcIsometry* iso, const double p[3], double o[3]) { iso3_point(&iso->fwd, p, o); }
 void orc_iso_inverse_transform_point(const OrcIsometry* iso, const double p[3], double o[3]) { iso3_point(&iso->inv, p, o); }

@@ -108,6 +108,8 @@ void orc_iso_new(const double t[3], const double euler_xyz[3], OrcIsometry* out)
 void orc_iso_append(const OrcIsometry* a, const OrcIsometry* b, OrcIsometry* out);      /* :216-223 */
 void orc_iso_from_view(const double p[3], const double dir[3], const double up[3], OrcIsometry* out); /* :166-185 */
 void orc_iso_transform_point(const OrcIsometry* iso, const double p[3], double out[3]);         /* :255-259 */
+void orc_define_up_direction(const double dir[3], double up[3]);                              /* ray.rs:818-838 */
+void orc_calc_new_up_direction(const double prev_dir[3], const double dir[3], double up[3]); /* ray.rs:842-860 */
 void orc_iso_inverse_transform_point(const OrcIsometry* iso, const double p[3], double out[3]); /* :280-284 */
 void orc_iso_transform_vector(const OrcIsometry* iso, const double v[3], double out[3]);        /* :350-352 */
 void orc_iso_inverse_transform_vector(const OrcIsometry* iso, const double v[3], double out[3]);/* :371-373 */

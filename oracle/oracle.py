@@ -374,6 +374,20 @@ def ray_new(pos, direction, wvl, e) -> np.ndarray:
     return out
 
 
+def define_up_direction(direction) -> np.ndarray:
+    """Ray::define_up_direction (ray.rs:818-838)"""
+    up = (C.c_double * 3)()
+    lib().orc_define_up_direction((C.c_double * 3)(*direction), up)
+    return np.array(up[:])
+
+
+def calc_new_up_direction(prev_dir, direction, up) -> np.ndarray:
+    """Ray::calc_new_up_direction (ray.rs:842-860): the rotated up-direction"""
+    u = (C.c_double * 3)(*up)
+    lib().orc_calc_new_up_direction((C.c_double * 3)(*prev_dir), (C.c_double * 3)(*direction), u)
+    return np.array(u[:])
+
+
 def rays_from_arrays(pos, direction, e, wvl) -> np.ndarray:
     n = len(e)
     out = np.zeros(n, dtype=RAY_DTYPE)

@@ -77,7 +77,13 @@ def _surface(geom, param, iso, coating):
 
 class ONode:
     def __init__(self, node_type, iso=None, p=(), index=None, coating_in=None, coating_out=None, aperture_in=None,
-                 aperture_out=None, alignment=None, lidt=1.0e4, parent=-1, parent_port=0, spectrum=None):
+                 aperture_out=None, alignment=None, lidt=1.0e4, parent=-1, parent_port=0, spectrum=None, distance=None):
+        # distance: NodeGroup::connect_nodes(.., distance) of a node WITHOUT an isometry of its own -- OScene.calc_node_positions
+        # places it (then `iso` is only a placeholder)
+        self._args = dict(node_type=node_type, p=p, index=index, coating_in=coating_in, coating_out=coating_out, aperture_in=aperture_in,
+                          aperture_out=aperture_out, alignment=alignment, lidt=lidt, parent=parent, parent_port=parent_port,
+                          spectrum=spectrum)
+        self.distance, self.placed, self.iso = distance, distance is None, iso or orc.Isometry.identity()
         self.type, self.p, self.index = node_type, tuple(p), index
         self.spectrum = spectrum  # (slots [um], values): FilterType::Spectrum / SplittingConfig::Spectrum
         self.parent, self.parent_port = parent, parent_port
@@ -125,6 +131,12 @@ class ONode:
         self.stored: np.ndarray | None = None
         self.split: np.ndarray | None = None
         self.stored_hist = self.split_hist = None  # orc.History of those bundles (raytrace(history=True))
+
+    def place(self, iso: "orc.Isometry"):
+        """OpticNode::set_isometry: rebuild the surfaces at the given node isometry"""
+        distance = self.distance
+        self.__init__(iso=iso, **self._args)
+        self.distance, self.placed = distance, True
 
 
 class OScene:
@@ -278,6 +290,84 @@ class OScene:
             if first:
                 main_out = rays
         return main_out
+
+    # ---- node positioning (nodes/node_group/analysis_raytrace.rs:92-212, optic_graph.rs:878-926)
+    def calc_node_positions(self, wavelength: float, cfg: RayTraceConfig | None = None) -> list:
+        """Places every node that has no isometry of its own at its edge distance behind its predecessor along the optical
+        axis: ONE axis ray (Rays::get_optical_axis_ray: origin, +z, `wavelength`, 1 J; nodes/source.rs:236-268) is passed from
+        node to node with each node's own `analyze` (beam splitter: only its input surface, both outputs carry the ray,
+        beam_splitter/analysis_raytrace.rs:40-93); an unplaced node gets Isometry::new_from_view(ray.propagate(distance),
+        up) (optic_graph.rs:903-905); `up` starts as Ray::define_up_direction of the source's axis ray and is rotated by every
+        node's last direction change (ray.rs:842-860).  Walk order = node index order.  Returns the node isometries."""
+        cfg = cfg or RayTraceConfig()
+        self.reset_data()
+        self.hist = None
+        out: dict[tuple[int, int], tuple[np.ndarray, np.ndarray | None]] = {}
+        up = np.array([0.0, 1.0, 0.0])  # analysis_raytrace.rs:103
+        for i, n in enumerate(self.nodes):
+            if n.type == SOURCE:
+                ray = orc.ray_new((0.0, 0.0, 0.0), (0.0, 0.0, 1.0), wavelength, 1.0)
+                orc.rays_transform(ray, n.s[0].eff_iso)  # axis_ray.transformed_ray(effective_surface_iso("input_1"))
+                out[(i, 0)] = (ray, None)
+                up = orc.define_up_direction(ray["dir"][0])
+                continue
+            parent = n.parent if n.parent >= 0 else i - 1
+            ray, prev_in = out[(parent, n.parent_port)]
+            ray = ray.copy()
+            if not n.placed:
+                r = ray[0]
+                pos = r["pos"] + n.distance * r["dir"]  # Ray::propagate (ray.rs:408-427)
+                n.place(orc.Isometry.from_view(pos, r["dir"], up))
+            prev_dir = prev_in  # a field of the ray: survives a node whose surface the ray does not reach
+
+            def refract(rays, s, idx, intended):
+                nonlocal prev_dir
+                before = rays[0].copy()
+                ch = self._refract(rays, s, idx, intended, cfg.missed_surface_strategy, record=False)
+                # prev_dir is set whenever the surface was reached (ray.rs:628-631,676), also on total reflection
+                moved = before["valid"] and (len(ch) > 0 or rays[0]["bounces"] != before["bounces"])
+                if moved:
+                    prev_dir = before["dir"].copy()
+                return ch
+
+            t = n.type
+            if t == BEAM_SPLITTER:
+                refract(ray, n.s[0], None, True)
+                out[(i, 0)] = out[(i, 1)] = (ray, prev_dir)
+                edges = 2
+            else:
+                if t in (LENS, CYLINDRIC_LENS, WEDGE):
+                    for s, idx in ((n.s[0], n.index), (n.s[1], self.ambient)):
+                        refract(ray, s, idx, True)
+                        orc.rays_apodize(ray, s.aperture, s.eff_iso, self.nt)
+                        orc.rays_threshold(ray, cfg.min_energy_per_ray, self.nt)
+                elif t in (THIN_MIRROR, PARABOLIC_MIRROR):
+                    ray = np.ascontiguousarray(refract(ray, n.s[0], None, False))
+                    orc.rays_apodize(ray, n.s[0].aperture, n.s[0].eff_iso, self.nt)
+                    orc.rays_threshold(ray, cfg.min_energy_per_ray, self.nt)
+                elif t == REFLECTIVE_GRATING:
+                    raise NotImplementedError("axis ray through a grating")
+                else:
+                    refract(ray, n.s[0], None, True)
+                    if t == PARAXIAL_SURFACE:
+                        if ray[0]["valid"]:
+                            prev_dir = ray[0]["dir"].copy()  # ray.rs:450
+                        orc.rays_refract_paraxial(ray, n.p[0], n.s[0].eff_iso)
+                    if t == IDEAL_FILTER:
+                        orc.rays_filter_energy(ray, n.p[0])
+                    orc.rays_apodize(ray, n.s[0].aperture, n.s[0].eff_iso, self.nt)
+                    orc.rays_threshold(ray, cfg.min_energy_per_ray, self.nt)
+                self._limits_rt(ray, cfg)
+                out[(i, 0)] = (ray, prev_dir)
+                edges = 1
+            if len(ray) == 0:
+                raise RuntimeError("no rays in this ray bundle. cannot position nodes")
+            for _ in range(edges):  # calc_new_up_direction once per outgoing edge (analysis_raytrace.rs:199-208)
+                if prev_dir is None:
+                    raise RuntimeError("no previous direction of ray defined to calculate new up-direction!")
+                up = orc.calc_new_up_direction(prev_dir, ray[0]["dir"], up)
+        self.reset_data()
+        return [n.iso for n in self.nodes]
 
     def node_fluence(self, node: int, nx=100, ny=83):  # fluence_detector/mod.rs:91-135 (Binning)
         fmap, lrtb = orc.fluence_binning(self.nodes[node].s[0].merged_hits(), nx, ny)

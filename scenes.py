@@ -2,8 +2,8 @@
 
 Harness code shared by tests/, bench.py and __graft_entry__.py -- not part of the product package.  The same
 description is turned into (a) the product's scene through the C ABI (`to_product`) and (b) the CPU oracle's scene
-(`to_oracle`, test infrastructure).  All nodes carry explicit isometries (node positioning is out of scope,
-SURVEY.md 8f-4); ambient medium = vacuum.  Glass data: H-K9L / H-ZF52 as shipped in the reference's examples
+(`to_oracle`, test infrastructure).  Nodes carry explicit isometries, or -- `distance=` -- the edge distance from their
+predecessor, to be placed by `calc_node_positions`; ambient medium = vacuum.  Glass data: H-K9L / H-ZF52 as shipped in the reference's examples
 (opossum/examples/hhts/hhts.rs:38-64, refr_index_sellmeier1.rs:237-243).
 """
 from __future__ import annotations
@@ -109,6 +109,26 @@ def c5_source(n_pos, n_wvl=64):
             "spectrum": ("gaussian", 950 * NM, 1150 * NM, n_wvl, 1053 * NM, 50 * NM, 1.0)}
 
 
+def folded_chain_by_distances():
+    """A folded beam path described the way the reference's examples do (examples/folded_telescope.rs, laser_system.rs): only
+    the source has an isometry, every other node hangs `distance` behind its predecessor and is placed by
+    `calc_node_positions`; the two mirrors carry their tilt as a local alignment, the wedge deflects the axis."""
+    return [
+        node("source", z=10 * MM, xy=(1 * MM, -2 * MM), euler=(0.02, -0.03, 0.0)),
+        node("lens", distance=100 * MM, p=(515.0 * MM, -515.0 * MM, 5.0 * MM), index=HK9L, coat_in=("fresnel",), coat_out=("fresnel",)),
+        node("thin_mirror", distance=150 * MM, alignment=((0.0, 0.0, 0.0), (math.radians(22.5), 0.0, 0.0))),
+        node("thin_mirror", distance=120 * MM, alignment=((0.0, 0.0, 0.0), (0.0, math.radians(-30.0), 0.0))),
+        node("wedge", distance=80 * MM, p=(8 * MM, math.radians(3.0)), index=HK9L),
+        node("beam_splitter", distance=60 * MM, p=(0.3,)),
+        node("paraxial_surface", distance=50 * MM, p=(400 * MM,)),
+        node("ideal_filter", distance=20 * MM, p=(0.8,)),
+        node("spot_diagram", distance=150 * MM),
+        node("fluence_detector", distance=10 * MM),
+        node("lens", distance=40 * MM, p=(300 * MM, math.inf, 4 * MM), index=NK9L_1054, parent=5, parent_port=1),
+        node("fluence_detector", distance=90 * MM),
+    ]
+
+
 # ---------------------------------------------------------------------------------------------------------------
 KIND_IDS = {"source": 0, "lens": 1, "cylindric_lens": 2, "wedge": 3, "thin_mirror": 4, "parabolic_mirror": 5, "beam_splitter": 6,
             "dummy": 7, "ideal_filter": 8, "paraxial_surface": 9, "spot_diagram": 10, "fluence_detector": 11, "reflective_grating": 12,
@@ -142,7 +162,7 @@ def to_product(ctx, nodes):
         if "spectrum" in d:  # (wavelength slots [um], values): FilterType::Spectrum / SplittingConfig::Spectrum
             n.with_spectrum(ob.Spectrum(ctx, *d["spectrum"]))
         n.fed_by(d.get("parent", -1), d.get("parent_port", 0))
-        sc.add_node(n)
+        sc.add_node(n, distance=d.get("distance"))
     return sc
 
 
@@ -164,7 +184,7 @@ def to_oracle(nodes, n_threads=1):
         align = orc.Isometry.new(*d["alignment"]) if "alignment" in d else None
         out.append(OS.ONode(KIND_IDS[d["kind"]], orc.Isometry.new(d["t"], d["euler"]), d.get("p", ()), idx, coat(d.get("coat_in")),
                             coat(d.get("coat_out")), ap(d.get("ap_in")), ap(d.get("ap_out")), align, d.get("lidt", 1.0e4),
-                            d.get("parent", -1), d.get("parent_port", 0), spectrum=d.get("spectrum")))
+                            d.get("parent", -1), d.get("parent_port", 0), spectrum=d.get("spectrum"), distance=d.get("distance")))
     return OS.OScene(out, n_threads=n_threads)
 
 

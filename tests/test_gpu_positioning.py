@@ -1,0 +1,143 @@
+"""Node positioning from the optical axis (NodeGroup::connect_nodes(.., distance) + calc_node_positions,
+nodes/node_group/analysis_raytrace.rs:92-212, optic_graph.rs:878-926) through the C ABI against the oracle: the node
+isometries of a folded chain described by edge distances only, the analysis of the placed scene, the equivalence with
+explicit isometries, and the error behaviour."""
+import math
+
+import numpy as np
+import pytest
+
+import opossum_b200 as ob
+import scenes
+from oracle import oracle as orc
+from helpers import RTOL, assert_map_match, assert_rays_match
+
+pytestmark = pytest.mark.gpu
+MM, NM = scenes.MM, scenes.NM
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = ob.Context(0)
+    yield c
+    c.close()
+
+
+def assert_isometries_match(psc, isos, what=""):
+    for k, want in enumerate(isos):
+        got = psc.node_isometry(k).matrices()
+        ref = want.matrices()
+        scale = max(1.0, float(np.abs(ref[1]).max()))
+        for g, r, name in zip(got, ref, ("rot", "t", "inv rot", "inv t")):
+            assert np.allclose(g, r, rtol=0, atol=RTOL * scale), f"{what} node {k} {name}: {g} vs {r}"
+
+
+def test_isometry_new_from_view_matches_oracle():
+    """utils/geom_transformation.rs:166-185"""
+    rng = np.random.default_rng(5)
+    for _ in range(50):
+        p, d = rng.normal(size=3), rng.normal(size=3)
+        up = orc.define_up_direction(d / np.linalg.norm(d))
+        a, b = ob.Isometry.new_from_view(p, d, up).matrices(), orc.Isometry.from_view(p, d, up).matrices()
+        for x, y in zip(a, b):
+            assert np.allclose(x, y, rtol=0, atol=1e-14 * max(1.0, np.abs(p).max()))
+    with pytest.raises(ob.OpossumError):
+        ob.Isometry.new_from_view((0, 0, 0), (0, 0, 1), (0, 0, 2))  # up collinear with the view
+    with pytest.raises(ob.OpossumError):
+        ob.Isometry.new_from_view((0, 0, 0), (0, 0, 0), (0, 1, 0))
+
+
+def test_folded_chain_positions_match_oracle(ctx):
+    """two tilted mirrors, a wedge that deflects the axis, a beam splitter with a side arm: every node isometry, then the
+    analysis of the placed scene"""
+    nodes = scenes.folded_chain_by_distances()
+    osc = scenes.to_oracle(nodes)
+    isos = osc.calc_node_positions(1054 * NM)
+    psc = scenes.to_product(ctx, nodes)
+    src = {"pos": ("fibonacci_ellipse", 3000, 4 * MM, 3 * MM), "energy": ("uniform", 1.0), "wvl": [1054 * NM], "w": [1.0]}
+    with pytest.raises(ob.OpossumError):  # analysed before it was placed: no effective isometry (analyzers/raytrace.rs:108-112)
+        psc.raytrace(scenes.source_to_product(src).generate(ctx))
+    with pytest.raises(ob.OpossumError):
+        psc.node_isometry(3)
+    psc.calc_node_positions(1054 * NM)
+    assert_isometries_match(psc, isos)
+    # the mirrors fold the path: the chain does not stay on the z axis
+    t8 = psc.node_isometry(8).matrices()[1]
+    assert abs(t8[0]) > 0.2 and abs(t8[1]) > 0.01
+    ref_out = osc.raytrace(scenes.source_to_oracle(src))
+    for mode in ("fast", "strict", "jit"):
+        ctx.set_jit(2 if mode == "jit" else 0, 1)
+        try:
+            rays = scenes.source_to_product(src).generate(ctx)
+            st = psc.raytrace(rays, strict=(mode == "strict"))
+            assert st.interactions == osc.interactions, mode
+            assert st.valid_out == orc.nr_of_rays(ref_out), mode
+            assert_rays_match(rays.to_array(), ref_out, what=mode)
+            for node in (9, 11):
+                fmap, lrtb, peak, tot = osc.node_fluence(node)
+                fd = psc.node_fluence(node)
+                assert np.allclose(fd.lrtb, lrtb, rtol=1e-7, atol=1e-15), mode
+                assert fd.total_energy == pytest.approx(tot, rel=1e-6), mode
+            s, ref_spot = psc.node_spot(8), osc.node_spot(8)
+            assert s.n_valid == ref_spot["n_valid"] and s.total_energy == pytest.approx(ref_spot["total_energy"], rel=RTOL)
+        finally:
+            ctx.set_jit(1, 200000)
+    # positioning is idempotent: placed nodes are left untouched (analysis_raytrace.rs:168-170)
+    psc.calc_node_positions(1054 * NM)
+    assert_isometries_match(psc, isos, "second pass")
+
+
+def test_distances_equal_explicit_isometries_on_axis(ctx):
+    """a centred, unfolded chain: placing by distances gives the isometries one would write by hand (each node `distance`
+    behind the last surface vertex of its predecessor) and the same analysis"""
+    by_distance = [scenes.node("source"),
+                   scenes.node("lens", distance=50 * MM, p=(205.55 * MM, -205.55 * MM, 2.79 * MM), index=scenes.NK9L_1054,
+                               coat_in=("fresnel",), coat_out=("fresnel",)),
+                   scenes.node("spot_diagram", distance=(200 - 2.79) * MM),
+                   scenes.node("fluence_detector", distance=10 * MM)]
+    a = scenes.to_product(ctx, by_distance)
+    a.calc_node_positions(1000 * NM)
+    b = scenes.to_product(ctx, scenes.c1_single_lens())
+    for k in range(4):
+        for x, y in zip(a.node_isometry(k).matrices(), b.node_isometry(k).matrices()):
+            assert np.allclose(x, y, rtol=0, atol=1e-15)
+    src = scenes.source_to_product(scenes.c1_source(60))
+    ra, rb = src.generate(ctx), src.generate(ctx)
+    sa, sb = a.raytrace(ra), b.raytrace(rb)
+    assert sa == sb
+    assert_rays_match(ra.to_array(), rb.to_array(), what="distance vs explicit")
+    assert_map_match(a.node_fluence(3).map, b.node_fluence(3).map)
+
+
+def test_positioning_with_a_paraxial_lens_off_axis_source(ctx):
+    """the axis ray of a decentred, tilted source through a paraxial surface (prev_dir of ray.rs:450) and a mirror; strict build"""
+    nodes = [scenes.node("source", xy=(2 * MM, 1 * MM), euler=(0.0, 0.05, 0.3)),
+             scenes.node("paraxial_surface", distance=40 * MM, p=(150 * MM,), alignment=((1 * MM, 0.0, 0.0), (0.0, 0.0, 0.0))),
+             scenes.node("thin_mirror", distance=70 * MM, alignment=((0.0, 0.0, 0.0), (0.0, math.radians(40.0), 0.0))),
+             scenes.node("dummy", distance=30 * MM),
+             scenes.node("spot_diagram", distance=25 * MM)]
+    osc = scenes.to_oracle(nodes)
+    isos = osc.calc_node_positions(800 * NM)
+    psc = scenes.to_product(ctx, nodes)
+    psc.calc_node_positions(800 * NM)
+    assert_isometries_match(psc, isos)
+    src = {"pos": ("grid", 30, 30, 6 * MM, 6 * MM), "energy": ("uniform", 1.0), "wvl": [800 * NM], "w": [1.0]}
+    ref_out = osc.raytrace(scenes.source_to_oracle(src))
+    rays = scenes.source_to_product(src).generate(ctx)
+    psc.raytrace(rays, strict=True)
+    assert_rays_match(rays.to_array(), ref_out, what="paraxial chain")
+
+
+def test_positioning_errors(ctx):
+    from opossum_b200 import scene as S
+    sc = S.Scene(ctx)
+    with pytest.raises(ob.OpossumError):  # the first node is the source and carries its own isometry
+        sc.add_node(S.Dummy(), distance=0.1)
+    sc.add_node(S.Source())
+    with pytest.raises(ob.OpossumError):  # "propagation length must be finite" (ray.rs:414-418)
+        sc.add_node(S.Dummy(), distance=math.inf)
+    sc.add_node(S.Dummy(), distance=0.1)
+    with pytest.raises(ob.OpossumError):
+        sc.calc_node_positions(0.0)
+    sc.calc_node_positions(1e-6)
+    assert np.allclose(sc.node_isometry(1).matrices()[1], (0.0, 0.0, 0.1), rtol=0, atol=1e-16)

@@ -737,3 +737,62 @@ def test_wavefront_statistics_kat():
     assert abs(ptv - 1.0) < 1e-12 and abs(rms - 0.5) < 1e-12
     with pytest.raises(orc.OracleError):
         orc.wavefront_statistics(np.zeros((0, 3)))
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# node positioning helpers
+# ---------------------------------------------------------------------------------------------------------------
+def test_define_up_direction_kats():
+    """ray.rs:1653-1755 define_up_direction_test (assert_relative_eq!; the last two with epsilon = 10 eps)"""
+    unit = lambda v: np.asarray(v, dtype=float) / np.linalg.norm(v)  # noqa: E731  (Ray::new normalises the direction)
+    x, y = np.array([1.0, 0.0, 0.0]), np.array([0.0, 1.0, 0.0])
+    cases = [((1, 0, 0), y, EPS), ((0, 1, 0), x, EPS), ((0, 0, 1), y, EPS), ((0, 1, 1), unit((0, 1, -1)), EPS), ((1, 0, 1), y, EPS),
+             ((1, 1, 0), unit((-1, 1, 0)), EPS), ((-1, 0, 3), y, EPS), ((1, 1, 1), unit((-1, 2, -1)), 10 * EPS),
+             ((-1, -1, -1), unit((-1, 2, -1)), 10 * EPS)]
+    for d, want, tol in cases:
+        got = orc.define_up_direction(unit(d))
+        assert np.all(np.abs(got - want) <= tol * np.maximum(1.0, np.abs(want))), (d, got, want)
+
+
+def test_calc_new_up_direction_kat():
+    """ray.rs:1757-1790 calc_new_up_direction_test: z -> y turns up = y into -z, y -> z turns it back, z -> x leaves y"""
+    up = np.array([0.0, 1.0, 0.0])
+    up = orc.calc_new_up_direction((0, 0, 1), (0, 1, 0), up)
+    assert np.allclose(up, (0, 0, -1), rtol=0, atol=EPS)
+    up = orc.calc_new_up_direction((0, 1, 0), (0, 0, 1), up)
+    assert np.allclose(up, (0, 1, 0), rtol=0, atol=EPS)
+    up = orc.calc_new_up_direction((0, 0, 1), (1, 0, 0), up)
+    assert np.allclose(up, (0, 1, 0), rtol=0, atol=EPS)
+    # unchanged direction (below 1000 eps): untouched, bit for bit
+    up2 = orc.calc_new_up_direction((0, 0, 1), (0, 1e-14, 1), np.array([0.3, 0.4, 0.5]))
+    assert np.array_equal(up2, (0.3, 0.4, 0.5))
+
+
+def test_calc_node_positions_on_a_straight_chain():
+    """nodes/node_group/analysis_raytrace.rs:92-212, optic_graph.rs:878-926: on an unfolded, centred chain a node sits `distance`
+    behind the LAST surface vertex of its predecessor (the axis ray leaves a lens at its rear vertex), unrotated"""
+    import scenes
+    MM = scenes.MM
+    nodes = [scenes.node("source"),
+             scenes.node("lens", distance=50 * MM, p=(205.55 * MM, -205.55 * MM, 2.79 * MM), index=scenes.NK9L_1054),
+             scenes.node("wedge", distance=30 * MM, p=(10 * MM, 0.0), index=scenes.HK9L),
+             scenes.node("spot_diagram", distance=100 * MM),
+             scenes.node("fluence_detector", distance=10 * MM)]
+    osc = scenes.to_oracle(nodes)
+    isos = osc.calc_node_positions(1000e-9)
+    want_z = [0.0, 50 * MM, (50 + 2.79 + 30) * MM, (50 + 2.79 + 30 + 10 + 100) * MM, (50 + 2.79 + 30 + 10 + 100 + 10) * MM]
+    for iso, z in zip(isos, want_z):
+        rot, t, _, _ = iso.matrices()
+        assert np.allclose(rot.reshape(3, 3), np.eye(3), rtol=0, atol=4 * EPS)
+        assert np.allclose(t, (0.0, 0.0, z), rtol=4 * EPS, atol=1e-18)
+    # and the placed scene traces like the one with explicit isometries
+    explicit = [dict(n) for n in nodes]
+    for n, z in zip(explicit, want_z):
+        n.pop("distance", None)
+        n["t"] = (0.0, 0.0, z)
+    src = scenes.source_to_oracle(scenes.c1_source(20))
+    a = osc.raytrace(src.copy())
+    b = scenes.to_oracle(explicit).raytrace(src.copy())
+    for f in ("pos", "dir", "e", "opl"):
+        assert np.allclose(a[f], b[f], rtol=1e-12, atol=1e-15), f
+    assert np.array_equal(a["valid"], b["valid"])
