@@ -208,3 +208,38 @@ def test_kde_errors_and_bounce_filter(ctx):
         with pytest.raises(ob.OpossumError) as ei:
             ob.fluence_kde(ctx, [h1], 8, 8)
         assert ei.value.code == F.OPM_ERR_KDE_BANDWIDTH
+
+
+@pytest.mark.parametrize("nx,ny", [(100, 83), (101, 101), (12, 9)])
+def test_binning_fixed_point_wide_energy_range(ctx, nx, ny):
+    """the CTA-private fixed-point sums (binning_smem_fixed_kernel): energies over 14 orders of magnitude in one map, many hits
+    per bin, hits of zero energy -- every bin within 1e-9 (floor 1e-9 of the peak) of the oracle's f64 sums, total energy 1e-12"""
+    rng = np.random.default_rng(11)
+    n = 300_000
+    x = mm(3.0) * rng.random(n) - mm(1.0)
+    y = mm(2.0) * rng.random(n) + mm(0.5)
+    e = 10.0 ** rng.uniform(-14.0, 0.0, n)
+    e[::97] = 0.0
+    e[5] = 3.0  # one hit far above the rest sets the unit of its CTA
+    ref_map, ref_lrtb = orc.fluence_binning(orc.hits_from_xye(x, y, e), nx, ny)
+    fd = ob.fluence_binning(ctx, [hitmap_from(ctx, x, y, e)], nx, ny)
+    assert fd.lrtb == ref_lrtb
+    assert_map_match(fd.map, ref_map)
+    assert fd.total_energy == pytest.approx(orc.fluence_total_energy(ref_map, ref_lrtb), rel=1e-12)
+    # tiny energies only: the unit follows the largest energy of the CTA's slots, nothing is rounded away
+    e2 = 1e-200 * (1.0 + rng.random(n))
+    ref2, _ = orc.fluence_binning(orc.hits_from_xye(x, y, e2), nx, ny)
+    assert_map_match(ob.fluence_binning(ctx, [hitmap_from(ctx, x, y, e2)], nx, ny).map, ref2)
+
+
+def test_binning_fixed_point_non_finite_energy(ctx):
+    """an infinite energy cannot be scaled: those taps go to the map as they are (like f64 adds: inf, or NaN where a tap weight
+    is 0), the finite bins stay exact"""
+    x = np.array([0.0, 1.0, 2.0, 3.0, 4.0, 2.0]) * mm(1.0)
+    y = np.array([0.0, 1.0, 2.0, 3.0, 4.0, 2.0]) * mm(1.0)
+    e = np.array([1.0, 2.0, np.inf, 4.0, 5.0, 1.0])
+    fd = ob.fluence_binning(ctx, [hitmap_from(ctx, x, y, e)], 5, 5)
+    assert not np.isfinite(fd.map[2, 2]) and np.isfinite(fd.map[0, 0]) and np.isfinite(fd.map[4, 4])
+    area = (mm(4.0) / 5) ** 2
+    assert fd.map[0, 0] == pytest.approx(1.0 / area, rel=1e-12) and fd.map[4, 4] == pytest.approx(5.0 / area, rel=1e-12)
+    assert fd.peak == pytest.approx(5.0 / area, rel=1e-12)  # fluence_data.rs:45-68: peak over the finite bins
