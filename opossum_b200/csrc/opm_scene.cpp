@@ -61,6 +61,9 @@ OpmIsometry iso_append(const OpmIsometry& a, const OpmIsometry& b) {
     return o;
 }
 
+// a per-bundle fluence check of the ghost-focus analysis whose result still sits on the device (opm_scene_gf.inc)
+struct GfCheck { SurfaceState* surface; uint64_t uuid; uint32_t lvl; };
+
 }  // namespace
 
 struct OpmScene {
@@ -74,10 +77,11 @@ struct OpmScene {
     // device buffers are recycled across analyses (cudaMalloc / cudaFree are synchronous and cost milliseconds)
     std::vector<OpmRays*> pool_rays;
     std::vector<OpmHitMap*> pool_hits;
-    // ghost focus: device scratch of the per-bundle 101x101 fluence check (map | range[4] | peak,total[2] | status) and its
-    // pinned mirror of the scalars, so a check costs one synchronisation and no allocation
+    // ghost focus: device scratch of the per-bundle 101x101 fluence checks (map | one slot of range[4] | peak,total[2] | status
+    // per check) and the pinned mirror of the slots: a check costs no synchronisation and no allocation
     void* gf_scratch = nullptr;
     void* gf_host = nullptr;
+    std::vector<GfCheck> gf_pending;
 };
 
 namespace {
@@ -281,11 +285,6 @@ struct Runner {
         total.first_valid_key = st.first_valid_key;
     }
 };
-
-bool is_detector(int type) {
-    return type == OPM_NODE_SPOT_DIAGRAM || type == OPM_NODE_FLUENCE_DETECTOR || type == OPM_NODE_RAY_PROPAGATION_VISUALIZER ||
-           type == OPM_NODE_SPECTROMETER || type == OPM_NODE_WAVEFRONT;
-}
 
 OpmHitMap* new_hitmap(OpmScene* sc, SurfaceState& s, uint64_t uuid, uint64_t n, OpmStatus* st) {
     OpmHitMap* h = nullptr;
