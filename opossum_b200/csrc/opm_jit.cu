@@ -202,7 +202,8 @@ std::string make_source(const DevOp* ops, int n_ops, bool compact, int block, in
          "        RayCtx x;\n"
          "        uint8_t vb;\n";
     s += pipe ? "        tile_load_staged(pipe, in, tile, n, x, vb);\n"
-              : "        tile_load(in, (uint64_t)tile * blockDim.x + threadIdx.x, n, x, vb);\n";
+              : "        tile_load(in, (uint64_t)tile * blockDim.x + threadIdx.x, n, x, vb);\n"
+                "        tile_prefetch(in, (uint64_t)(tile + gridDim.x) * blockDim.x + threadIdx.x, n);\n";
     s += body;
     appendf(s, "        tile_store<%s>(in, out, out_cap, out_tail, x, vb);\n", compact ? "true" : "false");
     s += "        tile_count(x, s_cnt, &s_status, &s_first_inv);\n"

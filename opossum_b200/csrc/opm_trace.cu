@@ -82,6 +82,7 @@ __device__ __forceinline__ void trace_body(const DevOp* __restrict__ g_ops, int 
         RayCtx x;
         uint8_t vb;
         tile_load(in, (uint64_t)tile * blockDim.x + threadIdx.x, n, x, vb);
+        tile_prefetch(in, (uint64_t)(tile + gridDim.x) * blockDim.x + threadIdx.x, n);
         for (int k = 0; k < n_ops; ++k) {
             const DevOp& op = ops[k];
             switch (op.kind) {  // warp-uniform

@@ -298,11 +298,39 @@ __device__ __forceinline__ void tile_load(const DevRays& in, uint64_t i, uint64_
     x.r.pos = v3(0, 0, 0); x.r.dir = v3(0, 0, 1); x.r.e = 0; x.r.wvl = 0; x.r.opl = 0; x.r.n = 1; x.r.bounces = 0; x.r.refr = 0; x.r.id = 0;
     vb = RAY_REMOVED;
     if (x.in_range) {
+#ifndef OPM_TILE_INDEPENDENT_LOADS
         vb = in.valid[i];
         if (vb != RAY_REMOVED) load_ray(in, i, x.r);
+#else   // probe (profiles/tile_load_variants.sh): the 13 field loads do not wait for the flag -- one round trip per tile instead
+        // of two.  Measured on C2: 1.335 ms against 1.318 ms; the other resident warps already cover the second round trip.
+        vb = in.valid[i];
+        load_ray(in, i, x.r);
+        if (vb == RAY_REMOVED) {
+            x.r.pos = v3(0, 0, 0); x.r.dir = v3(0, 0, 1); x.r.e = 0; x.r.wvl = 0; x.r.opl = 0; x.r.n = 1; x.r.bounces = 0; x.r.refr = 0; x.r.id = 0;
+        }
+#endif
     }
     x.alive = vb != RAY_REMOVED;
     x.valid = vb == RAY_VALID;
+}
+// probe (-DOPM_TILE_PREFETCH, profiles/tile_load_variants.sh): asks the L2 for the lines of the tile this CTA takes next (one
+// request per 128-byte line).  Measured on C2: 1.359 ms against 1.318 ms -- left off.
+__device__ __forceinline__ void tile_prefetch(const DevRays& in, uint64_t i, uint64_t n) {
+#ifdef OPM_TILE_PREFETCH
+    if (i >= n) return;
+    const unsigned lane = threadIdx.x & 31u;
+    if ((lane & 15u) == 0u) {
+        const double* f64[10] = {in.px, in.py, in.pz, in.dx, in.dy, in.dz, in.e, in.wvl, in.opl, in.n};
+#pragma unroll
+        for (int f = 0; f < 10; ++f) asm volatile("prefetch.global.L2 [%0];" ::"l"(f64[f] + i));
+        if (lane == 0u) {
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(in.bounces + i));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(in.refr + i));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(in.id + i));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(in.valid + i));
+        }
+    }
+#endif
 }
 
 // ---- staged tile loads (run-time specialised kernel) ---------------------------------------------------------------
