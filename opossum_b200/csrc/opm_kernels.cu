@@ -336,23 +336,29 @@ __device__ __forceinline__ double div_by_invariant(double x, double d, double in
     return fma(fma(-q, d, x), inv, q);
 }
 struct BinInv { double width_step, height_step, bin_area; };
-// bin_taps with the three divisions by loop-invariant numbers replaced by div_by_invariant
-__device__ __forceinline__ BinTaps bin_taps_inv(const BinParams& P, const BinInv& I, double x, double y, double e, unsigned* status) {
-    BinTaps t;
-    double ipx, ipy;
-    double fx = modf(div_by_invariant(x - P.left, P.width_step, I.width_step), &ipx);
-    double fy = modf(div_by_invariant(y - P.bottom, P.height_step, I.height_step), &ipy);
-    unsigned long long xi = f64_to_usize(ipx), yi = f64_to_usize(ipy);
-    double fl = div_by_invariant(e, P.bin_area, I.bin_area);
-    t.w00 = (1.0 - fx) * (1.0 - fy) * fl;
-    t.w10 = fx * (1.0 - fy) * fl;
-    t.w01 = (1.0 - fx) * fy * fl;
+// bin_taps for the shared-memory kernel (the map has fewer than 2^31 bins): the three divisions by loop-invariant numbers go
+// through div_by_invariant; modf(q) = (q - trunc(q), trunc(q)) for finite q (one FRND instead of the library routine); Rust's
+// saturating `f64 as usize` is what cvt.rzi.u64.f64 does (NaN and negatives -> 0, too large -> MAX); indices in 32 bits
+struct BinTaps32 { unsigned base; double w00, w10, w01, w11; bool ok, has_x, has_y; };
+__device__ __forceinline__ BinTaps32 bin_taps_inv(const BinParams& P, const BinInv& I, double x, double y, double e, unsigned* status) {
+    BinTaps32 t;
+    const double qx = div_by_invariant(x - P.left, P.width_step, I.width_step);
+    const double qy = div_by_invariant(y - P.bottom, P.height_step, I.height_step);
+    const double ipx = trunc(qx), ipy = trunc(qy);
+    const double fx = qx - ipx, fy = qy - ipy;
+    const unsigned long long xi = __double2ull_rz(ipx), yi = __double2ull_rz(ipy);
+    const double fl = div_by_invariant(e, P.bin_area, I.bin_area);
+    const double gx = 1.0 - fx, gy = 1.0 - fy;
+    t.w00 = gx * gy * fl;
+    t.w10 = fx * gy * fl;
+    t.w01 = gx * fy * fl;
     t.w11 = fx * fy * fl;
     t.ok = (xi < P.nx) && (yi < P.ny);
     if (!t.ok) *status |= 1u << OPM_ERR_BIN_RANGE;
-    t.has_x = xi < P.nx - 1;
-    t.has_y = yi < P.ny - 1;
-    t.base = xi * P.ny + yi;
+    const unsigned nx = (unsigned)P.nx, ny = (unsigned)P.ny, ux = (unsigned)xi, uy = (unsigned)yi;
+    t.has_x = ux + 1u < nx;
+    t.has_y = uy + 1u < ny;
+    t.base = ux * ny + uy;  // column-major ny x nx
     return t;
 }
 
@@ -429,7 +435,7 @@ __global__ void __launch_bounds__(BLOCK, MIN_CTAS) binning_smem_fixed_kernel(Dev
     const BinInv I{1.0 / P.width_step, 1.0 / P.height_step, 1.0 / P.bin_area};
     const bool scaled = flmax > 0.0 && isfinite(flmax);
     {
-        auto add = [&](unsigned long long b, double w) {
+        auto add = [&](unsigned b, double w) {
             if (w == 0.0) return;
             // NaN / infinite taps (a NaN hit position, an infinite energy) go to the global map as they are, like the f64 kernel's
             if (!scaled || !isfinite(w)) { atomicAdd(&map[b], w); return; }
@@ -442,7 +448,19 @@ __global__ void __launch_bounds__(BLOCK, MIN_CTAS) binning_smem_fixed_kernel(Dev
         auto splat = [&](uint64_t i, double x, double y, double e) {
             if (!(e >= 0.0)) return;
             if (bounce_filter >= 0 && (long long)H.bounce[i] != bounce_filter) return;
-            BinTaps t = FASTDIV ? bin_taps_inv(P, I, x, y, e, &status) : bin_taps(P, x, y, e, &status);
+            if (FASTDIV) {
+                const BinTaps32 t = bin_taps_inv(P, I, x, y, e, &status);
+                if (!t.ok) return;
+                const unsigned ny32 = (unsigned)P.ny;
+                add(t.base, t.w00);
+                if (t.has_x) {
+                    add(t.base + ny32, t.w10);
+                    if (t.has_y) add(t.base + ny32 + 1u, t.w11);
+                }
+                if (t.has_y) add(t.base + 1u, t.w01);
+                return;
+            }
+            BinTaps t = bin_taps(P, x, y, e, &status);
             if (!t.ok) return;
             add(t.base, t.w00);
             if (t.has_x) {
