@@ -176,8 +176,32 @@ size_t jit_dynamic_smem(bool has_fork, int block) {
 std::string make_source(const DevOp* ops, int n_ops, bool compact, int block, int min_ctas) {
     const bool pipe = jit_pipe_enabled() && block % 16 == 0;
     const size_t stash = jit_stash_bytes(program_has_fork(ops, n_ops), block);
+    // Body of the tile loop.  Rays that are (or become) invalid leave the straight-line code for a second copy of the program --
+    // the same op lines under the knowledge `x.valid == false`, which the compiler folds down to the ops' side effects for such a
+    // ray (empty hit records, detector copies, FORK / JOIN bookkeeping).  The live copy therefore has no `if (x.valid)` diamonds:
+    // no register moves where their two sides would meet again, no convergence barriers.  The two copies meet at the end of the
+    // tile, and behind a JOIN, where the parked (possibly valid) parent of a dead split-off ray returns to the live copy.
+    static const bool split = [] { const char* e = getenv("OPM_B200_JIT_SPLIT"); return !(e && e[0] == '0'); }();  // tuning switch
     std::string body;
-    for (int k = 0; k < n_ops; ++k) body += op_line(ops[k], k);
+    if (!split) {
+        for (int k = 0; k < n_ops; ++k) body += op_line(ops[k], k);
+    } else {
+        std::string dead;
+        for (int k = 0; k < n_ops; ++k) {
+            const std::string line = op_line(ops[k], k);
+            if (k > 0 && ops[k - 1].kind == OPK_JOIN) appendf(body, "      live_%d:\n", k);
+            appendf(body, "        if (!x.valid) goto dead_%d;\n        {\n", k);
+            body += line;
+            body += "        }\n";
+            appendf(dead, "      dead_%d:\n        x.valid = false;\n        {\n", k);
+            dead += line;
+            dead += "        }\n";
+            if (ops[k].kind == OPK_JOIN && k + 1 < n_ops) appendf(dead, "        if (x.valid) goto live_%d;\n", k + 1);
+        }
+        body += "        goto tile_done;\n";
+        body += dead;
+        body += "      tile_done:;\n";
+    }
     std::string s;
     s += "#include \"opm_trace_ops.cuh\"\nnamespace opm {\n";
     appendf(s, "extern \"C\" __constant__ DevOp opm_jit_ops[%d];\n", n_ops);
