@@ -446,36 +446,43 @@ __device__ __forceinline__ void tile_store(const DevRays& in, const DevRays& out
     }
 }
 
-// tile counters: one warp reduction per register, lane 0 adds the fields to the CTA totals in shared memory
-__device__ __forceinline__ void tile_count(const RayCtx& x, unsigned long long* s_cnt, unsigned* s_status, unsigned long long* s_first_inv) {
+// tile counters: one warp reduction per register, lane 0 adds the fields to the CTA totals in shared memory.  The CTA totals are
+// 32-bit (native shared-memory adds; 64-bit ones are compare-and-swap loops): a CTA sees at most rays / CTAs x ops interactions,
+// below 2^32 for any bundle that fits the device.
+typedef unsigned cta_count_t;
+__device__ __forceinline__ void tile_count(const RayCtx& x, cta_count_t* s_cnt, unsigned* s_status, unsigned long long* s_first_inv) {
     const unsigned ra = __reduce_add_sync(0xffffffffu, x.c.a), rb = __reduce_add_sync(0xffffffffu, x.c.b);
     const unsigned rp = __reduce_add_sync(0xffffffffu, x.c.apodized);
-    const unsigned live = __ballot_sync(0xffffffffu, x.alive), ok = __ballot_sync(0xffffffffu, x.valid && x.alive);
+    const bool v = x.valid && x.alive;
+    const unsigned live = __ballot_sync(0xffffffffu, x.alive), ok = __ballot_sync(0xffffffffu, v);
     const unsigned st = __reduce_or_sync(0xffffffffu, x.c.status);
-    if (ok) {  // first valid ray of the warp = lowest id: ~key is largest there
-        unsigned long long inv = (x.valid && x.alive) ? ~(((unsigned long long)x.r.id << 32) | x.r.bounces) : 0ull;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) { unsigned long long t = __shfl_xor_sync(0xffffffffu, inv, o); inv = t > inv ? t : inv; }
-        if ((threadIdx.x & 31) == 0) atomicMax(s_first_inv, inv);
+    const bool lane0 = (threadIdx.x & 31) == 0;
+    if (ok) {  // first valid ray of the warp = lowest (id, bounces): two 32-bit warp minima instead of a 64-bit shuffle tree
+        const unsigned idmin = __reduce_min_sync(0xffffffffu, v ? x.r.id : 0xffffffffu);
+        const unsigned bmin = __reduce_min_sync(0xffffffffu, (v && x.r.id == idmin) ? x.r.bounces : 0xffffffffu);
+        if (lane0) {
+            const unsigned long long inv = ~(((unsigned long long)idmin << 32) | bmin);  // largest for the first ray
+            if (inv > *(volatile unsigned long long*)s_first_inv) atomicMax(s_first_inv, inv);  // rarely after the CTA's first tiles
+        }
     }
-    if ((threadIdx.x & 31) == 0) {
-        if (ra & 0xffffu) atomicAdd(&s_cnt[CNT_INTERACTIONS], (unsigned long long)(ra & 0xffffu));
-        if (ra >> 16) atomicAdd(&s_cnt[CNT_HITS], (unsigned long long)(ra >> 16));
-        if (rb & 0xffffu) atomicAdd(&s_cnt[CNT_MISSED], (unsigned long long)(rb & 0xffffu));
-        if (rb >> 16) atomicAdd(&s_cnt[CNT_CHILDREN], (unsigned long long)(rb >> 16));
-        if (rp) atomicAdd(&s_cnt[CNT_APODIZED], (unsigned long long)rp);
-        if (live) atomicAdd(&s_cnt[CNT_ALIVE_OUT], (unsigned long long)__popc(live));
-        if (ok) atomicAdd(&s_cnt[CNT_VALID_OUT], (unsigned long long)__popc(ok));
+    if (lane0) {
+        if (ra & 0xffffu) atomicAdd(&s_cnt[CNT_INTERACTIONS], ra & 0xffffu);
+        if (ra >> 16) atomicAdd(&s_cnt[CNT_HITS], ra >> 16);
+        if (rb & 0xffffu) atomicAdd(&s_cnt[CNT_MISSED], rb & 0xffffu);
+        if (rb >> 16) atomicAdd(&s_cnt[CNT_CHILDREN], rb >> 16);
+        if (rp) atomicAdd(&s_cnt[CNT_APODIZED], rp);
+        if (live) atomicAdd(&s_cnt[CNT_ALIVE_OUT], (unsigned)__popc(live));
+        if (ok) atomicAdd(&s_cnt[CNT_VALID_OUT], (unsigned)__popc(ok));
         if (st) atomicOr(s_status, st);
     }
 }
 
 // CTA totals -> global statistics (call after __syncthreads())
-__device__ __forceinline__ void cta_flush(DevStats* stats, const unsigned long long* s_cnt, unsigned s_status, unsigned long long s_first_inv) {
+__device__ __forceinline__ void cta_flush(DevStats* stats, const cta_count_t* s_cnt, unsigned s_status, unsigned long long s_first_inv) {
     if (threadIdx.x < CNT_N && s_cnt[threadIdx.x]) {
         unsigned long long* dst[CNT_N] = {&stats->interactions, &stats->children, &stats->hits, &stats->missed,
                                           &stats->apodized, &stats->valid_out, &stats->alive_out};
-        atomicAdd(dst[threadIdx.x], s_cnt[threadIdx.x]);
+        atomicAdd(dst[threadIdx.x], (unsigned long long)s_cnt[threadIdx.x]);
     }
     if (threadIdx.x == 0 && s_status) atomicOr(&stats->status_bits, s_status);
     if (threadIdx.x == 0 && s_first_inv) atomicMax(&stats->first_inv, s_first_inv);
