@@ -300,6 +300,12 @@ void opm_rays_destroy(OpmRays* rays);
 uint64_t opm_rays_len(const OpmRays* rays);        /* slots in use (includes invalid and removed rays) */
 uint64_t opm_rays_capacity(const OpmRays* rays);
 OpmStatus opm_rays_clear(OpmRays* rays);
+/* Tells the library that (nearly) every ray of the bundle carries `wavelength_m` -- what a one-wavelength source produces
+ * (opm_source_generate and opm_rays_new_collimated_with_spectrum set it themselves; copies, split-off bundles and children
+ * inherit it; uploads clear it).  A performance hint only: the run-time specialised kernels then evaluate each index model
+ * once per CTA for that wavelength and check every ray against it, rays of another wavelength evaluate the model themselves.
+ * 0 = no hint. */
+OpmStatus opm_rays_set_wavelength_hint(OpmRays* rays, double wavelength_m);
 OpmStatus opm_rays_reserve(OpmRays* rays, uint64_t capacity);
 OpmStatus opm_rays_upload(OpmRays* rays, const OpmRay* host, uint64_t n);                 /* Rays::from(Vec<Ray>) */
 /* struct-of-arrays upload from (pinned) host memory; opl/n/bounces/refr/valid take their `Ray::new` defaults */

@@ -214,7 +214,7 @@ EXPORTS = [
     "opm_context_synchronize", "opm_context_stream", "opm_context_launch_count", "opm_context_set_kernel_timing",
     "opm_context_kernel_timing", "opm_context_set_jit", "opm_context_jit_wait", "opm_context_jit_stats", "opm_jit_selftest", "opm_isometry_identity",
     "opm_isometry_new", "opm_isometry_append", "opm_isometry_from_view", "opm_raytrace_config_default", "opm_rays_create", "opm_rays_destroy",
-    "opm_rays_len", "opm_rays_capacity", "opm_rays_clear", "opm_rays_reserve", "opm_rays_upload",
+    "opm_rays_len", "opm_rays_capacity", "opm_rays_clear", "opm_rays_set_wavelength_hint", "opm_rays_reserve", "opm_rays_upload",
     "opm_rays_upload_soa", "opm_rays_new_collimated_with_spectrum", "opm_rays_download", "opm_rays_copy", "opm_rays_append", "opm_rays_compact",
     "opm_rays_enable_position_history", "opm_rays_disable_position_history", "opm_rays_clear_position_history",
     "opm_rays_position_history_levels", "opm_rays_position_history",
@@ -281,6 +281,7 @@ def lib() -> C.CDLL:
         "opm_rays_capacity": (u64, [vp]),
         "opm_abi_sizeof": (u64, [C.c_char_p]),
         "opm_rays_clear": (i32, [vp]),
+        "opm_rays_set_wavelength_hint": (i32, [vp, C.c_double]),
         "opm_rays_reserve": (i32, [vp, u64]),
         "opm_rays_upload": (i32, [vp, vp, u64]),
         "opm_rays_upload_soa": (i32, [vp, C.POINTER(dp), C.POINTER(dp), dp, dp, u64]),

@@ -472,6 +472,10 @@ class Rays:
         _check(F.lib().opm_rays_clear(self.h))
 
     # ---- spectra / wavefront (spectrum.rs, nodes/spectrometer.rs, nodes/wavefront.rs)
+    def set_wavelength_hint(self, wavelength: float):
+        """performance hint: (nearly) every ray carries this wavelength [m]; checked per ray on the device, 0 = none"""
+        _check(F.lib().opm_rays_set_wavelength_hint(self.h, float(wavelength)))
+
     def wavelength_range(self):
         """(min, max, n_valid) of the valid rays' wavelengths"""
         mm = (C.c_double * 2)()

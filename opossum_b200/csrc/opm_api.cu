@@ -74,6 +74,9 @@ struct OpmRays {
     DevRays v{};
     unsigned long long* d_tail = nullptr;
     bool len_dirty = false;  // the device tail counter is ahead of `len` (asynchronous append)
+    // > 0: every ray of the bundle is believed to carry this wavelength (one-wavelength sources).  A hint for the specialised
+    // kernels (RefractCt HINT), which check it per ray: a stale value costs time, not correctness.
+    double mono_wvl = 0.0;
     // host upload in flight (opm_rays_new_collimated_with_spectrum): positions / energies / spectrum are copied into
     // this bundle's staging buffer on the context's copy stream; the expansion into the SoA arrays is enqueued on the
     // main stream the first time the bundle is used, so the copy overlaps whatever the main stream is doing until then
@@ -467,9 +470,14 @@ extern "C" uint64_t opm_rays_len(const OpmRays* r) {
     return r->len;
 }
 extern "C" uint64_t opm_rays_capacity(const OpmRays* r) { return r ? r->cap : 0; }
+extern "C" OpmStatus opm_rays_set_wavelength_hint(OpmRays* r, double wavelength) {
+    if (!r || !(wavelength >= 0.0) || !std::isfinite(wavelength)) return fail(OPM_ERR_ARG, "wavelength hint must be >= 0 and finite");
+    r->mono_wvl = wavelength;
+    return OPM_OK;
+}
 extern "C" OpmStatus opm_rays_clear(OpmRays* r) {
     if (!r) return fail(OPM_ERR_ARG, "rays is NULL");
-    r->len = 0; r->len_dirty = false; r->pending = false;
+    r->len = 0; r->len_dirty = false; r->pending = false; r->mono_wvl = 0.0;
     if (r->d_hist) { OpmStatus hs = hist_clear(r); if (hs) return hs; }  // new rays start without a history (ray.rs:126)
     CU(cudaMemsetAsync(r->d_tail, 0, 8, r->ctx->stream));
     return OPM_OK;
@@ -623,7 +631,7 @@ extern "C" OpmStatus opm_rays_position_history(const OpmRays* rc, int32_t with_c
 
 extern "C" OpmStatus opm_rays_upload(OpmRays* r, const OpmRay* host, uint64_t n) {
     if (!r || (!host && n)) return fail(OPM_ERR_ARG, "NULL argument");
-    r->pending = false;
+    r->pending = false; r->mono_wvl = 0.0;
     OpmContext* c = r->ctx;
     CU(cudaSetDevice(c->device));
     if (r->d_hist) { OpmStatus hs = hist_clear(r); if (hs) return hs; }  // new rays start without a history (ray.rs:126)
@@ -644,7 +652,7 @@ extern "C" OpmStatus opm_rays_upload_soa(OpmRays* r, const double* pos[3], const
     if (!r || !pos || !dir || !e || !wvl) return fail(OPM_ERR_ARG, "NULL argument");
     OpmContext* c = r->ctx;
     CU(cudaSetDevice(c->device));
-    r->pending = false;
+    r->pending = false; r->mono_wvl = 0.0;
     if (r->d_hist) { OpmStatus hs = hist_clear(r); if (hs) return hs; }  // new rays start without a history (ray.rs:126)
     OpmStatus s = opm_rays_reserve(r, n);
     if (s) return s;
@@ -667,6 +675,7 @@ extern "C" OpmStatus opm_rays_new_collimated_with_spectrum(OpmRays* r, const dou
         if (!(wvl[k] > 0.0) || !std::isfinite(wvl[k])) return fail(OPM_ERR_ARG, "wavelength must be >0");
     const uint64_t n_rays = n_pos * n_wvl;
     r->pending = false;  // an earlier upload that was never used is superseded
+    r->mono_wvl = n_wvl == 1 ? wvl[0] : 0.0;
     if (r->d_hist) { OpmStatus hs = hist_clear(r); if (hs) return hs; }  // new rays start without a history (ray.rs:126)
     OpmStatus s = opm_rays_reserve(r, n_rays);
     if (s) return s;
@@ -745,6 +754,7 @@ extern "C" OpmStatus opm_rays_copy(const OpmRays* src, OpmRays* dst) {
     if (s) return s;
     if (src->d_hist) { s = hist_copy(src, dst, src->hist_next, src->len); if (s) return s; }
     else if (dst->d_hist) { s = hist_clear(dst); if (s) return s; }
+    dst->mono_wvl = src->mono_wvl;
     return rays_set_len(dst, src->len);
 }
 extern "C" OpmStatus opm_rays_append(OpmRays* dst, const OpmRays* src) {
@@ -759,6 +769,7 @@ extern "C" OpmStatus opm_rays_append(OpmRays* dst, const OpmRays* src) {
     if (s) return s;
     s = copy_fields(src->v, 0, dst->v, dst->len, src->len, dst->ctx->stream);
     if (s) return s;
+    if (dst->len == 0) dst->mono_wvl = src->mono_wvl; else if (dst->mono_wvl != src->mono_wvl) dst->mono_wvl = 0.0;
     return rays_set_len(dst, dst->len + src->len);
 }
 extern "C" OpmStatus opm_rays_compact(OpmRays* r) {
@@ -1122,6 +1133,9 @@ static OpmStatus run_program(OpmRays* rays, const OpmOp* ops, int n_ops, int fla
 
     Compiled prog;
     s = compile_ops(c, ops, n_ops, n, prog);
+    if (!s && rays->mono_wvl > 0.0)  // one-wavelength bundle: the specialised kernels evaluate each index model once per CTA
+        for (DevOp& d : prog.ops)
+            if (d.kind == OPK_REFRACT && d.u.refract.has_index) d.u.refract.hint_wvl = rays->mono_wvl;
     auto free_temps = [&]() { for (void* p : prog.temp_dev) cudaFree(p); };
     if (s) { free_temps(); return s; }
 
@@ -1220,8 +1234,12 @@ static OpmStatus run_program(OpmRays* rays, const OpmOp* ops, int n_ops, int fla
         }
     // host-side lengths
     for (OpmHitMap* h : prog.hitmaps) h->len = n;
-    for (OpmRays* r : prog.slot_outputs) { s = rays_set_len(r, n); if (s) { free_temps(); return s; } }
-    for (OpmRays* r : prog.appended) r->len_dirty = true;
+    for (OpmRays* r : prog.slot_outputs) { s = rays_set_len(r, n); if (s) { free_temps(); return s; } r->mono_wvl = rays->mono_wvl; }
+    for (OpmRays* r : prog.appended) {  // children carry their parents' wavelengths
+        if (r->len == 0 && !r->len_dirty) r->mono_wvl = rays->mono_wvl; else if (r->mono_wvl != rays->mono_wvl) r->mono_wvl = 0.0;
+        r->len_dirty = true;
+    }
+    if (dst != rays) dst->mono_wvl = rays->mono_wvl;
     if (compact) dst->len_dirty = true;
     else if (dst != rays) { s = rays_set_len(dst, n); if (s) { free_temps(); return s; } }
 
@@ -2087,6 +2105,7 @@ static OpmStatus source_generate(OpmRays* rays, const OpmSourceDesc* desc, uint6
         S.energy_norm = norm;
     }
     rays->pending = false;
+    rays->mono_wvl = (desc->n_wavelengths == 1 && desc->wavelengths) ? desc->wavelengths[0] : 0.0;
     if (rays->d_hist) { OpmStatus hs = hist_clear(rays); if (hs) return hs; }  // new rays start without a history (ray.rs:126)
     uint64_t n_rays = n_pos * S.n_wavelengths;
     s = opm_rays_reserve(rays, n_rays);

@@ -45,6 +45,7 @@ struct DevRefract {
     DevIso fwd, inv;
     double ic[6];
     double wlo, whi;
+    double hint_wvl;                 // > 0: the bundle is (believed to be) monochromatic at this wavelength, see RefractCt HINT
     DevHits hits;                    // hits.e == nullptr: not recorded
     DevRays children;                // children.px == nullptr: not emitted
     unsigned long long* child_tail;  // device counter = current length of the children bundle

@@ -113,15 +113,29 @@ bool jit_rot_id_enabled() {
     return on;
 }
 
+// ops whose index model is evaluated once per CTA for the bundle's common wavelength (RefractCt HINT): refractions into a
+// wavelength-dependent medium of a bundle the launcher believes to be monochromatic
+bool op_has_hint(const DevOp& op) {
+    static const bool on = [] { const char* e = getenv("OPM_B200_JIT_MONO"); return !(e && e[0] == '0'); }();  // tuning switch
+    return on && op.kind == OPK_REFRACT && op.u.refract.has_index && op.u.refract.index_type != OPM_IDX_CONST && op.u.refract.hint_wvl > 0.0;
+}
+std::string refract_view(const DevRefract& o, int k, int hint_slot) {  // hint_slot < 0: no hint
+    const int rot_id = jit_rot_id_enabled() && rot_is_identity(o.inv) && rot_is_identity(o.fwd) ? 1 : 0;
+    std::string s;
+    appendf(s, "RefractCt<%d, %d, %d, %d, %d, %d, %d, %d, %d, %d>(opm_jit_ops[%d].u.refract", o.geom, o.coating, o.has_index ? 1 : 0, o.index_type,
+            o.strategy, o.flags, o.refraction_intended ? 1 : 0, o.hits.e ? 1 : 0, rot_id, hint_slot >= 0 ? 1 : 0, k);
+    if (hint_slot >= 0) appendf(s, ", s_hint + %d", 3 * hint_slot);
+    s += ")";
+    return s;
+}
+
 // one line of kernel body per op; the same text is the structural cache key
-std::string op_line(const DevOp& op, int k) {
+std::string op_line(const DevOp& op, int k, int hint_slot = -1) {
     std::string s;
     switch (op.kind) {
         case OPK_REFRACT: {
             const DevRefract& o = op.u.refract;
-            const int rot_id = jit_rot_id_enabled() && rot_is_identity(o.inv) && rot_is_identity(o.fwd) ? 1 : 0;
-            appendf(s, "        exec_refract(RefractCt<%d, %d, %d, %d, %d, %d, %d, %d, %d>(opm_jit_ops[%d].u.refract), x);\n", o.geom, o.coating,
-                    o.has_index ? 1 : 0, o.index_type, o.strategy, o.flags, o.refraction_intended ? 1 : 0, o.hits.e ? 1 : 0, rot_id, k);
+            s += "        exec_refract(" + refract_view(o, k, hint_slot) + ", x);\n";
             break;
         }
         case OPK_APODIZE: {
@@ -182,13 +196,25 @@ std::string make_source(const DevOp* ops, int n_ops, bool compact, int block, in
     // no register moves where their two sides would meet again, no convergence barriers.  The two copies meet at the end of the
     // tile, and behind a JOIN, where the parked (possibly valid) parent of a dead split-off ray returns to the live copy.
     static const bool split = [] { const char* e = getenv("OPM_B200_JIT_SPLIT"); return !(e && e[0] == '0'); }();  // tuning switch
-    std::string body;
+    std::string body, hint_init;
+    int n_hints = 0;
+    std::vector<int> hint_slot(n_ops, -1);
+    for (int k = 0; k < n_ops; ++k)
+        if (op_has_hint(ops[k])) {
+            hint_slot[k] = n_hints++;
+            appendf(hint_init, "    if (threadIdx.x == %d) {\n        const DevRefract& o = opm_jit_ops[%d].u.refract;\n        double n2 = 1.0;\n",
+                    hint_slot[k] % block, k);
+            hint_init += "        const int st = refractive_index(" + refract_view(ops[k].u.refract, k, -1) + ", o.hint_wvl, n2);\n";
+            appendf(hint_init, "        s_hint[%d] = st == OPM_OK ? o.hint_wvl : __longlong_as_double(0x7ff8000000000000ll);\n"
+                               "        s_hint[%d] = n2; s_hint[%d] = rcp_fast(n2);\n    }\n",
+                    3 * hint_slot[k], 3 * hint_slot[k] + 1, 3 * hint_slot[k] + 2);
+        }
     if (!split) {
-        for (int k = 0; k < n_ops; ++k) body += op_line(ops[k], k);
+        for (int k = 0; k < n_ops; ++k) body += op_line(ops[k], k, hint_slot[k]);
     } else {
         std::string dead;
         for (int k = 0; k < n_ops; ++k) {
-            const std::string line = op_line(ops[k], k);
+            const std::string line = op_line(ops[k], k, hint_slot[k]);
             if (k > 0 && ops[k - 1].kind == OPK_JOIN) appendf(body, "      live_%d:\n", k);
             appendf(body, "        if (!x.valid) goto dead_%d;\n        {\n", k);
             body += line;
@@ -214,8 +240,12 @@ std::string make_source(const DevOp* ops, int n_ops, bool compact, int block, in
          "    __shared__ unsigned s_status;\n"
          "    __shared__ unsigned long long s_first_inv;\n"
          "    if (threadIdx.x < CNT_N) s_cnt[threadIdx.x] = 0u;\n"
-         "    if (threadIdx.x == 0) { s_status = 0u; s_first_inv = 0ull; }\n"
-         "    __syncthreads();\n"
+         "    if (threadIdx.x == 0) { s_status = 0u; s_first_inv = 0ull; }\n";
+    if (n_hints) {
+        appendf(s, "    __shared__ double s_hint[%d];  // per hinted op: wavelength | n2 | 1 / n2\n", 3 * n_hints);
+        s += hint_init;
+    }
+    s += "    __syncthreads();\n"
          "    const unsigned tiles = (unsigned)((n + blockDim.x - 1) / blockDim.x);\n";
     if (pipe) {
         s += "    __shared__ unsigned long long s_bar[2];\n"

@@ -1,6 +1,8 @@
 """Edge cases of the GPU path against the oracle: empty and ragged bundles, a single ray, bundles without a valid ray,
 programs longer than one launch, detectors that nothing hits, zero-energy rays, and the interpreter / run-time
 specialised kernels against each other."""
+import math
+
 import numpy as np
 import pytest
 
@@ -137,3 +139,30 @@ def test_interpreter_and_specialised_kernels_agree(ctx):
     assert_rays_match(b, a, rtol=1e-13, what="specialised vs interpreter")
     assert np.array_equal(ha[4], hb[4]) and np.allclose(ha[0], hb[0], rtol=1e-13, atol=1e-18)
     assert ctx.jit_stats()["launches"] >= 1 and ctx.jit_stats()["compile_failures"] == 0
+
+
+def test_wavelength_hint_is_only_a_hint(ctx):
+    """run-time specialised kernel with the once-per-CTA index evaluation (RefractCt HINT): a bundle of three wavelengths under a
+    hint that names one of them, none of them, and one outside the glass's range -- rays of the hinted wavelength take the CTA's
+    value, the others evaluate the Sellmeier model themselves; the results are the oracle's either way"""
+    import scenes
+    MM, NM = scenes.MM, scenes.NM
+    nodes = [scenes.node("source"),
+             scenes.node("lens", z=30 * MM, p=(120 * MM, -150 * MM, 6 * MM), index=scenes.HK9L, coat_in=("fresnel",), coat_out=("fresnel",)),
+             scenes.node("wedge", z=80 * MM, p=(8 * MM, math.radians(4.0)), index=scenes.HZF52),
+             scenes.node("spot_diagram", z=200 * MM)]
+    src = {"pos": ("fibonacci_ellipse", 4000, 5 * MM, 4 * MM), "energy": ("uniform", 1.0), "wvl": [532 * NM, 1054 * NM, 1550 * NM], "w": [0.2, 0.5, 0.3]}
+    osc = scenes.to_oracle(nodes)
+    ref = osc.raytrace(scenes.source_to_oracle(src))
+    psc = scenes.to_product(ctx, nodes)
+    ctx.set_jit(2, 1)
+    try:
+        for hint in (0.0, 1054 * NM, 800 * NM, 5000 * NM):
+            rays = scenes.source_to_product(src).generate(ctx)
+            rays.set_wavelength_hint(hint)
+            st = psc.raytrace(rays)
+            assert st.interactions == osc.interactions, hint
+            assert_rays_match(rays.to_array(), ref, what=f"hint {hint}")
+    finally:
+        ctx.set_jit(1, 200000)
+    assert ctx.jit_stats()["compile_failures"] == 0
