@@ -106,6 +106,10 @@ struct OpmHitMap {
     uint64_t cap = 0, len = 0;
     void* base = nullptr;
     DevHits v{};
+    // bounding box of the recorded hits, kept by the specialised trace kernel while it writes the map (BBoxAccum); valid while
+    // the map holds exactly what that launch recorded
+    unsigned long long* d_acc = nullptr;
+    bool acc_valid = false;
 };
 
 static OpmStatus hist_resize(OpmRays* r, uint32_t levels, uint64_t stride);
@@ -818,7 +822,7 @@ static size_t hits_layout(uint64_t cap, void* base, DevHits* v) {
     auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return b ? b + o : nullptr; };
     v->x = (double*)take(cap * 8); v->y = (double*)take(cap * 8); v->z = (double*)take(cap * 8); v->e = (double*)take(cap * 8);
     v->bounce = (uint32_t*)take(cap * 4);
-    return off;
+    return off;  // the caller appends 64 bytes for the bounding-box accumulator
 }
 extern "C" OpmStatus opm_hitmap_create(OpmContext* ctx, uint64_t capacity, OpmHitMap** out) {
     if (!ctx || !out) return fail(OPM_ERR_ARG, "NULL argument");
@@ -827,9 +831,10 @@ extern "C" OpmStatus opm_hitmap_create(OpmContext* ctx, uint64_t capacity, OpmHi
     h->ctx = ctx; h->cap = capacity ? capacity : 1;
     DevHits tmp;
     size_t bytes = hits_layout(h->cap, nullptr, &tmp);
-    cudaError_t e = cudaMalloc(&h->base, bytes);
+    cudaError_t e = cudaMalloc(&h->base, bytes + 64);
     if (e != cudaSuccess) { delete h; return fail(OPM_ERR_CUDA, "cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e)); }
     hits_layout(h->cap, h->base, &h->v);
+    h->d_acc = (unsigned long long*)((unsigned char*)h->base + bytes);
     *out = h;
     return OPM_OK;
 }
@@ -846,6 +851,7 @@ extern "C" OpmStatus opm_hitmap_upload(OpmHitMap* h, const double* x, const doub
                                        const uint32_t* bounce, uint64_t n) {
     if (!h || !x || !y || !e) return fail(OPM_ERR_ARG, "NULL argument");
     if (n > h->cap) return fail(OPM_ERR_CAPACITY, "hit map capacity %llu < %llu", (unsigned long long)h->cap, (unsigned long long)n);
+    h->acc_valid = false;
     cudaStream_t st = h->ctx->stream;
     CU(cudaSetDevice(h->ctx->device));
     CU(cudaMemcpyAsync(h->v.x, x, n * 8, cudaMemcpyHostToDevice, st));
@@ -902,6 +908,7 @@ struct Compiled {
     std::vector<OpmRays*> slot_outputs; // split / snapshot outputs (len = n)
     std::vector<std::pair<int, OpmRays*>> slot_output_ops;  // the same with the index of their device op (position history)
     std::vector<OpmHitMap*> hitmaps;
+    std::vector<std::pair<int, OpmHitMap*>> hitmap_ops;  // the same with the index of the device op that records into them
     int fork_depth = 0;                 // inside an OPM_OP_FORK .. OPM_OP_JOIN range
     bool has_fork = false;
 };
@@ -956,6 +963,7 @@ static OpmStatus compile_ops(OpmContext* c, const OpmOp* ops, int n_ops, uint64_
                     if (r.hits->cap < n_rays) return fail(OPM_ERR_CAPACITY, "hit map capacity %llu < %llu rays", (unsigned long long)r.hits->cap, (unsigned long long)n_rays);
                     o.hits = r.hits->v;
                     out.hitmaps.push_back(r.hits);
+                    out.hitmap_ops.push_back({(int)out.ops.size(), r.hits});
                 }
                 if (r.flags & OPM_REFRACT_EMIT_CHILDREN) {
                     if (!r.children) return fail(OPM_ERR_ARG, "OPM_REFRACT_EMIT_CHILDREN without a children bundle");
@@ -1182,13 +1190,27 @@ static OpmStatus run_program(OpmRays* rays, const OpmOp* ops, int n_ops, int fla
         DevOp* h_slot = c->h_ops_ring + (size_t)slot * OPM_MAX_PROGRAM_OPS;
         DevOp* d_slot = c->d_ops + (size_t)slot * OPM_MAX_PROGRAM_OPS;
         CU(cudaEventSynchronize(c->ring_ev[slot]));  // the copy that last used this pinned slot has drained
-        memcpy(h_slot, prog.ops.data(), prog.ops.size() * sizeof(DevOp));
         const bool strict = (flags & OPM_TRACE_STRICT) != 0;
+        // hit maps that exactly one op of this launch records into get their bounding box from the specialised kernel (if that is
+        // the kernel that runs: the accumulator pointer is a structural fact of its source)
+        const bool jit_candidate = !strict && !use_hist && c->jit_enabled && n >= c->jit_min_rays && prog.ops.size() * sizeof(DevOp) <= 60 * 1024;
+        static const bool fuse_bbox = [] { const char* e = getenv("OPM_B200_JIT_BBOX"); return !(e && e[0] == '0'); }();  // tuning switch
+        std::vector<OpmHitMap*> fused;
+        if (jit_candidate && fuse_bbox)
+            for (auto& ho : prog.hitmap_ops) {
+                int uses = 0;
+                for (auto& other : prog.hitmap_ops) uses += other.second == ho.second ? 1 : 0;
+                if (uses != 1 || prog.ops[ho.first].kind != OPK_REFRACT) continue;
+                if (fused.size() == 2) break;  // 36 bytes of shared memory per thread and map, next to the parked rays of a FORK
+                prog.ops[ho.first].u.refract.hit_acc = ho.second->d_acc;
+                fused.push_back(ho.second);
+            }
+        memcpy(h_slot, prog.ops.data(), prog.ops.size() * sizeof(DevOp));
         int block = strict ? trace_block_strict() : trace_block_fast();
         // large bundles run the kernel compiled for the structure of this program (opm_jit.cu); otherwise, and whenever
         // that kernel cannot be had, the interpreter
         const JitKernel* jk = nullptr;
-        if (!strict && !use_hist && c->jit_enabled && n >= c->jit_min_rays && prog.ops.size() * sizeof(DevOp) <= 60 * 1024) {  // __constant__ holds 64 KB
+        if (jit_candidate) {  // __constant__ holds 64 KB
             const char* why = nullptr;
             jk = jit_get(c->jit, prog.ops.data(), (int)prog.ops.size(), compact, c->jit_block, c->jit_min_ctas, c->jit_sync, &why);
             if (jk) block = c->jit_block;
@@ -1201,6 +1223,15 @@ static OpmStatus run_program(OpmRays* rays, const OpmOp* ops, int n_ops, int fla
             KL(k_fetch_from_host(d_slot, h_slot, prog.ops.size() * sizeof(DevOp), c->stream));  // not a copy-engine transfer: see dev_put
             c->launches++;
         }
+        for (OpmHitMap* h : prog.hitmaps) h->acc_valid = false;
+        if (jk)
+            for (OpmHitMap* h : fused) {  // identity of the accumulator, then the kernel fills it
+                BBoxAccum init;
+                init.key[0] = ~0ull; init.key[1] = 0; init.key[2] = 0; init.key[3] = ~0ull; init.count = 0;
+                OpmStatus ps = dev_put(c, h->d_acc, &init, sizeof init);
+                if (ps) { free_temps(); return ps; }
+                h->acc_valid = true;
+            }
         CU(cudaMemsetAsync(c->d_stats, 0, sizeof(DevStats), c->stream));
         TraceLaunch L;
         L.ops = d_slot; L.n_ops = (int)prog.ops.size();
@@ -1746,12 +1777,23 @@ static OpmStatus check_same_ctx(OpmHitMap* const* maps, int n_maps, OpmContext**
 // scratch layout: [0,1024) accumulators, [1024,1028) status, [2048,2080) range, [2112,2192) spot sums, [2240,2264) radii,
 // [2304,2320) peak/total
 
+// used_acc: where the accumulator of this call lives on the device (the context's scratch, or the hit map's own)
+static OpmStatus bounding_box_async(OpmHitMap* const* maps, int32_t n_maps, int64_t bounce_filter, double* range_dev, const BBoxAccum** used_acc);
 extern "C" OpmStatus opm_hitmaps_bounding_box_async(OpmHitMap* const* maps, int32_t n_maps, int64_t bounce_filter, double* range_dev) {
+    return bounding_box_async(maps, n_maps, bounce_filter, range_dev, nullptr);
+}
+static OpmStatus bounding_box_async(OpmHitMap* const* maps, int32_t n_maps, int64_t bounce_filter, double* range_dev, const BBoxAccum** used_acc) {
     OpmContext* c;
     OpmStatus s = check_same_ctx(maps, n_maps, &c);
     if (s) return s;
     if (!range_dev) return fail(OPM_ERR_ARG, "range_dev is NULL");
     CU(cudaSetDevice(c->device));
+    if (used_acc) *used_acc = (const BBoxAccum*)c->d_scratch;
+    if (n_maps == 1 && bounce_filter < 0 && maps[0]->acc_valid && maps[0]->len) {  // the trace kernel kept the box while it recorded
+        if (used_acc) *used_acc = (const BBoxAccum*)maps[0]->d_acc;
+        KL(k_bbox_finalize((const BBoxAccum*)maps[0]->d_acc, range_dev, c->stream)); c->launches++;
+        return OPM_OK;
+    }
     BBoxAccum init;
     init.key[0] = ~0ull; init.key[1] = 0; init.key[2] = 0; init.key[3] = ~0ull; init.count = 0;
     BBoxAccum* d_acc = (BBoxAccum*)c->d_scratch;
@@ -1801,9 +1843,10 @@ extern "C" OpmStatus opm_hitmaps_bounding_box(OpmHitMap* const* maps, int32_t n_
     OpmContext* c;
     OpmStatus s = check_same_ctx(maps, n_maps, &c);
     if (s) return s;
-    s = opm_hitmaps_bounding_box_async(maps, n_maps, bounce_filter, scratch_range(c));
+    const BBoxAccum* d_used = nullptr;
+    s = bounding_box_async(maps, n_maps, bounce_filter, scratch_range(c), &d_used);
     if (s) return s;
-    CU(cudaMemcpyAsync(c->h_scratch, c->d_scratch, sizeof(BBoxAccum), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(c->h_scratch, d_used, sizeof(BBoxAccum), cudaMemcpyDeviceToHost, c->stream));
     double box[4];
     s = range_to_host(c, scratch_range(c), box, nullptr, nullptr);
     if (s) return s;

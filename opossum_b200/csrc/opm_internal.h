@@ -47,6 +47,8 @@ struct DevRefract {
     double wlo, whi;
     double hint_wvl;                 // > 0: the bundle is (believed to be) monochromatic at this wavelength, see RefractCt HINT
     DevHits hits;                    // hits.e == nullptr: not recorded
+    unsigned long long* hit_acc;     // bounding-box accumulator of the hit map (BBoxAccum: 4 ordered keys + count) the specialised
+                                     // kernel keeps while it records; nullptr: none
     DevRays children;                // children.px == nullptr: not emitted
     unsigned long long* child_tail;  // device counter = current length of the children bundle
     uint64_t child_cap;

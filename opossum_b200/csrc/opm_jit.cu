@@ -49,6 +49,7 @@ struct JitKernel {
     int n_ops = 0;
     int occupancy = 1;
     bool has_fork = false;
+    int bbox_slots = 0;  // hit maps whose bounding box the kernel keeps (36 bytes of shared memory per thread each)
     size_t smem = 0;  // dynamic shared memory per CTA
     std::string why;
 };
@@ -119,6 +120,12 @@ bool op_has_hint(const DevOp& op) {
     static const bool on = [] { const char* e = getenv("OPM_B200_JIT_MONO"); return !(e && e[0] == '0'); }();  // tuning switch
     return on && op.kind == OPK_REFRACT && op.u.refract.has_index && op.u.refract.index_type != OPM_IDX_CONST && op.u.refract.hint_wvl > 0.0;
 }
+bool op_has_bbox(const DevOp& op) { return op.kind == OPK_REFRACT && op.u.refract.hits.e && op.u.refract.hit_acc; }
+static int program_bbox_slots(const DevOp* ops, int n_ops) {
+    int n = 0;
+    for (int k = 0; k < n_ops; ++k) n += op_has_bbox(ops[k]) ? 1 : 0;
+    return n;
+}
 std::string refract_view(const DevRefract& o, int k, int hint_slot) {  // hint_slot < 0: no hint
     const int rot_id = jit_rot_id_enabled() && rot_is_identity(o.inv) && rot_is_identity(o.fwd) ? 1 : 0;
     std::string s;
@@ -135,7 +142,12 @@ std::string op_line(const DevOp& op, int k, int hint_slot = -1) {
     switch (op.kind) {
         case OPK_REFRACT: {
             const DevRefract& o = op.u.refract;
-            s += "        exec_refract(" + refract_view(o, k, hint_slot) + ", x);\n";
+            if (op_has_bbox(op)) {  // the kernel keeps the bounding box of the hits it records here (bbox_reg_*, opm_trace_ops.cuh)
+                s += "        { HitOut ho; exec_refract(" + refract_view(o, k, hint_slot) + ", x, &ho);";
+                appendf(s, " bbox_smem_add(bb_%d, ho); }\n", k);
+            } else {
+                s += "        exec_refract(" + refract_view(o, k, hint_slot) + ", x);\n";
+            }
             break;
         }
         case OPK_APODIZE: {
@@ -183,8 +195,13 @@ static bool program_has_fork(const DevOp* ops, int n_ops) {
 }
 // dynamic shared memory of a specialised kernel: [parked rays of a FORK | stage 0 | stage 1]
 static size_t jit_stash_bytes(bool has_fork, int block) { return has_fork ? (((size_t)block * kStashWords * 4 + 127) & ~(size_t)127) : 0; }
-size_t jit_dynamic_smem(bool has_fork, int block) {
+static int program_bbox_slots(const DevOp* ops, int n_ops);
+// [parked rays of a FORK | tile stages | running bounding boxes of the recorded hit maps]
+static size_t jit_bbox_offset(bool has_fork, int block) {
     return jit_stash_bytes(has_fork, block) + (jit_pipe_enabled() && block % 16 == 0 ? 2 * jit_stage_bytes(block) : 0);
+}
+size_t jit_dynamic_smem(bool has_fork, int block, int bbox_slots) {
+    return jit_bbox_offset(has_fork, block) + (size_t)bbox_slots * block * 36;
 }
 
 std::string make_source(const DevOp* ops, int n_ops, bool compact, int block, int min_ctas) {
@@ -252,6 +269,15 @@ std::string make_source(const DevOp* ops, int n_ops, bool compact, int block, in
              "    TilePipe pipe;\n";
         appendf(s, "    tile_pipe_init(pipe, opm_jit_smem + %zu, s_bar, in, n);\n", stash);
     }
+    {
+        const size_t bb0 = jit_bbox_offset(program_has_fork(ops, n_ops), block);
+        int j = 0;
+        for (int k = 0; k < n_ops; ++k)
+            if (op_has_bbox(ops[k])) {
+                appendf(s, "    unsigned char* const bb_%d = opm_jit_smem + %zu;\n    bbox_smem_init(bb_%d);\n", k, bb0 + (size_t)j * block * 36, k);
+                ++j;
+            }
+    }
     s += "    for (unsigned tile = blockIdx.x; tile < tiles; tile += gridDim.x) {\n"
          "        RayCtx x;\n"
          "        uint8_t vb;\n";
@@ -262,8 +288,10 @@ std::string make_source(const DevOp* ops, int n_ops, bool compact, int block, in
     appendf(s, "        tile_store<%s>(in, out, out_cap, out_tail, x, vb);\n", compact ? "true" : "false");
     s += "        tile_count(x, s_cnt, &s_status, &s_first_inv);\n"
          "    }\n"
-         "    __syncthreads();\n"
-         "    cta_flush(stats, s_cnt, s_status, s_first_inv);\n"
+         "    __syncthreads();\n";
+    for (int k = 0; k < n_ops; ++k)
+        if (op_has_bbox(ops[k])) appendf(s, "    bbox_reg_flush(bbox_smem_get(bb_%d), opm_jit_ops[%d].u.refract.hit_acc);\n", k, k);
+    s += "    cta_flush(stats, s_cnt, s_status, s_first_inv);\n"
          "}\n}  // namespace opm\n";
     return s;
 }
@@ -317,7 +345,7 @@ bool load(JitKernel& K, int n_ops, int block) {
     if (e != cudaSuccess) { K.why = std::string("cudaLibraryGetKernel/Global: ") + cudaGetErrorString(e); cudaGetLastError(); return false; }
     if (K.const_bytes < (size_t)n_ops * sizeof(DevOp)) { K.why = "constant array smaller than the program"; return false; }
     int nb = 0;
-    K.smem = jit_dynamic_smem(K.has_fork, block);
+    K.smem = jit_dynamic_smem(K.has_fork, block, K.bbox_slots);
     if (K.smem > 48 * 1024 &&
         cudaFuncSetAttribute((const void*)K.kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K.smem) != cudaSuccess) {
         K.why = "dynamic shared memory of the specialised kernel not available"; cudaGetLastError(); return false;
@@ -388,6 +416,7 @@ const JitKernel* jit_get(JitCache* cache, const DevOp* ops, int n_ops, bool comp
         it = cache->kernels.emplace(std::move(src), std::unique_ptr<JitKernel>(new JitKernel())).first;
         JitKernel* k = it->second.get();
         k->has_fork = program_has_fork(ops, n_ops);
+        k->bbox_slots = program_bbox_slots(ops, n_ops);
         if (!nvrtc_load(&k->why)) {
             k->state = JIT_FAILED;
             cache->failures++;

@@ -127,8 +127,10 @@ __device__ __forceinline__ void finish_children(const V& v, const RefractResult&
 
 // Rays::refract_on_surface (rays.rs:976-1047) for one ray + hit record + child emission / mirror continuation.  Returns
 // true when the ray reached the surface, i.e. when the reference pushes the old position to `pos_hist` (ray.rs:616).
+// the hit exec_refract recorded for this ray, for the bounding box the specialised kernel keeps next to the hit map
+struct HitOut { double x, y; bool ok; };
 template <class V>
-__device__ __forceinline__ bool exec_refract(const V& v, RayCtx& x) {
+__device__ __forceinline__ bool exec_refract(const V& v, RayCtx& x, HitOut* ho = nullptr) {
     const DevRefract& o = v.d();
     RefractResult res;
     res.has_child = false; res.moved = false; res.hit_e = -1.0; res.hit_bounce = 0; res.hit_local = v3(0, 0, 0);
@@ -141,16 +143,83 @@ __device__ __forceinline__ bool exec_refract(const V& v, RayCtx& x) {
             if (res.invalidated) x.valid = false;
         }
     }
+    if (ho) ho->ok = false;
     if (v.has_hits() && x.in_range) {  // slot-indexed hit record, e < 0 = empty
         OPM_ST(o.hits.e + x.i, res.hit_e);
         if (res.hit_e >= 0.0) {
             OPM_ST(o.hits.x + x.i, res.hit_local.x); OPM_ST(o.hits.y + x.i, res.hit_local.y);
             OPM_ST(o.hits.z + x.i, res.hit_local.z); OPM_ST(o.hits.bounce + x.i, res.hit_bounce);
             x.c.a += 1u << 16;
+            if (ho) { ho->ok = true; ho->x = res.hit_local.x; ho->y = res.hit_local.y; }
         }
     }
     finish_children(v, res, x);
     return res.moved;
+}
+
+// Bounding box of the hits a launch records (rays_hit_map.rs:522-562), kept by the specialised kernel while it writes the hit
+// map, so that the detector read-out needs no pass of its own over the map: per-thread running extrema across the tiles, one
+// reduction per CTA at the end of the kernel, ordered-key atomics into the hit map's accumulator (layout of BBoxAccum).
+// The running extrema live in dynamic shared memory, field-major per thread ([x0 | x1 | y0 | y1][blockDim] doubles, then
+// [n][blockDim] counts: 36 bytes per thread and hit map) -- registers held across the tile loop cost the kernel more than the
+// separate pass they replace.
+struct BBoxReg { double x0, x1, y0, y1; unsigned n; };
+__device__ __forceinline__ size_t bbox_slot_bytes() { return (size_t)blockDim.x * 36; }
+__device__ __forceinline__ void bbox_smem_init(unsigned char* slot) {
+    double* d = reinterpret_cast<double*>(slot);
+    const unsigned B = blockDim.x, t = threadIdx.x;
+    d[t] = 1.7976931348623157e308; d[B + t] = -1.7976931348623157e308; d[2 * B + t] = 1.7976931348623157e308; d[3 * B + t] = -1.7976931348623157e308;
+    reinterpret_cast<unsigned*>(d + 4 * B)[t] = 0u;
+}
+__device__ __forceinline__ void bbox_smem_add(unsigned char* slot, const HitOut& h) {
+    if (!h.ok) return;
+    double* d = reinterpret_cast<double*>(slot);
+    const unsigned B = blockDim.x, t = threadIdx.x;
+    // compare, store only on change: after a thread's first tiles its extrema rarely move
+    if (h.x < d[t]) d[t] = h.x;
+    if (h.x > d[B + t]) d[B + t] = h.x;
+    if (h.y < d[2 * B + t]) d[2 * B + t] = h.y;
+    if (h.y > d[3 * B + t]) d[3 * B + t] = h.y;
+    reinterpret_cast<unsigned*>(d + 4 * B)[t] += 1u;
+}
+__device__ __forceinline__ BBoxReg bbox_smem_get(const unsigned char* slot) {
+    const double* d = reinterpret_cast<const double*>(slot);
+    const unsigned B = blockDim.x, t = threadIdx.x;
+    BBoxReg b;
+    b.x0 = d[t]; b.x1 = d[B + t]; b.y0 = d[2 * B + t]; b.y1 = d[3 * B + t]; b.n = reinterpret_cast<const unsigned*>(d + 4 * B)[t];
+    return b;
+}
+__device__ __forceinline__ unsigned long long ordered_key(double d) {  // monotonic double -> uint64 (opm_kernels.cu dkey)
+    const unsigned long long u = (unsigned long long)__double_as_longlong(d);
+    return (u & 0x8000000000000000ull) ? ~u : (u | 0x8000000000000000ull);
+}
+// all threads of the CTA; ends with a barrier, so calls may follow one another
+__device__ __forceinline__ void bbox_reg_flush(BBoxReg b, unsigned long long* acc) {
+    __shared__ double sh[32][4];
+    __shared__ unsigned shn[32];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        b.x0 = fmin(b.x0, __shfl_xor_sync(0xffffffffu, b.x0, o)); b.x1 = fmax(b.x1, __shfl_xor_sync(0xffffffffu, b.x1, o));
+        b.y0 = fmin(b.y0, __shfl_xor_sync(0xffffffffu, b.y0, o)); b.y1 = fmax(b.y1, __shfl_xor_sync(0xffffffffu, b.y1, o));
+        b.n += __shfl_xor_sync(0xffffffffu, b.n, o);
+    }
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    if (l == 0) { sh[w][0] = b.x0; sh[w][1] = b.x1; sh[w][2] = b.y0; sh[w][3] = b.y1; shn[w] = b.n; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long n = 0;
+        for (int k = 0; k < (int)((blockDim.x + 31) >> 5); ++k) {
+            if (!shn[k]) continue;
+            n += shn[k];
+            b.x0 = fmin(b.x0, sh[k][0]); b.x1 = fmax(b.x1, sh[k][1]); b.y0 = fmin(b.y0, sh[k][2]); b.y1 = fmax(b.y1, sh[k][3]);
+        }
+        if (n) {
+            atomicMin(&acc[0], ordered_key(b.x0)); atomicMax(&acc[1], ordered_key(b.x1));
+            atomicMax(&acc[2], ordered_key(b.y1)); atomicMin(&acc[3], ordered_key(b.y0));
+            atomicAdd(&acc[4], n);
+        }
+    }
+    __syncthreads();
 }
 
 // Rays::diffract_on_periodic_surface (rays.rs:1058-1111) for one ray: reflective grating; returns like
