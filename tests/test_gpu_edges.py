@@ -166,3 +166,39 @@ def test_wavelength_hint_is_only_a_hint(ctx):
     finally:
         ctx.set_jit(1, 200000)
     assert ctx.jit_stats()["compile_failures"] == 0
+
+
+def test_bounding_box_kept_by_the_trace_kernel_equals_the_pass_over_the_map(ctx):
+    """the run-time specialised kernel keeps the bounding box (and the hit count) of a hit map it records; the read-out then
+    skips its own pass over the map: both must give the same bits, also for a detector most rays miss and for one nothing hits;
+    an upload into the map drops the kept box"""
+    import scenes
+    MM, NM = scenes.MM, scenes.NM
+    nodes = [scenes.node("source"),
+             scenes.node("lens", z=30 * MM, p=(120 * MM, -150 * MM, 6 * MM), index=scenes.HK9L, coat_in=("fresnel",), coat_out=("fresnel",)),
+             scenes.node("fluence_detector", z=60 * MM, ap_in=("circle", 1.5 * MM, 0.4 * MM, -0.2 * MM)),
+             scenes.node("dummy", z=90 * MM, ap_in=("circle", 0.1 * MM, 50 * MM, 0.0)),  # an aperture far off the beam: no ray survives
+             scenes.node("fluence_detector", z=120 * MM)]
+    src = {"pos": ("fibonacci_ellipse", 5000, 5 * MM, 4 * MM), "energy": ("uniform", 1.0), "wvl": [1054 * NM], "w": [1.0]}
+    out = {}
+    for mode in ("interpreter", "jit"):
+        ctx.set_jit(2 if mode == "jit" else 0, 1)
+        try:
+            psc = scenes.to_product(ctx, nodes)
+            psc.raytrace(scenes.source_to_product(src).generate(ctx))
+            boxes = []
+            for node in (2, 4):
+                hm = psc.node_hitmaps(node)
+                try:
+                    boxes.append(ob.hitmaps_bounding_box(hm))
+                except ob.OpossumError as e:
+                    boxes.append(("error", e.code))
+            out[mode] = boxes
+            if mode == "jit":  # a host upload replaces the map's content: the kept box must not survive it
+                h = psc.node_hitmaps(2)[0]
+                h.upload(np.array([1.0, 2.0]), np.array([-3.0, 4.0]), np.array([1.0, 1.0]))
+                assert ob.hitmaps_bounding_box([h]) == ((1.0, 2.0, 4.0, -3.0), 2)
+        finally:
+            ctx.set_jit(1, 200000)
+    assert out["jit"] == out["interpreter"]
+    assert out["jit"][0][1] > 0 and out["jit"][1][0] == "error"
