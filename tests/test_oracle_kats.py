@@ -796,3 +796,81 @@ def test_calc_node_positions_on_a_straight_chain():
     for f in ("pos", "dir", "e", "opl"):
         assert np.allclose(a[f], b[f], rtol=1e-12, atol=1e-15), f
     assert np.array_equal(a["valid"], b["valid"])
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# bundle-level tests of rays.rs that the per-ray transcriptions above do not cover
+# ---------------------------------------------------------------------------------------------------------------
+def test_bundle_refract_paraxial():
+    """rays.rs:2108-2146: focal length 0 / NaN / +-inf are errors; an on-axis ray is untouched, a ray 1 mm off axis turns to
+    normalize(0, -1, 100)"""
+    iso = orc.Isometry.identity()
+    empty = np.zeros(0, dtype=orc.RAY_DTYPE)
+    for bad in (0.0, math.nan, math.inf, -math.inf):
+        with pytest.raises(orc.OracleError):
+            orc.rays_refract_paraxial(empty, mm(bad) if math.isfinite(bad) else bad, iso)
+    orc.rays_refract_paraxial(empty, mm(100.0), iso)
+    rays = np.concatenate([orc.ray_new(mm(0.0, 0.0, 0.0), Z, nm(1053.0), 1.0), orc.ray_new(mm(0.0, 1.0, 0.0), Z, nm(1053.0), 1.0)])
+    before = rays.copy()
+    orc.rays_refract_paraxial(rays, mm(100.0), iso)
+    assert tuple(rays[0]["pos"]) == tuple(before[0]["pos"]) and tuple(rays[0]["dir"]) == tuple(before[0]["dir"])
+    assert tuple(rays[1]["pos"]) == tuple(before[1]["pos"])
+    want = np.array([0.0, -1.0, 100.0]) / math.sqrt(10001.0)
+    assert np.all(np.abs(rays[1]["dir"] - want) <= EPS)
+
+
+def test_bundle_refract_on_surface_same_index():
+    """rays.rs:2214-2245: n2 = None keeps every ray's own index (1.5 and 2.0): the directions do not change"""
+    rays = np.concatenate([orc.ray_new(mm(0.0, 0.0, -10.0), (0.0, 1.0, 1.0), nm(1053.0), 1.0),
+                           orc.ray_new(mm(0.0, 1.0, -10.0), (0.0, 1.0, 1.0), nm(1053.0), 1.0)])
+    rays["n"] = (1.5, 2.0)  # Ray::set_refractive_index
+    orc.rays_refract_on_surface(rays, plane(), None, True, orc.MISS_STOP)
+    want = np.array([0.0, 1.0, 1.0]) / math.sqrt(2.0)
+    for r in rays:
+        assert np.all(np.abs(r["dir"] - want) <= EPS)
+    assert tuple(rays["n"]) == (1.5, 2.0)
+
+
+def test_bundle_filter_energy():
+    """rays.rs:2288-2306: Constant(0.5) on an empty bundle is fine, -0.1 and 1.1 are errors; a bundle of one ray ends up like the
+    ray filtered on its own"""
+    empty = np.zeros(0, dtype=orc.RAY_DTYPE)
+    orc.rays_filter_energy(empty, 0.5)
+    for bad in (-0.1, 1.1):
+        with pytest.raises(orc.OracleError):
+            orc.rays_filter_energy(empty, bad)
+    ray = orc.ray_new(mm(0.0, 1.0, 0.0), Z, nm(1054.0), 1.0)
+    rays = ray.copy()
+    orc.rays_filter_energy(ray, 0.3)
+    orc.rays_filter_energy(rays, 0.3)
+    assert len(rays) == 1
+    for f in ("pos", "dir"):
+        assert tuple(rays[0][f]) == tuple(ray[0][f])
+    assert rays[0]["wvl"] == ray[0]["wvl"] and rays[0]["e"] == ray[0]["e"] == 0.3
+
+
+def test_bundle_split():
+    """rays.rs:2429-2459: ratios outside [0, 1] are errors; 1 J + 2 J split with ratio 0.2 leaves 0.6 J and splits off 2.4 J"""
+    rays = np.concatenate([orc.ray_new((0.0, 0.0, 0.0), Z, nm(1053.0), 1.0), orc.ray_new((0.0, 0.0, 0.0), Z, nm(1050.0), 2.0)])
+    for bad in (1.1, -0.1):
+        with pytest.raises(orc.OracleError):
+            orc.rays_split(rays.copy(), bad)
+    split = orc.rays_split(rays, 0.2)
+    assert abs(orc.total_energy(rays) - 0.6) <= EPS
+    assert abs(orc.total_energy(split) - 2.4) <= 10 * EPS
+    # an invalid ray is copied unchanged and counts for nothing (rays.rs:1258-1262, total_energy over valid rays)
+    rays = np.concatenate([orc.ray_new((0.0, 0.0, 0.0), Z, nm(1053.0), 1.0), orc.ray_new((0.0, 0.0, 0.0), Z, nm(1050.0), 2.0),
+                           orc.ray_new((0.0, 0.0, 0.0), Z, nm(1053.0), 5.0)])
+    rays["valid"][2] = 0
+    split = orc.rays_split(rays, 0.2)
+    assert abs(orc.total_energy(split) - 2.4) <= 10 * EPS and split[2]["e"] == 5.0 and split[2]["valid"] == 0
+
+
+def test_bundle_to_spectrum_range_follows_the_valid_rays():
+    """rays.rs:2352-2384 wavelength_range: the minimum / maximum wavelength of the VALID rays (1050..1053 nm with an invalid
+    1000 nm ray in the bundle) -- here through Rays::to_spectrum, whose slot range starts from it (rays.rs:1199-1215)"""
+    rays = np.concatenate([orc.ray_new((0.0, 0.0, 0.0), Z, nm(w), 1.0) for w in (1053.0, 1053.0, 1050.0, 1051.0, 1000.0)])
+    rays["valid"][4] = 0
+    lam, val = orc.rays_to_spectrum(rays, nm(0.5))
+    assert lam[0] * 1e-6 >= nm(1050.0) - nm(2.0) and lam[-1] * 1e-6 <= nm(1053.0) + nm(2.0)
+    assert lam[0] * 1e-6 > nm(1001.0)  # the invalid 1000 nm ray does not widen the range
