@@ -17,14 +17,17 @@ __device__ __forceinline__ unsigned lanemask_lt() {
     return m;
 }
 
-// warp-aggregated reservation of `want ? 1 : 0` slots per lane; returns this lane's slot
+// warp-aggregated reservation of `want ? 1 : 0` slots per lane; returns this lane's slot.  Aggregates over the lanes that arrive
+// here together (__activemask): the live and the dead copy of a specialised program call this from different places, each group
+// of lanes then reserves for itself
 __device__ __forceinline__ unsigned long long warp_reserve(bool want, unsigned long long* tail) {
-    unsigned mask = __ballot_sync(0xffffffffu, want);
+    const unsigned active = __activemask();
+    unsigned mask = __ballot_sync(active, want);
     if (mask == 0) return 0;
     int leader = __ffs(mask) - 1;
     unsigned long long base = 0;
     if ((threadIdx.x & 31) == leader) base = atomicAdd(tail, (unsigned long long)__popc(mask));
-    base = __shfl_sync(0xffffffffu, base, leader);
+    base = __shfl_sync(active, base, leader);
     return base + __popc(mask & lanemask_lt());
 }
 
