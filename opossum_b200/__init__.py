@@ -14,3 +14,4 @@ __all__ = ["Aperture", "Context", "FluenceData", "HitMap", "Isometry", "OpossumE
            "RAY_DTYPE", "RayTraceConfig", "Rays", "RefractiveIndex", "SourceDesc", "TraceStats", "fluence_binning",
            "fluence_kde", "fluence_peak_total", "hitmaps_bounding_box", "refr_index_vaccuum", "spectrum_gaussian", "Spectrum",
            "spectrum_total_energy", "spectrum_center_wavelength", "spectrum_get_value", "ffi"]
+from .opm_document import OpmDocument, OpmDocumentError, load_opm, loads_opm  # noqa: E402,F401  (.opm scene files)

@@ -141,3 +141,41 @@ def test_positioning_errors(ctx):
         sc.calc_node_positions(0.0)
     sc.calc_node_positions(1e-6)
     assert np.allclose(sc.node_isometry(1).matrices()[1], (0.0, 0.0, 0.1), rtol=0, atol=1e-16)
+
+
+def test_opm_document_end_to_end(ctx):
+    """a `.opm` file (tests/golden/opm/folded_chain_handwritten.opm: only the source has an isometry, edges carry distances)
+    read by opossum_b200/opm_document.py, placed by calc_node_positions and analysed, against the oracle's scene built from the
+    equivalent neutral description -- the mapping of the serialised properties, ports, alignment, source and edges end to end"""
+    from pathlib import Path
+
+    from opossum_b200 import opm_document as D
+    doc = D.load_opm(Path(__file__).parent / "golden" / "opm" / "folded_chain_handwritten.opm")
+    psc, sd, index = doc.build(ctx)
+    psc.calc_node_positions(doc.axis_wavelength())
+    nodes = [scenes.node("source", z=10 * MM, xy=(1 * MM, -2 * MM)),
+             scenes.node("lens", distance=100 * MM, p=(515.0 * MM, -515.0 * MM, 5.0 * MM), index=scenes.HK9L, coat_in=("fresnel",),
+                         coat_out=("fresnel",), ap_in=("circle", 3.5 * MM, 0.2 * MM, 0.0)),
+             scenes.node("thin_mirror", distance=150 * MM, alignment=((0.0, 0.0, 0.0), (math.radians(22.5), 0.0, 0.0)),
+                         coat_in=("constant_r", 0.98), coat_out=("constant_r", 0.98)),
+             scenes.node("beam_splitter", distance=120 * MM, p=(0.3,)),
+             scenes.node("ideal_filter", distance=50 * MM, p=(0.8,)),
+             scenes.node("spot_diagram", distance=80 * MM),
+             scenes.node("fluence_detector", distance=10 * MM),
+             scenes.node("fluence_detector", distance=90 * MM, parent=3, parent_port=1)]
+    src = {"pos": ("fibonacci_ellipse", 3000, 4 * MM, 3 * MM),
+           "energy": ("general_gaussian", 2.0, (0.3 * MM, -0.2 * MM), (2.5 * MM, 2.0 * MM), 2.0, 0.3, False),
+           "wvl": [1054 * NM, 527 * NM], "w": [0.7, 0.3]}
+    osc = scenes.to_oracle(nodes)
+    isos = osc.calc_node_positions(1054 * NM)
+    assert_isometries_match(psc, isos, ".opm")
+    ref_out = osc.raytrace(scenes.source_to_oracle(src))
+    rays = sd.generate(ctx)
+    st = psc.raytrace(rays, doc.raytrace_config())
+    assert st.interactions == osc.interactions and st.valid_out == orc.nr_of_rays(ref_out)
+    assert_rays_match(rays.to_array(), ref_out, what=".opm scene")
+    for node in (6, 7):
+        fmap, lrtb, peak, tot = osc.node_fluence(node)
+        fd = psc.node_fluence(node)
+        assert np.allclose(fd.lrtb, lrtb, rtol=1e-7, atol=1e-15) and fd.total_energy == pytest.approx(tot, rel=1e-6)
+    assert index[doc.nodes[-1].uuid] == 7
