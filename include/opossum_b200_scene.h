@@ -18,8 +18,8 @@
  *     (nodes/node_group/analysis_raytrace.rs:92-212, nodes/node_group/optic_graph.rs:878-926).
  *
  * Scope limits (SURVEY.md 8f "next"): the scene is a chain of nodes (explicit isometries, or edge distances placed by
- * opm_scene_calc_node_positions); a beam splitter may feed a side chain from its second output; .opm ingestion is out of
- * scope.  Fluence estimators on the device: Binning and KDE.
+ * opm_scene_calc_node_positions); a beam splitter may feed a side chain from its second output; `.opm` scene files are read
+ * by the host-side glue above this interface (opossum_b200/opm_document.py).  Fluence estimators on the device: Binning and KDE.
  */
 #ifndef OPOSSUM_B200_SCENE_H
 #define OPOSSUM_B200_SCENE_H
