@@ -292,6 +292,11 @@ void opm_isometry_append(const OpmIsometry* a, const OpmIsometry* b, OpmIsometry
 /* Isometry::new_from_view (:166-185): origin at `pos`, local z along `dir`, local y as close to `up` as orthogonality allows
  * (nalgebra Isometry3::face_towards(pos, pos + dir, up)); `up` must not be collinear with `dir` */
 OpmStatus opm_isometry_from_view(const double pos[3], const double dir[3], const double up[3], OpmIsometry* out);
+/* ParabolicMirror::calc_off_axis_isometry and calc_parent_focal_length (nodes/parabolic_mirror.rs:286-320): the anchor isometry of an
+ * off-axis parabola (decentre, z shift, rotation of the off-axis direction about z; collimating: half a turn about the surface normal
+ * at the off-axis point) and the focal length of its parent parabola.  dir_xy (0, 0) = the default direction (1, 0). */
+OpmStatus opm_parabola_off_axis_isometry(double focal_length, double oa_angle_rad, const double dir_xy[2], int32_t collimating,
+                                         OpmIsometry* out, double* parent_focal_length);
 void opm_raytrace_config_default(OpmRayTraceConfig* out);                                             /* analyzers/raytrace.rs:315-322 */
 
 /* ---- struct Rays (rays.rs:62-73) */

@@ -5,7 +5,7 @@
  * What it replaces in the reference (opossum/src/):
  *   - the node -> surface compilers `OpticNode::update_surfaces` of Lens (nodes/lens/mod.rs:226-293),
  *     CylindricLens (nodes/cylindric_lens/mod.rs:146-214), Wedge (nodes/wedge/mod.rs:116-160), ThinMirror
- *     (nodes/thin_mirror.rs:121-155), ParabolicMirror on axis (nodes/parabolic_mirror.rs:388-421), and the flat
+ *     (nodes/thin_mirror.rs:121-155), ParabolicMirror on and off axis (nodes/parabolic_mirror.rs:286-320,388-421), and the flat
  *     single-surface nodes (optic_node.rs:62-80): BeamSplitter, Dummy, IdealFilter, ParaxialSurface, Source,
  *     SpotDiagram, FluenceDetector;
  *   - each node's `AnalysisRayTrace::analyze` / `AnalysisGhostFocus::analyze` and the shared
@@ -56,7 +56,8 @@ typedef struct { int32_t type; int32_t _pad; double reflectivity; } OpmCoatingDe
  *   LENS / CYLINDRIC_LENS : p[0] front curvature, p[1] rear curvature (+-INFINITY = flat), p[2] centre thickness
  *   WEDGE                 : p[0] centre thickness, p[1] wedge angle [rad]
  *   THIN_MIRROR           : p[0] curvature (INFINITY = flat)
- *   PARABOLIC_MIRROR      : p[0] focal length (on axis)
+ *   PARABOLIC_MIRROR      : p[0] focal length, p[1] off-axis angle [rad] (0 = on axis), p[2], p[3] off-axis direction (x, y) in the
+ *                           local frame (0, 0 = the default (1, 0)), p[4] != 0: collimating (nodes/parabolic_mirror.rs:45-70)
  *   BEAM_SPLITTER         : p[0] splitting ratio (SplittingConfig::Ratio, ray.rs:36-46), or `spectrum` (SplittingConfig::Spectrum)
  *   IDEAL_FILTER          : p[0] transmission (FilterType::Constant), or `spectrum` (FilterType::Spectrum)
  *   PARAXIAL_SURFACE      : p[0] focal length
@@ -69,7 +70,7 @@ typedef struct {
     int32_t has_alignment;     /* local decenter/tilt appended to the node isometry (optic_node.rs:356-363) */
     OpmIsometry iso;           /* node isometry */
     OpmIsometry alignment;
-    double p[4];
+    double p[6];
     OpmIndexModel index;       /* glass of LENS / CYLINDRIC_LENS / WEDGE */
     OpmCoatingDesc coating_in, coating_out; /* per optic surface (input_1 / output_1) */
     OpmAperture aperture_in, aperture_out;

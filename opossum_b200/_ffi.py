@@ -176,7 +176,7 @@ class OpmCoatingDesc(C.Structure):
 
 class OpmNodeDesc(C.Structure):
     _fields_ = [("type", C.c_int32), ("parent", C.c_int32), ("parent_port", C.c_int32), ("has_alignment", C.c_int32),
-                ("iso", OpmIsometry), ("alignment", OpmIsometry), ("p", C.c_double * 4), ("index", OpmIndexModel),
+                ("iso", OpmIsometry), ("alignment", OpmIsometry), ("p", C.c_double * 6), ("index", OpmIndexModel),
                 ("coating_in", OpmCoatingDesc), ("coating_out", OpmCoatingDesc), ("aperture_in", OpmAperture),
                 ("aperture_out", OpmAperture), ("lidt", C.c_double), ("spectrum", C.c_void_p)]
 
@@ -213,7 +213,7 @@ EXPORTS = [
     "opm_abi_version", "opm_abi_sizeof", "opm_last_error", "opm_status_string", "opm_context_create", "opm_context_destroy",
     "opm_context_synchronize", "opm_context_stream", "opm_context_launch_count", "opm_context_set_kernel_timing",
     "opm_context_kernel_timing", "opm_context_set_jit", "opm_context_jit_wait", "opm_context_jit_stats", "opm_jit_selftest", "opm_isometry_identity",
-    "opm_isometry_new", "opm_isometry_append", "opm_isometry_from_view", "opm_raytrace_config_default", "opm_rays_create", "opm_rays_destroy",
+    "opm_isometry_new", "opm_isometry_append", "opm_isometry_from_view", "opm_parabola_off_axis_isometry", "opm_raytrace_config_default", "opm_rays_create", "opm_rays_destroy",
     "opm_rays_len", "opm_rays_capacity", "opm_rays_clear", "opm_rays_set_wavelength_hint", "opm_rays_reserve", "opm_rays_upload",
     "opm_rays_upload_soa", "opm_rays_new_collimated_with_spectrum", "opm_rays_download", "opm_rays_copy", "opm_rays_append", "opm_rays_compact",
     "opm_rays_enable_position_history", "opm_rays_disable_position_history", "opm_rays_clear_position_history",
@@ -274,6 +274,7 @@ def lib() -> C.CDLL:
         "opm_isometry_new": (i32, [dp, dp, C.POINTER(OpmIsometry)]),
         "opm_isometry_append": (None, [C.POINTER(OpmIsometry)] * 3),
         "opm_isometry_from_view": (i32, [dp, dp, dp, C.POINTER(OpmIsometry)]),
+        "opm_parabola_off_axis_isometry": (i32, [C.c_double, C.c_double, dp, i32, C.POINTER(OpmIsometry), dp]),
         "opm_raytrace_config_default": (None, [C.POINTER(OpmRayTraceConfig)]),
         "opm_rays_create": (i32, [vp, u64, pp]),
         "opm_rays_destroy": (None, [vp]),

@@ -71,6 +71,15 @@ class Isometry:
         _check(F.lib().opm_isometry_from_view(_d3(view_point), _d3(view_direction), _d3(up_direction), C.byref(o)))
         return Isometry(o)
 
+    @staticmethod
+    def parabola_off_axis(focal_length, oa_angle, oa_direction=(1.0, 0.0), collimating=False):
+        """ParabolicMirror::calc_off_axis_isometry / calc_parent_focal_length (nodes/parabolic_mirror.rs:286-320)
+        -> (anchor isometry, parent focal length)"""
+        o, pf = F.OpmIsometry(), C.c_double()
+        _check(F.lib().opm_parabola_off_axis_isometry(float(focal_length), float(oa_angle), (C.c_double * 2)(*oa_direction),
+                                                      int(bool(collimating)), C.byref(o), C.byref(pf)))
+        return Isometry(o), pf.value
+
     def append(self, rhs: "Isometry") -> "Isometry":
         o = F.OpmIsometry()
         F.lib().opm_isometry_append(C.byref(self.c), C.byref(rhs.c), C.byref(o))

@@ -383,6 +383,43 @@ extern "C" OpmStatus opm_isometry_from_view(const double p[3], const double dir[
     iso_invert(o->fwd, o->inv);
     return OPM_OK;
 }
+// ParabolicMirror::calc_off_axis_isometry / calc_parent_focal_length (nodes/parabolic_mirror.rs:286-320)
+extern "C" OpmStatus opm_parabola_off_axis_isometry(double f, double oa_angle, const double dir_xy[2], int32_t collimating, OpmIsometry* out,
+                                                    double* parent_focal_length) {
+    if (!out) return fail(OPM_ERR_ARG, "NULL argument");
+    if (!std::isnormal(f)) return fail(OPM_ERR_ARG, "focal length must not be 0.0 and finite");
+    if (!std::isfinite(oa_angle)) return fail(OPM_ERR_ARG, "off-axis angle must be finite");
+    double dx = dir_xy ? dir_xy[0] : 1.0, dy = dir_xy ? dir_xy[1] : 0.0;
+    if (dx == 0.0 && dy == 0.0) dx = 1.0;
+    const double tan_val = tan(oa_angle / 2.);
+    const double parent_f = f / fma(tan_val, tan_val, 1.);
+    const double decenter_x = sin(oa_angle) * f;
+    const double z_shift = f * (1. / fma(tan_val, tan_val, 1.) - cos(oa_angle));
+    const double z_rot = atan2(dy, dx);
+    OpmIsometry iso, rot_iso, tot;
+    const double tr[3] = {decenter_x, 0., z_shift}, zero[3] = {0., 0., 0.}, rz[3] = {0., 0., z_rot};
+    OpmStatus s = opm_isometry_new(tr, zero, &iso);
+    if (!s) s = opm_isometry_new(zero, rz, &rot_iso);
+    if (s) return s;
+    opm_isometry_append(&rot_iso, &iso, &tot);
+    if (collimating) {  // half a turn about the transformed normal vector (Isometry3::new(0, unit * pi)): R = 2 a a^T - 1
+        const double nv[3] = {decenter_x, 0., -2. * parent_f};
+        double a[3];
+        for (int r = 0; r < 3; ++r) a[r] = tot.fwd.rot[3 * r] * nv[0] + tot.fwd.rot[3 * r + 1] * nv[1] + tot.fwd.rot[3 * r + 2] * nv[2];
+        const double n = sqrt(a[0] * a[0] + a[1] * a[1] + a[2] * a[2]);
+        for (int r = 0; r < 3; ++r) a[r] /= n;
+        OpmIsometry rot, t2;
+        opm_isometry_identity(&rot);
+        for (int r = 0; r < 3; ++r)
+            for (int cidx = 0; cidx < 3; ++cidx) rot.fwd.rot[3 * r + cidx] = 2. * a[r] * a[cidx] - (r == cidx ? 1. : 0.);
+        iso_invert(rot.fwd, rot.inv);
+        opm_isometry_append(&rot, &tot, &t2);
+        tot = t2;
+    }
+    *out = tot;
+    if (parent_focal_length) *parent_focal_length = parent_f;
+    return OPM_OK;
+}
 extern "C" void opm_raytrace_config_default(OpmRayTraceConfig* c) {  // analyzers/raytrace.rs:315-322
     c->min_energy_per_ray = 1.0 * 1.0E-12;
     c->max_number_of_bounces = 1000;

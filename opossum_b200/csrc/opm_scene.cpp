@@ -181,10 +181,14 @@ OpmStatus update_surfaces(Node& n) {
             }
             break;
         }
-        case OPM_NODE_PARABOLIC_MIRROR: {  // nodes/parabolic_mirror.rs:388-421 with oa angle 0: Parabola(-f)
-            const double f = d.p[0];
-            if (!std::isnormal(f)) return OPM_ERR_ARG;
-            for (int k = 0; k < 2; ++k) n.s[k].surf = make_surface(OPM_GEOM_PARABOLA, -1.0 * f, node_iso, *coat[k]);
+        case OPM_NODE_PARABOLIC_MIRROR: {  // nodes/parabolic_mirror.rs:388-421: Parabola(-parent focal length) at the off-axis anchor
+            double parent_f = 0.0;
+            OpmIsometry off_axis;
+            if (opm_parabola_off_axis_isometry(d.p[0], d.p[1], &d.p[2], d.p[4] != 0.0, &off_axis, &parent_f)) return OPM_ERR_ARG;
+            for (int k = 0; k < 2; ++k) {
+                anchor[k] = off_axis;
+                n.s[k].surf = make_surface(OPM_GEOM_PARABOLA, -1.0 * parent_f, iso_append(node_iso, anchor[k]), *coat[k]);
+            }
             break;
         }
         default:  // optic_node.rs:62-80 update_flat_single_surfaces

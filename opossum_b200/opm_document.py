@@ -353,10 +353,10 @@ def _node(entry: dict) -> OpmNode:
         n.index = _index(props["refractive index"].single()) if "refractive index" in props else ("const", 1.5)
     elif t == "mirror":
         n.p = (_prop(props, "curvature", "Length", inf),)
-    elif t == "parabolic mirror":
-        if _prop(props, "oa angle", "Angle", 0.0) != 0.0:
-            raise OpmDocumentError("off-axis parabolic mirrors are not supported")
-        n.p = (_prop(props, "focal length", "Length", 1.0),)
+    elif t == "parabolic mirror":  # nodes/parabolic_mirror.rs:45-70
+        d = _prop(props, "oa direction", "Vec2", (1.0, 0.0))
+        n.p = (_prop(props, "focal length", "Length", 1.0), _prop(props, "oa angle", "Angle", 0.0), float(d[0]), float(d[1]),
+               1.0 if _prop(props, "collimating", "Bool", False) else 0.0)
     elif t == "beam splitter":
         cfg = props.get("splitter config")
         ratio = 0.5

@@ -112,9 +112,10 @@ def ThinMirror(curvature=math.inf, iso=None):
     return n
 
 
-def ParabolicMirror(focal_length, iso=None):
+def ParabolicMirror(focal_length, iso=None, oa_angle=0.0, oa_direction=(1.0, 0.0), collimating=False):
+    """ParabolicMirror::new / new_with_off_axis (nodes/parabolic_mirror.rs:88-150)"""
     n = Node(F.NODE_PARABOLIC_MIRROR, iso)
-    n.c.p[0] = focal_length
+    n.c.p[0], n.c.p[1], n.c.p[2], n.c.p[3], n.c.p[4] = focal_length, oa_angle, oa_direction[0], oa_direction[1], 1.0 if collimating else 0.0
     return n
 
 

@@ -179,6 +179,47 @@ void orc_iso_append(const OrcIsometry* a, const OrcIsometry* b, OrcIsometry* out
     iso3_mul(&a->fwd, &b->fwd, &t);
     iso_from_transform(&t, out);
 }
+/* nalgebra 0.33.2 Isometry3::new(translation, axisangle): rotation by |axisangle| about axisangle / |axisangle|
+ * (UnitQuaternion::from_scaled_axis: w = cos(angle / 2), (i, j, k) = axis * sin(angle / 2)); used by the off-axis parabola */
+void orc_iso_new_axis_angle(const double t[3], const double axisangle[3], OrcIsometry* out) {
+    OrcIso3 tr;
+    const double angle = norm3(axisangle);
+    if (angle == 0.0) { tr.q[0] = 1.0; tr.q[1] = tr.q[2] = tr.q[3] = 0.0; }
+    else {
+        const double h = 0.5 * angle, sn = sin(h);
+        tr.q[0] = cos(h);
+        tr.q[1] = axisangle[0] / angle * sn; tr.q[2] = axisangle[1] / angle * sn; tr.q[3] = axisangle[2] / angle * sn;
+    }
+    tr.t[0] = t[0]; tr.t[1] = t[1]; tr.t[2] = t[2];
+    iso_from_transform(&tr, out);
+}
+/* ParabolicMirror::calc_off_axis_isometry / calc_parent_focal_length (nodes/parabolic_mirror.rs:286-320) */
+void orc_parabola_off_axis_isometry(double focal_length, double oa_angle, double dir_x, double dir_y, int collimating,
+                                    OrcIsometry* out, double* parent_focal_length) {
+    const double tan_val = tan(oa_angle / 2.);
+    const double parent_f = focal_length / fma(tan_val, tan_val, 1.);
+    const double decenter_x = sin(oa_angle) * focal_length;
+    const double z_shift = focal_length * (1. / fma(tan_val, tan_val, 1.) - cos(oa_angle));
+    const double z_rot_angle = atan2(dir_y, dir_x);
+    const double zero[3] = { 0, 0, 0 }, tr[3] = { decenter_x, 0., z_shift }, rz[3] = { 0., 0., z_rot_angle };
+    OrcIsometry iso, rot_iso, tot;
+    orc_iso_new(tr, zero, &iso);        /* Isometry::new_translation */
+    orc_iso_new(zero, rz, &rot_iso);    /* Isometry::new_rotation */
+    orc_iso_append(&rot_iso, &iso, &tot);
+    if (collimating) {
+        const double nv[3] = { decenter_x, 0., -2. * parent_f };
+        double tn[3], axis[3], rot_v[3];
+        orc_iso_transform_vector(&tot, nv, tn);
+        normalize3(tn, axis);
+        rot_v[0] = axis[0] * M_PI; rot_v[1] = axis[1] * M_PI; rot_v[2] = axis[2] * M_PI;
+        OrcIsometry rot, t2;
+        orc_iso_new_axis_angle(zero, rot_v, &rot);
+        orc_iso_append(&rot, &tot, &t2);
+        tot = t2;
+    }
+    *out = tot;
+    if (parent_focal_length) *parent_focal_length = parent_f;
+}
 /* :166-185: Isometry3::face_towards(eye, eye+dir, up) */
 void orc_iso_from_view(const double p[3], const double dir[3], const double up[3], OrcIsometry* out) {
     double target[3] = { p[0] + dir[0], p[1] + dir[1], p[2] + dir[2] };

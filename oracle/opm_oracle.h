@@ -107,6 +107,9 @@ void orc_iso_identity(OrcIsometry* out);
 void orc_iso_new(const double t[3], const double euler_xyz[3], OrcIsometry* out);       /* :44-72 */
 void orc_iso_append(const OrcIsometry* a, const OrcIsometry* b, OrcIsometry* out);      /* :216-223 */
 void orc_iso_from_view(const double p[3], const double dir[3], const double up[3], OrcIsometry* out); /* :166-185 */
+void orc_iso_new_axis_angle(const double t[3], const double axisangle[3], OrcIsometry* out);   /* nalgebra Isometry3::new */
+void orc_parabola_off_axis_isometry(double focal_length, double oa_angle, double dir_x, double dir_y, int collimating,
+                                    OrcIsometry* out, double* parent_focal_length);  /* nodes/parabolic_mirror.rs:286-320 */
 void orc_iso_transform_point(const OrcIsometry* iso, const double p[3], double out[3]);         /* :255-259 */
 void orc_define_up_direction(const double dir[3], double up[3]);                              /* ray.rs:818-838 */
 void orc_calc_new_up_direction(const double prev_dir[3], const double dir[3], double up[3]); /* ray.rs:842-860 */

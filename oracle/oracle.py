@@ -77,6 +77,13 @@ class Isometry(C.Structure):
         lib().orc_iso_from_view((C.c_double * 3)(*p), (C.c_double * 3)(*direction), (C.c_double * 3)(*up), C.byref(o))
         return o
 
+    @staticmethod
+    def new_axis_angle(translation, axisangle) -> "Isometry":
+        """nalgebra Isometry3::new(translation, axisangle) wrapped by Isometry::new_from_transform"""
+        o = Isometry()
+        lib().orc_iso_new_axis_angle((C.c_double * 3)(*translation), (C.c_double * 3)(*axisangle), C.byref(o))
+        return o
+
     def append(self, rhs: "Isometry") -> "Isometry":
         o = Isometry()
         lib().orc_iso_append(C.byref(self), C.byref(rhs), C.byref(o))

@@ -71,6 +71,18 @@ class OSurface:
             self.critical[b.uuid] = (peak, orc.bounce_lvl(b.rays))
 
 
+def parabola_off_axis_isometry(focal_length, oa_angle=0.0, dir_x=1.0, dir_y=0.0, collimating=0.0):
+    """ParabolicMirror::calc_off_axis_isometry / calc_parent_focal_length (nodes/parabolic_mirror.rs:286-320)"""
+    if dir_x == 0.0 and dir_y == 0.0:
+        dir_x = 1.0  # the default off-axis direction (parabolic_mirror.rs:64-70)
+    import ctypes as C
+    tot, parent_f = orc.Isometry(), C.c_double()
+    orc.lib().orc_parabola_off_axis_isometry(C.c_double(focal_length), C.c_double(oa_angle), C.c_double(dir_x), C.c_double(dir_y),
+                                             int(bool(collimating)), C.byref(tot), C.byref(parent_f))
+    parent_f = parent_f.value
+    return tot, parent_f
+
+
 def _surface(geom, param, iso, coating):
     return orc.Surface(geom=geom, param=param, iso=iso, coating=coating[0], coating_r=coating[1])
 
@@ -123,8 +135,10 @@ class ONode:
             else:
                 anchor = [T(curv), T(curv)]
                 s0, s1 = (_surface(orc.GEOM_SPHERE, curv, node_iso.append(anchor[0]), c) for c in coats)
-        elif node_type == PARABOLIC_MIRROR:  # nodes/parabolic_mirror.rs:388-421 (on axis)
-            s0, s1 = (_surface(orc.GEOM_PARABOLA, -1.0 * self.p[0], node_iso, c) for c in coats)
+        elif node_type == PARABOLIC_MIRROR:  # nodes/parabolic_mirror.rs:388-421: p = (f, oa angle, oa dir x, oa dir y, collimating)
+            a_iso, parent_f = parabola_off_axis_isometry(*self.p)
+            anchor = [a_iso, a_iso]
+            s0, s1 = (_surface(orc.GEOM_PARABOLA, -1.0 * parent_f, node_iso.append(a_iso), c) for c in coats)
         else:  # optic_node.rs:62-80
             s0, s1 = (_surface(orc.GEOM_PLANE, 0.0, node_iso, c) for c in coats)
         self.s = [OSurface(s0, node_iso.append(anchor[0]), aps[0], lidt), OSurface(s1, node_iso.append(anchor[1]), aps[1], lidt)]

@@ -118,3 +118,31 @@ def test_jit_source_compiles_without_a_gpu():
     buf = C.create_string_buffer(4096)
     n = F.lib().opm_jit_selftest(buf, 4096)
     assert n > 10_000, buf.value.decode()
+
+
+def test_parabola_off_axis_isometry_host_helper():
+    """opm_parabola_off_axis_isometry (pure host math, no device): the reference's KAT nodes/parabolic_mirror.rs:901-951 and the
+    oracle's restatement"""
+    import math
+
+    import numpy as np
+
+    import opossum_b200 as ob
+    from oracle import scene as OS
+    iso, pf = ob.Isometry.parabola_off_axis(1.0, math.radians(45.0), (0.0, 1.0), True)
+    rot, t, _, _ = iso.matrices()
+    want_rot = np.array([-0.0, 1.0, -0.0, -0.7071067811865475, -0.0, -0.7071067811865476, -0.7071067811865476, 0.0, 0.7071067811865475])
+    want_t = np.array([-0.0, -0.6035533905932736, -0.3964466094067264])
+    eps = np.finfo(float).eps
+    assert np.all(np.abs(rot - want_rot) <= 3 * eps) and np.all(np.abs(t - want_t) <= 3 * eps)
+    assert ob.Isometry.parabola_off_axis(1.0, math.radians(90.0), (0.0, 1.0), True)[1] == 0.5000000000000001
+    for args in [(0.25, math.radians(30.0), (0.35, 8.35), False), (2.0, 0.0, (1.0, 0.0), True), (0.5, math.radians(-60.0), (-1.0, 0.3), True)]:
+        a, pfa = ob.Isometry.parabola_off_axis(*args)
+        b, pfb = OS.parabola_off_axis_isometry(args[0], args[1], args[2][0], args[2][1], args[3])
+        assert pfa == pfb and all(np.allclose(x, y, rtol=0, atol=1e-15) for x, y in zip(a.matrices(), b.matrices()))
+    for bad in (0.0, math.inf, math.nan):
+        try:
+            ob.Isometry.parabola_off_axis(bad, 0.1)
+            raise AssertionError("focal length must not be 0.0 and finite")
+        except ob.OpossumError:
+            pass

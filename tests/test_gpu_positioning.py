@@ -179,3 +179,32 @@ def test_opm_document_end_to_end(ctx):
         fd = psc.node_fluence(node)
         assert np.allclose(fd.lrtb, lrtb, rtol=1e-7, atol=1e-15) and fd.total_energy == pytest.approx(tot, rel=1e-6)
     assert index[doc.nodes[-1].uuid] == 7
+
+
+@pytest.mark.parametrize("collimating", [False, True])
+def test_off_axis_parabolic_mirror(ctx, collimating):
+    """ParabolicMirror with an off-axis angle (nodes/parabolic_mirror.rs:286-320,388-421): a collimated beam onto a 45 deg off-axis
+    parabola, detectors before and behind the focus, placed by distances; interpreter, strict and specialised kernels"""
+    nodes = [scenes.node("source"),
+             scenes.node("parabolic_mirror", distance=80 * MM, p=(250 * MM, math.radians(45.0), 0.3, 1.0, 1.0 if collimating else 0.0)),
+             scenes.node("spot_diagram", distance=200 * MM),
+             scenes.node("fluence_detector", distance=120 * MM)]
+    src = {"pos": ("hexapolar", 14, 6 * MM), "energy": ("uniform", 1.0), "wvl": [800 * NM], "w": [1.0]}
+    osc = scenes.to_oracle(nodes)
+    isos = osc.calc_node_positions(800 * NM)
+    psc = scenes.to_product(ctx, nodes)
+    psc.calc_node_positions(800 * NM)
+    assert_isometries_match(psc, isos, "oap")
+    ref_out = osc.raytrace(scenes.source_to_oracle(src))
+    assert orc.nr_of_rays(ref_out) == len(ref_out) > 500  # every ray is reflected and reaches the detectors
+    for mode in ("fast", "strict", "jit"):
+        ctx.set_jit(2 if mode == "jit" else 0, 1)
+        try:
+            rays = scenes.source_to_product(src).generate(ctx)
+            st = psc.raytrace(rays, strict=(mode == "strict"))
+            assert st.interactions == osc.interactions, mode
+            assert_rays_match(rays.to_array(), ref_out, what=f"oap {mode}")
+            s, ref_spot = psc.node_spot(2), osc.node_spot(2)
+            assert s.n_valid == ref_spot["n_valid"] and s.beam_radius_geo == pytest.approx(ref_spot["geo"], rel=1e-8)
+        finally:
+            ctx.set_jit(1, 200000)

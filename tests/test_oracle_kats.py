@@ -874,3 +874,17 @@ def test_bundle_to_spectrum_range_follows_the_valid_rays():
     lam, val = orc.rays_to_spectrum(rays, nm(0.5))
     assert lam[0] * 1e-6 >= nm(1050.0) - nm(2.0) and lam[-1] * 1e-6 <= nm(1053.0) + nm(2.0)
     assert lam[0] * 1e-6 > nm(1001.0)  # the invalid 1000 nm ray does not widen the range
+
+
+def test_parabola_off_axis_isometry_kats():
+    """nodes/parabolic_mirror.rs:901-951: the anchor isometry of a 1 m, 45 deg, collimating off-axis parabola with off-axis direction
+    (0, 1) (assert_relative_eq!, epsilon = 3 eps), and the parent focal length 0.5 m of a 90 deg one"""
+    from oracle import scene as OS
+    iso, _ = OS.parabola_off_axis_isometry(1.0, math.radians(45.0), 0.0, 1.0, 1.0)
+    rot, t, _, _ = iso.matrices()
+    want_rot = np.array([[-0.0, 1.0, -0.0], [-0.7071067811865475, -0.0, -0.7071067811865476], [-0.7071067811865476, 0.0, 0.7071067811865475]])
+    want_t = np.array([-0.0, -0.6035533905932736, -0.3964466094067264])
+    assert np.all(np.abs(rot.reshape(3, 3) - want_rot) <= 3 * EPS) and np.all(np.abs(t - want_t) <= 3 * EPS)
+    assert OS.parabola_off_axis_isometry(1.0, math.radians(90.0), 0.0, 1.0, 1.0)[1] == pytest.approx(0.5, rel=2 * EPS)
+    ident, pf = OS.parabola_off_axis_isometry(2.0)  # on axis: no anchor offset, the parabola of the node itself
+    assert np.array_equal(ident.matrices()[0], np.eye(3).ravel()) and np.array_equal(ident.matrices()[1], np.zeros(3)) and pf == 2.0
