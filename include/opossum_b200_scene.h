@@ -95,6 +95,11 @@ int32_t opm_scene_node_count(const OpmScene* scene);
  * (desc->iso is ignored; desc->parent / parent_port name the predecessor's output as in opm_scene_add_node; the local
  * `alignment` still applies, optic_node.rs:356-363).  The node cannot be analysed before it has been placed. */
 OpmStatus opm_scene_add_node_at_distance(OpmScene* scene, const OpmNodeDesc* desc, double distance_m, int32_t* node_index);
+/* OpticNode::align_like_node_at_distance (optic_node.rs:476-480, nodes/node_group/analysis_raytrace.rs:142-163): the node is not placed
+ * on the optical axis but gets the isometry of node `like_node` moved by `distance_m` along that node's local z; it is still fed by
+ * desc->parent.  If `like_node` has no isometry when its turn comes, the node is placed on the axis at `axis_distance_m` instead. */
+OpmStatus opm_scene_add_node_aligned_like(OpmScene* scene, const OpmNodeDesc* desc, int32_t like_node, double distance_m,
+                                          double axis_distance_m, int32_t* node_index);
 /* AnalysisRayTrace::calc_node_positions of the node group (nodes/node_group/analysis_raytrace.rs:92-212), which
  * RayTracingAnalyzer::analyze runs before the analysis proper (analyzers/raytrace.rs:44): ONE axis ray -- Rays::
  * get_optical_axis_ray = Ray::new_collimated(origin, axis_wavelength, 1 J) in the source's frame (nodes/source.rs:236-268,

@@ -201,7 +201,7 @@ class OpmCriticalFluence(C.Structure):
 # every symbol include/opossum_b200_scene.h declares
 SCENE_EXPORTS = [
     "opm_node_desc_init", "opm_scene_create", "opm_scene_destroy", "opm_scene_set_ambient", "opm_scene_add_node",
-    "opm_scene_add_node_at_distance", "opm_scene_calc_node_positions", "opm_scene_node_isometry",
+    "opm_scene_add_node_at_distance", "opm_scene_add_node_aligned_like", "opm_scene_calc_node_positions", "opm_scene_node_isometry",
     "opm_scene_node_count", "opm_scene_reset_data", "opm_scene_raytrace", "opm_scene_output_rays", "opm_scene_node_rays", "opm_scene_node_spot",
     "opm_scene_node_spot_partial", "opm_scene_node_spot_async",
     "opm_scene_node_fluence", "opm_scene_node_fluence_kde", "opm_scene_node_spectrum", "opm_scene_node_wavefront", "opm_scene_node_hitmaps", "opm_scene_ghostfocus", "opm_scene_gf_pass_tally",
@@ -363,6 +363,7 @@ def lib() -> C.CDLL:
         "opm_scene_set_ambient": (i32, [vp, C.POINTER(OpmIndexModel)]),
         "opm_scene_add_node": (i32, [vp, C.POINTER(OpmNodeDesc), C.POINTER(i32)]),
         "opm_scene_add_node_at_distance": (i32, [vp, C.POINTER(OpmNodeDesc), C.c_double, C.POINTER(i32)]),
+        "opm_scene_add_node_aligned_like": (i32, [vp, C.POINTER(OpmNodeDesc), i32, C.c_double, C.c_double, C.POINTER(i32)]),
         "opm_scene_calc_node_positions": (i32, [vp, C.c_double, C.POINTER(OpmRayTraceConfig)]),
         "opm_scene_node_isometry": (i32, [vp, i32, C.POINTER(OpmIsometry)]),
         "opm_scene_node_count": (i32, [vp]),

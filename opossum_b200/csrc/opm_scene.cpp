@@ -46,6 +46,8 @@ struct Node {
     int main_child = -1, split_child = -1;
     bool placed = true;         // false: waits for opm_scene_calc_node_positions (a node without an isometry of its own)
     double distance = 0.0;      // edge distance from the predecessor (NodeGroup::connect_nodes)
+    int align_like = -1;        // NodeAttr::align_like_node_at_distance: take that node's isometry, moved by align_distance along its z
+    double align_distance = 0.0;
     bool side_inlined = false;  // the second output's side chain ran inside the main launch (OPM_OP_FORK .. OPM_OP_JOIN)
 };
 
@@ -562,6 +564,17 @@ extern "C" OpmStatus opm_scene_add_node_at_distance(OpmScene* sc, const OpmNodeD
     if (idx) *idx = i;
     return OPM_OK;
 }
+extern "C" OpmStatus opm_scene_add_node_aligned_like(OpmScene* sc, const OpmNodeDesc* d, int32_t like_node, double distance,
+                                                     double axis_distance, int32_t* idx) {
+    if (!sc || like_node < 0 || like_node >= (int)sc->nodes.size() || !std::isfinite(distance)) return OPM_ERR_ARG;
+    int32_t i = -1;
+    OpmStatus st = opm_scene_add_node_at_distance(sc, d, axis_distance, &i);
+    if (st) return st;
+    sc->nodes[i]->align_like = like_node;
+    sc->nodes[i]->align_distance = distance;
+    if (idx) *idx = i;
+    return OPM_OK;
+}
 extern "C" OpmStatus opm_scene_node_isometry(const OpmScene* sc, int32_t node, OpmIsometry* out) {
     if (!sc || !out || node < 0 || node >= (int)sc->nodes.size() || !sc->nodes[node]->placed) return OPM_ERR_ARG;
     *out = sc->nodes[node]->d.iso;
@@ -675,6 +688,13 @@ extern "C" OpmStatus opm_scene_calc_node_positions(OpmScene* sc, double waveleng
         const AxisRay& in = (n.d.parent_port == 1 ? out_split : out_main)[n.parent];
         if (!in.set) return done(OPM_ERR_ARG);
         a = in;  // prev_dir is a field of the ray: it survives a node whose surface the ray does not reach
+        if (!n.placed && n.align_like >= 0 && sc->nodes[n.align_like]->placed) {
+            // analysis_raytrace.rs:142-155: the reference node's isometry (without its local alignment) o T(0, 0, distance)
+            n.d.iso = iso_append(sc->nodes[n.align_like]->d.iso, iso_z(n.align_distance));
+            st = update_surfaces(n);
+            if (st) return done(st);
+            n.placed = true;
+        }
         if (!n.placed) {  // optic_graph.rs:878-926: ray.propagate(distance), Isometry::new_from_view(position, direction, up)
             double pos[3];
             for (int c = 0; c < 3; ++c) pos[c] = a.ray.pos[c] + n.distance * a.ray.dir[c];

@@ -322,6 +322,7 @@ class OpmNode:
     source: OpmSource | None = None
     alignment_wavelength: float | None = None
     fluence_estimator: str | None = None
+    align_like: tuple | None = None   # NodeAttr::align_like_node_at_distance: (uuid, distance [m])
 
 
 def _node(entry: dict) -> OpmNode:
@@ -332,6 +333,9 @@ def _node(entry: dict) -> OpmNode:
     props = a.get("props") or {}
     n = OpmNode(uuid=a["uuid"], node_type=t, name=a.get("name", t), kind=NODE_TYPES[t], lidt=float(a.get("lidt", 1.0e4)),
                 isometry=_isometry(a.get("isometry")), alignment=_isometry(a.get("alignment")), inverted=bool(a.get("inverted", False)))
+    al = a.get("align_like_node_at_distance")
+    if al is not None:
+        n.align_like = (str(al[0]), float(al[1]))
     if n.inverted:
         raise OpmDocumentError(f"node {n.name!r} is inverted: not supported")
     ports = a.get("ports") or {}
@@ -527,7 +531,12 @@ class OpmDocument:
             if k > 0:
                 node.fed_by(parent, port)
             placed = n.isometry is not None or k == 0  # the source without an isometry sits at the origin
-            sc.add_node(node, distance=None if placed else dist)
+            like = None
+            if not placed and n.align_like is not None:
+                if n.align_like[0] not in index or index[n.align_like[0]] >= k:
+                    raise OpmDocumentError(f"node {n.name!r} is aligned like a node that comes after it")
+                like = (index[n.align_like[0]], n.align_like[1])
+            sc.add_node(node, distance=None if placed else dist, align_like=like)
         src = self.source_node().source
         sd = None
         if src is not None:

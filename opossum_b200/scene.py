@@ -212,12 +212,15 @@ class Scene:
     def set_ambient(self, index: RefractiveIndex):
         _check(F.lib().opm_scene_set_ambient(self.h, C.byref(index.c)))
 
-    def add_node(self, node: Node, distance: float | None = None) -> int:
+    def add_node(self, node: Node, distance: float | None = None, align_like: tuple | None = None) -> int:
         """NodeGroup::add_node (+ connect_nodes to the node named by `fed_by`, default the previous one).  distance = None: the
         node sits at its own isometry; else it has none and `calc_node_positions` places it `distance` [m] behind its
         predecessor along the optical axis (NodeGroup::connect_nodes(.., distance))"""
         idx = C.c_int32()
-        if distance is None:
+        if align_like is not None:  # (node index, distance): OpticNode::align_like_node_at_distance (optic_node.rs:476-480)
+            _check(F.lib().opm_scene_add_node_aligned_like(self.h, C.byref(node.c), int(align_like[0]), float(align_like[1]),
+                                                           float(distance or 0.0), C.byref(idx)))
+        elif distance is None:
             _check(F.lib().opm_scene_add_node(self.h, C.byref(node.c), C.byref(idx)))
         else:
             _check(F.lib().opm_scene_add_node_at_distance(self.h, C.byref(node.c), float(distance), C.byref(idx)))

@@ -89,13 +89,15 @@ def _surface(geom, param, iso, coating):
 
 class ONode:
     def __init__(self, node_type, iso=None, p=(), index=None, coating_in=None, coating_out=None, aperture_in=None,
-                 aperture_out=None, alignment=None, lidt=1.0e4, parent=-1, parent_port=0, spectrum=None, distance=None):
+                 aperture_out=None, alignment=None, lidt=1.0e4, parent=-1, parent_port=0, spectrum=None, distance=None, align_like=None):
+        # align_like = (node index, distance): NodeAttr::align_like_node_at_distance (analysis_raytrace.rs:142-163)
         # distance: NodeGroup::connect_nodes(.., distance) of a node WITHOUT an isometry of its own -- OScene.calc_node_positions
         # places it (then `iso` is only a placeholder)
         self._args = dict(node_type=node_type, p=p, index=index, coating_in=coating_in, coating_out=coating_out, aperture_in=aperture_in,
                           aperture_out=aperture_out, alignment=alignment, lidt=lidt, parent=parent, parent_port=parent_port,
                           spectrum=spectrum)
-        self.distance, self.placed, self.iso = distance, distance is None, iso or orc.Isometry.identity()
+        self.distance, self.placed, self.iso = distance, distance is None and align_like is None, iso or orc.Isometry.identity()
+        self.align_like = align_like
         self.type, self.p, self.index = node_type, tuple(p), index
         self.spectrum = spectrum  # (slots [um], values): FilterType::Spectrum / SplittingConfig::Spectrum
         self.parent, self.parent_port = parent, parent_port
@@ -148,9 +150,9 @@ class ONode:
 
     def place(self, iso: "orc.Isometry"):
         """OpticNode::set_isometry: rebuild the surfaces at the given node isometry"""
-        distance = self.distance
+        distance, align_like = self.distance, self.align_like
         self.__init__(iso=iso, **self._args)
-        self.distance, self.placed = distance, True
+        self.distance, self.align_like, self.placed = distance, align_like, True
 
 
 class OScene:
@@ -328,6 +330,8 @@ class OScene:
             parent = n.parent if n.parent >= 0 else i - 1
             ray, prev_in = out[(parent, n.parent_port)]
             ray = ray.copy()
+            if not n.placed and n.align_like is not None and self.nodes[n.align_like[0]].placed:
+                n.place(self.nodes[n.align_like[0]].iso.append(orc.Isometry.new_along_z(n.align_like[1])))
             if not n.placed:
                 r = ray[0]
                 pos = r["pos"] + n.distance * r["dir"]  # Ray::propagate (ray.rs:408-427)

@@ -162,7 +162,7 @@ def to_product(ctx, nodes):
         if "spectrum" in d:  # (wavelength slots [um], values): FilterType::Spectrum / SplittingConfig::Spectrum
             n.with_spectrum(ob.Spectrum(ctx, *d["spectrum"]))
         n.fed_by(d.get("parent", -1), d.get("parent_port", 0))
-        sc.add_node(n, distance=d.get("distance"))
+        sc.add_node(n, distance=d.get("distance"), align_like=d.get("align_like"))
     return sc
 
 
@@ -184,7 +184,8 @@ def to_oracle(nodes, n_threads=1):
         align = orc.Isometry.new(*d["alignment"]) if "alignment" in d else None
         out.append(OS.ONode(KIND_IDS[d["kind"]], orc.Isometry.new(d["t"], d["euler"]), d.get("p", ()), idx, coat(d.get("coat_in")),
                             coat(d.get("coat_out")), ap(d.get("ap_in")), ap(d.get("ap_out")), align, d.get("lidt", 1.0e4),
-                            d.get("parent", -1), d.get("parent_port", 0), spectrum=d.get("spectrum"), distance=d.get("distance")))
+                            d.get("parent", -1), d.get("parent_port", 0), spectrum=d.get("spectrum"), distance=d.get("distance"),
+                            align_like=d.get("align_like")))
     return OS.OScene(out, n_threads=n_threads)
 
 

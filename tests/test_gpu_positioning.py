@@ -208,3 +208,26 @@ def test_off_axis_parabolic_mirror(ctx, collimating):
             assert s.n_valid == ref_spot["n_valid"] and s.beam_radius_geo == pytest.approx(ref_spot["geo"], rel=1e-8)
         finally:
             ctx.set_jit(1, 200000)
+
+
+def test_align_like_node_at_distance(ctx):
+    """OpticNode::align_like_node_at_distance (optic_node.rs:476-480, analysis_raytrace.rs:142-163): a detector behind a deflecting
+    wedge that is not placed on the (deflected) axis but like the lens, 200 mm along the lens's z"""
+    nodes = [scenes.node("source", xy=(0.5 * MM, 0.0), euler=(0.01, 0.0, 0.0)),
+             scenes.node("lens", distance=50 * MM, p=(300 * MM, -300 * MM, 4 * MM), index=scenes.HK9L),
+             scenes.node("wedge", distance=30 * MM, p=(6 * MM, math.radians(5.0)), index=scenes.HK9L),
+             scenes.node("spot_diagram", distance=100 * MM, align_like=(1, 200 * MM)),
+             scenes.node("fluence_detector", distance=20 * MM)]
+    osc = scenes.to_oracle(nodes)
+    isos = osc.calc_node_positions(1000 * NM)
+    psc = scenes.to_product(ctx, nodes)
+    psc.calc_node_positions(1000 * NM)
+    assert_isometries_match(psc, isos, "align like")
+    lens, spot = psc.node_isometry(1).matrices(), psc.node_isometry(3).matrices()
+    assert np.allclose(spot[0], lens[0], rtol=0, atol=1e-15)                       # same orientation as the lens
+    assert np.allclose(spot[1] - lens[1], 0.2 * lens[0].reshape(3, 3)[:, 2], rtol=0, atol=1e-15)  # 200 mm along the lens's z
+    src = {"pos": ("grid", 25, 25, 5 * MM, 5 * MM), "energy": ("uniform", 1.0), "wvl": [1000 * NM], "w": [1.0]}
+    ref_out = osc.raytrace(scenes.source_to_oracle(src))
+    rays = scenes.source_to_product(src).generate(ctx)
+    psc.raytrace(rays)
+    assert_rays_match(rays.to_array(), ref_out, what="align like")
