@@ -388,9 +388,13 @@ extern "C" OpmStatus opm_parabola_off_axis_isometry(double f, double oa_angle, c
                                                     double* parent_focal_length) {
     if (!out) return fail(OPM_ERR_ARG, "NULL argument");
     if (!std::isnormal(f)) return fail(OPM_ERR_ARG, "focal length must not be 0.0 and finite");
-    if (!std::isfinite(oa_angle)) return fail(OPM_ERR_ARG, "off-axis angle must be finite");
+    // ParabolicMirror::check_attributes (nodes/parabolic_mirror.rs:231-259)
+    if (!std::isfinite(oa_angle)) return fail(OPM_ERR_ARG, "off-axis angle and finite");
+    if (std::fabs(oa_angle) >= M_PI) return fail(OPM_ERR_ARG, "off-axis angle must be smaller than 180 deg");
     double dx = dir_xy ? dir_xy[0] : 1.0, dy = dir_xy ? dir_xy[1] : 0.0;
-    if (dx == 0.0 && dy == 0.0) dx = 1.0;
+    if (dx == 0.0 && dy == 0.0) dx = 1.0;  // descriptor default: (1, 0)
+    if (!std::isfinite(dx) || !std::isfinite(dy) || std::sqrt(dx * dx + dy * dy) < 2.220446049250313e-16)
+        return fail(OPM_ERR_ARG, "off-axis direction values must be finite and the vector norm non-zero");
     const double tan_val = tan(oa_angle / 2.);
     const double parent_f = f / fma(tan_val, tan_val, 1.);
     const double decenter_x = sin(oa_angle) * f;

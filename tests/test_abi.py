@@ -140,9 +140,14 @@ def test_parabola_off_axis_isometry_host_helper():
         a, pfa = ob.Isometry.parabola_off_axis(*args)
         b, pfb = OS.parabola_off_axis_isometry(args[0], args[1], args[2][0], args[2][1], args[3])
         assert pfa == pfb and all(np.allclose(x, y, rtol=0, atol=1e-15) for x, y in zip(a.matrices(), b.matrices()))
-    for bad in (0.0, math.inf, math.nan):
+    # ParabolicMirror::check_attributes (nodes/parabolic_mirror.rs:231-259, tests :594-700)
+    def refused(*a):
         try:
-            ob.Isometry.parabola_off_axis(bad, 0.1)
-            raise AssertionError("focal length must not be 0.0 and finite")
+            ob.Isometry.parabola_off_axis(*a)
         except ob.OpossumError:
-            pass
+            return True
+        return False
+    assert all(refused(bad, 0.1) for bad in (0.0, math.inf, math.nan))
+    assert all(refused(1.0, math.radians(a)) for a in (180.0, 190.0, -180.0, -190.0, math.nan, math.inf, -math.inf))
+    assert not any(refused(1.0, math.radians(a)) for a in (45.0, -45.0, 0.0, 179.0))
+    assert refused(1.0, 0.5, (math.nan, 1.0)) and refused(1.0, 0.5, (1e-17, 0.0)) and not refused(1.0, 0.5, (-1.0, -1.0))
