@@ -47,7 +47,8 @@ typedef enum {
     OPM_NODE_RAY_PROPAGATION_VISUALIZER = 13, /* nodes/ray_propagation_visualizer.rs: a single-surface detector that keeps the bundle;
                                                  with OPM_SCENE_POSITION_HISTORY its rays carry their paths */
     OPM_NODE_SPECTROMETER = 14,  /* nodes/spectrometer.rs: detector, report = Rays::to_spectrum(0.2 nm) */
-    OPM_NODE_WAVEFRONT = 15      /* nodes/wavefront.rs: detector, report = wavefront error map, PtV, RMS */
+    OPM_NODE_WAVEFRONT = 15,     /* nodes/wavefront.rs: detector, report = wavefront error map, PtV, RMS */
+    OPM_NODE_ENERGY_METER = 16   /* nodes/energy_meter.rs: detector, report = Rays::total_energy of the bundle it keeps */
 } OpmNodeType;
 
 typedef struct { int32_t type; int32_t _pad; double reflectivity; } OpmCoatingDesc; /* coatings/mod.rs:17-29 */
@@ -149,6 +150,8 @@ OpmStatus opm_scene_node_fluence(OpmScene* scene, int32_t node, uint64_t nx, uin
 /* the same report with FluenceEstimator::KDE (rays_hit_map.rs:575-613, kde/mod.rs); band_width = the estimated kernel width */
 OpmStatus opm_scene_node_fluence_kde(OpmScene* scene, int32_t node, uint64_t nx, uint64_t ny, double* map_host, double lrtb[4],
                                      double* peak, double* total_energy, double* band_width);
+/* EnergyMeter::node_report (nodes/energy_meter.rs:136-151): total energy of the valid rays of the bundle the node keeps */
+OpmStatus opm_scene_node_energy(OpmScene* scene, int32_t node, double* energy_J);
 /* Spectrometer::node_report (nodes/spectrometer.rs:155-175): Rays::to_spectrum of the bundle the node keeps; resolution_m <= 0:
  * the node's 0.2 nm.  lambda_um == NULL: only *n_out.  Arguments as opm_rays_to_spectrum. */
 OpmStatus opm_scene_node_spectrum(OpmScene* scene, int32_t node, double resolution_m, const double* range_m, double* lambda_um,

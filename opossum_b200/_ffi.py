@@ -165,7 +165,7 @@ class OpmSourceDesc(C.Structure):
 
 (NODE_SOURCE, NODE_LENS, NODE_CYLINDRIC_LENS, NODE_WEDGE, NODE_THIN_MIRROR, NODE_PARABOLIC_MIRROR, NODE_BEAM_SPLITTER,
  NODE_DUMMY, NODE_IDEAL_FILTER, NODE_PARAXIAL_SURFACE, NODE_SPOT_DIAGRAM, NODE_FLUENCE_DETECTOR, NODE_REFLECTIVE_GRATING,
- NODE_RAY_PROPAGATION_VISUALIZER, NODE_SPECTROMETER, NODE_WAVEFRONT) = range(16)
+ NODE_RAY_PROPAGATION_VISUALIZER, NODE_SPECTROMETER, NODE_WAVEFRONT, NODE_ENERGY_METER) = range(17)
 SCENE_STRICT, SCENE_PER_SURFACE, SCENE_RECORD_ALL_HITS, SCENE_NO_SNAPSHOTS, SCENE_ASYNC, SCENE_KEEP_SOURCE = 2, 4, 8, 16, 32, 64
 SCENE_POSITION_HISTORY, SCENE_KEEP_LIGHT_DATA = 128, 256
 
@@ -204,7 +204,7 @@ SCENE_EXPORTS = [
     "opm_scene_add_node_at_distance", "opm_scene_add_node_aligned_like", "opm_scene_calc_node_positions", "opm_scene_node_isometry",
     "opm_scene_node_count", "opm_scene_reset_data", "opm_scene_raytrace", "opm_scene_output_rays", "opm_scene_node_rays", "opm_scene_node_spot",
     "opm_scene_node_spot_partial", "opm_scene_node_spot_async",
-    "opm_scene_node_fluence", "opm_scene_node_fluence_kde", "opm_scene_node_spectrum", "opm_scene_node_wavefront", "opm_scene_node_hitmaps", "opm_scene_ghostfocus", "opm_scene_gf_pass_tally",
+    "opm_scene_node_fluence", "opm_scene_node_fluence_kde", "opm_scene_node_energy", "opm_scene_node_spectrum", "opm_scene_node_wavefront", "opm_scene_node_hitmaps", "opm_scene_ghostfocus", "opm_scene_gf_pass_tally",
     "opm_scene_gf_pass_bundles", "opm_scene_node_critical_fluences", "opm_scene_node_peak_fluence",
 ]
 
@@ -363,6 +363,7 @@ def lib() -> C.CDLL:
         "opm_scene_set_ambient": (i32, [vp, C.POINTER(OpmIndexModel)]),
         "opm_scene_add_node": (i32, [vp, C.POINTER(OpmNodeDesc), C.POINTER(i32)]),
         "opm_scene_add_node_at_distance": (i32, [vp, C.POINTER(OpmNodeDesc), C.c_double, C.POINTER(i32)]),
+        "opm_scene_node_energy": (i32, [vp, i32, dp]),
         "opm_scene_add_node_aligned_like": (i32, [vp, C.POINTER(OpmNodeDesc), i32, C.c_double, C.c_double, C.POINTER(i32)]),
         "opm_scene_calc_node_positions": (i32, [vp, C.c_double, C.POINTER(OpmRayTraceConfig)]),
         "opm_scene_node_isometry": (i32, [vp, i32, C.POINTER(OpmIsometry)]),

@@ -426,6 +426,7 @@ OpmStatus compile_node_rt(OpmScene* sc, Node& n, const OpmRayTraceConfig& cfg, i
         case OPM_NODE_RAY_PROPAGATION_VISUALIZER:
         case OPM_NODE_SPECTROMETER:
         case OPM_NODE_WAVEFRONT:
+        case OPM_NODE_ENERGY_METER:
         case OPM_NODE_FLUENCE_DETECTOR: {  // pass_through_detector_surface analyzers/raytrace.rs:150-207
             OpmHitMap* h0 = hits_for(n.s[0]);
             if (st) return st;
@@ -806,6 +807,17 @@ extern "C" OpmStatus opm_scene_node_spot_async(OpmScene* sc, int32_t node, int32
     if (!n.stored) return OPM_ERR_ARG;
     return phase == 1 ? opm_rays_spot_sums_async(n.stored, &n.s[0].eff_iso, sums_dev)
                       : opm_rays_spot_radii_async(n.stored, &n.s[0].eff_iso, sums_dev, radii_dev);
+}
+// EnergyMeter::node_report (nodes/energy_meter.rs:136-151)
+extern "C" OpmStatus opm_scene_node_energy(OpmScene* sc, int32_t node, double* energy) {
+    if (!sc || !energy || node < 0 || node >= (int)sc->nodes.size()) return OPM_ERR_ARG;
+    Node& n = *sc->nodes[node];
+    if (!n.stored) return OPM_ERR_ARG;
+    OpmSpotStats ss;
+    OpmStatus st = opm_rays_spot_stats(n.stored, nullptr, &ss);
+    if (st) return st;
+    *energy = ss.total_energy;
+    return OPM_OK;
 }
 // Spectrometer::node_report (nodes/spectrometer.rs:155-175): to_spectrum(0.2 nm) of the kept bundle
 extern "C" OpmStatus opm_scene_node_spectrum(OpmScene* sc, int32_t node, double resolution_m, const double* range_m, double* lambda_um,

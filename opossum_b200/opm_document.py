@@ -179,7 +179,7 @@ def parse_ron(text: str):
 NODE_TYPES = {"source": 0, "lens": 1, "cylindric lens": 2, "wedge": 3, "mirror": 4, "parabolic mirror": 5, "beam splitter": 6,
               "dummy": 7, "ideal filter": 8, "paraxial surface": 9, "spot diagram": 10, "fluence detector": 11,
               "reflective grating": 12, "ray propagation": 13, "spectrometer": 14, "wavefront monitor": 15,
-              "energy meter": 7}  # an energy meter passes the rays like a dummy (nodes/energy_meter.rs:150-190)
+              "energy meter": 16}
 
 
 def _quat_to_euler_free(rot, trans):

@@ -173,6 +173,11 @@ def WaveFront(iso=None):
     return Node(F.NODE_WAVEFRONT, iso)
 
 
+def EnergyMeter(iso=None):
+    """nodes/energy_meter.rs: a detector whose report is the total energy of the rays that reach it"""
+    return Node(F.NODE_ENERGY_METER, iso)
+
+
 def RayPropagationVisualizer(iso=None):
     """nodes/ray_propagation_visualizer.rs: a single-surface detector that keeps the bundle; after
     raytrace(position_history=True) its rays (Scene.node_rays) carry their paths (Rays.position_history)"""
@@ -298,6 +303,12 @@ class Scene:
                                               m.ctypes.data_as(C.POINTER(C.c_double)) if download else None, lrtb,
                                               C.byref(peak), C.byref(tot)))
         return FluenceData(m.reshape(nx, ny).T.copy() if download else None, tuple(lrtb[:]), peak.value, tot.value)
+
+    def node_energy(self, node: int) -> float:
+        """EnergyMeter::node_report (nodes/energy_meter.rs:136-151)"""
+        e = C.c_double()
+        _check(F.lib().opm_scene_node_energy(self.h, node, C.byref(e)))
+        return e.value
 
     def node_spectrum(self, node: int, resolution: float = 0.0, wavelength_range=None):
         """Spectrometer::node_report (nodes/spectrometer.rs:155-175) -> (slots [um], values [1/um])"""

@@ -14,7 +14,7 @@ import numpy as np
 from . import oracle as orc
 
 (SOURCE, LENS, CYLINDRIC_LENS, WEDGE, THIN_MIRROR, PARABOLIC_MIRROR, BEAM_SPLITTER, DUMMY, IDEAL_FILTER, PARAXIAL_SURFACE,
- SPOT_DIAGRAM, FLUENCE_DETECTOR, REFLECTIVE_GRATING, RAY_PROPAGATION_VISUALIZER, SPECTROMETER, WAVEFRONT) = range(16)
+ SPOT_DIAGRAM, FLUENCE_DETECTOR, REFLECTIVE_GRATING, RAY_PROPAGATION_VISUALIZER, SPECTROMETER, WAVEFRONT, ENERGY_METER) = range(17)
 
 
 @dataclass
@@ -390,6 +390,9 @@ class OScene:
     def node_fluence(self, node: int, nx=100, ny=83):  # fluence_detector/mod.rs:91-135 (Binning)
         fmap, lrtb = orc.fluence_binning(self.nodes[node].s[0].merged_hits(), nx, ny)
         return fmap, lrtb, orc.fluence_peak(fmap), orc.fluence_total_energy(fmap, lrtb)
+
+    def node_energy(self, node: int) -> float:  # nodes/energy_meter.rs:136-151
+        return orc.total_energy(self.nodes[node].stored)
 
     def node_spectrum(self, node: int, resolution=0.2e-9):  # nodes/spectrometer.rs:155-175
         return orc.rays_to_spectrum(self.nodes[node].stored, resolution)

@@ -132,7 +132,7 @@ def folded_chain_by_distances():
 # ---------------------------------------------------------------------------------------------------------------
 KIND_IDS = {"source": 0, "lens": 1, "cylindric_lens": 2, "wedge": 3, "thin_mirror": 4, "parabolic_mirror": 5, "beam_splitter": 6,
             "dummy": 7, "ideal_filter": 8, "paraxial_surface": 9, "spot_diagram": 10, "fluence_detector": 11, "reflective_grating": 12,
-            "ray_propagation_visualizer": 13, "spectrometer": 14, "wavefront": 15}
+            "ray_propagation_visualizer": 13, "spectrometer": 14, "wavefront": 15, "energy_meter": 16}
 
 
 def to_product(ctx, nodes):

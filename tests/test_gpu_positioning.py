@@ -231,3 +231,23 @@ def test_align_like_node_at_distance(ctx):
     rays = scenes.source_to_product(src).generate(ctx)
     psc.raytrace(rays)
     assert_rays_match(rays.to_array(), ref_out, what="align like")
+
+
+def test_energy_meter_node(ctx):
+    """nodes/energy_meter.rs: a single-surface detector; report = total energy of the valid rays that reach it"""
+    nodes = [scenes.node("source"),
+             scenes.node("lens", distance=40 * MM, p=(200 * MM, -200 * MM, 5 * MM), index=scenes.HK9L, coat_in=("fresnel",), coat_out=("fresnel",)),
+             scenes.node("ideal_filter", distance=20 * MM, p=(0.6,), ap_in=("circle", 3.0 * MM, 0.5 * MM, 0.0)),
+             scenes.node("energy_meter", distance=30 * MM)]
+    src = {"pos": ("fibonacci_ellipse", 5000, 4 * MM, 4 * MM), "energy": ("uniform", 2.0), "wvl": [1054 * NM], "w": [1.0]}
+    osc, psc = scenes.to_oracle(nodes), scenes.to_product(ctx, nodes)
+    osc.calc_node_positions(1054 * NM)
+    psc.calc_node_positions(1054 * NM)
+    ref_out = osc.raytrace(scenes.source_to_oracle(src))
+    rays = scenes.source_to_product(src).generate(ctx)
+    psc.raytrace(rays)
+    assert_rays_match(rays.to_array(), ref_out, what="energy meter chain")
+    e = psc.node_energy(3)
+    assert e == pytest.approx(osc.node_energy(3), rel=RTOL) and 0.3 < e < 1.2  # 2 J x 0.6 x (1 - R)^2, clipped by the aperture
+    with pytest.raises(ob.OpossumError):
+        psc.node_energy(1)  # a lens keeps no bundle
