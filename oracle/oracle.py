@@ -605,6 +605,13 @@ def fluence_kde(hits: np.ndarray, nx: int, ny: int, ranges=None, n_threads=1):
     return m.reshape(nx, ny).T.copy(), tuple(lrtb[:]), bw.value
 
 
+def hits_bounding_box(hits: np.ndarray):
+    """RaysHitMap::calc_2d_bounding_box(margin 0) (rays_hit_map.rs:522-562) -> (left, right, top, bottom)"""
+    out = (C.c_double * 4)()
+    _check(lib().orc_hits_bounding_box(_vp(hits), len(hits), out))
+    return tuple(out[:])
+
+
 def fluence_peak(fmap: np.ndarray) -> float:
     m = np.ascontiguousarray(fmap, dtype=np.float64).ravel()
     return lib().orc_fluence_peak(_dptr(m), m.size)

@@ -151,3 +151,31 @@ def test_parabola_off_axis_isometry_host_helper():
     assert all(refused(1.0, math.radians(a)) for a in (180.0, 190.0, -180.0, -190.0, math.nan, math.inf, -math.inf))
     assert not any(refused(1.0, math.radians(a)) for a in (45.0, -45.0, 0.0, 179.0))
     assert refused(1.0, 0.5, (math.nan, 1.0)) and refused(1.0, 0.5, (1e-17, 0.0)) and not refused(1.0, 0.5, (-1.0, -1.0))
+
+
+def test_isometry_host_helpers_reference_kats():
+    """opm_isometry_new / _append (pure host math): utils/geom_transformation.rs:680-800 -- non-finite translations and angles are
+    errors, new_along_z, its inverse, append_z, append_with_rot, the Euler angles of Isometry::new(.., (10, 20, 30) deg)"""
+    import math
+
+    import numpy as np
+
+    import opossum_b200 as ob
+    for bad in (math.nan, math.inf, -math.inf):
+        for k in range(3):
+            v = [0.0, 0.0, 0.0]
+            v[k] = bad
+            for args in ((v, (0.0, 0.0, 0.0)), ((0.0, 0.0, 0.0), v)):
+                try:
+                    ob.Isometry.new(*args)
+                    raise AssertionError("non-finite isometry accepted")
+                except ob.OpossumError:
+                    pass
+    rot, t, rot_inv, t_inv = ob.Isometry.new_along_z(0.01).matrices()
+    assert np.array_equal(rot, np.eye(3).ravel()) and tuple(t) == (0.0, 0.0, 0.01) and tuple(t_inv) == (0.0, 0.0, -0.01)
+    assert tuple(ob.Isometry.new_along_z(0.01).append(ob.Isometry.new_along_z(0.02)).matrices()[1]) == (0.0, 0.0, 0.03)
+    r = ob.Isometry.new((0.0, 0.0, 0.01), (0.0, math.radians(90.0), 0.0)).append(ob.Isometry.new_along_z(0.02))
+    assert np.all(np.abs(r.matrices()[1] - (0.02, 0.0, 0.01)) <= np.finfo(float).eps)  # image of the origin
+    m = ob.Isometry.new((0.0, 0.0, 0.0), tuple(math.radians(a) for a in (10.0, 20.0, 30.0))).matrices()[0].reshape(3, 3)
+    got = np.array([math.atan2(m[2, 1], m[2, 2]), -math.asin(m[2, 0]), math.atan2(m[1, 0], m[0, 0])])
+    assert np.all(np.abs(got - np.radians([10.0, 20.0, 30.0])) <= np.finfo(float).eps)

@@ -888,3 +888,43 @@ def test_parabola_off_axis_isometry_kats():
     assert OS.parabola_off_axis_isometry(1.0, math.radians(90.0), 0.0, 1.0, 1.0)[1] == pytest.approx(0.5, rel=2 * EPS)
     ident, pf = OS.parabola_off_axis_isometry(2.0)  # on axis: no anchor offset, the parabola of the node itself
     assert np.array_equal(ident.matrices()[0], np.eye(3).ravel()) and np.array_equal(ident.matrices()[1], np.zeros(3)) and pf == 2.0
+
+
+def test_fluence_data_peak_and_total_energy_kats():
+    """nodes/fluence_detector/fluence_data.rs:278-300: peak of [[1, 2], [3, 4]] J/cm^2 is 4 J/cm^2; the total energy of
+    [[NaN, 8], [8, 4]] J/m^2 over the unit square is 5 J (NaN bins are skipped, every bin covers a quarter)"""
+    j_per_cm2 = 1.0e4
+    assert orc.fluence_peak(np.array([[1.0, 2.0], [3.0, 4.0]]) * j_per_cm2) == 4.0 * j_per_cm2
+    assert orc.fluence_total_energy(np.array([[math.nan, 8.0], [8.0, 4.0]]), (0.0, 1.0, 1.0, 0.0)) == 5.0
+
+
+def test_hit_map_bounding_box_kat():
+    """surface/hit_map/rays_hit_map.rs:1001-1060 calc_2d_bounding_box with margin 0 (what the Binning estimator uses,
+    :337-342): (left, right, top, bottom) grows with every hit; no hits is an error"""
+    with pytest.raises(orc.OracleError):
+        orc.hits_bounding_box(orc.hits_from_xye([], [], []))
+    pts = [(0.0, 0.0), (-1.0, 1.0), (-1.0, -1.0), (-1.0, 2.0), (1.0, 2.0)]
+    want = [(0.0, 0.0, 0.0, 0.0), (-1.0, 0.0, 1.0, 0.0), (-1.0, 0.0, 1.0, -1.0), (-1.0, 0.0, 2.0, -1.0), (-1.0, 1.0, 2.0, -1.0)]
+    for k in range(len(pts)):
+        x, y = zip(*pts[: k + 1])
+        assert orc.hits_bounding_box(orc.hits_from_xye(x, y, [1.0] * (k + 1))) == want[k]
+
+
+def test_isometry_kats():
+    """utils/geom_transformation.rs:680-800: new_along_z (translation (0, 0, 0.01), no rotation), its inverse (0, 0, -0.01),
+    append_z (10 mm then 20 mm = 0.03 m), append_with_rot (T(0, 0, 10 mm) R_y(90 deg) then T(0, 0, 20 mm) maps the origin to
+    (0.02, 0, 0.01)), rotation (Euler angles 10 / 20 / 30 deg come back out of the rotation matrix)"""
+    i = orc.Isometry.new_along_z(mm(10.0))
+    rot, t, rot_inv, t_inv = i.matrices()
+    assert np.array_equal(rot, np.eye(3).ravel()) and tuple(t) == (0.0, 0.0, 0.01)
+    assert np.array_equal(rot_inv, np.eye(3).ravel()) and tuple(t_inv) == (0.0, 0.0, -0.01)
+    both = i.append(orc.Isometry.new_along_z(mm(20.0)))
+    assert tuple(both.matrices()[1]) == (0.0, 0.0, 0.03)
+    r = orc.Isometry.new(mm(0.0, 0.0, 10.0), (0.0, math.radians(90.0), 0.0)).append(orc.Isometry.new_along_z(mm(20.0)))
+    p = r.transform_point((0.0, 0.0, 0.0))
+    assert np.all(np.abs(p - (0.02, 0.0, 0.01)) <= EPS)
+    m = orc.Isometry.new((0.0, 0.0, 0.0), tuple(math.radians(a) for a in (10.0, 20.0, 30.0))).matrices()[0].reshape(3, 3)
+    roll, pitch, yaw = math.atan2(m[2, 1], m[2, 2]), -math.asin(m[2, 0]), math.atan2(m[1, 0], m[0, 0])  # nalgebra euler_angles()
+    assert np.all(np.abs(np.array([roll, pitch, yaw]) - np.radians([10.0, 20.0, 30.0])) <= EPS)
+    ident = orc.Isometry.identity().matrices()
+    assert np.array_equal(ident[0], np.eye(3).ravel()) and not ident[1].any() and np.array_equal(ident[2], np.eye(3).ravel())
