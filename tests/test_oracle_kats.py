@@ -928,3 +928,38 @@ def test_isometry_kats():
     assert np.all(np.abs(np.array([roll, pitch, yaw]) - np.radians([10.0, 20.0, 30.0])) <= EPS)
     ident = orc.Isometry.identity().matrices()
     assert np.array_equal(ident[0], np.eye(3).ravel()) and not ident[1].any() and np.array_equal(ident[2], np.eye(3).ravel())
+
+
+def _one_node_chain(kind, ray, **node_kw):
+    """the ray through a source at the origin (identity, no aperture) and ONE node: what the reference's node tests do with
+    `AnalysisRayTrace::analyze(&mut node, input, &RayTraceConfig::default())`"""
+    import scenes
+    osc = scenes.to_oracle([scenes.node("source"), scenes.node(kind, **node_kw)])
+    return osc.raytrace(ray.copy())
+
+
+def test_paraxial_surface_node_kats():
+    """nodes/paraxial_surface.rs:316-458: analyze_geometric_ok (on axis: untouched, at z = 10 mm), test_shifted_x / _y (a lens
+    decentred by its focal length sends the axis ray to normalize(1, 0, 1) / (0, 1, 1): assert_eq!), test_rotated_y / _x (45 deg
+    tilts: position and direction with assert_relative_eq!)"""
+    ray = orc.ray_new((0.0, 0.0, 0.0), Z, nm(1000.0), 1.0)
+    out = _one_node_chain("paraxial_surface", ray, z=mm(10.0), p=(mm(10.0),))
+    assert orc.nr_of_rays(out) == 1 and tuple(out[0]["pos"]) == mm(0.0, 0.0, 10.0) and tuple(out[0]["dir"]) == Z
+    s = 1.0 / math.sqrt(2.0)
+    out = _one_node_chain("paraxial_surface", ray, z=mm(10.0), xy=(mm(10.0), 0.0), p=(mm(10.0),))
+    want = np.array([1.0, 0.0, 1.0]) / np.linalg.norm([1.0, 0.0, 1.0])
+    assert orc.nr_of_rays(out) == 1 and tuple(out[0]["pos"]) == mm(0.0, 0.0, 10.0) and np.array_equal(out[0]["dir"], want)
+    out = _one_node_chain("paraxial_surface", ray, z=mm(10.0), xy=(0.0, mm(10.0)), p=(mm(10.0),))
+    want = np.array([0.0, 1.0, 1.0]) / np.linalg.norm([0.0, 1.0, 1.0])
+    assert tuple(out[0]["pos"]) == mm(0.0, 0.0, 10.0) and np.array_equal(out[0]["dir"], want)
+    # tilted by 45 deg about x ("rotated_y"): the ray starts 10/sqrt(2) mm above the axis
+    ray = orc.ray_new(mm(0.0, 10.0 / math.sqrt(2.0), 0.0), Z, nm(1000.0), 1.0)
+    out = _one_node_chain("paraxial_surface", ray, z=mm(10.0), euler=(math.radians(45.0), 0.0, 0.0), p=(mm(10.0),))
+    rel = lambda a, b: abs(a - b) <= EPS or abs(a - b) <= EPS * max(abs(a), abs(b))  # noqa: E731  approx::relative_eq defaults
+    assert orc.nr_of_rays(out) == 1
+    assert abs(out[0]["pos"][0]) <= EPS and rel(out[0]["pos"][1], 0.01 / math.sqrt(2.0)) and rel(out[0]["pos"][2], 0.01 / math.sqrt(2.0) + 0.01)
+    assert np.all(np.abs(out[0]["dir"] - np.array([0.0, -1.0, 1.0]) * s) <= EPS)
+    ray = orc.ray_new(mm(-10.0 / math.sqrt(2.0), 0.0, 0.0), Z, nm(1000.0), 1.0)
+    out = _one_node_chain("paraxial_surface", ray, z=mm(10.0), euler=(0.0, math.radians(45.0), 0.0), p=(mm(10.0),))
+    assert rel(out[0]["pos"][0], -0.01 / math.sqrt(2.0)) and abs(out[0]["pos"][1]) <= EPS and rel(out[0]["pos"][2], 0.01 / math.sqrt(2.0) + 0.01)
+    assert np.all(np.abs(out[0]["dir"] - np.array([1.0, 0.0, 1.0]) * s) <= EPS)
