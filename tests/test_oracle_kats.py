@@ -963,3 +963,49 @@ def test_paraxial_surface_node_kats():
     out = _one_node_chain("paraxial_surface", ray, z=mm(10.0), euler=(0.0, math.radians(45.0), 0.0), p=(mm(10.0),))
     assert rel(out[0]["pos"][0], -0.01 / math.sqrt(2.0)) and abs(out[0]["pos"][1]) <= EPS and rel(out[0]["pos"][2], 0.01 / math.sqrt(2.0) + 0.01)
     assert np.all(np.abs(out[0]["dir"] - np.array([1.0, 0.0, 1.0]) * s) <= EPS)
+
+
+def _hexapolar_bundle(radius_mm, rings, wvl_nm=1000.0, energy=1.0):
+    """Rays::new_uniform_collimated(wavelength, energy, &Hexapolar::new(radius, rings)) (rays.rs:234-247)"""
+    xyz = orc.hexapolar(rings, mm(radius_mm))
+    return orc.rays_collimated_with_spectrum(xyz, orc.energy_uniform(len(xyz), energy), [nm(wvl_nm)], [1.0])
+
+
+@pytest.mark.parametrize("kind", ["lens", "cylindric_lens"])
+def test_lens_node_kats(kind):
+    """nodes/lens/mod.rs:440-501 and nodes/cylindric_lens/mod.rs:359-430: analyze_flatflat -- a 10 mm plane-parallel plate of index
+    2 at z = 10 mm leaves every ray of a hexapolar bundle along z with an optical path of exactly 30 mm (assert_eq!);
+    analyze_biconvex -- a biconvex lens of index 1 is neutral (Lens: assert_eq!, CylindricLens: assert_relative_eq!)"""
+    out = _one_node_chain(kind, _hexapolar_bundle(10.0, 3), z=mm(10.0), p=(math.inf, -math.inf, mm(10.0)), index=("const", 2.0))
+    assert len(out) == 37 and orc.nr_of_rays(out) == 37
+    for r in out:
+        assert tuple(r["dir"]) == Z and r["opl"] == mm(30.0)
+    out = _one_node_chain(kind, _hexapolar_bundle(10.0, 3), p=(mm(100.0), mm(-100.0), mm(10.0)), index=("const", 1.0))
+    for r in out:
+        if kind == "lens":
+            assert tuple(r["dir"]) == Z
+        else:
+            assert abs(r["dir"][0]) <= EPS and abs(r["dir"][1]) <= EPS and abs(r["dir"][2] - 1.0) <= EPS
+
+
+def test_thin_mirror_and_wedge_node_kats():
+    """nodes/thin_mirror.rs:376-399 (a flat mirror at z = 10 mm sends the axis ray back: position (0, 0, 10 mm), direction
+    (0, 0, -1)) and nodes/wedge/mod.rs:393-413 (the default wedge -- 10 mm thick, no wedge angle -- at z = 10 mm: the ray leaves
+    at (0, 0, 20 mm) along z); all assert_eq!"""
+    ray = orc.ray_new((0.0, 0.0, 0.0), Z, nm(1000.0), 1.0)  # Ray::origin_along_z
+    out = _one_node_chain("thin_mirror", ray, z=mm(10.0))
+    assert orc.nr_of_rays(out) == 1 and tuple(out[0]["pos"]) == mm(0.0, 0.0, 10.0) and tuple(out[0]["dir"]) == (0.0, 0.0, -1.0)
+    out = _one_node_chain("wedge", ray, z=mm(10.0), p=(mm(10.0), 0.0), index=("const", 1.5))
+    assert orc.nr_of_rays(out) == 1 and tuple(out[0]["pos"]) == mm(0.0, 0.0, 20.0) and tuple(out[0]["dir"]) == Z
+
+
+def test_beam_splitter_and_filter_node_kats():
+    """nodes/beam_splitter/analysis_raytrace.rs:122-147 analyze_one_input: Ratio(0.6) sends 0.6 J of a 1 J ray to the first output
+    and 0.4 J to the second (assert_eq!); nodes/ideal_filter.rs:373-399 analyzer_geometric_fixed: a Constant(0.3) filter leaves
+    0.3 J of a 1 J hexapolar bundle"""
+    import scenes
+    osc = scenes.to_oracle([scenes.node("source"), scenes.node("beam_splitter", p=(0.6,))])
+    out = osc.raytrace(orc.ray_new((0.0, 0.0, 0.0), Z, nm(1053.0), 1.0))
+    assert orc.total_energy(out) == 0.6 and orc.total_energy(osc.nodes[1].split) == 0.4
+    out = _one_node_chain("ideal_filter", _hexapolar_bundle(5.0, 1, 1054.0), p=(0.3,))
+    assert len(out) == 7 and abs(orc.total_energy(out) - 0.3) <= EPS
