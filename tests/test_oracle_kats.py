@@ -1009,3 +1009,17 @@ def test_beam_splitter_and_filter_node_kats():
     assert orc.total_energy(out) == 0.6 and orc.total_energy(osc.nodes[1].split) == 0.4
     out = _one_node_chain("ideal_filter", _hexapolar_bundle(5.0, 1, 1054.0), p=(0.3,))
     assert len(out) == 7 and abs(orc.total_energy(out) - 0.3) <= EPS
+
+
+def test_bundle_constructor_kats():
+    """rays.rs:1888-1927: new_collimated with a General2DGaussian energy distribution (hexapolar, 2 rings) carries 1 J in total;
+    new_uniform_collimated: 19 rays, 1 J within 10 eps; a hexapolar source of radius 0 is ONE ray at the origin along z"""
+    xyz = orc.hexapolar(2, mm(1.0))
+    e = orc.energy_general_gaussian(xyz, 1.0, (0.0, 0.0), mm(1.0, 1.0), 1.0, 0.0, True)
+    rays = orc.rays_collimated_with_spectrum(xyz, e, [nm(1054.0)], [1.0])
+    assert abs(orc.total_energy(rays) - 1.0) <= EPS
+    rays = orc.rays_collimated_with_spectrum(xyz, orc.energy_uniform(len(xyz), 1.0), [nm(1054.0)], [1.0])
+    assert orc.nr_of_rays(rays) == 19 and abs(orc.total_energy(rays) - 1.0) < 10 * EPS
+    xyz0 = orc.hexapolar(2, 0.0)
+    rays = orc.rays_collimated_with_spectrum(xyz0, orc.energy_uniform(len(xyz0), 1.0), [nm(1054.0)], [1.0])
+    assert orc.nr_of_rays(rays) == 1 and tuple(rays[0]["pos"]) == (0.0, 0.0, 0.0) and tuple(rays[0]["dir"]) == Z
