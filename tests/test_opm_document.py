@@ -79,3 +79,69 @@ def test_unsupported_content_is_refused():
         D.loads_opm(text.replace('name: "f",', 'name: "f", ').replace("inverted: false,\n                    ),\n                ),\n                (\n                    attributes: (\n                        node_type: \"spot diagram\"", "inverted: true,\n                    ),\n                ),\n                (\n                    attributes: (\n                        node_type: \"spot diagram\""))
     with pytest.raises(D.OpmDocumentError):
         D.loads_opm(text.replace('"input_1", 0.09', '"input_2", 0.09')).ordered()
+
+
+PORT = '(anchor_point_iso: (transform: (rotation: (0.0, 0.0, 0.0, 1.0), translation: (0.0, 0.0, 0.0))), %s coating: %s, lidt: 20000.0)'
+
+
+def _node_text(node_type, props, coat_in="IdealAR", ap_in="", outs=("output_1",), extra=""):
+    outs_text = ", ".join('"%s": %s' % (o, PORT % ("", "IdealAR")) for o in outs)
+    return ('(attributes: (node_type: "%s", name: "n", ports: (inputs: {"input_1": %s}, outputs: {%s}), '
+            'uuid: "00000000-0000-4000-8000-000000000001", lidt: 10000.0, props: {%s}, %s inverted: false))'
+            % (node_type, PORT % (ap_in, coat_in), outs_text, props, extra))
+
+
+def test_property_and_port_mapping_of_every_node_type():
+    """the serialised forms of the properties each node registers (see the module docstring for the reference lines) and of the
+    port fields (coating variants, the aperture configs of aperture.rs:123-340)"""
+    n = D._node(D.parse_ron(_node_text("wedge", '"center thickness": Length(0.008), "wedge": Angle(0.05), "refractive index": '
+                                       'RefractiveIndex(Schott((a0: 3.2, a1: -0.02, a2: 0.03, a3: 0.007, a4: -0.0009, a5: 0.00007, '
+                                       'wvl_range: (start: 0.0000003, end: 0.000002))))',
+                                       coat_in="ConstantR(reflectivity: 0.25)",
+                                       ap_in="aperture: BinaryRectangle((width: 0.01, height: 0.02, center: (0.001, -0.001), aperture_type: Obstruction)),")))
+    assert n.kind == 3 and n.p == (0.008, 0.05) and n.index == ("schott", 3.2, -0.02, 0.03, 0.007, -0.0009, 0.00007, 3e-7, 2e-6)
+    assert n.coatings[0] == ("constant_r", 0.25) and n.apertures[0] == ("rect", 0.01, 0.02, 0.001, -0.001, True)
+    n = D._node(D.parse_ron(_node_text("cylindric lens", '"front curvature": Length(inf), "rear curvature": Length(-0.2), "center thickness": '
+                                       'Length(0.004), "refractive index": RefractiveIndex(Conrady((n0: 1.5, a: 0.000000004, b: 0.0, '
+                                       'wvl_range: (start: 0.0000003, end: 0.0000025))))',
+                                       ap_in="aperture: Gaussian((sigma: (0.002, 0.003), center: (0.0, 0.0), aperture_type: Hole)),")))
+    assert n.kind == 2 and n.p == (math.inf, -0.2, 0.004) and n.index == ("conrady", 1.5, 4e-9, 0.0, 3e-7, 2.5e-6)
+    assert n.apertures[0] == ("gaussian", 0.002, 0.003, 0.0, 0.0, False) and n.coatings[1] == ("ideal_ar",)
+    n = D._node(D.parse_ron(_node_text("parabolic mirror", '"focal length": Length(0.25), "oa angle": Angle(0.7853981633974483), "collimating": '
+                                       'Bool(true), "oa direction": Vec2((0.0, 1.0))')))
+    assert n.kind == 5 and n.p == (0.25, 0.7853981633974483, 0.0, 1.0, 1.0)
+    n = D._node(D.parse_ron(_node_text("paraxial surface", '"focal length": Length(0.1)')))
+    assert n.kind == 9 and n.p == (0.1,)
+    n = D._node(D.parse_ron(_node_text("reflective grating", '"line density": LinearDensity(1200000.0), "diffraction order": I32(-2)')))
+    assert n.kind == 12 and n.p == (1200000.0, -2.0)
+    n = D._node(D.parse_ron(_node_text("energy meter", '"meter type": Metertype(IdealEnergyMeter)')))
+    assert n.kind == 16
+    n = D._node(D.parse_ron(_node_text("fluence detector", "")))
+    assert n.kind == 11 and n.fluence_estimator == "Voronoi"  # the reference's default estimator (fluence_detector/mod.rs:62)
+    n = D._node(D.parse_ron(_node_text("dummy", "", extra='align_like_node_at_distance: Some(("00000000-0000-4000-8000-000000000009", 0.3)),')))
+    assert n.align_like == ("00000000-0000-4000-8000-000000000009", 0.3)
+    for bad in ('"splitter config": SplitterType(Spectrum(()))',):
+        with pytest.raises(D.OpmDocumentError):
+            D._node(D.parse_ron(_node_text("beam splitter", bad, outs=("out1_trans1_refl2", "out2_trans2_refl1"))))
+
+
+def test_source_light_data_mapping():
+    """RayDataBuilder::Collimated with every distribution the device generates (position_distributions/, energy_distributions/,
+    spectral_distribution/)"""
+    def src(pos, energy, spec):
+        return D._node(D.parse_ron(_node_text("source", '"light data": LightDataBuilder(Some(Geometric(Collimated(pos_dist: %s, energy_dist: %s, '
+                                              'spect_dist: %s)))), "alignment wavelength": LengthOption(None)' % (pos, energy, spec))))
+    uni, line = "Uniform((total_energy: 1.5))", "LaserLines((lines: [(0.000001, 2.0)]))"
+    n = src("Grid((nr_of_points: (7, 5), side_length: (0.01, 0.02)))", uni, line)
+    assert n.source.pos == ("grid", 7, 5, 0.01, 0.02) and n.source.energy == ("uniform", 1.5) and n.alignment_wavelength is None
+    assert n.source.wavelengths == [1e-6] and n.source.weights == [1.0]  # weights are normalised
+    assert src("Hexapolar((nr_of_rings: 4, radius: 0.005))", uni, line).source.pos == ("hexapolar", 4, 0.005)
+    assert src("FibonacciRectangle((nr_of_rays: 100, side_length_x: 0.01, side_length_y: 0.02))", uni, line).source.pos == ("fibonacci_rectangle", 100, 0.01, 0.02)
+    g = src("FibonacciEllipse((nr_of_rays: 10, radius_x: 0.001, radius_y: 0.002))", uni,
+            "Gaussian((wvl_range: (0.00000095, 0.00000115), num_points: 64, mu: 0.000001053, fwhm: 0.00000005, power: 1.0))").source
+    assert g.spectrum == ("gaussian", 9.5e-7, 1.15e-6, 64, 1.053e-6, 5e-8, 1.0)
+    for bad_pos in ("Random((nr_of_points: 10, side_length_x: 0.01, side_length_y: 0.01))", "Sobol((nr_of_rays: 10))"):
+        with pytest.raises(D.OpmDocumentError, match="not generated on the device"):
+            src(bad_pos, uni, line)
+    empty = D._node(D.parse_ron(_node_text("source", '"light data": LightDataBuilder(None)')))
+    assert empty.source is None
