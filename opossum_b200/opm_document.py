@@ -19,7 +19,8 @@ variants `Name(..)`, strings, numbers, booleans, `Some`/`None`), then the mappin
 uom quantities are serialised as plain numbers in SI base units, nalgebra points as tuples, `Isometry` as its transform
 (rotation quaternion (i, j, k, w) + translation).  Scope: a chain of nodes with at most side chains behind beam splitters, one
 source, the node types of `include/opossum_b200_scene.h`; nested groups, reference nodes, `Raw` / `PointSrc` light data and
-spectrum-valued filters are rejected with `OpmDocumentError`.  Pinned by the reference's fixture files (tests/golden/opm/).
+spectrum-valued filters are rejected with `OpmDocumentError`.  Pinned by the reference's fixture files
+(opossum/files_for_testing/opm/, read by tests/test_opm_document.py where they lie).
 """
 from __future__ import annotations
 

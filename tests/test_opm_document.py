@@ -1,7 +1,9 @@
 """`.opm` reader (opossum_b200/opm_document.py) on the CPU: the RON subset parser and the interpretation of the
-serialised `OpmDocument`, pinned by the reference's own fixture files (copies of opossum/files_for_testing/opm/ in
-tests/golden/opm/: opticscenery.opm, optic_ref.opm, incorrect_opm.opm, empty.opm -- what opm_document.rs:300-420 tests load),
-plus a hand-written document that follows the same serde rules for the node types the fixtures do not contain."""
+serialised `OpmDocument`, pinned by the reference's own fixture files -- opossum/files_for_testing/opm/opticscenery.opm,
+optic_ref.opm, incorrect_opm.opm, empty.opm, what the tests of opm_document.rs load.  They are read where they lie under
+/root/reference (this container; the files are not copied into the repository, the tests that need them are skipped where the
+reference is absent) -- plus a hand-written document (tests/golden/opm/) that follows the same serde rules for the node types
+the fixtures do not contain."""
 import math
 from pathlib import Path
 
@@ -10,6 +12,8 @@ import pytest
 from opossum_b200 import opm_document as D
 
 OPM = Path(__file__).parent / "golden" / "opm"
+REF = Path("/root/reference/opossum/files_for_testing/opm")
+needs_reference = pytest.mark.skipif(not REF.is_dir(), reason="the reference's fixture files are not available here")
 
 
 def test_ron_subset():
@@ -22,10 +26,11 @@ def test_ron_subset():
             D.parse_ron(bad)
 
 
+@needs_reference
 def test_reference_fixture_opticscenery():
     """files_for_testing/opm/opticscenery.opm: two dummy nodes, one edge of distance 0, vacuum, a RayTrace analyzer with the
     default configuration"""
-    doc = D.load_opm(OPM / "opticscenery.opm")
+    doc = D.load_opm(REF / "opticscenery.opm")
     assert doc.version == "0" and doc.name == "OpticScenery demo"
     assert [(n.name, n.node_type) for n in doc.nodes] == [("dummy1", "dummy"), ("dummy2", "dummy")]
     assert doc.nodes[0].uuid == "484d82d5-656a-450a-a92d-ba67a77ef27e" and doc.nodes[1].uuid == "d5230f4f-45e7-4c74-9b26-032158d26076"
@@ -40,14 +45,15 @@ def test_reference_fixture_opticscenery():
         doc.source_node()
 
 
+@needs_reference
 def test_reference_fixture_optic_ref_and_broken_files():
     """optic_ref.opm is one serialised node (`OpticRef`), incorrect_opm.opm and empty.opm are the reference's negative cases
     ("parsing of model failed", opm_document.rs:116-121)"""
-    n = D._node(D.parse_ron((OPM / "optic_ref.opm").read_text()))
+    n = D._node(D.parse_ron((REF / "optic_ref.opm").read_text()))
     assert (n.name, n.node_type, n.uuid, n.lidt) == ("test123", "dummy", "98248e7f-dc4c-4131-8710-f3d5be2ff087", 10000.0)
     for bad in ("incorrect_opm.opm", "empty.opm"):
         with pytest.raises(D.OpmDocumentError, match="parsing of model failed"):
-            D.load_opm(OPM / bad)
+            D.load_opm(REF / bad)
 
 
 def test_handwritten_document_interpretation():
