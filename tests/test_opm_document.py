@@ -151,3 +151,64 @@ def test_source_light_data_mapping():
             src(bad_pos, uni, line)
     empty = D._node(D.parse_ron(_node_text("source", '"light data": LightDataBuilder(None)')))
     assert empty.source is None
+
+
+def _to_ron(v, indent=0):
+    """a serialiser for the subset, laid out like ron::ser::PrettyConfig does (one field per line, trailing commas)"""
+    pad, inner = "    " * indent, "    " * (indent + 1)
+    if v is None:
+        return "None"
+    if isinstance(v, bool):
+        return "true" if v else "false"
+    if isinstance(v, (int, float)):
+        return "inf" if v == math.inf else "-inf" if v == -math.inf else repr(v)
+    if isinstance(v, str):
+        return '"' + v.replace("\\", "\\\\").replace('"', '\\"') + '"'
+    if isinstance(v, list):
+        return "[\n" + "".join(inner + _to_ron(x, indent + 1) + ",\n" for x in v) + pad + "]" if v else "[]"
+    if isinstance(v, tuple):
+        return "(" + ", ".join(_to_ron(x, indent) for x in v) + ")"
+    if isinstance(v, D.Variant):
+        if v.fields is not None:
+            return v.name + "(\n" + "".join(inner + k + ": " + _to_ron(x, indent + 1) + ",\n" for k, x in v.fields.items()) + pad + ")"
+        return v.name + ("(" + ", ".join(_to_ron(x, indent) for x in v.args) + ")" if v.args else "")
+    if isinstance(v, dict) and v.get("__map__"):
+        items = [(k, x) for k, x in v.items() if k != "__map__"]
+        return "{\n" + "".join(inner + _to_ron(k, indent + 1) + ": " + _to_ron(x, indent + 1) + ",\n" for k, x in items) + pad + "}"
+    return "(\n" + "".join(inner + k + ": " + _to_ron(x, indent + 1) + ",\n" for k, x in v.items()) + pad + ")"
+
+
+def test_ron_round_trip_property():
+    """random nested documents survive serialise -> parse (hypothesis; finite numbers, identifiers that are no keywords)"""
+    from hypothesis import given, settings
+    from hypothesis import strategies as st
+    ident = st.from_regex(r"[a-z_][a-z0-9_]{0,8}", fullmatch=True).filter(lambda s: s not in ("true", "false", "inf", "e"))
+    upper = st.from_regex(r"[A-Z][A-Za-z0-9]{0,8}", fullmatch=True).filter(lambda s: s not in ("Some", "None", "NaN"))
+    leaf = st.one_of(st.booleans(), st.integers(-10**9, 10**9), st.floats(allow_nan=False, allow_infinity=True, width=64),
+                     st.text(alphabet=st.characters(min_codepoint=32, max_codepoint=126), max_size=12))
+
+    def extend(children):
+        struct = st.dictionaries(ident, children, min_size=1, max_size=4)
+        return st.one_of(st.lists(children, max_size=3), struct, st.tuples(children, children),
+                         st.dictionaries(st.text(alphabet="abc xyz", min_size=1, max_size=6), children, min_size=1, max_size=3)
+                         .map(lambda d: {**d, "__map__": True}),
+                         st.builds(lambda n, a: D.Variant(n, (a,)), upper, children), st.builds(lambda n, f: D.Variant(n, (), f), upper, struct),
+                         st.builds(D.Variant, upper))
+    docs = st.recursive(leaf, extend, max_leaves=25)
+
+    def strip(v):  # what the parser returns for a map: a plain dict
+        if isinstance(v, dict):
+            return {k: strip(x) for k, x in v.items() if k != "__map__"}
+        if isinstance(v, list):
+            return [strip(x) for x in v]
+        if isinstance(v, tuple):
+            return tuple(strip(x) for x in v)
+        if isinstance(v, D.Variant):
+            return D.Variant(v.name, tuple(strip(x) for x in v.args), None if v.fields is None else strip(v.fields))
+        return v
+
+    @settings(max_examples=200, deadline=None)
+    @given(docs)
+    def check(doc):
+        assert D.parse_ron(_to_ron(doc)) == strip(doc)
+    check()
