@@ -1023,3 +1023,19 @@ def test_bundle_constructor_kats():
     xyz0 = orc.hexapolar(2, 0.0)
     rays = orc.rays_collimated_with_spectrum(xyz0, orc.energy_uniform(len(xyz0), 1.0), [nm(1054.0)], [1.0])
     assert orc.nr_of_rays(rays) == 1 and tuple(rays[0]["pos"]) == (0.0, 0.0, 0.0) and tuple(rays[0]["dir"]) == Z
+
+
+def test_kde_fluence_end_to_end_kats():
+    """surface/hit_map/mod.rs:1124-1169 calc_combined_fluence_with_kde: five 1 J hits (the corners of a unit square and its centre)
+    on a 51 x 51 map give 5.474418964842738 J/m^2 in the centre bin; merged with five more (a square rotated by 45 deg and the
+    centre again) 8.969644069111087 -- the whole estimator (pair distances, Silverman bandwidth, range with its 3-bandwidth
+    margin, Gaussian sum) end to end, assert_relative_eq!"""
+    p1 = [(-0.5, -0.5), (0.0, 0.0), (-0.5, 0.5), (0.5, 0.5), (0.5, -0.5)]
+    r = math.sqrt(0.5)
+    p2 = [(r, 0.0), (0.0, r), (-r, 0.0), (0.0, -r), (0.0, 0.0)]
+    rel = lambda a, b: abs(a - b) <= EPS or abs(a - b) <= EPS * max(abs(a), abs(b))  # noqa: E731
+    fmap, _, _ = orc.fluence_kde(orc.hits_from_xye([p[0] for p in p1], [p[1] for p in p1], [1.0] * 5), 51, 51)
+    assert rel(fmap[25, 25], 5.474418964842738)
+    both = p1 + p2  # HitMap::get_merged_rays_hit_map: the hit points of both bundles in insertion order
+    fmap, _, _ = orc.fluence_kde(orc.hits_from_xye([p[0] for p in both], [p[1] for p in both], [1.0] * 10), 51, 51)
+    assert rel(fmap[25, 25], 8.969644069111087)
