@@ -261,6 +261,33 @@ class OScene:
             n.stored_hist = self.hist.copy() if self.hist is not None else None
         return rays
 
+    def beam_splitter_two_inputs(self, node: int, in1: np.ndarray | None, in2: np.ndarray | None, cfg: RayTraceConfig | None = None):
+        """BeamSplitter::analyze_raytrace with both inputs (nodes/beam_splitter/mod.rs:158-293): each input passes the node's flat
+        surface and input aperture and is split; output 1 = what input 1 keeps + what input 2 splits off, output 2 the other way
+        round; both outputs see output 1's aperture frame and the energy threshold.  (The product's scene layer is a tree and takes
+        one input; this restates the reference for its two-input test.)  Returns (out1, out2) or (None, None)."""
+        cfg = cfg or RayTraceConfig()
+        n = self.nodes[node]
+        if in1 is None and in2 is None:
+            return None, None
+        empty = np.zeros(0, dtype=orc.RAY_DTYPE)
+
+        def one(rays):
+            if rays is None:
+                return empty.copy(), empty.copy()
+            rays = np.ascontiguousarray(rays.copy())
+            self._refract(rays, n.s[0], None, True, cfg.missed_surface_strategy, record=False, want_children=False)
+            orc.rays_apodize(rays, n.s[0].aperture, n.s[0].eff_iso, self.nt)
+            split = orc.rays_split_spectrum(rays, *n.spectrum) if n.spectrum is not None else orc.rays_split(rays, n.p[0])
+            return rays, split
+        r1, sp1 = one(in1)
+        r2, sp2 = one(in2)
+        out1, out2 = np.concatenate([r1, sp2]), np.concatenate([r2, sp1])  # Rays::merge appends
+        for out in (out1, out2):
+            orc.rays_apodize(out, n.s[1].aperture, n.s[1].eff_iso, self.nt)
+            orc.rays_threshold(out, cfg.min_energy_per_ray, self.nt)
+        return out1, out2
+
     def _limits_rt(self, rays, cfg):  # node_group/analysis_raytrace.rs:20-27
         orc.rays_filter_bounces(rays, cfg.max_number_of_bounces)
         orc.rays_filter_refractions(rays, cfg.max_number_of_refractions)

@@ -1039,3 +1039,18 @@ def test_kde_fluence_end_to_end_kats():
     both = p1 + p2  # HitMap::get_merged_rays_hit_map: the hit points of both bundles in insertion order
     fmap, _, _ = orc.fluence_kde(orc.hits_from_xye([p[0] for p in both], [p[1] for p in both], [1.0] * 10), 51, 51)
     assert rel(fmap[25, 25], 8.969644069111087)
+
+
+def test_beam_splitter_two_inputs_kat():
+    """nodes/beam_splitter/analysis_raytrace.rs:148-178 analyze_two_input: Ratio(0.6) with 1 J at input 1 and 0.5 J at input 2 gives
+    0.8 J at the first output (0.6 * 1 + 0.4 * 0.5) and 0.7 J at the second (assert_abs_diff_eq!); no input, no output (:113-120)"""
+    import scenes
+    osc = scenes.to_oracle([scenes.node("source"), scenes.node("beam_splitter", p=(0.6,))])
+    in1 = orc.ray_new(mm(0.0, 0.0, -10.0), Z, nm(1053.0), 1.0)
+    in2 = orc.ray_new(mm(0.0, 0.0, -10.0), Z, nm(1053.0), 0.5)
+    out1, out2 = osc.beam_splitter_two_inputs(1, in1, in2)
+    assert abs(orc.total_energy(out1) - 0.8) <= EPS and abs(orc.total_energy(out2) - 0.7) <= EPS
+    assert len(out1) == 2 and len(out2) == 2
+    assert osc.beam_splitter_two_inputs(1, None, None) == (None, None)
+    only1 = osc.beam_splitter_two_inputs(1, in1, None)
+    assert orc.total_energy(only1[0]) == 0.6 and orc.total_energy(only1[1]) == 0.4
