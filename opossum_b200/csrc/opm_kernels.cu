@@ -16,8 +16,9 @@
 
 #include <cfloat>
 
-#include "opm_device.cuh"
+#include "opm_trace_ops.cuh"  // includes opm_device.cuh; the mbarrier / bulk-copy helpers
 #include <cstdlib>
+#include <cstring>
 
 #include <cub/device/device_radix_sort.cuh>
 
@@ -440,6 +441,12 @@ __global__ void __launch_bounds__(BLOCK, MIN_CTAS) binning_smem_fixed_kernel(Dev
             // NaN / infinite taps (a NaN hit position, an infinite energy) go to the global map as they are, like the f64 kernel's
             if (!scaled || !isfinite(w)) { atomicAdd(&map[b], w); return; }
             const unsigned long long q = __double2ull_rn(w * inv_unit);
+            // Taps below 2^32 units keep fewer than 32 significant bits in fixed point: they (and negative taps -- a hit left of or
+            // below an explicit range, which the reference adds as they are -- whose conversion saturates to 0) go to the global f64
+            // map directly.  Every fixed-point tap is therefore rounded by at most 2^-33 of itself, so a bin -- a sum of
+            // non-negative taps -- is within 1.2e-10 of the f64 sum RELATIVE TO ITS OWN VALUE, however small it is against the
+            // map's peak.  Such taps are rare (~1e-3 of all taps for a beam with a 100:1 energy range).
+            if (q < (1ull << 32)) { atomicAdd(&map[b], w); return; }
             const unsigned l = (unsigned)q;
             unsigned h = (unsigned)(q >> 32);
             if (l) { const unsigned old = atomicAdd(&lo[b], l); h += (unsigned)(old + l < old); }
@@ -534,6 +541,195 @@ __global__ void __launch_bounds__(256) binning_global_kernel(DevHits H, uint64_t
     if (status) atomicOr(status_out, status);
 }
 
+// Large maps, second form: every THREAD walks RUN consecutive slots and keeps the four taps of the bin it is in in registers.
+// Slots are in source order, and the sources that feed a large map are ordered (grid: y runs fastest), so consecutive hits fall
+// into the same bin or the one above / below it.  A step to the neighbouring row keeps the two taps the bins share
+// ((x, y+1) and (x+1, y+1) of the old bin are (x, y) and (x+1, y) of the new one) and flushes the other two; anything else flushes
+// all four.  A 10^8-hit C4 map (2.4 hits per bin along y) goes from 4 global f64 reductions per hit to about one, with no
+// shuffles.  Taps the reference does not add (x + 1 == nx, y + 1 == ny) are held as exact zeros and zeros are never flushed,
+// so the index arithmetic needs no edge cases.  Hits without locality cost what the un-merged splat costs.
+// A CTA owns a contiguous range of slots (not a grid-stride set): concurrently running CTAs then work on different parts of the
+// map and the reductions of one bin are not spread over a thousand CTAs at the same moment (the L2 serialises per address).
+template <int RUN>
+struct RunLoad {
+    double x[RUN], y[RUN], e[RUN];
+};
+template <int RUN>
+__device__ __forceinline__ void run_load(const DevHits& H, uint64_t s0, uint64_t n, RunLoad<RUN>& L) {
+    if (s0 + RUN <= n) {  // the arrays are 256-byte aligned and s0 is a multiple of RUN: 16-byte loads
+#pragma unroll
+        for (int u = 0; u < RUN; u += 2) {
+            // streaming (evict-first) loads: the hit records pass through the L2 once, the map's lines should stay
+            const double2 ev = __ldcs(reinterpret_cast<const double2*>(H.e + s0 + u));
+            const double2 xv = __ldcs(reinterpret_cast<const double2*>(H.x + s0 + u));
+            const double2 yv = __ldcs(reinterpret_cast<const double2*>(H.y + s0 + u));
+            L.e[u] = ev.x; L.e[u + 1] = ev.y; L.x[u] = xv.x; L.x[u + 1] = xv.y; L.y[u] = yv.x; L.y[u + 1] = yv.y;
+        }
+    } else {
+#pragma unroll
+        for (int u = 0; u < RUN; ++u) {
+            const bool in = s0 + u < n;
+            L.e[u] = in ? H.e[s0 + u] : -1.0; L.x[u] = in ? H.x[s0 + u] : 0.0; L.y[u] = in ? H.y[s0 + u] : 0.0;
+        }
+    }
+}
+// PREFETCH: the loads of the CTA's next chunk are issued before the current one is splatted (a second register set instead of more
+// resident warps)
+template <int BLOCK, int MIN_CTAS, int RUN, bool PREFETCH = false>
+__global__ void __launch_bounds__(BLOCK, MIN_CTAS) binning_runs_kernel(DevHits H, uint64_t n, long long bounce_filter, unsigned long long nx,
+                                                                       unsigned long long ny, const double* __restrict__ range,
+                                                                       double* __restrict__ map, unsigned* status_out, int interleave) {
+    static_assert(RUN % 2 == 0, "slots are loaded in pairs");
+    BinParams P;
+    if (!bin_params_from_range(nx, ny, range, P)) return;
+    const BinInv I{1.0 / P.width_step, 1.0 / P.height_step, 1.0 / P.bin_area};
+    const unsigned ny32 = (unsigned)P.ny;
+    unsigned status = 0;
+    const uint64_t chunk = (uint64_t)BLOCK * RUN;
+    const uint64_t n_chunks = (n + chunk - 1) / chunk;
+    const uint64_t per = (n_chunks + gridDim.x - 1) / gridDim.x;
+    uint64_t c0, c1, cstep;
+    if (interleave) { c0 = blockIdx.x; c1 = n_chunks; cstep = gridDim.x; }
+    else { c0 = blockIdx.x * per; c1 = c0 + per < n_chunks ? c0 + per : n_chunks; cstep = 1; }
+    RunLoad<RUN> N;
+    if (PREFETCH && c0 < c1) {
+        const uint64_t s = c0 * chunk + (uint64_t)threadIdx.x * RUN;
+        if (s < n) run_load(H, s, n, N);
+    }
+    for (uint64_t c = c0; c < c1; c += cstep) {
+        const uint64_t s0 = c * chunk + (uint64_t)threadIdx.x * RUN;
+        RunLoad<RUN> L;
+        if (PREFETCH) {
+            L = N;
+            const uint64_t s1 = (c + cstep) * chunk + (uint64_t)threadIdx.x * RUN;
+            if (c + cstep < c1 && s1 < n) run_load(H, s1, n, N);
+            if (s0 >= n) continue;
+        } else {
+            if (s0 >= n) continue;
+            run_load(H, s0, n, L);
+        }
+        bool open = false;
+        unsigned base = 0;
+        double a00 = 0.0, a10 = 0.0, a01 = 0.0, a11 = 0.0;
+        auto red = [&](unsigned b, double v) { if (v != 0.0) atomicAdd(&map[b], v); };
+#pragma unroll
+        for (int u = 0; u < RUN; ++u) {
+            if (!(L.e[u] >= 0.0)) continue;
+            if (bounce_filter >= 0 && (long long)H.bounce[s0 + u] != bounce_filter) continue;
+            BinTaps32 t = bin_taps_inv(P, I, L.x[u], L.y[u], L.e[u], &status);
+            if (!t.ok) continue;
+            if (!t.has_x) { t.w10 = 0.0; t.w11 = 0.0; }
+            if (!t.has_y) { t.w01 = 0.0; t.w11 = 0.0; }
+            if (open && t.base == base) { a00 += t.w00; a10 += t.w10; a01 += t.w01; a11 += t.w11; continue; }
+            if (open && t.base == base + 1u) {         // one row up (or the first bin of the next column: then a01 = a11 = 0)
+                red(base, a00); red(base + ny32, a10);
+                a00 = a01 + t.w00; a10 = a11 + t.w10; a01 = t.w01; a11 = t.w11;
+            } else if (open && t.base + 1u == base) {  // one row down
+                red(base + 1u, a01); red(base + ny32 + 1u, a11);
+                a01 = a00 + t.w01; a11 = a10 + t.w11; a00 = t.w00; a10 = t.w10;
+            } else {
+                if (open) { red(base, a00); red(base + ny32, a10); red(base + 1u, a01); red(base + ny32 + 1u, a11); }
+                a00 = t.w00; a10 = t.w10; a01 = t.w01; a11 = t.w11;
+                open = true;
+            }
+            base = t.base;
+        }
+        if (open) { red(base, a00); red(base + ny32, a10); red(base + 1u, a01); red(base + ny32 + 1u, a11); }
+    }
+    if (status) atomicOr(status_out, status);
+}
+
+// The same splat with the hit records staged through shared memory by TMA bulk copies (cp.async.bulk, one elected thread):
+// STAGES tiles of BLOCK * RUN slots (x | y | e) per CTA, one mbarrier per stage, so the HBM reads of the next tiles are in flight
+// while the warps splat the current one -- the direct-load form above waits on its loads (ncu: 9.4 warps per issue stalled on
+// the long scoreboard at half occupancy).  A stage is re-armed after the block barrier that follows its last read.
+template <int BLOCK, int MIN_CTAS, int RUN, int STAGES>
+__global__ void __launch_bounds__(BLOCK, MIN_CTAS) binning_runs_tma_kernel(DevHits H, uint64_t n, long long bounce_filter, unsigned long long nx,
+                                                                           unsigned long long ny, const double* __restrict__ range,
+                                                                           double* __restrict__ map, unsigned* status_out) {
+    extern __shared__ __align__(128) unsigned char tsm[];
+    __shared__ unsigned long long bar[STAGES];
+    BinParams P;
+    if (!bin_params_from_range(nx, ny, range, P)) return;
+    const BinInv I{1.0 / P.width_step, 1.0 / P.height_step, 1.0 / P.bin_area};
+    const unsigned ny32 = (unsigned)P.ny;
+    unsigned status = 0;
+    constexpr unsigned kTile = BLOCK * RUN;            // slots per tile
+    constexpr unsigned kArr = kTile * 8;               // bytes of one field of a tile
+    constexpr unsigned kStage = 3 * kArr;
+    const uint64_t n_full = n / kTile;                 // tiles [0, n_full) are complete: they travel by bulk copy
+    const uint64_t n_tiles = (n + kTile - 1) / kTile;
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int s = 0; s < STAGES; ++s) mbar_init(&bar[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    auto issue = [&](uint64_t tile, int s) {  // thread 0
+        unsigned char* st = tsm + (size_t)s * kStage;
+        mbar_expect_tx(&bar[s], kStage);
+        bulk_g2s(st, H.x + tile * kTile, kArr, &bar[s]);
+        bulk_g2s(st + kArr, H.y + tile * kTile, kArr, &bar[s]);
+        bulk_g2s(st + 2 * kArr, H.e + tile * kTile, kArr, &bar[s]);
+    };
+    if (threadIdx.x == 0)
+        for (int s = 0; s < STAGES - 1; ++s) {
+            const uint64_t t = blockIdx.x + (uint64_t)s * gridDim.x;
+            if (t < n_full) issue(t, s);
+        }
+    unsigned k = 0;
+    for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++k) {
+        const uint64_t s0 = tile * kTile + (uint64_t)threadIdx.x * RUN;
+        RunLoad<RUN> L;
+        if (tile < n_full) {
+            const int s = k % STAGES;
+            mbar_wait(&bar[s], (k / STAGES) & 1u);
+            const double2* sx = reinterpret_cast<const double2*>(tsm + (size_t)s * kStage) + (size_t)threadIdx.x * (RUN / 2);
+#pragma unroll
+            for (int u = 0; u < RUN; u += 2) {
+                const double2 xv = sx[u / 2], yv = sx[kTile / 2 + u / 2], ev = sx[kTile + u / 2];
+                L.x[u] = xv.x; L.x[u + 1] = xv.y; L.y[u] = yv.x; L.y[u + 1] = yv.y; L.e[u] = ev.x; L.e[u + 1] = ev.y;
+            }
+        } else {
+            if (s0 < n) run_load(H, s0, n, L);
+        }
+        __syncthreads();  // every thread holds its slots in registers: the stage of the PREVIOUS iteration's successor can be re-armed
+        if (threadIdx.x == 0) {
+            const uint64_t nt = tile + (uint64_t)(STAGES - 1) * gridDim.x;
+            if (nt < n_full) issue(nt, (k + STAGES - 1) % STAGES);
+        }
+        if (s0 >= n) continue;
+        bool open = false;
+        unsigned base = 0;
+        double a00 = 0.0, a10 = 0.0, a01 = 0.0, a11 = 0.0;
+        auto red = [&](unsigned b, double v) { if (v != 0.0) atomicAdd(&map[b], v); };
+#pragma unroll
+        for (int u = 0; u < RUN; ++u) {
+            if (s0 + u >= n || !(L.e[u] >= 0.0)) continue;
+            if (bounce_filter >= 0 && (long long)H.bounce[s0 + u] != bounce_filter) continue;
+            BinTaps32 t = bin_taps_inv(P, I, L.x[u], L.y[u], L.e[u], &status);
+            if (!t.ok) continue;
+            if (!t.has_x) { t.w10 = 0.0; t.w11 = 0.0; }
+            if (!t.has_y) { t.w01 = 0.0; t.w11 = 0.0; }
+            if (open && t.base == base) { a00 += t.w00; a10 += t.w10; a01 += t.w01; a11 += t.w11; continue; }
+            if (open && t.base == base + 1u) {
+                red(base, a00); red(base + ny32, a10);
+                a00 = a01 + t.w00; a10 = a11 + t.w10; a01 = t.w01; a11 = t.w11;
+            } else if (open && t.base + 1u == base) {
+                red(base + 1u, a01); red(base + ny32 + 1u, a11);
+                a01 = a00 + t.w01; a11 = a10 + t.w11; a00 = t.w00; a10 = t.w10;
+            } else {
+                if (open) { red(base, a00); red(base + ny32, a10); red(base + 1u, a01); red(base + ny32 + 1u, a11); }
+                a00 = t.w00; a10 = t.w10; a01 = t.w01; a11 = t.w11;
+                open = true;
+            }
+            base = t.base;
+        }
+        if (open) { red(base, a00); red(base + ny32, a10); red(base + 1u, a01); red(base + ny32 + 1u, a11); }
+    }
+    if (status) atomicOr(status_out, status);
+}
+
 // fluence_data.rs:45-68 (peak over finite bins) and :130-141 (sum over non-NaN bins)
 __global__ void __launch_bounds__(256) peak_total_kernel(const double* __restrict__ map, uint64_t nx, uint64_t ny,
                                                          const double* __restrict__ range, PeakAccum* acc) {
@@ -542,10 +738,30 @@ __global__ void __launch_bounds__(256) peak_total_kernel(const double* __restric
     const double dx = (range[1] - (-range[0])) / (double)nx, dy = (range[2] - (-range[3])) / (double)ny;
     const double area = dx * dy;
     double peak = -INFINITY, tot = 0.0;
-    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < bins; i += (uint64_t)gridDim.x * blockDim.x) {
-        double v = map[i];
-        if (isfinite(v)) peak = fmax(peak, v);
-        if (!isnan(v)) tot += area * v;
+    // four independent 16-byte loads per thread and iteration (a 4096 x 4096 map is 128 MiB: this pass is pure HBM streaming)
+    const uint64_t head = (reinterpret_cast<uintptr_t>(map) & 8u) ? 1 : 0;  // maps packed behind one another may start at 8 mod 16
+    const uint64_t pairs = (bins - (bins ? head : 0)) / 2, stride = (uint64_t)gridDim.x * blockDim.x;
+    const double2* __restrict__ m2 = reinterpret_cast<const double2*>(map + head);
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < pairs; i += 4 * stride) {
+        double2 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) v[u] = i + u * stride < pairs ? __ldcs(m2 + i + u * stride) : make_double2(NAN, NAN);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            if (isfinite(v[u].x)) peak = fmax(peak, v[u].x);
+            if (!isnan(v[u].x)) tot += area * v[u].x;
+            if (isfinite(v[u].y)) peak = fmax(peak, v[u].y);
+            if (!isnan(v[u].y)) tot += area * v[u].y;
+        }
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0 && bins) {  // the bins in front of / behind the 16-byte pairs
+        for (int k = 0; k < 2; ++k) {
+            const uint64_t j = k == 0 ? 0 : head + 2 * pairs;
+            if ((k == 0 && !head) || j >= bins) continue;
+            const double v = map[j];
+            if (isfinite(v)) peak = fmax(peak, v);
+            if (!isnan(v)) tot += area * v;
+        }
     }
     peak = warp_max(peak); tot = warp_sum(tot);
     if ((threadIdx.x & 31) == 0) { atomicMax(&acc->peak_key, dkey(peak)); atomicAdd(&acc->total, tot); }
@@ -887,7 +1103,42 @@ int k_binning(DevHits H, uint64_t n, long long bounce_filter, uint64_t nx, uint6
         // the privatised map takes most of an SM's shared memory: one CTA per SM, as many warps as it can hold
         binning_smem_kernel<<<grid_for(n, 1024, sms), 1024, bytes, ST>>>(H, n, bounce_filter, nx, ny, range_dev, map, status);
     } else {
-        binning_global_kernel<<<grid_for(n, 256, sms * 8), 256, 0, ST>>>(H, n, bounce_filter, nx, ny, range_dev, map, status);
+        // tuning switches (profiles/c4_binning_probe.py): OPM_B200_BINNING_LARGE=warp selects the warp-segmented kernel,
+        // OPM_B200_BINNING_RUNS="shape,ctas_per_sm,interleave" the launch shape of the run-merging one
+        const char* which = getenv("OPM_B200_BINNING_LARGE");
+        if ((which && !strcmp(which, "warp")) || nx * ny >= (1ull << 31)) {
+            binning_global_kernel<<<grid_for(n, 256, sms * 8), 256, 0, ST>>>(H, n, bounce_filter, nx, ny, range_dev, map, status);
+            return (int)cudaGetLastError();
+        }
+        int shape = 0, ctas = 0, interleave = 1;
+        if (const char* cfg = getenv("OPM_B200_BINNING_RUNS")) sscanf(cfg, "%d,%d,%d", &shape, &ctas, &interleave);
+#define OPM_RUNS(BLOCK, MINC, RUN, PF)                                                                                               \
+    {                                                                                                                                \
+        const int per_sm = ctas > 0 ? ctas : MINC;                                                                                   \
+        binning_runs_kernel<BLOCK, MINC, RUN, PF><<<grid_for((n + RUN - 1) / RUN, BLOCK, sms * per_sm), BLOCK, 0, ST>>>(             \
+            H, n, bounce_filter, nx, ny, range_dev, map, status, interleave);                                                        \
+    }
+#define OPM_RUNS_TMA(BLOCK, MINC, RUN, STAGES)                                                                                       \
+    {                                                                                                                                \
+        const int per_sm = ctas > 0 ? ctas : MINC;                                                                                   \
+        const size_t smem = (size_t)STAGES * 3 * BLOCK * RUN * 8;                                                                    \
+        auto kern = binning_runs_tma_kernel<BLOCK, MINC, RUN, STAGES>;                                                               \
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                          \
+        if (e != cudaSuccess) return (int)e;                                                                                         \
+        kern<<<grid_for((n + RUN - 1) / RUN, BLOCK, sms * per_sm), BLOCK, smem, ST>>>(H, n, bounce_filter, nx, ny, range_dev, map,   \
+                                                                                      status);                                     \
+    }
+        // measured on the C4 hit map (10^8 hits -> 4096 x 4096, profiles/r2_summary.md): 0 -> 0.709 ms (zero-fill + splat), 1 -> 0.739,
+        // 2 -> 0.765, 3 -> 0.720 (staged by TMA: no better -- the splat is bound by the SMs' rate of global reductions, not by the
+        // latency of its loads), the warp-segmented kernel of round 1 -> 1.261 ms
+        switch (shape) {
+            case 1: OPM_RUNS(256, 4, 4, false) break;
+            case 2: OPM_RUNS(256, 2, 8, false) break;
+            case 3: OPM_RUNS_TMA(512, 2, 4, 2) break;
+            default: OPM_RUNS(256, 3, 4, true) break;
+        }
+#undef OPM_RUNS
+#undef OPM_RUNS_TMA
     }
     return (int)cudaGetLastError();
 }
@@ -946,7 +1197,7 @@ int k_kde_2d(const double* hx, const double* hy, const double* he, uint64_t n, d
     return (int)cudaGetLastError();
 }
 int k_peak_total(const double* map, uint64_t nx, uint64_t ny, const double* range_dev, PeakAccum* acc, double* out2_dev, int sms, void* stream) {
-    peak_total_kernel<<<grid_for(nx * ny, 256, sms * 4), 256, 0, ST>>>(map, nx, ny, range_dev, acc);
+    peak_total_kernel<<<grid_for((nx * ny + 7) / 8, 256, sms * 8), 256, 0, ST>>>(map, nx, ny, range_dev, acc);
     if (out2_dev) peak_finalize_kernel<<<1, 1, 0, ST>>>(acc, out2_dev);
     return (int)cudaGetLastError();
 }
