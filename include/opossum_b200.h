@@ -262,7 +262,13 @@ const char* opm_status_string(OpmStatus s);
 /* device: CUDA ordinal; stream: a cudaStream_t the caller owns, or NULL for a library-owned stream */
 OpmStatus opm_context_create(int32_t device, void* stream, OpmContext** out);
 void opm_context_destroy(OpmContext* ctx);
+/* Waits for the context's stream.  Launches that do not read their statistics back (stats == NULL, OPM_SCENE_ASYNC) cannot return
+ * the per-ray error conditions on which the reference aborts an analysis (`?` in rays.rs:987-991: n2 invalid, wavelength outside an
+ * index model's range, non-finite hit point, apodisation factor outside (0, 1], full child bundle); their status bits are kept
+ * on the device and come back HERE as the error of the lowest such bit (then cleared). */
 OpmStatus opm_context_synchronize(OpmContext* ctx);
+/* the same check without waiting for anything but the copy of the status word; clear != 0: forget the bits afterwards */
+OpmStatus opm_context_check_errors(OpmContext* ctx, int32_t clear);
 void* opm_context_stream(OpmContext* ctx);
 /* number of kernels launched through this context so far (bench.py "gpu_launches") */
 uint64_t opm_context_launch_count(const OpmContext* ctx);

@@ -211,7 +211,7 @@ SCENE_EXPORTS = [
 # every symbol include/opossum_b200.h declares (tests/test_abi.py checks the library exports all of them)
 EXPORTS = [
     "opm_abi_version", "opm_abi_sizeof", "opm_last_error", "opm_status_string", "opm_context_create", "opm_context_destroy",
-    "opm_context_synchronize", "opm_context_stream", "opm_context_launch_count", "opm_context_set_kernel_timing",
+    "opm_context_synchronize", "opm_context_check_errors", "opm_context_stream", "opm_context_launch_count", "opm_context_set_kernel_timing",
     "opm_context_kernel_timing", "opm_context_set_jit", "opm_context_jit_wait", "opm_context_jit_stats", "opm_jit_selftest", "opm_isometry_identity",
     "opm_isometry_new", "opm_isometry_append", "opm_isometry_from_view", "opm_parabola_off_axis_isometry", "opm_raytrace_config_default", "opm_rays_create", "opm_rays_destroy",
     "opm_rays_len", "opm_rays_capacity", "opm_rays_clear", "opm_rays_set_wavelength_hint", "opm_rays_reserve", "opm_rays_upload",
@@ -262,6 +262,7 @@ def lib() -> C.CDLL:
         "opm_context_create": (i32, [i32, vp, pp]),
         "opm_context_destroy": (None, [vp]),
         "opm_context_synchronize": (i32, [vp]),
+        "opm_context_check_errors": (i32, [vp, i32]),
         "opm_context_stream": (vp, [vp]),
         "opm_context_launch_count": (u64, [vp]),
         "opm_context_set_kernel_timing": (i32, [vp, i32]),

@@ -228,8 +228,13 @@ class Context:
     """One CUDA device + stream.  Raises OpossumError(OPM_ERR_CUDA) when no B200 is visible (no CPU fallback)."""
 
     def __init__(self, device: int = 0, stream: int | None = None):
+        """stream: a cudaStream_t handle the library launches on (e.g. `torch.cuda.Stream().cuda_stream`); None = a private
+        non-blocking stream.  0 is CUDA's default stream (what `torch.cuda.default_stream().cuda_stream` returns): it is passed
+        on as cudaStreamLegacy, never silently replaced by a private stream."""
         h = C.c_void_p()
-        _check(F.lib().opm_context_create(device, C.c_void_p(stream) if stream else None, C.byref(h)))
+        if stream is not None and stream == 0:
+            stream = 0x1  # cudaStreamLegacy: the NULL stream under an explicit handle
+        _check(F.lib().opm_context_create(device, C.c_void_p(stream) if stream is not None else None, C.byref(h)))
         self.h = h
         self.device = device
         self._children = weakref.WeakSet()  # bundles / hit maps / scenes living on this context
@@ -238,7 +243,12 @@ class Context:
         self._children.add(child)
 
     def synchronize(self):
+        """waits for the stream; raises what asynchronous launches (sync=False) raised on the device meanwhile"""
         _check(F.lib().opm_context_synchronize(self.h))
+
+    def check_errors(self, clear=True):
+        """raise the error status asynchronous launches left on the device, without waiting for queued work"""
+        _check(F.lib().opm_context_check_errors(self.h, int(clear)))
 
     @property
     def stream(self) -> int:

@@ -237,6 +237,7 @@ extern "C" OpmStatus opm_context_create(int32_t device, void* stream, OpmContext
     CU(cudaMallocHost(&c->h_put_ring, OpmContext::kPutSlots * OpmContext::kPutBytes));
     for (int k = 0; k < OpmContext::kPutSlots; ++k) CU(cudaEventCreateWithFlags(&c->put_ev[k], cudaEventDisableTiming));
     CU(cudaMalloc(&c->d_stats, sizeof(DevStats)));
+    CU(cudaMemset(c->d_stats, 0, sizeof(DevStats)));
     CU(cudaMallocHost(&c->h_stats, sizeof(DevStats)));
     CU(cudaMalloc(&c->d_ops, sizeof(DevOp) * OPM_MAX_PROGRAM_OPS * OpmContext::kRing));
     CU(cudaMallocHost(&c->h_ops_ring, sizeof(DevOp) * OPM_MAX_PROGRAM_OPS * OpmContext::kRing));
@@ -262,11 +263,25 @@ extern "C" void opm_context_destroy(OpmContext* c) {
     if (c->own_stream) cudaStreamDestroy(c->stream);
     delete c;
 }
+// status bits raised by asynchronous launches since the last look (DevStats::sticky_bits); clear: forget them afterwards
+extern "C" OpmStatus opm_context_check_errors(OpmContext* c, int32_t clear) {
+    if (!c) return fail(OPM_ERR_ARG, "context is NULL");
+    CU(cudaSetDevice(c->device));
+    unsigned* h = (unsigned*)(c->h_scratch + 1032);
+    CU(cudaMemcpyAsync(h, &c->d_stats->sticky_bits, 4, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    const unsigned bits = *h;
+    if (bits && clear) CU(cudaMemsetAsync(&c->d_stats->sticky_bits, 0, 4, c->stream));
+    return status_from_bits(bits);
+}
+// Waits for the context's stream and reports what asynchronous launches raised meanwhile: a wavelength outside an index
+// model's range, an invalid n2, a non-finite hit point, a full child bundle, a bad apodisation factor -- conditions on which the
+// reference aborts the analysis (`?` in rays.rs:987-991) -- come back here as the error of the first such bit (then cleared).
 extern "C" OpmStatus opm_context_synchronize(OpmContext* c) {
     if (!c) return fail(OPM_ERR_ARG, "context is NULL");
     CU(cudaSetDevice(c->device));
     CU(cudaStreamSynchronize(c->stream));
-    return OPM_OK;
+    return opm_context_check_errors(c, 1);
 }
 // ---- run-time specialised kernels (opm_jit.cu)
 extern "C" uint64_t opm_jit_selftest(char* log, uint64_t cap) { return jit_selftest(log, cap); }
@@ -1273,7 +1288,7 @@ static OpmStatus run_program(OpmRays* rays, const OpmOp* ops, int n_ops, int fla
                 if (ps) { free_temps(); return ps; }
                 h->acc_valid = true;
             }
-        CU(cudaMemsetAsync(c->d_stats, 0, sizeof(DevStats), c->stream));
+        CU(cudaMemsetAsync(c->d_stats, 0, kDevStatsZeroBytes, c->stream));  // not the sticky status word
         TraceLaunch L;
         L.ops = d_slot; L.n_ops = (int)prog.ops.size();
         L.in = rays->v; L.out = dst->v; L.n = n; L.out_cap = dst->cap; L.out_tail = dst->d_tail;
@@ -1326,6 +1341,8 @@ static OpmStatus run_program(OpmRays* rays, const OpmOp* ops, int n_ops, int fla
         if (compact) { s = rays_refresh_len(dst); if (s) return s; }
         if (stats) {
             stats_to_public(*c->h_stats, stats);
+            // reported right here: not again at the next opm_context_synchronize
+            if (stats->status_bits) CU(cudaMemsetAsync(&c->d_stats->sticky_bits, 0, 4, c->stream));
             return status_from_bits(stats->status_bits);
         }
     }

@@ -556,7 +556,7 @@ __device__ __forceinline__ void cta_flush(DevStats* stats, const cta_count_t* s_
                                           &stats->apodized, &stats->valid_out, &stats->alive_out};
         atomicAdd(dst[threadIdx.x], (unsigned long long)s_cnt[threadIdx.x]);
     }
-    if (threadIdx.x == 0 && s_status) atomicOr(&stats->status_bits, s_status);
+    if (threadIdx.x == 0 && s_status) { atomicOr(&stats->status_bits, s_status); atomicOr(&stats->sticky_bits, s_status); }
     if (threadIdx.x == 0 && s_first_inv) atomicMax(&stats->first_inv, s_first_inv);
 }
 

@@ -77,16 +77,20 @@ def reduce_spot_sums(p, device="cpu"):
     """phase 1 -> global sums (fields of an OpmSpotPartial-like object are updated in place)"""
     sums = _reduce(list(p.sum), dist.ReduceOp.SUM, device)
     n = _reduce([int(p.n_valid), int(p.n_total)], dist.ReduceOp.SUM, device, torch.int64)
-    # bounce level = bounce count of the first valid ray (rays.rs:183-194): ids are local to a shard and shards are
-    # ordered by rank, so the global first valid ray is the first one of the lowest rank that has any
+    # bounce level = bounce count of the first valid ray (rays.rs:183-194).  Ray ids are GLOBAL source indices, so the first
+    # valid ray of the whole bundle is the one with the smallest id on any rank, whatever the partition (contiguous or
+    # interleaved); ties go to the lowest rank.  Same rule as the device path (opm_readout_combine_ranges_sums).
     rank = world()[0]
     big = (1 << 62)
-    key = ((rank << 32) | (int(p.first_key) & 0xFFFFFFFF)) if int(p.n_valid) > 0 else big
-    key = -_reduce([-key], dist.ReduceOp.MAX, device, torch.int64)[0]
+    has = int(p.n_valid) > 0 and int(p.first_key) != 0xFFFFFFFFFFFFFFFF
+    my_id = (int(p.first_key) >> 32) if has else big
+    min_id = -_reduce([-my_id], dist.ReduceOp.MAX, device, torch.int64)[0]
+    cand = ((rank << 32) | (int(p.first_key) & 0xFFFFFFFF)) if (has and my_id == min_id) else big
+    cand = -_reduce([-cand], dist.ReduceOp.MAX, device, torch.int64)[0]
     for j in range(7):
         p.sum[j] = sums[j]
     p.n_valid, p.n_total = n
-    p.first_key = 0xFFFFFFFFFFFFFFFF if key >= big else key
+    p.first_key = 0xFFFFFFFFFFFFFFFF if min_id >= big else ((min_id << 32) | (cand & 0xFFFFFFFF))
     return p
 
 
@@ -182,6 +186,12 @@ class DetectorReadout:
 
     def launch(self, download_maps: bool = False, slot: int = 0):
         """queue the whole read-out and its device->host copies on the current stream; nothing waits"""
+        # the library's kernels run on the context's stream; the torch side of the chain (collectives, status reset, pinned
+        # copies, the completion event) must be ordered with them: everything below is issued on that very stream
+        with torch.cuda.stream(torch.cuda.ExternalStream(self.ctx.stream, device=self.buf.device)):
+            self._launch(download_maps, slot)
+
+    def _launch(self, download_maps: bool, slot: int):
         L, C, F = self.F.lib(), self.C, self.F
         from .api import _check
         rank, w = world()

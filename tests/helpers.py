@@ -108,10 +108,22 @@ def assert_hits_match(gpu_xyzeb, ref_hits: np.ndarray, rtol=RTOL):
     assert (np.abs(e - ref_hits["e"]) / np.maximum(np.abs(ref_hits["e"]), 1e-30)).max() <= rtol
 
 
-def assert_map_match(gpu_map, ref_map, rtol=RTOL):
-    """fluence maps within 1e-9 relative per bin, absolute floor 1e-9 * peak."""
+def assert_map_match(gpu_map, ref_map, rtol=RTOL, floor=1e-12, what="fluence map"):
+    """BASELINE north_star: fluence maps within 1e-9 RELATIVE per bin.  Every bin is compared against its own value; bins below
+    `floor` x peak (1e-12: empty bins, and bins that hold nothing but the far tail of one tap) against floor x peak.  The worst
+    relative error is part of the failure message."""
     assert gpu_map.shape == ref_map.shape
-    peak = np.nanmax(np.abs(ref_map)) if ref_map.size else 0.0
-    err = np.abs(gpu_map - ref_map)
-    tol = rtol * np.maximum(np.abs(ref_map), peak)
-    assert np.all(err <= tol), f"fluence map max err {np.max(err / np.maximum(tol, 1e-300)):.3e} x tol"
+    if ref_map.size == 0:
+        return 0.0
+    nan_g, nan_r = np.isnan(gpu_map), np.isnan(ref_map)
+    assert np.array_equal(nan_g, nan_r), f"{what}: NaN bins differ"
+    same_inf = np.isinf(ref_map) & (gpu_map == ref_map)
+    skip = nan_r | same_inf
+    g, r = np.where(skip, 0.0, gpu_map), np.where(skip, 0.0, ref_map)
+    peak = np.max(np.abs(r[np.isfinite(r)])) if np.isfinite(r).any() else 0.0
+    rel = np.abs(g - r) / np.maximum(np.abs(r), floor * peak if peak > 0 else 1e-300)
+    worst = float(rel.max())
+    k = np.unravel_index(int(rel.argmax()), rel.shape)
+    assert worst <= rtol, (f"{what}: worst relative bin error {worst:.3e} at {k} (ref {r[k]:.6e} = {r[k] / peak if peak else 0:.2e} of the peak, "
+                           f"got {g[k]:.6e}); {int((rel > rtol).sum())} of {rel.size} bins above {rtol:g}")
+    return worst

@@ -56,7 +56,9 @@ def test_cuda_matches_golden(name, strict):
             assert np.allclose(fd.lrtb, gold[f"lrtb_{node}"], rtol=RTOL, atol=0.0)
             if tuple(fd.lrtb) == tuple(gold[f"lrtb_{node}"]):
                 assert_map_match(fd.map, gold[f"map_{node}"])
-            assert fd.total_energy == pytest.approx(float(gold[f"total_{node}"]), rel=1e-6)
+            same = ob.fluence_binning(ctx, sc.node_hitmaps(node, 0), *mg.MAP, lrtb=tuple(gold[f"lrtb_{node}"]))
+            assert_map_match(same.map, gold[f"map_{node}"], what=f"{name} node {node} on the golden grid")
+            assert fd.total_energy == pytest.approx(float(gold[f"total_{node}"]), rel=RTOL)
         if det["spot"] is not None:
             s = sc.node_spot(det["spot"])
             g = gold["spot"]
@@ -86,6 +88,6 @@ def test_cuda_matches_golden_ghost_focus():
             for surf in (0, 1):
                 ref = gold["peaks"][node, surf]
                 got = sc.node_peak_fluence(node, surf)
-                assert (got == pytest.approx(ref, rel=1e-6)) if np.isfinite(ref) else not np.isfinite(got)
+                assert (got == pytest.approx(ref, rel=RTOL)) if np.isfinite(ref) else not np.isfinite(got)
     finally:
         ctx.close()

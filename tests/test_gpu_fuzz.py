@@ -122,8 +122,11 @@ def test_random_scene_matches_oracle(ctx, seed):
                 fd = psc.node_fluence(node)
                 assert np.allclose(fd.lrtb, lrtb, rtol=RTOL, atol=1e-18), what
                 if fd.lrtb == lrtb:
-                    assert_map_match(fd.map, fmap)
-                assert fd.total_energy == pytest.approx(tot, rel=1e-6 if fd.lrtb != lrtb else RTOL), what
+                    assert_map_match(fd.map, fmap, what=what)
+                # the product's hit map on the oracle's grid: bins one to one in every kernel build
+                same = ob.fluence_binning(ctx, psc.node_hitmaps(node, 0), 100, 83, lrtb=lrtb)
+                assert_map_match(same.map, fmap, what=what + " (oracle's grid)")
+                assert fd.total_energy == pytest.approx(tot, rel=RTOL), what
             if any(n["kind"] == "beam_splitter" for n in nodes):  # the second output, traced through its side chain
                 sp = [n["kind"] for n in nodes].index("beam_splitter")
                 assert_rays_match(psc.node_rays(sp).to_array(), osc.chain_out[_side_start(nodes, sp)], what=what + " side arm")

@@ -207,6 +207,25 @@ def test_refract_errors_match_reference(ctx):
     assert eg.value.code == F.OPM_ERR_COATING
 
 
+def test_async_launch_errors_surface_at_synchronize(ctx):
+    """a launch that does not read its statistics back (sync=False: throughput runs, OPM_SCENE_ASYNC) cannot return the error on
+    which the reference aborts (rays.rs:987-991); the status bits stay on the device across later launches and come back from
+    Context.synchronize -- once"""
+    _, sg = surface_pair(F.GEOM_PLANE, iso=iso_pair((0, 0, mm(10.0))))
+    _, ig = index_pair("sellmeier1", *HK9L, nm(500.0), nm(2000.0))
+    bad = ob.Rays.from_array(ctx, make_bundle(64, wvl=(nm(400.0), nm(2100.0))))
+    good = ob.Rays.from_array(ctx, make_bundle(64, wvl=(nm(600.0), nm(1500.0))))
+    ctx.synchronize()
+    assert ob.Program().refract(sg, ig).run(bad, sync=False) is None
+    ob.Program().refract(sg, ig).run(good, sync=False)  # a clean launch afterwards clears nothing
+    with pytest.raises(ob.OpossumError) as e:
+        ctx.synchronize()
+    assert e.value.code == F.OPM_ERR_WVL_RANGE
+    ctx.synchronize()  # reported once
+    ob.Program().refract(sg, ig).run(good, sync=False)
+    ctx.check_errors()
+
+
 def test_mirror_drops_and_keeps_order(ctx):
     """refraction_intended = false (nodes/thin_mirror.rs:209-250, SURVEY C-1): the reflected bundle continues,
     invalid and missing rays leave the bundle; compact and in-place outputs agree"""

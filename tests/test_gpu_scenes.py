@@ -30,13 +30,22 @@ def run_both(ctx, nodes, src, **kw):
 
 
 def check_detector(osc, psc, node, nx=100, ny=83):
+    """FluenceDetector report vs the oracle.  (1) The product's own data-dependent map range agrees with the oracle's to 1e-9.
+    (2) The product's hit map binned into the ORACLE's grid (explicit range) is compared bin by bin at 1e-9 relative -- so every
+    kernel build is checked one to one, also when its bounding box differs from the oracle's in the last bit.  (3) When the two
+    boxes are bit-identical the product's own report is compared the same way."""
     fmap, lrtb, peak, tot = osc.node_fluence(node, nx, ny)
     fd = psc.node_fluence(node, nx, ny)
     assert np.allclose(fd.lrtb, lrtb, rtol=RTOL, atol=0.0)
-    if fd.lrtb == lrtb:  # identical bounding box: bins comparable one to one
-        assert_map_match(fd.map, fmap)
-    assert fd.peak == pytest.approx(peak, rel=1e-6 if fd.lrtb != lrtb else RTOL)
-    assert fd.total_energy == pytest.approx(tot, rel=1e-6 if fd.lrtb != lrtb else RTOL)
+    same = ob.fluence_binning(psc.ctx, psc.node_hitmaps(node, 0), nx, ny, lrtb=lrtb)
+    assert_map_match(same.map, fmap, what=f"node {node} map on the oracle's grid")
+    assert same.peak == pytest.approx(peak, rel=RTOL) and same.total_energy == pytest.approx(tot, rel=RTOL)
+    if fd.lrtb == lrtb:
+        assert_map_match(fd.map, fmap, what=f"node {node} map")
+        assert fd.peak == pytest.approx(peak, rel=RTOL) and fd.total_energy == pytest.approx(tot, rel=RTOL)
+    else:  # another grid (last-bit different range): the integral is grid independent, the peak moves with the bin edges
+        assert fd.total_energy == pytest.approx(tot, rel=RTOL)
+        assert fd.peak == pytest.approx(peak, rel=1e-6)
 
 
 @pytest.mark.parametrize("strict", [False, True], ids=["fast", "strict"])
@@ -167,14 +176,14 @@ def test_c3_ghost_focus(ctx, max_bounces):
             ref_peak = osc.nodes[node].s[surf].peak_seen
             got_peak = psc.node_peak_fluence(node, surf)
             if np.isfinite(ref_peak):
-                assert got_peak == pytest.approx(ref_peak, rel=1e-6), (node, surf)
+                assert got_peak == pytest.approx(ref_peak, rel=RTOL), (node, surf)
             else:
                 assert not np.isfinite(got_peak)
             ref_crit = sorted((pk, b) for pk, b in osc.nodes[node].s[surf].critical.values())
             got_crit = sorted((pk, b) for _, pk, b in psc.node_critical_fluences(node, surf))
             assert len(ref_crit) == len(got_crit)
             for (a, ab), (b, bb) in zip(ref_crit, got_crit):
-                assert ab == bb and b == pytest.approx(a, rel=1e-6)
+                assert ab == bb and b == pytest.approx(a, rel=RTOL)
 
 
 def test_sharded_trace_equals_whole_source(ctx):

@@ -101,8 +101,19 @@ def _worker(rank, world_size, port, q):
         blocks_ok = (torch.equal(B[: NX * NY].reshape(t.shape), t) and float(B[NX * NY]) == p.max_d2_mm2 and
                      abs(float(B[NX * NY + 1]) - p.sum_d2_mm2) <= 1e-12 * p.sum_d2_mm2 and int(A[13]) == 0 and int(A[14]) == 0 and
                      (-float(A[0]), float(A[1]), float(A[2]), -float(A[3])) == tuple(lrtb))
+        # interleaved shards (sharding.shard_strided): the first valid ray of the whole bundle can sit on any rank -- rank 0's first
+        # valid ray is id 4 (5 bounces), rank 1's is id 1 (2 bounces): the bundle's bounce level is 2 on both paths
+        ps = F.OpmSpotPartial()
+        ps.n_valid = ps.n_total = 1
+        ps.first_key = ((4 << 32) | 5) if rank == 0 else ((1 << 32) | 2)
+        sharding.reduce_spot_sums(ps)
+        rows = torch.zeros((2, 11), dtype=torch.float64)
+        rows[0, 7], rows[0, 9], rows[0, 10] = 1, 5, 4
+        rows[1, 7], rows[1, 9], rows[1, 10] = 1, 2, 1
+        As = sharding.combine_ranges_sums_reference(rows, 0, 1)
+        strided_ok = int(ps.first_key) == ((1 << 32) | 2) and int(As[9]) == 2 and int(As[10]) == 1
         if rank == 0:
-            q.put({"lrtb": lrtb, "map": t.numpy().copy(), "counts": counts, "energy": energy, "n_valid": st.n_valid,
+            q.put({"strided_ok": bool(strided_ok), "lrtb": lrtb, "map": t.numpy().copy(), "counts": counts, "energy": energy, "n_valid": st.n_valid,
                    "total_energy": st.total_energy, "centroid": list(st.energy_centroid), "geo": st.beam_radius_geo,
                    "rms": st.energy_beam_radius_rms, "bounce_lvl": st.bounce_lvl, "shard": (b, e), "blocks_ok": bool(blocks_ok)})
     finally:
@@ -147,6 +158,7 @@ def test_two_rank_reduction_equals_single_process():
     osc, out = _trace(src_all)
     fmap, lrtb = orc.fluence_binning(osc.nodes[3].s[0].merged_hits(), NX, NY)
     assert got["shard"] == (0, len(src_all) // 2)
+    assert got["strided_ok"]  # one rule for the bounce level on both multi-GPU paths: the smallest global ray id
     assert got["blocks_ok"]  # the gathered-block combination gives the same map, range, radii and first ray as the all-reduces
     assert got["lrtb"] == pytest.approx(lrtb, rel=0, abs=0)  # min/max are exact
     peak = fmap.max()
