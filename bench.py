@@ -99,46 +99,54 @@ class ClockSampler:
 _CPU = {}
 
 
-def _cpu_worker(k):
+def _cpu_worker(arg):
     import scenes
+    k, keep = arg
     src = _CPU["shards"][k]
     osc = _CPU.get("scene")
     if osc is None:
         osc = _CPU["scene"] = scenes.to_oracle(scenes.c2_laser_chain(), n_threads=1)
     t0 = time.perf_counter()
-    osc.raytrace(src, record_all=False)
-    for node in (9, 10):
-        osc.node_fluence(node, MAP_NX, MAP_NY)
-    osc.node_spot(8)
-    return osc.interactions, time.perf_counter() - t0
+    out = osc.raytrace(src, record_all=False)
+    maps = {node: osc.node_fluence(node, MAP_NX, MAP_NY) for node in (9, 10)}
+    spot = osc.node_spot(8)
+    dt = time.perf_counter() - t0
+    if keep:  # the shard the product is compared with (parity check of the bench's own workload; never inside a timed step)
+        return osc.interactions, dt, {"out": out, "side": osc.chain_out[10], "maps": maps, "spot": spot, "interactions": osc.interactions}
+    return osc.interactions, dt, None
 
 
 class CpuArm:
-    """The oracle's restatement of the reference's ray-trace analysis, sharded over `cores` worker processes."""
+    """The oracle's restatement of the reference's ray-trace analysis over the bench's OWN source (C2, `n_rays` rays, the same
+    FibonacciEllipse / General2DGaussian description the product generates on the device), sharded over `cores` worker
+    processes by source index i -> worker i mod cores (rays are independent: any partition is one analysis)."""
 
-    def __init__(self, rays_per_core: int, cores: int | None = None):
+    def __init__(self, n_rays: int, cores: int | None = None):
         import multiprocessing as mp
-
-        import numpy as np
 
         import scenes
         self.cores = cores or (len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else os.cpu_count() or 1)
-        self.n = rays_per_core * self.cores
+        self.n = n_rays
         src = scenes.source_to_oracle(scenes.c2_source(self.n))
-        _CPU["shards"] = np.array_split(src, self.cores)
+        _CPU["shards"] = [src[k::self.cores].copy() for k in range(self.cores)]
         _CPU.pop("scene", None)
         self.pool = mp.get_context("fork").Pool(self.cores) if self.cores > 1 else None
-        self.sample = (f"{self.n} rays of the C2 source ({rays_per_core} per worker process x {self.cores}), full chain + detector read-out; "
-                       "oracle port, per-surface passes over an AoS bundle like the reference")
+        self.sample = (f"the bench's own C2 source, all {self.n} rays, source index i -> worker process i mod {self.cores}; full chain + "
+                       "detector read-out per worker; oracle port, per-surface passes over an AoS bundle like the reference")
 
     def step(self):
         t0 = time.perf_counter()
-        res = self.pool.map(_cpu_worker, range(self.cores), chunksize=1) if self.pool else [_cpu_worker(0)]
+        args = [(k, False) for k in range(self.cores)]
+        res = self.pool.map(_cpu_worker, args, chunksize=1) if self.pool else [_cpu_worker(args[0])]
         dt = time.perf_counter() - t0
         return sum(r[0] for r in res), dt
 
+    def trace_kept(self, k=0):
+        """results of worker k's shard (untimed): final bundles, both maps, spot statistics"""
+        return (self.pool.apply(_cpu_worker, ((k, True),)) if self.pool else _cpu_worker((k, True)))[2]
+
     def single_thread(self):
-        inter, dt = _cpu_worker(0)
+        inter, dt, _ = _cpu_worker((0, False))
         return inter / dt
 
     def close(self):
@@ -151,7 +159,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    arm = CpuArm(args.cpu_rays_per_core)
+    arm = CpuArm(args.rays)
     for _ in range(args.warmup):
         arm.step()
     inter, dt = 0, 0.0
@@ -165,7 +173,8 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD_NAME, "rays_per_step": arm.n, "surfaces_per_ray": 13},
+        "config": {"workload": WORKLOAD_NAME, "rays_per_gpu": arm.n, "rays_total": arm.n, "surfaces_per_ray": 13,
+                   "fluence_map": f"{MAP_NX}x{MAP_NY} x2 (Binning, data-dependent range)"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": arm.cores, "kind": "port", "sample": arm.sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -200,6 +209,175 @@ def bind_to_gpu_numa_node(local: int) -> str:
         return "no numa information"
     except Exception as e:  # noqa: BLE001
         return f"not bound ({type(e).__name__})"
+
+
+def parity_vs_oracle(ctx, n, cores, kept):
+    """Untimed check of the bench's own workload against the CPU oracle: the product traces the shard of the 10^7-ray source one
+    CPU worker traced (source indices 0, cores, 2 cores, ...) and is compared ray by ray (integer state bit-exact, positions /
+    directions / energies / OPL at 1e-9 relative), both fluence maps bin by bin on the oracle's grid (1e-9 relative for bins
+    >= 1e-12 of the peak) and the spot statistics."""
+    import numpy as np
+
+    import opossum_b200 as ob
+    import scenes
+    sc = scenes.to_product(ctx, scenes.c2_laser_chain())
+    count = (n + cores - 1) // cores
+    rays = scenes.source_to_product(scenes.c2_source(n)).generate_strided(ctx, 0, count, cores)
+    ctx.set_jit(2, 200000)  # the specialised kernel (the one the timed steps run), waiting for its compilation
+    st = sc.raytrace(rays)
+    out = {"rays_traced": count, "kernel": "opm_jit_trace" if ctx.jit_stats()["launches"] else "interpreter"}
+
+    def rays_err(got, ref):
+        if len(got) != len(ref):
+            return {"len": [len(got), len(ref)]}
+        e = {"int_state_equal": bool(all(np.array_equal(got[f], ref[f]) for f in ("id", "valid", "bounces", "refr")))}
+        sp = np.maximum(np.linalg.norm(ref["pos"], axis=1), 1e-3)
+        e["pos"] = float((np.linalg.norm(got["pos"] - ref["pos"], axis=1) / sp).max())
+        e["dir"] = float(np.linalg.norm(got["dir"] - ref["dir"], axis=1).max())
+        for f, floor in (("e", 1e-30), ("opl", 1e-12)):
+            e[f] = float((np.abs(got[f] - ref[f]) / np.maximum(np.abs(ref[f]), floor)).max())
+        return e
+
+    out["main_bundle"] = rays_err(rays.to_array(), kept["out"])
+    out["split_off_bundle"] = rays_err(sc.node_rays(5).to_array(), kept["side"])
+    worst_bin = 0.0
+    for node in (9, 10):
+        fmap, lrtb, peak, tot = kept["maps"][node]
+        fd = ob.fluence_binning(ctx, sc.node_hitmaps(node, 0), MAP_NX, MAP_NY, lrtb=lrtb)
+        filled = np.abs(fmap) >= 1e-12 * np.abs(fmap).max()
+        rel = float((np.abs(fd.map - fmap)[filled] / np.abs(fmap)[filled]).max())
+        low = float(np.abs(fd.map - fmap)[~filled].max() / np.abs(fmap).max()) if (~filled).any() else 0.0
+        out[f"map_{node}"] = {"worst_rel_bin": rel, "below_floor_abs_over_peak": low, "peak_rel": abs(fd.peak - peak) / peak,
+                              "bbox_rel": float(max(abs(a - b) / abs(b) for a, b in zip(sc.node_fluence(node, MAP_NX, MAP_NY, download=False).lrtb, lrtb)))}
+        worst_bin = max(worst_bin, rel, low * 1e3)
+    s, r = sc.node_spot(8), kept["spot"]
+    out["spot"] = {"n_valid_equal": bool(s.n_valid == r["n_valid"]), "total_energy": abs(s.total_energy - r["total_energy"]) / r["total_energy"],
+                   "geo_radius": abs(s.beam_radius_geo - r["geo"]) / r["geo"], "rms_radius": abs(s.energy_beam_radius_rms - r["rms"]) / r["rms"]}
+    rb = [out["main_bundle"], out["split_off_bundle"]]
+    out["ok"] = bool(all("len" not in e and e["int_state_equal"] and max(e["pos"], e["dir"], e["e"], e["opl"]) <= 1e-9 for e in rb)
+                     and worst_bin <= 1e-9 and out["spot"]["n_valid_equal"]
+                     and max(out["spot"]["total_energy"], out["spot"]["geo_radius"], out["spot"]["rms_radius"]) <= 1e-9
+                     and st.interactions == kept_interactions(kept))
+    ctx.set_jit(1, 200000)
+    return out
+
+
+def kept_interactions(kept):
+    return kept.get("interactions", 0)
+
+
+C4_SIDE, C4_NX, C4_NY = 10_000, 4096, 4096
+
+
+def run_c4_strong(args, ctx, dev, stream, rank, world):
+    """BASELINE configs[3], the north-star scaling config: 10^8 rays IN TOTAL (grid 10^4 x 10^4) sharded over the ranks by
+    contiguous source-index ranges, lens + fluence detector, one 4096 x 4096 Binning map of all hits.  A step = trace of the
+    rank's shard + the detector read-out (common data-dependent range, windowed binning, column-slice merge over NVLink peer
+    memory, peak / total on every rank).  Strong scaling: total work fixed.  With N > 1 rank 0 also runs the WHOLE job alone in
+    the same process (untimed region of the others), which gives the speed-up basis on the same box and the parity reference
+    for the merged map."""
+    import torch
+    import torch.distributed as dist
+
+    import scenes
+    from opossum_b200 import sharding
+    steps = max(3, min(args.steps, 10))
+    n_total = C4_SIDE * C4_SIDE
+
+    def setup(first, count, peer, solo=False):
+        scene = scenes.to_product(ctx, scenes.c4_fluence())
+        src = scenes.source_to_product(scenes.c4_source(C4_SIDE)).generate(ctx, first, first + count)
+        st = scene.raytrace(src, keep_source=True, snapshots=False)
+        ro = sharding.DetectorReadout(ctx, scene, (2,), (), C4_NX, C4_NY, dev, peer=peer, solo=solo)
+        return scene, src, ro, st
+
+    def timed(scene, src, ro, barrier):
+        def step():
+            scene.raytrace(src, keep_source=True, snapshots=False, sync=False)
+            ro.launch(False, 0)
+        for _ in range(3):
+            step()
+        ro.collect(0)
+        barrier()
+        ctx.set_kernel_timing(True)
+        ctx.kernel_timing(reset=True)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(steps):
+            step()
+        e1.record(stream)
+        rep = ro.collect(0)
+        barrier()
+        ms = e0.elapsed_time(e1) / steps
+        kms, _ = ctx.kernel_timing(reset=True)
+        ctx.set_kernel_timing(False)
+        return ms, kms / steps, rep[2]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    b, e = sharding.shard_range(n_total, rank, world)
+    scene, src, ro, st = setup(b, e - b, None)
+    ctx.jit_wait()
+    ms, trace_ms, rep = timed(scene, src, ro, barrier)
+    t = torch.tensor([ms, trace_ms, float(st.interactions)], dtype=torch.float64, device=dev)
+    tsum = t.clone()
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+    ms, trace_ms, inter = t[0].item(), t[1].item(), tsum[2].item()
+    out = {"config": "C4: 10^8 rays total (grid 10^4 x 10^4, contiguous source-index shards), lens + fluence detector, 4096 x 4096 Binning "
+                     "map, data-dependent range", "scaling": "strong", "n_gpus": world, "rays_total": n_total, "rays_per_gpu": e - b,
+           "steps": steps, "ms_per_step": ms, "interactions_per_s": inter / (ms * 1e-3), "trace_ms": trace_ms, "readout_ms": ms - trace_ms,
+           "readout": ("bounding box kept by the trace kernel, zero-fill + run-merging splat, peak/total" if world == 1 else
+                       ("windowed splat + column-slice merge over NVLink peer memory, 3 flag meetings, no NCCL" if ro.peer is not None
+                        else "NCCL all-reduce of the whole map (peer memory unavailable)")),
+           "check": {"peak_J_m2": rep["peak"], "total_energy_J": rep["total_energy"], "lrtb": list(rep["lrtb"])}}
+    if world > 1:
+        # the collective part alone: three meetings of the ranks (what replaces all_gather + all_reduce + all_gather)
+        if ro.peer is not None:
+            blk = torch.zeros(4, dtype=torch.float64, device=dev)
+            got = torch.zeros((world, 4), dtype=torch.float64, device=dev)
+            for _ in range(3):
+                ro.peer[0].allgather(blk, got)
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            for _ in range(30):
+                ro.peer[0].allgather(blk, got)
+            e1.record(stream)
+            barrier()
+            tm = torch.tensor([e0.elapsed_time(e1) / 30], dtype=torch.float64, device=dev)
+            dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+            out["collective_ms"] = 3 * tm.item()
+            out["meeting_us"] = 1e3 * tm.item()
+        # merged map on rank 0 (gathered from the column slices) for the parity check below
+        merged = ro.run(download_maps=True)[2]
+        barrier()
+        del ro, src, scene
+        if rank == 0:  # the whole job on one GPU of the same box: speed-up basis + parity reference
+            scene1, src1, ro1, st1 = setup(0, n_total, False, solo=True)
+            ms1, trace1, rep1 = timed(scene1, src1, ro1, lambda: torch.cuda.synchronize())
+            ref = ro1.run(download_maps=True)[2]
+            import numpy as np
+            nz = ref["map"] > 0
+            rel = float((np.abs(merged["map"] - ref["map"])[nz] / ref["map"][nz]).max())
+            out["n1_same_box"] = {"ms_per_step": ms1, "trace_ms": trace1, "readout_ms": ms1 - trace1, "interactions_per_s": st1.interactions / (ms1 * 1e-3)}
+            out["speedup_vs_n1_basis"] = ms1 / ms
+            out["parity_vs_n1"] = {"map_worst_rel_bin": rel, "filled_bins_equal": bool(np.array_equal(nz, merged["map"] > 0)),
+                                   "range_equal": bool(tuple(merged["lrtb"]) == tuple(ref["lrtb"])),
+                                   "peak_rel": abs(merged["peak"] - ref["peak"]) / ref["peak"],
+                                   "total_rel": abs(merged["total_energy"] - ref["total_energy"]) / ref["total_energy"],
+                                   "interactions_equal": bool(int(inter) == st1.interactions),
+                                   "ok": bool(rel <= 1e-12 and tuple(merged["lrtb"]) == tuple(ref["lrtb"]) and int(inter) == st1.interactions)}
+            del ro1, src1, scene1
+        barrier()
+    else:
+        out["collective_ms"] = 0.0
+        out["speedup_vs_n1_basis"] = 1.0
+    return out
 
 
 def run_product(args):
@@ -359,6 +537,35 @@ def run_product(args):
         fp64_peak = ctx.measure_fp64_peak() if rank == 0 else 0.0
         jit = ctx.jit_stats()
 
+        # ---- N > 1: the merged reports of the sharded run against ONE GPU tracing the whole global source (untimed)
+        parity_n1 = None
+        if world > 1:
+            merged = readout.run(download_maps=True)
+            barrier()
+            if rank == 0:
+                scene_g = scenes.to_product(ctx, scenes.c2_laser_chain())
+                src_g = sd.generate(ctx)
+                scene_g.raytrace(src_g, keep_source=True)
+                solo = sharding.DetectorReadout(ctx, scene_g, (9, 10), (8,), MAP_NX, MAP_NY, dev, solo=True).run(download_maps=True)
+                worst = 0.0
+                for node in (9, 10):
+                    a, b = merged[node]["map"], solo[node]["map"]
+                    nz = b > 0
+                    worst = max(worst, float((np.abs(a - b)[nz] / b[nz]).max()), 0.0 if np.array_equal(nz, a > 0) else 1.0)
+                    worst = max(worst, 0.0 if tuple(merged[node]["lrtb"]) == tuple(solo[node]["lrtb"]) else 1.0)
+                sa, sb = merged[8], solo[8]
+                spot_rel = max(abs(sa.total_energy - sb.total_energy) / sb.total_energy, abs(sa.beam_radius_geo - sb.beam_radius_geo) / sb.beam_radius_geo,
+                               abs(sa.energy_beam_radius_rms - sb.energy_beam_radius_rms) / sb.energy_beam_radius_rms)
+                parity_n1 = {"what": f"reports of the {world}-GPU run vs the same {n * world}-ray source traced by GPU 0 alone",
+                             "maps_worst_rel_bin": worst, "spot_worst_rel": spot_rel, "spot_n_valid_equal": bool(sa.n_valid == sb.n_valid),
+                             "bounce_lvl_equal": bool(sa.bounce_lvl == sb.bounce_lvl),
+                             "ok": bool(worst <= 1e-12 and spot_rel <= 1e-12 and sa.n_valid == sb.n_valid and sa.bounce_lvl == sb.bounce_lvl)}
+                del scene_g, src_g
+            barrier()
+
+        # ---- BASELINE configs[3]: the north-star strong-scaling config (10^8 rays total, 4096^2 map)
+        c4 = None if args.no_c4 else run_c4_strong(args, ctx, dev, stream, rank, world)
+
     if rank == 0:
         peaks_file = ROOT / "MEASURED_PEAKS.json"
         if peaks_file.exists():
@@ -416,22 +623,29 @@ def run_product(args):
                                   "achieved_tflops_model": inter_per_step * flop_per_inter / (kern_ms_step * 1e-3) / 1e12}},
             "check": {"fluence_peak_J_m2": {str(k): v[0] for k, v in check.items() if k != "spot"},
                       "detector_energy_J": {str(k): v[1] for k, v in check.items() if k != "spot"}, "spot_valid_rays": check["spot"][0]},
+            "c4_strong": c4,
         }
+        if parity_n1 is not None:
+            line["parity_vs_one_gpu"] = parity_n1
     if world > 1:
         dist.barrier()
     # ---- cpu_baseline on rank 0 at N = 1 (test infrastructure timed beside the product; never on the product path)
     if rank == 0:
         if world == 1 and not args.no_cpu_baseline:
-            arm = CpuArm(args.cpu_rays_per_core)
+            arm = CpuArm(n)
             arm.step()
             best = 0.0
             for _ in range(2):
                 i, dt = arm.step()
                 best = max(best, i / dt)
             one = arm.single_thread()
+            kept = arm.trace_kept(0)
             arm.close()
             line["cpu_baseline"] = {"value": best, "unit": UNIT, "cores": arm.cores, "kind": "port", "sample": arm.sample,
                                     "single_thread_value": one}
+            # the same workload, product against oracle (the oracle as the checker)
+            with torch.cuda.stream(stream):
+                line["parity_vs_oracle"] = parity_vs_oracle(ctx, n, arm.cores, kept)
         else:
             line["cpu_baseline"] = None
         print(json.dumps(line))
@@ -447,7 +661,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="product", choices=["product", "reference"])
     ap.add_argument("--rays", type=int, default=10_000_000, help="rays per GPU (BASELINE.json configs[1]: 10^7)")
-    ap.add_argument("--cpu-rays-per-core", type=int, default=1_000_000)
+    ap.add_argument("--no-c4", action="store_true", help="skip the C4 strong-scaling object")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "product" else args.warmup

@@ -62,7 +62,8 @@ enum {
     OPM_ERR_KDE_BANDWIDTH = 15,  /* "bandwidth must be != 0.0 and finite"                      kde/mod.rs:36-42 */
     OPM_ERR_SPECTRUM = 16,       /* OpossumError::Spectrum; "wavelength of ray outside filter spectrum" ray.rs:716-720, :757-761;
                                     "ray bundle is empty - cannot create spectrum" rays.rs:1216-1220 */
-    OPM_ERR_EMPTY_WAVEFRONT = 17 /* "Empty wavefront-data vector!"                             nodes/wavefront.rs:121-123 */
+    OPM_ERR_EMPTY_WAVEFRONT = 17,/* "Empty wavefront-data vector!"                             nodes/wavefront.rs:121-123 */
+    OPM_ERR_PEER_TIMEOUT = 18    /* multi-GPU read-out: a peer rank did not arrive at a meeting in time (no reference counterpart) */
 };
 
 /* ------------------------------------------------------------------------------------------
@@ -491,6 +492,35 @@ OpmStatus opm_readout_combine_ranges_sums(OpmContext* ctx, const double* gathere
                                           double* out_dev);
 OpmStatus opm_readout_combine_maps_radii(OpmContext* ctx, const double* gathered_dev, int32_t world, uint64_t maps_len, int32_t n_spot,
                                          double* out_dev);
+
+/* ---- multi-GPU read-out of a LARGE fluence map over NVLink peer memory (opossum_b200/csrc/opm_peer.cu) ---------------
+ * The merge of the per-rank hit maps (hit_map/mod.rs:363-379) with the common data-dependent range (rays_hit_map.rs:522-562) when
+ * the hits are sharded over the GPUs of one box, one process per GPU.  Instead of an all-reduce of the whole map, every rank bins
+ * into the map columns its own hits span (its window), owns a slice of the columns and sums the overlapping windows of its peers
+ * by reading their memory directly; the ranks synchronise through flags in each other's memory.  Results: range, peak and total
+ * on every rank, the map distributed by column slices (gathered on demand).
+ *   create  : allocates this rank's exchange segment (control block + two buffers of map_bins doubles) and returns its CUDA IPC
+ *             handle (OPM_IPC_HANDLE_BYTES bytes);
+ *   connect : `handles` = the handles of all ranks in rank order (exchanged by the launcher: torch.distributed, MPI, a file);
+ *             maps every peer's segment into this process.  world == 1 needs no handles (NULL). */
+#define OPM_IPC_HANDLE_BYTES 64
+typedef struct OpmPeerGroup OpmPeerGroup;
+OpmStatus opm_peer_group_create(OpmContext* ctx, int32_t rank, int32_t world, uint64_t map_bins, OpmPeerGroup** out,
+                                uint8_t handle_out[OPM_IPC_HANDLE_BYTES]);
+OpmStatus opm_peer_group_connect(OpmPeerGroup* group, const uint8_t* handles);
+void opm_peer_group_destroy(OpmPeerGroup* group);
+/* one meeting of the ranks: all-gather of n <= 32 doubles (out_dev: world x n), also a barrier; asynchronous on the stream.
+ * A rank that waits longer than the group's time limit (default 20 s) gives up and raises OPM_ERR_PEER_TIMEOUT in the sticky
+ * status (opm_context_synchronize) instead of hanging the GPU. */
+OpmStatus opm_peer_allgather_async(OpmPeerGroup* group, const double* block_dev, int32_t n, double* out_dev);
+/* FluenceDetector report (Binning) of hit maps sharded over the ranks: range_dev[4] = (-left, right, top, -bottom) and
+ * peak_total_dev[2] on every rank; asynchronous, three meetings.  status_dev accumulates OpmStatus bits like
+ * opm_fluence_binning_async. */
+OpmStatus opm_peer_fluence_report_async(OpmPeerGroup* group, OpmHitMap* const* maps, int32_t n_maps, int64_t bounce_filter, uint64_t nx,
+                                        uint64_t ny, double* range_dev, double* peak_total_dev, uint32_t* status_dev);
+/* the whole map (nx * ny, column-major ny x nx) of the LAST report into map_dev on this rank: every rank's column slice is copied
+ * from its memory.  The ranks must not start another report before the copy has run (the caller's barrier). */
+OpmStatus opm_peer_fluence_gather_map(OpmPeerGroup* group, uint64_t nx, uint64_t ny, double* map_dev);
 
 /* measured FP64 FMA throughput of the device in TFLOP/s (FMA = 2 flop): roofline denominator of the fused trace kernel */
 OpmStatus opm_measure_fp64_peak(OpmContext* ctx, double* tflops);

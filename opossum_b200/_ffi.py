@@ -20,7 +20,7 @@ OPM_MAX_PROGRAM_OPS = 128
 (OPM_OK, OPM_ERR_N2_INVALID, OPM_ERR_WVL_RANGE, OPM_ERR_INDEX_MODEL, OPM_ERR_COATING, OPM_ERR_APODIZE_FACTOR,
  OPM_ERR_THRESHOLD, OPM_ERR_HITPOINT, OPM_ERR_SPLIT_RATIO, OPM_ERR_FOCAL_LENGTH, OPM_ERR_EMPTY_HITMAP,
  OPM_ERR_BIN_RANGE, OPM_ERR_ARG, OPM_ERR_CAPACITY, OPM_ERR_CUDA, OPM_ERR_KDE_BANDWIDTH,
- OPM_ERR_SPECTRUM, OPM_ERR_EMPTY_WAVEFRONT) = range(18)
+ OPM_ERR_SPECTRUM, OPM_ERR_EMPTY_WAVEFRONT, OPM_ERR_PEER_TIMEOUT) = range(19)
 
 GEOM_PLANE, GEOM_SPHERE, GEOM_CYLINDER, GEOM_PARABOLA = range(4)
 COAT_IDEAL_AR, COAT_CONSTANT_R, COAT_FRESNEL = range(3)
@@ -228,7 +228,8 @@ EXPORTS = [
     "opm_fluence_binning_async", "opm_fluence_peak_total_async", "opm_fluence_kde",
     "opm_spectrum_create", "opm_spectrum_destroy", "opm_spectrum_total_energy", "opm_spectrum_center_wavelength", "opm_spectrum_get_value",
     "opm_rays_wavelength_range", "opm_rays_to_spectrum", "opm_rays_filter_energy_spectrum", "opm_rays_split_spectrum",
-    "opm_rays_wavefront_error", "opm_readout_combine_ranges_sums", "opm_readout_combine_maps_radii", "opm_measure_fp64_peak", "opm_device_alloc",
+    "opm_rays_wavefront_error", "opm_readout_combine_ranges_sums", "opm_readout_combine_maps_radii", "opm_peer_group_create", "opm_peer_group_connect", "opm_peer_group_destroy",
+    "opm_peer_allgather_async", "opm_peer_fluence_report_async", "opm_peer_fluence_gather_map", "opm_measure_fp64_peak", "opm_device_alloc",
     "opm_device_free", "opm_device_memset", "opm_device_to_host", "opm_host_to_device", "opm_host_alloc_pinned", "opm_host_free_pinned",
     "opm_spectrum_gaussian", "opm_source_generate", "opm_source_generate_strided", "opm_source_energy_norm",
 ]
@@ -332,6 +333,12 @@ def lib() -> C.CDLL:
         "opm_rays_split_spectrum": (i32, [vp, vp, vp]),
         "opm_readout_combine_ranges_sums": (i32, [vp, vp, i32, i32, i32, vp]),
         "opm_readout_combine_maps_radii": (i32, [vp, vp, i32, u64, i32, vp]),
+        "opm_peer_group_create": (i32, [vp, i32, i32, u64, pp, vp]),
+        "opm_peer_group_connect": (i32, [vp, vp]),
+        "opm_peer_group_destroy": (None, [vp]),
+        "opm_peer_allgather_async": (i32, [vp, vp, i32, vp]),
+        "opm_peer_fluence_report_async": (i32, [vp, vp, i32, C.c_int64, u64, u64, vp, vp, vp]),
+        "opm_peer_fluence_gather_map": (i32, [vp, u64, u64, vp]),
         "opm_rays_wavefront_error": (i32, [vp, C.POINTER(OpmIsometry), C.c_double, dp, u64, C.POINTER(OpmWavefrontStats)]),
         "opm_rays_bounce_lvl": (i32, [vp, C.POINTER(C.c_uint32)]),
         "opm_rays_tally": (i32, [vp, C.c_uint32, C.POINTER(u64), dp]),

@@ -14,6 +14,7 @@
 
 #include "opm_internal.h"
 #include "opm_kernels.h"
+#include "opm_peer.h"
 #include "../../include/opossum_b200_scene.h"
 
 using namespace opm;
@@ -183,6 +184,7 @@ extern "C" const char* opm_status_string(OpmStatus s) {
         case OPM_ERR_KDE_BANDWIDTH: return "bandwidth must be != 0.0 and finite";
         case OPM_ERR_SPECTRUM: return "spectrum: wavelength outside the spectrum, no valid rays, or invalid range / resolution";
         case OPM_ERR_EMPTY_WAVEFRONT: return "Empty wavefront-data vector!";
+        case OPM_ERR_PEER_TIMEOUT: return "multi-GPU read-out: a peer rank did not arrive at a meeting in time";
         default: return "unknown status";
     }
 }
@@ -1478,6 +1480,144 @@ extern "C" OpmStatus opm_readout_combine_maps_radii(OpmContext* c, const double*
     if (!c || !gathered_dev || !out_dev || world < 1 || n_spot < 0) return fail(OPM_ERR_ARG, "bad argument");
     CU(cudaSetDevice(c->device));
     KL(k_readout_combine_b(gathered_dev, world, maps_len, n_spot, out_dev, c->sms, c->stream)); c->launches++;
+    return OPM_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// multi-GPU read-out over NVLink peer memory (opm_peer.cu)
+// ---------------------------------------------------------------------------------------------
+static OpmStatus check_same_ctx(OpmHitMap* const* maps, int n_maps, OpmContext** ctx);
+struct OpmPeerGroup {
+    OpmContext* ctx = nullptr;
+    int rank = 0, world = 1;
+    uint64_t map_bins = 0;
+    unsigned char* seg = nullptr;           // this rank's segment: [PeerCtrl | part | final]
+    void* peer_seg[kMaxPeers] = {};         // every rank's segment as mapped here (own: seg)
+    bool connected = false;
+    PeerView view{};
+    unsigned long long seq = 0;
+    unsigned long long timeout_ns = 20ull * 1000 * 1000 * 1000;
+    double* d_work = nullptr;               // [own range 4 | all ranges world x 4 | range 4 | peak block 2 | gathered peaks world x 2 | token 1 | gathered tokens world]
+};
+static size_t peer_seg_bytes(uint64_t bins) { return kPeerCtrlBytes + 2 * align_up(bins * sizeof(double), 256); }
+static double* peer_final(const OpmPeerGroup* g, int r) {
+    return (double*)((unsigned char*)g->peer_seg[r] + kPeerCtrlBytes + align_up(g->map_bins * sizeof(double), 256));
+}
+extern "C" OpmStatus opm_peer_group_create(OpmContext* c, int32_t rank, int32_t world, uint64_t map_bins, OpmPeerGroup** out,
+                                           uint8_t handle_out[OPM_IPC_HANDLE_BYTES]) {
+    if (!c || !out || world < 1 || world > kMaxPeers || rank < 0 || rank >= world || map_bins == 0)
+        return fail(OPM_ERR_ARG, "peer group: rank %d of %d (max %d ranks), %llu bins", rank, world, kMaxPeers, (unsigned long long)map_bins);
+    static_assert(sizeof(cudaIpcMemHandle_t) == OPM_IPC_HANDLE_BYTES, "CUDA IPC handle size");
+    CU(cudaSetDevice(c->device));
+    OpmPeerGroup* g = new OpmPeerGroup();
+    g->ctx = c; g->rank = rank; g->world = world; g->map_bins = map_bins;
+    if (const char* e = getenv("OPM_B200_PEER_TIMEOUT_MS")) g->timeout_ns = strtoull(e, nullptr, 10) * 1000000ull;
+    cudaError_t e = cudaMalloc(&g->seg, peer_seg_bytes(map_bins));
+    if (e == cudaSuccess) e = cudaMemset(g->seg, 0, kPeerCtrlBytes);
+    if (e == cudaSuccess) e = cudaMalloc(&g->d_work, (size_t)(16 + 8 * kMaxPeers) * sizeof(double));
+    if (e == cudaSuccess) e = cudaMemset(g->d_work, 0, (size_t)(16 + 8 * kMaxPeers) * sizeof(double));
+    if (e == cudaSuccess && world > 1 && handle_out) e = cudaIpcGetMemHandle((cudaIpcMemHandle_t*)handle_out, g->seg);
+    if (e != cudaSuccess) {
+        cudaFree(g->seg); cudaFree(g->d_work); delete g;
+        return fail(OPM_ERR_CUDA, "peer group: %s", cudaGetErrorString(e));
+    }
+    g->peer_seg[rank] = g->seg;
+    if (world == 1) { g->connected = true; }
+    *out = g;
+    return OPM_OK;
+}
+static void peer_build_view(OpmPeerGroup* g) {
+    memset(&g->view, 0, sizeof g->view);
+    g->view.rank = g->rank; g->view.world = g->world;
+    for (int r = 0; r < g->world; ++r) {
+        g->view.ctrl[r] = (PeerCtrl*)g->peer_seg[r];
+        g->view.part[r] = (double*)((unsigned char*)g->peer_seg[r] + kPeerCtrlBytes);
+    }
+}
+extern "C" OpmStatus opm_peer_group_connect(OpmPeerGroup* g, const uint8_t* handles) {
+    if (!g) return fail(OPM_ERR_ARG, "peer group is NULL");
+    CU(cudaSetDevice(g->ctx->device));
+    if (g->world > 1 && !g->connected) {
+        if (!handles) return fail(OPM_ERR_ARG, "peer group: handles of all ranks needed");
+        for (int r = 0; r < g->world; ++r) {
+            if (r == g->rank) continue;
+            cudaIpcMemHandle_t h;
+            memcpy(&h, handles + (size_t)r * OPM_IPC_HANDLE_BYTES, sizeof h);
+            cudaError_t e = cudaIpcOpenMemHandle(&g->peer_seg[r], h, cudaIpcMemLazyEnablePeerAccess);
+            if (e != cudaSuccess) {
+                cudaGetLastError();
+                return fail(OPM_ERR_CUDA, "peer group: cannot map the segment of rank %d (%s) -- no peer access between the GPUs?", r,
+                            cudaGetErrorString(e));
+            }
+        }
+        g->connected = true;
+    }
+    peer_build_view(g);
+    return OPM_OK;
+}
+extern "C" void opm_peer_group_destroy(OpmPeerGroup* g) {
+    if (!g) return;
+    cudaSetDevice(g->ctx->device);
+    cudaStreamSynchronize(g->ctx->stream);
+    for (int r = 0; r < g->world; ++r)
+        if (r != g->rank && g->peer_seg[r]) cudaIpcCloseMemHandle(g->peer_seg[r]);
+    cudaFree(g->seg); cudaFree(g->d_work);
+    delete g;
+}
+static OpmStatus peer_meet(OpmPeerGroup* g, const double* block, int n, double* out, int mode, double* out2) {
+    OpmContext* c = g->ctx;
+    if (!g->connected) return fail(OPM_ERR_ARG, "peer group is not connected");
+    if (g->view.world != g->world) peer_build_view(g);
+    KL(k_peer_meet(g->view, ++g->seq, block, n, out, mode, out2, &c->d_stats->sticky_bits, g->timeout_ns, c->stream));
+    c->launches++;
+    return OPM_OK;
+}
+extern "C" OpmStatus opm_peer_allgather_async(OpmPeerGroup* g, const double* block_dev, int32_t n, double* out_dev) {
+    if (!g || !block_dev || !out_dev || n < 1 || n > kPeerBlock) return fail(OPM_ERR_ARG, "peer all-gather: 1..%d doubles", kPeerBlock);
+    CU(cudaSetDevice(g->ctx->device));
+    return peer_meet(g, block_dev, n, out_dev, 0, nullptr);
+}
+extern "C" OpmStatus opm_peer_fluence_report_async(OpmPeerGroup* g, OpmHitMap* const* maps, int32_t n_maps, int64_t bounce_filter, uint64_t nx,
+                                                   uint64_t ny, double* range_dev, double* peak_total_dev, uint32_t* status_dev) {
+    if (!g || !range_dev || !peak_total_dev || !status_dev || nx < 2 || ny < 2 || nx * ny > g->map_bins) return fail(OPM_ERR_ARG, "peer fluence report: bad map arguments");
+    OpmContext* c;
+    OpmStatus s = check_same_ctx(maps, n_maps, &c);
+    if (s) return s;
+    if (c != g->ctx) return fail(OPM_ERR_ARG, "hit maps and peer group live on different contexts");
+    CU(cudaSetDevice(c->device));
+    if (g->view.world != g->world) peer_build_view(g);
+    double* own = g->d_work;                         // 4
+    double* all = own + 4;                           // world x 4
+    double* range = all + 4 * kMaxPeers;             // 4
+    double* pkb = range + 4;                         // 2
+    double* pks = pkb + 2;                           // world x 2
+    double* token = pks + 2 * kMaxPeers;             // 1
+    double* tokens = token + 1;                      // world
+    s = opm_hitmaps_bounding_box_async(maps, n_maps, bounce_filter, own);
+    if (s) return s;
+    s = peer_meet(g, own, 4, all, 1, range);                                       // meeting 1: every rank's own range, the common range
+    if (s) return s;
+    double* part = g->view.part[g->rank];
+    KL(k_peer_zero_window(part, nx, ny, own, range, c->sms, c->stream)); c->launches++;
+    for (int k = 0; k < n_maps; ++k)
+        if (maps[k]->len) { KL(k_binning(maps[k]->v, maps[k]->len, bounce_filter, nx, ny, range, part, status_dev, c->sms, c->stream)); c->launches++; }
+    s = peer_meet(g, token, 1, tokens, 0, nullptr);                                // meeting 2: every part is binned
+    if (s) return s;
+    KL(k_peer_reduce_slice(g->view, nx, ny, all, range, peer_final(g, g->rank), (PeakAccum*)c->d_scratch, pkb, c->sms, c->stream));
+    c->launches += 3;
+    s = peer_meet(g, pkb, 2, pks, 2, peak_total_dev);                              // meeting 3: peak and total of the whole map
+    if (s) return s;
+    CU(cudaMemcpyAsync(range_dev, range, 4 * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+    return OPM_OK;
+}
+extern "C" OpmStatus opm_peer_fluence_gather_map(OpmPeerGroup* g, uint64_t nx, uint64_t ny, double* map_dev) {
+    if (!g || !map_dev || nx * ny > g->map_bins) return fail(OPM_ERR_ARG, "peer gather: bad arguments");
+    OpmContext* c = g->ctx;
+    CU(cudaSetDevice(c->device));
+    for (int r = 0; r < g->world; ++r) {
+        const uint64_t c0 = (uint64_t)r * nx / g->world, c1 = (uint64_t)(r + 1) * nx / g->world;
+        if (c1 > c0) CU(cudaMemcpyAsync(map_dev + c0 * ny, peer_final(g, r) + c0 * ny, (c1 - c0) * ny * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+    }
     return OPM_OK;
 }
 

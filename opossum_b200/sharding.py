@@ -129,6 +129,48 @@ def combine_maps_radii_reference(gB: torch.Tensor, maps_len: int, ns: int) -> to
     return out
 
 
+class PeerGroup:
+    """This rank's side of the NVLink peer-memory exchange of a large fluence map (include/opossum_b200.h `OpmPeerGroup`,
+    opossum_b200/csrc/opm_peer.cu): allocates the rank's segment in the library, exchanges the CUDA IPC handles of all ranks
+    through `torch.distributed` (a host-side all_gather_object, once) and maps the peers' segments."""
+
+    def __init__(self, ctx, map_bins: int):
+        import ctypes as C
+
+        from . import _ffi as F
+        from .api import _check
+        self.ctx, self.map_bins = ctx, int(map_bins)
+        self.rank, self.world = world()
+        h = C.c_void_p()
+        handle = (C.c_uint8 * 64)()
+        _check(F.lib().opm_peer_group_create(ctx.h, self.rank, self.world, self.map_bins, C.byref(h), handle))
+        self.h = h
+        ctx._adopt(self)
+        self._close_order = 0  # before the context's bundles
+        if self.world > 1:
+            mine = bytes(handle)
+            every = [None] * self.world
+            dist.all_gather_object(every, mine)
+            blob = (C.c_uint8 * (64 * self.world)).from_buffer_copy(b"".join(every))
+            _check(F.lib().opm_peer_group_connect(self.h, blob))
+        else:
+            _check(F.lib().opm_peer_group_connect(self.h, None))
+
+    def allgather(self, block: torch.Tensor, out: torch.Tensor):
+        """one meeting: `block` (n <= 32 float64 on the device) of every rank -> out (world x n); also a barrier of the ranks"""
+        import ctypes as C
+
+        from . import _ffi as F
+        from .api import _check
+        _check(F.lib().opm_peer_allgather_async(self.h, C.c_void_p(block.data_ptr()), block.numel(), C.c_void_p(out.data_ptr())))
+
+    def close(self):
+        from . import _ffi as F
+        if getattr(self, "h", None):
+            F.lib().opm_peer_group_destroy(self.h)
+            self.h = None
+
+
 class DetectorReadout:
     """Reports of the detectors of a scene whose rays are sharded over the ranks: Binning fluence maps
     (`FluenceDetector::node_report`, nodes/fluence_detector/mod.rs:91-135) and spot-diagram statistics
@@ -148,7 +190,7 @@ class DetectorReadout:
     """
     FUSED_LIMIT = 8 * 1024 * 1024  # doubles in the gathered (maps | radii) buffer
 
-    def __init__(self, ctx, scene, fluence_nodes, spot_nodes, nx: int, ny: int, device):
+    def __init__(self, ctx, scene, fluence_nodes, spot_nodes, nx: int, ny: int, device, peer=None, solo=False):
         import ctypes as C
 
         from . import _ffi as F
@@ -167,11 +209,42 @@ class DetectorReadout:
                       "B": torch.zeros(max(self.nB, 1), dtype=torch.float64).pin_memory(),
                       "status": torch.zeros(self.status.numel(), dtype=torch.int32).pin_memory(),
                       "maps": None, "event": None, "with_maps": False} for _ in range(2)]
-        w = world()[1]
-        self.fused = w > 1 and self.mb.numel() * w <= self.FUSED_LIMIT
+        w = 1 if solo else world()[1]  # solo: this rank reads its own detectors out without meeting the others
+        self.w = w
+        self.fused = w > 1 and self.mb.numel() * w <= self.FUSED_LIMIT and peer is not True
+        # maps too large to gather: column-sliced merge over NVLink peer memory (PeerGroup), one group per detector; the NCCL
+        # all-reduce of the whole map remains as the fallback when the GPUs cannot map each other's memory
+        self.peer = None
+        if w > 1 and not self.fused and nf and peer is not False:
+            try:
+                self.peer = [PeerGroup(ctx, nx * ny) for _ in range(nf)]
+            except Exception as e:  # noqa: BLE001  (no peer access, IPC not permitted in this container, ...)
+                if peer is True:
+                    raise
+                import warnings
+                warnings.warn(f"peer-memory read-out unavailable ({e}); all-reducing whole fluence maps over NCCL instead")
+            flag = torch.tensor([1 if self.peer is not None else 0], dtype=torch.int32,
+                                device=device if dist.get_backend() == "nccl" else "cpu")
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)  # all ranks or none
+            if int(flag.item()) == 0:
+                self.peer = None
         self.gA = torch.zeros((w, self.nA), dtype=torch.float64, device=device) if w > 1 else None
         self.gMB = torch.zeros((w, self.mb.numel()), dtype=torch.float64, device=device) if self.fused else None
         self.gB = torch.zeros((w, max(self.nB, 1)), dtype=torch.float64, device=device) if (w > 1 and not self.fused) else None
+
+        ctx._adopt(self)       # closed with (and before) the context: the pinned report buffers were last used on ITS stream, and
+        self._close_order = -1  # torch's host allocator records an event on that stream when it takes them back
+
+    def close(self):
+        if getattr(self, "host", None) is None:
+            return
+        if torch.cuda.is_available():
+            torch.cuda.synchronize()
+        for g in (self.peer or []):
+            g.close()
+        self.peer = None
+        self.host = None
+        self.buf = self.mb = self.maps = self.status = self.gA = self.gMB = self.gB = None
 
     def _ptr(self, t: torch.Tensor, offset: int = 0) -> int:
         return t.data_ptr() + 8 * offset
@@ -194,21 +267,27 @@ class DetectorReadout:
     def _launch(self, download_maps: bool, slot: int):
         L, C, F = self.F.lib(), self.C, self.F
         from .api import _check
-        rank, w = world()
+        w = self.w
         nf, ns, nx, ny = len(self.fl), len(self.sp), self.nx, self.ny
         hits = [self._hit_arrays(n) for n in self.fl]
         vp = C.c_void_p
+        peer = self.peer is not None
         # ---- phase A
-        for j, (arr, n) in enumerate(hits):
-            _check(L.opm_hitmaps_bounding_box_async(arr, n, -1, vp(self._ptr(self.buf, 4 * j))))
+        if not peer:
+            for j, (arr, n) in enumerate(hits):
+                _check(L.opm_hitmaps_bounding_box_async(arr, n, -1, vp(self._ptr(self.buf, 4 * j))))
         for k, node in enumerate(self.sp):
             _check(L.opm_scene_node_spot_async(self.scene.h, node, 1, vp(self._ptr(self.buf, 4 * nf + 11 * k)), None))
-        if w > 1 and self.nA:
+        if w > 1 and self.nA and (ns or not peer):
             dist.all_gather_into_tensor(self.gA.view(-1), self.buf[: self.nA])
             _check(L.opm_readout_combine_ranges_sums(self.ctx.h, vp(self.gA.data_ptr()), w, nf, ns, vp(self.buf.data_ptr())))
         # ---- phase B
         self.status.zero_()
-        for j, (arr, n) in enumerate(hits):
+        if peer:  # range, windowed binning, column-slice merge, peak / total: three flag meetings over NVLink, no NCCL
+            for j, (arr, n) in enumerate(hits):
+                _check(L.opm_peer_fluence_report_async(self.peer[j].h, arr, n, -1, nx, ny, vp(self._ptr(self.buf, 4 * j)),
+                                                       vp(self._ptr(self.buf, self.nA + 2 * j)), vp(self.status.data_ptr() + 4 * j)))
+        for j, (arr, n) in enumerate(hits if not peer else []):
             _check(L.opm_fluence_binning_async(arr, n, -1, nx, ny, vp(self._ptr(self.buf, 4 * j)), 0,
                                                vp(self.maps[j].data_ptr()), vp(self.status.data_ptr() + 4 * j)))
         for k, node in enumerate(self.sp):
@@ -218,13 +297,13 @@ class DetectorReadout:
             dist.all_gather_into_tensor(self.gMB.view(-1), self.mb)
             _check(L.opm_readout_combine_maps_radii(self.ctx.h, vp(self.gMB.data_ptr()), w, self.maps_len, ns, vp(self.mb.data_ptr())))
         elif w > 1:
-            if nf:
+            if nf and not peer:
                 dist.all_reduce(self.maps, op=dist.ReduceOp.SUM)
             if ns:
                 dist.all_gather_into_tensor(self.gB.view(-1), self.mb[self.maps_len:])
                 _check(L.opm_readout_combine_maps_radii(self.ctx.h, vp(self.gB.data_ptr()), w, 0, ns, vp(self._ptr(self.mb, self.maps_len))))
         # ---- phase C
-        for j in range(nf):
+        for j in range(nf if not peer else 0):
             _check(L.opm_fluence_peak_total_async(self.ctx.h, vp(self.maps[j].data_ptr()), nx, ny, vp(self._ptr(self.buf, 4 * j)),
                                                   vp(self._ptr(self.buf, self.nA + 2 * j))))
         # ---- read
@@ -234,6 +313,9 @@ class DetectorReadout:
             H["B"].copy_(self.mb[self.maps_len:], non_blocking=True)
         H["status"].copy_(self.status, non_blocking=True)
         H["with_maps"] = bool(download_maps and nf)
+        if H["with_maps"] and peer:  # every rank collects the column slices of all ranks (peer copies)
+            for j in range(nf):
+                _check(L.opm_peer_fluence_gather_map(self.peer[j].h, nx, ny, vp(self.maps[j].data_ptr())))
         if H["with_maps"]:
             if H["maps"] is None:
                 H["maps"] = torch.zeros_like(self.maps, device="cpu").pin_memory()
@@ -249,6 +331,8 @@ class DetectorReadout:
         H = self.host[slot]
         H["event"].synchronize()
         h, download_maps = H["buf"], H["with_maps"]
+        if download_maps and self.peer is not None:
+            dist.barrier()  # no rank starts its next read-out while a peer still copies its slice
         out = {}
         for j, node in enumerate(self.fl):
             r = h[4 * j: 4 * j + 4].tolist()

@@ -60,7 +60,7 @@ def test_binning_auto_bbox_matches_oracle(ctx, nx, ny):
     assert n == len(x) and box == ref_lrtb == (x.min(), x.max(), y.max(), y.min())
     fd = ob.fluence_binning(ctx, [h], nx, ny)
     assert fd.lrtb == ref_lrtb
-    assert_map_match(fd.map, ref_map)
+    assert_map_match(fd.map, ref_map, same_hits=True)
     assert fd.peak == pytest.approx(orc.fluence_peak(ref_map), rel=RTOL)
     assert fd.total_energy == pytest.approx(orc.fluence_total_energy(ref_map, ref_lrtb), rel=RTOL)
 
@@ -72,7 +72,7 @@ def test_binning_coherent_runs(ctx):
     e = 1e-6 * (1.0 + 0.3 * np.cos(1e3 * x) * np.sin(2e3 * y))
     ref_map, ref_lrtb = orc.fluence_binning(orc.hits_from_xye(x, y, e), 300, 200)
     fd = ob.fluence_binning(ctx, [hitmap_from(ctx, x, y, e)], 300, 200)
-    assert_map_match(fd.map, ref_map)
+    assert_map_match(fd.map, ref_map, same_hits=True)
     assert fd.total_energy == pytest.approx(orc.fluence_total_energy(ref_map, ref_lrtb), rel=RTOL)
 
 
@@ -86,7 +86,7 @@ def test_binning_explicit_ranges_and_errors(ctx):
     h = hitmap_from(ctx, x, y, e)
     fd = ob.fluence_binning(ctx, [h], 64, 48, ranges=ranges)
     assert fd.lrtb == ref_lrtb == ranges
-    assert_map_match(fd.map, ref_map)
+    assert_map_match(fd.map, ref_map, same_hits=True)
     with pytest.raises(orc.OracleError):
         orc.fluence_binning(orc.hits_from_xye(x, y, e), 64, 48, (lo, mm(0.1), hi, lo))
     with pytest.raises(ob.OpossumError) as ei:
@@ -107,7 +107,7 @@ def test_binning_bounce_filter_and_accumulate(ctx):
     ref_map, ref_lrtb = orc.fluence_binning(orc.hits_from_xye(x[sel], y[sel], e[sel]), 101, 101)
     fd = ob.fluence_binning(ctx, [h], 101, 101, bounce=1)
     assert fd.lrtb == ref_lrtb
-    assert_map_match(fd.map, ref_map)
+    assert_map_match(fd.map, ref_map, same_hits=True)
     # two shards binned into one device map with a shared (externally reduced) bounding box: the multi-GPU pattern
     full_map, full_lrtb = orc.fluence_binning(orc.hits_from_xye(x, y, e), 200, 150)
     half = len(x) // 2
@@ -119,7 +119,7 @@ def test_binning_bounce_filter_and_accumulate(ctx):
     ob.fluence_binning(ctx, [ha], 200, 150, lrtb=box, map_dev=dev, download=False)
     fd = ob.fluence_binning(ctx, [hb], 200, 150, lrtb=box, map_dev=dev, accumulate=True)
     ctx.device_free(dev)
-    assert_map_match(fd.map, full_map)
+    assert_map_match(fd.map, full_map, same_hits=True)
 
 
 def test_sources_match_oracle(ctx):
@@ -184,7 +184,7 @@ def test_kde_fluence_matches_oracle(ctx, case):
     if case == "three_points":
         assert abs(bw - 0.00034057440111656337) < 1e-15  # kde/mod.rs:255-261
     assert np.allclose(fd.lrtb, ref_lrtb, rtol=1e-12, atol=1e-18)
-    assert_map_match(fd.map, ref_map)
+    assert_map_match(fd.map, ref_map, same_hits=True)
     assert fd.peak == pytest.approx(orc.fluence_peak(ref_map), rel=RTOL)
 
 
@@ -200,7 +200,7 @@ def test_kde_errors_and_bounce_filter(ctx):
     ref_map, _, ref_bw = orc.fluence_kde(orc.hits_from_xye(xyz[sel, 0], xyz[sel, 1], e[sel]), 32, 32)
     fd, bw = ob.fluence_kde(ctx, [hm], 32, 32, bounce=1)
     assert bw == pytest.approx(ref_bw, rel=1e-12)
-    assert_map_match(fd.map, ref_map)
+    assert_map_match(fd.map, ref_map, same_hits=True)
     for pts in ([[0.0, 0.0, 0.0]], [[1e-3, 2e-3, 0.0], [1e-3, 2e-3, 0.0]]):
         p = np.array(pts)
         h1 = ob.HitMap(ctx, len(p))
@@ -224,12 +224,12 @@ def test_binning_fixed_point_wide_energy_range(ctx, nx, ny):
     ref_map, ref_lrtb = orc.fluence_binning(orc.hits_from_xye(x, y, e), nx, ny)
     fd = ob.fluence_binning(ctx, [hitmap_from(ctx, x, y, e)], nx, ny)
     assert fd.lrtb == ref_lrtb
-    assert_map_match(fd.map, ref_map)
+    assert_map_match(fd.map, ref_map, same_hits=True)
     assert fd.total_energy == pytest.approx(orc.fluence_total_energy(ref_map, ref_lrtb), rel=1e-12)
     # tiny energies only: the unit follows the largest energy of the CTA's slots, nothing is rounded away
     e2 = 1e-200 * (1.0 + rng.random(n))
     ref2, _ = orc.fluence_binning(orc.hits_from_xye(x, y, e2), nx, ny)
-    assert_map_match(ob.fluence_binning(ctx, [hitmap_from(ctx, x, y, e2)], nx, ny).map, ref2)
+    assert_map_match(ob.fluence_binning(ctx, [hitmap_from(ctx, x, y, e2)], nx, ny).map, ref2, same_hits=True)
 
 
 def test_binning_fixed_point_non_finite_energy(ctx):
@@ -243,3 +243,44 @@ def test_binning_fixed_point_non_finite_energy(ctx):
     area = (mm(4.0) / 5) ** 2
     assert fd.map[0, 0] == pytest.approx(1.0 / area, rel=1e-12) and fd.map[4, 4] == pytest.approx(5.0 / area, rel=1e-12)
     assert fd.peak == pytest.approx(5.0 / area, rel=1e-12)  # fluence_data.rs:45-68: peak over the finite bins
+
+
+@pytest.mark.parametrize("order", ["rows_up", "rows_down", "with_holes"])
+def test_binning_large_map_run_merging(ctx, order):
+    """2048 x 2048 map (32 MiB: the run-merging kernel, opm_kernels.cu binning_runs_kernel) from grid-ordered hits, 2.2 hits per
+    bin along the fast axis like BASELINE configs[3]: consecutive hits share a bin or step to the next row (up, or down when the
+    order is reversed), columns change inside a thread's run, empty slots (e < 0) interrupt runs"""
+    g = orc.grid(900, 4500, mm(12.0), mm(9.0))  # x outer, y inner: y runs fastest in slot order
+    x = g[:, 0] * (1.0 + 0.02 * np.sin(300.0 * g[:, 1]))
+    y = g[:, 1] + mm(0.002) * np.cos(900.0 * g[:, 0])
+    e = 1e-9 * (1.0 + 0.5 * np.sin(1e3 * x) * np.cos(2e3 * y))
+    if order == "rows_down":
+        x, y, e = x[::-1].copy(), y[::-1].copy(), e[::-1].copy()
+    e_up = e.copy()
+    if order == "with_holes":
+        e_up[::7] = -1.0
+        e_up[1000:1100] = -1.0
+    ok = e_up >= 0.0
+    ref_map, ref_lrtb = orc.fluence_binning(orc.hits_from_xye(x[ok], y[ok], e[ok]), 2048, 2048)
+    fd = ob.fluence_binning(ctx, [hitmap_from(ctx, x, y, e_up)], 2048, 2048)
+    assert fd.lrtb == ref_lrtb
+    assert_map_match(fd.map, ref_map, what=f"2048^2 map, {order}", same_hits=True)
+    assert fd.peak == pytest.approx(orc.fluence_peak(ref_map), rel=RTOL)
+    assert fd.total_energy == pytest.approx(orc.fluence_total_energy(ref_map, ref_lrtb), rel=RTOL)
+
+
+@pytest.mark.parametrize("nx,ny", [(100, 83), (600, 500)])
+def test_binning_negative_taps_outside_an_explicit_range(ctx, nx, ny):
+    """a hit left of / below an explicit range start has a negative fractional index: the reference (rays_hit_map.rs:352-376) adds
+    the resulting NEGATIVE taps to column / row 0 and 1.  Both Binning kernels (fixed-point shared-memory splat for the small map,
+    run-merging global splat for the large one) must add them too."""
+    x, y, e = seeded_hits(30_000, spread=mm(1.0))
+    left, bottom = float(np.quantile(x, 0.02)), float(np.quantile(y, 0.03))  # 2-3 % of the hits lie outside
+    ranges = (left, float(x.max()), float(y.max()), bottom)
+    ref_map, ref_lrtb = orc.fluence_binning(orc.hits_from_xye(x, y, e), nx, ny, ranges)
+    assert (ref_map < 0).any()
+    fd = ob.fluence_binning(ctx, [hitmap_from(ctx, x, y, e)], nx, ny, ranges=ranges)
+    assert fd.lrtb == ref_lrtb
+    scale = np.abs(ref_map).max()
+    assert np.max(np.abs(fd.map - ref_map)) <= 1e-9 * scale  # sums of mixed sign: compare against the map's scale
+    assert ((fd.map < 0) == (ref_map < 0)).mean() > 0.999

@@ -216,7 +216,9 @@ def test_sharded_trace_equals_whole_source(ctx):
     for g, sc in enumerate(shards):
         fd = ob.fluence_binning(ctx, sc.node_hitmaps(9, 0), 100, 83, lrtb=lrtb, map_dev=dev_map, accumulate=g > 0, download=g == 1)
     ctx.device_free(dev_map)
-    assert_map_match(fd.map, ref_fd.map, rtol=1e-12)
+    # the same hit points binned in two pieces: the fixed-point splat rounds every tap to 2^-33 of itself (unit chosen per CTA), so
+    # a bin is reproducible to 2.4e-10 of its own value, not to the last bits
+    assert_map_match(fd.map, ref_fd.map, rtol=2.4e-10, same_hits=True)
     assert fd.peak == pytest.approx(ref_fd.peak, rel=1e-12) and fd.total_energy == pytest.approx(ref_fd.total_energy, rel=1e-12)
     # spot diagram: phase-1 partials summed, phase 2 about the global centroids, radius accumulators combined
     parts = [sc.node_spot_partial(8) for sc in shards]
