@@ -298,19 +298,28 @@ def run_c4_strong(args, ctx, dev, stream, rank, world):
         for _ in range(3):
             step()
         ro.collect(0)
+        # the trace kernel's share, measured in a pass of its own: the event pair around every trace launch stays out of the
+        # timed steps (it costs them a few microseconds each)
         barrier()
         ctx.set_kernel_timing(True)
         ctx.kernel_timing(reset=True)
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(stream)
         for _ in range(steps):
             step()
+        ro.collect(0)
+        barrier()
+        kms, _ = ctx.kernel_timing(reset=True)
+        ctx.set_kernel_timing(False)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        h0 = time.perf_counter()
+        for _ in range(steps):
+            step()
+        host_ms = 1e3 * (time.perf_counter() - h0) / steps  # what the host needs to queue one step (must stay below the step)
         e1.record(stream)
         rep = ro.collect(0)
         barrier()
         ms = e0.elapsed_time(e1) / steps
-        kms, _ = ctx.kernel_timing(reset=True)
-        ctx.set_kernel_timing(False)
+        timed.host_ms = host_ms
         return ms, kms / steps, rep[2]
 
     def barrier():
@@ -323,6 +332,7 @@ def run_c4_strong(args, ctx, dev, stream, rank, world):
     ctx.jit_wait()
     ms, trace_ms, rep = timed(scene, src, ro, barrier)
     t = torch.tensor([ms, trace_ms, float(st.interactions)], dtype=torch.float64, device=dev)
+    t_own = t.tolist()
     tsum = t.clone()
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -331,6 +341,7 @@ def run_c4_strong(args, ctx, dev, stream, rank, world):
     out = {"config": "C4: 10^8 rays total (grid 10^4 x 10^4, contiguous source-index shards), lens + fluence detector, 4096 x 4096 Binning "
                      "map, data-dependent range", "scaling": "strong", "n_gpus": world, "rays_total": n_total, "rays_per_gpu": e - b,
            "steps": steps, "ms_per_step": ms, "interactions_per_s": inter / (ms * 1e-3), "trace_ms": trace_ms, "readout_ms": ms - trace_ms,
+           "host_queue_ms_per_step": timed.host_ms,
            "readout": ("bounding box kept by the trace kernel, zero-fill + run-merging splat, peak/total" if world == 1 else
                        ("windowed splat + column-slice merge over NVLink peer memory, 3 flag meetings, no NCCL" if ro.peer is not None
                         else "NCCL all-reduce of the whole map (peer memory unavailable)")),
@@ -353,6 +364,23 @@ def run_c4_strong(args, ctx, dev, stream, rank, world):
             dist.all_reduce(tm, op=dist.ReduceOp.MAX)
             out["collective_ms"] = 3 * tm.item()
             out["meeting_us"] = 1e3 * tm.item()
+            # where the read-out's time goes on this rank (diagnostic, one extra untimed step)
+            import ctypes as C
+            from opossum_b200 import _ffi as F
+            ph = (C.c_float * 12)()
+            F.lib().opm_peer_group_phase_times(ro.peer[0].h, 1, None)
+            for _ in range(3):
+                scene.raytrace(src, keep_source=True, snapshots=False, sync=False)
+                ro.launch(False, 0)
+            F.lib().opm_peer_group_phase_times(ro.peer[0].h, 0, ph)
+            ro.collect(0)
+            pt = torch.tensor(list(ph) + [t_own[1]], dtype=torch.float64, device=dev)
+            allp = torch.zeros((world, 13), dtype=torch.float64, device=dev)
+            dist.all_gather_into_tensor(allp.view(-1), pt)
+            out["readout_phases_ms_per_rank"] = {k: [round(v, 4) for v in allp[:, j].tolist()]
+                                                 for j, k in enumerate(("meeting1", "zero_window", "splat", "reduce_meetings23", "t_splat_start", "t_range_posted",
+                                                                       "t_ranges_here", "t_reduce_start", "t_parts_binned", "t_last_cta_done",
+                                                                       "t_peaks_here", "t_first_cta_done", "trace"))}
         # merged map on rank 0 (gathered from the column slices) for the parity check below
         merged = ro.run(download_maps=True)[2]
         barrier()

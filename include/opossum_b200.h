@@ -514,10 +514,21 @@ void opm_peer_group_destroy(OpmPeerGroup* group);
  * status (opm_context_synchronize) instead of hanging the GPU. */
 OpmStatus opm_peer_allgather_async(OpmPeerGroup* group, const double* block_dev, int32_t n, double* out_dev);
 /* FluenceDetector report (Binning) of hit maps sharded over the ranks: range_dev[4] = (-left, right, top, -bottom) and
- * peak_total_dev[2] on every rank; asynchronous, three meetings.  status_dev accumulates OpmStatus bits like
- * opm_fluence_binning_async. */
+ * peak_total_dev[2] on every rank; asynchronous.  Three meetings in three launches when the trace kernel kept the hit map's
+ * bounding box: the kernel that zero-fills this rank's window carries meeting 1, the splat follows, the slice-reduce kernel
+ * carries meetings 2 and 3.  status_dev accumulates OpmStatus bits like opm_fluence_binning_async.
+ * host_report (may be NULL): 8 doubles of pinned, device-mapped host memory that the last kernel fills itself --
+ * [0..4) range, [4] peak, [5] total, [6] *status_dev, [7] a sequence number that changes with every report, stored last -- so a
+ * caller that only wants the report needs no device->host copy in the stream. */
 OpmStatus opm_peer_fluence_report_async(OpmPeerGroup* group, OpmHitMap* const* maps, int32_t n_maps, int64_t bounce_filter, uint64_t nx,
-                                        uint64_t ny, double* range_dev, double* peak_total_dev, uint32_t* status_dev);
+                                        uint64_t ny, double* range_dev, double* peak_total_dev, uint32_t* status_dev,
+                                        double* host_report);
+/* diagnostic: device time in ms of the four phases of the latest report (meeting 1 | zero-fill of the window | splat | slice
+ * reduce with meetings 2 and 3) in out_ms[0..4), then eight time stamps taken inside the kernels, in ms after the start of the
+ * splat kernel: [4] 0, [5] own range posted, [6] all ranges arrived, [7] slice reduce starts, [8] all parts binned, [9] last CTA
+ * of the reduce done, [10] all slices' peaks arrived, [11] first CTA done with its items.  enable != 0 records the phase
+ * boundaries of the reports that follow; out_ms may be NULL. */
+OpmStatus opm_peer_group_phase_times(OpmPeerGroup* group, int32_t enable, float out_ms[12]);
 /* the whole map (nx * ny, column-major ny x nx) of the LAST report into map_dev on this rank: every rank's column slice is copied
  * from its memory.  The ranks must not start another report before the copy has run (the caller's barrier). */
 OpmStatus opm_peer_fluence_gather_map(OpmPeerGroup* group, uint64_t nx, uint64_t ny, double* map_dev);

@@ -229,7 +229,7 @@ EXPORTS = [
     "opm_spectrum_create", "opm_spectrum_destroy", "opm_spectrum_total_energy", "opm_spectrum_center_wavelength", "opm_spectrum_get_value",
     "opm_rays_wavelength_range", "opm_rays_to_spectrum", "opm_rays_filter_energy_spectrum", "opm_rays_split_spectrum",
     "opm_rays_wavefront_error", "opm_readout_combine_ranges_sums", "opm_readout_combine_maps_radii", "opm_peer_group_create", "opm_peer_group_connect", "opm_peer_group_destroy",
-    "opm_peer_allgather_async", "opm_peer_fluence_report_async", "opm_peer_fluence_gather_map", "opm_measure_fp64_peak", "opm_device_alloc",
+    "opm_peer_allgather_async", "opm_peer_fluence_report_async", "opm_peer_fluence_gather_map", "opm_peer_group_phase_times", "opm_measure_fp64_peak", "opm_device_alloc",
     "opm_device_free", "opm_device_memset", "opm_device_to_host", "opm_host_to_device", "opm_host_alloc_pinned", "opm_host_free_pinned",
     "opm_spectrum_gaussian", "opm_source_generate", "opm_source_generate_strided", "opm_source_energy_norm",
 ]
@@ -337,8 +337,9 @@ def lib() -> C.CDLL:
         "opm_peer_group_connect": (i32, [vp, vp]),
         "opm_peer_group_destroy": (None, [vp]),
         "opm_peer_allgather_async": (i32, [vp, vp, i32, vp]),
-        "opm_peer_fluence_report_async": (i32, [vp, vp, i32, C.c_int64, u64, u64, vp, vp, vp]),
+        "opm_peer_fluence_report_async": (i32, [vp, vp, i32, C.c_int64, u64, u64, vp, vp, vp, vp]),
         "opm_peer_fluence_gather_map": (i32, [vp, u64, u64, vp]),
+        "opm_peer_group_phase_times": (i32, [vp, i32, vp]),
         "opm_rays_wavefront_error": (i32, [vp, C.POINTER(OpmIsometry), C.c_double, dp, u64, C.POINTER(OpmWavefrontStats)]),
         "opm_rays_bounce_lvl": (i32, [vp, C.POINTER(C.c_uint32)]),
         "opm_rays_tally": (i32, [vp, C.c_uint32, C.POINTER(u64), dp]),

@@ -1236,6 +1236,8 @@ static OpmStatus run_program(OpmRays* rays, const OpmOp* ops, int n_ops, int fla
         hp.base = dst->d_hist; hp.stride = dst->hist_stride;
         dst->hist_next = lv;
     }
+    std::vector<OpmRays*> planned;  // bundles whose length the prologue launch sets
+    auto is_planned = [&](OpmRays* r) { for (OpmRays* q : planned) if (q == r) return true; return false; };
     // a program whose ops were all elided (Aperture::None, negative threshold) still has to honour out/compact
     if (n > 0 && (!prog.ops.empty() || dst != rays)) {
         if (prog.ops.empty()) {  // pure copy: keep the kernel path uniform with a no-op limits check
@@ -1277,20 +1279,26 @@ static OpmStatus run_program(OpmRays* rays, const OpmOp* ops, int n_ops, int fla
                 fprintf(stderr, "opossum_b200: run-time kernel specialisation unavailable, using the interpreter kernel (%s)\n", why ? why : "?");
             }
         }
-        if (!jk) {
-            KL(k_fetch_from_host(d_slot, h_slot, prog.ops.size() * sizeof(DevOp), c->stream));  // not a copy-engine transfer: see dev_put
-            c->launches++;
-        }
+        // one prologue launch: descriptors to the device, statistics zeroed, bounding-box accumulators reset, output lengths set
+        ProloguePlan pp;
+        memset(&pp, 0, sizeof pp);
+        pp.dst = (unsigned long long*)(jk ? jit_const_ptr(jk) : (void*)d_slot);
+        pp.src_host = (const unsigned long long*)h_slot;
+        pp.words = (unsigned)(prog.ops.size() * sizeof(DevOp) / 8);
+        pp.stats = (unsigned long long*)c->d_stats; pp.stats_words = (unsigned)(kDevStatsZeroBytes / 8);  // not the sticky status word
         for (OpmHitMap* h : prog.hitmaps) h->acc_valid = false;
         if (jk)
-            for (OpmHitMap* h : fused) {  // identity of the accumulator, then the kernel fills it
-                BBoxAccum init;
-                init.key[0] = ~0ull; init.key[1] = 0; init.key[2] = 0; init.key[3] = ~0ull; init.count = 0;
-                OpmStatus ps = dev_put(c, h->d_acc, &init, sizeof init);
-                if (ps) { free_temps(); return ps; }
-                h->acc_valid = true;
-            }
-        CU(cudaMemsetAsync(c->d_stats, 0, kDevStatsZeroBytes, c->stream));  // not the sticky status word
+            for (size_t k = 0; k < fused.size(); ++k) { pp.acc[k] = (BBoxAccum*)fused[k]->d_acc; fused[k]->acc_valid = true; }
+        // slot-indexed outputs keep the input's length; the kernel does not touch their tail counters (only compacting stores and
+        // child emission do), so the prologue can set them
+        auto plan_len = [&](OpmRays* r) {
+            if (pp.n_tails < kPrologueTails) { pp.tail[pp.n_tails] = r->d_tail; pp.tail_val[pp.n_tails] = n; pp.n_tails++; r->len = n; r->len_dirty = false; return true; }
+            return false;
+        };
+        for (OpmRays* r : prog.slot_outputs) if (plan_len(r)) planned.push_back(r);
+        if (!compact && dst != rays && plan_len(dst)) planned.push_back(dst);
+        KL(k_trace_prologue(pp, c->stream));
+        c->launches++;
         TraceLaunch L;
         L.ops = d_slot; L.n_ops = (int)prog.ops.size();
         L.in = rays->v; L.out = dst->v; L.n = n; L.out_cap = dst->cap; L.out_tail = dst->d_tail;
@@ -1308,8 +1316,8 @@ static OpmStatus run_program(OpmRays* rays, const OpmOp* ops, int n_ops, int fla
             else { CU(cudaEventCreate(&tev.first)); CU(cudaEventCreate(&tev.second)); }
             CU(cudaEventRecord(tev.first, c->stream));
         }
-        int rc = jk ? jit_launch(c->jit, jk, L, h_slot) : strict ? launch_trace_strict(L) : launch_trace_fast(L);
-        c->launches += jk ? 2 : 1;
+        int rc = jk ? jit_launch(c->jit, jk, L, nullptr) : strict ? launch_trace_strict(L) : launch_trace_fast(L);
+        c->launches += 1;
         CU(cudaEventRecord(c->ring_ev[slot], c->stream));  // the pinned slot is free once the fetch kernel has read it
         if (c->timing) { CU(cudaEventRecord(tev.second, c->stream)); c->timing_events.push_back(tev); }
         if (rc != 0) { free_temps(); return fail(OPM_ERR_CUDA, "trace kernel launch failed: %s", cudaGetErrorString((cudaError_t)rc)); }
@@ -1323,14 +1331,17 @@ static OpmStatus run_program(OpmRays* rays, const OpmOp* ops, int n_ops, int fla
         }
     // host-side lengths
     for (OpmHitMap* h : prog.hitmaps) h->len = n;
-    for (OpmRays* r : prog.slot_outputs) { s = rays_set_len(r, n); if (s) { free_temps(); return s; } r->mono_wvl = rays->mono_wvl; }
+    for (OpmRays* r : prog.slot_outputs) {
+        if (!is_planned(r)) { s = rays_set_len(r, n); if (s) { free_temps(); return s; } }
+        r->mono_wvl = rays->mono_wvl;
+    }
     for (OpmRays* r : prog.appended) {  // children carry their parents' wavelengths
         if (r->len == 0 && !r->len_dirty) r->mono_wvl = rays->mono_wvl; else if (r->mono_wvl != rays->mono_wvl) r->mono_wvl = 0.0;
         r->len_dirty = true;
     }
     if (dst != rays) dst->mono_wvl = rays->mono_wvl;
     if (compact) dst->len_dirty = true;
-    else if (dst != rays) { s = rays_set_len(dst, n); if (s) { free_temps(); return s; } }
+    else if (dst != rays && !is_planned(dst)) { s = rays_set_len(dst, n); if (s) { free_temps(); return s; } }
 
     if (stats || !prog.temp_dev.empty()) {
         if (n > 0 && !prog.ops.empty())
@@ -1497,8 +1508,12 @@ struct OpmPeerGroup {
     PeerView view{};
     unsigned long long seq = 0;
     unsigned long long timeout_ns = 20ull * 1000 * 1000 * 1000;
-    double* d_work = nullptr;               // [own range 4 | all ranges world x 4 | range 4 | peak block 2 | gathered peaks world x 2 | token 1 | gathered tokens world]
+    cudaEvent_t tev[5] = {};                // diagnostic: phase boundaries of the latest report (opm_peer_group_phase_times)
+    bool timing = false;
+    double2* d_cta_peaks = nullptr;         // (peak, total) of every CTA of the slice reduce
+    double* d_work = nullptr;               // [own range 4 | all ranges world x 4 | range 4 | ... | last word: count of finished slice-reduce CTAs]
 };
+constexpr int kPeerWorkDoubles = 16 + 8 * kMaxPeers + 16;  // ... | 16 diagnostic time stamps at the end
 static size_t peer_seg_bytes(uint64_t bins) { return kPeerCtrlBytes + 2 * align_up(bins * sizeof(double), 256); }
 static double* peer_final(const OpmPeerGroup* g, int r) {
     return (double*)((unsigned char*)g->peer_seg[r] + kPeerCtrlBytes + align_up(g->map_bins * sizeof(double), 256));
@@ -1514,11 +1529,12 @@ extern "C" OpmStatus opm_peer_group_create(OpmContext* c, int32_t rank, int32_t 
     if (const char* e = getenv("OPM_B200_PEER_TIMEOUT_MS")) g->timeout_ns = strtoull(e, nullptr, 10) * 1000000ull;
     cudaError_t e = cudaMalloc(&g->seg, peer_seg_bytes(map_bins));
     if (e == cudaSuccess) e = cudaMemset(g->seg, 0, kPeerCtrlBytes);
-    if (e == cudaSuccess) e = cudaMalloc(&g->d_work, (size_t)(16 + 8 * kMaxPeers) * sizeof(double));
-    if (e == cudaSuccess) e = cudaMemset(g->d_work, 0, (size_t)(16 + 8 * kMaxPeers) * sizeof(double));
+    if (e == cudaSuccess) e = cudaMalloc(&g->d_work, (size_t)kPeerWorkDoubles * sizeof(double));
+    if (e == cudaSuccess) e = cudaMemset(g->d_work, 0, (size_t)kPeerWorkDoubles * sizeof(double));
+    if (e == cudaSuccess) e = cudaMalloc(&g->d_cta_peaks, (size_t)c->sms * kPeerReduceCtasPerSm * sizeof(double2));
     if (e == cudaSuccess && world > 1 && handle_out) e = cudaIpcGetMemHandle((cudaIpcMemHandle_t*)handle_out, g->seg);
     if (e != cudaSuccess) {
-        cudaFree(g->seg); cudaFree(g->d_work); delete g;
+        cudaFree(g->seg); cudaFree(g->d_work); cudaFree(g->d_cta_peaks); delete g;
         return fail(OPM_ERR_CUDA, "peer group: %s", cudaGetErrorString(e));
     }
     g->peer_seg[rank] = g->seg;
@@ -1561,14 +1577,15 @@ extern "C" void opm_peer_group_destroy(OpmPeerGroup* g) {
     cudaStreamSynchronize(g->ctx->stream);
     for (int r = 0; r < g->world; ++r)
         if (r != g->rank && g->peer_seg[r]) cudaIpcCloseMemHandle(g->peer_seg[r]);
-    cudaFree(g->seg); cudaFree(g->d_work);
+    cudaFree(g->seg); cudaFree(g->d_work); cudaFree(g->d_cta_peaks);
+    if (g->timing) for (auto& e : g->tev) cudaEventDestroy(e);
     delete g;
 }
 static OpmStatus peer_meet(OpmPeerGroup* g, const double* block, int n, double* out, int mode, double* out2) {
     OpmContext* c = g->ctx;
     if (!g->connected) return fail(OPM_ERR_ARG, "peer group is not connected");
     if (g->view.world != g->world) peer_build_view(g);
-    KL(k_peer_meet(g->view, ++g->seq, block, n, out, mode, out2, &c->d_stats->sticky_bits, g->timeout_ns, c->stream));
+    KL(k_peer_meet(g->view, ++g->seq, block, n, out, mode, out2, &c->d_stats->sticky_bits, g->timeout_ns, nullptr, nullptr, c->stream));
     c->launches++;
     return OPM_OK;
 }
@@ -1578,7 +1595,8 @@ extern "C" OpmStatus opm_peer_allgather_async(OpmPeerGroup* g, const double* blo
     return peer_meet(g, block_dev, n, out_dev, 0, nullptr);
 }
 extern "C" OpmStatus opm_peer_fluence_report_async(OpmPeerGroup* g, OpmHitMap* const* maps, int32_t n_maps, int64_t bounce_filter, uint64_t nx,
-                                                   uint64_t ny, double* range_dev, double* peak_total_dev, uint32_t* status_dev) {
+                                                   uint64_t ny, double* range_dev, double* peak_total_dev, uint32_t* status_dev,
+                                                   double* host_report) {
     if (!g || !range_dev || !peak_total_dev || !status_dev || nx < 2 || ny < 2 || nx * ny > g->map_bins) return fail(OPM_ERR_ARG, "peer fluence report: bad map arguments");
     OpmContext* c;
     OpmStatus s = check_same_ctx(maps, n_maps, &c);
@@ -1589,25 +1607,61 @@ extern "C" OpmStatus opm_peer_fluence_report_async(OpmPeerGroup* g, OpmHitMap* c
     double* own = g->d_work;                         // 4
     double* all = own + 4;                           // world x 4
     double* range = all + 4 * kMaxPeers;             // 4
-    double* pkb = range + 4;                         // 2
-    double* pks = pkb + 2;                           // world x 2
-    double* token = pks + 2 * kMaxPeers;             // 1
-    double* tokens = token + 1;                      // world
-    s = opm_hitmaps_bounding_box_async(maps, n_maps, bounce_filter, own);
-    if (s) return s;
-    s = peer_meet(g, own, 4, all, 1, range);                                       // meeting 1: every rank's own range, the common range
-    if (s) return s;
+    unsigned* done = (unsigned*)(g->d_work + 8 + 4 * kMaxPeers);          // finished CTAs of the slice reduce; left at 0 by every read-out
+    double2* cta_peaks = g->d_cta_peaks;
+    if (!g->connected) return fail(OPM_ERR_ARG, "peer group is not connected");
+    // meeting 1: every rank's own range, the common range.  When the trace kernel kept the bounding box while it recorded the hits
+    // the meeting kernel reads that accumulator itself
+    auto mark = [&](int k) { if (g->timing) cudaEventRecord(g->tev[k], c->stream); };
+    mark(0);
     double* part = g->view.part[g->rank];
-    KL(k_peer_zero_window(part, nx, ny, own, range, c->sms, c->stream)); c->launches++;
+    // meeting 1: every rank's own range, the common range.  When the trace kernel kept the bounding box while it recorded the hits,
+    // the kernel that zero-fills the window carries the meeting at its head; else bounding-box pass, meeting kernel, zero-fill
+    PeerHook hook;
+    memset(&hook, 0, sizeof hook);
+    if (n_maps == 1 && bounce_filter < 0 && maps[0]->acc_valid && maps[0]->len) {
+        hook.enabled = 1; hook.V = g->view; hook.seq = ++g->seq; hook.timeout_ns = g->timeout_ns;
+        hook.acc = (const BBoxAccum*)maps[0]->d_acc; hook.own_out = own; hook.all_out = all; hook.range_out = range;
+        hook.status = &c->d_stats->sticky_bits;
+        hook.stamps = g->timing ? (unsigned long long*)(g->d_work + kPeerWorkDoubles - 16) : nullptr;
+        mark(1);
+    } else {
+        s = opm_hitmaps_bounding_box_async(maps, n_maps, bounce_filter, own);
+        if (s) return s;
+        s = peer_meet(g, own, 4, all, 1, range);
+        if (s) return s;
+        mark(1);
+    }
+    KL(k_peer_zero_window(part, nx, ny, own, range, hook, c->sms, c->stream)); c->launches++;
+    mark(2);
     for (int k = 0; k < n_maps; ++k)
         if (maps[k]->len) { KL(k_binning(maps[k]->v, maps[k]->len, bounce_filter, nx, ny, range, part, status_dev, c->sms, c->stream)); c->launches++; }
-    s = peer_meet(g, token, 1, tokens, 0, nullptr);                                // meeting 2: every part is binned
-    if (s) return s;
-    KL(k_peer_reduce_slice(g->view, nx, ny, all, range, peer_final(g, g->rank), (PeakAccum*)c->d_scratch, pkb, c->sms, c->stream));
-    c->launches += 3;
-    s = peer_meet(g, pkb, 2, pks, 2, peak_total_dev);                              // meeting 3: peak and total of the whole map
-    if (s) return s;
-    CU(cudaMemcpyAsync(range_dev, range, 4 * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+    mark(3);
+    // meetings 2 ("every part is binned") and 3 (peak and total of the whole map) are the head and the tail of the slice reduce
+    const unsigned long long seq2 = ++g->seq;
+    ++g->seq;
+    KL(k_peer_reduce_slice(g->view, nx, ny, all, range, peer_final(g, g->rank), cta_peaks, done, seq2, peak_total_dev, range_dev,
+                           &c->d_stats->sticky_bits, g->timeout_ns, g->timing ? (unsigned long long*)(g->d_work + kPeerWorkDoubles - 16) : nullptr,
+                           status_dev, host_report, c->sms, c->stream));
+    c->launches++;
+    mark(4);
+    return OPM_OK;
+}
+// Diagnostic: device time of the phases of the latest opm_peer_fluence_report_async (meeting 1 | zero-fill of the window | splat |
+// slice reduce with meetings 2 and 3), in milliseconds.  enable != 0 switches the event records on for the following reports;
+// out_ms == NULL only switches.  Synchronises the stream.
+extern "C" OpmStatus opm_peer_group_phase_times(OpmPeerGroup* g, int32_t enable, float out_ms[12]) {
+    if (!g) return fail(OPM_ERR_ARG, "peer group is NULL");
+    CU(cudaSetDevice(g->ctx->device));
+    if (out_ms) {
+        if (!g->timing) return fail(OPM_ERR_ARG, "phase timing was not enabled");
+        CU(cudaStreamSynchronize(g->ctx->stream));
+        for (int k = 0; k < 4; ++k) CU(cudaEventElapsedTime(&out_ms[k], g->tev[k], g->tev[k + 1]));
+        unsigned long long st[8];  // in-kernel time stamps (globaltimer, ns) relative to the start of the splat kernel
+        CU(cudaMemcpy(st, g->d_work + kPeerWorkDoubles - 16, sizeof st, cudaMemcpyDeviceToHost));
+        for (int k = 0; k < 8; ++k) out_ms[4 + k] = (float)(((double)st[k] - (double)st[0]) * 1e-6);
+    }
+    if (enable && !g->timing) { for (auto& e : g->tev) CU(cudaEventCreate(&e)); g->timing = true; }
     return OPM_OK;
 }
 extern "C" OpmStatus opm_peer_fluence_gather_map(OpmPeerGroup* g, uint64_t nx, uint64_t ny, double* map_dev) {

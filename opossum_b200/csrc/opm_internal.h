@@ -149,6 +149,7 @@ void jit_cache_wait(JitCache* c);
 const JitKernel* jit_get(JitCache* cache, const DevOp* ops, int n_ops, bool compact, int block, int min_ctas, bool wait,
                          const char** why);
 int jit_occupancy(const JitKernel* k);
+void* jit_const_ptr(const JitKernel* k);  // the kernel's __constant__ descriptor table
 int jit_launch(JitCache* cache, const JitKernel* k, const TraceLaunch& L, const void* h_ops_pinned);
 size_t jit_selftest(char* why, size_t cap);  // compiles a program with every op kind to a cubin (no GPU needed); 0 = failed
 

@@ -455,6 +455,7 @@ const JitKernel* jit_get(JitCache* cache, const DevOp* ops, int n_ops, bool comp
 }
 
 int jit_occupancy(const JitKernel* K) { return K ? K->occupancy : 1; }
+void* jit_const_ptr(const JitKernel* K) { return K ? (void*)K->d_const : nullptr; }
 
 // Build check without a GPU: a program with one op of every kind, every geometry and coating is turned into source and
 // compiled to an sm_100a cubin.  Returns the cubin size, or 0 with the reason in `why`.
@@ -494,8 +495,10 @@ size_t jit_selftest(char* why, size_t cap) {
 // h_ops: the pinned, mapped copy of the program (the descriptors' numbers and pointers of THIS launch)
 int jit_launch(JitCache* cache, const JitKernel* K, const TraceLaunch& L, const void* h_ops) {
     cudaStream_t st = (cudaStream_t)L.stream;
-    int rc = k_fetch_from_host(K->d_const, h_ops, (size_t)L.n_ops * sizeof(DevOp), L.stream);
-    if (rc) return rc;
+    if (h_ops) {  // NULL: the caller's prologue launch has already brought the descriptors to jit_const_ptr()
+        int rc = k_fetch_from_host(K->d_const, h_ops, (size_t)L.n_ops * sizeof(DevOp), L.stream);
+        if (rc) return rc;
+    }
     DevRays in = L.in, out = L.out;
     unsigned long long n = L.n, cap = L.out_cap;
     unsigned long long* tail = L.out_tail;

@@ -1261,6 +1261,25 @@ int k_fetch_from_host(void* dst, const void* src_host, size_t bytes, void* strea
     fetch_from_host_kernel<<<1, 256, 0, ST>>>((unsigned long long*)dst, (const unsigned long long*)src_host, (unsigned)(bytes / 8));
     return (int)cudaGetLastError();
 }
+// Everything a trace launch needs on the device before it starts, in ONE small launch instead of four: the op descriptors of
+// this launch (pinned host -> device, over PCIe by the CTA itself), the per-launch statistics zeroed, the bounding-box
+// accumulators of the hit maps the kernel fills reset to their identity, and the lengths of the slot-indexed output bundles.
+__global__ void __launch_bounds__(256) trace_prologue_kernel(ProloguePlan P) {
+    for (unsigned k = threadIdx.x; k < P.words; k += blockDim.x) P.dst[k] = P.src_host[k];
+    if (threadIdx.x < P.stats_words) P.stats[threadIdx.x] = 0ull;
+    if (threadIdx.x >= 32 && threadIdx.x < 32 + 5 * 2) {
+        const unsigned a = (threadIdx.x - 32) / 5, j = (threadIdx.x - 32) % 5;
+        if (P.acc[a]) {
+            if (j < 4) P.acc[a]->key[j] = (j == 0 || j == 3) ? ~0ull : 0ull;
+            else P.acc[a]->count = 0ull;
+        }
+    }
+    if (threadIdx.x >= 64 && threadIdx.x < 64 + (unsigned)P.n_tails) *P.tail[threadIdx.x - 64] = P.tail_val[threadIdx.x - 64];
+}
+int k_trace_prologue(const ProloguePlan& P, void* stream) {
+    trace_prologue_kernel<<<1, 256, 0, ST>>>(P);
+    return (int)cudaGetLastError();
+}
 int k_set_u64(unsigned long long* p, unsigned long long v, void* stream) {
     set_u64_kernel<<<1, 1, 0, ST>>>(p, v);
     return (int)cudaGetLastError();

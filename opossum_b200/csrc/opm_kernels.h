@@ -84,6 +84,14 @@ int k_readout_combine_b(const double* g, int w, uint64_t maps_len, int ns, doubl
 int k_fp64_peak(double* out, int iters, int blocks, void* stream);
 int k_fetch_from_host(void* dst, const void* src_host, size_t bytes, void* stream);  // bytes % 8 == 0, src pinned + mapped
 int k_set_u64(unsigned long long* p, unsigned long long v, void* stream);
+constexpr int kPrologueTails = 8;
+struct ProloguePlan {
+    unsigned long long* dst; const unsigned long long* src_host; unsigned words;   // op descriptors (pinned + mapped source)
+    unsigned long long* stats; unsigned stats_words;                               // zeroed
+    BBoxAccum* acc[2];                                                             // reset to the identity (NULL: none)
+    unsigned long long* tail[kPrologueTails]; unsigned long long tail_val[kPrologueTails]; int n_tails;
+};
+int k_trace_prologue(const ProloguePlan& P, void* stream);
 int k_fill_u8(uint8_t* p, uint8_t v, uint64_t n, int sms, void* stream);
 
 }  // namespace opm

@@ -208,6 +208,7 @@ class DetectorReadout:
         self.host = [{"buf": torch.zeros(self.buf.numel(), dtype=torch.float64).pin_memory(),
                       "B": torch.zeros(max(self.nB, 1), dtype=torch.float64).pin_memory(),
                       "status": torch.zeros(self.status.numel(), dtype=torch.int32).pin_memory(),
+                      "report": torch.zeros(8 * max(nf, 1), dtype=torch.float64).pin_memory(), "lean": False,
                       "maps": None, "event": None, "with_maps": False} for _ in range(2)]
         w = 1 if solo else world()[1]  # solo: this rank reads its own detectors out without meeting the others
         self.w = w
@@ -282,11 +283,17 @@ class DetectorReadout:
             dist.all_gather_into_tensor(self.gA.view(-1), self.buf[: self.nA])
             _check(L.opm_readout_combine_ranges_sums(self.ctx.h, vp(self.gA.data_ptr()), w, nf, ns, vp(self.buf.data_ptr())))
         # ---- phase B
-        self.status.zero_()
+        H = self.host[slot]
+        # peer path with fluence detectors only and no map download: the last kernel of the report writes range, peak, total and
+        # status straight into this slot's pinned host block -- no status reset, no device->host copies in the stream
+        H["lean"] = lean = bool(peer and not ns and not download_maps)
+        if not lean:
+            self.status.zero_()
         if peer:  # range, windowed binning, column-slice merge, peak / total: three flag meetings over NVLink, no NCCL
             for j, (arr, n) in enumerate(hits):
                 _check(L.opm_peer_fluence_report_async(self.peer[j].h, arr, n, -1, nx, ny, vp(self._ptr(self.buf, 4 * j)),
-                                                       vp(self._ptr(self.buf, self.nA + 2 * j)), vp(self.status.data_ptr() + 4 * j)))
+                                                       vp(self._ptr(self.buf, self.nA + 2 * j)), vp(self.status.data_ptr() + 4 * j),
+                                                       vp(H["report"].data_ptr() + 64 * j) if lean else None))
         for j, (arr, n) in enumerate(hits if not peer else []):
             _check(L.opm_fluence_binning_async(arr, n, -1, nx, ny, vp(self._ptr(self.buf, 4 * j)), 0,
                                                vp(self.maps[j].data_ptr()), vp(self.status.data_ptr() + 4 * j)))
@@ -307,11 +314,11 @@ class DetectorReadout:
             _check(L.opm_fluence_peak_total_async(self.ctx.h, vp(self.maps[j].data_ptr()), nx, ny, vp(self._ptr(self.buf, 4 * j)),
                                                   vp(self._ptr(self.buf, self.nA + 2 * j))))
         # ---- read
-        H = self.host[slot]
-        H["buf"].copy_(self.buf, non_blocking=True)
-        if ns:
-            H["B"].copy_(self.mb[self.maps_len:], non_blocking=True)
-        H["status"].copy_(self.status, non_blocking=True)
+        if not lean:
+            H["buf"].copy_(self.buf, non_blocking=True)
+            if ns:
+                H["B"].copy_(self.mb[self.maps_len:], non_blocking=True)
+            H["status"].copy_(self.status, non_blocking=True)
         H["with_maps"] = bool(download_maps and nf)
         if H["with_maps"] and peer:  # every rank collects the column slices of all ranks (peer copies)
             for j in range(nf):
@@ -335,14 +342,20 @@ class DetectorReadout:
             dist.barrier()  # no rank starts its next read-out while a peer still copies its slice
         out = {}
         for j, node in enumerate(self.fl):
-            r = h[4 * j: 4 * j + 4].tolist()
+            if H["lean"]:
+                rep = H["report"][8 * j: 8 * j + 8].tolist()
+                r, pk, st = rep[0:4], rep[4:6], int(rep[6])
+                if st:
+                    self.status.zero_()  # sticky on this path: reported once
+            else:
+                r = h[4 * j: 4 * j + 4].tolist()
+                pk = h[self.nA + 2 * j: self.nA + 2 * j + 2].tolist()
+                st = int(H["status"][j])
             lrtb = (-r[0], r[1], r[2], -r[3])
             if not all(math.isfinite(v) for v in lrtb):
                 raise ValueError("could not calculate bounding box")
-            st = int(H["status"][j])
             if st:
                 raise RuntimeError(f"fluence binning raised status bits {st:#x}")
-            pk = h[self.nA + 2 * j: self.nA + 2 * j + 2].tolist()
             out[node] = {"lrtb": lrtb, "peak": pk[0], "total_energy": pk[1],
                          "map": H["maps"][j].numpy().reshape(nx, ny).T.copy() if download_maps else None}
         for k, node in enumerate(self.sp):

@@ -59,9 +59,14 @@ def _worker(rank, world_size, port, q):
         b, e = sharding.shard_range(SIDE * SIDE, rank, world_size)
         st, rep, ro = _report(ctx, b, e - b, True, world_size)
         used_peer = ro.peer is not None
+        # the lean form of the same read-out (no map download: the last kernel writes the report into pinned host memory)
+        dist.barrier()
+        lean = ro.run(download_maps=False)[2]
+        ok_lean = bool(ro.host[0]["lean"] and lean["lrtb"] == rep["lrtb"] and lean["peak"] == rep["peak"] and
+                       lean["total_energy"] == rep["total_energy"] and lean["map"] is None)
         # the same shards merged by the NCCL-free fallback cannot run under gloo; compare with the whole source instead (rank 0)
         if rank == 0:
-            q.put({"ok_meet": bool(ok_meet), "used_peer": used_peer, "lrtb": rep["lrtb"], "peak": rep["peak"], "total": rep["total_energy"],
+            q.put({"ok_meet": bool(ok_meet), "used_peer": used_peer, "ok_lean": ok_lean, "lrtb": rep["lrtb"], "peak": rep["peak"], "total": rep["total_energy"],
                    "map": rep["map"], "interactions": st.interactions})
         dist.barrier()
         del rep, ro
@@ -83,7 +88,7 @@ def test_peer_readout_two_ranks_on_one_gpu_equals_single_process():
     for p in procs:
         p.join(timeout=120)
         assert p.exitcode == 0
-    assert got["ok_meet"] and got["used_peer"]
+    assert got["ok_meet"] and got["used_peer"] and got["ok_lean"]
     ctx = ob.Context(0)
     try:
         st, rep, _ = _report(ctx, 0, SIDE * SIDE, None, 1)
