@@ -281,7 +281,7 @@ def run_c4_strong(args, ctx, dev, stream, rank, world):
 
     import scenes
     from opossum_b200 import sharding
-    steps = max(3, min(args.steps, 10))
+    steps = max(3, min(args.steps, 20))
     n_total = C4_SIDE * C4_SIDE
 
     def setup(first, count, peer, solo=False):
@@ -387,12 +387,20 @@ def run_c4_strong(args, ctx, dev, stream, rank, world):
         del ro, src, scene
         if rank == 0:  # the whole job on one GPU of the same box: speed-up basis + parity reference
             scene1, src1, ro1, st1 = setup(0, n_total, False, solo=True)
+            # the basis is the FASTER of two passes: the whole job on one GPU runs 7x longer per pass than a rank of the sharded
+            # run and meets the board's power cap sooner (profiles/r2_summary.md); the conservative speed-up uses the better one
             ms1, trace1, rep1 = timed(scene1, src1, ro1, lambda: torch.cuda.synchronize())
+            time.sleep(0.5)
+            ms1b, trace1b, rep1 = timed(scene1, src1, ro1, lambda: torch.cuda.synchronize())
+            n1_passes = [ms1, ms1b]
+            if ms1b < ms1:
+                ms1, trace1 = ms1b, trace1b
             ref = ro1.run(download_maps=True)[2]
             import numpy as np
             nz = ref["map"] > 0
             rel = float((np.abs(merged["map"] - ref["map"])[nz] / ref["map"][nz]).max())
-            out["n1_same_box"] = {"ms_per_step": ms1, "trace_ms": trace1, "readout_ms": ms1 - trace1, "interactions_per_s": st1.interactions / (ms1 * 1e-3)}
+            out["n1_same_box"] = {"ms_per_step": ms1, "trace_ms": trace1, "readout_ms": ms1 - trace1, "interactions_per_s": st1.interactions / (ms1 * 1e-3),
+                                   "passes_ms_per_step": n1_passes}
             out["speedup_vs_n1_basis"] = ms1 / ms
             out["parity_vs_n1"] = {"map_worst_rel_bin": rel, "filled_bins_equal": bool(np.array_equal(nz, merged["map"] > 0)),
                                    "range_equal": bool(tuple(merged["lrtb"]) == tuple(ref["lrtb"])),
