@@ -480,21 +480,24 @@ def run_product(args):
                 pipe["pending"] = None
             return pipe["last"]
 
-        # ---- e2e inputs: what the reference's distributions produce on the host (positions n x 3, energies n)
-        pos_h = torch.empty((n, 3), dtype=torch.float64).pin_memory()
-        e_h = torch.empty(n, dtype=torch.float64).pin_memory()
+        # ---- e2e inputs: what the reference's PositionDistribution produces on the host -- the points of this rank's shard, (x, y)
+        # only: every position distribution of the reference has z = 0 -- and the EnergyDistribution as a descriptor: the energies
+        # are a function of (x, y) (general_gaussian.rs:93-120) and are evaluated on the device, like the spectrum
+        pos_h = torch.empty((n, 2), dtype=torch.float64).pin_memory()
         tmp = np.empty(n)
-        for k, f in enumerate(("px", "py", "pz")):
+        for k, f in enumerate(("px", "py")):
             ctx.to_host(src.field_ptr(f), tmp)
             pos_h[:, k] = torch.from_numpy(tmp)
-        ctx.to_host(src.field_ptr("e"), tmp)
-        e_h.copy_(torch.from_numpy(tmp))
         e2e_rays = [ob.Rays(ctx, n), ob.Rays(ctx, n)]
         wvl, w = scenes.spectrum_of(scenes.c2_source(n))
+        sd_e2e = scenes.source_to_product(scenes.c2_source(n * world))
+        if world > 1:  # a shard cannot know the normalisation sum of the whole source: it is a property of the source, taken once
+            en = scenes.c2_source(n * world)["energy"]
+            sd_e2e.general_gaussian(en[2], en[3], en[4], en[5], en[6], norm=sd.energy_norm(ctx))
         e2e_k = [0]
 
         def upload(rays):
-            rays.new_collimated_with_spectrum(pos_h.data_ptr(), e_h.data_ptr(), n, wvl, w)
+            rays.new_collimated_xy(pos_h.data_ptr(), n, sd_e2e)
 
         def step_e2e():
             """host buffers -> reports.  Two bundles alternate: the upload of the NEXT step's inputs runs on the library's
@@ -503,6 +506,15 @@ def run_product(args):
             e2e_k[0] += 1
             upload(nxt)
             scene.raytrace(cur, sync=False)
+            return read_out(True)
+
+        doc_rays = ob.Rays(ctx, n)
+
+        def step_document():
+            """document level, what `OpmDocument::analyze` does (opm_document.rs:270-289): source DESCRIPTOR in (position, energy
+            and spectral distribution: a few hundred bytes) -> rays generated on the device -> trace -> reports on the host"""
+            sd.generate_strided(ctx, first, count, stride, rays=doc_rays)
+            scene.raytrace(doc_rays, sync=False)
             return read_out(True)
 
         def barrier():
@@ -557,15 +569,26 @@ def run_product(args):
             step_e2e()
         barrier()
         e2e_ms = 1e3 * (time.perf_counter() - t0)
+        # ---- document-level e2e: descriptors in, reports out
+        for _ in range(max(args.warmup, 1)):
+            step_document()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            doc_check = step_document()
+        barrier()
+        doc_ms = 1e3 * (time.perf_counter() - t0)
+        for key in (9, 10, "spot"):
+            assert np.allclose(np.asarray(doc_check[key], dtype=float), np.asarray(check[key], dtype=float), rtol=1e-9), (key, doc_check[key], check[key])
         clk = clocks.stop() if rank == 0 else None  # sampled over both timed regions (device-resident and e2e)
 
-        t = torch.tensor([ms, e2e_ms, float(inter_per_step), kern_ms], dtype=torch.float64, device=dev)
+        t = torch.tensor([ms, e2e_ms, float(inter_per_step), kern_ms, doc_ms], dtype=torch.float64, device=dev)
         if world > 1:
             tmax = t.clone()
             dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
             tsum = t.clone()
             dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
-            ms, e2e_ms, kern_ms = tmax[0].item(), tmax[1].item(), tmax[3].item()
+            ms, e2e_ms, kern_ms, doc_ms = tmax[0].item(), tmax[1].item(), tmax[3].item(), tmax[4].item()
             inter_total = tsum[2].item()
         else:
             inter_total = float(inter_per_step)
@@ -622,7 +645,7 @@ def run_product(args):
         achieved = bytes_step / (kern_ms_step * 1e-3) / 1e9
         unfused = inter_per_step * 146.0 / (kern_ms_step * 1e-3) / 1e9  # 146 B per stand-alone interaction
         flop_per_inter = 300.0  # SURVEY 8d estimate (FMA = 2 flop), sqrt/div counted as one
-        h2d = n * 32 + 16 * len(wvl)
+        h2d = n * 16 + 16 * len(wvl) + 256  # (x, y) of every position + spectrum + the energy distribution's descriptor
         d2h = 2 * MAP_NX * MAP_NY * 8 + 2 * 48 + 64
         # DRAM bytes of the same launch from the committed `ncu --set full` capture (never measured under the profiler here)
         traffic = None
@@ -644,8 +667,15 @@ def run_product(args):
                        "collective": "2 NCCL collectives per step: all_gather(map ranges | spot sums), all_gather(fluence maps | spot radii), each combined in rank order by one kernel" if world > 1 else "none (1 GPU)"},
             "e2e": {"value": inter_total * args.steps / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_ms / args.steps,
+                    "inputs": "the PositionDistribution's points as (x, y) in pinned host memory (z = 0 for every reference distribution); "
+                              "EnergyDistribution, spectrum and isometry as descriptors evaluated on the device "
+                              "(opm_rays_new_collimated_xy, rays.rs:264-297)",
                     "pipeline": "two bundles: H2D of step k+1 (copy stream) overlaps trace + read-out of step k",
-                    "host_binding": numa},
+                    "host_binding": numa,
+                    "document_level": {"value": inter_total * args.steps / (doc_ms * 1e-3), "unit": UNIT, "ms_per_step": doc_ms / args.steps,
+                                       "h2d_bytes_per_step": 512, "d2h_bytes_per_step": d2h,
+                                       "what": "source descriptor in (opm_source_generate on the device) -> trace -> reports on the host, "
+                                               "what OpmDocument::analyze does (opm_document.rs:270-289)"}},
             "gpu_launches": launches_per_step * args.steps,
             "clocks": clk,
             "roofline": {"bound": "hbm", "kernel": ("opm_jit_trace (fused surface sequence, compiled at run time for this op program)" if jit["launches"] else

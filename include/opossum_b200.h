@@ -184,8 +184,11 @@ typedef enum {
 
 enum {
     OPM_REFRACT_EMIT_CHILDREN = 1,   /* append reflected rays to `children` (warp-aggregated atomics) */
-    OPM_REFRACT_CONTINUE_AS_CHILD = 2 /* mirror in a sequence: the reflected ray continues, rays without one leave the bundle
+    OPM_REFRACT_CONTINUE_AS_CHILD = 2, /* mirror in a sequence: the reflected ray continues, rays without one leave the bundle
                                         (refraction_intended = false, nodes/thin_mirror.rs:209-250) */
+    OPM_REFRACT_STAT_KEY = 4         /* the launch statistic first_valid_key (Rays::bounce_lvl, rays.rs:183-194) is taken right after
+                                        this op instead of at the end of the program: the ghost-focus analysis reads the bounce
+                                        level between refract_on_surface and apodize (analyzers/raytrace.rs:118-133) */
 };
 
 typedef struct {
@@ -270,6 +273,10 @@ void opm_context_destroy(OpmContext* ctx);
 OpmStatus opm_context_synchronize(OpmContext* ctx);
 /* the same check without waiting for anything but the copy of the status word; clear != 0: forget the bits afterwards */
 OpmStatus opm_context_check_errors(OpmContext* ctx, int32_t clear);
+/* ray-surface interactions of all launches of the context so far (a device counter no launch resets); synchronises */
+OpmStatus opm_context_interactions_total(OpmContext* ctx, uint64_t* out);
+/* first_valid_key (OpmTraceStats) of the context's latest trace launch stored to dst_dev on the device, asynchronously */
+OpmStatus opm_context_last_first_valid_key_async(OpmContext* ctx, uint64_t* dst_dev);
 void* opm_context_stream(OpmContext* ctx);
 /* number of kernels launched through this context so far (bench.py "gpu_launches") */
 uint64_t opm_context_launch_count(const OpmContext* ctx);
@@ -310,6 +317,8 @@ void opm_raytrace_config_default(OpmRayTraceConfig* out);                       
 OpmStatus opm_rays_create(OpmContext* ctx, uint64_t capacity, OpmRays** out);
 void opm_rays_destroy(OpmRays* rays);
 uint64_t opm_rays_len(const OpmRays* rays);        /* slots in use (includes invalid and removed rays) */
+/* opm_rays_len of several bundles that asynchronous launches appended children to, with one synchronisation for all of them */
+OpmStatus opm_rays_refresh_lens(OpmRays* const* list, int32_t n);
 uint64_t opm_rays_capacity(const OpmRays* rays);
 OpmStatus opm_rays_clear(OpmRays* rays);
 /* Tells the library that (nearly) every ray of the bundle carries `wavelength_m` -- what a one-wavelength source produces
@@ -436,7 +445,22 @@ OpmStatus opm_fluence_binning(OpmHitMap* const* maps, int32_t n_maps, int64_t bo
                               double lrtb_out[4]);
 /* Device-chained forms (asynchronous, no host synchronisation).  The map range lives on the device as
  * range_dev[4] = (-left, right, top, -bottom): one element-wise MAX all-reduce merges the ranges of several GPUs and -inf
- * is the identity of a GPU without hits.  status_dev accumulates OpmStatus bits (OPM_ERR_BIN_RANGE). */
+ * is the identity of a GPU without hits.  status_dev accumulates OpmStatus bits (OPM_ERR_BIN_RANGE).
+ * bounce filter: >= 0 a bounce count, -1 all bounces, OPM_BOUNCE_OF_LAST_LAUNCH = Rays::bounce_lvl (rays.rs:183-194) of the
+ * bundle the context's latest trace launch ran on -- its first_valid_key statistic, read ON THE DEVICE, so that trace -> fluence
+ * check chains without the host (OpticSurface::evaluate_fluence_of_ray_bundle, optic_surface.rs:202-224). */
+#define OPM_BOUNCE_OF_LAST_LAUNCH INT64_MIN
+/* Peak fluence of ONE bundle's hits on a surface, the check the ghost-focus analysis makes per bundle and surface
+ * (OpticSurface::evaluate_fluence_of_ray_bundle, optic_surface.rs:202-224 -> RaysHitMap::get_max_fluence, rays_hit_map.rs:777-798):
+ * bounding box, Binning into a small nx x ny map (<= 160 KB), peak -- three launches, nothing uploaded, asynchronous.
+ * acc_dev: OPM_PEAK_CHECK_ACC_BYTES of device memory prepared ONCE by opm_fluence_peak_check_acc_init (every check leaves it
+ * ready for the next); map_dev: nx * ny doubles of scratch; result_dev: 8 doubles, of which [6] must be zero on entry:
+ * [0..4) range (-left, right, top, -bottom; -inf = the bundle recorded no hit of that bounce level), [4] peak, [5] total,
+ * [6] OpmStatus bits of the splat (u32), [7] first_valid_key of the launch when bounce_filter is OPM_BOUNCE_OF_LAST_LAUNCH (u64). */
+#define OPM_PEAK_CHECK_ACC_BYTES 64
+OpmStatus opm_fluence_peak_check_acc_init(OpmContext* ctx, void* acc_dev, uint64_t n);
+OpmStatus opm_fluence_peak_check_async(OpmHitMap* const* maps, int32_t n_maps, int64_t bounce_filter, uint64_t nx, uint64_t ny,
+                                       void* acc_dev, double* map_dev, double* result_dev);
 OpmStatus opm_hitmaps_bounding_box_async(OpmHitMap* const* maps, int32_t n_maps, int64_t bounce_filter_or_minus1, double* range_dev);
 OpmStatus opm_fluence_binning_async(OpmHitMap* const* maps, int32_t n_maps, int64_t bounce_filter_or_minus1, uint64_t nx, uint64_t ny,
                                     const double* range_dev, int32_t accumulate, double* map_dev, uint32_t* status_dev);
@@ -571,6 +595,14 @@ OpmStatus opm_source_generate(OpmRays* rays, const OpmSourceDesc* desc, uint64_t
 /* positions first_pos, first_pos + stride, ... (n_pos of them): a load-balanced shard of the source for rank g of G is
  * (first_pos = g, stride = G) -- rays are independent, so any partition of the source index set is a valid sharding */
 OpmStatus opm_source_generate_strided(OpmRays* rays, const OpmSourceDesc* desc, uint64_t first_pos, uint64_t n_pos, uint64_t stride);
+/* Rays::new_collimated_with_spectrum (rays.rs:264-297) from the PositionDistribution's (x, y) alone: pos_xy = n_pos x 2 doubles in
+ * (pinned) host memory -- every position distribution of the reference yields z = 0 (position_distributions/, every generator) -- while the
+ * EnergyDistribution (uniform.rs:37-41, general_gaussian.rs:93-120: a function of x and y), the spectrum and the source isometry
+ * are taken from `desc` and evaluated on the device: 16 bytes per position cross PCIe instead of 32.  Of `desc` the fields
+ * energy_dist, total_energy, mu / sigma / power / theta / rectangular, n_positions (positions of the WHOLE source; 0 = n_pos),
+ * energy_norm (0 = the given positions are the whole source: the sum is taken on the device), the spectrum and iso are used.
+ * Asynchronous like opm_rays_new_collimated_with_spectrum (copy stream; the expansion is queued when the bundle is first used). */
+OpmStatus opm_rays_new_collimated_xy(OpmRays* rays, const double* pos_xy, uint64_t n_pos, const OpmSourceDesc* desc);
 /* sum of unnormalised General2DGaussian weights over [pos_begin,pos_end) (for multi-GPU: allreduce, then set energy_norm) */
 OpmStatus opm_source_energy_norm(OpmContext* ctx, const OpmSourceDesc* desc, uint64_t pos_begin, uint64_t pos_end,
                                  double* partial_sum);

@@ -231,7 +231,8 @@ EXPORTS = [
     "opm_rays_wavefront_error", "opm_readout_combine_ranges_sums", "opm_readout_combine_maps_radii", "opm_peer_group_create", "opm_peer_group_connect", "opm_peer_group_destroy",
     "opm_peer_allgather_async", "opm_peer_fluence_report_async", "opm_peer_fluence_gather_map", "opm_peer_group_phase_times", "opm_measure_fp64_peak", "opm_device_alloc",
     "opm_device_free", "opm_device_memset", "opm_device_to_host", "opm_host_to_device", "opm_host_alloc_pinned", "opm_host_free_pinned",
-    "opm_spectrum_gaussian", "opm_source_generate", "opm_source_generate_strided", "opm_source_energy_norm",
+    "opm_spectrum_gaussian", "opm_source_generate", "opm_source_generate_strided", "opm_source_energy_norm", "opm_rays_new_collimated_xy", "opm_rays_refresh_lens", "opm_context_interactions_total",
+    "opm_context_last_first_valid_key_async", "opm_fluence_peak_check_acc_init", "opm_fluence_peak_check_async",
 ]
 
 _lib = None
@@ -364,6 +365,7 @@ def lib() -> C.CDLL:
         "opm_source_generate_strided": (i32, [vp, C.POINTER(OpmSourceDesc), u64, u64, u64]),
         "opm_spectrum_gaussian": (i32, [C.c_double, C.c_double, u64, C.c_double, C.c_double, C.c_double, dp, dp]),
         "opm_source_energy_norm": (i32, [vp, C.POINTER(OpmSourceDesc), u64, u64, dp]),
+        "opm_rays_new_collimated_xy": (i32, [vp, vp, u64, C.POINTER(OpmSourceDesc)]),
     }
     sig.update({
         "opm_node_desc_init": (None, [C.POINTER(OpmNodeDesc), i32]),

@@ -464,6 +464,11 @@ class Rays:
         _check(F.lib().opm_rays_new_collimated_with_spectrum(self.h, C.c_void_p(pos_xyz_ptr), C.c_void_p(e_pos_ptr), n_pos,
                                                              wv.ctypes.data_as(dp), wg.ctypes.data_as(dp), len(wv)))
 
+    def new_collimated_xy(self, pos_xy_ptr: int, n_pos: int, source: "SourceDesc"):
+        """Rays::new_collimated_with_spectrum from the position distribution's (x, y) alone (n_pos x 2 doubles, ideally pinned):
+        z = 0, energies from the source's EnergyDistribution descriptor, spectrum and isometry applied on the device."""
+        _check(F.lib().opm_rays_new_collimated_xy(self.h, C.c_void_p(pos_xy_ptr), n_pos, C.byref(source.c)))
+
     def to_array(self) -> np.ndarray:
         n = len(self)
         out = np.zeros(max(n, 1), dtype=RAY_DTYPE)

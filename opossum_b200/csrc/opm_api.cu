@@ -43,6 +43,7 @@ struct OpmContext {
     // so they never queue behind a bulk upload on the H2D copy engine
     static constexpr int kPutSlots = 32;
     static constexpr size_t kPutBytes = 256;
+    double* d_srcspec = nullptr;  // spectrum table of the source being generated (opm_source_generate, <= 16 lines)
     unsigned char* h_put_ring = nullptr;
     cudaEvent_t put_ev[kPutSlots] = {};
     int put_pos = 0;
@@ -87,6 +88,8 @@ struct OpmRays {
     size_t h_spec_bytes = 0;
     cudaEvent_t ev_uploaded = nullptr, ev_expanded = nullptr;
     bool pending = false;
+    int pend_kind = 0;         // 0: positions (n x 3) + energies; 1: xy only, energies from pend_src on the device
+    SourceParams pend_src{};
     uint64_t pend_n_pos = 0;
     uint32_t pend_n_wvl = 0;
     // optional per-ray position history (`pos_hist`, ray.rs:70): level-major log, see HistParams.
@@ -261,7 +264,7 @@ extern "C" void opm_context_destroy(OpmContext* c) {
     jit_cache_destroy(c->jit);
     for (int k = 0; k < OpmContext::kPutSlots; ++k) if (c->put_ev[k]) cudaEventDestroy(c->put_ev[k]);
     cudaFreeHost(c->h_put_ring);
-    cudaFree(c->d_stats); cudaFreeHost(c->h_stats); cudaFree(c->d_ops); cudaFree(c->d_scratch); cudaFreeHost(c->h_scratch);
+    cudaFree(c->d_stats); cudaFreeHost(c->h_stats); cudaFree(c->d_ops); cudaFree(c->d_scratch); cudaFreeHost(c->h_scratch); cudaFree(c->d_srcspec);
     if (c->own_stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -284,6 +287,23 @@ extern "C" OpmStatus opm_context_synchronize(OpmContext* c) {
     CU(cudaSetDevice(c->device));
     CU(cudaStreamSynchronize(c->stream));
     return opm_context_check_errors(c, 1);
+}
+// interactions of all launches of the context so far (a device counter no launch resets); synchronises the stream
+extern "C" OpmStatus opm_context_interactions_total(OpmContext* c, uint64_t* out) {
+    if (!c || !out) return fail(OPM_ERR_ARG, "NULL argument");
+    CU(cudaSetDevice(c->device));
+    unsigned long long* h = (unsigned long long*)(c->h_scratch + 1040);
+    CU(cudaMemcpyAsync(h, &c->d_stats->total_interactions, 8, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    *out = *h;
+    return OPM_OK;
+}
+// first_valid_key of the context's latest trace launch, copied on the device (asynchronous): ~0 when the bundle had no valid ray
+extern "C" OpmStatus opm_context_last_first_valid_key_async(OpmContext* c, uint64_t* dst_dev) {
+    if (!c || !dst_dev) return fail(OPM_ERR_ARG, "NULL argument");
+    CU(cudaSetDevice(c->device));
+    KL(k_first_key_store(&c->d_stats->first_inv, (unsigned long long*)dst_dev, c->stream)); c->launches++;
+    return OPM_OK;
 }
 // ---- run-time specialised kernels (opm_jit.cu)
 extern "C" uint64_t opm_jit_selftest(char* log, uint64_t cap) { return jit_selftest(log, cap); }
@@ -511,7 +531,13 @@ static OpmStatus rays_materialize(OpmRays* r) {
     double* d_e = d_xyz + 3 * n_pos;
     double* d_w = (double*)(r->d_stage + align_up(n_pos * 32, 256));
     CU(cudaStreamWaitEvent(c->stream, r->ev_uploaded, 0));
-    if (n_rays) { KL(k_expand_collimated(d_xyz, d_e, d_w, d_w + r->pend_n_wvl, r->pend_n_wvl, r->v, n_rays, c->sms, c->stream)); c->launches++; }
+    if (r->pend_kind == 1) {  // [xy n_pos x 2 | norm (8 bytes) ... | spectrum]
+        double* d_xy = (double*)r->d_stage;
+        double* d_norm = d_xy + 2 * n_pos;
+        double* d_spec = (double*)(r->d_stage + align_up(n_pos * 16 + 8, 256));
+        KL(k_expand_collimated_xy(d_xy, n_pos, r->pend_src, d_norm, d_spec, d_spec + r->pend_n_wvl, r->pend_n_wvl, r->v, n_rays, c->sms, c->stream));
+        c->launches += 1 + ((r->pend_src.energy_dist == OPM_EDIST_GENERAL_GAUSSIAN && !(r->pend_src.energy_norm > 0.0)) ? 1 : 0);
+    } else if (n_rays) { KL(k_expand_collimated(d_xyz, d_e, d_w, d_w + r->pend_n_wvl, r->pend_n_wvl, r->v, n_rays, c->sms, c->stream)); c->launches++; }
     CU(cudaEventRecord(r->ev_expanded, c->stream));
     KL(k_set_u64(r->d_tail, n_rays, c->stream)); c->launches++;
     return OPM_OK;
@@ -524,6 +550,37 @@ static OpmStatus rays_refresh_len(OpmRays* r) {
     CU(cudaStreamSynchronize(r->ctx->stream));
     r->len = t > r->cap ? r->cap : t;
     r->len_dirty = false;
+    return OPM_OK;
+}
+// lengths of several bundles that launches appended to (ghost-focus children), with ONE synchronisation
+extern "C" OpmStatus opm_rays_refresh_lens(OpmRays* const* list, int32_t n) {
+    if (n <= 0) return OPM_OK;
+    if (!list) return fail(OPM_ERR_ARG, "NULL argument");
+    OpmContext* c = nullptr;
+    std::vector<OpmRays*> dirty;
+    for (int k = 0; k < n; ++k) {
+        OpmRays* r = list[k];
+        if (!r) return fail(OPM_ERR_ARG, "NULL bundle");
+        if (r->pending) { OpmStatus s = rays_materialize(r); if (s) return s; }
+        if (!r->len_dirty) continue;
+        if (c && r->ctx != c) return fail(OPM_ERR_ARG, "bundles of different contexts");
+        c = r->ctx;
+        dirty.push_back(r);
+    }
+    if (dirty.empty()) return OPM_OK;
+    CU(cudaSetDevice(c->device));
+    constexpr size_t kBatch = 256;  // 2 KB of the pinned scratch area at a time
+    for (size_t b = 0; b < dirty.size(); b += kBatch) {
+        const size_t m = std::min(kBatch, dirty.size() - b);
+        unsigned long long* h = (unsigned long long*)(c->h_scratch + 2048);
+        for (size_t k = 0; k < m; ++k) CU(cudaMemcpyAsync(h + k, dirty[b + k]->d_tail, 8, cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+        for (size_t k = 0; k < m; ++k) {
+            OpmRays* r = dirty[b + k];
+            r->len = h[k] > r->cap ? r->cap : h[k];
+            r->len_dirty = false;
+        }
+    }
     return OPM_OK;
 }
 extern "C" uint64_t opm_rays_len(const OpmRays* r) {
@@ -775,8 +832,68 @@ extern "C" OpmStatus opm_rays_new_collimated_with_spectrum(OpmRays* r, const dou
     CU(cudaMemcpyAsync(d_e, e_pos, n_pos * 8, cudaMemcpyHostToDevice, c->copy_stream));
     CU(cudaMemcpyAsync(d_w, r->h_spec, (size_t)n_wvl * 16, cudaMemcpyHostToDevice, c->copy_stream));
     CU(cudaEventRecord(r->ev_uploaded, c->copy_stream));
-    r->pending = true; r->pend_n_pos = n_pos; r->pend_n_wvl = n_wvl;
+    r->pending = true; r->pend_kind = 0; r->pend_n_pos = n_pos; r->pend_n_wvl = n_wvl;
     r->len = n_rays; r->len_dirty = false;  // the device-side length is set when the expansion is enqueued
+    return OPM_OK;
+}
+static OpmStatus source_params(const OpmSourceDesc* d, SourceParams& S);
+// The same bundle from the PositionDistribution's (x, y) alone (16 bytes per position over PCIe instead of 32): z = 0 for every
+// position distribution of the reference, and the EnergyDistribution described by `desc` (energy_dist, total_energy, the Gaussian's
+// parameters; n_positions = positions of the WHOLE source for Uniform; energy_norm = sum of the unnormalised Gaussian weights over
+// the whole source, 0 = these positions are the whole source: sum them on the device) is evaluated on the device, like the
+// spectrum and the source isometry of `desc`.  pos_dist / grid_* / size_* of `desc` are not used.
+extern "C" OpmStatus opm_rays_new_collimated_xy(OpmRays* r, const double* pos_xy, uint64_t n_pos, const OpmSourceDesc* desc) {
+    if (!r || !pos_xy || !desc || !desc->wavelengths || desc->n_wavelengths == 0) return fail(OPM_ERR_ARG, "NULL argument");
+    OpmContext* c = r->ctx;
+    CU(cudaSetDevice(c->device));
+    const uint32_t n_wvl = desc->n_wavelengths;
+    for (uint32_t k = 0; k < n_wvl; ++k)  // Ray::new (ray.rs:114-116)
+        if (!(desc->wavelengths[k] > 0.0) || !std::isfinite(desc->wavelengths[k])) return fail(OPM_ERR_ARG, "wavelength must be >0");
+    OpmSourceDesc d2 = *desc;
+    d2.pos_dist = OPM_POS_FIBONACCI_RECT;  // the generator is not used here: skip its consistency checks
+    if (d2.n_positions == 0) d2.n_positions = n_pos;
+    SourceParams S;
+    OpmStatus s = source_params(&d2, S);
+    if (s) return s;
+    const uint64_t n_rays = n_pos * n_wvl;
+    r->pending = false;
+    r->mono_wvl = n_wvl == 1 ? desc->wavelengths[0] : 0.0;
+    if (r->d_hist) { OpmStatus hs = hist_clear(r); if (hs) return hs; }
+    s = opm_rays_reserve(r, n_rays);
+    if (s) return s;
+    const size_t need = align_up(n_pos * 16 + 8, 256) + (size_t)n_wvl * 16;
+    if (need > r->stage_bytes) {
+        CU(cudaStreamSynchronize(c->copy_stream));
+        CU(cudaStreamSynchronize(c->stream));
+        cudaFree(r->d_stage);
+        r->d_stage = nullptr; r->stage_bytes = 0;
+        CU(cudaMalloc(&r->d_stage, need));
+        r->stage_bytes = need;
+    }
+    if (!r->ev_uploaded) {
+        CU(cudaEventCreateWithFlags(&r->ev_uploaded, cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&r->ev_expanded, cudaEventDisableTiming));
+        CU(cudaEventRecord(r->ev_expanded, c->stream));
+        CU(cudaEventRecord(r->ev_uploaded, c->copy_stream));
+    }
+    double* d_xy = (double*)r->d_stage;
+    double* d_spec = (double*)(r->d_stage + align_up(n_pos * 16 + 8, 256));
+    CU(cudaEventSynchronize(r->ev_uploaded));
+    if ((size_t)n_wvl * 16 > r->h_spec_bytes) {
+        cudaFreeHost(r->h_spec);
+        r->h_spec = nullptr; r->h_spec_bytes = 0;
+        CU(cudaMallocHost(&r->h_spec, (size_t)n_wvl * 16));
+        r->h_spec_bytes = (size_t)n_wvl * 16;
+    }
+    memcpy(r->h_spec, desc->wavelengths, (size_t)n_wvl * 8);
+    if (desc->weights) memcpy(r->h_spec + n_wvl, desc->weights, (size_t)n_wvl * 8);
+    else for (uint32_t k = 0; k < n_wvl; ++k) r->h_spec[n_wvl + k] = 1.0;
+    CU(cudaStreamWaitEvent(c->copy_stream, r->ev_expanded, 0));
+    CU(cudaMemcpyAsync(d_xy, pos_xy, n_pos * 16, cudaMemcpyHostToDevice, c->copy_stream));
+    CU(cudaMemcpyAsync(d_spec, r->h_spec, (size_t)n_wvl * 16, cudaMemcpyHostToDevice, c->copy_stream));
+    CU(cudaEventRecord(r->ev_uploaded, c->copy_stream));
+    r->pending = true; r->pend_kind = 1; r->pend_src = S; r->pend_n_pos = n_pos; r->pend_n_wvl = n_wvl;
+    r->len = n_rays; r->len_dirty = false;
     return OPM_OK;
 }
 extern "C" OpmStatus opm_rays_download(const OpmRays* rc, OpmRay* host, uint64_t capacity, uint64_t* n_out) {
@@ -1619,7 +1736,8 @@ extern "C" OpmStatus opm_peer_fluence_report_async(OpmPeerGroup* g, OpmHitMap* c
     // the kernel that zero-fills the window carries the meeting at its head; else bounding-box pass, meeting kernel, zero-fill
     PeerHook hook;
     memset(&hook, 0, sizeof hook);
-    if (n_maps == 1 && bounce_filter < 0 && maps[0]->acc_valid && maps[0]->len) {
+    if (bounce_filter < -1) return fail(OPM_ERR_ARG, "bad bounce filter");
+    if (n_maps == 1 && bounce_filter == -1 && maps[0]->acc_valid && maps[0]->len) {
         hook.enabled = 1; hook.V = g->view; hook.seq = ++g->seq; hook.timeout_ns = g->timeout_ns;
         hook.acc = (const BBoxAccum*)maps[0]->d_acc; hook.own_out = own; hook.all_out = all; hook.range_out = range;
         hook.status = &c->d_stats->sticky_bits;
@@ -2040,8 +2158,10 @@ static OpmStatus bounding_box_async(OpmHitMap* const* maps, int32_t n_maps, int6
     if (s) return s;
     if (!range_dev) return fail(OPM_ERR_ARG, "range_dev is NULL");
     CU(cudaSetDevice(c->device));
+    if (bounce_filter == OPM_BOUNCE_OF_LAST_LAUNCH) bounce_filter = -(int64_t)(uintptr_t)&c->d_stats->first_inv;  // read on the device
+    else if (bounce_filter < -1) return fail(OPM_ERR_ARG, "bad bounce filter");
     if (used_acc) *used_acc = (const BBoxAccum*)c->d_scratch;
-    if (n_maps == 1 && bounce_filter < 0 && maps[0]->acc_valid && maps[0]->len) {  // the trace kernel kept the box while it recorded
+    if (n_maps == 1 && bounce_filter == -1 && maps[0]->acc_valid && maps[0]->len) {  // the trace kernel kept the box while it recorded
         if (used_acc) *used_acc = (const BBoxAccum*)maps[0]->d_acc;
         KL(k_bbox_finalize((const BBoxAccum*)maps[0]->d_acc, range_dev, c->stream)); c->launches++;
         return OPM_OK;
@@ -2062,9 +2182,46 @@ extern "C" OpmStatus opm_fluence_binning_async(OpmHitMap* const* maps, int32_t n
     if (s) return s;
     if (!map_dev || !range_dev || !status_dev || nx == 0 || ny == 0) return fail(OPM_ERR_ARG, "bad map arguments");
     CU(cudaSetDevice(c->device));
+    if (bounce_filter == OPM_BOUNCE_OF_LAST_LAUNCH) bounce_filter = -(int64_t)(uintptr_t)&c->d_stats->first_inv;  // read on the device
+    else if (bounce_filter < -1) return fail(OPM_ERR_ARG, "bad bounce filter");
     if (!accumulate) CU(cudaMemsetAsync(map_dev, 0, nx * ny * sizeof(double), c->stream));
     for (int k = 0; k < n_maps; ++k)
         if (maps[k]->len) { KL(k_binning(maps[k]->v, maps[k]->len, bounce_filter, nx, ny, range_dev, map_dev, status_dev, c->sms, c->stream)); c->launches++; }
+    return OPM_OK;
+}
+// ---- per-bundle peak-fluence check of the ghost-focus analysis: three launches, no parameter uploads (opm_kernels.cu)
+extern "C" OpmStatus opm_fluence_peak_check_acc_init(OpmContext* c, void* acc_dev, uint64_t n) {
+    if (!c || !acc_dev) return fail(OPM_ERR_ARG, "NULL argument");
+    static_assert(sizeof(PeakCheckAcc) == OPM_PEAK_CHECK_ACC_BYTES, "accumulator size");
+    CU(cudaSetDevice(c->device));
+    if (n) { KL(k_peakcheck_acc_init((PeakCheckAcc*)acc_dev, n, c->stream)); c->launches++; }
+    return OPM_OK;
+}
+extern "C" OpmStatus opm_fluence_peak_check_async(OpmHitMap* const* maps, int32_t n_maps, int64_t bounce_filter, uint64_t nx, uint64_t ny,
+                                                  void* acc_dev, double* map_dev, double* result_dev) {
+    OpmContext* c;
+    OpmStatus s = check_same_ctx(maps, n_maps, &c);
+    if (s) return s;
+    if (!acc_dev || !map_dev || !result_dev || nx < 2 || ny < 2 || nx * ny * sizeof(double) > 160 * 1024)
+        return fail(OPM_ERR_ARG, "peak check: bad arguments (maps up to 160 KB)");
+    CU(cudaSetDevice(c->device));
+    const unsigned long long* key_src = nullptr;
+    if (bounce_filter == OPM_BOUNCE_OF_LAST_LAUNCH) { key_src = &c->d_stats->first_inv; bounce_filter = -(int64_t)(uintptr_t)key_src; }
+    else if (bounce_filter < -1) return fail(OPM_ERR_ARG, "bad bounce filter");
+    int last = -1;
+    for (int k = 0; k < n_maps; ++k) if (maps[k]->len) last = k;
+    bool first = true;
+    for (int k = 0; k < n_maps; ++k) {
+        if (!maps[k]->len && !(last < 0 && k == n_maps - 1)) continue;
+        // (a check without any recorded slot still runs one launch: it zero-fills the map and writes the empty range)
+        KL(k_peakcheck_bbox(maps[k]->v, maps[k]->len, bounce_filter, (PeakCheckAcc*)acc_dev, result_dev, map_dev, nx * ny, first ? 1 : 0,
+                            (k == last || last < 0) ? 1 : 0, c->sms, c->stream));
+        c->launches++;
+        first = false;
+    }
+    for (int k = 0; k < n_maps; ++k)
+        if (maps[k]->len) { KL(k_binning(maps[k]->v, maps[k]->len, bounce_filter, nx, ny, result_dev, map_dev, (unsigned*)(result_dev + 6), c->sms, c->stream)); c->launches++; }
+    KL(k_peakcheck_peak(map_dev, nx, ny, key_src, result_dev, c->stream)); c->launches++;
     return OPM_OK;
 }
 extern "C" OpmStatus opm_fluence_peak_total_async(OpmContext* c, const double* map_dev, uint64_t nx, uint64_t ny, const double* range_dev,
@@ -2328,7 +2485,7 @@ extern "C" OpmStatus opm_spectrum_gaussian(double lo, double hi, uint64_t num, d
 }
 
 static OpmStatus source_params(const OpmSourceDesc* d, SourceParams& S) {
-    memset(&S, 0, sizeof S);
+    memset((void*)&S, 0, sizeof S);
     if (!d) return fail(OPM_ERR_ARG, "desc is NULL");
     if (d->n_positions == 0) return fail(OPM_ERR_ARG, "source has no positions");
     S.pos_dist = d->pos_dist; S.energy_dist = d->energy_dist; S.rectangular = d->rectangular;
@@ -2393,27 +2550,48 @@ static OpmStatus source_generate(OpmRays* rays, const OpmSourceDesc* desc, uint6
     if (s) return s;
     if (n_pos && pos_begin + (n_pos - 1) * stride >= desc->n_positions) return fail(OPM_ERR_ARG, "position range out of bounds");
     CU(cudaSetDevice(c->device));
-    if (S.energy_dist == OPM_EDIST_GENERAL_GAUSSIAN && !(S.energy_norm > 0.0)) {
-        double norm = 0.0;
-        s = opm_source_energy_norm(c, desc, 0, desc->n_positions, &norm);
-        if (s) return s;
-        S.energy_norm = norm;
-    }
+    const bool need_norm = S.energy_dist == OPM_EDIST_GENERAL_GAUSSIAN && !(S.energy_norm > 0.0);
+    const double* hw = desc->n_wavelengths ? desc->wavelengths : nullptr;
+    const double* hg = desc->n_wavelengths ? desc->weights : nullptr;
+    if (!hw) return fail(OPM_ERR_ARG, "source needs at least one wavelength");
     rays->pending = false;
     rays->mono_wvl = (desc->n_wavelengths == 1 && desc->wavelengths) ? desc->wavelengths[0] : 0.0;
     if (rays->d_hist) { OpmStatus hs = hist_clear(rays); if (hs) return hs; }  // new rays start without a history (ray.rs:126)
     uint64_t n_rays = n_pos * S.n_wavelengths;
     s = opm_rays_reserve(rays, n_rays);
     if (s) return s;
+    if ((size_t)S.n_wavelengths * 16 <= OpmContext::kPutBytes) {
+        // fully asynchronous: the spectrum table travels through the small-parameter ring, the normalisation sum of a Gaussian
+        // energy distribution (general_gaussian.rs:107-114, taken on every apply) stays on the device
+        if (!c->d_srcspec) CU(cudaMalloc(&c->d_srcspec, OpmContext::kPutBytes));
+        double tab[OpmContext::kPutBytes / 8];
+        for (uint32_t k = 0; k < S.n_wavelengths; ++k) { tab[k] = hw[k]; tab[S.n_wavelengths + k] = hg ? hg[k] : 1.0; }
+        s = dev_put(c, c->d_srcspec, tab, (size_t)S.n_wavelengths * 16);
+        if (s) return s;
+        double* d_norm = (double*)(c->d_scratch + 512);
+        if (need_norm) {
+            CU(cudaMemsetAsync(d_norm, 0, 8, c->stream));
+            KL(k_source_norm(S, 0, desc->n_positions, d_norm, c->sms, c->stream)); c->launches++;
+        }
+        if (n_rays) {
+            KL(k_source_generate(S, rays->v, pos_begin, stride, n_rays, c->d_srcspec, c->d_srcspec + S.n_wavelengths, need_norm ? d_norm : nullptr,
+                                 c->sms, c->stream));
+            c->launches++;
+        }
+        return rays_set_len(rays, n_rays);
+    }
+    if (need_norm) {
+        double norm = 0.0;
+        s = opm_source_energy_norm(c, desc, 0, desc->n_positions, &norm);
+        if (s) return s;
+        S.energy_norm = norm;
+    }
     double one = 1.0, *d_w = nullptr;
     CU(cudaMalloc(&d_w, (size_t)S.n_wavelengths * 16));
-    const double* hw = desc->n_wavelengths ? desc->wavelengths : nullptr;
-    const double* hg = desc->n_wavelengths ? desc->weights : nullptr;
-    if (!hw) { cudaFree(d_w); return fail(OPM_ERR_ARG, "source needs at least one wavelength"); }
     CU(cudaMemcpyAsync(d_w, hw, (size_t)S.n_wavelengths * 8, cudaMemcpyHostToDevice, c->stream));
     if (hg) CU(cudaMemcpyAsync(d_w + S.n_wavelengths, hg, (size_t)S.n_wavelengths * 8, cudaMemcpyHostToDevice, c->stream));
     else CU(cudaMemcpyAsync(d_w + S.n_wavelengths, &one, 8, cudaMemcpyHostToDevice, c->stream));
-    if (n_rays) { KL(k_source_generate(S, rays->v, pos_begin, stride, n_rays, d_w, d_w + S.n_wavelengths, c->sms, c->stream)); c->launches++; }
+    if (n_rays) { KL(k_source_generate(S, rays->v, pos_begin, stride, n_rays, d_w, d_w + S.n_wavelengths, nullptr, c->sms, c->stream)); c->launches++; }
     cudaError_t e = cudaStreamSynchronize(c->stream);
     cudaFree(d_w);
     if (e != cudaSuccess) return fail(OPM_ERR_CUDA, "source generation failed: %s", cudaGetErrorString(e));

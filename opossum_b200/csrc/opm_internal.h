@@ -113,6 +113,7 @@ struct DevStats {
     // looked (asynchronous launches do not read `status_bits` back -- their errors surface at opm_context_synchronize /
     // opm_context_check_errors, like the reference's `?` aborts the analysis, rays.rs:987-991)
     unsigned int sticky_bits, _pad2;
+    unsigned long long total_interactions;  // interactions of ALL launches of the context (ghost focus reads it once per analysis)
 };
 constexpr unsigned long long kDevStatsZeroBytes = 9 * 8;  // the per-launch part
 

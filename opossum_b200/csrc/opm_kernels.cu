@@ -231,7 +231,16 @@ __global__ void __launch_bounds__(256) tally_kernel(DevRays R, uint64_t n, uint3
 // ---------------------------------------------------------------------------------------------
 // hit map: bounding box and Binning
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) hits_bbox_kernel(DevHits H, uint64_t n, long long bounce_filter, BBoxAccum* acc) {
+// bounce filter of the hit-map kernels: >= 0 a bounce count, -1 none, < -1 the NEGATED device address of a launch statistic
+// `first_inv` (DevStats): the bounce level of the bundle the context's latest trace launch ran on, read here on the device, so
+// that the ghost-focus analysis chains trace -> per-bundle fluence check without a host round trip (Rays::bounce_lvl,
+// rays.rs:183-194: the bounce count of the first valid ray, 0 when there is none)
+__device__ __forceinline__ long long resolve_bounce_filter(long long f) {
+    if (f >= -1) return f;
+    const unsigned long long inv = *reinterpret_cast<const unsigned long long*>(-f);
+    return inv ? (long long)(~inv & 0xffffffffull) : 0ll;
+}
+__device__ __forceinline__ void hits_bbox_body(const DevHits& H, uint64_t n, long long bounce_filter, BBoxAccum* acc) {
     double xmin = DBL_MAX, xmax = -DBL_MAX, ymin = DBL_MAX, ymax = -DBL_MAX;
     unsigned long long cnt = 0;
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
@@ -276,6 +285,9 @@ __global__ void __launch_bounds__(256) hits_bbox_kernel(DevHits H, uint64_t n, l
             atomicAdd(&acc->count, c);
         }
     }
+}
+__global__ void __launch_bounds__(256) hits_bbox_kernel(DevHits H, uint64_t n, long long bounce_filter, BBoxAccum* acc) {
+    hits_bbox_body(H, n, resolve_bounce_filter(bounce_filter), acc);
 }
 
 // Rust `f64 as usize` (saturating, NaN -> 0)
@@ -339,7 +351,7 @@ __device__ __forceinline__ double div_by_invariant(double x, double d, double in
 struct BinInv { double width_step, height_step, bin_area; };
 // bin_taps for the shared-memory kernel (the map has fewer than 2^31 bins): the three divisions by loop-invariant numbers go
 // through div_by_invariant; modf(q) = (q - trunc(q), trunc(q)) for finite q (one FRND instead of the library routine); Rust's
-// saturating `f64 as usize` is what cvt.rzi.u64.f64 does (NaN and negatives -> 0, too large -> MAX); indices in 32 bits
+// saturating `f64 as usize` is cvt.rzi.u64.f64 behind a NaN / sign guard; indices in 32 bits
 struct BinTaps32 { unsigned base; double w00, w10, w01, w11; bool ok, has_x, has_y; };
 __device__ __forceinline__ BinTaps32 bin_taps_inv(const BinParams& P, const BinInv& I, double x, double y, double e, unsigned* status) {
     BinTaps32 t;
@@ -347,7 +359,10 @@ __device__ __forceinline__ BinTaps32 bin_taps_inv(const BinParams& P, const BinI
     const double qy = div_by_invariant(y - P.bottom, P.height_step, I.height_step);
     const double ipx = trunc(qx), ipy = trunc(qy);
     const double fx = qx - ipx, fy = qy - ipy;
-    const unsigned long long xi = __double2ull_rz(ipx), yi = __double2ull_rz(ipy);
+    // Rust's `f64 as usize`: NaN and negatives -> 0, too large -> MAX.  The conversion instruction saturates the same way but turns
+    // NaN into 2^63: a NaN index (a hit on a range of zero width: 0 / 0) must land in bin 0 like the reference's, not raise
+    // OPM_ERR_BIN_RANGE
+    const unsigned long long xi = ipx > 0.0 ? __double2ull_rz(ipx) : 0ull, yi = ipy > 0.0 ? __double2ull_rz(ipy) : 0ull;
     const double fl = div_by_invariant(e, P.bin_area, I.bin_area);
     const double gx = 1.0 - fx, gy = 1.0 - fy;
     t.w00 = gx * gy * fl;
@@ -367,6 +382,7 @@ __device__ __forceinline__ BinTaps32 bin_taps_inv(const BinParams& P, const BinI
 __global__ void __launch_bounds__(1024) binning_smem_kernel(DevHits H, uint64_t n, long long bounce_filter, unsigned long long nx,
                                                             unsigned long long ny, const double* __restrict__ range,
                                                             double* __restrict__ map, unsigned* status_out) {
+    bounce_filter = resolve_bounce_filter(bounce_filter);
     extern __shared__ double smap[];
     BinParams P;
     if (!bin_params_from_range(nx, ny, range, P)) return;  // no hit on any GPU: nothing to bin
@@ -407,6 +423,7 @@ __global__ void __launch_bounds__(BLOCK, MIN_CTAS) binning_smem_fixed_kernel(Dev
                                                                              unsigned long long nx, unsigned long long ny,
                                                                              const double* __restrict__ range, double* __restrict__ map,
                                                                              unsigned* status_out) {
+    bounce_filter = resolve_bounce_filter(bounce_filter);
     extern __shared__ unsigned sfix[];
     __shared__ unsigned long long s_emax_key;
     BinParams P;
@@ -501,6 +518,7 @@ __global__ void __launch_bounds__(BLOCK, MIN_CTAS) binning_smem_fixed_kernel(Dev
 __global__ void __launch_bounds__(256) binning_global_kernel(DevHits H, uint64_t n, long long bounce_filter, unsigned long long nx,
                                                              unsigned long long ny, const double* __restrict__ range,
                                                              double* __restrict__ map, unsigned* status_out) {
+    bounce_filter = resolve_bounce_filter(bounce_filter);
     BinParams P;
     if (!bin_params_from_range(nx, ny, range, P)) return;
     unsigned status = 0;
@@ -579,6 +597,7 @@ template <int BLOCK, int MIN_CTAS, int RUN, bool PREFETCH = false>
 __global__ void __launch_bounds__(BLOCK, MIN_CTAS) binning_runs_kernel(DevHits H, uint64_t n, long long bounce_filter, unsigned long long nx,
                                                                        unsigned long long ny, const double* __restrict__ range,
                                                                        double* __restrict__ map, unsigned* status_out, int interleave) {
+    bounce_filter = resolve_bounce_filter(bounce_filter);
     static_assert(RUN % 2 == 0, "slots are loaded in pairs");
     BinParams P;
     if (!bin_params_from_range(nx, ny, range, P)) return;
@@ -647,6 +666,7 @@ template <int BLOCK, int MIN_CTAS, int RUN, int STAGES>
 __global__ void __launch_bounds__(BLOCK, MIN_CTAS) binning_runs_tma_kernel(DevHits H, uint64_t n, long long bounce_filter, unsigned long long nx,
                                                                            unsigned long long ny, const double* __restrict__ range,
                                                                            double* __restrict__ map, unsigned* status_out) {
+    bounce_filter = resolve_bounce_filter(bounce_filter);
     extern __shared__ __align__(128) unsigned char tsm[];
     __shared__ unsigned long long bar[STAGES];
     BinParams P;
@@ -767,6 +787,60 @@ __global__ void __launch_bounds__(256) peak_total_kernel(const double* __restric
     if ((threadIdx.x & 31) == 0) { atomicMax(&acc->peak_key, dkey(peak)); atomicAdd(&acc->total, tot); }
 }
 
+// ---- per-bundle peak-fluence check of the ghost-focus analysis (OpticSurface::evaluate_fluence_of_ray_bundle,
+// optic_surface.rs:202-224; RaysHitMap::get_max_fluence, rays_hit_map.rs:777-798) in three launches without parameter uploads:
+//   1. bounding box of the bundle's hits; the CTA that finishes last turns it into the range (-l, r, t, -b) and restores the
+//      accumulator's identity for the next check; the first launch of a check also zero-fills the small map;
+//   2. the Binning splat (k_binning);
+//   3. one CTA: peak and total of the map, the bounce level the check used (the launch's first_valid_key).
+// result[8] = range 4 | peak | total | status bits (u32, accumulated by the splat) | first_valid_key (u64)
+__global__ void __launch_bounds__(256) peakcheck_bbox_kernel(DevHits H, uint64_t n, long long bounce_filter, PeakCheckAcc* acc,
+                                                             double* __restrict__ range_out, double* __restrict__ map, uint64_t bins,
+                                                             int first, int last) {
+    if (first)
+        for (uint64_t k = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; k < bins; k += (uint64_t)gridDim.x * blockDim.x) map[k] = 0.0;
+    hits_bbox_body(H, n, resolve_bounce_filter(bounce_filter), &acc->box);
+    if (!last || threadIdx.x != 0) return;
+    __threadfence();
+    if (atomicAdd(&acc->done, 1u) != gridDim.x - 1) return;
+    __threadfence();
+    const unsigned long long k0 = atomicMin(&acc->box.key[0], ~0ull), k1 = atomicMax(&acc->box.key[1], 0ull);
+    const unsigned long long k2 = atomicMax(&acc->box.key[2], 0ull), k3 = atomicMin(&acc->box.key[3], ~0ull);
+    const unsigned long long cnt = atomicAdd(&acc->box.count, 0ull);
+    if (cnt == 0) { range_out[0] = range_out[1] = range_out[2] = range_out[3] = -INFINITY; }
+    else { range_out[0] = -dkey_inv(k0); range_out[1] = dkey_inv(k1); range_out[2] = dkey_inv(k2); range_out[3] = -dkey_inv(k3); }
+    acc->box.key[0] = ~0ull; acc->box.key[1] = 0ull; acc->box.key[2] = 0ull; acc->box.key[3] = ~0ull; acc->box.count = 0ull; acc->done = 0u;
+}
+__global__ void __launch_bounds__(1024) peakcheck_peak_kernel(const double* __restrict__ map, uint64_t nx, uint64_t ny,
+                                                              const unsigned long long* first_inv, double* __restrict__ result) {
+    const double* range = result;
+    const uint64_t bins = nx * ny;
+    const double dx = (range[1] - (-range[0])) / (double)nx, dy = (range[2] - (-range[3])) / (double)ny;
+    const double area = dx * dy;
+    double peak = -INFINITY, tot = 0.0;
+    for (uint64_t k = threadIdx.x; k < bins; k += blockDim.x) {
+        const double v = map[k];
+        if (isfinite(v)) peak = fmax(peak, v);
+        if (!isnan(v)) tot += area * v;
+    }
+    peak = warp_max(peak); tot = warp_sum(tot);
+    __shared__ double sp[32], st[32];
+    if ((threadIdx.x & 31) == 0) { sp[threadIdx.x >> 5] = peak; st[threadIdx.x >> 5] = tot; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int k = 1; k < (int)(blockDim.x >> 5); ++k) { peak = fmax(peak, sp[k]); tot += st[k]; }
+        result[4] = peak; result[5] = tot;
+        const unsigned long long inv = first_inv ? *first_inv : 0ull;
+        reinterpret_cast<unsigned long long*>(result)[7] = inv ? ~inv : ~0ull;
+    }
+}
+__global__ void peakcheck_acc_init_kernel(PeakCheckAcc* acc, uint64_t n) {
+    for (uint64_t k = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; k < n; k += (uint64_t)gridDim.x * blockDim.x) {
+        acc[k].box.key[0] = ~0ull; acc[k].box.key[1] = 0ull; acc[k].box.key[2] = 0ull; acc[k].box.key[3] = ~0ull; acc[k].box.count = 0ull;
+        acc[k].done = 0u;
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // kernel density estimator (kde/mod.rs, kde/gaussian.rs): the KDE fluence estimator
 // ---------------------------------------------------------------------------------------------
@@ -774,6 +848,7 @@ __global__ void __launch_bounds__(256) peak_total_kernel(const double* __restric
 __global__ void __launch_bounds__(256) hits_pack_kernel(DevHits H, uint64_t n, long long bounce_filter, double* __restrict__ x,
                                                         double* __restrict__ y, double* __restrict__ e, unsigned long long* count,
                                                         unsigned long long cap) {
+    bounce_filter = resolve_bounce_filter(bounce_filter);
     const uint64_t n_round = (n + 31) / 32 * 32;
     for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n_round; i += (uint64_t)gridDim.x * blockDim.x) {
         bool ok = false;
@@ -914,8 +989,9 @@ __global__ void __launch_bounds__(256) source_norm_kernel(SourceParams S, uint64
 // rays.rs:264-297 (position-major, wavelength-minor) + nodes/source.rs:205-210 (source isometry)
 __global__ void __launch_bounds__(256) source_generate_kernel(SourceParams S, DevRays R, uint64_t pos_begin, uint64_t pos_stride,
                                                               uint64_t n_rays, const double* __restrict__ wvl,
-                                                              const double* __restrict__ wgt) {
+                                                              const double* __restrict__ wgt, const double* __restrict__ norm_dev) {
     const V3 zdir = iso_vector(S.iso, v3(0.0, 0.0, 1.0));
+    if (norm_dev) S.energy_norm = *norm_dev;  // the normalisation sum was taken on the device just before (source_norm_kernel)
     for (uint64_t k = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; k < n_rays; k += (uint64_t)gridDim.x * blockDim.x) {
         uint64_t ip = pos_begin + (k / S.n_wavelengths) * pos_stride;
         uint32_t iw = (uint32_t)(k % S.n_wavelengths);
@@ -942,6 +1018,37 @@ __global__ void __launch_bounds__(256) expand_collimated_kernel(const double* __
         R.px[k] = xyz[3 * ip]; R.py[k] = xyz[3 * ip + 1]; R.pz[k] = xyz[3 * ip + 2];
         R.dx[k] = 0.0; R.dy[k] = 0.0; R.dz[k] = 1.0;
         R.e[k] = e_pos[ip] * wgt[iw]; R.wvl[k] = wvl[iw]; R.opl[k] = 0.0; R.n[k] = 1.0;
+        R.bounces[k] = 0; R.refr[k] = 0; R.id[k] = (uint32_t)k; R.valid[k] = RAY_VALID;
+    }
+}
+
+// The same from the PositionDistribution's points alone: every position distribution of the reference yields z = 0
+// (position_distributions/*.rs) and the EnergyDistribution is a function of (x, y) (uniform.rs:37-41, general_gaussian.rs:93-120),
+// so the host hands over 16 bytes per position and the energies are evaluated here.  norm: sum of the unnormalised Gaussian
+// weights over all positions (S.energy_norm if the caller knows it, else *norm_dev from xy_norm_kernel).
+__global__ void __launch_bounds__(256) xy_norm_kernel(const double2* __restrict__ xy, uint64_t n_pos, SourceParams S, double* out) {
+    double s = 0.0;
+    for (uint64_t ip = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; ip < n_pos; ip += (uint64_t)gridDim.x * blockDim.x) {
+        const double2 p = xy[ip];
+        s += general_gaussian_weight(S, p.x, p.y);
+    }
+    s = warp_sum(s);
+    if ((threadIdx.x & 31) == 0) atomicAdd(out, s);
+}
+__global__ void __launch_bounds__(256) expand_collimated_xy_kernel(const double2* __restrict__ xy, SourceParams S, const double* __restrict__ norm_dev,
+                                                                   const double* __restrict__ wvl, const double* __restrict__ wgt,
+                                                                   uint32_t n_wvl, DevRays R, uint64_t n_rays) {
+    const V3 zdir = iso_vector(S.iso, v3(0.0, 0.0, 1.0));
+    const double norm = S.energy_norm > 0.0 ? S.energy_norm : (norm_dev ? *norm_dev : 1.0);
+    for (uint64_t k = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; k < n_rays; k += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t ip = k / n_wvl;
+        const uint32_t iw = (uint32_t)(k % n_wvl);
+        const double2 q = xy[ip];
+        const double e_pos = S.energy_dist == OPM_EDIST_UNIFORM ? S.e_uniform : S.total_energy * general_gaussian_weight(S, q.x, q.y) / norm;
+        const V3 p = iso_point(S.iso, v3(q.x, q.y, 0.0));
+        R.px[k] = p.x; R.py[k] = p.y; R.pz[k] = p.z;
+        R.dx[k] = zdir.x; R.dy[k] = zdir.y; R.dz[k] = zdir.z;
+        R.e[k] = e_pos * wgt[iw]; R.wvl[k] = wvl[iw]; R.opl[k] = 0.0; R.n[k] = 1.0;
         R.bounces[k] = 0; R.refr[k] = 0; R.id[k] = (uint32_t)k; R.valid[k] = RAY_VALID;
     }
 }
@@ -1077,6 +1184,19 @@ int k_tally(DevRays R, uint64_t n, uint32_t n_orders, unsigned long long* counts
 }
 int k_hits_bbox(DevHits H, uint64_t n, long long bounce_filter, BBoxAccum* acc, int sms, void* stream) {
     hits_bbox_kernel<<<grid_for(n, 256 * 4, sms * 8), 256, 0, ST>>>(H, n, bounce_filter, acc);
+    return (int)cudaGetLastError();
+}
+int k_peakcheck_acc_init(PeakCheckAcc* acc, uint64_t n, void* stream) {
+    peakcheck_acc_init_kernel<<<grid_for(n, 256, 64), 256, 0, ST>>>(acc, n);
+    return (int)cudaGetLastError();
+}
+int k_peakcheck_bbox(DevHits H, uint64_t n, long long bounce_filter, PeakCheckAcc* acc, double* range_out, double* map, uint64_t bins, int first,
+                     int last, int sms, void* stream) {
+    peakcheck_bbox_kernel<<<grid_for(n, 256 * 4, sms * 8), 256, 0, ST>>>(H, n, bounce_filter, acc, range_out, map, bins, first, last);
+    return (int)cudaGetLastError();
+}
+int k_peakcheck_peak(const double* map, uint64_t nx, uint64_t ny, const unsigned long long* first_inv, double* result, void* stream) {
+    peakcheck_peak_kernel<<<1, 1024, 0, ST>>>(map, nx, ny, first_inv, result);
     return (int)cudaGetLastError();
 }
 int k_bbox_finalize(const BBoxAccum* acc, double* range_dev, void* stream) {
@@ -1236,13 +1356,26 @@ int k_source_norm(const SourceParams& S, uint64_t b, uint64_t e, double* out, in
     return (int)cudaGetLastError();
 }
 int k_source_generate(const SourceParams& S, DevRays R, uint64_t pos_begin, uint64_t pos_stride, uint64_t n_rays, const double* wvl,
-                      const double* wgt, int sms, void* stream) {
-    source_generate_kernel<<<grid_for(n_rays, 256, sms * 8), 256, 0, ST>>>(S, R, pos_begin, pos_stride, n_rays, wvl, wgt);
+                      const double* wgt, const double* norm_dev, int sms, void* stream) {
+    source_generate_kernel<<<grid_for(n_rays, 256, sms * 8), 256, 0, ST>>>(S, R, pos_begin, pos_stride, n_rays, wvl, wgt, norm_dev);
     return (int)cudaGetLastError();
 }
 int k_expand_collimated(const double* xyz, const double* e_pos, const double* wvl, const double* wgt, uint32_t n_wvl, DevRays R,
                         uint64_t n_rays, int sms, void* stream) {
     expand_collimated_kernel<<<grid_for(n_rays, 256, sms * 8), 256, 0, ST>>>(xyz, e_pos, wvl, wgt, n_wvl, R, n_rays);
+    return (int)cudaGetLastError();
+}
+int k_expand_collimated_xy(const double* xy, uint64_t n_pos, const SourceParams& S, double* norm_dev, const double* wvl, const double* wgt,
+                           uint32_t n_wvl, DevRays R, uint64_t n_rays, int sms, void* stream) {
+    const bool need_norm = S.energy_dist == OPM_EDIST_GENERAL_GAUSSIAN && !(S.energy_norm > 0.0);
+    if (need_norm) {
+        cudaError_t e = cudaMemsetAsync(norm_dev, 0, 8, ST);
+        if (e != cudaSuccess) return (int)e;
+        if (n_pos) xy_norm_kernel<<<grid_for(n_pos, 256, sms * 8), 256, 0, ST>>>((const double2*)xy, n_pos, S, norm_dev);
+    }
+    if (n_rays)
+        expand_collimated_xy_kernel<<<grid_for(n_rays, 256, sms * 8), 256, 0, ST>>>((const double2*)xy, S, need_norm ? norm_dev : nullptr, wvl, wgt,
+                                                                                   n_wvl, R, n_rays);
     return (int)cudaGetLastError();
 }
 int k_compact(DevRays S, DevRays D, uint64_t n, unsigned* counts, unsigned long long* offsets, unsigned long long* total, void* stream) {
@@ -1278,6 +1411,15 @@ __global__ void __launch_bounds__(256) trace_prologue_kernel(ProloguePlan P) {
 }
 int k_trace_prologue(const ProloguePlan& P, void* stream) {
     trace_prologue_kernel<<<1, 256, 0, ST>>>(P);
+    return (int)cudaGetLastError();
+}
+// DevStats::first_inv (max of ~(id << 32 | bounces) over the valid rays, 0 = none) -> the public first_valid_key
+__global__ void first_key_store_kernel(const unsigned long long* first_inv, unsigned long long* out) {
+    const unsigned long long inv = *first_inv;
+    *out = inv ? ~inv : ~0ull;
+}
+int k_first_key_store(const unsigned long long* first_inv, unsigned long long* out, void* stream) {
+    first_key_store_kernel<<<1, 1, 0, ST>>>(first_inv, out);
     return (int)cudaGetLastError();
 }
 int k_set_u64(unsigned long long* p, unsigned long long v, void* stream) {

@@ -12,6 +12,7 @@ struct SpotAccum {
 };
 struct BBoxAccum { unsigned long long key[4]; unsigned long long count; };  // left,right,top,bottom as ordered keys
 struct PeakAccum { unsigned long long peak_key; double total; };
+struct PeakCheckAcc { BBoxAccum box; unsigned done, _pad; unsigned long long _pad2[2]; };  // 64 bytes (OPM_PEAK_CHECK_ACC_BYTES)
 struct WvlAccum { unsigned long long min_key, max_key, count; };  // init: key(+inf), key(-inf), 0
 // wavefront detector accumulators; init: min_r_key = key(+inf), first_slot = ~0, max_key = key(-inf), min_key = key(+inf), rest 0
 struct WfAccum { unsigned long long min_r_key, first_slot, max_key, min_key, count; double sum, sum2; };
@@ -54,6 +55,10 @@ int k_tally(DevRays R, uint64_t n, uint32_t n_orders, unsigned long long* counts
 int k_hits_bbox(DevHits H, uint64_t n, long long bounce_filter, BBoxAccum* acc, int sms, void* stream);
 // device-resident chaining: the map range lives on the device as (-left, right, top, -bottom), see opm_kernels.cu
 int k_bbox_finalize(const BBoxAccum* acc, double* range_dev, void* stream);
+int k_peakcheck_acc_init(PeakCheckAcc* acc, uint64_t n, void* stream);
+int k_peakcheck_bbox(DevHits H, uint64_t n, long long bounce_filter, PeakCheckAcc* acc, double* range_out, double* map, uint64_t bins, int first,
+                     int last, int sms, void* stream);
+int k_peakcheck_peak(const double* map, uint64_t nx, uint64_t ny, const unsigned long long* first_inv, double* result, void* stream);
 int k_binning(DevHits H, uint64_t n, long long bounce_filter, uint64_t nx, uint64_t ny, const double* range_dev, double* map,
               unsigned* status, int sms, void* stream);
 int k_peak_total(const double* map, uint64_t nx, uint64_t ny, const double* range_dev, PeakAccum* acc, double* out2_dev, int sms, void* stream);
@@ -69,7 +74,7 @@ int k_spot_sums_load(const double* sums_dev, SpotAccum* acc, void* stream);
 int k_spot_radii_store(const SpotAccum* acc, double* radii_dev, void* stream);
 int k_source_norm(const SourceParams& S, uint64_t b, uint64_t e, double* out, int sms, void* stream);
 int k_source_generate(const SourceParams& S, DevRays R, uint64_t pos_begin, uint64_t pos_stride, uint64_t n_rays, const double* wvl,
-                      const double* wgt, int sms, void* stream);
+                      const double* wgt, const double* norm_dev, int sms, void* stream);
 int k_expand_collimated(const double* xyz, const double* e_pos, const double* wvl, const double* wgt, uint32_t n_wvl, DevRays R,
                         uint64_t n_rays, int sms, void* stream);
 int k_compact(DevRays S, DevRays D, uint64_t n, unsigned* counts, unsigned long long* offsets, unsigned long long* total, void* stream);
@@ -84,6 +89,9 @@ int k_readout_combine_b(const double* g, int w, uint64_t maps_len, int ns, doubl
 int k_fp64_peak(double* out, int iters, int blocks, void* stream);
 int k_fetch_from_host(void* dst, const void* src_host, size_t bytes, void* stream);  // bytes % 8 == 0, src pinned + mapped
 int k_set_u64(unsigned long long* p, unsigned long long v, void* stream);
+int k_first_key_store(const unsigned long long* first_inv, unsigned long long* out, void* stream);
+int k_expand_collimated_xy(const double* xy, uint64_t n_pos, const SourceParams& S, double* norm_dev, const double* wvl, const double* wgt,
+                           uint32_t n_wvl, DevRays R, uint64_t n_rays, int sms, void* stream);
 constexpr int kPrologueTails = 8;
 struct ProloguePlan {
     unsigned long long* dst; const unsigned long long* src_host; unsigned words;   // op descriptors (pinned + mapped source)

@@ -70,7 +70,11 @@ __device__ __forceinline__ void store_ray(const DevRays& R, uint64_t i, const Ra
 // shared-memory atomic per field from lane 0; the CTA flushes its totals to the global statistics once.
 struct Counters {
     unsigned a, b, apodized, status;
+    // OPM_REFRACT_STAT_KEY: (id, bounces) of this ray right after the flagged refract op when it was valid there (kid = 0xffffffff:
+    // not valid); kid = kKeyUnset: no flagged op ran, the launch statistic `first_valid_key` looks at the end of the program
+    unsigned kid, kb;
 };
+constexpr unsigned kKeyUnset = 0xfffffffeu;
 enum { CNT_INTERACTIONS = 0, CNT_CHILDREN, CNT_HITS, CNT_MISSED, CNT_APODIZED, CNT_VALID_OUT, CNT_ALIVE_OUT, CNT_N };
 
 // one ray of the current tile
@@ -156,6 +160,8 @@ __device__ __forceinline__ bool exec_refract(const V& v, RayCtx& x, HitOut* ho =
             if (ho) { ho->ok = true; ho->x = res.hit_local.x; ho->y = res.hit_local.y; }
         }
     }
+    // Rays::bounce_lvl as the ghost-focus analysis reads it: between refract_on_surface and apodize (analyzers/raytrace.rs:118-133)
+    if (v.flags() & OPM_REFRACT_STAT_KEY) { x.c.kid = (x.valid && x.alive) ? x.r.id : 0xffffffffu; x.c.kb = x.r.bounces; }
     finish_children(v, res, x);
     return res.moved;
 }
@@ -366,7 +372,7 @@ __device__ __forceinline__ void exec_transform(const DevTransform& o, RayCtx& x)
 __device__ __forceinline__ void tile_load(const DevRays& in, uint64_t i, uint64_t n, RayCtx& x, uint8_t& vb) {
     x.i = i;
     x.in_range = i < n;
-    x.c.a = 0; x.c.b = 0; x.c.apodized = 0; x.c.status = 0;
+    x.c.a = 0; x.c.b = 0; x.c.apodized = 0; x.c.status = 0; x.c.kid = kKeyUnset; x.c.kb = 0;
     x.r.pos = v3(0, 0, 0); x.r.dir = v3(0, 0, 1); x.r.e = 0; x.r.wvl = 0; x.r.opl = 0; x.r.n = 1; x.r.bounces = 0; x.r.refr = 0; x.r.id = 0;
     vb = RAY_REMOVED;
     if (x.in_range) {
@@ -478,7 +484,7 @@ __device__ __forceinline__ void tile_load_staged(TilePipe& p, const DevRays& in,
     unsigned char* st = p.stage[s];
     mbar_wait(&p.bar[s], (p.iter >> 1) & 1u);
     x.i = i; x.in_range = true;
-    x.c.a = 0; x.c.b = 0; x.c.apodized = 0; x.c.status = 0;
+    x.c.a = 0; x.c.b = 0; x.c.apodized = 0; x.c.status = 0; x.c.kid = kKeyUnset; x.c.kb = 0;
     const double* d = reinterpret_cast<const double*>(st);
     x.r.pos = v3(d[t], d[B + t], d[2 * B + t]);
     x.r.dir = v3(d[3 * B + t], d[4 * B + t], d[5 * B + t]);
@@ -529,9 +535,11 @@ __device__ __forceinline__ void tile_count(const RayCtx& x, cta_count_t* s_cnt, 
     const unsigned live = __ballot_sync(0xffffffffu, x.alive), ok = __ballot_sync(0xffffffffu, v);
     const unsigned st = __reduce_or_sync(0xffffffffu, x.c.status);
     const bool lane0 = (threadIdx.x & 31) == 0;
-    if (ok) {  // first valid ray of the warp = lowest (id, bounces): two 32-bit warp minima instead of a 64-bit shuffle tree
-        const unsigned idmin = __reduce_min_sync(0xffffffffu, v ? x.r.id : 0xffffffffu);
-        const unsigned bmin = __reduce_min_sync(0xffffffffu, (v && x.r.id == idmin) ? x.r.bounces : 0xffffffffu);
+    const bool cap = x.c.kid != kKeyUnset;  // warp-uniform: the ops of a program are
+    const unsigned kid = cap ? x.c.kid : (v ? x.r.id : 0xffffffffu), kb = cap ? x.c.kb : x.r.bounces;
+    if (__ballot_sync(0xffffffffu, kid != 0xffffffffu)) {  // first valid ray of the warp = lowest (id, bounces): two 32-bit warp minima
+        const unsigned idmin = __reduce_min_sync(0xffffffffu, kid);
+        const unsigned bmin = __reduce_min_sync(0xffffffffu, (kid != 0xffffffffu && kid == idmin) ? kb : 0xffffffffu);
         if (lane0) {
             const unsigned long long inv = ~(((unsigned long long)idmin << 32) | bmin);  // largest for the first ray
             if (inv > *(volatile unsigned long long*)s_first_inv) atomicMax(s_first_inv, inv);  // rarely after the CTA's first tiles
@@ -555,6 +563,7 @@ __device__ __forceinline__ void cta_flush(DevStats* stats, const cta_count_t* s_
         unsigned long long* dst[CNT_N] = {&stats->interactions, &stats->children, &stats->hits, &stats->missed,
                                           &stats->apodized, &stats->valid_out, &stats->alive_out};
         atomicAdd(dst[threadIdx.x], (unsigned long long)s_cnt[threadIdx.x]);
+        if (threadIdx.x == CNT_INTERACTIONS) atomicAdd(&stats->total_interactions, (unsigned long long)s_cnt[threadIdx.x]);
     }
     if (threadIdx.x == 0 && s_status) { atomicOr(&stats->status_bits, s_status); atomicOr(&stats->sticky_bits, s_status); }
     if (threadIdx.x == 0 && s_first_inv) atomicMax(&stats->first_inv, s_first_inv);

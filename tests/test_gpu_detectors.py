@@ -284,3 +284,18 @@ def test_binning_negative_taps_outside_an_explicit_range(ctx, nx, ny):
     scale = np.abs(ref_map).max()
     assert np.max(np.abs(fd.map - ref_map)) <= 1e-9 * scale  # sums of mixed sign: compare against the map's scale
     assert ((fd.map < 0) == (ref_map < 0)).mean() > 0.999
+
+
+@pytest.mark.parametrize("nx,ny", [(101, 101), (400, 300)])
+def test_binning_of_a_single_hit_follows_the_reference_arithmetic(ctx, nx, ny):
+    """A hit map with ONE hit (a ghost bundle of which one ray reaches a detector): the bounding box has no extent, the
+    fractional indices are 0 / 0 = NaN, `NaN as usize` is 0 (rays_hit_map.rs:352-357) and four bins around (0, 0) receive NaN;
+    the peak over the finite bins is 0 (fluence_data.rs:45-68).  No error: the ghost-focus check records a peak of 0."""
+    x, y, e = np.array([mm(1.5)]), np.array([mm(-0.5)]), np.array([1e-6])
+    ref_map, ref_lrtb = orc.fluence_binning(orc.hits_from_xye(x, y, e), nx, ny)
+    assert np.isnan(ref_map).sum() == 4 and orc.fluence_peak(ref_map) == 0.0
+    fd = ob.fluence_binning(ctx, [hitmap_from(ctx, x, y, e)], nx, ny)
+    assert fd.lrtb == ref_lrtb
+    assert np.array_equal(np.isnan(fd.map), np.isnan(ref_map))
+    assert np.array_equal(fd.map[~np.isnan(fd.map)], ref_map[~np.isnan(ref_map)])
+    assert fd.peak == 0.0

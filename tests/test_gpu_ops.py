@@ -425,6 +425,44 @@ def test_new_collimated_with_spectrum_from_host_buffers(ctx):
         bufs[0].new_collimated_with_spectrum(xyz.ctypes.data, e.ctypes.data, len(xyz), [0.0], [1.0])  # Ray::new: wavelength must be > 0
 
 
+@pytest.mark.parametrize("energy", ["gaussian", "gaussian_known_norm", "uniform"])
+def test_new_collimated_xy_matches_oracle(ctx, energy):
+    """opm_rays_new_collimated_xy: the position distribution's (x, y) from the host (16 B per position), z = 0, the energy
+    distribution (general_gaussian.rs:93-120 / uniform.rs:37-41) evaluated on the device -- against the oracle's
+    Rays::new_collimated_with_spectrum (rays.rs:264-297) of the same points, twice into the same bundle."""
+    xyz = np.ascontiguousarray(orc.fibonacci_ellipse(3001, mm(5.0), mm(4.0)))
+    assert np.all(xyz[:, 2] == 0.0)
+    wvl, w = [nm(900.0), nm(1000.0), nm(1100.0)], [0.2, 0.5, 0.3]
+    sd = ob.SourceDesc(len(xyz), wvl, w, total_energy=2.0)
+    if energy == "uniform":
+        e = orc.energy_uniform(len(xyz), 2.0)
+    else:
+        e = np.ascontiguousarray(orc.energy_general_gaussian(xyz, 2.0, (mm(0.3), 0.0), (mm(3.0), mm(2.5)), 2.0, 0.2, False))
+        sd.general_gaussian((mm(0.3), 0.0), (mm(3.0), mm(2.5)), 2.0, 0.2, False)
+        if energy == "gaussian_known_norm":  # the sum over the whole source, as a sharded caller passes it
+            sd2 = ob.SourceDesc(len(xyz), wvl, w, total_energy=2.0).fibonacci_ellipse(mm(5.0), mm(4.0))
+            sd2.general_gaussian((mm(0.3), 0.0), (mm(3.0), mm(2.5)), 2.0, 0.2, False)
+            sd.general_gaussian((mm(0.3), 0.0), (mm(3.0), mm(2.5)), 2.0, 0.2, False, norm=sd2.energy_norm(ctx))
+    ref = orc.rays_collimated_with_spectrum(xyz, e, wvl, w)
+    xy = np.ascontiguousarray(xyz[:, :2])
+    r = ob.Rays(ctx, 1)
+    surf = surface_pair(F.GEOM_PLANE, iso=iso_pair((0.0, 0.0, mm(30.0))))
+    for k in range(2):
+        r.new_collimated_xy(xy.ctypes.data, len(xy), sd)
+        assert len(r) == len(ref) == 9003
+        got = r.to_array()
+        assert_rays_match(got, ref, what=f"xy upload {k}")
+        assert np.array_equal(got["wvl"], ref["wvl"]) and np.array_equal(got["pos"], ref["pos"])
+        assert abs(got["e"].sum() - 2.0) < 1e-12
+        r.refract_on_surface(surf[1], None, want_reflected=False)
+    # a shard of the positions with the whole source's normalisation = the matching slice of the whole bundle
+    if energy == "gaussian_known_norm":
+        half = np.ascontiguousarray(xy[1000:2000])
+        r.new_collimated_xy(half.ctypes.data, len(half), sd)
+        got = r.to_array()
+        assert np.allclose(got["e"], ref["e"][3000:6000], rtol=1e-12, atol=0)
+
+
 def test_source_generate_strided_is_a_slice_of_the_source(ctx):
     """opm_source_generate_strided: rank g of G gets positions g, g+G, ... of the same global source (ids stay global)"""
     sd = ob.SourceDesc(1001, [nm(1000.0), nm(1100.0)], [0.4, 0.6], total_energy=2.0).fibonacci_ellipse(mm(6.0), mm(5.0))

@@ -171,7 +171,13 @@ def test_c3_ghost_focus(ctx, max_bounces):
         assert np.array_equal(counts, ref_counts), f"pass {p}"
         assert np.allclose(energy, ref_energy, rtol=RTOL, atol=1e-30)
         assert nr == sum(len(r.rays) for r in ref_bundles)
-    for node in (0, 1, 2, 3):
+    _compare_surface_fluences(osc, psc, (0, 1, 2, 3))
+
+
+def _compare_surface_fluences(osc, psc, nodes):
+    """per surface: the largest per-bundle peak fluence and the critical-fluence records (peak, bounce level) of the LIDT check"""
+    n_crit = 0
+    for node in nodes:
         for surf in (0, 1):
             ref_peak = osc.nodes[node].s[surf].peak_seen
             got_peak = psc.node_peak_fluence(node, surf)
@@ -181,9 +187,35 @@ def test_c3_ghost_focus(ctx, max_bounces):
                 assert not np.isfinite(got_peak)
             ref_crit = sorted((pk, b) for pk, b in osc.nodes[node].s[surf].critical.values())
             got_crit = sorted((pk, b) for _, pk, b in psc.node_critical_fluences(node, surf))
-            assert len(ref_crit) == len(got_crit)
+            assert len(ref_crit) == len(got_crit), (node, surf)
             for (a, ab), (b, bb) in zip(ref_crit, got_crit):
                 assert ab == bb and b == pytest.approx(a, rel=RTOL)
+            n_crit += len(ref_crit)
+    return n_crit
+
+
+def test_ghost_focus_fluence_check_sees_the_bundle_before_the_aperture(ctx):
+    """The LIDT check of a surface reads the bundle's bounce level BETWEEN refract_on_surface and apodize
+    (analyzers/raytrace.rs:118-133).  Here the output aperture of the second lens clips every ray that reaches it: after the
+    surface pass those bundles hold no valid ray (bounce level 0), yet the reference has already evaluated their hits with
+    the level they arrived with -- ghost bundles of level 2 included.  A low LIDT turns every evaluation into a record."""
+    nodes = scenes.c3_telescope()
+    nodes[2] = dict(nodes[2], ap_out=("circle", 1.0e-3, 50.0e-3, 0.0), lidt=1.0e-6)
+    nodes[1] = dict(nodes[1], lidt=1.0e-6)
+    src = scenes.c3_source(2000)
+    osc = scenes.to_oracle(nodes)
+    ref_passes = osc.ghostfocus(scenes.source_to_oracle(src), 2)
+    psc = scenes.to_product(ctx, nodes)
+    st = psc.ghostfocus(scenes.source_to_product(src).generate(ctx), 2)
+    assert st.interactions == osc.interactions
+    for p, ref_bundles in enumerate(ref_passes):
+        got = psc.gf_pass_bundles(p)
+        assert len(got) == len(ref_bundles)
+        for g, r in zip(got, ref_bundles):
+            assert_rays_match(g.to_array(), r.rays, keyed=True, what=f"pass {p} bundle {r.uuid}", e_floor=1e-25)
+    assert _compare_surface_fluences(osc, psc, (0, 1, 2, 3)) > 4
+    levels = {b for _, _, b in psc.node_critical_fluences(2, 1)}
+    assert 2 in levels, levels  # a level-2 ghost bundle evaluated on the clipping surface
 
 
 def test_sharded_trace_equals_whole_source(ctx):
