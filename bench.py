@@ -618,7 +618,9 @@ def run_product(args):
                 parity_n1 = {"what": f"reports of the {world}-GPU run vs the same {n * world}-ray source traced by GPU 0 alone",
                              "maps_worst_rel_bin": worst, "spot_worst_rel": spot_rel, "spot_n_valid_equal": bool(sa.n_valid == sb.n_valid),
                              "bounce_lvl_equal": bool(sa.bounce_lvl == sb.bounce_lvl),
-                             "ok": bool(worst <= 1e-12 and spot_rel <= 1e-12 and sa.n_valid == sb.n_valid and sa.bounce_lvl == sb.bounce_lvl)}
+                             "bar": "maps 1e-9 relative per bin (the north star's bar: the small-map splat sums in fixed point, each tap rounded "
+                                    "by at most 2^-33 of itself, and the shards round different sets of taps), spot statistics 1e-12",
+                             "ok": bool(worst <= 1e-9 and spot_rel <= 1e-12 and sa.n_valid == sb.n_valid and sa.bounce_lvl == sb.bounce_lvl)}
                 del scene_g, src_g
             barrier()
 
@@ -644,18 +646,24 @@ def run_product(args):
         kern_ms_step = kern_ms / args.steps
         achieved = bytes_step / (kern_ms_step * 1e-3) / 1e9
         unfused = inter_per_step * 146.0 / (kern_ms_step * 1e-3) / 1e9  # 146 B per stand-alone interaction
-        flop_per_inter = 300.0  # SURVEY 8d estimate (FMA = 2 flop), sqrt/div counted as one
         h2d = n * 16 + 16 * len(wvl) + 256  # (x, y) of every position + spectrum + the energy distribution's descriptor
         d2h = 2 * MAP_NX * MAP_NY * 8 + 2 * 48 + 64
-        # DRAM bytes of the same launch from the committed `ncu --set full` capture (never measured under the profiler here)
-        traffic = None
+        # What only a profiler can count comes from the committed `ncu --set full` capture of the same launch (profiles/r2_traffic.json,
+        # never measured under the profiler here): DRAM bytes, executed FP64 instructions, issue-slot and pipe utilisation.  It is
+        # used only while it still describes this build's launch (same rays, launches per step and algorithmic bytes).
+        traffic, ncu = None, None
         try:
-            tr = json.loads((ROOT / "profiles" / "r1_traffic.json").read_text())
+            tr = json.loads((ROOT / "profiles" / "r2_traffic.json").read_text())["trace"]
             same_bytes = abs(tr["algorithmic_bytes_per_launch"] - bytes_step / max(launches_trace, 1)) < 0.02 * tr["algorithmic_bytes_per_launch"]
             if jit["launches"] and tr["workload_rays_per_gpu"] == n and tr["launches_per_step"] == launches_trace and same_bytes:
                 traffic = tr["dram_bytes_read"] + tr["dram_bytes_write"]
+                ncu = tr
         except (OSError, ValueError, KeyError):
             pass
+        # SURVEY 8(d)'s byte model: state S = 77 B per ray (9 f64 + u32 + u8), written without the read-only wavelength (69 B),
+        # 32 B per hit record; the split-off bundle is written once (77 B); NO copy of the bundle for the spot diagram
+        bytes_8d = n * 77 + alive_main * (69 + 32) + alive_side * (77 + 32)
+        kern_s = kern_ms_step * 1e-3
         line = {
             "metric": METRIC, "value": inter_total * args.steps / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -678,15 +686,30 @@ def run_product(args):
                                                "what OpmDocument::analyze does (opm_document.rs:270-289)"}},
             "gpu_launches": launches_per_step * args.steps,
             "clocks": clk,
-            "roofline": {"bound": "hbm", "kernel": ("opm_jit_trace (fused surface sequence, compiled at run time for this op program)" if jit["launches"] else
-                                                   "opm::trace_kernel (fused surface sequence, interpreter)"),
+            "roofline": {"bound": "issue",
+                         "bound_note": "the fused kernel is bound by instruction issue (ncu: issue slots 63 % busy, FP64 pipe 40 %, DRAM 50 %); "
+                                       "achieved / peak / frac below measure it against the HBM roof the north star names (bound: hbm there)",
+                         "kernel": ("opm_jit_trace (fused surface sequence, compiled at run time for this op program)" if jit["launches"] else
+                                    "opm::trace_kernel (fused surface sequence, interpreter)"),
                          "jit": jit, "achieved": achieved, "peak": hbm_peak,
                          "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": traffic, "peak_source": peak_src,
+                         "byte_model": "93 B ray state read, 93 B written per ray kept + 93 B spot-diagram copy + 36 B per hit record (DESIGN.md section 4)",
                          "algorithmic_bytes_per_launch": bytes_step / max(launches_trace, 1), "launches_per_step": launches_trace,
                          "kernel_ms_per_launch": kern_ms_step / max(launches_trace, 1), "kernel_share_of_step": kern_ms_step / (ms / args.steps),
+                         "survey_8d": {"bytes_per_launch": bytes_8d / max(launches_trace, 1), "achieved": bytes_8d / kern_s / 1e9,
+                                       "frac": bytes_8d / kern_s / 1e9 / hbm_peak,
+                                       "model": "SURVEY 8(d): 77 B read, 69 B written per ray kept, 77 B split-off bundle, 32 B per hit record, no spot-diagram copy"},
+                         "traffic_over_algorithmic": (traffic / (bytes_step / max(launches_trace, 1))) if traffic else None,
                          "unfused_equivalent_gbs": unfused,
-                         "fp64": {"peak_tflops_measured_dfma": fp64_peak, "flop_per_interaction_model": flop_per_inter,
-                                  "achieved_tflops_model": inter_per_step * flop_per_inter / (kern_ms_step * 1e-3) / 1e12}},
+                         "issue": ({"issue_slots_busy_pct": ncu["issue_active_pct"], "fp64_pipe_pct": ncu["fp64_pipe_pct"], "dram_pct": ncu["dram_throughput_pct"],
+                                    "warp_instructions_per_launch": ncu["warp_instructions"],
+                                    "ms_at_full_issue_rate": ncu["gpu_time_s"] * 1e3 * ncu["issue_active_pct"] / 100.0,
+                                    "source": "profiles/r2_traffic.json (ncu --set full of the same launch)"} if ncu else None),
+                         "fp64": {"peak_tflops_measured_dfma": fp64_peak,
+                                  "flop_per_launch_ncu": ncu["fp64_flop_per_launch"] if ncu else None,
+                                  "achieved_tflops": (ncu["fp64_flop_per_launch"] / kern_s / 1e12) if ncu else None,
+                                  "frac": (ncu["fp64_flop_per_launch"] / kern_s / 1e12 / fp64_peak) if (ncu and fp64_peak) else None,
+                                  "how": "executed DFMA x 2 + DMUL + DADD thread instructions of one launch counted by ncu, divided by this run's kernel time"}},
             "check": {"fluence_peak_J_m2": {str(k): v[0] for k, v in check.items() if k != "spot"},
                       "detector_energy_J": {str(k): v[1] for k, v in check.items() if k != "spot"}, "spot_valid_rays": check["spot"][0]},
             "c4_strong": c4,

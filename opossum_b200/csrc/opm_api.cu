@@ -603,13 +603,10 @@ extern "C" OpmStatus opm_rays_clear(OpmRays* r) {
 }
 static OpmStatus copy_fields(const DevRays& s, uint64_t soff, const DevRays& d, uint64_t doff, uint64_t n, cudaStream_t st) {
     if (n == 0) return OPM_OK;
-    const double* sd[10] = {s.px, s.py, s.pz, s.dx, s.dy, s.dz, s.e, s.wvl, s.opl, s.n};
-    double* dd[10] = {d.px, d.py, d.pz, d.dx, d.dy, d.dz, d.e, d.wvl, d.opl, d.n};
-    for (int k = 0; k < 10; ++k) CU(cudaMemcpyAsync(dd[k] + doff, sd[k] + soff, n * 8, cudaMemcpyDeviceToDevice, st));
-    CU(cudaMemcpyAsync(d.bounces + doff, s.bounces + soff, n * 4, cudaMemcpyDeviceToDevice, st));
-    CU(cudaMemcpyAsync(d.refr + doff, s.refr + soff, n * 4, cudaMemcpyDeviceToDevice, st));
-    CU(cudaMemcpyAsync(d.id + doff, s.id + soff, n * 4, cudaMemcpyDeviceToDevice, st));
-    CU(cudaMemcpyAsync(d.valid + doff, s.valid + soff, n, cudaMemcpyDeviceToDevice, st));
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    KL(k_copy_rays(s, soff, d, doff, n, sms, st));  // one launch for the fourteen arrays
     return OPM_OK;
 }
 extern "C" OpmStatus opm_rays_reserve(OpmRays* r, uint64_t capacity) {

@@ -1132,6 +1132,21 @@ __global__ void __launch_bounds__(256) fp64_peak_kernel(double* out, int iters, 
     if (s == 12345.678) out[0] = s;  // keeps the chains alive
 }
 __global__ void set_u64_kernel(unsigned long long* p, unsigned long long v) { *p = v; }
+// all fourteen arrays of a bundle in one launch (Rays::clone, growth of a bundle, append): n slots from S[soff..] to D[doff..]
+__global__ void __launch_bounds__(256) copy_rays_kernel(DevRays S, uint64_t soff, DevRays D, uint64_t doff, uint64_t n) {
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t a = soff + i, b = doff + i;
+        const double px = __ldcs(S.px + a), py = __ldcs(S.py + a), pz = __ldcs(S.pz + a), dx = __ldcs(S.dx + a), dy = __ldcs(S.dy + a);
+        const double dz = __ldcs(S.dz + a), e = __ldcs(S.e + a), w = __ldcs(S.wvl + a), o = __ldcs(S.opl + a), nn = __ldcs(S.n + a);
+        const uint32_t bo = __ldcs(S.bounces + a), rf = __ldcs(S.refr + a), id = __ldcs(S.id + a);
+        const uint8_t v = S.valid[a];
+        __stcs(D.px + b, px); __stcs(D.py + b, py); __stcs(D.pz + b, pz); __stcs(D.dx + b, dx); __stcs(D.dy + b, dy);
+        __stcs(D.dz + b, dz); __stcs(D.e + b, e); __stcs(D.wvl + b, w); __stcs(D.opl + b, o); __stcs(D.n + b, nn);
+        __stcs(D.bounces + b, bo); __stcs(D.refr + b, rf); __stcs(D.id + b, id);
+        D.valid[b] = v;
+    }
+}
+
 // small host -> device transfers that must not queue behind bulk uploads on the copy engine: the source is pinned host
 // memory mapped into the device address space (unified addressing), read over PCIe by one CTA
 __global__ void __launch_bounds__(256) fetch_from_host_kernel(unsigned long long* __restrict__ dst, const unsigned long long* __restrict__ src_host,
@@ -1420,6 +1435,10 @@ __global__ void first_key_store_kernel(const unsigned long long* first_inv, unsi
 }
 int k_first_key_store(const unsigned long long* first_inv, unsigned long long* out, void* stream) {
     first_key_store_kernel<<<1, 1, 0, ST>>>(first_inv, out);
+    return (int)cudaGetLastError();
+}
+int k_copy_rays(DevRays S, uint64_t soff, DevRays D, uint64_t doff, uint64_t n, int sms, void* stream) {
+    copy_rays_kernel<<<grid_for(n, 256, sms * 8), 256, 0, ST>>>(S, soff, D, doff, n);
     return (int)cudaGetLastError();
 }
 int k_set_u64(unsigned long long* p, unsigned long long v, void* stream) {

@@ -89,6 +89,7 @@ int k_readout_combine_b(const double* g, int w, uint64_t maps_len, int ns, doubl
 int k_fp64_peak(double* out, int iters, int blocks, void* stream);
 int k_fetch_from_host(void* dst, const void* src_host, size_t bytes, void* stream);  // bytes % 8 == 0, src pinned + mapped
 int k_set_u64(unsigned long long* p, unsigned long long v, void* stream);
+int k_copy_rays(DevRays S, uint64_t soff, DevRays D, uint64_t doff, uint64_t n, int sms, void* stream);
 int k_first_key_store(const unsigned long long* first_inv, unsigned long long* out, void* stream);
 int k_expand_collimated_xy(const double* xy, uint64_t n_pos, const SourceParams& S, double* norm_dev, const double* wvl, const double* wgt,
                            uint32_t n_wvl, DevRays R, uint64_t n_rays, int sms, void* stream);
