@@ -63,7 +63,8 @@ enum {
     OPM_ERR_SPECTRUM = 16,       /* OpossumError::Spectrum; "wavelength of ray outside filter spectrum" ray.rs:716-720, :757-761;
                                     "ray bundle is empty - cannot create spectrum" rays.rs:1216-1220 */
     OPM_ERR_EMPTY_WAVEFRONT = 17,/* "Empty wavefront-data vector!"                             nodes/wavefront.rs:121-123 */
-    OPM_ERR_PEER_TIMEOUT = 18    /* multi-GPU read-out: a peer rank did not arrive at a meeting in time (no reference counterpart) */
+    OPM_ERR_PEER_TIMEOUT = 18,   /* multi-GPU read-out: a peer rank did not arrive at a meeting in time (no reference counterpart) */
+    OPM_ERR_VORONOI = 19         /* Voronoi estimator: fewer than 3 hits, non-finite or collinear points  rays_hit_map.rs:416-420, griddata.rs:269-283 */
 };
 
 /* ------------------------------------------------------------------------------------------
@@ -473,6 +474,19 @@ OpmStatus opm_fluence_peak_total_async(OpmContext* ctx, const double* map_dev, u
  * memory for the bandwidth estimate: at most 50000 hit points. */
 OpmStatus opm_fluence_kde(OpmHitMap* const* maps, int32_t n_maps, int64_t bounce_filter_or_minus1, uint64_t nx, uint64_t ny,
                           const double* ranges_or_null, double* map_dev, double lrtb_out[4], double* band_width_out);
+/* RaysHitMap::calc_fluence_with_voronoi (rays_hit_map.rs:407-521), the reference's DEFAULT estimator (fluence_detector/mod.rs:61,
+ * analyzers/ghostfocus.rs:61), of ONE rays hit map (the hits that pass bounce_filter): per-hit Voronoi cells inside the convex
+ * hull pushed outwards (create_voronoi_cells, griddata.rs:265-345), fluence = E / cell area, natural-neighbour interpolation
+ * onto the grid (griddata.rs:387-436; NaN outside the convex hull).  BOTH axes take nx points (the reference uses
+ * nr_of_points.0 for the second axis too, :470 and :489): map_dev holds nx * nx doubles, column-major (x index * nx + y index),
+ * J/m^2.  ranges: NULL (the hits' limits) or {ax1.start, ax1.end, ax2.start, ax2.end} in metres.  accumulate != 0 adds to
+ * map_dev, which is how HitMap::calc_combined_fluence_with_voronoi (hit_map/mod.rs:232-262) sums the estimates of the rays hit
+ * maps of one surface on their common bounding box.  Synchronous. */
+OpmStatus opm_fluence_voronoi(OpmHitMap* const* maps, int32_t n_maps, int64_t bounce_filter_or_minus1, uint64_t nx,
+                              const double* ranges_or_null, int32_t accumulate, double* map_dev, double lrtb_out[4]);
+/* bit b of *mask is set when a recorded hit of the map has bounce count b (b < 64): the rays hit maps a slot-indexed hit map holds
+ * (hit_map/mod.rs:101-115 files hits under their bounce count) */
+OpmStatus opm_hitmap_bounce_levels(OpmHitMap* map, uint64_t* mask);
 /* FluenceData::new peak (fluence_data.rs:45-68) and total_energy (:130-141) of a device map */
 OpmStatus opm_fluence_peak_total(OpmContext* ctx, const double* map_dev, uint64_t nx, uint64_t ny, const double lrtb[4],
                                  double* peak, double* total_energy);

@@ -150,6 +150,12 @@ OpmStatus opm_scene_node_fluence(OpmScene* scene, int32_t node, uint64_t nx, uin
 /* the same report with FluenceEstimator::KDE (rays_hit_map.rs:575-613, kde/mod.rs); band_width = the estimated kernel width */
 OpmStatus opm_scene_node_fluence_kde(OpmScene* scene, int32_t node, uint64_t nx, uint64_t ny, double* map_host, double lrtb[4],
                                      double* peak, double* total_energy, double* band_width);
+/* the same report with FluenceEstimator::Voronoi, the node's default (nodes/fluence_detector/mod.rs:61): HitMap::
+ * calc_combined_fluence_with_voronoi (hit_map/mod.rs:232-262) -- one estimate per (bundle, bounce level) on the common bounding box,
+ * summed; NaN outside a bundle's convex hull.  nx x nx map; nx != ny is refused (OPM_ERR_ARG) where the reference panics on the
+ * dimensions of its matrix sum -- which is what its own (100, 83) report does. */
+OpmStatus opm_scene_node_fluence_voronoi(OpmScene* scene, int32_t node, uint64_t nx, uint64_t ny, double* map_host, double lrtb[4],
+                                         double* peak, double* total_energy);
 /* EnergyMeter::node_report (nodes/energy_meter.rs:136-151): total energy of the valid rays of the bundle the node keeps */
 OpmStatus opm_scene_node_energy(OpmScene* scene, int32_t node, double* energy_J);
 /* Spectrometer::node_report (nodes/spectrometer.rs:155-175): Rays::to_spectrum of the bundle the node keeps; resolution_m <= 0:

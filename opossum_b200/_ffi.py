@@ -20,7 +20,7 @@ OPM_MAX_PROGRAM_OPS = 128
 (OPM_OK, OPM_ERR_N2_INVALID, OPM_ERR_WVL_RANGE, OPM_ERR_INDEX_MODEL, OPM_ERR_COATING, OPM_ERR_APODIZE_FACTOR,
  OPM_ERR_THRESHOLD, OPM_ERR_HITPOINT, OPM_ERR_SPLIT_RATIO, OPM_ERR_FOCAL_LENGTH, OPM_ERR_EMPTY_HITMAP,
  OPM_ERR_BIN_RANGE, OPM_ERR_ARG, OPM_ERR_CAPACITY, OPM_ERR_CUDA, OPM_ERR_KDE_BANDWIDTH,
- OPM_ERR_SPECTRUM, OPM_ERR_EMPTY_WAVEFRONT, OPM_ERR_PEER_TIMEOUT) = range(19)
+ OPM_ERR_SPECTRUM, OPM_ERR_EMPTY_WAVEFRONT, OPM_ERR_PEER_TIMEOUT, OPM_ERR_VORONOI) = range(20)
 
 GEOM_PLANE, GEOM_SPHERE, GEOM_CYLINDER, GEOM_PARABOLA = range(4)
 COAT_IDEAL_AR, COAT_CONSTANT_R, COAT_FRESNEL = range(3)
@@ -204,7 +204,7 @@ SCENE_EXPORTS = [
     "opm_scene_add_node_at_distance", "opm_scene_add_node_aligned_like", "opm_scene_calc_node_positions", "opm_scene_node_isometry",
     "opm_scene_node_count", "opm_scene_reset_data", "opm_scene_raytrace", "opm_scene_output_rays", "opm_scene_node_rays", "opm_scene_node_spot",
     "opm_scene_node_spot_partial", "opm_scene_node_spot_async",
-    "opm_scene_node_fluence", "opm_scene_node_fluence_kde", "opm_scene_node_energy", "opm_scene_node_spectrum", "opm_scene_node_wavefront", "opm_scene_node_hitmaps", "opm_scene_ghostfocus", "opm_scene_gf_pass_tally",
+    "opm_scene_node_fluence", "opm_scene_node_fluence_kde", "opm_scene_node_fluence_voronoi", "opm_scene_node_energy", "opm_scene_node_spectrum", "opm_scene_node_wavefront", "opm_scene_node_hitmaps", "opm_scene_ghostfocus", "opm_scene_gf_pass_tally",
     "opm_scene_gf_pass_bundles", "opm_scene_node_critical_fluences", "opm_scene_node_peak_fluence",
 ]
 
@@ -232,7 +232,7 @@ EXPORTS = [
     "opm_peer_allgather_async", "opm_peer_fluence_report_async", "opm_peer_fluence_gather_map", "opm_peer_group_phase_times", "opm_measure_fp64_peak", "opm_device_alloc",
     "opm_device_free", "opm_device_memset", "opm_device_to_host", "opm_host_to_device", "opm_host_alloc_pinned", "opm_host_free_pinned",
     "opm_spectrum_gaussian", "opm_source_generate", "opm_source_generate_strided", "opm_source_energy_norm", "opm_rays_new_collimated_xy", "opm_rays_refresh_lens", "opm_context_interactions_total",
-    "opm_context_last_first_valid_key_async", "opm_fluence_peak_check_acc_init", "opm_fluence_peak_check_async",
+    "opm_context_last_first_valid_key_async", "opm_fluence_peak_check_acc_init", "opm_fluence_peak_check_async", "opm_fluence_voronoi", "opm_hitmap_bounce_levels",
 ]
 
 _lib = None
@@ -366,6 +366,8 @@ def lib() -> C.CDLL:
         "opm_spectrum_gaussian": (i32, [C.c_double, C.c_double, u64, C.c_double, C.c_double, C.c_double, dp, dp]),
         "opm_source_energy_norm": (i32, [vp, C.POINTER(OpmSourceDesc), u64, u64, dp]),
         "opm_rays_new_collimated_xy": (i32, [vp, vp, u64, C.POINTER(OpmSourceDesc)]),
+        "opm_fluence_voronoi": (i32, [vp, i32, C.c_int64, u64, dp, i32, vp, dp]),
+        "opm_hitmap_bounce_levels": (i32, [vp, C.POINTER(u64)]),
     }
     sig.update({
         "opm_node_desc_init": (None, [C.POINTER(OpmNodeDesc), i32]),
@@ -388,6 +390,7 @@ def lib() -> C.CDLL:
         "opm_scene_node_spot_async": (i32, [vp, i32, i32, vp, vp]),
         "opm_scene_node_fluence": (i32, [vp, i32, u64, u64, dp, dp, dp, dp]),
         "opm_scene_node_fluence_kde": (i32, [vp, i32, u64, u64, dp, dp, dp, dp, dp]),
+        "opm_scene_node_fluence_voronoi": (i32, [vp, i32, u64, u64, dp, dp, dp, dp]),
         "opm_scene_node_spectrum": (i32, [vp, i32, C.c_double, dp, dp, dp, u64, C.POINTER(u64)]),
         "opm_scene_node_wavefront": (i32, [vp, i32, dp, u64, C.POINTER(OpmWavefrontStats)]),
         "opm_scene_node_hitmaps": (i32, [vp, i32, i32, pp, i32]),

@@ -311,6 +311,9 @@ class Context:
     def device_free(self, p: int):
         F.lib().opm_device_free(self.h, C.c_void_p(p))
 
+    def device_memset(self, dev: int, value: int, nbytes: int):
+        _check(F.lib().opm_device_memset(self.h, C.c_void_p(dev), value, nbytes))
+
     def to_host(self, dev: int, arr: np.ndarray):
         _check(F.lib().opm_device_to_host(self.h, C.c_void_p(arr.ctypes.data), C.c_void_p(dev), arr.nbytes))
 
@@ -874,6 +877,61 @@ def fluence_kde(ctx: Context, hit_maps, nx: int, ny: int, ranges=None, bounce=-1
         flat = np.zeros(nx * ny)
         ctx.to_host(map_dev, flat)
         return FluenceData(flat.reshape(nx, ny).T.copy(), tuple(out[:]), peak.value, tot.value), bw.value
+    finally:
+        ctx.device_free(map_dev)
+
+
+def hitmap_bounce_levels(hit_map) -> list:
+    """the bounce counts under which the hits of a slot-indexed hit map are filed (hit_map/mod.rs:101-115), below 64"""
+    m = C.c_uint64()
+    _check(F.lib().opm_hitmap_bounce_levels(hit_map.h, C.byref(m)))
+    return [b for b in range(64) if (m.value >> b) & 1]
+
+
+def fluence_voronoi(ctx: Context, hit_maps, nx: int, ranges=None, bounce=-1, map_dev: int | None = None, accumulate=False) -> FluenceData:
+    """RaysHitMap::calc_fluence_with_voronoi (rays_hit_map.rs:407-521) of ONE rays hit map (the hits passing `bounce`): nx x nx map
+    (the reference gives both axes nr_of_points.0 points), ranges = (ax1.start, ax1.end, ax2.start, ax2.end) or None."""
+    L = F.lib()
+    own = map_dev is None
+    if own:
+        map_dev = ctx.device_alloc(nx * nx * 8)
+    try:
+        arr = (C.c_void_p * len(hit_maps))(*[h.h for h in hit_maps])
+        rg = (C.c_double * 4)(*ranges) if ranges is not None else None
+        out = (C.c_double * 4)()
+        _check(L.opm_fluence_voronoi(arr, len(hit_maps), bounce, nx, rg, int(accumulate), C.c_void_p(map_dev), out))
+        peak, tot = C.c_double(), C.c_double()
+        _check(L.opm_fluence_peak_total(ctx.h, C.c_void_p(map_dev), nx, nx, out, C.byref(peak), C.byref(tot)))
+        flat = np.zeros(nx * nx)
+        ctx.to_host(map_dev, flat)
+        return FluenceData(flat.reshape(nx, nx).T.copy(), tuple(out[:]), peak.value, tot.value)
+    finally:
+        if own:
+            ctx.device_free(map_dev)
+
+
+def fluence_voronoi_combined(ctx: Context, bundles, nx: int, ny: int) -> FluenceData:
+    """HitMap::calc_combined_fluence_with_voronoi (hit_map/mod.rs:232-262): `bundles` = one list of hit maps per ray bundle (uuid)
+    of the surface; every (bundle, bounce level) is a rays hit map of its own, estimated on the common bounding box
+    (get_bounding_box, :178-203) and summed.  The reference adds nx x nx estimates to an nx x ny matrix and panics unless
+    nx == ny; so does this (ValueError)."""
+    if nx != ny:
+        raise ValueError("calc_combined_fluence_with_voronoi: matrix dimensions mismatch (the reference panics unless nx == ny)")
+    every = [h for b in bundles for h in b]
+    l, r, t, b_ = hitmaps_bounding_box(every)[0]
+    map_dev = ctx.device_alloc(nx * nx * 8)
+    try:
+        ctx.device_memset(map_dev, 0, nx * nx * 8)
+        for maps in bundles:
+            levels = sorted({lv for h in maps for lv in hitmap_bounce_levels(h)})
+            for lv in levels:
+                fluence_voronoi(ctx, maps, nx, ranges=(l, r, b_, t), bounce=lv, map_dev=map_dev, accumulate=True)
+        out = (C.c_double * 4)(l, r, t, b_)
+        peak, tot = C.c_double(), C.c_double()
+        _check(F.lib().opm_fluence_peak_total(ctx.h, C.c_void_p(map_dev), nx, nx, out, C.byref(peak), C.byref(tot)))
+        flat = np.zeros(nx * nx)
+        ctx.to_host(map_dev, flat)
+        return FluenceData(flat.reshape(nx, nx).T.copy(), (l, r, t, b_), peak.value, tot.value)
     finally:
         ctx.device_free(map_dev)
 

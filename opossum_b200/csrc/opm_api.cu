@@ -12,7 +12,10 @@
 #include <string>
 #include <vector>
 
+#include <algorithm>
+
 #include "opm_internal.h"
+#define OPM_VORONOI_HOST
 #include "opm_kernels.h"
 #include "opm_peer.h"
 #include "../../include/opossum_b200_scene.h"
@@ -188,6 +191,7 @@ extern "C" const char* opm_status_string(OpmStatus s) {
         case OPM_ERR_SPECTRUM: return "spectrum: wavelength outside the spectrum, no valid rays, or invalid range / resolution";
         case OPM_ERR_EMPTY_WAVEFRONT: return "Empty wavefront-data vector!";
         case OPM_ERR_PEER_TIMEOUT: return "multi-GPU read-out: a peer rank did not arrive at a meeting in time";
+        case OPM_ERR_VORONOI: return "Voronoi diagram for fluence estimation could not be created";
         default: return "unknown status";
     }
 }
@@ -2393,6 +2397,189 @@ extern "C" OpmStatus opm_fluence_kde(OpmHitMap* const* maps, int32_t n_maps, int
     cleanup();
     if (rc || e != cudaSuccess) return fail(OPM_ERR_CUDA, "KDE map kernel failed");
     if (lrtb_out) { lrtb_out[0] = l; lrtb_out[1] = r; lrtb_out[2] = t; lrtb_out[3] = b; }
+    return OPM_OK;
+}
+
+// ---- Voronoi fluence estimator (opm_voronoi.cu): RaysHitMap::calc_fluence_with_voronoi, rays_hit_map.rs:407-521
+extern "C" OpmStatus opm_hitmap_bounce_levels(OpmHitMap* map, uint64_t* mask) {
+    if (!map || !mask) return fail(OPM_ERR_ARG, "NULL argument");
+    OpmContext* c = map->ctx;
+    CU(cudaSetDevice(c->device));
+    unsigned long long* d = (unsigned long long*)(c->d_scratch + 3072);
+    CU(cudaMemsetAsync(d, 0, 8, c->stream));
+    if (map->len) { KL(k_hits_bounce_mask(map->v, map->len, d, c->sms, c->stream)); c->launches++; }
+    unsigned long long* h = (unsigned long long*)(c->h_scratch + 3072);
+    CU(cudaMemcpyAsync(h, d, 8, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    *mask = *h;
+    return OPM_OK;
+}
+extern "C" OpmStatus opm_fluence_voronoi(OpmHitMap* const* maps, int32_t n_maps, int64_t bounce_filter, uint64_t nx, const double* ranges,
+                                         int32_t accumulate, double* map_dev, double lrtb_out[4]) {
+    OpmContext* c;
+    OpmStatus s = check_same_ctx(maps, n_maps, &c);
+    if (s) return s;
+    if (!map_dev || nx == 0 || nx > 46340) return fail(OPM_ERR_ARG, "bad map arguments");
+    if (bounce_filter < -1) return fail(OPM_ERR_ARG, "bad bounce filter");
+    CU(cudaSetDevice(c->device));
+    uint64_t slots = 0;
+    for (int k = 0; k < n_maps; ++k) slots += maps[k]->len;
+    if (slots > 0x7fffffffull) return fail(OPM_ERR_CAPACITY, "Voronoi estimator: too many hit slots");
+    std::vector<void*> dev;  // everything allocated here
+    auto cleanup = [&]() { cudaStreamSynchronize(c->stream); for (void* p : dev) cudaFree(p); };
+    auto alloc = [&](size_t bytes) -> void* { void* p = nullptr; if (cudaMalloc(&p, bytes ? bytes : 8) != cudaSuccess) { cudaGetLastError(); return nullptr; } dev.push_back(p); return p; };
+    // dense hit list
+    const size_t cap = slots ? slots : 1;
+    double* hx = (double*)alloc(cap * 4 * sizeof(double));
+    if (!hx) { cleanup(); return fail(OPM_ERR_CUDA, "out of device memory"); }
+    double *hy = hx + cap, *he = hy + cap, *fl = he + cap;
+    unsigned long long* d_count = (unsigned long long*)(c->d_scratch + 3072);
+    unsigned* d_status = (unsigned*)(c->d_scratch + 3072 + 8);
+    cudaMemsetAsync(d_count, 0, 16, c->stream);
+    for (int k = 0; k < n_maps; ++k)
+        if (maps[k]->len) {
+            int rc = k_hits_pack(maps[k]->v, maps[k]->len, bounce_filter, hx, hy, he, d_count, slots, c->sms, c->stream);
+            c->launches++;
+            if (rc) { cleanup(); return fail(OPM_ERR_CUDA, "hit packing failed"); }
+        }
+    unsigned long long n64 = 0;
+    cudaMemcpyAsync(&n64, d_count, 8, cudaMemcpyDeviceToHost, c->stream);
+    if (cudaStreamSynchronize(c->stream) != cudaSuccess) { cleanup(); return fail(OPM_ERR_CUDA, "hit packing failed"); }
+    const int n = (int)n64;
+    if (n < 3) { cleanup(); return fail(OPM_ERR_VORONOI, "Too few points (<3) on hitmap to calculate fluence!"); }
+    // the warp-aggregated packing does not keep the slot order; the estimate is a function of the SET of hits, but the last bits of
+    // the sums are not: sort the hits by (x, y, e) on the host so that equal hit sets give bit-equal maps
+    KL(k_voronoi_to_cm(n, hx, hy, c->stream)); c->launches++;
+    std::vector<double> x(n), y(n), e(n);
+    CU(cudaMemcpyAsync(x.data(), hx, (size_t)n * 8, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(y.data(), hy, (size_t)n * 8, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(e.data(), he, (size_t)n * 8, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    {
+        std::vector<int> ord(n);
+        for (int i = 0; i < n; ++i) ord[i] = i;
+        std::sort(ord.begin(), ord.end(), [&](int a, int b) { return x[a] != x[b] ? x[a] < x[b] : (y[a] != y[b] ? y[a] < y[b] : e[a] < e[b]); });
+        std::vector<double> t(n);
+        for (int i = 0; i < n; ++i) t[i] = x[ord[i]]; x.swap(t);
+        for (int i = 0; i < n; ++i) t[i] = y[ord[i]]; y.swap(t);
+        for (int i = 0; i < n; ++i) t[i] = e[ord[i]]; e.swap(t);
+        CU(cudaMemcpyAsync(hx, x.data(), (size_t)n * 8, cudaMemcpyHostToDevice, c->stream));
+        CU(cudaMemcpyAsync(hy, y.data(), (size_t)n * 8, cudaMemcpyHostToDevice, c->stream));
+        CU(cudaMemcpyAsync(he, e.data(), (size_t)n * 8, cudaMemcpyHostToDevice, c->stream));
+    }
+    for (int i = 0; i < n; ++i)
+        if (!std::isfinite(x[i]) || !std::isfinite(y[i])) { cleanup(); return fail(OPM_ERR_VORONOI, "Coordinate values for voronoi-diagram generation must be finite!"); }
+    if (vor_all_on_same_line(x.data(), y.data(), n)) { cleanup(); return fail(OPM_ERR_VORONOI, "All passed points lie on the same line! Triangulation not possible!"); }
+    // convex hull, bounding polygon (create_voronoi_cells, griddata.rs:284-343), grid
+    std::vector<int> hull;
+    int on_b = 0;
+    vor_convex_hull(x.data(), y.data(), n, hull, &on_b);
+    const int h = (int)hull.size();
+    if (h < 3) { cleanup(); return fail(OPM_ERR_VORONOI, "Could not create voronoi diagram!"); }
+    std::vector<double> px, py;
+    double pcx = 0.0, pcy = 0.0;
+    vor_bounding_polygon(x.data(), y.data(), hull, 2 * n - 2 - on_b, px, py, &pcx, &pcy);
+    const int m = (int)px.size();
+    std::vector<double> pol(4 * (size_t)m);  // px | py | outward normal x | y
+    double area2 = 0.0;
+    for (int i = 0; i < m; ++i) { const int j = (i + 1) % m; area2 += px[i] * py[j] - py[i] * px[j]; }
+    const double orient = area2 >= 0.0 ? 1.0 : -1.0;  // counter-clockwise: the interior is on the left of every edge
+    VorBound B;
+    memset(&B, 0, sizeof B);
+    B.x0 = B.x1 = px[0]; B.y0 = B.y1 = py[0];
+    double r_in = INFINITY;
+    for (int i = 0; i < m; ++i) {
+        const int j = (i + 1) % m;
+        const double ex = px[j] - px[i], ey = py[j] - py[i];
+        const double nxo = orient * ey, nyo = -orient * ex;  // outward normal of a counter-clockwise edge (ex, ey) is (ey, -ex)
+        pol[i] = px[i]; pol[m + i] = py[i]; pol[2 * m + i] = nxo; pol[3 * m + i] = nyo;
+        const double len = std::sqrt(nxo * nxo + nyo * nyo);
+        if (len > 0.0) r_in = std::min(r_in, ((px[i] - pcx) * nxo + (py[i] - pcy) * nyo) / len);
+        B.x0 = std::min(B.x0, px[i]); B.x1 = std::max(B.x1, px[i]); B.y0 = std::min(B.y0, py[i]); B.y1 = std::max(B.y1, py[i]);
+    }
+    r_in = std::isfinite(r_in) && r_in > 0.0 ? r_in * (1.0 - 1e-9) : 0.0;
+    B.cx = pcx; B.cy = pcy; B.r_in2 = r_in * r_in; B.m = m;
+    VorGrid G;
+    std::vector<int> cell_start, cell_sites;
+    vor_build_grid(x.data(), y.data(), n, G, cell_start, cell_sites);
+    double* d_pol = (double*)alloc(pol.size() * 8);
+    int* d_cells = (int*)alloc((cell_start.size() + cell_sites.size()) * 4);
+    if (!d_pol || !d_cells) { cleanup(); return fail(OPM_ERR_CUDA, "out of device memory"); }
+    CU(cudaMemcpyAsync(d_pol, pol.data(), pol.size() * 8, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(d_cells, cell_start.data(), cell_start.size() * 4, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(d_cells + cell_start.size(), cell_sites.data(), cell_sites.size() * 4, cudaMemcpyHostToDevice, c->stream));
+    B.px = d_pol; B.py = d_pol + m; B.nx = d_pol + 2 * m; B.ny = d_pol + 3 * m;
+    G.cell_start = d_cells; G.cell_sites = d_cells + cell_start.size();
+    // cells -> per-site fluence
+    KL(k_voronoi_cells(n, hx, hy, he, G, B, fl, d_status, c->stream)); c->launches++;
+    std::vector<double> z(n);
+    unsigned st_bits = 0;
+    CU(cudaMemcpyAsync(z.data(), fl, (size_t)n * 8, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(&st_bits, d_status, 4, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    if (st_bits) { cleanup(); return fail(OPM_ERR_CAPACITY, "Voronoi estimator: a cell has more than 64 vertices"); }
+    // interpolation over the sites with a finite value (griddata.rs:412): normally all of them
+    int nf = 0;
+    for (int i = 0; i < n; ++i) nf += std::isfinite(z[i]) ? 1 : 0;
+    const double *ix = hx, *iy = hy, *iz = fl;
+    std::vector<double> fx, fy, fz;
+    if (nf != n) {
+        for (int i = 0; i < n; ++i) if (std::isfinite(z[i])) { fx.push_back(x[i]); fy.push_back(y[i]); fz.push_back(z[i]); }
+        double* d_f = (double*)alloc((size_t)std::max(nf, 1) * 3 * 8);
+        if (!d_f) { cleanup(); return fail(OPM_ERR_CUDA, "out of device memory"); }
+        if (nf) {
+            CU(cudaMemcpyAsync(d_f, fx.data(), (size_t)nf * 8, cudaMemcpyHostToDevice, c->stream));
+            CU(cudaMemcpyAsync(d_f + nf, fy.data(), (size_t)nf * 8, cudaMemcpyHostToDevice, c->stream));
+            CU(cudaMemcpyAsync(d_f + 2 * (size_t)nf, fz.data(), (size_t)nf * 8, cudaMemcpyHostToDevice, c->stream));
+        }
+        ix = d_f; iy = d_f + nf; iz = d_f + 2 * (size_t)nf;
+        hull.clear();
+        if (nf >= 3) {
+            vor_convex_hull(fx.data(), fy.data(), nf, hull, nullptr);
+            vor_build_grid(fx.data(), fy.data(), nf, G, cell_start, cell_sites);
+            int* d_c2 = (int*)alloc((cell_start.size() + cell_sites.size()) * 4);
+            if (!d_c2) { cleanup(); return fail(OPM_ERR_CUDA, "out of device memory"); }
+            CU(cudaMemcpyAsync(d_c2, cell_start.data(), cell_start.size() * 4, cudaMemcpyHostToDevice, c->stream));
+            CU(cudaMemcpyAsync(d_c2 + cell_start.size(), cell_sites.data(), cell_sites.size() * 4, cudaMemcpyHostToDevice, c->stream));
+            G.cell_start = d_c2; G.cell_sites = d_c2 + cell_start.size();
+        }
+    }
+    const std::vector<double>& sxh = nf != n ? fx : x;
+    const std::vector<double>& syh = nf != n ? fy : y;
+    const std::vector<double>& szh = nf != n ? fz : z;
+    const int hh = (int)hull.size();
+    std::vector<double> hv(3 * (size_t)std::max(hh, 1));
+    for (int i = 0; i < hh; ++i) { hv[i] = sxh[hull[i]]; hv[hh + i] = syh[hull[i]]; hv[2 * hh + i] = szh[hull[i]]; }
+    double* d_hull = (double*)alloc(hv.size() * 8);
+    if (!d_hull) { cleanup(); return fail(OPM_ERR_CUDA, "out of device memory"); }
+    CU(cudaMemcpyAsync(d_hull, hv.data(), hv.size() * 8, cudaMemcpyHostToDevice, c->stream));
+    VorHull H{hh >= 3 ? hh : 0, d_hull, d_hull + hh, d_hull + 2 * hh};
+    // axes (rays_hit_map.rs:459-497): given ranges or the hits' limits, in centimetres; nx points on BOTH axes
+    double x0, x1, y0, y1;
+    if (ranges) { x0 = ranges[0] / 1.0E-2; x1 = ranges[1] / 1.0E-2; y0 = ranges[2] / 1.0E-2; y1 = ranges[3] / 1.0E-2; }
+    else {
+        x0 = y0 = INFINITY; x1 = y1 = -INFINITY;
+        for (int i = 0; i < n; ++i) { x0 = std::fmin(x0, x[i]); x1 = std::fmax(x1, x[i]); y0 = std::fmin(y0, y[i]); y1 = std::fmax(y1, y[i]); }
+    }
+    if (!std::isfinite(x0) || !std::isfinite(x1) || !std::isfinite(y0) || !std::isfinite(y1)) { cleanup(); return fail(OPM_ERR_VORONOI, "cannot construct voronoi cells with non-finite axes bounds!"); }
+    const double bin_x = nx > 1 ? (x1 - x0) / (double)(nx - 1) : 0.0, bin_y = nx > 1 ? (y1 - y0) / (double)(nx - 1) : 0.0;
+    double ext = 0.0;
+    for (int i = 0; i < (int)sxh.size(); ++i) ext = std::fmax(ext, std::fmax(std::fabs(sxh[i]), std::fabs(syh[i])));
+    const double big = 1.0e3 * (std::fmax(x1 - x0, y1 - y0) + ext + 1.0);
+    double* target = map_dev;
+    if (accumulate) { target = (double*)alloc((size_t)nx * nx * 8); if (!target) { cleanup(); return fail(OPM_ERR_CUDA, "out of device memory"); } }
+    CU(cudaMemsetAsync(d_status, 0, 4, c->stream));
+    KL(k_voronoi_interp((int)nx, (int)nx, x0, bin_x, y0, bin_y, nf, ix, iy, iz, G, H, big, target, d_status, c->stream)); c->launches++;
+    if (accumulate) { KL(k_voronoi_accumulate(nx * nx, map_dev, target, c->sms, c->stream)); c->launches++; }
+    CU(cudaMemcpyAsync(&st_bits, d_status, 4, cudaMemcpyDeviceToHost, c->stream));
+    cudaError_t ce = cudaStreamSynchronize(c->stream);
+    cleanup();
+    if (ce != cudaSuccess) return fail(OPM_ERR_CUDA, "Voronoi kernels failed: %s", cudaGetErrorString(ce));
+    if (st_bits) return fail(OPM_ERR_CAPACITY, "Voronoi estimator: a natural-neighbour cell exceeds the polygon capacity");
+    if (lrtb_out) {
+        if (ranges) { lrtb_out[0] = ranges[0]; lrtb_out[1] = ranges[1]; lrtb_out[2] = ranges[3]; lrtb_out[3] = ranges[2]; }
+        else { lrtb_out[0] = x0 * 1.0E-2; lrtb_out[1] = x1 * 1.0E-2; lrtb_out[2] = y1 * 1.0E-2; lrtb_out[3] = y0 * 1.0E-2; }
+    }
     return OPM_OK;
 }
 

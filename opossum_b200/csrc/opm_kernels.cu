@@ -1306,6 +1306,19 @@ int k_history_gather(const HistParams& hp, uint32_t levels, DevRays R, uint64_t 
     return (int)cudaGetLastError();
 }
 __global__ void peak_finalize_kernel(const PeakAccum* acc, double* out2) { out2[0] = dkey_inv(acc->peak_key); out2[1] = acc->total; }
+// bit b set when a recorded hit has bounce count b (< 64)
+__global__ void __launch_bounds__(256) hits_bounce_mask_kernel(DevHits H, uint64_t n, unsigned long long* mask) {
+    unsigned long long m = 0;
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
+        if (H.e[i] >= 0.0 && H.bounce[i] < 64u) m |= 1ull << H.bounce[i];
+    m |= __shfl_xor_sync(0xffffffffu, m, 16); m |= __shfl_xor_sync(0xffffffffu, m, 8); m |= __shfl_xor_sync(0xffffffffu, m, 4);
+    m |= __shfl_xor_sync(0xffffffffu, m, 2); m |= __shfl_xor_sync(0xffffffffu, m, 1);
+    if ((threadIdx.x & 31) == 0 && m) atomicOr(mask, m);
+}
+int k_hits_bounce_mask(DevHits H, uint64_t n, unsigned long long* mask, int sms, void* stream) {
+    hits_bounce_mask_kernel<<<grid_for(n, 256, sms * 8), 256, 0, ST>>>(H, n, mask);
+    return (int)cudaGetLastError();
+}
 int k_hits_pack(DevHits H, uint64_t n, long long bounce_filter, double* x, double* y, double* e, unsigned long long* count,
                 unsigned long long cap, int sms, void* stream) {
     hits_pack_kernel<<<grid_for(n, 256, sms * 8), 256, 0, ST>>>(H, n, bounce_filter, x, y, e, count, cap);

@@ -89,6 +89,28 @@ int k_readout_combine_b(const double* g, int w, uint64_t maps_len, int ns, doubl
 int k_fp64_peak(double* out, int iters, int blocks, void* stream);
 int k_fetch_from_host(void* dst, const void* src_host, size_t bytes, void* stream);  // bytes % 8 == 0, src pinned + mapped
 int k_set_u64(unsigned long long* p, unsigned long long v, void* stream);
+// ---- Voronoi fluence estimator (opm_voronoi.cu)
+struct VorGrid { double x0, y0, cs, inv_cs; int gx, gy; const int* cell_start; const int* cell_sites; };  // uniform grid over the sites
+struct VorBound {  // the reference's bounding polygon (convex, m edges: a point and the OUTWARD normal of each), a rectangle around it,
+    double x0, y0, x1, y1, cx, cy, r_in2;  // and the circle around (cx, cy) inscribed in it
+    int m;
+    const double *px, *py, *nx, *ny;
+};
+struct VorHull { int h; const double *x, *y, *z; };  // convex hull of the sites, counter-clockwise, with the sites' values
+int k_voronoi_to_cm(int n, double* x, double* y, void* stream);
+int k_voronoi_cells(int n, const double* sx, const double* sy, const double* e, const VorGrid& G, const VorBound& B, double* fluence,
+                    unsigned* status, void* stream);
+int k_voronoi_interp(int nx_pts, int ny_pts, double ax0, double ax_bin, double ay0, double ay_bin, int n, const double* sx, const double* sy,
+                     const double* sz, const VorGrid& G, const VorHull& H, double big, double* map, unsigned* status, void* stream);
+int k_voronoi_accumulate(uint64_t bins, double* map, const double* part, int sms, void* stream);
+#ifdef OPM_VORONOI_HOST  // host bookkeeping of the estimator (needs <vector>)
+void vor_convex_hull(const double* x, const double* y, int n, std::vector<int>& hull, int* on_boundary);
+bool vor_all_on_same_line(const double* x, const double* y, int n);
+void vor_bounding_polygon(const double* x, const double* y, const std::vector<int>& hull, int n_triangles, std::vector<double>& px,
+                          std::vector<double>& py, double* cx_out, double* cy_out);
+void vor_build_grid(const double* x, const double* y, int n, VorGrid& G, std::vector<int>& cell_start, std::vector<int>& cell_sites);
+#endif
+int k_hits_bounce_mask(DevHits H, uint64_t n, unsigned long long* mask, int sms, void* stream);
 int k_copy_rays(DevRays S, uint64_t soff, DevRays D, uint64_t doff, uint64_t n, int sms, void* stream);
 int k_first_key_store(const unsigned long long* first_inv, unsigned long long* out, void* stream);
 int k_expand_collimated_xy(const double* xy, uint64_t n_pos, const SourceParams& S, double* norm_dev, const double* wvl, const double* wgt,

@@ -285,8 +285,8 @@ class Scene:
         return p
 
     def node_fluence(self, node: int, nx=100, ny=83, download=True, estimator="binning") -> FluenceData:
-        """FluenceDetector::node_report (nodes/fluence_detector/mod.rs:91-135); estimator "binning" or "kde"
-        (FluenceEstimator::Binning / ::KDE)"""
+        """FluenceDetector::node_report (nodes/fluence_detector/mod.rs:91-135); estimator "binning", "kde" or "voronoi"
+        (FluenceEstimator::Binning / ::KDE / ::Voronoi, the reference's default: nx x nx map, nx must equal ny)"""
         m = np.zeros(nx * ny) if download else None
         lrtb = (C.c_double * 4)()
         peak, tot = C.c_double(), C.c_double()
@@ -297,8 +297,12 @@ class Scene:
             fd = FluenceData(m.reshape(nx, ny).T.copy() if download else None, tuple(lrtb[:]), peak.value, tot.value)
             fd.band_width = bw.value
             return fd
+        if estimator == "voronoi":
+            _check(F.lib().opm_scene_node_fluence_voronoi(self.h, node, nx, ny, m.ctypes.data_as(C.POINTER(C.c_double)) if download else None,
+                                                          lrtb, C.byref(peak), C.byref(tot)))
+            return FluenceData(m.reshape(nx, ny).T.copy() if download else None, tuple(lrtb[:]), peak.value, tot.value)
         if estimator != "binning":
-            raise ValueError("estimator must be 'binning' or 'kde' (the Voronoi estimator is out of scope, SURVEY 8f-1)")
+            raise ValueError("estimator must be 'binning', 'kde' or 'voronoi'")
         _check(F.lib().opm_scene_node_fluence(self.h, node, nx, ny,
                                               m.ctypes.data_as(C.POINTER(C.c_double)) if download else None, lrtb,
                                               C.byref(peak), C.byref(tot)))

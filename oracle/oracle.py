@@ -24,9 +24,8 @@ _LIB_PATH = _HERE / "libopm_oracle.so"
 
 def build(force: bool = False) -> Path:
     """Compile oracle/libopm_oracle.so with the committed Makefile (gcc only)."""
-    src = _HERE / "opm_oracle.c"
-    hdr = _HERE / "opm_oracle.h"
-    if force or not _LIB_PATH.exists() or _LIB_PATH.stat().st_mtime < max(src.stat().st_mtime, hdr.stat().st_mtime):
+    srcs = [_HERE / "opm_oracle.c", _HERE / "opm_voronoi.c", _HERE / "opm_oracle.h"]
+    if force or not _LIB_PATH.exists() or _LIB_PATH.stat().st_mtime < max(f.stat().st_mtime for f in srcs):
         env = dict(os.environ)
         env.pop("CC", None)
         subprocess.run(["make", "-C", str(_HERE), "-B" if force else "-s"], check=True, env=env,
@@ -571,6 +570,42 @@ def fluence_binning(hits: np.ndarray, nx: int, ny: int, ranges=None):
     rg = (C.c_double * 4)(*ranges) if ranges is not None else None
     _check(lib().orc_fluence_binning(_vp(hits), len(hits), nx, ny, rg, _dptr(m), lrtb))
     return m.reshape(nx, ny).T.copy(), tuple(lrtb[:])  # column-major ny x nx -> [row=y, col=x]
+
+
+def voronoi_site_fluence(x_cm, y_cm, e):
+    """per-site fluence E_i / area(Voronoi cell i) in J/cm^2 (rays_hit_map.rs:432-458); returns (fluence, hull area in cm^2)"""
+    x = np.ascontiguousarray(x_cm, dtype=np.float64); y = np.ascontiguousarray(y_cm, dtype=np.float64)
+    ee = np.ascontiguousarray(e, dtype=np.float64)
+    out = np.zeros(len(x))
+    area = C.c_double()
+    _check(lib().orc_voronoi_site_fluence(_dptr(x), _dptr(y), _dptr(ee), len(x), _dptr(out), C.byref(area)))
+    return out, area.value
+
+
+def fluence_voronoi(hits: np.ndarray, nx: int, ranges=None):
+    """RaysHitMap::calc_fluence_with_voronoi (rays_hit_map.rs:407-521) of ONE rays hit map.  ranges = (ax1.start, ax1.end,
+    ax2.start, ax2.end) in metres or None.  Returns (map[nx, nx] indexed [y index, x index] in J/m^2, (left, right, top, bottom))."""
+    m = np.zeros(nx * nx, dtype=np.float64)
+    lrtb = (C.c_double * 4)()
+    rg = (C.c_double * 4)(*ranges) if ranges is not None else None
+    _check(lib().orc_fluence_voronoi(_vp(hits), len(hits), nx, rg, _dptr(m), lrtb))
+    return m.reshape(nx, nx).T.copy(), tuple(lrtb[:])
+
+
+def fluence_voronoi_combined(hit_maps, nx: int, ny: int):
+    """HitMap::calc_combined_fluence_with_voronoi (hit_map/mod.rs:232-262): the bounding box of ALL rays hit maps
+    (get_bounding_box, :178-203), one Voronoi estimate per rays hit map -- per (bounce level, bundle) -- on that common grid, summed
+    (NaN outside a bundle's convex hull propagates).  The reference adds nx x nx estimates onto an nx x ny matrix: it panics
+    unless nx == ny (so does this: ValueError)."""
+    if nx != ny:
+        raise ValueError("calc_combined_fluence_with_voronoi: matrix dimensions mismatch (the reference panics unless nx == ny)")
+    x0 = min(float(h["x"].min()) for h in hit_maps); x1 = max(float(h["x"].max()) for h in hit_maps)
+    y0 = min(float(h["y"].min()) for h in hit_maps); y1 = max(float(h["y"].max()) for h in hit_maps)
+    total = np.zeros((nx, nx))
+    for h in hit_maps:
+        m, _ = fluence_voronoi(h, nx, (x0, x1, y0, y1))
+        total += m
+    return total, (x0, x1, y1, y0)
 
 
 def kde_distances_iqr(values) -> float:

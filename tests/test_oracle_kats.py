@@ -1054,3 +1054,52 @@ def test_beam_splitter_two_inputs_kat():
     assert osc.beam_splitter_two_inputs(1, None, None) == (None, None)
     only1 = osc.beam_splitter_two_inputs(1, in1, None)
     assert orc.total_energy(only1[0]) == 0.6 and orc.total_energy(only1[1]) == 0.4
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Voronoi fluence estimator (surface/hit_map/mod.rs:942-998, utils/griddata.rs tests)
+# ---------------------------------------------------------------------------------------------------------------
+def test_kat_voronoi_combined_fluence_centre_bins():
+    """hit_map/mod.rs:942-982 `calc_combined_fluence_with_voronoi`: five 1 J hits (unit square + centre) -> centre bin 2 J/m^2
+    (the centre's cell is the diamond of area 0.5 m^2); a second bundle (diamond + centre) on top -> 4 J/m^2"""
+    p1 = [(-0.5, -0.5), (0.0, 0.0), (-0.5, 0.5), (0.5, 0.5), (0.5, -0.5)]
+    h1 = orc.hits_from_xye(np.array([p[0] for p in p1]), np.array([p[1] for p in p1]), np.ones(5))
+    m, lrtb = orc.fluence_voronoi_combined([h1], 51, 51)
+    assert m[25, 25] == pytest.approx(2.0, rel=1e-14) and lrtb == (-0.5, 0.5, 0.5, -0.5)
+    r = math.sqrt(0.5)
+    p2 = [(r, 0.0), (0.0, r), (-r, 0.0), (0.0, -r), (0.0, 0.0)]
+    h2 = orc.hits_from_xye(np.array([p[0] for p in p2]), np.array([p[1] for p in p2]), np.ones(5))
+    m, _ = orc.fluence_voronoi_combined([h1, h2], 51, 51)
+    assert m[25, 25] == pytest.approx(4.0, rel=1e-14)
+
+
+def test_kat_voronoi_too_few_points_and_collinear():
+    """hit_map/mod.rs:984-998 (two hits: Err), griddata.rs `all_points_on_same_line_test` (collinear points: no triangulation)"""
+    two = orc.hits_from_xye(np.array([-0.5, 0.0]), np.array([-0.5, 0.0]), np.ones(2))
+    with pytest.raises(orc.OracleError):
+        orc.fluence_voronoi(two, 51)
+    line = orc.hits_from_xye(np.array([0.0, 1.0, 2.0]), np.array([0.0, 1.0, 2.0]), np.ones(3))
+    with pytest.raises(orc.OracleError):
+        orc.fluence_voronoi(line, 51)
+    ok = orc.hits_from_xye(np.array([0.0, 1.0, 2.0, 2.0]), np.array([0.0, 1.0, 2.0, 3.0]), np.ones(4))
+    orc.fluence_voronoi(ok, 11)
+
+
+def test_voronoi_cells_tile_the_bounding_polygon_and_interpolation_reproduces_linear_data():
+    """properties of the restatement (not reference KATs): the cells partition the bounding polygon, so sum(E_i / fluence_i) is its
+    area; natural-neighbour coordinates reproduce a linear function of (x, y) exactly inside the hull"""
+    rng = np.random.default_rng(5)
+    n = 400
+    x, y = rng.random(n) * 3.0 - 1.0, rng.random(n) * 2.0 + 0.5  # cm
+    fl, area_hull = orc.voronoi_site_fluence(x, y, np.ones(n))
+    total_cells = float(np.sum(1.0 / fl))
+    assert area_hull < total_cells < 1.25 * area_hull  # the hull pushed outwards by half a mean triangle height
+    # a rays hit map whose per-site fluence is linear in (x, y): E_i = f(x_i, y_i) * area_i
+    f = 2.0 + 0.7 * x - 0.3 * y
+    hits = orc.hits_from_xye(x * 1e-2, y * 1e-2, f / fl)
+    m, lrtb = orc.fluence_voronoi(hits, 41)
+    ax = np.linspace(x.min(), x.max(), 41); ay = np.linspace(y.min(), y.max(), 41)
+    want = (2.0 + 0.7 * ax[None, :] - 0.3 * ay[:, None]) * 1e4
+    inside = np.isfinite(m)
+    assert inside.sum() > 0.8 * m.size
+    assert np.allclose(m[inside], want[inside], rtol=1e-9)
