@@ -150,6 +150,13 @@ OpmStatus opm_scene_node_fluence(OpmScene* scene, int32_t node, uint64_t nx, uin
 /* the same report with FluenceEstimator::KDE (rays_hit_map.rs:575-613, kde/mod.rs); band_width = the estimated kernel width */
 OpmStatus opm_scene_node_fluence_kde(OpmScene* scene, int32_t node, uint64_t nx, uint64_t ny, double* map_host, double lrtb[4],
                                      double* peak, double* total_energy, double* band_width);
+/* BeamSplitter::analyze_raytrace with BOTH inputs (nodes/beam_splitter/mod.rs:158-293, analysis_raytrace.rs:12-39; the reference's
+ * test :149-181: 1 J and 0.5 J in at ratio 0.6 -> 0.8 J and 0.7 J out): out1 = what in1 keeps + what in2 splits off, out2 the other
+ * way round, after the input surface / aperture and before the output aperture and the energy threshold.  The scene GRAPH is a
+ * tree (one input per node); this is the node-level call for a caller that holds two bundles.  in1 or in2 may be NULL; the
+ * inputs are not modified; out1 / out2 are overwritten.  config NULL = RayTraceConfig::default(). */
+OpmStatus opm_scene_beam_splitter_two_inputs(OpmScene* scene, int32_t node, OpmRays* in1, OpmRays* in2, const OpmRayTraceConfig* config,
+                                             OpmRays* out1, OpmRays* out2);
 /* the same report with FluenceEstimator::Voronoi, the node's default (nodes/fluence_detector/mod.rs:61): HitMap::
  * calc_combined_fluence_with_voronoi (hit_map/mod.rs:232-262) -- one estimate per (bundle, bounce level) on the common bounding box,
  * summed; NaN outside a bundle's convex hull.  nx x nx map; nx != ny is refused (OPM_ERR_ARG) where the reference panics on the
@@ -169,7 +176,14 @@ OpmStatus opm_scene_node_wavefront(OpmScene* scene, int32_t node, double* xyw_ou
 int32_t opm_scene_node_hitmaps(OpmScene* scene, int32_t node, int32_t surface, OpmHitMap** out, int32_t capacity);
 
 /* ---- ghost focus (analyzers/ghostfocus.rs) */
-typedef struct { uint64_t max_bounces; } OpmGhostFocusConfig;  /* estimator: Binning */
+typedef enum { OPM_ESTIMATOR_BINNING = 0, OPM_ESTIMATOR_VORONOI = 1 } OpmFluenceEstimator;
+typedef struct {
+    uint64_t max_bounces;
+    uint32_t fluence_estimator;  /* OpmFluenceEstimator of the per-bundle LIDT check (GhostFocusConfig::fluence_estimator; the
+                                    reference's default is Voronoi, analyzers/ghostfocus.rs:61).  Binning chains on the device; a
+                                    Voronoi check synchronises (its cells are prepared on the host). */
+    uint32_t _pad;
+} OpmGhostFocusConfig;
 typedef struct {
     uint64_t interactions;
     uint64_t launches;

@@ -83,6 +83,7 @@ struct OpmScene {
     // per check) and the pinned mirror of the slots: a check costs no synchronisation and no allocation
     void* gf_scratch = nullptr;
     void* gf_host = nullptr;
+    void* gf_vor_map = nullptr;  // 101 x 101 map + the bounce-level key of a Voronoi LIDT check
     std::vector<GfCheck> gf_pending;
 };
 
@@ -528,6 +529,7 @@ extern "C" void opm_scene_destroy(OpmScene* sc) {
     for (OpmRays* r : sc->pool_rays) opm_rays_destroy(r);
     for (OpmHitMap* h : sc->pool_hits) opm_hitmap_destroy(h);
     if (sc->gf_scratch) opm_device_free(sc->ctx, sc->gf_scratch);
+    if (sc->gf_vor_map) opm_device_free(sc->ctx, sc->gf_vor_map);
     if (sc->gf_host) opm_host_free_pinned(sc->gf_host);
     delete sc;
 }
@@ -877,6 +879,52 @@ extern "C" OpmStatus opm_scene_node_fluence_kde(OpmScene* sc, int32_t node, uint
     if (!st && map_host) st = opm_device_to_host(sc->ctx, map_host, dev, nx * ny * sizeof(double));
     if (lrtb) memcpy(lrtb, box, sizeof box);
     opm_device_free(sc->ctx, dev);
+    return st;
+}
+
+// BeamSplitter::analyze_raytrace with BOTH inputs (nodes/beam_splitter/mod.rs:158-293; analysis_raytrace.rs:12-39): each input
+// passes the node's flat input surface and input aperture and is split (Rays::split, rays.rs:1253-1264); output 1 = what input 1
+// keeps merged with what input 2 splits off (Rays::merge appends), output 2 the other way round; both outputs are apodised by
+// the output aperture in the frame of output 1 and thresholded.  The scene graph itself is a tree (one input per node): this is
+// the node-level call for a caller that holds two bundles -- either input may be NULL (the reference's Rays::default()).
+extern "C" OpmStatus opm_scene_beam_splitter_two_inputs(OpmScene* sc, int32_t node, OpmRays* in1, OpmRays* in2, const OpmRayTraceConfig* cfg,
+                                                        OpmRays* out1, OpmRays* out2) {
+    if (!sc || node < 0 || node >= (int)sc->nodes.size() || !out1 || !out2 || out1 == out2) return OPM_ERR_ARG;
+    Node& n = *sc->nodes[node];
+    if (n.d.type != OPM_NODE_BEAM_SPLITTER || !n.placed) return OPM_ERR_ARG;
+    OpmRayTraceConfig def;
+    opm_raytrace_config_default(&def);
+    if (!cfg) cfg = &def;
+    OpmStatus st = opm_rays_clear(out1);
+    if (!st) st = opm_rays_clear(out2);
+    if (st || (!in1 && !in2)) return st;  // no input: no output (mod.rs:169-171)
+    OpmRays* split[2] = {nullptr, nullptr};  // what input k splits off
+    OpmRays* in[2] = {in1, in2};
+    OpmRays* keep[2] = {out1, out2};
+    for (int k = 0; k < 2 && !st; ++k) {
+        if (!in[k]) continue;
+        st = opm_rays_copy(in[k], keep[k]);  // the reference clones the incoming bundle
+        if (!st) st = acquire_rays(sc, opm_rays_len(in[k]) ? opm_rays_len(in[k]) : 1, &split[k]);
+        if (st) break;
+        std::vector<OpmOp> ops;
+        ops.push_back(op_refract(n.s[0], nullptr, true, cfg->missed_surface_strategy, 0, nullptr, nullptr));
+        ops.push_back(op_apodize(n.s[0].aperture, n.s[0].eff_iso));
+        OpmOp sp;
+        memset(&sp, 0, sizeof sp);
+        sp.kind = OPM_OP_SPLIT; sp.u.split.ratio = n.d.p[0]; sp.u.split.split_out = split[k]; sp.u.split.spectrum = n.d.spectrum;
+        ops.push_back(sp);
+        OpmTraceStats ts;
+        st = opm_trace_sequence(keep[k], ops.data(), (int32_t)ops.size(), 0, nullptr, &ts);
+    }
+    if (!st && split[1]) st = opm_rays_append(out1, split[1]);  // in_ray1.merge(&split2)
+    if (!st && split[0]) st = opm_rays_append(out2, split[0]);  // in_ray2.merge(&split1)
+    for (int k = 0; k < 2 && !st; ++k) {
+        if (opm_rays_len(keep[k]) == 0) continue;
+        std::vector<OpmOp> ops{op_apodize(n.s[1].aperture, n.s[1].eff_iso), op_threshold(cfg->min_energy_per_ray)};
+        OpmTraceStats ts;
+        st = opm_trace_sequence(keep[k], ops.data(), (int32_t)ops.size(), 0, nullptr, &ts);
+    }
+    for (OpmRays* r : split) if (r) sc->pool_rays.push_back(r);  // back to the scene's pool
     return st;
 }
 

@@ -341,10 +341,19 @@ class Scene:
         F.lib().opm_scene_node_hitmaps(self.h, node, surface, arr, n)
         return [_BorrowedHitMap(self.ctx, arr[k]) for k in range(n)]
 
+    def beam_splitter_two_inputs(self, node: int, in1: "Rays | None", in2: "Rays | None", cfg=None):
+        """BeamSplitter::analyze_raytrace with both inputs (nodes/beam_splitter/mod.rs:158-293) -> (out1, out2)"""
+        n = max(len(in1) if in1 is not None else 0, len(in2) if in2 is not None else 0, 1)
+        out1, out2 = Rays(self.ctx, 2 * n), Rays(self.ctx, 2 * n)
+        _check(F.lib().opm_scene_beam_splitter_two_inputs(self.h, node, in1.h if in1 is not None else None, in2.h if in2 is not None else None,
+                                                          C.byref(cfg.c) if cfg is not None else None, out1.h, out2.h))
+        return out1, out2
+
     # ---- ghost focus
-    def ghostfocus(self, source_rays: Rays, max_bounces: int = 1, strict=False) -> F.OpmGhostFocusStats:
-        """GhostFocusAnalyzer::analyze (analyzers/ghostfocus.rs:82-122), FluenceEstimator::Binning"""
-        cfg = F.OpmGhostFocusConfig(max_bounces=max_bounces)
+    def ghostfocus(self, source_rays: Rays, max_bounces: int = 1, strict=False, estimator="binning") -> F.OpmGhostFocusStats:
+        """GhostFocusAnalyzer::analyze (analyzers/ghostfocus.rs:82-122); estimator of the per-bundle LIDT check: "binning" or
+        "voronoi" (the reference's default)"""
+        cfg = F.OpmGhostFocusConfig(max_bounces=max_bounces, fluence_estimator={"binning": 0, "voronoi": 1}[estimator])
         st = F.OpmGhostFocusStats()
         _check(F.lib().opm_scene_ghostfocus(self.h, source_rays.h, C.byref(cfg), F.SCENE_STRICT if strict else 0, C.byref(st)))
         return st

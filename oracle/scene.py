@@ -57,12 +57,17 @@ class OSurface:
         parts = [h for lst in self.hit_map.values() for h in lst]
         return np.concatenate(parts) if parts else np.zeros(0, dtype=orc.HIT_DTYPE)
 
-    def evaluate_fluence_of_ray_bundle(self, b: Bundle):  # optic_surface.rs:202-224, Binning 101x101
+    estimator = "binning"  # GhostFocusConfig::fluence_estimator of the running analysis ("binning" | "voronoi")
+
+    def evaluate_fluence_of_ray_bundle(self, b: Bundle):  # optic_surface.rs:202-224 -> get_max_fluence (rays_hit_map.rs:777-783), 101x101
         lst = self.hit_map.get((orc.bounce_lvl(b.rays), b.uuid))
         if not lst:
             return
         try:
-            fmap, _ = orc.fluence_binning(np.concatenate(lst), 101, 101)
+            if OSurface.estimator == "voronoi":
+                fmap, _ = orc.fluence_voronoi(np.concatenate(lst), 101)
+            else:
+                fmap, _ = orc.fluence_binning(np.concatenate(lst), 101, 101)
         except orc.OracleError:
             return
         peak = orc.fluence_peak(fmap)
@@ -498,8 +503,9 @@ class OScene:
                     orc.rays_filter_energy(b.rays, n.p[0])
         return bundles
 
-    def ghostfocus(self, source_rays: np.ndarray, max_bounces: int = 1):
+    def ghostfocus(self, source_rays: np.ndarray, max_bounces: int = 1, estimator: str = "binning"):
         self.reset_data()
+        OSurface.estimator = estimator
         chain, i = [], 0
         while i is not None:
             chain.append(i)

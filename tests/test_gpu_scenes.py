@@ -94,6 +94,39 @@ def test_c2_laser_chain(ctx, mode):
         assert ctx.launch_count > 40
 
 
+def test_beam_splitter_with_two_inputs(ctx):
+    """BeamSplitter::analyze_raytrace with both inputs (nodes/beam_splitter/mod.rs:158-293).  The reference's known answer
+    (analysis_raytrace.rs:149-181): 1 J on input 1, 0.5 J on input 2, ratio 0.6 -> 0.8 J and 0.7 J out; then two bundles through a
+    splitter with apertures, ray by ray against the oracle; one missing input."""
+    MM, NM = scenes.MM, scenes.NM
+    nodes = [scenes.node("source"), scenes.node("beam_splitter", z=10 * MM, p=(0.6,))]
+    osc, psc = scenes.to_oracle(nodes), scenes.to_product(ctx, nodes)
+
+    def one_ray(e):
+        return orc.rays_collimated_with_spectrum(np.zeros((1, 3)), np.array([e]), [1053 * NM], [1.0])
+    a, b = one_ray(1.0), one_ray(0.5)
+    o1, o2 = psc.beam_splitter_two_inputs(1, ob.Rays.from_array(ctx, a), ob.Rays.from_array(ctx, b))
+    assert o1.to_array()["e"].sum() == pytest.approx(0.8, abs=1e-15) and o2.to_array()["e"].sum() == pytest.approx(0.7, abs=1e-15)
+    r1, r2 = osc.beam_splitter_two_inputs(1, a, b)
+    assert r1["e"].sum() == pytest.approx(0.8, abs=1e-15) and r2["e"].sum() == pytest.approx(0.7, abs=1e-15)
+    # bundles, apertures on both ports, a tilted splitter
+    nodes = [scenes.node("source"),
+             scenes.node("beam_splitter", z=40 * MM, euler=(0.3, 0.0, 0.0), p=(0.35,), ap_in=("circle", 6 * MM, 0.0, 0.0),
+                         ap_out=("rect", 9 * MM, 7 * MM, 0.5 * MM, 0.0))]
+    osc, psc = scenes.to_oracle(nodes), scenes.to_product(ctx, nodes)
+    in1 = scenes.source_to_oracle(scenes.c3_source(700))
+    in2 = scenes.source_to_oracle({"pos": ("grid", 20, 20, 11 * MM, 11 * MM), "energy": ("uniform", 0.4), "wvl": [1000 * NM], "w": [1.0]})
+    r1, r2 = osc.beam_splitter_two_inputs(1, in1, in2)
+    o1, o2 = psc.beam_splitter_two_inputs(1, ob.Rays.from_array(ctx, in1), ob.Rays.from_array(ctx, in2))
+    assert_rays_match(o1.to_array(), r1, what="output 1")  # order: input 1's rays, then what input 2 split off (Rays::merge appends)
+    assert_rays_match(o2.to_array(), r2, what="output 2")
+    assert (r1["valid"] == 0).sum() > 10  # the apertures clip
+    r1, r2 = osc.beam_splitter_two_inputs(1, None, in2)
+    o1, o2 = psc.beam_splitter_two_inputs(1, None, ob.Rays.from_array(ctx, in2))
+    assert_rays_match(o1.to_array(), r1, what="output 1, no input 1")
+    assert_rays_match(o2.to_array(), r2, what="output 2, no input 1")
+
+
 def test_c2_single_surface_nodes_and_limits(ctx):
     """dummy, paraxial surface, cylindric lens, parabolic mirror + the limits after every node
     (bounces > max, refractions >= max, node_group/analysis_raytrace.rs:20-27)"""
@@ -216,6 +249,33 @@ def test_ghost_focus_fluence_check_sees_the_bundle_before_the_aperture(ctx):
     assert _compare_surface_fluences(osc, psc, (0, 1, 2, 3)) > 4
     levels = {b for _, _, b in psc.node_critical_fluences(2, 1)}
     assert 2 in levels, levels  # a level-2 ghost bundle evaluated on the clipping surface
+
+
+def test_ghost_focus_with_the_voronoi_estimator(ctx):
+    """GhostFocusConfig::fluence_estimator = Voronoi, the reference's default (analyzers/ghostfocus.rs:61): the per-bundle LIDT check
+    takes the peak of a 101 x 101 Voronoi estimate of the bundle's hits (rays_hit_map.rs:777-783)"""
+    nodes = scenes.c3_telescope()
+    nodes[1] = dict(nodes[1], lidt=1.0e-6)
+    src = scenes.c3_source(400)
+    osc = scenes.to_oracle(nodes)
+    osc.ghostfocus(scenes.source_to_oracle(src), 1, estimator="voronoi")
+    psc = scenes.to_product(ctx, nodes)
+    st = psc.ghostfocus(scenes.source_to_product(src).generate(ctx), 1, estimator="voronoi")
+    assert st.interactions == osc.interactions
+    n_crit = 0
+    for node in (0, 1, 2, 3):
+        for surf in (0, 1):
+            ref_peak, got_peak = osc.nodes[node].s[surf].peak_seen, psc.node_peak_fluence(node, surf)
+            if np.isfinite(ref_peak):
+                assert got_peak == pytest.approx(ref_peak, rel=1e-6), (node, surf)  # cell areas: differences of products of positions
+            else:
+                assert not np.isfinite(got_peak)
+            ref_crit = sorted((pk, b) for pk, b in osc.nodes[node].s[surf].critical.values())
+            got_crit = sorted((pk, b) for _, pk, b in psc.node_critical_fluences(node, surf))
+            assert [b for _, b in ref_crit] == [b for _, b in got_crit]
+            n_crit += len(ref_crit)
+    assert n_crit >= 2
+    osc.ghostfocus(scenes.source_to_oracle(src), 1)  # back to the Binning estimator for the tests that follow
 
 
 def test_sharded_trace_equals_whole_source(ctx):
