@@ -416,6 +416,105 @@ def run_c4_strong(args, ctx, dev, stream, rank, world):
     return out
 
 
+C5_NPOS, C5_NWVL, C5_CHUNK, C5_NX = 100_000_000, 64, 1_562_500, 512
+
+
+def run_c5(args, ctx, dev, stream, rank, world):
+    """BASELINE configs[4]: broadband source (Gaussian spectrum, 64 lines over 950-1150 nm) through a Sellmeier lens and a prism pair,
+    10^8 positions x 64 wavelengths = 6.4 * 10^9 rays IN TOTAL, position-major (rays.rs:284-289), sharded over the ranks by
+    contiguous POSITION ranges (every rank owns whole 64-line groups) and streamed in chunks: the ray state is never resident in
+    full.  Pass 1 traces every chunk for the detector's data-dependent map range, the ranks' ranges meet in one 4-double
+    all-reduce(max); pass 2 traces again and bins into the common 512 x 512 grid; one all-reduce(sum) of the 2 MB map.  Strong
+    scaling.  At N > 1 a reduced source (10^6 positions) is also run sharded and on rank 0 alone and the two maps are compared."""
+    import ctypes as C
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import opossum_b200 as ob
+    import scenes
+    from opossum_b200 import _ffi as F
+    from opossum_b200 import sharding
+    L = F.lib()
+    nx = C5_NX
+    sc = scenes.to_product(ctx, scenes.c5_broadband())
+    rays = ob.Rays(ctx, C5_CHUNK * C5_NWVL)
+
+    def run(n_pos, shard_world, shard_rank, reduce):
+        sd = scenes.source_to_product(scenes.c5_source(n_pos, C5_NWVL))
+        b0, e0 = sharding.shard_range(n_pos, shard_rank, shard_world)
+        rng = torch.full((4,), -float("inf"), dtype=torch.float64, device=dev)
+        tmp = torch.zeros(4, dtype=torch.float64, device=dev)
+        fmap = torch.zeros(nx * nx, dtype=torch.float64, device=dev)
+        status = torch.zeros(1, dtype=torch.int32, device=dev)
+        if reduce:
+            dist.barrier()
+        torch.cuda.synchronize()
+        inter0 = ctx.interactions_total()
+        inter = 0
+        t0 = time.perf_counter()
+        for phase in (1, 2):
+            first = True
+            for b in range(b0, e0, C5_CHUNK):
+                e = min(b + C5_CHUNK, e0)
+                sd.generate(ctx, b, e, rays=rays)
+                sc.raytrace(rays, snapshots=False, sync=False)
+                hm = sc.node_hitmaps(4, 0)
+                arr = (C.c_void_p * len(hm))(*[h.h for h in hm])
+                if phase == 1:
+                    ob.api._check(L.opm_hitmaps_bounding_box_async(arr, len(hm), -1, C.c_void_p(tmp.data_ptr())))
+                    torch.maximum(rng, tmp, out=rng)
+                else:
+                    ob.api._check(L.opm_fluence_binning_async(arr, len(hm), -1, nx, nx, C.c_void_p(rng.data_ptr()), 0 if first else 1,
+                                                              C.c_void_p(fmap.data_ptr()), C.c_void_p(status.data_ptr())))
+                    first = False
+            if phase == 1:
+                inter = ctx.interactions_total() - inter0  # the launches raise no count on the host: read the device counter once
+                if reduce:
+                    dist.all_reduce(rng, op=dist.ReduceOp.MAX)  # (-l, r, t, -b): the common range is the element-wise maximum
+        if reduce:
+            dist.all_reduce(fmap, op=dist.ReduceOp.SUM)
+        torch.cuda.synchronize()
+        if reduce:
+            dist.barrier()
+        dt = time.perf_counter() - t0
+        r = rng.tolist()
+        return inter, dt, fmap, (-r[0], r[1], r[2], -r[3]), int(status.item())
+
+    with torch.cuda.stream(torch.cuda.ExternalStream(ctx.stream, device=dev)):
+        run(2 * C5_CHUNK * world, world, rank, world > 1)  # warm-up: kernels compiled, buffers sized
+        inter, dt, fmap, lrtb, status = run(C5_NPOS, world, rank, world > 1)
+        t = torch.tensor([float(inter), dt], dtype=torch.float64, device=dev)
+        if world > 1:
+            tsum, tmax = t.clone(), t.clone()
+            dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+            dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+            inter, dt = int(tsum[0].item()), tmax[1].item()
+        fd = ob.fluence_peak_total(ctx, fmap.data_ptr(), nx, nx, lrtb)
+        out = {"config": "C5: 10^8 positions x 64 wavelengths (Gaussian spectrum 950-1150 nm) = 6.4e9 rays total through a Sellmeier lens + prism pair, "
+                         "position-major, contiguous position shards, streamed in chunks of 1.5625e6 positions x 64 lines; two passes "
+                         "(range, then Binning into 512 x 512)", "scaling": "strong", "n_gpus": world, "rays_total": C5_NPOS * C5_NWVL,
+               "interactions_counted": inter, "interactions_traced": 2 * inter, "seconds": dt,
+               "interactions_per_s": inter / dt, "traced_interactions_per_s": 2 * inter / dt,
+               "collectives": "all_reduce(max) of the 4-double range, all_reduce(sum) of the 2 MB map (NCCL)" if world > 1 else "none",
+               "check": {"status_bits": status, "map_total_energy_J": fd.total_energy, "peak_J_m2": fd.peak, "lrtb": list(lrtb)}}
+        if world > 1:  # parity of the sharded path on a reduced source: merged map vs rank 0 alone
+            n_small = 1_000_000
+            _, _, fm, lr, _ = run(n_small, world, rank, True)
+            if rank == 0:
+                _, _, fm1, lr1, _ = run(n_small, 1, 0, False)
+                a, b = fm.cpu().numpy(), fm1.cpu().numpy()
+                nz = b > 0
+                out["parity_vs_one_gpu"] = {"positions": n_small, "range_equal": bool(tuple(lr) == tuple(lr1)),
+                                            "filled_bins_equal": bool(np.array_equal(nz, a > 0)),
+                                            "map_worst_rel_bin": float((np.abs(a - b)[nz] / b[nz]).max())}
+                out["parity_vs_one_gpu"]["ok"] = bool(out["parity_vs_one_gpu"]["range_equal"] and out["parity_vs_one_gpu"]["filled_bins_equal"]
+                                                      and out["parity_vs_one_gpu"]["map_worst_rel_bin"] <= 1e-9)
+            dist.barrier()
+    return out
+
+
 def run_product(args):
     import numpy as np
     import torch
@@ -626,6 +725,8 @@ def run_product(args):
 
         # ---- BASELINE configs[3]: the north-star strong-scaling config (10^8 rays total, 4096^2 map)
         c4 = None if args.no_c4 else run_c4_strong(args, ctx, dev, stream, rank, world)
+        # ---- BASELINE configs[4]: broadband source, 10^8 positions x 64 wavelengths, streamed
+        c5 = None if args.no_c5 else run_c5(args, ctx, dev, stream, rank, world)
 
     if rank == 0:
         peaks_file = ROOT / "MEASURED_PEAKS.json"
@@ -713,6 +814,7 @@ def run_product(args):
             "check": {"fluence_peak_J_m2": {str(k): v[0] for k, v in check.items() if k != "spot"},
                       "detector_energy_J": {str(k): v[1] for k, v in check.items() if k != "spot"}, "spot_valid_rays": check["spot"][0]},
             "c4_strong": c4,
+            "c5_broadband": c5,
         }
         if parity_n1 is not None:
             line["parity_vs_one_gpu"] = parity_n1
@@ -751,6 +853,7 @@ def main():
     ap.add_argument("--impl", default="product", choices=["product", "reference"])
     ap.add_argument("--rays", type=int, default=10_000_000, help="rays per GPU (BASELINE.json configs[1]: 10^7)")
     ap.add_argument("--no-c4", action="store_true", help="skip the C4 strong-scaling object")
+    ap.add_argument("--no-c5", action="store_true", help="skip the C5 broadband object")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "product" else args.warmup

@@ -311,6 +311,12 @@ class Context:
     def device_free(self, p: int):
         F.lib().opm_device_free(self.h, C.c_void_p(p))
 
+    def interactions_total(self) -> int:
+        """ray-surface interactions of all launches of the context so far (a device counter; synchronises)"""
+        out = C.c_uint64()
+        _check(F.lib().opm_context_interactions_total(self.h, C.byref(out)))
+        return out.value
+
     def device_memset(self, dev: int, value: int, nbytes: int):
         _check(F.lib().opm_device_memset(self.h, C.c_void_p(dev), value, nbytes))
 
