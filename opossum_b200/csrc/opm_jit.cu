@@ -126,27 +126,37 @@ static int program_bbox_slots(const DevOp* ops, int n_ops) {
     for (int k = 0; k < n_ops; ++k) n += op_has_bbox(ops[k]) ? 1 : 0;
     return n;
 }
-std::string refract_view(const DevRefract& o, int k, int hint_slot) {  // hint_slot < 0: no hint
+bool jit_unit_dir_enabled() {
+    static const bool on = [] { const char* e = getenv("OPM_B200_JIT_UNIT_DIR"); return !(e && e[0] == '0'); }();  // tuning switch
+    return on;
+}
+// does this op leave every ray that is still valid behind it with a unit direction (up to rounding)?  A refraction / reflection
+// (ray.rs:606-631) whose missed rays stop, and the paraxial surface (ray.rs:469), do; isometries and the energy ops keep what they
+// find.  (A surface whose missed rays carry on, and a grating, pass such rays through untouched: they establish nothing.)
+void unit_dir_after(const DevOp& op, bool& unit) {
+    if ((op.kind == OPK_REFRACT && op.u.refract.strategy == OPM_MISS_STOP) || op.kind == OPK_PARAXIAL) unit = true;
+}
+std::string refract_view(const DevRefract& o, int k, int hint_slot, bool unit_dir = false) {  // hint_slot < 0: no hint
     const int rot_id = jit_rot_id_enabled() && rot_is_identity(o.inv) && rot_is_identity(o.fwd) ? 1 : 0;
     std::string s;
-    appendf(s, "RefractCt<%d, %d, %d, %d, %d, %d, %d, %d, %d, %d>(opm_jit_ops[%d].u.refract", o.geom, o.coating, o.has_index ? 1 : 0, o.index_type,
-            o.strategy, o.flags, o.refraction_intended ? 1 : 0, o.hits.e ? 1 : 0, rot_id, hint_slot >= 0 ? 1 : 0, k);
+    appendf(s, "RefractCt<%d, %d, %d, %d, %d, %d, %d, %d, %d, %d, %d>(opm_jit_ops[%d].u.refract", o.geom, o.coating, o.has_index ? 1 : 0, o.index_type,
+            o.strategy, o.flags, o.refraction_intended ? 1 : 0, o.hits.e ? 1 : 0, rot_id, hint_slot >= 0 ? 1 : 0, unit_dir ? 1 : 0, k);
     if (hint_slot >= 0) appendf(s, ", s_hint + %d", 3 * hint_slot);
     s += ")";
     return s;
 }
 
 // one line of kernel body per op; the same text is the structural cache key
-std::string op_line(const DevOp& op, int k, int hint_slot = -1) {
+std::string op_line(const DevOp& op, int k, int hint_slot = -1, bool unit_dir = false) {
     std::string s;
     switch (op.kind) {
         case OPK_REFRACT: {
             const DevRefract& o = op.u.refract;
             if (op_has_bbox(op)) {  // the kernel keeps the bounding box of the hits it records here (bbox_reg_*, opm_trace_ops.cuh)
-                s += "        { HitOut ho; exec_refract(" + refract_view(o, k, hint_slot) + ", x, &ho);";
+                s += "        { HitOut ho; exec_refract(" + refract_view(o, k, hint_slot, unit_dir) + ", x, &ho);";
                 appendf(s, " bbox_smem_add(bb_%d, ho); }\n", k);
             } else {
-                s += "        exec_refract(" + refract_view(o, k, hint_slot) + ", x);\n";
+                s += "        exec_refract(" + refract_view(o, k, hint_slot, unit_dir) + ", x);\n";
             }
             break;
         }
@@ -226,12 +236,18 @@ std::string make_source(const DevOp* ops, int n_ops, bool compact, int block, in
                                "        s_hint[%d] = n2; s_hint[%d] = rcp_fast(n2);\n    }\n",
                     3 * hint_slot[k], 3 * hint_slot[k] + 1, 3 * hint_slot[k] + 2);
         }
+    // unit[k]: every ray that reaches op k has passed an op that leaves a unit direction
+    std::vector<char> unit(n_ops, 0);
+    {
+        bool u = false;
+        for (int k = 0; k < n_ops; ++k) { unit[k] = u && jit_unit_dir_enabled(); unit_dir_after(ops[k], u); }
+    }
     if (!split) {
-        for (int k = 0; k < n_ops; ++k) body += op_line(ops[k], k, hint_slot[k]);
+        for (int k = 0; k < n_ops; ++k) body += op_line(ops[k], k, hint_slot[k], unit[k] != 0);
     } else {
         std::string dead;
         for (int k = 0; k < n_ops; ++k) {
-            const std::string line = op_line(ops[k], k, hint_slot[k]);
+            const std::string line = op_line(ops[k], k, hint_slot[k], unit[k] != 0);
             if (k > 0 && ops[k - 1].kind == OPK_JOIN) appendf(body, "      live_%d:\n", k);
             appendf(body, "        if (!x.valid) goto dead_%d;\n        {\n", k);
             body += line;
@@ -246,6 +262,7 @@ std::string make_source(const DevOp* ops, int n_ops, bool compact, int block, in
         body += "      tile_done:;\n";
     }
     std::string s;
+    appendf(s, "#define OPM_JIT_BLOCK %d\n", block);
     s += "#include \"opm_trace_ops.cuh\"\nnamespace opm {\n";
     appendf(s, "extern \"C\" __constant__ DevOp opm_jit_ops[%d];\n", n_ops);
     appendf(s, "extern \"C\" __global__ void __launch_bounds__(%d, %d)\n", block, min_ctas);
@@ -263,7 +280,7 @@ std::string make_source(const DevOp* ops, int n_ops, bool compact, int block, in
         s += hint_init;
     }
     s += "    __syncthreads();\n"
-         "    const unsigned tiles = (unsigned)((n + blockDim.x - 1) / blockDim.x);\n";
+         "    const unsigned tiles = (unsigned)((n + OPM_BDIM - 1) / OPM_BDIM);\n";
     if (pipe) {
         s += "    __shared__ unsigned long long s_bar[2];\n"
              "    TilePipe pipe;\n";
@@ -282,8 +299,8 @@ std::string make_source(const DevOp* ops, int n_ops, bool compact, int block, in
          "        RayCtx x;\n"
          "        uint8_t vb;\n";
     s += pipe ? "        tile_load_staged(pipe, in, tile, n, x, vb);\n"
-              : "        tile_load(in, (uint64_t)tile * blockDim.x + threadIdx.x, n, x, vb);\n"
-                "        tile_prefetch(in, (uint64_t)(tile + gridDim.x) * blockDim.x + threadIdx.x, n);\n";
+              : "        tile_load(in, (uint64_t)tile * OPM_BDIM + threadIdx.x, n, x, vb);\n"
+                "        tile_prefetch(in, (uint64_t)(tile + gridDim.x) * OPM_BDIM + threadIdx.x, n);\n";
     s += body;
     appendf(s, "        tile_store<%s>(in, out, out_cap, out_tail, x, vb);\n", compact ? "true" : "false");
     s += "        tile_count(x, s_cnt, &s_status, &s_first_inv);\n"
@@ -409,7 +426,10 @@ const JitKernel* jit_get(JitCache* cache, const DevOp* ops, int n_ops, bool comp
     if (!cache || n_ops <= 0) { if (why) *why = "no program"; return nullptr; }
     std::string src = make_source(ops, n_ops, compact, block, min_ctas);
     if (const char* dump = getenv("OPM_B200_JIT_DUMP")) {  // diagnosis: the generated source, to compile offline with nvcc -Xptxas -v
-        if (FILE* f = fopen(dump, "w")) { fwrite(src.data(), 1, src.size(), f); fclose(f); }
+        // one file per distinct program: <dump>_<ops>_<hash>.cu
+        char name[1024];
+        snprintf(name, sizeof name, "%s_%d_%08zx.cu", dump, n_ops, std::hash<std::string>()(src) & 0xffffffffu);
+        if (FILE* f = fopen(name, "w")) { fwrite(src.data(), 1, src.size(), f); fclose(f); }
     }
     auto it = cache->kernels.find(src);
     if (it == cache->kernels.end()) {

@@ -11,6 +11,14 @@
 
 namespace opm {
 
+// CTA size: a compile-time constant in the run-time specialised kernel (the generator defines OPM_JIT_BLOCK: the parked rays of
+// a FORK and the running bounding boxes are then addressed as base + immediate), blockDim.x in the interpreter
+#ifdef OPM_JIT_BLOCK
+#define OPM_BDIM ((unsigned)(OPM_JIT_BLOCK))
+#else
+#define OPM_BDIM (blockDim.x)
+#endif
+
 __device__ __forceinline__ unsigned lanemask_lt() {
     unsigned m;
     asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
@@ -173,17 +181,17 @@ __device__ __forceinline__ bool exec_refract(const V& v, RayCtx& x, HitOut* ho =
 // [n][blockDim] counts: 36 bytes per thread and hit map) -- registers held across the tile loop cost the kernel more than the
 // separate pass they replace.
 struct BBoxReg { double x0, x1, y0, y1; unsigned n; };
-__device__ __forceinline__ size_t bbox_slot_bytes() { return (size_t)blockDim.x * 36; }
+__device__ __forceinline__ size_t bbox_slot_bytes() { return (size_t)OPM_BDIM * 36; }
 __device__ __forceinline__ void bbox_smem_init(unsigned char* slot) {
     double* d = reinterpret_cast<double*>(slot);
-    const unsigned B = blockDim.x, t = threadIdx.x;
+    const unsigned B = OPM_BDIM, t = threadIdx.x;
     d[t] = 1.7976931348623157e308; d[B + t] = -1.7976931348623157e308; d[2 * B + t] = 1.7976931348623157e308; d[3 * B + t] = -1.7976931348623157e308;
     reinterpret_cast<unsigned*>(d + 4 * B)[t] = 0u;
 }
 __device__ __forceinline__ void bbox_smem_add(unsigned char* slot, const HitOut& h) {
     if (!h.ok) return;
     double* d = reinterpret_cast<double*>(slot);
-    const unsigned B = blockDim.x, t = threadIdx.x;
+    const unsigned B = OPM_BDIM, t = threadIdx.x;
     // compare, store only on change: after a thread's first tiles its extrema rarely move
     if (h.x < d[t]) d[t] = h.x;
     if (h.x > d[B + t]) d[B + t] = h.x;
@@ -193,7 +201,7 @@ __device__ __forceinline__ void bbox_smem_add(unsigned char* slot, const HitOut&
 }
 __device__ __forceinline__ BBoxReg bbox_smem_get(const unsigned char* slot) {
     const double* d = reinterpret_cast<const double*>(slot);
-    const unsigned B = blockDim.x, t = threadIdx.x;
+    const unsigned B = OPM_BDIM, t = threadIdx.x;
     BBoxReg b;
     b.x0 = d[t]; b.x1 = d[B + t]; b.y0 = d[2 * B + t]; b.y1 = d[3 * B + t]; b.n = reinterpret_cast<const unsigned*>(d + 4 * B)[t];
     return b;
@@ -217,7 +225,7 @@ __device__ __forceinline__ void bbox_reg_flush(BBoxReg b, unsigned long long* ac
     __syncthreads();
     if (threadIdx.x == 0) {
         unsigned long long n = 0;
-        for (int k = 0; k < (int)((blockDim.x + 31) >> 5); ++k) {
+        for (int k = 0; k < (int)((OPM_BDIM + 31) >> 5); ++k) {
             if (!shn[k]) continue;
             n += shn[k];
             b.x0 = fmin(b.x0, sh[k][0]); b.x1 = fmax(b.x1, sh[k][1]); b.y0 = fmin(b.y0, sh[k][2]); b.y1 = fmax(b.y1, sh[k][3]);
@@ -321,11 +329,11 @@ __device__ __forceinline__ void exec_split(const DevSplit& o, RayCtx& x) {
 // same launch.  The main-bundle ray (E * ratio) is parked in shared memory, one 32-bit word per field and thread
 // (field-major, so consecutive lanes hit consecutive banks); the ops up to the JOIN see the split-off ray (E * (1 - ratio)).
 __device__ __forceinline__ void stash_put(unsigned* stash, int f, double v) {
-    stash[(2 * f) * blockDim.x + threadIdx.x] = (unsigned)__double2loint(v);
-    stash[(2 * f + 1) * blockDim.x + threadIdx.x] = (unsigned)__double2hiint(v);
+    stash[(2 * f) * OPM_BDIM + threadIdx.x] = (unsigned)__double2loint(v);
+    stash[(2 * f + 1) * OPM_BDIM + threadIdx.x] = (unsigned)__double2hiint(v);
 }
 __device__ __forceinline__ double stash_get(const unsigned* stash, int f) {
-    return __hiloint2double((int)stash[(2 * f + 1) * blockDim.x + threadIdx.x], (int)stash[(2 * f) * blockDim.x + threadIdx.x]);
+    return __hiloint2double((int)stash[(2 * f + 1) * OPM_BDIM + threadIdx.x], (int)stash[(2 * f) * OPM_BDIM + threadIdx.x]);
 }
 template <bool SPECTRAL = true>
 __device__ __forceinline__ void exec_fork(const DevFork& o, RayCtx& x, unsigned* stash) {
@@ -337,9 +345,9 @@ __device__ __forceinline__ void exec_fork(const DevFork& o, RayCtx& x, unsigned*
     stash_put(stash, 0, x.r.pos.x); stash_put(stash, 1, x.r.pos.y); stash_put(stash, 2, x.r.pos.z);
     stash_put(stash, 3, x.r.dir.x); stash_put(stash, 4, x.r.dir.y); stash_put(stash, 5, x.r.dir.z);
     stash_put(stash, 6, e_main); stash_put(stash, 7, x.r.opl); stash_put(stash, 8, x.r.n);
-    stash[18 * blockDim.x + threadIdx.x] = x.r.bounces;
-    stash[19 * blockDim.x + threadIdx.x] = x.r.refr;
-    stash[20 * blockDim.x + threadIdx.x] = (x.alive ? 1u : 0u) | (x.valid ? 2u : 0u);
+    stash[18 * OPM_BDIM + threadIdx.x] = x.r.bounces;
+    stash[19 * OPM_BDIM + threadIdx.x] = x.r.refr;
+    stash[20 * OPM_BDIM + threadIdx.x] = (x.alive ? 1u : 0u) | (x.valid ? 2u : 0u);
     if (x.valid) x.r.e *= 1.0 - ratio;
 }
 __device__ __forceinline__ void exec_join(const DevJoin& o, RayCtx& x, const unsigned* stash) {
@@ -350,9 +358,9 @@ __device__ __forceinline__ void exec_join(const DevJoin& o, RayCtx& x, const uns
     x.r.pos = v3(stash_get(stash, 0), stash_get(stash, 1), stash_get(stash, 2));
     x.r.dir = v3(stash_get(stash, 3), stash_get(stash, 4), stash_get(stash, 5));
     x.r.e = stash_get(stash, 6); x.r.opl = stash_get(stash, 7); x.r.n = stash_get(stash, 8);
-    x.r.bounces = stash[18 * blockDim.x + threadIdx.x];
-    x.r.refr = stash[19 * blockDim.x + threadIdx.x];
-    const unsigned fl = stash[20 * blockDim.x + threadIdx.x];
+    x.r.bounces = stash[18 * OPM_BDIM + threadIdx.x];
+    x.r.refr = stash[19 * OPM_BDIM + threadIdx.x];
+    const unsigned fl = stash[20 * OPM_BDIM + threadIdx.x];
     x.alive = (fl & 1u) != 0; x.valid = (fl & 2u) != 0;
 }
 // copy of the bundle a detector node keeps (analyzers/raytrace.rs:186-205)
@@ -412,7 +420,7 @@ __device__ __forceinline__ void tile_prefetch(const DevRays& in, uint64_t i, uin
 }
 
 // ---- staged tile loads (run-time specialised kernel) ---------------------------------------------------------------
-// One elected thread copies whole tiles of the bundle -- 14 contiguous field segments of blockDim.x rays -- into shared
+// One elected thread copies whole tiles of the bundle -- 14 contiguous field segments of OPM_BDIM rays -- into shared
 // memory with TMA bulk copies (cp.async.bulk -> UBLKCP) two tiles ahead of the compute; the CTA's warps find their ray
 // state on chip when they get to the tile instead of waiting on 14 global loads each.  Two stages, one mbarrier per
 // stage; a stage is re-armed after a block barrier that follows the last read of it.  A trailing partial tile takes the
@@ -444,11 +452,11 @@ struct TilePipe {
     unsigned long long* bar;  // [2]
     unsigned iter;            // tiles of this CTA consumed so far through the stages
     unsigned tiles;           // number of tiles of the launch
-    unsigned full_tiles;      // tiles [0, full_tiles) hold blockDim.x rays
+    unsigned full_tiles;      // tiles [0, full_tiles) hold OPM_BDIM rays
 };
 // thread 0: arm the stage's barrier and start the 14 copies of one full tile
 __device__ __forceinline__ void tile_issue(const DevRays& in, unsigned tile, unsigned char* st, unsigned long long* bar) {
-    const unsigned B = blockDim.x;
+    const unsigned B = OPM_BDIM;
     const size_t off = (size_t)tile * B;
     mbar_expect_tx(bar, B * kStageBytesPerRay);
     const double* f64[10] = {in.px, in.py, in.pz, in.dx, in.dy, in.dz, in.e, in.wvl, in.opl, in.n};
@@ -460,7 +468,7 @@ __device__ __forceinline__ void tile_issue(const DevRays& in, unsigned tile, uns
     bulk_g2s(st + (size_t)B * 92, in.valid + off, B, bar);
 }
 __device__ __forceinline__ void tile_pipe_init(TilePipe& p, unsigned char* smem, unsigned long long* bar, const DevRays& in, uint64_t n) {
-    const unsigned B = blockDim.x;
+    const unsigned B = OPM_BDIM;
     const unsigned stage_bytes = (B * kStageBytesPerRay + 127u) & ~127u;
     p.stage[0] = smem; p.stage[1] = smem + stage_bytes;
     p.bar = bar; p.iter = 0;
@@ -478,9 +486,9 @@ __device__ __forceinline__ void tile_pipe_init(TilePipe& p, unsigned char* smem,
     }
 }
 __device__ __forceinline__ void tile_load_staged(TilePipe& p, const DevRays& in, unsigned tile, uint64_t n, RayCtx& x, uint8_t& vb) {
-    const uint64_t i = (uint64_t)tile * blockDim.x + threadIdx.x;
+    const uint64_t i = (uint64_t)tile * OPM_BDIM + threadIdx.x;
     if (tile >= p.full_tiles) { tile_load(in, i, n, x, vb); return; }  // the trailing partial tile
-    const unsigned s = p.iter & 1u, B = blockDim.x, t = threadIdx.x;
+    const unsigned s = p.iter & 1u, B = OPM_BDIM, t = threadIdx.x;
     unsigned char* st = p.stage[s];
     mbar_wait(&p.bar[s], (p.iter >> 1) & 1u);
     x.i = i; x.in_range = true;
