@@ -39,6 +39,7 @@ UNIT = "interactions/s"
 RAY_BYTES = 93     # SoA bundle: 10 f64 + 3 u32 + 1 u8 (opossum_b200/csrc/opm_internal.h)
 RAY_BYTES_INPLACE = 81  # in-place write: wavelength and id never change
 HIT_BYTES = 36     # hit record: 4 f64 + u32
+SPOT_COPY_BYTES = 33  # spot-diagram copy of the bundle: position (3 f64) + energy + valid flag (OPM_SCENE_LEAN_SPOT_DATA)
 MAP_NX, MAP_NY = 100, 83  # nodes/fluence_detector/mod.rs:103
 
 
@@ -565,7 +566,7 @@ def run_product(args):
         def step_resident():
             """one analysis + read-out; the host reads the reports of step k-1 after it has queued step k (two sets of pinned
             report buffers), so the device never waits for the host between steps"""
-            scene.raytrace(src, keep_source=True, sync=False)
+            scene.raytrace(src, keep_source=True, sync=False, lean_spot_data=True)
             slot = pipe["k"] % 2
             pipe["k"] += 1
             readout.launch(False, slot)
@@ -604,7 +605,7 @@ def run_product(args):
             cur, nxt = e2e_rays[e2e_k[0] % 2], e2e_rays[(e2e_k[0] + 1) % 2]
             e2e_k[0] += 1
             upload(nxt)
-            scene.raytrace(cur, sync=False)
+            scene.raytrace(cur, sync=False, lean_spot_data=True)
             return read_out(True)
 
         doc_rays = ob.Rays(ctx, n)
@@ -613,7 +614,7 @@ def run_product(args):
             """document level, what `OpmDocument::analyze` does (opm_document.rs:270-289): source DESCRIPTOR in (position, energy
             and spectral distribution: a few hundred bytes) -> rays generated on the device -> trace -> reports on the host"""
             sd.generate_strided(ctx, first, count, stride, rays=doc_rays)
-            scene.raytrace(doc_rays, sync=False)
+            scene.raytrace(doc_rays, sync=False, lean_spot_data=True)
             return read_out(True)
 
         def barrier():
@@ -622,7 +623,7 @@ def run_product(args):
             torch.cuda.synchronize()
 
         # ---- one checked run: interactions per step, buffer populations for the byte model, launches per step
-        st = scene.raytrace(src, keep_source=True, sync=True)
+        st = scene.raytrace(src, keep_source=True, sync=True, lean_spot_data=True)
         check = read_out(False)
         inter_per_step = st.interactions
         alive_main = st.alive_out
@@ -703,7 +704,7 @@ def run_product(args):
             if rank == 0:
                 scene_g = scenes.to_product(ctx, scenes.c2_laser_chain())
                 src_g = sd.generate(ctx)
-                scene_g.raytrace(src_g, keep_source=True)
+                scene_g.raytrace(src_g, keep_source=True, lean_spot_data=True)
                 solo = sharding.DetectorReadout(ctx, scene_g, (9, 10), (8,), MAP_NX, MAP_NY, dev, solo=True).run(download_maps=True)
                 worst = 0.0
                 for node in (9, 10):
@@ -736,12 +737,12 @@ def run_product(args):
             hbm_peak, peak_src = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
         # algorithmic bytes of the trace launches of ONE step on this rank (DESIGN.md "byte model"): every buffer the step
         # must read or write, once.  Read the source bundle (n x 93 B); for the rays still in the bundle write the main
-        # output bundle, the spot diagram's copy of the bundle (93 B) and the fluence detector's hit record (36 B), and the
+        # output bundle, the spot diagram's copy of the bundle (33 B: position, energy, valid flag) and the fluence detector's hit record (36 B), and the
         # split-off bundle after its side chain with its hit record.  (The fluence detectors keep only hit maps: their
         # report reads nothing else, nodes/fluence_detector/mod.rs:91-135.)  When the side chain is its own launch
         # (2 trace launches per step) the split-off bundle is additionally written by the main launch and read back.
         launches_trace = kern_launches / args.steps
-        bytes_step = (n * RAY_BYTES + alive_main * (2 * RAY_BYTES + HIT_BYTES) + alive_side * (RAY_BYTES + HIT_BYTES))
+        bytes_step = (n * RAY_BYTES + alive_main * (RAY_BYTES + SPOT_COPY_BYTES + HIT_BYTES) + alive_side * (RAY_BYTES + HIT_BYTES))
         if launches_trace > 1.5:
             bytes_step += alive_side * (RAY_BYTES + RAY_BYTES_INPLACE)
         kern_ms_step = kern_ms / args.steps
@@ -794,7 +795,7 @@ def run_product(args):
                                     "opm::trace_kernel (fused surface sequence, interpreter)"),
                          "jit": jit, "achieved": achieved, "peak": hbm_peak,
                          "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": traffic, "peak_source": peak_src,
-                         "byte_model": "93 B ray state read, 93 B written per ray kept + 93 B spot-diagram copy + 36 B per hit record (DESIGN.md section 4)",
+                         "byte_model": "93 B ray state read, 93 B written per ray kept + 33 B spot-diagram copy (position, energy, valid flag: what the report reads; round 1 and early round 2 wrote all 93 B) + 36 B per hit record (DESIGN.md section 4)",
                          "algorithmic_bytes_per_launch": bytes_step / max(launches_trace, 1), "launches_per_step": launches_trace,
                          "kernel_ms_per_launch": kern_ms_step / max(launches_trace, 1), "kernel_share_of_step": kern_ms_step / (ms / args.steps),
                          "survey_8d": {"bytes_per_launch": bytes_8d / max(launches_trace, 1), "achieved": bytes_8d / kern_s / 1e9,

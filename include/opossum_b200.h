@@ -227,7 +227,14 @@ typedef struct { double focal_length; OpmIsometry iso; } OpmParaxialOp;
 typedef struct { double ratio; OpmRays* split_out; const OpmSpectrum* spectrum; } OpmSplitOp;
 typedef struct { double ratio; const OpmSpectrum* spectrum; } OpmForkOp;
 typedef struct { OpmRays* out; } OpmJoinOp;                         /* out: the split-off bundle after its side chain; NULL = discard */
-typedef struct { OpmRays* out; } OpmSnapshotOp;                     /* slot-indexed copy of the bundle at this point */
+/* slot-indexed copy of the bundle at this point.  fields = OPM_SNAPSHOT_SPOT: only what a spot-diagram report reads is copied
+ * (position, energy, valid flag -- nodes/spot_diagram.rs:101-163); the other arrays of `out` are left as they were.
+ * spot_frame: the frame the copy's statistics will be asked for in (opm_rays_spot_*, `frame_or_null` there; the detector's
+ * effective isometry, nodes/spot_diagram.rs:106-112) or NULL for none / world.  With want_spot_sums != 0 a launch that runs the
+ * specialised kernel takes the phase-1 sums of those statistics while it writes the copy (rays.rs:599-637); the next
+ * opm_rays_spot_* call on `out` with the same frame then has no first pass to make. */
+typedef enum { OPM_SNAPSHOT_ALL = 0, OPM_SNAPSHOT_SPOT = 1 } OpmSnapshotFields;
+typedef struct { OpmRays* out; int32_t fields; int32_t want_spot_sums; const OpmIsometry* spot_frame; } OpmSnapshotOp;
 typedef struct { OpmIsometry iso; int32_t inverse; int32_t _pad; } OpmTransformOp;
 
 typedef struct {

@@ -112,7 +112,7 @@ class OpmSplitOp(C.Structure):
 
 
 class OpmSnapshotOp(C.Structure):
-    _fields_ = [("out", C.c_void_p)]
+    _fields_ = [("out", C.c_void_p), ("fields", C.c_int32), ("want_spot_sums", C.c_int32), ("spot_frame", C.c_void_p)]
 
 
 class OpmTransformOp(C.Structure):
@@ -167,7 +167,8 @@ class OpmSourceDesc(C.Structure):
  NODE_DUMMY, NODE_IDEAL_FILTER, NODE_PARAXIAL_SURFACE, NODE_SPOT_DIAGRAM, NODE_FLUENCE_DETECTOR, NODE_REFLECTIVE_GRATING,
  NODE_RAY_PROPAGATION_VISUALIZER, NODE_SPECTROMETER, NODE_WAVEFRONT, NODE_ENERGY_METER) = range(17)
 SCENE_STRICT, SCENE_PER_SURFACE, SCENE_RECORD_ALL_HITS, SCENE_NO_SNAPSHOTS, SCENE_ASYNC, SCENE_KEEP_SOURCE = 2, 4, 8, 16, 32, 64
-SCENE_POSITION_HISTORY, SCENE_KEEP_LIGHT_DATA = 128, 256
+SCENE_POSITION_HISTORY, SCENE_KEEP_LIGHT_DATA, SCENE_LEAN_SPOT_DATA = 128, 256, 512
+SNAPSHOT_ALL, SNAPSHOT_SPOT = 0, 1
 
 
 class OpmCoatingDesc(C.Structure):

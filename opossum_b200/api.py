@@ -816,9 +816,16 @@ class Program:
         self.ops.append(op)
         return self
 
-    def snapshot(self, out: Rays) -> "Program":
+    def snapshot(self, out: Rays, spot_only=False, spot_frame: "Isometry | None" = None, want_spot_sums=False) -> "Program":
+        """copy of the bundle at this point; spot_only: position, energy and valid flag only; want_spot_sums: the launch takes the
+        phase-1 sums of out.spot_stats(spot_frame) on the way (specialised kernel)"""
         op = F.OpmOp(kind=F.OP_SNAPSHOT)
         op.u.snapshot.out = out.h
+        op.u.snapshot.fields = F.SNAPSHOT_SPOT if spot_only else F.SNAPSHOT_ALL
+        op.u.snapshot.want_spot_sums = 1 if want_spot_sums else 0
+        if spot_frame is not None:
+            op.u.snapshot.spot_frame = C.addressof(spot_frame.c)
+            self._keep.append(spot_frame)
         self._keep.append(out)
         self.ops.append(op)
         return self

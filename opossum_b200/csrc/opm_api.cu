@@ -55,6 +55,7 @@ struct OpmContext {
     bool jit_enabled = true;
     bool jit_sync = false;  // wait for the compiler instead of interpreting until the kernel is ready
     uint64_t jit_min_rays = 200000;
+    bool jit_fuse_spot = false;  // OPM_B200_JIT_SPOT=1: OPM_OP_SNAPSHOT want_spot_sums is honoured (see run_program)
     bool jit_warned = false;
     // CTA shape of the specialised kernels (tunable: OPM_B200_JIT_BLOCK / _MIN_CTAS).  One CTA of 32 warps per SM at 64 registers
     // per thread measured best on the C2 chain (profiles/r1_summary.md, CTA-shape sweep): the warps of one CTA walk the 70 KB of
@@ -100,6 +101,11 @@ struct OpmRays {
     double* d_hist = nullptr;
     uint32_t hist_levels = 0, hist_next = 0;
     uint64_t hist_stride = 0;
+    // phase-1 accumulators of the spot statistics (SpotAccum, 128 bytes behind the tail counter).  spot_acc_valid: the launch that
+    // wrote this bundle as an OPM_OP_SNAPSHOT copy also took the sums (specialised kernel), in the frame spot_inv (spot_has_frame)
+    SpotAccum* d_spot_acc = nullptr;
+    bool spot_acc_valid = false, spot_has_frame = false;
+    DevIso spot_inv{};
 };
 
 struct OpmSpectrum {  // spectrum.rs:35-37 on the device: [lam(n) | val(n)] in one allocation
@@ -241,6 +247,7 @@ extern "C" OpmStatus opm_context_create(int32_t device, void* stream, OpmContext
     c->jit = jit_cache_create();
     if (const char* e = getenv("OPM_B200_JIT")) { c->jit_enabled = atoi(e) != 0; c->jit_sync = atoi(e) == 2; }
     if (const char* e = getenv("OPM_B200_JIT_MIN_RAYS")) c->jit_min_rays = strtoull(e, nullptr, 10);
+    if (const char* e = getenv("OPM_B200_JIT_SPOT")) c->jit_fuse_spot = e[0] == '1';
     if (const char* e = getenv("OPM_B200_JIT_BLOCK")) { int v = atoi(e); if (v >= 32 && v <= 1024 && v % 32 == 0) c->jit_block = v; }
     if (const char* e = getenv("OPM_B200_JIT_MIN_CTAS")) { int v = atoi(e); if (v >= 1 && v <= 16) c->jit_min_ctas = v; }
     CU(cudaMallocHost(&c->h_put_ring, OpmContext::kPutSlots * OpmContext::kPutBytes));
@@ -477,7 +484,8 @@ extern "C" void opm_raytrace_config_default(OpmRayTraceConfig* c) {  // analyzer
 // rays storage
 // ---------------------------------------------------------------------------------------------
 
-static size_t rays_layout(uint64_t cap, void* base, DevRays* v, unsigned long long** tail) {
+static_assert(sizeof(SpotAccum) <= 128, "SpotAccum slot of a bundle");
+static size_t rays_layout(uint64_t cap, void* base, DevRays* v, unsigned long long** tail, SpotAccum** spot) {
     size_t off = 0;
     unsigned char* b = (unsigned char*)base;
     auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return b ? b + o : nullptr; };
@@ -488,16 +496,18 @@ static size_t rays_layout(uint64_t cap, void* base, DevRays* v, unsigned long lo
     v->id = (uint32_t*)take(cap * 4);
     v->valid = (uint8_t*)take(cap);
     *tail = (unsigned long long*)take(8);
+    if (spot) *spot = (SpotAccum*)take(128);
     return off;
 }
 
 static OpmStatus rays_alloc(OpmRays* r, uint64_t cap) {
-    DevRays tmp; unsigned long long* t;
-    size_t bytes = rays_layout(cap, nullptr, &tmp, &t);
+    DevRays tmp; unsigned long long* t; SpotAccum* sp;
+    size_t bytes = rays_layout(cap, nullptr, &tmp, &t, &sp);
     void* base = nullptr;
     CU(cudaMalloc(&base, bytes));
     r->base = base; r->cap = cap;
-    rays_layout(cap, base, &r->v, &r->d_tail);
+    rays_layout(cap, base, &r->v, &r->d_tail, &r->d_spot_acc);
+    r->spot_acc_valid = false;
     CU(cudaMemsetAsync(r->d_tail, 0, 8, r->ctx->stream));
     return OPM_OK;
 }
@@ -600,7 +610,7 @@ extern "C" OpmStatus opm_rays_set_wavelength_hint(OpmRays* r, double wavelength)
 }
 extern "C" OpmStatus opm_rays_clear(OpmRays* r) {
     if (!r) return fail(OPM_ERR_ARG, "rays is NULL");
-    r->len = 0; r->len_dirty = false; r->pending = false; r->mono_wvl = 0.0;
+    r->len = 0; r->len_dirty = false; r->pending = false; r->mono_wvl = 0.0; r->spot_acc_valid = false;
     if (r->d_hist) { OpmStatus hs = hist_clear(r); if (hs) return hs; }  // new rays start without a history (ray.rs:126)
     CU(cudaMemsetAsync(r->d_tail, 0, 8, r->ctx->stream));
     return OPM_OK;
@@ -751,7 +761,7 @@ extern "C" OpmStatus opm_rays_position_history(const OpmRays* rc, int32_t with_c
 
 extern "C" OpmStatus opm_rays_upload(OpmRays* r, const OpmRay* host, uint64_t n) {
     if (!r || (!host && n)) return fail(OPM_ERR_ARG, "NULL argument");
-    r->pending = false; r->mono_wvl = 0.0;
+    r->pending = false; r->mono_wvl = 0.0; r->spot_acc_valid = false;
     OpmContext* c = r->ctx;
     CU(cudaSetDevice(c->device));
     if (r->d_hist) { OpmStatus hs = hist_clear(r); if (hs) return hs; }  // new rays start without a history (ray.rs:126)
@@ -772,7 +782,7 @@ extern "C" OpmStatus opm_rays_upload_soa(OpmRays* r, const double* pos[3], const
     if (!r || !pos || !dir || !e || !wvl) return fail(OPM_ERR_ARG, "NULL argument");
     OpmContext* c = r->ctx;
     CU(cudaSetDevice(c->device));
-    r->pending = false; r->mono_wvl = 0.0;
+    r->pending = false; r->mono_wvl = 0.0; r->spot_acc_valid = false;
     if (r->d_hist) { OpmStatus hs = hist_clear(r); if (hs) return hs; }  // new rays start without a history (ray.rs:126)
     OpmStatus s = opm_rays_reserve(r, n);
     if (s) return s;
@@ -795,7 +805,7 @@ extern "C" OpmStatus opm_rays_new_collimated_with_spectrum(OpmRays* r, const dou
         if (!(wvl[k] > 0.0) || !std::isfinite(wvl[k])) return fail(OPM_ERR_ARG, "wavelength must be >0");
     const uint64_t n_rays = n_pos * n_wvl;
     r->pending = false;  // an earlier upload that was never used is superseded
-    r->mono_wvl = n_wvl == 1 ? wvl[0] : 0.0;
+    r->mono_wvl = n_wvl == 1 ? wvl[0] : 0.0; r->spot_acc_valid = false;
     if (r->d_hist) { OpmStatus hs = hist_clear(r); if (hs) return hs; }  // new rays start without a history (ray.rs:126)
     OpmStatus s = opm_rays_reserve(r, n_rays);
     if (s) return s;
@@ -858,7 +868,7 @@ extern "C" OpmStatus opm_rays_new_collimated_xy(OpmRays* r, const double* pos_xy
     if (s) return s;
     const uint64_t n_rays = n_pos * n_wvl;
     r->pending = false;
-    r->mono_wvl = n_wvl == 1 ? desc->wavelengths[0] : 0.0;
+    r->mono_wvl = n_wvl == 1 ? desc->wavelengths[0] : 0.0; r->spot_acc_valid = false;
     if (r->d_hist) { OpmStatus hs = hist_clear(r); if (hs) return hs; }
     s = opm_rays_reserve(r, n_rays);
     if (s) return s;
@@ -934,7 +944,7 @@ extern "C" OpmStatus opm_rays_copy(const OpmRays* src, OpmRays* dst) {
     if (s) return s;
     if (src->d_hist) { s = hist_copy(src, dst, src->hist_next, src->len); if (s) return s; }
     else if (dst->d_hist) { s = hist_clear(dst); if (s) return s; }
-    dst->mono_wvl = src->mono_wvl;
+    dst->mono_wvl = src->mono_wvl; dst->spot_acc_valid = false;
     return rays_set_len(dst, src->len);
 }
 extern "C" OpmStatus opm_rays_append(OpmRays* dst, const OpmRays* src) {
@@ -949,7 +959,7 @@ extern "C" OpmStatus opm_rays_append(OpmRays* dst, const OpmRays* src) {
     if (s) return s;
     s = copy_fields(src->v, 0, dst->v, dst->len, src->len, dst->ctx->stream);
     if (s) return s;
-    if (dst->len == 0) dst->mono_wvl = src->mono_wvl; else if (dst->mono_wvl != src->mono_wvl) dst->mono_wvl = 0.0;
+    if (dst->len == 0) dst->mono_wvl = src->mono_wvl; else if (dst->mono_wvl != src->mono_wvl) dst->mono_wvl = 0.0; dst->spot_acc_valid = false;
     return rays_set_len(dst, dst->len + src->len);
 }
 extern "C" OpmStatus opm_rays_compact(OpmRays* r) {
@@ -1085,6 +1095,7 @@ struct Compiled {
     std::vector<std::pair<int, OpmRays*>> slot_output_ops;  // the same with the index of their device op (position history)
     std::vector<OpmHitMap*> hitmaps;
     std::vector<std::pair<int, OpmHitMap*>> hitmap_ops;  // the same with the index of the device op that records into them
+    std::vector<std::pair<int, OpmRays*>> spot_ops;      // snapshot ops that want the phase-1 spot sums of their copy
     int fork_depth = 0;                 // inside an OPM_OP_FORK .. OPM_OP_JOIN range
     bool has_fork = false;
 };
@@ -1248,7 +1259,14 @@ static OpmStatus compile_ops(OpmContext* c, const OpmOp* ops, int n_ops, uint64_
                 if (!p.u.snapshot.out) return fail(OPM_ERR_ARG, "snapshot without output bundle");
                 OpmStatus s = opm_rays_reserve(p.u.snapshot.out, n_rays);
                 if (s) return s;
+                if (p.u.snapshot.fields != OPM_SNAPSHOT_ALL && p.u.snapshot.fields != OPM_SNAPSHOT_SPOT)
+                    return fail(OPM_ERR_ARG, "unknown snapshot field set %d", p.u.snapshot.fields);
                 d.kind = OPK_SNAPSHOT; d.u.snapshot.out = p.u.snapshot.out->v;
+                d.u.snapshot.fields = p.u.snapshot.fields;
+                d.u.snapshot.has_frame = p.u.snapshot.spot_frame ? 1 : 0;
+                if (p.u.snapshot.spot_frame) to_dev_iso(p.u.snapshot.spot_frame->inv, d.u.snapshot.inv);
+                d.u.snapshot.acc = nullptr;  // set by the launcher when the specialised kernel runs
+                if (p.u.snapshot.want_spot_sums) out.spot_ops.push_back({(int)out.ops.size(), p.u.snapshot.out});
                 out.slot_outputs.push_back(p.u.snapshot.out);
                 out.slot_output_ops.push_back({(int)out.ops.size(), p.u.snapshot.out});
                 break;
@@ -1383,6 +1401,24 @@ static OpmStatus run_program(OpmRays* rays, const OpmOp* ops, int n_ops, int fla
                 prog.ops[ho.first].u.refract.hit_acc = ho.second->d_acc;
                 fused.push_back(ho.second);
             }
+        // snapshot copies whose phase-1 spot sums the specialised kernel takes on the way (kSpotSmemBytes of shared memory per thread
+        // each, next to the parked rays of a FORK and the running boxes)
+        // Off unless OPM_B200_JIT_SPOT=1: measured on C2 (profiles/r2_summary.md) the sums cost the trace kernel 0.056 ms (0.12 ms when the
+        // running boxes already fill the shared memory and the L1 shrinks to its minimum) against the 0.085 ms pass they replace
+        const bool fuse_spot = c->jit_fuse_spot;  // read from the environment when the context was created
+        std::vector<std::pair<int, OpmRays*>> spot_fused;
+        if (jit_candidate && fuse_spot) {
+            size_t smem_need = (prog.has_fork ? (size_t)c->jit_block * kStashWords * 4 + 128 : 0) + fused.size() * (size_t)c->jit_block * 36;
+            for (auto& so : prog.spot_ops) {
+                if (spot_fused.size() == 2 || smem_need + (size_t)c->jit_block * kSpotSmemBytes > 222 * 1024) break;  // 227 KB per CTA, ~5 KB of it static
+                bool twice = false;
+                for (auto& q : spot_fused) twice |= q.second == so.second;
+                if (twice) continue;
+                smem_need += (size_t)c->jit_block * kSpotSmemBytes;
+                prog.ops[so.first].u.snapshot.acc = so.second->d_spot_acc;
+                spot_fused.push_back(so);
+            }
+        }
         memcpy(h_slot, prog.ops.data(), prog.ops.size() * sizeof(DevOp));
         int block = strict ? trace_block_strict() : trace_block_fast();
         // large bundles run the kernel compiled for the structure of this program (opm_jit.cu); otherwise, and whenever
@@ -1407,6 +1443,15 @@ static OpmStatus run_program(OpmRays* rays, const OpmOp* ops, int n_ops, int fla
         for (OpmHitMap* h : prog.hitmaps) h->acc_valid = false;
         if (jk)
             for (size_t k = 0; k < fused.size(); ++k) { pp.acc[k] = (BBoxAccum*)fused[k]->d_acc; fused[k]->acc_valid = true; }
+        for (OpmRays* r : prog.slot_outputs) r->spot_acc_valid = false;
+        rays->spot_acc_valid = false; dst->spot_acc_valid = false;
+        if (jk)
+            for (size_t k = 0; k < spot_fused.size(); ++k) {  // reset by the prologue launch, filled by the kernel
+                OpmRays* r = spot_fused[k].second;
+                const DevSnapshot& sn = prog.ops[spot_fused[k].first].u.snapshot;
+                pp.spot[k] = r->d_spot_acc;
+                r->spot_acc_valid = true; r->spot_has_frame = sn.has_frame != 0; r->spot_inv = sn.inv;
+            }
         // slot-indexed outputs keep the input's length; the kernel does not touch their tail counters (only compacting stores and
         // child emission do), so the prologue can set them
         auto plan_len = [&](OpmRays* r) {
@@ -1454,7 +1499,7 @@ static OpmStatus run_program(OpmRays* rays, const OpmOp* ops, int n_ops, int fla
         r->mono_wvl = rays->mono_wvl;
     }
     for (OpmRays* r : prog.appended) {  // children carry their parents' wavelengths
-        if (r->len == 0 && !r->len_dirty) r->mono_wvl = rays->mono_wvl; else if (r->mono_wvl != rays->mono_wvl) r->mono_wvl = 0.0;
+        if (r->len == 0 && !r->len_dirty) r->mono_wvl = rays->mono_wvl; else if (r->mono_wvl != rays->mono_wvl) r->mono_wvl = 0.0; r->spot_acc_valid = false;
         r->len_dirty = true;
     }
     if (dst != rays) dst->mono_wvl = rays->mono_wvl;
@@ -1997,6 +2042,15 @@ extern "C" OpmStatus opm_rays_spot_sums_async(const OpmRays* rc, const OpmIsomet
     CU(cudaSetDevice(c->device));
     OpmStatus s = rays_refresh_len(r);
     if (s) return s;
+    {   // the launch that wrote this copy took the sums on the way (OPM_OP_SNAPSHOT want_spot_sums), in this very frame?
+        DevIso want;
+        memset(&want, 0, sizeof want);
+        if (frame) to_dev_iso(frame->inv, want);
+        if (r->spot_acc_valid && r->spot_has_frame == (frame != nullptr) && (!frame || memcmp(&want, &r->spot_inv, sizeof want) == 0)) {
+            KL(k_spot_sums_store(r->d_spot_acc, sums_dev, c->stream)); c->launches++;
+            return OPM_OK;
+        }
+    }
     SpotAccum init;
     memset(&init, 0, sizeof init);
     init.first_key = ~0ull;
@@ -2739,7 +2793,7 @@ static OpmStatus source_generate(OpmRays* rays, const OpmSourceDesc* desc, uint6
     const double* hg = desc->n_wavelengths ? desc->weights : nullptr;
     if (!hw) return fail(OPM_ERR_ARG, "source needs at least one wavelength");
     rays->pending = false;
-    rays->mono_wvl = (desc->n_wavelengths == 1 && desc->wavelengths) ? desc->wavelengths[0] : 0.0;
+    rays->mono_wvl = (desc->n_wavelengths == 1 && desc->wavelengths) ? desc->wavelengths[0] : 0.0; rays->spot_acc_valid = false;
     if (rays->d_hist) { OpmStatus hs = hist_clear(rays); if (hs) return hs; }  // new rays start without a history (ray.rs:126)
     uint64_t n_rays = n_pos * S.n_wavelengths;
     s = opm_rays_reserve(rays, n_rays);

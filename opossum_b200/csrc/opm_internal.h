@@ -64,7 +64,11 @@ struct DevSpectrum { const double* lam; const double* val; uint64_t n; };
 struct DevFilter { double t; DevSpectrum s; };   // s.lam != nullptr: FilterType::Spectrum (ray.rs:712-721)
 struct DevParaxial { double f; DevIso fwd, inv; };
 struct DevSplit { double ratio; DevRays out; DevSpectrum s; };  // s.lam != nullptr: SplittingConfig::Spectrum (ray.rs:755-761)
-struct DevSnapshot { DevRays out; };
+// fields: OPM_SNAPSHOT_ALL (every array of the bundle) or OPM_SNAPSHOT_SPOT (position, energy, valid flag: what a spot-diagram report
+// reads).  acc != nullptr (specialised kernel only): the launch also takes the phase-1 sums of the spot statistics of the copy
+// (SpotAccum, rays.rs:599-637) with the positions in the frame `inv` (has_frame) -- no separate pass over the copy
+struct DevSnapshot { DevRays out; int32_t fields, has_frame; DevIso inv; void* acc; };
+constexpr int kSpotSmemBytes = 7 * 8 + 8;  // per thread: running sums x y z ex ey ez e + first (id, bounces) key
 struct DevFork { double ratio; DevSpectrum s; };
 struct DevJoin { DevRays out; };
 constexpr int kStashWords = 21;  // parked main-bundle ray of a FORK: pos, dir, e, opl, n (18 words) + bounces, refr, flags

@@ -50,6 +50,7 @@ struct JitKernel {
     int occupancy = 1;
     bool has_fork = false;
     int bbox_slots = 0;  // hit maps whose bounding box the kernel keeps (36 bytes of shared memory per thread each)
+    int spot_slots = 0;  // bundle copies whose phase-1 spot sums the kernel takes (kSpotSmemBytes per thread each)
     size_t smem = 0;  // dynamic shared memory per CTA
     std::string why;
 };
@@ -126,6 +127,12 @@ static int program_bbox_slots(const DevOp* ops, int n_ops) {
     for (int k = 0; k < n_ops; ++k) n += op_has_bbox(ops[k]) ? 1 : 0;
     return n;
 }
+bool op_has_spot(const DevOp& op) { return op.kind == OPK_SNAPSHOT && op.u.snapshot.acc; }
+static int program_spot_slots(const DevOp* ops, int n_ops) {
+    int n = 0;
+    for (int k = 0; k < n_ops; ++k) n += op_has_spot(ops[k]) ? 1 : 0;
+    return n;
+}
 bool jit_unit_dir_enabled() {
     static const bool on = [] { const char* e = getenv("OPM_B200_JIT_UNIT_DIR"); return !(e && e[0] == '0'); }();  // tuning switch
     return on;
@@ -175,7 +182,12 @@ std::string op_line(const DevOp& op, int k, int hint_slot = -1, bool unit_dir = 
         case OPK_FILTER: appendf(s, "        exec_filter<%s>(opm_jit_ops[%d].u.filter, x);\n", op.u.filter.s.lam ? "true" : "false", k); break;
         case OPK_PARAXIAL: appendf(s, "        exec_paraxial(opm_jit_ops[%d].u.paraxial, x);\n", k); break;
         case OPK_SPLIT: appendf(s, "        exec_split<%s>(opm_jit_ops[%d].u.split, x);\n", op.u.split.s.lam ? "true" : "false", k); break;
-        case OPK_SNAPSHOT: appendf(s, "        exec_snapshot(opm_jit_ops[%d].u.snapshot, x);\n", k); break;
+        case OPK_SNAPSHOT:
+            appendf(s, "        exec_snapshot_store<%s>(opm_jit_ops[%d].u.snapshot, x);\n", op.u.snapshot.fields == OPM_SNAPSHOT_SPOT ? "true" : "false", k);
+            if (op_has_spot(op))
+                appendf(s, "        spot_smem_add<%s, %s>(opm_jit_ops[%d].u.snapshot, sp_%d, s_spotn_%d, x);\n", op.u.snapshot.has_frame ? "true" : "false",
+                        jit_rot_id_enabled() && rot_is_identity(op.u.snapshot.inv) ? "true" : "false", k, k, k);
+            break;
         case OPK_TRANSFORM: appendf(s, "        exec_transform(opm_jit_ops[%d].u.transform, x);\n", k); break;
         case OPK_FORK: appendf(s, "        exec_fork<%s>(opm_jit_ops[%d].u.fork, x, opm_jit_stash);\n", op.u.fork.s.lam ? "true" : "false", k); break;
         case OPK_JOIN: appendf(s, "        exec_join(opm_jit_ops[%d].u.join, x, opm_jit_stash);\n", k); break;
@@ -206,12 +218,12 @@ static bool program_has_fork(const DevOp* ops, int n_ops) {
 // dynamic shared memory of a specialised kernel: [parked rays of a FORK | stage 0 | stage 1]
 static size_t jit_stash_bytes(bool has_fork, int block) { return has_fork ? (((size_t)block * kStashWords * 4 + 127) & ~(size_t)127) : 0; }
 static int program_bbox_slots(const DevOp* ops, int n_ops);
-// [parked rays of a FORK | tile stages | running bounding boxes of the recorded hit maps]
+// [parked rays of a FORK | tile stages | running bounding boxes of the recorded hit maps | running spot sums of the bundle copies]
 static size_t jit_bbox_offset(bool has_fork, int block) {
     return jit_stash_bytes(has_fork, block) + (jit_pipe_enabled() && block % 16 == 0 ? 2 * jit_stage_bytes(block) : 0);
 }
-size_t jit_dynamic_smem(bool has_fork, int block, int bbox_slots) {
-    return jit_bbox_offset(has_fork, block) + (size_t)bbox_slots * block * 36;
+size_t jit_dynamic_smem(bool has_fork, int block, int bbox_slots, int spot_slots) {
+    return jit_bbox_offset(has_fork, block) + (size_t)bbox_slots * block * 36 + (size_t)spot_slots * block * kSpotSmemBytes;
 }
 
 std::string make_source(const DevOp* ops, int n_ops, bool compact, int block, int min_ctas) {
@@ -279,6 +291,16 @@ std::string make_source(const DevOp* ops, int n_ops, bool compact, int block, in
         appendf(s, "    __shared__ double s_hint[%d];  // per hinted op: wavelength | n2 | 1 / n2\n", 3 * n_hints);
         s += hint_init;
     }
+    {
+        size_t sp0 = jit_bbox_offset(program_has_fork(ops, n_ops), block) + (size_t)program_bbox_slots(ops, n_ops) * block * 36;
+        sp0 = (sp0 + 7) & ~(size_t)7;
+        for (int k = 0; k < n_ops; ++k)
+            if (op_has_spot(ops[k])) {
+                appendf(s, "    unsigned char* const sp_%d = opm_jit_smem + %zu;\n    __shared__ unsigned s_spotn_%d[2];\n    spot_smem_init(sp_%d, s_spotn_%d);\n",
+                        k, sp0, k, k, k);
+                sp0 += (size_t)block * kSpotSmemBytes;
+            }
+    }
     s += "    __syncthreads();\n"
          "    const unsigned tiles = (unsigned)((n + OPM_BDIM - 1) / OPM_BDIM);\n";
     if (pipe) {
@@ -308,6 +330,8 @@ std::string make_source(const DevOp* ops, int n_ops, bool compact, int block, in
          "    __syncthreads();\n";
     for (int k = 0; k < n_ops; ++k)
         if (op_has_bbox(ops[k])) appendf(s, "    bbox_reg_flush(bbox_smem_get(bb_%d), opm_jit_ops[%d].u.refract.hit_acc);\n", k, k);
+    for (int k = 0; k < n_ops; ++k)
+        if (op_has_spot(ops[k])) appendf(s, "    spot_smem_flush(sp_%d, s_spotn_%d, opm_jit_ops[%d].u.snapshot.acc);\n", k, k, k);
     s += "    cta_flush(stats, s_cnt, s_status, s_first_inv);\n"
          "}\n}  // namespace opm\n";
     return s;
@@ -362,7 +386,7 @@ bool load(JitKernel& K, int n_ops, int block) {
     if (e != cudaSuccess) { K.why = std::string("cudaLibraryGetKernel/Global: ") + cudaGetErrorString(e); cudaGetLastError(); return false; }
     if (K.const_bytes < (size_t)n_ops * sizeof(DevOp)) { K.why = "constant array smaller than the program"; return false; }
     int nb = 0;
-    K.smem = jit_dynamic_smem(K.has_fork, block, K.bbox_slots);
+    K.smem = jit_dynamic_smem(K.has_fork, block, K.bbox_slots, K.spot_slots) + 8;
     if (K.smem > 48 * 1024 &&
         cudaFuncSetAttribute((const void*)K.kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K.smem) != cudaSuccess) {
         K.why = "dynamic shared memory of the specialised kernel not available"; cudaGetLastError(); return false;
@@ -437,6 +461,7 @@ const JitKernel* jit_get(JitCache* cache, const DevOp* ops, int n_ops, bool comp
         JitKernel* k = it->second.get();
         k->has_fork = program_has_fork(ops, n_ops);
         k->bbox_slots = program_bbox_slots(ops, n_ops);
+        k->spot_slots = program_spot_slots(ops, n_ops);
         if (!nvrtc_load(&k->why)) {
             k->state = JIT_FAILED;
             cache->failures++;
@@ -498,6 +523,10 @@ static size_t jit_selftest_impl(std::string& why) {
         for (int j = 0; j < 4; ++j) d->u.apodize.ap.items[j].type = OPM_AP_CIRCLE + j;
     }
     for (int kind : {OPK_THRESHOLD, OPK_LIMITS, OPK_FILTER, OPK_PARAXIAL, OPK_SPLIT, OPK_SNAPSHOT, OPK_TRANSFORM, OPK_DIFFRACT, OPK_FORK, OPK_JOIN}) push(kind);
+    {
+        DevOp* d = push(OPK_SNAPSHOT);  // spot-diagram copy with the phase-1 sums taken on the way
+        d->u.snapshot.fields = OPM_SNAPSHOT_SPOT; d->u.snapshot.has_frame = 1; d->u.snapshot.acc = (void*)8;
+    }
     std::vector<char> cubin;
     for (bool compact : {false, true}) {
         std::string src = make_source(ops.data(), (int)ops.size(), compact, 256, 2);

@@ -1436,6 +1436,12 @@ __global__ void __launch_bounds__(256) trace_prologue_kernel(ProloguePlan P) {
         }
     }
     if (threadIdx.x >= 64 && threadIdx.x < 64 + (unsigned)P.n_tails) *P.tail[threadIdx.x - 64] = P.tail_val[threadIdx.x - 64];
+    if (threadIdx.x >= 96 && threadIdx.x < 98 && P.spot[threadIdx.x - 96]) {
+        SpotAccum* a = P.spot[threadIdx.x - 96];
+        for (int j = 0; j < 7; ++j) a->sum[j] = 0.0;
+        a->n_valid = 0ull; a->n_total = 0ull; a->first_key = ~0ull;
+        a->max_d2_key = dkey(0.0); a->sum_d2 = 0.0; a->sum_ed2 = 0.0;
+    }
 }
 int k_trace_prologue(const ProloguePlan& P, void* stream) {
     trace_prologue_kernel<<<1, 256, 0, ST>>>(P);

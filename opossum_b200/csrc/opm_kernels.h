@@ -120,6 +120,7 @@ struct ProloguePlan {
     unsigned long long* dst; const unsigned long long* src_host; unsigned words;   // op descriptors (pinned + mapped source)
     unsigned long long* stats; unsigned stats_words;                               // zeroed
     BBoxAccum* acc[2];                                                             // reset to the identity (NULL: none)
+    SpotAccum* spot[2];                                                            // reset to the identity (NULL: none)
     unsigned long long* tail[kPrologueTails]; unsigned long long tail_val[kPrologueTails]; int n_tails;
 };
 int k_trace_prologue(const ProloguePlan& P, void* stream);

@@ -445,6 +445,11 @@ OpmStatus compile_node_rt(OpmScene* sc, Node& n, const OpmRayTraceConfig& cfg, i
                 OpmOp op;
                 memset(&op, 0, sizeof op);
                 op.kind = OPM_OP_SNAPSHOT; op.u.snapshot.out = n.stored;
+                if (n.d.type == OPM_NODE_SPOT_DIAGRAM) {  // the report is opm_scene_node_spot: statistics in the detector's frame
+                    op.u.snapshot.want_spot_sums = 1;
+                    op.u.snapshot.spot_frame = &n.s[0].eff_iso;
+                    if ((flags & OPM_SCENE_LEAN_SPOT_DATA) && !(flags & OPM_SCENE_POSITION_HISTORY)) op.u.snapshot.fields = OPM_SNAPSHOT_SPOT;
+                }
                 R.push(op);
             }
             break;

@@ -363,11 +363,100 @@ __device__ __forceinline__ void exec_join(const DevJoin& o, RayCtx& x, const uns
     const unsigned fl = stash[20 * OPM_BDIM + threadIdx.x];
     x.alive = (fl & 1u) != 0; x.valid = (fl & 2u) != 0;
 }
-// copy of the bundle a detector node keeps (analyzers/raytrace.rs:186-205)
-__device__ __forceinline__ void exec_snapshot(const DevSnapshot& o, RayCtx& x) {
+// copy of the bundle a detector node keeps (analyzers/raytrace.rs:186-205).  LEAN: only what a spot-diagram report reads
+// (nodes/spot_diagram.rs:101-163: positions, energies, which rays are valid)
+template <bool LEAN = false>
+__device__ __forceinline__ void exec_snapshot_store(const DevSnapshot& o, RayCtx& x) {
     if (!x.in_range) return;
-    if (x.alive) store_ray<true>(o.out, x.i, x.r, x.valid ? RAY_VALID : RAY_INVALID);
-    else o.out.valid[x.i] = RAY_REMOVED;
+    if (x.alive) {
+        if (LEAN) {
+            OPM_ST(o.out.px + x.i, x.r.pos.x); OPM_ST(o.out.py + x.i, x.r.pos.y); OPM_ST(o.out.pz + x.i, x.r.pos.z);
+            OPM_ST(o.out.e + x.i, x.r.e);
+            o.out.valid[x.i] = x.valid ? RAY_VALID : RAY_INVALID;
+        } else store_ray<true>(o.out, x.i, x.r, x.valid ? RAY_VALID : RAY_INVALID);
+    } else o.out.valid[x.i] = RAY_REMOVED;
+}
+__device__ __forceinline__ void exec_snapshot(const DevSnapshot& o, RayCtx& x) {  // interpreter: structural facts read at run time
+    if (o.fields == OPM_SNAPSHOT_SPOT) exec_snapshot_store<true>(o, x);
+    else exec_snapshot_store<false>(o, x);
+}
+// Phase-1 sums of the spot statistics (rays.rs:599-637: centroid and energy-weighted centroid of the valid rays, their number,
+// the first valid ray) taken while the copy is written.  Running sums per thread in dynamic shared memory, field-major
+// ([x | y | z | ex | ey | ez | e][OPM_BDIM] doubles, then [OPM_BDIM] keys): one reduction per CTA at the end of the kernel, one
+// set of atomics into the SpotAccum of the copy.  The ray counts go through two CTA counters (one ballot per warp and tile).
+__device__ __forceinline__ void spot_smem_init(unsigned char* slot, unsigned* s_n) {
+    double* d = reinterpret_cast<double*>(slot);
+    const unsigned B = OPM_BDIM, t = threadIdx.x;
+#pragma unroll
+    for (int j = 0; j < 7; ++j) d[j * B + t] = 0.0;
+    reinterpret_cast<unsigned long long*>(d + 7 * B)[t] = ~0ull;
+    if (t < 2) s_n[t] = 0u;
+}
+// HAS_FRAME / ROT_ID: positions go through the isometry `inv` / which is a pure translation
+template <bool HAS_FRAME, bool ROT_ID>
+__device__ __forceinline__ void spot_smem_add(const DevSnapshot& o, unsigned char* slot, unsigned* s_n, const RayCtx& x) {
+    const bool v = x.in_range && x.alive && x.valid;
+    const unsigned am = __activemask();  // the live and the dead copy of a specialised program call this separately
+    const unsigned mv = __ballot_sync(am, v), ma = __ballot_sync(am, x.in_range && x.alive);
+    if ((threadIdx.x & 31u) == (unsigned)(__ffs(am) - 1)) {
+        if (mv) atomicAdd(&s_n[0], (unsigned)__popc(mv));
+        if (ma) atomicAdd(&s_n[1], (unsigned)__popc(ma));
+    }
+    if (!v) return;
+    V3 p = x.r.pos;
+    if (HAS_FRAME) p = ROT_ID ? v3(p.x + o.inv.t[0], p.y + o.inv.t[1], p.z + o.inv.t[2]) : iso_point(o.inv, p);
+    double* d = reinterpret_cast<double*>(slot);
+    const unsigned B = OPM_BDIM, t = threadIdx.x;
+    const double e = x.r.e;
+    d[t] += p.x; d[B + t] += p.y; d[2 * B + t] += p.z;
+    d[3 * B + t] = fma(p.x, e, d[3 * B + t]); d[4 * B + t] = fma(p.y, e, d[4 * B + t]); d[5 * B + t] = fma(p.z, e, d[5 * B + t]);
+    d[6 * B + t] += e;
+    unsigned long long* k = reinterpret_cast<unsigned long long*>(d + 7 * B) + t;
+    const unsigned long long key = ((unsigned long long)x.r.id << 32) | x.r.bounces;
+    if (key < *k) *k = key;
+}
+// all threads of the CTA, after the tile loop and a barrier; ends with a barrier.  SpotAccum layout: sum[7] | n_valid | n_total |
+// first_key (opm_kernels.h)
+__device__ __forceinline__ void spot_smem_flush(const unsigned char* slot, const unsigned* s_n, void* acc_) {
+    __shared__ double sh[32][7];
+    __shared__ unsigned long long shk[32];
+    const double* d = reinterpret_cast<const double*>(slot);
+    const unsigned B = OPM_BDIM, t = threadIdx.x;
+    double s[7];
+#pragma unroll
+    for (int j = 0; j < 7; ++j) s[j] = d[j * B + t];
+    unsigned long long key = reinterpret_cast<const unsigned long long*>(d + 7 * B)[t];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+        for (int j = 0; j < 7; ++j) s[j] += __shfl_xor_sync(0xffffffffu, s[j], o);
+        const unsigned long long other = __shfl_xor_sync(0xffffffffu, key, o);
+        key = other < key ? other : key;
+    }
+    const int w = t >> 5, l = t & 31;
+    if (l == 0) {
+#pragma unroll
+        for (int j = 0; j < 7; ++j) sh[w][j] = s[j];
+        shk[w] = key;
+    }
+    __syncthreads();
+    if (t == 0 && s_n[1]) {
+        double* sum = reinterpret_cast<double*>(acc_);
+        unsigned long long* cnt = reinterpret_cast<unsigned long long*>(sum + 7);
+        for (int k = 1; k < (int)((B + 31) >> 5); ++k) {
+#pragma unroll
+            for (int j = 0; j < 7; ++j) s[j] += sh[k][j];
+            key = shk[k] < key ? shk[k] : key;
+        }
+        if (s_n[0]) {
+#pragma unroll
+            for (int j = 0; j < 7; ++j) atomicAdd(&sum[j], s[j]);
+            atomicAdd(&cnt[0], (unsigned long long)s_n[0]);
+            atomicMin(&cnt[2], key);
+        }
+        atomicAdd(&cnt[1], (unsigned long long)s_n[1]);
+    }
+    __syncthreads();
 }
 // ray.rs:787-804
 __device__ __forceinline__ void exec_transform(const DevTransform& o, RayCtx& x) {

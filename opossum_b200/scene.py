@@ -250,8 +250,10 @@ class Scene:
         return Isometry(o)
 
     def raytrace(self, source_rays: Rays, config: RayTraceConfig | None = None, strict=False, per_surface=False,
-                 record_all_hits=False, snapshots=True, sync=True, keep_source=False, position_history=False, keep_light_data=False) -> TraceStats | None:
-        """RayTracingAnalyzer::analyze (analyzers/raytrace.rs:36-49); traces `source_rays` in place."""
+                 record_all_hits=False, snapshots=True, sync=True, keep_source=False, position_history=False, keep_light_data=False,
+                 lean_spot_data=False) -> TraceStats | None:
+        """RayTracingAnalyzer::analyze (analyzers/raytrace.rs:36-49); traces `source_rays` in place.  lean_spot_data: SpotDiagram nodes
+        keep only position, energy and valid flag of their copy of the bundle (what their report reads)."""
         cfg = F.OpmRayTraceConfig()
         c = config or RayTraceConfig()
         cfg.min_energy_per_ray, cfg.max_number_of_bounces = c.min_energy_per_ray, c.max_number_of_bounces
@@ -259,7 +261,8 @@ class Scene:
         flags = ((F.SCENE_STRICT if strict else 0) | (F.SCENE_PER_SURFACE if per_surface else 0) |
                  (F.SCENE_RECORD_ALL_HITS if record_all_hits else 0) | (0 if snapshots else F.SCENE_NO_SNAPSHOTS) |
                  (0 if sync else F.SCENE_ASYNC) | (F.SCENE_KEEP_SOURCE if keep_source else 0) |
-                 (F.SCENE_POSITION_HISTORY if position_history else 0) | (F.SCENE_KEEP_LIGHT_DATA if keep_light_data else 0))
+                 (F.SCENE_POSITION_HISTORY if position_history else 0) | (F.SCENE_KEEP_LIGHT_DATA if keep_light_data else 0) |
+                 (F.SCENE_LEAN_SPOT_DATA if lean_spot_data else 0))
         st = F.OpmTraceStats()
         _check(F.lib().opm_scene_raytrace(self.h, source_rays.h, C.byref(cfg), flags, C.byref(st)))
         return TraceStats.of(st) if sync else None

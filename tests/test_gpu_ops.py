@@ -552,11 +552,15 @@ def test_fork_join_equals_split_and_separate_trace(ctx):
         assert st_b.valid_out == st_a.valid_out and st_b.alive_out == st_a.alive_out and st_b.apodized == st_a2.apodized
         ga, gb = a.to_array(), b.to_array()
         sa, sb = side_a.to_array(), side_b.to_array()
+        # the interpreter runs the same arithmetic in both forms: bit-identical.  The specialised kernel knows inside the fused program
+        # that the side chain's rays already carry unit directions (RefractCt UNIT_DIR) and skips a renormalisation the separate
+        # launch makes: last-bit differences
+        same = np.array_equal if jit == 0 else (lambda p, q: np.allclose(p, q, rtol=1e-13, atol=1e-300))
         for f in ga.dtype.names:
-            assert np.array_equal(ga[f], gb[f]), f"main bundle field {f} (jit={jit})"
-            assert np.array_equal(sa[f], sb[f]), f"side bundle field {f} (jit={jit})"
+            assert same(ga[f], gb[f]), f"main bundle field {f} (jit={jit})"
+            assert same(sa[f], sb[f]), f"side bundle field {f} (jit={jit})"
         for u, w in zip(hm_a.download(), hm_b.download()):
-            assert np.array_equal(u, w)
+            assert same(u, w)
     ctx.set_jit(1, 200000)
     with pytest.raises(ob.OpossumError):
         ob.Program().fork(0.5).refract(main_surf, None).run(ob.Rays.from_array(ctx, rays))  # FORK without JOIN

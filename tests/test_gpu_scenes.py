@@ -71,6 +71,57 @@ def test_c1_single_lens(ctx, strict):
                 assert_hits_match(maps[0].download(), ref_hits)
 
 
+def test_c2_specialised_kernel_spot_sums_and_lean_copy():
+    """C2 through the run-time specialised kernel: the SpotDiagram's copy holds position / energy / valid flag only
+    (OPM_SCENE_LEAN_SPOT_DATA) and its phase-1 sums come out of the trace launch (no first pass over the copy).  Every statistic
+    against the oracle, and against the two-pass path on a full copy."""
+    import os
+    src = scenes.c2_source(20000)
+    os.environ["OPM_B200_JIT_SPOT"] = "1"  # read when a context is created
+    ctx = ob.Context(0)
+    del os.environ["OPM_B200_JIT_SPOT"]
+    osc = scenes.to_oracle(scenes.c2_laser_chain())
+    ref_out = osc.raytrace(scenes.source_to_oracle(src))
+    ref = osc.node_spot(8)
+    stats = {}
+    try:
+        for mode in ("two_pass", "fused_full", "fused_lean"):
+            ctx.set_jit(2 if mode != "two_pass" else 0, 1)
+            psc = scenes.to_product(ctx, scenes.c2_laser_chain())
+            rays = scenes.source_to_product(src).generate(ctx)
+            n0 = ctx.launch_count
+            st = psc.raytrace(rays, lean_spot_data=(mode == "fused_lean"))
+            assert st.interactions == osc.interactions
+            assert_rays_match(rays.to_array(), ref_out, what=f"C2 main chain ({mode})")
+            n1 = ctx.launch_count
+            s = psc.node_spot(8)
+            stats[mode] = (s, ctx.launch_count - n1)
+            assert s.n_valid == ref["n_valid"] and s.n_total == len(ref_out) and s.bounce_lvl == 0
+            assert s.total_energy == pytest.approx(ref["total_energy"], rel=RTOL)
+            assert np.allclose(s.energy_centroid[:2], ref["centroid"][:2], rtol=RTOL, atol=1e-15)
+            assert s.beam_radius_geo == pytest.approx(ref["geo"], rel=RTOL)
+            assert s.energy_beam_radius_rms == pytest.approx(ref["rms"], rel=RTOL)
+            if mode == "fused_lean":  # the copy: positions, energies and flags of the full copy
+                full = osc.nodes[8].stored
+                got = psc.node_rays(8).to_array()
+                assert len(got) == len(full)
+                for f in ("pos", "e", "valid"):
+                    assert np.allclose(got[f], full[f], rtol=RTOL, atol=1e-300), f
+            check_detector(osc, psc, 9)
+    finally:
+        jit = ctx.jit_stats()
+        psc = rays = None  # owned by the context
+        import gc
+        gc.collect()
+        ctx.close()
+    assert jit["compile_failures"] == 0
+    a, b = stats["two_pass"][0], stats["fused_lean"][0]
+    for f in ("centroid", "energy_centroid"):
+        assert np.allclose(list(getattr(a, f)), list(getattr(b, f)), rtol=1e-12, atol=1e-18)
+    assert a.beam_radius_rms == pytest.approx(b.beam_radius_rms, rel=1e-12)
+    assert stats["fused_lean"][1] < stats["two_pass"][1]  # the pass over the copy that takes the sums is gone
+
+
 @pytest.mark.parametrize("mode", ["fused", "per_surface", "strict"])
 def test_c2_laser_chain(ctx, mode):
     """configs[1] at 20k rays: lens, two 45 deg mirrors (rays clipped at the first leave the bundle at the second), wedge
