@@ -1185,12 +1185,12 @@ static OpmStatus compile_ops(OpmContext* c, const OpmOp* ops, int n_ops, uint64_
             case OPM_OP_LIMITS:
                 if (!out.ops.empty() && !(out.ops.back().epi_flags & EPI_LIMITS)) {  // the epilogue runs threshold, then limits
                     DevOp& b = out.ops.back();
-                    b.epi_flags |= EPI_LIMITS | (p.u.limits.check_refractions ? EPI_CHECK_REFR : 0);
-                    b.epi_max_bounces = p.u.limits.max_bounces; b.epi_max_refr = p.u.limits.max_refractions;
+                    b.epi_flags |= EPI_LIMITS | ((p.u.limits.check_refractions && p.u.limits.max_refractions <= 0xffffffffull) ? EPI_CHECK_REFR : 0);
+                    b.epi_max_bounces = limit_sat32(p.u.limits.max_bounces); b.epi_max_refr = limit_sat32(p.u.limits.max_refractions);
                     continue;
                 }
-                d.kind = OPK_LIMITS; d.u.limits.max_bounces = p.u.limits.max_bounces; d.u.limits.max_refr = p.u.limits.max_refractions;
-                d.u.limits.check_refr = p.u.limits.check_refractions;
+                d.kind = OPK_LIMITS; d.u.limits.max_bounces = limit_sat32(p.u.limits.max_bounces); d.u.limits.max_refr = limit_sat32(p.u.limits.max_refractions);
+                d.u.limits.check_refr = (p.u.limits.check_refractions && p.u.limits.max_refractions <= 0xffffffffull) ? 1 : 0;
                 break;
             case OPM_OP_FILTER: {  // rays.rs:1120-1126
                 double t = p.u.filter.transmission;
@@ -1378,7 +1378,7 @@ static OpmStatus run_program(OpmRays* rays, const OpmOp* ops, int n_ops, int fla
     if (n > 0 && (!prog.ops.empty() || dst != rays)) {
         if (prog.ops.empty()) {  // pure copy: keep the kernel path uniform with a no-op limits check
             DevOp d; memset(&d, 0, sizeof d);
-            d.kind = OPK_LIMITS; d.u.limits.max_bounces = ~0ull; d.u.limits.max_refr = ~0ull; d.u.limits.check_refr = 0;
+            d.kind = OPK_LIMITS; d.u.limits.max_bounces = 0xffffffffu; d.u.limits.max_refr = 0xffffffffu; d.u.limits.check_refr = 0;
             prog.ops.push_back(d);
         }
         const int slot = c->ring_pos;

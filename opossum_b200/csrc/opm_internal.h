@@ -58,7 +58,10 @@ struct DevRefract {
 struct DevDiffract { DevRefract surf; double gvec[3]; double gnorm; double order; };
 struct DevApodize { DevIso inv; DevAperture ap; };
 struct DevThreshold { double min_energy; };
-struct DevLimits { uint64_t max_bounces, max_refr; int32_t check_refr, _pad; };
+// the counters of a ray are 32-bit: the limits travel saturated to 32 bits (bounces > 2^32 - 1 is never true; a refraction limit
+// above 2^32 - 1 clears check_refr instead), so each test is one 32-bit compare
+struct DevLimits { uint32_t max_bounces, max_refr; int32_t check_refr, _pad; };
+inline uint32_t limit_sat32(uint64_t v) { return v > 0xffffffffull ? 0xffffffffu : (uint32_t)v; }
 // a Spectrum (spectrum.rs:35-37) on the device: ascending wavelength slots [um] and their values; lam == nullptr: none
 struct DevSpectrum { const double* lam; const double* val; uint64_t n; };
 struct DevFilter { double t; DevSpectrum s; };   // s.lam != nullptr: FilterType::Spectrum (ray.rs:712-721)
@@ -81,7 +84,8 @@ enum : int32_t { EPI_THRESHOLD = 1, EPI_LIMITS = 2, EPI_CHECK_REFR = 4 };
 struct alignas(16) DevOp {
     int32_t kind, epi_flags;
     double epi_min_energy;
-    uint64_t epi_max_bounces, epi_max_refr;
+    uint32_t epi_max_bounces, epi_max_refr;  // saturated, see DevLimits
+    uint64_t _epi_pad;
     union {
         DevRefract refract;
         DevApodize apodize;

@@ -282,10 +282,10 @@ std::string make_source(const DevOp* ops, int n_ops, bool compact, int block, in
          "              DevStats* stats) {\n"
          "    extern __shared__ __align__(128) unsigned char opm_jit_smem[];  // [parked rays of a FORK | tile stages], sized by the launch\n"
          "    unsigned* opm_jit_stash = reinterpret_cast<unsigned*>(opm_jit_smem);\n"
-         "    __shared__ cta_count_t s_cnt[CNT_N];\n"
+         "    __shared__ cta_count_t s_cnt[kCntWords];\n"
          "    __shared__ unsigned s_status;\n"
          "    __shared__ unsigned long long s_first_inv;\n"
-         "    if (threadIdx.x < CNT_N) s_cnt[threadIdx.x] = 0u;\n"
+         "    cta_count_init(s_cnt);\n"
          "    if (threadIdx.x == 0) { s_status = 0u; s_first_inv = 0ull; }\n";
     if (n_hints) {
         appendf(s, "    __shared__ double s_hint[%d];  // per hinted op: wavelength | n2 | 1 / n2\n", 3 * n_hints);

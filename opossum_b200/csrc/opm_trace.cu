@@ -70,10 +70,10 @@ __device__ __forceinline__ void trace_body(const DevOp* __restrict__ g_ops, int 
     }
     bar.wait(std::move(token));
 
-    __shared__ cta_count_t s_cnt[CNT_N];
+    __shared__ cta_count_t s_cnt[kCntWords];
     __shared__ unsigned s_status;
     __shared__ unsigned long long s_first_inv;  // max of ~(id << 32 | bounces) over the valid rays this CTA wrote
-    if (threadIdx.x < CNT_N) s_cnt[threadIdx.x] = 0u;
+    cta_count_init(s_cnt);
     if (threadIdx.x == 0) { s_status = 0u; s_first_inv = 0ull; }
     __syncthreads();
 

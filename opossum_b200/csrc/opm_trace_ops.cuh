@@ -19,6 +19,13 @@ namespace opm {
 #define OPM_BDIM (blockDim.x)
 #endif
 
+// fire-and-forget add of ONE lane to a shared-memory counter.  Written as PTX: for an atomicAdd in divergent code the compiler
+// emits the warp-aggregated form (vote, leader election, popc, multiply: 12 instructions) although the caller has already
+// reduced over the warp and elected lane 0
+__device__ __forceinline__ void red_shared_add(unsigned* p, unsigned v) {
+    asm volatile("red.shared.add.u32 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(p)), "r"(v) : "memory");
+}
+
 __device__ __forceinline__ unsigned lanemask_lt() {
     unsigned m;
     asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
@@ -92,6 +99,11 @@ struct RayCtx {
     bool in_range;   // i < n
     bool alive;      // part of the bundle (not removed)
     bool valid;      // Ray::valid
+    // some slot of this warp's 32 held a ray when the tile was loaded: every slot-indexed store of the tile then writes ALL its
+    // in-range lanes (whatever the registers hold for a removed ray, flagged RAY_REMOVED / e < 0), so that every 32-byte sector
+    // reaches the L2 complete.  Sectors with holes are read back from DRAM before they can be written: on C2, where 8.6 % of the
+    // rays leave the bundle at scattered slots, that was 0.64 GB of reads per launch (ncu, profiles/r2_summary.md)
+    bool warp_live;
     Counters c;
 };
 
@@ -111,8 +123,8 @@ __device__ __forceinline__ void exec_epilogue(const E& e, const DevOp& op, RayCt
     if (f == 0 || !x.alive) return;
     if ((f & EPI_THRESHOLD) && x.r.e < op.epi_min_energy) x.valid = false;
     if (f & EPI_LIMITS) {
-        if ((uint64_t)x.r.bounces > op.epi_max_bounces) x.valid = false;
-        if ((f & EPI_CHECK_REFR) && (uint64_t)x.r.refr >= op.epi_max_refr) x.valid = false;
+        if (x.r.bounces > op.epi_max_bounces) x.valid = false;
+        if ((f & EPI_CHECK_REFR) && x.r.refr >= op.epi_max_refr) x.valid = false;
     }
 }
 
@@ -161,9 +173,11 @@ __device__ __forceinline__ bool exec_refract(const V& v, RayCtx& x, HitOut* ho =
     if (ho) ho->ok = false;
     if (v.has_hits() && x.in_range) {  // slot-indexed hit record, e < 0 = empty
         OPM_ST(o.hits.e + x.i, res.hit_e);
-        if (res.hit_e >= 0.0) {
+        if (res.hit_e >= 0.0 || x.warp_live) {  // full sectors (RayCtx::warp_live): the fields of a slot with e < 0 mean nothing
             OPM_ST(o.hits.x + x.i, res.hit_local.x); OPM_ST(o.hits.y + x.i, res.hit_local.y);
             OPM_ST(o.hits.z + x.i, res.hit_local.z); OPM_ST(o.hits.bounce + x.i, res.hit_bounce);
+        }
+        if (res.hit_e >= 0.0) {
             x.c.a += 1u << 16;
             if (ho) { ho->ok = true; ho->x = res.hit_local.x; ho->y = res.hit_local.y; }
         }
@@ -280,8 +294,8 @@ __device__ __forceinline__ void exec_threshold(const DevThreshold& o, RayCtx& x)
 // rays.rs:1386-1404
 __device__ __forceinline__ void exec_limits(const DevLimits& o, RayCtx& x) {
     if (!x.alive) return;
-    if ((uint64_t)x.r.bounces > o.max_bounces) x.valid = false;
-    if (o.check_refr && (uint64_t)x.r.refr >= o.max_refr) x.valid = false;
+    if (x.r.bounces > o.max_bounces) x.valid = false;
+    if (o.check_refr && x.r.refr >= o.max_refr) x.valid = false;
 }
 // the per-ray splitting ratio / transmission of a spectrum-driven op (ray.rs:712-721, 755-761); false = the wavelength is
 // outside the spectrum (the reference returns an error: the ray raises OPM_ERR_SPECTRUM)
@@ -322,7 +336,8 @@ __device__ __forceinline__ void exec_split(const DevSplit& o, RayCtx& x) {
         }
         if (o.out.px != nullptr) store_ray<true>(o.out, x.i, s, was_valid && x.valid ? RAY_VALID : RAY_INVALID);
     } else if (o.out.px != nullptr) {
-        o.out.valid[x.i] = RAY_REMOVED;
+        if (x.warp_live) store_ray<true>(o.out, x.i, x.r, RAY_REMOVED);  // full sectors
+        else o.out.valid[x.i] = RAY_REMOVED;
     }
 }
 // OPM_OP_FORK / OPM_OP_JOIN: Rays::split (rays.rs:1253-1264, ray.rs:752-772) whose split-off bundle runs its side chain in the
@@ -352,7 +367,7 @@ __device__ __forceinline__ void exec_fork(const DevFork& o, RayCtx& x, unsigned*
 }
 __device__ __forceinline__ void exec_join(const DevJoin& o, RayCtx& x, const unsigned* stash) {
     if (x.in_range && o.out.px != nullptr) {
-        if (x.alive) store_ray<true>(o.out, x.i, x.r, x.valid ? RAY_VALID : RAY_INVALID);
+        if (x.alive || x.warp_live) store_ray<true>(o.out, x.i, x.r, !x.alive ? RAY_REMOVED : x.valid ? RAY_VALID : RAY_INVALID);
         else o.out.valid[x.i] = RAY_REMOVED;
     }
     x.r.pos = v3(stash_get(stash, 0), stash_get(stash, 1), stash_get(stash, 2));
@@ -368,12 +383,13 @@ __device__ __forceinline__ void exec_join(const DevJoin& o, RayCtx& x, const uns
 template <bool LEAN = false>
 __device__ __forceinline__ void exec_snapshot_store(const DevSnapshot& o, RayCtx& x) {
     if (!x.in_range) return;
-    if (x.alive) {
+    if (x.alive || x.warp_live) {  // a removed ray: full sectors, flagged RAY_REMOVED
+        const uint8_t flag = !x.alive ? RAY_REMOVED : x.valid ? RAY_VALID : RAY_INVALID;
         if (LEAN) {
             OPM_ST(o.out.px + x.i, x.r.pos.x); OPM_ST(o.out.py + x.i, x.r.pos.y); OPM_ST(o.out.pz + x.i, x.r.pos.z);
             OPM_ST(o.out.e + x.i, x.r.e);
-            o.out.valid[x.i] = x.valid ? RAY_VALID : RAY_INVALID;
-        } else store_ray<true>(o.out, x.i, x.r, x.valid ? RAY_VALID : RAY_INVALID);
+            o.out.valid[x.i] = flag;
+        } else store_ray<true>(o.out, x.i, x.r, flag);
     } else o.out.valid[x.i] = RAY_REMOVED;
 }
 __device__ __forceinline__ void exec_snapshot(const DevSnapshot& o, RayCtx& x) {  // interpreter: structural facts read at run time
@@ -399,8 +415,8 @@ __device__ __forceinline__ void spot_smem_add(const DevSnapshot& o, unsigned cha
     const unsigned am = __activemask();  // the live and the dead copy of a specialised program call this separately
     const unsigned mv = __ballot_sync(am, v), ma = __ballot_sync(am, x.in_range && x.alive);
     if ((threadIdx.x & 31u) == (unsigned)(__ffs(am) - 1)) {
-        if (mv) atomicAdd(&s_n[0], (unsigned)__popc(mv));
-        if (ma) atomicAdd(&s_n[1], (unsigned)__popc(ma));
+        if (mv) red_shared_add(&s_n[0], (unsigned)__popc(mv));
+        if (ma) red_shared_add(&s_n[1], (unsigned)__popc(ma));
     }
     if (!v) return;
     V3 p = x.r.pos;
@@ -487,6 +503,7 @@ __device__ __forceinline__ void tile_load(const DevRays& in, uint64_t i, uint64_
     }
     x.alive = vb != RAY_REMOVED;
     x.valid = vb == RAY_VALID;
+    x.warp_live = __any_sync(0xffffffffu, x.alive);
 }
 // probe (-DOPM_TILE_PREFETCH, profiles/tile_load_variants.sh): asks the L2 for the lines of the tile this CTA takes next (one
 // request per 128-byte line).  Measured on C2: 1.359 ms against 1.318 ms -- left off.
@@ -594,6 +611,7 @@ __device__ __forceinline__ void tile_load_staged(TilePipe& p, const DevRays& in,
     }
     x.alive = vb != RAY_REMOVED;
     x.valid = vb == RAY_VALID;
+    x.warp_live = __any_sync(0xffffffffu, x.alive);
     __syncthreads();  // every thread has its ray in registers: the stage can take the tile after next
     if (t == 0) {
         const unsigned next = tile + 2u * gridDim.x;
@@ -612,19 +630,26 @@ __device__ __forceinline__ void tile_store(const DevRays& in, const DevRays& out
             else x.c.status |= 1u << OPM_ERR_CAPACITY;
         }
     } else if (x.in_range) {
-        if (x.alive) {
-            if (out.px == in.px) store_ray<false>(out, x.i, x.r, x.valid ? RAY_VALID : RAY_INVALID);
-            else store_ray<true>(out, x.i, x.r, x.valid ? RAY_VALID : RAY_INVALID);
+        if (x.alive || x.warp_live) {  // a removed ray: full sectors, flagged RAY_REMOVED (RayCtx::warp_live)
+            const uint8_t flag = !x.alive ? RAY_REMOVED : x.valid ? RAY_VALID : RAY_INVALID;
+            if (out.px == in.px) store_ray<false>(out, x.i, x.r, flag);
+            else store_ray<true>(out, x.i, x.r, flag);
         } else if (vb != RAY_REMOVED || out.px != in.px) {
             out.valid[x.i] = RAY_REMOVED;
         }
     }
 }
 
-// tile counters: one warp reduction per register, lane 0 adds the fields to the CTA totals in shared memory.  The CTA totals are
-// 32-bit (native shared-memory adds; 64-bit ones are compare-and-swap loops): a CTA sees at most rays / CTAs x ops interactions,
-// below 2^32 for any bundle that fits the device.
+// tile counters: one warp reduction per register, then lane k adds field k to THIS WARP's row of the CTA's counter table in
+// shared memory -- a plain load / add / store of 7 lanes, no atomics (an atomic add from divergent code is compiled into the
+// warp-aggregated form, a dozen instructions per counter).  32-bit counters: a warp sees at most rays / warps x ops
+// interactions, below 2^32 for any bundle that fits the device.  cta_flush sums the rows.
 typedef unsigned cta_count_t;
+constexpr int kCntStride = 8;                  // CNT_N fields per row, padded
+constexpr int kCntWords = 32 * kCntStride;     // one row per warp of the largest CTA
+__device__ __forceinline__ void cta_count_init(cta_count_t* s_cnt) {
+    for (unsigned k = threadIdx.x; k < (unsigned)kCntWords; k += blockDim.x) s_cnt[k] = 0u;
+}
 __device__ __forceinline__ void tile_count(const RayCtx& x, cta_count_t* s_cnt, unsigned* s_status, unsigned long long* s_first_inv) {
     const unsigned ra = __reduce_add_sync(0xffffffffu, x.c.a), rb = __reduce_add_sync(0xffffffffu, x.c.b);
     const unsigned rp = __reduce_add_sync(0xffffffffu, x.c.apodized);
@@ -642,25 +667,28 @@ __device__ __forceinline__ void tile_count(const RayCtx& x, cta_count_t* s_cnt, 
             if (inv > *(volatile unsigned long long*)s_first_inv) atomicMax(s_first_inv, inv);  // rarely after the CTA's first tiles
         }
     }
-    if (lane0) {
-        if (ra & 0xffffu) atomicAdd(&s_cnt[CNT_INTERACTIONS], ra & 0xffffu);
-        if (ra >> 16) atomicAdd(&s_cnt[CNT_HITS], ra >> 16);
-        if (rb & 0xffffu) atomicAdd(&s_cnt[CNT_MISSED], rb & 0xffffu);
-        if (rb >> 16) atomicAdd(&s_cnt[CNT_CHILDREN], rb >> 16);
-        if (rp) atomicAdd(&s_cnt[CNT_APODIZED], rp);
-        if (live) atomicAdd(&s_cnt[CNT_ALIVE_OUT], (unsigned)__popc(live));
-        if (ok) atomicAdd(&s_cnt[CNT_VALID_OUT], (unsigned)__popc(ok));
-        if (st) atomicOr(s_status, st);
-    }
+    const unsigned lane = threadIdx.x & 31u;
+    unsigned add = ra & 0xffffu;                                  // lane CNT_INTERACTIONS (0)
+    add = lane == CNT_CHILDREN ? rb >> 16 : add;
+    add = lane == CNT_HITS ? ra >> 16 : add;
+    add = lane == CNT_MISSED ? rb & 0xffffu : add;
+    add = lane == CNT_APODIZED ? rp : add;
+    add = lane == CNT_VALID_OUT ? (unsigned)__popc(ok) : add;
+    add = lane == CNT_ALIVE_OUT ? (unsigned)__popc(live) : add;
+    if (lane < (unsigned)CNT_N) s_cnt[(threadIdx.x >> 5) * kCntStride + lane] += add;
+    if (lane0 && st) atomicOr(s_status, st);
 }
 
 // CTA totals -> global statistics (call after __syncthreads())
 __device__ __forceinline__ void cta_flush(DevStats* stats, const cta_count_t* s_cnt, unsigned s_status, unsigned long long s_first_inv) {
-    if (threadIdx.x < CNT_N && s_cnt[threadIdx.x]) {
-        unsigned long long* dst[CNT_N] = {&stats->interactions, &stats->children, &stats->hits, &stats->missed,
-                                          &stats->apodized, &stats->valid_out, &stats->alive_out};
-        atomicAdd(dst[threadIdx.x], (unsigned long long)s_cnt[threadIdx.x]);
-        if (threadIdx.x == CNT_INTERACTIONS) atomicAdd(&stats->total_interactions, (unsigned long long)s_cnt[threadIdx.x]);
+    if (threadIdx.x < CNT_N) {
+        unsigned long long total = 0;
+        for (int w = 0; w < 32; ++w) total += s_cnt[w * kCntStride + threadIdx.x];
+        if (total) {
+            // DevStats starts with the counters in the order interactions, children, hits, missed, apodized, valid_out, alive_out = CNT_*
+            atomicAdd(&stats->interactions + threadIdx.x, total);
+            if (threadIdx.x == CNT_INTERACTIONS) atomicAdd(&stats->total_interactions, total);
+        }
     }
     if (threadIdx.x == 0 && s_status) { atomicOr(&stats->status_bits, s_status); atomicOr(&stats->sticky_bits, s_status); }
     if (threadIdx.x == 0 && s_first_inv) atomicMax(&stats->first_inv, s_first_inv);
