@@ -327,6 +327,12 @@ void opm_rays_destroy(OpmRays* rays);
 uint64_t opm_rays_len(const OpmRays* rays);        /* slots in use (includes invalid and removed rays) */
 /* opm_rays_len of several bundles that asynchronous launches appended children to, with one synchronisation for all of them */
 OpmStatus opm_rays_refresh_lens(OpmRays* const* list, int32_t n);
+/* The same without any synchronisation, for an EMPTY bundle that ONE launch emits children into (OPM_REFRACT_EMIT_CHILDREN): call
+ * before that launch.  The launch then writes the reflected child of the ray in slot i to slot i of this bundle and marks the
+ * slots without a child as removed rays -- which every consumer skips, like the rays a mirror drops -- so the bundle's extent is
+ * the launch's (opm_rays_len, known at once), the children keep their parents' order (the reference's, rays.rs:1002-1030), and
+ * the host never reads a device counter.  n_slots: capacity to reserve (the parent bundle's length). */
+OpmStatus opm_rays_expect_appends(OpmRays* rays, uint64_t n_slots);
 uint64_t opm_rays_capacity(const OpmRays* rays);
 OpmStatus opm_rays_clear(OpmRays* rays);
 /* Tells the library that (nearly) every ray of the bundle carries `wavelength_m` -- what a one-wavelength source produces
@@ -469,6 +475,14 @@ OpmStatus opm_fluence_binning(OpmHitMap* const* maps, int32_t n_maps, int64_t bo
 OpmStatus opm_fluence_peak_check_acc_init(OpmContext* ctx, void* acc_dev, uint64_t n);
 OpmStatus opm_fluence_peak_check_async(OpmHitMap* const* maps, int32_t n_maps, int64_t bounce_filter, uint64_t nx, uint64_t ny,
                                        void* acc_dev, double* map_dev, double* result_dev);
+/* The same check on the context's SIDE stream: ordered behind everything issued so far, concurrent with what the context is given
+ * afterwards (the next bundle's trace launch), so a chain of trace -> check -> trace -> check keeps only the traces on the
+ * critical path.  With OPM_BOUNCE_OF_LAST_LAUNCH the check takes its own copy of the launch statistic along (result_dev[7]).
+ * acc_dev and map_dev must be used by side-stream checks only (they run one after the other).  opm_context_join_side_stream orders
+ * the main stream behind the checks issued so far (before result_dev is read); opm_context_synchronize waits for both streams. */
+OpmStatus opm_fluence_peak_check_side_async(OpmHitMap* const* maps, int32_t n_maps, int64_t bounce_filter, uint64_t nx, uint64_t ny,
+                                            void* acc_dev, double* map_dev, double* result_dev);
+OpmStatus opm_context_join_side_stream(OpmContext* ctx);
 OpmStatus opm_hitmaps_bounding_box_async(OpmHitMap* const* maps, int32_t n_maps, int64_t bounce_filter_or_minus1, double* range_dev);
 OpmStatus opm_fluence_binning_async(OpmHitMap* const* maps, int32_t n_maps, int64_t bounce_filter_or_minus1, uint64_t nx, uint64_t ny,
                                     const double* range_dev, int32_t accumulate, double* map_dev, uint32_t* status_dev);

@@ -232,8 +232,8 @@ EXPORTS = [
     "opm_rays_wavefront_error", "opm_readout_combine_ranges_sums", "opm_readout_combine_maps_radii", "opm_peer_group_create", "opm_peer_group_connect", "opm_peer_group_destroy",
     "opm_peer_allgather_async", "opm_peer_fluence_report_async", "opm_peer_fluence_gather_map", "opm_peer_group_phase_times", "opm_measure_fp64_peak", "opm_device_alloc",
     "opm_device_free", "opm_device_memset", "opm_device_to_host", "opm_host_to_device", "opm_host_alloc_pinned", "opm_host_free_pinned",
-    "opm_spectrum_gaussian", "opm_source_generate", "opm_source_generate_strided", "opm_source_energy_norm", "opm_rays_new_collimated_xy", "opm_rays_refresh_lens", "opm_context_interactions_total",
-    "opm_context_last_first_valid_key_async", "opm_fluence_peak_check_acc_init", "opm_fluence_peak_check_async", "opm_fluence_voronoi", "opm_hitmap_bounce_levels",
+    "opm_spectrum_gaussian", "opm_source_generate", "opm_source_generate_strided", "opm_source_energy_norm", "opm_rays_new_collimated_xy", "opm_rays_refresh_lens", "opm_rays_expect_appends", "opm_context_interactions_total",
+    "opm_context_last_first_valid_key_async", "opm_fluence_peak_check_acc_init", "opm_fluence_peak_check_async", "opm_fluence_peak_check_side_async", "opm_context_join_side_stream", "opm_fluence_voronoi", "opm_hitmap_bounce_levels",
 ]
 
 _lib = None

@@ -62,6 +62,11 @@ struct OpmContext {
     // straight-line code together and share its instruction-cache lines.
     int jit_block = 1024, jit_min_ctas = 1;
     cudaStream_t copy_stream = nullptr;  // host uploads that are expanded on the device run here, overlapping the main stream
+    // side computations nobody waits for until opm_context_join_side_stream / opm_context_synchronize (the ghost-focus analysis'
+    // per-bundle fluence checks): created on first use
+    cudaStream_t side_stream = nullptr;
+    cudaEvent_t side_ev = nullptr;
+    bool side_busy = false;
     // optional per-launch timing of the fused trace kernel (CUDA events on the launching stream)
     bool timing = false;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timing_events;
@@ -103,6 +108,10 @@ struct OpmRays {
     uint64_t hist_stride = 0;
     // phase-1 accumulators of the spot statistics (SpotAccum, 128 bytes behind the tail counter).  spot_acc_valid: the launch that
     // wrote this bundle as an OPM_OP_SNAPSHOT copy also took the sums (specialised kernel), in the frame spot_inv (spot_has_frame)
+    // opm_rays_expect_appends: the extent a launch that appends to this bundle leaves it with (slots it does not fill are removed
+    // rays); 0 = none expected, the device tail counter decides (len_dirty)
+    uint64_t expected_len = 0;
+    bool sealed = false;  // took its appends under opm_rays_expect_appends: the device counter no longer describes it
     SpotAccum* d_spot_acc = nullptr;
     bool spot_acc_valid = false, spot_has_frame = false;
     DevIso spot_inv{};
@@ -272,6 +281,7 @@ extern "C" void opm_context_destroy(OpmContext* c) {
     for (auto* v : {&c->timing_events, &c->timing_free})
         for (auto& p : *v) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
     if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }
+    if (c->side_stream) { cudaStreamSynchronize(c->side_stream); cudaStreamDestroy(c->side_stream); cudaEventDestroy(c->side_ev); }
     jit_cache_destroy(c->jit);
     for (int k = 0; k < OpmContext::kPutSlots; ++k) if (c->put_ev[k]) cudaEventDestroy(c->put_ev[k]);
     cudaFreeHost(c->h_put_ring);
@@ -296,6 +306,7 @@ extern "C" OpmStatus opm_context_check_errors(OpmContext* c, int32_t clear) {
 extern "C" OpmStatus opm_context_synchronize(OpmContext* c) {
     if (!c) return fail(OPM_ERR_ARG, "context is NULL");
     CU(cudaSetDevice(c->device));
+    if (c->side_busy) { CU(cudaStreamSynchronize(c->side_stream)); c->side_busy = false; }
     CU(cudaStreamSynchronize(c->stream));
     return opm_context_check_errors(c, 1);
 }
@@ -597,6 +608,18 @@ extern "C" OpmStatus opm_rays_refresh_lens(OpmRays* const* list, int32_t n) {
     }
     return OPM_OK;
 }
+extern "C" OpmStatus opm_rays_expect_appends(OpmRays* r, uint64_t n_slots) {
+    if (!r) return fail(OPM_ERR_ARG, "NULL argument");
+    OpmContext* c = r->ctx;
+    CU(cudaSetDevice(c->device));
+    if (r->pending) { OpmStatus s = rays_materialize(r); if (s) return s; }
+    if (r->len != 0 || r->len_dirty) return fail(OPM_ERR_ARG, "opm_rays_expect_appends needs an empty bundle");
+    OpmStatus s = opm_rays_reserve(r, n_slots ? n_slots : 1);
+    if (s) return s;
+    r->expected_len = n_slots ? n_slots : 1;
+    r->spot_acc_valid = false;
+    return OPM_OK;
+}
 extern "C" uint64_t opm_rays_len(const OpmRays* r) {
     if (!r) return 0;
     rays_refresh_len(const_cast<OpmRays*>(r));
@@ -610,7 +633,7 @@ extern "C" OpmStatus opm_rays_set_wavelength_hint(OpmRays* r, double wavelength)
 }
 extern "C" OpmStatus opm_rays_clear(OpmRays* r) {
     if (!r) return fail(OPM_ERR_ARG, "rays is NULL");
-    r->len = 0; r->len_dirty = false; r->pending = false; r->mono_wvl = 0.0; r->spot_acc_valid = false;
+    r->len = 0; r->len_dirty = false; r->pending = false; r->mono_wvl = 0.0; r->spot_acc_valid = false; r->expected_len = 0; r->sealed = false;
     if (r->d_hist) { OpmStatus hs = hist_clear(r); if (hs) return hs; }  // new rays start without a history (ray.rs:126)
     CU(cudaMemsetAsync(r->d_tail, 0, 8, r->ctx->stream));
     return OPM_OK;
@@ -1144,7 +1167,7 @@ static OpmStatus compile_ops(OpmContext* c, const OpmOp* ops, int n_ops, uint64_
                 o.inv_abs_param = r.surface.geom != OPM_GEOM_PLANE ? 1.0 / std::fabs(r.surface.geom_param) : 0.0;
                 to_dev_iso(r.surface.iso.fwd, o.fwd); to_dev_iso(r.surface.iso.inv, o.inv);
                 o.has_index = r.has_index ? 1 : 0; o.refraction_intended = r.refraction_intended ? 1 : 0;
-                o.strategy = r.strategy; o.flags = r.flags; o.index_type = r.index.type;
+                o.strategy = r.strategy; o.flags = r.flags & 0xffff; o.index_type = r.index.type;
                 memcpy(o.ic, r.index.c, sizeof o.ic); o.wlo = r.index.wvl_lo; o.whi = r.index.wvl_hi;
                 if (r.hits) {
                     if (r.hits->cap < n_rays) return fail(OPM_ERR_CAPACITY, "hit map capacity %llu < %llu rays", (unsigned long long)r.hits->cap, (unsigned long long)n_rays);
@@ -1154,11 +1177,17 @@ static OpmStatus compile_ops(OpmContext* c, const OpmOp* ops, int n_ops, uint64_
                 }
                 if (r.flags & OPM_REFRACT_EMIT_CHILDREN) {
                     if (!r.children) return fail(OPM_ERR_ARG, "OPM_REFRACT_EMIT_CHILDREN without a children bundle");
+                    if (r.children->sealed) return fail(OPM_ERR_ARG, "the children bundle took its appends under opm_rays_expect_appends: clear it first");
                     OpmStatus s = rays_refresh_len(r.children);
                     if (s) return s;
                     s = opm_rays_reserve(r.children, r.children->len + n_rays);
                     if (s) return s;
                     o.children = r.children->v; o.child_tail = r.children->d_tail; o.child_cap = r.children->cap;
+                    if (r.children->expected_len) {  // opm_rays_expect_appends: child of slot i -> slot i, the extent is this launch's
+                        if (r.children->len != 0) return fail(OPM_ERR_ARG, "opm_rays_expect_appends needs an empty children bundle");
+                        o.flags |= kRefractChildrenBySlot;
+                        r.children->expected_len = n_rays ? n_rays : 1;
+                    }
                     out.appended.push_back(r.children);
                 }
                 break;
@@ -1292,6 +1321,7 @@ static OpmStatus compile_ops(OpmContext* c, const OpmOp* ops, int n_ops, uint64_
                     if (s) return s;
                     s = opm_rays_reserve(g.children, g.children->len + n_rays);
                     if (s) return s;
+                    if (g.children->expected_len || g.children->sealed) return fail(OPM_ERR_ARG, "opm_rays_expect_appends is for OPM_OP_REFRACT children");
                     o.surf.children = g.children->v; o.surf.child_tail = g.children->d_tail; o.surf.child_cap = g.children->cap;
                     out.appended.push_back(g.children);
                 }
@@ -1500,7 +1530,9 @@ static OpmStatus run_program(OpmRays* rays, const OpmOp* ops, int n_ops, int fla
     }
     for (OpmRays* r : prog.appended) {  // children carry their parents' wavelengths
         if (r->len == 0 && !r->len_dirty) r->mono_wvl = rays->mono_wvl; else if (r->mono_wvl != rays->mono_wvl) r->mono_wvl = 0.0; r->spot_acc_valid = false;
-        r->len_dirty = true;
+        if (r->expected_len) {  // opm_rays_expect_appends: the extent is known, unfilled slots are removed rays -- no read-back, ever
+            r->len = r->expected_len; r->expected_len = 0; r->len_dirty = false; r->sealed = true;
+        } else r->len_dirty = true;
     }
     if (dst != rays) dst->mono_wvl = rays->mono_wvl;
     if (compact) dst->len_dirty = true;
@@ -1513,7 +1545,7 @@ static OpmStatus run_program(OpmRays* rays, const OpmOp* ops, int n_ops, int fla
         cudaError_t e = cudaStreamSynchronize(c->stream);
         free_temps();
         if (e != cudaSuccess) return fail(OPM_ERR_CUDA, "kernel execution failed: %s", cudaGetErrorString(e));
-        for (OpmRays* r : prog.appended) { s = rays_refresh_len(r); if (s) return s; }
+        for (OpmRays* r : prog.appended) if (r->len_dirty) { s = rays_refresh_len(r); if (s) return s; }
         if (compact) { s = rays_refresh_len(dst); if (s) return s; }
         if (stats) {
             stats_to_public(*c->h_stats, stats);
@@ -2252,8 +2284,27 @@ extern "C" OpmStatus opm_fluence_peak_check_acc_init(OpmContext* c, void* acc_de
     if (n) { KL(k_peakcheck_acc_init((PeakCheckAcc*)acc_dev, n, c->stream)); c->launches++; }
     return OPM_OK;
 }
+static OpmStatus peak_check_impl(OpmHitMap* const* maps, int32_t n_maps, int64_t bounce_filter, uint64_t nx, uint64_t ny, void* acc_dev,
+                                 double* map_dev, double* result_dev, bool side);
 extern "C" OpmStatus opm_fluence_peak_check_async(OpmHitMap* const* maps, int32_t n_maps, int64_t bounce_filter, uint64_t nx, uint64_t ny,
                                                   void* acc_dev, double* map_dev, double* result_dev) {
+    return peak_check_impl(maps, n_maps, bounce_filter, nx, ny, acc_dev, map_dev, result_dev, false);
+}
+extern "C" OpmStatus opm_fluence_peak_check_side_async(OpmHitMap* const* maps, int32_t n_maps, int64_t bounce_filter, uint64_t nx, uint64_t ny,
+                                                       void* acc_dev, double* map_dev, double* result_dev) {
+    return peak_check_impl(maps, n_maps, bounce_filter, nx, ny, acc_dev, map_dev, result_dev, true);
+}
+extern "C" OpmStatus opm_context_join_side_stream(OpmContext* c) {
+    if (!c) return fail(OPM_ERR_ARG, "context is NULL");
+    if (!c->side_busy) return OPM_OK;
+    CU(cudaSetDevice(c->device));
+    CU(cudaEventRecord(c->side_ev, c->side_stream));
+    CU(cudaStreamWaitEvent(c->stream, c->side_ev, 0));
+    c->side_busy = false;
+    return OPM_OK;
+}
+static OpmStatus peak_check_impl(OpmHitMap* const* maps, int32_t n_maps, int64_t bounce_filter, uint64_t nx, uint64_t ny, void* acc_dev,
+                                 double* map_dev, double* result_dev, bool side) {
     OpmContext* c;
     OpmStatus s = check_same_ctx(maps, n_maps, &c);
     if (s) return s;
@@ -2261,8 +2312,23 @@ extern "C" OpmStatus opm_fluence_peak_check_async(OpmHitMap* const* maps, int32_
         return fail(OPM_ERR_ARG, "peak check: bad arguments (maps up to 160 KB)");
     CU(cudaSetDevice(c->device));
     const unsigned long long* key_src = nullptr;
-    if (bounce_filter == OPM_BOUNCE_OF_LAST_LAUNCH) { key_src = &c->d_stats->first_inv; bounce_filter = -(int64_t)(uintptr_t)key_src; }
-    else if (bounce_filter < -1) return fail(OPM_ERR_ARG, "bad bounce filter");
+    if (bounce_filter == OPM_BOUNCE_OF_LAST_LAUNCH) {
+        key_src = &c->d_stats->first_inv;
+        if (side) {  // the next trace launch resets the statistic: the check takes its own copy along (the result slot's key word)
+            unsigned long long* own = reinterpret_cast<unsigned long long*>(result_dev) + 7;
+            CU(cudaMemcpyAsync(own, key_src, 8, cudaMemcpyDeviceToDevice, c->stream));
+            key_src = own;
+        }
+        bounce_filter = -(int64_t)(uintptr_t)key_src;
+    } else if (bounce_filter < -1) return fail(OPM_ERR_ARG, "bad bounce filter");
+    cudaStream_t st = c->stream;
+    if (side) {  // behind everything the main stream holds so far, beside what it gets from now on
+        if (!c->side_stream) { CU(cudaStreamCreateWithFlags(&c->side_stream, cudaStreamNonBlocking)); CU(cudaEventCreateWithFlags(&c->side_ev, cudaEventDisableTiming)); }
+        CU(cudaEventRecord(c->side_ev, c->stream));
+        CU(cudaStreamWaitEvent(c->side_stream, c->side_ev, 0));
+        st = c->side_stream;
+        c->side_busy = true;
+    }
     int last = -1;
     for (int k = 0; k < n_maps; ++k) if (maps[k]->len) last = k;
     bool first = true;
@@ -2270,13 +2336,13 @@ extern "C" OpmStatus opm_fluence_peak_check_async(OpmHitMap* const* maps, int32_
         if (!maps[k]->len && !(last < 0 && k == n_maps - 1)) continue;
         // (a check without any recorded slot still runs one launch: it zero-fills the map and writes the empty range)
         KL(k_peakcheck_bbox(maps[k]->v, maps[k]->len, bounce_filter, (PeakCheckAcc*)acc_dev, result_dev, map_dev, nx * ny, first ? 1 : 0,
-                            (k == last || last < 0) ? 1 : 0, c->sms, c->stream));
+                            (k == last || last < 0) ? 1 : 0, c->sms, st));
         c->launches++;
         first = false;
     }
     for (int k = 0; k < n_maps; ++k)
-        if (maps[k]->len) { KL(k_binning(maps[k]->v, maps[k]->len, bounce_filter, nx, ny, result_dev, map_dev, (unsigned*)(result_dev + 6), c->sms, c->stream)); c->launches++; }
-    KL(k_peakcheck_peak(map_dev, nx, ny, key_src, result_dev, c->stream)); c->launches++;
+        if (maps[k]->len) { KL(k_binning(maps[k]->v, maps[k]->len, bounce_filter, nx, ny, result_dev, map_dev, (unsigned*)(result_dev + 6), c->sms, st)); c->launches++; }
+    KL(k_peakcheck_peak(map_dev, nx, ny, key_src, result_dev, st)); c->launches++;
     return OPM_OK;
 }
 extern "C" OpmStatus opm_fluence_peak_total_async(OpmContext* c, const double* map_dev, uint64_t nx, uint64_t ny, const double* range_dev,

@@ -35,6 +35,10 @@ struct DevAperture {
     const double* tris;  // device
 };
 
+// internal bit of DevRefract::flags (the public OPM_REFRACT_* flags use the low bits): the reflected child of the ray in slot i
+// goes to slot i of the children bundle, slots without a child become removed rays -- no append counter, no ordering left to
+// the scheduler (opm_rays_expect_appends)
+constexpr int32_t kRefractChildrenBySlot = 1 << 16;
 enum : int32_t { OPK_REFRACT = 1, OPK_APODIZE, OPK_THRESHOLD, OPK_LIMITS, OPK_FILTER, OPK_PARAXIAL, OPK_SPLIT, OPK_SNAPSHOT, OPK_TRANSFORM,
                  OPK_DIFFRACT, OPK_FORK, OPK_JOIN };
 

@@ -3,7 +3,10 @@
 // Pure host bookkeeping, O(#nodes): it compiles optic nodes into surface descriptors and `Rays` op programs
 // and drives them through the public C ABI (opossum_b200.h) exactly as a Rust host would through FFI.  No ray
 // arithmetic happens here.  Reference file:line citations are relative to opossum/src/.
+#include <chrono>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <memory>

@@ -133,7 +133,15 @@ __device__ __forceinline__ void exec_epilogue(const E& e, const DevOp& op, RayCt
 template <class V>
 __device__ __forceinline__ void finish_children(const V& v, const RefractResult& res, RayCtx& x) {
     const DevRefract& o = v.d();
-    if (v.flags() & OPM_REFRACT_EMIT_CHILDREN) {
+    if ((v.flags() & OPM_REFRACT_EMIT_CHILDREN) && (v.flags() & kRefractChildrenBySlot)) {
+        if (x.in_range) {
+            if (res.has_child || x.warp_live) {  // whole sectors: a slot without a child is a removed ray
+                RayState child = x.r;
+                if (res.has_child) { child_into(res, child); x.c.b += 1u << 16; }
+                store_ray<true>(o.children, x.i, child, res.has_child ? RAY_VALID : RAY_REMOVED);
+            } else o.children.valid[x.i] = RAY_REMOVED;
+        }
+    } else if (v.flags() & OPM_REFRACT_EMIT_CHILDREN) {
         unsigned long long slot = warp_reserve(res.has_child, o.child_tail);
         if (res.has_child) {
             if (slot < o.child_cap) {
