@@ -207,9 +207,51 @@ def bind_to_gpu_numa_node(local: int) -> str:
         if node >= 0 and ids:
             os.sched_setaffinity(0, ids)
             return f"numa node {node} ({len(ids)} cpus)"
-        return "no numa information"
+        return _bind_by_topo(local)
     except Exception as e:  # noqa: BLE001
         return f"not bound ({type(e).__name__})"
+
+
+def _bind_by_topo(local: int) -> str:
+    """sysfs has no numa_node in this container: take the GPU's "CPU Affinity" column of `nvidia-smi topo -m`"""
+    import subprocess
+    try:
+        out = subprocess.run(["nvidia-smi", "topo", "-m"], capture_output=True, text=True, timeout=20).stdout
+    except Exception:  # noqa: BLE001
+        return "no numa information"
+    import re
+    out = re.sub(r"\x1b\[[0-9;]*m", "", out)
+    lines = [ln for ln in out.splitlines() if ln.strip()]
+    if not lines:
+        return "no numa information"
+    header = [h.strip() for h in lines[0].split("\t")]
+    if "CPU Affinity" not in header:
+        return "no numa information"
+    col = header.index("CPU Affinity")
+    visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+    phys = local
+    if visible:
+        try:
+            phys = int(visible.split(",")[local])
+        except (ValueError, IndexError):
+            phys = local
+    for ln in lines[1:]:
+        cells = [c.strip() for c in ln.split("\t")]
+        if cells and cells[0] == f"GPU{phys}" and len(cells) > col:
+            ids = set()
+            try:
+                for part in cells[col].split(","):
+                    a, _, b = part.partition("-")
+                    ids.update(range(int(a), int(b or a) + 1))
+            except ValueError:
+                return "no numa information"
+            allowed = os.sched_getaffinity(0)
+            if ids and len(ids & allowed) and len(ids) < len(allowed):
+                os.sched_setaffinity(0, ids & allowed)
+                numa = cells[col + 1] if len(cells) > col + 1 else "?"
+                return f"nvidia-smi topo: cpus {cells[col]} (numa {numa})"
+            return f"nvidia-smi topo: one affinity domain ({cells[col]}), nothing to bind"
+    return "no numa information"
 
 
 def parity_vs_oracle(ctx, n, cores, kept):
