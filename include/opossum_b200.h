@@ -334,6 +334,21 @@ OpmStatus opm_rays_refresh_lens(OpmRays* const* list, int32_t n);
  * the host never reads a device counter.  n_slots: capacity to reserve (the parent bundle's length). */
 OpmStatus opm_rays_expect_appends(OpmRays* rays, uint64_t n_slots);
 uint64_t opm_rays_capacity(const OpmRays* rays);
+/* Fluence helper rays (FluenceRays, rays.rs:1470-1567; Ray::new_collimated_w_fluence_helper, ray.rs:157-166): every ray of the bundle
+ * gets three satellite rays on a triangle of area wavelength^2 around it and the effective energy init_fluence * wavelength^2
+ * (init_fluence_J_per_m2: HOST array of opm_rays_len values, finite and not negative).  From then on opm_trace_sequence and the
+ * single-op calls carry them along: a refraction records the FLUENCE of the helper triangle as it is BEFORE the helpers reach the
+ * surface in the hit map (a FluenceHitPoint, ray.rs:655-669) instead of the ray's energy, scales the effective energy by 1 - R
+ * (by R on the reflected ray a mirror keeps, whose helpers stay where they were and only take their reflected directions,
+ * rays.rs:996-1010), then refracts the helpers of every ray that was not missed or totally reflected; a paraxial surface
+ * refracts the valid helpers of every ray (rays.rs:953-955).  Hit maps written this way are read with opm_fluence_helper_rays.
+ * Bundles with helpers run the interpreter kernel; they cannot be compacted, keep a position history, emit children, be
+ * diffracted or be split inside a fused program (opm_rays_copy clones the helpers, like Rays::clone).
+ * opm_rays_download_fluence_helpers: 22 doubles per ray in the order of opm_rays_download -- helper positions [3][3], helper
+ * directions [3][3], the helpers' refractive indices [3] (negative: that helper was set invalid), the effective energy. */
+OpmStatus opm_rays_attach_fluence_helpers(OpmRays* rays, const double* init_fluence_J_per_m2);
+int32_t opm_rays_has_fluence_helpers(const OpmRays* rays);
+OpmStatus opm_rays_download_fluence_helpers(const OpmRays* rays, double* out, uint64_t capacity_rays, uint64_t* n_out);
 OpmStatus opm_rays_clear(OpmRays* rays);
 /* Tells the library that (nearly) every ray of the bundle carries `wavelength_m` -- what a one-wavelength source produces
  * (opm_source_generate and opm_rays_new_collimated_with_spectrum set it themselves; copies, split-off bundles and children
@@ -503,6 +518,13 @@ OpmStatus opm_fluence_kde(OpmHitMap* const* maps, int32_t n_maps, int64_t bounce
  * J/m^2.  ranges: NULL (the hits' limits) or {ax1.start, ax1.end, ax2.start, ax2.end} in metres.  accumulate != 0 adds to
  * map_dev, which is how HitMap::calc_combined_fluence_with_voronoi (hit_map/mod.rs:232-262) sums the estimates of the rays hit
  * maps of one surface on their common bounding box.  Synchronous. */
+/* RaysHitMap::calc_fluence_with_helper_rays (rays_hit_map.rs:627-722) of ONE rays hit map whose records carry fluences (written by
+ * the trace of a bundle with fluence helper rays): natural-neighbour interpolation of the recorded fluences, with voronator's four
+ * helper sites around the bounding polygon at the value 0 (:700-701), onto nx x nx points; arguments as opm_fluence_voronoi.
+ * HitMap::calc_combined_fluence_with_helper_rays (hit_map/mod.rs:283-310) is the sum over the rays hit maps of a surface on their
+ * common bounding box (accumulate != 0). */
+OpmStatus opm_fluence_helper_rays(OpmHitMap* const* maps, int32_t n_maps, int64_t bounce_filter_or_minus1, uint64_t nx,
+                                  const double* ranges_or_null, int32_t accumulate, double* map_dev, double lrtb_out[4]);
 OpmStatus opm_fluence_voronoi(OpmHitMap* const* maps, int32_t n_maps, int64_t bounce_filter_or_minus1, uint64_t nx,
                               const double* ranges_or_null, int32_t accumulate, double* map_dev, double lrtb_out[4]);
 /* bit b of *mask is set when a recorded hit of the map has bounce count b (b < 64): the rays hit maps a slot-indexed hit map holds

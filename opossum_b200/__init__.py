@@ -7,11 +7,11 @@ of include/opossum_b200.h).  There is no CPU implementation: importing works any
 from . import _ffi as ffi  # noqa: F401
 from .api import (Aperture, Context, FluenceData, HitMap, Isometry, OpossumError, OpticSurface, Program, RAY_DTYPE,  # noqa: F401
                   RayTraceConfig, Rays, RefractiveIndex, SourceDesc, TraceStats, fluence_binning, fluence_kde, fluence_peak_total,
-                  fluence_voronoi, fluence_voronoi_combined, hitmap_bounce_levels, hitmaps_bounding_box, refr_index_vaccuum, spectrum_gaussian, Spectrum, spectrum_total_energy,
+                  fluence_voronoi, fluence_voronoi_combined, fluence_helper_rays, hitmap_bounce_levels, hitmaps_bounding_box, refr_index_vaccuum, spectrum_gaussian, Spectrum, spectrum_total_energy,
                   spectrum_center_wavelength, spectrum_get_value)
 
 __all__ = ["Aperture", "Context", "FluenceData", "HitMap", "Isometry", "OpossumError", "OpticSurface", "Program",
            "RAY_DTYPE", "RayTraceConfig", "Rays", "RefractiveIndex", "SourceDesc", "TraceStats", "fluence_binning",
-           "fluence_kde", "fluence_peak_total", "fluence_voronoi", "fluence_voronoi_combined", "hitmap_bounce_levels", "hitmaps_bounding_box", "refr_index_vaccuum", "spectrum_gaussian", "Spectrum",
+           "fluence_kde", "fluence_peak_total", "fluence_voronoi", "fluence_voronoi_combined", "fluence_helper_rays", "hitmap_bounce_levels", "hitmaps_bounding_box", "refr_index_vaccuum", "spectrum_gaussian", "Spectrum",
            "spectrum_total_energy", "spectrum_center_wavelength", "spectrum_get_value", "ffi"]
 from .opm_document import OpmDocument, OpmDocumentError, load_opm, loads_opm  # noqa: E402,F401  (.opm scene files)

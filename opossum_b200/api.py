@@ -488,6 +488,28 @@ class Rays:
     def __len__(self):
         return F.lib().opm_rays_len(self.h)
 
+    def attach_fluence_helpers(self, init_fluence) -> "Rays":
+        """FluenceRays::new for every ray (rays.rs:1477-1516): three helper rays around it, effective energy = fluence * wavelength^2.
+        init_fluence: J/m^2, one value per ray (or a scalar)."""
+        fl = np.ascontiguousarray(np.broadcast_to(np.asarray(init_fluence, dtype=np.float64), (len(self),)))
+        _check(F.lib().opm_rays_attach_fluence_helpers(self.h, fl.ctypes.data_as(C.POINTER(C.c_double))))
+        return self
+
+    @property
+    def has_fluence_helpers(self) -> bool:
+        return bool(F.lib().opm_rays_has_fluence_helpers(self.h))
+
+    def fluence_helpers(self) -> dict:
+        """the FluenceRays of every ray in the order of to_array(): pos (n, 3, 3), dir (n, 3, 3), n (n, 3; negative = that helper is
+        invalid), eff (n,)"""
+        n = max(len(self), 1)
+        out = np.zeros((n, 22))
+        k = C.c_uint64()
+        _check(F.lib().opm_rays_download_fluence_helpers(self.h, out.ctypes.data_as(C.POINTER(C.c_double)), n, C.byref(k)))
+        out = out[: k.value]
+        return {"pos": out[:, 0:9].reshape(-1, 3, 3).copy(), "dir": out[:, 9:18].reshape(-1, 3, 3).copy(), "n": out[:, 18:21].copy(),
+                "eff": out[:, 21].copy()}
+
     def clone(self) -> "Rays":
         r = Rays(self.ctx, max(len(self), 1))
         _check(F.lib().opm_rays_copy(self.h, r.h))
@@ -913,6 +935,28 @@ def fluence_voronoi(ctx: Context, hit_maps, nx: int, ranges=None, bounce=-1, map
         rg = (C.c_double * 4)(*ranges) if ranges is not None else None
         out = (C.c_double * 4)()
         _check(L.opm_fluence_voronoi(arr, len(hit_maps), bounce, nx, rg, int(accumulate), C.c_void_p(map_dev), out))
+        peak, tot = C.c_double(), C.c_double()
+        _check(L.opm_fluence_peak_total(ctx.h, C.c_void_p(map_dev), nx, nx, out, C.byref(peak), C.byref(tot)))
+        flat = np.zeros(nx * nx)
+        ctx.to_host(map_dev, flat)
+        return FluenceData(flat.reshape(nx, nx).T.copy(), tuple(out[:]), peak.value, tot.value)
+    finally:
+        if own:
+            ctx.device_free(map_dev)
+
+
+def fluence_helper_rays(ctx: Context, hit_maps, nx: int, ranges=None, bounce=-1, map_dev: int | None = None, accumulate=False) -> FluenceData:
+    """RaysHitMap::calc_fluence_with_helper_rays (rays_hit_map.rs:627-722) of ONE rays hit map whose records carry fluences (the
+    trace of a bundle with fluence helper rays wrote them); arguments as fluence_voronoi."""
+    L = F.lib()
+    own = map_dev is None
+    if own:
+        map_dev = ctx.device_alloc(nx * nx * 8)
+    try:
+        arr = (C.c_void_p * len(hit_maps))(*[h.h for h in hit_maps])
+        rg = (C.c_double * 4)(*ranges) if ranges is not None else None
+        out = (C.c_double * 4)()
+        _check(L.opm_fluence_helper_rays(arr, len(hit_maps), bounce, nx, rg, int(accumulate), C.c_void_p(map_dev), out))
         peak, tot = C.c_double(), C.c_double()
         _check(L.opm_fluence_peak_total(ctx.h, C.c_void_p(map_dev), nx, nx, out, C.byref(peak), C.byref(tot)))
         flat = np.zeros(nx * nx)

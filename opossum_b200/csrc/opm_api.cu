@@ -110,6 +110,9 @@ struct OpmRays {
     // wrote this bundle as an OPM_OP_SNAPSHOT copy also took the sums (specialised kernel), in the frame spot_inv (spot_has_frame)
     // opm_rays_expect_appends: the extent a launch that appends to this bundle leaves it with (slots it does not fill are removed
     // rays); 0 = none expected, the device tail counter decides (len_dirty)
+    // fluence helper rays (FluenceRays, rays.rs:1470-1567): kHelperFields arrays of helper_stride doubles, see HelperParams; NULL: none
+    double* d_helpers = nullptr;
+    uint64_t helper_stride = 0;
     uint64_t expected_len = 0;
     bool sealed = false;  // took its appends under opm_rays_expect_appends: the device counter no longer describes it
     SpotAccum* d_spot_acc = nullptr;
@@ -540,6 +543,7 @@ extern "C" void opm_rays_destroy(OpmRays* r) {
     cudaStreamSynchronize(r->ctx->stream);
     cudaFree(r->base);
     cudaFree(r->d_hist);
+    cudaFree(r->d_helpers);
     cudaFree(r->d_stage);
     cudaFreeHost(r->h_spec);
     if (r->ev_uploaded) cudaEventDestroy(r->ev_uploaded);
@@ -635,7 +639,75 @@ extern "C" OpmStatus opm_rays_clear(OpmRays* r) {
     if (!r) return fail(OPM_ERR_ARG, "rays is NULL");
     r->len = 0; r->len_dirty = false; r->pending = false; r->mono_wvl = 0.0; r->spot_acc_valid = false; r->expected_len = 0; r->sealed = false;
     if (r->d_hist) { OpmStatus hs = hist_clear(r); if (hs) return hs; }  // new rays start without a history (ray.rs:126)
+    if (r->d_helpers) { CU(cudaStreamSynchronize(r->ctx->stream)); cudaFree(r->d_helpers); r->d_helpers = nullptr; r->helper_stride = 0; }
     CU(cudaMemsetAsync(r->d_tail, 0, 8, r->ctx->stream));
+    return OPM_OK;
+}
+// ---- fluence helper rays ------------------------------------------------------------------------
+static OpmStatus helpers_alloc(OpmRays* r, uint64_t stride) {
+    if (stride < 1) stride = 1;
+    if (r->d_helpers && r->helper_stride >= stride) return OPM_OK;
+    if (r->d_helpers) { CU(cudaStreamSynchronize(r->ctx->stream)); cudaFree(r->d_helpers); r->d_helpers = nullptr; }
+    CU(cudaMalloc(&r->d_helpers, (size_t)kHelperFields * stride * sizeof(double)));
+    r->helper_stride = stride;
+    return OPM_OK;
+}
+static OpmStatus helpers_copy(const OpmRays* src, OpmRays* dst, uint64_t n) {
+    OpmStatus s = helpers_alloc(dst, n);
+    if (s) return s;
+    if (n) CU(cudaMemcpy2DAsync(dst->d_helpers, dst->helper_stride * 8, src->d_helpers, src->helper_stride * 8, n * 8, kHelperFields,
+                                cudaMemcpyDeviceToDevice, dst->ctx->stream));
+    return OPM_OK;
+}
+extern "C" OpmStatus opm_rays_attach_fluence_helpers(OpmRays* r, const double* init_fluence) {
+    if (!r || !init_fluence) return fail(OPM_ERR_ARG, "NULL argument");
+    OpmContext* c = r->ctx;
+    CU(cudaSetDevice(c->device));
+    OpmStatus s = rays_refresh_len(r);
+    if (s) return s;
+    const uint64_t n = r->len;
+    for (uint64_t i = 0; i < n; ++i)  // FluenceRays::new (rays.rs:1484-1488)
+        if (!std::isfinite(init_fluence[i]) || std::signbit(init_fluence[i]))
+            return fail(OPM_ERR_ARG, "Initial fluence of Fluence Rays must be non-negative and finite!");
+    s = helpers_alloc(r, n);
+    if (s) return s;
+    if (n == 0) return OPM_OK;
+    double* eff = r->d_helpers + 21 * r->helper_stride;  // the fluences travel in the slot of the effective energy they become
+    CU(cudaMemcpyAsync(eff, init_fluence, n * 8, cudaMemcpyHostToDevice, c->stream));
+    double cs[6];
+    for (int k = 0; k < 3; ++k) {  // rays.rs:1495-1499: usize_to_f64(i) * 2. / 3. * PI
+        const double a = (double)k * 2. / 3. * 3.14159265358979323846264338327950288;
+        cs[2 * k] = std::cos(a); cs[2 * k + 1] = std::sin(a);
+    }
+    KL(k_helpers_init(r->v, n, r->d_helpers, r->helper_stride, cs, c->sms, c->stream)); c->launches++;
+    CU(cudaStreamSynchronize(c->stream));  // init_fluence is the caller's (pageable) memory
+    return OPM_OK;
+}
+extern "C" int32_t opm_rays_has_fluence_helpers(const OpmRays* r) { return r && r->d_helpers ? 1 : 0; }
+extern "C" OpmStatus opm_rays_download_fluence_helpers(const OpmRays* rc, double* out, uint64_t capacity, uint64_t* n_out) {
+    OpmRays* r = const_cast<OpmRays*>(rc);
+    if (!r || !out || !n_out) return fail(OPM_ERR_ARG, "NULL argument");
+    if (!r->d_helpers) return fail(OPM_ERR_ARG, "the bundle carries no fluence helper rays (opm_rays_attach_fluence_helpers)");
+    OpmContext* c = r->ctx;
+    CU(cudaSetDevice(c->device));
+    OpmStatus s = rays_refresh_len(r);
+    if (s) return s;
+    const uint64_t n = r->len;
+    *n_out = 0;
+    if (n == 0) return OPM_OK;
+    std::vector<double> tmp((size_t)kHelperFields * n);
+    std::vector<uint8_t> valid(n);
+    CU(cudaMemcpy2DAsync(tmp.data(), n * 8, r->d_helpers, r->helper_stride * 8, n * 8, kHelperFields, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(valid.data(), r->v.valid, n, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    uint64_t k = 0;
+    for (uint64_t i = 0; i < n; ++i) {
+        if (valid[i] == RAY_REMOVED) continue;  // the order and the rays of opm_rays_download
+        if (k >= capacity) return fail(OPM_ERR_CAPACITY, "download buffer too small");
+        for (int f = 0; f < kHelperFields; ++f) out[k * kHelperFields + f] = tmp[(size_t)f * n + i];
+        ++k;
+    }
+    *n_out = k;
     return OPM_OK;
 }
 static OpmStatus copy_fields(const DevRays& s, uint64_t soff, const DevRays& d, uint64_t doff, uint64_t n, cudaStream_t st) {
@@ -967,6 +1039,8 @@ extern "C" OpmStatus opm_rays_copy(const OpmRays* src, OpmRays* dst) {
     if (s) return s;
     if (src->d_hist) { s = hist_copy(src, dst, src->hist_next, src->len); if (s) return s; }
     else if (dst->d_hist) { s = hist_clear(dst); if (s) return s; }
+    if (src->d_helpers) { s = helpers_copy(src, dst, src->len); if (s) return s; }  // Rays::clone clones the FluenceRays
+    else if (dst->d_helpers) { CU(cudaStreamSynchronize(dst->ctx->stream)); cudaFree(dst->d_helpers); dst->d_helpers = nullptr; dst->helper_stride = 0; }
     dst->mono_wvl = src->mono_wvl; dst->spot_acc_valid = false;
     return rays_set_len(dst, src->len);
 }
@@ -1379,6 +1453,25 @@ static OpmStatus run_program(OpmRays* rays, const OpmOp* ops, int n_ops, int fla
         s = opm_rays_reserve(dst, n);
         if (s) { free_temps(); return s; }
     }
+    // fluence helper rays: the interpreter variant that carries them through refractions and paraxial surfaces
+    HelperParams help{};
+    const bool use_helpers = rays->d_helpers != nullptr;
+    if (use_helpers) {
+        auto no = [&](const char* what) { free_temps(); return fail(OPM_ERR_ARG, "a bundle with fluence helper rays cannot %s", what); };
+        if (compact) return no("be compacted by a trace");
+        if (rays->d_hist || dst->d_hist) return no("keep a position history");
+        if (n > rays->helper_stride) return no("have grown since the helpers were attached");
+        for (const DevOp& d : prog.ops) {
+            if (d.kind == OPK_SPLIT || d.kind == OPK_FORK || d.kind == OPK_JOIN) return no("be split in a fused program (copy the bundle and use opm_rays_split)");
+            if (d.kind == OPK_DIFFRACT) return no("be diffracted (the reference moves no helper ray there)");
+            if (d.kind == OPK_REFRACT && d.u.refract.children.px) return no("emit reflected children");
+        }
+        if (dst != rays) { s = helpers_alloc(dst, n); if (s) { free_temps(); return s; } }
+        help.in = rays->d_helpers; help.in_stride = rays->helper_stride;
+        help.out = dst->d_helpers; help.out_stride = dst->helper_stride;
+    } else if (dst != rays && dst->d_helpers) {
+        cudaStreamSynchronize(c->stream); cudaFree(dst->d_helpers); dst->d_helpers = nullptr; dst->helper_stride = 0;
+    }
     // position history: the bundle the program leaves its rays in logs one level per pushing op
     HistParams hp;
     const bool use_hist = rays->d_hist != nullptr || dst->d_hist != nullptr;
@@ -1419,7 +1512,7 @@ static OpmStatus run_program(OpmRays* rays, const OpmOp* ops, int n_ops, int fla
         const bool strict = (flags & OPM_TRACE_STRICT) != 0;
         // hit maps that exactly one op of this launch records into get their bounding box from the specialised kernel (if that is
         // the kernel that runs: the accumulator pointer is a structural fact of its source)
-        const bool jit_candidate = !strict && !use_hist && c->jit_enabled && n >= c->jit_min_rays && prog.ops.size() * sizeof(DevOp) <= 60 * 1024;
+        const bool jit_candidate = !strict && !use_hist && !use_helpers && c->jit_enabled && n >= c->jit_min_rays && prog.ops.size() * sizeof(DevOp) <= 60 * 1024;
         static const bool fuse_bbox = [] { const char* e = getenv("OPM_B200_JIT_BBOX"); return !(e && e[0] == '0'); }();  // tuning switch
         std::vector<OpmHitMap*> fused;
         if (jit_candidate && fuse_bbox)
@@ -1498,6 +1591,7 @@ static OpmStatus run_program(OpmRays* rays, const OpmOp* ops, int n_ops, int fla
         L.stats = c->d_stats; L.compact = compact ? 1 : 0; L.block = block; L.stream = c->stream;
         L.has_fork = prog.has_fork ? 1 : 0;
         L.hist = use_hist ? &hp : nullptr;
+        L.helpers = use_helpers ? &help : nullptr;
         size_t smem = prog.ops.size() * sizeof(DevOp) + (prog.has_fork ? (size_t)block * kStashWords * 4 : 0);
         int occ = jk ? jit_occupancy(jk) : strict ? trace_occupancy_strict(L.block, smem) : trace_occupancy_fast(L.block, smem);
         uint64_t tiles = (n + L.block - 1) / L.block;
@@ -2534,8 +2628,21 @@ extern "C" OpmStatus opm_hitmap_bounce_levels(OpmHitMap* map, uint64_t* mask) {
     *mask = *h;
     return OPM_OK;
 }
+static OpmStatus fluence_voronoi_impl(OpmHitMap* const* maps, int32_t n_maps, int64_t bounce_filter, uint64_t nx, const double* ranges,
+                                      int32_t accumulate, double* map_dev, double lrtb_out[4], bool helper_rays);
 extern "C" OpmStatus opm_fluence_voronoi(OpmHitMap* const* maps, int32_t n_maps, int64_t bounce_filter, uint64_t nx, const double* ranges,
                                          int32_t accumulate, double* map_dev, double lrtb_out[4]) {
+    return fluence_voronoi_impl(maps, n_maps, bounce_filter, nx, ranges, accumulate, map_dev, lrtb_out, false);
+}
+extern "C" OpmStatus opm_fluence_helper_rays(OpmHitMap* const* maps, int32_t n_maps, int64_t bounce_filter, uint64_t nx, const double* ranges,
+                                             int32_t accumulate, double* map_dev, double lrtb_out[4]) {
+    return fluence_voronoi_impl(maps, n_maps, bounce_filter, nx, ranges, accumulate, map_dev, lrtb_out, true);
+}
+// helper_rays: RaysHitMap::calc_fluence_with_helper_rays (rays_hit_map.rs:627-722) -- the hit records carry FLUENCES (the trace of a
+// bundle with fluence helper rays wrote them), the sites of the diagram take them as they are, voronator's four helper sites around
+// the bounding polygon take the value 0 (:700-701) and ALL of them go into the natural-neighbour interpolation
+static OpmStatus fluence_voronoi_impl(OpmHitMap* const* maps, int32_t n_maps, int64_t bounce_filter, uint64_t nx, const double* ranges,
+                                      int32_t accumulate, double* map_dev, double lrtb_out[4], bool helper_rays) {
     OpmContext* c;
     OpmStatus s = check_same_ctx(maps, n_maps, &c);
     if (s) return s;
@@ -2630,21 +2737,35 @@ extern "C" OpmStatus opm_fluence_voronoi(OpmHitMap* const* maps, int32_t n_maps,
     CU(cudaMemcpyAsync(d_cells + cell_start.size(), cell_sites.data(), cell_sites.size() * 4, cudaMemcpyHostToDevice, c->stream));
     B.px = d_pol; B.py = d_pol + m; B.nx = d_pol + 2 * m; B.ny = d_pol + 3 * m;
     G.cell_start = d_cells; G.cell_sites = d_cells + cell_start.size();
-    // cells -> per-site fluence
-    KL(k_voronoi_cells(n, hx, hy, he, G, B, fl, d_status, c->stream)); c->launches++;
     std::vector<double> z(n);
     unsigned st_bits = 0;
-    CU(cudaMemcpyAsync(z.data(), fl, (size_t)n * 8, cudaMemcpyDeviceToHost, c->stream));
-    CU(cudaMemcpyAsync(&st_bits, d_status, 4, cudaMemcpyDeviceToHost, c->stream));
-    CU(cudaStreamSynchronize(c->stream));
-    if (st_bits) { cleanup(); return fail(OPM_ERR_CAPACITY, "Voronoi estimator: a cell has more than 64 vertices"); }
+    if (!helper_rays) {
+        // cells -> per-site fluence
+        KL(k_voronoi_cells(n, hx, hy, he, G, B, fl, d_status, c->stream)); c->launches++;
+        CU(cudaMemcpyAsync(z.data(), fl, (size_t)n * 8, cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaMemcpyAsync(&st_bits, d_status, 4, cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+        if (st_bits) { cleanup(); return fail(OPM_ERR_CAPACITY, "Voronoi estimator: a cell has more than 64 vertices"); }
+    } else {
+        for (int i = 0; i < n; ++i) z[i] = e[i] / 1.0E4;  // get::<joule_per_square_centimeter>() of the SI value
+    }
     // interpolation over the sites with a finite value (griddata.rs:412): normally all of them
     int nf = 0;
     for (int i = 0; i < n; ++i) nf += std::isfinite(z[i]) ? 1 : 0;
     const double *ix = hx, *iy = hy, *iz = fl;
     std::vector<double> fx, fy, fz;
-    if (nf != n) {
+    if (nf != n || helper_rays) {
         for (int i = 0; i < n; ++i) if (std::isfinite(z[i])) { fx.push_back(x[i]); fy.push_back(y[i]); fz.push_back(z[i]); }
+        if (helper_rays) {
+            // voronator 0.2 VoronoiDiagram::with_bounding_polygon appends four helper sites to the point list (restated from the
+            // crate's source as remembered -- it is not under /root/reference): left, right, below and above the box of the
+            // bounding polygon, one box width / height away.  `sites.len() - hit_points.len()` of rays_hit_map.rs:701 is this 4.
+            const double w = B.x1 - B.x0, hgt = B.y1 - B.y0;
+            const double ex[4] = {B.x0 - w, B.x1 + w, B.x0 + w / 2.0, B.x0 + w / 2.0};
+            const double ey[4] = {B.y0 + hgt / 2.0, B.y0 + hgt / 2.0, B.y0 - hgt, B.y1 + hgt};
+            for (int k = 0; k < 4; ++k) { fx.push_back(ex[k]); fy.push_back(ey[k]); fz.push_back(0.0); }
+            nf = (int)fx.size();
+        }
         double* d_f = (double*)alloc((size_t)std::max(nf, 1) * 3 * 8);
         if (!d_f) { cleanup(); return fail(OPM_ERR_CUDA, "out of device memory"); }
         if (nf) {

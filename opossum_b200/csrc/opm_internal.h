@@ -116,6 +116,13 @@ struct HistParams {
     short level[OPM_MAX_PROGRAM_OPS];  // per device op, -1 = logs nothing
 };
 
+// Fluence helper rays (FluenceRays, rays.rs:1470-1567): three satellite rays per ray and the effective energy of the
+// area element they span, field-major beside the bundle: base[f * stride + slot], f = 0..8 helper positions (helper k, component
+// c at 3 k + c), 9..17 helper directions, 18..20 the helpers' refractive indices (NEGATIVE: that helper is invalid, ray.rs
+// set_invalid after a missed surface), 21 the effective energy.  in == out for a launch that leaves the rays where they were.
+constexpr int kHelperFields = 22;
+struct HelperParams { const double* in; double* out; uint64_t in_stride, out_stride; };
+
 // device mirror of OpmTraceStats (all counters are atomically accumulated)
 struct DevStats {
     unsigned long long interactions, children, hits, missed, apodized, valid_out, alive_out;
@@ -142,6 +149,7 @@ struct TraceLaunch {
     int32_t grid, block;
     void* stream;
     const HistParams* hist = nullptr;  // host pointer; non-NULL: the interpreter variant that logs positions (never compact)
+    const HelperParams* helpers = nullptr;  // host pointer; non-NULL: the interpreter variant that carries fluence helper rays
 };
 
 // launchers implemented in opm_trace.cu (compiled twice: contracted "fast" and -fmad=false "strict")

@@ -1464,6 +1464,33 @@ int k_set_u64(unsigned long long* p, unsigned long long v, void* stream) {
     set_u64_kernel<<<1, 1, 0, ST>>>(p, v);
     return (int)cudaGetLastError();
 }
+// FluenceRays::new (rays.rs:1477-1516): three helper rays on a triangle of area wavelength^2 around the ray (outer radius
+// sqrt(4 area / sqrt 27)), its direction (normalised by Ray::new, ray.rs:127), index 1; effective energy = fluence * area
+struct HelperTrig { double c[6]; };
+__global__ void __launch_bounds__(256) helpers_init_kernel(DevRays R, uint64_t n, double* __restrict__ base, uint64_t stride, HelperTrig T) {
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        const double wvl = R.wvl[i];
+        const double area = wvl * wvl;
+        const double fluence = base[21 * stride + i];
+        const double radius = sqrt(4. * area / sqrt(27.));
+        const V3 d = normalize(v3(R.dx[i], R.dy[i], R.dz[i]));
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            base[(3 * k) * stride + i] = R.px[i] + radius * T.c[2 * k];
+            base[(3 * k + 1) * stride + i] = R.py[i] + radius * T.c[2 * k + 1];
+            base[(3 * k + 2) * stride + i] = R.pz[i] + 0.;
+            base[(9 + 3 * k) * stride + i] = d.x; base[(9 + 3 * k + 1) * stride + i] = d.y; base[(9 + 3 * k + 2) * stride + i] = d.z;
+            base[(18 + k) * stride + i] = 1.0;
+        }
+        base[21 * stride + i] = fluence * area;
+    }
+}
+int k_helpers_init(DevRays R, uint64_t n, double* base, uint64_t stride, const double cs[6], int sms, void* stream) {
+    HelperTrig T;
+    for (int k = 0; k < 6; ++k) T.c[k] = cs[k];
+    helpers_init_kernel<<<grid_for(n, 256, sms * 4), 256, 0, ST>>>(R, n, base, stride, T);
+    return (int)cudaGetLastError();
+}
 int k_fill_u8(uint8_t* p, uint8_t v, uint64_t n, int sms, void* stream) {
     fill_u8_kernel<<<grid_for(n, 256, sms * 8), 256, 0, ST>>>(p, v, n);
     return (int)cudaGetLastError();

@@ -125,5 +125,7 @@ struct ProloguePlan {
 };
 int k_trace_prologue(const ProloguePlan& P, void* stream);
 int k_fill_u8(uint8_t* p, uint8_t v, uint64_t n, int sms, void* stream);
+// FluenceRays::new for every slot (rays.rs:1477-1516); base[21 * stride + slot] holds the initial fluence on entry; cs = cos, sin x 3
+int k_helpers_init(DevRays R, uint64_t n, double* base, uint64_t stride, const double cs[6], int sms, void* stream);
 
 }  // namespace opm

@@ -46,9 +46,10 @@ __device__ __forceinline__ void hist_push(const HistParams& hp, int level, uint6
     row[0] = p.x; row[hp.stride] = p.y; row[2 * hp.stride] = p.z;
 }
 
-template <bool COMPACT, bool HIST>
+template <bool COMPACT, bool HIST, bool HELP = false>
 __device__ __forceinline__ void trace_body(const DevOp* __restrict__ g_ops, int n_ops, const DevRays& in, const DevRays& out, uint64_t n,
-                                           uint64_t out_cap, unsigned long long* out_tail, DevStats* stats, const HistParams& hp) {
+                                           uint64_t out_cap, unsigned long long* out_tail, DevStats* stats, const HistParams& hp,
+                                           const HelperParams& hlp = HelperParams()) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     DevOp* ops = reinterpret_cast<DevOp*>(smem_raw);
     unsigned* stash = reinterpret_cast<unsigned*>(smem_raw + (size_t)n_ops * sizeof(DevOp));  // only sized when the program forks
@@ -83,12 +84,14 @@ __device__ __forceinline__ void trace_body(const DevOp* __restrict__ g_ops, int 
         uint8_t vb;
         tile_load(in, (uint64_t)tile * blockDim.x + threadIdx.x, n, x, vb);
         tile_prefetch(in, (uint64_t)(tile + gridDim.x) * blockDim.x + threadIdx.x, n);
+        HelperState hs;
+        if (HELP && x.in_range && x.alive) helpers_load(hlp, x.i, hs);
         for (int k = 0; k < n_ops; ++k) {
             const DevOp& op = ops[k];
             switch (op.kind) {  // warp-uniform
                 case OPK_REFRACT: {
                     const V3 p0 = x.r.pos;
-                    const bool moved = exec_refract(RefractRt(op.u.refract), x);
+                    const bool moved = HELP ? exec_refract_helpers(RefractRt(op.u.refract), x, hs) : exec_refract(RefractRt(op.u.refract), x);
                     if (HIST && moved && hp.level[k] >= 0) hist_push(hp, hp.level[k], x.i, p0);
                     break;
                 }
@@ -100,7 +103,10 @@ __device__ __forceinline__ void trace_body(const DevOp* __restrict__ g_ops, int 
                 case OPK_THRESHOLD: exec_threshold(op.u.threshold, x); break;
                 case OPK_LIMITS: exec_limits(op.u.limits, x); break;
                 case OPK_FILTER: exec_filter(op.u.filter, x); break;
-                case OPK_PARAXIAL: exec_paraxial(op.u.paraxial, x); break;
+                case OPK_PARAXIAL:
+                    if (HELP) exec_paraxial_helpers(op.u.paraxial, x, hs);
+                    else exec_paraxial(op.u.paraxial, x);
+                    break;
                 case OPK_SPLIT: exec_split(op.u.split, x); break;
                 case OPK_SNAPSHOT: exec_snapshot(op.u.snapshot, x); break;
                 case OPK_TRANSFORM: exec_transform(op.u.transform, x); break;
@@ -117,6 +123,7 @@ __device__ __forceinline__ void trace_body(const DevOp* __restrict__ g_ops, int 
             exec_epilogue(EpilogueRt(op.epi_flags), op, x);
         }
         tile_store<COMPACT>(in, out, out_cap, out_tail, x, vb);
+        if (HELP && x.in_range && x.alive) helpers_store(hlp, x.i, hs);
         tile_count(x, s_cnt, &s_status, &s_first_inv);
     }
     __syncthreads();
@@ -137,13 +144,26 @@ trace_history_kernel(const DevOp* __restrict__ g_ops, int n_ops, DevRays in, Dev
     trace_body<false, true>(g_ops, n_ops, in, out, n, 0, nullptr, stats, hp);
 }
 
+// the same program for a bundle that carries fluence helper rays: a separate kernel as well
+__global__ void __launch_bounds__(OPM_TRACE_BLOCK, 1)
+trace_helpers_kernel(const DevOp* __restrict__ g_ops, int n_ops, DevRays in, DevRays out, uint64_t n, DevStats* stats,
+                     const HelperParams hlp) {
+    HistParams none;
+    trace_body<false, false, true>(g_ops, n_ops, in, out, n, 0, nullptr, stats, none, hlp);
+}
+
 }  // namespace
 
 int OPM_VARIANT(launch_trace)(const TraceLaunch& L) {
     size_t smem = (size_t)L.n_ops * sizeof(DevOp) + (L.has_fork ? (size_t)L.block * kStashWords * 4 : 0);
     cudaStream_t st = (cudaStream_t)L.stream;
     cudaError_t err;
-    if (L.hist) {
+    if (L.helpers) {
+        if (L.compact || L.hist) return (int)cudaErrorInvalidValue;
+        err = cudaFuncSetAttribute(trace_helpers_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (err != cudaSuccess) return (int)err;
+        trace_helpers_kernel<<<L.grid, L.block, smem, st>>>(L.ops, L.n_ops, L.in, L.out, L.n, L.stats, *L.helpers);
+    } else if (L.hist) {
         if (L.compact) return (int)cudaErrorInvalidValue;
         err = cudaFuncSetAttribute(trace_history_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (err != cudaSuccess) return (int)err;

@@ -489,6 +489,115 @@ __device__ __forceinline__ void exec_transform(const DevTransform& o, RayCtx& x)
     x.r.dir = iso_vector(o.iso, x.r.dir);
 }
 
+// ---- fluence helper rays -------------------------------------------------------------------------
+// FluenceRays of one ray (rays.rs:1470-1516) in registers / local memory for the length of a program
+struct HelperState {
+    V3 pos[3], dir[3];
+    double n[3];   // negative: the helper has been set invalid (a missed surface under MissedSurfaceStrategy::Stop)
+    double eff;    // FluenceRays::effective_energy
+};
+__device__ __forceinline__ void helpers_load(const HelperParams& H, uint64_t i, HelperState& h) {
+    const double* b = H.in + i;
+    const uint64_t s = H.in_stride;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        h.pos[k] = v3(b[(3 * k) * s], b[(3 * k + 1) * s], b[(3 * k + 2) * s]);
+        h.dir[k] = v3(b[(9 + 3 * k) * s], b[(9 + 3 * k + 1) * s], b[(9 + 3 * k + 2) * s]);
+        h.n[k] = b[(18 + k) * s];
+    }
+    h.eff = b[21 * s];
+}
+__device__ __forceinline__ void helpers_store(const HelperParams& H, uint64_t i, const HelperState& h) {
+    double* b = H.out + i;
+    const uint64_t s = H.out_stride;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        b[(3 * k) * s] = h.pos[k].x; b[(3 * k + 1) * s] = h.pos[k].y; b[(3 * k + 2) * s] = h.pos[k].z;
+        b[(9 + 3 * k) * s] = h.dir[k].x; b[(9 + 3 * k + 1) * s] = h.dir[k].y; b[(9 + 3 * k + 2) * s] = h.dir[k].z;
+        b[(18 + k) * s] = h.n[k];
+    }
+    b[21 * s] = h.eff;
+}
+// Ray::helper_ray_fluence (ray.rs:172-198): effective energy over the area of the triangle the three helpers span
+__device__ __forceinline__ double helper_ray_fluence(const HelperState& h) {
+    const V3 ab = v3(h.pos[0].x - h.pos[1].x, h.pos[0].y - h.pos[1].y, h.pos[0].z - h.pos[1].z);
+    const V3 ac = v3(h.pos[0].x - h.pos[2].x, h.pos[0].y - h.pos[2].y, h.pos[0].z - h.pos[2].z);
+    const double cx = ab.y * ac.z - ab.z * ac.y, cy = ab.z * ac.x - ab.x * ac.z, cz = ab.x * ac.y - ab.y * ac.x;
+    const double area = 0.5 * sqrt(cx * cx + cy * cy + cz * cz);
+    return h.eff / area;
+}
+// Rays::refract_on_surface for a ray with FluenceRays (rays.rs:987-1012 with ray.rs:640-672).  In the reference's order: the main
+// ray is refracted first -- its hit point carries the fluence of the helper triangle AS IT STILL IS (the helpers have not reached
+// this surface yet), the effective energy takes the factor 1 - R (R for the reflected clone) -- then, if there is a reflected
+// clone, each helper is refracted on the same surface.  The clone keeps the helpers where they were and only takes their
+// reflected directions (rays.rs:1000-1010): that is what a mirror's continuing bundle carries.
+// Returns like exec_refract.
+template <class V>
+__device__ __forceinline__ bool exec_refract_helpers(const V& v, RayCtx& x, HelperState& h) {
+    const DevRefract& o = v.d();
+    RefractResult res;
+    res.has_child = false; res.moved = false; res.hit_e = -1.0; res.hit_bounce = 0; res.hit_local = v3(0, 0, 0);
+    double fluence = 0.0;
+    if (x.valid) {
+        x.c.a += 1u;
+        fluence = helper_ray_fluence(h);
+        RayState shadow = x.r;  // the same refraction with the effective energy in the place of the ray's: eff (1 - R) and eff R
+        shadow.e = h.eff;
+        res = refract_on_surface(v, x.r);
+        if (res.status != OPM_OK) { x.c.status |= 1u << res.status; x.valid = false; res.has_child = false; res.hit_e = -1.0; }
+        else {
+            if (res.missed) x.c.b += 1u;
+            if (res.invalidated) x.valid = false;
+        }
+        if (res.has_child) {
+            // FluenceHitPoint::new (hit_point.rs): the fluence must be finite and not negative
+            if (!isfinite(fluence) || signbit_(fluence)) { x.c.status |= 1u << OPM_ERR_HITPOINT; x.valid = false; res.has_child = false; res.hit_e = -1.0; }
+        }
+        if (res.has_child) {
+            res.hit_e = fluence;
+            const RefractResult rs = refract_on_surface(v, shadow);
+            const bool mirror = (v.flags() & OPM_REFRACT_CONTINUE_AS_CHILD) != 0;
+            h.eff = mirror ? rs.child_e : shadow.e;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                RayState hr = x.r;  // wavelength of the ray; the other fields below
+                hr.pos = h.pos[k]; hr.dir = h.dir[k]; hr.n = fabs(h.n[k]); hr.e = 1.0; hr.opl = 0.0; hr.bounces = 0; hr.refr = 0;
+                const RefractResult rh = refract_on_surface(v, hr);
+                // (a helper records no hit point: a hit-point error cannot come from it; the index / coating errors are the ray's own)
+                if (!mirror) {
+                    h.pos[k] = hr.pos; h.dir[k] = hr.dir;
+                    const bool inval = h.n[k] < 0.0 || (rh.status == OPM_OK && rh.invalidated);
+                    h.n[k] = inval ? -hr.n : hr.n;
+                } else if (rh.status == OPM_OK && rh.has_child) h.dir[k] = rh.child_dir;
+            }
+        }
+    }
+    if (v.has_hits() && x.in_range) {  // slot-indexed hit record, e < 0 = empty; here e is the FLUENCE of a FluenceHitPoint
+        OPM_ST(o.hits.e + x.i, res.hit_e);
+        if (res.hit_e >= 0.0 || x.warp_live) {
+            OPM_ST(o.hits.x + x.i, res.hit_local.x); OPM_ST(o.hits.y + x.i, res.hit_local.y);
+            OPM_ST(o.hits.z + x.i, res.hit_local.z); OPM_ST(o.hits.bounce + x.i, res.hit_bounce);
+        }
+        if (res.hit_e >= 0.0) x.c.a += 1u << 16;
+    }
+    if (v.flags() & OPM_REFRACT_STAT_KEY) { x.c.kid = (x.valid && x.alive) ? x.r.id : 0xffffffffu; x.c.kb = x.r.bounces; }
+    finish_children(v, res, x);
+    return res.moved;
+}
+// Rays::refract_paraxial (rays.rs:943-958): the ray if it is valid, and its valid helpers whether it is or not
+__device__ __forceinline__ void exec_paraxial_helpers(const DevParaxial& o, RayCtx& x, HelperState& h) {
+    if (x.valid) refract_paraxial(o, x.r);
+    if (!x.alive) return;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        if (h.n[k] < 0.0) continue;
+        RayState hr = x.r;
+        hr.pos = h.pos[k]; hr.dir = h.dir[k]; hr.opl = 0.0; hr.refr = 0;
+        refract_paraxial(o, hr);
+        h.pos[k] = hr.pos; h.dir[k] = hr.dir;
+    }
+}
+
 // ---- tile prologue / epilogue shared by both kernels -----------------------------------------------------------
 __device__ __forceinline__ void tile_load(const DevRays& in, uint64_t i, uint64_t n, RayCtx& x, uint8_t& vb) {
     x.i = i;

@@ -197,6 +197,8 @@ double orc_kde_value(const OrcHit* hits, uint64_t n, double band_width, double p
 /* Voronoi fluence estimator (opm_voronoi.c): RaysHitMap::calc_fluence_with_voronoi, rays_hit_map.rs:407-521 */
 int orc_voronoi_site_fluence(const double* x_cm, const double* y_cm, const double* e, uint64_t n, double* fluence, double* area_hull);
 int orc_fluence_voronoi(const OrcHit* hits, uint64_t n, uint64_t nx, const double* ranges, double* map, double lrtb_out[4]);
+/* RaysHitMap::calc_fluence_with_helper_rays, rays_hit_map.rs:627-722 (hits.e = fluence in J/m^2) */
+int orc_fluence_helper_rays(const OrcHit* hits, uint64_t n, uint64_t nx, const double* ranges, double* map, double lrtb_out[4]);
 int orc_fluence_kde(const OrcHit* hits, uint64_t n, uint64_t nx, uint64_t ny, const double* ranges, double* map, double lrtb_out[4],
                     double* band_width_out, int n_threads);                           /* rays_hit_map.rs:575-613 */
 

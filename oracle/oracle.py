@@ -12,6 +12,7 @@ walk and the ghost-focus pass loop (see oracle/scene.py).
 from __future__ import annotations
 
 import ctypes as C
+import math
 import os
 import subprocess
 from pathlib import Path
@@ -590,6 +591,137 @@ def fluence_voronoi(hits: np.ndarray, nx: int, ranges=None):
     rg = (C.c_double * 4)(*ranges) if ranges is not None else None
     _check(lib().orc_fluence_voronoi(_vp(hits), len(hits), nx, rg, _dptr(m), lrtb))
     return m.reshape(nx, nx).T.copy(), tuple(lrtb[:])
+
+
+def fluence_helper_rays(hits: np.ndarray, nx: int, ranges=None):
+    """RaysHitMap::calc_fluence_with_helper_rays (rays_hit_map.rs:627-722) of ONE rays hit map whose `e` field holds FLUENCES in
+    J/m^2 (FluenceHitPoint).  Returns like fluence_voronoi."""
+    m = np.zeros(nx * nx, dtype=np.float64)
+    lrtb = (C.c_double * 4)()
+    rg = (C.c_double * 4)(*ranges) if ranges is not None else None
+    _check(lib().orc_fluence_helper_rays(_vp(hits), len(hits), nx, rg, _dptr(m), lrtb))
+    return m.reshape(nx, nx).T.copy(), tuple(lrtb[:])
+
+
+def fluence_helper_rays_combined(hit_maps, nx: int, ny: int):
+    """HitMap::calc_combined_fluence_with_helper_rays (hit_map/mod.rs:283-310): every rays hit map on the common bounding box, summed
+    (nx x nx estimates onto an nx x ny matrix: the reference panics unless nx == ny)"""
+    if nx != ny:
+        raise ValueError("calc_combined_fluence_with_helper_rays: matrix dimensions mismatch (the reference panics unless nx == ny)")
+    x0 = min(float(h["x"].min()) for h in hit_maps); x1 = max(float(h["x"].max()) for h in hit_maps)
+    y0 = min(float(h["y"].min()) for h in hit_maps); y1 = max(float(h["y"].max()) for h in hit_maps)
+    total = np.zeros((nx, nx))
+    for h in hit_maps:
+        m, _ = fluence_helper_rays(h, nx, (x0, x1, y0, y1))
+        total += m
+    return total, (x0, x1, y1, y0)
+
+
+# ---------------------------------------------------------------------------
+# fluence helper rays (FluenceRays, rays.rs:1470-1567): pure-Python loops over the single-ray functions -- small bundles only
+# ---------------------------------------------------------------------------
+def fluence_general_gaussian(xy, total_energy, mu=(0.0, 0.0), sigma=(1.0, 1.0), theta=0.0) -> np.ndarray:
+    """fluence_distributions::General2DGaussian::apply (general_gaussian.rs:75-90, math_distribution_functions.rs:97-121): J/m^2"""
+    peak = total_energy / (2. * math.pi * sigma[0] * sigma[1])
+    st, ct = math.sin(theta), math.cos(theta)
+    out = np.zeros(len(xy))
+    for i, p in enumerate(np.asarray(xy, dtype=np.float64)):
+        x_rot = math.fma(p[0] - mu[0], ct, -((p[1] - mu[1]) * st)) if hasattr(math, "fma") else (p[0] - mu[0]) * ct - (p[1] - mu[1]) * st
+        y_rot = math.fma(p[1] - mu[1], ct, (p[0] - mu[0]) * st) if hasattr(math, "fma") else (p[1] - mu[1]) * ct + (p[0] - mu[0]) * st
+        q = (x_rot / sigma[0]) * (x_rot / sigma[0]) + (y_rot / sigma[1]) ** 2
+        out[i] = peak * math.exp(-0.5 * q)
+    return out
+
+
+def helpers_new(rays: np.ndarray, init_fluence) -> dict:
+    """FluenceRays::new for every ray (rays.rs:1477-1516; Ray::new_collimated_w_fluence_helper, ray.rs:157-166).
+    init_fluence in J/m^2.  Returns {"rays": (n, 3) RAY_DTYPE helper rays, "eff": (n,) effective energies}."""
+    n = len(rays)
+    fl = np.broadcast_to(np.asarray(init_fluence, dtype=np.float64), (n,))
+    if np.any(~np.isfinite(fl)) or np.any(np.signbit(fl)):
+        raise ValueError("Initial fluence of Fluence Rays must be non-negative and finite!")
+    h = np.zeros((n, 3), dtype=RAY_DTYPE)
+    eff = np.zeros(n)
+    for i in range(n):
+        area = rays["wvl"][i] * rays["wvl"][i]
+        eff[i] = fl[i] * area
+        radius = math.sqrt(4. * area / math.sqrt(27.))
+        for k in range(3):
+            ang = float(k) * 2. / 3. * math.pi
+            pos = rays["pos"][i] + np.array([radius * math.cos(ang), radius * math.sin(ang), 0.])
+            h[i, k] = ray_new(pos, rays["dir"][i], rays["wvl"][i], rays["e"][i])[0]
+    return {"rays": h, "eff": eff}
+
+
+def helper_ray_fluence(helpers: dict, i: int) -> float:
+    """Ray::helper_ray_fluence (ray.rs:172-198) in J/m^2"""
+    p = helpers["rays"]["pos"][i]
+    ab, ac = p[0] - p[1], p[0] - p[2]
+    c = (ab[1] * ac[2] - ab[2] * ac[1], ab[2] * ac[0] - ab[0] * ac[2], ab[0] * ac[1] - ab[1] * ac[0])
+    area = 0.5 * math.sqrt(c[0] * c[0] + c[1] * c[1] + c[2] * c[2])
+    with np.errstate(divide="ignore", invalid="ignore"):
+        return float(np.float64(helpers["eff"][i]) / np.float64(area))
+
+
+def rays_refract_on_surface_w_helpers(rays: np.ndarray, helpers: dict, surf: Surface, idx: IndexModel | None, refraction_intended=True,
+                                      strategy=MISS_STOP):
+    """Rays::refract_on_surface for a bundle with FluenceRays (rays.rs:976-1047 with ray.rs:640-672), in place.  The main ray is
+    refracted first: its hit point is a FluenceHitPoint with the fluence of the helper triangle as it still is, the effective
+    energy takes 1 - R (R on the reflected clone); then the helpers of a ray that has a reflected clone are refracted, and the
+    clone's helpers -- copies taken BEFORE that -- take the reflected directions (:996-1010).
+    Returns (children, child_helpers, hits) with hits["e"] = fluence in J/m^2.  For a mirror (refraction_intended = False) the
+    caller continues with the children, like nodes/thin_mirror.rs."""
+    n = len(rays)
+    children, hits, ch_rays, ch_eff = [], [], [], []
+    for i in range(n):
+        if rays["valid"][i] != 1:
+            continue
+        n2 = idx.get_refractive_index(float(rays["wvl"][i])) if idx is not None else None
+        fluence = helper_ray_fluence(helpers, i)  # evaluated inside the main ray's refraction (ray.rs:655)
+        shadow = rays[i:i + 1].copy()
+        shadow["e"] = helpers["eff"][i]
+        pre_helpers = helpers["rays"][i].copy()
+        child, hit = ray_refract_on_surface(rays[i:i + 1], surf, n2, strategy)
+        if child is None:
+            continue
+        if not math.isfinite(fluence) or fluence < 0 or (fluence == 0 and math.copysign(1.0, fluence) < 0):
+            raise ValueError("FluenceHitPoint: the fluence must be finite and not negative")
+        hit = hit.copy()
+        hit["e"] = fluence
+        hits.append(hit[0])
+        sh_child, _ = ray_refract_on_surface(shadow, surf, n2, strategy)  # the same arithmetic on the effective energy
+        helpers["eff"][i] = shadow["e"][0]
+        refl_helpers = pre_helpers.copy()
+        for k in range(3):
+            hk = helpers["rays"][i, k:k + 1]
+            hchild, _ = ray_refract_on_surface(hk, surf, n2, strategy)
+            if hchild is not None:
+                refl_helpers["dir"][k] = hchild["dir"][0]  # set_direction: stored as given (ray.rs set_direction)
+        c = child.copy()
+        if not refraction_intended:
+            c["bounces"] -= 1  # reduce_bounce_counter (rays.rs:1016)
+        children.append(c[0])
+        ch_rays.append(refl_helpers)
+        ch_eff.append(sh_child["e"][0])
+    ch = np.array(children, dtype=RAY_DTYPE) if children else np.zeros(0, dtype=RAY_DTYPE)
+    hh = np.array(hits, dtype=HIT_DTYPE) if hits else np.zeros(0, dtype=HIT_DTYPE)
+    chh = {"rays": np.array(ch_rays, dtype=RAY_DTYPE).reshape(-1, 3) if ch_rays else np.zeros((0, 3), dtype=RAY_DTYPE),
+           "eff": np.array(ch_eff, dtype=np.float64)}
+    return ch, chh, hh
+
+
+def rays_refract_paraxial_w_helpers(rays: np.ndarray, helpers: dict, f: float, iso: Isometry):
+    """Rays::refract_paraxial (rays.rs:943-958): the ray if it is valid, and its VALID helpers whether it is or not"""
+    rays_refract_paraxial(rays, f, iso)
+    for i in range(len(rays)):
+        rays_refract_paraxial(helpers["rays"][i], f, iso)
+
+
+def helpers_as_product_layout(helpers: dict) -> dict:
+    """the oracle's helper rays in the layout of opossum_b200.Rays.fluence_helpers()"""
+    h = helpers["rays"]
+    nn = np.where(h["valid"] == 1, h["n"], -h["n"]) if len(h) else np.zeros((0, 3))
+    return {"pos": h["pos"].copy(), "dir": h["dir"].copy(), "n": nn, "eff": helpers["eff"].copy()}
 
 
 def fluence_voronoi_combined(hit_maps, nx: int, ny: int):

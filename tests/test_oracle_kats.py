@@ -1103,3 +1103,64 @@ def test_voronoi_cells_tile_the_bounding_polygon_and_interpolation_reproduces_li
     inside = np.isfinite(m)
     assert inside.sum() > 0.8 * m.size
     assert np.allclose(m[inside], want[inside], rtol=1e-9)
+
+
+# ------------------------------------------------------------------ fluence helper rays
+def test_kat_helper_ray_fluence():
+    """ray.rs:1819-1843: a ray with FluenceRays of 1 J/cm^2 reports that fluence (1e-8); ray.rs:1892-1920: four times the effective
+    energy is four times the fluence; rays.rs:1484-1488: a negative or non-finite initial fluence is an error"""
+    r = orc.ray_new((1.0, 1.0, 1.0), (0.0, 0.0, 1.0), 1000e-9, 1.0)
+    h = orc.helpers_new(r, 1.0e4)
+    assert abs(orc.helper_ray_fluence(h, 0) / 10000.0 - 1.0) <= 1e-8
+    h["eff"] *= 4.0
+    assert abs(orc.helper_ray_fluence(h, 0) / 40000.0 - 1.0) <= 1e-8
+    for bad in (-1.0, math.nan, math.inf, -math.inf):
+        with pytest.raises(ValueError):
+            orc.helpers_new(r, bad)
+
+
+def test_kat_new_collimated_w_fluence_helper_gaussian():
+    """rays.rs:2846-2873: Hexapolar(15 mm, 5 rings) positions, General2DGaussian(1 J, sigma 2.5 mm) fluences: the first ray (the
+    centre) carries the peak fluence 1 / (2 pi sigma^2) to 2 ulp"""
+    xyz = orc.hexapolar(5, 15e-3)
+    fl = orc.fluence_general_gaussian(xyz[:, :2], 1.0, (0.0, 0.0), (2.5e-3, 2.5e-3), 0.0)
+    rays = orc.rays_from_arrays(xyz, np.tile([0.0, 0.0, 1.0], (len(xyz), 1)), np.ones(len(xyz)), np.full(len(xyz), 1000e-9))
+    h = orc.helpers_new(rays, fl)
+    assert tuple(xyz[0]) == (0.0, 0.0, 0.0)
+    assert abs(orc.helper_ray_fluence(h, 0) * (2.0 * math.pi * 0.0025 * 0.0025) - 1.0) <= 1e-9  # the triangle's area carries 1e-10 of rounding
+    assert abs(fl[0] * (2.0 * math.pi * 0.0025 * 0.0025) - 1.0) <= 2 * np.finfo(float).eps
+
+
+def test_kat_helper_rays_estimator():
+    """hit_map/mod.rs:1030-1068: five FluenceHitPoints of 1 J/cm^2 -> 10000 J/m^2 at the centre of a 51 x 51 map; a second bundle of
+    five on the common bounding box doubles it.  :1072-1091: fewer than three points is an error."""
+    p1 = [(-0.5, -0.5), (0.0, 0.0), (-0.5, 0.5), (0.5, 0.5), (0.5, -0.5)]
+    s = math.sqrt(0.5)
+    p2 = [(s, 0.0), (0.0, s), (-s, 0.0), (0.0, -s), (0.0, 0.0)]
+    h1 = orc.hits_from_xye([p[0] for p in p1], [p[1] for p in p1], [1.0e4] * 5)
+    h2 = orc.hits_from_xye([p[0] for p in p2], [p[1] for p in p2], [1.0e4] * 5)
+    m, lrtb = orc.fluence_helper_rays_combined([h1], 51, 51)
+    assert m[25, 25] == pytest.approx(10000.0, rel=1e-12)
+    m, lrtb = orc.fluence_helper_rays_combined([h1, h2], 51, 51)
+    assert m[25, 25] == pytest.approx(20000.0, rel=1e-12)
+    with pytest.raises(Exception):
+        orc.fluence_helper_rays(h1[:2], 50)
+
+
+def test_helper_rays_follow_a_plane_refraction():
+    """rays.rs:2165-2190 runs Rays::refract_on_surface on a helper-ray bundle (no assertion there).  Here with numbers: a collimated
+    bundle through a plane into n = 1.5 keeps its helper triangles (area wavelength^2), so the recorded FluenceHitPoint is the initial
+    fluence, and the effective energy drops by the Fresnel factor 1 - R = 0.96 at normal incidence"""
+    xyz = orc.hexapolar(2, 5e-3)
+    n = len(xyz)
+    rays = orc.rays_from_arrays(xyz, np.tile([0.0, 0.0, 1.0], (n, 1)), np.ones(n), np.full(n, 1000e-9))
+    h = orc.helpers_new(rays, 2.0e4)
+    surf = orc.Surface(geom=orc.GEOM_PLANE, coating=orc.COAT_FRESNEL, param=0.0, coating_r=0.0, iso=orc.Isometry.new((0.0, 0.0, 0.01)))
+    ch, chh, hits = orc.rays_refract_on_surface_w_helpers(rays, h, surf, orc.IndexModel.const(1.5))
+    assert len(hits) == n and np.allclose(hits["e"], 2.0e4, rtol=1e-8)
+    assert np.allclose(h["eff"], 2.0e4 * (1000e-9) ** 2 * 0.96, rtol=1e-12)
+    assert np.allclose(chh["eff"], 2.0e4 * (1000e-9) ** 2 * 0.04, rtol=1e-12)
+    assert np.allclose(h["rays"]["pos"][:, :, 2], 0.01, atol=1e-15) and np.allclose(chh["rays"]["pos"][:, :, 2], 0.0)  # the clone's helpers stay behind
+    assert np.allclose(chh["rays"]["dir"][:, :, 2], -1.0)  # ... with the reflected direction
+    for i in range(n):
+        assert abs(orc.helper_ray_fluence(h, i) / (2.0e4 * 0.96) - 1.0) <= 1e-7
