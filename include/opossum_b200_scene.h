@@ -163,6 +163,11 @@ OpmStatus opm_scene_beam_splitter_two_inputs(OpmScene* scene, int32_t node, OpmR
  * calc_combined_fluence_with_voronoi (hit_map/mod.rs:232-262) -- one estimate per (bundle, bounce level) on the common bounding box,
  * summed; NaN outside a bundle's convex hull.  nx x nx map; nx != ny is refused (OPM_ERR_ARG) where the reference panics on the
  * dimensions of its matrix sum -- which is what its own (100, 83) report does. */
+/* the same report with FluenceEstimator::HelperRays (HitMap::calc_combined_fluence_with_helper_rays, hit_map/mod.rs:283-310), for a
+ * scene that traced a bundle with fluence helper rays (opm_rays_attach_fluence_helpers): the detector's hit maps then hold
+ * FluenceHitPoints.  Such a bundle runs the whole chain in the interpreter kernel; beam splitters with a second output are refused. */
+OpmStatus opm_scene_node_fluence_helper_rays(OpmScene* scene, int32_t node, uint64_t nx, uint64_t ny, double* map_host, double lrtb[4],
+                                             double* peak, double* total);
 OpmStatus opm_scene_node_fluence_voronoi(OpmScene* scene, int32_t node, uint64_t nx, uint64_t ny, double* map_host, double lrtb[4],
                                          double* peak, double* total_energy);
 /* EnergyMeter::node_report (nodes/energy_meter.rs:136-151): total energy of the valid rays of the bundle the node keeps */

@@ -205,7 +205,7 @@ SCENE_EXPORTS = [
     "opm_scene_add_node_at_distance", "opm_scene_add_node_aligned_like", "opm_scene_calc_node_positions", "opm_scene_node_isometry",
     "opm_scene_node_count", "opm_scene_reset_data", "opm_scene_raytrace", "opm_scene_output_rays", "opm_scene_node_rays", "opm_scene_node_spot",
     "opm_scene_node_spot_partial", "opm_scene_node_spot_async",
-    "opm_scene_node_fluence", "opm_scene_node_fluence_kde", "opm_scene_node_fluence_voronoi", "opm_scene_beam_splitter_two_inputs", "opm_scene_node_energy", "opm_scene_node_spectrum", "opm_scene_node_wavefront", "opm_scene_node_hitmaps", "opm_scene_ghostfocus", "opm_scene_gf_pass_tally",
+    "opm_scene_node_fluence", "opm_scene_node_fluence_kde", "opm_scene_node_fluence_voronoi", "opm_scene_node_fluence_helper_rays", "opm_scene_beam_splitter_two_inputs", "opm_scene_node_energy", "opm_scene_node_spectrum", "opm_scene_node_wavefront", "opm_scene_node_hitmaps", "opm_scene_ghostfocus", "opm_scene_gf_pass_tally",
     "opm_scene_gf_pass_bundles", "opm_scene_node_critical_fluences", "opm_scene_node_peak_fluence",
 ]
 
@@ -400,6 +400,7 @@ def lib() -> C.CDLL:
         "opm_scene_node_fluence": (i32, [vp, i32, u64, u64, dp, dp, dp, dp]),
         "opm_scene_node_fluence_kde": (i32, [vp, i32, u64, u64, dp, dp, dp, dp, dp]),
         "opm_scene_node_fluence_voronoi": (i32, [vp, i32, u64, u64, dp, dp, dp, dp]),
+        "opm_scene_node_fluence_helper_rays": (i32, [vp, i32, u64, u64, dp, dp, dp, dp]),
         "opm_scene_beam_splitter_two_inputs": (i32, [vp, i32, vp, vp, vp, vp, vp]),
         "opm_scene_node_spectrum": (i32, [vp, i32, C.c_double, dp, dp, dp, u64, C.POINTER(u64)]),
         "opm_scene_node_wavefront": (i32, [vp, i32, dp, u64, C.POINTER(OpmWavefrontStats)]),

@@ -941,8 +941,20 @@ extern "C" OpmStatus opm_scene_beam_splitter_two_inputs(OpmScene* sc, int32_t no
 // per rays hit map, i.e. per (bundle, bounce level), on that common grid, summed.  The reference adds nx x nx estimates (both axes
 // take nr_of_points.0 points, rays_hit_map.rs:470,489) to an nx x ny matrix and panics unless nx == ny -- its own report asks for
 // (100, 83): refused here with OPM_ERR_ARG instead of a panic.
+static OpmStatus node_fluence_sites(OpmScene* sc, int32_t node, uint64_t nx, uint64_t ny, double* map_host, double lrtb[4], double* peak,
+                                    double* total, bool helper_rays);
 extern "C" OpmStatus opm_scene_node_fluence_voronoi(OpmScene* sc, int32_t node, uint64_t nx, uint64_t ny, double* map_host, double lrtb[4],
                                                     double* peak, double* total) {
+    return node_fluence_sites(sc, node, nx, ny, map_host, lrtb, peak, total, false);
+}
+// FluenceDetector::node_report with FluenceEstimator::HelperRays after the trace of a bundle with fluence helper rays:
+// HitMap::calc_combined_fluence_with_helper_rays (hit_map/mod.rs:283-310), same sum over the rays hit maps on the common box
+extern "C" OpmStatus opm_scene_node_fluence_helper_rays(OpmScene* sc, int32_t node, uint64_t nx, uint64_t ny, double* map_host, double lrtb[4],
+                                                        double* peak, double* total) {
+    return node_fluence_sites(sc, node, nx, ny, map_host, lrtb, peak, total, true);
+}
+static OpmStatus node_fluence_sites(OpmScene* sc, int32_t node, uint64_t nx, uint64_t ny, double* map_host, double lrtb[4], double* peak,
+                                    double* total, bool helper_rays) {
     if (!sc || node < 0 || node >= (int)sc->nodes.size() || nx == 0) return OPM_ERR_ARG;
     if (nx != ny) return OPM_ERR_ARG;  // "Matrix addition/subtraction dimensions mismatch" in the reference
     Node& n = *sc->nodes[node];
@@ -968,7 +980,9 @@ extern "C" OpmStatus opm_scene_node_fluence_voronoi(OpmScene* sc, int32_t node, 
         for (auto& h : n.s[0].hits)
             if (h.uuid == u) { mine.push_back(h.map); uint64_t m = 0; if (!st) st = opm_hitmap_bounce_levels(h.map, &m); levels |= m; }
         for (int b = 0; b < 64 && !st; ++b)
-            if ((levels >> b) & 1) st = opm_fluence_voronoi(mine.data(), (int32_t)mine.size(), b, nx, ranges, 1, (double*)dev, nullptr);
+            if ((levels >> b) & 1)
+                st = helper_rays ? opm_fluence_helper_rays(mine.data(), (int32_t)mine.size(), b, nx, ranges, 1, (double*)dev, nullptr)
+                                 : opm_fluence_voronoi(mine.data(), (int32_t)mine.size(), b, nx, ranges, 1, (double*)dev, nullptr);
     }
     if (!st) st = opm_fluence_peak_total(sc->ctx, (const double*)dev, nx, nx, box, peak, total);
     if (!st && map_host) st = opm_device_to_host(sc->ctx, map_host, dev, nx * nx * sizeof(double));

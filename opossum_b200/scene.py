@@ -300,12 +300,12 @@ class Scene:
             fd = FluenceData(m.reshape(nx, ny).T.copy() if download else None, tuple(lrtb[:]), peak.value, tot.value)
             fd.band_width = bw.value
             return fd
-        if estimator == "voronoi":
-            _check(F.lib().opm_scene_node_fluence_voronoi(self.h, node, nx, ny, m.ctypes.data_as(C.POINTER(C.c_double)) if download else None,
-                                                          lrtb, C.byref(peak), C.byref(tot)))
+        if estimator in ("voronoi", "helper_rays"):
+            fn = F.lib().opm_scene_node_fluence_voronoi if estimator == "voronoi" else F.lib().opm_scene_node_fluence_helper_rays
+            _check(fn(self.h, node, nx, ny, m.ctypes.data_as(C.POINTER(C.c_double)) if download else None, lrtb, C.byref(peak), C.byref(tot)))
             return FluenceData(m.reshape(nx, ny).T.copy() if download else None, tuple(lrtb[:]), peak.value, tot.value)
         if estimator != "binning":
-            raise ValueError("estimator must be 'binning', 'kde' or 'voronoi'")
+            raise ValueError("estimator must be 'binning', 'kde', 'voronoi' or 'helper_rays'")
         _check(F.lib().opm_scene_node_fluence(self.h, node, nx, ny,
                                               m.ctypes.data_as(C.POINTER(C.c_double)) if download else None, lrtb,
                                               C.byref(peak), C.byref(tot)))

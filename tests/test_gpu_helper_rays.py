@@ -172,3 +172,39 @@ def test_what_a_bundle_with_helpers_refuses(ctx):
         ob.Program().refract(plane, None).split(0.5, ob.Rays(ctx, 100)).run(r)
     with pytest.raises(ob.OpossumError):
         ob.Program().refract(plane, None, children=ob.Rays(ctx, 100)).run(r)
+
+
+def test_scene_with_helper_rays_and_report(ctx):
+    """the scene layer with a helper-ray bundle: source -> lens -> FluenceDetector, FluenceEstimator::HelperRays report
+    (HitMap::calc_combined_fluence_with_helper_rays) against the oracle run surface by surface"""
+    import scenes
+    MM = scenes.MM
+    nodes = [scenes.node("source"),
+             scenes.node("lens", z=30 * MM, p=(120 * MM, -120 * MM, 4 * MM), index=("const", 1.5), coat_in=("fresnel",), coat_out=("fresnel",)),
+             scenes.node("fluence_detector", z=60 * MM)]
+    xyz = orc.hexapolar(6, 6e-3)
+    n = len(xyz)
+    fl = orc.fluence_general_gaussian(xyz[:, :2], 1.0, (0.0, 0.0), (3e-3, 3e-3), 0.0)
+    rays = orc.rays_from_arrays(xyz, np.tile([0.0, 0.0, 1.0], (n, 1)), np.full(n, 1.0 / n), np.full(n, 1000e-9))
+    psc = scenes.to_product(ctx, nodes)
+    r = ob.Rays.from_array(ctx, rays).attach_fluence_helpers(fl)
+    st = psc.raytrace(r)
+    fd = psc.node_fluence(2, 31, 31, estimator="helper_rays")
+    # oracle: the same surfaces one by one (lens front, lens rear, detector plane), then the estimator on the detector's records
+    osc = scenes.to_oracle(nodes)
+    ref = rays.copy()
+    rh = orc.helpers_new(ref, fl)
+    lens, det = osc.nodes[1], osc.nodes[2]
+    glass = orc.IndexModel.const(1.5)
+    orc.rays_refract_on_surface_w_helpers(ref, rh, lens.s[0].surf, glass)
+    orc.rays_refract_on_surface_w_helpers(ref, rh, lens.s[1].surf, orc.IndexModel.const(1.0))
+    _, _, hits = orc.rays_refract_on_surface_w_helpers(ref, rh, det.s[0].surf, None)
+    assert st.interactions == 3 * n and len(hits) == n
+    assert_rays_match(r.to_array(), ref, what="scene with helpers")
+    assert_helpers_match(r.fluence_helpers(), orc.helpers_as_product_layout(rh), "scene")
+    ref_map, lrtb = orc.fluence_helper_rays_combined([hits], 31, 31)
+    assert np.allclose(fd.lrtb, lrtb, rtol=RTOL, atol=0)
+    ok = np.isfinite(ref_map)
+    assert np.array_equal(np.isfinite(fd.map), ok)
+    assert np.abs(fd.map[ok] - ref_map[ok]).max() / np.abs(ref_map[ok]).max() <= 1e-5  # the records are quotients by 1e-12 m^2 areas, see above
+    assert fd.peak == pytest.approx(np.nanmax(ref_map), rel=1e-5)
