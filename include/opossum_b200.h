@@ -347,6 +347,13 @@ uint64_t opm_rays_capacity(const OpmRays* rays);
  * opm_rays_download_fluence_helpers: 22 doubles per ray in the order of opm_rays_download -- helper positions [3][3], helper
  * directions [3][3], the helpers' refractive indices [3] (negative: that helper was set invalid), the effective energy. */
 OpmStatus opm_rays_attach_fluence_helpers(OpmRays* rays, const double* init_fluence_J_per_m2);
+/* Rays::new_collimated_w_fluence_helper (rays.rs:352-398): n rays along +z at pos_xyz (host, n x 3: the PositionDistribution's
+ * points), energy = area of the point's Voronoi cell (create_voronoi_cells, utils/griddata.rs:265-345) x its fluence (host, n
+ * values in J/m^2: the FluenceDistribution's), 0 for a cell of fewer than three vertices; each ray with its FluenceRays.
+ * opm_voronoi_cell_areas: those cell areas [m^2] by themselves (NaN: fewer than three vertices). */
+OpmStatus opm_rays_new_collimated_w_fluence_helper(OpmRays* rays, const double* pos_xyz, uint64_t n, double wavelength_m,
+                                                   const double* fluence_J_per_m2);
+OpmStatus opm_voronoi_cell_areas(OpmContext* ctx, const double* x_m, const double* y_m, uint64_t n, double* area_m2_out);
 int32_t opm_rays_has_fluence_helpers(const OpmRays* rays);
 OpmStatus opm_rays_download_fluence_helpers(const OpmRays* rays, double* out, uint64_t capacity_rays, uint64_t* n_out);
 OpmStatus opm_rays_clear(OpmRays* rays);

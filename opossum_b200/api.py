@@ -495,6 +495,14 @@ class Rays:
         _check(F.lib().opm_rays_attach_fluence_helpers(self.h, fl.ctypes.data_as(C.POINTER(C.c_double))))
         return self
 
+    def new_collimated_w_fluence_helper(self, pos_xyz, wavelength: float, fluence) -> "Rays":
+        """Rays::new_collimated_w_fluence_helper (rays.rs:352-398): energy = Voronoi cell area x fluence [J/m^2], FluenceRays attached"""
+        p = np.ascontiguousarray(pos_xyz, dtype=np.float64).reshape(-1, 3)
+        fl = np.ascontiguousarray(np.broadcast_to(np.asarray(fluence, dtype=np.float64), (len(p),)))
+        dp = C.POINTER(C.c_double)
+        _check(F.lib().opm_rays_new_collimated_w_fluence_helper(self.h, p.ctypes.data_as(dp), len(p), wavelength, fl.ctypes.data_as(dp)))
+        return self
+
     @property
     def has_fluence_helpers(self) -> bool:
         return bool(F.lib().opm_rays_has_fluence_helpers(self.h))

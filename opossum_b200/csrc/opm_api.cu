@@ -2628,8 +2628,49 @@ extern "C" OpmStatus opm_hitmap_bounce_levels(OpmHitMap* map, uint64_t* mask) {
     *mask = *h;
     return OPM_OK;
 }
+struct VorSites { std::vector<double> e, z; };  // sorted sites: what went in as `e`, and e / cell area [cm^2]
 static OpmStatus fluence_voronoi_impl(OpmHitMap* const* maps, int32_t n_maps, int64_t bounce_filter, uint64_t nx, const double* ranges,
-                                      int32_t accumulate, double* map_dev, double lrtb_out[4], bool helper_rays);
+                                      int32_t accumulate, double* map_dev, double lrtb_out[4], bool helper_rays, VorSites* cells_only = nullptr);
+// create_voronoi_cells (utils/griddata.rs:265-345) + calc_closed_poly_area of every cell, as Rays::new_collimated_w_fluence_helper
+// uses them (rays.rs:367-389): the area [m^2] of each point's Voronoi cell inside the pushed-out convex hull; NaN = fewer than
+// three vertices
+extern "C" OpmStatus opm_voronoi_cell_areas(OpmContext* c, const double* x_m, const double* y_m, uint64_t n, double* area_m2_out) {
+    if (!c || !x_m || !y_m || !area_m2_out) return fail(OPM_ERR_ARG, "NULL argument");
+    OpmHitMap* hm = nullptr;
+    OpmStatus s = opm_hitmap_create(c, n ? n : 1, &hm);
+    if (s) return s;
+    std::vector<double> tag(n);
+    for (uint64_t i = 0; i < n; ++i) tag[i] = (double)(i + 1);  // the sites come back sorted: the "energy" carries the index
+    s = opm_hitmap_upload(hm, x_m, y_m, nullptr, tag.data(), nullptr, n);
+    VorSites sites;
+    OpmHitMap* maps[1] = {hm};
+    if (!s) s = fluence_voronoi_impl(maps, 1, -1, 2, nullptr, 0, nullptr, nullptr, false, &sites);
+    opm_hitmap_destroy(hm);
+    if (s) return s;
+    if (sites.e.size() != n) return fail(OPM_ERR_VORONOI, "Voronoi cells: %zu sites for %llu points", sites.e.size(), (unsigned long long)n);
+    for (uint64_t k = 0; k < n; ++k) {
+        const uint64_t i = (uint64_t)sites.e[k] - 1;
+        area_m2_out[i] = (sites.e[k] / sites.z[k]) * 1.0E-4;  // cm^2 -> m^2
+    }
+    return OPM_OK;
+}
+// Rays::new_collimated_w_fluence_helper (rays.rs:352-398): rays along +z at the given positions, energy = Voronoi cell area x
+// fluence (0 for a cell of fewer than three vertices), each with its FluenceRays
+extern "C" OpmStatus opm_rays_new_collimated_w_fluence_helper(OpmRays* rays, const double* pos_xyz, uint64_t n, double wavelength_m,
+                                                              const double* fluence) {
+    if (!rays || !pos_xyz || !fluence || n == 0) return fail(OPM_ERR_ARG, "NULL argument");
+    std::vector<double> x(n), y(n), z(n), dx(n, 0.0), dy(n, 0.0), dz(n, 1.0), e(n), w(n, wavelength_m), area(n);
+    for (uint64_t i = 0; i < n; ++i) { x[i] = pos_xyz[3 * i]; y[i] = pos_xyz[3 * i + 1]; z[i] = pos_xyz[3 * i + 2]; }
+    OpmStatus s = opm_voronoi_cell_areas(rays->ctx, x.data(), y.data(), n, area.data());
+    if (s) return s;
+    for (uint64_t i = 0; i < n; ++i) e[i] = std::isfinite(area[i]) ? area[i] * fluence[i] : 0.0;
+    const double* P[3] = {x.data(), y.data(), z.data()};
+    const double* D[3] = {dx.data(), dy.data(), dz.data()};
+    s = opm_rays_upload_soa(rays, P, D, e.data(), w.data(), n);
+    if (s) return s;
+    CU(cudaStreamSynchronize(rays->ctx->stream));  // the staging vectors go out of scope
+    return opm_rays_attach_fluence_helpers(rays, fluence);
+}
 extern "C" OpmStatus opm_fluence_voronoi(OpmHitMap* const* maps, int32_t n_maps, int64_t bounce_filter, uint64_t nx, const double* ranges,
                                          int32_t accumulate, double* map_dev, double lrtb_out[4]) {
     return fluence_voronoi_impl(maps, n_maps, bounce_filter, nx, ranges, accumulate, map_dev, lrtb_out, false);
@@ -2642,11 +2683,11 @@ extern "C" OpmStatus opm_fluence_helper_rays(OpmHitMap* const* maps, int32_t n_m
 // bundle with fluence helper rays wrote them), the sites of the diagram take them as they are, voronator's four helper sites around
 // the bounding polygon take the value 0 (:700-701) and ALL of them go into the natural-neighbour interpolation
 static OpmStatus fluence_voronoi_impl(OpmHitMap* const* maps, int32_t n_maps, int64_t bounce_filter, uint64_t nx, const double* ranges,
-                                      int32_t accumulate, double* map_dev, double lrtb_out[4], bool helper_rays) {
+                                      int32_t accumulate, double* map_dev, double lrtb_out[4], bool helper_rays, VorSites* cells_only) {
     OpmContext* c;
     OpmStatus s = check_same_ctx(maps, n_maps, &c);
     if (s) return s;
-    if (!map_dev || nx == 0 || nx > 46340) return fail(OPM_ERR_ARG, "bad map arguments");
+    if ((!map_dev && !cells_only) || nx == 0 || nx > 46340) return fail(OPM_ERR_ARG, "bad map arguments");
     if (bounce_filter < -1) return fail(OPM_ERR_ARG, "bad bounce filter");
     CU(cudaSetDevice(c->device));
     uint64_t slots = 0;
@@ -2749,6 +2790,7 @@ static OpmStatus fluence_voronoi_impl(OpmHitMap* const* maps, int32_t n_maps, in
     } else {
         for (int i = 0; i < n; ++i) z[i] = e[i] / 1.0E4;  // get::<joule_per_square_centimeter>() of the SI value
     }
+    if (cells_only) { cells_only->e = e; cells_only->z = z; cleanup(); return OPM_OK; }
     // interpolation over the sites with a finite value (griddata.rs:412): normally all of them
     int nf = 0;
     for (int i = 0; i < n; ++i) nf += std::isfinite(z[i]) ? 1 : 0;

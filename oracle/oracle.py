@@ -653,6 +653,20 @@ def helpers_new(rays: np.ndarray, init_fluence) -> dict:
     return {"rays": h, "eff": eff}
 
 
+def rays_new_collimated_w_fluence_helper(xyz, wvl: float, fluence):
+    """Rays::new_collimated_w_fluence_helper (rays.rs:352-398): energy = Voronoi cell area x fluence (0 for a cell of fewer than three
+    vertices); fluence in J/m^2.  Returns (rays, helpers)."""
+    xyz = np.ascontiguousarray(xyz, dtype=np.float64)
+    n = len(xyz)
+    fl = np.broadcast_to(np.asarray(fluence, dtype=np.float64), (n,))
+    inv_area, _ = voronoi_site_fluence(xyz[:, 0] / 1.0E-2, xyz[:, 1] / 1.0E-2, np.ones(n))  # 1 / area [1/cm^2]
+    with np.errstate(divide="ignore", invalid="ignore"):
+        area_m2 = (1.0 / inv_area) * 1.0E-4
+    e = np.where(np.isfinite(area_m2), area_m2 * fl, 0.0)
+    rays = rays_from_arrays(xyz, np.tile([0.0, 0.0, 1.0], (n, 1)), e, np.full(n, wvl))
+    return rays, helpers_new(rays, fl)
+
+
 def helper_ray_fluence(helpers: dict, i: int) -> float:
     """Ray::helper_ray_fluence (ray.rs:172-198) in J/m^2"""
     p = helpers["rays"]["pos"][i]

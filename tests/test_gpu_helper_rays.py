@@ -208,3 +208,16 @@ def test_scene_with_helper_rays_and_report(ctx):
     assert np.array_equal(np.isfinite(fd.map), ok)
     assert np.abs(fd.map[ok] - ref_map[ok]).max() / np.abs(ref_map[ok]).max() <= 1e-5  # the records are quotients by 1e-12 m^2 areas, see above
     assert fd.peak == pytest.approx(np.nanmax(ref_map), rel=1e-5)
+
+
+def test_new_collimated_w_fluence_helper(ctx):
+    """Rays::new_collimated_w_fluence_helper (rays.rs:352-398): ray energies = Voronoi cell areas x fluences; the bundle's energy
+    approaches the distribution's total (1 J) as the reference's docstring promises"""
+    xyz = orc.hexapolar(7, 12e-3)
+    fl = orc.fluence_general_gaussian(xyz[:, :2], 1.0, (0.0, 0.0), (2.5e-3, 2.5e-3), 0.0)
+    ref, rh = orc.rays_new_collimated_w_fluence_helper(xyz, 1000e-9, fl)
+    r = ob.Rays(ctx, len(xyz)).new_collimated_w_fluence_helper(xyz, 1000e-9, fl)
+    got = r.to_array()
+    assert_rays_match(got, ref, what="new_collimated_w_fluence_helper")
+    assert_helpers_match(r.fluence_helpers(), orc.helpers_as_product_layout(rh), "new_collimated_w_fluence_helper")
+    assert abs(got["e"].sum() - 1.0) < 0.05
