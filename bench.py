@@ -39,7 +39,7 @@ UNIT = "interactions/s"
 RAY_BYTES = 93     # SoA bundle: 10 f64 + 3 u32 + 1 u8 (opossum_b200/csrc/opm_internal.h)
 RAY_BYTES_INPLACE = 81  # in-place write: wavelength and id never change
 HIT_BYTES = 36     # hit record: 4 f64 + u32
-SPOT_COPY_BYTES = 33  # spot-diagram copy of the bundle: position (3 f64) + energy + valid flag (OPM_SCENE_LEAN_SPOT_DATA)
+SPOT_COPY_BYTES = 41  # spot-diagram copy of the bundle: position (3 f64) + energy + id + bounce count + valid flag (OPM_SCENE_LEAN_SPOT_DATA)
 MAP_NX, MAP_NY = 100, 83  # nodes/fluence_detector/mod.rs:103
 
 
@@ -779,7 +779,7 @@ def run_product(args):
             hbm_peak, peak_src = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
         # algorithmic bytes of the trace launches of ONE step on this rank (DESIGN.md "byte model"): every buffer the step
         # must read or write, once.  Read the source bundle (n x 93 B); for the rays still in the bundle write the main
-        # output bundle, the spot diagram's copy of the bundle (33 B: position, energy, valid flag) and the fluence detector's hit record (36 B), and the
+        # output bundle, the spot diagram's copy of the bundle (41 B: position, energy, id, bounce count, valid flag) and the fluence detector's hit record (36 B), and the
         # split-off bundle after its side chain with its hit record.  (The fluence detectors keep only hit maps: their
         # report reads nothing else, nodes/fluence_detector/mod.rs:91-135.)  When the side chain is its own launch
         # (2 trace launches per step) the split-off bundle is additionally written by the main launch and read back.
@@ -837,7 +837,7 @@ def run_product(args):
                                     "opm::trace_kernel (fused surface sequence, interpreter)"),
                          "jit": jit, "achieved": achieved, "peak": hbm_peak,
                          "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": traffic, "peak_source": peak_src,
-                         "byte_model": "93 B ray state read, 93 B written per ray kept + 33 B spot-diagram copy (position, energy, valid flag: what the report reads; round 1 and early round 2 wrote all 93 B) + 36 B per hit record (DESIGN.md section 4)",
+                         "byte_model": "93 B ray state read, 93 B written per ray kept + 41 B spot-diagram copy (position, energy, id, bounce count, valid flag: what the report reads; round 1 and early round 2 wrote all 93 B) + 36 B per hit record (DESIGN.md section 4)",
                          "algorithmic_bytes_per_launch": bytes_step / max(launches_trace, 1), "launches_per_step": launches_trace,
                          "kernel_ms_per_launch": kern_ms_step / max(launches_trace, 1), "kernel_share_of_step": kern_ms_step / (ms / args.steps),
                          "survey_8d": {"bytes_per_launch": bytes_8d / max(launches_trace, 1), "achieved": bytes_8d / kern_s / 1e9,

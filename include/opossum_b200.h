@@ -227,8 +227,10 @@ typedef struct { double focal_length; OpmIsometry iso; } OpmParaxialOp;
 typedef struct { double ratio; OpmRays* split_out; const OpmSpectrum* spectrum; } OpmSplitOp;
 typedef struct { double ratio; const OpmSpectrum* spectrum; } OpmForkOp;
 typedef struct { OpmRays* out; } OpmJoinOp;                         /* out: the split-off bundle after its side chain; NULL = discard */
-/* slot-indexed copy of the bundle at this point.  fields = OPM_SNAPSHOT_SPOT: only what a spot-diagram report reads is copied
- * (position, energy, valid flag -- nodes/spot_diagram.rs:101-163); the other arrays of `out` are left as they were.
+/* slot-indexed copy of the bundle at this point.  fields = OPM_SNAPSHOT_SPOT: only what a spot-diagram report and the bundle
+ * statistics (opm_rays_spot_*, opm_rays_bounce_lvl, opm_rays_tally) read is copied -- position, energy, valid flag, id and bounce
+ * count (nodes/spot_diagram.rs:101-163, rays.rs:183-194, 521-701): 41 of the 93 bytes of a ray; the other arrays of `out`
+ * (direction, wavelength, path length, index, refraction count) are left as they were.
  * spot_frame: the frame the copy's statistics will be asked for in (opm_rays_spot_*, `frame_or_null` there; the detector's
  * effective isometry, nodes/spot_diagram.rs:106-112) or NULL for none / world.  With want_spot_sums != 0 a launch that runs the
  * specialised kernel takes the phase-1 sums of those statistics while it writes the copy (rays.rs:599-637); the next

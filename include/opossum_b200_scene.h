@@ -125,8 +125,9 @@ enum {
     OPM_SCENE_KEEP_SOURCE = 64,     /* leave `source_rays` untouched: the main chain's output goes to opm_scene_output_rays() */
     OPM_SCENE_KEEP_LIGHT_DATA = 256, /* FluenceDetector nodes also keep a copy of the bundle (the reference's `light_data`); no report
                                        reads it (nodes/fluence_detector/mod.rs:91-135), so by default only their hit map is kept */
-    OPM_SCENE_LEAN_SPOT_DATA = 512, /* SpotDiagram nodes keep only what their report reads of their copy of the bundle: position, energy and
-                                       valid flag per ray (nodes/spot_diagram.rs:101-163); the other arrays of opm_scene_node_rays() are undefined */
+    OPM_SCENE_LEAN_SPOT_DATA = 512, /* SpotDiagram nodes keep only what their report reads of their copy of the bundle: position, energy,
+                                       valid flag, id and bounce count per ray (OPM_SNAPSHOT_SPOT; nodes/spot_diagram.rs:101-163); the
+                                       other arrays of opm_scene_node_rays() are undefined */
     OPM_SCENE_POSITION_HISTORY = 128 /* keep the per-ray position history (`pos_hist`): read it with opm_rays_position_history() from the
                                        bundles of opm_scene_node_rays() / opm_scene_output_rays() / the traced source bundle */
 };

@@ -386,8 +386,8 @@ __device__ __forceinline__ void exec_join(const DevJoin& o, RayCtx& x, const uns
     const unsigned fl = stash[20 * OPM_BDIM + threadIdx.x];
     x.alive = (fl & 1u) != 0; x.valid = (fl & 2u) != 0;
 }
-// copy of the bundle a detector node keeps (analyzers/raytrace.rs:186-205).  LEAN: only what a spot-diagram report reads
-// (nodes/spot_diagram.rs:101-163: positions, energies, which rays are valid)
+// copy of the bundle a detector node keeps (analyzers/raytrace.rs:186-205).  LEAN: only what a spot-diagram report and the bundle
+// statistics read (nodes/spot_diagram.rs:101-163, rays.rs:521-701: positions, energies, which rays are valid, id and bounce count)
 template <bool LEAN = false>
 __device__ __forceinline__ void exec_snapshot_store(const DevSnapshot& o, RayCtx& x) {
     if (!x.in_range) return;
@@ -396,6 +396,7 @@ __device__ __forceinline__ void exec_snapshot_store(const DevSnapshot& o, RayCtx
         if (LEAN) {
             OPM_ST(o.out.px + x.i, x.r.pos.x); OPM_ST(o.out.py + x.i, x.r.pos.y); OPM_ST(o.out.pz + x.i, x.r.pos.z);
             OPM_ST(o.out.e + x.i, x.r.e);
+            OPM_ST(o.out.id + x.i, x.r.id); OPM_ST(o.out.bounces + x.i, x.r.bounces);  // Rays::bounce_lvl of the copy (rays.rs:183-194)
             o.out.valid[x.i] = flag;
         } else store_ray<true>(o.out, x.i, x.r, flag);
     } else o.out.valid[x.i] = RAY_REMOVED;

@@ -85,12 +85,12 @@ def test_c2_specialised_kernel_spot_sums_and_lean_copy():
     ref = osc.node_spot(8)
     stats = {}
     try:
-        for mode in ("two_pass", "fused_full", "fused_lean"):
-            ctx.set_jit(2 if mode != "two_pass" else 0, 1)
+        for mode in ("two_pass", "two_pass_lean", "fused_full", "fused_lean"):
+            ctx.set_jit(2 if mode.startswith("fused") else 0, 1)
             psc = scenes.to_product(ctx, scenes.c2_laser_chain())
             rays = scenes.source_to_product(src).generate(ctx)
             n0 = ctx.launch_count
-            st = psc.raytrace(rays, lean_spot_data=(mode == "fused_lean"))
+            st = psc.raytrace(rays, lean_spot_data=mode.endswith("lean"))
             assert st.interactions == osc.interactions
             assert_rays_match(rays.to_array(), ref_out, what=f"C2 main chain ({mode})")
             n1 = ctx.launch_count
@@ -101,12 +101,13 @@ def test_c2_specialised_kernel_spot_sums_and_lean_copy():
             assert np.allclose(s.energy_centroid[:2], ref["centroid"][:2], rtol=RTOL, atol=1e-15)
             assert s.beam_radius_geo == pytest.approx(ref["geo"], rel=RTOL)
             assert s.energy_beam_radius_rms == pytest.approx(ref["rms"], rel=RTOL)
-            if mode == "fused_lean":  # the copy: positions, energies and flags of the full copy
+            if mode.endswith("lean"):  # the copy: positions, energies, flags, ids and bounce counts of the full copy
                 full = osc.nodes[8].stored
                 got = psc.node_rays(8).to_array()
                 assert len(got) == len(full)
-                for f in ("pos", "e", "valid"):
+                for f in ("pos", "e", "valid", "id", "bounces"):
                     assert np.allclose(got[f], full[f], rtol=RTOL, atol=1e-300), f
+                assert psc.node_rays(8).bounce_lvl() == 0
             check_detector(osc, psc, 9)
     finally:
         jit = ctx.jit_stats()
