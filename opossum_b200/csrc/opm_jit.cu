@@ -387,6 +387,7 @@ bool load(JitKernel& K, int n_ops, int block) {
     if (K.const_bytes < (size_t)n_ops * sizeof(DevOp)) { K.why = "constant array smaller than the program"; return false; }
     int nb = 0;
     K.smem = jit_dynamic_smem(K.has_fork, block, K.bbox_slots, K.spot_slots) + 8;
+    if (const char* e = getenv("OPM_B200_JIT_SMEM_PAD_KB")) K.smem += (size_t)atoi(e) * 1024;  // probe: what the L1 share of the SM's memory is worth
     if (K.smem > 48 * 1024 &&
         cudaFuncSetAttribute((const void*)K.kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K.smem) != cudaSuccess) {
         K.why = "dynamic shared memory of the specialised kernel not available"; cudaGetLastError(); return false;
