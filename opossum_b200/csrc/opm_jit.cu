@@ -49,6 +49,7 @@ struct JitKernel {
     int n_ops = 0;
     int occupancy = 1;
     bool has_fork = false;
+    int stash_words = 0;  // shared-memory words per thread for the parked rays of the program's FORKs
     int bbox_slots = 0;  // hit maps whose bounding box the kernel keeps (36 bytes of shared memory per thread each)
     int spot_slots = 0;  // bundle copies whose phase-1 spot sums the kernel takes (kSpotSmemBytes per thread each)
     size_t smem = 0;  // dynamic shared memory per CTA
@@ -133,14 +134,14 @@ static int program_spot_slots(const DevOp* ops, int n_ops) {
     for (int k = 0; k < n_ops; ++k) n += op_has_spot(ops[k]) ? 1 : 0;
     return n;
 }
-bool jit_unit_dir_enabled() {
+static bool jit_unit_dir_enabled() {
     static const bool on = [] { const char* e = getenv("OPM_B200_JIT_UNIT_DIR"); return !(e && e[0] == '0'); }();  // tuning switch
     return on;
 }
 // does this op leave every ray that is still valid behind it with a unit direction (up to rounding)?  A refraction / reflection
 // (ray.rs:606-631) whose missed rays stop, and the paraxial surface (ray.rs:469), do; isometries and the energy ops keep what they
 // find.  (A surface whose missed rays carry on, and a grating, pass such rays through untouched: they establish nothing.)
-void unit_dir_after(const DevOp& op, bool& unit) {
+static void unit_dir_after(const DevOp& op, bool& unit) {
     if ((op.kind == OPK_REFRACT && op.u.refract.strategy == OPM_MISS_STOP) || op.kind == OPK_PARAXIAL) unit = true;
 }
 std::string refract_view(const DevRefract& o, int k, int hint_slot, bool unit_dir = false) {  // hint_slot < 0: no hint
@@ -154,7 +155,7 @@ std::string refract_view(const DevRefract& o, int k, int hint_slot, bool unit_di
 }
 
 // one line of kernel body per op; the same text is the structural cache key
-std::string op_line(const DevOp& op, int k, int hint_slot = -1, bool unit_dir = false) {
+std::string op_line(const DevOp& op, int k, int hint_slot = -1, bool unit_dir = false, int park = 63) {
     std::string s;
     switch (op.kind) {
         case OPK_REFRACT: {
@@ -189,8 +190,8 @@ std::string op_line(const DevOp& op, int k, int hint_slot = -1, bool unit_dir = 
                         jit_rot_id_enabled() && rot_is_identity(op.u.snapshot.inv) ? "true" : "false", k, k, k);
             break;
         case OPK_TRANSFORM: appendf(s, "        exec_transform(opm_jit_ops[%d].u.transform, x);\n", k); break;
-        case OPK_FORK: appendf(s, "        exec_fork<%s>(opm_jit_ops[%d].u.fork, x, opm_jit_stash);\n", op.u.fork.s.lam ? "true" : "false", k); break;
-        case OPK_JOIN: appendf(s, "        exec_join(opm_jit_ops[%d].u.join, x, opm_jit_stash);\n", k); break;
+        case OPK_FORK: appendf(s, "        exec_fork<%s, %d>(opm_jit_ops[%d].u.fork, x, opm_jit_stash);\n", op.u.fork.s.lam ? "true" : "false", park, k); break;
+        case OPK_JOIN: appendf(s, "        exec_join<%d>(opm_jit_ops[%d].u.join, x, opm_jit_stash);\n", park, k); break;
         case OPK_DIFFRACT: {
             const DevRefract& o = op.u.diffract.surf;
             appendf(s, "        exec_diffract(RefractCt<%d, %d, %d, %d, %d, %d, %d, %d>(opm_jit_ops[%d].u.diffract.surf), opm_jit_ops[%d].u.diffract, x);\n",
@@ -216,19 +217,67 @@ static bool program_has_fork(const DevOp* ops, int n_ops) {
     return false;
 }
 // dynamic shared memory of a specialised kernel: [parked rays of a FORK | stage 0 | stage 1]
-static size_t jit_stash_bytes(bool has_fork, int block) { return has_fork ? (((size_t)block * kStashWords * 4 + 127) & ~(size_t)127) : 0; }
+// shared-memory words per thread for the parked parent rays of the program's FORKs (0: no FORK)
+static size_t jit_stash_bytes(int stash_words, int block) { return stash_words ? (((size_t)block * stash_words * 4 + 127) & ~(size_t)127) : 0; }
+// STASH_* bits of opm_trace_ops.cuh (the generator does not include the device header)
+enum : int { JS_POS = 1, JS_DIR = 2, JS_OPL = 4, JS_N = 8, JS_BOUNCES = 16, JS_REFR = 32, JS_ALL = 63 };
+static int js_words(int park) {
+    return 3 + ((park & JS_POS) ? 6 : 0) + ((park & JS_DIR) ? 6 : 0) + ((park & JS_OPL) ? 2 : 0) + ((park & JS_N) ? 2 : 0) + ((park & JS_BOUNCES) ? 1 : 0) +
+           ((park & JS_REFR) ? 1 : 0);
+}
+static bool jit_unit_dir_enabled();
+static void unit_dir_after(const DevOp& op, bool& unit);
+// unit[k]: every ray that reaches op k has passed an op that leaves a unit direction
+static std::vector<char> program_unit_dirs(const DevOp* ops, int n_ops) {
+    std::vector<char> unit(n_ops, 0);
+    bool u = false;
+    for (int k = 0; k < n_ops; ++k) { unit[k] = u && jit_unit_dir_enabled(); unit_dir_after(ops[k], u); }
+    return unit;
+}
+// which fields of the parked parent the side chain of the FORK at op `f` can change (conservative; energy and flags are always
+// parked): the bits exec_fork / exec_join are instantiated with
+static int fork_park_mask(const DevOp* ops, int n_ops, int f, const std::vector<char>& unit) {
+    static const bool on = [] { const char* e = getenv("OPM_B200_JIT_PARK"); return !(e && e[0] == '0'); }();  // tuning switch
+    if (!on) return JS_ALL;
+    int m = 0;
+    for (int k = f + 1; k < n_ops && ops[k].kind != OPK_JOIN; ++k) {
+        const DevOp& d = ops[k];
+        switch (d.kind) {
+            case OPK_REFRACT: {
+                const DevRefract& o = d.u.refract;
+                m |= JS_POS | JS_OPL;
+                if (o.has_index || (o.flags & OPM_REFRACT_CONTINUE_AS_CHILD)) m |= JS_DIR | JS_N | JS_BOUNCES | JS_REFR;
+                else if (!(o.geom == OPM_GEOM_PLANE && unit[k])) m |= JS_DIR;  // a passive plane hands a unit direction back bit for bit
+                break;
+            }
+            case OPK_PARAXIAL: m |= JS_POS | JS_DIR | JS_OPL | JS_REFR; break;
+            case OPK_TRANSFORM: m |= JS_POS | JS_DIR; break;
+            case OPK_APODIZE: case OPK_THRESHOLD: case OPK_LIMITS: case OPK_FILTER: case OPK_SNAPSHOT: case OPK_SPLIT: break;  // energy, flags
+            default: return JS_ALL;  // gratings, anything new
+        }
+    }
+    return m;
+}
+static int program_stash_words(const DevOp* ops, int n_ops) {
+    const std::vector<char> unit = program_unit_dirs(ops, n_ops);
+    int w = 0;
+    for (int k = 0; k < n_ops; ++k)
+        if (ops[k].kind == OPK_FORK) w = std::max(w, js_words(fork_park_mask(ops, n_ops, k, unit)));
+    return w;
+}
 static int program_bbox_slots(const DevOp* ops, int n_ops);
 // [parked rays of a FORK | tile stages | running bounding boxes of the recorded hit maps | running spot sums of the bundle copies]
-static size_t jit_bbox_offset(bool has_fork, int block) {
-    return jit_stash_bytes(has_fork, block) + (jit_pipe_enabled() && block % 16 == 0 ? 2 * jit_stage_bytes(block) : 0);
+static size_t jit_bbox_offset(int stash_words, int block) {
+    return jit_stash_bytes(stash_words, block) + (jit_pipe_enabled() && block % 16 == 0 ? 2 * jit_stage_bytes(block) : 0);
 }
-size_t jit_dynamic_smem(bool has_fork, int block, int bbox_slots, int spot_slots) {
-    return jit_bbox_offset(has_fork, block) + (size_t)bbox_slots * block * 36 + (size_t)spot_slots * block * kSpotSmemBytes;
+size_t jit_dynamic_smem(int stash_words, int block, int bbox_slots, int spot_slots) {
+    return jit_bbox_offset(stash_words, block) + (size_t)bbox_slots * block * 36 + (size_t)spot_slots * block * kSpotSmemBytes;
 }
 
 std::string make_source(const DevOp* ops, int n_ops, bool compact, int block, int min_ctas) {
     const bool pipe = jit_pipe_enabled() && block % 16 == 0;
-    const size_t stash = jit_stash_bytes(program_has_fork(ops, n_ops), block);
+    const int stash_w = program_stash_words(ops, n_ops);
+    const size_t stash = jit_stash_bytes(stash_w, block);
     // Body of the tile loop.  Rays that are (or become) invalid leave the straight-line code for a second copy of the program --
     // the same op lines under the knowledge `x.valid == false`, which the compiler folds down to the ops' side effects for such a
     // ray (empty hit records, detector copies, FORK / JOIN bookkeeping).  The live copy therefore has no `if (x.valid)` diamonds:
@@ -248,18 +297,18 @@ std::string make_source(const DevOp* ops, int n_ops, bool compact, int block, in
                                "        s_hint[%d] = n2; s_hint[%d] = rcp_fast(n2);\n    }\n",
                     3 * hint_slot[k], 3 * hint_slot[k] + 1, 3 * hint_slot[k] + 2);
         }
-    // unit[k]: every ray that reaches op k has passed an op that leaves a unit direction
-    std::vector<char> unit(n_ops, 0);
-    {
-        bool u = false;
-        for (int k = 0; k < n_ops; ++k) { unit[k] = u && jit_unit_dir_enabled(); unit_dir_after(ops[k], u); }
+    const std::vector<char> unit = program_unit_dirs(ops, n_ops);
+    std::vector<int> park(n_ops, JS_ALL);  // FORK and its JOIN: the fields the side chain can change
+    for (int k = 0, open = -1; k < n_ops; ++k) {
+        if (ops[k].kind == OPK_FORK) { open = k; park[k] = fork_park_mask(ops, n_ops, k, unit); }
+        else if (ops[k].kind == OPK_JOIN && open >= 0) { park[k] = park[open]; open = -1; }
     }
     if (!split) {
-        for (int k = 0; k < n_ops; ++k) body += op_line(ops[k], k, hint_slot[k], unit[k] != 0);
+        for (int k = 0; k < n_ops; ++k) body += op_line(ops[k], k, hint_slot[k], unit[k] != 0, park[k]);
     } else {
         std::string dead;
         for (int k = 0; k < n_ops; ++k) {
-            const std::string line = op_line(ops[k], k, hint_slot[k], unit[k] != 0);
+            const std::string line = op_line(ops[k], k, hint_slot[k], unit[k] != 0, park[k]);
             if (k > 0 && ops[k - 1].kind == OPK_JOIN) appendf(body, "      live_%d:\n", k);
             appendf(body, "        if (!x.valid) goto dead_%d;\n        {\n", k);
             body += line;
@@ -292,7 +341,7 @@ std::string make_source(const DevOp* ops, int n_ops, bool compact, int block, in
         s += hint_init;
     }
     {
-        size_t sp0 = jit_bbox_offset(program_has_fork(ops, n_ops), block) + (size_t)program_bbox_slots(ops, n_ops) * block * 36;
+        size_t sp0 = jit_bbox_offset(stash_w, block) + (size_t)program_bbox_slots(ops, n_ops) * block * 36;
         sp0 = (sp0 + 7) & ~(size_t)7;
         for (int k = 0; k < n_ops; ++k)
             if (op_has_spot(ops[k])) {
@@ -309,7 +358,7 @@ std::string make_source(const DevOp* ops, int n_ops, bool compact, int block, in
         appendf(s, "    tile_pipe_init(pipe, opm_jit_smem + %zu, s_bar, in, n);\n", stash);
     }
     {
-        const size_t bb0 = jit_bbox_offset(program_has_fork(ops, n_ops), block);
+        const size_t bb0 = jit_bbox_offset(stash_w, block);
         int j = 0;
         for (int k = 0; k < n_ops; ++k)
             if (op_has_bbox(ops[k])) {
@@ -386,7 +435,7 @@ bool load(JitKernel& K, int n_ops, int block) {
     if (e != cudaSuccess) { K.why = std::string("cudaLibraryGetKernel/Global: ") + cudaGetErrorString(e); cudaGetLastError(); return false; }
     if (K.const_bytes < (size_t)n_ops * sizeof(DevOp)) { K.why = "constant array smaller than the program"; return false; }
     int nb = 0;
-    K.smem = jit_dynamic_smem(K.has_fork, block, K.bbox_slots, K.spot_slots) + 8;
+    K.smem = jit_dynamic_smem(K.stash_words, block, K.bbox_slots, K.spot_slots) + 8;
     if (const char* e = getenv("OPM_B200_JIT_SMEM_PAD_KB")) K.smem += (size_t)atoi(e) * 1024;  // probe: what the L1 share of the SM's memory is worth
     if (K.smem > 48 * 1024 &&
         cudaFuncSetAttribute((const void*)K.kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)K.smem) != cudaSuccess) {
@@ -461,6 +510,7 @@ const JitKernel* jit_get(JitCache* cache, const DevOp* ops, int n_ops, bool comp
         it = cache->kernels.emplace(std::move(src), std::unique_ptr<JitKernel>(new JitKernel())).first;
         JitKernel* k = it->second.get();
         k->has_fork = program_has_fork(ops, n_ops);
+        k->stash_words = program_stash_words(ops, n_ops);
         k->bbox_slots = program_bbox_slots(ops, n_ops);
         k->spot_slots = program_spot_slots(ops, n_ops);
         if (!nvrtc_load(&k->why)) {

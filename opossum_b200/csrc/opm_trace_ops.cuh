@@ -358,32 +358,54 @@ __device__ __forceinline__ void stash_put(unsigned* stash, int f, double v) {
 __device__ __forceinline__ double stash_get(const unsigned* stash, int f) {
     return __hiloint2double((int)stash[(2 * f + 1) * OPM_BDIM + threadIdx.x], (int)stash[(2 * f) * OPM_BDIM + threadIdx.x]);
 }
-template <bool SPECTRAL = true>
+// PARK: which fields of the parent the side chain can change (STASH_*; energy and flags are always parked).  The interpreter parks
+// everything; the specialised kernel parks what the ops between its FORK and JOIN can touch, the rest of the parent is still in
+// the registers when the JOIN comes (fewer shared-memory words per thread: more L1, fewer stores and loads).
+enum : int { STASH_POS = 1, STASH_DIR = 2, STASH_OPL = 4, STASH_N = 8, STASH_BOUNCES = 16, STASH_REFR = 32, STASH_ALL = 63 };
+__host__ __device__ constexpr int stash_words(int park) {
+    return 3 + ((park & STASH_POS) ? 6 : 0) + ((park & STASH_DIR) ? 6 : 0) + ((park & STASH_OPL) ? 2 : 0) + ((park & STASH_N) ? 2 : 0) +
+           ((park & STASH_BOUNCES) ? 1 : 0) + ((park & STASH_REFR) ? 1 : 0);
+}
+// word offset of a field's slot: energy 0-1, flags 2, then the parked fields in the order of their bits
+__host__ __device__ constexpr int stash_off(int park, int field) { return stash_words(park & (field - 1)); }
+__device__ __forceinline__ void stash_putw(unsigned* stash, int w, double v) {
+    stash[w * OPM_BDIM + threadIdx.x] = (unsigned)__double2loint(v);
+    stash[(w + 1) * OPM_BDIM + threadIdx.x] = (unsigned)__double2hiint(v);
+}
+__device__ __forceinline__ double stash_getw(const unsigned* stash, int w) {
+    return __hiloint2double((int)stash[(w + 1) * OPM_BDIM + threadIdx.x], (int)stash[w * OPM_BDIM + threadIdx.x]);
+}
+template <bool SPECTRAL = true, int PARK = STASH_ALL>
 __device__ __forceinline__ void exec_fork(const DevFork& o, RayCtx& x, unsigned* stash) {
     double ratio = o.ratio;
     if (SPECTRAL && x.valid && spectral_factor<true>(o.s, o.ratio, x, ratio) && o.s.lam != nullptr && !(ratio >= 0.0 && ratio <= 1.0)) {
         x.c.status |= 1u << OPM_ERR_SPLIT_RATIO; x.valid = false;
     }
     const double e_main = x.valid ? x.r.e * ratio : x.r.e;  // invalid rays are copied unchanged (rays.rs:1258-1262)
-    stash_put(stash, 0, x.r.pos.x); stash_put(stash, 1, x.r.pos.y); stash_put(stash, 2, x.r.pos.z);
-    stash_put(stash, 3, x.r.dir.x); stash_put(stash, 4, x.r.dir.y); stash_put(stash, 5, x.r.dir.z);
-    stash_put(stash, 6, e_main); stash_put(stash, 7, x.r.opl); stash_put(stash, 8, x.r.n);
-    stash[18 * OPM_BDIM + threadIdx.x] = x.r.bounces;
-    stash[19 * OPM_BDIM + threadIdx.x] = x.r.refr;
-    stash[20 * OPM_BDIM + threadIdx.x] = (x.alive ? 1u : 0u) | (x.valid ? 2u : 0u);
+    stash_putw(stash, 0, e_main);
+    stash[2 * OPM_BDIM + threadIdx.x] = (x.alive ? 1u : 0u) | (x.valid ? 2u : 0u);
+    if (PARK & STASH_POS) { const int w = stash_off(PARK, STASH_POS); stash_putw(stash, w, x.r.pos.x); stash_putw(stash, w + 2, x.r.pos.y); stash_putw(stash, w + 4, x.r.pos.z); }
+    if (PARK & STASH_DIR) { const int w = stash_off(PARK, STASH_DIR); stash_putw(stash, w, x.r.dir.x); stash_putw(stash, w + 2, x.r.dir.y); stash_putw(stash, w + 4, x.r.dir.z); }
+    if (PARK & STASH_OPL) stash_putw(stash, stash_off(PARK, STASH_OPL), x.r.opl);
+    if (PARK & STASH_N) stash_putw(stash, stash_off(PARK, STASH_N), x.r.n);
+    if (PARK & STASH_BOUNCES) stash[stash_off(PARK, STASH_BOUNCES) * OPM_BDIM + threadIdx.x] = x.r.bounces;
+    if (PARK & STASH_REFR) stash[stash_off(PARK, STASH_REFR) * OPM_BDIM + threadIdx.x] = x.r.refr;
     if (x.valid) x.r.e *= 1.0 - ratio;
 }
+template <int PARK = STASH_ALL>
 __device__ __forceinline__ void exec_join(const DevJoin& o, RayCtx& x, const unsigned* stash) {
     if (x.in_range && o.out.px != nullptr) {
         if (x.alive || x.warp_live) store_ray<true>(o.out, x.i, x.r, !x.alive ? RAY_REMOVED : x.valid ? RAY_VALID : RAY_INVALID);
         else o.out.valid[x.i] = RAY_REMOVED;
     }
-    x.r.pos = v3(stash_get(stash, 0), stash_get(stash, 1), stash_get(stash, 2));
-    x.r.dir = v3(stash_get(stash, 3), stash_get(stash, 4), stash_get(stash, 5));
-    x.r.e = stash_get(stash, 6); x.r.opl = stash_get(stash, 7); x.r.n = stash_get(stash, 8);
-    x.r.bounces = stash[18 * OPM_BDIM + threadIdx.x];
-    x.r.refr = stash[19 * OPM_BDIM + threadIdx.x];
-    const unsigned fl = stash[20 * OPM_BDIM + threadIdx.x];
+    x.r.e = stash_getw(stash, 0);
+    const unsigned fl = stash[2 * OPM_BDIM + threadIdx.x];
+    if (PARK & STASH_POS) { const int w = stash_off(PARK, STASH_POS); x.r.pos = v3(stash_getw(stash, w), stash_getw(stash, w + 2), stash_getw(stash, w + 4)); }
+    if (PARK & STASH_DIR) { const int w = stash_off(PARK, STASH_DIR); x.r.dir = v3(stash_getw(stash, w), stash_getw(stash, w + 2), stash_getw(stash, w + 4)); }
+    if (PARK & STASH_OPL) x.r.opl = stash_getw(stash, stash_off(PARK, STASH_OPL));
+    if (PARK & STASH_N) x.r.n = stash_getw(stash, stash_off(PARK, STASH_N));
+    if (PARK & STASH_BOUNCES) x.r.bounces = stash[stash_off(PARK, STASH_BOUNCES) * OPM_BDIM + threadIdx.x];
+    if (PARK & STASH_REFR) x.r.refr = stash[stash_off(PARK, STASH_REFR) * OPM_BDIM + threadIdx.x];
     x.alive = (fl & 1u) != 0; x.valid = (fl & 2u) != 0;
 }
 // copy of the bundle a detector node keeps (analyzers/raytrace.rs:186-205).  LEAN: only what a spot-diagram report and the bundle
