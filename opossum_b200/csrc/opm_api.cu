@@ -60,7 +60,10 @@ struct OpmContext {
     // CTA shape of the specialised kernels (tunable: OPM_B200_JIT_BLOCK / _MIN_CTAS).  One CTA of 32 warps per SM at 64 registers
     // per thread measured best on the C2 chain (profiles/r1_summary.md, CTA-shape sweep): the warps of one CTA walk the 70 KB of
     // straight-line code together and share its instruction-cache lines.
-    int jit_block = 1024, jit_min_ctas = 1;
+    // CTA shape of the specialised kernels.  jit_block 0 = by program: one CTA of 1024 threads per SM (64 registers), or of 896 (72
+    // registers) for a program with a FORK, whose parked-ray bookkeeping is what makes the 64-register build spill -- measured on
+    // C2 (FORK): 1.012 ms at 1024, 0.985 ms at 896 (960: 1.030, 832: 1.042); on C4 / C5 (no FORK) 1024 is 3-5 % ahead of 896
+    int jit_block = 0, jit_min_ctas = 1;
     cudaStream_t copy_stream = nullptr;  // host uploads that are expanded on the device run here, overlapping the main stream
     // side computations nobody waits for until opm_context_join_side_stream / opm_context_synchronize (the ghost-focus analysis'
     // per-bundle fluence checks): created on first use
@@ -1514,6 +1517,7 @@ static OpmStatus run_program(OpmRays* rays, const OpmOp* ops, int n_ops, int fla
         // the kernel that runs: the accumulator pointer is a structural fact of its source)
         const bool jit_candidate = !strict && !use_hist && !use_helpers && c->jit_enabled && n >= c->jit_min_rays && prog.ops.size() * sizeof(DevOp) <= 60 * 1024;
         static const bool fuse_bbox = [] { const char* e = getenv("OPM_B200_JIT_BBOX"); return !(e && e[0] == '0'); }();  // tuning switch
+        const int jit_block = c->jit_block ? c->jit_block : (prog.has_fork ? 896 : 1024);
         std::vector<OpmHitMap*> fused;
         if (jit_candidate && fuse_bbox)
             for (auto& ho : prog.hitmap_ops) {
@@ -1531,13 +1535,13 @@ static OpmStatus run_program(OpmRays* rays, const OpmOp* ops, int n_ops, int fla
         const bool fuse_spot = c->jit_fuse_spot;  // read from the environment when the context was created
         std::vector<std::pair<int, OpmRays*>> spot_fused;
         if (jit_candidate && fuse_spot) {
-            size_t smem_need = (prog.has_fork ? (size_t)c->jit_block * kStashWords * 4 + 128 : 0) + fused.size() * (size_t)c->jit_block * 36;
+            size_t smem_need = (prog.has_fork ? (size_t)jit_block * kStashWords * 4 + 128 : 0) + fused.size() * (size_t)jit_block * 36;
             for (auto& so : prog.spot_ops) {
-                if (spot_fused.size() == 2 || smem_need + (size_t)c->jit_block * kSpotSmemBytes > 222 * 1024) break;  // 227 KB per CTA, ~5 KB of it static
+                if (spot_fused.size() == 2 || smem_need + (size_t)jit_block * kSpotSmemBytes > 222 * 1024) break;  // 227 KB per CTA, ~5 KB of it static
                 bool twice = false;
                 for (auto& q : spot_fused) twice |= q.second == so.second;
                 if (twice) continue;
-                smem_need += (size_t)c->jit_block * kSpotSmemBytes;
+                smem_need += (size_t)jit_block * kSpotSmemBytes;
                 prog.ops[so.first].u.snapshot.acc = so.second->d_spot_acc;
                 spot_fused.push_back(so);
             }
@@ -1549,8 +1553,8 @@ static OpmStatus run_program(OpmRays* rays, const OpmOp* ops, int n_ops, int fla
         const JitKernel* jk = nullptr;
         if (jit_candidate) {  // __constant__ holds 64 KB
             const char* why = nullptr;
-            jk = jit_get(c->jit, prog.ops.data(), (int)prog.ops.size(), compact, c->jit_block, c->jit_min_ctas, c->jit_sync, &why);
-            if (jk) block = c->jit_block;
+            jk = jit_get(c->jit, prog.ops.data(), (int)prog.ops.size(), compact, jit_block, c->jit_min_ctas, c->jit_sync, &why);
+            if (jk) block = jit_block;
             if (!jk && why && !c->jit_warned) {  // why == NULL: still compiling, interpret meanwhile
                 c->jit_warned = true;
                 fprintf(stderr, "opossum_b200: run-time kernel specialisation unavailable, using the interpreter kernel (%s)\n", why ? why : "?");
