@@ -331,7 +331,7 @@ std::string make_source(const DevOp* ops, int n_ops, bool compact, int block, in
          "              DevStats* stats) {\n"
          "    extern __shared__ __align__(128) unsigned char opm_jit_smem[];  // [parked rays of a FORK | tile stages], sized by the launch\n"
          "    unsigned* opm_jit_stash = reinterpret_cast<unsigned*>(opm_jit_smem);\n"
-         "    __shared__ cta_count_t s_cnt[kCntWords];\n"
+         "    __shared__ __align__(16) cta_count_t s_cnt[kCntWords];\n"
          "    __shared__ unsigned s_status;\n"
          "    __shared__ unsigned long long s_first_inv;\n"
          "    cta_count_init(s_cnt);\n"
@@ -366,7 +366,8 @@ std::string make_source(const DevOp* ops, int n_ops, bool compact, int block, in
                 ++j;
             }
     }
-    s += "    for (unsigned tile = blockIdx.x; tile < tiles; tile += gridDim.x) {\n"
+    s += "    unsigned warp_best = 0xffffffffu;\n"
+         "    for (unsigned tile = blockIdx.x; tile < tiles; tile += gridDim.x) {\n"
          "        RayCtx x;\n"
          "        uint8_t vb;\n";
     s += pipe ? "        tile_load_staged(pipe, in, tile, n, x, vb);\n"
@@ -374,7 +375,7 @@ std::string make_source(const DevOp* ops, int n_ops, bool compact, int block, in
                 "        tile_prefetch(in, (uint64_t)(tile + gridDim.x) * OPM_BDIM + threadIdx.x, n);\n";
     s += body;
     appendf(s, "        tile_store<%s>(in, out, out_cap, out_tail, x, vb);\n", compact ? "true" : "false");
-    s += "        tile_count(x, s_cnt, &s_status, &s_first_inv);\n"
+    s += "        tile_count(x, s_cnt, &s_status, &s_first_inv, warp_best);\n"
          "    }\n"
          "    __syncthreads();\n";
     for (int k = 0; k < n_ops; ++k)

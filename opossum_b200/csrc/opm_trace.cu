@@ -71,7 +71,7 @@ __device__ __forceinline__ void trace_body(const DevOp* __restrict__ g_ops, int 
     }
     bar.wait(std::move(token));
 
-    __shared__ cta_count_t s_cnt[kCntWords];
+    __shared__ __align__(16) cta_count_t s_cnt[kCntWords];
     __shared__ unsigned s_status;
     __shared__ unsigned long long s_first_inv;  // max of ~(id << 32 | bounces) over the valid rays this CTA wrote
     cta_count_init(s_cnt);
@@ -79,6 +79,7 @@ __device__ __forceinline__ void trace_body(const DevOp* __restrict__ g_ops, int 
     __syncthreads();
 
     const unsigned tiles = (unsigned)((n + blockDim.x - 1) / blockDim.x);
+    unsigned warp_best = 0xffffffffu;
     for (unsigned tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
         RayCtx x;
         uint8_t vb;
@@ -124,7 +125,7 @@ __device__ __forceinline__ void trace_body(const DevOp* __restrict__ g_ops, int 
         }
         tile_store<COMPACT>(in, out, out_cap, out_tail, x, vb);
         if (HELP && x.in_range && x.alive) helpers_store(hlp, x.i, hs);
-        tile_count(x, s_cnt, &s_status, &s_first_inv);
+        tile_count(x, s_cnt, &s_status, &s_first_inv, warp_best);
     }
     __syncthreads();
     cta_flush(stats, s_cnt, s_status, s_first_inv);

@@ -790,7 +790,10 @@ constexpr int kCntWords = 32 * kCntStride;     // one row per warp of the larges
 __device__ __forceinline__ void cta_count_init(cta_count_t* s_cnt) {
     for (unsigned k = threadIdx.x; k < (unsigned)kCntWords; k += blockDim.x) s_cnt[k] = 0u;
 }
-__device__ __forceinline__ void tile_count(const RayCtx& x, cta_count_t* s_cnt, unsigned* s_status, unsigned long long* s_first_inv) {
+// warp_best: the smallest ray id this warp has offered for the launch's first valid ray so far (0xffffffff before its first tile);
+// a tile none of whose rays has an id at or below it cannot change the statistic and skips the two warp minima
+__device__ __forceinline__ void tile_count(const RayCtx& x, cta_count_t* s_cnt, unsigned* s_status, unsigned long long* s_first_inv,
+                                           unsigned& warp_best) {
     const unsigned ra = __reduce_add_sync(0xffffffffu, x.c.a), rb = __reduce_add_sync(0xffffffffu, x.c.b);
     const unsigned rp = __reduce_add_sync(0xffffffffu, x.c.apodized);
     const bool v = x.valid && x.alive;
@@ -799,25 +802,26 @@ __device__ __forceinline__ void tile_count(const RayCtx& x, cta_count_t* s_cnt, 
     const bool lane0 = (threadIdx.x & 31) == 0;
     const bool cap = x.c.kid != kKeyUnset;  // warp-uniform: the ops of a program are
     const unsigned kid = cap ? x.c.kid : (v ? x.r.id : 0xffffffffu), kb = cap ? x.c.kb : x.r.bounces;
-    if (__ballot_sync(0xffffffffu, kid != 0xffffffffu)) {  // first valid ray of the warp = lowest (id, bounces): two 32-bit warp minima
+    if (__any_sync(0xffffffffu, kid != 0xffffffffu && kid <= warp_best)) {  // first valid ray of the warp = lowest (id, bounces): two 32-bit warp minima
         const unsigned idmin = __reduce_min_sync(0xffffffffu, kid);
+        warp_best = idmin;
         const unsigned bmin = __reduce_min_sync(0xffffffffu, (kid != 0xffffffffu && kid == idmin) ? kb : 0xffffffffu);
         if (lane0) {
             const unsigned long long inv = ~(((unsigned long long)idmin << 32) | bmin);  // largest for the first ray
             if (inv > *(volatile unsigned long long*)s_first_inv) atomicMax(s_first_inv, inv);  // rarely after the CTA's first tiles
         }
     }
-    const unsigned lane = threadIdx.x & 31u;
-    unsigned add = ra & 0xffffu;                                  // lane CNT_INTERACTIONS (0)
-    add = lane == CNT_CHILDREN ? rb >> 16 : add;
-    add = lane == CNT_HITS ? ra >> 16 : add;
-    add = lane == CNT_MISSED ? rb & 0xffffu : add;
-    add = lane == CNT_APODIZED ? rp : add;
-    add = lane == CNT_VALID_OUT ? (unsigned)__popc(ok) : add;
-    add = lane == CNT_ALIVE_OUT ? (unsigned)__popc(live) : add;
-    if (lane < (unsigned)CNT_N) s_cnt[(threadIdx.x >> 5) * kCntStride + lane] += add;
-    if (lane0 && st) atomicOr(s_status, st);
+    if (lane0) {  // the warp's own row (32 bytes, CNT_* order): two vector loads, seven adds, two vector stores
+        uint4* row = reinterpret_cast<uint4*>(s_cnt + (threadIdx.x >> 5) * kCntStride);
+        uint4 a = row[0], b = row[1];
+        a.x += ra & 0xffffu; a.y += rb >> 16; a.z += ra >> 16; a.w += rb & 0xffffu;
+        b.x += rp; b.y += (unsigned)__popc(ok); b.z += (unsigned)__popc(live);
+        row[0] = a; row[1] = b;
+        if (st) atomicOr(s_status, st);
+    }
 }
+static_assert(CNT_INTERACTIONS == 0 && CNT_CHILDREN == 1 && CNT_HITS == 2 && CNT_MISSED == 3 && CNT_APODIZED == 4 && CNT_VALID_OUT == 5 &&
+              CNT_ALIVE_OUT == 6 && kCntStride == 8, "tile_count writes the counter row as two uint4");
 
 // CTA totals -> global statistics (call after __syncthreads())
 __device__ __forceinline__ void cta_flush(DevStats* stats, const cta_count_t* s_cnt, unsigned s_status, unsigned long long s_first_inv) {
