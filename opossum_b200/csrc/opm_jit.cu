@@ -367,11 +367,13 @@ std::string make_source(const DevOp* ops, int n_ops, bool compact, int block, in
             }
     }
     s += "    unsigned warp_best = 0xffffffffu;\n"
+         "    TileAhead ahead;\n"
+         "    tile_ahead_init(ahead, in, (uint64_t)blockIdx.x * OPM_BDIM + threadIdx.x, n);\n"
          "    for (unsigned tile = blockIdx.x; tile < tiles; tile += gridDim.x) {\n"
          "        RayCtx x;\n"
          "        uint8_t vb;\n";
     s += pipe ? "        tile_load_staged(pipe, in, tile, n, x, vb);\n"
-              : "        tile_load(in, (uint64_t)tile * OPM_BDIM + threadIdx.x, n, x, vb);\n"
+              : "        tile_load(in, (uint64_t)tile * OPM_BDIM + threadIdx.x, n, x, vb, ahead, (uint64_t)(tile + gridDim.x) * OPM_BDIM + threadIdx.x);\n"
                 "        tile_prefetch(in, (uint64_t)(tile + gridDim.x) * OPM_BDIM + threadIdx.x, n);\n";
     s += body;
     appendf(s, "        tile_store<%s>(in, out, out_cap, out_tail, x, vb);\n", compact ? "true" : "false");

@@ -645,9 +645,50 @@ __device__ __forceinline__ void tile_load(const DevRays& in, uint64_t i, uint64_
     x.valid = vb == RAY_VALID;
     x.warp_live = __any_sync(0xffffffffu, x.alive);
 }
+// The flag of the ray this thread takes in the CTA's NEXT tile, loaded one tile ahead (-DOPM_TILE_FLAG_AHEAD): the tile prologue
+// then waits for one round trip to the HBM (the 13 field loads) instead of two (flag, then fields) and still loads nothing
+// for a slot that holds no ray.  One register; nothing else writes the flag of a slot before its own thread gets to it.
+struct TileAhead { uint8_t vb; };
+__device__ __forceinline__ void tile_ahead_init(TileAhead& a, const DevRays& in, uint64_t i, uint64_t n) {
+    a.vb = RAY_REMOVED;
+#ifdef OPM_TILE_FLAG_AHEAD
+    if (i < n) a.vb = in.valid[i];
+#endif
+}
+__device__ __forceinline__ void tile_load(const DevRays& in, uint64_t i, uint64_t n, RayCtx& x, uint8_t& vb, TileAhead& a, uint64_t i_next) {
+#ifndef OPM_TILE_FLAG_AHEAD
+    tile_load(in, i, n, x, vb);
+#else
+    x.i = i;
+    x.in_range = i < n;
+    x.c.a = 0; x.c.b = 0; x.c.apodized = 0; x.c.status = 0; x.c.kid = kKeyUnset; x.c.kb = 0;
+    x.r.pos = v3(0, 0, 0); x.r.dir = v3(0, 0, 1); x.r.e = 0; x.r.wvl = 0; x.r.opl = 0; x.r.n = 1; x.r.bounces = 0; x.r.refr = 0; x.r.id = 0;
+    vb = a.vb;  // RAY_REMOVED beyond the bundle
+    if (vb != RAY_REMOVED) load_ray(in, i, x.r);
+    a.vb = RAY_REMOVED;
+    if (i_next < n) a.vb = in.valid[i_next];
+    x.alive = vb != RAY_REMOVED;
+    x.valid = vb == RAY_VALID;
+    x.warp_live = __any_sync(0xffffffffu, x.alive);
+#endif
+}
 // probe (-DOPM_TILE_PREFETCH, profiles/tile_load_variants.sh): asks the L2 for the lines of the tile this CTA takes next (one
 // request per 128-byte line).  Measured on C2: 1.359 ms against 1.318 ms -- left off.
+// -DOPM_TILE_BULK_PREFETCH: the same request as 14 bulk prefetches (cp.async.bulk.prefetch.L2, one per field segment of the
+// tile) from ONE thread of the CTA instead of two instructions per field from every warp.
 __device__ __forceinline__ void tile_prefetch(const DevRays& in, uint64_t i, uint64_t n) {
+#if defined(OPM_TILE_BULK_PREFETCH) && defined(OPM_JIT_BLOCK)
+    if (threadIdx.x == 0 && i + OPM_JIT_BLOCK <= n) {  // i = first ray of the next tile; whole tiles only (16-byte granules)
+        static_assert(OPM_JIT_BLOCK % 16 == 0, "bulk prefetch takes multiples of 16 bytes");
+        const double* f64[10] = {in.px, in.py, in.pz, in.dx, in.dy, in.dz, in.e, in.wvl, in.opl, in.n};
+#pragma unroll
+        for (int f = 0; f < 10; ++f) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(f64[f] + i), "r"(OPM_JIT_BLOCK * 8));
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(in.bounces + i), "r"(OPM_JIT_BLOCK * 4));
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(in.refr + i), "r"(OPM_JIT_BLOCK * 4));
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(in.id + i), "r"(OPM_JIT_BLOCK * 4));
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(in.valid + i), "r"(OPM_JIT_BLOCK));
+    }
+#endif
 #ifdef OPM_TILE_PREFETCH
     if (i >= n) return;
     const unsigned lane = threadIdx.x & 31u;
