@@ -552,6 +552,34 @@ void opm_spectrum_destroy(OpmSpectrum* spectrum);
 double opm_spectrum_total_energy(const double* lambda_um, const double* values, uint64_t n);
 double opm_spectrum_center_wavelength(const double* lambda_um, const double* values, uint64_t n);
 int32_t opm_spectrum_get_value(const double* lambda_um, const double* values, uint64_t n, double wavelength_m, double* out);
+/* host-side construction and combination of spectra (no device work; errors = OpossumError::Spectrum -> OPM_ERR_SPECTRUM).
+ * Arrays: lambda_um ascending slots, values per slot; a NULL lambda_um asks for the number of slots only (*n_out).
+ *  opm_spectrum_new                Spectrum::new (spectrum.rs:47-73): slots start + i * resolution, values 0
+ *  opm_spectrum_add_single_peak    Spectrum::add_single_peak (:193-227); a wavelength outside the range leaves the spectrum as it is
+ *  opm_spectrum_from_laser_lines   Spectrum::from_laser_lines (:126-148)
+ *  opm_spectrum_add_lorentzian_peak Spectrum::add_lorentzian_peak (:249-283)
+ *  opm_spectrum_scale_vertical     Spectrum::scale_vertical (:355-367) = Spectrum::filter_with_type(FilterType::Constant) (:445-453)
+ *  opm_spectrum_resample           Spectrum::resample (:377-428): the values of the source spectrum on the slots of (lambda_um, values)
+ *  opm_spectrum_combine            Spectrum::filter (:430-439), ::add (:483-492), ::sub (:497-507), ::split_by_spectrum (:456-472; values keep
+ *                                  the transmitted part, split_out[n] takes the rest): the other spectrum is resampled onto the slots first
+ *  opm_spectrum_average_resolution Spectrum::average_resolution (:172-176), metres
+ *  opm_spectrum_merge              merge_spectra (:622-650) of two present spectra
+ *  opm_spectrum_from_csv           Spectrum::from_csv (:89-117): `wavelength [nm];value [%]` records */
+enum { OPM_SPECTRUM_FILTER = 0, OPM_SPECTRUM_ADD = 1, OPM_SPECTRUM_SUB = 2, OPM_SPECTRUM_SPLIT = 3 };
+OpmStatus opm_spectrum_new(double start_m, double end_m, double resolution_m, double* lambda_um, double* values, uint64_t cap, uint64_t* n_out);
+OpmStatus opm_spectrum_add_single_peak(const double* lambda_um, double* values, uint64_t n, double wavelength_m, double value);
+OpmStatus opm_spectrum_from_laser_lines(const double* wavelengths_m, const double* energies, uint64_t n_lines, double resolution_m,
+                                        double* lambda_um, double* values, uint64_t cap, uint64_t* n_out);
+OpmStatus opm_spectrum_add_lorentzian_peak(const double* lambda_um, double* values, uint64_t n, double center_m, double width_m, double energy);
+OpmStatus opm_spectrum_scale_vertical(double* values, uint64_t n, double factor);
+OpmStatus opm_spectrum_resample(const double* lambda_um, double* values, uint64_t n, const double* src_lambda_um, const double* src_values,
+                                uint64_t n_src);
+OpmStatus opm_spectrum_combine(int32_t what, const double* lambda_um, double* values, uint64_t n, const double* other_lambda_um,
+                               const double* other_values, uint64_t n_other, double* split_out);
+double opm_spectrum_average_resolution(const double* lambda_um, uint64_t n);
+OpmStatus opm_spectrum_merge(const double* lambda1_um, const double* values1, uint64_t n1, const double* lambda2_um, const double* values2,
+                             uint64_t n2, double* lambda_um, double* values, uint64_t cap, uint64_t* n_out);
+OpmStatus opm_spectrum_from_csv(const char* path, double* lambda_um, double* values, uint64_t cap, uint64_t* n_out);
 /* smallest / largest wavelength and number of the valid rays (multi-GPU: reduce with min / max / sum, then pass the common
  * range to opm_rays_to_spectrum on every rank and sum the values) */
 OpmStatus opm_rays_wavelength_range(const OpmRays* rays, double min_max_m[2], uint64_t* n_valid);

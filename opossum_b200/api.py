@@ -433,6 +433,103 @@ def spectrum_get_value(lam, val, wavelength: float):
     return v.value if F.lib().opm_spectrum_get_value(lam.ctypes.data_as(dp), val.ctypes.data_as(dp), len(lam), wavelength, C.byref(v)) else None
 
 
+def _sp(lam, val):
+    lam, val = np.ascontiguousarray(lam, dtype=np.float64), np.ascontiguousarray(val, dtype=np.float64)
+    dp = C.POINTER(C.c_double)
+    return lam, val, lam.ctypes.data_as(dp), val.ctypes.data_as(dp)
+
+
+def _sp_sized(call):
+    """the two-call protocol of the functions that create a spectrum: slot count first, then the arrays"""
+    n = C.c_uint64()
+    _check(call(None, None, 0, C.byref(n)))
+    lam, val = np.zeros(max(n.value, 1)), np.zeros(max(n.value, 1))
+    dp = C.POINTER(C.c_double)
+    _check(call(lam.ctypes.data_as(dp), val.ctypes.data_as(dp), n.value, C.byref(n)))
+    return lam[: n.value], val[: n.value]
+
+
+def spectrum_new(start: float, end: float, resolution: float):
+    """Spectrum::new (spectrum.rs:47-73): (slots [um], zeros)"""
+    return _sp_sized(lambda l, v, cap, n: F.lib().opm_spectrum_new(start, end, resolution, l, v, cap, n))
+
+
+def spectrum_add_single_peak(lam, val, wavelength: float, value: float):
+    """Spectrum::add_single_peak (spectrum.rs:193-227), in place (val must be a contiguous float64 array)"""
+    dp = C.POINTER(C.c_double)
+    _check(F.lib().opm_spectrum_add_single_peak(lam.ctypes.data_as(dp), val.ctypes.data_as(dp), len(lam), wavelength, value))
+
+
+def spectrum_from_laser_lines(wavelengths, energies, resolution: float):
+    """Spectrum::from_laser_lines (spectrum.rs:126-148)"""
+    w, e, wp, ep = _sp(wavelengths, energies)
+    return _sp_sized(lambda l, v, cap, n: F.lib().opm_spectrum_from_laser_lines(wp, ep, len(w), resolution, l, v, cap, n))
+
+
+def spectrum_add_lorentzian_peak(lam, val, center: float, width: float, energy: float):
+    """Spectrum::add_lorentzian_peak (spectrum.rs:249-283), in place"""
+    dp = C.POINTER(C.c_double)
+    _check(F.lib().opm_spectrum_add_lorentzian_peak(lam.ctypes.data_as(dp), val.ctypes.data_as(dp), len(lam), center, width, energy))
+
+
+def spectrum_scale_vertical(val, factor: float):
+    """Spectrum::scale_vertical (spectrum.rs:355-367), in place"""
+    _check(F.lib().opm_spectrum_scale_vertical(val.ctypes.data_as(C.POINTER(C.c_double)), len(val), factor))
+
+
+def spectrum_resample(lam, val, src_lam, src_val):
+    """Spectrum::resample (spectrum.rs:377-428): val takes the source spectrum's values on the slots lam, in place"""
+    sl, sv, slp, svp = _sp(src_lam, src_val)
+    dp = C.POINTER(C.c_double)
+    _check(F.lib().opm_spectrum_resample(lam.ctypes.data_as(dp), val.ctypes.data_as(dp), len(lam), slp, svp, len(sl)))
+
+
+def _spectrum_combine(what, lam, val, o_lam, o_val, split=None):
+    ol, ov, olp, ovp = _sp(o_lam, o_val)
+    dp = C.POINTER(C.c_double)
+    _check(F.lib().opm_spectrum_combine(what, lam.ctypes.data_as(dp), val.ctypes.data_as(dp), len(lam), olp, ovp, len(ol),
+                                        split.ctypes.data_as(dp) if split is not None else None))
+
+
+def spectrum_filter(lam, val, f_lam, f_val):
+    """Spectrum::filter (spectrum.rs:430-439), in place"""
+    _spectrum_combine(0, lam, val, f_lam, f_val)
+
+
+def spectrum_add(lam, val, o_lam, o_val):
+    """Spectrum::add (spectrum.rs:483-492), in place"""
+    _spectrum_combine(1, lam, val, o_lam, o_val)
+
+
+def spectrum_sub(lam, val, o_lam, o_val):
+    """Spectrum::sub (spectrum.rs:497-507), in place"""
+    _spectrum_combine(2, lam, val, o_lam, o_val)
+
+
+def spectrum_split_by_spectrum(lam, val, f_lam, f_val) -> np.ndarray:
+    """Spectrum::split_by_spectrum (spectrum.rs:456-472): val keeps the transmitted part, the rest is returned"""
+    out = np.zeros(len(lam))
+    _spectrum_combine(3, lam, val, f_lam, f_val, out)
+    return out
+
+
+def spectrum_average_resolution(lam) -> float:
+    lam = np.ascontiguousarray(lam, dtype=np.float64)
+    return F.lib().opm_spectrum_average_resolution(lam.ctypes.data_as(C.POINTER(C.c_double)), len(lam))
+
+
+def spectrum_merge(l1, v1, l2, v2):
+    """merge_spectra (spectrum.rs:622-650)"""
+    a, b, ap, bp = _sp(l1, v1)
+    c, d, cp, dpp = _sp(l2, v2)
+    return _sp_sized(lambda l, v, cap, n: F.lib().opm_spectrum_merge(ap, bp, len(a), cp, dpp, len(c), l, v, cap, n))
+
+
+def spectrum_from_csv(path):
+    """Spectrum::from_csv (spectrum.rs:89-117)"""
+    return _sp_sized(lambda l, v, cap, n: F.lib().opm_spectrum_from_csv(str(path).encode(), l, v, cap, n))
+
+
 class Rays:
     """rays.rs `Rays`: a bundle held as struct-of-arrays f64 buffers in HBM."""
 

@@ -157,6 +157,10 @@ static OpmStatus fail(OpmStatus s, const char* fmt, ...) {
     g_last_error = buf;
     return s;
 }
+namespace opm {
+// for the host-only translation units of the library (opm_spectrum_host.cpp)
+OpmStatus host_fail(OpmStatus s, const char* msg) { return fail(s, "%s", msg); }
+}  // namespace opm
 #define CU(expr)                                                                                         \
     do {                                                                                                 \
         cudaError_t _e = (expr);                                                                         \
@@ -2019,7 +2023,7 @@ extern "C" double opm_spectrum_center_wavelength(const double* lambda_um, const 
 // Spectrum::get_value (spectrum.rs:321-349)
 extern "C" int32_t opm_spectrum_get_value(const double* lam, const double* val, uint64_t n, double wl_m, double* out) {
     if (!lam || !val || !out || n == 0) return 0;
-    const double w = wl_m / 1e-6;
+    const double w = wl_m * 1e6;
     if (w == lam[n - 1]) { *out = val[n - 1]; return 1; }
     if (!(lam[0] * 1e-6 <= wl_m && wl_m < lam[n - 1] * 1e-6)) return 0;
     uint64_t idx = n;
@@ -2058,7 +2062,7 @@ static OpmStatus spectrum_grid(double start_m, double end_m, double res_m, uint6
     if (std::signbit(start_m) || std::signbit(end_m)) return fail(OPM_ERR_SPECTRUM, "wavelength range limits must both be positive");
     const double cnt = std::round((end_m - start_m) / res_m);
     *n = cnt > 0.0 ? (uint64_t)cnt : 0;  // f64_to_usize (utils/math_utils.rs:38-43)
-    *start_um = start_m / 1e-6; *step_um = res_m / 1e-6;
+    *start_um = start_m * 1e6; *step_um = res_m * 1e6;
     return OPM_OK;
 }
 extern "C" OpmStatus opm_rays_to_spectrum(const OpmRays* rc, double resolution_m, const double* range_m, double* lambda_um, double* values,
@@ -2134,7 +2138,7 @@ extern "C" OpmStatus opm_rays_wavefront_error(const OpmRays* rc, const OpmIsomet
     DevIso inv;
     to_dev_iso(monitor_iso->inv, inv);
     cudaError_t e = cudaSuccess;
-    if (n) { e = (cudaError_t)k_wavefront(r->v, n, inv, wavelength_m / 1e-9, d_acc, d_xyw, c->sms, c->stream); c->launches += 4; }
+    if (n) { e = (cudaError_t)k_wavefront(r->v, n, inv, wavelength_m * (1.0 / 1e-9), d_acc, d_xyw, c->sms, c->stream); c->launches += 4; }
     WfAccum* h = (WfAccum*)(c->h_scratch + 3200);
     std::vector<double> tmp;
     if (e == cudaSuccess) e = cudaMemcpyAsync(h, d_acc, sizeof *h, cudaMemcpyDeviceToHost, c->stream);

@@ -160,7 +160,7 @@ __global__ void __launch_bounds__(256) spot_pass2_kernel(DevRays R, uint64_t n, 
     // rays.rs:599-612 / 618-637: centroid = sum / len ; energy centroid = sum(e*p) / sum(e)
     const double cx = acc->sum[0] / nvalid, cy = acc->sum[1] / nvalid;
     const double ex = acc->sum[3] / acc->sum[6], ey = acc->sum[4] / acc->sum[6];
-    const double cxm = cx / 1.0E-3, cym = cy / 1.0E-3;  // get::<millimeter>()
+    const double cxm = cx * 1.0E3, cym = cy * 1.0E3;  // get::<millimeter>()
     double mx = 0.0, s2 = 0.0, se = 0.0;
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     for (uint64_t base = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; base < n; base += 4 * stride) {
@@ -179,7 +179,7 @@ __global__ void __launch_bounds__(256) spot_pass2_kernel(DevRays R, uint64_t n, 
             if (!ok[u]) continue;
             V3 p = v3(px[u], py[u], pz[u]);
             if (use_frame) p = iso_point(inv, p);
-            double dx = cxm - p.x / 1.0E-3, dy = cym - p.y / 1.0E-3;
+            double dx = cxm - p.x * 1.0E3, dy = cym - p.y * 1.0E3;
             double d2 = dx * dx + dy * dy;
             mx = fmax(mx, d2);     // max of sqrt == sqrt of max (rays.rs:642-660)
             s2 += d2;              // rays.rs:666-684: distance(..).powi(2)
@@ -1531,7 +1531,7 @@ __global__ void __launch_bounds__(256) spectrum_splat_kernel(DevRays R, uint64_t
         const double wl = R.wvl[i], value = R.e[i];
         if (!(r0 <= wl && wl < r1)) continue;                          // "peak wavelength is not in spectrum range. Spectrum unmodified."
         if (value < 0.0 || nslots < 2) { status |= 1u << OPM_ERR_SPECTRUM; continue; }
-        const double w = wl / 1e-6;
+        const double w = wl * 1e6;
         // first slot with lambda >= w: estimate, then settle with the slots' own arithmetic
         double g = ceil((w - start) / step);
         long long idx = g > 0.0 ? (g < (double)nslots ? (long long)g : (long long)nslots) : 0;
@@ -1564,7 +1564,7 @@ __global__ void __launch_bounds__(256) spectrum_splat_kernel(DevRays R, uint64_t
 // the valid ray with the smallest x^2 + y^2, the first one in bundle order on ties.
 __device__ __forceinline__ void wf_xy(const DevRays& R, uint64_t i, const DevIso& inv, double& x, double& y) {
     const V3 p = iso_point(inv, v3(R.px[i], R.py[i], R.pz[i]));
-    x = p.x / 1e-3; y = p.y / 1e-3;
+    x = p.x * 1e3; y = p.y * 1e3;
 }
 __global__ void __launch_bounds__(256) wavefront_center1_kernel(DevRays R, uint64_t n, DevIso inv, WfAccum* acc) {
     double mn = INFINITY;
@@ -1595,7 +1595,7 @@ __global__ void __launch_bounds__(256) wavefront_center2_kernel(DevRays R, uint6
 __global__ void __launch_bounds__(256) wavefront_stats_kernel(DevRays R, uint64_t n, DevIso inv, double wvl_nm, WfAccum* acc,
                                                               double* __restrict__ xyw, int second) {
     const unsigned long long fs = acc->first_slot;
-    const double center = fs != ~0ull ? -(R.opl[fs] / 1e-9) : 0.0;
+    const double center = fs != ~0ull ? -(R.opl[fs] * (1.0 / 1e-9)) : 0.0;
     const double avg = second ? acc->sum / (double)acc->count : 0.0;
     double mx = -INFINITY, mn = INFINITY, sum = 0.0;
     unsigned long long cnt = 0;
@@ -1604,7 +1604,7 @@ __global__ void __launch_bounds__(256) wavefront_stats_kernel(DevRays R, uint64_
         double x = NAN, y = NAN, wf = NAN;
         if (ok) {
             wf_xy(R, i, inv, x, y);
-            wf = -(R.opl[i] / 1e-9);
+            wf = -(R.opl[i] * (1.0 / 1e-9));
             wf -= center;
             wf /= wvl_nm;
             if (second) { const double d = wf - avg; sum += d * d; }

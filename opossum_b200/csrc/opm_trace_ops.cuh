@@ -645,18 +645,20 @@ __device__ __forceinline__ void tile_load(const DevRays& in, uint64_t i, uint64_
     x.valid = vb == RAY_VALID;
     x.warp_live = __any_sync(0xffffffffu, x.alive);
 }
-// The flag of the ray this thread takes in the CTA's NEXT tile, loaded one tile ahead (-DOPM_TILE_FLAG_AHEAD): the tile prologue
-// then waits for one round trip to the HBM (the 13 field loads) instead of two (flag, then fields) and still loads nothing
-// for a slot that holds no ray.  One register; nothing else writes the flag of a slot before its own thread gets to it.
+// The flag of the ray this thread takes in the CTA's NEXT tile is loaded one tile ahead: the tile prologue then waits for one
+// round trip (the 13 field loads) instead of two (flag, then fields) and still loads nothing for a slot that holds no ray.
+// One register; nothing else writes the flag of a slot before its own thread gets to it.  Specialised kernel only; measured on
+// C2 (profiles/r2m_tile_variants.sh): 0.969 -> 0.959 ms alone, 0.916 -> 0.915 ms beside the bulk prefetch.  -DOPM_TILE_NO_FLAG_AHEAD
+// restores the dependent flag load.
 struct TileAhead { uint8_t vb; };
 __device__ __forceinline__ void tile_ahead_init(TileAhead& a, const DevRays& in, uint64_t i, uint64_t n) {
     a.vb = RAY_REMOVED;
-#ifdef OPM_TILE_FLAG_AHEAD
+#ifndef OPM_TILE_NO_FLAG_AHEAD
     if (i < n) a.vb = in.valid[i];
 #endif
 }
 __device__ __forceinline__ void tile_load(const DevRays& in, uint64_t i, uint64_t n, RayCtx& x, uint8_t& vb, TileAhead& a, uint64_t i_next) {
-#ifndef OPM_TILE_FLAG_AHEAD
+#ifdef OPM_TILE_NO_FLAG_AHEAD
     tile_load(in, i, n, x, vb);
 #else
     x.i = i;
@@ -674,10 +676,15 @@ __device__ __forceinline__ void tile_load(const DevRays& in, uint64_t i, uint64_
 }
 // probe (-DOPM_TILE_PREFETCH, profiles/tile_load_variants.sh): asks the L2 for the lines of the tile this CTA takes next (one
 // request per 128-byte line).  Measured on C2: 1.359 ms against 1.318 ms -- left off.
-// -DOPM_TILE_BULK_PREFETCH: the same request as 14 bulk prefetches (cp.async.bulk.prefetch.L2, one per field segment of the
-// tile) from ONE thread of the CTA instead of two instructions per field from every warp.
+// Specialised kernel (default; -DOPM_TILE_NO_BULK_PREFETCH turns it off): the same request as 14 bulk prefetches
+// (cp.async.bulk.prefetch.L2 -> UBLKPF, one per field segment of the tile) from ONE thread of the CTA instead of two instructions
+// per field from every warp: when the warps get to the tile, their loads hit the L2 instead of waiting for the HBM.  Measured on
+// C2 (profiles/r2m_tile_variants.sh): 0.969 -> 0.916 ms per launch (per-warp prefetches: 0.929 ms).
+#ifndef OPM_TILE_PREFETCH_DIST
+#define OPM_TILE_PREFETCH_DIST 1  // tiles of this CTA ahead
+#endif
 __device__ __forceinline__ void tile_prefetch(const DevRays& in, uint64_t i, uint64_t n) {
-#if defined(OPM_TILE_BULK_PREFETCH) && defined(OPM_JIT_BLOCK)
+#if !defined(OPM_TILE_NO_BULK_PREFETCH) && defined(OPM_JIT_BLOCK)
     if (threadIdx.x == 0 && i + OPM_JIT_BLOCK <= n) {  // i = first ray of the next tile; whole tiles only (16-byte granules)
         static_assert(OPM_JIT_BLOCK % 16 == 0, "bulk prefetch takes multiples of 16 bytes");
         const double* f64[10] = {in.px, in.py, in.pz, in.dx, in.dy, in.dz, in.e, in.wvl, in.opl, in.n};

@@ -339,8 +339,11 @@ double orc_powi(double a, int b) {
 /* ------------------------------------------------------------------------- */
 /* refractive index models                                                    */
 /* ------------------------------------------------------------------------- */
-/* uom: Length::get::<micrometer>() = value / 1e-6 */
-static inline double to_micrometer(double m) { return m / 1.0E-6; }
+/* uom 0.37 (Cargo.lock:7828; not under /root/reference): Length::get::<micrometer>() = value * (1 / 1e-6) = value * 1e6 -- a
+ * multiplication by the reciprocal of the unit's coefficient, not a division by it.  Pinned by the reference's own tests:
+ * spectrum.rs:763-766 expects nanometer!(800.0).get::<micrometer>() == 0.8 exactly (800e-9 * 1e6 = 0.8, 800e-9 / 1e-6 =
+ * 0.8000000000000002) and :757-761 expects nanometer!(380.0) -> 0.38, which rules out a division on the way in as well. */
+static inline double to_micrometer(double m) { return m * 1.0E6; }
 
 int orc_refractive_index(const OrcIndexModel* m, double wvl, double* n_out) {
     double n;
@@ -931,14 +934,14 @@ int orc_rays_energy_weighted_centroid(const OrcRay* rays, uint64_t n, double c[3
     c[0] = s0 / se; c[1] = s1 / se; c[2] = s2 / se;
     return 1;
 }
-/* uom: get::<millimeter>() = value / 1e-3 ; millimeter!(x) = x * 1e-3 */
+/* uom: get::<millimeter>() = value * 1e3 ; millimeter!(x) = x * 1e-3 */
 int orc_rays_beam_radius_geo(const OrcRay* rays, uint64_t n, double* r_m) { /* :642-660 */
     double c[3];
     if (!orc_rays_centroid(rays, n, c)) return 0;
-    double cx = c[0] / 1.0E-3, cy = c[1] / 1.0E-3;
+    double cx = c[0] * 1.0E3, cy = c[1] * 1.0E3;
     double max_dist = 0.0;
     for (uint64_t i = 0; i < n; ++i) if (rays[i].valid) {
-        double x = rays[i].pos[0] / 1.0E-3, y = rays[i].pos[1] / 1.0E-3;
+        double x = rays[i].pos[0] * 1.0E3, y = rays[i].pos[1] * 1.0E3;
         double dx = cx - x, dy = cy - y;
         double dist = sqrt(0.0 + (dx * dx + dy * dy));
         if (dist > max_dist) max_dist = dist;
@@ -949,10 +952,10 @@ int orc_rays_beam_radius_geo(const OrcRay* rays, uint64_t n, double* r_m) { /* :
 int orc_rays_beam_radius_rms(const OrcRay* rays, uint64_t n, double* r_m) { /* :666-684 */
     double c[3];
     if (!orc_rays_centroid(rays, n, c)) return 0;
-    double cx = c[0] / 1.0E-3, cy = c[1] / 1.0E-3;
+    double cx = c[0] * 1.0E3, cy = c[1] * 1.0E3;
     double sum = 0.0;
     for (uint64_t i = 0; i < n; ++i) if (rays[i].valid) {
-        double x = rays[i].pos[0] / 1.0E-3, y = rays[i].pos[1] / 1.0E-3;
+        double x = rays[i].pos[0] * 1.0E3, y = rays[i].pos[1] * 1.0E3;
         double dx = cx - x, dy = cy - y;
         sum += orc_powi(sqrt(0.0 + (dx * dx + dy * dy)), 2);
     }
@@ -1272,7 +1275,7 @@ int orc_rays_collimated_with_spectrum(const double* xyz, const double* e_pos, ui
 
 /* ---------------------------------------------------------------------------------------------
  * spectrum.rs: Spectrum = Vec<(wavelength in micrometers, value in 1/micrometers)>, here two arrays.
- * uom: micrometer!(x) = x * 1e-6, get::<micrometer>() = value / 1e-6, get::<nanometer>() = value / 1e-9
+ * uom: micrometer!(x) = x * 1e-6, get::<micrometer>() = value * 1e6, get::<nanometer>() = value * (1.0 / 1e-9)
  * ------------------------------------------------------------------------------------------- */
 /* Spectrum::new (spectrum.rs:47-73); lambda == NULL: only the number of slots is returned */
 int orc_spectrum_new(double start_m, double end_m, double res_m, double* lambda, double* data, uint64_t cap, uint64_t* n_out) {
@@ -1281,7 +1284,7 @@ int orc_spectrum_new(double start_m, double end_m, double res_m, double* lambda,
     if (signbit(start_m) || signbit(end_m)) return ORC_ERR_SPECTRUM;
     double cnt = round((end_m - start_m) / res_m);
     uint64_t n = cnt > 0.0 ? (uint64_t)cnt : 0;             /* f64_to_usize: `as usize` */
-    double start = start_m / 1e-6, step = res_m / 1e-6;
+    double start = start_m * 1e6, step = res_m * 1e6;
     if (n_out) *n_out = n;
     if (!lambda) return ORC_OK;
     if (n > cap) return ORC_ERR_ARG;
@@ -1294,7 +1297,7 @@ int orc_spectrum_add_single_peak(const double* lambda, double* data, uint64_t n,
     double r0 = lambda[0] * 1e-6, r1 = lambda[n - 1] * 1e-6;     /* range(): micrometer!(first)..micrometer!(last) */
     if (!(r0 <= wl_m && wl_m < r1)) return ORC_OK;               /* warn!("peak wavelength is not in spectrum range. Spectrum unmodified.") */
     if (value < 0.0) return ORC_ERR_SPECTRUM;                    /* "energy must be positive" */
-    double w = wl_m / 1e-6;
+    double w = wl_m * 1e6;
     if (n < 2) return ORC_ERR_SPECTRUM;                          /* "spectrum size is too small" */
     uint64_t idx = n;
     for (uint64_t i = 0; i < n; ++i) if (lambda[i] >= w) { idx = i; break; }
@@ -1362,7 +1365,7 @@ double orc_spectrum_center_wavelength(const double* lambda, const double* data, 
 /* Spectrum::get_value (spectrum.rs:321-349): returns 1 = Some(*out), 0 = None */
 int orc_spectrum_get_value(const double* lambda, const double* data, uint64_t n, double wl_m, double* out) {
     if (n == 0) return 0;
-    double w = wl_m / 1e-6;
+    double w = wl_m * 1e6;
     if (w == lambda[n - 1]) { *out = data[n - 1]; return 1; }
     double r0 = lambda[0] * 1e-6, r1 = lambda[n - 1] * 1e-6;
     if (!(r0 <= wl_m && wl_m < r1)) return 0;
@@ -1402,16 +1405,16 @@ int orc_rays_split_spectrum(OrcRay* rays, uint64_t n, const double* lambda, cons
  * valid rays in order, relative to the ray closest to the monitor axis (the first one on ties) */
 int orc_rays_wavefront_error(const OrcRay* rays, uint64_t n, double wavelength_m, const OrcIsometry* monitor_iso, double* xyw,
                              uint64_t* n_out) {
-    double wvl = wavelength_m / 1e-9;
+    double wvl = wavelength_m * (1.0 / 1e-9);
     double min_radius = INFINITY, center = 0.0;
     uint64_t k = 0;
     for (uint64_t i = 0; i < n; ++i) {
         if (!rays[i].valid) continue;
         double p[3];
         iso3_point(&monitor_iso->inv, rays[i].pos, p);
-        double x = p[0] / 1e-3, y = p[1] / 1e-3;
+        double x = p[0] * 1e3, y = p[1] * 1e3;
         xyw[3 * k] = x; xyw[3 * k + 1] = y;
-        xyw[3 * k + 2] = -(rays[i].opl / 1e-9);
+        xyw[3 * k + 2] = -(rays[i].opl * (1.0 / 1e-9));
         double radius = fma(x, x, y * y);
         if (radius < min_radius) { min_radius = radius; center = xyw[3 * k + 2]; }
         ++k;

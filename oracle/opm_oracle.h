@@ -227,6 +227,20 @@ int orc_rays_to_spectrum(const OrcRay* rays, uint64_t n, double res_m, double* l
 double orc_spectrum_total_energy(const double* lambda, const double* data, uint64_t n);                                       /* :289-298 */
 double orc_spectrum_center_wavelength(const double* lambda, const double* data, uint64_t n);                                  /* :304-316, metres */
 int orc_spectrum_get_value(const double* lambda, const double* data, uint64_t n, double wl_m, double* out);                   /* :321-349 */
+/* opm_spectrum.c: the remaining Spectrum operations (line numbers: opossum/src/spectrum.rs) */
+int orc_spectrum_add_lorentzian_peak(const double* lambda, double* data, uint64_t n, double center_m, double width_m, double energy); /* :249-283 */
+int orc_spectrum_scale_vertical(double* data, uint64_t n, double factor);                                                     /* :355-367 */
+double orc_spectrum_calc_ratio(double bucket_left, double bucket_right, double source_left, double source_right);             /* :588-606 */
+void orc_spectrum_resample(const double* lambda, double* data, uint64_t n, const double* sl, const double* sd, uint64_t ns);  /* :377-428 */
+int orc_spectrum_filter(const double* lambda, double* data, uint64_t n, const double* fl, const double* fd, uint64_t nf);     /* :430-439 */
+int orc_spectrum_split_by_spectrum(const double* lambda, double* data, uint64_t n, const double* fl, const double* fd, uint64_t nf,
+                                   double* split_out);                                                                        /* :456-472 */
+int orc_spectrum_add(const double* lambda, double* data, uint64_t n, const double* ol, const double* od, uint64_t no);        /* :483-492 */
+int orc_spectrum_sub(const double* lambda, double* data, uint64_t n, const double* ol, const double* od, uint64_t no);        /* :497-507 */
+double orc_spectrum_average_resolution(const double* lambda, uint64_t n);                                                     /* :172-176, metres */
+int orc_spectrum_merge(const double* l1, const double* d1, uint64_t n1, const double* l2, const double* d2, uint64_t n2, double* lambda,
+                       double* data, uint64_t cap, uint64_t* n_out);                                                          /* :622-650 */
+int orc_spectrum_from_csv(const char* path, double* lambda, double* data, uint64_t cap, uint64_t* n_out);                     /* :89-117 */
 int orc_rays_filter_energy_spectrum(OrcRay* rays, uint64_t n, const double* lambda, const double* data, uint64_t ns);         /* ray.rs:712-721 */
 int orc_rays_split_spectrum(OrcRay* rays, uint64_t n, const double* lambda, const double* data, uint64_t ns, OrcRay* split_out); /* ray.rs:752-772 */
 int orc_rays_wavefront_error(const OrcRay* rays, uint64_t n, double wavelength_m, const OrcIsometry* monitor_iso, double* xyw,

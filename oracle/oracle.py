@@ -25,7 +25,7 @@ _LIB_PATH = _HERE / "libopm_oracle.so"
 
 def build(force: bool = False) -> Path:
     """Compile oracle/libopm_oracle.so with the committed Makefile (gcc only)."""
-    srcs = [_HERE / "opm_oracle.c", _HERE / "opm_voronoi.c", _HERE / "opm_oracle.h"]
+    srcs = [_HERE / "opm_oracle.c", _HERE / "opm_voronoi.c", _HERE / "opm_spectrum.c", _HERE / "opm_oracle.h"]
     if force or not _LIB_PATH.exists() or _LIB_PATH.stat().st_mtime < max(f.stat().st_mtime for f in srcs):
         env = dict(os.environ)
         env.pop("CC", None)
@@ -328,6 +328,19 @@ def lib():
     L.orc_spectrum_center_wavelength.argtypes = [dp, dp, C.c_uint64]
     L.orc_spectrum_center_wavelength.restype = C.c_double
     L.orc_spectrum_get_value.argtypes = [dp, dp, C.c_uint64, C.c_double, dp]
+    L.orc_spectrum_add_lorentzian_peak.argtypes = [dp, dp, C.c_uint64, C.c_double, C.c_double, C.c_double]
+    L.orc_spectrum_scale_vertical.argtypes = [dp, C.c_uint64, C.c_double]
+    L.orc_spectrum_calc_ratio.argtypes = [C.c_double] * 4
+    L.orc_spectrum_calc_ratio.restype = C.c_double
+    L.orc_spectrum_resample.argtypes = [dp, dp, C.c_uint64, dp, dp, C.c_uint64]
+    L.orc_spectrum_resample.restype = None
+    for name in ("orc_spectrum_filter", "orc_spectrum_add", "orc_spectrum_sub"):
+        getattr(L, name).argtypes = [dp, dp, C.c_uint64, dp, dp, C.c_uint64]
+    L.orc_spectrum_split_by_spectrum.argtypes = [dp, dp, C.c_uint64, dp, dp, C.c_uint64, dp]
+    L.orc_spectrum_average_resolution.argtypes = [dp, C.c_uint64]
+    L.orc_spectrum_average_resolution.restype = C.c_double
+    L.orc_spectrum_merge.argtypes = [dp, dp, C.c_uint64, dp, dp, C.c_uint64, dp, dp, C.c_uint64, u64p]
+    L.orc_spectrum_from_csv.argtypes = [C.c_char_p, dp, dp, C.c_uint64, u64p]
     L.orc_rays_filter_energy_spectrum.argtypes = [vp, C.c_uint64, dp, dp, C.c_uint64]
     L.orc_rays_split_spectrum.argtypes = [vp, C.c_uint64, dp, dp, C.c_uint64, vp]
     L.orc_rays_wavefront_error.argtypes = [vp, C.c_uint64, C.c_double, C.POINTER(Isometry), dp, u64p]
@@ -913,6 +926,76 @@ def spectrum_get_value(lam, data, wl_m: float):
     lam, data = np.ascontiguousarray(lam, dtype=np.float64), np.ascontiguousarray(data, dtype=np.float64)
     v = C.c_double()
     return v.value if lib().orc_spectrum_get_value(_dptr(lam), _dptr(data), len(lam), wl_m, C.byref(v)) else None
+
+
+def _spec(lam, data):
+    return np.ascontiguousarray(lam, dtype=np.float64), np.ascontiguousarray(data, dtype=np.float64)
+
+
+def spectrum_add_lorentzian_peak(lam, data, center_m: float, width_m: float, energy: float):
+    """Spectrum::add_lorentzian_peak (spectrum.rs:249-283), in place"""
+    _check(lib().orc_spectrum_add_lorentzian_peak(_dptr(lam), _dptr(data), len(lam), center_m, width_m, energy))
+
+
+def spectrum_scale_vertical(data, factor: float):
+    _check(lib().orc_spectrum_scale_vertical(_dptr(data), len(data), factor))
+
+
+def spectrum_calc_ratio(bl, br, sl, sr) -> float:
+    return lib().orc_spectrum_calc_ratio(bl, br, sl, sr)
+
+
+def spectrum_resample(lam, data, src_lam, src_data):
+    """Spectrum::resample (spectrum.rs:377-428): (lam, data) takes the values of the source spectrum, in place"""
+    sl, sd = _spec(src_lam, src_data)
+    lib().orc_spectrum_resample(_dptr(lam), _dptr(data), len(lam), _dptr(sl), _dptr(sd), len(sl))
+
+
+def spectrum_filter(lam, data, f_lam, f_data):
+    fl, fd = _spec(f_lam, f_data)
+    _check(lib().orc_spectrum_filter(_dptr(lam), _dptr(data), len(lam), _dptr(fl), _dptr(fd), len(fl)))
+
+
+def spectrum_split_by_spectrum(lam, data, f_lam, f_data) -> np.ndarray:
+    fl, fd = _spec(f_lam, f_data)
+    out = np.zeros(len(lam))
+    _check(lib().orc_spectrum_split_by_spectrum(_dptr(lam), _dptr(data), len(lam), _dptr(fl), _dptr(fd), len(fl), _dptr(out)))
+    return out
+
+
+def spectrum_add(lam, data, o_lam, o_data):
+    ol, od = _spec(o_lam, o_data)
+    _check(lib().orc_spectrum_add(_dptr(lam), _dptr(data), len(lam), _dptr(ol), _dptr(od), len(ol)))
+
+
+def spectrum_sub(lam, data, o_lam, o_data):
+    ol, od = _spec(o_lam, o_data)
+    _check(lib().orc_spectrum_sub(_dptr(lam), _dptr(data), len(lam), _dptr(ol), _dptr(od), len(ol)))
+
+
+def spectrum_average_resolution(lam) -> float:
+    lam = np.ascontiguousarray(lam, dtype=np.float64)
+    return lib().orc_spectrum_average_resolution(_dptr(lam), len(lam))
+
+
+def spectrum_merge(l1, d1, l2, d2):
+    """merge_spectra (spectrum.rs:622-650) of two present spectra"""
+    l1, d1 = _spec(l1, d1)
+    l2, d2 = _spec(l2, d2)
+    n = C.c_uint64()
+    _check(lib().orc_spectrum_merge(_dptr(l1), _dptr(d1), len(l1), _dptr(l2), _dptr(d2), len(l2), None, None, 0, C.byref(n)))
+    lam, data = np.zeros(max(n.value, 1)), np.zeros(max(n.value, 1))
+    _check(lib().orc_spectrum_merge(_dptr(l1), _dptr(d1), len(l1), _dptr(l2), _dptr(d2), len(l2), _dptr(lam), _dptr(data), n.value, C.byref(n)))
+    return lam[: n.value], data[: n.value]
+
+
+def spectrum_from_csv(path):
+    """Spectrum::from_csv (spectrum.rs:89-117)"""
+    n = C.c_uint64()
+    _check(lib().orc_spectrum_from_csv(str(path).encode(), None, None, 0, C.byref(n)))
+    lam, data = np.zeros(n.value), np.zeros(n.value)
+    _check(lib().orc_spectrum_from_csv(str(path).encode(), _dptr(lam), _dptr(data), n.value, C.byref(n)))
+    return lam, data
 
 
 def rays_filter_energy_spectrum(rays, lam, data):
