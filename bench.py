@@ -831,7 +831,9 @@ def run_product(args):
             "gpu_launches": launches_per_step * args.steps,
             "clocks": clk,
             "roofline": {"bound": "issue",
-                         "bound_note": "the fused kernel is bound by instruction issue (ncu: issue slots 63 % busy, FP64 pipe 40 %, DRAM 50 %); "
+                         "bound_note": ("the fused kernel is bound by instruction issue (ncu: issue slots %.0f %% busy, FP64 pipe %.0f %%, DRAM %.0f %%); "
+                                        % (ncu["issue_active_pct"], ncu["fp64_pipe_pct"], ncu["dram_throughput_pct"]) if ncu else
+                                        "the fused kernel is bound by instruction issue (no ncu capture of this build's launch is committed); ") +
                                        "achieved / peak / frac below measure it against the HBM roof the north star names (bound: hbm there)",
                          "kernel": ("opm_jit_trace (fused surface sequence, compiled at run time for this op program)" if jit["launches"] else
                                     "opm::trace_kernel (fused surface sequence, interpreter)"),

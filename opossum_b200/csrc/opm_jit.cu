@@ -274,10 +274,11 @@ size_t jit_dynamic_smem(int stash_words, int block, int bbox_slots, int spot_slo
     return jit_bbox_offset(stash_words, block) + (size_t)bbox_slots * block * 36 + (size_t)spot_slots * block * kSpotSmemBytes;
 }
 
-// Bulk L2 prefetch of the CTA's next tile (tile_prefetch, opm_trace_ops.cuh): only for programs whose tiles keep a warp busy for long
-// compared with a round trip to the HBM -- five or more surfaces.  Measured (profiles/r2n_gpu_run.sh): C2 (13 surfaces, bound by
-// instruction issue) 0.969 -> 0.915 ms per launch; C4 (3 surfaces, at the HBM roof already) 3.75 -> 5.39 ms with it -- the warps
-// reach the next tile while its prefetch is still on the way and the lines are read twice.  OPM_B200_JIT_PREFETCH=0|1 forces it.
+// Bulk L2 prefetch of the CTA's next tile and its flags loaded one tile ahead (tile_prefetch / TileAhead, opm_trace_ops.cuh): only
+// for programs whose tiles keep a warp busy for long compared with a round trip to the HBM -- five or more surfaces.  Measured
+// (profiles/r2n_gpu_run.sh, r2o_gpu_run.sh): C2 (13 surfaces, bound by instruction issue) 0.969 -> 0.915 ms per launch; C4
+// (3 surfaces, at the HBM roof already) 3.74 -> 5.31 ms with the prefetch -- the warps reach the next tile while its prefetch is
+// still on the way and the lines are read twice -- and 3.74 -> 4.22 ms with the flags alone.  OPM_B200_JIT_PREFETCH=0|1 forces both.
 static bool program_wants_prefetch(const DevOp* ops, int n_ops) {
     static const int forced = [] { const char* e = getenv("OPM_B200_JIT_PREFETCH"); return e ? (e[0] == '0' ? 0 : 1) : -1; }();
     if (forced >= 0) return forced != 0;
@@ -336,7 +337,7 @@ std::string make_source(const DevOp* ops, int n_ops, bool compact, int block, in
     }
     std::string s;
     appendf(s, "#define OPM_JIT_BLOCK %d\n", block);
-    if (!program_wants_prefetch(ops, n_ops)) s += "#define OPM_TILE_NO_BULK_PREFETCH 1\n";
+    if (!program_wants_prefetch(ops, n_ops)) s += "#define OPM_TILE_NO_BULK_PREFETCH 1\n#define OPM_TILE_NO_FLAG_AHEAD 1\n";
     s += "#include \"opm_trace_ops.cuh\"\nnamespace opm {\n";
     appendf(s, "extern \"C\" __constant__ DevOp opm_jit_ops[%d];\n", n_ops);
     appendf(s, "extern \"C\" __global__ void __launch_bounds__(%d, %d)\n", block, min_ctas);

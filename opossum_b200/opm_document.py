@@ -232,11 +232,30 @@ def _coating(v):
 
 
 def _aperture(v):
-    """Aperture (aperture.rs:66-84); the polygon and stack forms are not read"""
+    """Aperture (aperture.rs:66-84).  A BinaryPolygon is serialised with its earcut triangulation (PolygonConfig: points,
+    aperture_type, triangle_indices; aperture.rs:247-251), which is what `in_polygon` tests a point against (:289-316) -- the
+    triangles are read, nothing is triangulated here.  A Stack (StackConfig, :385-416) is read when it is a flat list of simple
+    apertures with at most one polygon, which is what the device aperture holds."""
     if v is None or v.name == "None":
         return None
     c = v.single()
     obstruction = c["aperture_type"].name == "Obstruction"
+    if v.name == "BinaryPolygon":
+        pts = [(float(q[0]), float(q[1])) for q in c["points"]]
+        tris = []
+        for tri in c["triangle_indices"]:
+            idx = [int(i) for i in tri]
+            if len(idx) != 3 or any(i < 0 or i >= len(pts) for i in idx):
+                raise OpmDocumentError("polygon aperture: a triangle does not name three of its points")
+            tris.append([coord for i in idx for coord in pts[i]])
+        if not tris:
+            raise OpmDocumentError("polygon aperture without triangles")
+        return ("polygon", tris, obstruction)
+    if v.name == "Stack":
+        items = [_aperture(a) for a in c["apertures"]]
+        if any(a is None or a[0] == "stack" for a in items) or sum(a[0] == "polygon" for a in items) > 1:
+            raise OpmDocumentError("aperture stack: only flat stacks of simple apertures with at most one polygon are supported")
+        return ("stack", items, obstruction)
     cx, cy = (float(t) for t in c["center"])
     if v.name == "BinaryCircle":
         return ("circle", float(c["radius"]), cx, cy, obstruction)
@@ -512,6 +531,8 @@ class OpmDocument:
         def ap(a):
             if a is None:
                 return None
+            if a[0] == "stack":
+                return Aperture.stack([ap(item) for item in a[1]], obstruction=a[-1])
             return getattr(Aperture, a[0])(*a[1:-1], obstruction=a[-1])
 
         def coat(c):

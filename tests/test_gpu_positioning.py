@@ -181,6 +181,53 @@ def test_opm_document_end_to_end(ctx):
     assert index[doc.nodes[-1].uuid] == 7
 
 
+def test_opm_document_polygon_and_stack_apertures_end_to_end(ctx):
+    """the same file with the lens' circular input aperture replaced by (a) a BinaryPolygon as the reference serialises it -- points
+    plus earcut's triangle indices (aperture.rs:247-251) -- and (b) a Stack of that polygon and a Gaussian: the document's analysis
+    against the oracle's scene with the same triangles"""
+    from pathlib import Path
+
+    from opossum_b200 import opm_document as D
+    text = (Path(__file__).parent / "golden" / "opm" / "folded_chain_handwritten.opm").read_text()
+    circle = "BinaryCircle((radius: 0.0035, center: (0.0002, 0.0), aperture_type: Hole))"
+    assert circle in text
+    pts = [(-0.003, -0.002), (0.0025, -0.0028), (0.0032, 0.001), (0.0004, 0.0034), (-0.0028, 0.0015)]  # a convex pentagon around the axis
+    fan = [(0, 1, 2), (0, 2, 3), (0, 3, 4)]
+    poly = ("BinaryPolygon((points: [%s], aperture_type: Hole, triangle_indices: [%s]))"
+            % (", ".join("(%r, %r)" % q for q in pts), ", ".join("[%d, %d, %d]" % t for t in fan)))
+    tris = [[c for i in t for c in pts[i]] for t in fan]
+    gauss = "Gaussian((sigma: (0.004, 0.003), center: (0.0, 0.0), aperture_type: Hole))"
+    cases = {"polygon": (poly, ("polygon", tris, False)),
+             "stack": ("Stack((apertures: [%s, %s], aperture_type: Hole))" % (gauss, poly),
+                       ("stack", [orc.ap_gaussian(0.004, 0.003), orc.ap_polygon(tris)], False))}
+    for name, (ron, neutral) in cases.items():
+        doc = D.loads_opm(text.replace(circle, ron))
+        psc, sd, _ = doc.build(ctx)
+        psc.calc_node_positions(doc.axis_wavelength())
+        nodes = [scenes.node("source", z=10 * MM, xy=(1 * MM, -2 * MM)),
+                 scenes.node("lens", distance=100 * MM, p=(515.0 * MM, -515.0 * MM, 5.0 * MM), index=scenes.HK9L, coat_in=("fresnel",),
+                             coat_out=("fresnel",), ap_in=neutral),
+                 scenes.node("thin_mirror", distance=150 * MM, alignment=((0.0, 0.0, 0.0), (math.radians(22.5), 0.0, 0.0)),
+                             coat_in=("constant_r", 0.98), coat_out=("constant_r", 0.98)),
+                 scenes.node("beam_splitter", distance=120 * MM, p=(0.3,)),
+                 scenes.node("ideal_filter", distance=50 * MM, p=(0.8,)),
+                 scenes.node("spot_diagram", distance=80 * MM),
+                 scenes.node("fluence_detector", distance=10 * MM),
+                 scenes.node("fluence_detector", distance=90 * MM, parent=3, parent_port=1)]
+        src = {"pos": ("fibonacci_ellipse", 3000, 4 * MM, 3 * MM),
+               "energy": ("general_gaussian", 2.0, (0.3 * MM, -0.2 * MM), (2.5 * MM, 2.0 * MM), 2.0, 0.3, False),
+               "wvl": [1054 * NM, 527 * NM], "w": [0.7, 0.3]}
+        osc = scenes.to_oracle(nodes)
+        osc.calc_node_positions(1054 * NM)
+        ref_out = osc.raytrace(scenes.source_to_oracle(src))
+        rays = sd.generate(ctx)
+        st = psc.raytrace(rays, doc.raytrace_config())
+        n_valid = orc.nr_of_rays(ref_out)
+        assert 0 < n_valid < len(ref_out), name  # the aperture clips some rays, not all
+        assert st.interactions == osc.interactions and st.valid_out == n_valid, name
+        assert_rays_match(rays.to_array(), ref_out, what=f".opm scene, {name} aperture")
+
+
 @pytest.mark.parametrize("collimating", [False, True])
 def test_off_axis_parabolic_mirror(ctx, collimating):
     """ParabolicMirror with an off-axis angle (nodes/parabolic_mirror.rs:286-320,388-421): a collimated beam onto a 45 deg off-axis

@@ -126,6 +126,19 @@ def test_property_and_port_mapping_of_every_node_type():
     assert n.kind == 11 and n.fluence_estimator == "Voronoi"  # the reference's default estimator (fluence_detector/mod.rs:62)
     n = D._node(D.parse_ron(_node_text("dummy", "", extra='align_like_node_at_distance: Some(("00000000-0000-4000-8000-000000000009", 0.3)),')))
     assert n.align_like == ("00000000-0000-4000-8000-000000000009", 0.3)
+    # PolygonConfig travels with its triangulation (aperture.rs:247-251); StackConfig as a list of apertures (:385-390)
+    poly = ("BinaryPolygon((points: [(0.0, 0.0), (0.01, 0.0), (0.01, 0.01), (0.0, 0.01)], aperture_type: Hole, "
+            "triangle_indices: [[3, 0, 1], [1, 2, 3]]))")
+    n = D._node(D.parse_ron(_node_text("dummy", "", ap_in="aperture: %s," % poly)))
+    assert n.apertures[0] == ("polygon", [[0.0, 0.01, 0.0, 0.0, 0.01, 0.0], [0.01, 0.0, 0.01, 0.01, 0.0, 0.01]], False)
+    n = D._node(D.parse_ron(_node_text("dummy", "", ap_in="aperture: Stack((apertures: [BinaryCircle((radius: 0.02, center: (0.0, 0.0), "
+                                       "aperture_type: Hole)), %s], aperture_type: Obstruction))," % poly)))
+    assert n.apertures[0][0] == "stack" and n.apertures[0][-1] is True
+    assert [a[0] for a in n.apertures[0][1]] == ["circle", "polygon"]
+    with pytest.raises(D.OpmDocumentError, match="triangle"):
+        D._node(D.parse_ron(_node_text("dummy", "", ap_in="aperture: %s," % poly.replace("[1, 2, 3]", "[1, 2, 7]"))))
+    with pytest.raises(D.OpmDocumentError, match="flat stacks"):
+        D._node(D.parse_ron(_node_text("dummy", "", ap_in="aperture: Stack((apertures: [%s, %s], aperture_type: Hole))," % (poly, poly))))
     for bad in ('"splitter config": SplitterType(Spectrum(()))',):
         with pytest.raises(D.OpmDocumentError):
             D._node(D.parse_ron(_node_text("beam splitter", bad, outs=("out1_trans1_refl2", "out2_trans2_refl1"))))
