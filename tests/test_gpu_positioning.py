@@ -223,7 +223,7 @@ def test_opm_document_polygon_and_stack_apertures_end_to_end(ctx):
         rays = sd.generate(ctx)
         st = psc.raytrace(rays, doc.raytrace_config())
         n_valid = orc.nr_of_rays(ref_out)
-        assert 0 < n_valid < len(ref_out), name  # the aperture clips some rays, not all
+        assert 0 < n_valid < 6000, name  # the aperture clips some of the 3000 x 2 rays, not all (the mirror drops them from its output)
         assert st.interactions == osc.interactions and st.valid_out == n_valid, name
         assert_rays_match(rays.to_array(), ref_out, what=f".opm scene, {name} aperture")
 
