@@ -507,6 +507,16 @@ OpmStatus opm_fluence_peak_check_async(OpmHitMap* const* maps, int32_t n_maps, i
 OpmStatus opm_fluence_peak_check_side_async(OpmHitMap* const* maps, int32_t n_maps, int64_t bounce_filter, uint64_t nx, uint64_t ny,
                                             void* acc_dev, double* map_dev, double* result_dev);
 OpmStatus opm_context_join_side_stream(OpmContext* ctx);
+/* MANY such checks in three launches -- for a caller that can defer them, as the ghost-focus analysis can: the verdicts of
+ * evaluate_fluence_of_ray_bundle steer no control flow and the hit maps stay until the surfaces are reset.  Check k takes ONE hit map
+ * maps[k], accumulator k of acc_dev (n_checks x OPM_PEAK_CHECK_ACC_BYTES, prepared once by opm_fluence_peak_check_acc_init), map k of
+ * maps_dev (n_checks maps of nx * ny doubles, each padded to a multiple of 8 doubles) and the result slot results_dev[k] (8 doubles
+ * as above, [6] zero on entry).  bounce_filters: NULL = every check uses the key word [7] of its own result slot, which
+ * opm_fluence_peak_check_capture_key_async put there right after the bundle's trace launch (Rays::bounce_lvl of that moment,
+ * analyzers/raytrace.rs:118-133); else one filter per check (a level, -1, or OPM_BOUNCE_OF_LAST_LAUNCH for the captured key). */
+OpmStatus opm_fluence_peak_check_capture_key_async(OpmContext* ctx, double* result_dev);
+OpmStatus opm_fluence_peak_check_batch_async(OpmHitMap* const* maps, int32_t n_checks, const int64_t* bounce_filters, uint64_t nx, uint64_t ny,
+                                             void* acc_dev, double* maps_dev, double* const* results_dev);
 OpmStatus opm_hitmaps_bounding_box_async(OpmHitMap* const* maps, int32_t n_maps, int64_t bounce_filter_or_minus1, double* range_dev);
 OpmStatus opm_fluence_binning_async(OpmHitMap* const* maps, int32_t n_maps, int64_t bounce_filter_or_minus1, uint64_t nx, uint64_t ny,
                                     const double* range_dev, int32_t accumulate, double* map_dev, uint32_t* status_dev);

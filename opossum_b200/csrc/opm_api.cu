@@ -70,6 +70,11 @@ struct OpmContext {
     cudaStream_t side_stream = nullptr;
     cudaEvent_t side_ev = nullptr;
     bool side_busy = false;
+    // job list of opm_fluence_peak_check_batch_async: pinned staging + device copy, reused once jobs_ev says the copy has drained
+    PeakCheckJob* h_jobs = nullptr;
+    PeakCheckJob* d_jobs = nullptr;
+    int jobs_cap = 0;
+    cudaEvent_t jobs_ev = nullptr;
     // optional per-launch timing of the fused trace kernel (CUDA events on the launching stream)
     bool timing = false;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timing_events;
@@ -292,6 +297,8 @@ extern "C" void opm_context_destroy(OpmContext* c) {
         for (auto& p : *v) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
     if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }
     if (c->side_stream) { cudaStreamSynchronize(c->side_stream); cudaStreamDestroy(c->side_stream); cudaEventDestroy(c->side_ev); }
+    if (c->jobs_ev) cudaEventDestroy(c->jobs_ev);
+    cudaFreeHost(c->h_jobs); cudaFree(c->d_jobs);
     jit_cache_destroy(c->jit);
     for (int k = 0; k < OpmContext::kPutSlots; ++k) if (c->put_ev[k]) cudaEventDestroy(c->put_ev[k]);
     cudaFreeHost(c->h_put_ring);
@@ -2445,6 +2452,52 @@ static OpmStatus peak_check_impl(OpmHitMap* const* maps, int32_t n_maps, int64_t
     for (int k = 0; k < n_maps; ++k)
         if (maps[k]->len) { KL(k_binning(maps[k]->v, maps[k]->len, bounce_filter, nx, ny, result_dev, map_dev, (unsigned*)(result_dev + 6), c->sms, st)); c->launches++; }
     KL(k_peakcheck_peak(map_dev, nx, ny, key_src, result_dev, st)); c->launches++;
+    return OPM_OK;
+}
+// the bundle's bounce level for a deferred check: the latest launch's first_valid_key statistic, copied into the key word of the
+// check's result slot in stream order (the next trace launch resets the statistic)
+extern "C" OpmStatus opm_fluence_peak_check_capture_key_async(OpmContext* c, double* result_dev) {
+    if (!c || !result_dev) return fail(OPM_ERR_ARG, "NULL argument");
+    CU(cudaSetDevice(c->device));
+    CU(cudaMemcpyAsync(reinterpret_cast<unsigned long long*>(result_dev) + 7, &c->d_stats->first_inv, 8, cudaMemcpyDeviceToDevice, c->stream));
+    return OPM_OK;
+}
+extern "C" OpmStatus opm_fluence_peak_check_batch_async(OpmHitMap* const* maps, int32_t n_checks, const int64_t* bounce_filters, uint64_t nx,
+                                                        uint64_t ny, void* acc_dev, double* maps_dev, double* const* results_dev) {
+    if (n_checks == 0) return OPM_OK;
+    OpmContext* c;
+    OpmStatus s = check_same_ctx(maps, n_checks, &c);
+    if (s) return s;
+    if (!acc_dev || !maps_dev || !results_dev || nx < 2 || ny < 2 || nx * ny * sizeof(double) > 160 * 1024 || n_checks > 65535)
+        return fail(OPM_ERR_ARG, "peak check batch: bad arguments (maps up to 160 KB, at most 65535 checks)");
+    CU(cudaSetDevice(c->device));
+    if (n_checks > c->jobs_cap) {
+        if (c->jobs_ev) CU(cudaEventSynchronize(c->jobs_ev));
+        cudaFreeHost(c->h_jobs); cudaFree(c->d_jobs);
+        c->h_jobs = nullptr; c->d_jobs = nullptr; c->jobs_cap = 0;
+        const int cap = n_checks < 256 ? 256 : n_checks;
+        CU(cudaMallocHost(&c->h_jobs, sizeof(PeakCheckJob) * cap));
+        CU(cudaMalloc(&c->d_jobs, sizeof(PeakCheckJob) * cap));
+        if (!c->jobs_ev) CU(cudaEventCreateWithFlags(&c->jobs_ev, cudaEventDisableTiming));
+        c->jobs_cap = cap;
+    } else CU(cudaEventSynchronize(c->jobs_ev));  // the previous batch's copy has read the pinned list
+    const size_t map_stride = (nx * ny + 7) / 8 * 8;
+    uint64_t max_n = 0;
+    for (int k = 0; k < n_checks; ++k) {
+        if (!results_dev[k]) return fail(OPM_ERR_ARG, "peak check batch: NULL result slot");
+        PeakCheckJob& j = c->h_jobs[k];
+        j.H = maps[k]->v; j.n = maps[k]->len;
+        const int64_t f = bounce_filters ? bounce_filters[k] : OPM_BOUNCE_OF_LAST_LAUNCH;
+        if (f == OPM_BOUNCE_OF_LAST_LAUNCH) j.bounce_filter = -(long long)(uintptr_t)(reinterpret_cast<unsigned long long*>(results_dev[k]) + 7);
+        else if (f < -1) return fail(OPM_ERR_ARG, "bad bounce filter");
+        else j.bounce_filter = f;
+        j.acc = (PeakCheckAcc*)acc_dev + k; j.result = results_dev[k]; j.map = maps_dev + (size_t)k * map_stride;
+        if (j.n > max_n) max_n = j.n;
+    }
+    CU(cudaMemcpyAsync(c->d_jobs, c->h_jobs, sizeof(PeakCheckJob) * n_checks, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaEventRecord(c->jobs_ev, c->stream));
+    KL(k_peakcheck_batch(c->d_jobs, n_checks, max_n, nx, ny, c->sms, c->stream));
+    c->launches += 3;
     return OPM_OK;
 }
 extern "C" OpmStatus opm_fluence_peak_total_async(OpmContext* c, const double* map_dev, uint64_t nx, uint64_t ny, const double* range_dev,

@@ -418,11 +418,10 @@ __global__ void __launch_bounds__(1024) binning_smem_kernel(DevHits H, uint64_t 
 // 2^62 units: a tap is rounded to 2^-62 x (slots per CTA) of the largest possible tap (<= 2^-45 relative to it for 10^5 slots per
 // CTA), and the CTA's sums do not depend on the order of the adds. Taps, indices and the flush into the global f64 map are
 // those of the kernel above.
-template <int BLOCK, int MIN_CTAS, int UNROLL, bool FASTDIV>
-__global__ void __launch_bounds__(BLOCK, MIN_CTAS) binning_smem_fixed_kernel(DevHits H, uint64_t n, long long bounce_filter,
-                                                                             unsigned long long nx, unsigned long long ny,
-                                                                             const double* __restrict__ range, double* __restrict__ map,
-                                                                             unsigned* status_out) {
+template <int BLOCK, int UNROLL, bool FASTDIV>
+__device__ __forceinline__ void binning_smem_fixed_body(const DevHits& H, uint64_t n, long long bounce_filter, unsigned long long nx,
+                                                        unsigned long long ny, const double* __restrict__ range, double* __restrict__ map,
+                                                        unsigned* status_out) {
     bounce_filter = resolve_bounce_filter(bounce_filter);
     extern __shared__ unsigned sfix[];
     __shared__ unsigned long long s_emax_key;
@@ -511,6 +510,13 @@ __global__ void __launch_bounds__(BLOCK, MIN_CTAS) binning_smem_fixed_kernel(Dev
         if (q) atomicAdd(&map[k], (double)q * unit);
     }
     if (status) atomicOr(status_out, status);
+}
+template <int BLOCK, int MIN_CTAS, int UNROLL, bool FASTDIV>
+__global__ void __launch_bounds__(BLOCK, MIN_CTAS) binning_smem_fixed_kernel(DevHits H, uint64_t n, long long bounce_filter,
+                                                                             unsigned long long nx, unsigned long long ny,
+                                                                             const double* __restrict__ range, double* __restrict__ map,
+                                                                             unsigned* status_out) {
+    binning_smem_fixed_body<BLOCK, UNROLL, FASTDIV>(H, n, bounce_filter, nx, ny, range, map, status_out);
 }
 
 // large maps: consecutive lanes that fall into the same bin (a run) are summed with a segmented warp
@@ -794,9 +800,9 @@ __global__ void __launch_bounds__(256) peak_total_kernel(const double* __restric
 //   2. the Binning splat (k_binning);
 //   3. one CTA: peak and total of the map, the bounce level the check used (the launch's first_valid_key).
 // result[8] = range 4 | peak | total | status bits (u32, accumulated by the splat) | first_valid_key (u64)
-__global__ void __launch_bounds__(256) peakcheck_bbox_kernel(DevHits H, uint64_t n, long long bounce_filter, PeakCheckAcc* acc,
-                                                             double* __restrict__ range_out, double* __restrict__ map, uint64_t bins,
-                                                             int first, int last) {
+__device__ __forceinline__ void peakcheck_bbox_body(const DevHits& H, uint64_t n, long long bounce_filter, PeakCheckAcc* acc,
+                                                    double* __restrict__ range_out, double* __restrict__ map, uint64_t bins, int first,
+                                                    int last) {
     if (first)
         for (uint64_t k = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; k < bins; k += (uint64_t)gridDim.x * blockDim.x) map[k] = 0.0;
     hits_bbox_body(H, n, resolve_bounce_filter(bounce_filter), &acc->box);
@@ -811,8 +817,13 @@ __global__ void __launch_bounds__(256) peakcheck_bbox_kernel(DevHits H, uint64_t
     else { range_out[0] = -dkey_inv(k0); range_out[1] = dkey_inv(k1); range_out[2] = dkey_inv(k2); range_out[3] = -dkey_inv(k3); }
     acc->box.key[0] = ~0ull; acc->box.key[1] = 0ull; acc->box.key[2] = 0ull; acc->box.key[3] = ~0ull; acc->box.count = 0ull; acc->done = 0u;
 }
-__global__ void __launch_bounds__(1024) peakcheck_peak_kernel(const double* __restrict__ map, uint64_t nx, uint64_t ny,
-                                                              const unsigned long long* first_inv, double* __restrict__ result) {
+__global__ void __launch_bounds__(256) peakcheck_bbox_kernel(DevHits H, uint64_t n, long long bounce_filter, PeakCheckAcc* acc,
+                                                             double* __restrict__ range_out, double* __restrict__ map, uint64_t bins,
+                                                             int first, int last) {
+    peakcheck_bbox_body(H, n, bounce_filter, acc, range_out, map, bins, first, last);
+}
+__device__ __forceinline__ void peakcheck_peak_body(const double* __restrict__ map, uint64_t nx, uint64_t ny,
+                                                    const unsigned long long* first_inv, double* __restrict__ result) {
     const double* range = result;
     const uint64_t bins = nx * ny;
     const double dx = (range[1] - (-range[0])) / (double)nx, dy = (range[2] - (-range[3])) / (double)ny;
@@ -833,6 +844,30 @@ __global__ void __launch_bounds__(1024) peakcheck_peak_kernel(const double* __re
         const unsigned long long inv = first_inv ? *first_inv : 0ull;
         reinterpret_cast<unsigned long long*>(result)[7] = inv ? ~inv : ~0ull;
     }
+}
+__global__ void __launch_bounds__(1024) peakcheck_peak_kernel(const double* __restrict__ map, uint64_t nx, uint64_t ny,
+                                                              const unsigned long long* first_inv, double* __restrict__ result) {
+    peakcheck_peak_body(map, nx, ny, first_inv, result);
+}
+// The same three steps for MANY checks at once (the ghost-focus analysis defers its per-bundle checks: their verdicts steer no
+// control flow and the hit maps stay): blockIdx.y (bbox, splat) / blockIdx.x (peak) picks the check, every check has its own
+// accumulator, map and result slot; the bounce level of check k is the key word of its result slot (captured right after the
+// bundle's launch).  Three launches for up to a few hundred checks instead of three latency-bound launches each.
+__global__ void __launch_bounds__(256) peakcheck_bbox_batch_kernel(const PeakCheckJob* __restrict__ jobs, uint64_t bins) {
+    const PeakCheckJob j = jobs[blockIdx.y];
+    peakcheck_bbox_body(j.H, j.n, j.bounce_filter, j.acc, j.result, j.map, bins, 1, 1);
+}
+template <int BLOCK, int MIN_CTAS, int UNROLL, bool FASTDIV>
+__global__ void __launch_bounds__(BLOCK, MIN_CTAS) binning_fixed_batch_kernel(const PeakCheckJob* __restrict__ jobs, unsigned long long nx,
+                                                                              unsigned long long ny) {
+    const PeakCheckJob j = jobs[blockIdx.y];
+    if (j.n == 0) return;  // a check without recorded slots has no splat (its range is empty)
+    binning_smem_fixed_body<BLOCK, UNROLL, FASTDIV>(j.H, j.n, j.bounce_filter, nx, ny, j.result, j.map,
+                                                    reinterpret_cast<unsigned*>(j.result + 6));
+}
+__global__ void __launch_bounds__(1024) peakcheck_peak_batch_kernel(const PeakCheckJob* __restrict__ jobs, uint64_t nx, uint64_t ny) {
+    const PeakCheckJob j = jobs[blockIdx.x];
+    peakcheck_peak_body(j.map, nx, ny, reinterpret_cast<const unsigned long long*>(j.result) + 7, j.result);
 }
 __global__ void peakcheck_acc_init_kernel(PeakCheckAcc* acc, uint64_t n) {
     for (uint64_t k = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; k < n; k += (uint64_t)gridDim.x * blockDim.x) {
@@ -1208,6 +1243,24 @@ int k_peakcheck_acc_init(PeakCheckAcc* acc, uint64_t n, void* stream) {
 int k_peakcheck_bbox(DevHits H, uint64_t n, long long bounce_filter, PeakCheckAcc* acc, double* range_out, double* map, uint64_t bins, int first,
                      int last, int sms, void* stream) {
     peakcheck_bbox_kernel<<<grid_for(n, 256 * 4, sms * 8), 256, 0, ST>>>(H, n, bounce_filter, acc, range_out, map, bins, first, last);
+    return (int)cudaGetLastError();
+}
+// n_jobs checks in three launches; the CTAs of a launch are shared out among the checks (a few waves in total: the splat's
+// CTA-private map is flushed once per CTA, so a check gets no more CTAs than keep the SMs busy)
+int k_peakcheck_batch(const PeakCheckJob* d_jobs, int n_jobs, uint64_t max_n, uint64_t nx, uint64_t ny, int sms, void* stream) {
+    if (n_jobs <= 0) return 0;
+    const uint64_t bins = nx * ny;
+    const size_t bytes = (size_t)bins * sizeof(double);
+    if (bytes > 160 * 1024 || n_jobs > 65535) return (int)cudaErrorInvalidValue;
+    auto share = [&](int total, int most) { int g = (total + n_jobs - 1) / n_jobs; return g < 1 ? 1 : (g > most ? most : g); };
+    const int g_bbox = share(sms * 8, grid_for(max_n, 256 * 4, sms * 8));
+    peakcheck_bbox_batch_kernel<<<dim3(g_bbox, n_jobs), 256, 0, ST>>>(d_jobs, bins);
+    const int ctas = (2 * (bytes + 1024) <= 227 * 1024) ? 2 : 1;
+    const int g_bin = share(sms * ctas * 2, grid_for(max_n, 1024, sms * ctas));
+    cudaError_t e = cudaFuncSetAttribute(binning_fixed_batch_kernel<1024, 2, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e != cudaSuccess) return (int)e;
+    binning_fixed_batch_kernel<1024, 2, 2, true><<<dim3(g_bin, n_jobs), 1024, bytes, ST>>>(d_jobs, nx, ny);
+    peakcheck_peak_batch_kernel<<<n_jobs, 1024, 0, ST>>>(d_jobs, nx, ny);
     return (int)cudaGetLastError();
 }
 int k_peakcheck_peak(const double* map, uint64_t nx, uint64_t ny, const unsigned long long* first_inv, double* result, void* stream) {

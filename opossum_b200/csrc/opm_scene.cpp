@@ -24,6 +24,10 @@ struct Bundle {
     OpmRays* rays = nullptr;
     uint64_t uuid = 0;
     uint64_t parent = 0;
+    // ghost focus: a clone of a cached bundle that has not been written yet -- its first launch reads `lazy_src` and writes `rays`
+    // (opm_scene_gf.inc); lazy_limits: the clone still owes the ray limits of the node it was injected behind
+    std::shared_ptr<Bundle> lazy_src;
+    bool lazy_limits = false;
 };
 
 // surface/optic_surface.rs:29-43
@@ -88,6 +92,9 @@ struct OpmScene {
     void* gf_host = nullptr;
     void* gf_vor_map = nullptr;  // 101 x 101 map + the bounce-level key of a Voronoi LIDT check
     std::vector<GfCheck> gf_pending;
+    void* gf_batch_mem = nullptr;               // maps and accumulators of the deferred checks (opm_scene_gf.inc)
+    std::vector<OpmHitMap*> gf_batch_maps;      // deferred checks not launched yet: hit map ...
+    std::vector<double*> gf_batch_slots;        // ... and result slot
 };
 
 namespace {
@@ -538,6 +545,7 @@ extern "C" void opm_scene_destroy(OpmScene* sc) {
     for (OpmHitMap* h : sc->pool_hits) opm_hitmap_destroy(h);
     if (sc->gf_scratch) opm_device_free(sc->ctx, sc->gf_scratch);
     if (sc->gf_vor_map) opm_device_free(sc->ctx, sc->gf_vor_map);
+    if (sc->gf_batch_mem) opm_device_free(sc->ctx, sc->gf_batch_mem);
     if (sc->gf_host) opm_host_free_pinned(sc->gf_host);
     delete sc;
 }

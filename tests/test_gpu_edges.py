@@ -202,3 +202,63 @@ def test_bounding_box_kept_by_the_trace_kernel_equals_the_pass_over_the_map(ctx)
             ctx.set_jit(1, 200000)
     assert out["jit"] == out["interpreter"]
     assert out["jit"][0][1] > 0 and out["jit"][1][0] == "error"
+
+
+def test_peak_checks_in_a_batch_equal_the_checks_one_at_a_time_and_the_oracle(ctx):
+    """opm_fluence_peak_check_batch_async (what the ghost-focus analysis defers its per-bundle checks to): five hit maps of
+    different sizes and bounce mixes -- one without a hit of its level, one with a single hit, one empty -- through the batch, through
+    opm_fluence_peak_check_async one at a time, and through the oracle's 101 x 101 Binning map of the hits of that level
+    (RaysHitMap::get_max_fluence, rays_hit_map.rs:777-798)"""
+    import ctypes as C
+    rng = np.random.default_rng(77)
+    N = 101
+    pad = (N * N + 7) // 8 * 8
+    sizes, levels = [50_000, 1234, 700, 1, 0], [1, 0, 3, 2, 0]
+    maps, data = [], []
+    for n, lvl in zip(sizes, levels):
+        x, y = rng.normal(0.0, 2e-3, n), rng.normal(1e-3, 1e-3, n)
+        e = rng.uniform(0.0, 1.0, n)
+        b = rng.integers(0, 3, n).astype(np.uint32) if n > 1 else np.full(n, lvl, dtype=np.uint32)
+        e[rng.random(n) < 0.1] = -1.0  # empty slots
+        hm = ob.HitMap(ctx, max(n, 1))
+        if n:
+            hm.upload(x, y, e, bounce=b)
+        maps.append(hm)
+        data.append((x, y, e, b))
+    k = len(maps)
+    acc = ctx.device_alloc(64 * k)
+    assert F.lib().opm_fluence_peak_check_acc_init(ctx.h, C.c_void_p(acc), k) == 0
+    d_maps = ctx.device_alloc(pad * 8 * k)
+    d_res = ctx.device_alloc(64 * k)
+    ctx.device_memset(d_res, 0, 64 * k)
+    arr = (C.c_void_p * k)(*[m.h for m in maps])
+    slots = (C.c_void_p * k)(*[d_res + 64 * i for i in range(k)])
+    filt = (C.c_int64 * k)(*levels)
+    assert F.lib().opm_fluence_peak_check_batch_async(arr, k, filt, N, N, C.c_void_p(acc), C.c_void_p(d_maps), slots) == 0
+    batch = np.zeros((k, 8))
+    ctx.to_host(d_res, batch)
+    # one at a time
+    acc1, map1, res1 = ctx.device_alloc(64), ctx.device_alloc(pad * 8), ctx.device_alloc(64)
+    assert F.lib().opm_fluence_peak_check_acc_init(ctx.h, C.c_void_p(acc1), 1) == 0
+    for i in range(k):
+        ctx.device_memset(res1, 0, 64)
+        one = (C.c_void_p * 1)(maps[i].h)
+        assert F.lib().opm_fluence_peak_check_async(one, 1, levels[i], N, N, C.c_void_p(acc1), C.c_void_p(map1), C.c_void_p(res1)) == 0
+        single = np.zeros(8)
+        ctx.to_host(res1, single)
+        assert np.array_equal(batch[i, :4], single[:4]), i                      # the range: bit for bit
+        assert batch[i, 6:7].view(np.uint32)[0] == single[6:7].view(np.uint32)[0], i
+        x, y, e, b = data[i]
+        sel = (e >= 0.0) & (b == levels[i]) if len(e) else np.zeros(0, dtype=bool)
+        if not sel.any():
+            assert np.all(np.isneginf(batch[i, :4])), i                         # get_rays_hit_map(bounce, uuid) == None
+            continue
+        assert batch[i, 4] == pytest.approx(single[4], rel=1e-9, nan_ok=True) and batch[i, 5] == pytest.approx(single[5], rel=1e-9, nan_ok=True), i
+        hits = orc.hits_from_xye(x[sel], y[sel], e[sel])
+        if sel.sum() == 1:
+            continue  # a range of zero width: no map to compare (the reference's NaN bin index lands in bin 0)
+        ref_map, ref_lrtb = orc.fluence_binning(hits, N, N)
+        assert np.allclose([-batch[i, 0], batch[i, 1], batch[i, 2], -batch[i, 3]], ref_lrtb, rtol=1e-15, atol=0), i
+        assert batch[i, 4] == pytest.approx(np.nanmax(ref_map), rel=1e-9), i
+    for p in (acc, d_maps, d_res, acc1, map1, res1):
+        ctx.device_free(p)
