@@ -517,6 +517,10 @@ OpmStatus opm_context_join_side_stream(OpmContext* ctx);
 OpmStatus opm_fluence_peak_check_capture_key_async(OpmContext* ctx, double* result_dev);
 OpmStatus opm_fluence_peak_check_batch_async(OpmHitMap* const* maps, int32_t n_checks, const int64_t* bounce_filters, uint64_t nx, uint64_t ny,
                                              void* acc_dev, double* maps_dev, double* const* results_dev);
+/* the batch on the context's side stream (see opm_fluence_peak_check_side_async): behind everything issued so far, beside what
+ * follows; acc_dev / maps_dev then belong to side-stream batches only */
+OpmStatus opm_fluence_peak_check_batch_side_async(OpmHitMap* const* maps, int32_t n_checks, const int64_t* bounce_filters, uint64_t nx,
+                                                  uint64_t ny, void* acc_dev, double* maps_dev, double* const* results_dev);
 OpmStatus opm_hitmaps_bounding_box_async(OpmHitMap* const* maps, int32_t n_maps, int64_t bounce_filter_or_minus1, double* range_dev);
 OpmStatus opm_fluence_binning_async(OpmHitMap* const* maps, int32_t n_maps, int64_t bounce_filter_or_minus1, uint64_t nx, uint64_t ny,
                                     const double* range_dev, int32_t accumulate, double* map_dev, uint32_t* status_dev);

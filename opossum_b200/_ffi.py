@@ -236,7 +236,7 @@ EXPORTS = [
     "opm_peer_allgather_async", "opm_peer_fluence_report_async", "opm_peer_fluence_gather_map", "opm_peer_group_phase_times", "opm_measure_fp64_peak", "opm_device_alloc",
     "opm_device_free", "opm_device_memset", "opm_device_to_host", "opm_host_to_device", "opm_host_alloc_pinned", "opm_host_free_pinned",
     "opm_spectrum_gaussian", "opm_source_generate", "opm_source_generate_strided", "opm_source_energy_norm", "opm_rays_new_collimated_xy", "opm_rays_refresh_lens", "opm_rays_expect_appends", "opm_context_interactions_total",
-    "opm_context_last_first_valid_key_async", "opm_fluence_peak_check_acc_init", "opm_fluence_peak_check_async", "opm_fluence_peak_check_side_async", "opm_context_join_side_stream", "opm_fluence_peak_check_capture_key_async", "opm_fluence_peak_check_batch_async", "opm_fluence_voronoi", "opm_hitmap_bounce_levels", "opm_rays_attach_fluence_helpers", "opm_rays_has_fluence_helpers",
+    "opm_context_last_first_valid_key_async", "opm_fluence_peak_check_acc_init", "opm_fluence_peak_check_async", "opm_fluence_peak_check_side_async", "opm_context_join_side_stream", "opm_fluence_peak_check_capture_key_async", "opm_fluence_peak_check_batch_async", "opm_fluence_peak_check_batch_side_async", "opm_fluence_voronoi", "opm_hitmap_bounce_levels", "opm_rays_attach_fluence_helpers", "opm_rays_has_fluence_helpers",
     "opm_rays_download_fluence_helpers", "opm_fluence_helper_rays", "opm_rays_new_collimated_w_fluence_helper", "opm_voronoi_cell_areas",
 ]
 
@@ -394,6 +394,7 @@ def lib() -> C.CDLL:
         "opm_context_join_side_stream": (i32, [vp]),
         "opm_fluence_peak_check_capture_key_async": (i32, [vp, vp]),
         "opm_fluence_peak_check_batch_async": (i32, [vp, i32, vp, u64, u64, vp, vp, vp]),
+        "opm_fluence_peak_check_batch_side_async": (i32, [vp, i32, vp, u64, u64, vp, vp, vp]),
     }
     sig.update({
         "opm_node_desc_init": (None, [C.POINTER(OpmNodeDesc), i32]),

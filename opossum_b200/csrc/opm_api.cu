@@ -71,10 +71,11 @@ struct OpmContext {
     cudaEvent_t side_ev = nullptr;
     bool side_busy = false;
     // job list of opm_fluence_peak_check_batch_async: pinned staging + device copy, reused once jobs_ev says the copy has drained
+    static constexpr int kJobRing = 4;  // batches whose job lists may be in flight before the host has to wait for the oldest copy
     PeakCheckJob* h_jobs = nullptr;
     PeakCheckJob* d_jobs = nullptr;
-    int jobs_cap = 0;
-    cudaEvent_t jobs_ev = nullptr;
+    int jobs_cap = 0, jobs_pos = 0;
+    cudaEvent_t jobs_ev[kJobRing] = {};
     // optional per-launch timing of the fused trace kernel (CUDA events on the launching stream)
     bool timing = false;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timing_events;
@@ -297,7 +298,7 @@ extern "C" void opm_context_destroy(OpmContext* c) {
         for (auto& p : *v) { cudaEventDestroy(p.first); cudaEventDestroy(p.second); }
     if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }
     if (c->side_stream) { cudaStreamSynchronize(c->side_stream); cudaStreamDestroy(c->side_stream); cudaEventDestroy(c->side_ev); }
-    if (c->jobs_ev) cudaEventDestroy(c->jobs_ev);
+    for (int k = 0; k < OpmContext::kJobRing; ++k) if (c->jobs_ev[k]) cudaEventDestroy(c->jobs_ev[k]);
     cudaFreeHost(c->h_jobs); cudaFree(c->d_jobs);
     jit_cache_destroy(c->jit);
     for (int k = 0; k < OpmContext::kPutSlots; ++k) if (c->put_ev[k]) cudaEventDestroy(c->put_ev[k]);
@@ -2462,8 +2463,18 @@ extern "C" OpmStatus opm_fluence_peak_check_capture_key_async(OpmContext* c, dou
     CU(cudaMemcpyAsync(reinterpret_cast<unsigned long long*>(result_dev) + 7, &c->d_stats->first_inv, 8, cudaMemcpyDeviceToDevice, c->stream));
     return OPM_OK;
 }
+static OpmStatus peak_check_batch_impl(OpmHitMap* const* maps, int32_t n_checks, const int64_t* bounce_filters, uint64_t nx, uint64_t ny,
+                                       void* acc_dev, double* maps_dev, double* const* results_dev, bool side);
 extern "C" OpmStatus opm_fluence_peak_check_batch_async(OpmHitMap* const* maps, int32_t n_checks, const int64_t* bounce_filters, uint64_t nx,
                                                         uint64_t ny, void* acc_dev, double* maps_dev, double* const* results_dev) {
+    return peak_check_batch_impl(maps, n_checks, bounce_filters, nx, ny, acc_dev, maps_dev, results_dev, false);
+}
+extern "C" OpmStatus opm_fluence_peak_check_batch_side_async(OpmHitMap* const* maps, int32_t n_checks, const int64_t* bounce_filters, uint64_t nx,
+                                                             uint64_t ny, void* acc_dev, double* maps_dev, double* const* results_dev) {
+    return peak_check_batch_impl(maps, n_checks, bounce_filters, nx, ny, acc_dev, maps_dev, results_dev, true);
+}
+static OpmStatus peak_check_batch_impl(OpmHitMap* const* maps, int32_t n_checks, const int64_t* bounce_filters, uint64_t nx, uint64_t ny,
+                                       void* acc_dev, double* maps_dev, double* const* results_dev, bool side) {
     if (n_checks == 0) return OPM_OK;
     OpmContext* c;
     OpmStatus s = check_same_ctx(maps, n_checks, &c);
@@ -2472,20 +2483,25 @@ extern "C" OpmStatus opm_fluence_peak_check_batch_async(OpmHitMap* const* maps, 
         return fail(OPM_ERR_ARG, "peak check batch: bad arguments (maps up to 160 KB, at most 65535 checks)");
     CU(cudaSetDevice(c->device));
     if (n_checks > c->jobs_cap) {
-        if (c->jobs_ev) CU(cudaEventSynchronize(c->jobs_ev));
+        if (c->jobs_cap) { CU(cudaStreamSynchronize(c->stream)); if (c->side_stream) CU(cudaStreamSynchronize(c->side_stream)); }  // lists in flight
         cudaFreeHost(c->h_jobs); cudaFree(c->d_jobs);
         c->h_jobs = nullptr; c->d_jobs = nullptr; c->jobs_cap = 0;
         const int cap = n_checks < 256 ? 256 : n_checks;
-        CU(cudaMallocHost(&c->h_jobs, sizeof(PeakCheckJob) * cap));
-        CU(cudaMalloc(&c->d_jobs, sizeof(PeakCheckJob) * cap));
-        if (!c->jobs_ev) CU(cudaEventCreateWithFlags(&c->jobs_ev, cudaEventDisableTiming));
+        CU(cudaMallocHost(&c->h_jobs, sizeof(PeakCheckJob) * cap * OpmContext::kJobRing));
+        CU(cudaMalloc(&c->d_jobs, sizeof(PeakCheckJob) * cap * OpmContext::kJobRing));
+        for (int k = 0; k < OpmContext::kJobRing; ++k) if (!c->jobs_ev[k]) CU(cudaEventCreateWithFlags(&c->jobs_ev[k], cudaEventDisableTiming));
         c->jobs_cap = cap;
-    } else CU(cudaEventSynchronize(c->jobs_ev));  // the previous batch's copy has read the pinned list
+    }
+    const int ring = c->jobs_pos;
+    c->jobs_pos = (c->jobs_pos + 1) % OpmContext::kJobRing;
+    CU(cudaEventSynchronize(c->jobs_ev[ring]));  // the batch that last used this slot of the ring has finished with its lists
+    PeakCheckJob* const h_list = c->h_jobs + (size_t)ring * c->jobs_cap;
+    PeakCheckJob* const d_list = c->d_jobs + (size_t)ring * c->jobs_cap;
     const size_t map_stride = (nx * ny + 7) / 8 * 8;
     uint64_t max_n = 0;
     for (int k = 0; k < n_checks; ++k) {
         if (!results_dev[k]) return fail(OPM_ERR_ARG, "peak check batch: NULL result slot");
-        PeakCheckJob& j = c->h_jobs[k];
+        PeakCheckJob& j = h_list[k];
         j.H = maps[k]->v; j.n = maps[k]->len;
         const int64_t f = bounce_filters ? bounce_filters[k] : OPM_BOUNCE_OF_LAST_LAUNCH;
         if (f == OPM_BOUNCE_OF_LAST_LAUNCH) j.bounce_filter = -(long long)(uintptr_t)(reinterpret_cast<unsigned long long*>(results_dev[k]) + 7);
@@ -2494,9 +2510,17 @@ extern "C" OpmStatus opm_fluence_peak_check_batch_async(OpmHitMap* const* maps, 
         j.acc = (PeakCheckAcc*)acc_dev + k; j.result = results_dev[k]; j.map = maps_dev + (size_t)k * map_stride;
         if (j.n > max_n) max_n = j.n;
     }
-    CU(cudaMemcpyAsync(c->d_jobs, c->h_jobs, sizeof(PeakCheckJob) * n_checks, cudaMemcpyHostToDevice, c->stream));
-    CU(cudaEventRecord(c->jobs_ev, c->stream));
-    KL(k_peakcheck_batch(c->d_jobs, n_checks, max_n, nx, ny, c->sms, c->stream));
+    cudaStream_t st = c->stream;
+    if (side) {  // behind everything the main stream holds so far (the traces that recorded the hits, the captured keys), beside what follows
+        if (!c->side_stream) { CU(cudaStreamCreateWithFlags(&c->side_stream, cudaStreamNonBlocking)); CU(cudaEventCreateWithFlags(&c->side_ev, cudaEventDisableTiming)); }
+        CU(cudaEventRecord(c->side_ev, c->stream));
+        CU(cudaStreamWaitEvent(c->side_stream, c->side_ev, 0));
+        st = c->side_stream;
+        c->side_busy = true;
+    }
+    CU(cudaMemcpyAsync(d_list, h_list, sizeof(PeakCheckJob) * n_checks, cudaMemcpyHostToDevice, st));
+    KL(k_peakcheck_batch(d_list, n_checks, max_n, nx, ny, c->sms, st));
+    CU(cudaEventRecord(c->jobs_ev[ring], st));  // both lists of this slot are free once the batch's last kernel has run
     c->launches += 3;
     return OPM_OK;
 }
