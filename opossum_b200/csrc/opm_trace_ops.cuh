@@ -684,7 +684,20 @@ __device__ __forceinline__ void tile_load(const DevRays& in, uint64_t i, uint64_
 #define OPM_TILE_PREFETCH_DIST 1  // tiles of this CTA ahead
 #endif
 __device__ __forceinline__ void tile_prefetch(const DevRays& in, uint64_t i, uint64_t n) {
-#if !defined(OPM_TILE_NO_BULK_PREFETCH) && defined(OPM_JIT_BLOCK)
+#if !defined(OPM_TILE_NO_BULK_PREFETCH) && defined(OPM_JIT_BLOCK) && defined(OPM_TILE_BULK_PREFETCH_PER_WARP)
+    // probe: every warp asks for its own 32 rays of the next tile (14 requests of 256 / 128 / 32 bytes from lane 0) -- the request
+    // then leads the warp's own loads by exactly one tile of that warp, however far the warps of the CTA have drifted apart.
+    // Measured on C2 (profiles/r2y_variants.txt): 0.958 ms against 0.915 ms for the 14 requests per CTA -- left off.
+    if ((threadIdx.x & 31u) == 0u && i + 32 <= n) {
+        const double* f64[10] = {in.px, in.py, in.pz, in.dx, in.dy, in.dz, in.e, in.wvl, in.opl, in.n};
+#pragma unroll
+        for (int f = 0; f < 10; ++f) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(f64[f] + i), "r"(256));
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(in.bounces + i), "r"(128));
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(in.refr + i), "r"(128));
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(in.id + i), "r"(128));
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(in.valid + i), "r"(32));
+    }
+#elif !defined(OPM_TILE_NO_BULK_PREFETCH) && defined(OPM_JIT_BLOCK)
     if (threadIdx.x == 0 && i + OPM_JIT_BLOCK <= n) {  // i = first ray of the next tile; whole tiles only (16-byte granules)
         static_assert(OPM_JIT_BLOCK % 16 == 0, "bulk prefetch takes multiples of 16 bytes");
         const double* f64[10] = {in.px, in.py, in.pz, in.dx, in.dy, in.dz, in.e, in.wvl, in.opl, in.n};
