@@ -187,9 +187,12 @@ enum {
     OPM_REFRACT_EMIT_CHILDREN = 1,   /* append reflected rays to `children` (warp-aggregated atomics) */
     OPM_REFRACT_CONTINUE_AS_CHILD = 2, /* mirror in a sequence: the reflected ray continues, rays without one leave the bundle
                                         (refraction_intended = false, nodes/thin_mirror.rs:209-250) */
-    OPM_REFRACT_STAT_KEY = 4         /* the launch statistic first_valid_key (Rays::bounce_lvl, rays.rs:183-194) is taken right after
+    OPM_REFRACT_STAT_KEY = 4,        /* the launch statistic first_valid_key (Rays::bounce_lvl, rays.rs:183-194) is taken right after
                                         this op instead of at the end of the program: the ghost-focus analysis reads the bounce
                                         level between refract_on_surface and apodize (analyzers/raytrace.rs:118-133) */
+    OPM_REFRACT_STAT_KEY2 = 8        /* a SECOND such statistic, taken right after this op: a launch that covers both surfaces of a
+                                        lens yields the bundle's bounce level behind each of its two refractions
+                                        (opm_fluence_peak_check_capture_key_async with slot 1) */
 };
 
 typedef struct {
@@ -512,9 +515,10 @@ OpmStatus opm_context_join_side_stream(OpmContext* ctx);
  * maps[k], accumulator k of acc_dev (n_checks x OPM_PEAK_CHECK_ACC_BYTES, prepared once by opm_fluence_peak_check_acc_init), map k of
  * maps_dev (n_checks maps of nx * ny doubles, each padded to a multiple of 8 doubles) and the result slot results_dev[k] (8 doubles
  * as above, [6] zero on entry).  bounce_filters: NULL = every check uses the key word [7] of its own result slot, which
- * opm_fluence_peak_check_capture_key_async put there right after the bundle's trace launch (Rays::bounce_lvl of that moment,
+ * opm_fluence_peak_check_capture_key_async put there right after the bundle's trace launch (Rays::bounce_lvl at the flagged op,
  * analyzers/raytrace.rs:118-133); else one filter per check (a level, -1, or OPM_BOUNCE_OF_LAST_LAUNCH for the captured key). */
-OpmStatus opm_fluence_peak_check_capture_key_async(OpmContext* ctx, double* result_dev);
+OpmStatus opm_fluence_peak_check_capture_key_async(OpmContext* ctx, double* result_dev, int32_t slot /* 0: OPM_REFRACT_STAT_KEY (or the
+                                                   end of the program), 1: OPM_REFRACT_STAT_KEY2 */);
 OpmStatus opm_fluence_peak_check_batch_async(OpmHitMap* const* maps, int32_t n_checks, const int64_t* bounce_filters, uint64_t nx, uint64_t ny,
                                              void* acc_dev, double* maps_dev, double* const* results_dev);
 /* the batch on the context's side stream (see opm_fluence_peak_check_side_async): behind everything issued so far, beside what

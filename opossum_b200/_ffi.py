@@ -392,7 +392,7 @@ def lib() -> C.CDLL:
         "opm_rays_expect_appends": (i32, [vp, u64]),
         "opm_fluence_peak_check_side_async": (i32, [vp, i32, C.c_int64, u64, u64, vp, vp, vp]),
         "opm_context_join_side_stream": (i32, [vp]),
-        "opm_fluence_peak_check_capture_key_async": (i32, [vp, vp]),
+        "opm_fluence_peak_check_capture_key_async": (i32, [vp, vp, i32]),
         "opm_fluence_peak_check_batch_async": (i32, [vp, i32, vp, u64, u64, vp, vp, vp]),
         "opm_fluence_peak_check_batch_side_async": (i32, [vp, i32, vp, u64, u64, vp, vp, vp]),
     }

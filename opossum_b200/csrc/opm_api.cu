@@ -2457,10 +2457,11 @@ static OpmStatus peak_check_impl(OpmHitMap* const* maps, int32_t n_maps, int64_t
 }
 // the bundle's bounce level for a deferred check: the latest launch's first_valid_key statistic, copied into the key word of the
 // check's result slot in stream order (the next trace launch resets the statistic)
-extern "C" OpmStatus opm_fluence_peak_check_capture_key_async(OpmContext* c, double* result_dev) {
-    if (!c || !result_dev) return fail(OPM_ERR_ARG, "NULL argument");
+extern "C" OpmStatus opm_fluence_peak_check_capture_key_async(OpmContext* c, double* result_dev, int32_t slot) {
+    if (!c || !result_dev || slot < 0 || slot > 1) return fail(OPM_ERR_ARG, "NULL argument / key slot not 0 or 1");
     CU(cudaSetDevice(c->device));
-    CU(cudaMemcpyAsync(reinterpret_cast<unsigned long long*>(result_dev) + 7, &c->d_stats->first_inv, 8, cudaMemcpyDeviceToDevice, c->stream));
+    const unsigned long long* src = slot ? &c->d_stats->first_inv2 : &c->d_stats->first_inv;
+    CU(cudaMemcpyAsync(reinterpret_cast<unsigned long long*>(result_dev) + 7, src, 8, cudaMemcpyDeviceToDevice, c->stream));
     return OPM_OK;
 }
 static OpmStatus peak_check_batch_impl(OpmHitMap* const* maps, int32_t n_checks, const int64_t* bounce_filters, uint64_t nx, uint64_t ny,

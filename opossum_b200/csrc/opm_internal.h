@@ -128,13 +128,14 @@ struct DevStats {
     unsigned long long interactions, children, hits, missed, apodized, valid_out, alive_out;
     unsigned int status_bits, _pad;
     unsigned long long first_inv;  // max over valid rays of ~(id << 32 | bounces); 0 = no valid ray (zero-initialised)
+    unsigned long long first_inv2; // the same right after the op flagged OPM_REFRACT_STAT_KEY2 (0: no such op, or no valid ray there)
     // Everything above is zeroed before every launch.  The word below is not: status bits raised by ANY launch since the host last
     // looked (asynchronous launches do not read `status_bits` back -- their errors surface at opm_context_synchronize /
     // opm_context_check_errors, like the reference's `?` aborts the analysis, rays.rs:987-991)
     unsigned int sticky_bits, _pad2;
     unsigned long long total_interactions;  // interactions of ALL launches of the context (ghost focus reads it once per analysis)
 };
-constexpr unsigned long long kDevStatsZeroBytes = 9 * 8;  // the per-launch part
+constexpr unsigned long long kDevStatsZeroBytes = 10 * 8;  // the per-launch part
 
 struct TraceLaunch {
     const DevOp* ops;  // device

@@ -348,8 +348,9 @@ std::string make_source(const DevOp* ops, int n_ops, bool compact, int block, in
          "    __shared__ __align__(16) cta_count_t s_cnt[kCntWords];\n"
          "    __shared__ unsigned s_status;\n"
          "    __shared__ unsigned long long s_first_inv;\n"
+         "    __shared__ unsigned long long s_first_inv2;\n"
          "    cta_count_init(s_cnt);\n"
-         "    if (threadIdx.x == 0) { s_status = 0u; s_first_inv = 0ull; }\n";
+         "    if (threadIdx.x == 0) { s_status = 0u; s_first_inv = 0ull; s_first_inv2 = 0ull; }\n";
     if (n_hints) {
         appendf(s, "    __shared__ double s_hint[%d];  // per hinted op: wavelength | n2 | 1 / n2\n", 3 * n_hints);
         s += hint_init;
@@ -391,14 +392,14 @@ std::string make_source(const DevOp* ops, int n_ops, bool compact, int block, in
                 "        tile_prefetch(in, (uint64_t)(tile + OPM_TILE_PREFETCH_DIST * gridDim.x) * OPM_BDIM + threadIdx.x, n);\n";
     s += body;
     appendf(s, "        tile_store<%s>(in, out, out_cap, out_tail, x, vb);\n", compact ? "true" : "false");
-    s += "        tile_count(x, s_cnt, &s_status, &s_first_inv, warp_best);\n"
+    s += "        tile_count(x, s_cnt, &s_status, &s_first_inv, warp_best, &s_first_inv2);\n"
          "    }\n"
          "    __syncthreads();\n";
     for (int k = 0; k < n_ops; ++k)
         if (op_has_bbox(ops[k])) appendf(s, "    bbox_reg_flush(bbox_smem_get(bb_%d), opm_jit_ops[%d].u.refract.hit_acc);\n", k, k);
     for (int k = 0; k < n_ops; ++k)
         if (op_has_spot(ops[k])) appendf(s, "    spot_smem_flush(sp_%d, s_spotn_%d, opm_jit_ops[%d].u.snapshot.acc);\n", k, k, k);
-    s += "    cta_flush(stats, s_cnt, s_status, s_first_inv);\n"
+    s += "    cta_flush(stats, s_cnt, s_status, s_first_inv, s_first_inv2);\n"
          "}\n}  // namespace opm\n";
     return s;
 }

@@ -74,8 +74,9 @@ __device__ __forceinline__ void trace_body(const DevOp* __restrict__ g_ops, int 
     __shared__ __align__(16) cta_count_t s_cnt[kCntWords];
     __shared__ unsigned s_status;
     __shared__ unsigned long long s_first_inv;  // max of ~(id << 32 | bounces) over the valid rays this CTA wrote
+    __shared__ unsigned long long s_first_inv2; // the same right after the op flagged OPM_REFRACT_STAT_KEY2
     cta_count_init(s_cnt);
-    if (threadIdx.x == 0) { s_status = 0u; s_first_inv = 0ull; }
+    if (threadIdx.x == 0) { s_status = 0u; s_first_inv = 0ull; s_first_inv2 = 0ull; }
     __syncthreads();
 
     const unsigned tiles = (unsigned)((n + blockDim.x - 1) / blockDim.x);
@@ -125,10 +126,10 @@ __device__ __forceinline__ void trace_body(const DevOp* __restrict__ g_ops, int 
         }
         tile_store<COMPACT>(in, out, out_cap, out_tail, x, vb);
         if (HELP && x.in_range && x.alive) helpers_store(hlp, x.i, hs);
-        tile_count(x, s_cnt, &s_status, &s_first_inv, warp_best);
+        tile_count(x, s_cnt, &s_status, &s_first_inv, warp_best, &s_first_inv2);
     }
     __syncthreads();
-    cta_flush(stats, s_cnt, s_status, s_first_inv);
+    cta_flush(stats, s_cnt, s_status, s_first_inv, s_first_inv2);
 }
 
 template <bool COMPACT>

@@ -88,6 +88,9 @@ struct Counters {
     // OPM_REFRACT_STAT_KEY: (id, bounces) of this ray right after the flagged refract op when it was valid there (kid = 0xffffffff:
     // not valid); kid = kKeyUnset: no flagged op ran, the launch statistic `first_valid_key` looks at the end of the program
     unsigned kid, kb;
+    // OPM_REFRACT_STAT_KEY2: the same pair right after a second flagged op (kid2 = kKeyUnset: no such op in the program -- the
+    // specialised kernels then carry nothing of it)
+    unsigned kid2, kb2;
 };
 constexpr unsigned kKeyUnset = 0xfffffffeu;
 enum { CNT_INTERACTIONS = 0, CNT_CHILDREN, CNT_HITS, CNT_MISSED, CNT_APODIZED, CNT_VALID_OUT, CNT_ALIVE_OUT, CNT_N };
@@ -192,6 +195,7 @@ __device__ __forceinline__ bool exec_refract(const V& v, RayCtx& x, HitOut* ho =
     }
     // Rays::bounce_lvl as the ghost-focus analysis reads it: between refract_on_surface and apodize (analyzers/raytrace.rs:118-133)
     if (v.flags() & OPM_REFRACT_STAT_KEY) { x.c.kid = (x.valid && x.alive) ? x.r.id : 0xffffffffu; x.c.kb = x.r.bounces; }
+    if (v.flags() & OPM_REFRACT_STAT_KEY2) { x.c.kid2 = (x.valid && x.alive) ? x.r.id : 0xffffffffu; x.c.kb2 = x.r.bounces; }
     finish_children(v, res, x);
     return res.moved;
 }
@@ -604,6 +608,7 @@ __device__ __forceinline__ bool exec_refract_helpers(const V& v, RayCtx& x, Help
         if (res.hit_e >= 0.0) x.c.a += 1u << 16;
     }
     if (v.flags() & OPM_REFRACT_STAT_KEY) { x.c.kid = (x.valid && x.alive) ? x.r.id : 0xffffffffu; x.c.kb = x.r.bounces; }
+    if (v.flags() & OPM_REFRACT_STAT_KEY2) { x.c.kid2 = (x.valid && x.alive) ? x.r.id : 0xffffffffu; x.c.kb2 = x.r.bounces; }
     finish_children(v, res, x);
     return res.moved;
 }
@@ -625,7 +630,7 @@ __device__ __forceinline__ void exec_paraxial_helpers(const DevParaxial& o, RayC
 __device__ __forceinline__ void tile_load(const DevRays& in, uint64_t i, uint64_t n, RayCtx& x, uint8_t& vb) {
     x.i = i;
     x.in_range = i < n;
-    x.c.a = 0; x.c.b = 0; x.c.apodized = 0; x.c.status = 0; x.c.kid = kKeyUnset; x.c.kb = 0;
+    x.c.a = 0; x.c.b = 0; x.c.apodized = 0; x.c.status = 0; x.c.kid = kKeyUnset; x.c.kb = 0; x.c.kid2 = kKeyUnset; x.c.kb2 = 0;
     x.r.pos = v3(0, 0, 0); x.r.dir = v3(0, 0, 1); x.r.e = 0; x.r.wvl = 0; x.r.opl = 0; x.r.n = 1; x.r.bounces = 0; x.r.refr = 0; x.r.id = 0;
     vb = RAY_REMOVED;
     if (x.in_range) {
@@ -663,7 +668,7 @@ __device__ __forceinline__ void tile_load(const DevRays& in, uint64_t i, uint64_
 #else
     x.i = i;
     x.in_range = i < n;
-    x.c.a = 0; x.c.b = 0; x.c.apodized = 0; x.c.status = 0; x.c.kid = kKeyUnset; x.c.kb = 0;
+    x.c.a = 0; x.c.b = 0; x.c.apodized = 0; x.c.status = 0; x.c.kid = kKeyUnset; x.c.kb = 0; x.c.kid2 = kKeyUnset; x.c.kb2 = 0;
     x.r.pos = v3(0, 0, 0); x.r.dir = v3(0, 0, 1); x.r.e = 0; x.r.wvl = 0; x.r.opl = 0; x.r.n = 1; x.r.bounces = 0; x.r.refr = 0; x.r.id = 0;
     vb = a.vb;  // RAY_REMOVED beyond the bundle
     if (vb != RAY_REMOVED) load_ray(in, i, x.r);
@@ -799,7 +804,7 @@ __device__ __forceinline__ void tile_load_staged(TilePipe& p, const DevRays& in,
     unsigned char* st = p.stage[s];
     mbar_wait(&p.bar[s], (p.iter >> 1) & 1u);
     x.i = i; x.in_range = true;
-    x.c.a = 0; x.c.b = 0; x.c.apodized = 0; x.c.status = 0; x.c.kid = kKeyUnset; x.c.kb = 0;
+    x.c.a = 0; x.c.b = 0; x.c.apodized = 0; x.c.status = 0; x.c.kid = kKeyUnset; x.c.kb = 0; x.c.kid2 = kKeyUnset; x.c.kb2 = 0;
     const double* d = reinterpret_cast<const double*>(st);
     x.r.pos = v3(d[t], d[B + t], d[2 * B + t]);
     x.r.dir = v3(d[3 * B + t], d[4 * B + t], d[5 * B + t]);
@@ -854,7 +859,17 @@ __device__ __forceinline__ void cta_count_init(cta_count_t* s_cnt) {
 // warp_best: the smallest ray id this warp has offered for the launch's first valid ray so far (0xffffffff before its first tile);
 // a tile none of whose rays has an id at or below it cannot change the statistic and skips the two warp minima
 __device__ __forceinline__ void tile_count(const RayCtx& x, cta_count_t* s_cnt, unsigned* s_status, unsigned long long* s_first_inv,
-                                           unsigned& warp_best) {
+                                           unsigned& warp_best, unsigned long long* s_first_inv2) {
+    if (x.c.kid2 != kKeyUnset) {  // warp-uniform; a program without an OPM_REFRACT_STAT_KEY2 op never gets here
+        if (__any_sync(0xffffffffu, x.c.kid2 != 0xffffffffu)) {
+            const unsigned idmin = __reduce_min_sync(0xffffffffu, x.c.kid2);
+            const unsigned bmin = __reduce_min_sync(0xffffffffu, x.c.kid2 == idmin ? x.c.kb2 : 0xffffffffu);
+            if ((threadIdx.x & 31) == 0) {
+                const unsigned long long inv = ~(((unsigned long long)idmin << 32) | bmin);
+                if (inv > *(volatile unsigned long long*)s_first_inv2) atomicMax(s_first_inv2, inv);
+            }
+        }
+    }
     const unsigned ra = __reduce_add_sync(0xffffffffu, x.c.a), rb = __reduce_add_sync(0xffffffffu, x.c.b);
     const unsigned rp = __reduce_add_sync(0xffffffffu, x.c.apodized);
     const bool v = x.valid && x.alive;
@@ -885,7 +900,9 @@ static_assert(CNT_INTERACTIONS == 0 && CNT_CHILDREN == 1 && CNT_HITS == 2 && CNT
               CNT_ALIVE_OUT == 6 && kCntStride == 8, "tile_count writes the counter row as two uint4");
 
 // CTA totals -> global statistics (call after __syncthreads())
-__device__ __forceinline__ void cta_flush(DevStats* stats, const cta_count_t* s_cnt, unsigned s_status, unsigned long long s_first_inv) {
+__device__ __forceinline__ void cta_flush(DevStats* stats, const cta_count_t* s_cnt, unsigned s_status, unsigned long long s_first_inv,
+                                          unsigned long long s_first_inv2) {
+    if (threadIdx.x == 0 && s_first_inv2) atomicMax(&stats->first_inv2, s_first_inv2);
     if (threadIdx.x < CNT_N) {
         unsigned long long total = 0;
         for (int w = 0; w < 32; ++w) total += s_cnt[w * kCntStride + threadIdx.x];
