@@ -517,6 +517,8 @@ OpmStatus opm_context_join_side_stream(OpmContext* ctx);
  * as above, [6] zero on entry).  bounce_filters: NULL = every check uses the key word [7] of its own result slot, which
  * opm_fluence_peak_check_capture_key_async put there right after the bundle's trace launch (Rays::bounce_lvl at the flagged op,
  * analyzers/raytrace.rs:118-133); else one filter per check (a level, -1, or OPM_BOUNCE_OF_LAST_LAUNCH for the captured key). */
+/* capture: no copy of its own -- the statistic stays in place until the context's NEXT trace launch, whose prologue writes it to
+ * result_dev[7] before it resets it; a batch launch, opm_context_join_side_stream and opm_context_synchronize deliver what is left */
 OpmStatus opm_fluence_peak_check_capture_key_async(OpmContext* ctx, double* result_dev, int32_t slot /* 0: OPM_REFRACT_STAT_KEY (or the
                                                    end of the program), 1: OPM_REFRACT_STAT_KEY2 */);
 OpmStatus opm_fluence_peak_check_batch_async(OpmHitMap* const* maps, int32_t n_checks, const int64_t* bounce_filters, uint64_t nx, uint64_t ny,

@@ -71,6 +71,9 @@ struct OpmContext {
     cudaEvent_t side_ev = nullptr;
     bool side_busy = false;
     // job list of opm_fluence_peak_check_batch_async: pinned staging + device copy, reused once jobs_ev says the copy has drained
+    // opm_fluence_peak_check_capture_key_async: where the latest launch's first-valid-ray keys are still to be copied -- the next
+    // trace launch's prologue takes them along (it is what resets them), flush_pending_keys() copies what is left
+    unsigned long long* pending_key[2] = {nullptr, nullptr};
     static constexpr int kJobRing = 4;  // batches whose job lists may be in flight before the host has to wait for the oldest copy
     PeakCheckJob* h_jobs = nullptr;
     PeakCheckJob* d_jobs = nullptr;
@@ -163,6 +166,7 @@ static OpmStatus fail(OpmStatus s, const char* fmt, ...) {
     g_last_error = buf;
     return s;
 }
+static OpmStatus flush_pending_keys(OpmContext* c);
 namespace opm {
 // for the host-only translation units of the library (opm_spectrum_host.cpp)
 OpmStatus host_fail(OpmStatus s, const char* msg) { return fail(s, "%s", msg); }
@@ -324,6 +328,7 @@ extern "C" OpmStatus opm_context_check_errors(OpmContext* c, int32_t clear) {
 extern "C" OpmStatus opm_context_synchronize(OpmContext* c) {
     if (!c) return fail(OPM_ERR_ARG, "context is NULL");
     CU(cudaSetDevice(c->device));
+    if (OpmStatus s = flush_pending_keys(c)) return s;
     if (c->side_busy) { CU(cudaStreamSynchronize(c->side_stream)); c->side_busy = false; }
     CU(cudaStreamSynchronize(c->stream));
     return opm_context_check_errors(c, 1);
@@ -1579,6 +1584,7 @@ static OpmStatus run_program(OpmRays* rays, const OpmOp* ops, int n_ops, int fla
         pp.src_host = (const unsigned long long*)h_slot;
         pp.words = (unsigned)(prog.ops.size() * sizeof(DevOp) / 8);
         pp.stats = (unsigned long long*)c->d_stats; pp.stats_words = (unsigned)(kDevStatsZeroBytes / 8);  // not the sticky status word
+        for (int k = 0; k < 2; ++k) { pp.key_dst[k] = c->pending_key[k]; c->pending_key[k] = nullptr; }
         for (OpmHitMap* h : prog.hitmaps) h->acc_valid = false;
         if (jk)
             for (size_t k = 0; k < fused.size(); ++k) { pp.acc[k] = (BBoxAccum*)fused[k]->d_acc; fused[k]->acc_valid = true; }
@@ -2406,8 +2412,9 @@ extern "C" OpmStatus opm_fluence_peak_check_side_async(OpmHitMap* const* maps, i
 }
 extern "C" OpmStatus opm_context_join_side_stream(OpmContext* c) {
     if (!c) return fail(OPM_ERR_ARG, "context is NULL");
-    if (!c->side_busy) return OPM_OK;
     CU(cudaSetDevice(c->device));
+    if (OpmStatus s = flush_pending_keys(c)) return s;
+    if (!c->side_busy) return OPM_OK;
     CU(cudaEventRecord(c->side_ev, c->side_stream));
     CU(cudaStreamWaitEvent(c->stream, c->side_ev, 0));
     c->side_busy = false;
@@ -2457,11 +2464,21 @@ static OpmStatus peak_check_impl(OpmHitMap* const* maps, int32_t n_maps, int64_t
 }
 // the bundle's bounce level for a deferred check: the latest launch's first_valid_key statistic, copied into the key word of the
 // check's result slot in stream order (the next trace launch resets the statistic)
+static OpmStatus flush_pending_keys(OpmContext* c) {
+    for (int k = 0; k < 2; ++k) {
+        if (!c->pending_key[k]) continue;
+        const unsigned long long* src = k ? &c->d_stats->first_inv2 : &c->d_stats->first_inv;
+        CU(cudaMemcpyAsync(c->pending_key[k], src, 8, cudaMemcpyDeviceToDevice, c->stream));
+        c->pending_key[k] = nullptr;
+    }
+    return OPM_OK;
+}
 extern "C" OpmStatus opm_fluence_peak_check_capture_key_async(OpmContext* c, double* result_dev, int32_t slot) {
     if (!c || !result_dev || slot < 0 || slot > 1) return fail(OPM_ERR_ARG, "NULL argument / key slot not 0 or 1");
     CU(cudaSetDevice(c->device));
-    const unsigned long long* src = slot ? &c->d_stats->first_inv2 : &c->d_stats->first_inv;
-    CU(cudaMemcpyAsync(reinterpret_cast<unsigned long long*>(result_dev) + 7, src, 8, cudaMemcpyDeviceToDevice, c->stream));
+    if (c->pending_key[slot]) { OpmStatus s = flush_pending_keys(c); if (s) return s; }  // one destination per key and launch
+    // no copy now: the statistic stays where it is until the next trace launch, whose prologue delivers it before resetting it
+    c->pending_key[slot] = reinterpret_cast<unsigned long long*>(result_dev) + 7;
     return OPM_OK;
 }
 static OpmStatus peak_check_batch_impl(OpmHitMap* const* maps, int32_t n_checks, const int64_t* bounce_filters, uint64_t nx, uint64_t ny,
@@ -2511,6 +2528,8 @@ static OpmStatus peak_check_batch_impl(OpmHitMap* const* maps, int32_t n_checks,
         j.acc = (PeakCheckAcc*)acc_dev + k; j.result = results_dev[k]; j.map = maps_dev + (size_t)k * map_stride;
         if (j.n > max_n) max_n = j.n;
     }
+    s = flush_pending_keys(c);
+    if (s) return s;
     cudaStream_t st = c->stream;
     if (side) {  // behind everything the main stream holds so far (the traces that recorded the hits, the captured keys), beside what follows
         if (!c->side_stream) { CU(cudaStreamCreateWithFlags(&c->side_stream, cudaStreamNonBlocking)); CU(cudaEventCreateWithFlags(&c->side_ev, cudaEventDisableTiming)); }

@@ -338,6 +338,9 @@ std::string make_source(const DevOp* ops, int n_ops, bool compact, int block, in
     std::string s;
     appendf(s, "#define OPM_JIT_BLOCK %d\n", block);
     if (!program_wants_prefetch(ops, n_ops)) s += "#define OPM_TILE_NO_BULK_PREFETCH 1\n#define OPM_TILE_NO_FLAG_AHEAD 1\n";
+    bool key2 = false;  // a second first-valid-ray key (OPM_REFRACT_STAT_KEY2): compiled in only for programs that ask for it
+    for (int k = 0; k < n_ops; ++k) key2 |= ops[k].kind == OPK_REFRACT && (ops[k].u.refract.flags & OPM_REFRACT_STAT_KEY2) != 0;
+    if (key2) s += "#define OPM_STAT_KEY2 1\n";
     s += "#include \"opm_trace_ops.cuh\"\nnamespace opm {\n";
     appendf(s, "extern \"C\" __constant__ DevOp opm_jit_ops[%d];\n", n_ops);
     appendf(s, "extern \"C\" __global__ void __launch_bounds__(%d, %d)\n", block, min_ctas);
@@ -348,9 +351,17 @@ std::string make_source(const DevOp* ops, int n_ops, bool compact, int block, in
          "    __shared__ __align__(16) cta_count_t s_cnt[kCntWords];\n"
          "    __shared__ unsigned s_status;\n"
          "    __shared__ unsigned long long s_first_inv;\n"
+         "#ifdef OPM_STAT_KEY2\n"
          "    __shared__ unsigned long long s_first_inv2;\n"
+         "    if (threadIdx.x == 0) s_first_inv2 = 0ull;\n"
+         "#define OPM_JIT_KEY2_PTR (&s_first_inv2)\n"
+         "#define OPM_JIT_KEY2_VAL s_first_inv2\n"
+         "#else\n"
+         "#define OPM_JIT_KEY2_PTR ((unsigned long long*)0)\n"
+         "#define OPM_JIT_KEY2_VAL 0ull\n"
+         "#endif\n"
          "    cta_count_init(s_cnt);\n"
-         "    if (threadIdx.x == 0) { s_status = 0u; s_first_inv = 0ull; s_first_inv2 = 0ull; }\n";
+         "    if (threadIdx.x == 0) { s_status = 0u; s_first_inv = 0ull; }\n";
     if (n_hints) {
         appendf(s, "    __shared__ double s_hint[%d];  // per hinted op: wavelength | n2 | 1 / n2\n", 3 * n_hints);
         s += hint_init;
@@ -392,14 +403,14 @@ std::string make_source(const DevOp* ops, int n_ops, bool compact, int block, in
                 "        tile_prefetch(in, (uint64_t)(tile + OPM_TILE_PREFETCH_DIST * gridDim.x) * OPM_BDIM + threadIdx.x, n);\n";
     s += body;
     appendf(s, "        tile_store<%s>(in, out, out_cap, out_tail, x, vb);\n", compact ? "true" : "false");
-    s += "        tile_count(x, s_cnt, &s_status, &s_first_inv, warp_best, &s_first_inv2);\n"
+    s += "        tile_count(x, s_cnt, &s_status, &s_first_inv, warp_best, OPM_JIT_KEY2_PTR);\n"
          "    }\n"
          "    __syncthreads();\n";
     for (int k = 0; k < n_ops; ++k)
         if (op_has_bbox(ops[k])) appendf(s, "    bbox_reg_flush(bbox_smem_get(bb_%d), opm_jit_ops[%d].u.refract.hit_acc);\n", k, k);
     for (int k = 0; k < n_ops; ++k)
         if (op_has_spot(ops[k])) appendf(s, "    spot_smem_flush(sp_%d, s_spotn_%d, opm_jit_ops[%d].u.snapshot.acc);\n", k, k, k);
-    s += "    cta_flush(stats, s_cnt, s_status, s_first_inv, s_first_inv2);\n"
+    s += "    cta_flush(stats, s_cnt, s_status, s_first_inv, OPM_JIT_KEY2_VAL);\n"
          "}\n}  // namespace opm\n";
     return s;
 }
@@ -581,6 +592,8 @@ static size_t jit_selftest_impl(std::string& why) {
         DevOp* d = push(OPK_REFRACT);
         d->u.refract.geom = geom; d->u.refract.coating = geom % 3; d->u.refract.has_index = 1; d->u.refract.index_type = geom;
         d->u.refract.refraction_intended = 1; d->u.refract.hits.e = (double*)8; d->epi_flags = EPI_THRESHOLD | EPI_LIMITS | EPI_CHECK_REFR;
+        if (geom == OPM_GEOM_PLANE) d->u.refract.flags = OPM_REFRACT_STAT_KEY;       // the two first-valid-ray keys of a fused lens launch
+        if (geom == OPM_GEOM_SPHERE) d->u.refract.flags = OPM_REFRACT_STAT_KEY2;
     }
     {
         DevOp* d = push(OPK_REFRACT);  // mirror that also emits its children

@@ -1480,7 +1480,13 @@ int k_fetch_from_host(void* dst, const void* src_host, size_t bytes, void* strea
 // accumulators of the hit maps the kernel fills reset to their identity, and the lengths of the slot-indexed output bundles.
 __global__ void __launch_bounds__(256) trace_prologue_kernel(ProloguePlan P) {
     for (unsigned k = threadIdx.x; k < P.words; k += blockDim.x) P.dst[k] = P.src_host[k];
-    if (threadIdx.x < P.stats_words) P.stats[threadIdx.x] = 0ull;
+    if (threadIdx.x < P.stats_words) {
+        // deferred opm_fluence_peak_check_capture_key_async: the previous launch's keys leave with the launch that resets them
+        static_assert(offsetof(DevStats, first_inv) == 8 * 8 && offsetof(DevStats, first_inv2) == 9 * 8, "key words of DevStats");
+        if (threadIdx.x == 8 && P.key_dst[0]) *P.key_dst[0] = P.stats[8];
+        if (threadIdx.x == 9 && P.key_dst[1]) *P.key_dst[1] = P.stats[9];
+        P.stats[threadIdx.x] = 0ull;
+    }
     if (threadIdx.x >= 32 && threadIdx.x < 32 + 5 * 2) {
         const unsigned a = (threadIdx.x - 32) / 5, j = (threadIdx.x - 32) % 5;
         if (P.acc[a]) {

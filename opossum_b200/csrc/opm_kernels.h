@@ -123,6 +123,7 @@ constexpr int kPrologueTails = 8;
 struct ProloguePlan {
     unsigned long long* dst; const unsigned long long* src_host; unsigned words;   // op descriptors (pinned + mapped source)
     unsigned long long* stats; unsigned stats_words;                               // zeroed
+    unsigned long long* key_dst[2];  // NULL, or where the first-valid-ray keys of the PREVIOUS launch go before the statistics are zeroed
     BBoxAccum* acc[2];                                                             // reset to the identity (NULL: none)
     SpotAccum* spot[2];                                                            // reset to the identity (NULL: none)
     unsigned long long* tail[kPrologueTails]; unsigned long long tail_val[kPrologueTails]; int n_tails;

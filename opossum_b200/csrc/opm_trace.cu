@@ -20,6 +20,7 @@
 #include <cuda/barrier>
 #include <cuda_runtime.h>
 
+#define OPM_STAT_KEY2 1  // the interpreter runs any program: OPM_REFRACT_STAT_KEY2 included
 #include "opm_trace_ops.cuh"
 
 #ifdef OPM_STRICT

@@ -88,10 +88,18 @@ struct Counters {
     // OPM_REFRACT_STAT_KEY: (id, bounces) of this ray right after the flagged refract op when it was valid there (kid = 0xffffffff:
     // not valid); kid = kKeyUnset: no flagged op ran, the launch statistic `first_valid_key` looks at the end of the program
     unsigned kid, kb;
-    // OPM_REFRACT_STAT_KEY2: the same pair right after a second flagged op (kid2 = kKeyUnset: no such op in the program -- the
-    // specialised kernels then carry nothing of it)
+    // OPM_REFRACT_STAT_KEY2: the same pair right after a second flagged op (kid2 = kKeyUnset: no such op ran).  Compiled in where
+    // OPM_STAT_KEY2 is defined: the interpreter, and the specialised kernels of programs that hold such an op -- the others carry
+    // nothing of it
+#ifdef OPM_STAT_KEY2
     unsigned kid2, kb2;
+#endif
 };
+#ifdef OPM_STAT_KEY2
+#define OPM_KEY2_RESET(c) do { (c).kid2 = kKeyUnset; (c).kb2 = 0; } while (0)
+#else
+#define OPM_KEY2_RESET(c) do { } while (0)
+#endif
 constexpr unsigned kKeyUnset = 0xfffffffeu;
 enum { CNT_INTERACTIONS = 0, CNT_CHILDREN, CNT_HITS, CNT_MISSED, CNT_APODIZED, CNT_VALID_OUT, CNT_ALIVE_OUT, CNT_N };
 
@@ -195,7 +203,9 @@ __device__ __forceinline__ bool exec_refract(const V& v, RayCtx& x, HitOut* ho =
     }
     // Rays::bounce_lvl as the ghost-focus analysis reads it: between refract_on_surface and apodize (analyzers/raytrace.rs:118-133)
     if (v.flags() & OPM_REFRACT_STAT_KEY) { x.c.kid = (x.valid && x.alive) ? x.r.id : 0xffffffffu; x.c.kb = x.r.bounces; }
+#ifdef OPM_STAT_KEY2
     if (v.flags() & OPM_REFRACT_STAT_KEY2) { x.c.kid2 = (x.valid && x.alive) ? x.r.id : 0xffffffffu; x.c.kb2 = x.r.bounces; }
+#endif
     finish_children(v, res, x);
     return res.moved;
 }
@@ -608,7 +618,9 @@ __device__ __forceinline__ bool exec_refract_helpers(const V& v, RayCtx& x, Help
         if (res.hit_e >= 0.0) x.c.a += 1u << 16;
     }
     if (v.flags() & OPM_REFRACT_STAT_KEY) { x.c.kid = (x.valid && x.alive) ? x.r.id : 0xffffffffu; x.c.kb = x.r.bounces; }
+#ifdef OPM_STAT_KEY2
     if (v.flags() & OPM_REFRACT_STAT_KEY2) { x.c.kid2 = (x.valid && x.alive) ? x.r.id : 0xffffffffu; x.c.kb2 = x.r.bounces; }
+#endif
     finish_children(v, res, x);
     return res.moved;
 }
@@ -630,7 +642,7 @@ __device__ __forceinline__ void exec_paraxial_helpers(const DevParaxial& o, RayC
 __device__ __forceinline__ void tile_load(const DevRays& in, uint64_t i, uint64_t n, RayCtx& x, uint8_t& vb) {
     x.i = i;
     x.in_range = i < n;
-    x.c.a = 0; x.c.b = 0; x.c.apodized = 0; x.c.status = 0; x.c.kid = kKeyUnset; x.c.kb = 0; x.c.kid2 = kKeyUnset; x.c.kb2 = 0;
+    x.c.a = 0; x.c.b = 0; x.c.apodized = 0; x.c.status = 0; x.c.kid = kKeyUnset; x.c.kb = 0; OPM_KEY2_RESET(x.c);
     x.r.pos = v3(0, 0, 0); x.r.dir = v3(0, 0, 1); x.r.e = 0; x.r.wvl = 0; x.r.opl = 0; x.r.n = 1; x.r.bounces = 0; x.r.refr = 0; x.r.id = 0;
     vb = RAY_REMOVED;
     if (x.in_range) {
@@ -668,7 +680,7 @@ __device__ __forceinline__ void tile_load(const DevRays& in, uint64_t i, uint64_
 #else
     x.i = i;
     x.in_range = i < n;
-    x.c.a = 0; x.c.b = 0; x.c.apodized = 0; x.c.status = 0; x.c.kid = kKeyUnset; x.c.kb = 0; x.c.kid2 = kKeyUnset; x.c.kb2 = 0;
+    x.c.a = 0; x.c.b = 0; x.c.apodized = 0; x.c.status = 0; x.c.kid = kKeyUnset; x.c.kb = 0; OPM_KEY2_RESET(x.c);
     x.r.pos = v3(0, 0, 0); x.r.dir = v3(0, 0, 1); x.r.e = 0; x.r.wvl = 0; x.r.opl = 0; x.r.n = 1; x.r.bounces = 0; x.r.refr = 0; x.r.id = 0;
     vb = a.vb;  // RAY_REMOVED beyond the bundle
     if (vb != RAY_REMOVED) load_ray(in, i, x.r);
@@ -804,7 +816,7 @@ __device__ __forceinline__ void tile_load_staged(TilePipe& p, const DevRays& in,
     unsigned char* st = p.stage[s];
     mbar_wait(&p.bar[s], (p.iter >> 1) & 1u);
     x.i = i; x.in_range = true;
-    x.c.a = 0; x.c.b = 0; x.c.apodized = 0; x.c.status = 0; x.c.kid = kKeyUnset; x.c.kb = 0; x.c.kid2 = kKeyUnset; x.c.kb2 = 0;
+    x.c.a = 0; x.c.b = 0; x.c.apodized = 0; x.c.status = 0; x.c.kid = kKeyUnset; x.c.kb = 0; OPM_KEY2_RESET(x.c);
     const double* d = reinterpret_cast<const double*>(st);
     x.r.pos = v3(d[t], d[B + t], d[2 * B + t]);
     x.r.dir = v3(d[3 * B + t], d[4 * B + t], d[5 * B + t]);
@@ -860,7 +872,8 @@ __device__ __forceinline__ void cta_count_init(cta_count_t* s_cnt) {
 // a tile none of whose rays has an id at or below it cannot change the statistic and skips the two warp minima
 __device__ __forceinline__ void tile_count(const RayCtx& x, cta_count_t* s_cnt, unsigned* s_status, unsigned long long* s_first_inv,
                                            unsigned& warp_best, unsigned long long* s_first_inv2) {
-    if (x.c.kid2 != kKeyUnset) {  // warp-uniform; a program without an OPM_REFRACT_STAT_KEY2 op never gets here
+#ifdef OPM_STAT_KEY2
+    if (x.c.kid2 != kKeyUnset) {  // warp-uniform
         if (__any_sync(0xffffffffu, x.c.kid2 != 0xffffffffu)) {
             const unsigned idmin = __reduce_min_sync(0xffffffffu, x.c.kid2);
             const unsigned bmin = __reduce_min_sync(0xffffffffu, x.c.kid2 == idmin ? x.c.kb2 : 0xffffffffu);
@@ -870,6 +883,9 @@ __device__ __forceinline__ void tile_count(const RayCtx& x, cta_count_t* s_cnt, 
             }
         }
     }
+#else
+    (void)s_first_inv2;
+#endif
     const unsigned ra = __reduce_add_sync(0xffffffffu, x.c.a), rb = __reduce_add_sync(0xffffffffu, x.c.b);
     const unsigned rp = __reduce_add_sync(0xffffffffu, x.c.apodized);
     const bool v = x.valid && x.alive;
@@ -902,7 +918,11 @@ static_assert(CNT_INTERACTIONS == 0 && CNT_CHILDREN == 1 && CNT_HITS == 2 && CNT
 // CTA totals -> global statistics (call after __syncthreads())
 __device__ __forceinline__ void cta_flush(DevStats* stats, const cta_count_t* s_cnt, unsigned s_status, unsigned long long s_first_inv,
                                           unsigned long long s_first_inv2) {
+#ifdef OPM_STAT_KEY2
     if (threadIdx.x == 0 && s_first_inv2) atomicMax(&stats->first_inv2, s_first_inv2);
+#else
+    (void)s_first_inv2;
+#endif
     if (threadIdx.x < CNT_N) {
         unsigned long long total = 0;
         for (int w = 0; w < 32; ++w) total += s_cnt[w * kCntStride + threadIdx.x];
