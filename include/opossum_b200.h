@@ -511,8 +511,9 @@ OpmStatus opm_fluence_peak_check_side_async(OpmHitMap* const* maps, int32_t n_ma
                                             void* acc_dev, double* map_dev, double* result_dev);
 OpmStatus opm_context_join_side_stream(OpmContext* ctx);
 /* MANY such checks in three launches -- for a caller that can defer them, as the ghost-focus analysis can: the verdicts of
- * evaluate_fluence_of_ray_bundle steer no control flow and the hit maps stay until the surfaces are reset.  Check k takes ONE hit map
- * maps[k], accumulator k of acc_dev (n_checks x OPM_PEAK_CHECK_ACC_BYTES, prepared once by opm_fluence_peak_check_acc_init), map k of
+ * evaluate_fluence_of_ray_bundle steer no control flow and the hit maps stay until the surfaces are reset.  Check k takes
+ * maps_per_check[k] (1 to 4; NULL: one each) consecutive hit maps of the flat list `maps` -- the maps of one bundle id on one surface,
+ * summed into one fluence map like HitMap::get_rays_hit_map's --, accumulator k of acc_dev (n_checks x OPM_PEAK_CHECK_ACC_BYTES, prepared once by opm_fluence_peak_check_acc_init), map k of
  * maps_dev (n_checks maps of nx * ny doubles, each padded to a multiple of 8 doubles) and the result slot results_dev[k] (8 doubles
  * as above, [6] zero on entry).  bounce_filters: NULL = every check uses the key word [7] of its own result slot, which
  * opm_fluence_peak_check_capture_key_async put there right after the bundle's trace launch (Rays::bounce_lvl at the flagged op,
@@ -521,12 +522,14 @@ OpmStatus opm_context_join_side_stream(OpmContext* ctx);
  * result_dev[7] before it resets it; a batch launch, opm_context_join_side_stream and opm_context_synchronize deliver what is left */
 OpmStatus opm_fluence_peak_check_capture_key_async(OpmContext* ctx, double* result_dev, int32_t slot /* 0: OPM_REFRACT_STAT_KEY (or the
                                                    end of the program), 1: OPM_REFRACT_STAT_KEY2 */);
-OpmStatus opm_fluence_peak_check_batch_async(OpmHitMap* const* maps, int32_t n_checks, const int64_t* bounce_filters, uint64_t nx, uint64_t ny,
-                                             void* acc_dev, double* maps_dev, double* const* results_dev);
+OpmStatus opm_fluence_peak_check_batch_async(OpmHitMap* const* maps, const int32_t* maps_per_check, int32_t n_checks,
+                                             const int64_t* bounce_filters, uint64_t nx, uint64_t ny, void* acc_dev, double* maps_dev,
+                                             double* const* results_dev);
 /* the batch on the context's side stream (see opm_fluence_peak_check_side_async): behind everything issued so far, beside what
  * follows; acc_dev / maps_dev then belong to side-stream batches only */
-OpmStatus opm_fluence_peak_check_batch_side_async(OpmHitMap* const* maps, int32_t n_checks, const int64_t* bounce_filters, uint64_t nx,
-                                                  uint64_t ny, void* acc_dev, double* maps_dev, double* const* results_dev);
+OpmStatus opm_fluence_peak_check_batch_side_async(OpmHitMap* const* maps, const int32_t* maps_per_check, int32_t n_checks,
+                                                  const int64_t* bounce_filters, uint64_t nx, uint64_t ny, void* acc_dev, double* maps_dev,
+                                                  double* const* results_dev);
 OpmStatus opm_hitmaps_bounding_box_async(OpmHitMap* const* maps, int32_t n_maps, int64_t bounce_filter_or_minus1, double* range_dev);
 OpmStatus opm_fluence_binning_async(OpmHitMap* const* maps, int32_t n_maps, int64_t bounce_filter_or_minus1, uint64_t nx, uint64_t ny,
                                     const double* range_dev, int32_t accumulate, double* map_dev, uint32_t* status_dev);

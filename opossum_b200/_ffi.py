@@ -393,8 +393,8 @@ def lib() -> C.CDLL:
         "opm_fluence_peak_check_side_async": (i32, [vp, i32, C.c_int64, u64, u64, vp, vp, vp]),
         "opm_context_join_side_stream": (i32, [vp]),
         "opm_fluence_peak_check_capture_key_async": (i32, [vp, vp, i32]),
-        "opm_fluence_peak_check_batch_async": (i32, [vp, i32, vp, u64, u64, vp, vp, vp]),
-        "opm_fluence_peak_check_batch_side_async": (i32, [vp, i32, vp, u64, u64, vp, vp, vp]),
+        "opm_fluence_peak_check_batch_async": (i32, [vp, vp, i32, vp, u64, u64, vp, vp, vp]),
+        "opm_fluence_peak_check_batch_side_async": (i32, [vp, vp, i32, vp, u64, u64, vp, vp, vp]),
     }
     sig.update({
         "opm_node_desc_init": (None, [C.POINTER(OpmNodeDesc), i32]),

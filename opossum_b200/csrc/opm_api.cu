@@ -2481,21 +2481,32 @@ extern "C" OpmStatus opm_fluence_peak_check_capture_key_async(OpmContext* c, dou
     c->pending_key[slot] = reinterpret_cast<unsigned long long*>(result_dev) + 7;
     return OPM_OK;
 }
-static OpmStatus peak_check_batch_impl(OpmHitMap* const* maps, int32_t n_checks, const int64_t* bounce_filters, uint64_t nx, uint64_t ny,
-                                       void* acc_dev, double* maps_dev, double* const* results_dev, bool side);
-extern "C" OpmStatus opm_fluence_peak_check_batch_async(OpmHitMap* const* maps, int32_t n_checks, const int64_t* bounce_filters, uint64_t nx,
-                                                        uint64_t ny, void* acc_dev, double* maps_dev, double* const* results_dev) {
-    return peak_check_batch_impl(maps, n_checks, bounce_filters, nx, ny, acc_dev, maps_dev, results_dev, false);
+static OpmStatus peak_check_batch_impl(OpmHitMap* const* maps, const int32_t* maps_per_check, int32_t n_checks, const int64_t* bounce_filters,
+                                       uint64_t nx, uint64_t ny, void* acc_dev, double* maps_dev, double* const* results_dev, bool side);
+extern "C" OpmStatus opm_fluence_peak_check_batch_async(OpmHitMap* const* maps, const int32_t* maps_per_check, int32_t n_checks,
+                                                        const int64_t* bounce_filters, uint64_t nx, uint64_t ny, void* acc_dev, double* maps_dev,
+                                                        double* const* results_dev) {
+    return peak_check_batch_impl(maps, maps_per_check, n_checks, bounce_filters, nx, ny, acc_dev, maps_dev, results_dev, false);
 }
-extern "C" OpmStatus opm_fluence_peak_check_batch_side_async(OpmHitMap* const* maps, int32_t n_checks, const int64_t* bounce_filters, uint64_t nx,
-                                                             uint64_t ny, void* acc_dev, double* maps_dev, double* const* results_dev) {
-    return peak_check_batch_impl(maps, n_checks, bounce_filters, nx, ny, acc_dev, maps_dev, results_dev, true);
+extern "C" OpmStatus opm_fluence_peak_check_batch_side_async(OpmHitMap* const* maps, const int32_t* maps_per_check, int32_t n_checks,
+                                                             const int64_t* bounce_filters, uint64_t nx, uint64_t ny, void* acc_dev,
+                                                             double* maps_dev, double* const* results_dev) {
+    return peak_check_batch_impl(maps, maps_per_check, n_checks, bounce_filters, nx, ny, acc_dev, maps_dev, results_dev, true);
 }
-static OpmStatus peak_check_batch_impl(OpmHitMap* const* maps, int32_t n_checks, const int64_t* bounce_filters, uint64_t nx, uint64_t ny,
-                                       void* acc_dev, double* maps_dev, double* const* results_dev, bool side) {
+static OpmStatus peak_check_batch_impl(OpmHitMap* const* maps, const int32_t* maps_per_check, int32_t n_checks, const int64_t* bounce_filters,
+                                       uint64_t nx, uint64_t ny, void* acc_dev, double* maps_dev, double* const* results_dev, bool side) {
     if (n_checks == 0) return OPM_OK;
+    if (n_checks < 0) return fail(OPM_ERR_ARG, "negative number of checks");
+    int64_t total_maps = 0;
+    int max_maps = 1;
+    for (int k = 0; k < n_checks; ++k) {
+        const int m = maps_per_check ? maps_per_check[k] : 1;
+        if (m < 1 || m > kPeakCheckMaps) return fail(OPM_ERR_ARG, "peak check batch: a check takes 1 to %d hit maps", kPeakCheckMaps);
+        total_maps += m;
+        if (m > max_maps) max_maps = m;
+    }
     OpmContext* c;
-    OpmStatus s = check_same_ctx(maps, n_checks, &c);
+    OpmStatus s = check_same_ctx(maps, (int32_t)total_maps, &c);
     if (s) return s;
     if (!acc_dev || !maps_dev || !results_dev || nx < 2 || ny < 2 || nx * ny * sizeof(double) > 160 * 1024 || n_checks > 65535)
         return fail(OPM_ERR_ARG, "peak check batch: bad arguments (maps up to 160 KB, at most 65535 checks)");
@@ -2517,16 +2528,21 @@ static OpmStatus peak_check_batch_impl(OpmHitMap* const* maps, int32_t n_checks,
     PeakCheckJob* const d_list = c->d_jobs + (size_t)ring * c->jobs_cap;
     const size_t map_stride = (nx * ny + 7) / 8 * 8;
     uint64_t max_n = 0;
+    int64_t next_map = 0;
     for (int k = 0; k < n_checks; ++k) {
         if (!results_dev[k]) return fail(OPM_ERR_ARG, "peak check batch: NULL result slot");
         PeakCheckJob& j = h_list[k];
-        j.H = maps[k]->v; j.n = maps[k]->len;
+        memset(&j, 0, sizeof j);
+        j.n_maps = maps_per_check ? maps_per_check[k] : 1;
+        for (int m = 0; m < j.n_maps; ++m, ++next_map) {
+            j.H[m] = maps[next_map]->v; j.n[m] = maps[next_map]->len;
+            if (j.n[m] > max_n) max_n = j.n[m];
+        }
         const int64_t f = bounce_filters ? bounce_filters[k] : OPM_BOUNCE_OF_LAST_LAUNCH;
         if (f == OPM_BOUNCE_OF_LAST_LAUNCH) j.bounce_filter = -(long long)(uintptr_t)(reinterpret_cast<unsigned long long*>(results_dev[k]) + 7);
         else if (f < -1) return fail(OPM_ERR_ARG, "bad bounce filter");
         else j.bounce_filter = f;
         j.acc = (PeakCheckAcc*)acc_dev + k; j.result = results_dev[k]; j.map = maps_dev + (size_t)k * map_stride;
-        if (j.n > max_n) max_n = j.n;
     }
     s = flush_pending_keys(c);
     if (s) return s;
@@ -2539,9 +2555,12 @@ static OpmStatus peak_check_batch_impl(OpmHitMap* const* maps, int32_t n_checks,
         c->side_busy = true;
     }
     CU(cudaMemcpyAsync(d_list, h_list, sizeof(PeakCheckJob) * n_checks, cudaMemcpyHostToDevice, st));
-    KL(k_peakcheck_batch(d_list, n_checks, max_n, nx, ny, c->sms, st));
+    int active[kPeakCheckMaps] = {};
+    for (int k = 0; k < n_checks; ++k)
+        for (int m = 0; m < h_list[k].n_maps; ++m) active[m]++;
+    KL(k_peakcheck_batch(d_list, n_checks, max_maps, active, max_n, nx, ny, c->sms, st));
     CU(cudaEventRecord(c->jobs_ev[ring], st));  // both lists of this slot are free once the batch's last kernel has run
-    c->launches += 3;
+    c->launches += 2 * max_maps + 1;
     return OPM_OK;
 }
 extern "C" OpmStatus opm_fluence_peak_total_async(OpmContext* c, const double* map_dev, uint64_t nx, uint64_t ny, const double* range_dev,

@@ -853,21 +853,41 @@ __global__ void __launch_bounds__(1024) peakcheck_peak_kernel(const double* __re
 // control flow and the hit maps stay): blockIdx.y (bbox, splat) / blockIdx.x (peak) picks the check, every check has its own
 // accumulator, map and result slot; the bounce level of check k is the key word of its result slot (captured right after the
 // bundle's launch).  Three launches for up to a few hundred checks instead of three latency-bound launches each.
-__global__ void __launch_bounds__(256) peakcheck_bbox_batch_kernel(const PeakCheckJob* __restrict__ jobs, uint64_t bins) {
-    const PeakCheckJob j = jobs[blockIdx.y];
-    peakcheck_bbox_body(j.H, j.n, j.bounce_filter, j.acc, j.result, j.map, bins, 1, 1);
+// `mi`: which of the check's hit maps this launch takes (a batch runs max(n_maps) bounding-box launches, then as many splats: the
+// first bounding-box launch zero-fills the map, a check's last one finalises its range, every splat adds to the map)
+__global__ void __launch_bounds__(256) peakcheck_bbox_batch_kernel(const PeakCheckJob* __restrict__ jobs, uint64_t bins, int mi) {
+    const PeakCheckJob* j = jobs + blockIdx.y;
+    const int n_maps = j->n_maps;
+    if (mi >= n_maps) return;
+    const DevHits H = j->H[mi];  // by value: the body's loops must not go back to the job list for the array pointers
+    const uint64_t n = j->n[mi];
+    const long long filter = j->bounce_filter;
+    PeakCheckAcc* const acc = j->acc;
+    double* const result = j->result;
+    double* const map = j->map;
+    peakcheck_bbox_body(H, n, filter, acc, result, map, bins, mi == 0, mi == n_maps - 1);
 }
 template <int BLOCK, int MIN_CTAS, int UNROLL, bool FASTDIV>
 __global__ void __launch_bounds__(BLOCK, MIN_CTAS) binning_fixed_batch_kernel(const PeakCheckJob* __restrict__ jobs, unsigned long long nx,
-                                                                              unsigned long long ny) {
-    const PeakCheckJob j = jobs[blockIdx.y];
-    if (j.n == 0) return;  // a check without recorded slots has no splat (its range is empty)
-    binning_smem_fixed_body<BLOCK, UNROLL, FASTDIV>(j.H, j.n, j.bounce_filter, nx, ny, j.result, j.map,
-                                                    reinterpret_cast<unsigned*>(j.result + 6));
+                                                                              unsigned long long ny, int mi) {
+    const PeakCheckJob* j = jobs + blockIdx.y;
+    if (mi >= j->n_maps || j->n[mi] == 0) return;  // a hit map without recorded slots has no splat
+    // the check's arguments staged in shared memory: at 32 registers per thread (two CTAs of 1024 threads per SM) five array pointers
+    // held by value are spilled and reloaded from local memory in the splat loop; the single-check kernel has them in the constant bank
+    __shared__ DevHits sH;
+    __shared__ uint64_t sn;
+    __shared__ long long sfilter;
+    __shared__ double* sresult;
+    __shared__ double* smap;
+    if (threadIdx.x == 0) { sH = j->H[mi]; sn = j->n[mi]; sfilter = j->bounce_filter; sresult = j->result; smap = j->map; }
+    __syncthreads();
+    binning_smem_fixed_body<BLOCK, UNROLL, FASTDIV>(sH, sn, sfilter, nx, ny, sresult, smap, reinterpret_cast<unsigned*>(sresult + 6));
 }
 __global__ void __launch_bounds__(1024) peakcheck_peak_batch_kernel(const PeakCheckJob* __restrict__ jobs, uint64_t nx, uint64_t ny) {
-    const PeakCheckJob j = jobs[blockIdx.x];
-    peakcheck_peak_body(j.map, nx, ny, reinterpret_cast<const unsigned long long*>(j.result) + 7, j.result);
+    const PeakCheckJob* j = jobs + blockIdx.x;
+    double* const result = j->result;
+    const double* const map = j->map;
+    peakcheck_peak_body(map, nx, ny, reinterpret_cast<const unsigned long long*>(result) + 7, result);
 }
 __global__ void peakcheck_acc_init_kernel(PeakCheckAcc* acc, uint64_t n) {
     for (uint64_t k = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; k < n; k += (uint64_t)gridDim.x * blockDim.x) {
@@ -1247,19 +1267,31 @@ int k_peakcheck_bbox(DevHits H, uint64_t n, long long bounce_filter, PeakCheckAc
 }
 // n_jobs checks in three launches; the CTAs of a launch are shared out among the checks (a few waves in total: the splat's
 // CTA-private map is flushed once per CTA, so a check gets no more CTAs than keep the SMs busy)
-int k_peakcheck_batch(const PeakCheckJob* d_jobs, int n_jobs, uint64_t max_n, uint64_t nx, uint64_t ny, int sms, void* stream) {
+// active[mi]: checks that have a hit map number mi (the others' CTAs of that launch return at once, so the launch's CTAs are shared
+// out among the active ones: a second-map launch with two active checks gives each of them half the GPU, not a sixteenth)
+int k_peakcheck_batch(const PeakCheckJob* d_jobs, int n_jobs, int max_maps, const int* active, uint64_t max_n, uint64_t nx, uint64_t ny, int sms,
+                      void* stream) {
     if (n_jobs <= 0) return 0;
+    if (max_maps < 1 || max_maps > kPeakCheckMaps) return (int)cudaErrorInvalidValue;
     const uint64_t bins = nx * ny;
     const size_t bytes = (size_t)bins * sizeof(double);
     if (bytes > 160 * 1024 || n_jobs > 65535) return (int)cudaErrorInvalidValue;
-    auto share = [&](int total, int most) { int g = (total + n_jobs - 1) / n_jobs; return g < 1 ? 1 : (g > most ? most : g); };
-    const int g_bbox = share(sms * 8, grid_for(max_n, 256 * 4, sms * 8));
-    peakcheck_bbox_batch_kernel<<<dim3(g_bbox, n_jobs), 256, 0, ST>>>(d_jobs, bins);
+    auto share = [&](int total, int most, int among) {
+        if (among < 1) among = 1;
+        int g = (total + among - 1) / among;
+        return g < 1 ? 1 : (g > most ? most : g);
+    };
+    for (int mi = 0; mi < max_maps; ++mi) {
+        const int g_bbox = share(sms * 8, grid_for(max_n, 256 * 4, sms * 8), active ? active[mi] : n_jobs);
+        peakcheck_bbox_batch_kernel<<<dim3(g_bbox, n_jobs), 256, 0, ST>>>(d_jobs, bins, mi);
+    }
     const int ctas = (2 * (bytes + 1024) <= 227 * 1024) ? 2 : 1;
-    const int g_bin = share(sms * ctas * 2, grid_for(max_n, 1024, sms * ctas));
     cudaError_t e = cudaFuncSetAttribute(binning_fixed_batch_kernel<1024, 2, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
     if (e != cudaSuccess) return (int)e;
-    binning_fixed_batch_kernel<1024, 2, 2, true><<<dim3(g_bin, n_jobs), 1024, bytes, ST>>>(d_jobs, nx, ny);
+    for (int mi = 0; mi < max_maps; ++mi) {
+        const int g_bin = share(sms * ctas * 2, grid_for(max_n, 1024, sms * ctas), active ? active[mi] : n_jobs);
+        binning_fixed_batch_kernel<1024, 2, 2, true><<<dim3(g_bin, n_jobs), 1024, bytes, ST>>>(d_jobs, nx, ny, mi);
+    }
     peakcheck_peak_batch_kernel<<<n_jobs, 1024, 0, ST>>>(d_jobs, nx, ny);
     return (int)cudaGetLastError();
 }

@@ -61,8 +61,11 @@ int k_peakcheck_bbox(DevHits H, uint64_t n, long long bounce_filter, PeakCheckAc
 int k_peakcheck_peak(const double* map, uint64_t nx, uint64_t ny, const unsigned long long* first_inv, double* result, void* stream);
 // one deferred peak check: hit map, the bounce filter (>= 0, -1, or the negated address of the key word), its accumulator,
 // result slot (range 4 | peak | total | status | key) and map
-struct PeakCheckJob { DevHits H; uint64_t n; long long bounce_filter; PeakCheckAcc* acc; double* result; double* map; };
-int k_peakcheck_batch(const PeakCheckJob* d_jobs, int n_jobs, uint64_t max_n, uint64_t nx, uint64_t ny, int sms, void* stream);
+// (a check may sum several hit maps: the same bundle id met the surface more than once -- HitMap::get_rays_hit_map(bounce, uuid))
+constexpr int kPeakCheckMaps = 4;
+struct PeakCheckJob { DevHits H[kPeakCheckMaps]; uint64_t n[kPeakCheckMaps]; int n_maps, _pad; long long bounce_filter; PeakCheckAcc* acc; double* result; double* map; };
+int k_peakcheck_batch(const PeakCheckJob* d_jobs, int n_jobs, int max_maps, const int* active, uint64_t max_n, uint64_t nx, uint64_t ny, int sms,
+                      void* stream);
 int k_binning(DevHits H, uint64_t n, long long bounce_filter, uint64_t nx, uint64_t ny, const double* range_dev, double* map,
               unsigned* status, int sms, void* stream);
 int k_peak_total(const double* map, uint64_t nx, uint64_t ny, const double* range_dev, PeakAccum* acc, double* out2_dev, int sms, void* stream);

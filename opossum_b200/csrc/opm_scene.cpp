@@ -93,8 +93,9 @@ struct OpmScene {
     void* gf_vor_map = nullptr;  // 101 x 101 map + the bounce-level key of a Voronoi LIDT check
     std::vector<GfCheck> gf_pending;
     void* gf_batch_mem = nullptr;               // maps and accumulators of the deferred checks (opm_scene_gf.inc)
-    std::vector<OpmHitMap*> gf_batch_maps;      // deferred checks not launched yet: hit map ...
-    std::vector<double*> gf_batch_slots;        // ... and result slot
+    std::vector<OpmHitMap*> gf_batch_maps;      // deferred checks not launched yet: their hit maps (flat) ...
+    std::vector<int32_t> gf_batch_counts;       // ... how many of them each check takes ...
+    std::vector<double*> gf_batch_slots;        // ... and the checks' result slots
 };
 
 namespace {

@@ -225,16 +225,21 @@ def test_peak_checks_in_a_batch_equal_the_checks_one_at_a_time_and_the_oracle(ct
             hm.upload(x, y, e, bounce=b)
         maps.append(hm)
         data.append((x, y, e, b))
-    k = len(maps)
+    # a sixth check sums TWO hit maps (the same bundle id met the surface twice): maps 0 and 1 at bounce level 1
+    groups = [[i] for i in range(len(maps))] + [[0, 1]]
+    levels = levels + [1]
+    k = len(groups)
     acc = ctx.device_alloc(64 * k)
     assert F.lib().opm_fluence_peak_check_acc_init(ctx.h, C.c_void_p(acc), k) == 0
     d_maps = ctx.device_alloc(pad * 8 * k)
     d_res = ctx.device_alloc(64 * k)
     ctx.device_memset(d_res, 0, 64 * k)
-    arr = (C.c_void_p * k)(*[m.h for m in maps])
+    flat = [maps[i].h for g in groups for i in g]
+    arr = (C.c_void_p * len(flat))(*flat)
+    per = (C.c_int32 * k)(*[len(g) for g in groups])
     slots = (C.c_void_p * k)(*[d_res + 64 * i for i in range(k)])
     filt = (C.c_int64 * k)(*levels)
-    assert F.lib().opm_fluence_peak_check_batch_async(arr, k, filt, N, N, C.c_void_p(acc), C.c_void_p(d_maps), slots) == 0
+    assert F.lib().opm_fluence_peak_check_batch_async(arr, per, k, filt, N, N, C.c_void_p(acc), C.c_void_p(d_maps), slots) == 0
     batch = np.zeros((k, 8))
     ctx.to_host(d_res, batch)
     # one at a time
@@ -242,13 +247,13 @@ def test_peak_checks_in_a_batch_equal_the_checks_one_at_a_time_and_the_oracle(ct
     assert F.lib().opm_fluence_peak_check_acc_init(ctx.h, C.c_void_p(acc1), 1) == 0
     for i in range(k):
         ctx.device_memset(res1, 0, 64)
-        one = (C.c_void_p * 1)(maps[i].h)
-        assert F.lib().opm_fluence_peak_check_async(one, 1, levels[i], N, N, C.c_void_p(acc1), C.c_void_p(map1), C.c_void_p(res1)) == 0
+        one = (C.c_void_p * len(groups[i]))(*[maps[j].h for j in groups[i]])
+        assert F.lib().opm_fluence_peak_check_async(one, len(groups[i]), levels[i], N, N, C.c_void_p(acc1), C.c_void_p(map1), C.c_void_p(res1)) == 0
         single = np.zeros(8)
         ctx.to_host(res1, single)
         assert np.array_equal(batch[i, :4], single[:4]), i                      # the range: bit for bit
         assert batch[i, 6:7].view(np.uint32)[0] == single[6:7].view(np.uint32)[0], i
-        x, y, e, b = data[i]
+        x, y, e, b = (np.concatenate([data[j][f] for j in groups[i]]) for f in range(4))
         sel = (e >= 0.0) & (b == levels[i]) if len(e) else np.zeros(0, dtype=bool)
         if not sel.any():
             assert np.all(np.isneginf(batch[i, :4])), i                         # get_rays_hit_map(bounce, uuid) == None
