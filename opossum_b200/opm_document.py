@@ -18,8 +18,8 @@ variants `Name(..)`, strings, numbers, booleans, `Some`/`None`), then the mappin
   position_distributions/, energy_distributions/, spectral_distribution/.
 uom quantities are serialised as plain numbers in SI base units, nalgebra points as tuples, `Isometry` as its transform
 (rotation quaternion (i, j, k, w) + translation).  Scope: a chain of nodes with at most side chains behind beam splitters, one
-source, the node types of `include/opossum_b200_scene.h`; nested groups, reference nodes, `Raw` / `PointSrc` light data and
-spectrum-valued filters are rejected with `OpmDocumentError`.  Pinned by the reference's fixture files
+source, the node types of `include/opossum_b200_scene.h`; nested `NodeGroup`s are taken apart (`_flatten_graph`); inverted nodes and
+groups, reference nodes, `Raw` / `PointSrc` light data and spectrum-valued filters are rejected with `OpmDocumentError`.  Pinned by the reference's fixture files
 (opossum/files_for_testing/opm/, read by tests/test_opm_document.py where they lie).
 """
 from __future__ import annotations
@@ -579,6 +579,71 @@ class OpmDocument:
         return sc, sd, index
 
 
+def _port_map(v) -> dict:
+    """PortMap (port_map.rs:12): a newtype around {external port name: (node uuid, internal port name)}"""
+    if v is None:
+        return {}
+    m = v[0] if isinstance(v, tuple) and len(v) == 1 else v
+    if not isinstance(m, dict):
+        raise OpmDocumentError("port map of a group is not a map")
+    return {str(k): (str(t[0]), str(t[1])) for k, t in m.items()}
+
+
+def _flatten_graph(graph: dict, doc: "OpmDocument"):
+    """The nodes and edges of an OpticGraph (nodes/node_group/optic_graph.rs:1040-1071) into the document's flat lists.  A nested
+    NodeGroup (an entry with a `graph` of its own, optic_ref.rs:76-99) is taken apart: its nodes join the list, and an edge that ends
+    at one of its external ports is re-attached to the inner node and port the group's input_map / output_map names -- which is what
+    the reference's analysis does with the light that arrives there (node_group/analysis_raytrace.rs:29-91: `get_incoming` hands the
+    external port's light to the mapped inner node, the mapped output ports carry the sub-graph's results out) and what its node
+    positioning does with the edge's distance (`set_external_distances`, :96-98; optic_graph.rs:878-926: the inner node is placed that
+    distance behind the predecessor OUTSIDE the group).  The group node's own isometry places nothing.  Deviation: the reference starts
+    every group's positioning with the up direction +y (:102), the flat scene carries the up direction on from the outside; the two
+    differ only when the beam has been turned about its own axis before it enters the group.  Refused: inverted groups, reference
+    nodes."""
+    groups: dict[str, tuple[dict, dict]] = {}
+
+    def walk(g: dict):
+        for entry in g.get("nodes") or []:
+            a = entry.get("attributes") or entry.get("node_attr") or {}
+            t = a.get("node_type")
+            if t == "reference":
+                raise OpmDocumentError("node type 'reference' (a node that stands for another node) is not supported")
+            if t == "group":
+                if bool(a.get("inverted", False)):
+                    raise OpmDocumentError(f"group {a.get('name', '')!r} is inverted: not supported")
+                sub = entry.get("graph")
+                if not isinstance(sub, dict):
+                    raise OpmDocumentError(f"group {a.get('name', '')!r} has no graph")
+                groups[str(a["uuid"])] = (_port_map(sub.get("input_map")), _port_map(sub.get("output_map")))
+                walk(sub)
+                continue
+            doc.nodes.append(_node(entry))
+        for e in g.get("edges") or []:
+            doc.edges.append((str(e[0]), str(e[1]), str(e[2]), str(e[3]), float(e[4])))
+
+    walk(graph)
+    if not groups:
+        return
+    resolved = []
+    for (s, sp, t, tp, d) in doc.edges:
+        for _ in range(64):  # a port of a group may itself be mapped to a port of a group nested in it
+            if s not in groups:
+                break
+            if sp not in groups[s][1]:
+                raise OpmDocumentError(f"edge leaves a group at port {sp!r}, which its output map does not name")
+            s, sp = groups[s][1][sp]
+        for _ in range(64):
+            if t not in groups:
+                break
+            if tp not in groups[t][0]:
+                raise OpmDocumentError(f"edge enters a group at port {tp!r}, which its input map does not name")
+            t, tp = groups[t][0][tp]
+        if s in groups or t in groups:
+            raise OpmDocumentError("port maps of nested groups do not end at a node")
+        resolved.append((s, sp, t, tp, d))
+    doc.edges[:] = resolved
+
+
 def loads_opm(text: str) -> OpmDocument:
     """OpmDocument::from_string (opm_document.rs:116-121)"""
     try:
@@ -591,13 +656,7 @@ def loads_opm(text: str) -> OpmDocument:
     attr = scenery.get("node_attr") or {}
     graph = scenery.get("graph") or {}
     doc = OpmDocument(version=str(root["opm_file_version"]), name=attr.get("name", ""))
-    for entry in graph.get("nodes") or []:
-        a = entry.get("attributes") or entry.get("node_attr") or {}
-        if a.get("node_type") in ("group", "reference"):
-            raise OpmDocumentError(f"node type {a.get('node_type')!r} (nested groups, references) is not supported")
-        doc.nodes.append(_node(entry))
-    for e in graph.get("edges") or []:
-        doc.edges.append((e[0], e[1], e[2], e[3], float(e[4])))
+    _flatten_graph(graph, doc)
     g = root.get("global") or {}
     if "ambient_refr_index" in g:
         doc.ambient = _index(g["ambient_refr_index"])

@@ -5,6 +5,7 @@ optic_ref.opm, incorrect_opm.opm, empty.opm, what the tests of opm_document.rs l
 reference is absent) -- plus a hand-written document (tests/golden/opm/) that follows the same serde rules for the node types
 the fixtures do not contain."""
 import math
+import re
 from pathlib import Path
 
 import pytest
@@ -85,6 +86,62 @@ def test_unsupported_content_is_refused():
         D.loads_opm(text.replace('name: "f",', 'name: "f", ').replace("inverted: false,\n                    ),\n                ),\n                (\n                    attributes: (\n                        node_type: \"spot diagram\"", "inverted: true,\n                    ),\n                ),\n                (\n                    attributes: (\n                        node_type: \"spot diagram\""))
     with pytest.raises(D.OpmDocumentError):
         D.loads_opm(text.replace('"input_1", 0.09', '"input_2", 0.09')).ordered()
+
+
+def _nested_variant(text: str, inner_again: bool = False) -> str:
+    """the handwritten document with the ideal filter and the spot diagram moved into a nested NodeGroup (optic_ref.rs:76-99: an
+    entry with `attributes` and a `graph` of its own), external ports "in" / "out" mapped onto them; with `inner_again` the filter
+    sits in a group inside that group"""
+    lines = text.split("\n")
+    starts = [i for i, l in enumerate(lines) if l == "                ("]
+    ends = [i for i, l in enumerate(lines) if l == "                ),"]
+    assert len(starts) == len(ends) == 8
+    f, spot = (lines[starts[k]: ends[k] + 1] for k in (4, 5))
+    U = "00000000-0000-4000-8000-0000000000"
+
+    def group(uuid, name, nodes, edges, imap, omap):
+        head = ['(', '    attributes: (', '        node_type: "group",', f'        name: "{name}",', '        ports: (inputs: {}, outputs: {}),',
+                f'        uuid: "{uuid}",', '        lidt: 10000.0,', '        props: {},', '        inverted: false,', '    ),', '    graph: (',
+                '        nodes: [']
+        tail = ['        ],', '        edges: [' + ", ".join(edges) + '],', '        input_map: ({' + imap + '}),', '        output_map: ({' + omap + '}),',
+                '    ),', '),']
+        return head + ["        " + l.strip() for l in nodes] + tail
+
+    f_id, spot_id = U + "05", U + "06"
+    if inner_again:
+        f_part = group(U + "bb", "innermost", f, [], f'"a": ("{f_id}", "input_1")', f'"b": ("{f_id}", "output_1")')
+        first, first_in, first_out = U + "bb", "a", "b"
+    else:
+        f_part, first, first_in, first_out = f, f_id, "input_1", "output_1"
+    g = group(U + "aa", "inner", f_part + spot, [f'("{first}", "{first_out}", "{spot_id}", "input_1", 0.08)'],
+              f'"in": ("{first}", "{first_in}")', f'"out": ("{spot_id}", "output_1")')
+    out = lines[: starts[4]] + ["                " + l for l in g] + lines[ends[5] + 1:]
+    t = "\n".join(out)
+    t = t.replace(f'"out1_trans1_refl2", "{f_id}", "input_1", 0.05', f'"out1_trans1_refl2", "{U}aa", "in", 0.05')
+    t = t.replace(f'                ("{f_id}", "output_1", "{spot_id}", "input_1", 0.08),\n', "")
+    t = t.replace(f'("{spot_id}", "output_1", "{U}07", "input_1", 0.01)', f'("{U}aa", "out", "{U}07", "input_1", 0.01)')
+    return t
+
+
+def test_nested_groups_are_taken_apart():
+    """a NodeGroup inside the scenery (and one inside that): the flattened document is the flat one -- same nodes, same chain, same
+    distances; inverted groups and unmapped ports are refused"""
+    text = (OPM / "folded_chain_handwritten.opm").read_text()
+    flat = D.loads_opm(text)
+    want = [(n.name, p, port, d) for n, p, port, d in flat.ordered()[0]]
+    for again in (False, True):
+        nested_text = _nested_variant(text, again)
+        assert nested_text.count('node_type: "group"') == (3 if again else 2)
+        doc = D.loads_opm(nested_text)
+        assert sorted(n.uuid for n in doc.nodes) == sorted(n.uuid for n in flat.nodes)
+        assert [(n.name, p, port, d) for n, p, port, d in doc.ordered()[0]] == want
+        by, by_flat = {n.uuid: n for n in doc.nodes}, {n.uuid: n for n in flat.nodes}
+        assert all(by[u] == by_flat[u] for u in by)
+    nested_text = _nested_variant(text)
+    with pytest.raises(D.OpmDocumentError, match="input map"):
+        D.loads_opm(nested_text.replace('"in": (', '"elsewhere": ('))
+    with pytest.raises(D.OpmDocumentError, match="inverted"):
+        D.loads_opm(re.sub(r'(name: "inner",.*?props: \{\},\s*inverted: )false', r'\1true', nested_text, count=1, flags=re.S))
 
 
 PORT = '(anchor_point_iso: (transform: (rotation: (0.0, 0.0, 0.0, 1.0), translation: (0.0, 0.0, 0.0))), %s coating: %s, lidt: 20000.0)'
