@@ -603,6 +603,11 @@ double opm_spectrum_average_resolution(const double* lambda_um, uint64_t n);
 OpmStatus opm_spectrum_merge(const double* lambda1_um, const double* values1, uint64_t n1, const double* lambda2_um, const double* values2,
                              uint64_t n2, double* lambda_um, double* values, uint64_t cap, uint64_t* n_out);
 OpmStatus opm_spectrum_from_csv(const char* path, double* lambda_um, double* values, uint64_t cap, uint64_t* n_out);
+/* generate_filter_spectrum (spectrum_helper.rs:124-190): ideal short- / long-pass transmission curves (step, or a sine of the given
+ * width around the cut-off) on the slots of Spectrum::new(start, end, resolution) */
+enum { OPM_FILTER_SHORT_PASS_STEP = 0, OPM_FILTER_SHORT_PASS_SMOOTH = 1, OPM_FILTER_LONG_PASS_STEP = 2, OPM_FILTER_LONG_PASS_SMOOTH = 3 };
+OpmStatus opm_spectrum_generate_filter(int32_t kind, double start_m, double end_m, double resolution_m, double cut_off_m, double width_m,
+                                       double* lambda_um, double* values, uint64_t cap, uint64_t* n_out);
 /* smallest / largest wavelength and number of the valid rays (multi-GPU: reduce with min / max / sum, then pass the common
  * range to opm_rays_to_spectrum on every rank and sum the values) */
 OpmStatus opm_rays_wavelength_range(const OpmRays* rays, double min_max_m[2], uint64_t* n_valid);

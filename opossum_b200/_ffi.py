@@ -230,7 +230,7 @@ EXPORTS = [
     "opm_spectrum_create", "opm_spectrum_destroy", "opm_spectrum_total_energy", "opm_spectrum_center_wavelength", "opm_spectrum_get_value",
     "opm_spectrum_new", "opm_spectrum_add_single_peak", "opm_spectrum_from_laser_lines", "opm_spectrum_add_lorentzian_peak",
     "opm_spectrum_scale_vertical", "opm_spectrum_resample", "opm_spectrum_combine", "opm_spectrum_average_resolution", "opm_spectrum_merge",
-    "opm_spectrum_from_csv",
+    "opm_spectrum_from_csv", "opm_spectrum_generate_filter",
     "opm_rays_wavelength_range", "opm_rays_to_spectrum", "opm_rays_filter_energy_spectrum", "opm_rays_split_spectrum",
     "opm_rays_wavefront_error", "opm_readout_combine_ranges_sums", "opm_readout_combine_maps_radii", "opm_peer_group_create", "opm_peer_group_connect", "opm_peer_group_destroy",
     "opm_peer_allgather_async", "opm_peer_fluence_report_async", "opm_peer_fluence_gather_map", "opm_peer_group_phase_times", "opm_measure_fp64_peak", "opm_device_alloc",
@@ -343,6 +343,7 @@ def lib() -> C.CDLL:
         "opm_spectrum_average_resolution": (C.c_double, [dp, u64]),
         "opm_spectrum_merge": (i32, [dp, dp, u64, dp, dp, u64, dp, dp, u64, C.POINTER(u64)]),
         "opm_spectrum_from_csv": (i32, [C.c_char_p, dp, dp, u64, C.POINTER(u64)]),
+        "opm_spectrum_generate_filter": (i32, [i32] + [C.c_double] * 5 + [dp, dp, u64, C.POINTER(u64)]),
         "opm_rays_wavelength_range": (i32, [vp, dp, C.POINTER(u64)]),
         "opm_rays_to_spectrum": (i32, [vp, C.c_double, dp, dp, dp, u64, C.POINTER(u64)]),
         "opm_rays_filter_energy_spectrum": (i32, [vp, vp]),

@@ -525,6 +525,15 @@ def spectrum_merge(l1, v1, l2, v2):
     return _sp_sized(lambda l, v, cap, n: F.lib().opm_spectrum_merge(ap, bp, len(a), cp, dpp, len(c), l, v, cap, n))
 
 
+FILTER_KINDS = {"short_pass_step": 0, "short_pass_smooth": 1, "long_pass_step": 2, "long_pass_smooth": 3}
+
+
+def spectrum_generate_filter(kind: str, start: float, end: float, resolution: float, cut_off: float, width: float = 0.0):
+    """generate_filter_spectrum (spectrum_helper.rs:124-190): (slots [um], transmission)"""
+    k = FILTER_KINDS[kind]
+    return _sp_sized(lambda l, v, cap, n: F.lib().opm_spectrum_generate_filter(k, start, end, resolution, cut_off, width, l, v, cap, n))
+
+
 def spectrum_from_csv(path):
     """Spectrum::from_csv (spectrum.rs:89-117)"""
     return _sp_sized(lambda l, v, cap, n: F.lib().opm_spectrum_from_csv(str(path).encode(), l, v, cap, n))

@@ -230,6 +230,37 @@ extern "C" OpmStatus opm_spectrum_merge(const double* l1, const double* v1, uint
     return opm_spectrum_combine(OPM_SPECTRUM_ADD, lambda_um, values, n, l2, v2, n2, nullptr);
 }
 
+// generate_filter_spectrum (spectrum_helper.rs:124-190): the transmission curve of an ideal short- / long-pass filter on the slots of
+// Spectrum::new(range, resolution) -- what a caller hands to opm_spectrum_create for an IdealFilter with FilterType::Spectrum.  A cut-off
+// outside the range is a warning in the reference, not an error.  The smooth forms follow the reference's code: full transmission /
+// absorption up to cut_off - width / 2, the sine in between, and the other end at cut_off + width (:156, :182).
+extern "C" OpmStatus opm_spectrum_generate_filter(int32_t kind, double start_m, double end_m, double resolution_m, double cut_off_m,
+                                                  double width_m, double* lambda_um, double* values, uint64_t cap, uint64_t* n_out) {
+    uint64_t n = 0;
+    if (OpmStatus st = opm_spectrum_new(start_m, end_m, resolution_m, lambda_um, values, cap, &n)) return st;
+    if (n_out) *n_out = n;
+    if (kind < OPM_FILTER_SHORT_PASS_STEP || kind > OPM_FILTER_LONG_PASS_SMOOTH) return host_fail(OPM_ERR_ARG, "unknown filter type");
+    const bool smooth = kind == OPM_FILTER_SHORT_PASS_SMOOTH || kind == OPM_FILTER_LONG_PASS_SMOOTH;
+    if (smooth && (width_m == 0.0 || !std::isnormal(width_m) || std::signbit(width_m)))
+        return host_fail(OPM_ERR_SPECTRUM, "width must be positive and finite");
+    if (!lambda_um) return OPM_OK;
+    const double cut = cut_off_m * kPerMicro, width = width_m * kPerMicro;
+    const double pi = 3.14159265358979323846264338327950288;
+    const bool short_pass = kind == OPM_FILTER_SHORT_PASS_STEP || kind == OPM_FILTER_SHORT_PASS_SMOOTH;
+    const double pass = 1.0, block = 0.0;
+    for (uint64_t i = 0; i < n; ++i) {
+        const double l = lambda_um[i];
+        if (!smooth) { values[i] = (short_pass ? l < cut : l > cut) ? pass : block; continue; }
+        if (l <= cut - width / 2.0) values[i] = short_pass ? pass : block;
+        else if (l >= cut + width) values[i] = short_pass ? block : pass;
+        else {
+            const double s = std::sin(pi / width * (l - cut));
+            values[i] = std::fma(0.5, short_pass ? -s : s, 0.5);
+        }
+    }
+    return OPM_OK;
+}
+
 // Spectrum::from_csv (:89-117): records of `wavelength in nm ; value in percent` (a Thorlabs transmission export).  The csv crate as
 // the reference configures it: no header row, ';', empty lines skipped, every record as long as the first one; a field must parse
 // as a whole (Rust's str::parse::<f64>: no blanks, no hexadecimal).

@@ -241,6 +241,8 @@ double orc_spectrum_average_resolution(const double* lambda, uint64_t n);       
 int orc_spectrum_merge(const double* l1, const double* d1, uint64_t n1, const double* l2, const double* d2, uint64_t n2, double* lambda,
                        double* data, uint64_t cap, uint64_t* n_out);                                                          /* :622-650 */
 int orc_spectrum_from_csv(const char* path, double* lambda, double* data, uint64_t cap, uint64_t* n_out);                     /* :89-117 */
+int orc_spectrum_generate_filter(int kind, double start_m, double end_m, double res_m, double cut_off_m, double width_m, double* lambda,
+                                 double* data, uint64_t cap, uint64_t* n_out);                                                /* spectrum_helper.rs:124-190 */
 int orc_rays_filter_energy_spectrum(OrcRay* rays, uint64_t n, const double* lambda, const double* data, uint64_t ns);         /* ray.rs:712-721 */
 int orc_rays_split_spectrum(OrcRay* rays, uint64_t n, const double* lambda, const double* data, uint64_t ns, OrcRay* split_out); /* ray.rs:752-772 */
 int orc_rays_wavefront_error(const OrcRay* rays, uint64_t n, double wavelength_m, const OrcIsometry* monitor_iso, double* xyw,

@@ -219,3 +219,37 @@ int orc_spectrum_from_csv(const char* path, double* lambda, double* data, uint64
     if (lambda && n > cap) return ORC_ERR_ARG;
     return ORC_OK;
 }
+
+/* spectrum_helper.rs:124-190 generate_filter_spectrum: kind 0 ShortPassStep, 1 ShortPassSmooth, 2 LongPassStep, 3 LongPassSmooth.
+ * lambda == NULL: only the number of slots.  (The smooth forms reach 0 / 1 at cut_off + width, not + width / 2: the reference's
+ * code, :156 and :182, not its doc comment.) */
+int orc_spectrum_generate_filter(int kind, double start_m, double end_m, double res_m, double cut_off_m, double width_m, double* lambda,
+                                 double* data, uint64_t cap, uint64_t* n_out) {
+    uint64_t n = 0;
+    int rc = orc_spectrum_new(start_m, end_m, res_m, lambda, data, cap, &n);
+    if (n_out) *n_out = n;
+    if (rc) return rc;
+    if (kind < 0 || kind > 3) return ORC_ERR_ARG;
+    if (kind == 1 || kind == 3) { /* width.is_zero() || !width.is_normal() || width.is_sign_negative() */
+        if (width_m == 0.0 || !isnormal(width_m) || signbit(width_m)) return ORC_ERR_SPECTRUM;
+    }
+    if (!lambda) return ORC_OK;
+    double cut = cut_off_m * 1e6, w = width_m * 1e6;
+    for (uint64_t i = 0; i < n; ++i) {
+        double l = lambda[i];
+        switch (kind) {
+            case 0: data[i] = l < cut ? 1.0 : 0.0; break;
+            case 2: data[i] = l > cut ? 1.0 : 0.0; break;
+            default: {
+                double lo = kind == 1 ? 1.0 : 0.0, hi = kind == 1 ? 0.0 : 1.0;
+                if (l <= cut - w / 2.0) data[i] = lo;
+                else if (l >= cut + w) data[i] = hi;
+                else {
+                    double angle = M_PI / w * (l - cut);
+                    data[i] = kind == 1 ? fma(0.5, -sin(angle), 0.5) : fma(0.5, sin(angle), 0.5);
+                }
+            }
+        }
+    }
+    return ORC_OK;
+}

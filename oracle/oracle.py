@@ -341,6 +341,7 @@ def lib():
     L.orc_spectrum_average_resolution.restype = C.c_double
     L.orc_spectrum_merge.argtypes = [dp, dp, C.c_uint64, dp, dp, C.c_uint64, dp, dp, C.c_uint64, u64p]
     L.orc_spectrum_from_csv.argtypes = [C.c_char_p, dp, dp, C.c_uint64, u64p]
+    L.orc_spectrum_generate_filter.argtypes = [C.c_int] + [C.c_double] * 5 + [dp, dp, C.c_uint64, u64p]
     L.orc_rays_filter_energy_spectrum.argtypes = [vp, C.c_uint64, dp, dp, C.c_uint64]
     L.orc_rays_split_spectrum.argtypes = [vp, C.c_uint64, dp, dp, C.c_uint64, vp]
     L.orc_rays_wavefront_error.argtypes = [vp, C.c_uint64, C.c_double, C.POINTER(Isometry), dp, u64p]
@@ -986,6 +987,19 @@ def spectrum_merge(l1, d1, l2, d2):
     _check(lib().orc_spectrum_merge(_dptr(l1), _dptr(d1), len(l1), _dptr(l2), _dptr(d2), len(l2), None, None, 0, C.byref(n)))
     lam, data = np.zeros(max(n.value, 1)), np.zeros(max(n.value, 1))
     _check(lib().orc_spectrum_merge(_dptr(l1), _dptr(d1), len(l1), _dptr(l2), _dptr(d2), len(l2), _dptr(lam), _dptr(data), n.value, C.byref(n)))
+    return lam[: n.value], data[: n.value]
+
+
+FILTER_KINDS = {"short_pass_step": 0, "short_pass_smooth": 1, "long_pass_step": 2, "long_pass_smooth": 3}
+
+
+def spectrum_generate_filter(kind: str, start_m, end_m, res_m, cut_off_m, width_m=0.0):
+    """generate_filter_spectrum (spectrum_helper.rs:124-190)"""
+    k = FILTER_KINDS[kind]
+    n = C.c_uint64()
+    _check(lib().orc_spectrum_generate_filter(k, start_m, end_m, res_m, cut_off_m, width_m, None, None, 0, C.byref(n)))
+    lam, data = np.zeros(max(n.value, 1)), np.zeros(max(n.value, 1))
+    _check(lib().orc_spectrum_generate_filter(k, start_m, end_m, res_m, cut_off_m, width_m, _dptr(lam), _dptr(data), n.value, C.byref(n)))
     return lam[: n.value], data[: n.value]
 
 

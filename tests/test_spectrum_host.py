@@ -27,6 +27,8 @@ class _Orc:
     average_resolution = staticmethod(orc.spectrum_average_resolution)
     merge = staticmethod(orc.spectrum_merge)
     from_csv = staticmethod(orc.spectrum_from_csv)
+    generate_filter = staticmethod(orc.spectrum_generate_filter)
+    get_value = staticmethod(orc.spectrum_get_value)
     total_energy = staticmethod(orc.spectrum_total_energy)
     error = orc.OracleError if hasattr(orc, "OracleError") else Exception
 
@@ -45,6 +47,8 @@ class _Lib:
     average_resolution = staticmethod(ob.spectrum_average_resolution)
     merge = staticmethod(ob.spectrum_merge)
     from_csv = staticmethod(ob.spectrum_from_csv)
+    generate_filter = staticmethod(ob.spectrum_generate_filter)
+    get_value = staticmethod(ob.spectrum_get_value)
     total_energy = staticmethod(ob.spectrum_total_energy)
     error = Exception
 
@@ -270,3 +274,34 @@ def test_merge_spans_both_spectra_at_the_finer_resolution():
     assert abs(ob.spectrum_total_energy(lam, val) - 2.6) < 1e-9
     lo, vo = orc.spectrum_merge(l1, v1, l2, v2)
     assert np.array_equal(lo, lam) and np.array_equal(vo, val)
+
+
+@pytest.mark.parametrize("S", IMPLS)
+def test_generate_filter_spectrum_kats(S):
+    """spectrum_helper.rs:203-366: short / long pass, step and smooth"""
+    S.generate_filter("short_pass_step", 1.0 * UM, 5.0 * UM, 1.0 * UM, 7.0 * UM)  # cut-off outside the range: a warning, not an error
+    lam, val = S.generate_filter("short_pass_step", 1.0 * UM, 5.0 * UM, 1.0 * UM, 3.0 * UM)
+    assert [S.get_value(lam, val, w * UM) for w in (1.0, 2.0, 3.0, 4.0)] == [1.0, 1.0, 0.0, 0.0]
+    lam, val = S.generate_filter("long_pass_step", 1.0 * UM, 5.0 * UM, 1.0 * UM, 3.0 * UM)
+    assert [S.get_value(lam, val, w * UM) for w in (1.0, 2.0, 3.0, 4.0)] == [0.0, 0.0, 0.0, 1.0]
+    for kind in ("short_pass_smooth", "long_pass_smooth"):
+        for bad in (0.0, -1.0 * UM):
+            with pytest.raises(S.error):
+                S.generate_filter(kind, 1.0 * UM, 5.0 * UM, 0.5 * UM, 3.0 * UM, bad)
+    lam, val = S.generate_filter("short_pass_smooth", 1.0 * UM, 5.0 * UM, 0.5 * UM, 3.0 * UM, 1.0 * UM)
+    assert [S.get_value(lam, val, w * UM) for w in (1.0, 2.0, 2.5, 3.0)] == [1.0, 1.0, 1.0, 0.5]
+    assert S.get_value(lam, val, 4.0 * UM) == 0.0 and abs(S.get_value(lam, val, 3.5 * UM)) < 1e-15  # 0.5 - 0.5 sin(pi / 2)
+    lam, val = S.generate_filter("long_pass_smooth", 1.0 * UM, 5.0 * UM, 0.5 * UM, 3.0 * UM, 1.0 * UM)
+    assert [S.get_value(lam, val, w * UM) for w in (1.0, 2.0, 2.5, 3.0)] == [0.0, 0.0, 0.0, 0.5]
+    assert S.get_value(lam, val, 4.0 * UM) == 1.0 and abs(S.get_value(lam, val, 3.5 * UM) - 1.0) < 1e-15
+
+
+def test_generate_filter_library_matches_oracle():
+    rng = np.random.default_rng(5)
+    for _ in range(100):
+        kind = list(orc.FILTER_KINDS)[int(rng.integers(0, 4))]
+        a = rng.uniform(0.3, 1.0) * UM
+        args = (a, a + rng.uniform(0.2, 2.0) * UM, rng.uniform(0.5, 30.0) * NM, rng.uniform(0.2, 3.2) * UM, rng.uniform(1.0, 400.0) * NM)
+        lo, vo = orc.spectrum_generate_filter(kind, *args)
+        ll, vl = ob.spectrum_generate_filter(kind, *args)
+        assert np.array_equal(lo, ll) and np.array_equal(vo, vl), (kind, args)
